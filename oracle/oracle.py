@@ -1,0 +1,300 @@
+"""ctypes driver for the CPU oracle (liboracle.so) -- TEST INFRASTRUCTURE ONLY.
+
+Restates, for result comparison, the reference's output path:
+  Vector.GetValue   /root/reference/pkg/chunk/vector.go:76-186
+  Value.String      /root/reference/pkg/chunk/value.go:26-70
+  Chunk.SaveToFile  /root/reference/pkg/chunk/chunk.go:196-220 (tab separated rows)
+  ORDER BY keys     /root/reference/pkg/compute/sort_encoder.go:65-81
+  LIMIT             /root/reference/pkg/compute/executor_limit.go:120-137
+"""
+import ctypes as C
+import datetime
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+CMP_EQ, CMP_NE, CMP_LT, CMP_LE, CMP_GT, CMP_GE = range(6)
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE, "liboracle.so"])
+
+
+class Dec(C.Structure):
+    _fields_ = [("coef", C.c_uint64), ("scale", C.c_int8), ("neg", C.c_uint8)]
+
+    def tuple(self):
+        return (int(self.coef), int(self.scale), int(self.neg))
+
+
+class Huge(C.Structure):
+    _fields_ = [("lower", C.c_uint64), ("upper", C.c_int64)]
+
+    def value(self):
+        return (int(self.upper) << 64) + int(self.lower)
+
+
+class Q6Result(C.Structure):
+    _fields_ = [("rows_in", C.c_int64), ("rows_selected", C.c_int64), ("sum", Dec),
+                ("has_row", C.c_int), ("exact_lo", C.c_uint64), ("exact_hi", C.c_int64),
+                ("error", C.c_int)]
+
+
+class Q1Group(C.Structure):
+    _fields_ = [("rf", C.c_uint8), ("ls", C.c_uint8), ("sum_qty", Huge),
+                ("sum_base", Dec), ("sum_disc_price", Dec), ("sum_charge", Dec),
+                ("avg_qty_sum", C.c_double), ("avg_price_sum", Dec), ("avg_disc_sum", Dec),
+                ("count", C.c_uint64), ("avg_qty", C.c_double), ("avg_price", Dec), ("avg_disc", Dec),
+                ("x_base_lo", C.c_uint64), ("x_disc_price_lo", C.c_uint64), ("x_charge_lo", C.c_uint64),
+                ("x_disc_lo", C.c_uint64), ("x_base_hi", C.c_int64), ("x_disc_price_hi", C.c_int64),
+                ("x_charge_hi", C.c_int64), ("x_disc_hi", C.c_int64), ("x_qty", C.c_int64),
+                ("first_row", C.c_int64)]
+
+
+class Q1Result(C.Structure):
+    _fields_ = [("rows_in", C.c_int64), ("rows_selected", C.c_int64), ("ngroups", C.c_int),
+                ("error", C.c_int), ("g", Q1Group * 64)]
+
+
+class Q3Group(C.Structure):
+    _fields_ = [("orderkey", C.c_int64), ("orderdate", C.c_int32), ("shippriority", C.c_int32),
+                ("revenue", Dec), ("x_rev_lo", C.c_uint64), ("x_rev_hi", C.c_int64),
+                ("first_row", C.c_int64)]
+
+
+class Q3Result(C.Structure):
+    _fields_ = [("n_cust_sel", C.c_int64), ("n_orders_sel", C.c_int64), ("n_orders_joined", C.c_int64),
+                ("n_line_sel", C.c_int64), ("n_line_joined", C.c_int64), ("ngroups", C.c_int64),
+                ("nout", C.c_int64), ("error", C.c_int)]
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        L.tg_num_orders.restype = C.c_int64
+        L.tg_num_orders.argtypes = [C.c_double]
+        L.tg_num_customers.restype = C.c_int64
+        L.tg_num_customers.argtypes = [C.c_double]
+        L.tg_count_lineitems.restype = C.c_int64
+        L.tg_count_lineitems.argtypes = [C.c_double, C.c_int64, C.c_int64]
+        L.tg_gen_orders_lineitem.restype = C.c_int64
+        L.tg_gen_orders_lineitem.argtypes = [C.c_double, C.c_int64, C.c_int64] + [C.c_void_p] * 19
+        L.tg_gen_customer.restype = None
+        L.tg_gen_customer.argtypes = [C.c_double, C.c_int64, C.c_int64] + [C.c_void_p] * 3
+        L.tg_segment_name.restype = C.c_char_p
+        L.tg_segment_name.argtypes = [C.c_int]
+        L.orc_q6.restype = None
+        L.orc_q6.argtypes = [C.c_int64] + [C.c_void_p] * 4 + [C.c_int32, C.c_int32, C.c_double, C.c_double,
+                                                             C.c_int32, C.POINTER(Q6Result)]
+        L.orc_q1.restype = None
+        L.orc_q1.argtypes = [C.c_int64] + [C.c_void_p] * 7 + [C.c_int32, C.POINTER(Q1Result)]
+        L.orc_q3.restype = None
+        L.orc_q3.argtypes = ([C.c_int64, C.c_void_p, C.c_void_p, C.c_uint8] +
+                             [C.c_int64] + [C.c_void_p] * 4 + [C.c_int32] +
+                             [C.c_int64] + [C.c_void_p] * 4 + [C.c_int32] +
+                             [C.c_void_p, C.c_int64, C.POINTER(Q3Result)])
+        L.orc_format_decimal.restype = C.c_int
+        L.orc_format_decimal.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]
+        L.orc_decimal_sortkey.restype = C.c_int
+        L.orc_decimal_sortkey.argtypes = [C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        for name in ("orc_dec_add", "orc_dec_mul", "orc_dec_quo"):
+            f = getattr(L, name)
+            f.restype = C.c_int
+            f.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int,
+                          C.POINTER(C.c_uint64), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.orc_dec_float64.restype = C.c_double
+        L.orc_dec_float64.argtypes = [C.c_uint64, C.c_int, C.c_int]
+        assert L.orc_sizeof_q1_group() == C.sizeof(Q1Group), (L.orc_sizeof_q1_group(), C.sizeof(Q1Group))
+        assert L.orc_sizeof_q1_result() == C.sizeof(Q1Result)
+        assert L.orc_sizeof_q3_group() == C.sizeof(Q3Group)
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+# ------------------------------------------------------------------ data --
+
+def days(y, m, d):
+    return (datetime.date(y, m, d) - datetime.date(1970, 1, 1)).days
+
+
+SEGMENTS = ["AUTOMOBILE", "BUILDING", "FURNITURE", "HOUSEHOLD", "MACHINERY"]
+
+LINEITEM_COLS = [("l_orderkey", np.int64), ("l_partkey", np.int32), ("l_suppkey", np.int32),
+                 ("l_linenumber", np.int32), ("l_quantity", np.int32), ("l_extendedprice", np.int64),
+                 ("l_discount", np.int64), ("l_tax", np.int64), ("l_returnflag", np.uint8),
+                 ("l_linestatus", np.uint8), ("l_shipdate", np.int32), ("l_commitdate", np.int32),
+                 ("l_receiptdate", np.int32)]
+ORDERS_COLS = [("o_orderkey", np.int64), ("o_custkey", np.int32), ("o_orderdate", np.int32),
+               ("o_shippriority", np.int32), ("o_totalprice", np.int64), ("o_orderstatus", np.uint8)]
+
+
+def gen_orders_lineitem(sf, o_lo=0, o_hi=None, lineitem_cols=None, orders_cols=None):
+    """dbgen-equivalent orders [o_lo,o_hi) and their lineitems as numpy columns."""
+    L = lib()
+    if o_hi is None:
+        o_hi = L.tg_num_orders(sf)
+    nline = L.tg_count_lineitems(sf, o_lo, o_hi)
+    want_l = set(c for c, _ in LINEITEM_COLS) if lineitem_cols is None else set(lineitem_cols)
+    want_o = set(c for c, _ in ORDERS_COLS) if orders_cols is None else set(orders_cols)
+    orders = {c: (np.empty(o_hi - o_lo, dtype=t) if c in want_o else None) for c, t in ORDERS_COLS}
+    line = {c: (np.empty(nline, dtype=t) if c in want_l else None) for c, t in LINEITEM_COLS}
+    args = [_p(orders[c]) for c, _ in ORDERS_COLS] + [_p(line[c]) for c, _ in LINEITEM_COLS]
+    n = L.tg_gen_orders_lineitem(sf, o_lo, o_hi, *args)
+    assert n == nline
+    return ({k: v for k, v in orders.items() if v is not None},
+            {k: v for k, v in line.items() if v is not None})
+
+
+def gen_customer(sf, c_lo=0, c_hi=None):
+    L = lib()
+    if c_hi is None:
+        c_hi = L.tg_num_customers(sf)
+    out = {"c_custkey": np.empty(c_hi - c_lo, np.int32), "c_mktsegment": np.empty(c_hi - c_lo, np.uint8),
+           "c_nationkey": np.empty(c_hi - c_lo, np.int32)}
+    L.tg_gen_customer(sf, c_lo, c_hi, _p(out["c_custkey"]), _p(out["c_mktsegment"]), _p(out["c_nationkey"]))
+    return out
+
+
+# --------------------------------------------------------------- queries --
+
+def _i128(lo, hi):
+    return (int(hi) << 64) + int(lo)
+
+
+def q6(line, date_lo=days(1994, 1, 1), date_hi=days(1995, 1, 1), disc_lit=0.03, disc_eps=0.01, qty_lt=24):
+    r = Q6Result()
+    n = len(line["l_shipdate"])
+    lib().orc_q6(n, _p(line["l_shipdate"]), _p(line["l_discount"]), _p(line["l_quantity"]),
+                 _p(line["l_extendedprice"]), date_lo, date_hi, disc_lit, disc_eps, qty_lt, C.byref(r))
+    assert r.error == 0
+    return {"rows_in": r.rows_in, "rows_selected": r.rows_selected, "has_row": bool(r.has_row),
+            "sum": r.sum.tuple(), "exact": _i128(r.exact_lo, r.exact_hi)}
+
+
+def q1(line, ship_le=days(1998, 8, 11)):
+    r = Q1Result()
+    n = len(line["l_shipdate"])
+    lib().orc_q1(n, _p(line["l_shipdate"]), _p(line["l_returnflag"]), _p(line["l_linestatus"]),
+                 _p(line["l_quantity"]), _p(line["l_extendedprice"]), _p(line["l_discount"]),
+                 _p(line["l_tax"]), ship_le, C.byref(r))
+    assert r.error == 0, r.error
+    groups = []
+    for i in range(r.ngroups):
+        g = r.g[i]
+        groups.append({
+            "l_returnflag": chr(g.rf), "l_linestatus": chr(g.ls),
+            "sum_qty": g.sum_qty.value(), "sum_base_price": g.sum_base.tuple(),
+            "sum_disc_price": g.sum_disc_price.tuple(), "sum_charge": g.sum_charge.tuple(),
+            "avg_qty": g.avg_qty, "avg_price": g.avg_price.tuple(), "avg_disc": g.avg_disc.tuple(),
+            "count_order": int(g.count),
+            "x_qty": int(g.x_qty), "x_base": _i128(g.x_base_lo, g.x_base_hi),
+            "x_disc_price": _i128(g.x_disc_price_lo, g.x_disc_price_hi),
+            "x_charge": _i128(g.x_charge_lo, g.x_charge_hi), "x_disc": _i128(g.x_disc_lo, g.x_disc_hi),
+            "first_row": int(g.first_row)})
+    return {"rows_in": r.rows_in, "rows_selected": r.rows_selected, "groups": groups}
+
+
+def q3(cust, orders, line, segment="HOUSEHOLD", odate_lt=days(1995, 3, 29), ship_gt=days(1995, 3, 29),
+       capacity=None):
+    r = Q3Result()
+    seg_code = SEGMENTS.index(segment) if isinstance(segment, str) else int(segment)
+    if capacity is None:
+        capacity = max(len(orders["o_orderkey"]), 1)
+    out = (Q3Group * capacity)()
+    lib().orc_q3(len(cust["c_custkey"]), _p(cust["c_custkey"]), _p(cust["c_mktsegment"]), seg_code,
+                 len(orders["o_orderkey"]), _p(orders["o_orderkey"]), _p(orders["o_custkey"]),
+                 _p(orders["o_orderdate"]), _p(orders["o_shippriority"]), odate_lt,
+                 len(line["l_orderkey"]), _p(line["l_orderkey"]), _p(line["l_extendedprice"]),
+                 _p(line["l_discount"]), _p(line["l_shipdate"]), ship_gt,
+                 C.cast(out, C.c_void_p), capacity, C.byref(r))
+    assert r.error == 0, r.error
+    groups = [{"l_orderkey": int(g.orderkey), "revenue": g.revenue.tuple(), "o_orderdate": int(g.orderdate),
+               "o_shippriority": int(g.shippriority), "x_revenue": _i128(g.x_rev_lo, g.x_rev_hi),
+               "first_row": int(g.first_row)} for g in out[:r.nout]]
+    stats = {k: int(getattr(r, k)) for k in ("n_cust_sel", "n_orders_sel", "n_orders_joined",
+                                              "n_line_sel", "n_line_joined", "ngroups")}
+    return {"groups": groups, "stats": stats}
+
+
+# ------------------------------------------------------------- formatting --
+
+def fmt_decimal(dec, type_scale):
+    buf = C.create_string_buffer(64)
+    n = lib().orc_format_decimal(dec[0], dec[1], dec[2], type_scale, buf, 64)
+    assert n >= 0
+    return buf.value.decode()
+
+
+def decimal_sortkey(dec):
+    w, f = C.c_int64(), C.c_int64()
+    ok = lib().orc_decimal_sortkey(dec[0], dec[1], dec[2], C.byref(w), C.byref(f))
+    assert ok
+    return (w.value, f.value)
+
+
+def fmt_date(d):
+    return (datetime.date(1970, 1, 1) + datetime.timedelta(days=int(d))).isoformat()
+
+
+def fmt_double(x):
+    """Go fmt %v for float64: shortest round-trip, 'e' form for exp < -4 || exp >= 21."""
+    r = repr(float(x))
+    if "e" in r or "inf" in r or "nan" in r:
+        m, _, e = r.partition("e")
+        if e:
+            e = int(e)
+            return "%se%s%02d" % (m, "+" if e >= 0 else "-", abs(e))
+        return {"inf": "+Inf", "-inf": "-Inf", "nan": "NaN"}[r]
+    if r.endswith(".0"):
+        r = r[:-2]
+        if len(r.lstrip("-")) > 21:
+            return "%e" % x
+    return r
+
+
+def q1_text(res):
+    """Rows as the reference writes them (ORDER BY l_returnflag, l_linestatus)."""
+    rows = sorted(res["groups"], key=lambda g: (g["l_returnflag"], g["l_linestatus"]))
+    lines = ["#" + "\t" * 9]
+    for g in rows:
+        lines.append("\t".join([
+            g["l_returnflag"], g["l_linestatus"], str(g["sum_qty"]),
+            fmt_decimal(g["sum_base_price"], 2), fmt_decimal(g["sum_disc_price"], 4),
+            fmt_decimal(g["sum_charge"], 8), fmt_double(g["avg_qty"]),
+            fmt_decimal(g["avg_price"], 2), fmt_decimal(g["avg_disc"], 2), str(g["count_order"])]))
+    return "\n".join(lines) + "\n"
+
+
+def q6_text(res):
+    lines = ["#"]
+    if res["has_row"]:
+        lines.append(fmt_decimal(res["sum"], 4))
+    return "\n".join(lines) + "\n"
+
+
+def q3_topk(res, limit=10):
+    """ORDER BY revenue DESC (key rounded to 2 digits), o_orderdate ; LIMIT."""
+    def key(g):
+        w, f = decimal_sortkey(g["revenue"])
+        return (-w, -f, g["o_orderdate"])
+    return sorted(res["groups"], key=key)[:limit]
+
+
+def q3_text(res, limit=10):
+    lines = ["#" + "\t" * 3]
+    for g in q3_topk(res, limit):
+        lines.append("\t".join([str(g["l_orderkey"]), fmt_decimal(g["revenue"], 4),
+                                fmt_date(g["o_orderdate"]), str(g["o_shippriority"])]))
+    return "\n".join(lines) + "\n"

@@ -1,0 +1,178 @@
+/*
+ * oracle/tpchgen.c -- TEST INFRASTRUCTURE (CPU). Not part of the product path.
+ *
+ * dbgen-equivalent TPC-H generator for the columns the hot path touches
+ * (lineitem, orders, customer).  The reference loads official dbgen SF1 data
+ * (/root/reference/Makefile:47,57-67) and its golden results
+ * (cases/tpch/1g/plan/q{1,3,6}.txt) are computed on it, so this generator
+ * restates dbgen's published algorithm bit for bit for those columns:
+ *   - Park-Miller LCG  seed' = seed*16807 mod (2^31-1), one stream per column,
+ *     UnifInt = lo + (int64)((double)seed/2147483647.0 * (hi-lo+1));
+ *   - every lineitem stream is consumed exactly 7 times per order (row_stop
+ *     advances the unused draws), so stream position = 7*order_index + line,
+ *     which makes any order range independently generable (jump-ahead by
+ *     modular exponentiation);
+ *   - sparse order keys (8 of every 32), customer mortality (custkey%3 != 0),
+ *     retail price from partkey, R/A return flag drawn only when
+ *     receiptdate <= 1995-06-17.
+ * Pinned by tests/test_tpchgen.py against the first rows of the official SF1
+ * lineitem/orders/customer tables and, end to end, by the reference's golden
+ * Q1/Q6/Q3 results.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define TG_M 2147483647LL
+#define TG_A 16807LL
+
+/* dbgen stream seeds (Seed[] table of dbgen's rnd.h, by column) */
+enum {
+    SD_L_QTY = 209208115, SD_L_DCNT = 554590007, SD_L_TAX = 721958466,
+    SD_L_PKEY = 1808217256, SD_L_SKEY = 2095021727, SD_L_SDTE = 1769349045,
+    SD_L_CDTE = 904914315, SD_L_RDTE = 373135028, SD_L_RFLG = 717419739,
+    SD_O_ODATE = 1066728069, SD_O_CKEY = 851767375, SD_O_LCNT = 1434868289,
+    SD_C_MSEG = 1140279430, SD_C_NTRG = 1489529863
+};
+
+#define EPOCH_1992_01_01 8035   /* days from 1970-01-01 to 1992-01-01 */
+#define ODATE_SPAN 2406         /* 1992-01-01 .. 1998-08-02 inclusive  */
+#define CURRENT_OFF 1263        /* 1995-06-17 as offset from 1992-01-01 */
+
+static inline int64_t tg_mulmod(int64_t a, int64_t b) { return (int64_t)(((__int128)a * b) % TG_M); }
+
+static int64_t tg_powmod(int64_t n)
+{
+    int64_t r = 1, b = TG_A;
+    while (n > 0) {
+        if (n & 1) r = tg_mulmod(r, b);
+        b = tg_mulmod(b, b);
+        n >>= 1;
+    }
+    return r;
+}
+
+/* state of a stream after n draws from its initial seed */
+static inline int64_t tg_jump(int64_t seed, int64_t n) { return tg_mulmod(seed, tg_powmod(n)); }
+
+static inline int64_t tg_draw(int64_t *s, int64_t lo, int64_t hi)
+{
+    *s = (*s * TG_A) % TG_M;
+    double r = (double)(hi - lo + 1);
+    return lo + (int64_t)(((double)*s / 2147483647.0) * r);
+}
+
+int64_t tg_num_orders(double sf) { return (int64_t)(1500000.0 * sf + 0.5); }
+int64_t tg_num_customers(double sf) { return (int64_t)(150000.0 * sf + 0.5); }
+static int64_t tg_num_parts(double sf) { return (int64_t)(200000.0 * sf + 0.5); }
+static int64_t tg_num_supp(double sf) { int64_t n = (int64_t)(10000.0 * sf + 0.5); return n < 4 ? 4 : n; }
+
+/* number of lineitem rows belonging to orders [o_lo, o_hi) (0-based order index) */
+int64_t tg_count_lineitems(double sf, int64_t o_lo, int64_t o_hi)
+{
+    (void)sf;
+    int64_t s = tg_jump(SD_O_LCNT, o_lo), n = 0;
+    for (int64_t i = o_lo; i < o_hi; i++) n += tg_draw(&s, 1, 7);
+    return n;
+}
+
+static inline int64_t tg_orderkey(int64_t idx1)   /* idx1 is 1-based */
+{
+    return ((idx1 >> 3) << 5) | (idx1 & 7);
+}
+
+/*
+ * Generate orders [o_lo,o_hi) and their lineitems.  Any output pointer may be
+ * NULL.  Lineitem arrays must hold tg_count_lineitems(sf,o_lo,o_hi) rows.
+ * DECIMAL(15,2) columns are int64 unscaled (cents); dates are int32 days since
+ * 1970-01-01; flags are raw bytes.
+ * Returns the number of lineitem rows written.
+ */
+int64_t tg_gen_orders_lineitem(double sf, int64_t o_lo, int64_t o_hi,
+    /* orders */
+    int64_t *o_orderkey, int32_t *o_custkey, int32_t *o_orderdate, int32_t *o_shippriority,
+    int64_t *o_totalprice, uint8_t *o_orderstatus,
+    /* lineitem */
+    int64_t *l_orderkey, int32_t *l_partkey, int32_t *l_suppkey, int32_t *l_linenumber,
+    int32_t *l_quantity, int64_t *l_extendedprice, int64_t *l_discount, int64_t *l_tax,
+    uint8_t *l_returnflag, uint8_t *l_linestatus,
+    int32_t *l_shipdate, int32_t *l_commitdate, int32_t *l_receiptdate)
+{
+    const int64_t ncust = tg_num_customers(sf), npart = tg_num_parts(sf), nsupp = tg_num_supp(sf);
+    int64_t s_ckey = tg_jump(SD_O_CKEY, o_lo), s_odate = tg_jump(SD_O_ODATE, o_lo),
+            s_lcnt = tg_jump(SD_O_LCNT, o_lo);
+    int64_t row = 0;
+    for (int64_t i = o_lo; i < o_hi; i++) {
+        int64_t okey = tg_orderkey(i + 1);
+        int64_t ck = tg_draw(&s_ckey, 1, ncust);
+        int64_t delta = 1;
+        while (ck % 3 == 0) { ck += delta; if (ck > ncust) ck = ncust; delta = -delta; }
+        int64_t od = tg_draw(&s_odate, 0, ODATE_SPAN - 1);
+        int64_t lines = tg_draw(&s_lcnt, 1, 7);
+        int64_t base = 7 * i;
+        int64_t s_qty = tg_jump(SD_L_QTY, base), s_dc = tg_jump(SD_L_DCNT, base),
+                s_tax = tg_jump(SD_L_TAX, base), s_pk = tg_jump(SD_L_PKEY, base),
+                s_sk = tg_jump(SD_L_SKEY, base), s_sd = tg_jump(SD_L_SDTE, base),
+                s_cd = tg_jump(SD_L_CDTE, base), s_rd = tg_jump(SD_L_RDTE, base),
+                s_rf = tg_jump(SD_L_RFLG, base);
+        int64_t total = 0; int shipped = 0;
+        for (int64_t j = 0; j < lines; j++, row++) {
+            int64_t qty = tg_draw(&s_qty, 1, 50);
+            int64_t dc = tg_draw(&s_dc, 0, 10);
+            int64_t tax = tg_draw(&s_tax, 0, 8);
+            int64_t pk = tg_draw(&s_pk, 1, npart);
+            int64_t sn = tg_draw(&s_sk, 0, 3);
+            int64_t sd = od + tg_draw(&s_sd, 1, 121);
+            int64_t cd = od + tg_draw(&s_cd, 30, 90);
+            int64_t rd = sd + tg_draw(&s_rd, 1, 30);
+            int64_t price = 90000 + (pk / 10) % 20001 + (pk % 1000) * 100;
+            int64_t ep = price * qty;
+            int64_t sk = (pk + sn * (nsupp / 4 + (pk - 1) / nsupp)) % nsupp + 1;
+            uint8_t rf = 'N';
+            if (rd <= CURRENT_OFF) rf = (tg_draw(&s_rf, 1, 2) == 1) ? 'R' : 'A';
+            uint8_t ls = 'O';
+            if (sd <= CURRENT_OFF) { ls = 'F'; shipped++; }
+            total += ((ep * (100 - dc)) / 100) * (100 + tax) / 100;
+            if (l_orderkey) l_orderkey[row] = okey;
+            if (l_partkey) l_partkey[row] = (int32_t)pk;
+            if (l_suppkey) l_suppkey[row] = (int32_t)sk;
+            if (l_linenumber) l_linenumber[row] = (int32_t)(j + 1);
+            if (l_quantity) l_quantity[row] = (int32_t)qty;
+            if (l_extendedprice) l_extendedprice[row] = ep;
+            if (l_discount) l_discount[row] = dc;
+            if (l_tax) l_tax[row] = tax;
+            if (l_returnflag) l_returnflag[row] = rf;
+            if (l_linestatus) l_linestatus[row] = ls;
+            if (l_shipdate) l_shipdate[row] = (int32_t)(EPOCH_1992_01_01 + sd);
+            if (l_commitdate) l_commitdate[row] = (int32_t)(EPOCH_1992_01_01 + cd);
+            if (l_receiptdate) l_receiptdate[row] = (int32_t)(EPOCH_1992_01_01 + rd);
+        }
+        int64_t k = i - o_lo;
+        if (o_orderkey) o_orderkey[k] = okey;
+        if (o_custkey) o_custkey[k] = (int32_t)ck;
+        if (o_orderdate) o_orderdate[k] = (int32_t)(EPOCH_1992_01_01 + od);
+        if (o_shippriority) o_shippriority[k] = 0;
+        if (o_totalprice) o_totalprice[k] = total;
+        if (o_orderstatus) o_orderstatus[k] = shipped == 0 ? 'O' : (shipped == lines ? 'F' : 'P');
+    }
+    return row;
+}
+
+/* customer segment dictionary, dists.dss "msegmnt" order */
+static const char *TG_SEGMENTS[5] = {"AUTOMOBILE", "BUILDING", "FURNITURE", "HOUSEHOLD", "MACHINERY"};
+const char *tg_segment_name(int code) { return (code >= 0 && code < 5) ? TG_SEGMENTS[code] : ""; }
+
+/* customers [c_lo,c_hi) (0-based); c_mktsegment is the dictionary code 0..4 */
+void tg_gen_customer(double sf, int64_t c_lo, int64_t c_hi,
+                     int32_t *c_custkey, uint8_t *c_mktsegment, int32_t *c_nationkey)
+{
+    (void)sf;
+    int64_t s_seg = tg_jump(SD_C_MSEG, c_lo), s_nat = tg_jump(SD_C_NTRG, c_lo);
+    for (int64_t i = c_lo; i < c_hi; i++) {
+        int64_t seg = tg_draw(&s_seg, 1, 5);
+        int64_t nat = tg_draw(&s_nat, 0, 24);
+        if (c_custkey) c_custkey[i - c_lo] = (int32_t)(i + 1);
+        if (c_mktsegment) c_mktsegment[i - c_lo] = (uint8_t)(seg - 1);
+        if (c_nationkey) c_nationkey[i - c_lo] = (int32_t)nat;
+    }
+}
