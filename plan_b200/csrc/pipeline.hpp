@@ -1,0 +1,93 @@
+// pipeline.hpp -- plan / result objects shared by the pipeline builders.
+#pragma once
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "plan_ir.hpp"
+
+namespace pg {
+
+struct ResCol {
+    int type = 0, width = 0, scale = 0;
+    std::vector<uint8_t> data;
+    template <typename T> void push(const T &v)
+    {
+        size_t n = data.size();
+        data.resize(n + sizeof(T));
+        memcpy(data.data() + n, &v, sizeof(T));
+    }
+};
+
+struct Pipeline {
+    std::string explain;
+    virtual ~Pipeline();
+    virtual int run(pg_result *res) = 0;
+};
+
+// RAII device / pinned buffers
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    int alloc(size_t n)
+    {
+        release();
+        if (n == 0) n = 16;
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e != cudaSuccess) { p = nullptr; set_error("cudaMalloc(%zu) failed: %s", n, cudaGetErrorString(e)); return PG_ENOMEM; }
+        bytes = n;
+        return PG_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    ~DevBuf() { release(); }
+    template <typename T> T *as() const { return (T *)p; }
+};
+struct PinBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    int alloc(size_t n)
+    {
+        release();
+        if (n == 0) n = 16;
+        cudaError_t e = cudaMallocHost(&p, n);
+        if (e != cudaSuccess) { p = nullptr; set_error("cudaMallocHost(%zu) failed: %s", n, cudaGetErrorString(e)); return PG_ENOMEM; }
+        bytes = n;
+        return PG_OK;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; bytes = 0; }
+    ~PinBuf() { release(); }
+    template <typename T> T *as() const { return (T *)p; }
+};
+
+struct EventPair {
+    cudaEvent_t a = nullptr, b = nullptr;
+    int init()
+    {
+        if (a) return PG_OK;
+        PG_CUDA(cudaEventCreate(&a));
+        PG_CUDA(cudaEventCreate(&b));
+        return PG_OK;
+    }
+    ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+    float ms() const { float m = 0; cudaEventElapsedTime(&m, a, b); return m; }
+};
+
+// all-gather `bytes` from every rank into recv[world][bytes] (comm.cu); world==1 copies.
+int comm_allgather(const void *d_send, void *d_recv, size_t bytes, cudaStream_t stream);
+
+}  // namespace pg
+
+struct pg_result {
+    std::vector<pg::ResCol> cols;
+    pg::i64 nrows = 0, cursor = 0;
+    pg_stats stats{};
+};
+
+struct pg_plan {
+    pg::Node root;
+    std::vector<pg_table *> slots;
+    std::vector<uint64_t> bound_versions;
+    int pipe_world = 1;
+    std::unique_ptr<pg::Pipeline> pipe;
+};

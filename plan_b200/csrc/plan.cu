@@ -1,0 +1,203 @@
+// plan.cu -- pg_plan / pg_result: compile a plan descriptor, pick fused kernels, run,
+// finalise in exact arithmetic, hand results back as native columns.
+//
+// Plays the role of the reference's executor tree for the off-loaded subtree
+// (/root/reference/pkg/compute/executor.go:305-350 buildOperatorExec,
+//  executor_aggr.go:106-262 aggExecutor.Execute): HAS_INIT drains the child completely,
+// HAS_SCAN emits groups in first-insertion order (aggregate_hash.go:424-438).
+#include <chrono>
+#include <memory>
+
+#include "common.cuh"
+#include "hostdec.hpp"
+#include "pipeline.hpp"
+#include "plan_ir.hpp"
+
+namespace pg {
+
+Pipeline::~Pipeline() {}
+
+int build_scan_agg(pg_plan *plan, const Node &agg, const Node &scan, std::unique_ptr<Pipeline> *out);
+int build_join_agg(pg_plan *plan, const Node &agg, const Node &join, std::unique_ptr<Pipeline> *out);
+
+static const Node *skip_filters(const Node *n, std::vector<Expr> *extra)
+{
+    while (n->op == PG_OP_FILTER) {
+        for (auto &f : n->filters) extra->push_back(f);
+        n = &n->children[0];
+    }
+    return n;
+}
+
+static int build_pipeline(pg_plan *plan)
+{
+    const Node &root = plan->root;
+    if (root.op != PG_OP_AGG) PG_FAIL(PG_EUNSUPPORTED, "plan root must be an aggregate (got op %d)", root.op);
+    std::vector<Expr> extra;
+    const Node *child = skip_filters(&root.children[0], &extra);
+    if (child->op == PG_OP_SCAN) {
+        Node scan = *child;
+        for (auto &f : extra) scan.filters.push_back(f);
+        return build_scan_agg(plan, root, scan, &plan->pipe);
+    }
+    if (child->op == PG_OP_JOIN) {
+        if (!extra.empty()) PG_FAIL(PG_EUNSUPPORTED, "filter between aggregate and join is not supported");
+        return build_join_agg(plan, root, *child, &plan->pipe);
+    }
+    PG_FAIL(PG_EUNSUPPORTED, "unsupported aggregate input (op %d)", child->op);
+}
+
+}  // namespace pg
+
+using namespace pg;
+
+extern "C" {
+
+int pg_plan_compile(const int64_t *desc, size_t nwords, pg_plan **out)
+{
+    if (!desc || !out || nwords < 3) PG_FAIL(PG_EINVAL, "pg_plan_compile: bad arguments");
+    if (desc[0] != PG_DESC_MAGIC || desc[1] != PG_DESC_VERSION)
+        PG_FAIL(PG_EINVAL, "pg_plan_compile: bad magic/version (%lld, %lld)", (long long)desc[0], (long long)desc[1]);
+    DescReader rd(desc + 2, nwords - 2);
+    std::unique_ptr<pg_plan> p(new pg_plan());
+    if (!rd.node(&p->root) || !rd.ok()) PG_FAIL(PG_EINVAL, "pg_plan_compile: malformed descriptor near word %zu", rd.pos() + 2);
+    if (rd.pos() != nwords - 2) PG_FAIL(PG_EINVAL, "pg_plan_compile: %zu trailing words", nwords - 2 - rd.pos());
+    // number of table slots = max scan slot + 1
+    int nslots = 0;
+    std::vector<const Node *> todo{&p->root};
+    while (!todo.empty()) {
+        const Node *n = todo.back();
+        todo.pop_back();
+        if (n->op == PG_OP_SCAN) {
+            if (n->slot < 0 || n->slot > 63) PG_FAIL(PG_EINVAL, "pg_plan_compile: scan slot %d out of range", n->slot);
+            nslots = std::max(nslots, n->slot + 1);
+        }
+        for (auto &c : n->children) todo.push_back(&c);
+    }
+    p->slots.assign((size_t)nslots, nullptr);
+    // structural check now, kernel selection when the tables are bound
+    if (p->root.op != PG_OP_AGG) PG_FAIL(PG_EUNSUPPORTED, "pg_plan_compile: only aggregate-rooted pipelines are off-loaded");
+    *out = p.release();
+    return PG_OK;
+}
+
+int pg_plan_bind(pg_plan *p, int slot, pg_table *t)
+{
+    if (!p || !t || slot < 0 || slot >= (int)p->slots.size()) PG_FAIL(PG_EINVAL, "pg_plan_bind: bad arguments");
+    if (!t->sealed) PG_FAIL(PG_ESTATE, "pg_plan_bind: table %s is not sealed", t->name.c_str());
+    p->slots[(size_t)slot] = t;
+    p->pipe.reset();
+    return PG_OK;
+}
+
+static int ensure_pipeline(pg_plan *p)
+{
+    for (size_t i = 0; i < p->slots.size(); i++)
+        if (!p->slots[i]) PG_FAIL(PG_ESTATE, "plan slot %zu is not bound", i);
+    bool stale = !p->pipe;
+    if (p->pipe) {
+        for (size_t i = 0; i < p->slots.size(); i++)
+            if (p->bound_versions[i] != p->slots[i]->version) stale = true;
+        if (p->pipe_world != ctx().world) stale = true;
+    }
+    if (!stale) return PG_OK;
+    p->pipe.reset();
+    PG_CUDA(cudaSetDevice(ctx().device));
+    PG_TRY(build_pipeline(p));
+    p->bound_versions.resize(p->slots.size());
+    for (size_t i = 0; i < p->slots.size(); i++) p->bound_versions[i] = p->slots[i]->version;
+    p->pipe_world = ctx().world;
+    return PG_OK;
+}
+
+int pg_plan_prepare(pg_plan *p)
+{
+    if (!p) PG_FAIL(PG_EINVAL, "pg_plan_prepare: null plan");
+    if (!ctx().ready) PG_FAIL(PG_ESTATE, "pg_plan_prepare: call pg_init first");
+    return ensure_pipeline(p);
+}
+
+const char *pg_plan_explain(pg_plan *p)
+{
+    if (!p) return "";
+    if (ensure_pipeline(p) != PG_OK) return get_error();
+    return p->pipe->explain.c_str();
+}
+
+int pg_plan_execute(pg_plan *p, pg_result **out)
+{
+    if (!p || !out) PG_FAIL(PG_EINVAL, "pg_plan_execute: bad arguments");
+    if (!ctx().ready) PG_FAIL(PG_ESTATE, "pg_plan_execute: call pg_init first");
+    PG_TRY(ensure_pipeline(p));
+    PG_CUDA(cudaSetDevice(ctx().device));
+    std::unique_ptr<pg_result> r(new pg_result());
+    auto t0 = std::chrono::steady_clock::now();
+    PG_TRY(p->pipe->run(r.get()));
+    auto t1 = std::chrono::steady_clock::now();
+    r->stats.exec_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    *out = r.release();
+    return PG_OK;
+}
+
+void pg_plan_free(pg_plan *p)
+{
+    if (!p) return;
+    if (ctx().ready) cudaSetDevice(ctx().device);
+    delete p;
+}
+
+int pg_result_num_columns(const pg_result *r, int *ncol)
+{
+    if (!r || !ncol) PG_FAIL(PG_EINVAL, "pg_result_num_columns: bad arguments");
+    *ncol = (int)r->cols.size();
+    return PG_OK;
+}
+
+int pg_result_column_type(const pg_result *r, int col, int32_t *type, int32_t *width, int32_t *scale)
+{
+    if (!r || col < 0 || col >= (int)r->cols.size()) PG_FAIL(PG_EINVAL, "pg_result_column_type: bad arguments");
+    if (type) *type = r->cols[(size_t)col].type;
+    if (width) *width = r->cols[(size_t)col].width;
+    if (scale) *scale = r->cols[(size_t)col].scale;
+    return PG_OK;
+}
+
+int pg_result_rows(const pg_result *r, int64_t *nrows)
+{
+    if (!r || !nrows) PG_FAIL(PG_EINVAL, "pg_result_rows: bad arguments");
+    *nrows = r->nrows;
+    return PG_OK;
+}
+
+int pg_result_next(pg_result *r, int64_t max_rows, int64_t *nrows, const void **cols, const uint8_t **valid)
+{
+    if (!r || !nrows || max_rows <= 0) PG_FAIL(PG_EINVAL, "pg_result_next: bad arguments");
+    i64 n = std::min<i64>(max_rows, r->nrows - r->cursor);
+    if (n < 0) n = 0;
+    for (size_t i = 0; i < r->cols.size(); i++) {
+        ResCol &c = r->cols[i];
+        if (cols) cols[i] = n > 0 ? (const void *)(c.data.data() + (size_t)r->cursor * (size_t)type_size(c.type)) : nullptr;
+        if (valid) valid[i] = nullptr;   // BASELINE pipelines produce no NULLs (empty input => no row)
+    }
+    *nrows = n;
+    r->cursor += n;
+    return PG_OK;
+}
+
+int pg_result_rewind(pg_result *r)
+{
+    if (!r) PG_FAIL(PG_EINVAL, "pg_result_rewind: null");
+    r->cursor = 0;
+    return PG_OK;
+}
+
+int pg_result_stats(const pg_result *r, pg_stats *out)
+{
+    if (!r || !out) PG_FAIL(PG_EINVAL, "pg_result_stats: bad arguments");
+    *out = r->stats;
+    return PG_OK;
+}
+
+void pg_result_free(pg_result *r) { delete r; }
+
+}  // extern "C"

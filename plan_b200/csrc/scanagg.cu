@@ -1,0 +1,544 @@
+// scanagg.cu -- `Agg <- Scan[filters]` pipelines: shape matching, launch, exact finalise.
+//
+// Reference operators replaced: aggExecutor over scanExecutor with pushed-down filters
+// (/root/reference/pkg/compute/executor_aggr.go:106-262, executor_scan.go:225-241);
+// plan shapes per SURVEY.md 3.4 (Q6: const group + sum(DEC*DEC); Q1: 2 x VARCHAR(1) keys,
+// 8 aggregates).
+#include <algorithm>
+
+#include "hostdec.hpp"
+#include "pipeline.hpp"
+#include "scanagg.cuh"
+
+namespace pg {
+
+static i128 maxabs(i64 lo, i64 hi)
+{
+    i128 a = lo < 0 ? -(i128)lo : (i128)lo, b = hi < 0 ? -(i128)hi : (i128)hi;
+    return a > b ? a : b;
+}
+
+static void clamp_to_stats(Range &r, const Column &c)
+{
+    if (c.stats_ok) {
+        if (r.lo < c.vmin) r.lo = c.vmin;
+        if (r.hi > c.vmax) r.hi = c.vmax;
+    }
+}
+
+static Range find_range(const std::vector<Range> &rs, int col)
+{
+    for (auto &r : rs) if (r.col == col) return r;
+    Range r;
+    r.col = col;
+    return r;
+}
+
+static int grid_for(const void *kernel, int threads, size_t smem, i64 ntiles)
+{
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
+    if (per_sm < 1) per_sm = 1;
+    i64 g = (i64)ctx().prop.multiProcessorCount * per_sm;
+    if (g > ntiles) g = ntiles;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+static pg_decimal to_pg_decimal(const HDec &d)
+{
+    pg_decimal o;
+    o.coef = d.coef;
+    o.scale = d.scale;
+    o.neg = d.neg ? 1u : 0u;
+    return o;
+}
+
+static i128 make_i128(u64 lo, u64 hi) { return (i128)(((u128)hi << 64) | (u128)lo); }
+
+// ------------------------------------------------------------------- sumprod --
+
+struct SumProdPipeline : Pipeline {
+    const pg_table *table = nullptr;
+    SumProdParams prm{};
+    bool has_a = false, has_b = false;
+    int grid = 1, vscale = 0;
+    AggExpr agg;
+    std::vector<std::pair<int, int>> outs;
+    int bytes_per_row = 16;
+    DevBuf d_part, d_final, d_gather;
+    PinBuf h_final;
+    EventPair ev_all, ev_main;
+
+    int launch()
+    {
+        cudaStream_t st = ctx().stream;
+#define PG_SP(A, B) sumprod_kernel<A, B, 4><<<grid, SA_THREADS, 0, st>>>(prm, d_part.as<i64>())
+        if (has_a && has_b) PG_SP(true, true);
+        else if (has_a) PG_SP(true, false);
+        else if (has_b) PG_SP(false, true);
+        else PG_SP(false, false);
+#undef PG_SP
+        PG_CUDA(cudaGetLastError());
+        return PG_OK;
+    }
+
+    int run(pg_result *res) override
+    {
+        Context &c = ctx();
+        cudaStream_t st = c.stream;
+        PG_TRY(ev_all.init());
+        PG_TRY(ev_main.init());
+        PG_CUDA(cudaEventRecord(ev_all.a, st));
+        PG_CUDA(cudaEventRecord(ev_main.a, st));
+        PG_TRY(launch());
+        PG_CUDA(cudaEventRecord(ev_main.b, st));
+        finalize128_kernel<<<1, 32, 0, st>>>(d_part.as<i64>(), grid, 2, d_final.as<u64>());
+        PG_CUDA(cudaGetLastError());
+        const void *src = d_final.p;
+        if (c.world > 1) {
+            PG_TRY(comm_allgather(d_final.p, d_gather.p, 32, st));
+            src = d_gather.p;
+        }
+        PG_CUDA(cudaMemcpyAsync(h_final.p, src, 32 * (size_t)c.world, cudaMemcpyDeviceToHost, st));
+        PG_CUDA(cudaEventRecord(ev_all.b, st));
+        PG_CUDA(cudaStreamSynchronize(st));
+        const u64 *h = h_final.as<u64>();
+        i128 sum = 0, cnt = 0;
+        for (int r = 0; r < c.world; r++) {   // merged in rank order (shards are contiguous row ranges)
+            sum += make_i128(h[4 * r], h[4 * r + 1]);
+            cnt += make_i128(h[4 * r + 2], h[4 * r + 3]);
+        }
+        res->stats.kernel_ms = ev_all.ms();
+        res->stats.main_kernel_ms = ev_main.ms();
+        res->stats.rows_scanned = table->nrows;
+        res->stats.algorithmic_bytes = table->nrows * bytes_per_row;
+        res->stats.main_kernel_bytes = res->stats.algorithmic_bytes;
+        res->stats.kernel_launches = 2;
+        res->stats.aux[0] = (i64)cnt;
+        // the reference emits no row at all when nothing reached the aggregate
+        // (aggregate_exec.go:160-185)
+        res->nrows = cnt > 0 ? 1 : 0;
+        for (auto &o : outs) {
+            (void)o;
+            ResCol col;
+            col.type = PG_T_DECIMAL128;
+            col.width = agg.width;
+            col.scale = agg.scale;
+            if (cnt > 0) {
+                HDec d;
+                // TODO(rounding regime): a total beyond 19 digits needs the sequential
+                // half-even emulation; until then refuse instead of rounding differently.
+                if (!hd_from_i128(sum, vscale, &d) || hd_digits((u128)(sum < 0 ? -sum : sum)) > HD_MAXPREC)
+                    PG_FAIL(PG_EOVERFLOW, "sum exceeds 19 significant digits (order-dependent rounding regime)");
+                col.push(to_pg_decimal(d));
+            }
+            res->cols.push_back(col);
+        }
+        return PG_OK;
+    }
+};
+
+static int try_sumprod(pg_plan *plan, const Node &aggn, const Node &scan, const std::vector<Range> &ranges,
+                       const std::vector<AffProd> &args, std::unique_ptr<Pipeline> *out, std::string *why)
+{
+    const pg_table *t = plan->slots[(size_t)scan.slot];
+    if (!aggn.groups.empty()) { *why = "has group keys"; return PG_EUNSUPPORTED; }
+    if (aggn.aggs.size() != 1 || aggn.aggs[0].fn != PG_AGG_SUM || aggn.aggs[0].ltype != PG_LT_DECIMAL) { *why = "not a single DECIMAL sum"; return PG_EUNSUPPORTED; }
+    const AffProd &ap = args[0];
+    if (ap.f.size() != 2 || ap.f[0].c != 0 || ap.f[0].s != 1 || ap.f[1].c != 0 || ap.f[1].s != 1) { *why = "argument is not column*column"; return PG_EUNSUPPORTED; }
+    const Column &ca = t->cols[(size_t)ap.f[0].col], &cb = t->cols[(size_t)ap.f[1].col];
+    if (type_size(ca.type) != 8 || type_size(cb.type) != 8) { *why = "factor columns are not 64-bit"; return PG_EUNSUPPORTED; }
+    std::unique_ptr<SumProdPipeline> p(new SumProdPipeline());
+    p->table = t;
+    p->agg = aggn.aggs[0];
+    p->outs = aggn.outs;
+    for (auto &o : aggn.outs) if (o.first != 1 || o.second != 0) { *why = "output list refers to something else than the aggregate"; return PG_EUNSUPPORTED; }
+    p->vscale = ap.vscale();
+    SumProdParams &q = p->prm;
+    q.nrows = t->nrows;
+    q.fa = (const i64 *)ca.d_data;
+    q.fb = (const i64 *)cb.d_data;
+    Range ra = find_range(ranges, ap.f[0].col), rb = find_range(ranges, ap.f[1].col);
+    clamp_to_stats(ra, ca);
+    clamp_to_stats(rb, cb);
+    q.fa_lo = ra.lo; q.fa_hi = ra.hi; q.fb_lo = rb.lo; q.fb_hi = rb.hi;
+    q.pa = q.pb = nullptr;
+    q.a_lo = q.b_lo = INT32_MIN;
+    q.a_hi = q.b_hi = INT32_MAX;
+    int n32 = 0;
+    for (auto &r : ranges) {
+        if (r.col == ap.f[0].col || r.col == ap.f[1].col) continue;
+        const Column &col = t->cols[(size_t)r.col];
+        if (type_size(col.type) != 4) { *why = "predicate on a column that is neither a factor nor 32-bit"; return PG_EUNSUPPORTED; }
+        if (n32 == 2) { *why = "more than two 32-bit predicate columns"; return PG_EUNSUPPORTED; }
+        int lo = (int)std::max<i64>(r.lo, INT32_MIN), hi = (int)std::min<i64>(r.hi, INT32_MAX);
+        if (r.lo > r.hi) { lo = 1; hi = 0; }
+        if (n32 == 0) { q.pa = (const int *)col.d_data; q.a_lo = lo; q.a_hi = hi; p->has_a = true; }
+        else { q.pb = (const int *)col.d_data; q.b_lo = lo; q.b_hi = hi; p->has_b = true; }
+        n32++;
+    }
+    p->bytes_per_row = 16 + 4 * n32;
+    i64 ntiles = (t->nrows + SA_TILE - 1) / SA_TILE;
+    const void *kern = p->has_a && p->has_b ? (const void *)sumprod_kernel<true, true, 4>
+                       : p->has_a           ? (const void *)sumprod_kernel<true, false, 4>
+                       : p->has_b           ? (const void *)sumprod_kernel<false, true, 4>
+                                            : (const void *)sumprod_kernel<false, false, 4>;
+    p->grid = grid_for(kern, SA_THREADS, 0, ntiles);
+    // per-CTA int64 partials must be exact: bound them with the column statistics
+    i128 per_row = maxabs(ra.lo, ra.hi) * maxabs(rb.lo, rb.hi);
+    i128 rows_per_cta = (i128)((ntiles + p->grid - 1) / p->grid) * SA_TILE;
+    if (ra.lo <= ra.hi && rb.lo <= rb.hi && per_row * rows_per_cta >= ((i128)1 << 62)) {
+        *why = "per-CTA partial sum could exceed int64";
+        return PG_EUNSUPPORTED;
+    }
+    PG_TRY(p->d_part.alloc(sizeof(i64) * 2 * (size_t)p->grid));
+    PG_TRY(p->d_final.alloc(32));
+    PG_TRY(p->d_gather.alloc(32 * (size_t)ctx().world));
+    PG_TRY(p->h_final.alloc(32 * (size_t)ctx().world));
+    char buf[512];
+    snprintf(buf, sizeof buf,
+             "ScanAgg[sumprod] table=%s rows=%lld kernel=sumprod_kernel<%d,%d,4> grid=%d block=%d "
+             "bytes/row=%d ranges: a=[%d,%d] b=[%d,%d] fa=[%lld,%lld] fb=[%lld,%lld] value_scale=%d",
+             t->name.c_str(), (long long)t->nrows, (int)p->has_a, (int)p->has_b, p->grid, SA_THREADS,
+             p->bytes_per_row, q.a_lo, q.a_hi, q.b_lo, q.b_hi, (long long)q.fa_lo, (long long)q.fa_hi,
+             (long long)q.fb_lo, (long long)q.fb_hi, p->vscale);
+    p->explain = buf;
+    *out = std::move(p);
+    return PG_OK;
+}
+
+// ------------------------------------------------------------- lowcard chain --
+
+struct LowcardPipeline : Pipeline {
+    const pg_table *table = nullptr;
+    LowcardParams prm{};
+    bool has_key1 = false;
+    int grid = 1, G = 1;
+    size_t smem = 0;
+    int nkeys = 0;
+    int key_col[2] = {-1, -1};
+    std::vector<uint8_t> vals[2];        // dense id -> byte code, per key
+    std::vector<AggExpr> aggs;
+    std::vector<int> slot;               // accumulator slot per aggregate
+    std::vector<int> slot_scale;         // value scale per accumulator slot
+    std::vector<bool> agg_is_int;        // integer (HUGEINT / DOUBLE) vs DECIMAL result
+    std::vector<std::pair<int, int>> outs;
+    int bytes_per_row = 34;
+    DevBuf d_part, d_final, d_first, d_luts, d_gather;
+    PinBuf h_final;
+    EventPair ev_all, ev_main;
+
+    size_t rank_bytes() const { return (size_t)G * LC_K * 16 + (size_t)LC_MAXG * 8; }
+
+    int run(pg_result *res) override
+    {
+        Context &c = ctx();
+        cudaStream_t st = c.stream;
+        PG_TRY(ev_all.init());
+        PG_TRY(ev_main.init());
+        // d_final layout: [G*K][2] u64 totals followed by first_row[LC_MAXG]
+        i64 *d_firstrow = (i64 *)((char *)d_final.p + (size_t)G * LC_K * 16);
+        PG_CUDA(cudaEventRecord(ev_all.a, st));
+        PG_CUDA(cudaMemsetAsync(d_firstrow, 0x7f, LC_MAXG * 8, st));   // 0x7f7f.. = "unset"
+        PG_CUDA(cudaEventRecord(ev_main.a, st));
+        if (has_key1) lowcard_chain_kernel<true, 2><<<grid, SA_THREADS, smem, st>>>(prm, d_part.as<i64>(), d_firstrow);
+        else lowcard_chain_kernel<false, 2><<<grid, SA_THREADS, smem, st>>>(prm, d_part.as<i64>(), d_firstrow);
+        PG_CUDA(cudaGetLastError());
+        PG_CUDA(cudaEventRecord(ev_main.b, st));
+        finalize128_kernel<<<1, 64, 0, st>>>(d_part.as<i64>(), grid, G * LC_K, d_final.as<u64>());
+        PG_CUDA(cudaGetLastError());
+        const void *src = d_final.p;
+        if (c.world > 1) {
+            PG_TRY(comm_allgather(d_final.p, d_gather.p, rank_bytes(), st));
+            src = d_gather.p;
+        }
+        PG_CUDA(cudaMemcpyAsync(h_final.p, src, rank_bytes() * (size_t)c.world, cudaMemcpyDeviceToHost, st));
+        PG_CUDA(cudaEventRecord(ev_all.b, st));
+        PG_CUDA(cudaStreamSynchronize(st));
+
+        // merge ranks in order; 128-bit exact
+        std::vector<i128> tot((size_t)G * LC_K, 0);
+        std::vector<i64> first((size_t)G, INT64_MAX);
+        for (int r = 0; r < c.world; r++) {
+            const char *base = (const char *)h_final.p + rank_bytes() * (size_t)r;
+            const u64 *h = (const u64 *)base;
+            const i64 *f = (const i64 *)(base + (size_t)G * LC_K * 16);
+            for (int v = 0; v < G * LC_K; v++) tot[(size_t)v] += make_i128(h[2 * v], h[2 * v + 1]);
+            for (int g = 0; g < G; g++) if (f[g] != 0x7f7f7f7f7f7f7f7fLL && f[g] < first[(size_t)g]) first[(size_t)g] = f[g];
+        }
+        res->stats.kernel_ms = ev_all.ms();
+        res->stats.main_kernel_ms = ev_main.ms();
+        res->stats.rows_scanned = table->nrows;
+        res->stats.algorithmic_bytes = table->nrows * bytes_per_row;
+        res->stats.main_kernel_bytes = res->stats.algorithmic_bytes;
+        res->stats.kernel_launches = 2;
+
+        // groups in first-insertion order (aggregate_hash.go:424-438)
+        std::vector<int> order;
+        for (int g = 0; g < G; g++) if (tot[(size_t)g * LC_K] > 0) order.push_back(g);
+        std::sort(order.begin(), order.end(), [&](int a, int b) { return first[(size_t)a] < first[(size_t)b]; });
+        i64 selected = 0;
+        for (int g : order) selected += (i64)tot[(size_t)g * LC_K];
+        res->stats.aux[0] = selected;
+        res->nrows = (i64)order.size();
+        for (auto &o : outs) {
+            ResCol col;
+            if (o.first == 0) {
+                const Column &kc = table->cols[(size_t)key_col[o.second]];
+                col.type = kc.type;
+                for (int g : order) {
+                    int id = (nkeys == 2) ? (o.second == 0 ? g / prm.n1 : g % prm.n1) : g;
+                    col.push<uint8_t>(vals[o.second][(size_t)id]);
+                }
+            } else {
+                const AggExpr &a = aggs[(size_t)o.second];
+                int s = slot[(size_t)o.second];
+                bool is_int = agg_is_int[(size_t)o.second];
+                col.width = a.width;
+                col.scale = a.scale;
+                if (a.fn == PG_AGG_COUNT) col.type = PG_T_HUGEINT;
+                else if (a.fn == PG_AGG_SUM) col.type = is_int ? PG_T_HUGEINT : PG_T_DECIMAL128;
+                else col.type = is_int ? PG_T_FLOAT64 : PG_T_DECIMAL128;
+                for (int g : order) {
+                    i128 v = tot[(size_t)g * LC_K + (size_t)s];
+                    i128 n = tot[(size_t)g * LC_K];
+                    if (a.fn == PG_AGG_COUNT || (a.fn == PG_AGG_SUM && is_int)) {
+                        pg_hugeint h;
+                        h.lower = (u64)v;
+                        h.upper = (i64)(v >> 64);
+                        col.push(h);
+                    } else if (a.fn == PG_AGG_SUM) {
+                        HDec d;
+                        if (!hd_from_i128(v, slot_scale[(size_t)s], &d) || hd_digits((u128)(v < 0 ? -v : v)) > HD_MAXPREC)
+                            PG_FAIL(PG_EOVERFLOW, "sum exceeds 19 significant digits (order-dependent rounding regime)");
+                        col.push(to_pg_decimal(d));
+                    } else if (is_int) {   // avg(INT32): float64 sum / float64 count
+                        i128 mag = v < 0 ? -v : v;
+                        if (mag >= ((i128)1 << 53)) PG_FAIL(PG_EOVERFLOW, "avg(INT32): sum not exact in float64");
+                        double x = (double)(i64)v / (double)(i64)n;
+                        col.push(x);
+                    } else {               // avg(DECIMAL) = sum.Quo(count)
+                        HDec sd, nd, qd;
+                        if (!hd_from_i128(v, slot_scale[(size_t)s], &sd) || hd_digits((u128)(v < 0 ? -v : v)) > HD_MAXPREC)
+                            PG_FAIL(PG_EOVERFLOW, "avg: sum exceeds 19 significant digits");
+                        hd_from_i128(n, 0, &nd);
+                        if (!hd_quo(sd, nd, &qd)) PG_FAIL(PG_EOVERFLOW, "avg: decimal division failed");
+                        col.push(to_pg_decimal(qd));
+                    }
+                }
+            }
+            res->cols.push_back(col);
+        }
+        return PG_OK;
+    }
+};
+
+static bool prefix_match(const AffProd &a, const AffProd &chain, size_t n)
+{
+    if (a.f.size() != n || chain.f.size() < n) return false;
+    for (size_t i = 0; i < n; i++) if (!(a.f[i] == chain.f[i])) return false;
+    return true;
+}
+
+static int try_lowcard(pg_plan *plan, const Node &aggn, const Node &scan, const std::vector<Range> &ranges,
+                       const std::vector<AffProd> &args, std::unique_ptr<Pipeline> *out, std::string *why)
+{
+    const pg_table *t = plan->slots[(size_t)scan.slot];
+    if (aggn.groups.empty() || aggn.groups.size() > 2) { *why = "needs 1 or 2 group keys"; return PG_EUNSUPPORTED; }
+    if (!aggn.having.empty()) { *why = "HAVING not supported in this shape"; return PG_EUNSUPPORTED; }
+    std::unique_ptr<LowcardPipeline> p(new LowcardPipeline());
+    p->table = t;
+    p->nkeys = (int)aggn.groups.size();
+    std::vector<uint8_t> luts(512, 0);
+    int dims[2] = {1, 1};
+    for (int k = 0; k < p->nkeys; k++) {
+        const Expr &ge = aggn.groups[(size_t)k];
+        if (ge.kind != PG_TK_COL) { *why = "group key is not a column"; return PG_EUNSUPPORTED; }
+        const Column &col = t->cols[(size_t)ge.idx];
+        if (!is_byte_family(col.type) || col.has_nulls) { *why = "group key is not a non-null byte-coded column"; return PG_EUNSUPPORTED; }
+        p->key_col[k] = ge.idx;
+        // dense ids over the codes that occur anywhere (union over ranks so every rank agrees)
+        uint32_t present[8];
+        memcpy(present, col.present, sizeof present);
+        if (ctx().world > 1) {
+            DevBuf ds, dr;
+            PG_TRY(ds.alloc(32));
+            PG_TRY(dr.alloc(32 * (size_t)ctx().world));
+            PG_CUDA(cudaMemcpyAsync(ds.p, present, 32, cudaMemcpyHostToDevice, ctx().stream));
+            PG_TRY(comm_allgather(ds.p, dr.p, 32, ctx().stream));
+            std::vector<uint32_t> all(8 * (size_t)ctx().world);
+            PG_CUDA(cudaMemcpyAsync(all.data(), dr.p, 32 * (size_t)ctx().world, cudaMemcpyDeviceToHost, ctx().stream));
+            PG_CUDA(cudaStreamSynchronize(ctx().stream));
+            for (int r = 0; r < ctx().world; r++) for (int w = 0; w < 8; w++) present[w] |= all[(size_t)r * 8 + (size_t)w];
+        }
+        for (int code = 0; code < 256; code++)
+            if (present[code >> 5] & (1u << (code & 31))) {
+                luts[(size_t)k * 256 + (size_t)code] = (uint8_t)p->vals[k].size();
+                p->vals[k].push_back((uint8_t)code);
+            }
+        if (p->vals[k].empty()) p->vals[k].push_back(0);   // empty table
+        dims[k] = (int)p->vals[k].size();
+    }
+    p->G = dims[0] * dims[1];
+    if (p->G > LC_MAXG) { *why = "more dense groups than the low-cardinality kernel holds"; return PG_EUNSUPPORTED; }
+    p->has_key1 = p->nkeys == 2;
+
+    // the longest product is the chain A*(c1+s1*B)*(c2+s2*C)
+    AffProd chain;
+    for (auto &a : args) if (a.f.size() > chain.f.size()) chain = a;
+    if (chain.f.size() > 3) { *why = "product of more than three factors"; return PG_EUNSUPPORTED; }
+    int colA = -1, colB = -1, colC = -1, colQ = -1;
+    if (!chain.f.empty()) {
+        if (chain.f[0].c != 0 || chain.f[0].s != 1) { *why = "first factor of the chain is not a plain column"; return PG_EUNSUPPORTED; }
+        colA = chain.f[0].col;
+        if (chain.f.size() > 1) colB = chain.f[1].col;
+        if (chain.f.size() > 2) colC = chain.f[2].col;
+    }
+    p->aggs = aggn.aggs;
+    p->outs = aggn.outs;
+    p->slot_scale.assign(LC_K, 0);
+    for (size_t i = 0; i < aggn.aggs.size(); i++) {
+        const AggExpr &a = aggn.aggs[i];
+        const AffProd &ap = args[i];
+        int s = -1;
+        bool is_int = false;
+        if (a.fn == PG_AGG_COUNT) { s = 0; is_int = true; }
+        else if (a.fn != PG_AGG_SUM && a.fn != PG_AGG_AVG) { *why = "aggregate other than sum/avg/count"; return PG_EUNSUPPORTED; }
+        else if (ap.f.size() == 1 && ap.f[0].c == 0 && ap.f[0].s == 1 && type_size(t->cols[(size_t)ap.f[0].col].type) == 4) {
+            if (colQ >= 0 && colQ != ap.f[0].col) { *why = "two different 32-bit aggregate columns"; return PG_EUNSUPPORTED; }
+            colQ = ap.f[0].col;
+            s = 1;
+            is_int = true;
+        } else if (prefix_match(ap, chain, 1)) s = 2;
+        else if (prefix_match(ap, chain, 2)) s = 3;
+        else if (prefix_match(ap, chain, 3)) s = 4;
+        else if (ap.f.size() == 1 && ap.f[0].c == 0 && ap.f[0].s == 1 && ap.f[0].col == colB) s = 5;
+        else { *why = "aggregate argument does not map onto the chain accumulators"; return PG_EUNSUPPORTED; }
+        if (s >= 2) {
+            int sc = 0;
+            if (s == 5) sc = t->cols[(size_t)colB].type == PG_T_DECIMAL64 ? t->cols[(size_t)colB].scale : 0;
+            else for (int k = 0; k < s - 1; k++) sc += chain.f[(size_t)k].scale;
+            p->slot_scale[(size_t)s] = sc;
+            is_int = a.ltype == PG_LT_HUGEINT || a.ltype == PG_LT_DOUBLE;
+            if (is_int && sc != 0) { *why = "integer aggregate over a scaled value"; return PG_EUNSUPPORTED; }
+        }
+        if (a.fn == PG_AGG_SUM && !is_int && a.ltype != PG_LT_DECIMAL) { *why = "sum result type mismatch"; return PG_EUNSUPPORTED; }
+        p->slot.push_back(s);
+        p->agg_is_int.push_back(is_int);
+    }
+    for (auto &o : aggn.outs) {
+        if (o.first == 0 && (o.second < 0 || o.second >= p->nkeys)) { *why = "bad group output index"; return PG_EUNSUPPORTED; }
+        if (o.first == 1 && (o.second < 0 || o.second >= (int)aggn.aggs.size())) { *why = "bad aggregate output index"; return PG_EUNSUPPORTED; }
+        if (o.first != 0 && o.first != 1) { *why = "bad output kind"; return PG_EUNSUPPORTED; }
+    }
+    // predicate: at most one range, on a 32-bit column
+    if (ranges.size() > 1) { *why = "more than one predicate column"; return PG_EUNSUPPORTED; }
+    int colP = -1;
+    int lo = INT32_MIN, hi = INT32_MAX;
+    if (ranges.size() == 1) {
+        colP = ranges[0].col;
+        if (type_size(t->cols[(size_t)colP].type) != 4) { *why = "predicate column is not 32-bit"; return PG_EUNSUPPORTED; }
+        lo = (int)std::max<i64>(ranges[0].lo, INT32_MIN);
+        hi = (int)std::min<i64>(ranges[0].hi, INT32_MAX);
+        if (ranges[0].lo > ranges[0].hi) { lo = 1; hi = 0; }
+    }
+    // every kernel input must exist: alias the missing ones to a column that is read anyway
+    if (colA < 0) { *why = "no 64-bit aggregate column"; return PG_EUNSUPPORTED; }
+    for (int cidx : {colA, colB, colC}) if (cidx >= 0 && type_size(t->cols[(size_t)cidx].type) != 8) { *why = "chain column is not 64-bit"; return PG_EUNSUPPORTED; }
+    LowcardParams &q = p->prm;
+    q.nrows = t->nrows;
+    q.row_base = t->global_offset;
+    q.A = (const i64 *)t->cols[(size_t)colA].d_data;
+    q.c1 = 1; q.s1 = 0; q.c2 = 1; q.s2 = 0;
+    q.B = q.A; q.C = q.A;
+    int ncol8 = 1;
+    if (colB >= 0) { q.B = (const i64 *)t->cols[(size_t)colB].d_data; q.c1 = chain.f[1].c; q.s1 = chain.f[1].s; ncol8++; }
+    if (colC >= 0) { q.C = (const i64 *)t->cols[(size_t)colC].d_data; q.c2 = chain.f[2].c; q.s2 = chain.f[2].s; ncol8++; }
+    int ncol4 = 0;
+    if (colQ >= 0) { q.q = (const int *)t->cols[(size_t)colQ].d_data; ncol4++; }
+    if (colP >= 0) { q.pred = (const int *)t->cols[(size_t)colP].d_data; if (colP != colQ) ncol4++; }
+    if (colQ < 0 && colP < 0) { *why = "no 32-bit column at all"; return PG_EUNSUPPORTED; }
+    if (colQ < 0) q.q = q.pred;
+    if (colP < 0) q.pred = q.q;
+    q.lo = lo; q.hi = hi;
+    q.key0 = (const uint8_t *)t->cols[(size_t)p->key_col[0]].d_data;
+    q.key1 = p->has_key1 ? (const uint8_t *)t->cols[(size_t)p->key_col[1]].d_data : nullptr;
+    q.n1 = dims[1];
+    q.ngroups = p->G;
+    p->bytes_per_row = 8 * ncol8 + 4 * ncol4 + p->nkeys;
+    p->smem = (size_t)p->G * LC_K * SA_THREADS * sizeof(i64);
+    const void *kern = p->has_key1 ? (const void *)lowcard_chain_kernel<true, 2> : (const void *)lowcard_chain_kernel<false, 2>;
+    PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+    i64 ntiles = (t->nrows + SA_TILE - 1) / SA_TILE;
+    p->grid = grid_for(kern, SA_THREADS, p->smem, ntiles);
+    // exactness proof from column statistics
+    {
+        const Column &cA = t->cols[(size_t)colA];
+        i128 bound = maxabs(cA.vmin, cA.vmax);
+        if (colB >= 0) {
+            const Column &cB = t->cols[(size_t)colB];
+            i128 f = std::max(maxabs(q.c1 + q.s1 * cB.vmin, q.c1 + q.s1 * cB.vmax), maxabs(cB.vmin, cB.vmax));
+            bound *= f > 1 ? f : 1;
+        }
+        if (colC >= 0) {
+            const Column &cC = t->cols[(size_t)colC];
+            i128 f = maxabs(q.c2 + q.s2 * cC.vmin, q.c2 + q.s2 * cC.vmax);
+            bound *= f > 1 ? f : 1;
+        }
+        i128 rows_per_cta = (i128)((ntiles + p->grid - 1) / p->grid) * SA_TILE;
+        if (bound * rows_per_cta >= ((i128)1 << 62)) { *why = "per-CTA partial sum could exceed int64"; return PG_EUNSUPPORTED; }
+    }
+    PG_TRY(p->d_part.alloc(sizeof(i64) * (size_t)p->grid * (size_t)p->G * LC_K));
+    PG_TRY(p->d_final.alloc(p->rank_bytes()));
+    PG_TRY(p->d_gather.alloc(p->rank_bytes() * (size_t)ctx().world));
+    PG_TRY(p->h_final.alloc(p->rank_bytes() * (size_t)ctx().world));
+    PG_TRY(p->d_luts.alloc(512));
+    PG_CUDA(cudaMemcpyAsync(p->d_luts.p, luts.data(), 512, cudaMemcpyHostToDevice, ctx().stream));
+    PG_CUDA(cudaStreamSynchronize(ctx().stream));
+    q.luts = p->d_luts.as<uint8_t>();
+    char buf[512];
+    snprintf(buf, sizeof buf,
+             "ScanAgg[lowcard-chain] table=%s rows=%lld kernel=lowcard_chain_kernel<%d,2> grid=%d block=%d smem=%zu "
+             "groups=%dx%d bytes/row=%d pred=[%d,%d] chain: A*(%lld%+lld*B)*(%lld%+lld*C)",
+             t->name.c_str(), (long long)t->nrows, (int)p->has_key1, p->grid, SA_THREADS, p->smem, dims[0], dims[1],
+             p->bytes_per_row, lo, hi, (long long)q.c1, (long long)q.s1, (long long)q.c2, (long long)q.s2);
+    p->explain = buf;
+    *out = std::move(p);
+    return PG_OK;
+}
+
+// ---------------------------------------------------------------------- entry --
+
+int build_scan_agg(pg_plan *plan, const Node &aggn, const Node &scan, std::unique_ptr<Pipeline> *out)
+{
+    const pg_table *t = plan->slots[(size_t)scan.slot];
+    LowerCtx cx;
+    cx.table = t;
+    std::vector<Range> ranges;
+    if (!lower_filters(cx, scan.filters, ranges)) PG_FAIL(PG_EUNSUPPORTED, "scan filter not off-loadable: %s", cx.why.c_str());
+    std::vector<AffProd> args(aggn.aggs.size());
+    for (size_t i = 0; i < aggn.aggs.size(); i++) {
+        const AggExpr &a = aggn.aggs[i];
+        if (a.fn == PG_AGG_COUNT) {
+            // count(*) is rewritten to count(<first column>) by the binder (builder_binder.go:207-228);
+            // on a NOT NULL column that is the row count
+            if (!a.star) {
+                const Expr *e = strip_value_preserving_casts(&a.arg);
+                if (e->kind != PG_TK_COL || e->idx < 0 || e->idx >= (int)t->cols.size() || t->cols[(size_t)e->idx].has_nulls)
+                    PG_FAIL(PG_EUNSUPPORTED, "count() over a nullable or computed argument");
+            }
+            continue;
+        }
+        if (a.star) PG_FAIL(PG_EINVAL, "aggregate %zu has no argument", i);
+        if (!lower_affprod(cx, a.arg, args[i])) PG_FAIL(PG_EUNSUPPORTED, "aggregate argument not off-loadable: %s", cx.why.c_str());
+    }
+    std::string why1, why2;
+    int s = try_sumprod(plan, aggn, scan, ranges, args, out, &why1);
+    if (s != PG_EUNSUPPORTED) return s;
+    s = try_lowcard(plan, aggn, scan, ranges, args, out, &why2);
+    if (s != PG_EUNSUPPORTED) return s;
+    PG_FAIL(PG_EUNSUPPORTED, "no fused scan-aggregate kernel for this shape (sumprod: %s; lowcard: %s)", why1.c_str(), why2.c_str());
+}
+
+}  // namespace pg

@@ -1,0 +1,192 @@
+"""TPC-H physical plans as the reference's planner emits them, plus the
+in-box generated tables.  The planner itself stays in Go; these builders stand in for
+`genPhyPlan` (/root/reference/pkg/compute/executor.go:76-114) in tests and benchmarks.
+
+Typing follows the reference binder:
+  - `1 - l_discount`: INTEGER literal cast to DECIMAL(15,2), DECIMAL subtract -> DECIMAL(16,2)
+  - `a * b` on DECIMALs: scale = sum of scales (function_scalar.go:429-475)
+  - `l_discount between 0.03-0.01 and 0.03+0.01`: FLOAT literals, folded in float32, column
+    cast to FLOAT (builder_binder.go:517-580)
+  - date +/- interval folded to a DATE constant (rule_constant_folding.go:34-100)
+  - sum(DECIMAL(w,s)) -> DECIMAL(38,s); avg(INT) -> DOUBLE; sum(INT)/count -> HUGEINT
+"""
+import ctypes as C
+import datetime
+
+import numpy as np
+
+from . import _lib as L
+from . import chunk as K
+from .compute import (JOIN_INNER, POT_Agg, POT_Join, POT_Scan, AggOpInfo, DeviceTable, JoinOpInfo,
+                      PhysicalOperator, ScanOpInfo, cast, col, const, func)
+
+SEGMENTS = ["AUTOMOBILE", "BUILDING", "FURNITURE", "HOUSEHOLD", "MACHINERY"]
+
+LINEITEM = [("l_orderkey", L.PG_T_INT64, 0, 0, None), ("l_partkey", L.PG_T_INT32, 0, 0, None),
+            ("l_suppkey", L.PG_T_INT32, 0, 0, None), ("l_linenumber", L.PG_T_INT32, 0, 0, None),
+            ("l_quantity", L.PG_T_INT32, 0, 0, None), ("l_extendedprice", L.PG_T_DECIMAL64, 15, 2, None),
+            ("l_discount", L.PG_T_DECIMAL64, 15, 2, None), ("l_tax", L.PG_T_DECIMAL64, 15, 2, None),
+            ("l_returnflag", L.PG_T_CHAR1, 0, 0, None), ("l_linestatus", L.PG_T_CHAR1, 0, 0, None),
+            ("l_shipdate", L.PG_T_DATE32, 0, 0, None), ("l_commitdate", L.PG_T_DATE32, 0, 0, None),
+            ("l_receiptdate", L.PG_T_DATE32, 0, 0, None)]
+ORDERS = [("o_orderkey", L.PG_T_INT64, 0, 0, None), ("o_custkey", L.PG_T_INT32, 0, 0, None),
+          ("o_orderdate", L.PG_T_DATE32, 0, 0, None), ("o_shippriority", L.PG_T_INT32, 0, 0, None),
+          ("o_totalprice", L.PG_T_DECIMAL64, 15, 2, None), ("o_orderstatus", L.PG_T_CHAR1, 0, 0, None)]
+CUSTOMER = [("c_custkey", L.PG_T_INT32, 0, 0, None), ("c_mktsegment", L.PG_T_DICT8, 0, 0, SEGMENTS),
+            ("c_nationkey", L.PG_T_INT32, 0, 0, None)]
+
+LI = {c[0]: i for i, c in enumerate(LINEITEM)}
+OI = {c[0]: i for i, c in enumerate(ORDERS)}
+CI = {c[0]: i for i, c in enumerate(CUSTOMER)}
+
+DEC15_2 = K.DecimalType(15, 2)
+
+
+def days(y, m, d):
+    return (datetime.date(y, m, d) - datetime.date(1970, 1, 1)).days
+
+
+def _ltype_of(coldef):
+    _, t, w, s, _ = coldef
+    return {L.PG_T_INT32: K.IntegerType(), L.PG_T_INT64: K.BigintType(), L.PG_T_DATE32: K.DateType(),
+            L.PG_T_DECIMAL64: K.DecimalType(w, s), L.PG_T_CHAR1: K.VarcharType(), L.PG_T_DICT8: K.VarcharType()}[t]
+
+
+def lcol(name, side=0):
+    return col(side, LI[name], _ltype_of(LINEITEM[LI[name]]))
+
+
+def ocol(name, side=0):
+    return col(side, OI[name], _ltype_of(ORDERS[OI[name]]))
+
+
+def ccol(name, side=0):
+    return col(side, CI[name], _ltype_of(CUSTOMER[CI[name]]))
+
+
+# ------------------------------------------------------------------ plans --
+
+def q6_plan(date_lo=None, date_hi=None, disc_lit=0.03, disc_eps=0.01, qty_lt=24):
+    """Agg(no group; sum(l_extendedprice*l_discount)) <- Scan(lineitem; 5 comparisons)."""
+    date_lo = days(1994, 1, 1) if date_lo is None else date_lo
+    date_hi = days(1995, 1, 1) if date_hi is None else date_hi
+    B = K.LType(K.LTID_BOOLEAN)
+    f32 = np.float32
+    flo = float(f32(disc_lit) - f32(disc_eps))     # subFloat32 folded at plan time
+    fhi = float(f32(disc_lit) + f32(disc_eps))
+    discf = cast(lcol("l_discount"), K.FloatType())
+    filters = [
+        func(">=", B, lcol("l_shipdate"), const(date_lo, K.DateType())),
+        func("<", B, lcol("l_shipdate"), const(date_hi, K.DateType())),
+        func("and", B, func(">=", B, discf, const(flo, K.FloatType())),
+             func("<=", B, discf, const(fhi, K.FloatType()))),
+        func("<", B, lcol("l_quantity"), const(qty_lt, K.IntegerType())),
+    ]
+    scan = PhysicalOperator(POT_Scan, Filters=filters, Info=ScanOpInfo("lineitem"))
+    arg = func("*", K.DecimalType(18, 4), lcol("l_extendedprice"), lcol("l_discount"))
+    agg = func("sum", K.DecimalType(38, 4), arg)
+    return PhysicalOperator(POT_Agg, Outputs=[col(1, 0, K.DecimalType(38, 4))], Children=[scan],
+                            Info=AggOpInfo([agg], []))
+
+
+def _one_minus_disc():
+    one = cast(const(1, K.IntegerType()), DEC15_2)
+    return func("-", K.DecimalType(16, 2), one, lcol("l_discount"))
+
+
+def _disc_price():
+    return func("*", K.DecimalType(18, 4), cast(lcol("l_extendedprice"), K.DecimalType(16, 2)), _one_minus_disc())
+
+
+def q1_plan(ship_le=None):
+    """Agg(group by l_returnflag,l_linestatus; 8 aggregates) <- Scan(lineitem; l_shipdate <= c)."""
+    ship_le = days(1998, 8, 11) if ship_le is None else ship_le    # 1998-12-01 - 112 days, folded
+    B = K.LType(K.LTID_BOOLEAN)
+    scan = PhysicalOperator(POT_Scan, Filters=[func("<=", B, lcol("l_shipdate"), const(ship_le, K.DateType()))],
+                            Info=ScanOpInfo("lineitem"))
+    one_plus_tax = func("+", K.DecimalType(16, 2), cast(const(1, K.IntegerType()), DEC15_2), lcol("l_tax"))
+    charge = func("*", K.DecimalType(18, 8), _disc_price(), cast(one_plus_tax, K.DecimalType(18, 4)))
+    aggs = [
+        func("sum", K.HugeintType(), lcol("l_quantity")),
+        func("sum", K.DecimalType(38, 2), lcol("l_extendedprice")),
+        func("sum", K.DecimalType(38, 4), _disc_price()),
+        func("sum", K.DecimalType(38, 8), charge),
+        func("avg", K.DoubleType(), lcol("l_quantity")),
+        func("avg", K.DecimalType(38, 2), lcol("l_extendedprice")),
+        func("avg", K.DecimalType(38, 2), lcol("l_discount")),
+        func("count", K.HugeintType(), lcol("l_orderkey")),     # count(*) -> count(first column)
+    ]
+    groups = [lcol("l_returnflag"), lcol("l_linestatus")]
+    outs = [col(0, 0, K.VarcharType()), col(0, 1, K.VarcharType())] + [col(1, i, a.DataTyp) for i, a in enumerate(aggs)]
+    return PhysicalOperator(POT_Agg, Outputs=outs, Children=[scan], Info=AggOpInfo(aggs, groups))
+
+
+def q3_plan(segment="HOUSEHOLD", odate_lt=None, ship_gt=None):
+    """Agg(group by l_orderkey,o_orderdate,o_shippriority; sum(ext*(1-disc)))
+         <- Join(l_orderkey = o_orderkey) <- { Scan(lineitem; l_shipdate > d),
+              Join(o_custkey = c_custkey) <- { Scan(orders; o_orderdate < d),
+                                               Scan(customer; c_mktsegment = seg) } }
+    Probe/left = larger relation, build/right = Children[1] (optimizer_joinorder.go:1028-1030)."""
+    odate_lt = days(1995, 3, 29) if odate_lt is None else odate_lt
+    ship_gt = days(1995, 3, 29) if ship_gt is None else ship_gt
+    B = K.LType(K.LTID_BOOLEAN)
+    cust = PhysicalOperator(POT_Scan, Filters=[func("=", B, ccol("c_mktsegment"), const(segment, K.VarcharType()))],
+                            Info=ScanOpInfo("customer"))
+    orders = PhysicalOperator(POT_Scan, Filters=[func("<", B, ocol("o_orderdate"), const(odate_lt, K.DateType()))],
+                              Info=ScanOpInfo("orders"))
+    line = PhysicalOperator(POT_Scan, Filters=[func(">", B, lcol("l_shipdate"), const(ship_gt, K.DateType()))],
+                            Info=ScanOpInfo("lineitem"))
+    j1 = PhysicalOperator(
+        POT_Join, Children=[orders, cust],
+        Outputs=[col(0, OI["o_orderkey"], K.BigintType()), col(0, OI["o_orderdate"], K.DateType()),
+                 col(0, OI["o_shippriority"], K.IntegerType())],
+        Info=JoinOpInfo(JOIN_INNER, [func("=", B, ocol("o_custkey", 0), ccol("c_custkey", 1))]))
+    j2 = PhysicalOperator(
+        POT_Join, Children=[line, j1],
+        Outputs=[col(0, LI["l_orderkey"], K.BigintType()), col(0, LI["l_extendedprice"], DEC15_2),
+                 col(0, LI["l_discount"], DEC15_2), col(1, 1, K.DateType()), col(1, 2, K.IntegerType())],
+        Info=JoinOpInfo(JOIN_INNER, [func("=", B, lcol("l_orderkey", 0), col(1, 0, K.BigintType()))]))
+    one = cast(const(1, K.IntegerType()), DEC15_2)
+    rev = func("*", K.DecimalType(18, 4), cast(col(0, 1, DEC15_2), K.DecimalType(16, 2)),
+               func("-", K.DecimalType(16, 2), one, col(0, 2, DEC15_2)))
+    agg = func("sum", K.DecimalType(38, 4), rev)
+    groups = [col(0, 0, K.BigintType()), col(0, 3, K.DateType()), col(0, 4, K.IntegerType())]
+    outs = [col(0, 0, K.BigintType()), col(1, 0, K.DecimalType(38, 4)), col(0, 1, K.DateType()),
+            col(0, 2, K.IntegerType())]
+    return PhysicalOperator(POT_Agg, Outputs=outs, Children=[j2], Info=AggOpInfo([agg], groups))
+
+
+# ----------------------------------------------------------------- tables --
+
+def generate_device_tables(sf, order_lo=0, order_hi=None, want=("lineitem", "orders", "customer")):
+    """dbgen-equivalent tables generated directly in HBM (plangpu_tpch.h)."""
+    lib = L.lib()
+    if order_hi is None:
+        order_hi = lib.pg_tpch_num_orders(sf)
+    out = {}
+    ho, hl = C.c_void_p(), C.c_void_p()
+    if "lineitem" in want or "orders" in want:
+        L.check(lib.pg_tpch_orders_lineitem(sf, order_lo, order_hi,
+                                            C.byref(ho) if "orders" in want else None,
+                                            C.byref(hl) if "lineitem" in want else None))
+        if "orders" in want:
+            out["orders"] = DeviceTable("orders", ho, ORDERS)
+        if "lineitem" in want:
+            out["lineitem"] = DeviceTable("lineitem", hl, LINEITEM)
+    if "customer" in want:
+        hc = C.c_void_p()
+        L.check(lib.pg_tpch_customer(sf, 0, lib.pg_tpch_num_customers(sf), C.byref(hc)))
+        out["customer"] = DeviceTable("customer", hc, CUSTOMER)
+    return out
+
+
+def upload_tables(host, global_offsets=None):
+    """host: {table: {column: numpy array}} (e.g. from the CPU generator) -> sealed DeviceTables."""
+    schemas = {"lineitem": LINEITEM, "orders": ORDERS, "customer": CUSTOMER}
+    out = {}
+    for name, cols in host.items():
+        t = DeviceTable.create(name, schemas[name])
+        t.append([cols[c[0]] for c in schemas[name]])
+        t.seal((global_offsets or {}).get(name, 0))
+        out[name] = t
+    return out

@@ -1,0 +1,208 @@
+"""GPU parity: fused scan+filter+aggregate pipelines (Q6 / Q1 shapes) vs the CPU oracle.
+
+Bit-exact for DECIMAL sums, counts and keys; avg(INT32) is an IEEE double compared exactly
+(north_star tolerance for AVG is 1e-12 relative -- we require equality)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(plan, tables):
+    from plan_b200 import compute as X
+    ex = X.gpuPipelineExec(plan, tables)
+    ex.Init()
+    chunks = X.drain(ex)
+    stats = ex.stats
+    explain = ex.Explain()
+    ex.Close()
+    return chunks, stats, explain
+
+
+def _rows(chunks):
+    rows = []
+    for c in chunks:
+        for r in range(c.Card()):
+            rows.append([v.GetValue(r) for v in c.Data])
+    return rows
+
+
+def _dec(vec, r):
+    x = vec.Data[r]
+    return (int(x["coef"]), int(x["scale"]), int(x["neg"]))
+
+
+def _dec_value(t):
+    return (-1 if t[2] else 1) * t[0], t[1]
+
+
+def _same_decimal(a, b):
+    """value equality of (coef, scale, neg) triples"""
+    (va, sa), (vb, sb) = _dec_value(a), _dec_value(b)
+    s = max(sa, sb)
+    return va * 10 ** (s - sa) == vb * 10 ** (s - sb)
+
+
+def check_q6(oracle, tables, line, **kw):
+    from plan_b200 import tpch as T
+    plan = T.q6_plan(**{k: v for k, v in kw.items()})
+    chunks, stats, explain = _run(plan, tables)
+    ref = oracle.q6(line, **kw)
+    assert "sumprod" in explain
+    assert stats.aux[0] == ref["rows_selected"]
+    if not ref["has_row"]:
+        assert chunks == []
+        return
+    assert len(chunks) == 1 and chunks[0].Card() == 1
+    got = _dec(chunks[0].Data[0], 0)
+    assert _dec_value(got)[0] * 10 ** (4 - got[1]) == ref["exact"]
+    assert _same_decimal(got, ref["sum"])
+    assert chunks[0].Data[0].GetValue(0).String() == oracle.fmt_decimal(ref["sum"], 4)
+
+
+def check_q1(oracle, tables, line, **kw):
+    from plan_b200 import tpch as T
+    plan = T.q1_plan(**kw)
+    chunks, stats, explain = _run(plan, tables)
+    ref = oracle.q1(line, **kw)
+    assert "lowcard" in explain
+    assert stats.aux[0] == ref["rows_selected"]
+    ngot = sum(c.Card() for c in chunks)
+    assert ngot == len(ref["groups"])
+    if ngot == 0:
+        return
+    c = chunks[0]
+    # group order = first-insertion order, like the reference's group scan
+    for r, g in enumerate(sorted(ref["groups"], key=lambda g: g["first_row"])):
+        assert chr(int(c.Data[0].Data[r])) == g["l_returnflag"]
+        assert chr(int(c.Data[1].Data[r])) == g["l_linestatus"]
+        hq = c.Data[2].Data[r]
+        assert (int(hq["upper"]) << 64) + int(hq["lower"]) == g["sum_qty"] == g["x_qty"]
+        for colidx, key, xkey, sc in ((3, "sum_base_price", "x_base", 2), (4, "sum_disc_price", "x_disc_price", 4),
+                                      (5, "sum_charge", "x_charge", 6)):
+            got = _dec(c.Data[colidx], r)
+            assert _dec_value(got)[0] * 10 ** (sc - got[1]) == g[xkey], key
+            assert _same_decimal(got, g[key]), key
+        assert float(c.Data[6].Data[r]) == g["avg_qty"]
+        assert _same_decimal(_dec(c.Data[7], r), g["avg_price"])
+        assert _same_decimal(_dec(c.Data[8], r), g["avg_disc"])
+        hc = c.Data[9].Data[r]
+        assert int(hc["lower"]) == g["count_order"] and int(hc["upper"]) == 0
+    # and the reference's text rendering of the rows
+    got_txt = sorted("\t".join(v.GetValue(r).String() for v in c.Data) for r in range(c.Card()))
+    ref_txt = sorted(oracle.q1_text(ref).strip("\n").split("\n")[1:])
+    assert got_txt == ref_txt
+
+
+@pytest.fixture(scope="module")
+def uploaded(pg, sf01_host):
+    from plan_b200 import tpch as T
+    t = T.upload_tables({"lineitem": sf01_host["lineitem"]})
+    yield t
+    for x in t.values():
+        x.free()
+
+
+def test_q6_sf01_uploaded(pg, oracle, uploaded, sf01_host):
+    check_q6(oracle, uploaded, sf01_host["lineitem"])
+
+
+def test_q1_sf01_uploaded(pg, oracle, uploaded, sf01_host):
+    check_q1(oracle, uploaded, sf01_host["lineitem"])
+
+
+@pytest.mark.parametrize("kw", [
+    dict(qty_lt=1),                                   # nothing passes -> no row at all
+    dict(qty_lt=51),                                  # quantity predicate always true
+    dict(disc_lit=0.05, disc_eps=0.02),
+    dict(disc_lit=0.07, disc_eps=0.0),
+    dict(disc_lit=0.10, disc_eps=0.011),
+    dict(date_lo=0, date_hi=40000),                   # date predicate always true
+])
+def test_q6_predicate_variants(pg, oracle, uploaded, sf01_host, kw):
+    check_q6(oracle, uploaded, sf01_host["lineitem"], **kw)
+
+
+@pytest.mark.parametrize("ship_le", [0, 8035 + 200, 8035 + 1263, 8035 + 1500, 40000])
+def test_q1_predicate_variants(pg, oracle, uploaded, sf01_host, ship_le):
+    check_q1(oracle, uploaded, sf01_host["lineitem"], ship_le=ship_le)
+
+
+@pytest.mark.parametrize("nrows", [0, 1, 3, 1023, 1024, 1025, 4097, 100003])
+def test_ragged_sizes(pg, oracle, sf01_host, nrows):
+    """Empty, single-row and non-tile-multiple inputs (tile = 1024 rows, vector = 4 rows)."""
+    from plan_b200 import tpch as T
+    line = {k: v[:nrows].copy() for k, v in sf01_host["lineitem"].items()}
+    t = T.upload_tables({"lineitem": line})
+    try:
+        check_q6(oracle, t, line, qty_lt=51, date_lo=0, date_hi=40000, disc_lit=0.05, disc_eps=0.06)
+        check_q6(oracle, t, line)
+        check_q1(oracle, t, line)
+    finally:
+        t["lineitem"].free()
+
+
+def test_append_in_chunks(pg, oracle, sf01_host):
+    """Ingest 2048-row chunk by chunk (how the shim drains scanExecutor) == bulk ingest."""
+    from plan_b200 import compute as X, tpch as T
+    n = 50000
+    line = {k: v[:n].copy() for k, v in sf01_host["lineitem"].items()}
+    t = X.DeviceTable.create("lineitem", T.LINEITEM)
+    for off in range(0, n, 2048):
+        t.append([line[c[0]][off:off + 2048] for c in T.LINEITEM])
+    t.seal()
+    try:
+        assert t.rows() == n
+        for c in ("l_extendedprice", "l_shipdate", "l_returnflag"):
+            assert np.array_equal(t.read_column(c), line[c])
+        check_q1(oracle, {"lineitem": t}, line)
+        check_q6(oracle, {"lineitem": t}, line)
+    finally:
+        t.free()
+
+
+def test_device_generator_matches_cpu_generator(pg, oracle, sf01_host):
+    """The CUDA dbgen restatement and the C one agree on every column of every table."""
+    from plan_b200 import tpch as T
+    t = T.generate_device_tables(0.1)
+    try:
+        for name in ("lineitem", "orders", "customer"):
+            assert t[name].rows() == len(next(iter(sf01_host[name].values())))
+            for cname, *_ in t[name].columns:
+                assert np.array_equal(t[name].read_column(cname), sf01_host[name][cname]), (name, cname)
+        check_q6(oracle, t, sf01_host["lineitem"])
+        check_q1(oracle, t, sf01_host["lineitem"])
+    finally:
+        for x in t.values():
+            x.free()
+
+
+def test_device_generator_order_ranges(pg, oracle):
+    """Any order range is generated independently (row-range shards built in place)."""
+    from plan_b200 import tpch as T
+    sf = 0.05
+    n = oracle.lib().tg_num_orders(sf)
+    lo, hi = n // 3, n // 3 + 20011
+    orders, line = oracle.gen_orders_lineitem(sf, lo, hi)
+    t = T.generate_device_tables(sf, lo, hi, want=("lineitem", "orders"))
+    try:
+        for cname, *_ in t["lineitem"].columns:
+            assert np.array_equal(t["lineitem"].read_column(cname), line[cname]), cname
+        for cname, *_ in t["orders"].columns:
+            assert np.array_equal(t["orders"].read_column(cname), orders[cname]), cname
+    finally:
+        for x in t.values():
+            x.free()
+
+
+def test_unsupported_shape_is_refused_not_emulated(pg, uploaded):
+    """A shape without a fused kernel yields PG_EUNSUPPORTED (plan selection falls back to the
+    stock executors at plan-build time) -- never a silent CPU path."""
+    from plan_b200 import _lib as L, chunk as K, compute as X, tpch as T
+    plan = T.q6_plan()
+    plan.Info.Aggs[0] = X.func("max", K.DecimalType(38, 4), plan.Info.Aggs[0].Children[0])
+    ex = X.gpuPipelineExec(plan, uploaded)
+    with pytest.raises(L.PlanGpuError) as ei:
+        ex.Init()
+    assert ei.value.status == L.PG_EUNSUPPORTED
+    ex.Close()
