@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""bench.py -- TPC-H Q1/Q6/Q3 lineitem rows/s + HBM roofline fraction at SF100 on N B200s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--sf 100] [--queries q6,q1,q3]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference ...      # the reference's CPU path (oracle port) on host cores
+
+A "step" = one execution of every query of the workload over the (row-range sharded)
+SF100 tables resident in HBM.  `value` = lineitem rows scanned by all queries of a step,
+over all ranks, per second (barrier + device sync on both sides, max over ranks).
+`e2e` = the same with HOST column buffers: pg_table_create/append/seal (H2D) + execute +
+result fetch inside the timed region.  `roofline` is for the dominant kernel (the Q1
+scan): algorithmic bytes / CUDA-event duration measured by the library on its own stream.
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LINEITEM_ROWS_PER_SF = 6_000_000   # nominal; the exact generated count is reported
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--sf", type=float, default=100.0)
+    ap.add_argument("--queries", default="q6,q1,q3")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-sf", type=float, default=1.0, help="CPU baseline sample: this SF worth of rows")
+    return ap.parse_args()
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.path = device, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons, smax = [], set(), None
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=smax, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ----------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation of the path = the oracle port
+# ----------------------------------------------------------------------------------------
+
+def cpu_reference_run(queries, sample_sf, steps, warmup):
+    """Time the C restatement of the reference executor (oracle/refexec.c), single thread
+    (the reference executes on one goroutine), on a bounded dbgen-equivalent sample."""
+    from oracle import oracle as O
+    O.build()
+    orders, line = O.gen_orders_lineitem(sample_sf)
+    cust = O.gen_customer(sample_sf)
+    nline = len(line["l_orderkey"])
+
+    def step():
+        for q in queries:
+            if q == "q6":
+                O.q6(line)
+            elif q == "q1":
+                O.q1(line)
+            elif q == "q3":
+                O.q3(cust, orders, line, capacity=16)
+    for _ in range(warmup):
+        step()
+    per_q = {}
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        for q in queries:
+            t = time.perf_counter()
+            {"q6": lambda: O.q6(line), "q1": lambda: O.q1(line),
+             "q3": lambda: O.q3(cust, orders, line, capacity=16)}[q]()
+            per_q[q] = per_q.get(q, 0.0) + (time.perf_counter() - t)
+    dt = time.perf_counter() - t0
+    rows = nline * len(queries) * steps
+    return {"rows_per_s": rows / dt, "ms_per_step": dt / steps * 1e3, "lineitem_rows": nline,
+            "per_query_rows_per_s": {q: nline * steps / per_q[q] for q in queries}}
+
+
+def run_reference_arm(args, queries):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_sf = min(args.cpu_sample_sf, args.sf)
+    steps, warmup = max(1, args.steps), max(0, min(args.warmup, 1))
+    # bound the whole run to a few minutes: ~6 s per SF1 step for q6+q1+q3 on one core
+    while steps * sample_sf * 7.0 > 240 and sample_sf > 0.05:
+        sample_sf /= 2
+    r = cpu_reference_run(queries, sample_sf, steps, warmup)
+    sample = "dbgen-equivalent SF%g sample (%d lineitem rows) of the SF%g workload, per step" % (
+        sample_sf, r["lineitem_rows"], args.sf)
+    line = {
+        "impl": "reference", "metric": "tpch_q1_q6_q3_lineitem_rows_per_s", "value": r["rows_per_s"],
+        "unit": "rows/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int64/decimal(19)",
+        "data": "synthetic (dbgen-equivalent generator, in-box)",
+        "config": {"workload": "TPC-H " + "+".join(q.upper() for q in queries) + " at SF%g" % args.sf,
+                   "queries": queries, "sf": args.sf, "sample": sample},
+        "cpu_baseline": {"value": r["rows_per_s"], "unit": "rows/s", "cores": 1, "kind": "port", "sample": sample,
+                         "note": "C restatement of the reference's single-goroutine executor (no Go toolchain on "
+                                 "the box); per query: " + json.dumps(r["per_query_rows_per_s"])},
+        "e2e": {"value": r["rows_per_s"], "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------
+
+def main():
+    args = parse_args()
+    queries = [q.strip() for q in args.queries.split(",") if q.strip()]
+    if args.impl == "reference":
+        run_reference_arm(args, queries)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("WORLD_SIZE %d != --gpus %d" % (world, args.gpus))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from plan_b200 import _lib as L
+    from plan_b200 import compute as X
+    from plan_b200 import tpch as T
+    import ctypes as C
+    lib = L.lib()
+    L.check(lib.pg_init(local_rank))
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (C.c_uint8 * 128)()
+            L.check(lib.pg_comm_unique_id(buf))
+            uid = torch.tensor(list(buf), dtype=torch.uint8)
+        uid = uid.cuda()
+        dist.broadcast(uid, 0)
+        raw = bytes(uid.cpu().tolist())
+        L.check(lib.pg_comm_init(world, rank, raw))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- data: this rank's contiguous order range, generated in HBM -------------------------
+    n_orders = lib.pg_tpch_num_orders(args.sf)
+    o_lo, o_hi = n_orders * rank // world, n_orders * (rank + 1) // world
+    want = ["lineitem"] + (["orders", "customer"] if "q3" in queries else [])
+    t_gen = time.perf_counter()
+    tables = T.generate_device_tables(args.sf, o_lo, o_hi, want=tuple(want))
+    gen_s = time.perf_counter() - t_gen
+    local_rows = tables["lineitem"].rows()
+    total_rows = int(sum_over_ranks(float(local_rows)))
+
+    plans = {"q6": T.q6_plan, "q1": T.q1_plan, "q3": T.q3_plan}
+    execs = {}
+    for q in queries:
+        ex = X.gpuPipelineExec(plans[q](), tables)
+        ex.Init()
+        execs[q] = ex
+
+    def run_query(q):
+        ex = execs[q]
+        ex.Reset()
+        chunks = X.drain(ex)
+        return chunks, ex.stats
+
+    def step(acc=None):
+        for q in queries:
+            _, st = run_query(q)
+            if acc is not None:
+                a = acc.setdefault(q, {"kernel_ms": 0.0, "main_ms": 0.0, "exec_ms": 0.0, "launches": 0, "n": 0,
+                                       "bytes": st.algorithmic_bytes, "main_bytes": st.main_kernel_bytes})
+                a["kernel_ms"] += st.kernel_ms
+                a["main_ms"] += st.main_kernel_ms
+                a["exec_ms"] += st.exec_ms
+                a["launches"] += st.kernel_launches
+                a["n"] += 1
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    acc = {}
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step(acc)
+    barrier()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = dt / args.steps * 1e3
+    value = total_rows * len(queries) * args.steps / dt
+
+    # ---- roofline of the dominant kernel (largest share of device time) ---------------------
+    peak, peak_src = measured_peak_gbs()
+    per_query = {}
+    for q in queries:
+        a = acc[q]
+        main_ms = max_over_ranks(a["main_ms"] / a["n"])
+        kern_ms = max_over_ranks(a["kernel_ms"] / a["n"])
+        exec_ms = max_over_ranks(a["exec_ms"] / a["n"])
+        gbs = a["main_bytes"] / (a["main_ms"] / a["n"] * 1e-3) / 1e9 if a["main_ms"] > 0 else 0.0
+        per_query[q] = {"rows_per_s": total_rows / (exec_ms * 1e-3), "exec_ms": exec_ms, "kernel_ms": kern_ms,
+                        "main_kernel_ms": main_ms, "main_kernel_bytes": a["main_bytes"],
+                        "achieved_gbs_per_gpu": gbs, "frac_of_measured_peak": gbs / peak}
+    dom = max(queries, key=lambda q: per_query[q]["main_kernel_ms"])
+    roofline = {"bound": "hbm", "achieved": per_query[dom]["achieved_gbs_per_gpu"], "peak": peak, "unit": "GB/s",
+                "frac": per_query[dom]["achieved_gbs_per_gpu"] / peak, "traffic": None,
+                "kernel": execs[dom].Explain().split(" kernel=")[1].split(" ")[0] if " kernel=" in execs[dom].Explain() else dom,
+                "query": dom, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": per_query[dom]["main_kernel_bytes"],
+                "avg_launch_ms": per_query[dom]["main_kernel_ms"]}
+    launches = sum(a["launches"] for a in acc.values())
+
+    # ---- e2e: host buffers through the C ABI (H2D inside the timed region) -------------------
+    e2e = None
+    if not args.no_e2e:
+        need = {"lineitem": ["l_quantity", "l_extendedprice", "l_discount", "l_tax", "l_returnflag", "l_linestatus",
+                             "l_shipdate"] + (["l_orderkey"] if "q3" in queries else [])}
+        if "q3" in queries:
+            need["orders"] = ["o_orderkey", "o_custkey", "o_orderdate", "o_shippriority"]
+            need["customer"] = ["c_custkey", "c_mktsegment"]
+        schemas = {"lineitem": T.LINEITEM, "orders": T.ORDERS, "customer": T.CUSTOMER}
+        host = {}
+        h2d_bytes = 0
+        for tname, cols in need.items():
+            host[tname] = {}
+            for cdef in schemas[tname]:
+                if cdef[0] in cols:
+                    dt_ = np.dtype(__import__("plan_b200.chunk", fromlist=["x"]).native_dtype(cdef[1]))
+                    n = tables[tname].rows()
+                    pinned = torch.empty(max(n, 1) * dt_.itemsize, dtype=torch.uint8, pin_memory=True)
+                    arr = pinned.numpy()[:n * dt_.itemsize].view(dt_)
+                    ci = [c[0] for c in schemas[tname]].index(cdef[0])
+                    L.check(lib.pg_table_read_column(tables[tname].handle, ci, 0, n, arr.ctypes.data))
+                    host[tname][cdef[0]] = (arr, pinned)
+                    h2d_bytes += n * dt_.itemsize
+        # the e2e tables carry only the referenced columns; plans are built on that pruned schema
+        sub = T.FULL.pruned(need)
+        sub_schema = sub.tables
+        offsets = {"lineitem": 0, "orders": o_lo, "customer": 0}
+        e_plans = {q: plans[q](schema=sub) for q in queries}
+        # free the resident tables' HBM is not needed: 180 GB holds both copies at SF100
+
+        def e2e_step():
+            d2h = 0
+            tabs = {}
+            for tname in need:
+                t = X.DeviceTable.create(tname, sub_schema[tname])
+                t.append([host[tname][c[0]][0] for c in sub_schema[tname]])
+                t.seal(offsets[tname])
+                tabs[tname] = t
+            for q in queries:
+                ex = X.gpuPipelineExec(e_plans[q], tabs)
+                ex.Init()
+                chunks = X.drain(ex)
+                d2h += sum(v.Data.nbytes for c in chunks for v in c.Data)
+                ex.Close()
+            for t in tabs.values():
+                t.free()
+            return d2h
+        e2e_step()                                  # warm-up (allocator, pinned paths)
+        barrier()
+        t0 = time.perf_counter()
+        d2h = 0
+        for _ in range(max(1, args.e2e_steps)):
+            d2h = e2e_step()
+        barrier()
+        edt = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": total_rows * len(queries) * max(1, args.e2e_steps) / edt, "unit": "rows/s",
+               "h2d_bytes_per_step": int(sum_over_ranks(float(h2d_bytes))), "d2h_bytes_per_step": int(sum_over_ranks(float(d2h))),
+               "ms_per_step": edt / max(1, args.e2e_steps) * 1e3, "steps": max(1, args.e2e_steps),
+               "includes": "pg_table_create+append(H2D from pinned host)+seal(stats)+plan compile/execute+result fetch"}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) -------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sample_sf = min(args.cpu_sample_sf, args.sf)
+        r = cpu_reference_run(queries, sample_sf, 1, 0)
+        cpu = {"value": r["rows_per_s"], "unit": "rows/s", "cores": 1, "kind": "port",
+               "sample": "dbgen-equivalent SF%g sample (%d lineitem rows), one pass of %s" % (
+                   sample_sf, r["lineitem_rows"], "+".join(queries)),
+               "host_cores": os.cpu_count(), "per_query_rows_per_s": r["per_query_rows_per_s"]}
+
+    if rank == 0:
+        out = {
+            "metric": "tpch_q1_q6_q3_lineitem_rows_per_s", "value": value, "unit": "rows/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "int64 fixed-point (128-bit merge)",
+            "data": "synthetic (dbgen-equivalent TPC-H generator, in HBM)",
+            "config": {"workload": "TPC-H " + "+".join(q.upper() for q in queries) + " at SF%g, lineitem/orders row-range "
+                                   "sharded over %d GPU(s)" % (args.sf, world),
+                       "queries": queries, "sf": args.sf, "lineitem_rows": total_rows,
+                       "l2": "inputs larger than L2 (%.1f GB of columns per GPU vs 126 MB)" % (
+                           per_query[dom]["main_kernel_bytes"] / 1e9),
+                       "parallelism": "row-range shard x%d, NCCL all-gather merge of partial aggregates" % world},
+            "queries": per_query, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+            "clocks": clocks, "datagen_s": gen_s,
+        }
+        print(json.dumps(out))
+    for ex in execs.values():
+        ex.Close()
+    for t in tables.values():
+        t.free()
+    if world > 1:
+        lib.pg_comm_destroy()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

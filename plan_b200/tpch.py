@@ -35,10 +35,6 @@ ORDERS = [("o_orderkey", L.PG_T_INT64, 0, 0, None), ("o_custkey", L.PG_T_INT32, 
 CUSTOMER = [("c_custkey", L.PG_T_INT32, 0, 0, None), ("c_mktsegment", L.PG_T_DICT8, 0, 0, SEGMENTS),
             ("c_nationkey", L.PG_T_INT32, 0, 0, None)]
 
-LI = {c[0]: i for i, c in enumerate(LINEITEM)}
-OI = {c[0]: i for i, c in enumerate(ORDERS)}
-CI = {c[0]: i for i, c in enumerate(CUSTOMER)}
-
 DEC15_2 = K.DecimalType(15, 2)
 
 
@@ -52,103 +48,116 @@ def _ltype_of(coldef):
             L.PG_T_DECIMAL64: K.DecimalType(w, s), L.PG_T_CHAR1: K.VarcharType(), L.PG_T_DICT8: K.VarcharType()}[t]
 
 
-def lcol(name, side=0):
-    return col(side, LI[name], _ltype_of(LINEITEM[LI[name]]))
+class Schema:
+    """Column layout of the bound tables (ScanOpInfo.Columns / ColName2Idx).  The default is
+    the full generated tables; a caller that uploads only the referenced columns passes the
+    pruned layout so column references index the right positions."""
+
+    def __init__(self, lineitem=None, orders=None, customer=None):
+        self.tables = {"lineitem": lineitem or LINEITEM, "orders": orders or ORDERS, "customer": customer or CUSTOMER}
+        self.idx = {t: {c[0]: i for i, c in enumerate(cols)} for t, cols in self.tables.items()}
+
+    def col(self, table, name, side=0):
+        i = self.idx[table][name]
+        return col(side, i, _ltype_of(self.tables[table][i]))
+
+    def pruned(self, need):
+        """need: {table: [column names]} -> Schema holding only those columns (original order)."""
+        kw = {t: [c for c in self.tables[t] if c[0] in need[t]] for t in need}
+        return Schema(**kw)
 
 
-def ocol(name, side=0):
-    return col(side, OI[name], _ltype_of(ORDERS[OI[name]]))
-
-
-def ccol(name, side=0):
-    return col(side, CI[name], _ltype_of(CUSTOMER[CI[name]]))
+FULL = Schema()
 
 
 # ------------------------------------------------------------------ plans --
 
-def q6_plan(date_lo=None, date_hi=None, disc_lit=0.03, disc_eps=0.01, qty_lt=24):
+def q6_plan(date_lo=None, date_hi=None, disc_lit=0.03, disc_eps=0.01, qty_lt=24, schema=FULL):
     """Agg(no group; sum(l_extendedprice*l_discount)) <- Scan(lineitem; 5 comparisons)."""
+    S = schema
     date_lo = days(1994, 1, 1) if date_lo is None else date_lo
     date_hi = days(1995, 1, 1) if date_hi is None else date_hi
     B = K.LType(K.LTID_BOOLEAN)
     f32 = np.float32
     flo = float(f32(disc_lit) - f32(disc_eps))     # subFloat32 folded at plan time
     fhi = float(f32(disc_lit) + f32(disc_eps))
-    discf = cast(lcol("l_discount"), K.FloatType())
+    discf = cast(S.col("lineitem", "l_discount"), K.FloatType())
     filters = [
-        func(">=", B, lcol("l_shipdate"), const(date_lo, K.DateType())),
-        func("<", B, lcol("l_shipdate"), const(date_hi, K.DateType())),
+        func(">=", B, S.col("lineitem", "l_shipdate"), const(date_lo, K.DateType())),
+        func("<", B, S.col("lineitem", "l_shipdate"), const(date_hi, K.DateType())),
         func("and", B, func(">=", B, discf, const(flo, K.FloatType())),
              func("<=", B, discf, const(fhi, K.FloatType()))),
-        func("<", B, lcol("l_quantity"), const(qty_lt, K.IntegerType())),
+        func("<", B, S.col("lineitem", "l_quantity"), const(qty_lt, K.IntegerType())),
     ]
     scan = PhysicalOperator(POT_Scan, Filters=filters, Info=ScanOpInfo("lineitem"))
-    arg = func("*", K.DecimalType(18, 4), lcol("l_extendedprice"), lcol("l_discount"))
+    arg = func("*", K.DecimalType(18, 4), S.col("lineitem", "l_extendedprice"), S.col("lineitem", "l_discount"))
     agg = func("sum", K.DecimalType(38, 4), arg)
     return PhysicalOperator(POT_Agg, Outputs=[col(1, 0, K.DecimalType(38, 4))], Children=[scan],
                             Info=AggOpInfo([agg], []))
 
 
-def _one_minus_disc():
+def _disc_price(ext, disc):
+    """l_extendedprice * (1 - l_discount): INTEGER 1 cast to DECIMAL(15,2), DECIMAL(16,2) subtract,
+    left operand cast to DECIMAL(16,2), product DECIMAL(18,4)."""
     one = cast(const(1, K.IntegerType()), DEC15_2)
-    return func("-", K.DecimalType(16, 2), one, lcol("l_discount"))
+    return func("*", K.DecimalType(18, 4), cast(ext, K.DecimalType(16, 2)), func("-", K.DecimalType(16, 2), one, disc))
 
 
-def _disc_price():
-    return func("*", K.DecimalType(18, 4), cast(lcol("l_extendedprice"), K.DecimalType(16, 2)), _one_minus_disc())
-
-
-def q1_plan(ship_le=None):
+def q1_plan(ship_le=None, schema=FULL):
     """Agg(group by l_returnflag,l_linestatus; 8 aggregates) <- Scan(lineitem; l_shipdate <= c)."""
+    S = schema
+    lc = lambda n: S.col("lineitem", n)   # noqa: E731
     ship_le = days(1998, 8, 11) if ship_le is None else ship_le    # 1998-12-01 - 112 days, folded
     B = K.LType(K.LTID_BOOLEAN)
-    scan = PhysicalOperator(POT_Scan, Filters=[func("<=", B, lcol("l_shipdate"), const(ship_le, K.DateType()))],
+    scan = PhysicalOperator(POT_Scan, Filters=[func("<=", B, lc("l_shipdate"), const(ship_le, K.DateType()))],
                             Info=ScanOpInfo("lineitem"))
-    one_plus_tax = func("+", K.DecimalType(16, 2), cast(const(1, K.IntegerType()), DEC15_2), lcol("l_tax"))
-    charge = func("*", K.DecimalType(18, 8), _disc_price(), cast(one_plus_tax, K.DecimalType(18, 4)))
+    one_plus_tax = func("+", K.DecimalType(16, 2), cast(const(1, K.IntegerType()), DEC15_2), lc("l_tax"))
+    charge = func("*", K.DecimalType(18, 8), _disc_price(lc("l_extendedprice"), lc("l_discount")),
+                  cast(one_plus_tax, K.DecimalType(18, 4)))
+    count_col = S.tables["lineitem"][0]        # count(*) -> count(first column) (builder_binder.go:207-228)
     aggs = [
-        func("sum", K.HugeintType(), lcol("l_quantity")),
-        func("sum", K.DecimalType(38, 2), lcol("l_extendedprice")),
-        func("sum", K.DecimalType(38, 4), _disc_price()),
+        func("sum", K.HugeintType(), lc("l_quantity")),
+        func("sum", K.DecimalType(38, 2), lc("l_extendedprice")),
+        func("sum", K.DecimalType(38, 4), _disc_price(lc("l_extendedprice"), lc("l_discount"))),
         func("sum", K.DecimalType(38, 8), charge),
-        func("avg", K.DoubleType(), lcol("l_quantity")),
-        func("avg", K.DecimalType(38, 2), lcol("l_extendedprice")),
-        func("avg", K.DecimalType(38, 2), lcol("l_discount")),
-        func("count", K.HugeintType(), lcol("l_orderkey")),     # count(*) -> count(first column)
+        func("avg", K.DoubleType(), lc("l_quantity")),
+        func("avg", K.DecimalType(38, 2), lc("l_extendedprice")),
+        func("avg", K.DecimalType(38, 2), lc("l_discount")),
+        func("count", K.HugeintType(), col(0, 0, _ltype_of(count_col))),
     ]
-    groups = [lcol("l_returnflag"), lcol("l_linestatus")]
+    groups = [lc("l_returnflag"), lc("l_linestatus")]
     outs = [col(0, 0, K.VarcharType()), col(0, 1, K.VarcharType())] + [col(1, i, a.DataTyp) for i, a in enumerate(aggs)]
     return PhysicalOperator(POT_Agg, Outputs=outs, Children=[scan], Info=AggOpInfo(aggs, groups))
 
 
-def q3_plan(segment="HOUSEHOLD", odate_lt=None, ship_gt=None):
+def q3_plan(segment="HOUSEHOLD", odate_lt=None, ship_gt=None, schema=FULL):
     """Agg(group by l_orderkey,o_orderdate,o_shippriority; sum(ext*(1-disc)))
          <- Join(l_orderkey = o_orderkey) <- { Scan(lineitem; l_shipdate > d),
               Join(o_custkey = c_custkey) <- { Scan(orders; o_orderdate < d),
                                                Scan(customer; c_mktsegment = seg) } }
     Probe/left = larger relation, build/right = Children[1] (optimizer_joinorder.go:1028-1030)."""
+    S = schema
     odate_lt = days(1995, 3, 29) if odate_lt is None else odate_lt
     ship_gt = days(1995, 3, 29) if ship_gt is None else ship_gt
     B = K.LType(K.LTID_BOOLEAN)
-    cust = PhysicalOperator(POT_Scan, Filters=[func("=", B, ccol("c_mktsegment"), const(segment, K.VarcharType()))],
-                            Info=ScanOpInfo("customer"))
-    orders = PhysicalOperator(POT_Scan, Filters=[func("<", B, ocol("o_orderdate"), const(odate_lt, K.DateType()))],
-                              Info=ScanOpInfo("orders"))
-    line = PhysicalOperator(POT_Scan, Filters=[func(">", B, lcol("l_shipdate"), const(ship_gt, K.DateType()))],
-                            Info=ScanOpInfo("lineitem"))
+    cust = PhysicalOperator(POT_Scan, Info=ScanOpInfo("customer"),
+                            Filters=[func("=", B, S.col("customer", "c_mktsegment"), const(segment, K.VarcharType()))])
+    orders = PhysicalOperator(POT_Scan, Info=ScanOpInfo("orders"),
+                              Filters=[func("<", B, S.col("orders", "o_orderdate"), const(odate_lt, K.DateType()))])
+    line = PhysicalOperator(POT_Scan, Info=ScanOpInfo("lineitem"),
+                            Filters=[func(">", B, S.col("lineitem", "l_shipdate"), const(ship_gt, K.DateType()))])
+    OI, LI = S.idx["orders"], S.idx["lineitem"]
     j1 = PhysicalOperator(
         POT_Join, Children=[orders, cust],
         Outputs=[col(0, OI["o_orderkey"], K.BigintType()), col(0, OI["o_orderdate"], K.DateType()),
                  col(0, OI["o_shippriority"], K.IntegerType())],
-        Info=JoinOpInfo(JOIN_INNER, [func("=", B, ocol("o_custkey", 0), ccol("c_custkey", 1))]))
+        Info=JoinOpInfo(JOIN_INNER, [func("=", B, S.col("orders", "o_custkey", 0), S.col("customer", "c_custkey", 1))]))
     j2 = PhysicalOperator(
         POT_Join, Children=[line, j1],
         Outputs=[col(0, LI["l_orderkey"], K.BigintType()), col(0, LI["l_extendedprice"], DEC15_2),
                  col(0, LI["l_discount"], DEC15_2), col(1, 1, K.DateType()), col(1, 2, K.IntegerType())],
-        Info=JoinOpInfo(JOIN_INNER, [func("=", B, lcol("l_orderkey", 0), col(1, 0, K.BigintType()))]))
-    one = cast(const(1, K.IntegerType()), DEC15_2)
-    rev = func("*", K.DecimalType(18, 4), cast(col(0, 1, DEC15_2), K.DecimalType(16, 2)),
-               func("-", K.DecimalType(16, 2), one, col(0, 2, DEC15_2)))
+        Info=JoinOpInfo(JOIN_INNER, [func("=", B, S.col("lineitem", "l_orderkey", 0), col(1, 0, K.BigintType()))]))
+    rev = _disc_price(col(0, 1, DEC15_2), col(0, 2, DEC15_2))
     agg = func("sum", K.DecimalType(38, 4), rev)
     groups = [col(0, 0, K.BigintType()), col(0, 3, K.DateType()), col(0, 4, K.IntegerType())]
     outs = [col(0, 0, K.BigintType()), col(1, 0, K.DecimalType(38, 4)), col(0, 1, K.DateType()),
@@ -180,9 +189,9 @@ def generate_device_tables(sf, order_lo=0, order_hi=None, want=("lineitem", "ord
     return out
 
 
-def upload_tables(host, global_offsets=None):
+def upload_tables(host, global_offsets=None, schema=FULL):
     """host: {table: {column: numpy array}} (e.g. from the CPU generator) -> sealed DeviceTables."""
-    schemas = {"lineitem": LINEITEM, "orders": ORDERS, "customer": CUSTOMER}
+    schemas = schema.tables
     out = {}
     for name, cols in host.items():
         t = DeviceTable.create(name, schemas[name])
