@@ -263,11 +263,14 @@ def main():
                 a["launches"] += st.kernel_launches
                 a["n"] += 1
 
-    for _ in range(max(args.warmup, 3)):
-        step()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        t_wait = time.perf_counter()          # nvidia-smi needs a moment before its first sample
+        while time.perf_counter() - t_wait < 3.0 and not (os.path.exists(sampler.path) and os.path.getsize(sampler.path) > 0):
+            time.sleep(0.05)
+    for _ in range(max(args.warmup, 3)):
+        step()
     acc = {}
     barrier()
     t0 = time.perf_counter()
@@ -275,7 +278,14 @@ def main():
         step(acc)
     barrier()
     dt = max_over_ranks(time.perf_counter() - t0)
+    # the timed region can be a few milliseconds: keep the same steps running (untimed) until the
+    # 100 ms sampler has seen the GPU under this load a few times
+    t_keep = time.perf_counter()
+    while time.perf_counter() - t_keep < 0.6:
+        step()
     clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["note"] = "sampled every 100 ms from warm-up through the timed steps and 0.6 s of the same steps after"
     ms_per_step = dt / args.steps * 1e3
     value = total_rows * len(queries) * args.steps / dt
 

@@ -228,8 +228,173 @@ struct LowcardPipeline : Pipeline {
     DevBuf d_part, d_final, d_first, d_luts, d_gather;
     PinBuf h_final;
     EventPair ev_all, ev_main;
+    bool nonneg[LC_K] = {true, true, true, true, true, true};   // slot values proven >= 0 from statistics
+    int emulations = 0;                                         // (group, slot) sums that took the ordered path
 
     size_t rank_bytes() const { return (size_t)G * LC_K * 16 + (size_t)LC_MAXG * 8; }
+
+    int ord_summaries(int g, int s, i64 tb, i64 te, std::vector<OrdSummary> *out)
+    {
+        out->resize((size_t)std::max<i64>(te - tb, 0));
+        if (te <= tb) return PG_OK;
+        cudaStream_t st = ctx().stream;
+        DevBuf d;
+        PG_TRY(d.alloc(sizeof(OrdSummary) * (size_t)(te - tb)));
+        OrdParams op;
+        op.base = prm;
+        op.group = g;
+        op.slot = s;
+        op.tile_begin = tb;
+        op.tile_end = te;
+        int gr = (int)std::min<i64>(te - tb, (i64)ctx().prop.multiProcessorCount * 8);
+        if (has_key1) ord_tile_kernel<true><<<gr, SA_THREADS, 0, st>>>(op, d.as<OrdSummary>());
+        else ord_tile_kernel<false><<<gr, SA_THREADS, 0, st>>>(op, d.as<OrdSummary>());
+        PG_CUDA(cudaGetLastError());
+        PG_CUDA(cudaMemcpyAsync(out->data(), d.p, sizeof(OrdSummary) * (size_t)(te - tb), cudaMemcpyDeviceToHost, st));
+        PG_CUDA(cudaStreamSynchronize(st));
+        return PG_OK;
+    }
+
+    // The value the reference's sequential Decimal.Add fold holds for (group g, slot s) when the
+    // exact total needs 20 digits (see the comment above ord_tile_kernel).  Collective: every
+    // rank calls it with the same arguments.  rank_tot[r] = exact total of rank r.
+    int emulate_rounded_sum(int g, int s, const std::vector<i128> &rank_tot, int vscale, HDec *out)
+    {
+        Context &c = ctx();
+        cudaStream_t st = c.stream;
+        const i128 THR = (i128)10000000000000000000ULL;    // 10^19
+        i128 total = 0;
+        for (auto v : rank_tot) total += v;
+        if (!nonneg[s]) PG_FAIL(PG_EOVERFLOW, "sum needs 20 digits and its addends may be negative: rounding order emulation not available");
+        if (total >= THR * 10) PG_FAIL(PG_EOVERFLOW, "sum needs more than 20 digits");
+        if (!prm.contig) PG_FAIL(PG_EOVERFLOW, "internal: ordered partials were not produced");
+        if (vscale < 1) PG_FAIL(PG_EOVERFLOW, "decimal overflow: integer part exceeds 19 digits");
+        int rstar = 0;
+        i128 P0 = 0;
+        while (P0 + rank_tot[(size_t)rstar] < THR) { P0 += rank_tot[(size_t)rstar]; rstar++; }
+        const i64 ntiles = (prm.nrows + SA_TILE - 1) / SA_TILE;
+        // per-rank contribution: absolute state (rank == rstar) or a transducer summary (rank > rstar)
+        struct Contrib { u64 kind, s_lo, s_hi, q_lo, q_hi; u64 c0, c1, p0p1; } mine{};
+        if (c.rank == rstar) {
+            // a. which CTA range crosses
+            std::vector<i64> part((size_t)grid * (size_t)G * LC_K);
+            PG_CUDA(cudaMemcpyAsync(part.data(), d_part.p, part.size() * sizeof(i64), cudaMemcpyDeviceToHost, st));
+            PG_CUDA(cudaStreamSynchronize(st));
+            i64 per = (ntiles + grid - 1) / grid;
+            i128 P = P0;
+            int cstar = 0;
+            for (; cstar < grid; cstar++) {
+                i128 v = part[(size_t)cstar * (size_t)G * LC_K + (size_t)g * LC_K + (size_t)s];
+                if (P + v >= THR) break;
+                P += v;
+            }
+            if (cstar == grid) PG_FAIL(PG_ECUDA, "internal: crossing CTA not found");
+            // b. which tile of that CTA crosses
+            i64 tb = (i64)cstar * per, te = std::min<i64>(ntiles, tb + per);
+            std::vector<OrdSummary> sums;
+            PG_TRY(ord_summaries(g, s, tb, te, &sums));
+            i64 tstar = tb;
+            for (; tstar < te; tstar++) {
+                i128 v = sums[(size_t)(tstar - tb)].sum_x;
+                if (P + v >= THR) break;
+                P += v;
+            }
+            if (tstar == te) PG_FAIL(PG_ECUDA, "internal: crossing tile not found");
+            // c. that tile row by row, exactly as the reference would add them
+            i64 row0 = tstar * SA_TILE;
+            int n = (int)std::min<i64>(SA_TILE, prm.nrows - row0);
+            std::vector<int> h_pred((size_t)n);
+            std::vector<uint8_t> h_k0((size_t)n), h_k1((size_t)n), h_lut(512);
+            std::vector<i64> h_a((size_t)n), h_b((size_t)n), h_c((size_t)n);
+            PG_CUDA(cudaMemcpyAsync(h_pred.data(), prm.pred + row0, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+            PG_CUDA(cudaMemcpyAsync(h_k0.data(), prm.key0 + row0, (size_t)n, cudaMemcpyDeviceToHost, st));
+            if (has_key1) PG_CUDA(cudaMemcpyAsync(h_k1.data(), prm.key1 + row0, (size_t)n, cudaMemcpyDeviceToHost, st));
+            PG_CUDA(cudaMemcpyAsync(h_a.data(), prm.A + row0, sizeof(i64) * (size_t)n, cudaMemcpyDeviceToHost, st));
+            PG_CUDA(cudaMemcpyAsync(h_b.data(), prm.B + row0, sizeof(i64) * (size_t)n, cudaMemcpyDeviceToHost, st));
+            PG_CUDA(cudaMemcpyAsync(h_c.data(), prm.C + row0, sizeof(i64) * (size_t)n, cudaMemcpyDeviceToHost, st));
+            PG_CUDA(cudaMemcpyAsync(h_lut.data(), prm.luts, 512, cudaMemcpyDeviceToHost, st));
+            PG_CUDA(cudaStreamSynchronize(st));
+            bool rounded = false;
+            u128 S = 0;
+            for (int i = 0; i < n; i++) {
+                if (h_pred[(size_t)i] < prm.lo || h_pred[(size_t)i] > prm.hi) continue;
+                int gg = h_lut[h_k0[(size_t)i]];
+                if (has_key1) gg = gg * prm.n1 + h_lut[256 + h_k1[(size_t)i]];
+                if (gg != g) continue;
+                i64 a = h_a[(size_t)i], b = h_b[(size_t)i], cc = h_c[(size_t)i];
+                i64 t2 = a * (prm.c1 + prm.s1 * b);
+                i64 x = s == 2 ? a : s == 3 ? t2 : s == 4 ? t2 * (prm.c2 + prm.s2 * cc) : b;
+                if (!rounded) {
+                    P += x;
+                    if (P >= THR) { S = hd_shift_right_even((u128)P, 1); rounded = true; }
+                } else {
+                    u128 q = (u128)(x / 10), t = S + q;
+                    int d = (int)(x % 10);
+                    S = t + ((d > 5 || (d == 5 && (t & 1))) ? 1 : 0);
+                }
+            }
+            if (!rounded) PG_FAIL(PG_ECUDA, "internal: crossing row not found");
+            // d. the rest of this rank's rows, tile summaries composed in order
+            PG_TRY(ord_summaries(g, s, tstar + 1, ntiles, &sums));
+            for (auto &o : sums) S += (u128)o.sum_q + ((S & 1) ? o.c1 : o.c0);
+            mine.kind = 1;
+            mine.s_lo = (u64)S;
+            mine.s_hi = (u64)(S >> 64);
+        } else if (c.rank > rstar) {
+            std::vector<OrdSummary> sums;
+            PG_TRY(ord_summaries(g, s, 0, ntiles, &sums));
+            i128 q = 0;
+            u64 cc[2] = {0, 0}, pp[2] = {0, 1};
+            for (auto &o : sums) {
+                q += o.sum_q;
+                for (int k = 0; k < 2; k++) {
+                    cc[k] += pp[k] ? o.c1 : o.c0;
+                    pp[k] = pp[k] ? o.p1 : o.p0;
+                }
+            }
+            mine.kind = 2;
+            mine.q_lo = (u64)q;
+            mine.q_hi = (u64)((u128)q >> 64);
+            mine.c0 = cc[0];
+            mine.c1 = cc[1];
+            mine.p0p1 = pp[0] | (pp[1] << 1);
+        }
+        std::vector<Contrib> all((size_t)c.world);
+        if (c.world > 1) {
+            DevBuf ds, dr;
+            PG_TRY(ds.alloc(sizeof(Contrib)));
+            PG_TRY(dr.alloc(sizeof(Contrib) * (size_t)c.world));
+            PG_CUDA(cudaMemcpyAsync(ds.p, &mine, sizeof(Contrib), cudaMemcpyHostToDevice, st));
+            PG_TRY(comm_allgather(ds.p, dr.p, sizeof(Contrib), st));
+            PG_CUDA(cudaMemcpyAsync(all.data(), dr.p, sizeof(Contrib) * (size_t)c.world, cudaMemcpyDeviceToHost, st));
+            PG_CUDA(cudaStreamSynchronize(st));
+        } else {
+            all[0] = mine;
+        }
+        if (all[(size_t)rstar].kind != 1) PG_FAIL(PG_ECUDA, "internal: crossing rank did not report a state");
+        u128 S = ((u128)all[(size_t)rstar].s_hi << 64) | all[(size_t)rstar].s_lo;
+        for (int r = rstar + 1; r < c.world; r++) {
+            const Contrib &k = all[(size_t)r];
+            u128 q = ((u128)k.q_hi << 64) | k.q_lo;
+            S += q + ((S & 1) ? k.c1 : k.c0);
+        }
+        if (S > (u128)HD_MAXCOEF) PG_FAIL(PG_EOVERFLOW, "sum needs more than 19 digits after rounding");
+        out->coef = (u64)S;
+        out->scale = vscale - 1;
+        out->neg = false;
+        emulations++;
+        return PG_OK;
+    }
+
+    // exact total -> the Decimal the reference would hold (rank_tot = per-rank exact totals)
+    int decimal_sum(int g, int s, const std::vector<i128> &rank_tot, HDec *out)
+    {
+        i128 v = 0;
+        for (auto x : rank_tot) v += x;
+        if (hd_digits((u128)(v < 0 ? -v : v)) > HD_MAXPREC) return emulate_rounded_sum(g, s, rank_tot, slot_scale[(size_t)s], out);
+        if (!hd_from_i128(v, slot_scale[(size_t)s], out)) PG_FAIL(PG_EOVERFLOW, "decimal overflow");
+        return PG_OK;
+    }
 
     int run(pg_result *res) override
     {
@@ -259,12 +424,17 @@ struct LowcardPipeline : Pipeline {
 
         // merge ranks in order; 128-bit exact
         std::vector<i128> tot((size_t)G * LC_K, 0);
+        std::vector<std::vector<i128>> rtot((size_t)G * LC_K, std::vector<i128>((size_t)c.world, 0));
         std::vector<i64> first((size_t)G, INT64_MAX);
+        emulations = 0;
         for (int r = 0; r < c.world; r++) {
             const char *base = (const char *)h_final.p + rank_bytes() * (size_t)r;
             const u64 *h = (const u64 *)base;
             const i64 *f = (const i64 *)(base + (size_t)G * LC_K * 16);
-            for (int v = 0; v < G * LC_K; v++) tot[(size_t)v] += make_i128(h[2 * v], h[2 * v + 1]);
+            for (int v = 0; v < G * LC_K; v++) {
+                rtot[(size_t)v][(size_t)r] = make_i128(h[2 * v], h[2 * v + 1]);
+                tot[(size_t)v] += rtot[(size_t)v][(size_t)r];
+            }
             for (int g = 0; g < G; g++) if (f[g] != 0x7f7f7f7f7f7f7f7fLL && f[g] < first[(size_t)g]) first[(size_t)g] = f[g];
         }
         res->stats.kernel_ms = ev_all.ms();
@@ -282,6 +452,7 @@ struct LowcardPipeline : Pipeline {
         for (int g : order) selected += (i64)tot[(size_t)g * LC_K];
         res->stats.aux[0] = selected;
         res->nrows = (i64)order.size();
+
         for (auto &o : outs) {
             ResCol col;
             if (o.first == 0) {
@@ -310,8 +481,7 @@ struct LowcardPipeline : Pipeline {
                         col.push(h);
                     } else if (a.fn == PG_AGG_SUM) {
                         HDec d;
-                        if (!hd_from_i128(v, slot_scale[(size_t)s], &d) || hd_digits((u128)(v < 0 ? -v : v)) > HD_MAXPREC)
-                            PG_FAIL(PG_EOVERFLOW, "sum exceeds 19 significant digits (order-dependent rounding regime)");
+                        PG_TRY(decimal_sum(g, s, rtot[(size_t)g * LC_K + (size_t)s], &d));
                         col.push(to_pg_decimal(d));
                     } else if (is_int) {   // avg(INT32): float64 sum / float64 count
                         i128 mag = v < 0 ? -v : v;
@@ -320,8 +490,7 @@ struct LowcardPipeline : Pipeline {
                         col.push(x);
                     } else {               // avg(DECIMAL) = sum.Quo(count)
                         HDec sd, nd, qd;
-                        if (!hd_from_i128(v, slot_scale[(size_t)s], &sd) || hd_digits((u128)(v < 0 ? -v : v)) > HD_MAXPREC)
-                            PG_FAIL(PG_EOVERFLOW, "avg: sum exceeds 19 significant digits");
+                        PG_TRY(decimal_sum(g, s, rtot[(size_t)g * LC_K + (size_t)s], &sd));
                         hd_from_i128(n, 0, &nd);
                         if (!hd_quo(sd, nd, &qd)) PG_FAIL(PG_EOVERFLOW, "avg: decimal division failed");
                         col.push(to_pg_decimal(qd));
@@ -330,6 +499,7 @@ struct LowcardPipeline : Pipeline {
             }
             res->cols.push_back(col);
         }
+        res->stats.aux[1] = emulations;
         return PG_OK;
     }
 };
@@ -488,6 +658,20 @@ static int try_lowcard(pg_plan *plan, const Node &aggn, const Node &scan, const 
         }
         i128 rows_per_cta = (i128)((ntiles + p->grid - 1) / p->grid) * SA_TILE;
         if (bound * rows_per_cta >= ((i128)1 << 62)) { *why = "per-CTA partial sum could exceed int64"; return PG_EUNSUPPORTED; }
+        // can any DECIMAL total need 20 digits?  Then the CTAs take contiguous tile runs so that
+        // their partials are ordered (sequential-rounding emulation); the bound uses the largest
+        // table any rank could hold relative to this one (shards are balanced to within 2x).
+        i128 table_bound = bound * (i128)std::max<i64>(t->nrows, 1) * (i128)ctx().world * 2;
+        q.contig = table_bound >= (i128)1000000000000000000LL ? 1 : 0;   // 10^18: generous margin
+        const char *force = getenv("PG_LOWCARD_CONTIG");
+        if (force) q.contig = atoi(force) ? 1 : 0;
+        bool a_pos = cA.vmin >= 0;
+        bool f1_pos = colB < 0 || (q.c1 + q.s1 * t->cols[(size_t)colB].vmin >= 0 && q.c1 + q.s1 * t->cols[(size_t)colB].vmax >= 0);
+        bool f2_pos = colC < 0 || (q.c2 + q.s2 * t->cols[(size_t)colC].vmin >= 0 && q.c2 + q.s2 * t->cols[(size_t)colC].vmax >= 0);
+        p->nonneg[2] = a_pos;
+        p->nonneg[3] = a_pos && f1_pos;
+        p->nonneg[4] = a_pos && f1_pos && f2_pos;
+        p->nonneg[5] = colB < 0 || t->cols[(size_t)colB].vmin >= 0;
     }
     PG_TRY(p->d_part.alloc(sizeof(i64) * (size_t)p->grid * (size_t)p->G * LC_K));
     PG_TRY(p->d_final.alloc(p->rank_bytes()));
@@ -500,9 +684,10 @@ static int try_lowcard(pg_plan *plan, const Node &aggn, const Node &scan, const 
     char buf[512];
     snprintf(buf, sizeof buf,
              "ScanAgg[lowcard-chain] table=%s rows=%lld kernel=lowcard_chain_kernel<%d,2> grid=%d block=%d smem=%zu "
-             "groups=%dx%d bytes/row=%d pred=[%d,%d] chain: A*(%lld%+lld*B)*(%lld%+lld*C)",
+             "groups=%dx%d bytes/row=%d pred=[%d,%d] chain: A*(%lld%+lld*B)*(%lld%+lld*C) tiles=%s",
              t->name.c_str(), (long long)t->nrows, (int)p->has_key1, p->grid, SA_THREADS, p->smem, dims[0], dims[1],
-             p->bytes_per_row, lo, hi, (long long)q.c1, (long long)q.s1, (long long)q.c2, (long long)q.s2);
+             p->bytes_per_row, lo, hi, (long long)q.c1, (long long)q.s1, (long long)q.c2, (long long)q.s2,
+             q.contig ? "contiguous-per-CTA(ordered partials)" : "interleaved");
     p->explain = buf;
     *out = std::move(p);
     return PG_OK;

@@ -147,7 +147,31 @@ struct LowcardParams {
     int ngroups;
     i64 nrows;
     i64 row_base;                        // global row id of local row 0 (for first_row)
+    int contig;                          // 1: each CTA owns a contiguous run of tiles, so the per-CTA
+                                         // partials are ORDERED partial sums (needed by the sequential
+                                         // rounding emulation); 0: tiles interleaved across CTAs
 };
+
+// tile iteration space of one CTA: tiles t0 + u*ustride, t0 = tbeg, tbeg+tstep, ... < tend
+struct TileIter { i64 tbeg, tend, tstep, ustride; };
+template <int UNROLL>
+__device__ __forceinline__ TileIter tile_iter(i64 ntiles, int contig)
+{
+    TileIter it;
+    if (contig) {
+        i64 per = (ntiles + gridDim.x - 1) / gridDim.x;
+        it.tbeg = (i64)blockIdx.x * per;
+        it.tend = it.tbeg + per < ntiles ? it.tbeg + per : ntiles;
+        it.tstep = UNROLL;
+        it.ustride = 1;
+    } else {
+        it.tbeg = blockIdx.x;
+        it.tend = ntiles;
+        it.tstep = (i64)gridDim.x * UNROLL;
+        it.ustride = gridDim.x;
+    }
+    return it;
+}
 
 template <bool HAS_KEY1, int UNROLL>
 __global__ void __launch_bounds__(SA_THREADS)
@@ -164,15 +188,16 @@ lowcard_chain_kernel(const LowcardParams p, i64 *__restrict__ partials /* [grid]
     __syncthreads();
 
     const i64 ntiles = (p.nrows + SA_TILE - 1) / SA_TILE;
+    const TileIter it = tile_iter<UNROLL>(ntiles, p.contig);
     i64 *my = s_acc + threadIdx.x;
-    for (i64 tile0 = blockIdx.x; tile0 < ntiles; tile0 += (i64)gridDim.x * UNROLL) {
+    for (i64 tile0 = it.tbeg; tile0 < it.tend; tile0 += it.tstep) {
         int4 d[UNROLL], q[UNROLL];
         unsigned k0[UNROLL], k1[UNROLL];
         longlong2 a[UNROLL][2], b[UNROLL][2], c[UNROLL][2];
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) {
-            i64 tile = tile0 + (i64)u * gridDim.x;
-            if (tile < ntiles) {
+            i64 tile = tile0 + (i64)u * it.ustride;
+            if (tile < it.tend) {
                 i64 row = tile * SA_TILE + threadIdx.x * SA_VEC;
                 d[u] = ld_stream16(p.pred + row);
                 k0[u] = ld_stream4(p.key0 + row);
@@ -185,8 +210,8 @@ lowcard_chain_kernel(const LowcardParams p, i64 *__restrict__ partials /* [grid]
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) {
-            i64 tile = tile0 + (i64)u * gridDim.x;
-            if (tile < ntiles) {
+            i64 tile = tile0 + (i64)u * it.ustride;
+            if (tile < it.tend) {
                 i64 row = tile * SA_TILE + threadIdx.x * SA_VEC;
                 i64 rem = p.nrows - row;
                 int dv[4] = {d[u].x, d[u].y, d[u].z, d[u].w};
@@ -228,6 +253,121 @@ lowcard_chain_kernel(const LowcardParams p, i64 *__restrict__ partials /* [grid]
     }
     if (threadIdx.x < G && s_first[threadIdx.x] != INT64_MAX)
         atomicMin((long long *)&first_row[threadIdx.x], (long long)s_first[threadIdx.x]);
+}
+
+// ------------------------------------------------------------------------------
+// Sequential-rounding emulation (govalues >19-digit regime).
+//
+// The reference folds sum(DECIMAL) with Decimal.Add in scan order
+// (function_aggr.go:684-689).  Once a running sum needs 20 digits the library keeps 19 and
+// rounds EVERY further addition half-to-even, so the result depends on row order:
+//     S' = S + floor(x/10) + carry,  carry = [d>5] or ([d==5] and (S + floor(x/10)) odd),
+// with d = x mod 10.  Each row is therefore a map parity(S) -> (parity(S'), carry) plus an
+// exact floor(x/10); maps compose associatively, so a tile is summarised in parallel and
+// tiles are composed in order on the host.  Only the rows after the crossing point are
+// re-read (about 8% of lineitem for Q1's (N,O) sum_charge at SF100).
+// ------------------------------------------------------------------------------
+struct OrdParams {
+    LowcardParams base;
+    int group;       // dense group id to follow
+    int slot;        // accumulator slot whose value sequence is followed (2..5)
+    i64 tile_begin, tile_end;
+};
+
+struct OrdSummary {        // one per tile
+    i64 sum_q;             // sum of floor(x/10)            (transducer kernel)
+    i64 sum_x;             // exact sum of x                (both kernels)
+    unsigned c0, c1;       // carries produced when entering with even / odd parity
+    unsigned p0, p1;       // parity on exit
+};
+
+__device__ __forceinline__ i64 ord_value(const LowcardParams &p, int slot, i64 a, i64 b, i64 c)
+{
+    i64 t2 = a * (p.c1 + p.s1 * b);
+    switch (slot) {
+    case 2: return a;
+    case 3: return t2;
+    case 4: return t2 * (p.c2 + p.s2 * c);
+    default: return b;
+    }
+}
+
+struct OrdState { i64 sq, sx; unsigned c0, c1, p0, p1; };
+__device__ __forceinline__ OrdState ord_compose(const OrdState &l, const OrdState &r)
+{
+    OrdState o;
+    o.sq = l.sq + r.sq;
+    o.sx = l.sx + r.sx;
+    o.p0 = l.p0 ? r.p1 : r.p0;
+    o.c0 = l.c0 + (l.p0 ? r.c1 : r.c0);
+    o.p1 = l.p1 ? r.p1 : r.p0;
+    o.c1 = l.c1 + (l.p1 ? r.c1 : r.c0);
+    return o;
+}
+
+template <bool HAS_KEY1>
+__global__ void __launch_bounds__(SA_THREADS)
+ord_tile_kernel(const OrdParams op, OrdSummary *__restrict__ out /* [tile_end - tile_begin] */)
+{
+    const LowcardParams &p = op.base;
+    __shared__ uint8_t s_lut[2][256];
+    __shared__ OrdState s_w[SA_THREADS / 32];
+    for (int i = threadIdx.x; i < 512; i += SA_THREADS) s_lut[i >> 8][i & 255] = p.luts[i];
+    __syncthreads();
+    for (i64 tile = op.tile_begin + blockIdx.x; tile < op.tile_end; tile += gridDim.x) {
+        i64 row = tile * SA_TILE + threadIdx.x * SA_VEC;
+        i64 rem = p.nrows - row;
+        int4 d = ld_stream16(p.pred + row);
+        unsigned k0 = ld_stream4(p.key0 + row), k1 = HAS_KEY1 ? ld_stream4(p.key1 + row) : 0;
+        longlong2 a0 = ld_stream16_ll(p.A + row), a1 = ld_stream16_ll(p.A + row + 2);
+        longlong2 b0 = ld_stream16_ll(p.B + row), b1 = ld_stream16_ll(p.B + row + 2);
+        longlong2 c0 = ld_stream16_ll(p.C + row), c1 = ld_stream16_ll(p.C + row + 2);
+        int dv[4] = {d.x, d.y, d.z, d.w};
+        i64 av[4] = {a0.x, a0.y, a1.x, a1.y}, bv[4] = {b0.x, b0.y, b1.x, b1.y}, cv[4] = {c0.x, c0.y, c1.x, c1.y};
+        OrdState st = {0, 0, 0, 0, 0, 1};   // identity: parity preserved, no carries
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            bool ok = j < rem && dv[j] >= p.lo && dv[j] <= p.hi;
+            int g = s_lut[0][(k0 >> (8 * j)) & 255];
+            if (HAS_KEY1) g = g * p.n1 + s_lut[1][(k1 >> (8 * j)) & 255];
+            if (ok && g == op.group) {
+                i64 x = ord_value(p, op.slot, av[j], bv[j], cv[j]);
+                i64 q = x / 10;
+                unsigned dgt = (unsigned)(x - q * 10), qb = (unsigned)(q & 1);
+                OrdState r;
+                r.sq = q;
+                r.sx = x;
+                unsigned t0 = qb, t1 = qb ^ 1u;     // parity of S + q when entering even / odd
+                r.c0 = (dgt > 5u) | ((dgt == 5u) & t0);
+                r.c1 = (dgt > 5u) | ((dgt == 5u) & t1);
+                r.p0 = t0 ^ r.c0;
+                r.p1 = t1 ^ r.c1;
+                st = ord_compose(st, r);
+            }
+        }
+        // ordered composition across the warp, then across the 8 warps
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            OrdState r;
+            r.sq = __shfl_down_sync(0xffffffffu, st.sq, o);
+            r.sx = __shfl_down_sync(0xffffffffu, st.sx, o);
+            r.c0 = __shfl_down_sync(0xffffffffu, st.c0, o);
+            r.c1 = __shfl_down_sync(0xffffffffu, st.c1, o);
+            r.p0 = __shfl_down_sync(0xffffffffu, st.p0, o);
+            r.p1 = __shfl_down_sync(0xffffffffu, st.p1, o);
+            if ((threadIdx.x & 31) + o < 32) st = ord_compose(st, r);
+        }
+        if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = st;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            OrdState t = s_w[0];
+            for (int w = 1; w < SA_THREADS / 32; w++) t = ord_compose(t, s_w[w]);
+            OrdSummary o;
+            o.sum_q = t.sq; o.sum_x = t.sx; o.c0 = t.c0; o.c1 = t.c1; o.p0 = t.p0; o.p1 = t.p1;
+            out[tile - op.tile_begin] = o;
+        }
+        __syncthreads();
+    }
 }
 
 // ------------------------------------------------------------------------------
