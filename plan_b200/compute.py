@@ -358,3 +358,42 @@ def drain(exec_):
         if out.Card() > 0:
             chunks.append(out)
     return chunks
+
+
+def order_limit(chunks, order_by, limit=None):
+    """Host stand-in for the parents that stay in Go: Order (normalized keys,
+    /root/reference/pkg/compute/sort_encoder.go:65-81: a DECIMAL key is Int64(2), i.e. rounded
+    to two fractional digits; DESC inverts) and Limit (executor_limit.go:120-137).
+    order_by: [(column index, descending)] ; returns a list of rows of Values."""
+    rows = []
+    for c in chunks:
+        for r in range(c.Card()):
+            rows.append([v.GetValue(r) for v in c.Data])
+
+    def key(row):
+        k = []
+        for idx, desc in order_by:
+            v = row[idx]
+            if v.Typ.Id == K.LTID_DECIMAL:
+                coef, scale, neg = K.new_from_int64(v.I64, v.I64_1, v.Typ.Scale) if not v.Str else (None, None, None)
+                w, f = K.decimal_int64(coef, scale, neg, 2)
+                part = (w, f)
+            elif v.Typ.Id in (K.LTID_DOUBLE, K.LTID_FLOAT):
+                part = (v.F64,)
+            elif v.Typ.Id == K.LTID_VARCHAR:
+                part = (v.Str,)
+            elif v.Typ.Id == K.LTID_HUGEINT:
+                part = ((v.I64 << 64) + (v.I64_1 & 0xFFFFFFFFFFFFFFFF),)
+            else:
+                part = (v.I64,)
+            if desc:
+                part = tuple(-x for x in part)
+            k.append(part)
+        return k
+    rows.sort(key=key)
+    return rows if limit is None else rows[:limit]
+
+
+def rows_text(rows, ncols):
+    """Chunk.SaveToFile text of a row list, with the reference's '#' headline."""
+    return "#" + "\t" * (ncols - 1) + "\n" + "".join("\t".join(v.String() for v in r) + "\n" for r in rows)

@@ -1,0 +1,254 @@
+// join.cuh -- hash join build / probe and high-cardinality group-by kernels (sm_100a).
+//
+// Reference code replaced:
+//   JoinHashTable.Build / Finalize / InsertHashesLoop   pkg/compute/join_table.go:85-288
+//     (chained table: bucket heads of nextpow2(2n) pointers, next pointer inside the row)
+//   Scan.Next / InnerJoin / resolvePredicates / Match    pkg/compute/join_scan.go:182-299
+//   GroupedAggrHashTable.FindOrCreateGroups + UpdateStates  pkg/compute/aggregate_hash.go:201-391,
+//                                                          aggregate_exec.go:456
+//
+// Design for B200 (HBM-bound, random-sector-bound on the table):
+//   * BUCKETIZED open addressing: a bucket is one 64-byte line of 8 keys (2 sectors) plus a
+//     parallel 64-byte line of 8 payloads read only on a match; duplicates occupy further
+//     slots of the probe sequence, an empty slot ends it (no deletes).  Payload = row id of
+//     the build-side source row: columns are gathered late, only for matches.
+//   * an exact key-domain BITMAP (1 bit per key in [kmin,kmax] of the build column
+//     statistics) screens probes before the table is touched.  For dense keys it is a few
+//     MB, L2-resident, and TPC-H fact tables are clustered on their join keys so
+//     consecutive probes hit the same sectors.
+//   * group-by on high-cardinality keys: global open-addressing table in HBM, 64-bit CAS
+//     on the key words, 64-bit atomic adds on the accumulators (red.global.add.u64).
+#pragma once
+#include "common.cuh"
+#include "scanagg.cuh"
+
+namespace pg {
+
+constexpr i64 HT_EMPTY = (i64)0x8080808080808080ULL;   // memset(0x80) pattern
+constexpr int HT_BUCKET = 8;
+
+__host__ __device__ __forceinline__ u64 mix64(u64 x)
+{
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return x;
+}
+
+struct JoinTable {
+    i64 *keys;          // [nbuckets][8]
+    u64 *pay;           // [nbuckets][8]
+    u64 bucket_mask;    // nbuckets - 1 (power of two)
+    unsigned *bitmap;   // may be null
+    i64 bm_min, bm_max; // key domain covered by the bitmap
+};
+
+__device__ __forceinline__ bool bitmap_test(const JoinTable &t, i64 key)
+{
+    if (key < t.bm_min || key > t.bm_max) return false;
+    u64 off = (u64)(key - t.bm_min);
+    return (__ldg(t.bitmap + (off >> 5)) >> (off & 31)) & 1u;
+}
+
+__device__ __forceinline__ void jt_insert(const JoinTable &t, i64 key, u64 payload)
+{
+    if (t.bitmap) {
+        u64 off = (u64)(key - t.bm_min);
+        atomicOr(t.bitmap + (off >> 5), 1u << (off & 31));
+    }
+    u64 b = mix64((u64)key) & t.bucket_mask;
+    for (;;) {
+        i64 *line = t.keys + b * HT_BUCKET;
+#pragma unroll
+        for (int s = 0; s < HT_BUCKET; s++) {
+            if (line[s] == HT_EMPTY) {
+                i64 old = (i64)atomicCAS((unsigned long long *)&line[s], (unsigned long long)HT_EMPTY, (unsigned long long)key);
+                if (old == HT_EMPTY) { t.pay[b * HT_BUCKET + s] = payload; return; }
+            }
+        }
+        b = (b + 1) & t.bucket_mask;
+    }
+}
+
+// calls f(payload) for every build row with this key (INNER join emits every pair)
+template <typename F>
+__device__ __forceinline__ void jt_probe(const JoinTable &t, i64 key, F f)
+{
+    u64 b = mix64((u64)key) & t.bucket_mask;
+    for (;;) {
+        const longlong2 *line = (const longlong2 *)(t.keys + b * HT_BUCKET);
+        longlong2 k01 = __ldg(line), k23 = __ldg(line + 1), k45 = __ldg(line + 2), k67 = __ldg(line + 3);
+        i64 k[8] = {k01.x, k01.y, k23.x, k23.y, k45.x, k45.y, k67.x, k67.y};
+        bool end = false;
+#pragma unroll
+        for (int s = 0; s < HT_BUCKET; s++) {
+            if (k[s] == key) f(__ldg(t.pay + b * HT_BUCKET + s));
+            end = end || k[s] == HT_EMPTY;
+        }
+        if (end) return;
+        b = (b + 1) & t.bucket_mask;
+    }
+}
+
+// a column of a base table read by row id with its native width
+struct TypedCol {
+    const void *p;
+    int width;      // 1, 4 or 8 bytes
+};
+__device__ __forceinline__ i64 load_typed(const TypedCol &c, i64 row)
+{
+    switch (c.width) {
+    case 8: return __ldg((const i64 *)c.p + row);
+    case 4: return (i64)__ldg((const int *)c.p + row);
+    default: return (i64)__ldg((const uint8_t *)c.p + row);
+    }
+}
+
+struct SrcPred {          // inclusive range on a source column
+    TypedCol col;
+    i64 lo, hi;
+};
+
+constexpr int PIPE_MAXPRED = 3;
+
+// ---------------------------------------------------------------- pipelines --
+// One kernel family: stream a source table, apply range predicates, optionally probe one
+// join table with a source key column, and feed a sink:
+//   SINK_COUNT   count surviving (joined) rows            -> sizing pass
+//   SINK_INSERT  insert (key column, source row id) into a join table  -> build side
+//   SINK_GROUP   update the global group table            -> aggregate over the join
+enum { SINK_COUNT = 0, SINK_INSERT = 1, SINK_GROUP = 2 };
+
+constexpr int GT_MAXACC = 4;
+constexpr int GT_MAXKEYPARTS = 3;
+
+struct GroupTable {
+    i64 *klo, *khi;       // [cap] key words, HT_EMPTY when free
+    i64 *acc;             // [nacc + 1][cap]; the last plane counts rows
+    u64 mask;             // cap - 1
+    int nacc;
+    int *overflow;        // set when a probe sequence exceeds the limit (table too small)
+};
+
+// where a value comes from: the streamed source row or the matched build row
+struct ValRef {
+    TypedCol col;
+    int from_build;       // 0: source row id, 1: build row id (late gather)
+};
+
+struct GroupSpec {
+    // key = up to 3 parts: part 0 -> klo; parts 1,2 -> khi = (p1 << 32) | (p2 & 0xffffffff)
+    int nparts;
+    ValRef part[GT_MAXKEYPARTS];
+    // accumulator a = product over its factors of (c + s * value)
+    int nacc;
+    int nfac[GT_MAXACC];
+    ValRef fac[GT_MAXACC][3];
+    i64 fc[GT_MAXACC][3];
+    int fs[GT_MAXACC][3];
+};
+
+struct PipeParams {
+    i64 nrows;
+    int npred;
+    SrcPred pred[PIPE_MAXPRED];
+    int has_probe;
+    TypedCol probe_key;
+    JoinTable probe;
+    // SINK_INSERT
+    TypedCol ins_key;
+    JoinTable ins;
+    // SINK_GROUP
+    GroupTable gt;
+    GroupSpec gs;
+    // SINK_COUNT / statistics: [0] rows passing the predicates, [1] joined rows
+    unsigned long long *counters;
+};
+
+__device__ __forceinline__ void gt_update(const GroupTable &g, i64 klo, i64 khi, const i64 *vals)
+{
+    u64 cap = g.mask + 1;
+    u64 i = mix64((u64)klo * 0x9E3779B97F4A7C15ULL ^ (u64)khi) & g.mask;
+    for (u64 n = 0; n <= g.mask; n++) {
+        i64 cur = g.klo[i];
+        if (cur == HT_EMPTY) cur = (i64)atomicCAS((unsigned long long *)&g.klo[i], (unsigned long long)HT_EMPTY, (unsigned long long)klo);
+        if (cur == HT_EMPTY || cur == klo) {
+            i64 h = g.khi[i];
+            if (h == HT_EMPTY) h = (i64)atomicCAS((unsigned long long *)&g.khi[i], (unsigned long long)HT_EMPTY, (unsigned long long)khi);
+            if (h == HT_EMPTY || h == khi) {
+                for (int a = 0; a < g.nacc; a++) atomicAdd((unsigned long long *)&g.acc[(u64)a * cap + i], (unsigned long long)vals[a]);
+                atomicAdd((unsigned long long *)&g.acc[(u64)g.nacc * cap + i], 1ULL);
+                return;
+            }
+        }
+        i = (i + 1) & g.mask;
+        if (n > 4096) break;
+    }
+    *g.overflow = 1;
+}
+
+template <int SINK>
+__global__ void __launch_bounds__(256)
+pipeline_kernel(const PipeParams p)
+{
+    unsigned long long n_pass = 0, n_join = 0;
+    for (i64 row = (i64)blockIdx.x * blockDim.x + threadIdx.x; row < p.nrows; row += (i64)gridDim.x * blockDim.x) {
+        bool ok = true;
+        for (int k = 0; k < p.npred && ok; k++) {
+            i64 v = load_typed(p.pred[k].col, row);
+            ok = v >= p.pred[k].lo && v <= p.pred[k].hi;
+        }
+        if (!ok) continue;
+        n_pass++;
+        auto sink = [&](u64 build_row) {
+            n_join++;
+            if (SINK == SINK_INSERT) {
+                jt_insert(p.ins, load_typed(p.ins_key, row), (u64)row);
+            } else if (SINK == SINK_GROUP) {
+                auto val = [&](const ValRef &r) { return load_typed(r.col, r.from_build ? (i64)build_row : row); };
+                i64 klo = val(p.gs.part[0]);
+                i64 khi = 0;
+                if (p.gs.nparts > 1) khi = val(p.gs.part[1]) << 32;
+                if (p.gs.nparts > 2) khi |= val(p.gs.part[2]) & 0xffffffffLL;
+                i64 vals[GT_MAXACC];
+                for (int a = 0; a < p.gs.nacc; a++) {
+                    i64 x = 1;
+                    for (int f = 0; f < p.gs.nfac[a]; f++) x *= p.gs.fc[a][f] + p.gs.fs[a][f] * val(p.gs.fac[a][f]);
+                    vals[a] = x;
+                }
+                gt_update(p.gt, klo, khi, vals);
+            }
+        };
+        if (p.has_probe) {
+            i64 key = load_typed(p.probe_key, row);
+            if (p.probe.bitmap && !bitmap_test(p.probe, key)) continue;
+            jt_probe(p.probe, key, sink);
+        } else {
+            sink(0);
+        }
+    }
+    // block-aggregate the two counters
+    n_pass = (unsigned long long)warp_sum((i64)n_pass);
+    n_join = (unsigned long long)warp_sum((i64)n_join);
+    if ((threadIdx.x & 31) == 0) {
+        if (n_pass) atomicAdd(&p.counters[0], n_pass);
+        if (n_join) atomicAdd(&p.counters[1], n_join);
+    }
+}
+
+// compact the occupied slots of a group table into dense output arrays
+static __global__ void gt_compact_kernel(const GroupTable g, i64 *__restrict__ out_klo, i64 *__restrict__ out_khi,
+                                  i64 *__restrict__ out_acc /* [nacc+1][max_out] */, i64 max_out,
+                                  unsigned long long *__restrict__ counter)
+{
+    u64 cap = g.mask + 1;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (u64)gridDim.x * blockDim.x) {
+        i64 k = g.klo[i];
+        if (k == HT_EMPTY) continue;
+        unsigned long long o = atomicAdd(counter, 1ULL);
+        if ((i64)o >= max_out) continue;
+        out_klo[o] = k;
+        out_khi[o] = g.khi[i];
+        for (int a = 0; a <= g.nacc; a++) out_acc[(u64)a * (u64)max_out + o] = g.acc[(u64)a * cap + i];
+    }
+}
+
+}  // namespace pg

@@ -376,7 +376,7 @@ ord_tile_kernel(const OrdParams op, OrdSummary *__restrict__ out /* [tile_end - 
 // 19-digit Decimal (:684-689); per-CTA sums are proven < 2^63 at plan time from the
 // column statistics, the cross-CTA total is carried in 128 bits.
 // ------------------------------------------------------------------------------
-__global__ void finalize128_kernel(const i64 *__restrict__ partials, int nblocks, int nvals,
+static __global__ void finalize128_kernel(const i64 *__restrict__ partials, int nblocks, int nvals,
                                    u64 *__restrict__ out /* [nvals][2] */)
 {
     int v = blockIdx.x * blockDim.x + threadIdx.x;

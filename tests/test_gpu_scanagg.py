@@ -209,7 +209,7 @@ def test_unsupported_shape_is_refused_not_emulated(pg, uploaded):
     ex.Close()
 
 
-@pytest.mark.parametrize("nrows,mult", [(20000, 40001), (60000, 12007), (5000, 150001)])
+@pytest.mark.parametrize("nrows,mult", [(20000, 40001), (60000, 12007), (200000, 3001)])
 def test_q1_sequential_rounding_regime(pg, oracle, sf01_host, nrows, mult):
     """sum_charge beyond 19 digits: govalues keeps 19 digits and rounds every further addition
     half-to-even, so the result depends on row order (happens for Q1's (N,O)
@@ -224,5 +224,22 @@ def test_q1_sequential_rounding_regime(pg, oracle, sf01_host, nrows, mult):
     t = T.upload_tables({"lineitem": line})
     try:
         check_q1(oracle, t, line)
+    finally:
+        t["lineitem"].free()
+
+
+def test_inexact_partials_are_refused(pg, sf01_host):
+    """Values so large that a per-CTA int64 partial could overflow: refuse at plan time
+    (PG_EUNSUPPORTED -> stock executors), never compute a wrong sum."""
+    from plan_b200 import _lib as L, compute as X, tpch as T
+    line = {k: v[:5000].copy() for k, v in sf01_host["lineitem"].items()}
+    line["l_extendedprice"] = line["l_extendedprice"] * 150001
+    t = T.upload_tables({"lineitem": line})
+    try:
+        ex = X.gpuPipelineExec(T.q1_plan(), t)
+        with pytest.raises(L.PlanGpuError) as ei:
+            ex.Init()
+        assert ei.value.status == L.PG_EUNSUPPORTED
+        ex.Close()
     finally:
         t["lineitem"].free()
