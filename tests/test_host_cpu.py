@@ -1,0 +1,121 @@
+"""CPU: the C-ABI library loads and exports every declared symbol; the host-side mirror
+(descriptor serialisation, formatting, Order/Limit stand-ins) behaves; malformed descriptors are
+refused.  No compute call is made (there is no GPU here)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from plan_b200 import build as B
+    B.build()
+    from plan_b200 import _lib as L
+    return L.lib()
+
+
+def _declared_symbols():
+    names = set()
+    for h in ("plangpu.h", "plangpu_tpch.h"):
+        src = open(os.path.join(ROOT, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b(pg_[a-z0-9_]+)\s*\(", src))
+    return names
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from plan_b200 import _lib as L
+    declared = _declared_symbols()
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(lib, name), "libplangpu.so does not export %s" % name
+    assert declared == {s[0] for s in L.SIGNATURES}, "ctypes bindings and headers disagree"
+    assert lib.pg_abi_version() == 1
+
+
+def test_sass_is_sm100_only():
+    """The product is built for sm_100a only (no multi-arch fat binary)."""
+    import subprocess
+    out = subprocess.run(["cuobjdump", "--list-elf", os.path.join(ROOT, "plan_b200", "libplangpu.so")],
+                         capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_calls_without_init_fail_loudly(lib):
+    from plan_b200 import _lib as L
+    h = C.c_void_p()
+    desc = (L.ColDesc * 1)()
+    desc[0].name, desc[0].type = b"x", L.PG_T_INT32
+    assert lib.pg_table_create(b"t", 1, desc, C.byref(h)) == L.PG_ESTATE
+    assert b"pg_init" in lib.pg_last_error()
+
+
+def test_descriptor_roundtrip_and_validation(lib):
+    from plan_b200 import _lib as L, compute as X, tpch as T
+    for plan, nslots in ((T.q6_plan(), 1), (T.q1_plan(), 1), (T.q3_plan(), 3)):
+        d, slots = X.serialize_plan(plan)
+        assert d[0] == 0x31504750 and d[1] == 1 and len(slots) == nslots
+        p = C.c_void_p()
+        assert lib.pg_plan_compile(d.ctypes.data_as(C.POINTER(C.c_int64)), len(d), C.byref(p)) == L.PG_OK
+        # executing needs pg_init (a GPU): refused, not emulated
+        r = C.c_void_p()
+        assert lib.pg_plan_execute(p, C.byref(r)) == L.PG_ESTATE
+        lib.pg_plan_free(p)
+        # truncated and corrupted descriptors
+        for bad in (d[:len(d) // 2], np.concatenate([d, [7]]), np.concatenate([[1, 1], d[2:]])):
+            bad = np.ascontiguousarray(bad, dtype=np.int64)
+            p = C.c_void_p()
+            assert lib.pg_plan_compile(bad.ctypes.data_as(C.POINTER(C.c_int64)), len(bad), C.byref(p)) == L.PG_EINVAL
+        d2 = d.copy()
+        d2[2] = 99                                       # unknown operator
+        p = C.c_void_p()
+        assert lib.pg_plan_compile(d2.ctypes.data_as(C.POINTER(C.c_int64)), len(d2), C.byref(p)) == L.PG_EINVAL
+
+
+def test_value_formatting_follows_the_reference():
+    from plan_b200 import chunk as K
+    dec = np.zeros(3, dtype=K.DECIMAL128)
+    dec[0] = (5656804138090, 2, 0)
+    dec[1] = (3827312915, 5, 0)
+    dec[2] = (10861784737714287, 5, 0)
+    v = K.Vector(K.DecimalType(38, 2), dec)
+    assert v.GetValue(0).String() == "56568041380.9"         # trailing zero stripped
+    assert v.GetValue(1).String() == "38273.13"              # Int64(2) rounds half-even
+    v8 = K.Vector(K.DecimalType(38, 8), dec)
+    assert v8.GetValue(2).String() == "108617847377.14287"
+    h = np.zeros(1, dtype=K.HUGEINT)
+    h[0] = (37734107, 0)
+    assert K.Vector(K.HugeintType(), h).GetValue(0).String() == "37734107"
+    assert K.Vector(K.DateType(), np.array([9217], np.int32)).GetValue(0).String() == "1995-03-28"
+    assert K.Vector(K.DoubleType(), np.array([25.522005853257337])).GetValue(0).String() == "25.522005853257337"
+    assert K.go_float_string(1e21) == "1e+21" and K.go_float_string(0.00001) == "1e-05"
+    assert K.decimal_int64(125, 3, False, 2) == (0, 12) and K.decimal_int64(135, 3, False, 2) == (0, 14)
+
+
+def test_order_limit_standins():
+    from plan_b200 import chunk as K, compute as X
+    dec = np.zeros(4, dtype=K.DECIMAL128)
+    for i, c in enumerate((100049, 100051, 99, 100049)):      # keys are rounded to 2 digits: 10.00 10.01 0.01 10.00
+        dec[i] = (c, 4, 0)
+    ch = K.Chunk()
+    ch.Data = [K.Vector(K.BigintType(), np.array([1, 2, 3, 4], np.int64)), K.Vector(K.DecimalType(38, 4), dec),
+               K.Vector(K.DateType(), np.array([30, 20, 10, 5], np.int32))]
+    ch.Count = 4
+    rows = X.order_limit([ch], [(1, True), (2, False)], 3)
+    assert [r[0].I64 for r in rows] == [2, 4, 1]              # 10.01 first; tie on 10.00 broken by date
+
+
+def test_oracle_is_not_reachable_from_the_product():
+    """The product path must never import or link the oracle."""
+    for root, _, files in os.walk(os.path.join(ROOT, "plan_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
+                src = open(os.path.join(root, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
+                assert not [ln for ln in src.splitlines() if ln.lstrip().startswith("#include") and "oracle" in ln], f

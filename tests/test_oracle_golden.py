@@ -1,0 +1,113 @@
+"""CPU: the oracle (C restatement of the reference executor + dbgen-equivalent generator) is
+pinned against the reference's own SF1 golden result files and known official dbgen rows."""
+import os
+
+import numpy as np
+import pytest
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def sf1(oracle):
+    orders, line = oracle.gen_orders_lineitem(1.0)
+    return {"orders": orders, "lineitem": line, "customer": oracle.gen_customer(1.0)}
+
+
+def test_generator_row_counts_match_official_dbgen(oracle):
+    L = oracle.lib()
+    assert L.tg_count_lineitems(1.0, 0, 1500000) == 6001215       # official SF1 lineitem cardinality
+    assert L.tg_count_lineitems(10.0, 0, 15000000) == 59986052    # SF10
+
+
+def test_generator_first_rows_match_official_dbgen(oracle, sf1):
+    """First rows of the official SF1 lineitem.tbl / orders.tbl / customer.tbl."""
+    l, o, c = sf1["lineitem"], sf1["orders"], sf1["customer"]
+    d = oracle.days
+    want = [  # orderkey partkey suppkey line qty extprice disc tax rf ls ship commit receipt
+        (1, 155190, 7706, 1, 17, 2116823, 4, 2, "N", "O", d(1996, 3, 13), d(1996, 2, 12), d(1996, 3, 22)),
+        (1, 67310, 7311, 2, 36, 4598316, 9, 6, "N", "O", d(1996, 4, 12), d(1996, 2, 28), d(1996, 4, 20)),
+        (1, 63700, 3701, 3, 8, 1330960, 10, 2, "N", "O", d(1996, 1, 29), d(1996, 3, 5), d(1996, 1, 31)),
+        (1, 2132, 4633, 4, 28, 2895564, 9, 6, "N", "O", d(1996, 4, 21), d(1996, 3, 30), d(1996, 5, 16)),
+        (1, 24027, 1534, 5, 24, 2282448, 10, 4, "N", "O", d(1996, 3, 30), d(1996, 3, 14), d(1996, 4, 1)),
+        (1, 15635, 638, 6, 32, 4962016, 7, 2, "N", "O", d(1996, 1, 30), d(1996, 2, 7), d(1996, 2, 3)),
+        (2, 106170, 1191, 1, 38, 4469446, 0, 5, "N", "O", d(1997, 1, 28), d(1997, 1, 14), d(1997, 2, 2)),
+        (3, 4297, 1798, 1, 45, 5405805, 6, 0, "R", "F", d(1994, 2, 2), d(1994, 1, 4), d(1994, 2, 23)),
+        (3, 19036, 6540, 2, 49, 4679647, 10, 0, "R", "F", d(1993, 11, 9), d(1993, 12, 20), d(1993, 11, 24)),
+        (3, 128449, 3474, 3, 27, 3989088, 6, 7, "A", "F", d(1994, 1, 16), d(1993, 11, 22), d(1994, 1, 23)),
+    ]
+    cols = ["l_orderkey", "l_partkey", "l_suppkey", "l_linenumber", "l_quantity", "l_extendedprice", "l_discount",
+            "l_tax", "l_returnflag", "l_linestatus", "l_shipdate", "l_commitdate", "l_receiptdate"]
+    for r, row in enumerate(want):
+        got = tuple(chr(int(l[cn][r])) if cn in ("l_returnflag", "l_linestatus") else int(l[cn][r]) for cn in cols)
+        assert got == row, (r, got, row)
+    # orders.tbl: 1|36901|O|173665.47|1996-01-02 ; 2|78002|O|46929.18|1996-12-01 ; 3|123314|F|193846.25|1993-10-14
+    assert [int(x) for x in o["o_orderkey"][:9]] == [1, 2, 3, 4, 5, 6, 7, 32, 33]
+    assert [int(x) for x in o["o_custkey"][:3]] == [36901, 78002, 123314]
+    assert [int(x) for x in o["o_totalprice"][:3]] == [17366547, 4692918, 19384625]
+    assert [chr(int(x)) for x in o["o_orderstatus"][:3]] == ["O", "O", "F"]
+    assert [int(x) for x in o["o_orderdate"][:3]] == [d(1996, 1, 2), d(1996, 12, 1), d(1993, 10, 14)]
+    segs = [oracle.SEGMENTS[int(x)] for x in c["c_mktsegment"][:10]]
+    assert segs == ["BUILDING", "AUTOMOBILE", "AUTOMOBILE", "MACHINERY", "HOUSEHOLD", "AUTOMOBILE", "AUTOMOBILE",
+                    "BUILDING", "FURNITURE", "HOUSEHOLD"]
+
+
+def test_generator_ranges_are_independent(oracle, sf1):
+    o2, l2 = oracle.gen_orders_lineitem(1.0, 700000, 700100)
+    first = int(np.searchsorted(sf1["lineitem"]["l_orderkey"], l2["l_orderkey"][0]))
+    for k, v in l2.items():
+        assert np.array_equal(v, sf1["lineitem"][k][first:first + len(v)]), k
+    for k, v in o2.items():
+        assert np.array_equal(v, sf1["orders"][k][700000:700100]), k
+
+
+def test_q6_reproduces_reference_golden(oracle, sf1):
+    assert oracle.q6_text(oracle.q6(sf1["lineitem"])) == open(os.path.join(GOLDEN, "ref_sf1_q6.txt")).read()
+
+
+def test_q1_reproduces_reference_golden(oracle, sf1):
+    res = oracle.q1(sf1["lineitem"])
+    assert oracle.q1_text(res) == open(os.path.join(GOLDEN, "ref_sf1_q1.txt")).read()
+    assert res["rows_selected"] == 1478493 + 38854 + 2874145 + 1478870
+    for g in res["groups"]:        # data-independent KATs of SURVEY.md 8c: avg = sum / count
+        assert repr(g["avg_qty"]) == repr(float(g["sum_qty"]) / float(g["count_order"]))
+
+
+def test_q3_reproduces_reference_golden(oracle, sf1):
+    res = oracle.q3(sf1["customer"], sf1["orders"], sf1["lineitem"])
+    assert oracle.q3_text(res) == open(os.path.join(GOLDEN, "ref_sf1_q3.txt")).read()
+
+
+def test_decimal_contract(oracle):
+    """govalues contract points the restatement relies on."""
+    import ctypes as C
+    L = oracle.lib()
+
+    def op(name, a, b):
+        oc, os_, on = C.c_uint64(), C.c_int(), C.c_int()
+        rc = getattr(L, name)(a[0], a[1], a[2], b[0], b[1], b[2], C.byref(oc), C.byref(os_), C.byref(on))
+        return rc, (oc.value, os_.value, on.value)
+    assert op("orc_dec_add", (150, 2, 0), (25, 1, 0)) == (0, (400, 2, 0))                 # scale = max
+    assert op("orc_dec_mul", (150, 2, 0), (25, 1, 0)) == (0, (3750, 3, 0))                # scale = sum
+    assert op("orc_dec_add", (100, 2, 0), (250, 2, 1)) == (0, (150, 2, 1))                # sign
+    # 20-digit result: keep 19 digits, half-even
+    assert op("orc_dec_add", (9999999999999999999, 6, 0), (6, 6, 0)) == (0, (1000000000000000000, 5, 0))
+    assert op("orc_dec_add", (9999999999999999990, 6, 0), (15, 6, 0)) == (0, (1000000000000000000, 5, 0))   # tie -> even
+    assert op("orc_dec_add", (9999999999999999990, 6, 0), (25, 6, 0)) == (0, (1000000000000000002, 5, 0))   # tie -> even
+    assert op("orc_dec_add", (9999999999999999999, 0, 0), (1, 0, 0))[0] != 0              # integer part overflows
+    # Quo: exact when it terminates, else 19 significant digits; trailing zeros trimmed
+    assert op("orc_dec_quo", (100, 2, 0), (4, 0, 0)) == (0, (25, 2, 0))
+    assert op("orc_dec_quo", (1, 0, 0), (3, 0, 0)) == (0, (3333333333333333333, 19, 0))
+    rc, (coef, scale, neg) = op("orc_dec_quo", (5658655440073, 2, 0), (1478493, 0, 0))            # 38273.1297...
+    assert rc == 0 and neg == 0 and str(coef).startswith("3827312973462167") and coef * 10 ** (19 - scale) // 10 ** 19 == 38273
+    # formatting: Int64(scale) rounds half-even, NewFromInt64 strips trailing zeros
+    assert oracle.fmt_decimal((5656804138090, 2, 0), 2) == "56568041380.9"
+    assert oracle.fmt_decimal((3827312915, 5, 0), 2) == "38273.13"
+    assert oracle.fmt_decimal((125, 3, 0), 2) == "0.12" and oracle.fmt_decimal((135, 3, 0), 2) == "0.14"
+    assert oracle.fmt_double(25.522005853257337) == "25.522005853257337"
+    assert oracle.fmt_double(1e21) == "1e+21" and oracle.fmt_double(100.0) == "100"
+    # the float32 cast the reference applies to DECIMAL columns in range predicates
+    f = np.float32
+    lo, hi = f(0.03) - f(0.01), f(0.03) + f(0.01)
+    passing = [c for c in range(0, 11) if lo <= f(L.orc_dec_float64(c, 2, 0)) <= hi]
+    assert passing == [2, 3, 4]
