@@ -198,15 +198,8 @@ def main():
     lib = L.lib()
     L.check(lib.pg_init(local_rank))
     if world > 1:
-        uid = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            buf = (C.c_uint8 * 128)()
-            L.check(lib.pg_comm_unique_id(buf))
-            uid = torch.tensor(list(buf), dtype=torch.uint8)
-        uid = uid.cuda()
-        dist.broadcast(uid, 0)
-        raw = bytes(uid.cpu().tolist())
-        L.check(lib.pg_comm_init(world, rank, raw))
+        from plan_b200 import dist as D
+        D.init_comm(lib, L.check)
 
     def barrier():
         torch.cuda.synchronize()
@@ -234,6 +227,8 @@ def main():
     want = ["lineitem"] + (["orders", "customer"] if "q3" in queries else [])
     t_gen = time.perf_counter()
     tables = T.generate_device_tables(args.sf, o_lo, o_hi, want=tuple(want))
+    if "customer" in tables:
+        tables["customer"].set_replicated()        # small dimension table: whole copy on every rank
     gen_s = time.perf_counter() - t_gen
     local_rows = tables["lineitem"].rows()
     total_rows = int(sum_over_ranks(float(local_rows)))
@@ -347,6 +342,8 @@ def main():
                 t = X.DeviceTable.create(tname, sub_schema[tname])
                 t.append([host[tname][c[0]][0] for c in sub_schema[tname]])
                 t.seal(offsets[tname])
+                if tname == "customer":
+                    t.set_replicated()
                 tabs[tname] = t
             for q in queries:
                 ex = X.gpuPipelineExec(e_plans[q], tabs)

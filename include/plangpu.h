@@ -135,6 +135,14 @@ int pg_table_set_rows(pg_table *t, int64_t nrows);
  * the device.  `global_row_offset` is this rank's first row in the unsharded table
  * (0 on a single GPU); shards are contiguous row ranges in rank order.            */
 int pg_table_seal(pg_table *t, int64_t global_row_offset);
+/* How the table relates to the other ranks when a communicator is up (default SHARDED):
+ * SHARDED    = this rank holds one contiguous row range of the table (rank order = row order);
+ * REPLICATED = every rank holds the whole table (small dimension tables).
+ * Joins between sharded tables run shard-local when the column statistics prove the shards
+ * are co-partitioned on the join key (disjoint key ranges); otherwise PG_EUNSUPPORTED.     */
+#define PG_DIST_SHARDED 0
+#define PG_DIST_REPLICATED 1
+int pg_table_set_distribution(pg_table *t, int dist);
 int pg_table_rows(const pg_table *t, int64_t *nrows);
 void pg_table_free(pg_table *t);
 

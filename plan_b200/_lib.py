@@ -9,6 +9,7 @@ PG_OK, PG_EINVAL, PG_ENOMEM, PG_ECUDA, PG_ENCCL, PG_EOVERFLOW, PG_EUNSUPPORTED, 
 STATUS_NAMES = ["PG_OK", "PG_EINVAL", "PG_ENOMEM", "PG_ECUDA", "PG_ENCCL", "PG_EOVERFLOW", "PG_EUNSUPPORTED",
                 "PG_ESTATE"]
 
+PG_DIST_SHARDED, PG_DIST_REPLICATED = 0, 1
 PG_T_INT32, PG_T_INT64, PG_T_DATE32, PG_T_DECIMAL64, PG_T_CHAR1, PG_T_DICT8, PG_T_FLOAT64, PG_T_HUGEINT, \
     PG_T_DECIMAL128 = range(1, 10)
 
@@ -62,6 +63,7 @@ SIGNATURES = [
     ("pg_table_device_column", C.c_int, [_P, C.c_int, C.POINTER(_P)]),
     ("pg_table_set_rows", C.c_int, [_P, C.c_int64]),
     ("pg_table_seal", C.c_int, [_P, C.c_int64]),
+    ("pg_table_set_distribution", C.c_int, [_P, C.c_int]),
     ("pg_table_rows", C.c_int, [_P, C.POINTER(C.c_int64)]),
     ("pg_table_free", None, [_P]),
     ("pg_plan_compile", C.c_int, [C.POINTER(C.c_int64), C.c_size_t, C.POINTER(_P)]),

@@ -223,6 +223,10 @@ class DeviceTable:
         L.check(L.lib().pg_table_seal(self.handle, global_row_offset))
         return self
 
+    def set_replicated(self, replicated=True):
+        L.check(L.lib().pg_table_set_distribution(self.handle, L.PG_DIST_REPLICATED if replicated else L.PG_DIST_SHARDED))
+        return self
+
     def rows(self):
         n = C.c_int64()
         L.check(L.lib().pg_table_rows(self.handle, C.byref(n)))

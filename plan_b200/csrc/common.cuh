@@ -94,6 +94,7 @@ struct pg_table {
     std::vector<pg::Column> cols;
     pg::i64 nrows = 0, capacity = 0;
     bool sealed = false;
+    int dist = 0;              // PG_DIST_*
     pg::i64 global_offset = 0;
     uint64_t version = 0;   // bumped whenever contents change (plan caches key on it)
 };

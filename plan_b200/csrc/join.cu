@@ -76,6 +76,8 @@ struct JoinAggPipeline : Pipeline {
     u64 gt_cap = 0;
     i64 out_cap = 0;
     EventPair ev_all, ev_main;
+    bool gather_ranks = false;     // probe side is sharded: every rank ends with the union of all groups
+    DevBuf d_g_klo, d_g_khi, d_g_acc, d_g_cnt;
 
     const pg_table *tab(int slot) const { return plan->slots[(size_t)slot]; }
 
@@ -181,7 +183,6 @@ struct JoinAggPipeline : Pipeline {
     {
         Context &c = ctx();
         cudaStream_t st = c.stream;
-        if (c.world > 1) PG_FAIL(PG_EUNSUPPORTED, "multi-GPU join pipelines are not built yet");
         PG_TRY(ev_all.init());
         PG_TRY(ev_main.init());
         PG_CUDA(cudaEventRecord(ev_all.a, st));
@@ -246,13 +247,74 @@ struct JoinAggPipeline : Pipeline {
         unsigned long long ng2[2];
         PG_TRY(read_counters(ng2));
         i64 ngroups = (i64)ng2[0];
-        std::vector<i64> h_klo((size_t)ngroups), h_khi((size_t)ngroups), h_acc((size_t)ngroups * (size_t)(gs.nacc + 1));
-        if (ngroups > 0) {
-            PG_CUDA(cudaMemcpyAsync(h_klo.data(), d_out_klo.p, (size_t)ngroups * 8, cudaMemcpyDeviceToHost, st));
-            PG_CUDA(cudaMemcpyAsync(h_khi.data(), d_out_khi.p, (size_t)ngroups * 8, cudaMemcpyDeviceToHost, st));
-            for (int a = 0; a <= gs.nacc; a++)
-                PG_CUDA(cudaMemcpyAsync(h_acc.data() + (size_t)a * (size_t)ngroups, d_out_acc.as<i64>() + (size_t)a * (size_t)out_cap,
-                                        (size_t)ngroups * 8, cudaMemcpyDeviceToHost, st));
+        const int planes = gs.nacc + 1;
+        std::vector<i64> h_klo, h_khi, h_acc;
+        if (gather_ranks && c.world > 1) {
+            // shard-local groups are disjoint across ranks (co-partitioned on the join key, checked
+            // at plan time): all-gather the per-rank lists over NVLink, every rank ends with the union
+            std::vector<i64> counts((size_t)c.world);
+            PG_CUDA(cudaMemcpyAsync(d_counters.p, &ngroups, 8, cudaMemcpyHostToDevice, st));
+            PG_TRY(d_g_cnt.alloc(8 * (size_t)c.world));
+            PG_TRY(comm_allgather(d_counters.p, d_g_cnt.p, 8, st));
+            PG_CUDA(cudaMemcpyAsync(counts.data(), d_g_cnt.p, 8 * (size_t)c.world, cudaMemcpyDeviceToHost, st));
+            PG_CUDA(cudaStreamSynchronize(st));
+            i64 maxn = 1, total = 0;
+            for (i64 x : counts) { maxn = std::max(maxn, x); total += x; }
+            if (maxn > out_cap) {          // send buffers must hold maxn elements
+                DevBuf nk, nh, na;
+                PG_TRY(nk.alloc((size_t)maxn * 8));
+                PG_TRY(nh.alloc((size_t)maxn * 8));
+                PG_TRY(na.alloc((size_t)maxn * 8 * (size_t)planes));
+                PG_CUDA(cudaMemcpyAsync(nk.p, d_out_klo.p, (size_t)ngroups * 8, cudaMemcpyDeviceToDevice, st));
+                PG_CUDA(cudaMemcpyAsync(nh.p, d_out_khi.p, (size_t)ngroups * 8, cudaMemcpyDeviceToDevice, st));
+                for (int a = 0; a < planes; a++)
+                    PG_CUDA(cudaMemcpyAsync(na.as<i64>() + (size_t)a * (size_t)maxn, d_out_acc.as<i64>() + (size_t)a * (size_t)out_cap,
+                                            (size_t)ngroups * 8, cudaMemcpyDeviceToDevice, st));
+                PG_CUDA(cudaStreamSynchronize(st));
+                std::swap(d_out_klo.p, nk.p); std::swap(d_out_klo.bytes, nk.bytes);
+                std::swap(d_out_khi.p, nh.p); std::swap(d_out_khi.bytes, nh.bytes);
+                std::swap(d_out_acc.p, na.p); std::swap(d_out_acc.bytes, na.bytes);
+                out_cap = maxn;
+            }
+            size_t seg = (size_t)maxn * 8;
+            if (d_g_klo.bytes < seg * (size_t)c.world) {
+                PG_TRY(d_g_klo.alloc(seg * (size_t)c.world));
+                PG_TRY(d_g_khi.alloc(seg * (size_t)c.world));
+                PG_TRY(d_g_acc.alloc(seg * (size_t)c.world * (size_t)planes));
+            }
+            PG_TRY(comm_allgather(d_out_klo.p, d_g_klo.p, seg, st));
+            PG_TRY(comm_allgather(d_out_khi.p, d_g_khi.p, seg, st));
+            for (int a = 0; a < planes; a++)
+                PG_TRY(comm_allgather(d_out_acc.as<i64>() + (size_t)a * (size_t)out_cap,
+                                      (char *)d_g_acc.p + (size_t)a * seg * (size_t)c.world, seg, st));
+            h_klo.resize((size_t)total);
+            h_khi.resize((size_t)total);
+            h_acc.resize((size_t)total * (size_t)planes);
+            i64 off = 0;
+            for (int r = 0; r < c.world; r++) {
+                size_t n = (size_t)counts[(size_t)r];
+                if (n) {
+                    PG_CUDA(cudaMemcpyAsync(h_klo.data() + off, (char *)d_g_klo.p + seg * (size_t)r, n * 8, cudaMemcpyDeviceToHost, st));
+                    PG_CUDA(cudaMemcpyAsync(h_khi.data() + off, (char *)d_g_khi.p + seg * (size_t)r, n * 8, cudaMemcpyDeviceToHost, st));
+                    for (int a = 0; a < planes; a++)
+                        PG_CUDA(cudaMemcpyAsync(h_acc.data() + (size_t)a * (size_t)total + (size_t)off,
+                                                (char *)d_g_acc.p + (size_t)a * seg * (size_t)c.world + seg * (size_t)r, n * 8,
+                                                cudaMemcpyDeviceToHost, st));
+                }
+                off += (i64)n;
+            }
+            ngroups = total;
+        } else {
+            h_klo.resize((size_t)ngroups);
+            h_khi.resize((size_t)ngroups);
+            h_acc.resize((size_t)ngroups * (size_t)planes);
+            if (ngroups > 0) {
+                PG_CUDA(cudaMemcpyAsync(h_klo.data(), d_out_klo.p, (size_t)ngroups * 8, cudaMemcpyDeviceToHost, st));
+                PG_CUDA(cudaMemcpyAsync(h_khi.data(), d_out_khi.p, (size_t)ngroups * 8, cudaMemcpyDeviceToHost, st));
+                for (int a = 0; a < planes; a++)
+                    PG_CUDA(cudaMemcpyAsync(h_acc.data() + (size_t)a * (size_t)ngroups, d_out_acc.as<i64>() + (size_t)a * (size_t)out_cap,
+                                            (size_t)ngroups * 8, cudaMemcpyDeviceToHost, st));
+            }
         }
         PG_CUDA(cudaEventRecord(ev_all.b, st));
         PG_CUDA(cudaStreamSynchronize(st));
@@ -535,6 +597,61 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &join, std::uniqu
             i64 b = t->nrows * type_size(t->cols[(size_t)u.second].type);
             p->algorithmic_bytes += b;
             if (u.first == p->src_slot) p->main_bytes += b;
+        }
+    }
+    // multi-GPU: which joins are shard-local?  A REPLICATED build side is complete everywhere.  Two
+    // SHARDED sides must be co-partitioned on the join key: no rank's probe-key range may touch
+    // another rank's build-key range (proved from the column statistics, exchanged once here).
+    if (ctx().world > 1) {
+        const int W = ctx().world;
+        auto copartitioned = [&](const pg_table *pt, int pcol, const pg_table *btab, int bcol, bool *ok) -> int {
+            i64 mine[6] = {pt->cols[(size_t)pcol].vmin, pt->cols[(size_t)pcol].vmax, pt->nrows,
+                           btab->cols[(size_t)bcol].vmin, btab->cols[(size_t)bcol].vmax, btab->nrows};
+            DevBuf ds, dr;
+            PG_TRY(ds.alloc(sizeof mine));
+            PG_TRY(dr.alloc(sizeof mine * (size_t)W));
+            PG_CUDA(cudaMemcpyAsync(ds.p, mine, sizeof mine, cudaMemcpyHostToDevice, ctx().stream));
+            PG_TRY(comm_allgather(ds.p, dr.p, sizeof mine, ctx().stream));
+            std::vector<i64> all(6 * (size_t)W);
+            PG_CUDA(cudaMemcpyAsync(all.data(), dr.p, sizeof mine * (size_t)W, cudaMemcpyDeviceToHost, ctx().stream));
+            PG_CUDA(cudaStreamSynchronize(ctx().stream));
+            *ok = true;
+            for (int r = 0; r < W; r++)
+                for (int q = 0; q < W; q++) {
+                    if (r == q || all[(size_t)r * 6 + 2] == 0 || all[(size_t)q * 6 + 5] == 0) continue;
+                    if (all[(size_t)r * 6] <= all[(size_t)q * 6 + 4] && all[(size_t)q * 6 + 3] <= all[(size_t)r * 6 + 1]) *ok = false;
+                }
+            return PG_OK;
+        };
+        // every rank must take the same decisions: they depend only on gathered data and the plan
+        // (a) inner build stages probing earlier stages
+        for (auto &sp : p->stages) {
+            if (!sp->has_probe) continue;
+            const Stage &inner = *p->stages[(size_t)sp->probe_stage];
+            const pg_table *pt = p->tab(sp->src_slot), *ib = p->tab(inner.src_slot);
+            if (ib->dist == PG_DIST_REPLICATED) continue;
+            if (pt->dist == PG_DIST_REPLICATED) PG_FAIL(PG_EUNSUPPORTED, "replicated table probing a sharded one");
+            bool ok = false;
+            PG_TRY(copartitioned(pt, sp->probe_key_col, ib, inner.ins_key_col, &ok));
+            if (!ok) PG_FAIL(PG_EUNSUPPORTED, "sharded join sides are not co-partitioned on the key (needs the all-to-all shuffle path)");
+        }
+        // (b) the top join
+        if (bt->dist != PG_DIST_REPLICATED) {
+            if (st->dist == PG_DIST_REPLICATED) PG_FAIL(PG_EUNSUPPORTED, "replicated table probing a sharded one");
+            bool ok = false;
+            PG_TRY(copartitioned(st, p->probe_key_col, bt, bs.ins_key_col, &ok));
+            if (!ok) PG_FAIL(PG_EUNSUPPORTED, "sharded join sides are not co-partitioned on the key (needs the all-to-all shuffle path)");
+        }
+        if (st->dist != PG_DIST_REPLICATED) {
+            // groups of different ranks must be disjoint: the first group key is the probe join key and the
+            // probe key ranges of the ranks do not overlap
+            BaseCol g0;
+            const Expr *ge = strip_value_preserving_casts(&aggn.groups[0]);
+            bool ok = resolve(join, ge->idx, &g0) && g0.slot == p->src_slot && g0.col == p->probe_key_col;
+            bool disjoint = false;
+            if (ok) PG_TRY(copartitioned(st, p->probe_key_col, st, p->probe_key_col, &disjoint));
+            if (!ok || !disjoint) PG_FAIL(PG_EUNSUPPORTED, "groups are not partitioned by the shard key (needs the all-to-all shuffle path)");
+            p->gather_ranks = true;
         }
     }
     PG_TRY(p->d_counters.alloc(16));

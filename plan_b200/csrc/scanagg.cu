@@ -96,16 +96,17 @@ struct SumProdPipeline : Pipeline {
         finalize128_kernel<<<1, 32, 0, st>>>(d_part.as<i64>(), grid, 2, d_final.as<u64>());
         PG_CUDA(cudaGetLastError());
         const void *src = d_final.p;
-        if (c.world > 1) {
+        const int nmerge = table->dist == PG_DIST_REPLICATED ? 1 : c.world;   // a replicated table is complete on every rank
+        if (nmerge > 1) {
             PG_TRY(comm_allgather(d_final.p, d_gather.p, 32, st));
             src = d_gather.p;
         }
-        PG_CUDA(cudaMemcpyAsync(h_final.p, src, 32 * (size_t)c.world, cudaMemcpyDeviceToHost, st));
+        PG_CUDA(cudaMemcpyAsync(h_final.p, src, 32 * (size_t)nmerge, cudaMemcpyDeviceToHost, st));
         PG_CUDA(cudaEventRecord(ev_all.b, st));
         PG_CUDA(cudaStreamSynchronize(st));
         const u64 *h = h_final.as<u64>();
         i128 sum = 0, cnt = 0;
-        for (int r = 0; r < c.world; r++) {   // merged in rank order (shards are contiguous row ranges)
+        for (int r = 0; r < nmerge; r++) {   // merged in rank order (shards are contiguous row ranges)
             sum += make_i128(h[4 * r], h[4 * r + 1]);
             cnt += make_i128(h[4 * r + 2], h[4 * r + 3]);
         }
@@ -231,6 +232,10 @@ struct LowcardPipeline : Pipeline {
     bool nonneg[LC_K] = {true, true, true, true, true, true};   // slot values proven >= 0 from statistics
     int emulations = 0;                                         // (group, slot) sums that took the ordered path
 
+    // ranks whose partials are merged: a replicated table is complete on every rank
+    int nranks() const { return table->dist == PG_DIST_REPLICATED ? 1 : ctx().world; }
+    int myrank() const { return table->dist == PG_DIST_REPLICATED ? 0 : ctx().rank; }
+
     size_t rank_bytes() const { return (size_t)G * LC_K * 16 + (size_t)LC_MAXG * 8; }
 
     int ord_summaries(int g, int s, i64 tb, i64 te, std::vector<OrdSummary> *out)
@@ -275,7 +280,7 @@ struct LowcardPipeline : Pipeline {
         const i64 ntiles = (prm.nrows + SA_TILE - 1) / SA_TILE;
         // per-rank contribution: absolute state (rank == rstar) or a transducer summary (rank > rstar)
         struct Contrib { u64 kind, s_lo, s_hi, q_lo, q_hi; u64 c0, c1, p0p1; } mine{};
-        if (c.rank == rstar) {
+        if (myrank() == rstar) {
             // a. which CTA range crosses
             std::vector<i64> part((size_t)grid * (size_t)G * LC_K);
             PG_CUDA(cudaMemcpyAsync(part.data(), d_part.p, part.size() * sizeof(i64), cudaMemcpyDeviceToHost, st));
@@ -340,7 +345,7 @@ struct LowcardPipeline : Pipeline {
             mine.kind = 1;
             mine.s_lo = (u64)S;
             mine.s_hi = (u64)(S >> 64);
-        } else if (c.rank > rstar) {
+        } else if (myrank() > rstar) {
             std::vector<OrdSummary> sums;
             PG_TRY(ord_summaries(g, s, 0, ntiles, &sums));
             i128 q = 0;
@@ -359,21 +364,21 @@ struct LowcardPipeline : Pipeline {
             mine.c1 = cc[1];
             mine.p0p1 = pp[0] | (pp[1] << 1);
         }
-        std::vector<Contrib> all((size_t)c.world);
-        if (c.world > 1) {
+        std::vector<Contrib> all((size_t)nranks());
+        if (nranks() > 1) {
             DevBuf ds, dr;
             PG_TRY(ds.alloc(sizeof(Contrib)));
-            PG_TRY(dr.alloc(sizeof(Contrib) * (size_t)c.world));
+            PG_TRY(dr.alloc(sizeof(Contrib) * (size_t)nranks()));
             PG_CUDA(cudaMemcpyAsync(ds.p, &mine, sizeof(Contrib), cudaMemcpyHostToDevice, st));
             PG_TRY(comm_allgather(ds.p, dr.p, sizeof(Contrib), st));
-            PG_CUDA(cudaMemcpyAsync(all.data(), dr.p, sizeof(Contrib) * (size_t)c.world, cudaMemcpyDeviceToHost, st));
+            PG_CUDA(cudaMemcpyAsync(all.data(), dr.p, sizeof(Contrib) * (size_t)nranks(), cudaMemcpyDeviceToHost, st));
             PG_CUDA(cudaStreamSynchronize(st));
         } else {
             all[0] = mine;
         }
         if (all[(size_t)rstar].kind != 1) PG_FAIL(PG_ECUDA, "internal: crossing rank did not report a state");
         u128 S = ((u128)all[(size_t)rstar].s_hi << 64) | all[(size_t)rstar].s_lo;
-        for (int r = rstar + 1; r < c.world; r++) {
+        for (int r = rstar + 1; r < nranks(); r++) {
             const Contrib &k = all[(size_t)r];
             u128 q = ((u128)k.q_hi << 64) | k.q_lo;
             S += q + ((S & 1) ? k.c1 : k.c0);
@@ -414,20 +419,20 @@ struct LowcardPipeline : Pipeline {
         finalize128_kernel<<<1, 64, 0, st>>>(d_part.as<i64>(), grid, G * LC_K, d_final.as<u64>());
         PG_CUDA(cudaGetLastError());
         const void *src = d_final.p;
-        if (c.world > 1) {
+        if (nranks() > 1) {
             PG_TRY(comm_allgather(d_final.p, d_gather.p, rank_bytes(), st));
             src = d_gather.p;
         }
-        PG_CUDA(cudaMemcpyAsync(h_final.p, src, rank_bytes() * (size_t)c.world, cudaMemcpyDeviceToHost, st));
+        PG_CUDA(cudaMemcpyAsync(h_final.p, src, rank_bytes() * (size_t)nranks(), cudaMemcpyDeviceToHost, st));
         PG_CUDA(cudaEventRecord(ev_all.b, st));
         PG_CUDA(cudaStreamSynchronize(st));
 
         // merge ranks in order; 128-bit exact
         std::vector<i128> tot((size_t)G * LC_K, 0);
-        std::vector<std::vector<i128>> rtot((size_t)G * LC_K, std::vector<i128>((size_t)c.world, 0));
+        std::vector<std::vector<i128>> rtot((size_t)G * LC_K, std::vector<i128>((size_t)nranks(), 0));
         std::vector<i64> first((size_t)G, INT64_MAX);
         emulations = 0;
-        for (int r = 0; r < c.world; r++) {
+        for (int r = 0; r < nranks(); r++) {
             const char *base = (const char *)h_final.p + rank_bytes() * (size_t)r;
             const u64 *h = (const u64 *)base;
             const i64 *f = (const i64 *)(base + (size_t)G * LC_K * 16);
@@ -531,7 +536,7 @@ static int try_lowcard(pg_plan *plan, const Node &aggn, const Node &scan, const 
         // dense ids over the codes that occur anywhere (union over ranks so every rank agrees)
         uint32_t present[8];
         memcpy(present, col.present, sizeof present);
-        if (ctx().world > 1) {
+        if (ctx().world > 1 && t->dist != PG_DIST_REPLICATED) {
             DevBuf ds, dr;
             PG_TRY(ds.alloc(32));
             PG_TRY(dr.alloc(32 * (size_t)ctx().world));
@@ -675,8 +680,8 @@ static int try_lowcard(pg_plan *plan, const Node &aggn, const Node &scan, const 
     }
     PG_TRY(p->d_part.alloc(sizeof(i64) * (size_t)p->grid * (size_t)p->G * LC_K));
     PG_TRY(p->d_final.alloc(p->rank_bytes()));
-    PG_TRY(p->d_gather.alloc(p->rank_bytes() * (size_t)ctx().world));
-    PG_TRY(p->h_final.alloc(p->rank_bytes() * (size_t)ctx().world));
+    PG_TRY(p->d_gather.alloc(p->rank_bytes() * (size_t)p->nranks()));
+    PG_TRY(p->h_final.alloc(p->rank_bytes() * (size_t)p->nranks()));
     PG_TRY(p->d_luts.alloc(512));
     PG_CUDA(cudaMemcpyAsync(p->d_luts.p, luts.data(), 512, cudaMemcpyHostToDevice, ctx().stream));
     PG_CUDA(cudaStreamSynchronize(ctx().stream));

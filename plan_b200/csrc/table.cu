@@ -385,6 +385,14 @@ int pg_table_seal(pg_table *t, int64_t global_row_offset)
     return PG_OK;
 }
 
+int pg_table_set_distribution(pg_table *t, int dist)
+{
+    if (!t || (dist != PG_DIST_SHARDED && dist != PG_DIST_REPLICATED)) PG_FAIL(PG_EINVAL, "pg_table_set_distribution: bad arguments");
+    t->dist = dist;
+    t->version++;
+    return PG_OK;
+}
+
 int pg_table_rows(const pg_table *t, int64_t *nrows)
 {
     if (!t || !nrows) PG_FAIL(PG_EINVAL, "pg_table_rows: bad arguments");

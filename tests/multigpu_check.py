@@ -1,0 +1,68 @@
+"""Launched by tests/test_gpu_multi.py under torchrun: every rank builds its row-range shard in
+HBM, runs Q6 / Q1 / Q3 through the C ABI with the NCCL communicator up, and compares the merged
+result with the CPU oracle over the WHOLE table.  Exit code 0 = parity on every rank."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from oracle import oracle as O
+    from plan_b200 import _lib as L, compute as X, dist as D, tpch as T
+    import test_gpu_scanagg as SA
+    import test_gpu_join as J
+
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = L.lib()
+    L.check(lib.pg_init(local))
+    D.init_comm(lib, L.check)
+    sf = 0.05
+    n_orders = lib.pg_tpch_num_orders(sf)
+    lo, hi = D.shard_range(n_orders, rank, world)
+    tables = T.generate_device_tables(sf, lo, hi)
+    tables["customer"].set_replicated()
+    orders, line = O.gen_orders_lineitem(sf)
+    host = {"orders": orders, "lineitem": line, "customer": O.gen_customer(sf)}
+    total = torch.tensor([tables["lineitem"].rows()], device="cuda")
+    dist.all_reduce(total)
+    assert int(total.item()) == len(line["l_orderkey"])
+
+    SA.check_q6(O, tables, line)
+    SA.check_q6(O, tables, line, qty_lt=1)
+    SA.check_q1(O, tables, line)
+    SA.check_q1(O, tables, line, ship_le=8035 + 1263)
+    J.check_q3(O, tables, host, check_counts=False)
+    J.check_q3(O, tables, host, check_counts=False, segment="BUILDING", odate_lt=8035 + 3000, ship_gt=8035 - 10)
+
+    # order-dependent rounding regime across shards: inflate prices on the uploaded shard
+    first = int(np.searchsorted(line["l_orderkey"], orders["o_orderkey"][lo]))
+    last = len(line["l_orderkey"]) if hi == n_orders else int(np.searchsorted(line["l_orderkey"], orders["o_orderkey"][hi]))
+    big = {k: v.copy() for k, v in line.items()}
+    big["l_extendedprice"] = big["l_extendedprice"] * 3001
+    ref = O.q1(big)
+    assert any(g["x_charge"] >= 10 ** 19 for g in ref["groups"])
+    shard = {k: v[first:last] for k, v in big.items()}
+    t = X.DeviceTable.create("lineitem", T.LINEITEM)
+    t.append([shard[c[0]] for c in T.LINEITEM])
+    t.seal(first)
+    SA.check_q1(O, {"lineitem": t}, big)
+    t.free()
+
+    for x in tables.values():
+        x.free()
+    lib.pg_comm_destroy()
+    dist.barrier()
+    dist.destroy_process_group()
+    print("rank %d/%d: multi-GPU parity OK" % (rank, world))
+
+
+if __name__ == "__main__":
+    main()

@@ -32,7 +32,7 @@ def _q3_groups(chunks):
     return out
 
 
-def check_q3(oracle, tables, host, **kw):
+def check_q3(oracle, tables, host, check_counts=True, **kw):
     from plan_b200 import tpch as T
     chunks, stats, explain = _run(T.q3_plan(**kw), tables)
     ref = oracle.q3(host["customer"], host["orders"], host["lineitem"], **kw)
@@ -41,10 +41,11 @@ def check_q3(oracle, tables, host, **kw):
     want = {(g["l_orderkey"], g["o_orderdate"], g["o_shippriority"]): g["x_revenue"] for g in ref["groups"]}
     assert len(got) == ref["stats"]["ngroups"] == len(want)
     assert got == want                                   # row set and exact DECIMAL sums
-    assert stats.aux[0] == ref["stats"]["n_line_sel"]    # rows passing the lineitem filter
-    assert stats.aux[1] == ref["stats"]["n_line_joined"]
-    assert stats.aux[3] == ref["stats"]["n_cust_sel"]
-    assert stats.aux[5] == ref["stats"]["n_orders_joined"]
+    if check_counts:                                     # per-rank counters when sharded
+        assert stats.aux[0] == ref["stats"]["n_line_sel"]    # rows passing the lineitem filter
+        assert stats.aux[1] == ref["stats"]["n_line_joined"]
+        assert stats.aux[3] == ref["stats"]["n_cust_sel"]
+        assert stats.aux[5] == ref["stats"]["n_orders_joined"]
     return chunks, ref
 
 
