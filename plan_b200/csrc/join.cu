@@ -36,6 +36,9 @@ struct Stage {
     JoinTable jt{};
     i64 capacity_rows = 0;
     i64 built_rows = 0;
+    bool payload_needed = false;     // some column of this build side is read above the join
+    i64 dup_keys = 0;                // duplicates seen while building (bitmap builds only)
+    bool bitmap_only() const { return jt.bitmap && !payload_needed && dup_keys == 0; }
 };
 
 static u64 next_pow2(u64 x)
@@ -78,6 +81,7 @@ struct JoinAggPipeline : Pipeline {
     EventPair ev_all, ev_main;
     bool gather_ranks = false;     // probe side is sharded: every rank ends with the union of all groups
     DevBuf d_g_klo, d_g_khi, d_g_acc, d_g_cnt;
+    PinBuf h_out;                  // pinned landing zone of the group lists: [klo | khi | acc planes]
 
     const pg_table *tab(int slot) const { return plan->slots[(size_t)slot]; }
 
@@ -95,7 +99,7 @@ struct JoinAggPipeline : Pipeline {
 
     int read_counters(unsigned long long *out2)
     {
-        PG_CUDA(cudaMemcpyAsync(out2, d_counters.p, 16, cudaMemcpyDeviceToHost, ctx().stream));
+        PG_CUDA(cudaMemcpyAsync(out2, d_counters.p, 32, cudaMemcpyDeviceToHost, ctx().stream));
         PG_CUDA(cudaStreamSynchronize(ctx().stream));
         return PG_OK;
     }
@@ -106,6 +110,28 @@ struct JoinAggPipeline : Pipeline {
         i64 cap = (i64)ctx().prop.multiProcessorCount * 8;
         if (g > cap) g = cap;
         return (int)std::max<i64>(g, 1);
+    }
+
+    // launch the pipeline kernel for `pp`: the vectorised variant when the shape allows it
+    template <int SINK>
+    int launch_pipe(const PipeParams &pp, const pg_table *t)
+    {
+        cudaStream_t st = ctx().stream;
+        bool fast = pp.has_probe && pp.probe.bitmap && pp.npred <= 1 && (pp.npred == 0 || pp.pred[0].col.width == 4) &&
+                    (pp.probe_key.width == 4 || pp.probe_key.width == 8) && !getenv("PG_JOIN_GENERIC");
+        if (!fast) {
+            pipeline_kernel<SINK><<<grid_rows(t->nrows), 256, 0, st>>>(pp);
+        } else {
+            i64 ntiles = (t->nrows + SA_TILE - 1) / SA_TILE;
+            int grid = (int)std::max<i64>(std::min<i64>(ntiles, (i64)ctx().prop.multiProcessorCount * 6), 1);
+            bool k8 = pp.probe_key.width == 8, hp = pp.npred == 1;
+            if (k8 && hp) fast_pipeline_kernel<8, SINK, true, 2><<<grid, SA_THREADS, 0, st>>>(pp);
+            else if (k8) fast_pipeline_kernel<8, SINK, false, 2><<<grid, SA_THREADS, 0, st>>>(pp);
+            else if (hp) fast_pipeline_kernel<4, SINK, true, 2><<<grid, SA_THREADS, 0, st>>>(pp);
+            else fast_pipeline_kernel<4, SINK, false, 2><<<grid, SA_THREADS, 0, st>>>(pp);
+        }
+        PG_CUDA(cudaGetLastError());
+        return PG_OK;
     }
 
     // size + (re)initialise the join table a stage builds
@@ -149,21 +175,24 @@ struct JoinAggPipeline : Pipeline {
         if (s.has_probe) {
             pp.probe_key = typed(t, s.probe_key_col);
             pp.probe = stages[(size_t)s.probe_stage]->jt;
+            pp.probe_bitmap_only = stages[(size_t)s.probe_stage]->bitmap_only() ? 1 : 0;
         }
         pp.counters = d_counters.as<unsigned long long>();
         // sizing pass: how many rows reach the sink
-        PG_CUDA(cudaMemsetAsync(d_counters.p, 0, 16, st));
-        pipeline_kernel<SINK_COUNT><<<grid_rows(t->nrows), 256, 0, st>>>(pp);
-        PG_CUDA(cudaGetLastError());
-        unsigned long long cnt[2];
+        PG_CUDA(cudaMemsetAsync(d_counters.p, 0, 32, st));
+        PG_TRY(launch_pipe<SINK_COUNT>(pp, t));
+        unsigned long long cnt[4];
         PG_TRY(read_counters(cnt));
         s.built_rows = (i64)cnt[1];
         PG_TRY(prepare_table(s, s.built_rows, t->cols[(size_t)s.ins_key_col]));
         pp.ins_key = typed(t, s.ins_key_col);
+        s.jt.dups = d_counters.as<unsigned long long>() + 2;
         pp.ins = s.jt;
-        PG_CUDA(cudaMemsetAsync(d_counters.p, 0, 16, st));
-        pipeline_kernel<SINK_INSERT><<<grid_rows(t->nrows), 256, 0, st>>>(pp);
-        PG_CUDA(cudaGetLastError());
+        PG_CUDA(cudaMemsetAsync(d_counters.p, 0, 32, st));
+        PG_TRY(launch_pipe<SINK_INSERT>(pp, t));
+        unsigned long long c2[4];
+        PG_TRY(read_counters(c2));
+        s.dup_keys = (i64)c2[2];
         res->stats.kernel_launches += 2;
         if (idx < 4) { res->stats.aux[2 + 2 * idx] = (i64)cnt[0]; res->stats.aux[3 + 2 * idx] = (i64)cnt[1]; }
         return PG_OK;
@@ -185,9 +214,10 @@ struct JoinAggPipeline : Pipeline {
         cudaStream_t st = c.stream;
         PG_TRY(ev_all.init());
         PG_TRY(ev_main.init());
+        Trace tr("joinagg");
         PG_CUDA(cudaEventRecord(ev_all.a, st));
         res->stats.kernel_launches = 0;
-        for (size_t i = 0; i < stages.size(); i++) PG_TRY(run_build_stage(*stages[i], res, (int)i));
+        for (size_t i = 0; i < stages.size(); i++) { PG_TRY(run_build_stage(*stages[i], res, (int)i)); tr.mark("build stage"); }
 
         const pg_table *t = tab(src_slot);
         Stage &last = *stages.back();
@@ -197,13 +227,14 @@ struct JoinAggPipeline : Pipeline {
         pp.has_probe = 1;
         pp.probe_key = typed(t, probe_key_col);
         pp.probe = last.jt;
+        pp.probe_bitmap_only = last.bitmap_only() ? 1 : 0;
         pp.counters = d_counters.as<unsigned long long>();
         pp.gs = gs;
         // group table: start at twice the build-side rows (each joined row matches a build row),
         // grow x2 and rerun if a probe sequence overflows (the reference resizes x2 as well,
         // aggregate_hash.go:538-540)
         u64 cap = next_pow2((u64)std::max<i64>(last.built_rows * 2, 1024));
-        unsigned long long cnt[2] = {0, 0};
+        unsigned long long cnt[4] = {0, 0, 0, 0};
         for (int attempt = 0;; attempt++) {
             PG_TRY(ensure_group_table(cap));
             cap = gt_cap;
@@ -211,7 +242,7 @@ struct JoinAggPipeline : Pipeline {
             PG_CUDA(cudaMemsetAsync(d_khi.p, 0x80, cap * 8, st));
             PG_CUDA(cudaMemsetAsync(d_acc.p, 0, cap * 8 * (size_t)(gs.nacc + 1), st));
             PG_CUDA(cudaMemsetAsync(d_overflow.p, 0, 4, st));
-            PG_CUDA(cudaMemsetAsync(d_counters.p, 0, 16, st));
+            PG_CUDA(cudaMemsetAsync(d_counters.p, 0, 32, st));
             pp.gt.klo = d_klo.as<i64>();
             pp.gt.khi = d_khi.as<i64>();
             pp.gt.acc = d_acc.as<i64>();
@@ -219,13 +250,13 @@ struct JoinAggPipeline : Pipeline {
             pp.gt.nacc = gs.nacc;
             pp.gt.overflow = d_overflow.as<int>();
             PG_CUDA(cudaEventRecord(ev_main.a, st));
-            pipeline_kernel<SINK_GROUP><<<grid_rows(t->nrows), 256, 0, st>>>(pp);
-            PG_CUDA(cudaGetLastError());
+            PG_TRY(launch_pipe<SINK_GROUP>(pp, t));
             PG_CUDA(cudaEventRecord(ev_main.b, st));
             res->stats.kernel_launches += 1;
             int ovf = 0;
             PG_CUDA(cudaMemcpyAsync(&ovf, d_overflow.p, 4, cudaMemcpyDeviceToHost, st));
             PG_TRY(read_counters(cnt));
+            tr.mark("probe+group kernel");
             if (!ovf) break;
             if (attempt > 8) PG_FAIL(PG_ENOMEM, "group table keeps overflowing");
             cap *= 2;
@@ -239,16 +270,25 @@ struct JoinAggPipeline : Pipeline {
             PG_TRY(d_out_acc.alloc((size_t)max_out * 8 * (size_t)(gs.nacc + 1)));
             out_cap = max_out;
         }
-        PG_CUDA(cudaMemsetAsync(d_counters.p, 0, 16, st));
+        PG_CUDA(cudaMemsetAsync(d_counters.p, 0, 32, st));
         gt_compact_kernel<<<(int)std::min<u64>((cap + 255) / 256, (u64)c.prop.multiProcessorCount * 8), 256, 0, st>>>(
             pp.gt, d_out_klo.as<i64>(), d_out_khi.as<i64>(), d_out_acc.as<i64>(), out_cap, d_counters.as<unsigned long long>());
         PG_CUDA(cudaGetLastError());
         res->stats.kernel_launches += 1;
-        unsigned long long ng2[2];
+        unsigned long long ng2[4];
         PG_TRY(read_counters(ng2));
         i64 ngroups = (i64)ng2[0];
+        tr.mark("compact");
         const int planes = gs.nacc + 1;
-        std::vector<i64> h_klo, h_khi, h_acc;
+        i64 *h_klo = nullptr, *h_khi = nullptr, *h_acc = nullptr;
+        auto host_arrays = [&](i64 n) -> int {
+            size_t need = (size_t)std::max<i64>(n, 1) * 8 * (size_t)(2 + planes);
+            if (h_out.bytes < need) PG_TRY(h_out.alloc(need + need / 4));
+            h_klo = h_out.as<i64>();
+            h_khi = h_klo + n;
+            h_acc = h_khi + n;
+            return PG_OK;
+        };
         if (gather_ranks && c.world > 1) {
             // shard-local groups are disjoint across ranks (co-partitioned on the join key, checked
             // at plan time): all-gather the per-rank lists over NVLink, every rank ends with the union
@@ -287,17 +327,15 @@ struct JoinAggPipeline : Pipeline {
             for (int a = 0; a < planes; a++)
                 PG_TRY(comm_allgather(d_out_acc.as<i64>() + (size_t)a * (size_t)out_cap,
                                       (char *)d_g_acc.p + (size_t)a * seg * (size_t)c.world, seg, st));
-            h_klo.resize((size_t)total);
-            h_khi.resize((size_t)total);
-            h_acc.resize((size_t)total * (size_t)planes);
+            PG_TRY(host_arrays(total));
             i64 off = 0;
             for (int r = 0; r < c.world; r++) {
                 size_t n = (size_t)counts[(size_t)r];
                 if (n) {
-                    PG_CUDA(cudaMemcpyAsync(h_klo.data() + off, (char *)d_g_klo.p + seg * (size_t)r, n * 8, cudaMemcpyDeviceToHost, st));
-                    PG_CUDA(cudaMemcpyAsync(h_khi.data() + off, (char *)d_g_khi.p + seg * (size_t)r, n * 8, cudaMemcpyDeviceToHost, st));
+                    PG_CUDA(cudaMemcpyAsync(h_klo + off, (char *)d_g_klo.p + seg * (size_t)r, n * 8, cudaMemcpyDeviceToHost, st));
+                    PG_CUDA(cudaMemcpyAsync(h_khi + off, (char *)d_g_khi.p + seg * (size_t)r, n * 8, cudaMemcpyDeviceToHost, st));
                     for (int a = 0; a < planes; a++)
-                        PG_CUDA(cudaMemcpyAsync(h_acc.data() + (size_t)a * (size_t)total + (size_t)off,
+                        PG_CUDA(cudaMemcpyAsync(h_acc + (size_t)a * (size_t)total + (size_t)off,
                                                 (char *)d_g_acc.p + (size_t)a * seg * (size_t)c.world + seg * (size_t)r, n * 8,
                                                 cudaMemcpyDeviceToHost, st));
                 }
@@ -305,19 +343,18 @@ struct JoinAggPipeline : Pipeline {
             }
             ngroups = total;
         } else {
-            h_klo.resize((size_t)ngroups);
-            h_khi.resize((size_t)ngroups);
-            h_acc.resize((size_t)ngroups * (size_t)planes);
+            PG_TRY(host_arrays(ngroups));
             if (ngroups > 0) {
-                PG_CUDA(cudaMemcpyAsync(h_klo.data(), d_out_klo.p, (size_t)ngroups * 8, cudaMemcpyDeviceToHost, st));
-                PG_CUDA(cudaMemcpyAsync(h_khi.data(), d_out_khi.p, (size_t)ngroups * 8, cudaMemcpyDeviceToHost, st));
+                PG_CUDA(cudaMemcpyAsync(h_klo, d_out_klo.p, (size_t)ngroups * 8, cudaMemcpyDeviceToHost, st));
+                PG_CUDA(cudaMemcpyAsync(h_khi, d_out_khi.p, (size_t)ngroups * 8, cudaMemcpyDeviceToHost, st));
                 for (int a = 0; a < planes; a++)
-                    PG_CUDA(cudaMemcpyAsync(h_acc.data() + (size_t)a * (size_t)ngroups, d_out_acc.as<i64>() + (size_t)a * (size_t)out_cap,
+                    PG_CUDA(cudaMemcpyAsync(h_acc + (size_t)a * (size_t)ngroups, d_out_acc.as<i64>() + (size_t)a * (size_t)out_cap,
                                             (size_t)ngroups * 8, cudaMemcpyDeviceToHost, st));
             }
         }
         PG_CUDA(cudaEventRecord(ev_all.b, st));
         PG_CUDA(cudaStreamSynchronize(st));
+        tr.mark("gather+d2h");
         res->stats.kernel_ms = ev_all.ms();
         res->stats.main_kernel_ms = ev_main.ms();
         res->stats.rows_scanned = t->nrows;
@@ -335,13 +372,21 @@ struct JoinAggPipeline : Pipeline {
             if (o.first == 0) {
                 int k = o.second;
                 col.type = group_out_type[(size_t)k];
-                col.data.resize((size_t)ngroups * (size_t)type_size(col.type));
-                for (i64 i = 0; i < ngroups; i++) {
-                    i64 v = k == 0 ? h_klo[(size_t)i] : k == 1 ? (h_khi[(size_t)i] >> 32) : (i64)(int32_t)(h_khi[(size_t)i] & 0xffffffffLL);
-                    switch (type_size(col.type)) {
-                    case 8: ((i64 *)col.data.data())[i] = v; break;
-                    case 4: ((int32_t *)col.data.data())[i] = (int32_t)v; break;
-                    default: col.data[(size_t)i] = (uint8_t)v; break;
+                const int w = type_size(col.type);
+                col.data.resize((size_t)ngroups * (size_t)w);
+                if (k == 0 && w == 8) {
+                    if (ngroups) memcpy(col.data.data(), h_klo, (size_t)ngroups * 8);
+                } else if (k == 0) {
+                    int32_t *d = (int32_t *)col.data.data();
+                    for (i64 i = 0; i < ngroups; i++) d[i] = (int32_t)h_klo[i];
+                } else if (w == 4) {
+                    int32_t *d = (int32_t *)col.data.data();
+                    if (k == 1) for (i64 i = 0; i < ngroups; i++) d[i] = (int32_t)(h_khi[i] >> 32);
+                    else for (i64 i = 0; i < ngroups; i++) d[i] = (int32_t)(h_khi[i] & 0xffffffffLL);
+                } else {
+                    for (i64 i = 0; i < ngroups; i++) {
+                        i64 v = k == 1 ? (h_khi[i] >> 32) : (i64)(int32_t)(h_khi[i] & 0xffffffffLL);
+                        if (w == 8) ((i64 *)col.data.data())[i] = v; else col.data[(size_t)i] = (uint8_t)v;
                     }
                 }
             } else {
@@ -351,16 +396,18 @@ struct JoinAggPipeline : Pipeline {
                 col.scale = a.scale;
                 col.data.resize((size_t)ngroups * sizeof(pg_decimal));
                 pg_decimal *d = (pg_decimal *)col.data.data();
-                const i64 *src = h_acc.data() + (size_t)o.second * (size_t)ngroups;
+                const i64 *src = h_acc + (size_t)o.second * (size_t)ngroups;
+                const int32_t sc = agg_scale[(size_t)o.second];
                 for (i64 i = 0; i < ngroups; i++) {
-                    i64 v = src[(size_t)i];
+                    i64 v = src[i];
                     d[i].neg = v < 0;
                     d[i].coef = v < 0 ? (u64)(-(v + 1)) + 1 : (u64)v;
-                    d[i].scale = agg_scale[(size_t)o.second];
+                    d[i].scale = sc;
                 }
             }
             res->cols.push_back(std::move(col));
         }
+        tr.mark("result columns");
         return PG_OK;
     }
 };
@@ -564,6 +611,12 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &join, std::uniqu
     }
     // 64-bit accumulators: a group can at most receive every probe row
     if (worst * (i128)std::max<i64>(st->nrows, 1) >= ((i128)1 << 63)) PG_FAIL(PG_EUNSUPPORTED, "group sums could exceed int64");
+    {   // does anything above the top join read a build-side column?
+        bool need = false;
+        for (int k = 0; k < p->nparts; k++) need = need || p->gs.part[k].from_build;
+        for (int a = 0; a < p->gs.nacc; a++) for (int f = 0; f < p->gs.nfac[a]; f++) need = need || p->gs.fac[a][f].from_build;
+        p->stages[(size_t)top_stage]->payload_needed = need;
+    }
     for (auto &o : aggn.outs) {
         if (o.first == 0 && (o.second < 0 || o.second >= p->nparts)) PG_FAIL(PG_EUNSUPPORTED, "bad group output index");
         if (o.first == 1 && (o.second < 0 || o.second >= (int)aggn.aggs.size())) PG_FAIL(PG_EUNSUPPORTED, "bad aggregate output index");
@@ -654,7 +707,7 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &join, std::uniqu
             p->gather_ranks = true;
         }
     }
-    PG_TRY(p->d_counters.alloc(16));
+    PG_TRY(p->d_counters.alloc(64));
     PG_TRY(p->d_overflow.alloc(4));
     std::string ex = "JoinAgg[inner hash join chain -> global group table] stages:";
     for (auto &sp : p->stages) {

@@ -1,5 +1,9 @@
 // pipeline.hpp -- plan / result objects shared by the pipeline builders.
 #pragma once
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <chrono>
 #include <memory>
 #include <string>
 #include <vector>
@@ -71,6 +75,29 @@ struct EventPair {
     }
     ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
     float ms() const { float m = 0; cudaEventElapsedTime(&m, a, b); return m; }
+};
+
+// PG_TRACE=1: per-phase wall-clock breakdown of pg_plan_execute on stderr (syncs the stream at
+// every mark, so use it for diagnosis only -- never while benchmarking)
+struct Trace {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    const char *who;
+    explicit Trace(const char *w) : who(w)
+    {
+        const char *e = getenv("PG_TRACE");
+        on = e && atoi(e) != 0;
+        if (on) { cudaStreamSynchronize(ctx().stream); t0 = std::chrono::steady_clock::now(); }
+    }
+    void mark(const char *what)
+    {
+        if (!on) return;
+        cudaStreamSynchronize(ctx().stream);
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[pg trace r%d] %s: %-28s %8.3f ms\n", ctx().rank, who, what,
+                std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
 };
 
 // all-gather `bytes` from every rank into recv[world][bytes] (comm.cu); world==1 copies.

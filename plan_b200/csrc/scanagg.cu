@@ -238,13 +238,30 @@ struct LowcardPipeline : Pipeline {
 
     size_t rank_bytes() const { return (size_t)G * LC_K * 16 + (size_t)LC_MAXG * 8; }
 
-    int ord_summaries(int g, int s, i64 tb, i64 te, std::vector<OrdSummary> *out)
+    // scratch of the ordered-rounding path, allocated once (no cudaMalloc while executing)
+    DevBuf d_ord, d_contrib;
+    PinBuf h_ord, h_part, h_tile, h_contrib;
+
+    int ensure_ord_buffers()
     {
-        out->resize((size_t)std::max<i64>(te - tb, 0));
+        if (d_ord.p) return PG_OK;
+        const i64 ntiles = (prm.nrows + SA_TILE - 1) / SA_TILE;
+        PG_TRY(d_ord.alloc(sizeof(OrdSummary) * (size_t)std::max<i64>(ntiles, 1)));
+        PG_TRY(h_ord.alloc(sizeof(OrdSummary) * (size_t)std::max<i64>(ntiles, 1)));
+        PG_TRY(h_part.alloc(sizeof(i64) * (size_t)grid * (size_t)G * LC_K));
+        PG_TRY(h_tile.alloc((size_t)SA_TILE * 32 + 512));
+        PG_TRY(d_contrib.alloc(64 * (size_t)(ctx().world + 1)));
+        PG_TRY(h_contrib.alloc(64 * (size_t)(ctx().world + 1)));
+        return PG_OK;
+    }
+
+    // per-tile summaries of tiles [tb, te) for (group, slot) -> h_ord (pinned)
+    int ord_summaries(int g, int s, i64 tb, i64 te, const OrdSummary **out, i64 *n)
+    {
+        *n = std::max<i64>(te - tb, 0);
+        *out = h_ord.as<OrdSummary>();
         if (te <= tb) return PG_OK;
         cudaStream_t st = ctx().stream;
-        DevBuf d;
-        PG_TRY(d.alloc(sizeof(OrdSummary) * (size_t)(te - tb)));
         OrdParams op;
         op.base = prm;
         op.group = g;
@@ -252,10 +269,10 @@ struct LowcardPipeline : Pipeline {
         op.tile_begin = tb;
         op.tile_end = te;
         int gr = (int)std::min<i64>(te - tb, (i64)ctx().prop.multiProcessorCount * 8);
-        if (has_key1) ord_tile_kernel<true><<<gr, SA_THREADS, 0, st>>>(op, d.as<OrdSummary>());
-        else ord_tile_kernel<false><<<gr, SA_THREADS, 0, st>>>(op, d.as<OrdSummary>());
+        if (has_key1) ord_tile_kernel<true><<<gr, SA_THREADS, 0, st>>>(op, d_ord.as<OrdSummary>());
+        else ord_tile_kernel<false><<<gr, SA_THREADS, 0, st>>>(op, d_ord.as<OrdSummary>());
         PG_CUDA(cudaGetLastError());
-        PG_CUDA(cudaMemcpyAsync(out->data(), d.p, sizeof(OrdSummary) * (size_t)(te - tb), cudaMemcpyDeviceToHost, st));
+        PG_CUDA(cudaMemcpyAsync(h_ord.p, d_ord.p, sizeof(OrdSummary) * (size_t)(te - tb), cudaMemcpyDeviceToHost, st));
         PG_CUDA(cudaStreamSynchronize(st));
         return PG_OK;
     }
@@ -278,12 +295,15 @@ struct LowcardPipeline : Pipeline {
         i128 P0 = 0;
         while (P0 + rank_tot[(size_t)rstar] < THR) { P0 += rank_tot[(size_t)rstar]; rstar++; }
         const i64 ntiles = (prm.nrows + SA_TILE - 1) / SA_TILE;
+        PG_TRY(ensure_ord_buffers());
+        const OrdSummary *sums = nullptr;
+        i64 nsums = 0;
         // per-rank contribution: absolute state (rank == rstar) or a transducer summary (rank > rstar)
         struct Contrib { u64 kind, s_lo, s_hi, q_lo, q_hi; u64 c0, c1, p0p1; } mine{};
         if (myrank() == rstar) {
             // a. which CTA range crosses
-            std::vector<i64> part((size_t)grid * (size_t)G * LC_K);
-            PG_CUDA(cudaMemcpyAsync(part.data(), d_part.p, part.size() * sizeof(i64), cudaMemcpyDeviceToHost, st));
+            const i64 *part = h_part.as<i64>();
+            PG_CUDA(cudaMemcpyAsync(h_part.p, d_part.p, sizeof(i64) * (size_t)grid * (size_t)G * LC_K, cudaMemcpyDeviceToHost, st));
             PG_CUDA(cudaStreamSynchronize(st));
             i64 per = (ntiles + grid - 1) / grid;
             i128 P = P0;
@@ -296,11 +316,10 @@ struct LowcardPipeline : Pipeline {
             if (cstar == grid) PG_FAIL(PG_ECUDA, "internal: crossing CTA not found");
             // b. which tile of that CTA crosses
             i64 tb = (i64)cstar * per, te = std::min<i64>(ntiles, tb + per);
-            std::vector<OrdSummary> sums;
-            PG_TRY(ord_summaries(g, s, tb, te, &sums));
+            PG_TRY(ord_summaries(g, s, tb, te, &sums, &nsums));
             i64 tstar = tb;
             for (; tstar < te; tstar++) {
-                i128 v = sums[(size_t)(tstar - tb)].sum_x;
+                i128 v = sums[tstar - tb].sum_x;
                 if (P + v >= THR) break;
                 P += v;
             }
@@ -308,16 +327,17 @@ struct LowcardPipeline : Pipeline {
             // c. that tile row by row, exactly as the reference would add them
             i64 row0 = tstar * SA_TILE;
             int n = (int)std::min<i64>(SA_TILE, prm.nrows - row0);
-            std::vector<int> h_pred((size_t)n);
-            std::vector<uint8_t> h_k0((size_t)n), h_k1((size_t)n), h_lut(512);
-            std::vector<i64> h_a((size_t)n), h_b((size_t)n), h_c((size_t)n);
-            PG_CUDA(cudaMemcpyAsync(h_pred.data(), prm.pred + row0, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
-            PG_CUDA(cudaMemcpyAsync(h_k0.data(), prm.key0 + row0, (size_t)n, cudaMemcpyDeviceToHost, st));
-            if (has_key1) PG_CUDA(cudaMemcpyAsync(h_k1.data(), prm.key1 + row0, (size_t)n, cudaMemcpyDeviceToHost, st));
-            PG_CUDA(cudaMemcpyAsync(h_a.data(), prm.A + row0, sizeof(i64) * (size_t)n, cudaMemcpyDeviceToHost, st));
-            PG_CUDA(cudaMemcpyAsync(h_b.data(), prm.B + row0, sizeof(i64) * (size_t)n, cudaMemcpyDeviceToHost, st));
-            PG_CUDA(cudaMemcpyAsync(h_c.data(), prm.C + row0, sizeof(i64) * (size_t)n, cudaMemcpyDeviceToHost, st));
-            PG_CUDA(cudaMemcpyAsync(h_lut.data(), prm.luts, 512, cudaMemcpyDeviceToHost, st));
+            // pinned staging: [A | B | C] int64, [pred] int32, [key0 | key1] bytes, [luts]
+            i64 *h_a = h_tile.as<i64>(), *h_b = h_a + SA_TILE, *h_c = h_b + SA_TILE;
+            int *h_pred = (int *)(h_c + SA_TILE);
+            uint8_t *h_k0 = (uint8_t *)(h_pred + SA_TILE), *h_k1 = h_k0 + SA_TILE, *h_lut = h_k1 + SA_TILE;
+            PG_CUDA(cudaMemcpyAsync(h_pred, prm.pred + row0, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+            PG_CUDA(cudaMemcpyAsync(h_k0, prm.key0 + row0, (size_t)n, cudaMemcpyDeviceToHost, st));
+            if (has_key1) PG_CUDA(cudaMemcpyAsync(h_k1, prm.key1 + row0, (size_t)n, cudaMemcpyDeviceToHost, st));
+            PG_CUDA(cudaMemcpyAsync(h_a, prm.A + row0, sizeof(i64) * (size_t)n, cudaMemcpyDeviceToHost, st));
+            PG_CUDA(cudaMemcpyAsync(h_b, prm.B + row0, sizeof(i64) * (size_t)n, cudaMemcpyDeviceToHost, st));
+            PG_CUDA(cudaMemcpyAsync(h_c, prm.C + row0, sizeof(i64) * (size_t)n, cudaMemcpyDeviceToHost, st));
+            PG_CUDA(cudaMemcpyAsync(h_lut, prm.luts, 512, cudaMemcpyDeviceToHost, st));
             PG_CUDA(cudaStreamSynchronize(st));
             bool rounded = false;
             u128 S = 0;
@@ -340,17 +360,17 @@ struct LowcardPipeline : Pipeline {
             }
             if (!rounded) PG_FAIL(PG_ECUDA, "internal: crossing row not found");
             // d. the rest of this rank's rows, tile summaries composed in order
-            PG_TRY(ord_summaries(g, s, tstar + 1, ntiles, &sums));
-            for (auto &o : sums) S += (u128)o.sum_q + ((S & 1) ? o.c1 : o.c0);
+            PG_TRY(ord_summaries(g, s, tstar + 1, ntiles, &sums, &nsums));
+            for (i64 i = 0; i < nsums; i++) S += (u128)sums[i].sum_q + ((S & 1) ? sums[i].c1 : sums[i].c0);
             mine.kind = 1;
             mine.s_lo = (u64)S;
             mine.s_hi = (u64)(S >> 64);
         } else if (myrank() > rstar) {
-            std::vector<OrdSummary> sums;
-            PG_TRY(ord_summaries(g, s, 0, ntiles, &sums));
+            PG_TRY(ord_summaries(g, s, 0, ntiles, &sums, &nsums));
             i128 q = 0;
             u64 cc[2] = {0, 0}, pp[2] = {0, 1};
-            for (auto &o : sums) {
+            for (i64 i = 0; i < nsums; i++) {
+                const OrdSummary &o = sums[i];
                 q += o.sum_q;
                 for (int k = 0; k < 2; k++) {
                     cc[k] += pp[k] ? o.c1 : o.c0;
@@ -364,14 +384,13 @@ struct LowcardPipeline : Pipeline {
             mine.c1 = cc[1];
             mine.p0p1 = pp[0] | (pp[1] << 1);
         }
-        std::vector<Contrib> all((size_t)nranks());
+        static_assert(sizeof(Contrib) == 64, "Contrib is exchanged as 64 bytes");
+        Contrib *all = h_contrib.as<Contrib>() + 1;
         if (nranks() > 1) {
-            DevBuf ds, dr;
-            PG_TRY(ds.alloc(sizeof(Contrib)));
-            PG_TRY(dr.alloc(sizeof(Contrib) * (size_t)nranks()));
-            PG_CUDA(cudaMemcpyAsync(ds.p, &mine, sizeof(Contrib), cudaMemcpyHostToDevice, st));
-            PG_TRY(comm_allgather(ds.p, dr.p, sizeof(Contrib), st));
-            PG_CUDA(cudaMemcpyAsync(all.data(), dr.p, sizeof(Contrib) * (size_t)nranks(), cudaMemcpyDeviceToHost, st));
+            h_contrib.as<Contrib>()[0] = mine;
+            PG_CUDA(cudaMemcpyAsync(d_contrib.p, h_contrib.p, 64, cudaMemcpyHostToDevice, st));
+            PG_TRY(comm_allgather(d_contrib.p, (char *)d_contrib.p + 64, 64, st));
+            PG_CUDA(cudaMemcpyAsync(all, (char *)d_contrib.p + 64, 64 * (size_t)nranks(), cudaMemcpyDeviceToHost, st));
             PG_CUDA(cudaStreamSynchronize(st));
         } else {
             all[0] = mine;
@@ -407,6 +426,7 @@ struct LowcardPipeline : Pipeline {
         cudaStream_t st = c.stream;
         PG_TRY(ev_all.init());
         PG_TRY(ev_main.init());
+        Trace tr("lowcard");
         // d_final layout: [G*K][2] u64 totals followed by first_row[LC_MAXG]
         i64 *d_firstrow = (i64 *)((char *)d_final.p + (size_t)G * LC_K * 16);
         PG_CUDA(cudaEventRecord(ev_all.a, st));
@@ -426,6 +446,7 @@ struct LowcardPipeline : Pipeline {
         PG_CUDA(cudaMemcpyAsync(h_final.p, src, rank_bytes() * (size_t)nranks(), cudaMemcpyDeviceToHost, st));
         PG_CUDA(cudaEventRecord(ev_all.b, st));
         PG_CUDA(cudaStreamSynchronize(st));
+        tr.mark("kernels+gather+d2h");
 
         // merge ranks in order; 128-bit exact
         std::vector<i128> tot((size_t)G * LC_K, 0);
@@ -505,6 +526,7 @@ struct LowcardPipeline : Pipeline {
             res->cols.push_back(col);
         }
         res->stats.aux[1] = emulations;
+        tr.mark("finalise(+rounding emulation)");
         return PG_OK;
     }
 };
