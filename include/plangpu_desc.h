@@ -7,7 +7,11 @@
  * appends int64 words.  No pointers, no Go structs.
  *
  *   desc  := PG_DESC_MAGIC PG_DESC_VERSION node
- *   node  := PG_OP_SCAN   slot nfilters expr*
+ *   node  := PG_OP_TOPK   nkeys (out_idx desc)* limit node      -- Limit <- Order [<- Project] <- Agg fused:
+ *                         ORDER BY output columns of the aggregate below (executor_order.go,
+ *                         sort_encoder.go:65-81 key semantics), keep the first `limit` rows
+ *                         (executor_limit.go:120-137); limit < 0 = no limit.  Root only.
+ *          | PG_OP_SCAN   slot nfilters expr*
  *          | PG_OP_FILTER nfilters expr* node
  *          | PG_OP_JOIN   jointype nconds (expr_probe expr_build)* nout (side idx)* node_probe node_build
  *          | PG_OP_AGG    ngroups expr* naggs (aggfn ltype width scale expr)* nhaving expr* nout (kind idx)* node
@@ -39,6 +43,7 @@
 #define PG_OP_FILTER 2
 #define PG_OP_JOIN 3
 #define PG_OP_AGG 4
+#define PG_OP_TOPK 5
 
 /* join types (LOT_JoinType) */
 #define PG_JOIN_INNER 1

@@ -209,7 +209,10 @@ def q1(line, ship_le=days(1998, 8, 11)):
 def q3(cust, orders, line, segment="HOUSEHOLD", odate_lt=days(1995, 3, 29), ship_gt=days(1995, 3, 29),
        capacity=None):
     r = Q3Result()
-    seg_code = SEGMENTS.index(segment) if isinstance(segment, str) else int(segment)
+    if isinstance(segment, str):
+        seg_code = SEGMENTS.index(segment) if segment in SEGMENTS else 255     # unknown literal matches nothing
+    else:
+        seg_code = int(segment)
     if capacity is None:
         capacity = max(len(orders["o_orderkey"]), 1)
     out = (Q3Group * capacity)()

@@ -81,6 +81,16 @@ class AggOpInfo:
         self.Aggs, self.GroupBys = Aggs, GroupBys         # Aggs[i] = func("sum"|..., result type, arg)
 
 
+class OrderOpInfo:
+    def __init__(self, OrderBys):
+        self.OrderBys = OrderBys            # [(Expr column ref into the child's outputs, descending)]
+
+
+class LimitOpInfo:
+    def __init__(self, Limit):
+        self.Limit = Limit
+
+
 class PhysicalOperator:
     def __init__(self, Typ, Outputs=None, Filters=None, Children=None, Info=None):
         self.Typ, self.Outputs, self.Filters = Typ, Outputs or [], Filters or []
@@ -125,6 +135,20 @@ def _expr_words(e):
 
 
 def _node_words(op, slots):
+    if op.Typ == POT_Limit and op.Children[0].Typ == POT_Order and op.Children[0].Children[0].Typ == POT_Agg:
+        # Limit <- Order <- Agg with ORDER BY on plain output columns fuses into PG_OP_TOPK
+        order = op.Children[0]
+        w = [5, len(order.Info.OrderBys)]
+        for e, desc in order.Info.OrderBys:
+            w += [e.ColRef[1], 1 if desc else 0]
+        w.append(op.Info.Limit)
+        return w + _node_words(order.Children[0], slots)
+    if op.Typ == POT_Order and op.Children[0].Typ == POT_Agg:
+        w = [5, len(op.Info.OrderBys)]
+        for e, desc in op.Info.OrderBys:
+            w += [e.ColRef[1], 1 if desc else 0]
+        w.append(-1)
+        return w + _node_words(op.Children[0], slots)
     if op.Typ == POT_Scan:
         if op.Info.Table not in slots:
             slots[op.Info.Table] = len(slots)
@@ -315,11 +339,12 @@ class gpuPipelineExec(OperatorExec):
             output.Data, output.Count = [], 0
             return Done, None
         vecs = []
+        agg = self._agg_op()
         for i, (t, w, s) in enumerate(self.coltypes):
             dt = np.dtype(K.native_dtype(t))
             buf = (C.c_char * (dt.itemsize * n.value)).from_address(cols[i])
             data = np.frombuffer(buf, dtype=dt, count=n.value).copy()
-            typ = self.op.Outputs[i].DataTyp if i < len(self.op.Outputs) else K.LType(0)
+            typ = agg.Outputs[i].DataTyp if i < len(agg.Outputs) else K.LType(0)
             d = None
             if t == L.PG_T_DICT8:
                 d = self._dict_for_output(i)
@@ -327,12 +352,19 @@ class gpuPipelineExec(OperatorExec):
         output.Data, output.Count = vecs, n.value
         return haveMoreOutput, None
 
+    def _agg_op(self):
+        op = self.op
+        while op.Typ in (POT_Limit, POT_Order):
+            op = op.Children[0]
+        return op
+
     def _dict_for_output(self, i):
         # a DICT8 group key comes straight from a scan column: find its dictionary
-        o = self.op.Outputs[i]
-        if self.op.Typ == POT_Agg and o.ColRef[0] == 0:
-            g = self.op.Info.GroupBys[o.ColRef[1]]
-            node = self.op.Children[0]
+        agg = self._agg_op()
+        o = agg.Outputs[i]
+        if agg.Typ == POT_Agg and o.ColRef[0] == 0:
+            g = agg.Info.GroupBys[o.ColRef[1]]
+            node = agg.Children[0]
             while node.Typ not in (POT_Scan,):
                 node = node.Children[g.ColRef[0]] if node.Typ == POT_Join else node.Children[0]
             return self.tables[node.Info.Table].columns[g.ColRef[1]][4]

@@ -82,6 +82,65 @@ struct JoinAggPipeline : Pipeline {
     bool gather_ranks = false;     // probe side is sharded: every rank ends with the union of all groups
     DevBuf d_g_klo, d_g_khi, d_g_acc, d_g_cnt;
     PinBuf h_out;                  // pinned landing zone of the group lists: [klo | khi | acc planes]
+    // fused ORDER BY ... LIMIT k: device pre-selection on the primary key
+    bool has_topk = false;
+    TopkKey topk_key{};
+    i64 topk_limit = -1;
+    DevBuf d_hist, d_cand_klo, d_cand_khi, d_cand_acc;
+    i64 cand_cap = 0;
+
+    // replace the compacted group list (d_out_*, n groups) by the candidates for the first k rows
+    int topk_preselect(i64 *ngroups, pg_result *res)
+    {
+        cudaStream_t st = ctx().stream;
+        i64 n = *ngroups, k = topk_limit;
+        if (k < 0 || n <= k) return PG_OK;
+        if (k == 0) { *ngroups = 0; return PG_OK; }
+        const int planes = gs.nacc + 1;
+        if (!d_hist.p) PG_TRY(d_hist.alloc(256 * 8));
+        int grid = (int)std::max<i64>(std::min<i64>((n + 255) / 256, (i64)ctx().prop.multiProcessorCount * 4), 1);
+        u64 prefix = 0;
+        i64 remaining = k;       // we look for the remaining-th smallest key among those matching the prefix
+        unsigned long long hist[256];
+        i64 n_equal = 0;
+        for (int pass = 0; pass < 8; pass++) {
+            PG_CUDA(cudaMemsetAsync(d_hist.p, 0, 256 * 8, st));
+            topk_hist_kernel<<<grid, 256, 0, st>>>(topk_key, d_out_klo.as<i64>(), d_out_khi.as<i64>(), d_out_acc.as<i64>(), out_cap, n,
+                                                   prefix, pass * 8, d_hist.as<unsigned long long>());
+            PG_CUDA(cudaGetLastError());
+            PG_CUDA(cudaMemcpyAsync(hist, d_hist.p, 256 * 8, cudaMemcpyDeviceToHost, st));
+            PG_CUDA(cudaStreamSynchronize(st));
+            int d = 0;
+            for (; d < 256; d++) {
+                if ((i64)hist[d] >= remaining) break;
+                remaining -= (i64)hist[d];
+            }
+            if (d == 256) PG_FAIL(PG_ECUDA, "internal: top-k radix select ran off the histogram");
+            prefix = (prefix << 8) | (u64)d;
+            n_equal = (i64)hist[d];
+            res->stats.kernel_launches += 1;
+        }
+        i64 ncand = (k - remaining) + n_equal;      // strictly smaller keys + every tie of the k-th key
+        if (ncand > cand_cap) {
+            PG_TRY(d_cand_klo.alloc((size_t)ncand * 8));
+            PG_TRY(d_cand_khi.alloc((size_t)ncand * 8));
+            PG_TRY(d_cand_acc.alloc((size_t)ncand * 8 * (size_t)planes));
+            cand_cap = ncand;
+        }
+        PG_CUDA(cudaMemsetAsync(d_counters.p, 0, 32, st));
+        topk_collect_kernel<<<grid, 256, 0, st>>>(topk_key, d_out_klo.as<i64>(), d_out_khi.as<i64>(), d_out_acc.as<i64>(), out_cap, n, planes,
+                                                  prefix, d_cand_klo.as<i64>(), d_cand_khi.as<i64>(), d_cand_acc.as<i64>(), cand_cap,
+                                                  d_counters.as<unsigned long long>());
+        PG_CUDA(cudaGetLastError());
+        res->stats.kernel_launches += 1;
+        // the candidate arrays become the output arrays
+        std::swap(d_out_klo.p, d_cand_klo.p); std::swap(d_out_klo.bytes, d_cand_klo.bytes);
+        std::swap(d_out_khi.p, d_cand_khi.p); std::swap(d_out_khi.bytes, d_cand_khi.bytes);
+        std::swap(d_out_acc.p, d_cand_acc.p); std::swap(d_out_acc.bytes, d_cand_acc.bytes);
+        std::swap(out_cap, cand_cap);
+        *ngroups = ncand;
+        return PG_OK;
+    }
 
     const pg_table *tab(int slot) const { return plan->slots[(size_t)slot]; }
 
@@ -278,7 +337,9 @@ struct JoinAggPipeline : Pipeline {
         unsigned long long ng2[4];
         PG_TRY(read_counters(ng2));
         i64 ngroups = (i64)ng2[0];
+        res->stats.aux[6] = ngroups;          // groups before any LIMIT
         tr.mark("compact");
+        if (has_topk) { PG_TRY(topk_preselect(&ngroups, res)); tr.mark("top-k preselect"); }
         const int planes = gs.nacc + 1;
         i64 *h_klo = nullptr, *h_khi = nullptr, *h_acc = nullptr;
         auto host_arrays = [&](i64 n) -> int {
@@ -706,6 +767,24 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &join, std::uniqu
             if (!ok || !disjoint) PG_FAIL(PG_EUNSUPPORTED, "groups are not partitioned by the shard key (needs the all-to-all shuffle path)");
             p->gather_ranks = true;
         }
+    }
+    if (plan->topk && !plan->topk->order.empty()) {
+        // primary ORDER BY key -> where it lives in the group table
+        auto o = aggn.outs[(size_t)plan->topk->order[0].first];
+        TopkKey tk{};
+        tk.desc = plan->topk->order[0].second ? 1 : 0;
+        tk.div = 1;
+        if (o.first == 0) {
+            tk.src = o.second;            // 0: klo, 1: khi high, 2: khi low
+        } else {
+            tk.src = 3;
+            tk.plane = o.second;
+            int sc = p->agg_scale[(size_t)o.second];
+            for (int i = 2; i < sc; i++) tk.div *= 10;     // DECIMAL keys compare at two fractional digits
+        }
+        p->has_topk = true;
+        p->topk_key = tk;
+        p->topk_limit = plan->topk->limit;
     }
     PG_TRY(p->d_counters.alloc(64));
     PG_TRY(p->d_overflow.alloc(4));

@@ -271,6 +271,13 @@ fast_pipeline_kernel(const PipeParams p)
             gt_update(p.gt, klo, khi, vals);
         }
     };
+    // WARP-COOPERATIVE slow path: rows whose key bit is set are queued per warp in shared memory
+    // (ballot + prefix), then the 32 lanes drain the queue in parallel -- a matching order's rows
+    // (adjacent in the table) are spread over lanes instead of serialising in the lane that
+    // streamed them, and the probe/sink code exists once.
+    __shared__ i64 s_queue[SA_THREADS / 32][32 * SA_VEC * UNROLL];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
     for (i64 tile0 = blockIdx.x; tile0 < ntiles; tile0 += (i64)gridDim.x * UNROLL) {
         int4 d[UNROLL];
         i64 k[UNROLL][4];
@@ -289,31 +296,33 @@ fast_pipeline_kernel(const PipeParams p)
                 }
             }
         }
+        int nq = 0;
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) {
-            i64 tile = tile0 + (i64)u * gridDim.x;
+            i64 tile = tile0 + (i64)u * gridDim.x;     // warp-uniform
             if (tile < ntiles) {
                 i64 row = tile * SA_TILE + threadIdx.x * SA_VEC;
                 i64 rem = p.nrows - row;
                 int dv[4] = {d[u].x, d[u].y, d[u].z, d[u].w};
-                bool hit[4];
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     bool ok = j < rem;
                     if (HAS_PRED) ok = ok && !pempty && dv[j] >= plo && dv[j] <= phi;
                     n_pass += ok ? 1 : 0;
-                    hit[j] = ok && bitmap_test(p.probe, k[u][j]);
-                }
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    if (hit[j]) {
-                        i64 r = row + j;
-                        if (p.probe_bitmap_only) sink(r, 0);
-                        else jt_probe(p.probe, k[u][j], [&](u64 pay) { sink(r, pay); });
-                    }
+                    bool hit = ok && bitmap_test(p.probe, k[u][j]);
+                    unsigned m = __ballot_sync(0xffffffffu, hit);
+                    if (hit) s_queue[warp][nq + __popc(m & lt_mask)] = row + j;
+                    nq += __popc(m);
                 }
             }
         }
+        __syncwarp();
+        for (int i = lane; i < nq; i += 32) {
+            i64 r = s_queue[warp][i];
+            if (p.probe_bitmap_only) sink(r, 0);
+            else jt_probe(p.probe, load_typed(p.probe_key, r), [&](u64 pay) { sink(r, pay); });
+        }
+        __syncwarp();
     }
     n_pass = (unsigned long long)warp_sum((i64)n_pass);
     n_join = (unsigned long long)warp_sum((i64)n_join);
@@ -337,6 +346,62 @@ static __global__ void gt_compact_kernel(const GroupTable g, i64 *__restrict__ o
         out_klo[o] = k;
         out_khi[o] = g.khi[i];
         for (int a = 0; a <= g.nacc; a++) out_acc[(u64)a * (u64)max_out + o] = g.acc[(u64)a * cap + i];
+    }
+}
+
+// ------------------------------------------------------------------ top-k --
+// Limit <- Order <- Agg fused onto the device: instead of shipping every group
+// to the host to sort, radix-select the k-th smallest PRIMARY sort key over the compacted group
+// list (8 histogram passes of 8 bits), collect the groups at or before it (k plus ties) and let
+// the host order those few rows with the full key list.  Keys follow sort_encoder.go:65-81:
+// a DECIMAL key is the value rounded half-even to two fractional digits.
+struct TopkKey {
+    int src;        // 0: klo, 1: khi >> 32, 2: low 32 bits of khi (sign extended), 3: accumulator plane
+    int plane;
+    int desc;
+    i64 div;        // DECIMAL: 10^(scale-2) (1 = no rounding)
+};
+
+__device__ __forceinline__ u64 topk_u64(const TopkKey &k, const i64 *klo, const i64 *khi, const i64 *acc, i64 stride, i64 i)
+{
+    i64 v = k.src == 0 ? klo[i] : k.src == 1 ? (khi[i] >> 32) : k.src == 2 ? (i64)(int)(khi[i] & 0xffffffffLL) : acc[(i64)k.plane * stride + i];
+    if (k.div > 1) {
+        bool neg = v < 0;
+        u64 m = neg ? (u64)(-(v + 1)) + 1 : (u64)v, q = m / (u64)k.div, r = m % (u64)k.div;
+        if (2 * r > (u64)k.div || (2 * r == (u64)k.div && (q & 1))) q++;
+        v = neg ? -(i64)q : (i64)q;
+    }
+    u64 u = (u64)v ^ 0x8000000000000000ULL;     // order preserving
+    return k.desc ? ~u : u;                     // output order = ascending u
+}
+
+static __global__ void topk_hist_kernel(TopkKey key, const i64 *klo, const i64 *khi, const i64 *acc, i64 stride, i64 n,
+                                        u64 prefix, int prefix_bits, unsigned long long *hist /* [256] */)
+{
+    __shared__ unsigned s_h[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_h[i] = 0;
+    __syncthreads();
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        u64 u = topk_u64(key, klo, khi, acc, stride, i);
+        if (prefix_bits == 0 || (u >> (64 - prefix_bits)) == prefix) atomicAdd(&s_h[(u >> (56 - prefix_bits)) & 255], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        if (s_h[i]) atomicAdd(&hist[i], (unsigned long long)s_h[i]);
+}
+
+// copy every group whose primary key is <= threshold to the candidate arrays
+static __global__ void topk_collect_kernel(TopkKey key, const i64 *klo, const i64 *khi, const i64 *acc, i64 stride, i64 n, int planes,
+                                           u64 threshold, i64 *out_klo, i64 *out_khi, i64 *out_acc, i64 out_cap,
+                                           unsigned long long *counter)
+{
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        if (topk_u64(key, klo, khi, acc, stride, i) > threshold) continue;
+        unsigned long long o = atomicAdd(counter, 1ULL);
+        if ((i64)o >= out_cap) continue;
+        out_klo[o] = klo[i];
+        out_khi[o] = khi[i];
+        for (int a = 0; a < planes; a++) out_acc[(i64)a * out_cap + (i64)o] = acc[(i64)a * stride + i];
     }
 }
 

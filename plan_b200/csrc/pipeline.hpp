@@ -113,6 +113,8 @@ struct pg_result {
 
 struct pg_plan {
     pg::Node root;
+    const pg::Node *topk = nullptr;     // root when it is a PG_OP_TOPK, else null
+    const pg::Node &agg_root() const { return topk ? root.children[0] : root; }
     std::vector<pg_table *> slots;
     std::vector<uint64_t> bound_versions;
     int pipe_world = 1;

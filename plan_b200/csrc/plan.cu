@@ -5,6 +5,7 @@
 // (/root/reference/pkg/compute/executor.go:305-350 buildOperatorExec,
 //  executor_aggr.go:106-262 aggExecutor.Execute): HAS_INIT drains the child completely,
 // HAS_SCAN emits groups in first-insertion order (aggregate_hash.go:424-438).
+#include <algorithm>
 #include <chrono>
 #include <memory>
 
@@ -29,9 +30,65 @@ static const Node *skip_filters(const Node *n, std::vector<Expr> *extra)
     return n;
 }
 
+// ORDER BY + LIMIT over a (small) result: the reference's Order operator compares normalized keys
+// (sort_encoder.go:65-81): a DECIMAL key is Int64(2) -- the value rounded half-even to two
+// fractional digits -- integers/dates by value, DESC inverts; ties keep an arbitrary order.
+static i128 order_key(const ResCol &c, i64 row)
+{
+    const uint8_t *p = c.data.data() + (size_t)row * (size_t)type_size(c.type);
+    switch (c.type) {
+    case PG_T_INT32: case PG_T_DATE32: { int32_t v; memcpy(&v, p, 4); return v; }
+    case PG_T_INT64: case PG_T_DECIMAL64: { i64 v; memcpy(&v, p, 8); return v; }
+    case PG_T_CHAR1: case PG_T_DICT8: return *p;
+    case PG_T_HUGEINT: { pg_hugeint h; memcpy(&h, p, 16); return (i128)(((u128)(u64)h.upper << 64) | h.lower); }
+    case PG_T_DECIMAL128: {
+        pg_decimal d;
+        memcpy(&d, p, 16);
+        u128 m = d.coef;
+        if (d.scale > 2) m = hd_shift_right_even(m, d.scale - 2);
+        else m *= hd_pow10(2 - d.scale);
+        return d.neg ? -(i128)m : (i128)m;
+    }
+    default: return 0;
+    }
+}
+
+static int sort_result(pg_result *r, const std::vector<std::pair<int, int>> &order, i64 limit)
+{
+    for (auto &o : order)
+        if (o.first < 0 || o.first >= (int)r->cols.size()) PG_FAIL(PG_EINVAL, "ORDER BY column %d out of range", o.first);
+    std::vector<i64> idx((size_t)r->nrows);
+    for (i64 i = 0; i < r->nrows; i++) idx[(size_t)i] = i;
+    auto less = [&](i64 a, i64 b) {
+        for (auto &o : order) {
+            const ResCol &c = r->cols[(size_t)o.first];
+            if (c.type == PG_T_FLOAT64) {
+                double x, y;
+                memcpy(&x, c.data.data() + (size_t)a * 8, 8);
+                memcpy(&y, c.data.data() + (size_t)b * 8, 8);
+                if (x != y) return o.second ? x > y : x < y;
+                continue;
+            }
+            i128 x = order_key(c, a), y = order_key(c, b);
+            if (x != y) return o.second ? x > y : x < y;
+        }
+        return false;
+    };
+    std::stable_sort(idx.begin(), idx.end(), less);
+    i64 n = limit >= 0 && limit < r->nrows ? limit : r->nrows;
+    for (ResCol &c : r->cols) {
+        size_t w = (size_t)type_size(c.type);
+        std::vector<uint8_t> out((size_t)n * w);
+        for (i64 i = 0; i < n; i++) memcpy(out.data() + (size_t)i * w, c.data.data() + (size_t)idx[(size_t)i] * w, w);
+        c.data.swap(out);
+    }
+    r->nrows = n;
+    return PG_OK;
+}
+
 static int build_pipeline(pg_plan *plan)
 {
-    const Node &root = plan->root;
+    const Node &root = plan->agg_root();
     if (root.op != PG_OP_AGG) PG_FAIL(PG_EUNSUPPORTED, "plan root must be an aggregate (got op %d)", root.op);
     std::vector<Expr> extra;
     const Node *child = skip_filters(&root.children[0], &extra);
@@ -76,7 +133,12 @@ int pg_plan_compile(const int64_t *desc, size_t nwords, pg_plan **out)
     }
     p->slots.assign((size_t)nslots, nullptr);
     // structural check now, kernel selection when the tables are bound
-    if (p->root.op != PG_OP_AGG) PG_FAIL(PG_EUNSUPPORTED, "pg_plan_compile: only aggregate-rooted pipelines are off-loaded");
+    if (p->root.op == PG_OP_TOPK) {
+        p->topk = &p->root;
+        for (auto &o : p->root.order)
+            if (o.first < 0 || o.first >= (int)p->root.children[0].outs.size()) PG_FAIL(PG_EINVAL, "pg_plan_compile: ORDER BY refers to output %d", o.first);
+    }
+    if (p->agg_root().op != PG_OP_AGG) PG_FAIL(PG_EUNSUPPORTED, "pg_plan_compile: only aggregate-rooted pipelines are off-loaded");
     *out = p.release();
     return PG_OK;
 }
@@ -133,6 +195,7 @@ int pg_plan_execute(pg_plan *p, pg_result **out)
     std::unique_ptr<pg_result> r(new pg_result());
     auto t0 = std::chrono::steady_clock::now();
     PG_TRY(p->pipe->run(r.get()));
+    if (p->topk) PG_TRY(sort_result(r.get(), p->topk->order, p->topk->limit));   // pipelines pre-select candidates on the device
     auto t1 = std::chrono::steady_clock::now();
     r->stats.exec_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
     *out = r.release();

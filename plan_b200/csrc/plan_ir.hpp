@@ -50,6 +50,8 @@ struct Node {
     std::vector<Expr> groups;                        // AGG
     std::vector<AggExpr> aggs;
     std::vector<Expr> having;
+    std::vector<std::pair<int, int>> order;          // TOPK (output index, descending)
+    i64 limit = -1;                                  // TOPK
     std::vector<Node> children;
 };
 
@@ -114,6 +116,16 @@ public:
         if (depth > 16) return ok_ = false;
         out->op = (int)next();
         switch (out->op) {
+        case PG_OP_TOPK: {
+            if (depth != 0) return ok_ = false;
+            i64 nk = next();
+            if (!ok_ || nk < 0 || nk > 16) return ok_ = false;
+            out->order.resize((size_t)nk);
+            for (auto &o : out->order) { o.first = (int)next(); o.second = (int)next(); }
+            out->limit = next();
+            out->children.resize(1);
+            return node(&out->children[0], depth + 1);
+        }
         case PG_OP_SCAN: {
             out->slot = (int)next();
             i64 nf = next();

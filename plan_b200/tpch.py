@@ -17,8 +17,8 @@ import numpy as np
 
 from . import _lib as L
 from . import chunk as K
-from .compute import (JOIN_INNER, POT_Agg, POT_Join, POT_Scan, AggOpInfo, DeviceTable, JoinOpInfo,
-                      PhysicalOperator, ScanOpInfo, cast, col, const, func)
+from .compute import (JOIN_INNER, POT_Agg, POT_Join, POT_Limit, POT_Order, POT_Scan, AggOpInfo, DeviceTable, JoinOpInfo,
+                      LimitOpInfo, OrderOpInfo, PhysicalOperator, ScanOpInfo, cast, col, const, func)
 
 SEGMENTS = ["AUTOMOBILE", "BUILDING", "FURNITURE", "HOUSEHOLD", "MACHINERY"]
 
@@ -163,6 +163,15 @@ def q3_plan(segment="HOUSEHOLD", odate_lt=None, ship_gt=None, schema=FULL):
     outs = [col(0, 0, K.BigintType()), col(1, 0, K.DecimalType(38, 4)), col(0, 1, K.DateType()),
             col(0, 2, K.IntegerType())]
     return PhysicalOperator(POT_Agg, Outputs=outs, Children=[j2], Info=AggOpInfo([agg], groups))
+
+
+def q3_topk_plan(limit=10, **kw):
+    """Limit <- Order(revenue desc, o_orderdate) <- Agg(...) : the whole Q3 tail below the final
+    Project, fused into the GPU pipeline (device top-k)."""
+    agg = q3_plan(**kw)
+    order = PhysicalOperator(POT_Order, Outputs=agg.Outputs, Children=[agg],
+                             Info=OrderOpInfo([(col(0, 1, K.DecimalType(38, 4)), True), (col(0, 2, K.DateType()), False)]))
+    return PhysicalOperator(POT_Limit, Outputs=agg.Outputs, Children=[order], Info=LimitOpInfo(limit))
 
 
 # ----------------------------------------------------------------- tables --

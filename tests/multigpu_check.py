@@ -42,6 +42,9 @@ def main():
     J.check_q3(O, tables, host, check_counts=False)
     J.check_q3(O, tables, host, check_counts=False, segment="BUILDING", odate_lt=8035 + 3000, ship_gt=8035 - 10)
 
+    J.check_q3_topk(O, tables, host, 10)
+    J.check_q3_topk(O, tables, host, 1000, segment="BUILDING")
+
     # order-dependent rounding regime across shards: inflate prices on the uploaded shard
     first = int(np.searchsorted(line["l_orderkey"], orders["o_orderkey"][lo]))
     last = len(line["l_orderkey"]) if hi == n_orders else int(np.searchsorted(line["l_orderkey"], orders["o_orderkey"][hi]))

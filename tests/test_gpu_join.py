@@ -82,6 +82,28 @@ def test_q3_variants(pg, oracle, uploaded, sf01_host, kw):
     check_q3(oracle, uploaded, sf01_host, **kw)
 
 
+def check_q3_topk(oracle, tables, host, limit, **kw):
+    """Limit <- Order <- Agg fused on the device == oracle ORDER BY revenue desc, o_orderdate LIMIT k."""
+    from plan_b200 import compute as X, tpch as T
+    chunks, stats, _ = _run(T.q3_topk_plan(limit=limit, **kw), tables)
+    ref = oracle.q3(host["customer"], host["orders"], host["lineitem"], **kw)
+    rows = [[v.GetValue(r) for v in c.Data] for c in chunks for r in range(c.Card())]
+    assert len(rows) == min(limit, ref["stats"]["ngroups"])
+    assert X.rows_text(rows, 4) == oracle.q3_text(ref, limit)     # already ordered and limited by the GPU path
+    return stats
+
+
+@pytest.mark.parametrize("limit", [0, 1, 10, 100, 5000])
+def test_q3_topk_pushdown(pg, oracle, uploaded, sf01_host, limit):
+    stats = check_q3_topk(oracle, uploaded, sf01_host, limit)
+    assert stats.aux[6] > 1000          # the aggregate itself produced many groups; only `limit` came back
+
+
+def test_q3_topk_other_parameters(pg, oracle, uploaded, sf01_host):
+    check_q3_topk(oracle, uploaded, sf01_host, 10, segment="BUILDING", odate_lt=8035 + 3000, ship_gt=8035 - 10)
+    check_q3_topk(oracle, uploaded, sf01_host, 10, segment="NOSUCHSEGMENT")
+
+
 def test_join_duplicate_build_keys_emit_every_pair(pg, oracle, sf01_host):
     """INNER join semantics with a non-unique build side (join_scan.go:182-299 follows the whole
     chain): duplicating every customer doubles every revenue, duplicating orders too -> x4."""
@@ -120,6 +142,8 @@ def test_reference_golden_files_sf1_on_gpu(pg):
         assert X.rows_text(X.order_limit(chunks, [(0, False), (1, False)]), 10) == open(os.path.join(GOLDEN, "ref_sf1_q1.txt")).read()
         chunks, _, _ = _run(T.q3_plan(), t)
         assert X.rows_text(X.order_limit(chunks, [(1, True), (2, False)], 10), 4) == open(os.path.join(GOLDEN, "ref_sf1_q3.txt")).read()
+        chunks, _, _ = _run(T.q3_topk_plan(10), t)      # ORDER BY + LIMIT fused into the GPU pipeline
+        assert X.rows_text(X.order_limit(chunks, []), 4) == open(os.path.join(GOLDEN, "ref_sf1_q3.txt")).read()
     finally:
         for x in t.values():
             x.free()
