@@ -32,7 +32,7 @@ struct Stage {
     int probe_stage = -1;            // which earlier stage built the probed table
     int ins_key_col = -1;            // SINK_INSERT: key column on the source table
     // device state of the table this stage builds
-    DevBuf d_keys, d_pay, d_bitmap;
+    DevBuf d_slots, d_bitmap;
     JoinTable jt{};
     i64 capacity_rows = 0;
     i64 built_rows = 0;
@@ -184,10 +184,20 @@ struct JoinAggPipeline : Pipeline {
             i64 ntiles = (t->nrows + SA_TILE - 1) / SA_TILE;
             int grid = (int)std::max<i64>(std::min<i64>(ntiles, (i64)ctx().prop.multiProcessorCount * 6), 1);
             bool k8 = pp.probe_key.width == 8, hp = pp.npred == 1;
-            if (k8 && hp) fast_pipeline_kernel<8, SINK, true, 2><<<grid, SA_THREADS, 0, st>>>(pp);
-            else if (k8) fast_pipeline_kernel<8, SINK, false, 2><<<grid, SA_THREADS, 0, st>>>(pp);
-            else if (hp) fast_pipeline_kernel<4, SINK, true, 2><<<grid, SA_THREADS, 0, st>>>(pp);
-            else fast_pipeline_kernel<4, SINK, false, 2><<<grid, SA_THREADS, 0, st>>>(pp);
+            static const int unroll = getenv("PG_JOIN_UNROLL") ? atoi(getenv("PG_JOIN_UNROLL")) : 2;
+            static const int gmul = getenv("PG_JOIN_GRIDMUL") ? atoi(getenv("PG_JOIN_GRIDMUL")) : 6;
+            grid = (int)std::max<i64>(std::min<i64>(ntiles, (i64)ctx().prop.multiProcessorCount * gmul), 1);
+            if (unroll == 4) {
+                if (k8 && hp) fast_pipeline_kernel<8, SINK, true, 4><<<grid, SA_THREADS, 0, st>>>(pp);
+                else if (k8) fast_pipeline_kernel<8, SINK, false, 4><<<grid, SA_THREADS, 0, st>>>(pp);
+                else if (hp) fast_pipeline_kernel<4, SINK, true, 4><<<grid, SA_THREADS, 0, st>>>(pp);
+                else fast_pipeline_kernel<4, SINK, false, 4><<<grid, SA_THREADS, 0, st>>>(pp);
+            } else {
+                if (k8 && hp) fast_pipeline_kernel<8, SINK, true, 2><<<grid, SA_THREADS, 0, st>>>(pp);
+                else if (k8) fast_pipeline_kernel<8, SINK, false, 2><<<grid, SA_THREADS, 0, st>>>(pp);
+                else if (hp) fast_pipeline_kernel<4, SINK, true, 2><<<grid, SA_THREADS, 0, st>>>(pp);
+                else fast_pipeline_kernel<4, SINK, false, 2><<<grid, SA_THREADS, 0, st>>>(pp);
+            }
         }
         PG_CUDA(cudaGetLastError());
         return PG_OK;
@@ -198,16 +208,14 @@ struct JoinAggPipeline : Pipeline {
     {
         cudaStream_t st = ctx().stream;
         u64 nb = next_pow2((u64)std::max<i64>((nbuild * 2 + HT_BUCKET - 1) / HT_BUCKET, 16));
-        if (nbuild > s.capacity_rows || !s.d_keys.p) {
-            PG_TRY(s.d_keys.alloc(nb * HT_BUCKET * sizeof(i64)));
-            PG_TRY(s.d_pay.alloc(nb * HT_BUCKET * sizeof(u64)));
+        if (nbuild > s.capacity_rows || !s.d_slots.p) {
+            PG_TRY(s.d_slots.alloc(nb * HT_BUCKET * sizeof(longlong2)));
             s.capacity_rows = (i64)(nb * HT_BUCKET / 2);
         } else {
-            nb = s.d_keys.bytes / (HT_BUCKET * sizeof(i64));
+            nb = next_pow2((u64)std::max<i64>((nbuild * 2 + HT_BUCKET - 1) / HT_BUCKET, 16));   // fits: capacity only grows
         }
-        PG_CUDA(cudaMemsetAsync(s.d_keys.p, 0x80, nb * HT_BUCKET * sizeof(i64), st));
-        s.jt.keys = s.d_keys.as<i64>();
-        s.jt.pay = s.d_pay.as<u64>();
+        PG_CUDA(cudaMemsetAsync(s.d_slots.p, 0x80, nb * HT_BUCKET * sizeof(longlong2), st));
+        s.jt.slots = s.d_slots.as<longlong2>();
         s.jt.bucket_mask = nb - 1;
         // exact key-domain bitmap when the build column's value range is small enough
         s.jt.bitmap = nullptr;

@@ -25,7 +25,7 @@
 namespace pg {
 
 constexpr i64 HT_EMPTY = (i64)0x8080808080808080ULL;   // memset(0x80) pattern
-constexpr int HT_BUCKET = 8;
+constexpr int HT_BUCKET = 4;      // slots per 64-byte bucket line: {key, payload} pairs
 
 __host__ __device__ __forceinline__ u64 mix64(u64 x)
 {
@@ -34,8 +34,8 @@ __host__ __device__ __forceinline__ u64 mix64(u64 x)
 }
 
 struct JoinTable {
-    i64 *keys;          // [nbuckets][8]
-    u64 *pay;           // [nbuckets][8]
+    longlong2 *slots;   // [nbuckets][4] of {x = key, y = payload}: key and payload share a 32-byte sector,
+                        // so an insert or a matching probe touches ONE random sector, not two
     u64 bucket_mask;    // nbuckets - 1 (power of two)
     unsigned *bitmap;   // may be null
     i64 bm_min, bm_max; // key domain covered by the bitmap
@@ -58,12 +58,12 @@ __device__ __forceinline__ void jt_insert(const JoinTable &t, i64 key, u64 paylo
     }
     u64 b = mix64((u64)key) & t.bucket_mask;
     for (;;) {
-        i64 *line = t.keys + b * HT_BUCKET;
+        longlong2 *line = t.slots + b * HT_BUCKET;
 #pragma unroll
         for (int s = 0; s < HT_BUCKET; s++) {
-            if (line[s] == HT_EMPTY) {
-                i64 old = (i64)atomicCAS((unsigned long long *)&line[s], (unsigned long long)HT_EMPTY, (unsigned long long)key);
-                if (old == HT_EMPTY) { t.pay[b * HT_BUCKET + s] = payload; return; }
+            if (line[s].x == HT_EMPTY) {
+                i64 old = (i64)atomicCAS((unsigned long long *)&line[s].x, (unsigned long long)HT_EMPTY, (unsigned long long)key);
+                if (old == HT_EMPTY) { line[s].y = (i64)payload; return; }
             }
         }
         b = (b + 1) & t.bucket_mask;
@@ -76,16 +76,13 @@ __device__ __forceinline__ void jt_probe(const JoinTable &t, i64 key, F f)
 {
     u64 b = mix64((u64)key) & t.bucket_mask;
     for (;;) {
-        const longlong2 *line = (const longlong2 *)(t.keys + b * HT_BUCKET);
-        longlong2 k01 = __ldg(line), k23 = __ldg(line + 1), k45 = __ldg(line + 2), k67 = __ldg(line + 3);
-        i64 k[8] = {k01.x, k01.y, k23.x, k23.y, k45.x, k45.y, k67.x, k67.y};
-        bool end = false;
-#pragma unroll
-        for (int s = 0; s < HT_BUCKET; s++) {
-            if (k[s] == key) f(__ldg(t.pay + b * HT_BUCKET + s));
-            end = end || k[s] == HT_EMPTY;
-        }
-        if (end) return;
+        const longlong2 *line = t.slots + b * HT_BUCKET;
+        longlong2 s0 = __ldg(line), s1 = __ldg(line + 1), s2 = __ldg(line + 2), s3 = __ldg(line + 3);
+        if (s0.x == key) f((u64)s0.y);
+        if (s1.x == key) f((u64)s1.y);
+        if (s2.x == key) f((u64)s2.y);
+        if (s3.x == key) f((u64)s3.y);
+        if (s0.x == HT_EMPTY || s1.x == HT_EMPTY || s2.x == HT_EMPTY || s3.x == HT_EMPTY) return;
         b = (b + 1) & t.bucket_mask;
     }
 }
@@ -275,7 +272,12 @@ fast_pipeline_kernel(const PipeParams p)
     // (ballot + prefix), then the 32 lanes drain the queue in parallel -- a matching order's rows
     // (adjacent in the table) are spread over lanes instead of serialising in the lane that
     // streamed them, and the probe/sink code exists once.
-    __shared__ i64 s_queue[SA_THREADS / 32][32 * SA_VEC * UNROLL];
+    // The queue is drained only once it holds at least a warp's worth of rows (or at the end): with a
+    // ~1% match rate a drain after every batch would stall the warp's streaming for one full random-
+    // access latency chain to serve two or three rows.
+    constexpr int QCAP = 32 * SA_VEC * UNROLL + 32;
+    __shared__ i64 s_queue[SA_THREADS / 32][QCAP];
+    int nq = 0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     for (i64 tile0 = blockIdx.x; tile0 < ntiles; tile0 += (i64)gridDim.x * UNROLL) {
@@ -296,33 +298,43 @@ fast_pipeline_kernel(const PipeParams p)
                 }
             }
         }
-        int nq = 0;
+        // all bitmap words of the batch are requested before any is consumed
+        bool hit[UNROLL][4];
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) {
             i64 tile = tile0 + (i64)u * gridDim.x;     // warp-uniform
-            if (tile < ntiles) {
-                i64 row = tile * SA_TILE + threadIdx.x * SA_VEC;
-                i64 rem = p.nrows - row;
-                int dv[4] = {d[u].x, d[u].y, d[u].z, d[u].w};
+            i64 row = tile * SA_TILE + threadIdx.x * SA_VEC;
+            i64 rem = tile < ntiles ? p.nrows - row : 0;
+            int dv[4] = {d[u].x, d[u].y, d[u].z, d[u].w};
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    bool ok = j < rem;
-                    if (HAS_PRED) ok = ok && !pempty && dv[j] >= plo && dv[j] <= phi;
-                    n_pass += ok ? 1 : 0;
-                    bool hit = ok && bitmap_test(p.probe, k[u][j]);
-                    unsigned m = __ballot_sync(0xffffffffu, hit);
-                    if (hit) s_queue[warp][nq + __popc(m & lt_mask)] = row + j;
-                    nq += __popc(m);
-                }
+            for (int j = 0; j < 4; j++) {
+                bool ok = j < rem;
+                if (HAS_PRED) ok = ok && !pempty && dv[j] >= plo && dv[j] <= phi;
+                n_pass += ok ? 1 : 0;
+                hit[u][j] = ok && bitmap_test(p.probe, k[u][j]);
             }
         }
-        __syncwarp();
-        for (int i = lane; i < nq; i += 32) {
-            i64 r = s_queue[warp][i];
-            if (p.probe_bitmap_only) sink(r, 0);
-            else jt_probe(p.probe, load_typed(p.probe_key, r), [&](u64 pay) { sink(r, pay); });
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            i64 row = (tile0 + (i64)u * gridDim.x) * SA_TILE + threadIdx.x * SA_VEC;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                unsigned m = __ballot_sync(0xffffffffu, hit[u][j]);
+                if (hit[u][j]) s_queue[warp][nq + __popc(m & lt_mask)] = row + j;
+                nq += __popc(m);
+            }
         }
-        __syncwarp();
+        const bool last = tile0 + (i64)gridDim.x * UNROLL >= ntiles;    // warp-uniform
+        if (nq >= 32 || last) {
+            __syncwarp();
+            for (int i = lane; i < nq; i += 32) {
+                i64 r = s_queue[warp][i];
+                if (p.probe_bitmap_only) sink(r, 0);
+                else jt_probe(p.probe, load_typed(p.probe_key, r), [&](u64 pay) { sink(r, pay); });
+            }
+            __syncwarp();
+            nq = 0;
+        }
     }
     n_pass = (unsigned long long)warp_sum((i64)n_pass);
     n_join = (unsigned long long)warp_sum((i64)n_join);

@@ -174,7 +174,7 @@ __device__ __forceinline__ TileIter tile_iter(i64 ntiles, int contig)
 }
 
 template <bool HAS_KEY1, int UNROLL>
-__global__ void __launch_bounds__(SA_THREADS)
+__global__ void __launch_bounds__(SA_THREADS)   // 2 CTAs/SM; forcing 3 (80 regs + max SMEM carve-out) measured 1.8x SLOWER
 lowcard_chain_kernel(const LowcardParams p, i64 *__restrict__ partials /* [grid][G*K] */,
                      i64 *__restrict__ first_row /* [G], pre-set to INT64_MAX */)
 {
