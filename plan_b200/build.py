@@ -43,7 +43,19 @@ def build(force=False, verbose=False):
     if not ok:
         raise RuntimeError("libplangpu build failed")
     subprocess.check_call([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT] + objs + ["-lcudart", "-ldl"])
+    build_host()
     return OUT
+
+
+HOST_BIN = os.path.join(HERE, "host", "planhost_run")
+
+
+def build_host():
+    """The C++ host shim above the C ABI (plan_b200/host): a driver binary linked against libplangpu.so only."""
+    cxx = os.environ.get("CXX", "g++")
+    subprocess.check_call([cxx, "-std=c++17", "-O2", "-Wall", "-o", HOST_BIN, os.path.join(HERE, "host", "shim_main.cc"),
+                           "-L" + HERE, "-lplangpu", "-Wl,-rpath," + HERE, "-Wl,-rpath,/usr/local/cuda/lib64"])
+    return HOST_BIN
 
 
 if __name__ == "__main__":

@@ -1,0 +1,126 @@
+// tpch_plans.hpp -- the physical plans the reference's planner emits for TPC-H Q6 / Q1 / Q3
+// (typing per SURVEY.md 8c-1), built by hand because the planner stays in Go.
+#pragma once
+#include <math.h>
+
+#include "../../include/plangpu_tpch.h"
+#include "gpu_exec.hpp"
+
+namespace planhost {
+
+inline int32_t days_from_civil(int y, unsigned m, unsigned d)
+{
+    y -= m <= 2;
+    const int era = (y >= 0 ? y : y - 399) / 400;
+    const unsigned yoe = (unsigned)(y - era * 400);
+    const unsigned doy = (153 * (m + (m > 2 ? -3 : 9)) + 2) / 5 + d - 1;
+    const unsigned doe = yoe * 365 + yoe / 4 - yoe / 100 + doy;
+    return era * 146097 + (int)doe - 719468;
+}
+
+inline LType lineitem_type(int c)
+{
+    switch (c) {
+    case PG_L_ORDERKEY: return LType::Bigint();
+    case PG_L_EXTENDEDPRICE: case PG_L_DISCOUNT: case PG_L_TAX: return LType::Decimal(15, 2);
+    case PG_L_RETURNFLAG: case PG_L_LINESTATUS: return LType::Varchar();
+    case PG_L_SHIPDATE: case PG_L_COMMITDATE: case PG_L_RECEIPTDATE: return LType::Date();
+    default: return LType::Integer();
+    }
+}
+inline Expr lcol(int c, int side = 0) { return col(side, c, lineitem_type(c)); }
+
+inline Op make(POT t) { auto p = std::make_shared<PhysicalOperator>(); p->Typ = t; return p; }
+
+inline Expr disc_price(Expr ext, Expr disc)
+{
+    Expr one = cast(constI(1, LType::Integer()), LType::Decimal(15, 2));
+    return func("*", LType::Decimal(18, 4), {cast(std::move(ext), LType::Decimal(16, 2)),
+                                             func("-", LType::Decimal(16, 2), {one, std::move(disc)})});
+}
+
+inline Op q6_plan()
+{
+    LType B = LType::Boolean();
+    float flo = (float)0.03 - (float)0.01, fhi = (float)0.03 + (float)0.01;   // subFloat32 / addFloat32 folding
+    Expr discf = cast(lcol(PG_L_DISCOUNT), LType::Float());
+    Op scan = make(POT_Scan);
+    scan->Table = "lineitem";
+    scan->Filters = {
+        func(">=", B, {lcol(PG_L_SHIPDATE), constI(days_from_civil(1994, 1, 1), LType::Date())}),
+        func("<", B, {lcol(PG_L_SHIPDATE), constI(days_from_civil(1995, 1, 1), LType::Date())}),
+        func("and", B, {func(">=", B, {discf, constF(flo, LType::Float())}), func("<=", B, {discf, constF(fhi, LType::Float())})}),
+        func("<", B, {lcol(PG_L_QUANTITY), constI(24, LType::Integer())})};
+    Op agg = make(POT_Agg);
+    agg->Aggs = {func("sum", LType::Decimal(38, 4), {func("*", LType::Decimal(18, 4), {lcol(PG_L_EXTENDEDPRICE), lcol(PG_L_DISCOUNT)})})};
+    agg->Outputs = {col(1, 0, LType::Decimal(38, 4))};
+    agg->Children = {scan};
+    return agg;
+}
+
+inline Op q1_plan()     // Order(l_returnflag, l_linestatus) <- Agg <- Scan
+{
+    LType B = LType::Boolean();
+    Op scan = make(POT_Scan);
+    scan->Table = "lineitem";
+    scan->Filters = {func("<=", B, {lcol(PG_L_SHIPDATE), constI(days_from_civil(1998, 8, 11), LType::Date())})};
+    Expr one_plus_tax = func("+", LType::Decimal(16, 2), {cast(constI(1, LType::Integer()), LType::Decimal(15, 2)), lcol(PG_L_TAX)});
+    Expr charge = func("*", LType::Decimal(18, 8), {disc_price(lcol(PG_L_EXTENDEDPRICE), lcol(PG_L_DISCOUNT)), cast(one_plus_tax, LType::Decimal(18, 4))});
+    Op agg = make(POT_Agg);
+    agg->GroupBys = {lcol(PG_L_RETURNFLAG), lcol(PG_L_LINESTATUS)};
+    agg->Aggs = {func("sum", LType::Hugeint(), {lcol(PG_L_QUANTITY)}),
+                 func("sum", LType::Decimal(38, 2), {lcol(PG_L_EXTENDEDPRICE)}),
+                 func("sum", LType::Decimal(38, 4), {disc_price(lcol(PG_L_EXTENDEDPRICE), lcol(PG_L_DISCOUNT))}),
+                 func("sum", LType::Decimal(38, 8), {charge}),
+                 func("avg", LType::Double(), {lcol(PG_L_QUANTITY)}),
+                 func("avg", LType::Decimal(38, 2), {lcol(PG_L_EXTENDEDPRICE)}),
+                 func("avg", LType::Decimal(38, 2), {lcol(PG_L_DISCOUNT)}),
+                 func("count", LType::Hugeint(), {lcol(PG_L_ORDERKEY)})};
+    agg->Outputs = {col(0, 0, LType::Varchar()), col(0, 1, LType::Varchar())};
+    for (size_t i = 0; i < agg->Aggs.size(); i++) agg->Outputs.push_back(col(1, (int)i, agg->Aggs[i].DataTyp));
+    agg->Children = {scan};
+    Op order = make(POT_Order);
+    order->OrderBys = {{col(0, 0, LType::Varchar()), false}, {col(0, 1, LType::Varchar()), false}};
+    order->Outputs = agg->Outputs;
+    order->Children = {agg};
+    return order;
+}
+
+inline Op q3_plan(int64_t limit = 10)   // Limit <- Order(revenue desc, o_orderdate) <- Agg <- Join <- {lineitem, Join <- {orders, customer}}
+{
+    LType B = LType::Boolean();
+    int32_t d = days_from_civil(1995, 3, 29);
+    Op cust = make(POT_Scan);
+    cust->Table = "customer";
+    cust->Filters = {func("=", B, {col(0, PG_C_MKTSEGMENT, LType::Varchar()), constS("HOUSEHOLD")})};
+    Op ord = make(POT_Scan);
+    ord->Table = "orders";
+    ord->Filters = {func("<", B, {col(0, PG_O_ORDERDATE, LType::Date()), constI(d, LType::Date())})};
+    Op line = make(POT_Scan);
+    line->Table = "lineitem";
+    line->Filters = {func(">", B, {lcol(PG_L_SHIPDATE), constI(d, LType::Date())})};
+    Op j1 = make(POT_Join);
+    j1->Children = {ord, cust};
+    j1->OnConds = {func("=", B, {col(0, PG_O_CUSTKEY, LType::Integer()), col(1, PG_C_CUSTKEY, LType::Integer())})};
+    j1->Outputs = {col(0, PG_O_ORDERKEY, LType::Bigint()), col(0, PG_O_ORDERDATE, LType::Date()), col(0, PG_O_SHIPPRIORITY, LType::Integer())};
+    Op j2 = make(POT_Join);
+    j2->Children = {line, j1};
+    j2->OnConds = {func("=", B, {lcol(PG_L_ORDERKEY), col(1, 0, LType::Bigint())})};
+    j2->Outputs = {lcol(PG_L_ORDERKEY), lcol(PG_L_EXTENDEDPRICE), lcol(PG_L_DISCOUNT), col(1, 1, LType::Date()), col(1, 2, LType::Integer())};
+    Op agg = make(POT_Agg);
+    agg->GroupBys = {col(0, 0, LType::Bigint()), col(0, 3, LType::Date()), col(0, 4, LType::Integer())};
+    agg->Aggs = {func("sum", LType::Decimal(38, 4), {disc_price(col(0, 1, LType::Decimal(15, 2)), col(0, 2, LType::Decimal(15, 2)))})};
+    agg->Outputs = {col(0, 0, LType::Bigint()), col(1, 0, LType::Decimal(38, 4)), col(0, 1, LType::Date()), col(0, 2, LType::Integer())};
+    agg->Children = {j2};
+    Op order = make(POT_Order);
+    order->OrderBys = {{col(0, 1, LType::Decimal(38, 4)), true}, {col(0, 2, LType::Date()), false}};
+    order->Outputs = agg->Outputs;
+    order->Children = {agg};
+    Op lim = make(POT_Limit);
+    lim->Limit = limit;
+    lim->Outputs = agg->Outputs;
+    lim->Children = {order};
+    return lim;
+}
+
+}  // namespace planhost

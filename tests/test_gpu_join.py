@@ -147,3 +147,15 @@ def test_reference_golden_files_sf1_on_gpu(pg):
     finally:
         for x in t.values():
             x.free()
+
+
+@pytest.mark.parametrize("query,golden", [(6, "ref_sf1_q6.txt"), (1, "ref_sf1_q1.txt"), (3, "ref_sf1_q3.txt")])
+def test_cpp_host_shim_reproduces_golden_files(query, golden):
+    """The C++ host shim (plan_b200/host: OperatorExec / PhysicalOperator / Chunk mirrors above the C
+    ABI, standing in for the Go side) run like `tester tpch1g --query_id N`: its stdout is the
+    reference's result file, byte for byte."""
+    import subprocess
+    from plan_b200 import build as B
+    r = subprocess.run([B.HOST_BIN, "1", str(query)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout == open(os.path.join(GOLDEN, golden)).read()
