@@ -54,7 +54,7 @@ def build_host():
     """The C++ host shim above the C ABI (plan_b200/host): a driver binary linked against libplangpu.so only."""
     cxx = os.environ.get("CXX", "g++")
     subprocess.check_call([cxx, "-std=c++17", "-O2", "-Wall", "-o", HOST_BIN, os.path.join(HERE, "host", "shim_main.cc"),
-                           "-L" + HERE, "-lplangpu", "-Wl,-rpath," + HERE, "-Wl,-rpath,/usr/local/cuda/lib64"])
+                           "-L" + HERE, "-lplangpu", "-Wl,-rpath,$ORIGIN/..", "-Wl,-rpath," + HERE, "-Wl,-rpath,/usr/local/cuda/lib64"])
     return HOST_BIN
 
 

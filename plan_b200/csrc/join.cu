@@ -428,7 +428,7 @@ struct JoinAggPipeline : Pipeline {
         res->stats.main_kernel_ms = ev_main.ms();
         res->stats.rows_scanned = t->nrows;
         res->stats.algorithmic_bytes = algorithmic_bytes;
-        res->stats.main_kernel_bytes = main_bytes;
+        res->stats.main_kernel_bytes = main_bytes + (i64)cnt[1] * 32 * (gs.nparts + 2 * gs.nacc);   // streamed + gathered sectors
         res->stats.aux[0] = (i64)cnt[0];
         res->stats.aux[1] = (i64)cnt[1];
 
@@ -717,9 +717,14 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &join, std::uniqu
         for (auto &u : used) {
             const pg_table *t = p->tab(u.first);
             i64 b = t->nrows * type_size(t->cols[(size_t)u.second].type);
-            p->algorithmic_bytes += b;
-            if (u.first == p->src_slot) p->main_bytes += b;
+            p->algorithmic_bytes += b;      // every referenced column read once
         }
+        // the probe kernel itself STREAMS only the predicate and key columns; the other probe-side
+        // columns are gathered for matching rows (added per run: 32-byte sector per value)
+        for (auto &r : p->ranges) p->main_bytes += st->nrows * type_size(st->cols[(size_t)r.col].type);
+        bool key_is_pred = false;
+        for (auto &r : p->ranges) key_is_pred = key_is_pred || r.col == p->probe_key_col;
+        if (!key_is_pred) p->main_bytes += st->nrows * type_size(st->cols[(size_t)p->probe_key_col].type);
     }
     // multi-GPU: which joins are shard-local?  A REPLICATED build side is complete everywhere.  Two
     // SHARDED sides must be co-partitioned on the join key: no rank's probe-key range may touch
