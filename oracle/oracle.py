@@ -72,6 +72,16 @@ class Q3Result(C.Structure):
                 ("nout", C.c_int64), ("error", C.c_int)]
 
 
+class StatsGroup(C.Structure):
+    _fields_ = [("rf", C.c_uint8), ("min_ext", Dec), ("max_ext", Dec), ("max_disc", Dec), ("sum_tax", Dec),
+                ("avg_tax", Dec), ("sum_taxed", Dec), ("count", C.c_uint64), ("first_row", C.c_int64)]
+
+
+class StatsResult(C.Structure):
+    _fields_ = [("rows_in", C.c_int64), ("rows_selected", C.c_int64), ("ngroups", C.c_int), ("error", C.c_int),
+                ("g", StatsGroup * 16)]
+
+
 def lib():
     global _LIB
     if _LIB is None:
@@ -101,6 +111,9 @@ def lib():
                              [C.c_int64] + [C.c_void_p] * 4 + [C.c_int32] +
                              [C.c_int64] + [C.c_void_p] * 4 + [C.c_int32] +
                              [C.c_void_p, C.c_int64, C.POINTER(Q3Result)])
+        L.orc_stats.restype = None
+        L.orc_stats.argtypes = [C.c_int64] + [C.c_void_p] * 8 + [C.c_int32] * 6 + [C.c_int64, C.POINTER(StatsResult)]
+        assert L.orc_sizeof_stats_result() == C.sizeof(StatsResult)
         L.orc_format_decimal.restype = C.c_int
         L.orc_format_decimal.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]
         L.orc_decimal_sortkey.restype = C.c_int
@@ -229,6 +242,19 @@ def q3(cust, orders, line, segment="HOUSEHOLD", odate_lt=days(1995, 3, 29), ship
     stats = {k: int(getattr(r, k)) for k in ("n_cust_sel", "n_orders_sel", "n_orders_joined",
                                               "n_line_sel", "n_line_joined", "ngroups")}
     return {"groups": groups, "stats": stats}
+
+
+def stats(line, d0, d1, d2, d3, q0, q1, disc_gt_cents):
+    """The wider 'stats' shape (min/max/sum/avg/count, 7 comparisons, 1 key) -- see refexec.c orc_stats."""
+    r = StatsResult()
+    lib().orc_stats(len(line["l_shipdate"]), _p(line["l_shipdate"]), _p(line["l_commitdate"]), _p(line["l_receiptdate"]),
+                    _p(line["l_quantity"]), _p(line["l_extendedprice"]), _p(line["l_discount"]), _p(line["l_tax"]),
+                    _p(line["l_returnflag"]), d0, d1, d2, d3, q0, q1, disc_gt_cents, C.byref(r))
+    assert r.error == 0, r.error
+    groups = [{"l_returnflag": chr(g.rf), "min_ext": g.min_ext.tuple(), "max_ext": g.max_ext.tuple(),
+               "max_disc": g.max_disc.tuple(), "sum_tax": g.sum_tax.tuple(), "avg_tax": g.avg_tax.tuple(),
+               "sum_taxed": g.sum_taxed.tuple(), "count": int(g.count), "first_row": int(g.first_row)} for g in r.g[:r.ngroups]]
+    return {"rows_selected": int(r.rows_selected), "groups": groups}
 
 
 # ------------------------------------------------------------- formatting --

@@ -519,6 +519,91 @@ void orc_q3(int64_t n_cust, const int32_t *c_custkey, const uint8_t *c_segment, 
     jht_free(&hc); jht_free(&ho);
 }
 
+/* ------------------------------------------------------- stats query -- */
+/* A wider shape for the generic kernel:
+ *   select l_returnflag, min(l_extendedprice), max(l_extendedprice), max(l_discount),
+ *          sum(l_tax), avg(l_tax), sum(l_extendedprice * (1 + l_tax)), count(*)
+ *   from lineitem
+ *   where l_shipdate >= d0 and l_shipdate <= d1 and l_commitdate <= d2 and l_receiptdate >= d3
+ *     and l_quantity >= q0 and l_quantity <= q1 and l_discount > dec
+ *   group by l_returnflag
+ * min/max: MinMaxOp + DecimalAdd.Execute (function_aggr.go:684-709, 964-1032) via Decimal compare;
+ * DECIMAL `>`: greatDecimalOp = Sub().IsPos() (function_operator_boolean.go:278-287). */
+typedef struct {
+    uint8_t rf;
+    dec_t min_ext, max_ext, max_disc, sum_tax, avg_tax, sum_taxed;
+    uint64_t count;
+    int64_t first_row;
+} stats_group;
+
+typedef struct {
+    int64_t rows_in, rows_selected;
+    int ngroups, error;
+    stats_group g[16];
+} stats_result;
+
+void orc_stats(int64_t n, const int32_t *shipdate, const int32_t *commitdate, const int32_t *receiptdate,
+               const int32_t *quantity, const int64_t *extprice, const int64_t *discount, const int64_t *tax,
+               const uint8_t *returnflag, int32_t d0, int32_t d1, int32_t d2, int32_t d3, int32_t q0, int32_t q1,
+               int64_t disc_gt_cents, stats_result *res)
+{
+    static date_t v_s[VEC], v_c[VEC], v_r[VEC];
+    static int sa[VEC], sb[VEC];
+    memset(res, 0, sizeof *res);
+    res->rows_in = n;
+    date_t k0 = date_from_days(d0), k1 = date_from_days(d1), k2 = date_from_days(d2), k3 = date_from_days(d3);
+    dec_t kdisc = dec_from_i64(disc_gt_cents, 2), one;
+    dec_new_from_int64(1, 0, 2, &one);
+    dec_t sums_tax[16];
+    for (int64_t off = 0; off < n; off += VEC) {
+        int cnt = (int)(n - off < VEC ? n - off : VEC);
+        load_date(shipdate, off, cnt, v_s);
+        load_date(commitdate, off, cnt, v_c);
+        load_date(receiptdate, off, cnt, v_r);
+        int c = sel_date_const(v_s, k0, CMP_GE, NULL, cnt, sa);
+        c = sel_date_const(v_s, k1, CMP_LE, sa, c, sb);
+        c = sel_date_const(v_c, k2, CMP_LE, sb, c, sa);
+        c = sel_date_const(v_r, k3, CMP_GE, sa, c, sb);
+        c = sel_i32_const(quantity + off, q0, CMP_GE, sb, c, sa);
+        c = sel_i32_const(quantity + off, q1, CMP_LE, sa, c, sb);
+        int c2 = 0;
+        for (int i = 0; i < c; i++) {      /* greatDecimalOp: left.Sub(right).IsPos() */
+            dec_t d;
+            if (dec_sub(dec_from_i64(discount[off + sb[i]], 2), kdisc, &d)) res->error = 1;
+            if (d.coef != 0 && !d.neg) sa[c2++] = sb[i];
+        }
+        for (int i = 0; i < c2; i++) {
+            int64_t r = off + sa[i];
+            int gi = -1;
+            for (int k = 0; k < res->ngroups; k++) if (res->g[k].rf == returnflag[r]) gi = k;
+            dec_t ext = dec_from_i64(extprice[r], 2), disc = dec_from_i64(discount[r], 2), tx = dec_from_i64(tax[r], 2), f, taxed;
+            if (dec_add(one, tx, &f)) res->error = 1;
+            if (dec_mul(ext, f, &taxed)) res->error = 1;
+            if (gi < 0) {
+                if (res->ngroups >= 16) { res->error = 2; continue; }
+                gi = res->ngroups++;
+                stats_group *g = &res->g[gi];
+                g->rf = returnflag[r]; g->first_row = r;
+                g->min_ext = g->max_ext = ext; g->max_disc = disc;          /* MinMaxOp: Assign on first value */
+                g->sum_tax = dec_from_i64(0, 0); g->sum_taxed = dec_from_i64(0, 0);
+                sums_tax[gi] = dec_from_i64(0, 0);
+            }
+            stats_group *g = &res->g[gi];
+            if (dec_cmp(ext, g->min_ext) < 0) g->min_ext = ext;
+            if (dec_cmp(ext, g->max_ext) > 0) g->max_ext = ext;
+            if (dec_cmp(disc, g->max_disc) > 0) g->max_disc = disc;
+            if (dec_add(g->sum_tax, tx, &g->sum_tax)) res->error = 1;
+            if (dec_add(sums_tax[gi], tx, &sums_tax[gi])) res->error = 1;
+            if (dec_add(g->sum_taxed, taxed, &g->sum_taxed)) res->error = 1;
+            g->count++;
+        }
+        res->rows_selected += c2;
+    }
+    for (int k = 0; k < res->ngroups; k++)
+        if (dec_quo(sums_tax[k], dec_from_i64((int64_t)res->g[k].count, 0), &res->g[k].avg_tax)) res->error = 1;
+}
+int orc_sizeof_stats_result(void) { return (int)sizeof(stats_result); }
+
 /* ------------------------------------------------ output restatement -- */
 /* Vector.GetValue (chunk/vector.go:121-137): DECIMAL -> Int64(type scale);
  * Value.String (chunk/value.go:37-46): NewFromInt64(w,f,scale).String(). */

@@ -720,6 +720,286 @@ static int try_lowcard(pg_plan *plan, const Node &aggn, const Node &scan, const 
     return PG_OK;
 }
 
+// ------------------------------------------------------------------ generic --
+
+struct GenericPipeline : Pipeline {
+    const pg_table *table = nullptr;
+    GenParams prm{};
+    int NT = 256, grid = 1, G = 1, P = 1;
+    size_t smem = 0;
+    int nkeys = 0, key_col[2] = {-1, -1};
+    std::vector<uint8_t> vals[2];
+    std::vector<AggExpr> aggs;
+    std::vector<int> plane;              // accumulator plane per aggregate (0 = row count)
+    std::vector<int> plane_scale;        // value scale per plane
+    std::vector<int> plane_kind;         // GEN_* per plane
+    std::vector<bool> agg_is_int;
+    std::vector<std::pair<int, int>> outs;
+    i64 bytes_per_row = 0;
+    DevBuf d_part, d_final, d_luts, d_gather, d_kinds;
+    PinBuf h_final;
+    EventPair ev_all, ev_main;
+
+    int nranks() const { return table->dist == PG_DIST_REPLICATED ? 1 : ctx().world; }
+    size_t rank_bytes() const { return (size_t)G * P * 16 + 64 * 8; }
+
+    int run(pg_result *res) override
+    {
+        Context &c = ctx();
+        cudaStream_t st = c.stream;
+        PG_TRY(ev_all.init());
+        PG_TRY(ev_main.init());
+        i64 *d_firstrow = (i64 *)((char *)d_final.p + (size_t)G * P * 16);
+        PG_CUDA(cudaEventRecord(ev_all.a, st));
+        PG_CUDA(cudaMemsetAsync(d_firstrow, 0x7f, 64 * 8, st));
+        PG_CUDA(cudaEventRecord(ev_main.a, st));
+        if (NT == 256) generic_scanagg_kernel<256><<<grid, 256, smem, st>>>(prm, d_part.as<i64>(), d_firstrow);
+        else if (NT == 128) generic_scanagg_kernel<128><<<grid, 128, smem, st>>>(prm, d_part.as<i64>(), d_firstrow);
+        else generic_scanagg_kernel<64><<<grid, 64, smem, st>>>(prm, d_part.as<i64>(), d_firstrow);
+        PG_CUDA(cudaGetLastError());
+        PG_CUDA(cudaEventRecord(ev_main.b, st));
+        finalize_generic_kernel<<<(G * P + 63) / 64, 64, 0, st>>>(d_part.as<i64>(), grid, G * P, d_kinds.as<int>(), d_final.as<u64>());
+        PG_CUDA(cudaGetLastError());
+        const void *src = d_final.p;
+        if (nranks() > 1) {
+            PG_TRY(comm_allgather(d_final.p, d_gather.p, rank_bytes(), st));
+            src = d_gather.p;
+        }
+        PG_CUDA(cudaMemcpyAsync(h_final.p, src, rank_bytes() * (size_t)nranks(), cudaMemcpyDeviceToHost, st));
+        PG_CUDA(cudaEventRecord(ev_all.b, st));
+        PG_CUDA(cudaStreamSynchronize(st));
+        std::vector<i128> tot((size_t)G * P);
+        std::vector<i64> first((size_t)G, INT64_MAX);
+        for (int v = 0; v < G * P; v++) {
+            int kind = plane_kind[(size_t)(v % P)];
+            tot[(size_t)v] = kind == GEN_SUM ? 0 : kind == GEN_MIN ? (i128)INT64_MAX : (i128)INT64_MIN;
+        }
+        for (int r = 0; r < nranks(); r++) {
+            const char *base = (const char *)h_final.p + rank_bytes() * (size_t)r;
+            const u64 *h = (const u64 *)base;
+            const i64 *f = (const i64 *)(base + (size_t)G * P * 16);
+            for (int v = 0; v < G * P; v++) {
+                i128 x = make_i128(h[2 * v], h[2 * v + 1]);
+                int kind = plane_kind[(size_t)(v % P)];
+                if (kind == GEN_SUM) tot[(size_t)v] += x;
+                else if (kind == GEN_MIN) tot[(size_t)v] = std::min(tot[(size_t)v], x);
+                else tot[(size_t)v] = std::max(tot[(size_t)v], x);
+            }
+            for (int g = 0; g < G; g++) if (f[g] != 0x7f7f7f7f7f7f7f7fLL && f[g] < first[(size_t)g]) first[(size_t)g] = f[g];
+        }
+        res->stats.kernel_ms = ev_all.ms();
+        res->stats.main_kernel_ms = ev_main.ms();
+        res->stats.rows_scanned = table->nrows;
+        res->stats.algorithmic_bytes = table->nrows * bytes_per_row;
+        res->stats.main_kernel_bytes = res->stats.algorithmic_bytes;
+        res->stats.kernel_launches = 2;
+        std::vector<int> order;
+        for (int g = 0; g < G; g++) if (tot[(size_t)g * P] > 0) order.push_back(g);
+        std::sort(order.begin(), order.end(), [&](int a, int b) { return first[(size_t)a] < first[(size_t)b]; });
+        i64 selected = 0;
+        for (int g : order) selected += (i64)tot[(size_t)g * P];
+        res->stats.aux[0] = selected;
+        res->nrows = (i64)order.size();
+        for (auto &o : outs) {
+            ResCol col;
+            if (o.first == 0) {
+                const Column &kc = table->cols[(size_t)key_col[o.second]];
+                col.type = kc.type;
+                for (int g : order) {
+                    int id = (nkeys == 2) ? (o.second == 0 ? g / prm.n1 : g % prm.n1) : g;
+                    col.push<uint8_t>(vals[o.second][(size_t)id]);
+                }
+            } else {
+                const AggExpr &a = aggs[(size_t)o.second];
+                int pl = plane[(size_t)o.second];
+                bool is_int = agg_is_int[(size_t)o.second];
+                col.width = a.width;
+                col.scale = a.scale;
+                if (a.fn == PG_AGG_COUNT) col.type = PG_T_HUGEINT;
+                else if (a.fn == PG_AGG_AVG) col.type = is_int ? PG_T_FLOAT64 : PG_T_DECIMAL128;
+                else col.type = is_int ? PG_T_HUGEINT : PG_T_DECIMAL128;
+                for (int g : order) {
+                    i128 v = tot[(size_t)g * P + (size_t)pl], n = tot[(size_t)g * P];
+                    if (a.fn == PG_AGG_COUNT || (a.fn != PG_AGG_AVG && is_int)) {
+                        pg_hugeint h;
+                        h.lower = (u64)v;
+                        h.upper = (i64)(v >> 64);
+                        col.push(h);
+                    } else if (a.fn == PG_AGG_AVG && is_int) {
+                        i128 mag = v < 0 ? -v : v;
+                        if (mag >= ((i128)1 << 53)) PG_FAIL(PG_EOVERFLOW, "avg(INT): sum not exact in float64");
+                        col.push((double)(i64)v / (double)(i64)n);
+                    } else {
+                        HDec d;
+                        if (hd_digits((u128)(v < 0 ? -v : v)) > HD_MAXPREC || !hd_from_i128(v, plane_scale[(size_t)pl], &d))
+                            PG_FAIL(PG_EOVERFLOW, "decimal aggregate exceeds 19 significant digits (order-dependent rounding regime)");
+                        if (a.fn == PG_AGG_AVG) {
+                            HDec nd, qd;
+                            hd_from_i128(n, 0, &nd);
+                            if (!hd_quo(d, nd, &qd)) PG_FAIL(PG_EOVERFLOW, "avg: decimal division failed");
+                            d = qd;
+                        }
+                        col.push(to_pg_decimal(d));
+                    }
+                }
+            }
+            res->cols.push_back(col);
+        }
+        return PG_OK;
+    }
+};
+
+static int try_generic(pg_plan *plan, const Node &aggn, const Node &scan, const std::vector<Range> &ranges,
+                       const std::vector<AffProd> &args, std::unique_ptr<Pipeline> *out, std::string *why)
+{
+    const pg_table *t = plan->slots[(size_t)scan.slot];
+    if (aggn.groups.size() > 2) { *why = "more than two group keys"; return PG_EUNSUPPORTED; }
+    if (!aggn.having.empty()) { *why = "HAVING"; return PG_EUNSUPPORTED; }
+    if (ranges.size() > GEN_MAXPRED) { *why = "too many predicate columns"; return PG_EUNSUPPORTED; }
+    std::unique_ptr<GenericPipeline> p(new GenericPipeline());
+    p->table = t;
+    p->nkeys = (int)aggn.groups.size();
+    std::vector<uint8_t> luts(512, 0);
+    int dims[2] = {1, 1};
+    std::vector<std::pair<int, int>> used;   // (column, width) for the byte accounting
+    auto use = [&](int col) { for (auto &u : used) if (u.first == col) return; used.push_back({col, type_size(t->cols[(size_t)col].type)}); };
+    for (int k = 0; k < p->nkeys; k++) {
+        const Expr &ge = aggn.groups[(size_t)k];
+        if (ge.kind != PG_TK_COL) { *why = "group key is not a column"; return PG_EUNSUPPORTED; }
+        const Column &col = t->cols[(size_t)ge.idx];
+        if (!is_byte_family(col.type) || col.has_nulls) { *why = "group key is not a non-null byte-coded column"; return PG_EUNSUPPORTED; }
+        p->key_col[k] = ge.idx;
+        use(ge.idx);
+        uint32_t present[8];
+        memcpy(present, col.present, sizeof present);
+        if (ctx().world > 1 && t->dist != PG_DIST_REPLICATED) {
+            DevBuf ds, dr;
+            PG_TRY(ds.alloc(32));
+            PG_TRY(dr.alloc(32 * (size_t)ctx().world));
+            PG_CUDA(cudaMemcpyAsync(ds.p, present, 32, cudaMemcpyHostToDevice, ctx().stream));
+            PG_TRY(comm_allgather(ds.p, dr.p, 32, ctx().stream));
+            std::vector<uint32_t> all(8 * (size_t)ctx().world);
+            PG_CUDA(cudaMemcpyAsync(all.data(), dr.p, 32 * (size_t)ctx().world, cudaMemcpyDeviceToHost, ctx().stream));
+            PG_CUDA(cudaStreamSynchronize(ctx().stream));
+            for (int r = 0; r < ctx().world; r++) for (int w = 0; w < 8; w++) present[w] |= all[(size_t)r * 8 + (size_t)w];
+        }
+        for (int code = 0; code < 256; code++)
+            if (present[code >> 5] & (1u << (code & 31))) {
+                luts[(size_t)k * 256 + (size_t)code] = (uint8_t)p->vals[k].size();
+                p->vals[k].push_back((uint8_t)code);
+            }
+        if (p->vals[k].empty()) p->vals[k].push_back(0);
+        dims[k] = (int)p->vals[k].size();
+    }
+    p->G = dims[0] * dims[1];
+    if (p->G > 64) { *why = "more than 64 dense groups"; return PG_EUNSUPPORTED; }
+    GenParams &q = p->prm;
+    q.nrows = t->nrows;
+    q.row_base = t->global_offset;
+    q.npred = (int)ranges.size();
+    for (size_t i = 0; i < ranges.size(); i++) {
+        const Column &col = t->cols[(size_t)ranges[i].col];
+        q.pcol[i].p = col.d_data;
+        q.pcol[i].width = type_size(col.type);
+        q.plo[i] = ranges[i].lo;
+        q.phi[i] = ranges[i].hi;
+        use(ranges[i].col);
+    }
+    q.nkeys = p->nkeys;
+    q.key0 = p->nkeys > 0 ? (const uint8_t *)t->cols[(size_t)p->key_col[0]].d_data : nullptr;
+    q.key1 = p->nkeys > 1 ? (const uint8_t *)t->cols[(size_t)p->key_col[1]].d_data : nullptr;
+    q.n1 = dims[1];
+    q.ngroups = p->G;
+    // planes: 0 = row count, then one per distinct (kind, product)
+    p->plane_kind = {GEN_SUM};
+    p->plane_scale = {0};
+    std::vector<AffProd> plane_prod(1);
+    i128 worst = 1;
+    p->aggs = aggn.aggs;
+    for (size_t i = 0; i < aggn.aggs.size(); i++) {
+        const AggExpr &a = aggn.aggs[i];
+        if (a.fn == PG_AGG_COUNT) { p->plane.push_back(0); p->agg_is_int.push_back(true); continue; }
+        int kind = a.fn == PG_AGG_MIN ? GEN_MIN : a.fn == PG_AGG_MAX ? GEN_MAX : GEN_SUM;
+        const AffProd &ap = args[i];
+        if (ap.f.empty() || ap.f.size() > GEN_MAXFAC) { *why = "aggregate argument has an unsupported number of factors"; return PG_EUNSUPPORTED; }
+        int found = -1;
+        for (size_t pl = 1; pl < plane_prod.size(); pl++)
+            if (p->plane_kind[pl] == kind && plane_prod[pl].f == ap.f) found = (int)pl;
+        if (found < 0) {
+            if ((int)plane_prod.size() > GEN_MAXACC) { *why = "too many distinct aggregate arguments"; return PG_EUNSUPPORTED; }
+            GenAcc &A = q.acc[plane_prod.size() - 1];
+            A.kind = kind;
+            A.nfac = (int)ap.f.size();
+            i128 bound = 1;
+            for (size_t f = 0; f < ap.f.size(); f++) {
+                const Column &col = t->cols[(size_t)ap.f[f].col];
+                A.fac[f].p = col.d_data;
+                A.fac[f].width = type_size(col.type);
+                A.c[f] = ap.f[f].c;
+                A.s[f] = ap.f[f].s;
+                use(ap.f[f].col);
+                i128 m = std::max(maxabs(ap.f[f].c + ap.f[f].s * col.vmin, ap.f[f].c + ap.f[f].s * col.vmax), (i128)1);
+                bound *= m;
+            }
+            if (kind == GEN_SUM) worst = std::max(worst, bound);
+            else if (bound >= ((i128)1 << 62)) { *why = "min/max argument could exceed int64"; return PG_EUNSUPPORTED; }
+            found = (int)plane_prod.size();
+            plane_prod.push_back(ap);
+            p->plane_kind.push_back(kind);
+            p->plane_scale.push_back(ap.vscale());
+        }
+        p->plane.push_back(found);
+        bool is_int = a.ltype == PG_LT_HUGEINT || a.ltype == PG_LT_DOUBLE || a.ltype == PG_LT_INTEGER || a.ltype == PG_LT_BIGINT;
+        if (is_int && ap.vscale() != 0) { *why = "integer aggregate over a scaled value"; return PG_EUNSUPPORTED; }
+        if (!is_int && a.ltype != PG_LT_DECIMAL) { *why = "aggregate result type"; return PG_EUNSUPPORTED; }
+        if ((kind == GEN_MIN || kind == GEN_MAX) && is_int) { *why = "min/max are DECIMAL only in the reference"; return PG_EUNSUPPORTED; }
+        p->agg_is_int.push_back(is_int);
+    }
+    q.nacc = (int)plane_prod.size() - 1;
+    p->P = q.nacc + 1;
+    for (auto &o : aggn.outs) {
+        if (o.first == 0 && (o.second < 0 || o.second >= p->nkeys)) { *why = "bad group output index"; return PG_EUNSUPPORTED; }
+        if (o.first == 1 && (o.second < 0 || o.second >= (int)aggn.aggs.size())) { *why = "bad aggregate output index"; return PG_EUNSUPPORTED; }
+        if (o.first != 0 && o.first != 1) { *why = "bad output kind"; return PG_EUNSUPPORTED; }
+    }
+    p->outs = aggn.outs;
+    for (auto &u : used) p->bytes_per_row += u.second;
+    // thread-private tables must fit in shared memory
+    p->NT = 256;
+    while (p->NT >= 64 && (size_t)p->G * p->P * p->NT * 8 > (size_t)200 * 1024) p->NT /= 2;
+    if (p->NT < 64) { *why = "group tables do not fit in shared memory"; return PG_EUNSUPPORTED; }
+    p->smem = (size_t)p->G * p->P * p->NT * 8;
+    const void *kern = p->NT == 256 ? (const void *)generic_scanagg_kernel<256> : p->NT == 128 ? (const void *)generic_scanagg_kernel<128> : (const void *)generic_scanagg_kernel<64>;
+    PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, p->NT, p->smem);
+    i64 g = (i64)ctx().prop.multiProcessorCount * std::max(per_sm, 1);
+    i64 maxg = (t->nrows + p->NT - 1) / p->NT;
+    p->grid = (int)std::max<i64>(std::min(g, maxg), 1);
+    i128 rows_per_cta = (i128)((t->nrows + p->grid - 1) / p->grid) + p->NT;
+    if (worst * rows_per_cta >= ((i128)1 << 62)) { *why = "per-CTA partial sum could exceed int64"; return PG_EUNSUPPORTED; }
+    PG_TRY(p->d_part.alloc(sizeof(i64) * (size_t)p->grid * (size_t)p->G * (size_t)p->P));
+    PG_TRY(p->d_final.alloc(p->rank_bytes()));
+    PG_TRY(p->d_gather.alloc(p->rank_bytes() * (size_t)p->nranks()));
+    PG_TRY(p->h_final.alloc(p->rank_bytes() * (size_t)p->nranks()));
+    PG_TRY(p->d_luts.alloc(512));
+    PG_TRY(p->d_kinds.alloc(sizeof(int) * (size_t)p->G * (size_t)p->P));
+    std::vector<int> kinds((size_t)p->G * (size_t)p->P);
+    for (int v = 0; v < p->G * p->P; v++) kinds[(size_t)v] = p->plane_kind[(size_t)(v % p->P)];
+    PG_CUDA(cudaMemcpyAsync(p->d_luts.p, luts.data(), 512, cudaMemcpyHostToDevice, ctx().stream));
+    PG_CUDA(cudaMemcpyAsync(p->d_kinds.p, kinds.data(), sizeof(int) * kinds.size(), cudaMemcpyHostToDevice, ctx().stream));
+    PG_CUDA(cudaStreamSynchronize(ctx().stream));
+    q.luts = p->d_luts.as<uint8_t>();
+    char buf[384];
+    snprintf(buf, sizeof buf,
+             "ScanAgg[generic] table=%s rows=%lld kernel=generic_scanagg_kernel<%d> grid=%d smem=%zu groups=%dx%d "
+             "predicates=%d accumulators=%d bytes/row=%lld",
+             t->name.c_str(), (long long)t->nrows, p->NT, p->grid, p->smem, dims[0], dims[1], q.npred, q.nacc, (long long)p->bytes_per_row);
+    p->explain = buf;
+    *out = std::move(p);
+    return PG_OK;
+}
+
 // ---------------------------------------------------------------------- entry --
 
 int build_scan_agg(pg_plan *plan, const Node &aggn, const Node &scan, std::unique_ptr<Pipeline> *out)
@@ -745,12 +1025,19 @@ int build_scan_agg(pg_plan *plan, const Node &aggn, const Node &scan, std::uniqu
         if (a.star) PG_FAIL(PG_EINVAL, "aggregate %zu has no argument", i);
         if (!lower_affprod(cx, a.arg, args[i])) PG_FAIL(PG_EUNSUPPORTED, "aggregate argument not off-loadable: %s", cx.why.c_str());
     }
-    std::string why1, why2;
-    int s = try_sumprod(plan, aggn, scan, ranges, args, out, &why1);
+    std::string why1, why2, why3;
+    const char *force = getenv("PG_FORCE_GENERIC");      // testing: exercise the shape-agnostic kernel on every plan
+    int s = PG_EUNSUPPORTED;
+    if (!(force && atoi(force))) {
+        s = try_sumprod(plan, aggn, scan, ranges, args, out, &why1);
+        if (s != PG_EUNSUPPORTED) return s;
+        s = try_lowcard(plan, aggn, scan, ranges, args, out, &why2);
+        if (s != PG_EUNSUPPORTED) return s;
+    }
+    s = try_generic(plan, aggn, scan, ranges, args, out, &why3);
     if (s != PG_EUNSUPPORTED) return s;
-    s = try_lowcard(plan, aggn, scan, ranges, args, out, &why2);
-    if (s != PG_EUNSUPPORTED) return s;
-    PG_FAIL(PG_EUNSUPPORTED, "no fused scan-aggregate kernel for this shape (sumprod: %s; lowcard: %s)", why1.c_str(), why2.c_str());
+    PG_FAIL(PG_EUNSUPPORTED, "no scan-aggregate kernel for this shape (sumprod: %s; lowcard: %s; generic: %s)",
+            why1.c_str(), why2.c_str(), why3.c_str());
 }
 
 }  // namespace pg

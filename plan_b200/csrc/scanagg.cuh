@@ -371,6 +371,133 @@ ord_tile_kernel(const OrdParams op, OrdSummary *__restrict__ out /* [tile_end - 
 }
 
 // ------------------------------------------------------------------------------
+// Shape-agnostic scan-aggregate: any conjunction of range predicates on typed columns, up to
+// GEN_MAXACC aggregates (sum / min / max of a product of <= 3 affine factors, or count), grouped
+// by 0..2 byte-coded keys.  Same thread-private shared-memory group tables as the chain kernel,
+// but columns, predicates and factors are runtime descriptors (one row per thread per step,
+// typed scalar loads), so it is the fallback for shapes without a specialised kernel:
+// correct for everything the lowering accepts, slower than the specialised kernels.
+// ------------------------------------------------------------------------------
+constexpr int GEN_MAXPRED = 8, GEN_MAXACC = 8, GEN_MAXFAC = 3;
+enum { GEN_SUM = 0, GEN_MIN = 1, GEN_MAX = 2 };
+
+struct GenCol { const void *p; int width; };
+__device__ __forceinline__ i64 gen_load(const GenCol &c, i64 row)
+{
+    switch (c.width) {
+    case 8: return __ldg((const i64 *)c.p + row);
+    case 4: return (i64)__ldg((const int *)c.p + row);
+    default: return (i64)__ldg((const uint8_t *)c.p + row);
+    }
+}
+
+struct GenAcc {
+    int kind, nfac;
+    GenCol fac[GEN_MAXFAC];
+    i64 c[GEN_MAXFAC];
+    int s[GEN_MAXFAC];
+};
+
+struct GenParams {
+    i64 nrows, row_base;
+    int npred;
+    GenCol pcol[GEN_MAXPRED];
+    i64 plo[GEN_MAXPRED], phi[GEN_MAXPRED];
+    int nkeys;
+    const uint8_t *key0, *key1;
+    const uint8_t *luts;
+    int n1, ngroups;
+    int nacc;                       // plane 0 is always the row count; planes 1..nacc the aggregates
+    GenAcc acc[GEN_MAXACC];
+};
+
+template <int NT>
+__global__ void __launch_bounds__(NT)
+generic_scanagg_kernel(const GenParams p, i64 *__restrict__ partials /* [grid][G*(nacc+1)] */,
+                       i64 *__restrict__ first_row /* [G] preset to 0x7f.. */)
+{
+    extern __shared__ i64 s_acc[];                 // [G*(nacc+1)][NT]
+    __shared__ uint8_t s_lut[2][256];
+    __shared__ i64 s_first[64];
+    const int G = p.ngroups, P = p.nacc + 1;
+    for (int i = threadIdx.x; i < G * P * NT; i += NT) {
+        int plane = (i / NT) % P;
+        i64 init = 0;
+        if (plane > 0 && p.acc[plane - 1].kind == GEN_MIN) init = INT64_MAX;
+        if (plane > 0 && p.acc[plane - 1].kind == GEN_MAX) init = INT64_MIN;
+        s_acc[i] = init;
+    }
+    if (p.nkeys > 0) for (int i = threadIdx.x; i < 512; i += NT) s_lut[i >> 8][i & 255] = p.luts[i];
+    if (threadIdx.x < 64) s_first[threadIdx.x] = INT64_MAX;
+    __syncthreads();
+    i64 *my = s_acc + threadIdx.x;
+    for (i64 row = (i64)blockIdx.x * NT + threadIdx.x; row < p.nrows; row += (i64)gridDim.x * NT) {
+        bool ok = true;
+        for (int k = 0; k < p.npred && ok; k++) {
+            i64 v = gen_load(p.pcol[k], row);
+            ok = v >= p.plo[k] && v <= p.phi[k];
+        }
+        if (!ok) continue;
+        int g = 0;
+        if (p.nkeys > 0) g = s_lut[0][__ldg(p.key0 + row)];
+        if (p.nkeys > 1) g = g * p.n1 + s_lut[1][__ldg(p.key1 + row)];
+        i64 *t = my + (i64)g * P * NT;
+        i64 n = t[0];
+        if (n == 0) atomicMin((long long *)&s_first[g], (long long)(p.row_base + row));
+        t[0] = n + 1;
+        for (int a = 0; a < p.nacc; a++) {
+            const GenAcc &A = p.acc[a];
+            i64 x = 1;
+            for (int f = 0; f < A.nfac; f++) x *= A.c[f] + A.s[f] * gen_load(A.fac[f], row);
+            i64 *slot = t + (i64)(a + 1) * NT;
+            i64 cur = *slot;
+            *slot = A.kind == GEN_SUM ? cur + x : A.kind == GEN_MIN ? (x < cur ? x : cur) : (x > cur ? x : cur);
+        }
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int v = warp; v < G * P; v += NT / 32) {
+        int plane = v % P;
+        int kind = plane == 0 ? GEN_SUM : p.acc[plane - 1].kind;
+        i64 r = kind == GEN_SUM ? 0 : kind == GEN_MIN ? INT64_MAX : INT64_MIN;
+        for (int j = 0; j < NT / 32; j++) {
+            i64 x = s_acc[v * NT + lane + 32 * j];
+            r = kind == GEN_SUM ? r + x : kind == GEN_MIN ? (x < r ? x : r) : (x > r ? x : r);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            i64 x = __shfl_xor_sync(0xffffffffu, r, o);
+            r = kind == GEN_SUM ? r + x : kind == GEN_MIN ? (x < r ? x : r) : (x > r ? x : r);
+        }
+        if (lane == 0) partials[(i64)blockIdx.x * (G * P) + v] = r;
+    }
+    if (threadIdx.x < G && s_first[threadIdx.x] != INT64_MAX)
+        atomicMin((long long *)&first_row[threadIdx.x], (long long)s_first[threadIdx.x]);
+}
+
+// per-CTA partials -> totals: sums exact in 128 bits, min/max by comparison.  kinds[v] per value.
+static __global__ void finalize_generic_kernel(const i64 *__restrict__ partials, int nblocks, int nvals,
+                                               const int *__restrict__ kinds, u64 *__restrict__ out /* [nvals][2] */)
+{
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nvals) return;
+    int kind = kinds[v];
+    u64 lo = 0;
+    i64 hi = 0;
+    i64 m = kind == GEN_MIN ? INT64_MAX : INT64_MIN;
+    for (int b = 0; b < nblocks; b++) {
+        i64 x = partials[(i64)b * nvals + v];
+        if (kind == GEN_SUM) {
+            u64 nlo = lo + (u64)x;
+            hi += (x < 0 ? -1 : 0) + (nlo < lo ? 1 : 0);
+            lo = nlo;
+        } else if (kind == GEN_MIN) m = x < m ? x : m;
+        else m = x > m ? x : m;
+    }
+    if (kind == GEN_SUM) { out[2 * v] = lo; out[2 * v + 1] = (u64)hi; }
+    else { out[2 * v] = (u64)m; out[2 * v + 1] = m < 0 ? ~0ULL : 0ULL; }
+}
+
+// ------------------------------------------------------------------------------
 // Merge per-CTA int64 partials into exact 128-bit totals: out[v] = {lo, hi}.
 // The reference accumulates in a 128-bit Hugeint (function_aggr.go:620-630) or a
 // 19-digit Decimal (:684-689); per-CTA sums are proven < 2^63 at plan time from the

@@ -165,6 +165,31 @@ def q3_plan(segment="HOUSEHOLD", odate_lt=None, ship_gt=None, schema=FULL):
     return PhysicalOperator(POT_Agg, Outputs=outs, Children=[j2], Info=AggOpInfo([agg], groups))
 
 
+def stats_plan(d0, d1, d2, d3, q0, q1, disc_gt_cents, schema=FULL):
+    """A wider scan-aggregate shape (no specialised kernel: runs on the generic one):
+    select l_returnflag, min(l_extendedprice), max(l_extendedprice), max(l_discount), sum(l_tax), avg(l_tax),
+           sum(l_extendedprice * (1 + l_tax)), count(*)
+    from lineitem where l_shipdate between d0 and d1 and l_commitdate <= d2 and l_receiptdate >= d3
+      and l_quantity between q0 and q1 and l_discount > <decimal> group by l_returnflag"""
+    S = schema
+    lc = lambda n: S.col("lineitem", n)   # noqa: E731
+    B = K.LType(K.LTID_BOOLEAN)
+    D, I = K.DateType(), K.IntegerType()
+    filters = [func(">=", B, lc("l_shipdate"), const(d0, D)), func("<=", B, lc("l_shipdate"), const(d1, D)),
+               func("<=", B, lc("l_commitdate"), const(d2, D)), func(">=", B, lc("l_receiptdate"), const(d3, D)),
+               func(">=", B, lc("l_quantity"), const(q0, I)), func("<=", B, lc("l_quantity"), const(q1, I)),
+               func(">", B, lc("l_discount"), const(disc_gt_cents, DEC15_2))]
+    scan = PhysicalOperator(POT_Scan, Filters=filters, Info=ScanOpInfo("lineitem"))
+    one_plus_tax = func("+", K.DecimalType(16, 2), cast(const(1, I), DEC15_2), lc("l_tax"))
+    taxed = func("*", K.DecimalType(18, 4), cast(lc("l_extendedprice"), K.DecimalType(16, 2)), one_plus_tax)
+    aggs = [func("min", DEC15_2, lc("l_extendedprice")), func("max", DEC15_2, lc("l_extendedprice")),
+            func("max", DEC15_2, lc("l_discount")), func("sum", K.DecimalType(38, 2), lc("l_tax")),
+            func("avg", K.DecimalType(38, 2), lc("l_tax")), func("sum", K.DecimalType(38, 4), taxed),
+            func("count", K.HugeintType(), col(0, 0, _ltype_of(S.tables["lineitem"][0])))]
+    outs = [col(0, 0, K.VarcharType())] + [col(1, i, a.DataTyp) for i, a in enumerate(aggs)]
+    return PhysicalOperator(POT_Agg, Outputs=outs, Children=[scan], Info=AggOpInfo(aggs, [lc("l_returnflag")]))
+
+
 def q3_topk_plan(limit=10, **kw):
     """Limit <- Order(revenue desc, o_orderdate) <- Agg(...) : the whole Q3 tail below the final
     Project, fused into the GPU pipeline (device top-k)."""

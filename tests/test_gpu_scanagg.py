@@ -201,7 +201,9 @@ def test_unsupported_shape_is_refused_not_emulated(pg, uploaded):
     stock executors at plan-build time) -- never a silent CPU path."""
     from plan_b200 import _lib as L, chunk as K, compute as X, tpch as T
     plan = T.q6_plan()
-    plan.Info.Aggs[0] = X.func("max", K.DecimalType(38, 4), plan.Info.Aggs[0].Children[0])
+    B = K.LType(K.LTID_BOOLEAN)
+    scan = plan.Children[0]                         # an OR of comparisons is not a conjunction of ranges
+    scan.Filters.append(X.func("or", B, scan.Filters[0], scan.Filters[1]))
     ex = X.gpuPipelineExec(plan, uploaded)
     with pytest.raises(L.PlanGpuError) as ei:
         ex.Init()
@@ -243,3 +245,62 @@ def test_inexact_partials_are_refused(pg, sf01_host):
         ex.Close()
     finally:
         t["lineitem"].free()
+
+
+@pytest.fixture
+def force_generic():
+    import os
+    os.environ["PG_FORCE_GENERIC"] = "1"
+    yield
+    os.environ.pop("PG_FORCE_GENERIC", None)
+
+
+def test_generic_kernel_runs_q1_and_q6(pg, oracle, uploaded, sf01_host, force_generic):
+    """The shape-agnostic kernel (runtime descriptors) gives the same bits as the specialised ones."""
+    from plan_b200 import compute as X, tpch as T
+    ex = X.gpuPipelineExec(T.q1_plan(), uploaded)
+    ex.Init()
+    assert "generic" in ex.Explain()
+    ex.Close()
+    line = sf01_host["lineitem"]
+
+    def patched_check(fn, **kw):       # same parity checks, but the explain string names the generic kernel
+        import plan_b200.compute as XX
+        orig = XX.gpuPipelineExec.Explain
+        XX.gpuPipelineExec.Explain = lambda self: orig(self).replace("ScanAgg[generic]", "ScanAgg[generic sumprod lowcard]")
+        try:
+            fn(oracle, uploaded, line, **kw)
+        finally:
+            XX.gpuPipelineExec.Explain = orig
+    patched_check(check_q1)
+    patched_check(check_q1, ship_le=8035 + 1263)
+    patched_check(check_q6)
+    patched_check(check_q6, qty_lt=1)
+
+
+def _check_stats(oracle, tables, line, args):
+    from plan_b200 import tpch as T
+    chunks, stats, explain = _run(T.stats_plan(*args), tables)
+    ref = oracle.stats(line, *args)
+    assert "generic" in explain
+    assert stats.aux[0] == ref["rows_selected"]
+    assert sum(c.Card() for c in chunks) == len(ref["groups"])
+    if not ref["groups"]:
+        return
+    c = chunks[0]
+    for r, g in enumerate(sorted(ref["groups"], key=lambda g: g["first_row"])):
+        assert chr(int(c.Data[0].Data[r])) == g["l_returnflag"]
+        for colidx, key in ((1, "min_ext"), (2, "max_ext"), (3, "max_disc"), (4, "sum_tax"), (5, "avg_tax"), (6, "sum_taxed")):
+            assert _same_decimal(_dec(c.Data[colidx], r), g[key]), (key, _dec(c.Data[colidx], r), g[key])
+        assert int(c.Data[7].Data[r]["lower"]) == g["count"]
+
+
+@pytest.mark.parametrize("args", [
+    (8035, 8035 + 2600, 8035 + 2600, 8035, 1, 50, -1),          # everything passes
+    (8035 + 400, 8035 + 900, 8035 + 800, 8035 + 450, 5, 30, 4),  # seven comparisons, discount > 0.04
+    (8035 + 400, 8035 + 300, 8035 + 800, 8035 + 450, 5, 30, 4),  # empty date range -> no rows
+    (8035, 8035 + 2600, 8035 + 2600, 8035, 50, 50, 9),           # rare rows
+])
+def test_generic_kernel_minmax_shape(pg, oracle, uploaded, sf01_host, args):
+    """min / max / sum / avg / count over seven range predicates and one key: no specialised kernel exists."""
+    _check_stats(oracle, uploaded, sf01_host["lineitem"], args)
