@@ -257,6 +257,25 @@ def stats(line, d0, d1, d2, d3, q0, q1, disc_gt_cents):
     return {"rows_selected": int(r.rows_selected), "groups": groups}
 
 
+def groupby_sum(line, key="l_orderkey", value="l_quantity", having_gt=None, ship_le=None):
+    """numpy restatement of a high-cardinality hash aggregate (exact int64 arithmetic):
+    GroupedAggrHashTable.FindOrCreateGroups (aggregate_hash.go:201-391) + sum(INT32)->HUGEINT /
+    sum(DECIMAL) / count (function_aggr.go:620-650, 950-962) + HAVING via greatHugeintOp
+    (function_operator_boolean.go:255-263).  Returns {key: (sum, count)}."""
+    k, v = line[key], line[value].astype(np.int64)
+    if ship_le is not None:
+        m = line["l_shipdate"] <= ship_le
+        k, v = k[m], v[m]
+    uk, inv = np.unique(k, return_inverse=True)
+    sums = np.zeros(len(uk), dtype=np.int64)
+    np.add.at(sums, inv, v)
+    cnts = np.bincount(inv, minlength=len(uk))
+    out = {int(a): (int(b), int(c)) for a, b, c in zip(uk, sums, cnts)}
+    if having_gt is not None:
+        out = {a: bc for a, bc in out.items() if bc[0] > having_gt}
+    return out
+
+
 # ------------------------------------------------------------- formatting --
 
 def fmt_decimal(dec, type_scale):

@@ -83,6 +83,29 @@ int comm_allgather(const void *d_send, void *d_recv, size_t bytes, cudaStream_t 
     return PG_OK;
 }
 
+// variable all-to-all of fixed-size rows: counts/offsets in rows, grouped ncclSend/ncclRecv (one pair
+// per peer; NVSwitch gives every pair full bandwidth, so no ordering tricks are needed)
+int comm_alltoallv(const void *d_send, const i64 *send_cnt, const i64 *send_off, void *d_recv, const i64 *recv_cnt,
+                   const i64 *recv_off, size_t row_bytes, cudaStream_t stream)
+{
+    Context &c = ctx();
+    if (c.world <= 1) {
+        PG_CUDA(cudaMemcpyAsync(d_recv, d_send, (size_t)send_cnt[0] * row_bytes, cudaMemcpyDeviceToDevice, stream));
+        return PG_OK;
+    }
+    PG_NCCL(nccl().GroupStart());
+    for (int r = 0; r < c.world; r++) {
+        if (send_cnt[r] > 0)
+            PG_NCCL(nccl().Send((const char *)d_send + (size_t)send_off[r] * row_bytes, (size_t)send_cnt[r] * row_bytes, ncclInt8, r,
+                                (ncclComm_t)c.nccl_comm, stream));
+        if (recv_cnt[r] > 0)
+            PG_NCCL(nccl().Recv((char *)d_recv + (size_t)recv_off[r] * row_bytes, (size_t)recv_cnt[r] * row_bytes, ncclInt8, r,
+                                (ncclComm_t)c.nccl_comm, stream));
+    }
+    PG_NCCL(nccl().GroupEnd());
+    return PG_OK;
+}
+
 }  // namespace pg
 
 using namespace pg;

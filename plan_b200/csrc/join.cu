@@ -71,6 +71,11 @@ struct JoinAggPipeline : Pipeline {
     int part_type[GT_MAXKEYPARTS] = {0, 0, 0};
     std::vector<AggExpr> aggs;
     std::vector<int> agg_scale;
+    std::vector<int> agg_plane;                  // accumulator plane of each aggregate (count(*) = the row-count plane)
+    bool no_join = false;                        // Agg <- Scan on high-cardinality keys: no probe at all
+    int hav_plane = -1;                          // HAVING <aggregate> in [hav_lo, hav_hi]
+    i64 hav_lo = INT64_MIN, hav_hi = INT64_MAX;
+    i64 group_hint = 0;                          // expected number of groups (no-join case)
     std::vector<std::pair<int, int>> outs;
     std::vector<int> group_out_type;             // pg_type of each group key
     i64 algorithmic_bytes = 0, main_bytes = 0;
@@ -79,6 +84,7 @@ struct JoinAggPipeline : Pipeline {
     u64 gt_cap = 0;
     i64 out_cap = 0;
     EventPair ev_all, ev_main;
+    bool shuffle = false;          // local groups of different ranks may collide: hash-partition + all-to-all + merge
     bool gather_ranks = false;     // probe side is sharded: every rank ends with the union of all groups
     DevBuf d_g_klo, d_g_khi, d_g_acc, d_g_cnt;
     PinBuf h_out;                  // pinned landing zone of the group lists: [klo | khi | acc planes]
@@ -275,6 +281,81 @@ struct JoinAggPipeline : Pipeline {
         return PG_OK;
     }
 
+    // ---- all-to-all hash-partitioned exchange of the local group lists ----
+    // rows are packed AoS: [klo, khi, plane 0 .. plane nacc] (W = 3 + nacc words); destination rank =
+    // mix64(klo ^ rot(khi)) % world.  Counts travel with an all-gather, rows with grouped
+    // ncclSend/ncclRecv over NVLink, then every rank merges what it owns into its (reset) table.
+    DevBuf d_sx_send, d_sx_recv, d_sx_cnt, d_sx_cursor, d_sx_allcnt;
+    size_t sx_send_rows = 0, sx_recv_rows = 0;
+
+    int shuffle_groups(i64 *ngroups, PipeParams &pp, pg_result *res)
+    {
+        Context &c = ctx();
+        cudaStream_t st = c.stream;
+        const int W = c.world, planes = gs.nacc + 1, RW = 2 + planes;
+        i64 n = *ngroups;
+        if (!d_sx_cnt.p) {
+            PG_TRY(d_sx_cnt.alloc(8 * (size_t)W));
+            PG_TRY(d_sx_cursor.alloc(8 * (size_t)W));
+            PG_TRY(d_sx_allcnt.alloc(8 * (size_t)W * (size_t)W));
+        }
+        if ((size_t)n > sx_send_rows) { PG_TRY(d_sx_send.alloc((size_t)std::max<i64>(n, 1) * RW * 8)); sx_send_rows = (size_t)n; }
+        int grid = (int)std::max<i64>(std::min<i64>((n + 255) / 256, (i64)c.prop.multiProcessorCount * 4), 1);
+        // 1. count rows per destination
+        PG_CUDA(cudaMemsetAsync(d_sx_cnt.p, 0, 8 * (size_t)W, st));
+        shuffle_count_kernel<<<grid, 256, 0, st>>>(d_out_klo.as<i64>(), d_out_khi.as<i64>(), n, W, d_sx_cnt.as<unsigned long long>());
+        PG_CUDA(cudaGetLastError());
+        // 2. everybody learns the whole count matrix
+        PG_TRY(comm_allgather(d_sx_cnt.p, d_sx_allcnt.p, 8 * (size_t)W, st));
+        std::vector<i64> all((size_t)W * (size_t)W);
+        PG_CUDA(cudaMemcpyAsync(all.data(), d_sx_allcnt.p, 8 * (size_t)W * (size_t)W, cudaMemcpyDeviceToHost, st));
+        PG_CUDA(cudaStreamSynchronize(st));
+        std::vector<i64> send_cnt((size_t)W), send_off((size_t)W), recv_cnt((size_t)W), recv_off((size_t)W);
+        i64 so = 0, ro = 0;
+        for (int r = 0; r < W; r++) {
+            send_cnt[(size_t)r] = all[(size_t)c.rank * W + r]; send_off[(size_t)r] = so; so += send_cnt[(size_t)r];
+            recv_cnt[(size_t)r] = all[(size_t)r * W + c.rank]; recv_off[(size_t)r] = ro; ro += recv_cnt[(size_t)r];
+        }
+        if ((size_t)ro > sx_recv_rows) { PG_TRY(d_sx_recv.alloc((size_t)std::max<i64>(ro, 1) * RW * 8)); sx_recv_rows = (size_t)ro; }
+        // 3. scatter rows into destination order
+        PG_CUDA(cudaMemcpyAsync(d_sx_cursor.p, send_off.data(), 8 * (size_t)W, cudaMemcpyHostToDevice, st));
+        shuffle_scatter_kernel<<<grid, 256, 0, st>>>(d_out_klo.as<i64>(), d_out_khi.as<i64>(), d_out_acc.as<i64>(), out_cap, n, planes, W,
+                                                     d_sx_cursor.as<unsigned long long>(), d_sx_send.as<i64>());
+        PG_CUDA(cudaGetLastError());
+        // 4. the exchange
+        PG_TRY(comm_alltoallv(d_sx_send.p, send_cnt.data(), send_off.data(), d_sx_recv.p, recv_cnt.data(), recv_off.data(), (size_t)RW * 8, st));
+        // 5. merge what this rank owns
+        PG_CUDA(cudaMemsetAsync(d_klo.p, 0x80, gt_cap * 8, st));
+        PG_CUDA(cudaMemsetAsync(d_khi.p, 0x80, gt_cap * 8, st));
+        PG_CUDA(cudaMemsetAsync(d_acc.p, 0, gt_cap * 8 * (size_t)planes, st));
+        PG_CUDA(cudaMemsetAsync(d_overflow.p, 0, 4, st));
+        int g2 = (int)std::max<i64>(std::min<i64>((ro + 255) / 256, (i64)c.prop.multiProcessorCount * 4), 1);
+        shuffle_merge_kernel<<<g2, 256, 0, st>>>(pp.gt, d_sx_recv.as<i64>(), ro, planes);
+        PG_CUDA(cudaGetLastError());
+        int ovf = 0;
+        PG_CUDA(cudaMemcpyAsync(&ovf, d_overflow.p, 4, cudaMemcpyDeviceToHost, st));
+        PG_CUDA(cudaStreamSynchronize(st));
+        if (ovf) PG_FAIL(PG_ENOMEM, "group table overflow while merging shuffled groups");
+        // 6. compact again (HAVING applies to the merged totals)
+        if (ro > out_cap) {
+            PG_TRY(d_out_klo.alloc((size_t)ro * 8));
+            PG_TRY(d_out_khi.alloc((size_t)ro * 8));
+            PG_TRY(d_out_acc.alloc((size_t)ro * 8 * (size_t)planes));
+            out_cap = ro;
+        }
+        PG_CUDA(cudaMemsetAsync(d_counters.p, 0, 32, st));
+        gt_compact_kernel<<<(int)std::min<u64>((gt_cap + 255) / 256, (u64)c.prop.multiProcessorCount * 8), 256, 0, st>>>(
+            pp.gt, d_out_klo.as<i64>(), d_out_khi.as<i64>(), d_out_acc.as<i64>(), out_cap, d_counters.as<unsigned long long>(),
+            hav_plane, hav_lo, hav_hi);
+        PG_CUDA(cudaGetLastError());
+        unsigned long long ng2[4];
+        PG_TRY(read_counters(ng2));
+        *ngroups = (i64)ng2[0];
+        res->stats.kernel_launches += 4;
+        res->stats.aux[7] = so;        // rows this rank sent
+        return PG_OK;
+    }
+
     int run(pg_result *res) override
     {
         Context &c = ctx();
@@ -287,20 +368,22 @@ struct JoinAggPipeline : Pipeline {
         for (size_t i = 0; i < stages.size(); i++) { PG_TRY(run_build_stage(*stages[i], res, (int)i)); tr.mark("build stage"); }
 
         const pg_table *t = tab(src_slot);
-        Stage &last = *stages.back();
         PipeParams pp{};
         pp.nrows = t->nrows;
         PG_TRY(fill_preds(pp, ranges, src_slot));
-        pp.has_probe = 1;
-        pp.probe_key = typed(t, probe_key_col);
-        pp.probe = last.jt;
-        pp.probe_bitmap_only = last.bitmap_only() ? 1 : 0;
+        pp.has_probe = no_join ? 0 : 1;
+        if (!no_join) {
+            Stage &last = *stages.back();
+            pp.probe_key = typed(t, probe_key_col);
+            pp.probe = last.jt;
+            pp.probe_bitmap_only = last.bitmap_only() ? 1 : 0;
+        }
         pp.counters = d_counters.as<unsigned long long>();
         pp.gs = gs;
         // group table: start at twice the build-side rows (each joined row matches a build row),
         // grow x2 and rerun if a probe sequence overflows (the reference resizes x2 as well,
         // aggregate_hash.go:538-540)
-        u64 cap = next_pow2((u64)std::max<i64>(last.built_rows * 2, 1024));
+        u64 cap = next_pow2((u64)std::max<i64>((no_join ? group_hint : stages.back()->built_rows) * 2, 1024));
         unsigned long long cnt[4] = {0, 0, 0, 0};
         for (int attempt = 0;; attempt++) {
             PG_TRY(ensure_group_table(cap));
@@ -329,6 +412,7 @@ struct JoinAggPipeline : Pipeline {
             cap *= 2;
         }
         // compact
+        const bool do_shuffle = shuffle && c.world > 1;
         i64 max_out = (i64)std::min<u64>(cap, (u64)cnt[1]);
         if (max_out < 1) max_out = 1;
         if (max_out > out_cap) {
@@ -339,12 +423,14 @@ struct JoinAggPipeline : Pipeline {
         }
         PG_CUDA(cudaMemsetAsync(d_counters.p, 0, 32, st));
         gt_compact_kernel<<<(int)std::min<u64>((cap + 255) / 256, (u64)c.prop.multiProcessorCount * 8), 256, 0, st>>>(
-            pp.gt, d_out_klo.as<i64>(), d_out_khi.as<i64>(), d_out_acc.as<i64>(), out_cap, d_counters.as<unsigned long long>());
+            pp.gt, d_out_klo.as<i64>(), d_out_khi.as<i64>(), d_out_acc.as<i64>(), out_cap, d_counters.as<unsigned long long>(),
+            do_shuffle ? -1 : hav_plane, hav_lo, hav_hi);
         PG_CUDA(cudaGetLastError());
         res->stats.kernel_launches += 1;
         unsigned long long ng2[4];
         PG_TRY(read_counters(ng2));
         i64 ngroups = (i64)ng2[0];
+        if (do_shuffle) { PG_TRY(shuffle_groups(&ngroups, pp, res)); tr.mark("all-to-all shuffle + merge"); }
         res->stats.aux[6] = ngroups;          // groups before any LIMIT
         tr.mark("compact");
         if (has_topk) { PG_TRY(topk_preselect(&ngroups, res)); tr.mark("top-k preselect"); }
@@ -460,18 +546,25 @@ struct JoinAggPipeline : Pipeline {
                 }
             } else {
                 const AggExpr &a = aggs[(size_t)o.second];
-                col.type = PG_T_DECIMAL128;
                 col.width = a.width;
                 col.scale = a.scale;
-                col.data.resize((size_t)ngroups * sizeof(pg_decimal));
-                pg_decimal *d = (pg_decimal *)col.data.data();
-                const i64 *src = h_acc + (size_t)o.second * (size_t)ngroups;
-                const int32_t sc = agg_scale[(size_t)o.second];
-                for (i64 i = 0; i < ngroups; i++) {
-                    i64 v = src[i];
-                    d[i].neg = v < 0;
-                    d[i].coef = v < 0 ? (u64)(-(v + 1)) + 1 : (u64)v;
-                    d[i].scale = sc;
+                const i64 *src = h_acc + (size_t)agg_plane[(size_t)o.second] * (size_t)ngroups;
+                if (a.ltype == PG_LT_HUGEINT) {          // sum(INT) / count -> 128-bit integer
+                    col.type = PG_T_HUGEINT;
+                    col.data.resize((size_t)ngroups * sizeof(pg_hugeint));
+                    pg_hugeint *d = (pg_hugeint *)col.data.data();
+                    for (i64 i = 0; i < ngroups; i++) { d[i].lower = (u64)src[i]; d[i].upper = src[i] < 0 ? -1 : 0; }
+                } else {
+                    col.type = PG_T_DECIMAL128;
+                    col.data.resize((size_t)ngroups * sizeof(pg_decimal));
+                    pg_decimal *d = (pg_decimal *)col.data.data();
+                    const int32_t sc = agg_scale[(size_t)o.second];
+                    for (i64 i = 0; i < ngroups; i++) {
+                        i64 v = src[i];
+                        d[i].neg = v < 0;
+                        d[i].coef = v < 0 ? (u64)(-(v + 1)) + 1 : (u64)v;
+                        d[i].scale = sc;
+                    }
                 }
             }
             res->cols.push_back(std::move(col));
@@ -566,15 +659,20 @@ static int add_build_stage(JoinAggPipeline *p, const Node &n0, int key_idx, int 
     return PG_OK;
 }
 
+// `join` is the aggregate's input: an INNER join tree, or (high-cardinality group-by straight over a
+// table) a SCAN whose filters the caller already merged.
 int build_join_agg(pg_plan *plan, const Node &aggn, const Node &join, std::unique_ptr<Pipeline> *out)
 {
     std::unique_ptr<JoinAggPipeline> p(new JoinAggPipeline());
     p->plan = plan;
-    if (join.jointype != PG_JOIN_INNER) PG_FAIL(PG_EUNSUPPORTED, "only INNER joins are off-loaded");
-    if (join.conds.size() != 1) PG_FAIL(PG_EUNSUPPORTED, "multi-column join keys are not off-loaded");
-    if (!aggn.having.empty()) PG_FAIL(PG_EUNSUPPORTED, "HAVING over a join aggregate is not off-loaded");
+    p->no_join = join.op == PG_OP_SCAN;
+    if (!p->no_join) {
+        if (join.jointype != PG_JOIN_INNER) PG_FAIL(PG_EUNSUPPORTED, "only INNER joins are off-loaded");
+        if (join.conds.size() != 1) PG_FAIL(PG_EUNSUPPORTED, "multi-column join keys are not off-loaded");
+    }
+    if (aggn.having.size() > 1) PG_FAIL(PG_EUNSUPPORTED, "HAVING with more than one conjunct is not off-loaded");
     // probe side: filtered scan
-    const Node *src = &join.children[0];
+    const Node *src = p->no_join ? &join : &join.children[0];
     std::vector<Expr> pf;
     while (src->op == PG_OP_FILTER) { for (auto &f : src->filters) pf.push_back(f); src = &src->children[0]; }
     if (src->op != PG_OP_SCAN) PG_FAIL(PG_EUNSUPPORTED, "probe side of the top join must be a scan");
@@ -587,17 +685,21 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &join, std::uniqu
         for (auto &f : pf) fl.push_back(f);
         if (!lower_filters(cx, fl, p->ranges)) PG_FAIL(PG_EUNSUPPORTED, "probe-side filter not off-loadable: %s", cx.why.c_str());
     }
-    const Expr *pe = strip_value_preserving_casts(&join.conds[0].first);
-    const Expr *be = strip_value_preserving_casts(&join.conds[0].second);
-    if (pe->kind != PG_TK_COL || be->kind != PG_TK_COL) PG_FAIL(PG_EUNSUPPORTED, "join condition is not column = column");
-    BaseCol pk;
-    if (!resolve(join.children[0], pe->idx, &pk) || pk.slot != src->slot) PG_FAIL(PG_EUNSUPPORTED, "probe key is not a column of the probe scan");
-    if (!is_int_family(st->cols[(size_t)pk.col].type) || st->cols[(size_t)pk.col].has_nulls) PG_FAIL(PG_EUNSUPPORTED, "probe key must be a non-null integer column");
-    p->probe_key_col = pk.col;
     int top_stage = -1;
-    PG_TRY(add_build_stage(p.get(), join.children[1], be->idx, &top_stage));
-    const Stage &bs = *p->stages[(size_t)top_stage];
-    const pg_table *bt = p->tab(bs.src_slot);
+    const pg_table *bt = nullptr;
+    int build_slot = -1;
+    if (!p->no_join) {
+        const Expr *pe = strip_value_preserving_casts(&join.conds[0].first);
+        const Expr *be = strip_value_preserving_casts(&join.conds[0].second);
+        if (pe->kind != PG_TK_COL || be->kind != PG_TK_COL) PG_FAIL(PG_EUNSUPPORTED, "join condition is not column = column");
+        BaseCol pk;
+        if (!resolve(join.children[0], pe->idx, &pk) || pk.slot != src->slot) PG_FAIL(PG_EUNSUPPORTED, "probe key is not a column of the probe scan");
+        if (!is_int_family(st->cols[(size_t)pk.col].type) || st->cols[(size_t)pk.col].has_nulls) PG_FAIL(PG_EUNSUPPORTED, "probe key must be a non-null integer column");
+        p->probe_key_col = pk.col;
+        PG_TRY(add_build_stage(p.get(), join.children[1], be->idx, &top_stage));
+        build_slot = p->stages[(size_t)top_stage]->src_slot;
+        bt = p->tab(build_slot);
+    }
 
     // a value above the join: output idx of the join -> (source | build) typed column
     auto valref = [&](int join_out, ValRef *vr, const Column **colp) -> bool {
@@ -605,7 +707,7 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &join, std::uniqu
         if (!resolve(join, join_out, &bc)) return false;
         const pg_table *t = nullptr;
         if (bc.slot == p->src_slot) { vr->from_build = 0; t = st; }
-        else if (bc.slot == bs.src_slot) { vr->from_build = 1; t = bt; }
+        else if (bc.slot == build_slot) { vr->from_build = 1; t = bt; }
         else return false;
         vr->col = typed(t, bc.col);
         *colp = &t->cols[(size_t)bc.col];
@@ -628,13 +730,24 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &join, std::uniqu
         p->group_out_type.push_back(col->type);
     }
     // aggregates: sum of affine products over reachable columns
-    if (aggn.aggs.empty() || aggn.aggs.size() > GT_MAXACC) PG_FAIL(PG_EUNSUPPORTED, "join aggregate supports 1..%d sums", GT_MAXACC);
-    p->gs.nacc = (int)aggn.aggs.size();
+    if (aggn.aggs.empty() || aggn.aggs.size() > GT_MAXACC) PG_FAIL(PG_EUNSUPPORTED, "high-cardinality aggregate supports 1..%d aggregates", GT_MAXACC);
     p->aggs = aggn.aggs;
     i128 worst = 0;
-    for (size_t a = 0; a < aggn.aggs.size(); a++) {
-        const AggExpr &ae = aggn.aggs[a];
-        if (ae.fn != PG_AGG_SUM || ae.ltype != PG_LT_DECIMAL) PG_FAIL(PG_EUNSUPPORTED, "join aggregate supports sum(DECIMAL) only");
+    int nsum = 0;
+    for (auto &ae : aggn.aggs) if (ae.fn != PG_AGG_COUNT) nsum++;
+    p->gs.nacc = nsum;
+    p->agg_plane.assign(aggn.aggs.size(), nsum);      // count(*) reads the row-count plane (index nacc)
+    p->agg_scale.assign(aggn.aggs.size(), 0);
+    int next_plane = 0;
+    for (size_t ai = 0; ai < aggn.aggs.size(); ai++) {
+        const AggExpr &ae = aggn.aggs[ai];
+        if (ae.fn == PG_AGG_COUNT) {
+            if (ae.ltype != PG_LT_HUGEINT) PG_FAIL(PG_EUNSUPPORTED, "count result type");
+            continue;
+        }
+        const size_t a = (size_t)next_plane;
+        p->agg_plane[ai] = next_plane++;
+        if (ae.fn != PG_AGG_SUM || (ae.ltype != PG_LT_DECIMAL && ae.ltype != PG_LT_HUGEINT)) PG_FAIL(PG_EUNSUPPORTED, "high-cardinality aggregate supports sum and count only");
         // lower against a virtual table made of the join's outputs: reuse lower_affprod on the
         // probe table for factors, resolving columns by hand
         struct Tmp { std::vector<Factor> f; } tmp;
@@ -675,8 +788,30 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &join, std::uniqu
             i128 m = std::max(lo < 0 ? -lo : lo, hi < 0 ? -hi : hi);
             bound *= m > 1 ? m : 1;
         }
-        p->agg_scale.push_back(scale);
+        if (ae.ltype == PG_LT_HUGEINT && scale != 0) PG_FAIL(PG_EUNSUPPORTED, "integer sum over a scaled value");
+        p->agg_scale[ai] = scale;
         worst = std::max(worst, bound);
+    }
+    // HAVING <aggregate> <cmp> <constant>  ->  inclusive range on that accumulator plane
+    if (aggn.having.size() == 1) {
+        const Expr &h = aggn.having[0];
+        if (h.kind != PG_TK_FUNC || !is_cmp(h.fn) || h.args.size() != 2) PG_FAIL(PG_EUNSUPPORTED, "HAVING is not a comparison");
+        const Expr *l = strip_value_preserving_casts(&h.args[0]), *r = strip_value_preserving_casts(&h.args[1]);
+        int op = h.fn;
+        if (l->kind == PG_TK_CONST) { std::swap(l, r); op = flip_cmp(op); }
+        if (l->kind != PG_TK_COL || l->side != 1 || r->kind != PG_TK_CONST || l->idx < 0 || l->idx >= (int)aggn.aggs.size())
+            PG_FAIL(PG_EUNSUPPORTED, "HAVING must compare an aggregate with a constant");
+        i64 k;
+        if (!const_at_scale(r, p->agg_scale[(size_t)l->idx], &k)) PG_FAIL(PG_EUNSUPPORTED, "HAVING constant does not fit the aggregate scale");
+        p->hav_plane = p->agg_plane[(size_t)l->idx];
+        switch (op) {
+        case PG_FN_EQ: p->hav_lo = p->hav_hi = k; break;
+        case PG_FN_LT: p->hav_hi = k - 1; break;
+        case PG_FN_LE: p->hav_hi = k; break;
+        case PG_FN_GT: p->hav_lo = k + 1; break;
+        case PG_FN_GE: p->hav_lo = k; break;
+        default: PG_FAIL(PG_EUNSUPPORTED, "HAVING <> is not a range");
+        }
     }
     // 64-bit accumulators: a group can at most receive every probe row
     if (worst * (i128)std::max<i64>(st->nrows, 1) >= ((i128)1 << 63)) PG_FAIL(PG_EUNSUPPORTED, "group sums could exceed int64");
@@ -684,7 +819,16 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &join, std::uniqu
         bool need = false;
         for (int k = 0; k < p->nparts; k++) need = need || p->gs.part[k].from_build;
         for (int a = 0; a < p->gs.nacc; a++) for (int f = 0; f < p->gs.nfac[a]; f++) need = need || p->gs.fac[a][f].from_build;
-        p->stages[(size_t)top_stage]->payload_needed = need;
+        if (!p->no_join) p->stages[(size_t)top_stage]->payload_needed = need;
+    }
+    if (p->no_join) {
+        // expected groups: bounded by the rows and by the key domain of the first key
+        BaseCol g0;
+        const Expr *ge = strip_value_preserving_casts(&aggn.groups[0]);
+        resolve(join, ge->idx, &g0);
+        const Column &kc = st->cols[(size_t)g0.col];
+        i128 domain = (i128)kc.vmax - (i128)kc.vmin + 1;
+        p->group_hint = (i64)std::min<i128>(std::max<i128>(domain, 1), (i128)std::max<i64>(st->nrows / 2, 1));
     }
     for (auto &o : aggn.outs) {
         if (o.first == 0 && (o.second < 0 || o.second >= p->nparts)) PG_FAIL(PG_EUNSUPPORTED, "bad group output index");
@@ -698,7 +842,7 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &join, std::uniqu
         std::vector<std::pair<int, int>> used;   // (slot, col)
         auto use = [&](int slot, int col) { if (std::find(used.begin(), used.end(), std::make_pair(slot, col)) == used.end()) used.push_back({slot, col}); };
         for (auto &r : p->ranges) use(p->src_slot, r.col);
-        use(p->src_slot, p->probe_key_col);
+        if (!p->no_join) use(p->src_slot, p->probe_key_col);
         for (auto &sp : p->stages) {
             for (auto &r : sp->ranges) use(sp->src_slot, r.col);
             use(sp->src_slot, sp->ins_key_col);
@@ -722,9 +866,10 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &join, std::uniqu
         // the probe kernel itself STREAMS only the predicate and key columns; the other probe-side
         // columns are gathered for matching rows (added per run: 32-byte sector per value)
         for (auto &r : p->ranges) p->main_bytes += st->nrows * type_size(st->cols[(size_t)r.col].type);
-        bool key_is_pred = false;
+        bool key_is_pred = p->no_join;
         for (auto &r : p->ranges) key_is_pred = key_is_pred || r.col == p->probe_key_col;
         if (!key_is_pred) p->main_bytes += st->nrows * type_size(st->cols[(size_t)p->probe_key_col].type);
+        if (p->no_join) p->main_bytes = p->algorithmic_bytes;
     }
     // multi-GPU: which joins are shard-local?  A REPLICATED build side is complete everywhere.  Two
     // SHARDED sides must be co-partitioned on the join key: no rank's probe-key range may touch
@@ -763,22 +908,25 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &join, std::uniqu
             if (!ok) PG_FAIL(PG_EUNSUPPORTED, "sharded join sides are not co-partitioned on the key (needs the all-to-all shuffle path)");
         }
         // (b) the top join
-        if (bt->dist != PG_DIST_REPLICATED) {
+        if (!p->no_join && bt->dist != PG_DIST_REPLICATED) {
             if (st->dist == PG_DIST_REPLICATED) PG_FAIL(PG_EUNSUPPORTED, "replicated table probing a sharded one");
             bool ok = false;
-            PG_TRY(copartitioned(st, p->probe_key_col, bt, bs.ins_key_col, &ok));
+            PG_TRY(copartitioned(st, p->probe_key_col, bt, p->stages[(size_t)top_stage]->ins_key_col, &ok));
             if (!ok) PG_FAIL(PG_EUNSUPPORTED, "sharded join sides are not co-partitioned on the key (needs the all-to-all shuffle path)");
         }
         if (st->dist != PG_DIST_REPLICATED) {
-            // groups of different ranks must be disjoint: the first group key is the probe join key and the
-            // probe key ranges of the ranks do not overlap
+            // Are the groups of different ranks disjoint?  Yes when the first group key is a probe-side
+            // column whose value ranges do not overlap between ranks (the shard key).  Otherwise the
+            // local group lists are hash-partitioned and exchanged (all-to-all over NVLink) and merged.
             BaseCol g0;
             const Expr *ge = strip_value_preserving_casts(&aggn.groups[0]);
-            bool ok = resolve(join, ge->idx, &g0) && g0.slot == p->src_slot && g0.col == p->probe_key_col;
+            bool ok = resolve(join, ge->idx, &g0) && g0.slot == p->src_slot;
             bool disjoint = false;
-            if (ok) PG_TRY(copartitioned(st, p->probe_key_col, st, p->probe_key_col, &disjoint));
-            if (!ok || !disjoint) PG_FAIL(PG_EUNSUPPORTED, "groups are not partitioned by the shard key (needs the all-to-all shuffle path)");
+            if (ok) PG_TRY(copartitioned(st, g0.col, st, g0.col, &disjoint));
+            const char *force = getenv("PG_FORCE_SHUFFLE");
+            if (force && atoi(force)) disjoint = false;
             p->gather_ranks = true;
+            p->shuffle = !(ok && disjoint);
         }
     }
     if (plan->topk && !plan->topk->order.empty()) {
@@ -791,7 +939,7 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &join, std::uniqu
             tk.src = o.second;            // 0: klo, 1: khi high, 2: khi low
         } else {
             tk.src = 3;
-            tk.plane = o.second;
+            tk.plane = p->agg_plane[(size_t)o.second];
             int sc = p->agg_scale[(size_t)o.second];
             for (int i = 2; i < sc; i++) tk.div *= 10;     // DECIMAL keys compare at two fractional digits
         }
@@ -808,10 +956,16 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &join, std::uniqu
                  p->tab(sp->src_slot)->cols[(size_t)sp->ins_key_col].name.c_str(), sp->has_probe ? " probing previous" : "");
         ex += b;
     }
-    char b[256];
-    snprintf(b, sizeof b, " probe(%s key=%s) kernel=pipeline_kernel<SINK_GROUP> group_keys=%d sums=%d", st->name.c_str(),
-             st->cols[(size_t)p->probe_key_col].name.c_str(), p->nparts, p->gs.nacc);
-    ex += b;
+    char b[320];
+    if (p->no_join)
+        snprintf(b, sizeof b, "GroupBy[global open-addressing table] scan(%s) kernel=pipeline_kernel<SINK_GROUP> group_keys=%d sums=%d%s%s",
+                 st->name.c_str(), p->nparts, p->gs.nacc, p->hav_plane >= 0 ? " having" : "",
+                 p->shuffle ? " exchange=all-to-all(hash-partitioned)" : "");
+    else
+        snprintf(b, sizeof b, " probe(%s key=%s) kernel=fast_pipeline_kernel<SINK_GROUP> group_keys=%d sums=%d%s", st->name.c_str(),
+                 st->cols[(size_t)p->probe_key_col].name.c_str(), p->nparts, p->gs.nacc,
+                 p->shuffle ? " exchange=all-to-all(hash-partitioned)" : "");
+    if (p->no_join) ex = b; else ex += b;
     p->explain = ex;
     *out = std::move(p);
     return PG_OK;

@@ -345,14 +345,19 @@ fast_pipeline_kernel(const PipeParams p)
 }
 
 // compact the occupied slots of a group table into dense output arrays
+// (HAVING on one aggregate -- an inclusive range on accumulator plane `hav_plane` -- is applied here)
 static __global__ void gt_compact_kernel(const GroupTable g, i64 *__restrict__ out_klo, i64 *__restrict__ out_khi,
                                   i64 *__restrict__ out_acc /* [nacc+1][max_out] */, i64 max_out,
-                                  unsigned long long *__restrict__ counter)
+                                  unsigned long long *__restrict__ counter, int hav_plane, i64 hav_lo, i64 hav_hi)
 {
     u64 cap = g.mask + 1;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (u64)gridDim.x * blockDim.x) {
         i64 k = g.klo[i];
         if (k == HT_EMPTY) continue;
+        if (hav_plane >= 0) {
+            i64 v = g.acc[(u64)hav_plane * cap + i];
+            if (v < hav_lo || v > hav_hi) { atomicAdd(counter + 1, 1ULL); continue; }
+        }
         unsigned long long o = atomicAdd(counter, 1ULL);
         if ((i64)o >= max_out) continue;
         out_klo[o] = k;
@@ -414,6 +419,66 @@ static __global__ void topk_collect_kernel(TopkKey key, const i64 *klo, const i6
         out_klo[o] = klo[i];
         out_khi[o] = khi[i];
         for (int a = 0; a < planes; a++) out_acc[(i64)a * out_cap + (i64)o] = acc[(i64)a * stride + i];
+    }
+}
+
+// -------------------------------------------------------------- shuffle --
+__device__ __forceinline__ int shuffle_dest(i64 klo, i64 khi, int world)
+{
+    return (int)(mix64((u64)klo ^ ((u64)khi * 0x9E3779B97F4A7C15ULL)) % (u64)world);
+}
+
+static __global__ void shuffle_count_kernel(const i64 *klo, const i64 *khi, i64 n, int world, unsigned long long *cnt)
+{
+    __shared__ unsigned s_c[64];
+    if (threadIdx.x < 64) s_c[threadIdx.x] = 0;
+    __syncthreads();
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
+        atomicAdd(&s_c[shuffle_dest(klo[i], khi[i], world)], 1u);
+    __syncthreads();
+    if (threadIdx.x < world && s_c[threadIdx.x]) atomicAdd(&cnt[threadIdx.x], (unsigned long long)s_c[threadIdx.x]);
+}
+
+// pack rows [klo, khi, planes...] grouped by destination rank (cursor[d] starts at the d-th send offset)
+static __global__ void shuffle_scatter_kernel(const i64 *klo, const i64 *khi, const i64 *acc, i64 stride, i64 n, int planes, int world,
+                                              unsigned long long *cursor, i64 *send)
+{
+    const int RW = 2 + planes;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        i64 a = klo[i], b = khi[i];
+        unsigned long long pos = atomicAdd(&cursor[shuffle_dest(a, b, world)], 1ULL);
+        i64 *row = send + pos * RW;
+        row[0] = a;
+        row[1] = b;
+        for (int p = 0; p < planes; p++) row[2 + p] = acc[(i64)p * stride + i];
+    }
+}
+
+// add received partial groups (all planes, the last one being the row count) into the group table
+static __global__ void shuffle_merge_kernel(const GroupTable g, const i64 *rows, i64 n, int planes)
+{
+    const int RW = 2 + planes;
+    u64 cap = g.mask + 1;
+    for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (i64)gridDim.x * blockDim.x) {
+        const i64 *row = rows + r * RW;
+        i64 klo = row[0], khi = row[1];
+        u64 i = mix64((u64)klo * 0x9E3779B97F4A7C15ULL ^ (u64)khi) & g.mask;
+        bool done = false;
+        for (u64 k = 0; k <= g.mask && k <= 4096; k++) {
+            i64 cur = g.klo[i];
+            if (cur == HT_EMPTY) cur = (i64)atomicCAS((unsigned long long *)&g.klo[i], (unsigned long long)HT_EMPTY, (unsigned long long)klo);
+            if (cur == HT_EMPTY || cur == klo) {
+                i64 h = g.khi[i];
+                if (h == HT_EMPTY) h = (i64)atomicCAS((unsigned long long *)&g.khi[i], (unsigned long long)HT_EMPTY, (unsigned long long)khi);
+                if (h == HT_EMPTY || h == khi) {
+                    for (int p = 0; p < planes; p++) atomicAdd((unsigned long long *)&g.acc[(u64)p * cap + i], (unsigned long long)row[2 + p]);
+                    done = true;
+                    break;
+                }
+            }
+            i = (i + 1) & g.mask;
+        }
+        if (!done) *g.overflow = 1;
     }
 }
 

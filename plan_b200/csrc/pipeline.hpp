@@ -102,6 +102,9 @@ struct Trace {
 
 // all-gather `bytes` from every rank into recv[world][bytes] (comm.cu); world==1 copies.
 int comm_allgather(const void *d_send, void *d_recv, size_t bytes, cudaStream_t stream);
+// variable all-to-all of fixed-size rows (counts / offsets in rows) over grouped ncclSend/ncclRecv
+int comm_alltoallv(const void *d_send, const i64 *send_cnt, const i64 *send_off, void *d_recv, const i64 *recv_cnt,
+                   const i64 *recv_off, size_t row_bytes, cudaStream_t stream);
 
 }  // namespace pg
 
@@ -114,6 +117,7 @@ struct pg_result {
 struct pg_plan {
     pg::Node root;
     const pg::Node *topk = nullptr;     // root when it is a PG_OP_TOPK, else null
+    pg::Node scan_copy;                 // scan with merged filters (high-cardinality Agg <- Scan)
     const pg::Node &agg_root() const { return topk ? root.children[0] : root; }
     std::vector<pg_table *> slots;
     std::vector<uint64_t> bound_versions;

@@ -95,6 +95,18 @@ static int build_pipeline(pg_plan *plan)
     if (child->op == PG_OP_SCAN) {
         Node scan = *child;
         for (auto &f : extra) scan.filters.push_back(f);
+        // byte-coded (or no) group keys -> the shared-memory scan-aggregate kernels; integer keys of
+        // arbitrary cardinality -> the global open-addressing group table (same machinery as the joins)
+        bool int_keys = !root.groups.empty();
+        for (auto &g : root.groups) {
+            const Expr *e = strip_value_preserving_casts(&g);
+            const pg_table *t = plan->slots[(size_t)scan.slot];
+            if (e->kind != PG_TK_COL || e->idx < 0 || e->idx >= (int)t->cols.size() || !is_int_family(t->cols[(size_t)e->idx].type)) int_keys = false;
+        }
+        if (int_keys) {
+            plan->scan_copy = scan;
+            return build_join_agg(plan, root, plan->scan_copy, &plan->pipe);
+        }
         return build_scan_agg(plan, root, scan, &plan->pipe);
     }
     if (child->op == PG_OP_JOIN) {

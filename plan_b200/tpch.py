@@ -190,6 +190,34 @@ def stats_plan(d0, d1, d2, d3, q0, q1, disc_gt_cents, schema=FULL):
     return PhysicalOperator(POT_Agg, Outputs=outs, Children=[scan], Info=AggOpInfo(aggs, [lc("l_returnflag")]))
 
 
+def groupby_plan(key="l_orderkey", value="l_quantity", having_gt=None, ship_le=None, topk=None, schema=FULL):
+    """High-cardinality group-by straight over lineitem (the inner aggregate of TPC-H Q18 when
+    key = l_orderkey, having_gt = 314):
+        select <key>, sum(<value>), count(*) from lineitem [where l_shipdate <= d]
+        group by <key> [having sum(<value>) > k] [order by 2 desc, 1 limit n]
+    sum(INTEGER) -> HUGEINT; `sum > 314` compares HUGEINTs (greatHugeintOp,
+    function_operator_boolean.go:255-263) after the literal is cast INTEGER -> HUGEINT."""
+    S = schema
+    lc = lambda n: S.col("lineitem", n)   # noqa: E731
+    B = K.LType(K.LTID_BOOLEAN)
+    filters = [] if ship_le is None else [func("<=", B, lc("l_shipdate"), const(ship_le, K.DateType()))]
+    scan = PhysicalOperator(POT_Scan, Filters=filters, Info=ScanOpInfo("lineitem"))
+    vt = _ltype_of(S.tables["lineitem"][S.idx["lineitem"][value]])
+    sum_t = K.HugeintType() if vt.Id in (K.LTID_INTEGER, K.LTID_BIGINT) else K.DecimalType(38, vt.Scale)
+    aggs = [func("sum", sum_t, lc(value)), func("count", K.HugeintType(), col(0, 0, _ltype_of(S.tables["lineitem"][0])))]
+    kt = _ltype_of(S.tables["lineitem"][S.idx["lineitem"][key]])
+    outs = [col(0, 0, kt), col(1, 0, sum_t), col(1, 1, K.HugeintType())]
+    having = []
+    if having_gt is not None:
+        having = [func(">", B, col(1, 0, sum_t), cast(const(having_gt, K.IntegerType()), sum_t))]
+    agg = PhysicalOperator(POT_Agg, Outputs=outs, Filters=having, Children=[scan], Info=AggOpInfo(aggs, [lc(key)]))
+    if topk is None:
+        return agg
+    order = PhysicalOperator(POT_Order, Outputs=outs, Children=[agg],
+                             Info=OrderOpInfo([(col(0, 1, sum_t), True), (col(0, 0, kt), False)]))
+    return PhysicalOperator(POT_Limit, Outputs=outs, Children=[order], Info=LimitOpInfo(topk))
+
+
 def q3_topk_plan(limit=10, **kw):
     """Limit <- Order(revenue desc, o_orderdate) <- Agg(...) : the whole Q3 tail below the final
     Project, fused into the GPU pipeline (device top-k)."""

@@ -45,6 +45,18 @@ def main():
     J.check_q3_topk(O, tables, host, 10)
     J.check_q3_topk(O, tables, host, 1000, segment="BUILDING")
 
+    # high-cardinality group-by: l_orderkey is the shard key (groups disjoint, concatenated) while
+    # l_partkey / l_suppkey groups collide across ranks -> NCCL all-to-all hash-partitioned shuffle + merge
+    st = J.check_groupby(O, tables, line, key="l_orderkey", value="l_quantity", having_gt=200)
+    st = J.check_groupby(O, tables, line, key="l_partkey", value="l_quantity")
+    assert st.aux[7] > 0, "the shuffle path did not run"
+    J.check_groupby(O, tables, line, key="l_suppkey", value="l_extendedprice", ship_le=8035 + 1263)
+    os.environ["PG_FORCE_SHUFFLE"] = "1"          # the general path must also be right when it is not needed
+    J.check_groupby(O, tables, line, key="l_orderkey", value="l_quantity", having_gt=200)
+    J.check_q3(O, tables, host, check_counts=False)
+    J.check_q3_topk(O, tables, host, 10)
+    os.environ.pop("PG_FORCE_SHUFFLE")
+
     # order-dependent rounding regime across shards: inflate prices on the uploaded shard
     first = int(np.searchsorted(line["l_orderkey"], orders["o_orderkey"][lo]))
     last = len(line["l_orderkey"]) if hi == n_orders else int(np.searchsorted(line["l_orderkey"], orders["o_orderkey"][hi]))

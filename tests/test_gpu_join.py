@@ -159,3 +159,51 @@ def test_cpp_host_shim_reproduces_golden_files(query, golden):
     r = subprocess.run([B.HOST_BIN, "1", str(query)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     assert r.stdout == open(os.path.join(GOLDEN, golden)).read()
+
+
+def _groupby_result(chunks):
+    out = {}
+    for c in chunks:
+        k, s, n = (v.Data for v in c.Data)
+        for r in range(c.Card()):
+            sv = s[r]
+            if s.dtype.names and "coef" in s.dtype.names:
+                val = (-1 if sv["neg"] else 1) * int(sv["coef"])
+            else:
+                val = (int(sv["upper"]) << 64) + int(sv["lower"])
+            assert int(k[r]) not in out
+            out[int(k[r])] = (val, int(n[r]["lower"]))
+    return out
+
+
+def check_groupby(oracle, tables, line, **kw):
+    from plan_b200 import tpch as T
+    chunks, stats, explain = _run(T.groupby_plan(**kw), tables)
+    assert "global open-addressing table" in explain
+    want = oracle.groupby_sum(line, **kw)
+    got = _groupby_result(chunks)
+    assert len(got) == len(want)
+    assert got == want
+    return stats
+
+
+@pytest.mark.parametrize("kw", [
+    dict(key="l_orderkey", value="l_quantity"),                           # 150k groups at SF0.1
+    dict(key="l_orderkey", value="l_quantity", having_gt=200),            # Q18's inner aggregate shape
+    dict(key="l_partkey", value="l_quantity", ship_le=8035 + 1263),       # 20k groups, many rows per group
+    dict(key="l_suppkey", value="l_extendedprice"),                       # sum(DECIMAL), 1000 hot groups
+    dict(key="l_orderkey", value="l_quantity", having_gt=10 ** 6),        # HAVING removes everything
+])
+def test_high_cardinality_groupby(pg, oracle, uploaded, sf01_host, kw):
+    check_groupby(oracle, uploaded, sf01_host["lineitem"], **kw)
+
+
+def test_high_cardinality_groupby_topk(pg, oracle, uploaded, sf01_host):
+    from plan_b200 import tpch as T
+    chunks, _, _ = _run(T.groupby_plan(key="l_orderkey", value="l_quantity", having_gt=150, topk=20), uploaded)
+    want = oracle.groupby_sum(sf01_host["lineitem"], having_gt=150)
+    top = sorted(want.items(), key=lambda kv: (-kv[1][0], kv[0]))[:20]
+    got = _groupby_result(chunks)
+    rows = [(int(c.Data[0].Data[r]),) for c in chunks for r in range(c.Card())]
+    assert [k for (k,) in rows] == [k for k, _ in top]          # already ordered: sum desc, key asc
+    assert all(got[k] == v for k, v in top)
