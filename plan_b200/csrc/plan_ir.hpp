@@ -277,7 +277,8 @@ inline const Expr *strip_value_preserving_casts(const Expr *e)
     while (e->kind == PG_TK_FUNC && e->fn == PG_FN_CAST && e->args.size() == 1) {
         const Expr &a = e->args[0];
         bool dec2dec = e->ltype == PG_LT_DECIMAL && a.ltype == PG_LT_DECIMAL && e->scale >= a.scale;
-        bool int2int = (e->ltype == PG_LT_BIGINT || e->ltype == PG_LT_INTEGER) && (a.ltype == PG_LT_INTEGER || a.ltype == PG_LT_BIGINT);
+        bool int2int = (e->ltype == PG_LT_BIGINT || e->ltype == PG_LT_INTEGER || e->ltype == PG_LT_HUGEINT) &&
+                       (a.ltype == PG_LT_INTEGER || a.ltype == PG_LT_BIGINT);   // incl. tryCastInt32ToHugeint (function_cast.go:321-325)
         bool int2dec = e->ltype == PG_LT_DECIMAL && (a.ltype == PG_LT_INTEGER || a.ltype == PG_LT_BIGINT) && a.kind == PG_TK_CONST;
         if (!(dec2dec || int2int || int2dec)) break;
         e = &a;
