@@ -84,6 +84,7 @@ struct Column {
     // statistics computed at seal
     bool stats_ok = false;
     i64 vmin = 0, vmax = 0;
+    i64 adjacent_equal = 0;                           // rows whose value equals the next row's (clustering)
     uint32_t present[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // byte columns: which codes occur
 };
 

@@ -76,11 +76,13 @@ struct JoinAggPipeline : Pipeline {
     int hav_plane = -1;                          // HAVING <aggregate> in [hav_lo, hav_hi]
     i64 hav_lo = INT64_MIN, hav_hi = INT64_MAX;
     i64 group_hint = 0;                          // expected number of groups (no-join case)
+    i64 key_min = 0;                             // statistics of the first group key (no-join case)
+    u64 key_domain = 0;
     std::vector<std::pair<int, int>> outs;
     std::vector<int> group_out_type;             // pg_type of each group key
     i64 algorithmic_bytes = 0, main_bytes = 0;
     // device scratch
-    DevBuf d_counters, d_klo, d_khi, d_acc, d_overflow, d_out_klo, d_out_khi, d_out_acc;
+    DevBuf d_counters, d_gt, d_overflow, d_out_klo, d_out_khi, d_out_acc;
     u64 gt_cap = 0;
     i64 out_cap = 0;
     EventPair ev_all, ev_main;
@@ -274,9 +276,7 @@ struct JoinAggPipeline : Pipeline {
     int ensure_group_table(u64 cap)
     {
         if (cap <= gt_cap) return PG_OK;
-        PG_TRY(d_klo.alloc(cap * 8));
-        PG_TRY(d_khi.alloc(cap * 8));
-        PG_TRY(d_acc.alloc(cap * 8 * (size_t)(gs.nacc + 1)));
+        PG_TRY(d_gt.alloc(cap * 8 * (size_t)gt_slot_words(gs.nacc)));
         gt_cap = cap;
         return PG_OK;
     }
@@ -325,9 +325,7 @@ struct JoinAggPipeline : Pipeline {
         // 4. the exchange
         PG_TRY(comm_alltoallv(d_sx_send.p, send_cnt.data(), send_off.data(), d_sx_recv.p, recv_cnt.data(), recv_off.data(), (size_t)RW * 8, st));
         // 5. merge what this rank owns
-        PG_CUDA(cudaMemsetAsync(d_klo.p, 0x80, gt_cap * 8, st));
-        PG_CUDA(cudaMemsetAsync(d_khi.p, 0x80, gt_cap * 8, st));
-        PG_CUDA(cudaMemsetAsync(d_acc.p, 0, gt_cap * 8 * (size_t)planes, st));
+        PG_CUDA(cudaMemsetAsync(d_gt.p, 0x80, gt_cap * 8 * (size_t)gt_slot_words(gs.nacc), st));
         PG_CUDA(cudaMemsetAsync(d_overflow.p, 0, 4, st));
         int g2 = (int)std::max<i64>(std::min<i64>((ro + 255) / 256, (i64)c.prop.multiProcessorCount * 4), 1);
         shuffle_merge_kernel<<<g2, 256, 0, st>>>(pp.gt, d_sx_recv.as<i64>(), ro, planes);
@@ -388,19 +386,49 @@ struct JoinAggPipeline : Pipeline {
         for (int attempt = 0;; attempt++) {
             PG_TRY(ensure_group_table(cap));
             cap = gt_cap;
-            PG_CUDA(cudaMemsetAsync(d_klo.p, 0x80, cap * 8, st));
-            PG_CUDA(cudaMemsetAsync(d_khi.p, 0x80, cap * 8, st));
-            PG_CUDA(cudaMemsetAsync(d_acc.p, 0, cap * 8 * (size_t)(gs.nacc + 1), st));
+            PG_CUDA(cudaMemsetAsync(d_gt.p, 0x80, cap * 8 * (size_t)gt_slot_words(gs.nacc), st));
             PG_CUDA(cudaMemsetAsync(d_overflow.p, 0, 4, st));
             PG_CUDA(cudaMemsetAsync(d_counters.p, 0, 32, st));
-            pp.gt.klo = d_klo.as<i64>();
-            pp.gt.khi = d_khi.as<i64>();
-            pp.gt.acc = d_acc.as<i64>();
+            pp.gt.slots = d_gt.as<i64>();
             pp.gt.mask = cap - 1;
             pp.gt.nacc = gs.nacc;
+            pp.gt.rw = gt_slot_words(gs.nacc);
+            pp.gt.two_words = gs.nparts > 1 ? 1 : 0;
+            pp.gt.order_preserving = 0;
+            if (no_join && gs.run_aggregate && key_domain > 0 && key_domain <= ((u64)1 << 34) && !(shuffle && c.world > 1)) {
+                int lg = 0;
+                while (((u64)1 << lg) < cap) lg++;
+                if (lg <= 29) {      // (key - kmin) << log2cap must fit in 64 bits
+                    pp.gt.order_preserving = getenv("PG_ORDER_PRESERVING") ? atoi(getenv("PG_ORDER_PRESERVING")) : 1;
+                    pp.gt.kmin = key_min;
+                    pp.gt.domain = key_domain;
+                    pp.gt.log2cap = lg;
+                }
+            }
             pp.gt.overflow = d_overflow.as<int>();
             PG_CUDA(cudaEventRecord(ev_main.a, st));
-            PG_TRY(launch_pipe<SINK_GROUP>(pp, t));
+            if (no_join) {
+                // the specialised vectorised kernel when the shape is: 1 key, 1 summed column, <=1 32-bit predicate
+                const bool one = gs.nparts == 1 && gs.nacc == 1 && gs.nfac[0] == 1 && pp.npred <= 1 &&
+                                 (pp.npred == 0 || pp.pred[0].col.width == 4) && gs.part[0].col.width >= 4 &&
+                                 gs.fac[0][0].col.width >= 4 && !getenv("PG_GROUP_GENERIC");
+                if (one) {
+                    i64 ntiles = (t->nrows + SA_TILE - 1) / SA_TILE;
+                    int grid = (int)std::max<i64>(std::min<i64>(ntiles, (i64)c.prop.multiProcessorCount * 8), 1);
+                    const bool k8 = gs.part[0].col.width == 8, v8 = gs.fac[0][0].col.width == 8, hp = pp.npred == 1;
+#define PG_G1(K, V, P) group1_kernel<K, V, P><<<grid, SA_THREADS, 0, st>>>(pp)
+                    if (k8 && v8) { if (hp) PG_G1(8, 8, true); else PG_G1(8, 8, false); }
+                    else if (k8) { if (hp) PG_G1(8, 4, true); else PG_G1(8, 4, false); }
+                    else if (v8) { if (hp) PG_G1(4, 8, true); else PG_G1(4, 8, false); }
+                    else { if (hp) PG_G1(4, 4, true); else PG_G1(4, 4, false); }
+#undef PG_G1
+                } else {
+                    scan_group_kernel<<<grid_rows(t->nrows), 256, 0, st>>>(pp);
+                }
+                PG_CUDA(cudaGetLastError());
+            } else {
+                PG_TRY(launch_pipe<SINK_GROUP>(pp, t));
+            }
             PG_CUDA(cudaEventRecord(ev_main.b, st));
             res->stats.kernel_launches += 1;
             int ovf = 0;
@@ -828,7 +856,12 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &join, std::uniqu
         resolve(join, ge->idx, &g0);
         const Column &kc = st->cols[(size_t)g0.col];
         i128 domain = (i128)kc.vmax - (i128)kc.vmin + 1;
-        p->group_hint = (i64)std::min<i128>(std::max<i128>(domain, 1), (i128)std::max<i64>(st->nrows / 2, 1));
+        p->group_hint = (i64)std::min<i128>(std::max<i128>(domain, 1), (i128)std::max<i64>(st->nrows / 4, 1));   // grows x2 on overflow
+        // clustered key (most rows repeat their neighbour's key, e.g. l_orderkey): combine runs in the warp first
+        p->key_min = kc.vmin;
+        p->key_domain = domain > 0 && domain < ((i128)1 << 62) ? (u64)domain : 0;
+        p->gs.run_aggregate = kc.stats_ok && kc.adjacent_equal * 2 >= st->nrows ? 1 : 0;
+        if (getenv("PG_RUN_AGGREGATE")) p->gs.run_aggregate = atoi(getenv("PG_RUN_AGGREGATE"));
     }
     for (auto &o : aggn.outs) {
         if (o.first == 0 && (o.second < 0 || o.second >= p->nparts)) PG_FAIL(PG_EUNSUPPORTED, "bad group output index");

@@ -119,13 +119,33 @@ enum { SINK_COUNT = 0, SINK_INSERT = 1, SINK_GROUP = 2 };
 constexpr int GT_MAXACC = 4;
 constexpr int GT_MAXKEYPARTS = 3;
 
+// Slots are records {klo, khi, acc[0..nacc-1], count} padded to `rw` = 4 or 8 words, so one group
+// update touches ONE 32-byte sector (64 bytes for more than one sum) instead of one sector per
+// field.  The whole table is initialised with memset(0x80): key words read HT_EMPTY when free and
+// every accumulator starts at HT_EMPTY, which compaction subtracts again (64-bit wrap-around
+// arithmetic keeps the sums exact).
 struct GroupTable {
-    i64 *klo, *khi;       // [cap] key words, HT_EMPTY when free
-    i64 *acc;             // [nacc + 1][cap]; the last plane counts rows
+    i64 *slots;           // [cap][rw]
     u64 mask;             // cap - 1
     int nacc;
+    int rw;               // words per slot (4 or 8)
     int *overflow;        // set when a probe sequence exceeds the limit (table too small)
+    // Slot choice.  Default: mix64 hash.  For keys that are CLUSTERED in row order (statistics:
+    // most rows repeat their neighbour's key, e.g. l_orderkey) an ORDER-PRESERVING map of the key
+    // domain onto the table is used instead: consecutive rows then touch consecutive slots, so the
+    // table is written like a stream rather than at random DRAM pages (measured 36 -> ~ms class).
+    int two_words;        // keys use both words (more than one key column)
+    int order_preserving;
+    i64 kmin;
+    u64 domain;           // kmax - kmin + 1  (<= 2^34 when order_preserving)
+    int log2cap;
 };
+__device__ __forceinline__ u64 gt_home(const GroupTable &g, i64 klo, i64 khi)
+{
+    if (g.order_preserving) return (((u64)(klo - g.kmin)) << g.log2cap) / g.domain;
+    return mix64((u64)klo * 0x9E3779B97F4A7C15ULL ^ (u64)khi) & g.mask;
+}
+__host__ __device__ __forceinline__ int gt_slot_words(int nacc) { return nacc <= 1 ? 4 : 8; }
 
 // where a value comes from: the streamed source row or the matched build row
 struct ValRef {
@@ -137,6 +157,8 @@ struct GroupSpec {
     // key = up to 3 parts: part 0 -> klo; parts 1,2 -> khi = (p1 << 32) | (p2 & 0xffffffff)
     int nparts;
     ValRef part[GT_MAXKEYPARTS];
+    int run_aggregate;   // group keys are clustered in row order: combine runs of equal keys across adjacent
+                         // lanes (segmented warp scan) and issue ONE table update per run
     // accumulator a = product over its factors of (c + s * value)
     int nacc;
     int nfac[GT_MAXACC];
@@ -163,26 +185,59 @@ struct PipeParams {
     unsigned long long *counters;
 };
 
-__device__ __forceinline__ void gt_update(const GroupTable &g, i64 klo, i64 khi, const i64 *vals)
+// add `vals` (nacc sums) and `count` rows to group (klo, khi); claims a free slot with 64-bit CAS
+__device__ __forceinline__ void gt_add(const GroupTable &g, i64 klo, i64 khi, const i64 *vals, i64 count)
 {
-    u64 cap = g.mask + 1;
-    u64 i = mix64((u64)klo * 0x9E3779B97F4A7C15ULL ^ (u64)khi) & g.mask;
-    for (u64 n = 0; n <= g.mask; n++) {
-        i64 cur = g.klo[i];
-        if (cur == HT_EMPTY) cur = (i64)atomicCAS((unsigned long long *)&g.klo[i], (unsigned long long)HT_EMPTY, (unsigned long long)klo);
+    u64 i = gt_home(g, klo, khi);
+    for (u64 n = 0; n <= g.mask && n <= 4096; n++) {
+        i64 *slot = g.slots + i * (u64)g.rw;
+        i64 cur = slot[0];
+        if (cur == HT_EMPTY) cur = (i64)atomicCAS((unsigned long long *)&slot[0], (unsigned long long)HT_EMPTY, (unsigned long long)klo);
         if (cur == HT_EMPTY || cur == klo) {
-            i64 h = g.khi[i];
-            if (h == HT_EMPTY) h = (i64)atomicCAS((unsigned long long *)&g.khi[i], (unsigned long long)HT_EMPTY, (unsigned long long)khi);
+            i64 h = khi;
+            if (g.two_words) {      // single-column keys never touch the second key word
+                h = slot[1];
+                if (h == HT_EMPTY) h = (i64)atomicCAS((unsigned long long *)&slot[1], (unsigned long long)HT_EMPTY, (unsigned long long)khi);
+            }
             if (h == HT_EMPTY || h == khi) {
-                for (int a = 0; a < g.nacc; a++) atomicAdd((unsigned long long *)&g.acc[(u64)a * cap + i], (unsigned long long)vals[a]);
-                atomicAdd((unsigned long long *)&g.acc[(u64)g.nacc * cap + i], 1ULL);
+                for (int a = 0; a < g.nacc; a++) atomicAdd((unsigned long long *)&slot[2 + a], (unsigned long long)vals[a]);
+                atomicAdd((unsigned long long *)&slot[2 + g.nacc], (unsigned long long)count);
                 return;
             }
         }
         i = (i + 1) & g.mask;
-        if (n > 4096) break;
     }
     *g.overflow = 1;
+}
+__device__ __forceinline__ void gt_update(const GroupTable &g, i64 klo, i64 khi, const i64 *vals) { gt_add(g, klo, khi, vals, 1); }
+
+// Segmented inclusive sum over the warp: lanes with equal (klo, khi) that are ADJACENT form a run;
+// the last lane of a run ends up with the run's totals and performs the single table update.
+// All 32 lanes must call it; `valid` = this lane has a row.
+__device__ __forceinline__ void gt_update_runs(const GroupTable &g, bool valid, i64 klo, i64 khi, i64 *vals)
+{
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    i64 pk = __shfl_up_sync(full, klo, 1), ph = __shfl_up_sync(full, khi, 1);
+    int pv = __shfl_up_sync(full, (int)valid, 1);
+    int head = lane == 0 || !valid || !pv || pk != klo || ph != khi;
+    int nhead = __shfl_down_sync(full, head, 1);
+    bool tail = lane == 31 || nhead;
+    i64 cnt = valid ? 1 : 0;
+    int f = head;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int fu = __shfl_up_sync(full, f, o);
+        i64 cu = __shfl_up_sync(full, cnt, o);
+        i64 vu[GT_MAXACC];
+        for (int a = 0; a < g.nacc; a++) vu[a] = __shfl_up_sync(full, vals[a], o);
+        if (lane >= o && !f) {
+            cnt += cu;
+            for (int a = 0; a < g.nacc; a++) vals[a] += vu[a];
+            f |= fu;
+        }
+    }
+    if (valid && tail) gt_add(g, klo, khi, vals, cnt);
 }
 
 template <int SINK>
@@ -232,6 +287,103 @@ pipeline_kernel(const PipeParams p)
     if ((threadIdx.x & 31) == 0) {
         if (n_pass) atomicAdd(&p.counters[0], n_pass);
         if (n_join) atomicAdd(&p.counters[1], n_join);
+    }
+}
+
+// Group-by straight over a table (no probe): warp-converged loop so that runs of equal keys in
+// adjacent lanes can be combined before they reach the table.
+__global__ void __launch_bounds__(256)
+static scan_group_kernel(const PipeParams p)
+{
+    unsigned long long n_pass = 0;
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    const i64 nround = (p.nrows + stride - 1) / stride;     // same trip count for every thread
+    for (i64 it = 0; it < nround; it++) {
+        i64 row = it * stride + (i64)blockIdx.x * blockDim.x + threadIdx.x;
+        bool ok = row < p.nrows;
+        for (int k = 0; k < p.npred && ok; k++) {
+            i64 v = load_typed(p.pred[k].col, row);
+            ok = v >= p.pred[k].lo && v <= p.pred[k].hi;
+        }
+        i64 klo = 0, khi = 0, vals[GT_MAXACC];
+        if (ok) {
+            n_pass++;
+            klo = load_typed(p.gs.part[0].col, row);
+            if (p.gs.nparts > 1) khi = load_typed(p.gs.part[1].col, row) << 32;
+            if (p.gs.nparts > 2) khi |= load_typed(p.gs.part[2].col, row) & 0xffffffffLL;
+            for (int a = 0; a < p.gs.nacc; a++) {
+                i64 x = 1;
+                for (int f = 0; f < p.gs.nfac[a]; f++) x *= p.gs.fc[a][f] + p.gs.fs[a][f] * load_typed(p.gs.fac[a][f].col, row);
+                vals[a] = x;
+            }
+        }
+        if (p.gs.run_aggregate) gt_update_runs(p.gt, ok, klo, khi, vals);
+        else if (ok) gt_add(p.gt, klo, khi, vals, 1);
+    }
+    n_pass = (unsigned long long)warp_sum((i64)n_pass);
+    if ((threadIdx.x & 31) == 0 && n_pass) {
+        atomicAdd(&p.counters[0], n_pass);
+        atomicAdd(&p.counters[1], n_pass);
+    }
+}
+
+// Specialised, vectorised group-by for the dominant high-cardinality shape -- ONE integer key,
+// ONE summed column (plus the row count), at most one 32-bit range predicate: e.g. TPC-H Q18's
+// `group by l_orderkey having sum(l_quantity) > 314`.  16-byte streaming loads (4 rows per thread),
+// runs of equal keys are first combined inside the thread's 4 rows, then one compact table update
+// per run.  Everything is compile-time except pointers and constants.
+template <int KEYW, int VALW, bool HAS_PRED>
+__global__ void __launch_bounds__(SA_THREADS)
+group1_kernel(const PipeParams p)
+{
+    unsigned long long n_pass = 0;
+    const i64 ntiles = (p.nrows + SA_TILE - 1) / SA_TILE;
+    const int plo = (int)(p.pred[0].lo < INT32_MIN ? INT32_MIN : p.pred[0].lo);
+    const int phi = (int)(p.pred[0].hi > INT32_MAX ? INT32_MAX : p.pred[0].hi);
+    const bool pempty = p.pred[0].lo > p.pred[0].hi;
+    const void *kp = p.gs.part[0].col.p, *vp = p.gs.fac[0][0].col.p;
+    const i64 fc = p.gs.fc[0][0];
+    const int fs = p.gs.fs[0][0];
+    for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        i64 row = tile * SA_TILE + threadIdx.x * SA_VEC;
+        i64 rem = p.nrows - row;
+        int4 d = make_int4(0, 0, 0, 0);
+        if (HAS_PRED) d = ld_stream16((const int *)p.pred[0].col.p + row);
+        i64 k[4], v[4];
+        if (KEYW == 8) {
+            longlong2 a = ld_stream16_ll((const i64 *)kp + row), b = ld_stream16_ll((const i64 *)kp + row + 2);
+            k[0] = a.x; k[1] = a.y; k[2] = b.x; k[3] = b.y;
+        } else {
+            int4 a = ld_stream16((const int *)kp + row);
+            k[0] = a.x; k[1] = a.y; k[2] = a.z; k[3] = a.w;
+        }
+        if (VALW == 8) {
+            longlong2 a = ld_stream16_ll((const i64 *)vp + row), b = ld_stream16_ll((const i64 *)vp + row + 2);
+            v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+        } else {
+            int4 a = ld_stream16((const int *)vp + row);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        }
+        int dv[4] = {d.x, d.y, d.z, d.w};
+        // fold the 4 rows into runs of equal keys
+        i64 run_key = 0, run_sum = 0, run_cnt = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            bool ok = j < rem;
+            if (HAS_PRED) ok = ok && !pempty && dv[j] >= plo && dv[j] <= phi;
+            if (!ok) continue;
+            n_pass++;
+            i64 x = fc + fs * v[j];
+            if (run_cnt > 0 && k[j] == run_key) { run_sum += x; run_cnt++; continue; }
+            if (run_cnt > 0) gt_add(p.gt, run_key, 0, &run_sum, run_cnt);
+            run_key = k[j]; run_sum = x; run_cnt = 1;
+        }
+        if (run_cnt > 0) gt_add(p.gt, run_key, 0, &run_sum, run_cnt);
+    }
+    n_pass = (unsigned long long)warp_sum((i64)n_pass);
+    if ((threadIdx.x & 31) == 0 && n_pass) {
+        atomicAdd(&p.counters[0], n_pass);
+        atomicAdd(&p.counters[1], n_pass);
     }
 }
 
@@ -350,19 +502,44 @@ static __global__ void gt_compact_kernel(const GroupTable g, i64 *__restrict__ o
                                   i64 *__restrict__ out_acc /* [nacc+1][max_out] */, i64 max_out,
                                   unsigned long long *__restrict__ counter, int hav_plane, i64 hav_lo, i64 hav_hi)
 {
-    u64 cap = g.mask + 1;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (u64)gridDim.x * blockDim.x) {
-        i64 k = g.klo[i];
-        if (k == HT_EMPTY) continue;
-        if (hav_plane >= 0) {
-            i64 v = g.acc[(u64)hav_plane * cap + i];
-            if (v < hav_lo || v > hav_hi) { atomicAdd(counter + 1, 1ULL); continue; }
+    // one output-position atomic per BLOCK step (256 slots), not per surviving slot
+    __shared__ unsigned s_warp[8];
+    __shared__ unsigned long long s_base;
+    const u64 cap = g.mask + 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u64 nstep = (cap + blockDim.x - 1) / blockDim.x;
+    for (u64 step = blockIdx.x; step < nstep; step += gridDim.x) {
+        u64 i = step * blockDim.x + threadIdx.x;
+        const i64 *slot = g.slots + i * (u64)g.rw;
+        bool keep = false, dropped = false;
+        i64 k = HT_EMPTY;
+        if (i < cap) {
+            k = slot[0];
+            keep = k != HT_EMPTY;
+            if (keep && hav_plane >= 0) {
+                i64 v = (i64)((u64)slot[2 + hav_plane] - (u64)HT_EMPTY);
+                if (v < hav_lo || v > hav_hi) { keep = false; dropped = true; }
+            }
         }
-        unsigned long long o = atomicAdd(counter, 1ULL);
-        if ((i64)o >= max_out) continue;
-        out_klo[o] = k;
-        out_khi[o] = g.khi[i];
-        for (int a = 0; a <= g.nacc; a++) out_acc[(u64)a * (u64)max_out + o] = g.acc[(u64)a * cap + i];
+        unsigned m = __ballot_sync(0xffffffffu, keep), md = __ballot_sync(0xffffffffu, dropped);
+        if (lane == 0) s_warp[warp] = __popc(m) | (__popc(md) << 16);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned tot = 0, totd = 0;
+            for (int w = 0; w < 8; w++) { unsigned c = s_warp[w] & 0xffff; totd += s_warp[w] >> 16; s_warp[w] = tot; tot += c; }
+            s_base = tot ? atomicAdd(counter, (unsigned long long)tot) : 0;
+            if (totd) atomicAdd(counter + 1, (unsigned long long)totd);
+        }
+        __syncthreads();
+        if (keep) {
+            unsigned long long o = s_base + s_warp[warp] + __popc(m & ((1u << lane) - 1u));
+            if ((i64)o < max_out) {
+                out_klo[o] = k;
+                out_khi[o] = g.two_words ? slot[1] : 0;
+                for (int a = 0; a <= g.nacc; a++) out_acc[(u64)a * (u64)max_out + o] = (i64)((u64)slot[2 + a] - (u64)HT_EMPTY);
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -458,27 +635,9 @@ static __global__ void shuffle_scatter_kernel(const i64 *klo, const i64 *khi, co
 static __global__ void shuffle_merge_kernel(const GroupTable g, const i64 *rows, i64 n, int planes)
 {
     const int RW = 2 + planes;
-    u64 cap = g.mask + 1;
     for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (i64)gridDim.x * blockDim.x) {
         const i64 *row = rows + r * RW;
-        i64 klo = row[0], khi = row[1];
-        u64 i = mix64((u64)klo * 0x9E3779B97F4A7C15ULL ^ (u64)khi) & g.mask;
-        bool done = false;
-        for (u64 k = 0; k <= g.mask && k <= 4096; k++) {
-            i64 cur = g.klo[i];
-            if (cur == HT_EMPTY) cur = (i64)atomicCAS((unsigned long long *)&g.klo[i], (unsigned long long)HT_EMPTY, (unsigned long long)klo);
-            if (cur == HT_EMPTY || cur == klo) {
-                i64 h = g.khi[i];
-                if (h == HT_EMPTY) h = (i64)atomicCAS((unsigned long long *)&g.khi[i], (unsigned long long)HT_EMPTY, (unsigned long long)khi);
-                if (h == HT_EMPTY || h == khi) {
-                    for (int p = 0; p < planes; p++) atomicAdd((unsigned long long *)&g.acc[(u64)p * cap + i], (unsigned long long)row[2 + p]);
-                    done = true;
-                    break;
-                }
-            }
-            i = (i + 1) & g.mask;
-        }
-        if (!done) *g.overflow = 1;
+        gt_add(g, row[0], row[1], row + 2, row[2 + g.nacc]);
     }
 }
 
