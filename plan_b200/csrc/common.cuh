@@ -85,6 +85,7 @@ struct Column {
     bool stats_ok = false;
     i64 vmin = 0, vmax = 0;
     i64 adjacent_equal = 0;                           // rows whose value equals the next row's (clustering)
+    i64 adjacent_descents = 0;                        // rows whose value is >= the next row's; 0 => strictly increasing => unique
     uint32_t present[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // byte columns: which codes occur
 };
 

@@ -37,6 +37,8 @@ struct Stage {
     i64 capacity_rows = 0;
     i64 built_rows = 0;
     bool payload_needed = false;     // some column of this build side is read above the join
+    bool unique_key = false;         // build key is strictly increasing in row order (statistics) => unique
+    bool no_table = false;           // unique + payload-free + no probe of its own: the exact bitmap IS the build side
     i64 dup_keys = 0;                // duplicates seen while building (bitmap builds only)
     bool bitmap_only() const { return jt.bitmap && !payload_needed && dup_keys == 0; }
 };
@@ -95,6 +97,7 @@ struct JoinAggPipeline : Pipeline {
     TopkKey topk_key{};
     i64 topk_limit = -1;
     DevBuf d_hist, d_cand_klo, d_cand_khi, d_cand_acc;
+    PinBuf h_hist;
     i64 cand_cap = 0;
 
     // replace the compacted group list (d_out_*, n groups) by the candidates for the first k rows
@@ -105,26 +108,27 @@ struct JoinAggPipeline : Pipeline {
         if (k < 0 || n <= k) return PG_OK;
         if (k == 0) { *ngroups = 0; return PG_OK; }
         const int planes = gs.nacc + 1;
-        if (!d_hist.p) PG_TRY(d_hist.alloc(256 * 8));
+        constexpr int NB = 1 << TOPK_DIGIT_BITS;
+        if (!d_hist.p) { PG_TRY(d_hist.alloc(NB * 4)); PG_TRY(h_hist.alloc(NB * 4)); }
         int grid = (int)std::max<i64>(std::min<i64>((n + 255) / 256, (i64)ctx().prop.multiProcessorCount * 4), 1);
         u64 prefix = 0;
         i64 remaining = k;       // we look for the remaining-th smallest key among those matching the prefix
-        unsigned long long hist[256];
+        const unsigned *hist = h_hist.as<unsigned>();
         i64 n_equal = 0;
-        for (int pass = 0; pass < 8; pass++) {
-            PG_CUDA(cudaMemsetAsync(d_hist.p, 0, 256 * 8, st));
+        for (int pass = 0; pass < 64 / TOPK_DIGIT_BITS; pass++) {
+            PG_CUDA(cudaMemsetAsync(d_hist.p, 0, NB * 4, st));
             topk_hist_kernel<<<grid, 256, 0, st>>>(topk_key, d_out_klo.as<i64>(), d_out_khi.as<i64>(), d_out_acc.as<i64>(), out_cap, n,
-                                                   prefix, pass * 8, d_hist.as<unsigned long long>());
+                                                   prefix, pass * TOPK_DIGIT_BITS, d_hist.as<unsigned>());
             PG_CUDA(cudaGetLastError());
-            PG_CUDA(cudaMemcpyAsync(hist, d_hist.p, 256 * 8, cudaMemcpyDeviceToHost, st));
+            PG_CUDA(cudaMemcpyAsync(h_hist.p, d_hist.p, NB * 4, cudaMemcpyDeviceToHost, st));
             PG_CUDA(cudaStreamSynchronize(st));
             int d = 0;
-            for (; d < 256; d++) {
+            for (; d < NB; d++) {
                 if ((i64)hist[d] >= remaining) break;
                 remaining -= (i64)hist[d];
             }
-            if (d == 256) PG_FAIL(PG_ECUDA, "internal: top-k radix select ran off the histogram");
-            prefix = (prefix << 8) | (u64)d;
+            if (d == NB) PG_FAIL(PG_ECUDA, "internal: top-k radix select ran off the histogram");
+            prefix = (prefix << TOPK_DIGIT_BITS) | (u64)d;
             n_equal = (i64)hist[d];
             res->stats.kernel_launches += 1;
         }
@@ -253,6 +257,28 @@ struct JoinAggPipeline : Pipeline {
             pp.probe_bitmap_only = stages[(size_t)s.probe_stage]->bitmap_only() ? 1 : 0;
         }
         pp.counters = d_counters.as<unsigned long long>();
+        s.no_table = false;
+        if (s.unique_key && !s.payload_needed && !s.has_probe && !getenv("PG_JOIN_NO_BITMAP_BUILD")) {
+            // unique keys, nothing but existence is needed: one pass that sets key bits, no hash table at all
+            PG_TRY(prepare_table(s, 0, t->cols[(size_t)s.ins_key_col]));
+            if (s.jt.bitmap) {
+                pp.ins_key = typed(t, s.ins_key_col);
+                pp.ins = s.jt;
+                PG_CUDA(cudaMemsetAsync(d_counters.p, 0, 32, st));
+                PG_TRY(launch_pipe<SINK_BITMAP>(pp, t));
+                s.no_table = true;
+                s.dup_keys = 0;
+                res->stats.kernel_launches += 1;
+                if (idx < 4) {       // counters are read lazily with the next stage's; keep the API cheap
+                    unsigned long long c0[4];
+                    PG_TRY(read_counters(c0));
+                    s.built_rows = (i64)c0[1];
+                    res->stats.aux[2 + 2 * idx] = (i64)c0[0];
+                    res->stats.aux[3 + 2 * idx] = (i64)c0[1];
+                }
+                return PG_OK;
+            }
+        }
         // sizing pass: how many rows reach the sink
         PG_CUDA(cudaMemsetAsync(d_counters.p, 0, 32, st));
         PG_TRY(launch_pipe<SINK_COUNT>(pp, t));
@@ -682,6 +708,7 @@ static int add_build_stage(JoinAggPipeline *p, const Node &n0, int key_idx, int 
     if (!is_int_family(kc.type) || kc.has_nulls) PG_FAIL(PG_EUNSUPPORTED, "join key must be a non-null integer column");
     if (kc.vmin <= HT_EMPTY && kc.vmax >= HT_EMPTY) PG_FAIL(PG_EUNSUPPORTED, "join key range contains the empty-slot sentinel");
     s->ins_key_col = key.col;
+    s->unique_key = kc.stats_ok && kc.adjacent_descents == 0;
     p->stages.push_back(std::move(s));
     *stage_out = (int)p->stages.size() - 1;
     return PG_OK;

@@ -114,7 +114,7 @@ constexpr int PIPE_MAXPRED = 3;
 //   SINK_COUNT   count surviving (joined) rows            -> sizing pass
 //   SINK_INSERT  insert (key column, source row id) into a join table  -> build side
 //   SINK_GROUP   update the global group table            -> aggregate over the join
-enum { SINK_COUNT = 0, SINK_INSERT = 1, SINK_GROUP = 2 };
+enum { SINK_COUNT = 0, SINK_INSERT = 1, SINK_GROUP = 2, SINK_BITMAP = 3 };   // BITMAP: set the key bit only (unique, payload-free build side)
 
 constexpr int GT_MAXACC = 4;
 constexpr int GT_MAXKEYPARTS = 3;
@@ -257,6 +257,9 @@ pipeline_kernel(const PipeParams p)
             n_join++;
             if (SINK == SINK_INSERT) {
                 jt_insert(p.ins, load_typed(p.ins_key, row), (u64)row);
+            } else if (SINK == SINK_BITMAP) {
+                u64 off = (u64)(load_typed(p.ins_key, row) - p.ins.bm_min);
+                atomicOr(p.ins.bitmap + (off >> 5), 1u << (off & 31));
             } else if (SINK == SINK_GROUP) {
                 auto val = [&](const ValRef &r) { return load_typed(r.col, r.from_build ? (i64)build_row : row); };
                 i64 klo = val(p.gs.part[0]);
@@ -569,8 +572,11 @@ __device__ __forceinline__ u64 topk_u64(const TopkKey &k, const i64 *klo, const 
     return k.desc ? ~u : u;                     // output order = ascending u
 }
 
+// one radix-select pass over an 8-bit digit, histogram privatised in shared memory (a 16-bit digit
+// with global atomics was tried: 7x slower, the top digits of real keys collide in one bin)
+constexpr int TOPK_DIGIT_BITS = 8;
 static __global__ void topk_hist_kernel(TopkKey key, const i64 *klo, const i64 *khi, const i64 *acc, i64 stride, i64 n,
-                                        u64 prefix, int prefix_bits, unsigned long long *hist /* [256] */)
+                                        u64 prefix, int prefix_bits, unsigned *hist /* [256] */)
 {
     __shared__ unsigned s_h[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_h[i] = 0;
@@ -581,7 +587,7 @@ static __global__ void topk_hist_kernel(TopkKey key, const i64 *klo, const i64 *
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 256; i += blockDim.x)
-        if (s_h[i]) atomicAdd(&hist[i], (unsigned long long)s_h[i]);
+        if (s_h[i]) atomicAdd(&hist[i], s_h[i]);
 }
 
 // copy every group whose primary key is <= threshold to the candidate arrays

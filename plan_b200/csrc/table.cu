@@ -44,10 +44,17 @@ __global__ void stats_minmax_kernel(const T *__restrict__ v, i64 n, i64 *out_min
         i64 x = (i64)v[i];
         lo = x < lo ? x : lo;
         hi = x > hi ? x : hi;
-        if (i + 1 < n && (i64)v[i + 1] == x) adj++;     // the neighbour load hits the same line
+        if (i + 1 < n) {                                // the neighbour load hits the same line
+            i64 y = (i64)v[i + 1];
+            if (y == x) adj += 1;
+            if (y <= x) adj += 1ULL << 32;              // high half counts "not strictly increasing" steps
+        }
     }
     for (int o = 16; o > 0; o >>= 1) adj += __shfl_xor_sync(0xffffffffu, adj, o);
-    if ((threadIdx.x & 31) == 0 && adj) atomicAdd(out_adj, adj);
+    if ((threadIdx.x & 31) == 0 && adj) {
+        if (adj & 0xffffffffULL) atomicAdd(out_adj, adj & 0xffffffffULL);
+        if (adj >> 32) atomicAdd(out_adj + 1, adj >> 32);
+    }
     for (int o = 16; o > 0; o >>= 1) {
         i64 l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
         lo = l2 < lo ? l2 : lo;
@@ -99,8 +106,8 @@ static int compute_stats(pg_table *t)
     int *d_flag = nullptr;
     unsigned long long *d_adj = nullptr;
     size_t ncol = t->cols.size();
-    PG_CUDA(cudaMalloc(&d_adj, sizeof(unsigned long long) * ncol));
-    PG_CUDA(cudaMemsetAsync(d_adj, 0, sizeof(unsigned long long) * ncol, c.stream));
+    PG_CUDA(cudaMalloc(&d_adj, sizeof(unsigned long long) * 2 * ncol));
+    PG_CUDA(cudaMemsetAsync(d_adj, 0, sizeof(unsigned long long) * 2 * ncol, c.stream));
     PG_CUDA(cudaMalloc(&d_mm, sizeof(i64) * 2 * ncol));
     PG_CUDA(cudaMalloc(&d_present, sizeof(uint32_t) * 8 * ncol));
     PG_CUDA(cudaMalloc(&d_flag, sizeof(int) * ncol));
@@ -114,10 +121,10 @@ static int compute_stats(pg_table *t)
         Column &col = t->cols[i];
         switch (col.type) {
         case PG_T_INT32: case PG_T_DATE32:
-            stats_minmax_kernel<int32_t><<<grid, 256, 0, c.stream>>>((const int32_t *)col.d_data, t->nrows, d_mm + 2 * i, d_mm + 2 * i + 1, d_adj + i);
+            stats_minmax_kernel<int32_t><<<grid, 256, 0, c.stream>>>((const int32_t *)col.d_data, t->nrows, d_mm + 2 * i, d_mm + 2 * i + 1, d_adj + 2 * i);
             break;
         case PG_T_INT64: case PG_T_DECIMAL64:
-            stats_minmax_kernel<i64><<<grid, 256, 0, c.stream>>>((const i64 *)col.d_data, t->nrows, d_mm + 2 * i, d_mm + 2 * i + 1, d_adj + i);
+            stats_minmax_kernel<i64><<<grid, 256, 0, c.stream>>>((const i64 *)col.d_data, t->nrows, d_mm + 2 * i, d_mm + 2 * i + 1, d_adj + 2 * i);
             break;
         case PG_T_CHAR1: case PG_T_DICT8:
             stats_bytes_kernel<<<grid, 256, 0, c.stream>>>((const uint8_t *)col.d_data, t->nrows, d_present + 8 * i);
@@ -129,8 +136,8 @@ static int compute_stats(pg_table *t)
     PG_CUDA(cudaGetLastError());
     std::vector<uint32_t> h_present(8 * ncol);
     std::vector<int> h_flag(ncol);
-    std::vector<unsigned long long> h_adj(ncol);
-    PG_CUDA(cudaMemcpyAsync(h_adj.data(), d_adj, sizeof(unsigned long long) * ncol, cudaMemcpyDeviceToHost, c.stream));
+    std::vector<unsigned long long> h_adj(2 * ncol);
+    PG_CUDA(cudaMemcpyAsync(h_adj.data(), d_adj, sizeof(unsigned long long) * 2 * ncol, cudaMemcpyDeviceToHost, c.stream));
     PG_CUDA(cudaMemcpyAsync(h_mm.data(), d_mm, sizeof(i64) * 2 * ncol, cudaMemcpyDeviceToHost, c.stream));
     PG_CUDA(cudaMemcpyAsync(h_present.data(), d_present, sizeof(uint32_t) * 8 * ncol, cudaMemcpyDeviceToHost, c.stream));
     PG_CUDA(cudaMemcpyAsync(h_flag.data(), d_flag, sizeof(int) * ncol, cudaMemcpyDeviceToHost, c.stream));
@@ -141,7 +148,8 @@ static int compute_stats(pg_table *t)
         col.vmax = t->nrows > 0 ? h_mm[2 * i + 1] : 0;
         memcpy(col.present, &h_present[8 * i], sizeof col.present);
         col.has_nulls = col.d_valid != nullptr && h_flag[i] != 0;
-        col.adjacent_equal = (i64)h_adj[i];
+        col.adjacent_equal = (i64)h_adj[2 * i];
+        col.adjacent_descents = (i64)h_adj[2 * i + 1];
         col.stats_ok = true;
     }
     cudaFree(d_adj);
