@@ -238,6 +238,8 @@ struct LowcardPipeline : Pipeline {
 
     size_t rank_bytes() const { return (size_t)G * LC_K * 16 + (size_t)LC_MAXG * 8; }
 
+    static constexpr int ORD_CHUNK = 16;   // tiles composed per summary on the device (tail pass)
+    bool part_on_host = false;             // run() already copied the per-CTA partials to h_part
     // scratch of the ordered-rounding path, allocated once (no cudaMalloc while executing)
     DevBuf d_ord, d_contrib;
     PinBuf h_ord, h_part, h_tile, h_contrib;
@@ -255,10 +257,11 @@ struct LowcardPipeline : Pipeline {
         return PG_OK;
     }
 
-    // per-tile summaries of tiles [tb, te) for (group, slot) -> h_ord (pinned)
-    int ord_summaries(int g, int s, i64 tb, i64 te, const OrdSummary **out, i64 *n)
+    // summaries of tiles [tb, te) for (group, slot), `chunk` consecutive tiles composed per summary
+    // (chunk = 1 where the crossing tile is searched) -> h_ord (pinned)
+    int ord_summaries(int g, int s, i64 tb, i64 te, int chunk, const OrdSummary **out, i64 *n)
     {
-        *n = std::max<i64>(te - tb, 0);
+        *n = te > tb ? (te - tb + chunk - 1) / chunk : 0;
         *out = h_ord.as<OrdSummary>();
         if (te <= tb) return PG_OK;
         cudaStream_t st = ctx().stream;
@@ -268,11 +271,12 @@ struct LowcardPipeline : Pipeline {
         op.slot = s;
         op.tile_begin = tb;
         op.tile_end = te;
-        int gr = (int)std::min<i64>(te - tb, (i64)ctx().prop.multiProcessorCount * 8);
+        op.chunk = chunk;
+        int gr = (int)std::min<i64>(*n, (i64)ctx().prop.multiProcessorCount * 8);
         if (has_key1) ord_tile_kernel<true><<<gr, SA_THREADS, 0, st>>>(op, d_ord.as<OrdSummary>());
         else ord_tile_kernel<false><<<gr, SA_THREADS, 0, st>>>(op, d_ord.as<OrdSummary>());
         PG_CUDA(cudaGetLastError());
-        PG_CUDA(cudaMemcpyAsync(h_ord.p, d_ord.p, sizeof(OrdSummary) * (size_t)(te - tb), cudaMemcpyDeviceToHost, st));
+        PG_CUDA(cudaMemcpyAsync(h_ord.p, d_ord.p, sizeof(OrdSummary) * (size_t)*n, cudaMemcpyDeviceToHost, st));
         PG_CUDA(cudaStreamSynchronize(st));
         return PG_OK;
     }
@@ -303,8 +307,10 @@ struct LowcardPipeline : Pipeline {
         if (myrank() == rstar) {
             // a. which CTA range crosses
             const i64 *part = h_part.as<i64>();
-            PG_CUDA(cudaMemcpyAsync(h_part.p, d_part.p, sizeof(i64) * (size_t)grid * (size_t)G * LC_K, cudaMemcpyDeviceToHost, st));
-            PG_CUDA(cudaStreamSynchronize(st));
+            if (!part_on_host) {
+                PG_CUDA(cudaMemcpyAsync(h_part.p, d_part.p, sizeof(i64) * (size_t)grid * (size_t)G * LC_K, cudaMemcpyDeviceToHost, st));
+                PG_CUDA(cudaStreamSynchronize(st));
+            }
             i64 per = (ntiles + grid - 1) / grid;
             i128 P = P0;
             int cstar = 0;
@@ -316,7 +322,7 @@ struct LowcardPipeline : Pipeline {
             if (cstar == grid) PG_FAIL(PG_ECUDA, "internal: crossing CTA not found");
             // b. which tile of that CTA crosses
             i64 tb = (i64)cstar * per, te = std::min<i64>(ntiles, tb + per);
-            PG_TRY(ord_summaries(g, s, tb, te, &sums, &nsums));
+            PG_TRY(ord_summaries(g, s, tb, te, 1, &sums, &nsums));
             i64 tstar = tb;
             for (; tstar < te; tstar++) {
                 i128 v = sums[tstar - tb].sum_x;
@@ -360,13 +366,13 @@ struct LowcardPipeline : Pipeline {
             }
             if (!rounded) PG_FAIL(PG_ECUDA, "internal: crossing row not found");
             // d. the rest of this rank's rows, tile summaries composed in order
-            PG_TRY(ord_summaries(g, s, tstar + 1, ntiles, &sums, &nsums));
+            PG_TRY(ord_summaries(g, s, tstar + 1, ntiles, ORD_CHUNK, &sums, &nsums));
             for (i64 i = 0; i < nsums; i++) S += (u128)sums[i].sum_q + ((S & 1) ? sums[i].c1 : sums[i].c0);
             mine.kind = 1;
             mine.s_lo = (u64)S;
             mine.s_hi = (u64)(S >> 64);
         } else if (myrank() > rstar) {
-            PG_TRY(ord_summaries(g, s, 0, ntiles, &sums, &nsums));
+            PG_TRY(ord_summaries(g, s, 0, ntiles, ORD_CHUNK, &sums, &nsums));
             i128 q = 0;
             u64 cc[2] = {0, 0}, pp[2] = {0, 1};
             for (i64 i = 0; i < nsums; i++) {
@@ -444,6 +450,12 @@ struct LowcardPipeline : Pipeline {
             src = d_gather.p;
         }
         PG_CUDA(cudaMemcpyAsync(h_final.p, src, rank_bytes() * (size_t)nranks(), cudaMemcpyDeviceToHost, st));
+        part_on_host = false;
+        if (prm.contig) {      // the ordered partials ride along: the rounding path then needs no extra round trip
+            PG_TRY(ensure_ord_buffers());
+            PG_CUDA(cudaMemcpyAsync(h_part.p, d_part.p, sizeof(i64) * (size_t)grid * (size_t)G * LC_K, cudaMemcpyDeviceToHost, st));
+            part_on_host = true;
+        }
         PG_CUDA(cudaEventRecord(ev_all.b, st));
         PG_CUDA(cudaStreamSynchronize(st));
         tr.mark("kernels+gather+d2h");

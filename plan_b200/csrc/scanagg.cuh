@@ -272,6 +272,7 @@ struct OrdParams {
     int group;       // dense group id to follow
     int slot;        // accumulator slot whose value sequence is followed (2..5)
     i64 tile_begin, tile_end;
+    int chunk;       // consecutive tiles composed (in order) into ONE output summary by a CTA
 };
 
 struct OrdSummary {        // one per tile
@@ -307,66 +308,72 @@ __device__ __forceinline__ OrdState ord_compose(const OrdState &l, const OrdStat
 
 template <bool HAS_KEY1>
 __global__ void __launch_bounds__(SA_THREADS)
-ord_tile_kernel(const OrdParams op, OrdSummary *__restrict__ out /* [tile_end - tile_begin] */)
+ord_tile_kernel(const OrdParams op, OrdSummary *__restrict__ out /* [ceil((tile_end - tile_begin) / chunk)] */)
 {
     const LowcardParams &p = op.base;
     __shared__ uint8_t s_lut[2][256];
     __shared__ OrdState s_w[SA_THREADS / 32];
     for (int i = threadIdx.x; i < 512; i += SA_THREADS) s_lut[i >> 8][i & 255] = p.luts[i];
     __syncthreads();
-    for (i64 tile = op.tile_begin + blockIdx.x; tile < op.tile_end; tile += gridDim.x) {
-        i64 row = tile * SA_TILE + threadIdx.x * SA_VEC;
-        i64 rem = p.nrows - row;
-        int4 d = ld_stream16(p.pred + row);
-        unsigned k0 = ld_stream4(p.key0 + row), k1 = HAS_KEY1 ? ld_stream4(p.key1 + row) : 0;
-        longlong2 a0 = ld_stream16_ll(p.A + row), a1 = ld_stream16_ll(p.A + row + 2);
-        longlong2 b0 = ld_stream16_ll(p.B + row), b1 = ld_stream16_ll(p.B + row + 2);
-        longlong2 c0 = ld_stream16_ll(p.C + row), c1 = ld_stream16_ll(p.C + row + 2);
-        int dv[4] = {d.x, d.y, d.z, d.w};
-        i64 av[4] = {a0.x, a0.y, a1.x, a1.y}, bv[4] = {b0.x, b0.y, b1.x, b1.y}, cv[4] = {c0.x, c0.y, c1.x, c1.y};
-        OrdState st = {0, 0, 0, 0, 0, 1};   // identity: parity preserved, no carries
+    const i64 nchunks = (op.tile_end - op.tile_begin + op.chunk - 1) / op.chunk;
+    for (i64 ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+        OrdState run = {0, 0, 0, 0, 0, 1};      // thread 0: ordered composition of the chunk's tiles
+        const i64 t0 = op.tile_begin + ch * op.chunk, t1 = t0 + op.chunk < op.tile_end ? t0 + op.chunk : op.tile_end;
+        for (i64 tile = t0; tile < t1; tile++) {
+            i64 row = tile * SA_TILE + threadIdx.x * SA_VEC;
+            i64 rem = p.nrows - row;
+            int4 d = ld_stream16(p.pred + row);
+            unsigned k0 = ld_stream4(p.key0 + row), k1 = HAS_KEY1 ? ld_stream4(p.key1 + row) : 0;
+            longlong2 a0 = ld_stream16_ll(p.A + row), a1 = ld_stream16_ll(p.A + row + 2);
+            longlong2 b0 = ld_stream16_ll(p.B + row), b1 = ld_stream16_ll(p.B + row + 2);
+            longlong2 c0 = ld_stream16_ll(p.C + row), c1 = ld_stream16_ll(p.C + row + 2);
+            int dv[4] = {d.x, d.y, d.z, d.w};
+            i64 av[4] = {a0.x, a0.y, a1.x, a1.y}, bv[4] = {b0.x, b0.y, b1.x, b1.y}, cv[4] = {c0.x, c0.y, c1.x, c1.y};
+            OrdState st = {0, 0, 0, 0, 0, 1};   // identity: parity preserved, no carries
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            bool ok = j < rem && dv[j] >= p.lo && dv[j] <= p.hi;
-            int g = s_lut[0][(k0 >> (8 * j)) & 255];
-            if (HAS_KEY1) g = g * p.n1 + s_lut[1][(k1 >> (8 * j)) & 255];
-            if (ok && g == op.group) {
-                i64 x = ord_value(p, op.slot, av[j], bv[j], cv[j]);
-                i64 q = x / 10;
-                unsigned dgt = (unsigned)(x - q * 10), qb = (unsigned)(q & 1);
-                OrdState r;
-                r.sq = q;
-                r.sx = x;
-                unsigned t0 = qb, t1 = qb ^ 1u;     // parity of S + q when entering even / odd
-                r.c0 = (dgt > 5u) | ((dgt == 5u) & t0);
-                r.c1 = (dgt > 5u) | ((dgt == 5u) & t1);
-                r.p0 = t0 ^ r.c0;
-                r.p1 = t1 ^ r.c1;
-                st = ord_compose(st, r);
+            for (int j = 0; j < 4; j++) {
+                bool ok = j < rem && dv[j] >= p.lo && dv[j] <= p.hi;
+                int g = s_lut[0][(k0 >> (8 * j)) & 255];
+                if (HAS_KEY1) g = g * p.n1 + s_lut[1][(k1 >> (8 * j)) & 255];
+                if (ok && g == op.group) {
+                    i64 x = ord_value(p, op.slot, av[j], bv[j], cv[j]);
+                    i64 q = x / 10;
+                    unsigned dgt = (unsigned)(x - q * 10), qb = (unsigned)(q & 1);
+                    OrdState r;
+                    r.sq = q;
+                    r.sx = x;
+                    unsigned t0b = qb, t1b = qb ^ 1u;     // parity of S + q when entering even / odd
+                    r.c0 = (dgt > 5u) | ((dgt == 5u) & t0b);
+                    r.c1 = (dgt > 5u) | ((dgt == 5u) & t1b);
+                    r.p0 = t0b ^ r.c0;
+                    r.p1 = t1b ^ r.c1;
+                    st = ord_compose(st, r);
+                }
             }
-        }
-        // ordered composition across the warp, then across the 8 warps
+            // ordered composition across the warp, then across the 8 warps
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            OrdState r;
-            r.sq = __shfl_down_sync(0xffffffffu, st.sq, o);
-            r.sx = __shfl_down_sync(0xffffffffu, st.sx, o);
-            r.c0 = __shfl_down_sync(0xffffffffu, st.c0, o);
-            r.c1 = __shfl_down_sync(0xffffffffu, st.c1, o);
-            r.p0 = __shfl_down_sync(0xffffffffu, st.p0, o);
-            r.p1 = __shfl_down_sync(0xffffffffu, st.p1, o);
-            if ((threadIdx.x & 31) + o < 32) st = ord_compose(st, r);
+            for (int o = 1; o < 32; o <<= 1) {
+                OrdState r;
+                r.sq = __shfl_down_sync(0xffffffffu, st.sq, o);
+                r.sx = __shfl_down_sync(0xffffffffu, st.sx, o);
+                r.c0 = __shfl_down_sync(0xffffffffu, st.c0, o);
+                r.c1 = __shfl_down_sync(0xffffffffu, st.c1, o);
+                r.p0 = __shfl_down_sync(0xffffffffu, st.p0, o);
+                r.p1 = __shfl_down_sync(0xffffffffu, st.p1, o);
+                if ((threadIdx.x & 31) + o < 32) st = ord_compose(st, r);
+            }
+            if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = st;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                for (int w = 0; w < SA_THREADS / 32; w++) run = ord_compose(run, s_w[w]);
+            }
+            __syncthreads();
         }
-        if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = st;
-        __syncthreads();
         if (threadIdx.x == 0) {
-            OrdState t = s_w[0];
-            for (int w = 1; w < SA_THREADS / 32; w++) t = ord_compose(t, s_w[w]);
             OrdSummary o;
-            o.sum_q = t.sq; o.sum_x = t.sx; o.c0 = t.c0; o.c1 = t.c1; o.p0 = t.p0; o.p1 = t.p1;
-            out[tile - op.tile_begin] = o;
+            o.sum_q = run.sq; o.sum_x = run.sx; o.c0 = run.c0; o.c1 = run.c1; o.p0 = run.p0; o.p1 = run.p1;
+            out[ch] = o;
         }
-        __syncthreads();
     }
 }
 
