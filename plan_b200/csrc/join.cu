@@ -28,6 +28,8 @@ struct Stage {
     int src_slot = -1;
     std::vector<Range> ranges;
     bool has_probe = false;
+    int probe_mode = 0;              // 0 INNER, 1 SEMI, 2 ANTI -- how this stage's own probe filters its source rows
+    bool existence_only = false;     // the join consuming this build side is SEMI/ANTI: only key existence matters
     int probe_key_col = -1;          // on the source table
     int probe_stage = -1;            // which earlier stage built the probed table
     int ins_key_col = -1;            // SINK_INSERT: key column on the source table
@@ -40,7 +42,7 @@ struct Stage {
     bool unique_key = false;         // build key is strictly increasing in row order (statistics) => unique
     bool no_table = false;           // unique + payload-free + no probe of its own: the exact bitmap IS the build side
     i64 dup_keys = 0;                // duplicates seen while building (bitmap builds only)
-    bool bitmap_only() const { return jt.bitmap && !payload_needed && dup_keys == 0; }
+    bool bitmap_only() const { return jt.bitmap && !payload_needed && (dup_keys == 0 || existence_only); }
 };
 
 static u64 next_pow2(u64 x)
@@ -75,6 +77,7 @@ struct JoinAggPipeline : Pipeline {
     std::vector<int> agg_scale;
     std::vector<int> agg_plane;                  // accumulator plane of each aggregate (count(*) = the row-count plane)
     bool no_join = false;                        // Agg <- Scan on high-cardinality keys: no probe at all
+    int top_probe_mode = 0;                      // INNER / SEMI / ANTI of the top join
     int hav_plane = -1;                          // HAVING <aggregate> in [hav_lo, hav_hi]
     i64 hav_lo = INT64_MIN, hav_hi = INT64_MAX;
     i64 group_hint = 0;                          // expected number of groups (no-join case)
@@ -255,10 +258,11 @@ struct JoinAggPipeline : Pipeline {
             pp.probe_key = typed(t, s.probe_key_col);
             pp.probe = stages[(size_t)s.probe_stage]->jt;
             pp.probe_bitmap_only = stages[(size_t)s.probe_stage]->bitmap_only() ? 1 : 0;
+            pp.probe_mode = s.probe_mode;
         }
         pp.counters = d_counters.as<unsigned long long>();
         s.no_table = false;
-        if (s.unique_key && !s.payload_needed && !s.has_probe && !getenv("PG_JOIN_NO_BITMAP_BUILD")) {
+        if ((s.existence_only || (s.unique_key && !s.has_probe)) && !s.payload_needed && !getenv("PG_JOIN_NO_BITMAP_BUILD")) {
             // unique keys, nothing but existence is needed: one pass that sets key bits, no hash table at all
             PG_TRY(prepare_table(s, 0, t->cols[(size_t)s.ins_key_col]));
             if (s.jt.bitmap) {
@@ -401,6 +405,7 @@ struct JoinAggPipeline : Pipeline {
             pp.probe_key = typed(t, probe_key_col);
             pp.probe = last.jt;
             pp.probe_bitmap_only = last.bitmap_only() ? 1 : 0;
+            pp.probe_mode = top_probe_mode;
         }
         pp.counters = d_counters.as<unsigned long long>();
         pp.gs = gs;
@@ -675,8 +680,10 @@ static int add_build_stage(JoinAggPipeline *p, const Node &n0, int key_idx, int 
         if (!lower_filters(cx, fl, s->ranges)) PG_FAIL(PG_EUNSUPPORTED, "build-side filter not off-loadable: %s", cx.why.c_str());
     } else if (n->op == PG_OP_JOIN) {
         if (!extra.empty()) PG_FAIL(PG_EUNSUPPORTED, "filter above a build-side join");
-        if (n->jointype != PG_JOIN_INNER) PG_FAIL(PG_EUNSUPPORTED, "only INNER joins are off-loaded");
+        if (n->jointype != PG_JOIN_INNER && n->jointype != PG_JOIN_SEMI && n->jointype != PG_JOIN_ANTI)
+            PG_FAIL(PG_EUNSUPPORTED, "only INNER / SEMI / ANTI joins are off-loaded");
         if (n->conds.size() != 1) PG_FAIL(PG_EUNSUPPORTED, "multi-column join keys are not off-loaded");
+        for (auto &o : n->outs) if (n->jointype != PG_JOIN_INNER && o.first != 0) PG_FAIL(PG_EUNSUPPORTED, "SEMI/ANTI join output refers to the build side");
         const Node &probe = n->children[0];
         const Node *src = &probe;
         std::vector<Expr> pf;
@@ -697,6 +704,8 @@ static int add_build_stage(JoinAggPipeline *p, const Node &n0, int key_idx, int 
         int inner = -1;
         PG_TRY(add_build_stage(p, n->children[1], be->idx, &inner));
         s->has_probe = true;
+        s->probe_mode = n->jointype == PG_JOIN_SEMI ? 1 : n->jointype == PG_JOIN_ANTI ? 2 : 0;
+        if (s->probe_mode != 0) p->stages[(size_t)inner]->existence_only = true;
         s->probe_key_col = pk.col;
         s->probe_stage = inner;
         if (key.slot != s->src_slot) PG_FAIL(PG_EUNSUPPORTED, "join key of the outer join comes from the inner build side");
@@ -722,8 +731,11 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &join, std::uniqu
     p->plan = plan;
     p->no_join = join.op == PG_OP_SCAN;
     if (!p->no_join) {
-        if (join.jointype != PG_JOIN_INNER) PG_FAIL(PG_EUNSUPPORTED, "only INNER joins are off-loaded");
+        if (join.jointype != PG_JOIN_INNER && join.jointype != PG_JOIN_SEMI && join.jointype != PG_JOIN_ANTI)
+            PG_FAIL(PG_EUNSUPPORTED, "only INNER / SEMI / ANTI joins are off-loaded");
         if (join.conds.size() != 1) PG_FAIL(PG_EUNSUPPORTED, "multi-column join keys are not off-loaded");
+        p->top_probe_mode = join.jointype == PG_JOIN_SEMI ? 1 : join.jointype == PG_JOIN_ANTI ? 2 : 0;
+        for (auto &o : join.outs) if (p->top_probe_mode != 0 && o.first != 0) PG_FAIL(PG_EUNSUPPORTED, "SEMI/ANTI join output refers to the build side");
     }
     if (aggn.having.size() > 1) PG_FAIL(PG_EUNSUPPORTED, "HAVING with more than one conjunct is not off-loaded");
     // probe side: filtered scan
@@ -752,6 +764,7 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &join, std::uniqu
         if (!is_int_family(st->cols[(size_t)pk.col].type) || st->cols[(size_t)pk.col].has_nulls) PG_FAIL(PG_EUNSUPPORTED, "probe key must be a non-null integer column");
         p->probe_key_col = pk.col;
         PG_TRY(add_build_stage(p.get(), join.children[1], be->idx, &top_stage));
+        if (p->top_probe_mode != 0) p->stages[(size_t)top_stage]->existence_only = true;
         build_slot = p->stages[(size_t)top_stage]->src_slot;
         bt = p->tab(build_slot);
     }

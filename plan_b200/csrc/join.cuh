@@ -172,7 +172,9 @@ struct PipeParams {
     int npred;
     SrcPred pred[PIPE_MAXPRED];
     int has_probe;
-    int probe_bitmap_only;   // build keys are unique and no build column is needed: the exact bitmap IS the join
+    int probe_mode;          // 0 INNER: every match reaches the sink; 1 SEMI: the row once if any match;
+                             // 2 ANTI: the row once if no match (join_scan.go:90-165 NextSemiOrAntiJoin)
+    int probe_bitmap_only;   // the exact key bitmap decides alone: unique payload-free INNER build side, or SEMI/ANTI
     TypedCol probe_key;
     JoinTable probe;
     // SINK_INSERT
@@ -277,9 +279,16 @@ pipeline_kernel(const PipeParams p)
         };
         if (p.has_probe) {
             i64 key = load_typed(p.probe_key, row);
-            if (p.probe.bitmap && !bitmap_test(p.probe, key)) continue;
-            if (p.probe_bitmap_only) sink(0);
-            else jt_probe(p.probe, key, sink);
+            if (p.probe_mode == 0) {
+                if (p.probe.bitmap && !bitmap_test(p.probe, key)) continue;
+                if (p.probe_bitmap_only) sink(0);
+                else jt_probe(p.probe, key, sink);
+            } else {
+                bool found;
+                if (p.probe.bitmap) found = bitmap_test(p.probe, key);       // exact existence
+                else { found = false; jt_probe(p.probe, key, [&](u64) { found = true; }); }
+                if (found == (p.probe_mode == 1)) sink(0);
+            }
         } else {
             sink(0);
         }
@@ -408,6 +417,9 @@ fast_pipeline_kernel(const PipeParams p)
         n_join++;
         if (SINK == SINK_INSERT) {
             jt_insert(p.ins, load_typed(p.ins_key, row), (u64)row);
+        } else if (SINK == SINK_BITMAP) {
+            u64 off = (u64)(load_typed(p.ins_key, row) - p.ins.bm_min);
+            atomicOr(p.ins.bitmap + (off >> 5), 1u << (off & 31));
         } else if (SINK == SINK_GROUP) {
             auto val = [&](const ValRef &r) { return load_typed(r.col, r.from_build ? (i64)build_row : row); };
             i64 klo = val(p.gs.part[0]);
@@ -466,7 +478,7 @@ fast_pipeline_kernel(const PipeParams p)
                 bool ok = j < rem;
                 if (HAS_PRED) ok = ok && !pempty && dv[j] >= plo && dv[j] <= phi;
                 n_pass += ok ? 1 : 0;
-                hit[u][j] = ok && bitmap_test(p.probe, k[u][j]);
+                hit[u][j] = ok && (bitmap_test(p.probe, k[u][j]) != (p.probe_mode == 2));   // ANTI keeps the misses
             }
         }
 #pragma unroll
@@ -484,7 +496,7 @@ fast_pipeline_kernel(const PipeParams p)
             __syncwarp();
             for (int i = lane; i < nq; i += 32) {
                 i64 r = s_queue[warp][i];
-                if (p.probe_bitmap_only) sink(r, 0);
+                if (p.probe_bitmap_only || p.probe_mode != 0) sink(r, 0);
                 else jt_probe(p.probe, load_typed(p.probe_key, r), [&](u64 pay) { sink(r, pay); });
             }
             __syncwarp();

@@ -17,7 +17,7 @@ import numpy as np
 
 from . import _lib as L
 from . import chunk as K
-from .compute import (JOIN_INNER, POT_Agg, POT_Join, POT_Limit, POT_Order, POT_Scan, AggOpInfo, DeviceTable, JoinOpInfo,
+from .compute import (JOIN_ANTI, JOIN_SEMI, JOIN_INNER, POT_Agg, POT_Join, POT_Limit, POT_Order, POT_Scan, AggOpInfo, DeviceTable, JoinOpInfo,
                       LimitOpInfo, OrderOpInfo, PhysicalOperator, ScanOpInfo, cast, col, const, func)
 
 SEGMENTS = ["AUTOMOBILE", "BUILDING", "FURNITURE", "HOUSEHOLD", "MACHINERY"]
@@ -216,6 +216,31 @@ def groupby_plan(key="l_orderkey", value="l_quantity", having_gt=None, ship_le=N
     order = PhysicalOperator(POT_Order, Outputs=outs, Children=[agg],
                              Info=OrderOpInfo([(col(0, 1, sum_t), True), (col(0, 0, kt), False)]))
     return PhysicalOperator(POT_Limit, Outputs=outs, Children=[order], Info=LimitOpInfo(topk))
+
+
+def semi_plan(anti=False, odate_lt=None, ship_gt=None, schema=FULL):
+    """SEMI / ANTI hash join under an aggregate (the `IN (subquery)` / `NOT IN` shape of Q18 / Q4 / Q21/Q22):
+        select o_custkey, sum(o_totalprice), count(*) from orders
+        where o_orderdate < d and o_orderkey [NOT] IN (select l_orderkey from lineitem where l_shipdate > s)
+        group by o_custkey
+    The subquery becomes the build side (Children[1]) of a SEMI / ANTI join (join_scan.go:90-165)."""
+    S = schema
+    odate_lt = days(1995, 3, 29) if odate_lt is None else odate_lt
+    ship_gt = days(1995, 3, 29) if ship_gt is None else ship_gt
+    B = K.LType(K.LTID_BOOLEAN)
+    orders = PhysicalOperator(POT_Scan, Info=ScanOpInfo("orders"),
+                              Filters=[func("<", B, S.col("orders", "o_orderdate"), const(odate_lt, K.DateType()))])
+    line = PhysicalOperator(POT_Scan, Info=ScanOpInfo("lineitem"),
+                            Filters=[func(">", B, S.col("lineitem", "l_shipdate"), const(ship_gt, K.DateType()))])
+    OI = S.idx["orders"]
+    j = PhysicalOperator(
+        POT_Join, Children=[orders, line],
+        Outputs=[col(0, OI["o_custkey"], K.IntegerType()), col(0, OI["o_totalprice"], DEC15_2)],
+        Info=JoinOpInfo(JOIN_ANTI if anti else JOIN_SEMI,
+                        [func("=", B, S.col("orders", "o_orderkey", 0), S.col("lineitem", "l_orderkey", 1))]))
+    aggs = [func("sum", K.DecimalType(38, 2), col(0, 1, DEC15_2)), func("count", K.HugeintType(), col(0, 0, K.IntegerType()))]
+    outs = [col(0, 0, K.IntegerType()), col(1, 0, K.DecimalType(38, 2)), col(1, 1, K.HugeintType())]
+    return PhysicalOperator(POT_Agg, Outputs=outs, Children=[j], Info=AggOpInfo(aggs, [col(0, 0, K.IntegerType())]))
 
 
 def q3_topk_plan(limit=10, **kw):

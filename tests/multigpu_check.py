@@ -51,6 +51,9 @@ def main():
     st = J.check_groupby(O, tables, line, key="l_partkey", value="l_quantity")
     assert st.aux[7] > 0, "the shuffle path did not run"
     J.check_groupby(O, tables, line, key="l_suppkey", value="l_extendedprice", ship_le=8035 + 1263)
+    # SEMI / ANTI join of co-partitioned shards; its groups (o_custkey) collide across ranks -> shuffle
+    J.check_semi(O, tables, host, anti=False)
+    J.check_semi(O, tables, host, anti=True)
     os.environ["PG_FORCE_SHUFFLE"] = "1"          # the general path must also be right when it is not needed
     J.check_groupby(O, tables, line, key="l_orderkey", value="l_quantity", having_gt=200)
     J.check_q3(O, tables, host, check_counts=False)
