@@ -74,7 +74,8 @@ class Q3Result(C.Structure):
 
 class StatsGroup(C.Structure):
     _fields_ = [("rf", C.c_uint8), ("min_ext", Dec), ("max_ext", Dec), ("max_disc", Dec), ("sum_tax", Dec),
-                ("avg_tax", Dec), ("sum_taxed", Dec), ("count", C.c_uint64), ("first_row", C.c_int64)]
+                ("avg_tax", Dec), ("sum_taxed", Dec), ("count", C.c_uint64), ("first_row", C.c_int64),
+                ("n_ext", C.c_uint64), ("n_tax", C.c_uint64), ("n_taxed", C.c_uint64)]
 
 
 class StatsResult(C.Structure):
@@ -112,7 +113,7 @@ def lib():
                              [C.c_int64] + [C.c_void_p] * 4 + [C.c_int32] +
                              [C.c_void_p, C.c_int64, C.POINTER(Q3Result)])
         L.orc_stats.restype = None
-        L.orc_stats.argtypes = [C.c_int64] + [C.c_void_p] * 8 + [C.c_int32] * 6 + [C.c_int64, C.POINTER(StatsResult)]
+        L.orc_stats.argtypes = [C.c_int64] + [C.c_void_p] * 8 + [C.c_int32] * 6 + [C.c_int64] + [C.c_void_p] * 3 + [C.POINTER(StatsResult)]
         assert L.orc_sizeof_stats_result() == C.sizeof(StatsResult)
         L.orc_format_decimal.restype = C.c_int
         L.orc_format_decimal.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]
@@ -244,16 +245,24 @@ def q3(cust, orders, line, segment="HOUSEHOLD", odate_lt=days(1995, 3, 29), ship
     return {"groups": groups, "stats": stats}
 
 
-def stats(line, d0, d1, d2, d3, q0, q1, disc_gt_cents):
-    """The wider 'stats' shape (min/max/sum/avg/count, 7 comparisons, 1 key) -- see refexec.c orc_stats."""
+def stats(line, d0, d1, d2, d3, q0, q1, disc_gt_cents, valid=None):
+    """The wider 'stats' shape (min/max/sum/avg/count, 7 comparisons, 1 key) -- see refexec.c orc_stats.
+    valid: optional {column: bool array} for l_quantity / l_extendedprice / l_tax (False = NULL); aggregate
+    results whose inputs were all NULL come back as None."""
     r = StatsResult()
+    valid = valid or {}
+    vb = {k: np.ascontiguousarray(v, dtype=np.uint8) for k, v in valid.items()}
     lib().orc_stats(len(line["l_shipdate"]), _p(line["l_shipdate"]), _p(line["l_commitdate"]), _p(line["l_receiptdate"]),
                     _p(line["l_quantity"]), _p(line["l_extendedprice"]), _p(line["l_discount"]), _p(line["l_tax"]),
-                    _p(line["l_returnflag"]), d0, d1, d2, d3, q0, q1, disc_gt_cents, C.byref(r))
+                    _p(line["l_returnflag"]), d0, d1, d2, d3, q0, q1, disc_gt_cents,
+                    _p(vb.get("l_quantity")), _p(vb.get("l_extendedprice")), _p(vb.get("l_tax")), C.byref(r))
     assert r.error == 0, r.error
-    groups = [{"l_returnflag": chr(g.rf), "min_ext": g.min_ext.tuple(), "max_ext": g.max_ext.tuple(),
-               "max_disc": g.max_disc.tuple(), "sum_tax": g.sum_tax.tuple(), "avg_tax": g.avg_tax.tuple(),
-               "sum_taxed": g.sum_taxed.tuple(), "count": int(g.count), "first_row": int(g.first_row)} for g in r.g[:r.ngroups]]
+    groups = [{"l_returnflag": chr(g.rf),
+               "min_ext": g.min_ext.tuple() if g.n_ext else None, "max_ext": g.max_ext.tuple() if g.n_ext else None,
+               "max_disc": g.max_disc.tuple(), "sum_tax": g.sum_tax.tuple() if g.n_tax else None,
+               "avg_tax": g.avg_tax.tuple() if g.n_tax else None,
+               "sum_taxed": g.sum_taxed.tuple() if g.n_taxed else None,
+               "count": int(g.count), "first_row": int(g.first_row)} for g in r.g[:r.ngroups]]
     return {"rows_selected": int(r.rows_selected), "groups": groups}
 
 

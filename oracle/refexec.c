@@ -534,6 +534,9 @@ typedef struct {
     dec_t min_ext, max_ext, max_disc, sum_tax, avg_tax, sum_taxed;
     uint64_t count;
     int64_t first_row;
+    /* NULL handling: aggregates ignore NULL inputs (IgnoreNull); no valid input at all => NULL result
+     * (Sum/Avg/MinMax Finalize, function_aggr.go:815-1032) */
+    uint64_t n_ext, n_tax, n_taxed;
 } stats_group;
 
 typedef struct {
@@ -542,10 +545,14 @@ typedef struct {
     stats_group g[16];
 } stats_result;
 
+/* v_qty / v_ext / v_tax: optional validity (one byte per row, 1 = not NULL) of l_quantity, l_extendedprice,
+ * l_tax.  A NULL comparison operand is never selected (selectFlatLoop checks the mask,
+ * function_operator_boolean.go:780-868); a NULL operand makes the arithmetic result NULL (mask AND,
+ * function_operator_binary.go:267-481). */
 void orc_stats(int64_t n, const int32_t *shipdate, const int32_t *commitdate, const int32_t *receiptdate,
                const int32_t *quantity, const int64_t *extprice, const int64_t *discount, const int64_t *tax,
                const uint8_t *returnflag, int32_t d0, int32_t d1, int32_t d2, int32_t d3, int32_t q0, int32_t q1,
-               int64_t disc_gt_cents, stats_result *res)
+               int64_t disc_gt_cents, const uint8_t *v_qty, const uint8_t *v_ext, const uint8_t *v_tax, stats_result *res)
 {
     static date_t v_s[VEC], v_c[VEC], v_r[VEC];
     static int sa[VEC], sb[VEC];
@@ -564,6 +571,11 @@ void orc_stats(int64_t n, const int32_t *shipdate, const int32_t *commitdate, co
         c = sel_date_const(v_s, k1, CMP_LE, sa, c, sb);
         c = sel_date_const(v_c, k2, CMP_LE, sb, c, sa);
         c = sel_date_const(v_r, k3, CMP_GE, sa, c, sb);
+        if (v_qty) {      /* rows whose quantity is NULL never pass a comparison on it */
+            int k = 0;
+            for (int i = 0; i < c; i++) if (v_qty[off + sb[i]]) sb[k++] = sb[i];
+            c = k;
+        }
         c = sel_i32_const(quantity + off, q0, CMP_GE, sb, c, sa);
         c = sel_i32_const(quantity + off, q1, CMP_LE, sa, c, sb);
         int c2 = 0;
@@ -579,28 +591,39 @@ void orc_stats(int64_t n, const int32_t *shipdate, const int32_t *commitdate, co
             dec_t ext = dec_from_i64(extprice[r], 2), disc = dec_from_i64(discount[r], 2), tx = dec_from_i64(tax[r], 2), f, taxed;
             if (dec_add(one, tx, &f)) res->error = 1;
             if (dec_mul(ext, f, &taxed)) res->error = 1;
+            int ext_ok = !v_ext || v_ext[r], tax_ok = !v_tax || v_tax[r];
             if (gi < 0) {
                 if (res->ngroups >= 16) { res->error = 2; continue; }
                 gi = res->ngroups++;
                 stats_group *g = &res->g[gi];
                 g->rf = returnflag[r]; g->first_row = r;
-                g->min_ext = g->max_ext = ext; g->max_disc = disc;          /* MinMaxOp: Assign on first value */
+                g->max_disc = disc;                                          /* MinMaxOp: Assign on first value */
                 g->sum_tax = dec_from_i64(0, 0); g->sum_taxed = dec_from_i64(0, 0);
                 sums_tax[gi] = dec_from_i64(0, 0);
             }
             stats_group *g = &res->g[gi];
-            if (dec_cmp(ext, g->min_ext) < 0) g->min_ext = ext;
-            if (dec_cmp(ext, g->max_ext) > 0) g->max_ext = ext;
+            if (ext_ok) {
+                if (g->n_ext == 0) g->min_ext = g->max_ext = ext;
+                if (dec_cmp(ext, g->min_ext) < 0) g->min_ext = ext;
+                if (dec_cmp(ext, g->max_ext) > 0) g->max_ext = ext;
+                g->n_ext++;
+            }
             if (dec_cmp(disc, g->max_disc) > 0) g->max_disc = disc;
-            if (dec_add(g->sum_tax, tx, &g->sum_tax)) res->error = 1;
-            if (dec_add(sums_tax[gi], tx, &sums_tax[gi])) res->error = 1;
-            if (dec_add(g->sum_taxed, taxed, &g->sum_taxed)) res->error = 1;
+            if (tax_ok) {
+                if (dec_add(g->sum_tax, tx, &g->sum_tax)) res->error = 1;
+                if (dec_add(sums_tax[gi], tx, &sums_tax[gi])) res->error = 1;
+                g->n_tax++;
+            }
+            if (ext_ok && tax_ok) {
+                if (dec_add(g->sum_taxed, taxed, &g->sum_taxed)) res->error = 1;
+                g->n_taxed++;
+            }
             g->count++;
         }
         res->rows_selected += c2;
     }
     for (int k = 0; k < res->ngroups; k++)
-        if (dec_quo(sums_tax[k], dec_from_i64((int64_t)res->g[k].count, 0), &res->g[k].avg_tax)) res->error = 1;
+        if (res->g[k].n_tax > 0 && dec_quo(sums_tax[k], dec_from_i64((int64_t)res->g[k].n_tax, 0), &res->g[k].avg_tax)) res->error = 1;
 }
 int orc_sizeof_stats_result(void) { return (int)sizeof(stats_result); }
 

@@ -334,7 +334,8 @@ class gpuPipelineExec(OperatorExec):
             self._run()
         n = C.c_int64()
         cols = (C.c_void_p * self.ncols)()
-        L.check(lib.pg_result_next(self.result, K.DEFAULT_VECTOR_SIZE, C.byref(n), cols, None))
+        valids = (C.c_void_p * self.ncols)()
+        L.check(lib.pg_result_next(self.result, K.DEFAULT_VECTOR_SIZE, C.byref(n), cols, valids))
         if n.value == 0:
             output.Data, output.Count = [], 0
             return Done, None
@@ -348,7 +349,11 @@ class gpuPipelineExec(OperatorExec):
             d = None
             if t == L.PG_T_DICT8:
                 d = self._dict_for_output(i)
-            vecs.append(K.Vector(typ, data, dictionary=d))
+            mask = None
+            if valids[i]:       # packed validity bits, 1 = valid (pkg/util/bitmap.go)
+                nb = (n.value + 7) // 8
+                mask = np.frombuffer((C.c_char * nb).from_address(valids[i]), dtype=np.uint8, count=nb).copy()
+            vecs.append(K.Vector(typ, data, mask=mask, dictionary=d))
         output.Data, output.Count = vecs, n.value
         return haveMoreOutput, None
 

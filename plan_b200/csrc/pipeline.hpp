@@ -16,6 +16,14 @@ namespace pg {
 struct ResCol {
     int type = 0, width = 0, scale = 0;
     std::vector<uint8_t> data;
+    std::vector<uint8_t> valid;     // one byte per row (1 = not NULL); empty = no NULLs in this column
+    void push_null(size_t rows_before, size_t elem)
+    {
+        if (valid.empty()) valid.assign(rows_before, 1);
+        valid.push_back(0);
+        data.resize(data.size() + elem);
+    }
+    void mark_valid() { if (!valid.empty()) valid.push_back(1); }
     template <typename T> void push(const T &v)
     {
         size_t n = data.size();
@@ -110,6 +118,7 @@ int comm_alltoallv(const void *d_send, const i64 *send_cnt, const i64 *send_off,
 
 struct pg_result {
     std::vector<pg::ResCol> cols;
+    std::vector<std::vector<uint8_t>> valid_scratch;   // packed validity bitmaps handed out by pg_result_next
     pg::i64 nrows = 0, cursor = 0;
     pg_stats stats{};
 };

@@ -81,6 +81,11 @@ static int sort_result(pg_result *r, const std::vector<std::pair<int, int>> &ord
         std::vector<uint8_t> out((size_t)n * w);
         for (i64 i = 0; i < n; i++) memcpy(out.data() + (size_t)i * w, c.data.data() + (size_t)idx[(size_t)i] * w, w);
         c.data.swap(out);
+        if (!c.valid.empty()) {
+            std::vector<uint8_t> v((size_t)n);
+            for (i64 i = 0; i < n; i++) v[(size_t)i] = c.valid[(size_t)idx[(size_t)i]];
+            c.valid.swap(v);
+        }
     }
     r->nrows = n;
     return PG_OK;
@@ -252,7 +257,17 @@ int pg_result_next(pg_result *r, int64_t max_rows, int64_t *nrows, const void **
     for (size_t i = 0; i < r->cols.size(); i++) {
         ResCol &c = r->cols[i];
         if (cols) cols[i] = n > 0 ? (const void *)(c.data.data() + (size_t)r->cursor * (size_t)type_size(c.type)) : nullptr;
-        if (valid) valid[i] = nullptr;   // BASELINE pipelines produce no NULLs (empty input => no row)
+        if (valid) {
+            valid[i] = nullptr;
+            bool any_null = false;
+            for (i64 k = 0; k < n && !c.valid.empty(); k++) any_null = any_null || !c.valid[(size_t)(r->cursor + k)];
+            if (any_null) {      // packed bits, 1 = valid, LSB first (pkg/util/bitmap.go); owned by the result
+                r->valid_scratch.emplace_back((size_t)(n + 7) / 8, 0);
+                std::vector<uint8_t> &bm = r->valid_scratch.back();
+                for (i64 k = 0; k < n; k++) if (c.valid[(size_t)(r->cursor + k)]) bm[(size_t)k >> 3] |= (uint8_t)(1u << (k & 7));
+                valid[i] = bm.data();
+            }
+        }
     }
     *nrows = n;
     r->cursor += n;

@@ -265,6 +265,8 @@ inline void float_cmp_to_range(int op, float k, int scale, i64 vmin, i64 vmax, i
 
 struct LowerCtx {
     const pg_table *table = nullptr;
+    bool allow_nulls = false;   // the consumer handles validity bitmaps (generic scan-aggregate kernel)
+    bool saw_nulls = false;     // some referenced column actually holds NULLs
     std::string why;   // reason of the last failure
 };
 
@@ -317,7 +319,10 @@ inline bool lower_compare(LowerCtx &cx, const Expr &e, std::vector<Range> &range
     if (c->kind != PG_TK_COL) return fail(cx, "comparison left side is not a column");
     if (c->idx < 0 || c->idx >= (int)cx.table->cols.size()) return fail(cx, "column index out of range");
     const Column &col = cx.table->cols[(size_t)c->idx];
-    if (col.has_nulls) return fail(cx, "nullable column in predicate");
+    if (col.has_nulls) {
+        if (!cx.allow_nulls) return fail(cx, "nullable column in predicate");
+        cx.saw_nulls = true;
+    }
     Range rg;
     rg.col = c->idx;
     if (float_cast) {
@@ -406,7 +411,10 @@ inline bool lower_affprod(LowerCtx &cx, const Expr &e0, AffProd &out)
         if (c->idx < 0 || c->idx >= (int)cx.table->cols.size()) return false;
         const Column &col = cx.table->cols[(size_t)c->idx];
         if (!is_int_family(col.type) || col.type == PG_T_DATE32) return false;
-        if (col.has_nulls) return false;
+        if (col.has_nulls) {
+            if (!cx.allow_nulls) return false;
+            cx.saw_nulls = true;
+        }
         f->col = c->idx;
         f->c = 0;
         f->s = 1;

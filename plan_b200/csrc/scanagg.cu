@@ -738,6 +738,7 @@ struct GenericPipeline : Pipeline {
     const pg_table *table = nullptr;
     GenParams prm{};
     int NT = 256, grid = 1, G = 1, P = 1;
+    bool nulls = false;                  // some referenced column holds NULLs: per-aggregate valid counts are kept
     size_t smem = 0;
     int nkeys = 0, key_col[2] = {-1, -1};
     std::vector<uint8_t> vals[2];
@@ -765,9 +766,12 @@ struct GenericPipeline : Pipeline {
         PG_CUDA(cudaEventRecord(ev_all.a, st));
         PG_CUDA(cudaMemsetAsync(d_firstrow, 0x7f, 64 * 8, st));
         PG_CUDA(cudaEventRecord(ev_main.a, st));
-        if (NT == 256) generic_scanagg_kernel<256><<<grid, 256, smem, st>>>(prm, d_part.as<i64>(), d_firstrow);
-        else if (NT == 128) generic_scanagg_kernel<128><<<grid, 128, smem, st>>>(prm, d_part.as<i64>(), d_firstrow);
-        else generic_scanagg_kernel<64><<<grid, 64, smem, st>>>(prm, d_part.as<i64>(), d_firstrow);
+#define PG_GEN(N) do { if (nulls) generic_scanagg_kernel<N, true><<<grid, N, smem, st>>>(prm, d_part.as<i64>(), d_firstrow); \
+                       else generic_scanagg_kernel<N, false><<<grid, N, smem, st>>>(prm, d_part.as<i64>(), d_firstrow); } while (0)
+        if (NT == 256) PG_GEN(256);
+        else if (NT == 128) PG_GEN(128);
+        else PG_GEN(64);
+#undef PG_GEN
         PG_CUDA(cudaGetLastError());
         PG_CUDA(cudaEventRecord(ev_main.b, st));
         finalize_generic_kernel<<<(G * P + 63) / 64, 64, 0, st>>>(d_part.as<i64>(), grid, G * P, d_kinds.as<int>(), d_final.as<u64>());
@@ -830,8 +834,17 @@ struct GenericPipeline : Pipeline {
                 if (a.fn == PG_AGG_COUNT) col.type = PG_T_HUGEINT;
                 else if (a.fn == PG_AGG_AVG) col.type = is_int ? PG_T_FLOAT64 : PG_T_DECIMAL128;
                 else col.type = is_int ? PG_T_HUGEINT : PG_T_DECIMAL128;
+                size_t nrow = 0;
                 for (int g : order) {
                     i128 v = tot[(size_t)g * P + (size_t)pl], n = tot[(size_t)g * P];
+                    if (nulls && pl > 0) {
+                        // NULL inputs were skipped: the count that matters is the aggregate's own; no valid
+                        // input at all => NULL (SumOp/AvgOp/CountOp/MinMaxOp.Finalize, function_aggr.go:815-1032)
+                        n = tot[(size_t)g * P + (size_t)(prm.nacc + pl)];
+                        if (n == 0) { col.push_null(nrow++, (size_t)type_size(col.type)); continue; }
+                    }
+                    col.mark_valid();
+                    nrow++;
                     if (a.fn == PG_AGG_COUNT || (a.fn != PG_AGG_AVG && is_int)) {
                         pg_hugeint h;
                         h.lower = (u64)v;
@@ -913,6 +926,8 @@ static int try_generic(pg_plan *plan, const Node &aggn, const Node &scan, const 
         const Column &col = t->cols[(size_t)ranges[i].col];
         q.pcol[i].p = col.d_data;
         q.pcol[i].width = type_size(col.type);
+        q.pcol[i].valid = col.has_nulls ? col.d_valid : nullptr;
+        if (col.has_nulls) p->nulls = true;
         q.plo[i] = ranges[i].lo;
         q.phi[i] = ranges[i].hi;
         use(ranges[i].col);
@@ -930,8 +945,8 @@ static int try_generic(pg_plan *plan, const Node &aggn, const Node &scan, const 
     p->aggs = aggn.aggs;
     for (size_t i = 0; i < aggn.aggs.size(); i++) {
         const AggExpr &a = aggn.aggs[i];
-        if (a.fn == PG_AGG_COUNT) { p->plane.push_back(0); p->agg_is_int.push_back(true); continue; }
-        int kind = a.fn == PG_AGG_MIN ? GEN_MIN : a.fn == PG_AGG_MAX ? GEN_MAX : GEN_SUM;
+        if (a.fn == PG_AGG_COUNT && args[i].f.empty()) { p->plane.push_back(0); p->agg_is_int.push_back(true); continue; }
+        int kind = a.fn == PG_AGG_COUNT ? GEN_COUNTV : a.fn == PG_AGG_MIN ? GEN_MIN : a.fn == PG_AGG_MAX ? GEN_MAX : GEN_SUM;
         const AffProd &ap = args[i];
         if (ap.f.empty() || ap.f.size() > GEN_MAXFAC) { *why = "aggregate argument has an unsupported number of factors"; return PG_EUNSUPPORTED; }
         int found = -1;
@@ -947,6 +962,8 @@ static int try_generic(pg_plan *plan, const Node &aggn, const Node &scan, const 
                 const Column &col = t->cols[(size_t)ap.f[f].col];
                 A.fac[f].p = col.d_data;
                 A.fac[f].width = type_size(col.type);
+                A.fac[f].valid = col.has_nulls ? col.d_valid : nullptr;
+                if (col.has_nulls) p->nulls = true;
                 A.c[f] = ap.f[f].c;
                 A.s[f] = ap.f[f].s;
                 use(ap.f[f].col);
@@ -954,7 +971,7 @@ static int try_generic(pg_plan *plan, const Node &aggn, const Node &scan, const 
                 bound *= m;
             }
             if (kind == GEN_SUM) worst = std::max(worst, bound);
-            else if (bound >= ((i128)1 << 62)) { *why = "min/max argument could exceed int64"; return PG_EUNSUPPORTED; }
+            else if (kind != GEN_COUNTV && bound >= ((i128)1 << 62)) { *why = "min/max argument could exceed int64"; return PG_EUNSUPPORTED; }
             found = (int)plane_prod.size();
             plane_prod.push_back(ap);
             p->plane_kind.push_back(kind);
@@ -962,13 +979,15 @@ static int try_generic(pg_plan *plan, const Node &aggn, const Node &scan, const 
         }
         p->plane.push_back(found);
         bool is_int = a.ltype == PG_LT_HUGEINT || a.ltype == PG_LT_DOUBLE || a.ltype == PG_LT_INTEGER || a.ltype == PG_LT_BIGINT;
-        if (is_int && ap.vscale() != 0) { *why = "integer aggregate over a scaled value"; return PG_EUNSUPPORTED; }
+        if (is_int && ap.vscale() != 0 && kind != GEN_COUNTV) { *why = "integer aggregate over a scaled value"; return PG_EUNSUPPORTED; }
         if (!is_int && a.ltype != PG_LT_DECIMAL) { *why = "aggregate result type"; return PG_EUNSUPPORTED; }
         if ((kind == GEN_MIN || kind == GEN_MAX) && is_int) { *why = "min/max are DECIMAL only in the reference"; return PG_EUNSUPPORTED; }
         p->agg_is_int.push_back(is_int);
     }
     q.nacc = (int)plane_prod.size() - 1;
-    p->P = q.nacc + 1;
+    p->P = p->nulls ? 1 + 2 * q.nacc : 1 + q.nacc;
+    for (int a = 0; a < q.nacc; a++) if (p->plane_kind[(size_t)(a + 1)] == GEN_COUNTV) p->plane_kind[(size_t)(a + 1)] = GEN_SUM;
+    if (p->nulls) for (int a = 0; a < q.nacc; a++) { p->plane_kind.push_back(GEN_SUM); p->plane_scale.push_back(0); }
     for (auto &o : aggn.outs) {
         if (o.first == 0 && (o.second < 0 || o.second >= p->nkeys)) { *why = "bad group output index"; return PG_EUNSUPPORTED; }
         if (o.first == 1 && (o.second < 0 || o.second >= (int)aggn.aggs.size())) { *why = "bad aggregate output index"; return PG_EUNSUPPORTED; }
@@ -981,7 +1000,8 @@ static int try_generic(pg_plan *plan, const Node &aggn, const Node &scan, const 
     while (p->NT >= 64 && (size_t)p->G * p->P * p->NT * 8 > (size_t)200 * 1024) p->NT /= 2;
     if (p->NT < 64) { *why = "group tables do not fit in shared memory"; return PG_EUNSUPPORTED; }
     p->smem = (size_t)p->G * p->P * p->NT * 8;
-    const void *kern = p->NT == 256 ? (const void *)generic_scanagg_kernel<256> : p->NT == 128 ? (const void *)generic_scanagg_kernel<128> : (const void *)generic_scanagg_kernel<64>;
+    const void *kern = p->nulls ? (p->NT == 256 ? (const void *)generic_scanagg_kernel<256, true> : p->NT == 128 ? (const void *)generic_scanagg_kernel<128, true> : (const void *)generic_scanagg_kernel<64, true>)
+                                : (p->NT == 256 ? (const void *)generic_scanagg_kernel<256, false> : p->NT == 128 ? (const void *)generic_scanagg_kernel<128, false> : (const void *)generic_scanagg_kernel<64, false>);
     PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, p->NT, p->smem);
@@ -1005,8 +1025,9 @@ static int try_generic(pg_plan *plan, const Node &aggn, const Node &scan, const 
     char buf[384];
     snprintf(buf, sizeof buf,
              "ScanAgg[generic] table=%s rows=%lld kernel=generic_scanagg_kernel<%d> grid=%d smem=%zu groups=%dx%d "
-             "predicates=%d accumulators=%d bytes/row=%lld",
-             t->name.c_str(), (long long)t->nrows, p->NT, p->grid, p->smem, dims[0], dims[1], q.npred, q.nacc, (long long)p->bytes_per_row);
+             "predicates=%d accumulators=%d bytes/row=%lld%s",
+             t->name.c_str(), (long long)t->nrows, p->NT, p->grid, p->smem, dims[0], dims[1], q.npred, q.nacc, (long long)p->bytes_per_row,
+             p->nulls ? " nulls=validity-bitmaps" : "");
     p->explain = buf;
     *out = std::move(p);
     return PG_OK;
@@ -1019,6 +1040,7 @@ int build_scan_agg(pg_plan *plan, const Node &aggn, const Node &scan, std::uniqu
     const pg_table *t = plan->slots[(size_t)scan.slot];
     LowerCtx cx;
     cx.table = t;
+    cx.allow_nulls = true;     // columns that hold NULLs route the plan to the NULL-aware generic kernel
     std::vector<Range> ranges;
     if (!lower_filters(cx, scan.filters, ranges)) PG_FAIL(PG_EUNSUPPORTED, "scan filter not off-loadable: %s", cx.why.c_str());
     std::vector<AffProd> args(aggn.aggs.size());
@@ -1029,18 +1051,24 @@ int build_scan_agg(pg_plan *plan, const Node &aggn, const Node &scan, std::uniqu
             // on a NOT NULL column that is the row count
             if (!a.star) {
                 const Expr *e = strip_value_preserving_casts(&a.arg);
-                if (e->kind != PG_TK_COL || e->idx < 0 || e->idx >= (int)t->cols.size() || t->cols[(size_t)e->idx].has_nulls)
-                    PG_FAIL(PG_EUNSUPPORTED, "count() over a nullable or computed argument");
+                if (e->kind != PG_TK_COL || e->idx < 0 || e->idx >= (int)t->cols.size())
+                    PG_FAIL(PG_EUNSUPPORTED, "count() over a computed argument");
+                if (t->cols[(size_t)e->idx].has_nulls) {      // count(col) = rows where col is not NULL
+                    Factor f;
+                    f.col = e->idx;
+                    args[i].f.push_back(f);
+                    cx.saw_nulls = true;
+                }
             }
             continue;
         }
         if (a.star) PG_FAIL(PG_EINVAL, "aggregate %zu has no argument", i);
         if (!lower_affprod(cx, a.arg, args[i])) PG_FAIL(PG_EUNSUPPORTED, "aggregate argument not off-loadable: %s", cx.why.c_str());
     }
-    std::string why1, why2, why3;
+    std::string why1 = "NULLs present", why2 = "NULLs present", why3;
     const char *force = getenv("PG_FORCE_GENERIC");      // testing: exercise the shape-agnostic kernel on every plan
     int s = PG_EUNSUPPORTED;
-    if (!(force && atoi(force))) {
+    if (!(force && atoi(force)) && !cx.saw_nulls) {
         s = try_sumprod(plan, aggn, scan, ranges, args, out, &why1);
         if (s != PG_EUNSUPPORTED) return s;
         s = try_lowcard(plan, aggn, scan, ranges, args, out, &why2);

@@ -386,9 +386,13 @@ ord_tile_kernel(const OrdParams op, OrdSummary *__restrict__ out /* [ceil((tile_
 // correct for everything the lowering accepts, slower than the specialised kernels.
 // ------------------------------------------------------------------------------
 constexpr int GEN_MAXPRED = 8, GEN_MAXACC = 8, GEN_MAXFAC = 3;
-enum { GEN_SUM = 0, GEN_MIN = 1, GEN_MAX = 2 };
+enum { GEN_SUM = 0, GEN_MIN = 1, GEN_MAX = 2, GEN_COUNTV = 3 };   // COUNTV: count(column) = rows where it is not NULL
 
-struct GenCol { const void *p; int width; };
+struct GenCol { const void *p; int width; const uint8_t *valid; };   // valid: packed bits, 1 = not NULL; null = no NULLs
+__device__ __forceinline__ bool gen_valid(const GenCol &c, i64 row)
+{
+    return c.valid == nullptr || ((__ldg(c.valid + (row >> 3)) >> (row & 7)) & 1);
+}
 __device__ __forceinline__ i64 gen_load(const GenCol &c, i64 row)
 {
     switch (c.width) {
@@ -414,25 +418,33 @@ struct GenParams {
     const uint8_t *key0, *key1;
     const uint8_t *luts;
     int n1, ngroups;
-    int nacc;                       // plane 0 is always the row count; planes 1..nacc the aggregates
+    int nacc;                       // plane 0 is always the row count; planes 1..nacc the aggregates;
+                                    // with NULLS, planes nacc+1..2*nacc count the non-NULL inputs of each aggregate
     GenAcc acc[GEN_MAXACC];
 };
+__host__ __device__ __forceinline__ int gen_plane_kind(const GenParams &p, int plane)
+{
+    if (plane == 0 || plane > p.nacc) return GEN_SUM;
+    int k = p.acc[plane - 1].kind;
+    return k == GEN_COUNTV ? GEN_SUM : k;
+}
 
-template <int NT>
+// NULL semantics of the reference (masks AND-ed through expressions, function_operator_binary.go:267-481;
+// selection skips NULL operands, function_operator_boolean.go:780-868; aggregates ignore NULL inputs,
+// function_aggr.go IgnoreNull): a row with a NULL predicate operand is not selected; an aggregate
+// skips rows where any column of its argument is NULL.
+template <int NT, bool NULLS>
 __global__ void __launch_bounds__(NT)
-generic_scanagg_kernel(const GenParams p, i64 *__restrict__ partials /* [grid][G*(nacc+1)] */,
+generic_scanagg_kernel(const GenParams p, i64 *__restrict__ partials /* [grid][G*P] */,
                        i64 *__restrict__ first_row /* [G] preset to 0x7f.. */)
 {
-    extern __shared__ i64 s_acc[];                 // [G*(nacc+1)][NT]
+    extern __shared__ i64 s_acc[];                 // [G*P][NT]
     __shared__ uint8_t s_lut[2][256];
     __shared__ i64 s_first[64];
-    const int G = p.ngroups, P = p.nacc + 1;
+    const int G = p.ngroups, P = NULLS ? 1 + 2 * p.nacc : 1 + p.nacc;
     for (int i = threadIdx.x; i < G * P * NT; i += NT) {
-        int plane = (i / NT) % P;
-        i64 init = 0;
-        if (plane > 0 && p.acc[plane - 1].kind == GEN_MIN) init = INT64_MAX;
-        if (plane > 0 && p.acc[plane - 1].kind == GEN_MAX) init = INT64_MIN;
-        s_acc[i] = init;
+        int kind = gen_plane_kind(p, (i / NT) % P);
+        s_acc[i] = kind == GEN_MIN ? INT64_MAX : kind == GEN_MAX ? INT64_MIN : 0;
     }
     if (p.nkeys > 0) for (int i = threadIdx.x; i < 512; i += NT) s_lut[i >> 8][i & 255] = p.luts[i];
     if (threadIdx.x < 64) s_first[threadIdx.x] = INT64_MAX;
@@ -441,6 +453,7 @@ generic_scanagg_kernel(const GenParams p, i64 *__restrict__ partials /* [grid][G
     for (i64 row = (i64)blockIdx.x * NT + threadIdx.x; row < p.nrows; row += (i64)gridDim.x * NT) {
         bool ok = true;
         for (int k = 0; k < p.npred && ok; k++) {
+            if (NULLS && !gen_valid(p.pcol[k], row)) { ok = false; break; }
             i64 v = gen_load(p.pcol[k], row);
             ok = v >= p.plo[k] && v <= p.phi[k];
         }
@@ -455,17 +468,22 @@ generic_scanagg_kernel(const GenParams p, i64 *__restrict__ partials /* [grid][G
         for (int a = 0; a < p.nacc; a++) {
             const GenAcc &A = p.acc[a];
             i64 x = 1;
-            for (int f = 0; f < A.nfac; f++) x *= A.c[f] + A.s[f] * gen_load(A.fac[f], row);
+            bool vok = true;
+            for (int f = 0; f < A.nfac; f++) {
+                if (NULLS && !gen_valid(A.fac[f], row)) { vok = false; break; }
+                x *= A.c[f] + A.s[f] * gen_load(A.fac[f], row);
+            }
+            if (!vok) continue;
             i64 *slot = t + (i64)(a + 1) * NT;
             i64 cur = *slot;
-            *slot = A.kind == GEN_SUM ? cur + x : A.kind == GEN_MIN ? (x < cur ? x : cur) : (x > cur ? x : cur);
+            *slot = A.kind == GEN_SUM ? cur + x : A.kind == GEN_MIN ? (x < cur ? x : cur) : A.kind == GEN_MAX ? (x > cur ? x : cur) : cur + 1;
+            if (NULLS) t[(i64)(p.nacc + 1 + a) * NT] += 1;
         }
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int v = warp; v < G * P; v += NT / 32) {
-        int plane = v % P;
-        int kind = plane == 0 ? GEN_SUM : p.acc[plane - 1].kind;
+        int kind = gen_plane_kind(p, v % P);
         i64 r = kind == GEN_SUM ? 0 : kind == GEN_MIN ? INT64_MAX : INT64_MIN;
         for (int j = 0; j < NT / 32; j++) {
             i64 x = s_acc[v * NT + lane + 32 * j];

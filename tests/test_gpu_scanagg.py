@@ -304,3 +304,44 @@ def _check_stats(oracle, tables, line, args):
 def test_generic_kernel_minmax_shape(pg, oracle, uploaded, sf01_host, args):
     """min / max / sum / avg / count over seven range predicates and one key: no specialised kernel exists."""
     _check_stats(oracle, uploaded, sf01_host["lineitem"], args)
+
+
+def _pack_bits(valid):
+    return np.packbits(np.asarray(valid, dtype=np.uint8), bitorder="little")
+
+
+@pytest.mark.parametrize("null_cols,frac", [
+    (("l_tax",), 0.1), (("l_extendedprice", "l_tax"), 0.3), (("l_quantity",), 0.2),
+    (("l_quantity", "l_extendedprice", "l_tax"), 0.05), (("l_extendedprice",), 1.0),
+])
+def test_nulls_follow_the_reference(pg, oracle, sf01_host, null_cols, frac):
+    """NULL inputs (validity bitmaps at the boundary): a NULL comparison operand is never selected, an
+    aggregate ignores NULL inputs, and an aggregate with no valid input at all is NULL in the result."""
+    from plan_b200 import compute as X, tpch as T
+    n = 60000
+    rng = np.random.default_rng(7)
+    line = {k: v[:n].copy() for k, v in sf01_host["lineitem"].items()}
+    valid = {c: rng.random(n) >= frac for c in null_cols}
+    t = X.DeviceTable.create("lineitem", T.LINEITEM)
+    vlist = [(_pack_bits(valid[c[0]]) if c[0] in valid else None) for c in T.LINEITEM]
+    t.append([line[c[0]] for c in T.LINEITEM], valid=vlist)
+    t.seal()
+    try:
+        args = (8035 + 100, 8035 + 2300, 8035 + 2400, 8035 + 50, 3, 45, 2)
+        chunks, stats, explain = _run(T.stats_plan(*args), {"lineitem": t})
+        assert "nulls=validity-bitmaps" in explain
+        ref = oracle.stats(line, *args, valid=valid)
+        assert stats.aux[0] == ref["rows_selected"]
+        assert sum(c.Card() for c in chunks) == len(ref["groups"])
+        c = chunks[0]
+        for r, g in enumerate(sorted(ref["groups"], key=lambda g: g["first_row"])):
+            assert chr(int(c.Data[0].Data[r])) == g["l_returnflag"]
+            for colidx, key in ((1, "min_ext"), (2, "max_ext"), (3, "max_disc"), (4, "sum_tax"), (5, "avg_tax"), (6, "sum_taxed")):
+                v = c.Data[colidx].GetValue(r)
+                if g[key] is None:
+                    assert v.IsNull and v.String() == "NULL", key
+                else:
+                    assert not v.IsNull and _same_decimal(_dec(c.Data[colidx], r), g[key]), key
+            assert int(c.Data[7].Data[r]["lower"]) == g["count"]
+    finally:
+        t.free()
