@@ -285,13 +285,19 @@ def groupby_sum(line, key="l_orderkey", value="l_quantity", having_gt=None, ship
     return out
 
 
-def semi_groupby(orders, line, anti=False, odate_lt=days(1995, 3, 29), ship_gt=days(1995, 3, 29)):
+def semi_groupby(orders, line, anti=False, odate_lt=days(1995, 3, 29), ship_gt=days(1995, 3, 29),
+                 valid_okey=None, valid_lkey=None):
     """numpy restatement of a SEMI / ANTI hash join under a hash aggregate: a probe row is emitted once
     iff some / no build row has its key (Scan.NextSemiOrAntiJoin, join_scan.go:90-165; NULL keys never
     match, join_table.go:152-195).  Returns {o_custkey: (sum(o_totalprice) cents, count)}."""
-    build_keys = line["l_orderkey"][line["l_shipdate"] > ship_gt]
+    bm = line["l_shipdate"] > ship_gt
+    if valid_lkey is not None:
+        bm = bm & valid_lkey                      # NULL build keys are dropped (join_table.go:152-195)
+    build_keys = line["l_orderkey"][bm]
     m = orders["o_orderdate"] < odate_lt
     hit = np.isin(orders["o_orderkey"], build_keys)
+    if valid_okey is not None:
+        hit = hit & valid_okey                    # a NULL probe key finds no match: SEMI drops it, ANTI keeps it
     m &= ~hit if anti else hit
     k, v = orders["o_custkey"][m], orders["o_totalprice"][m].astype(np.int64)
     uk, inv = np.unique(k, return_inverse=True)

@@ -57,6 +57,7 @@ static TypedCol typed(const pg_table *t, int col)
     TypedCol c;
     c.p = t->cols[(size_t)col].d_data;
     c.width = type_size(t->cols[(size_t)col].type);
+    c.valid = t->cols[(size_t)col].has_nulls ? t->cols[(size_t)col].d_valid : nullptr;
     return c;
 }
 
@@ -191,8 +192,10 @@ struct JoinAggPipeline : Pipeline {
     int launch_pipe(const PipeParams &pp, const pg_table *t)
     {
         cudaStream_t st = ctx().stream;
+        bool any_valid = pp.probe_key.valid != nullptr || (SINK == SINK_INSERT || SINK == SINK_BITMAP ? pp.ins_key.valid != nullptr : false);
+        for (int k = 0; k < pp.npred; k++) any_valid = any_valid || pp.pred[k].col.valid != nullptr;
         bool fast = pp.has_probe && pp.probe.bitmap && pp.npred <= 1 && (pp.npred == 0 || pp.pred[0].col.width == 4) &&
-                    (pp.probe_key.width == 4 || pp.probe_key.width == 8) && !getenv("PG_JOIN_GENERIC");
+                    (pp.probe_key.width == 4 || pp.probe_key.width == 8) && !any_valid && !getenv("PG_JOIN_GENERIC");
         if (!fast) {
             pipeline_kernel<SINK><<<grid_rows(t->nrows), 256, 0, st>>>(pp);
         } else {
@@ -440,7 +443,9 @@ struct JoinAggPipeline : Pipeline {
             PG_CUDA(cudaEventRecord(ev_main.a, st));
             if (no_join) {
                 // the specialised vectorised kernel when the shape is: 1 key, 1 summed column, <=1 32-bit predicate
-                const bool one = gs.nparts == 1 && gs.nacc == 1 && gs.nfac[0] == 1 && pp.npred <= 1 &&
+                bool pred_valid = false;
+                for (int k = 0; k < pp.npred; k++) pred_valid = pred_valid || pp.pred[k].col.valid != nullptr;
+                const bool one = !pred_valid && gs.nparts == 1 && gs.nacc == 1 && gs.nfac[0] == 1 && pp.npred <= 1 &&
                                  (pp.npred == 0 || pp.pred[0].col.width == 4) && gs.part[0].col.width >= 4 &&
                                  gs.fac[0][0].col.width >= 4 && !getenv("PG_GROUP_GENERIC");
                 if (one) {
@@ -675,6 +680,7 @@ static int add_build_stage(JoinAggPipeline *p, const Node &n0, int key_idx, int 
         s->src_slot = n->slot;
         LowerCtx cx;
         cx.table = p->tab(n->slot);
+        cx.allow_nulls = true;
         std::vector<Expr> fl = n->filters;
         for (auto &f : extra) fl.push_back(f);
         if (!lower_filters(cx, fl, s->ranges)) PG_FAIL(PG_EUNSUPPORTED, "build-side filter not off-loadable: %s", cx.why.c_str());
@@ -692,6 +698,7 @@ static int add_build_stage(JoinAggPipeline *p, const Node &n0, int key_idx, int 
         s->src_slot = src->slot;
         LowerCtx cx;
         cx.table = p->tab(src->slot);
+        cx.allow_nulls = true;
         std::vector<Expr> fl = src->filters;
         for (auto &f : pf) fl.push_back(f);
         if (!lower_filters(cx, fl, s->ranges)) PG_FAIL(PG_EUNSUPPORTED, "probe-side filter not off-loadable: %s", cx.why.c_str());
@@ -714,7 +721,7 @@ static int add_build_stage(JoinAggPipeline *p, const Node &n0, int key_idx, int 
     }
     if (key.slot != s->src_slot) PG_FAIL(PG_EUNSUPPORTED, "build key is not on the build source table");
     const Column &kc = p->tab(key.slot)->cols[(size_t)key.col];
-    if (!is_int_family(kc.type) || kc.has_nulls) PG_FAIL(PG_EUNSUPPORTED, "join key must be a non-null integer column");
+    if (!is_int_family(kc.type)) PG_FAIL(PG_EUNSUPPORTED, "join key must be an integer column");
     if (kc.vmin <= HT_EMPTY && kc.vmax >= HT_EMPTY) PG_FAIL(PG_EUNSUPPORTED, "join key range contains the empty-slot sentinel");
     s->ins_key_col = key.col;
     s->unique_key = kc.stats_ok && kc.adjacent_descents == 0;
@@ -748,6 +755,7 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &join, std::uniqu
     {
         LowerCtx cx;
         cx.table = st;
+        cx.allow_nulls = true;
         std::vector<Expr> fl = src->filters;
         for (auto &f : pf) fl.push_back(f);
         if (!lower_filters(cx, fl, p->ranges)) PG_FAIL(PG_EUNSUPPORTED, "probe-side filter not off-loadable: %s", cx.why.c_str());
@@ -761,7 +769,7 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &join, std::uniqu
         if (pe->kind != PG_TK_COL || be->kind != PG_TK_COL) PG_FAIL(PG_EUNSUPPORTED, "join condition is not column = column");
         BaseCol pk;
         if (!resolve(join.children[0], pe->idx, &pk) || pk.slot != src->slot) PG_FAIL(PG_EUNSUPPORTED, "probe key is not a column of the probe scan");
-        if (!is_int_family(st->cols[(size_t)pk.col].type) || st->cols[(size_t)pk.col].has_nulls) PG_FAIL(PG_EUNSUPPORTED, "probe key must be a non-null integer column");
+        if (!is_int_family(st->cols[(size_t)pk.col].type)) PG_FAIL(PG_EUNSUPPORTED, "probe key must be an integer column");
         p->probe_key_col = pk.col;
         PG_TRY(add_build_stage(p.get(), join.children[1], be->idx, &top_stage));
         if (p->top_probe_mode != 0) p->stages[(size_t)top_stage]->existence_only = true;

@@ -90,8 +90,13 @@ __device__ __forceinline__ void jt_probe(const JoinTable &t, i64 key, F f)
 // a column of a base table read by row id with its native width
 struct TypedCol {
     const void *p;
-    int width;      // 1, 4 or 8 bytes
+    int width;             // 1, 4 or 8 bytes
+    const uint8_t *valid;  // packed validity (1 = not NULL) or null when the column holds no NULLs
 };
+__device__ __forceinline__ bool typed_valid(const TypedCol &c, i64 row)
+{
+    return c.valid == nullptr || ((__ldg(c.valid + (row >> 3)) >> (row & 7)) & 1);
+}
 __device__ __forceinline__ i64 load_typed(const TypedCol &c, i64 row)
 {
     switch (c.width) {
@@ -251,11 +256,12 @@ pipeline_kernel(const PipeParams p)
         bool ok = true;
         for (int k = 0; k < p.npred && ok; k++) {
             i64 v = load_typed(p.pred[k].col, row);
-            ok = v >= p.pred[k].lo && v <= p.pred[k].hi;
+            ok = typed_valid(p.pred[k].col, row) && v >= p.pred[k].lo && v <= p.pred[k].hi;   // NULL is never selected
         }
         if (!ok) continue;
         n_pass++;
         auto sink = [&](u64 build_row) {
+            if ((SINK == SINK_INSERT || SINK == SINK_BITMAP) && !typed_valid(p.ins_key, row)) return;   // NULL keys are not built (join_table.go:152-195)
             n_join++;
             if (SINK == SINK_INSERT) {
                 jt_insert(p.ins, load_typed(p.ins_key, row), (u64)row);
@@ -279,6 +285,10 @@ pipeline_kernel(const PipeParams p)
         };
         if (p.has_probe) {
             i64 key = load_typed(p.probe_key, row);
+            if (!typed_valid(p.probe_key, row)) {      // a NULL key matches nothing: only ANTI keeps the row
+                if (p.probe_mode == 2) sink(0);
+                continue;
+            }
             if (p.probe_mode == 0) {
                 if (p.probe.bitmap && !bitmap_test(p.probe, key)) continue;
                 if (p.probe_bitmap_only) sink(0);
@@ -315,7 +325,7 @@ static scan_group_kernel(const PipeParams p)
         bool ok = row < p.nrows;
         for (int k = 0; k < p.npred && ok; k++) {
             i64 v = load_typed(p.pred[k].col, row);
-            ok = v >= p.pred[k].lo && v <= p.pred[k].hi;
+            ok = typed_valid(p.pred[k].col, row) && v >= p.pred[k].lo && v <= p.pred[k].hi;
         }
         i64 klo = 0, khi = 0, vals[GT_MAXACC];
         if (ok) {

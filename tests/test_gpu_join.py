@@ -235,3 +235,31 @@ def test_semi_join_without_bitmap(pg, oracle, uploaded, sf01_host, monkeypatch):
     monkeypatch.setenv("PG_JOIN_GENERIC", "1")
     check_semi(oracle, uploaded, sf01_host, anti=False)
     check_semi(oracle, uploaded, sf01_host, anti=True)
+
+
+@pytest.mark.parametrize("anti", [False, True])
+def test_null_join_keys_never_match(pg, oracle, sf01_host, anti):
+    """NULL keys on either side never match (join_table.go:152-195): dropped from the build side, and a
+    probe row with a NULL key survives only an ANTI join."""
+    from plan_b200 import compute as X, tpch as T
+    rng = np.random.default_rng(11)
+    n_o = 40000
+    orders = {k: v[:n_o].copy() for k, v in sf01_host["orders"].items()}
+    nl = int(np.searchsorted(sf01_host["lineitem"]["l_orderkey"], orders["o_orderkey"][-1], side="right"))
+    line = {k: v[:nl].copy() for k, v in sf01_host["lineitem"].items()}
+    v_ok, v_lk = rng.random(n_o) >= 0.2, rng.random(nl) >= 0.3
+    pack = lambda v: np.packbits(v.astype(np.uint8), bitorder="little")   # noqa: E731
+    to = X.DeviceTable.create("orders", T.ORDERS)
+    to.append([orders[c[0]] for c in T.ORDERS], valid=[pack(v_ok) if c[0] == "o_orderkey" else None for c in T.ORDERS])
+    to.seal()
+    tl = X.DeviceTable.create("lineitem", T.LINEITEM)
+    tl.append([line[c[0]] for c in T.LINEITEM], valid=[pack(v_lk) if c[0] == "l_orderkey" else None for c in T.LINEITEM])
+    tl.seal()
+    try:
+        kw = dict(anti=anti, odate_lt=8035 + 3000, ship_gt=8035 + 900)
+        chunks, _, _ = _run(T.semi_plan(**kw), {"orders": to, "lineitem": tl})
+        want = oracle.semi_groupby(orders, line, valid_okey=v_ok, valid_lkey=v_lk, **kw)
+        assert _groupby_result(chunks) == want
+    finally:
+        to.free()
+        tl.free()
