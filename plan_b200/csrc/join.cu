@@ -235,6 +235,16 @@ struct JoinAggPipeline : Pipeline {
         PG_CUDA(cudaMemsetAsync(s.d_slots.p, 0x80, nb * HT_BUCKET * sizeof(longlong2), st));
         s.jt.slots = s.d_slots.as<longlong2>();
         s.jt.bucket_mask = nb - 1;
+        {   // ascending build key (>= 99% of adjacent rows increase): order-preserving buckets
+            i128 dom = (i128)keycol.vmax - (i128)keycol.vmin + 1;
+            int lg = 0;
+            while (((u64)1 << lg) < nb) lg++;
+            bool asc = keycol.stats_ok && keycol.adjacent_descents * 100 <= std::max<i64>(nbuild, 1) && dom > 0 && dom <= ((i128)1 << 34) && lg <= 29;
+            if (getenv("PG_JOIN_ORDER_PRESERVING")) asc = asc && atoi(getenv("PG_JOIN_ORDER_PRESERVING")) != 0;
+            s.jt.order_preserving = asc ? 1 : 0;
+            s.jt.log2buckets = lg;
+            s.jt.domain = dom > 0 ? (u64)dom : 1;
+        }
         // exact key-domain bitmap when the build column's value range is small enough
         s.jt.bitmap = nullptr;
         s.jt.bm_min = keycol.vmin;

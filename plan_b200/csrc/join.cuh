@@ -40,7 +40,21 @@ struct JoinTable {
     unsigned *bitmap;   // may be null
     i64 bm_min, bm_max; // key domain covered by the bitmap
     unsigned long long *dups;   // number of inserted keys that were already present (bitmap builds only)
+    // Bucket choice: mix64 hash by default; for a build key that ascends in row order (statistics) an
+    // ORDER-PRESERVING map of the key domain onto the buckets, so the build writes the table like a
+    // stream and a probe side clustered on the same key (TPC-H fact tables) reads it like one.
+    int order_preserving;
+    int log2buckets;
+    u64 domain;                 // bm_max - bm_min + 1
 };
+__device__ __forceinline__ u64 jt_home(const JoinTable &t, i64 key)
+{
+    if (t.order_preserving) {
+        u64 off = (u64)(key - t.bm_min);
+        return off < t.domain ? (off << t.log2buckets) / t.domain : (mix64((u64)key) & t.bucket_mask);
+    }
+    return mix64((u64)key) & t.bucket_mask;
+}
 
 __device__ __forceinline__ bool bitmap_test(const JoinTable &t, i64 key)
 {
@@ -56,7 +70,7 @@ __device__ __forceinline__ void jt_insert(const JoinTable &t, i64 key, u64 paylo
         unsigned bit = 1u << (off & 31);
         if (atomicOr(t.bitmap + (off >> 5), bit) & bit) atomicAdd(t.dups, 1ULL);
     }
-    u64 b = mix64((u64)key) & t.bucket_mask;
+    u64 b = jt_home(t, key);
     for (;;) {
         longlong2 *line = t.slots + b * HT_BUCKET;
 #pragma unroll
@@ -74,7 +88,7 @@ __device__ __forceinline__ void jt_insert(const JoinTable &t, i64 key, u64 paylo
 template <typename F>
 __device__ __forceinline__ void jt_probe(const JoinTable &t, i64 key, F f)
 {
-    u64 b = mix64((u64)key) & t.bucket_mask;
+    u64 b = jt_home(t, key);
     for (;;) {
         const longlong2 *line = t.slots + b * HT_BUCKET;
         longlong2 s0 = __ldg(line), s1 = __ldg(line + 1), s2 = __ldg(line + 2), s3 = __ldg(line + 3);
