@@ -305,6 +305,16 @@ def main():
                 "query": dom, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": per_query[dom]["main_kernel_bytes"],
                 "avg_launch_ms": per_query[dom]["main_kernel_ms"]}
+    # DRAM traffic of the dominant kernel: ncu's dram bytes per launch relative to the algorithmic bytes,
+    # from the committed capture of the same kernel (profiles/traffic_ratio.json), scaled to this launch
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_ratio.json")))
+        for kname, info in tr["kernels"].items():
+            if kname in roofline["kernel"]:
+                roofline["traffic"] = info["ratio"] * roofline["algorithmic_bytes_per_launch"]
+                roofline["traffic_source"] = tr["source"] + "; ratio %.5f applied to this launch's algorithmic bytes" % info["ratio"]
+    except Exception:
+        pass
     launches = sum(a["launches"] for a in acc.values())
 
     # ---- e2e: host buffers through the C ABI (H2D inside the timed region) -------------------

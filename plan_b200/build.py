@@ -9,7 +9,7 @@ SOURCES = ["table.cu", "plan.cu", "scanagg.cu", "join.cu", "comm.cu", "tpchgen.c
 OUT = os.path.join(HERE, "libplangpu.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-         "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr"]
+         "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr"] + os.environ.get("PG_NVCC_EXTRA", "").split()
 
 
 def needs_build():

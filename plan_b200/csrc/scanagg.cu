@@ -247,11 +247,11 @@ struct LowcardPipeline : Pipeline {
     int ensure_ord_buffers()
     {
         if (d_ord.p) return PG_OK;
-        const i64 ntiles = (prm.nrows + SA_TILE - 1) / SA_TILE;
+        const i64 ntiles = (prm.nrows + LC_TILE - 1) / LC_TILE;
         PG_TRY(d_ord.alloc(sizeof(OrdSummary) * (size_t)std::max<i64>(ntiles, 1)));
         PG_TRY(h_ord.alloc(sizeof(OrdSummary) * (size_t)std::max<i64>(ntiles, 1)));
         PG_TRY(h_part.alloc(sizeof(i64) * (size_t)grid * (size_t)G * LC_K));
-        PG_TRY(h_tile.alloc((size_t)SA_TILE * 32 + 512));
+        PG_TRY(h_tile.alloc((size_t)LC_TILE * 32 + 512));
         PG_TRY(d_contrib.alloc(64 * (size_t)(ctx().world + 1)));
         PG_TRY(h_contrib.alloc(64 * (size_t)(ctx().world + 1)));
         return PG_OK;
@@ -273,8 +273,8 @@ struct LowcardPipeline : Pipeline {
         op.tile_end = te;
         op.chunk = chunk;
         int gr = (int)std::min<i64>(*n, (i64)ctx().prop.multiProcessorCount * 8);
-        if (has_key1) ord_tile_kernel<true><<<gr, SA_THREADS, 0, st>>>(op, d_ord.as<OrdSummary>());
-        else ord_tile_kernel<false><<<gr, SA_THREADS, 0, st>>>(op, d_ord.as<OrdSummary>());
+        if (has_key1) ord_tile_kernel<true><<<gr, LC_THREADS, 0, st>>>(op, d_ord.as<OrdSummary>());
+        else ord_tile_kernel<false><<<gr, LC_THREADS, 0, st>>>(op, d_ord.as<OrdSummary>());
         PG_CUDA(cudaGetLastError());
         PG_CUDA(cudaMemcpyAsync(h_ord.p, d_ord.p, sizeof(OrdSummary) * (size_t)*n, cudaMemcpyDeviceToHost, st));
         PG_CUDA(cudaStreamSynchronize(st));
@@ -298,7 +298,7 @@ struct LowcardPipeline : Pipeline {
         int rstar = 0;
         i128 P0 = 0;
         while (P0 + rank_tot[(size_t)rstar] < THR) { P0 += rank_tot[(size_t)rstar]; rstar++; }
-        const i64 ntiles = (prm.nrows + SA_TILE - 1) / SA_TILE;
+        const i64 ntiles = (prm.nrows + LC_TILE - 1) / LC_TILE;
         PG_TRY(ensure_ord_buffers());
         const OrdSummary *sums = nullptr;
         i64 nsums = 0;
@@ -331,12 +331,12 @@ struct LowcardPipeline : Pipeline {
             }
             if (tstar == te) PG_FAIL(PG_ECUDA, "internal: crossing tile not found");
             // c. that tile row by row, exactly as the reference would add them
-            i64 row0 = tstar * SA_TILE;
-            int n = (int)std::min<i64>(SA_TILE, prm.nrows - row0);
+            i64 row0 = tstar * LC_TILE;
+            int n = (int)std::min<i64>(LC_TILE, prm.nrows - row0);
             // pinned staging: [A | B | C] int64, [pred] int32, [key0 | key1] bytes, [luts]
-            i64 *h_a = h_tile.as<i64>(), *h_b = h_a + SA_TILE, *h_c = h_b + SA_TILE;
-            int *h_pred = (int *)(h_c + SA_TILE);
-            uint8_t *h_k0 = (uint8_t *)(h_pred + SA_TILE), *h_k1 = h_k0 + SA_TILE, *h_lut = h_k1 + SA_TILE;
+            i64 *h_a = h_tile.as<i64>(), *h_b = h_a + LC_TILE, *h_c = h_b + LC_TILE;
+            int *h_pred = (int *)(h_c + LC_TILE);
+            uint8_t *h_k0 = (uint8_t *)(h_pred + LC_TILE), *h_k1 = h_k0 + LC_TILE, *h_lut = h_k1 + LC_TILE;
             PG_CUDA(cudaMemcpyAsync(h_pred, prm.pred + row0, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
             PG_CUDA(cudaMemcpyAsync(h_k0, prm.key0 + row0, (size_t)n, cudaMemcpyDeviceToHost, st));
             if (has_key1) PG_CUDA(cudaMemcpyAsync(h_k1, prm.key1 + row0, (size_t)n, cudaMemcpyDeviceToHost, st));
@@ -438,8 +438,8 @@ struct LowcardPipeline : Pipeline {
         PG_CUDA(cudaEventRecord(ev_all.a, st));
         PG_CUDA(cudaMemsetAsync(d_firstrow, 0x7f, LC_MAXG * 8, st));   // 0x7f7f.. = "unset"
         PG_CUDA(cudaEventRecord(ev_main.a, st));
-        if (has_key1) lowcard_chain_kernel<true, 2><<<grid, SA_THREADS, smem, st>>>(prm, d_part.as<i64>(), d_firstrow);
-        else lowcard_chain_kernel<false, 2><<<grid, SA_THREADS, smem, st>>>(prm, d_part.as<i64>(), d_firstrow);
+        if (has_key1) lowcard_chain_kernel<true, 2><<<grid, LC_THREADS, smem, st>>>(prm, d_part.as<i64>(), d_firstrow);
+        else lowcard_chain_kernel<false, 2><<<grid, LC_THREADS, smem, st>>>(prm, d_part.as<i64>(), d_firstrow);
         PG_CUDA(cudaGetLastError());
         PG_CUDA(cudaEventRecord(ev_main.b, st));
         finalize128_kernel<<<1, 64, 0, st>>>(d_part.as<i64>(), grid, G * LC_K, d_final.as<u64>());
@@ -676,11 +676,11 @@ static int try_lowcard(pg_plan *plan, const Node &aggn, const Node &scan, const 
     q.n1 = dims[1];
     q.ngroups = p->G;
     p->bytes_per_row = 8 * ncol8 + 4 * ncol4 + p->nkeys;
-    p->smem = (size_t)p->G * LC_K * SA_THREADS * sizeof(i64);
+    p->smem = (size_t)p->G * LC_K * LC_THREADS * sizeof(i64);
     const void *kern = p->has_key1 ? (const void *)lowcard_chain_kernel<true, 2> : (const void *)lowcard_chain_kernel<false, 2>;
     PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
-    i64 ntiles = (t->nrows + SA_TILE - 1) / SA_TILE;
-    p->grid = grid_for(kern, SA_THREADS, p->smem, ntiles);
+    i64 ntiles = (t->nrows + LC_TILE - 1) / LC_TILE;
+    p->grid = grid_for(kern, LC_THREADS, p->smem, ntiles);
     // exactness proof from column statistics
     {
         const Column &cA = t->cols[(size_t)colA];
@@ -695,7 +695,7 @@ static int try_lowcard(pg_plan *plan, const Node &aggn, const Node &scan, const 
             i128 f = maxabs(q.c2 + q.s2 * cC.vmin, q.c2 + q.s2 * cC.vmax);
             bound *= f > 1 ? f : 1;
         }
-        i128 rows_per_cta = (i128)((ntiles + p->grid - 1) / p->grid) * SA_TILE;
+        i128 rows_per_cta = (i128)((ntiles + p->grid - 1) / p->grid) * LC_TILE;
         if (bound * rows_per_cta >= ((i128)1 << 62)) { *why = "per-CTA partial sum could exceed int64"; return PG_EUNSUPPORTED; }
         // can any DECIMAL total need 20 digits?  Then the CTAs take contiguous tile runs so that
         // their partials are ordered (sequential-rounding emulation); the bound uses the largest
@@ -724,7 +724,7 @@ static int try_lowcard(pg_plan *plan, const Node &aggn, const Node &scan, const 
     snprintf(buf, sizeof buf,
              "ScanAgg[lowcard-chain] table=%s rows=%lld kernel=lowcard_chain_kernel<%d,2> grid=%d block=%d smem=%zu "
              "groups=%dx%d bytes/row=%d pred=[%d,%d] chain: A*(%lld%+lld*B)*(%lld%+lld*C) tiles=%s",
-             t->name.c_str(), (long long)t->nrows, (int)p->has_key1, p->grid, SA_THREADS, p->smem, dims[0], dims[1],
+             t->name.c_str(), (long long)t->nrows, (int)p->has_key1, p->grid, LC_THREADS, p->smem, dims[0], dims[1],
              p->bytes_per_row, lo, hi, (long long)q.c1, (long long)q.s1, (long long)q.c2, (long long)q.s2,
              q.contig ? "contiguous-per-CTA(ordered partials)" : "interleaved");
     p->explain = buf;

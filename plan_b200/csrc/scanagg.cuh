@@ -133,6 +133,11 @@ sumprod_kernel(const SumProdParams p, i64 *__restrict__ partials /* [grid][2] = 
 // reduction at the end, one partial per CTA, 128-bit merge in finalize128_kernel.
 // Algorithmic bytes per row: 4 + nkeys + 4 + 24 (= 34 for Q1).
 // ------------------------------------------------------------------------------
+#ifndef PG_LC_THREADS
+#define PG_LC_THREADS 256
+#endif
+constexpr int LC_THREADS = PG_LC_THREADS;          // threads per CTA of the low-cardinality kernels
+constexpr int LC_TILE = LC_THREADS * SA_VEC;       // rows per tile of the low-cardinality kernels
 constexpr int LC_K = 6;
 constexpr int LC_MAXG = 8;
 
@@ -174,20 +179,20 @@ __device__ __forceinline__ TileIter tile_iter(i64 ntiles, int contig)
 }
 
 template <bool HAS_KEY1, int UNROLL>
-__global__ void __launch_bounds__(SA_THREADS)   // 2 CTAs/SM; forcing 3 (80 regs + max SMEM carve-out) measured 1.8x SLOWER
+__global__ void __launch_bounds__(LC_THREADS)   // 2 CTAs/SM; forcing 3 (80 regs + max SMEM carve-out) measured 1.8x SLOWER
 lowcard_chain_kernel(const LowcardParams p, i64 *__restrict__ partials /* [grid][G*K] */,
                      i64 *__restrict__ first_row /* [G], pre-set to INT64_MAX */)
 {
-    extern __shared__ i64 s_acc[];                 // [G*K][SA_THREADS]
+    extern __shared__ i64 s_acc[];                 // [G*K][LC_THREADS]
     __shared__ uint8_t s_lut[2][256];
     __shared__ i64 s_first[LC_MAXG];
     const int G = p.ngroups;
-    for (int i = threadIdx.x; i < G * LC_K * SA_THREADS; i += SA_THREADS) s_acc[i] = 0;
-    for (int i = threadIdx.x; i < 512; i += SA_THREADS) s_lut[i >> 8][i & 255] = p.luts[i];
+    for (int i = threadIdx.x; i < G * LC_K * LC_THREADS; i += LC_THREADS) s_acc[i] = 0;
+    for (int i = threadIdx.x; i < 512; i += LC_THREADS) s_lut[i >> 8][i & 255] = p.luts[i];
     if (threadIdx.x < LC_MAXG) s_first[threadIdx.x] = INT64_MAX;
     __syncthreads();
 
-    const i64 ntiles = (p.nrows + SA_TILE - 1) / SA_TILE;
+    const i64 ntiles = (p.nrows + LC_TILE - 1) / LC_TILE;
     const TileIter it = tile_iter<UNROLL>(ntiles, p.contig);
     i64 *my = s_acc + threadIdx.x;
     for (i64 tile0 = it.tbeg; tile0 < it.tend; tile0 += it.tstep) {
@@ -198,7 +203,7 @@ lowcard_chain_kernel(const LowcardParams p, i64 *__restrict__ partials /* [grid]
         for (int u = 0; u < UNROLL; u++) {
             i64 tile = tile0 + (i64)u * it.ustride;
             if (tile < it.tend) {
-                i64 row = tile * SA_TILE + threadIdx.x * SA_VEC;
+                i64 row = tile * LC_TILE + threadIdx.x * SA_VEC;
                 d[u] = ld_stream16(p.pred + row);
                 k0[u] = ld_stream4(p.key0 + row);
                 if (HAS_KEY1) k1[u] = ld_stream4(p.key1 + row);
@@ -212,7 +217,7 @@ lowcard_chain_kernel(const LowcardParams p, i64 *__restrict__ partials /* [grid]
         for (int u = 0; u < UNROLL; u++) {
             i64 tile = tile0 + (i64)u * it.ustride;
             if (tile < it.tend) {
-                i64 row = tile * SA_TILE + threadIdx.x * SA_VEC;
+                i64 row = tile * LC_TILE + threadIdx.x * SA_VEC;
                 i64 rem = p.nrows - row;
                 int dv[4] = {d[u].x, d[u].y, d[u].z, d[u].w};
                 int qv[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
@@ -225,17 +230,17 @@ lowcard_chain_kernel(const LowcardParams p, i64 *__restrict__ partials /* [grid]
                     if (ok) {
                         int g = s_lut[0][(k0[u] >> (8 * j)) & 255];
                         if (HAS_KEY1) g = g * p.n1 + s_lut[1][(k1[u] >> (8 * j)) & 255];
-                        i64 *t = my + g * (LC_K * SA_THREADS);
+                        i64 *t = my + g * (LC_K * LC_THREADS);
                         i64 n = t[0];
                         if (n == 0) atomicMin((long long *)&s_first[g], (long long)(p.row_base + row + j));
                         i64 t2 = av[j] * (p.c1 + p.s1 * bv[j]);
                         i64 t3 = t2 * (p.c2 + p.s2 * cv[j]);
                         t[0] = n + 1;
-                        t[1 * SA_THREADS] += qv[j];
-                        t[2 * SA_THREADS] += av[j];
-                        t[3 * SA_THREADS] += t2;
-                        t[4 * SA_THREADS] += t3;
-                        t[5 * SA_THREADS] += bv[j];
+                        t[1 * LC_THREADS] += qv[j];
+                        t[2 * LC_THREADS] += av[j];
+                        t[3 * LC_THREADS] += t2;
+                        t[4 * LC_THREADS] += t3;
+                        t[5 * LC_THREADS] += bv[j];
                     }
                 }
             }
@@ -244,10 +249,10 @@ lowcard_chain_kernel(const LowcardParams p, i64 *__restrict__ partials /* [grid]
     __syncthreads();
     // block reduction: warp w sums slots w, w+8, ... across the 256 private copies
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int v = warp; v < G * LC_K; v += SA_THREADS / 32) {
+    for (int v = warp; v < G * LC_K; v += LC_THREADS / 32) {
         i64 s = 0;
 #pragma unroll
-        for (int j = 0; j < SA_THREADS / 32; j++) s += s_acc[v * SA_THREADS + lane + 32 * j];
+        for (int j = 0; j < LC_THREADS / 32; j++) s += s_acc[v * LC_THREADS + lane + 32 * j];
         s = warp_sum(s);
         if (lane == 0) partials[(i64)blockIdx.x * (G * LC_K) + v] = s;
     }
@@ -307,20 +312,20 @@ __device__ __forceinline__ OrdState ord_compose(const OrdState &l, const OrdStat
 }
 
 template <bool HAS_KEY1>
-__global__ void __launch_bounds__(SA_THREADS)
+__global__ void __launch_bounds__(LC_THREADS)
 ord_tile_kernel(const OrdParams op, OrdSummary *__restrict__ out /* [ceil((tile_end - tile_begin) / chunk)] */)
 {
     const LowcardParams &p = op.base;
     __shared__ uint8_t s_lut[2][256];
-    __shared__ OrdState s_w[SA_THREADS / 32];
-    for (int i = threadIdx.x; i < 512; i += SA_THREADS) s_lut[i >> 8][i & 255] = p.luts[i];
+    __shared__ OrdState s_w[LC_THREADS / 32];
+    for (int i = threadIdx.x; i < 512; i += LC_THREADS) s_lut[i >> 8][i & 255] = p.luts[i];
     __syncthreads();
     const i64 nchunks = (op.tile_end - op.tile_begin + op.chunk - 1) / op.chunk;
     for (i64 ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
         OrdState run = {0, 0, 0, 0, 0, 1};      // thread 0: ordered composition of the chunk's tiles
         const i64 t0 = op.tile_begin + ch * op.chunk, t1 = t0 + op.chunk < op.tile_end ? t0 + op.chunk : op.tile_end;
         for (i64 tile = t0; tile < t1; tile++) {
-            i64 row = tile * SA_TILE + threadIdx.x * SA_VEC;
+            i64 row = tile * LC_TILE + threadIdx.x * SA_VEC;
             i64 rem = p.nrows - row;
             int4 d = ld_stream16(p.pred + row);
             unsigned k0 = ld_stream4(p.key0 + row), k1 = HAS_KEY1 ? ld_stream4(p.key1 + row) : 0;
@@ -365,7 +370,7 @@ ord_tile_kernel(const OrdParams op, OrdSummary *__restrict__ out /* [ceil((tile_
             if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = st;
             __syncthreads();
             if (threadIdx.x == 0) {
-                for (int w = 0; w < SA_THREADS / 32; w++) run = ord_compose(run, s_w[w]);
+                for (int w = 0; w < LC_THREADS / 32; w++) run = ord_compose(run, s_w[w]);
             }
             __syncthreads();
         }
