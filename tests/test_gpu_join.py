@@ -263,3 +263,60 @@ def test_null_join_keys_never_match(pg, oracle, sf01_host, anti):
     finally:
         to.free()
         tl.free()
+
+
+@pytest.mark.parametrize("empty", ["customer", "orders", "lineitem", "all"])
+def test_q3_with_empty_tables(pg, oracle, sf01_host, empty):
+    """Empty inputs on any side of the join tree: no rows, no crash (the reference emits nothing)."""
+    from plan_b200 import tpch as T
+    host = {}
+    for name, cols in sf01_host.items():
+        n = 0 if empty in (name, "all") else 3000
+        host[name] = {k: v[:n].copy() for k, v in cols.items()}
+    t = T.upload_tables(host)
+    try:
+        for plan in (T.q3_plan(odate_lt=8035 + 3000, ship_gt=8035 - 10), T.q3_topk_plan(10, odate_lt=8035 + 3000, ship_gt=8035 - 10)):
+            chunks, stats, _ = _run(plan, t)
+            if empty == "lineitem" or empty == "all" or empty == "orders" or empty == "customer":
+                ref = oracle.q3(host["customer"], host["orders"], host["lineitem"], odate_lt=8035 + 3000, ship_gt=8035 - 10) \
+                    if len(host["orders"]["o_orderkey"]) and len(host["customer"]["c_custkey"]) and len(host["lineitem"]["l_orderkey"]) else None
+                assert ref is None
+                assert chunks == []
+        chunks, _, _ = _run(T.groupby_plan(key="l_orderkey", value="l_quantity"), t)
+        assert (chunks == []) == (len(host["lineitem"]["l_orderkey"]) == 0)
+    finally:
+        for x in t.values():
+            x.free()
+
+
+def test_sentinel_key_values_are_refused(pg, sf01_host):
+    """A key column whose value range contains the table's empty-slot sentinel cannot use the open
+    addressing tables: refused at plan time (PG_EUNSUPPORTED), never a wrong group."""
+    from plan_b200 import _lib as L, compute as X, tpch as T
+    line = {k: v[:5000].copy() for k, v in sf01_host["lineitem"].items()}
+    line["l_orderkey"][17] = np.int64(-0x7f7f7f7f7f7f7f80)        # == HT_EMPTY (0x8080808080808080)
+    line["l_orderkey"][18] = np.int64(2 ** 62)
+    t = T.upload_tables({"lineitem": line})
+    try:
+        ex = X.gpuPipelineExec(T.groupby_plan(key="l_orderkey", value="l_quantity"), t)
+        with pytest.raises(L.PlanGpuError) as ei:
+            ex.Init()
+        assert ei.value.status == L.PG_EUNSUPPORTED
+        ex.Close()
+    finally:
+        t["lineitem"].free()
+
+
+def test_extreme_key_values_group_correctly(pg, oracle, sf01_host):
+    """Keys spread over almost the whole int64 range (but not the sentinel): hashed slots, exact sums."""
+    from plan_b200 import tpch as T
+    n = 20000
+    line = {k: v[:n].copy() for k, v in sf01_host["lineitem"].items()}
+    rng = np.random.default_rng(3)
+    keys = rng.integers(-2 ** 62, 2 ** 62, size=500, dtype=np.int64)
+    line["l_orderkey"] = keys[rng.integers(0, 500, size=n)]
+    t = T.upload_tables({"lineitem": line})
+    try:
+        check_groupby(oracle, t, line, key="l_orderkey", value="l_extendedprice")
+    finally:
+        t["lineitem"].free()
