@@ -96,6 +96,9 @@ struct JoinAggPipeline : Pipeline {
     bool gather_ranks = false;     // probe side is sharded: every rank ends with the union of all groups
     DevBuf d_g_klo, d_g_khi, d_g_acc, d_g_cnt;
     PinBuf h_out;                  // pinned landing zone of the group lists: [klo | khi | acc planes]
+    static constexpr int SG_CAP = 256;   // rows per rank in the single-message gather of top-k candidates
+    DevBuf d_sg;
+    PinBuf h_sg;
     // fused ORDER BY ... LIMIT k: device pre-selection on the primary key
     bool has_topk = false;
     TopkKey topk_key{};
@@ -308,9 +311,12 @@ struct JoinAggPipeline : Pipeline {
         pp.ins = s.jt;
         PG_CUDA(cudaMemsetAsync(d_counters.p, 0, 32, st));
         PG_TRY(launch_pipe<SINK_INSERT>(pp, t));
-        unsigned long long c2[4];
-        PG_TRY(read_counters(c2));
-        s.dup_keys = (i64)c2[2];
+        s.dup_keys = 1;                          // unknown: assume duplicates...
+        if (!s.payload_needed && s.jt.bitmap) {  // ...unless it decides whether the bitmap alone can answer probes
+            unsigned long long c2[4];
+            PG_TRY(read_counters(c2));
+            s.dup_keys = (i64)c2[2];
+        }
         res->stats.kernel_launches += 2;
         if (idx < 4) { res->stats.aux[2 + 2 * idx] = (i64)cnt[0]; res->stats.aux[3 + 2 * idx] = (i64)cnt[1]; }
         return PG_OK;
@@ -518,7 +524,47 @@ struct JoinAggPipeline : Pipeline {
             h_acc = h_khi + n;
             return PG_OK;
         };
-        if (gather_ranks && c.world > 1) {
+        bool small_done = false;
+        if (gather_ranks && c.world > 1 && has_topk && topk_limit >= 0 && topk_limit <= SG_CAP / 2) {
+            // LIMIT k with small k: every rank has at most k (+ties) candidates -> ONE fixed-size all-gather
+            // [count | klo[SG_CAP] | khi[SG_CAP] | planes x acc[SG_CAP]] and one read-back.  A rank with more
+            // than SG_CAP candidates publishes count = -1 and everybody takes the general path below.
+            const size_t words = 1 + (size_t)SG_CAP * (size_t)(2 + planes);
+            if (!d_sg.p) { PG_TRY(d_sg.alloc(words * 8 * (size_t)(c.world + 1))); PG_TRY(h_sg.alloc(words * 8 * (size_t)c.world)); }
+            i64 *send = d_sg.as<i64>();
+            i64 cnt_word = ngroups <= SG_CAP ? ngroups : -1;
+            PG_CUDA(cudaMemcpyAsync(send, &cnt_word, 8, cudaMemcpyHostToDevice, st));
+            if (cnt_word > 0) {
+                PG_CUDA(cudaMemcpyAsync(send + 1, d_out_klo.p, (size_t)ngroups * 8, cudaMemcpyDeviceToDevice, st));
+                PG_CUDA(cudaMemcpyAsync(send + 1 + SG_CAP, d_out_khi.p, (size_t)ngroups * 8, cudaMemcpyDeviceToDevice, st));
+                for (int a = 0; a < planes; a++)
+                    PG_CUDA(cudaMemcpyAsync(send + 1 + (size_t)SG_CAP * (size_t)(2 + a), d_out_acc.as<i64>() + (size_t)a * (size_t)out_cap,
+                                            (size_t)ngroups * 8, cudaMemcpyDeviceToDevice, st));
+            }
+            PG_TRY(comm_allgather(send, send + words, words * 8, st));
+            PG_CUDA(cudaMemcpyAsync(h_sg.p, send + words, words * 8 * (size_t)c.world, cudaMemcpyDeviceToHost, st));
+            PG_CUDA(cudaStreamSynchronize(st));
+            const i64 *hs = h_sg.as<i64>();
+            i64 total = 0;
+            bool ok = true;
+            for (int r = 0; r < c.world; r++) { i64 x = hs[(size_t)r * words]; if (x < 0) ok = false; else total += x; }
+            if (ok) {
+                PG_TRY(host_arrays(total));
+                i64 off = 0;
+                for (int r = 0; r < c.world; r++) {
+                    const i64 *rec = hs + (size_t)r * words;
+                    i64 nr = rec[0];
+                    memcpy(h_klo + off, rec + 1, (size_t)nr * 8);
+                    memcpy(h_khi + off, rec + 1 + SG_CAP, (size_t)nr * 8);
+                    for (int a = 0; a < planes; a++) memcpy(h_acc + (size_t)a * (size_t)total + (size_t)off, rec + 1 + (size_t)SG_CAP * (size_t)(2 + a), (size_t)nr * 8);
+                    off += nr;
+                }
+                ngroups = total;
+                small_done = true;
+            }
+        }
+        if (small_done) {
+        } else if (gather_ranks && c.world > 1) {
             // shard-local groups are disjoint across ranks (co-partitioned on the join key, checked
             // at plan time): all-gather the per-rank lists over NVLink, every rank ends with the union
             std::vector<i64> counts((size_t)c.world);

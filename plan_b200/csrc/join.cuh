@@ -626,6 +626,8 @@ static __global__ void topk_hist_kernel(TopkKey key, const i64 *klo, const i64 *
         if (s_h[i]) atomicAdd(&hist[i], s_h[i]);
 }
 
+// (A single-block, single-launch radix select was tried to save the 8 host round trips at small n: one SM
+// evaluating every key 8 times took 0.66 ms at 113 k groups against 0.16 ms for the multi-block passes.)
 // copy every group whose primary key is <= threshold to the candidate arrays
 static __global__ void topk_collect_kernel(TopkKey key, const i64 *klo, const i64 *khi, const i64 *acc, i64 stride, i64 n, int planes,
                                            u64 threshold, i64 *out_klo, i64 *out_khi, i64 *out_acc, i64 out_cap,

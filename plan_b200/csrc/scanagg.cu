@@ -259,10 +259,10 @@ struct LowcardPipeline : Pipeline {
 
     // summaries of tiles [tb, te) for (group, slot), `chunk` consecutive tiles composed per summary
     // (chunk = 1 where the crossing tile is searched) -> h_ord (pinned)
-    int ord_summaries(int g, int s, i64 tb, i64 te, int chunk, const OrdSummary **out, i64 *n)
+    int ord_summaries(int g, int s, i64 tb, i64 te, int chunk, const OrdSummary **out, i64 *n, i64 at = 0, bool sync = true)
     {
         *n = te > tb ? (te - tb + chunk - 1) / chunk : 0;
-        *out = h_ord.as<OrdSummary>();
+        *out = h_ord.as<OrdSummary>() + at;
         if (te <= tb) return PG_OK;
         cudaStream_t st = ctx().stream;
         OrdParams op;
@@ -273,11 +273,11 @@ struct LowcardPipeline : Pipeline {
         op.tile_end = te;
         op.chunk = chunk;
         int gr = (int)std::min<i64>(*n, (i64)ctx().prop.multiProcessorCount * 8);
-        if (has_key1) ord_tile_kernel<true><<<gr, LC_THREADS, 0, st>>>(op, d_ord.as<OrdSummary>());
-        else ord_tile_kernel<false><<<gr, LC_THREADS, 0, st>>>(op, d_ord.as<OrdSummary>());
+        if (has_key1) ord_tile_kernel<true><<<gr, LC_THREADS, 0, st>>>(op, d_ord.as<OrdSummary>() + at);
+        else ord_tile_kernel<false><<<gr, LC_THREADS, 0, st>>>(op, d_ord.as<OrdSummary>() + at);
         PG_CUDA(cudaGetLastError());
-        PG_CUDA(cudaMemcpyAsync(h_ord.p, d_ord.p, sizeof(OrdSummary) * (size_t)*n, cudaMemcpyDeviceToHost, st));
-        PG_CUDA(cudaStreamSynchronize(st));
+        PG_CUDA(cudaMemcpyAsync(h_ord.as<OrdSummary>() + at, d_ord.as<OrdSummary>() + at, sizeof(OrdSummary) * (size_t)*n, cudaMemcpyDeviceToHost, st));
+        if (sync) PG_CUDA(cudaStreamSynchronize(st));
         return PG_OK;
     }
 
@@ -320,9 +320,13 @@ struct LowcardPipeline : Pipeline {
                 P += v;
             }
             if (cstar == grid) PG_FAIL(PG_ECUDA, "internal: crossing CTA not found");
-            // b. which tile of that CTA crosses
+            // b. per-tile summaries of the crossing CTA's tiles and, in the same round trip, chunk summaries
+            //    of every tile after that CTA's range
             i64 tb = (i64)cstar * per, te = std::min<i64>(ntiles, tb + per);
-            PG_TRY(ord_summaries(g, s, tb, te, 1, &sums, &nsums));
+            const OrdSummary *tail = nullptr;
+            i64 ntail = 0;
+            PG_TRY(ord_summaries(g, s, tb, te, 1, &sums, &nsums, 0, false));
+            PG_TRY(ord_summaries(g, s, te, ntiles, ORD_CHUNK, &tail, &ntail, te - tb, true));
             i64 tstar = tb;
             for (; tstar < te; tstar++) {
                 i128 v = sums[tstar - tb].sum_x;
@@ -365,9 +369,9 @@ struct LowcardPipeline : Pipeline {
                 }
             }
             if (!rounded) PG_FAIL(PG_ECUDA, "internal: crossing row not found");
-            // d. the rest of this rank's rows, tile summaries composed in order
-            PG_TRY(ord_summaries(g, s, tstar + 1, ntiles, ORD_CHUNK, &sums, &nsums));
-            for (i64 i = 0; i < nsums; i++) S += (u128)sums[i].sum_q + ((S & 1) ? sums[i].c1 : sums[i].c0);
+            // d. the rest of the crossing CTA's tiles (per-tile summaries), then the chunk summaries after it
+            for (i64 t = tstar + 1; t < te; t++) S += (u128)sums[t - tb].sum_q + ((S & 1) ? sums[t - tb].c1 : sums[t - tb].c0);
+            for (i64 i = 0; i < ntail; i++) S += (u128)tail[i].sum_q + ((S & 1) ? tail[i].c1 : tail[i].c0);
             mine.kind = 1;
             mine.s_lo = (u64)S;
             mine.s_hi = (u64)(S >> 64);
