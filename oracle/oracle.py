@@ -113,7 +113,7 @@ def lib():
                              [C.c_int64] + [C.c_void_p] * 4 + [C.c_int32] +
                              [C.c_void_p, C.c_int64, C.POINTER(Q3Result)])
         L.orc_stats.restype = None
-        L.orc_stats.argtypes = [C.c_int64] + [C.c_void_p] * 8 + [C.c_int32] * 6 + [C.c_int64] + [C.c_void_p] * 3 + [C.POINTER(StatsResult)]
+        L.orc_stats.argtypes = [C.c_int64] + [C.c_void_p] * 8 + [C.c_int32] * 6 + [C.c_int64] + [C.c_void_p] * 6 + [C.POINTER(StatsResult)]
         assert L.orc_sizeof_stats_result() == C.sizeof(StatsResult)
         L.orc_format_decimal.restype = C.c_int
         L.orc_format_decimal.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]
@@ -245,7 +245,16 @@ def q3(cust, orders, line, segment="HOUSEHOLD", odate_lt=days(1995, 3, 29), ship
     return {"groups": groups, "stats": stats}
 
 
-def stats(line, d0, d1, d2, d3, q0, q1, disc_gt_cents, valid=None):
+def _lut(chars):
+    if chars is None:
+        return None
+    t = np.zeros(256, dtype=np.uint8)
+    for ch in chars:
+        t[ord(ch)] = 1
+    return t
+
+
+def stats(line, d0, d1, d2, d3, q0, q1, disc_gt_cents, valid=None, linestatus_in=None, returnflag_in=None):
     """The wider 'stats' shape (min/max/sum/avg/count, 7 comparisons, 1 key) -- see refexec.c orc_stats.
     valid: optional {column: bool array} for l_quantity / l_extendedprice / l_tax (False = NULL); aggregate
     results whose inputs were all NULL come back as None."""
@@ -255,7 +264,8 @@ def stats(line, d0, d1, d2, d3, q0, q1, disc_gt_cents, valid=None):
     lib().orc_stats(len(line["l_shipdate"]), _p(line["l_shipdate"]), _p(line["l_commitdate"]), _p(line["l_receiptdate"]),
                     _p(line["l_quantity"]), _p(line["l_extendedprice"]), _p(line["l_discount"]), _p(line["l_tax"]),
                     _p(line["l_returnflag"]), d0, d1, d2, d3, q0, q1, disc_gt_cents,
-                    _p(vb.get("l_quantity")), _p(vb.get("l_extendedprice")), _p(vb.get("l_tax")), C.byref(r))
+                    _p(vb.get("l_quantity")), _p(vb.get("l_extendedprice")), _p(vb.get("l_tax")),
+                    _p(line["l_linestatus"]), _p(_lut(linestatus_in)), _p(_lut(returnflag_in)), C.byref(r))
     assert r.error == 0, r.error
     groups = [{"l_returnflag": chr(g.rf),
                "min_ext": g.min_ext.tuple() if g.n_ext else None, "max_ext": g.max_ext.tuple() if g.n_ext else None,

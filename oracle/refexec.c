@@ -552,8 +552,11 @@ typedef struct {
 void orc_stats(int64_t n, const int32_t *shipdate, const int32_t *commitdate, const int32_t *receiptdate,
                const int32_t *quantity, const int64_t *extprice, const int64_t *discount, const int64_t *tax,
                const uint8_t *returnflag, int32_t d0, int32_t d1, int32_t d2, int32_t d3, int32_t q0, int32_t q1,
-               int64_t disc_gt_cents, const uint8_t *v_qty, const uint8_t *v_ext, const uint8_t *v_tax, stats_result *res)
-{
+               int64_t disc_gt_cents, const uint8_t *v_qty, const uint8_t *v_ext, const uint8_t *v_tax,
+               const uint8_t *linestatus, const uint8_t *ls_lut, const uint8_t *rf_lut, stats_result *res)
+{   /* ls_lut / rf_lut: optional 256-entry tables, 1 = the code passes -- restates `l_linestatus <> 'O'`,
+     * `l_returnflag in ('A','R')`, `a = x or a = y` (equalStrOp / inOp / execSelectOr,
+     * function_operator_boolean.go:99-104,393-504, expr_exec.go:482-530) */
     static date_t v_s[VEC], v_c[VEC], v_r[VEC];
     static int sa[VEC], sb[VEC];
     memset(res, 0, sizeof *res);
@@ -578,6 +581,16 @@ void orc_stats(int64_t n, const int32_t *shipdate, const int32_t *commitdate, co
         }
         c = sel_i32_const(quantity + off, q0, CMP_GE, sb, c, sa);
         c = sel_i32_const(quantity + off, q1, CMP_LE, sa, c, sb);
+        if (ls_lut || rf_lut) {
+            int k = 0;
+            for (int i = 0; i < c; i++) {
+                int64_t r = off + sb[i];
+                if (ls_lut && !ls_lut[linestatus[r]]) continue;
+                if (rf_lut && !rf_lut[returnflag[r]]) continue;
+                sb[k++] = sb[i];
+            }
+            c = k;
+        }
         int c2 = 0;
         for (int i = 0; i < c; i++) {      /* greatDecimalOp: left.Sub(right).IsPos() */
             dec_t d;

@@ -194,6 +194,9 @@ private:
 struct Range {
     int col = -1;
     i64 lo = INT64_MIN, hi = INT64_MAX;   // inclusive; lo > hi selects nothing
+    // byte-coded columns (VARCHAR(1) / dictionary): `<>`, IN lists and ORs of equalities are code SETS
+    bool is_set = false;
+    uint32_t set[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 struct Factor {
@@ -228,6 +231,15 @@ inline void range_and(Range &r, i64 lo, i64 hi)
 {
     if (lo > r.lo) r.lo = lo;
     if (hi < r.hi) r.hi = hi;
+}
+
+// fold range bounds into the code set of a byte column (so that ranges and sets on one column intersect)
+inline void range_to_set(Range &r)
+{
+    if (r.is_set) return;
+    r.is_set = true;
+    for (int c = 0; c < 256; c++)
+        if ((i64)c >= r.lo && (i64)c <= r.hi) r.set[c >> 5] |= 1u << (c & 31);
 }
 
 // float32(Float64(decimal c * 10^-scale)) exactly as the reference casts a DECIMAL to FLOAT
@@ -288,6 +300,57 @@ inline const Expr *strip_value_preserving_casts(const Expr *e)
     return e;
 }
 
+inline i64 byte_code(const Column &col, const std::string &s)
+{
+    if (col.type == PG_T_CHAR1) return s.size() == 1 ? (i64)(uint8_t)s[0] : -1;
+    for (size_t i = 0; i < col.dict.size(); i++) if (col.dict[i] == s) return (i64)i;
+    return -1;
+}
+
+inline bool lower_compare(LowerCtx &cx, const Expr &e, std::vector<Range> &ranges);
+
+// `col IN (...)` and `a = x OR a = y OR ...` on ONE byte-coded column -> a code set
+inline bool lower_byte_set(LowerCtx &cx, const Expr &e, std::vector<Range> &ranges)
+{
+    Range acc;
+    acc.is_set = true;
+    std::vector<const Expr *> todo{&e};
+    while (!todo.empty()) {
+        const Expr *x = todo.back();
+        todo.pop_back();
+        if (x->kind == PG_TK_FUNC && x->fn == PG_FN_OR) { for (auto &a : x->args) todo.push_back(&a); continue; }
+        std::vector<Range> one;
+        if (x->kind == PG_TK_FUNC && x->fn == PG_FN_IN && x->args.size() >= 2) {
+            const Expr *c = strip_value_preserving_casts(&x->args[0]);
+            if (c->kind != PG_TK_COL || c->idx < 0 || c->idx >= (int)cx.table->cols.size()) return fail(cx, "IN over a non-column");
+            const Column &col = cx.table->cols[(size_t)c->idx];
+            if (!is_byte_family(col.type)) return fail(cx, "IN is supported on dictionary/char columns only");
+            if (col.has_nulls) { if (!cx.allow_nulls) return fail(cx, "nullable column in predicate"); cx.saw_nulls = true; }
+            Range r;
+            r.col = c->idx;
+            r.is_set = true;
+            for (size_t i = 1; i < x->args.size(); i++) {
+                const Expr *k = strip_value_preserving_casts(&x->args[i]);
+                if (k->kind != PG_TK_STR) return fail(cx, "IN list element is not a string literal");
+                i64 code = byte_code(col, k->str);
+                if (code >= 0) r.set[code >> 5] |= 1u << (code & 31);
+            }
+            one.push_back(r);
+        } else if (!lower_compare(cx, *x, one) || one.size() != 1) {
+            return fail(cx, "OR branch is not a single comparison");
+        }
+        Range &r = one[0];
+        if (!is_byte_family(cx.table->cols[(size_t)r.col].type)) return fail(cx, "OR / IN is supported on dictionary/char columns only");
+        if (acc.col >= 0 && acc.col != r.col) return fail(cx, "OR over different columns");
+        acc.col = r.col;
+        range_to_set(r);
+        for (int w = 0; w < 8; w++) acc.set[w] |= r.set[w];
+    }
+    if (acc.col < 0) return fail(cx, "empty OR");
+    ranges.push_back(acc);
+    return true;
+}
+
 // One conjunct `col <cmp> const` (either order) -> range on a table column.
 inline bool lower_compare(LowerCtx &cx, const Expr &e, std::vector<Range> &ranges)
 {
@@ -296,6 +359,7 @@ inline bool lower_compare(LowerCtx &cx, const Expr &e, std::vector<Range> &range
         for (auto &a : e.args) if (!lower_compare(cx, a, ranges)) return false;
         return true;
     }
+    if (e.fn == PG_FN_OR || e.fn == PG_FN_IN) return lower_byte_set(cx, e, ranges);
     if (!is_cmp(e.fn) || e.args.size() != 2) return fail(cx, "filter is not a comparison/AND");
     const Expr *l = &e.args[0], *r = &e.args[1];
     int op = e.fn;
@@ -340,14 +404,14 @@ inline bool lower_compare(LowerCtx &cx, const Expr &e, std::vector<Range> &range
     }
     if (is_byte_family(col.type)) {
         if (k->kind != PG_TK_STR) return fail(cx, "byte column compared with non-string");
-        if (op != PG_FN_EQ) return fail(cx, "only = is supported on dictionary/char columns");
-        i64 code = -1;
-        if (col.type == PG_T_CHAR1) {
-            if (k->str.size() == 1) code = (uint8_t)k->str[0];
-        } else {
-            for (size_t i = 0; i < col.dict.size(); i++) if (col.dict[i] == k->str) code = (i64)i;
+        if (op != PG_FN_EQ && op != PG_FN_NE) return fail(cx, "only = and <> are supported on dictionary/char columns");
+        i64 code = byte_code(col, k->str);
+        if (op == PG_FN_EQ) {
+            if (code < 0) { rg.lo = 1; rg.hi = 0; } else { rg.lo = rg.hi = code; }
+        } else {                       // <> : every code but this one (equalStrOp negated, function_operator_boolean.go:99-104)
+            rg.is_set = true;
+            for (int c = 0; c < 256; c++) if (c != code) rg.set[c >> 5] |= 1u << (c & 31);
         }
-        if (code < 0) { rg.lo = 1; rg.hi = 0; } else { rg.lo = rg.hi = code; }
         ranges.push_back(rg);
         return true;
     }
@@ -381,7 +445,17 @@ inline bool lower_filters(LowerCtx &cx, const std::vector<Expr> &filters, std::v
     for (auto &f : filters) if (!lower_compare(cx, f, raw)) return false;
     for (auto &r : raw) {
         bool merged = false;
-        for (auto &o : out) if (o.col == r.col) { range_and(o, r.lo, r.hi); merged = true; }
+        for (auto &o : out) if (o.col == r.col) {
+            if (o.is_set || r.is_set) {          // intersect as code sets
+                Range rr = r;
+                range_to_set(o);
+                range_to_set(rr);
+                for (int w = 0; w < 8; w++) o.set[w] &= rr.set[w];
+            } else {
+                range_and(o, r.lo, r.hi);
+            }
+            merged = true;
+        }
         if (!merged) out.push_back(r);
     }
     return true;

@@ -934,6 +934,8 @@ static int try_generic(pg_plan *plan, const Node &aggn, const Node &scan, const 
         if (col.has_nulls) p->nulls = true;
         q.plo[i] = ranges[i].lo;
         q.phi[i] = ranges[i].hi;
+        q.pset[i] = ranges[i].is_set ? 1 : 0;
+        memcpy(q.pmask[i], ranges[i].set, sizeof q.pmask[i]);
         use(ranges[i].col);
     }
     q.nkeys = p->nkeys;
@@ -1069,10 +1071,12 @@ int build_scan_agg(pg_plan *plan, const Node &aggn, const Node &scan, std::uniqu
         if (a.star) PG_FAIL(PG_EINVAL, "aggregate %zu has no argument", i);
         if (!lower_affprod(cx, a.arg, args[i])) PG_FAIL(PG_EUNSUPPORTED, "aggregate argument not off-loadable: %s", cx.why.c_str());
     }
-    std::string why1 = "NULLs present", why2 = "NULLs present", why3;
+    std::string why1 = "NULLs or code-set predicates present", why2 = why1, why3;
     const char *force = getenv("PG_FORCE_GENERIC");      // testing: exercise the shape-agnostic kernel on every plan
     int s = PG_EUNSUPPORTED;
-    if (!(force && atoi(force)) && !cx.saw_nulls) {
+    bool any_set = false;
+    for (auto &r : ranges) any_set = any_set || r.is_set;
+    if (!(force && atoi(force)) && !cx.saw_nulls && !any_set) {
         s = try_sumprod(plan, aggn, scan, ranges, args, out, &why1);
         if (s != PG_EUNSUPPORTED) return s;
         s = try_lowcard(plan, aggn, scan, ranges, args, out, &why2);

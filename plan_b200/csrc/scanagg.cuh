@@ -419,6 +419,8 @@ struct GenParams {
     int npred;
     GenCol pcol[GEN_MAXPRED];
     i64 plo[GEN_MAXPRED], phi[GEN_MAXPRED];
+    int pset[GEN_MAXPRED];                 // 1: the predicate is a code set on a byte column (IN, <>, OR of =)
+    unsigned pmask[GEN_MAXPRED][8];
     int nkeys;
     const uint8_t *key0, *key1;
     const uint8_t *luts;
@@ -460,7 +462,7 @@ generic_scanagg_kernel(const GenParams p, i64 *__restrict__ partials /* [grid][G
         for (int k = 0; k < p.npred && ok; k++) {
             if (NULLS && !gen_valid(p.pcol[k], row)) { ok = false; break; }
             i64 v = gen_load(p.pcol[k], row);
-            ok = v >= p.plo[k] && v <= p.phi[k];
+            ok = p.pset[k] ? ((p.pmask[k][(v >> 5) & 7] >> (v & 31)) & 1u) != 0 : (v >= p.plo[k] && v <= p.phi[k]);
         }
         if (!ok) continue;
         int g = 0;

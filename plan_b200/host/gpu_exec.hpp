@@ -65,7 +65,7 @@ public:
     static int fn_id(const std::string &n)
     {
         static const std::map<std::string, int> m = {{"+", PG_FN_ADD}, {"-", PG_FN_SUB}, {"*", PG_FN_MUL}, {"/", PG_FN_DIV},
-            {"=", PG_FN_EQ}, {"<>", PG_FN_NE}, {"<", PG_FN_LT}, {"<=", PG_FN_LE}, {">", PG_FN_GT}, {">=", PG_FN_GE},
+            {"=", PG_FN_EQ}, {"<>", PG_FN_NE}, {"<", PG_FN_LT}, {"<=", PG_FN_LE}, {">", PG_FN_GT}, {">=", PG_FN_GE}, {"in", PG_FN_IN},
             {"and", PG_FN_AND}, {"or", PG_FN_OR}, {"not", PG_FN_NOT}, {"cast", PG_FN_CAST}};
         auto it = m.find(n);
         if (it == m.end()) throw PlanError(PG_EUNSUPPORTED, "function " + n + " cannot be off-loaded");

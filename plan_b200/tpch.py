@@ -165,7 +165,7 @@ def q3_plan(segment="HOUSEHOLD", odate_lt=None, ship_gt=None, schema=FULL):
     return PhysicalOperator(POT_Agg, Outputs=outs, Children=[j2], Info=AggOpInfo([agg], groups))
 
 
-def stats_plan(d0, d1, d2, d3, q0, q1, disc_gt_cents, schema=FULL):
+def stats_plan(d0, d1, d2, d3, q0, q1, disc_gt_cents, schema=FULL, linestatus_ne=None, returnflag_in=None, returnflag_or=None):
     """A wider scan-aggregate shape (no specialised kernel: runs on the generic one):
     select l_returnflag, min(l_extendedprice), max(l_extendedprice), max(l_discount), sum(l_tax), avg(l_tax),
            sum(l_extendedprice * (1 + l_tax)), count(*)
@@ -179,6 +179,16 @@ def stats_plan(d0, d1, d2, d3, q0, q1, disc_gt_cents, schema=FULL):
                func("<=", B, lc("l_commitdate"), const(d2, D)), func(">=", B, lc("l_receiptdate"), const(d3, D)),
                func(">=", B, lc("l_quantity"), const(q0, I)), func("<=", B, lc("l_quantity"), const(q1, I)),
                func(">", B, lc("l_discount"), const(disc_gt_cents, DEC15_2))]
+    V = K.VarcharType()
+    if linestatus_ne is not None:          # l_linestatus <> 'O'
+        filters.append(func("<>", B, lc("l_linestatus"), const(linestatus_ne, V)))
+    if returnflag_in is not None:          # l_returnflag in ('A', 'R')
+        filters.append(func("in", B, lc("l_returnflag"), *[const(x, V) for x in returnflag_in]))
+    if returnflag_or is not None:          # l_returnflag = 'A' or l_returnflag = 'N'
+        e = func("=", B, lc("l_returnflag"), const(returnflag_or[0], V))
+        for x in returnflag_or[1:]:
+            e = func("or", B, e, func("=", B, lc("l_returnflag"), const(x, V)))
+        filters.append(e)
     scan = PhysicalOperator(POT_Scan, Filters=filters, Info=ScanOpInfo("lineitem"))
     one_plus_tax = func("+", K.DecimalType(16, 2), cast(const(1, I), DEC15_2), lc("l_tax"))
     taxed = func("*", K.DecimalType(18, 4), cast(lc("l_extendedprice"), K.DecimalType(16, 2)), one_plus_tax)

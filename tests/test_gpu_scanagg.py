@@ -345,3 +345,26 @@ def test_nulls_follow_the_reference(pg, oracle, sf01_host, null_cols, frac):
             assert int(c.Data[7].Data[r]["lower"]) == g["count"]
     finally:
         t.free()
+
+
+@pytest.mark.parametrize("kw,okw", [
+    (dict(linestatus_ne="O"), dict(linestatus_in="F")),
+    (dict(returnflag_in=["A", "R"]), dict(returnflag_in="AR")),
+    (dict(returnflag_or=["A", "N"]), dict(returnflag_in="AN")),
+    (dict(returnflag_in=["A", "X"], linestatus_ne="F"), dict(returnflag_in="A", linestatus_in="O")),
+    (dict(returnflag_in=["Z"]), dict(returnflag_in="Z")),                   # nothing matches
+])
+def test_code_set_predicates(pg, oracle, uploaded, sf01_host, kw, okw):
+    """`<>`, IN lists and ORs of equalities on VARCHAR(1)/dictionary columns become code sets."""
+    from plan_b200 import tpch as T
+    args = (8035, 8035 + 2600, 8035 + 2600, 8035, 1, 50, -1)
+    line = sf01_host["lineitem"]
+    chunks, stats, explain = _run(T.stats_plan(*args, **kw), uploaded)
+    ref = oracle.stats(line, *args, **okw)
+    assert "generic" in explain
+    assert stats.aux[0] == ref["rows_selected"]
+    got = {chr(int(c.Data[0].Data[r])): (int(c.Data[7].Data[r]["lower"]), _dec(c.Data[6], r)) for c in chunks for r in range(c.Card())}
+    want = {g["l_returnflag"]: (g["count"], g["sum_taxed"]) for g in ref["groups"]}
+    assert set(got) == set(want)
+    for k in want:
+        assert got[k][0] == want[k][0] and _same_decimal(got[k][1], want[k][1])
