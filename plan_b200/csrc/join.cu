@@ -191,36 +191,55 @@ struct JoinAggPipeline : Pipeline {
         return (int)std::max<i64>(g, 1);
     }
 
-    // launch the pipeline kernel for `pp`: the vectorised variant when the shape allows it
+    // scratch of the two-phase path: hit list (row ids) and its device-side cursor
+    DevBuf d_hits, d_hit_count;
+    static constexpr i64 HIT_CHUNK = (i64)1 << 26;     // rows screened per filter launch (256 MB of row ids at most)
+
+    static bool two_phase_ok(const PipeParams &pp, const pg_table *t, bool ins_sink)
+    {
+        bool any_valid = pp.probe_key.valid != nullptr || (ins_sink && pp.ins_key.valid != nullptr);
+        for (int k = 0; k < pp.npred; k++) any_valid = any_valid || pp.pred[k].col.valid != nullptr;
+        return pp.has_probe && pp.probe.bitmap && pp.npred <= 1 && (pp.npred == 0 || pp.pred[0].col.width == 4) &&
+               (pp.probe_key.width == 4 || pp.probe_key.width == 8) && !any_valid && t->nrows < ((i64)1 << 32) &&
+               !getenv("PG_JOIN_GENERIC");
+    }
+
+    // phase 1 over rows [lo, hi): fills d_hits / d_hit_count (cursor reset first)
+    int launch_filter(PipeParams &pp, i64 lo, i64 hi)
+    {
+        cudaStream_t st = ctx().stream;
+        if (!d_hit_count.p) PG_TRY(d_hit_count.alloc(8));
+        size_t need = (size_t)std::max<i64>(hi - lo, 1) * 4;
+        if (d_hits.bytes < need) PG_TRY(d_hits.alloc(need));
+        PG_CUDA(cudaMemsetAsync(d_hit_count.p, 0, 8, st));
+        pp.row_begin = lo;
+        pp.row_end = hi;
+        pp.hits = d_hits.as<unsigned>();
+        pp.hit_count = d_hit_count.as<unsigned long long>();
+        i64 ntiles = (hi - lo + SA_TILE - 1) / SA_TILE;
+        int grid = (int)std::max<i64>(std::min<i64>(ntiles, (i64)ctx().prop.multiProcessorCount * 8), 1);
+        const bool k8 = pp.probe_key.width == 8, hp = pp.npred == 1;
+        if (k8 && hp) filter_hits_kernel<8, true, 2><<<grid, SA_THREADS, 0, st>>>(pp);
+        else if (k8) filter_hits_kernel<8, false, 2><<<grid, SA_THREADS, 0, st>>>(pp);
+        else if (hp) filter_hits_kernel<4, true, 2><<<grid, SA_THREADS, 0, st>>>(pp);
+        else filter_hits_kernel<4, false, 2><<<grid, SA_THREADS, 0, st>>>(pp);
+        PG_CUDA(cudaGetLastError());
+        return PG_OK;
+    }
+
+    template <int SINK>
+    int launch_sink(const PipeParams &pp)
+    {
+        hits_sink_kernel<SINK><<<ctx().prop.multiProcessorCount * 8, 256, 0, ctx().stream>>>(pp);
+        PG_CUDA(cudaGetLastError());
+        return PG_OK;
+    }
+
+    // one-kernel path (no exact bitmap on the probed table, NULLs, wide predicates ...)
     template <int SINK>
     int launch_pipe(const PipeParams &pp, const pg_table *t)
     {
-        cudaStream_t st = ctx().stream;
-        bool any_valid = pp.probe_key.valid != nullptr || (SINK == SINK_INSERT || SINK == SINK_BITMAP ? pp.ins_key.valid != nullptr : false);
-        for (int k = 0; k < pp.npred; k++) any_valid = any_valid || pp.pred[k].col.valid != nullptr;
-        bool fast = pp.has_probe && pp.probe.bitmap && pp.npred <= 1 && (pp.npred == 0 || pp.pred[0].col.width == 4) &&
-                    (pp.probe_key.width == 4 || pp.probe_key.width == 8) && !any_valid && !getenv("PG_JOIN_GENERIC");
-        if (!fast) {
-            pipeline_kernel<SINK><<<grid_rows(t->nrows), 256, 0, st>>>(pp);
-        } else {
-            i64 ntiles = (t->nrows + SA_TILE - 1) / SA_TILE;
-            int grid = (int)std::max<i64>(std::min<i64>(ntiles, (i64)ctx().prop.multiProcessorCount * 6), 1);
-            bool k8 = pp.probe_key.width == 8, hp = pp.npred == 1;
-            static const int unroll = getenv("PG_JOIN_UNROLL") ? atoi(getenv("PG_JOIN_UNROLL")) : 2;
-            static const int gmul = getenv("PG_JOIN_GRIDMUL") ? atoi(getenv("PG_JOIN_GRIDMUL")) : 6;
-            grid = (int)std::max<i64>(std::min<i64>(ntiles, (i64)ctx().prop.multiProcessorCount * gmul), 1);
-            if (unroll == 4) {
-                if (k8 && hp) fast_pipeline_kernel<8, SINK, true, 4><<<grid, SA_THREADS, 0, st>>>(pp);
-                else if (k8) fast_pipeline_kernel<8, SINK, false, 4><<<grid, SA_THREADS, 0, st>>>(pp);
-                else if (hp) fast_pipeline_kernel<4, SINK, true, 4><<<grid, SA_THREADS, 0, st>>>(pp);
-                else fast_pipeline_kernel<4, SINK, false, 4><<<grid, SA_THREADS, 0, st>>>(pp);
-            } else {
-                if (k8 && hp) fast_pipeline_kernel<8, SINK, true, 2><<<grid, SA_THREADS, 0, st>>>(pp);
-                else if (k8) fast_pipeline_kernel<8, SINK, false, 2><<<grid, SA_THREADS, 0, st>>>(pp);
-                else if (hp) fast_pipeline_kernel<4, SINK, true, 2><<<grid, SA_THREADS, 0, st>>>(pp);
-                else fast_pipeline_kernel<4, SINK, false, 2><<<grid, SA_THREADS, 0, st>>>(pp);
-            }
-        }
+        pipeline_kernel<SINK><<<grid_rows(t->nrows), 256, 0, ctx().stream>>>(pp);
         PG_CUDA(cudaGetLastError());
         return PG_OK;
     }
@@ -299,6 +318,32 @@ struct JoinAggPipeline : Pipeline {
                 }
                 return PG_OK;
             }
+        }
+        if (two_phase_ok(pp, t, true)) {
+            // phase 1 screens the whole source once: the hit list doubles as the sizing pass
+            PG_CUDA(cudaMemsetAsync(d_counters.p, 0, 32, st));
+            PG_TRY(launch_filter(pp, 0, t->nrows));
+            const bool exact = pp.probe_bitmap_only || pp.probe_mode != 0;      // one sink row per hit
+            if (!exact) PG_TRY(launch_sink<SINK_COUNT>(pp));
+            unsigned long long cnt[4], nh = 0;
+            PG_CUDA(cudaMemcpyAsync(&nh, d_hit_count.p, 8, cudaMemcpyDeviceToHost, st));
+            PG_TRY(read_counters(cnt));
+            s.built_rows = exact ? (i64)nh : (i64)cnt[1];
+            PG_TRY(prepare_table(s, s.built_rows, t->cols[(size_t)s.ins_key_col]));
+            pp.ins_key = typed(t, s.ins_key_col);
+            s.jt.dups = d_counters.as<unsigned long long>() + 2;
+            pp.ins = s.jt;
+            PG_CUDA(cudaMemsetAsync(d_counters.p, 0, 32, st));
+            PG_TRY(launch_sink<SINK_INSERT>(pp));
+            s.dup_keys = 1;
+            if (!s.payload_needed && s.jt.bitmap) {
+                unsigned long long c2[4];
+                PG_TRY(read_counters(c2));
+                s.dup_keys = (i64)c2[2];
+            }
+            res->stats.kernel_launches += exact ? 2 : 3;
+            if (idx < 4) { res->stats.aux[2 + 2 * idx] = (i64)cnt[0]; res->stats.aux[3 + 2 * idx] = s.built_rows; }
+            return PG_OK;
         }
         // sizing pass: how many rows reach the sink
         PG_CUDA(cudaMemsetAsync(d_counters.p, 0, 32, st));
@@ -458,7 +503,16 @@ struct JoinAggPipeline : Pipeline {
             }
             pp.gt.overflow = d_overflow.as<int>();
             PG_CUDA(cudaEventRecord(ev_main.a, st));
-            if (no_join) {
+            if (!no_join && two_phase_ok(pp, t, false)) {
+                // phase 1 at scan speed over chunks of the fact table, phase 2 over each chunk's hit list
+                // (no host round trip in between: the sink kernel reads the hit count from device memory)
+                for (i64 lo = 0; lo < t->nrows; lo += HIT_CHUNK) {
+                    PG_TRY(launch_filter(pp, lo, std::min<i64>(t->nrows, lo + HIT_CHUNK)));
+                    PG_TRY(launch_sink<SINK_GROUP>(pp));
+                    res->stats.kernel_launches += 2;
+                }
+                res->stats.kernel_launches -= 1;
+            } else if (no_join) {
                 // the specialised vectorised kernel when the shape is: 1 key, 1 summed column, <=1 32-bit predicate
                 bool pred_valid = false;
                 for (int k = 0; k < pp.npred; k++) pred_valid = pred_valid || pp.pred[k].col.valid != nullptr;
@@ -1100,7 +1154,7 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &join, std::uniqu
                  st->name.c_str(), p->nparts, p->gs.nacc, p->hav_plane >= 0 ? " having" : "",
                  p->shuffle ? " exchange=all-to-all(hash-partitioned)" : "");
     else
-        snprintf(b, sizeof b, " probe(%s key=%s) kernel=fast_pipeline_kernel<SINK_GROUP> group_keys=%d sums=%d%s", st->name.c_str(),
+        snprintf(b, sizeof b, " probe(%s key=%s) kernel=filter_hits_kernel+hits_sink_kernel<SINK_GROUP> group_keys=%d sums=%d%s", st->name.c_str(),
                  st->cols[(size_t)p->probe_key_col].name.c_str(), p->nparts, p->gs.nacc,
                  p->shuffle ? " exchange=all-to-all(hash-partitioned)" : "");
     if (p->no_join) ex = b; else ex += b;

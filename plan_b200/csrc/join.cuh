@@ -204,6 +204,12 @@ struct PipeParams {
     GroupSpec gs;
     // SINK_COUNT / statistics: [0] rows passing the predicates, [1] joined rows
     unsigned long long *counters;
+    // two-phase execution (filter_hits_kernel -> hits_sink_kernel): rows [row_begin, row_end) of the source
+    // are screened, the row ids of the hits are appended to `hits` (capacity >= row_end - row_begin),
+    // `hit_count` is the device-side cursor
+    i64 row_begin, row_end;
+    unsigned *hits;
+    unsigned long long *hit_count;
 };
 
 // add `vals` (nacc sums) and `count` rows to group (klo, khi); claims a free slot with 64-bit CAS
@@ -423,54 +429,37 @@ group1_kernel(const PipeParams p)
     }
 }
 
-// Vectorised variant for the big scans (fact-table side): at most one 32-bit range predicate,
-// a 4- or 8-byte probe key and an exact bitmap on the probed table.  Each thread streams 4 rows
-// per tile with 16-byte loads, UNROLL tiles in flight; only rows whose key bit is set (a few
-// percent in TPC-H Q3) leave the streaming path to touch the hash table / the sink.
-// Bytes streamed per row: 4*[HAS_PRED] + KEYW; everything else is gathered for matches only.
-template <int KEYW, int SINK, bool HAS_PRED, int UNROLL>
-__global__ void __launch_bounds__(SA_THREADS)     // capping registers at 64 for 4 CTAs/SM was measured 14% slower (spills)
-fast_pipeline_kernel(const PipeParams p)
+// ---------------------------------------------------------------- two-phase --
+// Phase 1 (streaming, HBM-bound): screen rows [row_begin,row_end) with the range predicate and the exact
+// key bitmap of the probed table and append the row ids of the hits to a compact list (one global
+// cursor bump per warp step).  Nothing random is touched here, so it runs at scan speed.
+// Phase 2 (latency-bound, massively parallel): one thread per hit does the hash-table probe / insert /
+// group update.  Splitting the two lets each kernel have the occupancy it needs: measured at SF100, the
+// fused warp-queue kernel streamed lineitem at 3.1 TB/s; see profiles/ for the split numbers.
+template <int KEYW, bool HAS_PRED, int UNROLL>
+__global__ void __launch_bounds__(SA_THREADS)
+filter_hits_kernel(const PipeParams p)
 {
-    unsigned long long n_pass = 0, n_join = 0;
-    const i64 ntiles = (p.nrows + SA_TILE - 1) / SA_TILE;
+    unsigned long long n_pass = 0;
+    const i64 nloc = p.row_end - p.row_begin;
+    const i64 ntiles = (nloc + SA_TILE - 1) / SA_TILE;
     const int plo = (int)(p.pred[0].lo < INT32_MIN ? INT32_MIN : p.pred[0].lo);
     const int phi = (int)(p.pred[0].hi > INT32_MAX ? INT32_MAX : p.pred[0].hi);
     const bool pempty = p.pred[0].lo > p.pred[0].hi;
-    auto sink = [&](i64 row, u64 build_row) {
-        n_join++;
-        if (SINK == SINK_INSERT) {
-            jt_insert(p.ins, load_typed(p.ins_key, row), (u64)row);
-        } else if (SINK == SINK_BITMAP) {
-            u64 off = (u64)(load_typed(p.ins_key, row) - p.ins.bm_min);
-            atomicOr(p.ins.bitmap + (off >> 5), 1u << (off & 31));
-        } else if (SINK == SINK_GROUP) {
-            auto val = [&](const ValRef &r) { return load_typed(r.col, r.from_build ? (i64)build_row : row); };
-            i64 klo = val(p.gs.part[0]);
-            i64 khi = 0;
-            if (p.gs.nparts > 1) khi = val(p.gs.part[1]) << 32;
-            if (p.gs.nparts > 2) khi |= val(p.gs.part[2]) & 0xffffffffLL;
-            i64 vals[GT_MAXACC];
-            for (int a = 0; a < p.gs.nacc; a++) {
-                i64 x = 1;
-                for (int f = 0; f < p.gs.nfac[a]; f++) x *= p.gs.fc[a][f] + p.gs.fs[a][f] * val(p.gs.fac[a][f]);
-                vals[a] = x;
-            }
-            gt_update(p.gt, klo, khi, vals);
-        }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool anti = p.probe_mode == 2;
+    constexpr int WBUF = 1024;                       // >= 32 * 4 * UNROLL hits of one step
+    __shared__ unsigned s_buf[SA_THREADS / 32][WBUF];
+    int nbuf = 0;                                    // warp-uniform fill level
+    auto flush = [&]() {
+        if (nbuf == 0) return;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(p.hit_count, (unsigned long long)nbuf);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int i = lane; i < nbuf; i += 32) p.hits[base + i] = s_buf[warp][i];
+        __syncwarp();
+        nbuf = 0;
     };
-    // WARP-COOPERATIVE slow path: rows whose key bit is set are queued per warp in shared memory
-    // (ballot + prefix), then the 32 lanes drain the queue in parallel -- a matching order's rows
-    // (adjacent in the table) are spread over lanes instead of serialising in the lane that
-    // streamed them, and the probe/sink code exists once.
-    // The queue is drained only once it holds at least a warp's worth of rows (or at the end): with a
-    // ~1% match rate a drain after every batch would stall the warp's streaming for one full random-
-    // access latency chain to serve two or three rows.
-    constexpr int QCAP = 32 * SA_VEC * UNROLL + 32;
-    __shared__ i64 s_queue[SA_THREADS / 32][QCAP];
-    int nq = 0;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const unsigned lt_mask = (1u << lane) - 1u;
     for (i64 tile0 = blockIdx.x; tile0 < ntiles; tile0 += (i64)gridDim.x * UNROLL) {
         int4 d[UNROLL];
         i64 k[UNROLL][4];
@@ -478,7 +467,7 @@ fast_pipeline_kernel(const PipeParams p)
         for (int u = 0; u < UNROLL; u++) {
             i64 tile = tile0 + (i64)u * gridDim.x;
             if (tile < ntiles) {
-                i64 row = tile * SA_TILE + threadIdx.x * SA_VEC;
+                i64 row = p.row_begin + tile * SA_TILE + threadIdx.x * SA_VEC;
                 if (HAS_PRED) d[u] = ld_stream16((const int *)p.pred[0].col.p + row);
                 if (KEYW == 8) {
                     longlong2 a = ld_stream16_ll((const i64 *)p.probe_key.p + row), b = ld_stream16_ll((const i64 *)p.probe_key.p + row + 2);
@@ -489,53 +478,86 @@ fast_pipeline_kernel(const PipeParams p)
                 }
             }
         }
-        // all bitmap words of the batch are requested before any is consumed
-        bool hit[UNROLL][4];
+        unsigned hitmask = 0;      // bit (4u + j): row j of tile u is a hit
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) {
-            i64 tile = tile0 + (i64)u * gridDim.x;     // warp-uniform
-            i64 row = tile * SA_TILE + threadIdx.x * SA_VEC;
-            i64 rem = tile < ntiles ? p.nrows - row : 0;
+            i64 tile = tile0 + (i64)u * gridDim.x;
+            i64 row = p.row_begin + tile * SA_TILE + threadIdx.x * SA_VEC;
+            i64 rem = tile < ntiles ? p.row_end - row : 0;
             int dv[4] = {d[u].x, d[u].y, d[u].z, d[u].w};
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 bool ok = j < rem;
                 if (HAS_PRED) ok = ok && !pempty && dv[j] >= plo && dv[j] <= phi;
                 n_pass += ok ? 1 : 0;
-                hit[u][j] = ok && (bitmap_test(p.probe, k[u][j]) != (p.probe_mode == 2));   // ANTI keeps the misses
+                if (ok && (bitmap_test(p.probe, k[u][j]) != anti)) hitmask |= 1u << (4 * u + j);
             }
         }
+        // append to the warp's private staging buffer in shared memory (exclusive scan of the per-lane hit
+        // counts); the buffer is flushed to the global list with ONE cursor bump when it is nearly full --
+        // a bump per warp step put 2.3 M atomics on one address and cost more than the scan itself
+        int c = __popc(hitmask), incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0) continue;
+        if (nbuf + total > WBUF) { flush(); }
+        int pos = nbuf + incl - c;
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) {
-            i64 row = (tile0 + (i64)u * gridDim.x) * SA_TILE + threadIdx.x * SA_VEC;
+            i64 row = p.row_begin + (tile0 + (i64)u * gridDim.x) * SA_TILE + threadIdx.x * SA_VEC;
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                unsigned m = __ballot_sync(0xffffffffu, hit[u][j]);
-                if (hit[u][j]) s_queue[warp][nq + __popc(m & lt_mask)] = row + j;
-                nq += __popc(m);
-            }
+            for (int j = 0; j < 4; j++)
+                if (hitmask & (1u << (4 * u + j))) s_buf[warp][pos++] = (unsigned)(row + j);
         }
-        const bool last = tile0 + (i64)gridDim.x * UNROLL >= ntiles;    // warp-uniform
-        if (nq >= 32 || last) {
-            __syncwarp();
-            for (int i = lane; i < nq; i += 32) {
-                i64 r = s_queue[warp][i];
-                if (p.probe_bitmap_only || p.probe_mode != 0) sink(r, 0);
-                else jt_probe(p.probe, load_typed(p.probe_key, r), [&](u64 pay) { sink(r, pay); });
-            }
-            __syncwarp();
-            nq = 0;
-        }
+        nbuf += total;
+        __syncwarp();
     }
+    flush();
     n_pass = (unsigned long long)warp_sum((i64)n_pass);
-    n_join = (unsigned long long)warp_sum((i64)n_join);
-    if ((threadIdx.x & 31) == 0) {
-        if (n_pass) atomicAdd(&p.counters[0], n_pass);
-        if (n_join) atomicAdd(&p.counters[1], n_join);
-    }
+    if (lane == 0 && n_pass) atomicAdd(&p.counters[0], n_pass);
 }
 
-// compact the occupied slots of a group table into dense output arrays
+template <int SINK>
+__global__ void __launch_bounds__(256)
+hits_sink_kernel(const PipeParams p)
+{
+    const unsigned long long n = *p.hit_count;
+    unsigned long long n_join = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const i64 row = (i64)p.hits[i];
+        auto sink = [&](u64 build_row) {
+            n_join++;
+            if (SINK == SINK_INSERT) {
+                jt_insert(p.ins, load_typed(p.ins_key, row), (u64)row);
+            } else if (SINK == SINK_BITMAP) {
+                u64 off = (u64)(load_typed(p.ins_key, row) - p.ins.bm_min);
+                atomicOr(p.ins.bitmap + (off >> 5), 1u << (off & 31));
+            } else if (SINK == SINK_GROUP) {
+                auto val = [&](const ValRef &r) { return load_typed(r.col, r.from_build ? (i64)build_row : row); };
+                i64 klo = val(p.gs.part[0]);
+                i64 khi = 0;
+                if (p.gs.nparts > 1) khi = val(p.gs.part[1]) << 32;
+                if (p.gs.nparts > 2) khi |= val(p.gs.part[2]) & 0xffffffffLL;
+                i64 vals[GT_MAXACC];
+                for (int a = 0; a < p.gs.nacc; a++) {
+                    i64 x = 1;
+                    for (int f = 0; f < p.gs.nfac[a]; f++) x *= p.gs.fc[a][f] + p.gs.fs[a][f] * val(p.gs.fac[a][f]);
+                    vals[a] = x;
+                }
+                gt_update(p.gt, klo, khi, vals);
+            }
+        };
+        if (p.probe_bitmap_only || p.probe_mode != 0) sink(0);
+        else jt_probe(p.probe, load_typed(p.probe_key, row), sink);
+    }
+    n_join = (unsigned long long)warp_sum((i64)n_join);
+    if ((threadIdx.x & 31) == 0 && n_join) atomicAdd(&p.counters[1], n_join);
+}
+
 // (HAVING on one aggregate -- an inclusive range on accumulator plane `hav_plane` -- is applied here)
 static __global__ void gt_compact_kernel(const GroupTable g, i64 *__restrict__ out_klo, i64 *__restrict__ out_khi,
                                   i64 *__restrict__ out_acc /* [nacc+1][max_out] */, i64 max_out,
