@@ -13,6 +13,8 @@
 //   build(customer) -> build(orders probing customer) -> lineitem probing orders -> group-by
 #include <algorithm>
 
+#include <cub/device/device_scan.cuh>
+
 #include "hostdec.hpp"
 #include "join.cuh"
 #include "pipeline.hpp"
@@ -34,8 +36,9 @@ struct Stage {
     int probe_stage = -1;            // which earlier stage built the probed table
     int ins_key_col = -1;            // SINK_INSERT: key column on the source table
     // device state of the table this stage builds
-    DevBuf d_slots, d_bitmap;
+    DevBuf d_slots, d_bitmap, d_rank_prefix, d_rank_payload, d_keys_tmp, d_scan_tmp;
     JoinTable jt{};
+    bool rank_index = false;         // unique keys + bitmap: the table is bitmap + rank prefix + payload (join.cuh jt_rank)
     i64 capacity_rows = 0;
     i64 built_rows = 0;
     bool payload_needed = false;     // some column of this build side is read above the join
@@ -116,18 +119,34 @@ struct JoinAggPipeline : Pipeline {
         if (k == 0) { *ngroups = 0; return PG_OK; }
         const int planes = gs.nacc + 1;
         constexpr int NB = 1 << TOPK_DIGIT_BITS;
-        if (!d_hist.p) { PG_TRY(d_hist.alloc(NB * 4)); PG_TRY(h_hist.alloc(NB * 4)); }
+        // hist buffer: [256 bins][min, max as two u64]
+        if (!d_hist.p) { PG_TRY(d_hist.alloc(NB * 4 + 16)); PG_TRY(h_hist.alloc(NB * 4 + 16)); }
         int grid = (int)std::max<i64>(std::min<i64>((n + 255) / 256, (i64)ctx().prop.multiProcessorCount * 4), 1);
         u64 prefix = 0;
         i64 remaining = k;       // we look for the remaining-th smallest key among those matching the prefix
         const unsigned *hist = h_hist.as<unsigned>();
-        i64 n_equal = 0;
-        for (int pass = 0; pass < 64 / TOPK_DIGIT_BITS; pass++) {
+        unsigned long long *d_minmax = (unsigned long long *)(d_hist.as<unsigned>() + NB);
+        const unsigned long long *h_minmax = (const unsigned long long *)(hist + NB);
+        i64 n_equal = n;
+        // The passes stop as soon as the bin holding the k-th key is small (the host orders the few
+        // candidates anyway), and the first pass also yields min/max so that digits common to every key
+        // are skipped: a revenue column uses ~26 of its 64 key bits -> 3 passes instead of 8.
+        const i64 stop_at = std::max<i64>(128 - k, 16);
+        const int npass = 64 / TOPK_DIGIT_BITS;
+        int pass = 0;
+        while (pass < npass && (pass == 0 || n_equal > stop_at)) {
             PG_CUDA(cudaMemsetAsync(d_hist.p, 0, NB * 4, st));
-            topk_hist_kernel<<<grid, 256, 0, st>>>(topk_key, d_out_klo.as<i64>(), d_out_khi.as<i64>(), d_out_acc.as<i64>(), out_cap, n,
-                                                   prefix, pass * TOPK_DIGIT_BITS, d_hist.as<unsigned>());
+            if (pass == 0) {
+                PG_CUDA(cudaMemsetAsync(d_minmax, 0xff, 8, st));
+                PG_CUDA(cudaMemsetAsync(d_minmax + 1, 0, 8, st));
+                topk_hist_kernel<true><<<grid, 256, 0, st>>>(topk_key, d_out_klo.as<i64>(), d_out_khi.as<i64>(), d_out_acc.as<i64>(), out_cap, n,
+                                                             prefix, 0, d_hist.as<unsigned>(), d_minmax);
+            } else {
+                topk_hist_kernel<false><<<grid, 256, 0, st>>>(topk_key, d_out_klo.as<i64>(), d_out_khi.as<i64>(), d_out_acc.as<i64>(), out_cap, n,
+                                                              prefix, pass * TOPK_DIGIT_BITS, d_hist.as<unsigned>(), d_minmax);
+            }
             PG_CUDA(cudaGetLastError());
-            PG_CUDA(cudaMemcpyAsync(h_hist.p, d_hist.p, NB * 4, cudaMemcpyDeviceToHost, st));
+            PG_CUDA(cudaMemcpyAsync(h_hist.p, d_hist.p, NB * 4 + 16, cudaMemcpyDeviceToHost, st));
             PG_CUDA(cudaStreamSynchronize(st));
             int d = 0;
             for (; d < NB; d++) {
@@ -138,7 +157,24 @@ struct JoinAggPipeline : Pipeline {
             prefix = (prefix << TOPK_DIGIT_BITS) | (u64)d;
             n_equal = (i64)hist[d];
             res->stats.kernel_launches += 1;
+            pass++;
+            if (pass == 1) {
+                // digits shared by every key: jump over them (all n keys carry that prefix, none is smaller)
+                const u64 diff = (u64)h_minmax[0] ^ (u64)h_minmax[1];
+                int common = 64;
+                if (diff) { common = 0; while (!((diff << common) >> 63)) common++; }
+                const int skip_to = std::min(common / TOPK_DIGIT_BITS, npass);
+                if (skip_to > pass) {
+                    pass = skip_to;
+                    prefix = pass == npass ? (u64)h_minmax[0] : (u64)h_minmax[0] >> (64 - pass * TOPK_DIGIT_BITS);
+                    remaining = k;
+                    n_equal = n;
+                }
+            }
         }
+        // keys <= threshold are the candidates: the prefix, widened by the digits that were not examined
+        const int rest_bits = 64 - pass * TOPK_DIGIT_BITS;
+        if (rest_bits > 0) prefix = (prefix << rest_bits) | ((((u64)1) << rest_bits) - 1);
         i64 ncand = (k - remaining) + n_equal;      // strictly smaller keys + every tie of the k-th key
         if (ncand > cand_cap) {
             PG_TRY(d_cand_klo.alloc((size_t)ncand * 8));
@@ -193,7 +229,8 @@ struct JoinAggPipeline : Pipeline {
 
     // scratch of the two-phase path: hit list (row ids) and its device-side cursor
     DevBuf d_hits, d_hit_count;
-    static constexpr i64 HIT_CHUNK = (i64)1 << 26;     // rows screened per filter launch (256 MB of row ids at most)
+    static constexpr i64 HIT_CHUNK = (i64)1 << 30;     // rows screened per filter launch: row-id scratch of at most 4 GB
+                                                       // (180 GB of HBM3e; SF100 lineitem needs 2.4 GB and ONE launch)
 
     static bool two_phase_ok(const PipeParams &pp, const pg_table *t, bool ins_sink)
     {
@@ -219,10 +256,12 @@ struct JoinAggPipeline : Pipeline {
         i64 ntiles = (hi - lo + SA_TILE - 1) / SA_TILE;
         int grid = (int)std::max<i64>(std::min<i64>(ntiles, (i64)ctx().prop.multiProcessorCount * 8), 1);
         const bool k8 = pp.probe_key.width == 8, hp = pp.npred == 1;
-        if (k8 && hp) filter_hits_kernel<8, true, 2><<<grid, SA_THREADS, 0, st>>>(pp);
-        else if (k8) filter_hits_kernel<8, false, 2><<<grid, SA_THREADS, 0, st>>>(pp);
-        else if (hp) filter_hits_kernel<4, true, 2><<<grid, SA_THREADS, 0, st>>>(pp);
-        else filter_hits_kernel<4, false, 2><<<grid, SA_THREADS, 0, st>>>(pp);
+        // (two tiles per step were measured slower for both key widths: 90 registers cost more occupancy
+        //  than the extra loads in flight bring)
+#define PG_FH(K, P) filter_hits_kernel<K, P, 1><<<grid, SA_THREADS, 0, st>>>(pp)
+        if (k8) { if (hp) PG_FH(8, true); else PG_FH(8, false); }
+        else { if (hp) PG_FH(4, true); else PG_FH(4, false); }
+#undef PG_FH
         PG_CUDA(cudaGetLastError());
         return PG_OK;
     }
@@ -268,17 +307,71 @@ struct JoinAggPipeline : Pipeline {
             s.jt.log2buckets = lg;
             s.jt.domain = dom > 0 ? (u64)dom : 1;
         }
+        s.jt.rank_prefix = nullptr;
+        s.jt.rank_payload = nullptr;
+        s.rank_index = false;
         // exact key-domain bitmap when the build column's value range is small enough
         s.jt.bitmap = nullptr;
         s.jt.bm_min = keycol.vmin;
         s.jt.bm_max = keycol.vmax;
         i128 domain = (i128)keycol.vmax - (i128)keycol.vmin + 1;
         if (keycol.stats_ok && domain > 0 && domain <= ((i128)1 << 32)) {
-            size_t words = (size_t)((domain + 31) / 32);
+            size_t words = ((size_t)((domain + 31) / 32) + 7) / 8 * 8;      // whole 256-bit blocks (rank index)
             if (s.d_bitmap.bytes < words * 4) PG_TRY(s.d_bitmap.alloc(words * 4));
             PG_CUDA(cudaMemsetAsync(s.d_bitmap.p, 0, words * 4, st));
             s.jt.bitmap = s.d_bitmap.as<unsigned>();
         }
+        return PG_OK;
+    }
+
+    // Unique build keys inside a bitmap-able domain: no hash table.  The hit list of the stage's filter
+    // pass becomes bitmap + per-block rank prefix + payload[rank] (three streaming-friendly passes without
+    // CAS, probing or 64-byte buckets).  *done = 0 when the keys turn out not to be unique: the caller
+    // falls back to the hash build over the same hit list.
+    int build_rank_index(Stage &s, PipeParams &pp, const pg_table *t, i64 nh, pg_result *res, int *done)
+    {
+        cudaStream_t st = ctx().stream;
+        *done = 0;
+        const Column &keycol = t->cols[(size_t)s.ins_key_col];
+        PG_TRY(prepare_table(s, 0, keycol));
+        if (!s.jt.bitmap) return PG_OK;
+        const int grid = ctx().prop.multiProcessorCount * 8;
+        if (s.d_keys_tmp.bytes < (size_t)std::max<i64>(nh, 1) * 8) PG_TRY(s.d_keys_tmp.alloc((size_t)std::max<i64>(nh, 1) * 8));
+        pp.ins_key = typed(t, s.ins_key_col);
+        s.jt.dups = d_counters.as<unsigned long long>() + 2;
+        pp.ins = s.jt;
+        PG_CUDA(cudaMemsetAsync(d_counters.p, 0, 32, st));
+        if (s.unique_key) {
+            rank_mark_kernel<false><<<grid, 256, 0, st>>>(pp, s.d_keys_tmp.as<i64>());
+            s.dup_keys = 0;
+        } else {
+            rank_mark_kernel<true><<<grid, 256, 0, st>>>(pp, s.d_keys_tmp.as<i64>());
+            unsigned long long c2[4];
+            PG_TRY(read_counters(c2));
+            s.dup_keys = (i64)c2[2];
+        }
+        PG_CUDA(cudaGetLastError());
+        res->stats.kernel_launches += 1;
+        if (s.dup_keys != 0) return PG_OK;            // not unique: hash table (prepare_table resets the bitmap)
+        if (!s.payload_needed) { *done = 1; return PG_OK; }      // the exact bitmap alone answers every probe
+        const u64 nblocks = (s.jt.domain + 255) / 256;
+        if (s.d_rank_prefix.bytes < nblocks * 4) PG_TRY(s.d_rank_prefix.alloc(nblocks * 4));
+        if (s.d_rank_payload.bytes < (size_t)std::max<i64>(nh, 1) * 4) PG_TRY(s.d_rank_payload.alloc((size_t)std::max<i64>(nh, 1) * 4));
+        unsigned *prefix = s.d_rank_prefix.as<unsigned>();
+        rank_count_kernel<<<(int)std::min<u64>((nblocks + 255) / 256, (u64)grid), 256, 0, st>>>(s.jt.bitmap, nblocks, prefix);
+        PG_CUDA(cudaGetLastError());
+        size_t tmp_bytes = 0;
+        PG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, prefix, prefix, (int)nblocks, st));
+        if (s.d_scan_tmp.bytes < tmp_bytes) PG_TRY(s.d_scan_tmp.alloc(tmp_bytes));
+        PG_CUDA(cub::DeviceScan::ExclusiveSum(s.d_scan_tmp.p, tmp_bytes, prefix, prefix, (int)nblocks, st));
+        s.jt.rank_prefix = prefix;
+        s.jt.rank_payload = s.d_rank_payload.as<unsigned>();
+        pp.ins = s.jt;
+        rank_fill_kernel<<<grid, 256, 0, st>>>(pp, s.d_keys_tmp.as<i64>(), s.d_rank_payload.as<unsigned>());
+        PG_CUDA(cudaGetLastError());
+        res->stats.kernel_launches += 3;
+        s.rank_index = true;
+        *done = 1;
         return PG_OK;
     }
 
@@ -329,6 +422,15 @@ struct JoinAggPipeline : Pipeline {
             PG_CUDA(cudaMemcpyAsync(&nh, d_hit_count.p, 8, cudaMemcpyDeviceToHost, st));
             PG_TRY(read_counters(cnt));
             s.built_rows = exact ? (i64)nh : (i64)cnt[1];
+            if (exact && !getenv("PG_JOIN_NO_RANK_INDEX")) {
+                int done = 0;
+                PG_TRY(build_rank_index(s, pp, t, (i64)nh, res, &done));
+                if (done) {
+                    res->stats.kernel_launches += 1;
+                    if (idx < 4) { res->stats.aux[2 + 2 * idx] = (i64)cnt[0]; res->stats.aux[3 + 2 * idx] = s.built_rows; }
+                    return PG_OK;
+                }
+            }
             PG_TRY(prepare_table(s, s.built_rows, t->cols[(size_t)s.ins_key_col]));
             pp.ins_key = typed(t, s.ins_key_col);
             s.jt.dups = d_counters.as<unsigned long long>() + 2;
@@ -479,6 +581,23 @@ struct JoinAggPipeline : Pipeline {
         // aggregate_hash.go:538-540)
         u64 cap = next_pow2((u64)std::max<i64>((no_join ? group_hint : stages.back()->built_rows) * 2, 1024));
         unsigned long long cnt[4] = {0, 0, 0, 0};
+        // two-phase, whole source in one filter launch: the hit count is known before the group table is
+        // sized, so the table (memset + compaction cost) follows the joined rows, not the build side
+        const bool two_phase = !no_join && two_phase_ok(pp, t, false);
+        const bool single_filter = two_phase && t->nrows <= HIT_CHUNK;
+        unsigned long long filter_pass = 0;
+        if (single_filter) {
+            PG_CUDA(cudaMemsetAsync(d_counters.p, 0, 32, st));
+            PG_CUDA(cudaEventRecord(ev_main.a, st));
+            PG_TRY(launch_filter(pp, 0, t->nrows));
+            unsigned long long c0[4];
+            PG_TRY(read_counters(c0));
+            filter_pass = c0[0];
+            const bool exact = pp.probe_bitmap_only || pp.probe_mode != 0 || stages.back()->dup_keys == 0 || stages.back()->unique_key;   // at most one joined row per hit
+            if (exact) cap = next_pow2((u64)std::max<i64>((i64)std::min<unsigned long long>(c0[3], (unsigned long long)cap / 2) * 2, 1024));
+            res->stats.kernel_launches += 1;
+            tr.mark("probe filter");
+        }
         for (int attempt = 0;; attempt++) {
             PG_TRY(ensure_group_table(cap));
             cap = gt_cap;
@@ -502,8 +621,10 @@ struct JoinAggPipeline : Pipeline {
                 }
             }
             pp.gt.overflow = d_overflow.as<int>();
-            PG_CUDA(cudaEventRecord(ev_main.a, st));
-            if (!no_join && two_phase_ok(pp, t, false)) {
+            if (!single_filter) PG_CUDA(cudaEventRecord(ev_main.a, st));
+            if (single_filter) {
+                PG_TRY(launch_sink<SINK_GROUP>(pp));
+            } else if (two_phase) {
                 // phase 1 at scan speed over chunks of the fact table, phase 2 over each chunk's hit list
                 // (no host round trip in between: the sink kernel reads the hit count from device memory)
                 for (i64 lo = 0; lo < t->nrows; lo += HIT_CHUNK) {
@@ -541,6 +662,7 @@ struct JoinAggPipeline : Pipeline {
             int ovf = 0;
             PG_CUDA(cudaMemcpyAsync(&ovf, d_overflow.p, 4, cudaMemcpyDeviceToHost, st));
             PG_TRY(read_counters(cnt));
+            if (single_filter) cnt[0] = filter_pass;
             tr.mark("probe+group kernel");
             if (!ovf) break;
             if (attempt > 8) PG_FAIL(PG_ENOMEM, "group table keeps overflowing");

@@ -46,7 +46,30 @@ struct JoinTable {
     int order_preserving;
     int log2buckets;
     u64 domain;                 // bm_max - bm_min + 1
+    // RANK INDEX (unique build keys + bitmap): no slots at all.  The r-th set bit of the bitmap owns
+    // rank_payload[r]; rank = rank_prefix[256-bit block] + popcount inside the block, and a block is one
+    // 32-byte sector, so a lookup is branch-free: bitmap sector + prefix word -> payload word.
+    const unsigned *rank_prefix;
+    const unsigned *rank_payload;
 };
+
+// rank of key offset `off` (its bit must be set): number of set bits before it
+__device__ __forceinline__ unsigned jt_rank(const JoinTable &t, u64 off, bool *set)
+{
+    const uint4 *blk = (const uint4 *)(t.bitmap + ((off >> 8) << 3));
+    const uint4 a = __ldg(blk), b = __ldg(blk + 1);
+    const unsigned base = __ldg(t.rank_prefix + (off >> 8));
+    const unsigned w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    const unsigned wi = (unsigned)(off >> 5) & 7u, bit = (unsigned)off & 31u;
+    unsigned r = base, word = 0;
+#pragma unroll
+    for (unsigned i = 0; i < 8; i++) {
+        r += i < wi ? __popc(w[i]) : 0;
+        word = i == wi ? w[i] : word;
+    }
+    *set = (word >> bit) & 1u;
+    return r + __popc(word & ((1u << bit) - 1u));
+}
 __device__ __forceinline__ u64 jt_home(const JoinTable &t, i64 key)
 {
     if (t.order_preserving) {
@@ -88,6 +111,14 @@ __device__ __forceinline__ void jt_insert(const JoinTable &t, i64 key, u64 paylo
 template <typename F>
 __device__ __forceinline__ void jt_probe(const JoinTable &t, i64 key, F f)
 {
+    if (t.rank_prefix) {
+        const u64 off = (u64)key - (u64)t.bm_min;
+        if (off >= t.domain) return;
+        bool set;
+        const unsigned r = jt_rank(t, off, &set);
+        if (set) f((u64)__ldg(t.rank_payload + r));
+        return;
+    }
     u64 b = jt_home(t, key);
     for (;;) {
         const longlong2 *line = t.slots + b * HT_BUCKET;
@@ -436,11 +467,10 @@ group1_kernel(const PipeParams p)
 // Phase 2 (latency-bound, massively parallel): one thread per hit does the hash-table probe / insert /
 // group update.  Splitting the two lets each kernel have the occupancy it needs: measured at SF100, the
 // fused warp-queue kernel streamed lineitem at 3.1 TB/s; see profiles/ for the split numbers.
-template <int KEYW, bool HAS_PRED, int UNROLL>
+template <int KEYW, bool HAS_PRED, int NT>
 __global__ void __launch_bounds__(SA_THREADS)
 filter_hits_kernel(const PipeParams p)
 {
-    unsigned long long n_pass = 0;
     const i64 nloc = p.row_end - p.row_begin;
     const i64 ntiles = (nloc + SA_TILE - 1) / SA_TILE;
     const int plo = (int)(p.pred[0].lo < INT32_MIN ? INT32_MIN : p.pred[0].lo);
@@ -448,9 +478,13 @@ filter_hits_kernel(const PipeParams p)
     const bool pempty = p.pred[0].lo > p.pred[0].hi;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool anti = p.probe_mode == 2;
-    constexpr int WBUF = 1024;                       // >= 32 * 4 * UNROLL hits of one step
+    const unsigned *__restrict__ bm = p.probe.bitmap;
+    const u64 bmin = (u64)p.probe.bm_min, dom = p.probe.domain;
+    const i64 G = gridDim.x;
+    constexpr int WBUF = 1024;                       // >= 32 * 4 * NT hits of one step
     __shared__ unsigned s_buf[SA_THREADS / 32][WBUF];
     int nbuf = 0;                                    // warp-uniform fill level
+    unsigned n_pass = 0, n_hits = 0;
     auto flush = [&]() {
         if (nbuf == 0) return;
         unsigned long long base = 0;
@@ -458,67 +492,101 @@ filter_hits_kernel(const PipeParams p)
         base = __shfl_sync(0xffffffffu, base, 0);
         for (int i = lane; i < nbuf; i += 32) p.hits[base + i] = s_buf[warp][i];
         __syncwarp();
+        n_hits += lane == 0 ? (unsigned)nbuf : 0u;
         nbuf = 0;
     };
-    for (i64 tile0 = blockIdx.x; tile0 < ntiles; tile0 += (i64)gridDim.x * UNROLL) {
-        int4 d[UNROLL];
-        i64 k[UNROLL][4];
+    // one step = NT tiles (tile0 + u * G); the column buffers carry ROW_PAD rows of slack, so a
+    // whole-vector load of a partial tile is in bounds
+    auto load = [&](i64 tile0, int4 (&d)[NT], i64 (&k)[NT][4]) {
 #pragma unroll
-        for (int u = 0; u < UNROLL; u++) {
-            i64 tile = tile0 + (i64)u * gridDim.x;
-            if (tile < ntiles) {
-                i64 row = p.row_begin + tile * SA_TILE + threadIdx.x * SA_VEC;
-                if (HAS_PRED) d[u] = ld_stream16((const int *)p.pred[0].col.p + row);
-                if (KEYW == 8) {
-                    longlong2 a = ld_stream16_ll((const i64 *)p.probe_key.p + row), b = ld_stream16_ll((const i64 *)p.probe_key.p + row + 2);
-                    k[u][0] = a.x; k[u][1] = a.y; k[u][2] = b.x; k[u][3] = b.y;
-                } else {
-                    int4 a = ld_stream16((const int *)p.probe_key.p + row);
-                    k[u][0] = a.x; k[u][1] = a.y; k[u][2] = a.z; k[u][3] = a.w;
-                }
+        for (int u = 0; u < NT; u++) {
+            const i64 tile = tile0 + u * G;
+            if (tile >= ntiles) continue;
+            const i64 row = p.row_begin + tile * SA_TILE + threadIdx.x * SA_VEC;
+            if (HAS_PRED) d[u] = ld_stream16((const int *)p.pred[0].col.p + row);
+            if (KEYW == 8) {
+                longlong2 a = ld_stream16_ll((const i64 *)p.probe_key.p + row), b = ld_stream16_ll((const i64 *)p.probe_key.p + row + 2);
+                k[u][0] = a.x; k[u][1] = a.y; k[u][2] = b.x; k[u][3] = b.y;
+            } else {
+                int4 a = ld_stream16((const int *)p.probe_key.p + row);
+                k[u][0] = a.x; k[u][1] = a.y; k[u][2] = a.z; k[u][3] = a.w;
+            }
+        }
+    };
+    auto process = [&](i64 tile0, const int4 (&d)[NT], const i64 (&k)[NT][4]) {
+        bool ok[NT][4];
+        unsigned w[NT][4];
+        u64 off[NT][4];
+        // the bitmap words are fetched with predicated loads issued back to back (no branches)
+#pragma unroll
+        for (int u = 0; u < NT; u++) {
+            const i64 tile = tile0 + u * G;
+            const i64 row = p.row_begin + tile * SA_TILE + threadIdx.x * SA_VEC;
+            const i64 rem = tile < ntiles ? p.row_end - row : 0;
+            const int dv[4] = {d[u].x, d[u].y, d[u].z, d[u].w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                ok[u][j] = j < rem;
+                if (HAS_PRED) ok[u][j] = ok[u][j] && !pempty && dv[j] >= plo && dv[j] <= phi;
+                off[u][j] = (u64)k[u][j] - bmin;            // one unsigned compare covers both ends of the domain
+                const bool in = ok[u][j] && off[u][j] < dom;
+                w[u][j] = in ? __ldg(bm + (unsigned)(off[u][j] >> 5)) : 0u;
             }
         }
         unsigned hitmask = 0;      // bit (4u + j): row j of tile u is a hit
 #pragma unroll
-        for (int u = 0; u < UNROLL; u++) {
-            i64 tile = tile0 + (i64)u * gridDim.x;
-            i64 row = p.row_begin + tile * SA_TILE + threadIdx.x * SA_VEC;
-            i64 rem = tile < ntiles ? p.row_end - row : 0;
-            int dv[4] = {d[u].x, d[u].y, d[u].z, d[u].w};
+        for (int u = 0; u < NT; u++)
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                bool ok = j < rem;
-                if (HAS_PRED) ok = ok && !pempty && dv[j] >= plo && dv[j] <= phi;
-                n_pass += ok ? 1 : 0;
-                if (ok && (bitmap_test(p.probe, k[u][j]) != anti)) hitmask |= 1u << (4 * u + j);
+                n_pass += ok[u][j] ? 1u : 0u;
+                const bool set = (w[u][j] >> ((unsigned)off[u][j] & 31u)) & 1u;
+                if (ok[u][j] && set != anti) hitmask |= 1u << (4 * u + j);
             }
-        }
         // append to the warp's private staging buffer in shared memory (exclusive scan of the per-lane hit
         // counts); the buffer is flushed to the global list with ONE cursor bump when it is nearly full --
         // a bump per warp step put 2.3 M atomics on one address and cost more than the scan itself
-        int c = __popc(hitmask), incl = c;
+        const int c = __popc(hitmask);
+        int incl = c;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             int v = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += v;
         }
-        int total = __shfl_sync(0xffffffffu, incl, 31);
-        if (total == 0) continue;
-        if (nbuf + total > WBUF) { flush(); }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0) return;
+        if (nbuf + total > WBUF) flush();
         int pos = nbuf + incl - c;
 #pragma unroll
-        for (int u = 0; u < UNROLL; u++) {
-            i64 row = p.row_begin + (tile0 + (i64)u * gridDim.x) * SA_TILE + threadIdx.x * SA_VEC;
+        for (int u = 0; u < NT; u++) {
+            const i64 row = p.row_begin + (tile0 + u * G) * SA_TILE + threadIdx.x * SA_VEC;
 #pragma unroll
             for (int j = 0; j < 4; j++)
                 if (hitmask & (1u << (4 * u + j))) s_buf[warp][pos++] = (unsigned)(row + j);
         }
         nbuf += total;
         __syncwarp();
+    };
+    // software pipeline: the next step's vectors are in flight while the current step is screened
+    int4 dA[NT], dB[NT];
+    i64 kA[NT][4], kB[NT][4];
+#pragma unroll
+    for (int u = 0; u < NT; u++) dA[u] = dB[u] = make_int4(0, 0, 0, 0);
+    i64 tile = blockIdx.x;
+    const i64 step = G * NT;
+    if (tile < ntiles) load(tile, dA, kA);
+    while (tile < ntiles) {
+        if (tile + step < ntiles) load(tile + step, dB, kB);
+        process(tile, dA, kA);
+        tile += step;
+        if (tile >= ntiles) break;
+        if (tile + step < ntiles) load(tile + step, dA, kA);
+        process(tile, dB, kB);
+        tile += step;
     }
     flush();
-    n_pass = (unsigned long long)warp_sum((i64)n_pass);
-    if (lane == 0 && n_pass) atomicAdd(&p.counters[0], n_pass);
+    unsigned long long np = (unsigned long long)warp_sum((i64)n_pass), nh = (unsigned long long)warp_sum((i64)n_hits);
+    if (lane == 0 && np) atomicAdd(&p.counters[0], np);
+    if (lane == 0 && nh) atomicAdd(&p.counters[3], nh);
 }
 
 template <int SINK>
@@ -556,6 +624,49 @@ hits_sink_kernel(const PipeParams p)
     }
     n_join = (unsigned long long)warp_sum((i64)n_join);
     if ((threadIdx.x & 31) == 0 && n_join) atomicAdd(&p.counters[1], n_join);
+}
+
+// ---------------------------------------------------------------- rank index build --
+// pass 1 over the hit list: gather the build key, remember it, set its bit (DETECT: count keys seen twice)
+template <bool DETECT>
+static __global__ void __launch_bounds__(256)
+rank_mark_kernel(const PipeParams p, i64 *__restrict__ keys_tmp)
+{
+    const unsigned long long n = *p.hit_count;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned long long dups = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const i64 key = load_typed(p.ins_key, (i64)p.hits[i]);
+        keys_tmp[i] = key;
+        const u64 off = (u64)key - (u64)p.ins.bm_min;
+        const unsigned bit = 1u << (off & 31);
+        if (DETECT) dups += (atomicOr(p.ins.bitmap + (off >> 5), bit) & bit) ? 1 : 0;
+        else atomicOr(p.ins.bitmap + (off >> 5), bit);      // result unused: a fire-and-forget RED
+    }
+    if (DETECT) {
+        dups = (unsigned long long)warp_sum((i64)dups);
+        if ((threadIdx.x & 31) == 0 && dups) atomicAdd(p.ins.dups, dups);
+    }
+}
+// set bits per 256-bit block (exclusive-summed into rank_prefix by the caller)
+static __global__ void rank_count_kernel(const unsigned *__restrict__ bitmap, u64 nblocks, unsigned *__restrict__ counts)
+{
+    for (u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x; b < nblocks; b += (u64)gridDim.x * blockDim.x) {
+        const uint4 x = __ldg((const uint4 *)(bitmap + b * 8)), y = __ldg((const uint4 *)(bitmap + b * 8) + 1);
+        counts[b] = __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w) + __popc(y.x) + __popc(y.y) + __popc(y.z) + __popc(y.w);
+    }
+}
+// pass 2 over the hit list: payload[rank(key)] = build row id
+static __global__ void __launch_bounds__(256)
+rank_fill_kernel(const PipeParams p, const i64 *__restrict__ keys_tmp, unsigned *__restrict__ payload)
+{
+    const unsigned long long n = *p.hit_count;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        bool set;
+        const unsigned r = jt_rank(p.ins, (u64)keys_tmp[i] - (u64)p.ins.bm_min, &set);
+        payload[r] = p.hits[i];
+    }
 }
 
 // (HAVING on one aggregate -- an inclusive range on accumulator plane `hav_plane` -- is applied here)
@@ -631,17 +742,31 @@ __device__ __forceinline__ u64 topk_u64(const TopkKey &k, const i64 *klo, const 
 }
 
 // one radix-select pass over an 8-bit digit, histogram privatised in shared memory (a 16-bit digit
-// with global atomics was tried: 7x slower, the top digits of real keys collide in one bin)
+// with global atomics was tried: 7x slower, the top digits of real keys collide in one bin).
+// MINMAX (first pass only): also reduce the smallest / largest key into minmax[0..1], so the host can
+// skip every digit the keys have in common.
 constexpr int TOPK_DIGIT_BITS = 8;
+template <bool MINMAX>
 static __global__ void topk_hist_kernel(TopkKey key, const i64 *klo, const i64 *khi, const i64 *acc, i64 stride, i64 n,
-                                        u64 prefix, int prefix_bits, unsigned *hist /* [256] */)
+                                        u64 prefix, int prefix_bits, unsigned *hist /* [256] */, unsigned long long *minmax)
 {
     __shared__ unsigned s_h[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_h[i] = 0;
     __syncthreads();
+    u64 lo = ~0ULL, hi = 0;
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
         u64 u = topk_u64(key, klo, khi, acc, stride, i);
+        if (MINMAX) { lo = u < lo ? u : lo; hi = u > hi ? u : hi; }
         if (prefix_bits == 0 || (u >> (64 - prefix_bits)) == prefix) atomicAdd(&s_h[(u >> (56 - prefix_bits)) & 255], 1u);
+    }
+    if (MINMAX) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            u64 l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+            lo = l2 < lo ? l2 : lo;
+            hi = h2 > hi ? h2 : hi;
+        }
+        if ((threadIdx.x & 31) == 0) { atomicMin(&minmax[0], lo); atomicMax(&minmax[1], hi); }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 256; i += blockDim.x)
