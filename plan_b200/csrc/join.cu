@@ -87,6 +87,8 @@ struct JoinAggPipeline : Pipeline {
     i64 group_hint = 0;                          // expected number of groups (no-join case)
     i64 key_min = 0;                             // statistics of the first group key (no-join case)
     u64 key_domain = 0;
+    bool key_sorted = false;                     // first group key never descends in row order (no-join case)
+    DevBuf d_edges;
     std::vector<std::pair<int, int>> outs;
     std::vector<int> group_out_type;             // pg_type of each group key
     i64 algorithmic_bytes = 0, main_bytes = 0;
@@ -598,7 +600,63 @@ struct JoinAggPipeline : Pipeline {
             res->stats.kernel_launches += 1;
             tr.mark("probe filter");
         }
-        for (int attempt = 0;; attempt++) {
+        // the shape the vectorised no-join kernels take: 1 key, 1 summed column, <=1 32-bit predicate
+        bool one_shape = false;
+        if (no_join) {
+            bool pred_valid = false;
+            for (int k = 0; k < pp.npred; k++) pred_valid = pred_valid || pp.pred[k].col.valid != nullptr;
+            one_shape = !pred_valid && gs.nparts == 1 && gs.nacc == 1 && gs.nfac[0] == 1 && pp.npred <= 1 &&
+                        (pp.npred == 0 || pp.pred[0].col.width == 4) && gs.part[0].col.width >= 4 &&
+                        gs.fac[0][0].col.width >= 4 && !getenv("PG_GROUP_GENERIC");
+        }
+        const bool sorted_runs = one_shape && key_sorted && t->nrows > 0 && !(shuffle && c.world > 1) && !getenv("PG_NO_SORTED_RUNS");
+        i64 ngroups = 0;
+        if (sorted_runs) {
+            // key sorted in row order: fused reduce-by-key at scan speed, no table, no compaction
+            // one chunk of 128-row tiles per warp
+            constexpr int WPB = SA_THREADS / 32;
+            const i64 ntiles = (t->nrows + RUN_WTILE - 1) / RUN_WTILE;
+            i64 nwarps = std::max<i64>(std::min<i64>(ntiles, (i64)c.prop.multiProcessorCount * 4 * WPB), 1);
+            const i64 chunk_tiles = (ntiles + nwarps - 1) / nwarps;
+            nwarps = (ntiles + chunk_tiles - 1) / chunk_tiles;
+            const i64 grid = (nwarps + WPB - 1) / WPB;
+            const i64 nchunks = grid * WPB;
+            if (d_edges.bytes < (size_t)nchunks * 2 * sizeof(RunEdge)) PG_TRY(d_edges.alloc((size_t)nchunks * 2 * sizeof(RunEdge)));
+            RunEdge *first = d_edges.as<RunEdge>(), *last = first + nchunks;
+            // output capacity: a HAVING keeps few groups (the list grows and the pass reruns if not)
+            i64 want = hav_plane >= 0 ? std::max<i64>(t->nrows / 64, 1 << 16) : std::min<i64>(t->nrows, group_hint * 4);
+            for (int attempt = 0;; attempt++) {
+                if (want > out_cap) {
+                    PG_TRY(d_out_klo.alloc((size_t)want * 8));
+                    PG_TRY(d_out_khi.alloc((size_t)want * 8));
+                    PG_TRY(d_out_acc.alloc((size_t)want * 8 * (size_t)(gs.nacc + 1)));
+                    out_cap = want;
+                }
+                PG_CUDA(cudaMemsetAsync(d_counters.p, 0, 32, st));
+                RunOut ro{d_out_klo.as<i64>(), d_out_khi.as<i64>(), d_out_acc.as<i64>(), out_cap, d_counters.as<unsigned long long>() + 2,
+                          hav_plane, hav_lo, hav_hi};
+                PG_CUDA(cudaEventRecord(ev_main.a, st));
+                const bool k8 = gs.part[0].col.width == 8, v8 = gs.fac[0][0].col.width == 8, hp = pp.npred == 1;
+#define PG_RG(K, V, P) run_group_kernel<K, V, P><<<(int)grid, SA_THREADS, 0, st>>>(pp, ro, first, last, chunk_tiles)
+                if (k8 && v8) { if (hp) PG_RG(8, 8, true); else PG_RG(8, 8, false); }
+                else if (k8) { if (hp) PG_RG(8, 4, true); else PG_RG(8, 4, false); }
+                else if (v8) { if (hp) PG_RG(4, 8, true); else PG_RG(4, 8, false); }
+                else { if (hp) PG_RG(4, 4, true); else PG_RG(4, 4, false); }
+#undef PG_RG
+                PG_CUDA(cudaGetLastError());
+                run_fixup_kernel<<<1, 256, 0, st>>>(first, last, (int)nchunks, ro);
+                PG_CUDA(cudaGetLastError());
+                PG_CUDA(cudaEventRecord(ev_main.b, st));
+                res->stats.kernel_launches += 2;
+                PG_TRY(read_counters(cnt));
+                ngroups = (i64)cnt[2];
+                if (ngroups <= out_cap) break;
+                if (attempt > 2) PG_FAIL(PG_ECUDA, "internal: sorted-run output keeps overflowing");
+                want = ngroups;
+            }
+            tr.mark("sorted-run group-by");
+        }
+        for (int attempt = 0; !sorted_runs; attempt++) {
             PG_TRY(ensure_group_table(cap));
             cap = gt_cap;
             PG_CUDA(cudaMemsetAsync(d_gt.p, 0x80, cap * 8 * (size_t)gt_slot_words(gs.nacc), st));
@@ -635,12 +693,7 @@ struct JoinAggPipeline : Pipeline {
                 res->stats.kernel_launches -= 1;
             } else if (no_join) {
                 // the specialised vectorised kernel when the shape is: 1 key, 1 summed column, <=1 32-bit predicate
-                bool pred_valid = false;
-                for (int k = 0; k < pp.npred; k++) pred_valid = pred_valid || pp.pred[k].col.valid != nullptr;
-                const bool one = !pred_valid && gs.nparts == 1 && gs.nacc == 1 && gs.nfac[0] == 1 && pp.npred <= 1 &&
-                                 (pp.npred == 0 || pp.pred[0].col.width == 4) && gs.part[0].col.width >= 4 &&
-                                 gs.fac[0][0].col.width >= 4 && !getenv("PG_GROUP_GENERIC");
-                if (one) {
+                if (one_shape) {
                     i64 ntiles = (t->nrows + SA_TILE - 1) / SA_TILE;
                     int grid = (int)std::max<i64>(std::min<i64>(ntiles, (i64)c.prop.multiProcessorCount * 8), 1);
                     const bool k8 = gs.part[0].col.width == 8, v8 = gs.fac[0][0].col.width == 8, hp = pp.npred == 1;
@@ -670,6 +723,7 @@ struct JoinAggPipeline : Pipeline {
         }
         // compact
         const bool do_shuffle = shuffle && c.world > 1;
+        if (!sorted_runs) {
         i64 max_out = (i64)std::min<u64>(cap, (u64)cnt[1]);
         if (max_out < 1) max_out = 1;
         if (max_out > out_cap) {
@@ -686,7 +740,8 @@ struct JoinAggPipeline : Pipeline {
         res->stats.kernel_launches += 1;
         unsigned long long ng2[4];
         PG_TRY(read_counters(ng2));
-        i64 ngroups = (i64)ng2[0];
+        ngroups = (i64)ng2[0];
+        }
         if (do_shuffle) { PG_TRY(shuffle_groups(&ngroups, pp, res)); tr.mark("all-to-all shuffle + merge"); }
         res->stats.aux[6] = ngroups;          // groups before any LIMIT
         tr.mark("compact");
@@ -1142,6 +1197,7 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &join, std::uniqu
         p->key_min = kc.vmin;
         p->key_domain = domain > 0 && domain < ((i128)1 << 62) ? (u64)domain : 0;
         p->gs.run_aggregate = kc.stats_ok && kc.adjacent_equal * 2 >= st->nrows ? 1 : 0;
+        p->key_sorted = kc.stats_ok && kc.adjacent_descents == kc.adjacent_equal;
         if (getenv("PG_RUN_AGGREGATE")) p->gs.run_aggregate = atoi(getenv("PG_RUN_AGGREGATE"));
     }
     for (auto &o : aggn.outs) {
@@ -1272,8 +1328,9 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &join, std::uniqu
     }
     char b[320];
     if (p->no_join)
-        snprintf(b, sizeof b, "GroupBy[global open-addressing table] scan(%s) kernel=pipeline_kernel<SINK_GROUP> group_keys=%d sums=%d%s%s",
+        snprintf(b, sizeof b, "GroupBy[global open-addressing table] scan(%s) kernel=pipeline_kernel<SINK_GROUP> group_keys=%d sums=%d%s%s%s",
                  st->name.c_str(), p->nparts, p->gs.nacc, p->hav_plane >= 0 ? " having" : "",
+                 p->key_sorted ? " sorted-run reduce-by-key when the shape allows (run_group_kernel)" : "",
                  p->shuffle ? " exchange=all-to-all(hash-partitioned)" : "");
     else
         snprintf(b, sizeof b, " probe(%s key=%s) kernel=filter_hits_kernel+hits_sink_kernel<SINK_GROUP> group_keys=%d sums=%d%s", st->name.c_str(),

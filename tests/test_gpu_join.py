@@ -322,6 +322,54 @@ def test_extreme_key_values_group_correctly(pg, oracle, sf01_host):
         t["lineitem"].free()
 
 
+def _sorted_run_case(name, n, rng):
+    """Key layouts that stress the sorted-run reduce-by-key: edges of 4-row vectors, 1024-row tiles, block chunks."""
+    if name == "one_run":
+        return np.full(n, 7, dtype=np.int64)
+    if name == "all_distinct":
+        return np.arange(n, dtype=np.int64) * 3 - 5
+    if name == "tile_aligned":                      # every run is exactly one 1024-row tile
+        return np.arange(n, dtype=np.int64) // 1024
+    if name == "vector_aligned":                    # every run is exactly one 4-row vector
+        return np.arange(n, dtype=np.int64) // 4
+    if name == "long_then_short":                   # one run over many tiles, then runs of 1..7
+        head = n // 2 + 3
+        tail = np.repeat(np.arange(1, n), rng.integers(1, 8, size=n - 1))[: n - head]
+        return np.concatenate([np.zeros(head, dtype=np.int64), tail.astype(np.int64)])[:n]
+    if name == "mixed":
+        lens = rng.choice([1, 2, 3, 5, 31, 257, 1023, 1025, 4099], size=n)
+        return np.repeat(np.arange(n, dtype=np.int64) * 2, lens)[:n]
+    raise AssertionError(name)
+
+
+@pytest.mark.parametrize("name", ["one_run", "all_distinct", "tile_aligned", "vector_aligned", "long_then_short", "mixed"])
+@pytest.mark.parametrize("n", [1, 5, 1024, 40000, 300001])
+def test_sorted_run_groupby_edges(pg, oracle, sf01_host, monkeypatch, name, n):
+    """Sorted group key => fused reduce-by-key (run_group_kernel + run_fixup_kernel): exact against the oracle,
+    with and without a predicate that empties whole runs, with and without HAVING, and identical to the
+    table-based path it replaces."""
+    from plan_b200 import tpch as T
+    rng = np.random.default_rng(n * 31 + len(name))
+    line = {k: v[:n].copy() for k, v in sf01_host["lineitem"].items()}
+    line["l_orderkey"] = _sorted_run_case(name, n, rng)
+    assert len(line["l_orderkey"]) == n
+    t = T.upload_tables({"lineitem": line})
+    try:
+        for extra in (dict(), dict(ship_le=8035 + 1200), dict(having_gt=100), dict(value="l_extendedprice", ship_le=8035 + 600)):
+            kw = dict(key="l_orderkey", value="l_quantity")
+            kw.update(extra)
+            chunks, stats, explain = _run(T.groupby_plan(**kw), t)
+            assert "sorted-run" in explain
+            got = _groupby_result(chunks)
+            assert got == oracle.groupby_sum(line, **kw)
+            monkeypatch.setenv("PG_NO_SORTED_RUNS", "1")
+            chunks2, _, _ = _run(T.groupby_plan(**kw), t)
+            monkeypatch.delenv("PG_NO_SORTED_RUNS")
+            assert _groupby_result(chunks2) == got
+    finally:
+        t["lineitem"].free()
+
+
 def test_full_size_sf100_matches_the_oracle_fixtures(pg):
     """BASELINE's full size: SF100 (600,037,902 lineitem rows) generated in HBM, Q6 / Q1 / Q3(top 10)
     through the C ABI == the CPU oracle's SF100 results (tests/golden/oracle_sf100_*.txt, produced once by
