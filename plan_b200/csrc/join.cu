@@ -644,7 +644,7 @@ struct JoinAggPipeline : Pipeline {
                 else { if (hp) PG_RG(4, 4, true); else PG_RG(4, 4, false); }
 #undef PG_RG
                 PG_CUDA(cudaGetLastError());
-                run_fixup_kernel<<<1, 256, 0, st>>>(first, last, (int)nchunks, ro);
+                run_fixup_kernel<<<(int)((nchunks + 255) / 256), 256, 0, st>>>(first, last, (int)nchunks, ro);
                 PG_CUDA(cudaGetLastError());
                 PG_CUDA(cudaEventRecord(ev_main.b, st));
                 res->stats.kernel_launches += 2;

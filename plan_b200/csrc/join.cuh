@@ -489,9 +489,11 @@ __device__ __forceinline__ bool run_passes(const RunOut &o, i64 sum, i64 cnt)
 
 constexpr int RUN_H = 1, RUN_S = 2;                    // segment head | run touches the start of the warp's chunk
 constexpr int RUN_WTILE = 32 * SA_VEC;                 // rows per warp tile
+// (register double-buffering and prefetch.global.L2 of later tiles were both measured: no gain, the kernel
+//  is issue-bound at ~75 % issue utilisation, not latency-bound)
 
 template <int KEYW, int VALW, bool HAS_PRED>
-__global__ void __launch_bounds__(SA_THREADS)
+__global__ void __launch_bounds__(SA_THREADS, 4)
 run_group_kernel(const PipeParams p, const RunOut out, RunEdge *__restrict__ first, RunEdge *__restrict__ last, i64 chunk_tiles)
 {
     const unsigned full = 0xffffffffu;
@@ -508,6 +510,7 @@ run_group_kernel(const PipeParams p, const RunOut out, RunEdge *__restrict__ fir
     const bool pempty = p.pred[0].lo > p.pred[0].hi;
     const void *kp = p.gs.part[0].col.p, *vp = p.gs.fac[0][0].col.p;
     const i64 fc = p.gs.fc[0][0], fs = p.gs.fs[0][0];
+    const bool plain = fc == 0 && fs == 1;             // sum(column): no multiply
     const i64 tail_key = KEYW == 8 ? __ldg((const i64 *)kp + (p.nrows - 1)) : (i64)__ldg((const int *)kp + (p.nrows - 1));
     // the warp's open run, carried across tiles (warp-uniform); cf == 0: none yet
     int cf = 0;
@@ -542,33 +545,28 @@ run_group_kernel(const PipeParams p, const RunOut out, RunEdge *__restrict__ fir
             bool ok = j < rem;
             if (!ok) k[j] = tail_key;                  // pad rows join the table's last run and add nothing
             if (HAS_PRED) ok = ok && !pempty && dv[j] >= plo && dv[j] <= phi;
-            x[j] = ok ? fc + fs * v[j] : 0;
+            x[j] = ok ? (plain ? v[j] : fc + fs * v[j]) : 0;
             c[j] = ok ? 1 : 0;
             n_pass += ok ? 1u : 0u;
         }
-        // lane-local runs: leading (may continue the previous lane's), interior (complete), trailing (open)
-        i64 ek[4], es[4], ec[4];                        // records this lane closes: [0] the previous lane's run,
-        bool ev[4] = {false, false, false, false};      // [1] its leading run, [2..3] interior runs
-        i64 lead_s = x[0];
-        int lead_c = c[0];
-        i64 cur_k = k[0], cur_s = x[0];
-        int cur_c = c[0], nheads = 0;
-#pragma unroll
-        for (int j = 1; j < 4; j++) {
-            if (k[j] != cur_k) {
-                if (nheads == 0) { lead_s = cur_s; lead_c = cur_c; }
-                else {
-#pragma unroll
-                    for (int r = 2; r < 4; r++)         // static indices keep the records in registers
-                        if (1 + nheads == r) { ek[r] = cur_k; es[r] = cur_s; ec[r] = cur_c; ev[r] = true; }
-                }
-                nheads++;
-                cur_k = k[j]; cur_s = 0; cur_c = 0;
-            }
-            cur_s += x[j]; cur_c += c[j];
-        }
-        const bool single = nheads == 0;
-        if (single) { lead_s = cur_s; lead_c = cur_c; }
+        // lane-local runs, branch-free: prefix sums + the three head flags between the four rows.
+        //   leading run  = rows before the first head (may continue the previous lane's run)
+        //   trailing run = rows from the last head on (still open)
+        //   interior runs (complete): [1, 2 or 3) when h1 and a later head exist; [2, 3) when h2 and h3
+        const bool h1 = k[1] != k[0], h2 = k[2] != k[1], h3 = k[3] != k[2];
+        const i64 p0 = x[0], p1 = p0 + x[1], p2 = p1 + x[2], p3 = p2 + x[3];
+        const int n0 = c[0], n1 = n0 + c[1], n2 = n1 + c[2], n3 = n2 + c[3];
+        const bool single = !(h1 || h2 || h3);
+        const i64 lead_s = h1 ? p0 : h2 ? p1 : h3 ? p2 : p3;
+        const int lead_c = h1 ? n0 : h2 ? n1 : h3 ? n2 : n3;
+        const i64 cur_s = p3 - (h3 ? p2 : h2 ? p1 : h1 ? p0 : 0);
+        const int cur_c = n3 - (h3 ? n2 : h2 ? n1 : h1 ? n0 : 0);
+        // records this lane may close: a = the previous lane's run, b = its leading run, m / n = interior runs
+        bool eva = false, evb = false;
+        i64 eka = 0, esa = 0, eca = 0, ekb = 0, esb = 0, ecb = 0;
+        bool evm = h1 && (h2 || h3), evn = h2 && h3;
+        const i64 ekm = k[1], esm = (h2 ? p1 : p2) - p0, ekn = k[2], esn = x[2];
+        const int ecm = (h2 ? n1 : n2) - n0, ecn = c[2];
         // element of the warp-wide segmented scan: the run that is still open at the end of this lane
         const i64 kfirst = k[0], klast = k[3];
         i64 pk = __shfl_up_sync(full, klast, 1);
@@ -595,23 +593,23 @@ run_group_kernel(const PipeParams p, const RunOut out, RunEdge *__restrict__ fir
         // close runs
         if (pvalid && !cont) {                          // the previous run ended exactly at my first row
             if (qf & RUN_S) { first[gw].key = pk; first[gw].sum = qs; first[gw].cnt = qc; first[gw].spans = 0; first[gw].valid = 1; }
-            else if (run_passes(out, qs, qc)) { ek[0] = pk; es[0] = qs; ec[0] = qc; ev[0] = true; }
+            else if (run_passes(out, qs, qc)) { eka = pk; esa = qs; eca = qc; eva = true; }
         }
         if (!single) {                                  // my leading run ends inside me
             const i64 ts = lead_s + (cont ? qs : 0), tc = (i64)lead_c + (cont ? qc : 0);
             const bool touches = cont ? (qf & RUN_S) != 0 : chunk_start;
             if (touches) { first[gw].key = kfirst; first[gw].sum = ts; first[gw].cnt = tc; first[gw].spans = 0; first[gw].valid = 1; }
-            else if (run_passes(out, ts, tc)) { ek[1] = kfirst; es[1] = ts; ec[1] = tc; ev[1] = true; }
-#pragma unroll
-            for (int r = 2; r < 4; r++) ev[r] = ev[r] && run_passes(out, es[r], ec[r]);
+            else if (run_passes(out, ts, tc)) { ekb = kfirst; esb = ts; ecb = tc; evb = true; }
         }
+        evm = evm && run_passes(out, esm, (i64)ecm);
+        evn = evn && run_passes(out, esn, (i64)ecn);
         // carry into the next tile: lane 31's open run
         cf = __shfl_sync(full, f, 31) | RUN_H;
         ck = __shfl_sync(full, klast, 31);
         cs = __shfl_sync(full, ss, 31);
         cc = __shfl_sync(full, sc, 31);
         // append the closed runs: one cursor bump per warp tile
-        const int mine = (int)ev[0] + (int)ev[1] + (int)ev[2] + (int)ev[3];
+        const int mine = (int)eva + (int)evb + (int)evm + (int)evn;
         if (__any_sync(full, mine != 0)) {
             int incl = mine;
 #pragma unroll
@@ -624,17 +622,15 @@ run_group_kernel(const PipeParams p, const RunOut out, RunEdge *__restrict__ fir
             if (lane == 0) base = atomicAdd(out.count, (unsigned long long)total);
             base = __shfl_sync(full, base, 0);
             unsigned long long pos = base + (unsigned long long)(incl - mine);
-#pragma unroll
-            for (int r = 0; r < 4; r++) {
-                if (!ev[r]) continue;
-                if ((i64)pos < out.cap) {
-                    out.klo[pos] = ek[r];
-                    out.khi[pos] = 0;
-                    out.acc[pos] = es[r];
-                    out.acc[out.cap + (i64)pos] = ec[r];
-                }
+            auto put = [&](bool on, i64 key, i64 sum, i64 cnt) {
+                if (!on) return;
+                if ((i64)pos < out.cap) { out.klo[pos] = key; out.khi[pos] = 0; out.acc[pos] = sum; out.acc[out.cap + (i64)pos] = cnt; }
                 pos++;
-            }
+            };
+            put(eva, eka, esa, eca);
+            put(evb, ekb, esb, ecb);
+            put(evm, ekm, esm, (i64)ecm);
+            put(evn, ekn, esn, (i64)ecn);
         }
     }
     if (lane == 0) {     // the run still open at the end of the chunk
@@ -644,41 +640,36 @@ run_group_kernel(const PipeParams p, const RunOut out, RunEdge *__restrict__ fir
     if (lane == 0 && np) { atomicAdd(&p.counters[0], np); atomicAdd(&p.counters[1], np); }
 }
 
-// stitch the runs that touch chunk edges: batches of edges are staged in shared memory by the whole
-// block, thread 0 walks them in order (a few thousand records)
+// Stitch the runs that touch chunk edges, one thread per chunk.  Thread b emits first[b] when it does not
+// continue the run left open by chunk b-1, and OWNS the run left open at the end of chunk b if that run
+// starts in chunk b: it walks forward over chunks the run spans entirely until the chunk that closes it
+// (sorted keys: equal keys in neighbouring edge records always mean the same run).
 static __global__ void __launch_bounds__(256)
 run_fixup_kernel(const RunEdge *__restrict__ first, const RunEdge *__restrict__ last, int nchunks, const RunOut out)
 {
-    __shared__ RunEdge s_f[256], s_l[256];
-    bool open = false;
-    i64 ok = 0, os = 0, oc = 0;
+    const int b = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (b >= nchunks) return;
     auto emit = [&](i64 k, i64 s, i64 c) {
         if (!run_passes(out, s, c)) return;
         unsigned long long pos = atomicAdd(out.count, 1ULL);
         if ((i64)pos < out.cap) { out.klo[pos] = k; out.khi[pos] = 0; out.acc[pos] = s; out.acc[out.cap + (i64)pos] = c; }
     };
-    for (int b0 = 0; b0 < nchunks; b0 += 256) {
-        const int b = b0 + (int)threadIdx.x;
-        if (b < nchunks) { s_f[threadIdx.x] = first[b]; s_l[threadIdx.x] = last[b]; }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const int nb = nchunks - b0 < 256 ? nchunks - b0 : 256;
-            for (int i = 0; i < nb; i++) {
-                const RunEdge F = s_f[i], L = s_l[i];
-                if (F.valid) {
-                    if (open && ok == F.key) emit(ok, os + F.sum, oc + F.cnt);
-                    else { if (open) emit(ok, os, oc); emit(F.key, F.sum, F.cnt); }
-                    open = false;
-                }
-                if (L.valid) {
-                    if (L.spans && open && ok == L.key) { os += L.sum; oc += L.cnt; }
-                    else { if (open) emit(ok, os, oc); open = true; ok = L.key; os = L.sum; oc = L.cnt; }
-                }
-            }
-        }
-        __syncthreads();
+    const RunEdge F = first[b], L = last[b];
+    bool has_prev = false;
+    i64 pkey = 0;
+    if (b > 0) { has_prev = last[b - 1].valid != 0; pkey = last[b - 1].key; }
+    if (F.valid && !(has_prev && pkey == F.key)) emit(F.key, F.sum, F.cnt);
+    if (!L.valid) return;
+    if (L.spans && has_prev && pkey == L.key) return;       // a continuation: the thread where the run starts owns it
+    i64 s = L.sum, c = L.cnt;
+    for (int j = b + 1; j < nchunks; j++) {
+        const RunEdge Fj = first[j];
+        if (Fj.valid) { if (Fj.key == L.key) { s += Fj.sum; c += Fj.cnt; } break; }
+        const RunEdge Lj = last[j];
+        if (!(Lj.valid && Lj.spans && Lj.key == L.key)) break;
+        s += Lj.sum; c += Lj.cnt;
     }
-    if (threadIdx.x == 0 && open) emit(ok, os, oc);
+    emit(L.key, s, c);
 }
 
 // ---------------------------------------------------------------- two-phase --
