@@ -381,6 +381,48 @@ def q3_topk(res, limit=10):
     return sorted(res["groups"], key=key)[:limit]
 
 
+def customer_name(custkey):
+    """dbgen C_NAME: the tag "Customer" + '#' + the key zero-padded to 9 digits (TPC-H spec 4.2.3)."""
+    return "Customer#%09d" % int(custkey)
+
+
+def q18(cust, orders, line, qty_gt=314, limit=100):
+    """TPC-H Q18 as the reference plans it (cases/tpch/query/q18.sql): the IN-subquery is a SEMI join on
+    o_orderkey against `group by l_orderkey having sum(l_quantity) > k` (builder_plan.go:234-262; the
+    HAVING compares HUGEINTs, function_operator_boolean.go:255-263); the outer aggregate groups by
+    (c_name, c_custkey, o_orderkey, o_orderdate, o_totalprice) with sum(l_quantity) -> HUGEINT
+    (function_aggr.go:620-650); ORDER BY o_totalprice DESC (DECIMAL key = Int64(2), sort_encoder.go:65-70),
+    o_orderdate; LIMIT (executor_limit.go:120-137).  Returns the ordered rows as dicts."""
+    lk, lq = line["l_orderkey"], line["l_quantity"].astype(np.int64)
+    uk, inv = np.unique(lk, return_inverse=True)
+    sums = np.zeros(len(uk), dtype=np.int64)
+    np.add.at(sums, inv, lq)
+    big = uk[sums > qty_gt]
+    sel = np.nonzero(np.isin(orders["o_orderkey"], big))[0]
+    ckeys = set(int(x) for x in cust["c_custkey"])
+    qsum = dict(zip((int(k) for k in uk), (int(v) for v in sums)))
+    rows = []
+    for i in sel:
+        ck = int(orders["o_custkey"][i])
+        if ck not in ckeys:                     # INNER join customer: unmatched orders disappear
+            continue
+        ok = int(orders["o_orderkey"][i])
+        rows.append({"c_name": customer_name(ck), "c_custkey": ck, "o_orderkey": ok,
+                     "o_orderdate": int(orders["o_orderdate"][i]), "o_totalprice": int(orders["o_totalprice"][i]),
+                     "sum_qty": qsum[ok]})
+    rows.sort(key=lambda r: (-r["o_totalprice"], r["o_orderdate"]))
+    return rows if limit is None else rows[:limit]
+
+
+def q18_text(rows):
+    lines = ["#" + "\t" * 5]
+    for r in rows:
+        tp = r["o_totalprice"]
+        lines.append("\t".join([r["c_name"], str(r["c_custkey"]), str(r["o_orderkey"]), fmt_date(r["o_orderdate"]),
+                                fmt_decimal((abs(tp), 2, tp < 0), 2), str(r["sum_qty"])]))
+    return "\n".join(lines) + "\n"
+
+
 def q3_text(res, limit=10):
     lines = ["#" + "\t" * 3]
     for g in q3_topk(res, limit):

@@ -73,6 +73,12 @@ def test_q1_reproduces_reference_golden(oracle, sf1):
         assert repr(g["avg_qty"]) == repr(float(g["sum_qty"]) / float(g["count_order"]))
 
 
+def test_q18_reproduces_reference_golden(oracle, sf1):
+    """cases/tpch/1g/plan/q18.txt: HAVING on a HUGEINT sum, SEMI join, 5-key group-by, DECIMAL sort key, LIMIT."""
+    rows = oracle.q18(sf1["customer"], sf1["orders"], sf1["lineitem"])
+    assert oracle.q18_text(rows) == open(os.path.join(GOLDEN, "ref_sf1_q18.txt")).read()
+
+
 def test_q3_reproduces_reference_golden(oracle, sf1):
     res = oracle.q3(sf1["customer"], sf1["orders"], sf1["lineitem"])
     assert oracle.q3_text(res) == open(os.path.join(GOLDEN, "ref_sf1_q3.txt")).read()
