@@ -22,7 +22,7 @@ enum { PG_L_ORDERKEY = 0, PG_L_PARTKEY, PG_L_SUPPKEY, PG_L_LINENUMBER, PG_L_QUAN
        PG_L_RECEIPTDATE, PG_L_NCOLS };
 enum { PG_O_ORDERKEY = 0, PG_O_CUSTKEY, PG_O_ORDERDATE, PG_O_SHIPPRIORITY, PG_O_TOTALPRICE, PG_O_ORDERSTATUS,
        PG_O_NCOLS };
-enum { PG_C_CUSTKEY = 0, PG_C_MKTSEGMENT, PG_C_NATIONKEY, PG_C_NCOLS };
+enum { PG_C_CUSTKEY = 0, PG_C_MKTSEGMENT, PG_C_NATIONKEY, PG_C_NAME, PG_C_NCOLS };
 
 int64_t pg_tpch_num_orders(double sf);
 int64_t pg_tpch_num_customers(double sf);

@@ -178,6 +178,7 @@ def gen_customer(sf, c_lo=0, c_hi=None):
     out = {"c_custkey": np.empty(c_hi - c_lo, np.int32), "c_mktsegment": np.empty(c_hi - c_lo, np.uint8),
            "c_nationkey": np.empty(c_hi - c_lo, np.int32)}
     L.tg_gen_customer(sf, c_lo, c_hi, _p(out["c_custkey"]), _p(out["c_mktsegment"]), _p(out["c_nationkey"]))
+    out["c_name"] = np.array([customer_name(k).encode() for k in out["c_custkey"]], dtype=object)
     return out
 
 

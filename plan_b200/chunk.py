@@ -83,6 +83,8 @@ class Vector:
         if t == LTID_HUGEINT:
             return Value(self._Typ, i64=int(x["upper"]), i64_1=int(x["lower"]))
         if t == LTID_VARCHAR:
+            if isinstance(x, (bytes, str)):          # full VARCHAR column: the string itself
+                return Value(self._Typ, s=x.decode() if isinstance(x, bytes) else x)
             if self.Dict is not None:
                 return Value(self._Typ, s=self.Dict[int(x)])
             return Value(self._Typ, s=chr(int(x)))
@@ -189,7 +191,11 @@ def go_float_string(x):
     return r
 
 
+# pg_string {const char *data; int64_t len} (include/plangpu.h; the layout of common.String)
+PG_STRING = np.dtype([("data", np.uint64), ("len", np.int64)])
+
+
 def native_dtype(pg_type):
     return {L.PG_T_INT32: np.int32, L.PG_T_INT64: np.int64, L.PG_T_DATE32: np.int32, L.PG_T_DECIMAL64: np.int64,
             L.PG_T_CHAR1: np.uint8, L.PG_T_DICT8: np.uint8, L.PG_T_FLOAT64: np.float64, L.PG_T_HUGEINT: HUGEINT,
-            L.PG_T_DECIMAL128: DECIMAL128}[pg_type]
+            L.PG_T_DECIMAL128: DECIMAL128, L.PG_T_VARCHAR: PG_STRING}[pg_type]

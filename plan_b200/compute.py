@@ -227,6 +227,19 @@ class DeviceTable:
         ptrs = (C.c_void_p * n)()
         nrows = None
         for i, a in enumerate(arrays):
+            if self.columns[i][1] == L.PG_T_VARCHAR:
+                # list / array of bytes|str -> one pg_string per row over a single contiguous buffer
+                raw = [x.encode() if isinstance(x, str) else bytes(x) for x in a]
+                lens = np.fromiter((len(x) for x in raw), dtype=np.int64, count=len(raw))
+                blob = np.frombuffer(b"".join(raw) + b"\0", dtype=np.uint8)
+                sv = np.empty(len(raw), dtype=K.PG_STRING)
+                sv["len"] = lens
+                sv["data"] = blob.ctypes.data + np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.uint64) if len(raw) else 0
+                arrays[i] = (sv, blob)
+                ptrs[i] = sv.ctypes.data
+                nrows = len(raw) if nrows is None else nrows
+                assert len(raw) == nrows
+                continue
             if isinstance(a, np.ndarray):
                 a = np.ascontiguousarray(a, dtype=K.native_dtype(self.columns[i][1]))
                 arrays[i] = a
@@ -345,6 +358,8 @@ class gpuPipelineExec(OperatorExec):
             dt = np.dtype(K.native_dtype(t))
             buf = (C.c_char * (dt.itemsize * n.value)).from_address(cols[i])
             data = np.frombuffer(buf, dtype=dt, count=n.value).copy()
+            if t == L.PG_T_VARCHAR:      # pg_string rows -> python strings (the result owns the bytes until Close)
+                data = np.array([C.string_at(int(r["data"]), int(r["len"])) for r in data], dtype=object)
             typ = agg.Outputs[i].DataTyp if i < len(agg.Outputs) else K.LType(0)
             d = None
             if t == L.PG_T_DICT8:

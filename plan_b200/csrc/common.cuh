@@ -67,7 +67,7 @@ inline int type_size(int t)
     case PG_T_INT32: case PG_T_DATE32: return 4;
     case PG_T_INT64: case PG_T_DECIMAL64: case PG_T_FLOAT64: return 8;
     case PG_T_CHAR1: case PG_T_DICT8: return 1;
-    case PG_T_HUGEINT: case PG_T_DECIMAL128: return 16;
+    case PG_T_HUGEINT: case PG_T_DECIMAL128: case PG_T_VARCHAR: return 16;
     default: return 0;
     }
 }
@@ -87,6 +87,9 @@ struct Column {
     i64 adjacent_equal = 0;                           // rows whose value equals the next row's (clustering)
     i64 adjacent_descents = 0;                        // rows whose value is >= the next row's; 0 => strictly increasing => unique
     uint32_t present[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // byte columns: which codes occur
+    // PG_T_VARCHAR: host-resident payload, row r = h_bytes[h_off[r] .. h_off[r+1]) (h_off holds nrows+1 entries)
+    std::vector<int64_t> h_off;
+    std::string h_bytes;
 };
 
 }  // namespace pg

@@ -39,6 +39,14 @@ struct Stage {
     DevBuf d_slots, d_bitmap, d_rank_prefix, d_rank_payload, d_keys_tmp, d_scan_tmp;
     JoinTable jt{};
     bool rank_index = false;         // unique keys + bitmap: the table is bitmap + rank prefix + payload (join.cuh jt_rank)
+    // further existence tests on this stage's source rows (pushed-down SEMI / ANTI joins, INNER joins
+    // against unique keys): {mode 0 INNER / 1 SEMI / 2 ANTI, key column on the source table, probed stage}
+    struct Extra { int mode, key_col, stage; };
+    std::vector<Extra> extras;
+    // build side that is itself an aggregate (`key IN (select k from t group by k having ...)`): its
+    // group keys are computed on the device by a nested pipeline and become an existence bitmap
+    std::unique_ptr<Pipeline> sub;
+    Node sub_scan;
     i64 capacity_rows = 0;
     i64 built_rows = 0;
     bool payload_needed = false;     // some column of this build side is read above the join
@@ -88,6 +96,18 @@ struct JoinAggPipeline : Pipeline {
     i64 key_min = 0;                             // statistics of the first group key (no-join case)
     u64 key_domain = 0;
     bool key_sorted = false;                     // first group key never descends in row order (no-join case)
+    bool device_only = false;                    // nested use: stop after the group list is on the device
+    i64 dev_ngroups = 0;
+    std::vector<Stage::Extra> extras;            // existence tests on the top probe's source rows
+    // Group keys functionally dependent on the top join's unique build key (TPC-H Q18 groups by five
+    // columns of one orders row): the group table is keyed by the build ROW ID alone and the key columns
+    // are fetched once per output group.  kind 0: column of the top build table at that row; kind 1: the
+    // row's `via_key_col` looked up in the rank index of the deeper unique build side `via_stage`.
+    bool fd_mode = false;
+    struct FdOut { int kind, slot, col, via_key_col, via_stage; };
+    std::vector<FdOut> fd;
+    DevBuf d_fd;
+    PinBuf h_fd;
     DevBuf d_edges;
     std::vector<std::pair<int, int>> outs;
     std::vector<int> group_out_type;             // pg_type of each group key
@@ -214,6 +234,23 @@ struct JoinAggPipeline : Pipeline {
         return PG_OK;
     }
 
+    int fill_extras(PipeParams &pp, const std::vector<Stage::Extra> &ex, int slot)
+    {
+        if (ex.size() > PIPE_MAXEXTRA) PG_FAIL(PG_EUNSUPPORTED, "more than %d existence joins on one scan", PIPE_MAXEXTRA);
+        pp.nextra = (int)ex.size();
+        for (size_t i = 0; i < ex.size(); i++) {
+            const Stage &b = *stages[(size_t)ex[i].stage];
+            if (!b.jt.bitmap) PG_FAIL(PG_EUNSUPPORTED, "existence join against a key domain too wide for a bitmap");
+            if (ex[i].mode == 0 && b.dup_keys != 0 && !b.unique_key) PG_FAIL(PG_EUNSUPPORTED, "INNER join pushed to an existence test found duplicate build keys");
+            pp.extra[i].key = typed(tab(slot), ex[i].key_col);
+            pp.extra[i].bitmap = b.jt.bitmap;
+            pp.extra[i].bm_min = b.jt.bm_min;
+            pp.extra[i].domain = b.jt.domain;
+            pp.extra[i].anti = ex[i].mode == 2 ? 1 : 0;
+        }
+        return PG_OK;
+    }
+
     int read_counters(unsigned long long *out2)
     {
         PG_CUDA(cudaMemcpyAsync(out2, d_counters.p, 32, cudaMemcpyDeviceToHost, ctx().stream));
@@ -238,7 +275,9 @@ struct JoinAggPipeline : Pipeline {
     {
         bool any_valid = pp.probe_key.valid != nullptr || (ins_sink && pp.ins_key.valid != nullptr);
         for (int k = 0; k < pp.npred; k++) any_valid = any_valid || pp.pred[k].col.valid != nullptr;
-        return pp.has_probe && pp.probe.bitmap && pp.npred <= 1 && (pp.npred == 0 || pp.pred[0].col.width == 4) &&
+        // (a build stage without a probe of its own also qualifies: the filter pass then lists every row that
+        //  passes the predicate -- pp.probe_key must name the key column so the vector loads have a source)
+        return (pp.has_probe ? pp.probe.bitmap != nullptr : ins_sink) && pp.npred <= 1 && (pp.npred == 0 || pp.pred[0].col.width == 4) &&
                (pp.probe_key.width == 4 || pp.probe_key.width == 8) && !any_valid && t->nrows < ((i64)1 << 32) &&
                !getenv("PG_JOIN_GENERIC");
     }
@@ -381,19 +420,46 @@ struct JoinAggPipeline : Pipeline {
     {
         cudaStream_t st = ctx().stream;
         const pg_table *t = tab(s.src_slot);
+        if (s.sub) {
+            // the build side is a sub-aggregate: run it on the device, turn its group keys into the bitmap
+            JoinAggPipeline *sp = static_cast<JoinAggPipeline *>(s.sub.get());
+            const i64 launches = res->stats.kernel_launches;
+            const pg_stats keep = res->stats;
+            PG_TRY(sp->run(res));
+            const i64 sub_launches = res->stats.kernel_launches;
+            res->stats = keep;
+            res->stats.kernel_launches = launches + sub_launches + 1;
+            PG_TRY(prepare_table(s, 0, t->cols[(size_t)s.ins_key_col]));
+            if (!s.jt.bitmap) PG_FAIL(PG_EUNSUPPORTED, "sub-aggregate build side: key domain too wide for a bitmap");
+            const i64 nk = sp->dev_ngroups;
+            if (nk > 0) {
+                keys_bitmap_kernel<<<(int)std::max<i64>(std::min<i64>((nk + 255) / 256, (i64)ctx().prop.multiProcessorCount * 8), 1), 256, 0, st>>>(
+                    sp->d_out_klo.as<i64>(), nk, s.jt);
+                PG_CUDA(cudaGetLastError());
+            }
+            s.no_table = true;
+            s.dup_keys = 0;
+            s.built_rows = nk;
+            if (idx < 4) { res->stats.aux[2 + 2 * idx] = sp->tab(sp->src_slot)->nrows; res->stats.aux[3 + 2 * idx] = nk; }
+            return PG_OK;
+        }
         PipeParams pp{};
         pp.nrows = t->nrows;
         PG_TRY(fill_preds(pp, s.ranges, s.src_slot));
+        PG_TRY(fill_extras(pp, s.extras, s.src_slot));
         pp.has_probe = s.has_probe ? 1 : 0;
         if (s.has_probe) {
             pp.probe_key = typed(t, s.probe_key_col);
             pp.probe = stages[(size_t)s.probe_stage]->jt;
             pp.probe_bitmap_only = stages[(size_t)s.probe_stage]->bitmap_only() ? 1 : 0;
             pp.probe_mode = s.probe_mode;
+        } else {
+            pp.probe_key = typed(t, s.ins_key_col);      // the filter pass streams the key column itself
         }
         pp.counters = d_counters.as<unsigned long long>();
         s.no_table = false;
         if ((s.existence_only || (s.unique_key && !s.has_probe)) && !s.payload_needed && !getenv("PG_JOIN_NO_BITMAP_BUILD")) {
+            // (a stage with a probe of its own, SEMI/ANTI-consumed, also lands here: pipeline_kernel probes + applies extras)
             // unique keys, nothing but existence is needed: one pass that sets key bits, no hash table at all
             PG_TRY(prepare_table(s, 0, t->cols[(size_t)s.ins_key_col]));
             if (s.jt.bitmap) {
@@ -414,11 +480,11 @@ struct JoinAggPipeline : Pipeline {
                 return PG_OK;
             }
         }
-        if (two_phase_ok(pp, t, true)) {
+        if (two_phase_ok(pp, t, true) && (s.has_probe || (s.unique_key && s.payload_needed))) {
             // phase 1 screens the whole source once: the hit list doubles as the sizing pass
             PG_CUDA(cudaMemsetAsync(d_counters.p, 0, 32, st));
             PG_TRY(launch_filter(pp, 0, t->nrows));
-            const bool exact = pp.probe_bitmap_only || pp.probe_mode != 0;      // one sink row per hit
+            const bool exact = !pp.has_probe || pp.probe_bitmap_only || pp.probe_mode != 0;      // at most one sink row per hit
             if (!exact) PG_TRY(launch_sink<SINK_COUNT>(pp));
             unsigned long long cnt[4], nh = 0;
             PG_CUDA(cudaMemcpyAsync(&nh, d_hit_count.p, 8, cudaMemcpyDeviceToHost, st));
@@ -576,6 +642,7 @@ struct JoinAggPipeline : Pipeline {
             pp.probe_bitmap_only = last.bitmap_only() ? 1 : 0;
             pp.probe_mode = top_probe_mode;
         }
+        PG_TRY(fill_extras(pp, extras, src_slot));
         pp.counters = d_counters.as<unsigned long long>();
         pp.gs = gs;
         // group table: start at twice the build-side rows (each joined row matches a build row),
@@ -745,7 +812,41 @@ struct JoinAggPipeline : Pipeline {
         if (do_shuffle) { PG_TRY(shuffle_groups(&ngroups, pp, res)); tr.mark("all-to-all shuffle + merge"); }
         res->stats.aux[6] = ngroups;          // groups before any LIMIT
         tr.mark("compact");
-        if (has_topk) { PG_TRY(topk_preselect(&ngroups, res)); tr.mark("top-k preselect"); }
+        if (device_only) { dev_ngroups = ngroups; return PG_OK; }
+        // (FD mode: the ORDER BY keys are fetched below, the host orders the groups)
+        if (has_topk && !fd_mode) { PG_TRY(topk_preselect(&ngroups, res)); tr.mark("top-k preselect"); }
+        const i64 *h_fd_cols = nullptr;
+        if (fd_mode) {
+            const size_t nf = fd.size();
+            const size_t need = (size_t)std::max<i64>(ngroups, 1) * 8 * nf;
+            if (d_fd.bytes < need) PG_TRY(d_fd.alloc(need));
+            if (h_fd.bytes < need) PG_TRY(h_fd.alloc(need));
+            if (ngroups > 0) {
+                const int grid = (int)std::max<i64>(std::min<i64>((ngroups + 255) / 256, (i64)c.prop.multiProcessorCount * 8), 1);
+                const pg_table *bt = tab(stages.back()->src_slot);
+                for (size_t f = 0; f < nf; f++) {
+                    const FdOut &o = fd[f];
+                    const pg_table *ct = tab(o.slot);
+                    const bool host_col = ct->cols[(size_t)o.col].type == PG_T_VARCHAR;
+                    TypedCol none{nullptr, 8, nullptr};
+                    TypedCol colref = host_col ? none : typed(ct, o.col);
+                    if (o.kind == 0) {
+                        fd_gather_kernel<<<grid, 256, 0, st>>>(d_out_klo.as<i64>(), ngroups, colref, 0, none, JoinTable{}, none, host_col ? 1 : 0,
+                                                               d_fd.as<i64>() + f * (size_t)ngroups);
+                    } else {
+                        const Stage &d = *stages[(size_t)o.via_stage];
+                        if (!d.rank_index) PG_FAIL(PG_EUNSUPPORTED, "functionally dependent group key: the deeper build side has no unique-key index");
+                        fd_gather_kernel<<<grid, 256, 0, st>>>(d_out_klo.as<i64>(), ngroups, none, 1, typed(bt, o.via_key_col), d.jt, colref,
+                                                               host_col ? 1 : 0, d_fd.as<i64>() + f * (size_t)ngroups);
+                    }
+                    PG_CUDA(cudaGetLastError());
+                    res->stats.kernel_launches += 1;
+                }
+                PG_CUDA(cudaMemcpyAsync(h_fd.p, d_fd.p, (size_t)ngroups * 8 * nf, cudaMemcpyDeviceToHost, st));
+            }
+            h_fd_cols = h_fd.as<i64>();
+            tr.mark("dependent key gather");
+        }
         const int planes = gs.nacc + 1;
         i64 *h_klo = nullptr, *h_khi = nullptr, *h_acc = nullptr;
         auto host_arrays = [&](i64 n) -> int {
@@ -876,7 +977,39 @@ struct JoinAggPipeline : Pipeline {
         res->nrows = ngroups;
         for (auto &o : outs) {
             ResCol col;
-            if (o.first == 0) {
+            if (o.first == 0 && fd_mode) {
+                const FdOut &fo = fd[(size_t)o.second];
+                const Column &cc = tab(fo.slot)->cols[(size_t)fo.col];
+                const i64 *src = h_fd_cols + (size_t)o.second * (size_t)ngroups;
+                col.type = cc.type;
+                col.width = cc.width;
+                col.scale = cc.scale;
+                const int w = type_size(cc.type);
+                col.data.resize((size_t)ngroups * (size_t)w);
+                if (cc.type == PG_T_VARCHAR) {
+                    size_t total = 0;
+                    for (i64 i = 0; i < ngroups; i++) {
+                        if (src[i] < 0 || src[i] + 1 >= (i64)cc.h_off.size()) PG_FAIL(PG_ECUDA, "internal: dependent key row %lld out of range", (long long)src[i]);
+                        total += (size_t)(cc.h_off[(size_t)src[i] + 1] - cc.h_off[(size_t)src[i]]);
+                    }
+                    col.heap.resize(total + 1);
+                    pg_string *d = (pg_string *)col.data.data();
+                    size_t at = 0;
+                    for (i64 i = 0; i < ngroups; i++) {
+                        const size_t b = (size_t)cc.h_off[(size_t)src[i]], n = (size_t)cc.h_off[(size_t)src[i] + 1] - b;
+                        memcpy(col.heap.data() + at, cc.h_bytes.data() + b, n);
+                        d[i].data = col.heap.data() + at;
+                        d[i].len = (int64_t)n;
+                        at += n;
+                    }
+                } else {
+                    for (i64 i = 0; i < ngroups; i++) {
+                        if (w == 8) ((i64 *)col.data.data())[i] = src[i];
+                        else if (w == 4) ((int32_t *)col.data.data())[i] = (int32_t)src[i];
+                        else col.data[(size_t)i] = (uint8_t)src[i];
+                    }
+                }
+            } else if (o.first == 0) {
                 int k = o.second;
                 col.type = group_out_type[(size_t)k];
                 const int w = type_size(col.type);
@@ -941,6 +1074,13 @@ bool resolve(const Node &n, int idx, BaseCol *out)
         if (o.first != 0 && o.first != 1) return false;
         return resolve(n.children[(size_t)o.first], o.second, out);
     }
+    if (n.op == PG_OP_AGG) {        // an aggregate's group-key output is the grouped column itself
+        if (idx < 0 || idx >= (int)n.outs.size()) return false;
+        auto o = n.outs[(size_t)idx];
+        if (o.first != 0 || o.second < 0 || o.second >= (int)n.groups.size()) return false;
+        const Expr *ge = strip_value_preserving_casts(&n.groups[(size_t)o.second]);
+        return ge->kind == PG_TK_COL && resolve(n.children[0], ge->idx, out);
+    }
     return false;
 }
 
@@ -954,6 +1094,8 @@ const Node *source_scan(const Node &n)   // probe-side source of a join chain, o
 }
 
 }  // namespace
+
+int build_join_agg(pg_plan *plan, const Node &aggn, const Node &join, std::unique_ptr<Pipeline> *out, bool nested);
 
 // build the stage that materialises `n` (a build side) keyed on output `key_idx` of n
 static int add_build_stage(JoinAggPipeline *p, const Node &n0, int key_idx, int *stage_out)
@@ -1004,6 +1146,22 @@ static int add_build_stage(JoinAggPipeline *p, const Node &n0, int key_idx, int 
         s->probe_key_col = pk.col;
         s->probe_stage = inner;
         if (key.slot != s->src_slot) PG_FAIL(PG_EUNSUPPORTED, "join key of the outer join comes from the inner build side");
+    } else if (n->op == PG_OP_AGG) {
+        // `key IN (select k from t [where ...] group by k [having ...])`: the group keys of a nested
+        // high-cardinality aggregate; only their existence can be consumed (SEMI / ANTI)
+        if (!extra.empty()) PG_FAIL(PG_EUNSUPPORTED, "filter above a build-side aggregate");
+        if (n->groups.size() != 1 || n->outs.size() != 1 || n->outs[0] != std::make_pair(0, 0))
+            PG_FAIL(PG_EUNSUPPORTED, "a build-side aggregate must output exactly its single group key");
+        std::vector<Expr> fl;
+        const Node *src = &n->children[0];
+        while (src->op == PG_OP_FILTER) { for (auto &f : src->filters) fl.push_back(f); src = &src->children[0]; }
+        if (src->op != PG_OP_SCAN) PG_FAIL(PG_EUNSUPPORTED, "build-side aggregate over a non-scan input");
+        s->sub_scan = *src;
+        for (auto &f : fl) s->sub_scan.filters.push_back(f);
+        s->src_slot = src->slot;
+        PG_TRY(build_join_agg(p->plan, *n, s->sub_scan, &s->sub, true));
+        static_cast<JoinAggPipeline *>(s->sub.get())->device_only = true;
+        s->existence_only = true;
     } else {
         PG_FAIL(PG_EUNSUPPORTED, "unsupported build side (op %d)", n->op);
     }
@@ -1012,7 +1170,7 @@ static int add_build_stage(JoinAggPipeline *p, const Node &n0, int key_idx, int 
     if (!is_int_family(kc.type)) PG_FAIL(PG_EUNSUPPORTED, "join key must be an integer column");
     if (kc.vmin <= HT_EMPTY && kc.vmax >= HT_EMPTY) PG_FAIL(PG_EUNSUPPORTED, "join key range contains the empty-slot sentinel");
     s->ins_key_col = key.col;
-    s->unique_key = kc.stats_ok && kc.adjacent_descents == 0;
+    s->unique_key = s->sub ? true : (kc.stats_ok && kc.adjacent_descents == 0);     // group keys are unique by construction
     p->stages.push_back(std::move(s));
     *stage_out = (int)p->stages.size() - 1;
     return PG_OK;
@@ -1020,10 +1178,38 @@ static int add_build_stage(JoinAggPipeline *p, const Node &n0, int key_idx, int 
 
 // `join` is the aggregate's input: an INNER join tree, or (high-cardinality group-by straight over a
 // table) a SCAN whose filters the caller already merged.
-int build_join_agg(pg_plan *plan, const Node &aggn, const Node &join, std::unique_ptr<Pipeline> *out)
+int build_join_agg(pg_plan *plan, const Node &aggn, const Node &top, std::unique_ptr<Pipeline> *out, bool nested)
 {
     std::unique_ptr<JoinAggPipeline> p(new JoinAggPipeline());
     p->plan = plan;
+    // SEMI / ANTI joins whose probe side is itself a join (`... where k IN (subquery)` above the FROM-list
+    // joins, builder_plan.go:234-262) only filter on one base column: they are pushed down to the scan
+    // that owns that column as an existence test (a semi join commutes with the inner joins below it).
+    // `top` keeps resolving output indices; `join` is the join whose two sides become the pipelines.
+    struct Pending { int mode; BaseCol key; int stage; };
+    std::vector<Pending> pending;
+    const Node *jn = &top;
+    while (jn->op == PG_OP_JOIN && (jn->jointype == PG_JOIN_SEMI || jn->jointype == PG_JOIN_ANTI)) {
+        const Node *ps = &jn->children[0];
+        while (ps->op == PG_OP_FILTER) ps = &ps->children[0];
+        if (ps->op != PG_OP_JOIN) break;
+        if (jn->children[0].op != PG_OP_JOIN) PG_FAIL(PG_EUNSUPPORTED, "filter between a SEMI/ANTI join and the join below it");
+        if (jn->conds.size() != 1) PG_FAIL(PG_EUNSUPPORTED, "multi-column join keys are not off-loaded");
+        for (auto &o : jn->outs) if (o.first != 0) PG_FAIL(PG_EUNSUPPORTED, "SEMI/ANTI join output refers to the build side");
+        const Expr *pe = strip_value_preserving_casts(&jn->conds[0].first);
+        const Expr *be = strip_value_preserving_casts(&jn->conds[0].second);
+        if (pe->kind != PG_TK_COL || be->kind != PG_TK_COL) PG_FAIL(PG_EUNSUPPORTED, "join condition is not column = column");
+        Pending pd;
+        pd.mode = jn->jointype == PG_JOIN_SEMI ? 1 : 2;
+        if (!resolve(jn->children[0], pe->idx, &pd.key)) PG_FAIL(PG_EUNSUPPORTED, "SEMI/ANTI probe key is not a base column");
+        const Column &kc = plan->slots[(size_t)pd.key.slot]->cols[(size_t)pd.key.col];
+        if (!is_int_family(kc.type)) PG_FAIL(PG_EUNSUPPORTED, "probe key must be an integer column");
+        PG_TRY(add_build_stage(p.get(), jn->children[1], be->idx, &pd.stage));      // built before the stages that test it
+        p->stages[(size_t)pd.stage]->existence_only = true;
+        pending.push_back(pd);
+        jn = &jn->children[0];
+    }
+    const Node &join = *jn;
     p->no_join = join.op == PG_OP_SCAN;
     if (!p->no_join) {
         if (join.jointype != PG_JOIN_INNER && join.jointype != PG_JOIN_SEMI && join.jointype != PG_JOIN_ANTI)
@@ -1065,10 +1251,78 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &join, std::uniqu
         bt = p->tab(build_slot);
     }
 
+    // pushed-down SEMI / ANTI joins become existence tests on the stage (or the top probe) that scans the key's table
+    for (const auto &pd : pending) {
+        if (p->no_join) PG_FAIL(PG_EUNSUPPORTED, "internal: pushed-down join without a join below it");
+        Stage::Extra ex{pd.mode, pd.key.col, pd.stage};
+        if (pd.key.slot == p->src_slot) { p->extras.push_back(ex); continue; }
+        Stage *owner = nullptr;
+        for (auto &sp : p->stages) if (!sp->sub && sp->src_slot == pd.key.slot) owner = sp.get();
+        if (!owner) PG_FAIL(PG_EUNSUPPORTED, "SEMI/ANTI probe key belongs to no scanned table");
+        // Make the (selective) existence test the stage's MAIN probe when its current one is an INNER join
+        // against unique keys, i.e. itself only an existence filter for this stage: the filter pass then
+        // lists a handful of rows instead of every row that has a matching build key.
+        if (owner->has_probe && owner->probe_mode == 0 && p->stages[(size_t)owner->probe_stage]->unique_key) {
+            Stage::Extra old_main{0, owner->probe_key_col, owner->probe_stage};
+            owner->probe_mode = pd.mode;
+            owner->probe_key_col = pd.key.col;
+            owner->probe_stage = pd.stage;
+            owner->extras.push_back(old_main);
+        } else {
+            owner->extras.push_back(ex);
+        }
+    }
+    for (auto &sp : p->stages)
+        for (auto &ex : sp->extras) {
+            const Stage &b = *p->stages[(size_t)ex.stage];
+            const Column &bk = p->tab(b.src_slot)->cols[(size_t)b.ins_key_col];
+            if ((i128)bk.vmax - (i128)bk.vmin + 1 > ((i128)1 << 32)) PG_FAIL(PG_EUNSUPPORTED, "existence join against a key domain too wide for a bitmap");
+            if (ex.mode == 0 && !b.unique_key) PG_FAIL(PG_EUNSUPPORTED, "INNER join as an existence test needs unique build keys");
+        }
+
+    // Group keys functionally dependent on the top join's unique build key -> group by the build row id
+    // (see JoinAggPipeline::fd).  Used only when the packed key cannot hold the keys: more than three
+    // columns, a VARCHAR, or a column of a deeper build side.
+    if (!p->no_join && p->top_probe_mode == 0) {
+        Stage &T = *p->stages[(size_t)top_stage];
+        bool anchor = false, ok = T.unique_key && !T.sub, need = aggn.groups.size() > GT_MAXKEYPARTS;
+        std::vector<JoinAggPipeline::FdOut> fd;
+        for (size_t k = 0; k < aggn.groups.size() && ok; k++) {
+            const Expr *ge = strip_value_preserving_casts(&aggn.groups[k]);
+            BaseCol bc;
+            if (ge->kind != PG_TK_COL || !resolve(top, ge->idx, &bc)) { ok = false; break; }
+            const Column &cc = p->tab(bc.slot)->cols[(size_t)bc.col];
+            if (cc.has_nulls) { ok = false; break; }
+            if (cc.type == PG_T_VARCHAR) need = true;
+            if (bc.slot == build_slot) {
+                if (bc.col == T.ins_key_col) anchor = true;
+                fd.push_back({0, bc.slot, bc.col, -1, -1});
+            } else if (bc.slot == p->src_slot && bc.col == p->probe_key_col) {
+                anchor = true;                                   // equal to the build key by the join condition
+                fd.push_back({0, build_slot, T.ins_key_col, -1, -1});
+            } else {
+                // a column of a build side the top build stage itself joins INNER on unique keys
+                int via_stage = -1, via_key = -1;
+                if (T.has_probe && T.probe_mode == 0 && p->stages[(size_t)T.probe_stage]->src_slot == bc.slot) { via_stage = T.probe_stage; via_key = T.probe_key_col; }
+                for (auto &ex : T.extras)
+                    if (ex.mode == 0 && p->stages[(size_t)ex.stage]->src_slot == bc.slot) { via_stage = ex.stage; via_key = ex.key_col; }
+                if (via_stage < 0 || !p->stages[(size_t)via_stage]->unique_key || p->stages[(size_t)via_stage]->sub) { ok = false; break; }
+                need = true;
+                fd.push_back({1, bc.slot, bc.col, via_key, via_stage});
+            }
+        }
+        if (ok && anchor && need) {
+            if (ctx().world > 1) PG_FAIL(PG_EUNSUPPORTED, "functionally dependent group keys are single-GPU for now");
+            p->fd_mode = true;
+            p->fd = fd;
+            for (auto &f : fd) if (f.kind == 1) p->stages[(size_t)f.via_stage]->payload_needed = true;
+        }
+    }
+
     // a value above the join: output idx of the join -> (source | build) typed column
     auto valref = [&](int join_out, ValRef *vr, const Column **colp) -> bool {
         BaseCol bc;
-        if (!resolve(join, join_out, &bc)) return false;
+        if (!resolve(top, join_out, &bc)) return false;
         const pg_table *t = nullptr;
         if (bc.slot == p->src_slot) { vr->from_build = 0; t = st; }
         else if (bc.slot == build_slot) { vr->from_build = 1; t = bt; }
@@ -1079,10 +1333,19 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &join, std::uniqu
     };
 
     // group keys: up to 3 parts packed into two 64-bit words
-    if (aggn.groups.empty() || aggn.groups.size() > GT_MAXKEYPARTS) PG_FAIL(PG_EUNSUPPORTED, "join aggregate needs 1..3 group keys");
-    p->nparts = (int)aggn.groups.size();
-    p->gs.nparts = p->nparts;
-    for (int k = 0; k < p->nparts; k++) {
+    if (p->fd_mode) {
+        p->nparts = 1;
+        p->gs.nparts = 1;
+        p->gs.part[0].col = TypedCol{nullptr, 8, nullptr};
+        p->gs.part[0].from_build = 2;                  // the build row id is the group key
+        p->group_out_type.push_back(PG_T_INT64);
+    } else if (aggn.groups.empty() || aggn.groups.size() > GT_MAXKEYPARTS) {
+        PG_FAIL(PG_EUNSUPPORTED, "join aggregate needs 1..3 group keys (or keys functionally dependent on a unique build key)");
+    } else {
+        p->nparts = (int)aggn.groups.size();
+        p->gs.nparts = p->nparts;
+    }
+    for (int k = 0; k < p->nparts && !p->fd_mode; k++) {
         const Expr *ge = strip_value_preserving_casts(&aggn.groups[(size_t)k]);
         const Column *col = nullptr;
         if (ge->kind != PG_TK_COL || !valref(ge->idx, &p->gs.part[k], &col)) PG_FAIL(PG_EUNSUPPORTED, "group key %d is not a reachable non-null column", k);
@@ -1181,7 +1444,7 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &join, std::uniqu
     if (worst * (i128)std::max<i64>(st->nrows, 1) >= ((i128)1 << 63)) PG_FAIL(PG_EUNSUPPORTED, "group sums could exceed int64");
     {   // does anything above the top join read a build-side column?
         bool need = false;
-        for (int k = 0; k < p->nparts; k++) need = need || p->gs.part[k].from_build;
+        for (int k = 0; k < p->nparts; k++) need = need || p->gs.part[k].from_build != 0;
         for (int a = 0; a < p->gs.nacc; a++) for (int f = 0; f < p->gs.nfac[a]; f++) need = need || p->gs.fac[a][f].from_build;
         if (!p->no_join) p->stages[(size_t)top_stage]->payload_needed = need;
     }
@@ -1189,7 +1452,7 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &join, std::uniqu
         // expected groups: bounded by the rows and by the key domain of the first key
         BaseCol g0;
         const Expr *ge = strip_value_preserving_casts(&aggn.groups[0]);
-        resolve(join, ge->idx, &g0);
+        resolve(top, ge->idx, &g0);
         const Column &kc = st->cols[(size_t)g0.col];
         i128 domain = (i128)kc.vmax - (i128)kc.vmin + 1;
         p->group_hint = (i64)std::min<i128>(std::max<i128>(domain, 1), (i128)std::max<i64>(st->nrows / 4, 1));   // grows x2 on overflow
@@ -1201,7 +1464,7 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &join, std::uniqu
         if (getenv("PG_RUN_AGGREGATE")) p->gs.run_aggregate = atoi(getenv("PG_RUN_AGGREGATE"));
     }
     for (auto &o : aggn.outs) {
-        if (o.first == 0 && (o.second < 0 || o.second >= p->nparts)) PG_FAIL(PG_EUNSUPPORTED, "bad group output index");
+        if (o.first == 0 && (o.second < 0 || o.second >= (p->fd_mode ? (int)p->fd.size() : p->nparts))) PG_FAIL(PG_EUNSUPPORTED, "bad group output index");
         if (o.first == 1 && (o.second < 0 || o.second >= (int)aggn.aggs.size())) PG_FAIL(PG_EUNSUPPORTED, "bad aggregate output index");
         if (o.first != 0 && o.first != 1) PG_FAIL(PG_EUNSUPPORTED, "bad output kind");
     }
@@ -1218,13 +1481,19 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &join, std::uniqu
             use(sp->src_slot, sp->ins_key_col);
             if (sp->has_probe) use(sp->src_slot, sp->probe_key_col);
         }
-        for (int k = 0; k < p->nparts; k++) { BaseCol bc; const Expr *ge = strip_value_preserving_casts(&aggn.groups[(size_t)k]); if (resolve(join, ge->idx, &bc)) use(bc.slot, bc.col); }
+        for (size_t k = 0; k < aggn.groups.size(); k++) {
+            BaseCol bc;
+            const Expr *ge = strip_value_preserving_casts(&aggn.groups[k]);
+            if (resolve(top, ge->idx, &bc) && p->tab(bc.slot)->cols[(size_t)bc.col].type != PG_T_VARCHAR) use(bc.slot, bc.col);
+        }
+        for (auto &sp : p->stages) for (auto &ex : sp->extras) use(sp->src_slot, ex.key_col);
+        for (auto &ex : p->extras) use(p->src_slot, ex.key_col);
         for (size_t a = 0; a < aggn.aggs.size(); a++) {
             std::vector<const Expr *> todo{&aggn.aggs[a].arg};
             while (!todo.empty()) {
                 const Expr *e = todo.back();
                 todo.pop_back();
-                if (e->kind == PG_TK_COL) { BaseCol bc; if (resolve(join, e->idx, &bc)) use(bc.slot, bc.col); }
+                if (e->kind == PG_TK_COL) { BaseCol bc; if (resolve(top, e->idx, &bc)) use(bc.slot, bc.col); }
                 for (auto &ch : e->args) todo.push_back(&ch);
             }
         }
@@ -1290,7 +1559,7 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &join, std::uniqu
             // local group lists are hash-partitioned and exchanged (all-to-all over NVLink) and merged.
             BaseCol g0;
             const Expr *ge = strip_value_preserving_casts(&aggn.groups[0]);
-            bool ok = resolve(join, ge->idx, &g0) && g0.slot == p->src_slot;
+            bool ok = resolve(top, ge->idx, &g0) && g0.slot == p->src_slot;
             bool disjoint = false;
             if (ok) PG_TRY(copartitioned(st, g0.col, st, g0.col, &disjoint));
             const char *force = getenv("PG_FORCE_SHUFFLE");
@@ -1299,7 +1568,7 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &join, std::uniqu
             p->shuffle = !(ok && disjoint);
         }
     }
-    if (plan->topk && !plan->topk->order.empty()) {
+    if (plan->topk && !plan->topk->order.empty() && !nested && !p->fd_mode) {
         // primary ORDER BY key -> where it lives in the group table
         auto o = aggn.outs[(size_t)plan->topk->order[0].first];
         TopkKey tk{};
@@ -1322,10 +1591,12 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &join, std::uniqu
     std::string ex = "JoinAgg[inner hash join chain -> global group table] stages:";
     for (auto &sp : p->stages) {
         char b[256];
-        snprintf(b, sizeof b, " build(%s key=%s%s)", p->tab(sp->src_slot)->name.c_str(),
-                 p->tab(sp->src_slot)->cols[(size_t)sp->ins_key_col].name.c_str(), sp->has_probe ? " probing previous" : "");
+        snprintf(b, sizeof b, " build(%s%s key=%s%s%s)", sp->sub ? "aggregate over " : "", p->tab(sp->src_slot)->name.c_str(),
+                 p->tab(sp->src_slot)->cols[(size_t)sp->ins_key_col].name.c_str(), sp->has_probe ? " probing previous" : "",
+                 sp->extras.empty() ? "" : " +existence tests");
         ex += b;
     }
+    if (p->fd_mode) ex += " group-by=build row id (dependent keys fetched per group)";
     char b[320];
     if (p->no_join)
         snprintf(b, sizeof b, "GroupBy[global open-addressing table] scan(%s) kernel=pipeline_kernel<SINK_GROUP> group_keys=%d sums=%d%s%s%s",

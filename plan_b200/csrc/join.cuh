@@ -158,6 +158,18 @@ struct SrcPred {          // inclusive range on a source column
 
 constexpr int PIPE_MAXPRED = 3;
 
+// A further existence test on a source row besides the pipeline's main probe (a SEMI / ANTI join pushed
+// down to the scan that owns its key, or an INNER join against unique keys whose columns are fetched
+// late): the exact key bitmap of the probed build side decides.
+constexpr int PIPE_MAXEXTRA = 2;
+struct ExtraProbe {
+    TypedCol key;
+    const unsigned *bitmap;
+    i64 bm_min;
+    u64 domain;
+    int anti;              // 1: keep the row when the key is ABSENT (a NULL key is absent)
+};
+
 // ---------------------------------------------------------------- pipelines --
 // One kernel family: stream a source table, apply range predicates, optionally probe one
 // join table with a source key column, and feed a sink:
@@ -200,7 +212,9 @@ __host__ __device__ __forceinline__ int gt_slot_words(int nacc) { return nacc <=
 // where a value comes from: the streamed source row or the matched build row
 struct ValRef {
     TypedCol col;
-    int from_build;       // 0: source row id, 1: build row id (late gather)
+    int from_build;       // 0: column at the source row, 1: column at the matched build row (late gather),
+                          // 2: the matched build row id itself (group keys functionally dependent on a
+                          //    unique build key are fetched once per GROUP after the aggregation)
 };
 
 struct GroupSpec {
@@ -235,6 +249,8 @@ struct PipeParams {
     GroupSpec gs;
     // SINK_COUNT / statistics: [0] rows passing the predicates, [1] joined rows
     unsigned long long *counters;
+    int nextra;
+    ExtraProbe extra[PIPE_MAXEXTRA];
     // two-phase execution (filter_hits_kernel -> hits_sink_kernel): rows [row_begin, row_end) of the source
     // are screened, the row ids of the hits are appended to `hits` (capacity >= row_end - row_begin),
     // `hit_count` is the device-side cursor
@@ -242,6 +258,20 @@ struct PipeParams {
     unsigned *hits;
     unsigned long long *hit_count;
 };
+
+__device__ __forceinline__ bool extras_pass(const PipeParams &p, i64 row)
+{
+    for (int e = 0; e < p.nextra; e++) {
+        const ExtraProbe &x = p.extra[e];
+        bool found = false;
+        if (typed_valid(x.key, row)) {
+            const u64 off = (u64)load_typed(x.key, row) - (u64)x.bm_min;
+            if (off < x.domain) found = (__ldg(x.bitmap + (off >> 5)) >> (off & 31)) & 1u;
+        }
+        if (found == (x.anti != 0)) return false;
+    }
+    return true;
+}
 
 // add `vals` (nacc sums) and `count` rows to group (klo, khi); claims a free slot with 64-bit CAS
 __device__ __forceinline__ void gt_add(const GroupTable &g, i64 klo, i64 khi, const i64 *vals, i64 count)
@@ -311,6 +341,7 @@ pipeline_kernel(const PipeParams p)
         }
         if (!ok) continue;
         n_pass++;
+        if (p.nextra && !extras_pass(p, row)) continue;
         auto sink = [&](u64 build_row) {
             if ((SINK == SINK_INSERT || SINK == SINK_BITMAP) && !typed_valid(p.ins_key, row)) return;   // NULL keys are not built (join_table.go:152-195)
             n_join++;
@@ -320,7 +351,7 @@ pipeline_kernel(const PipeParams p)
                 u64 off = (u64)(load_typed(p.ins_key, row) - p.ins.bm_min);
                 atomicOr(p.ins.bitmap + (off >> 5), 1u << (off & 31));
             } else if (SINK == SINK_GROUP) {
-                auto val = [&](const ValRef &r) { return load_typed(r.col, r.from_build ? (i64)build_row : row); };
+                auto val = [&](const ValRef &r) { return r.from_build == 2 ? (i64)build_row : load_typed(r.col, r.from_build ? (i64)build_row : row); };
                 i64 klo = val(p.gs.part[0]);
                 i64 khi = 0;
                 if (p.gs.nparts > 1) khi = val(p.gs.part[1]) << 32;
@@ -741,7 +772,7 @@ filter_hits_kernel(const PipeParams p)
                 ok[u][j] = j < rem;
                 if (HAS_PRED) ok[u][j] = ok[u][j] && !pempty && dv[j] >= plo && dv[j] <= phi;
                 off[u][j] = (u64)k[u][j] - bmin;            // one unsigned compare covers both ends of the domain
-                const bool in = ok[u][j] && off[u][j] < dom;
+                const bool in = ok[u][j] && bm != nullptr && off[u][j] < dom;
                 w[u][j] = in ? __ldg(bm + (unsigned)(off[u][j] >> 5)) : 0u;
             }
         }
@@ -751,7 +782,7 @@ filter_hits_kernel(const PipeParams p)
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 n_pass += ok[u][j] ? 1u : 0u;
-                const bool set = (w[u][j] >> ((unsigned)off[u][j] & 31u)) & 1u;
+                const bool set = bm == nullptr || ((w[u][j] >> ((unsigned)off[u][j] & 31u)) & 1u);   // no probe: every row that passes is a hit
                 if (ok[u][j] && set != anti) hitmask |= 1u << (4 * u + j);
             }
         // append to the warp's private staging buffer in shared memory (exclusive scan of the per-lane hit
@@ -809,6 +840,7 @@ hits_sink_kernel(const PipeParams p)
     unsigned long long n_join = 0;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
         const i64 row = (i64)p.hits[i];
+        if (p.nextra && !extras_pass(p, row)) continue;
         auto sink = [&](u64 build_row) {
             n_join++;
             if (SINK == SINK_INSERT) {
@@ -817,7 +849,7 @@ hits_sink_kernel(const PipeParams p)
                 u64 off = (u64)(load_typed(p.ins_key, row) - p.ins.bm_min);
                 atomicOr(p.ins.bitmap + (off >> 5), 1u << (off & 31));
             } else if (SINK == SINK_GROUP) {
-                auto val = [&](const ValRef &r) { return load_typed(r.col, r.from_build ? (i64)build_row : row); };
+                auto val = [&](const ValRef &r) { return r.from_build == 2 ? (i64)build_row : load_typed(r.col, r.from_build ? (i64)build_row : row); };
                 i64 klo = val(p.gs.part[0]);
                 i64 khi = 0;
                 if (p.gs.nparts > 1) khi = val(p.gs.part[1]) << 32;
@@ -831,7 +863,7 @@ hits_sink_kernel(const PipeParams p)
                 gt_update(p.gt, klo, khi, vals);
             }
         };
-        if (p.probe_bitmap_only || p.probe_mode != 0) sink(0);
+        if (!p.has_probe || p.probe_bitmap_only || p.probe_mode != 0) sink(0);
         else jt_probe(p.probe, load_typed(p.probe_key, row), sink);
     }
     n_join = (unsigned long long)warp_sum((i64)n_join);
@@ -848,6 +880,7 @@ rank_mark_kernel(const PipeParams p, i64 *__restrict__ keys_tmp)
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     unsigned long long dups = 0;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if (p.nextra && !extras_pass(p, (i64)p.hits[i])) { keys_tmp[i] = HT_EMPTY; continue; }   // HT_EMPTY is never a key
         const i64 key = load_typed(p.ins_key, (i64)p.hits[i]);
         keys_tmp[i] = key;
         const u64 off = (u64)key - (u64)p.ins.bm_min;
@@ -875,9 +908,34 @@ rank_fill_kernel(const PipeParams p, const i64 *__restrict__ keys_tmp, unsigned 
     const unsigned long long n = *p.hit_count;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if (keys_tmp[i] == HT_EMPTY) continue;
         bool set;
         const unsigned r = jt_rank(p.ins, (u64)keys_tmp[i] - (u64)p.ins.bm_min, &set);
         payload[r] = p.hits[i];
+    }
+}
+
+// existence-only build side made of a key LIST (the groups of a sub-aggregate): set the key bits
+static __global__ void keys_bitmap_kernel(const i64 *__restrict__ keys, i64 n, JoinTable jt)
+{
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        const u64 off = (u64)keys[i] - (u64)jt.bm_min;
+        if (off < jt.domain) atomicOr(jt.bitmap + (off >> 5), 1u << (off & 31));
+    }
+}
+
+// Late materialisation of one functionally dependent group key for the n output groups: brow[i] is the
+// build row a group stands for.  direct: out = col[brow].  via: key = via_key[brow] is looked up in the
+// rank index `dt` of a deeper build side, out = dcol[drow] (or drow itself for host-resident columns).
+static __global__ void fd_gather_kernel(const i64 *__restrict__ brow, i64 n, TypedCol direct, int via, TypedCol via_key, JoinTable dt,
+                                        TypedCol dcol, int want_rowid, i64 *__restrict__ out)
+{
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        const i64 b = brow[i];
+        if (!via) { out[i] = want_rowid ? b : load_typed(direct, b); continue; }
+        i64 drow = -1;
+        jt_probe(dt, load_typed(via_key, b), [&](u64 r) { drow = (i64)r; });
+        out[i] = drow < 0 ? -1 : (want_rowid ? drow : load_typed(dcol, drow));
     }
 }
 

@@ -17,6 +17,7 @@ struct ResCol {
     int type = 0, width = 0, scale = 0;
     std::vector<uint8_t> data;
     std::vector<uint8_t> valid;     // one byte per row (1 = not NULL); empty = no NULLs in this column
+    std::vector<char> heap;         // PG_T_VARCHAR: the bytes the pg_string rows point into (sized once, never regrown)
     void push_null(size_t rows_before, size_t elem)
     {
         if (valid.empty()) valid.assign(rows_before, 1);

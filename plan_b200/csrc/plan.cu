@@ -19,7 +19,7 @@ namespace pg {
 Pipeline::~Pipeline() {}
 
 int build_scan_agg(pg_plan *plan, const Node &agg, const Node &scan, std::unique_ptr<Pipeline> *out);
-int build_join_agg(pg_plan *plan, const Node &agg, const Node &join, std::unique_ptr<Pipeline> *out);
+int build_join_agg(pg_plan *plan, const Node &agg, const Node &join, std::unique_ptr<Pipeline> *out, bool nested = false);
 
 static const Node *skip_filters(const Node *n, std::vector<Expr> *extra)
 {

@@ -166,6 +166,7 @@ static int grow(pg_table *t, i64 need_rows)
     i64 cap = std::max<i64>(round_up(need_rows, ROW_PAD), t->capacity + t->capacity / 2);
     cap = round_up(cap, ROW_PAD);
     for (Column &col : t->cols) {
+        if (col.type == PG_T_VARCHAR) continue;      // host-resident
         size_t esz = (size_t)type_size(col.type);
         void *nd = nullptr;
         PG_CUDA(cudaMalloc(&nd, esz * (size_t)cap));
@@ -351,6 +352,17 @@ int pg_table_append(pg_table *t, int64_t nrows, const void *const *cols, const u
     for (size_t i = 0; i < t->cols.size(); i++) {
         Column &col = t->cols[i];
         if (!cols[i]) PG_FAIL(PG_EINVAL, "pg_table_append: column %zu (%s) is NULL", i, col.name.c_str());
+        if (col.type == PG_T_VARCHAR) {
+            if (valid && valid[i]) PG_FAIL(PG_EUNSUPPORTED, "pg_table_append: NULLs in VARCHAR column %s", col.name.c_str());
+            const pg_string *sv = (const pg_string *)cols[i];
+            if (col.h_off.empty()) col.h_off.push_back(0);
+            for (int64_t r = 0; r < nrows; r++) {
+                if (sv[r].len < 0 || (sv[r].len > 0 && !sv[r].data)) PG_FAIL(PG_EINVAL, "pg_table_append: bad string in column %s", col.name.c_str());
+                col.h_bytes.append(sv[r].data ? sv[r].data : "", (size_t)sv[r].len);
+                col.h_off.push_back((int64_t)col.h_bytes.size());
+            }
+            continue;
+        }
         size_t esz = (size_t)type_size(col.type);
         PG_TRY(h2d((char *)col.d_data + esz * (size_t)t->nrows, cols[i], esz * (size_t)nrows));
         if (valid && valid[i]) {
@@ -379,6 +391,7 @@ int pg_table_device_column(pg_table *t, int col, void **dev_ptr)
 {
     if (!t || !dev_ptr || col < 0 || col >= (int)t->cols.size()) PG_FAIL(PG_EINVAL, "pg_table_device_column: bad arguments");
     if (t->capacity == 0) PG_FAIL(PG_ESTATE, "pg_table_device_column: reserve rows first");
+    if (t->cols[col].type == PG_T_VARCHAR) PG_FAIL(PG_EUNSUPPORTED, "pg_table_device_column: VARCHAR columns are host-resident");
     *dev_ptr = t->cols[col].d_data;
     return PG_OK;
 }
@@ -398,6 +411,12 @@ int pg_table_seal(pg_table *t, int64_t global_row_offset)
     PG_CUDA(cudaSetDevice(ctx().device));
     if (t->capacity == 0) PG_TRY(grow(t, 1));
     t->global_offset = global_row_offset;
+    for (Column &col : t->cols) {
+        if (col.type != PG_T_VARCHAR) continue;
+        if (col.h_off.empty()) col.h_off.push_back(0);
+        if ((int64_t)col.h_off.size() != t->nrows + 1)
+            PG_FAIL(PG_ESTATE, "pg_table_seal: VARCHAR column %s holds %zu strings for %lld rows", col.name.c_str(), col.h_off.size() - 1, (long long)t->nrows);
+    }
     PG_TRY(compute_stats(t));
     t->sealed = true;
     t->version++;

@@ -238,7 +238,8 @@ int pg_tpch_customer(double sf, int64_t cust_lo, int64_t cust_hi, pg_table **cus
     static const char *segs[5] = {"AUTOMOBILE", "BUILDING", "FURNITURE", "HOUSEHOLD", "MACHINERY"};
     pg_coldesc cd[PG_C_NCOLS] = {{"c_custkey", PG_T_INT32, 0, 0, 0, nullptr},
                                  {"c_mktsegment", PG_T_DICT8, 0, 0, 5, segs},
-                                 {"c_nationkey", PG_T_INT32, 0, 0, 0, nullptr}};
+                                 {"c_nationkey", PG_T_INT32, 0, 0, 0, nullptr},
+                                 {"c_name", PG_T_VARCHAR, 25, 0, 0, nullptr}};
     pg_table *t = nullptr;
     PG_TRY(pg_table_create("customer", PG_C_NCOLS, cd, &t));
     i64 n = cust_hi - cust_lo;
@@ -251,6 +252,20 @@ int pg_tpch_customer(double sf, int64_t cust_lo, int64_t cust_hi, pg_table **cus
     }
     PG_CUDA(cudaStreamSynchronize(c.stream));
     PG_TRY(pg_table_set_rows(t, n));
+    {   // C_NAME = "Customer#" + key zero-padded to 9 digits (TPC-H 4.2.3); VARCHAR columns live on the host
+        Column &nm = t->cols[PG_C_NAME];
+        nm.h_off.resize((size_t)n + 1);
+        nm.h_bytes.resize((size_t)n * 18);
+        char *b = &nm.h_bytes[0];
+        for (i64 i = 0; i < n; i++) {
+            char *s = b + (size_t)i * 18;
+            memcpy(s, "Customer#", 9);
+            i64 key = cust_lo + i + 1;
+            for (int d = 17; d >= 9; d--) { s[d] = (char)('0' + key % 10); key /= 10; }
+            nm.h_off[(size_t)i] = i * 18;
+        }
+        nm.h_off[(size_t)n] = n * 18;
+    }
     PG_TRY(pg_table_seal(t, cust_lo));
     *customer = t;
     return PG_OK;
@@ -261,6 +276,7 @@ int pg_table_read_column(pg_table *t, int col, int64_t row, int64_t nrows, void 
     if (!t || !host_out || col < 0 || col >= (int)t->cols.size() || row < 0 || nrows < 0 || row + nrows > t->nrows)
         PG_FAIL(PG_EINVAL, "pg_table_read_column: bad arguments");
     PG_CUDA(cudaSetDevice(ctx().device));
+    if (t->cols[(size_t)col].type == PG_T_VARCHAR) PG_FAIL(PG_EUNSUPPORTED, "pg_table_read_column: VARCHAR columns are host-resident");
     size_t esz = (size_t)type_size(t->cols[(size_t)col].type);
     PG_CUDA(cudaMemcpyAsync(host_out, (const char *)t->cols[(size_t)col].d_data + esz * (size_t)row, esz * (size_t)nrows,
                             cudaMemcpyDeviceToHost, ctx().stream));

@@ -33,7 +33,7 @@ ORDERS = [("o_orderkey", L.PG_T_INT64, 0, 0, None), ("o_custkey", L.PG_T_INT32, 
           ("o_orderdate", L.PG_T_DATE32, 0, 0, None), ("o_shippriority", L.PG_T_INT32, 0, 0, None),
           ("o_totalprice", L.PG_T_DECIMAL64, 15, 2, None), ("o_orderstatus", L.PG_T_CHAR1, 0, 0, None)]
 CUSTOMER = [("c_custkey", L.PG_T_INT32, 0, 0, None), ("c_mktsegment", L.PG_T_DICT8, 0, 0, SEGMENTS),
-            ("c_nationkey", L.PG_T_INT32, 0, 0, None)]
+            ("c_nationkey", L.PG_T_INT32, 0, 0, None), ("c_name", L.PG_T_VARCHAR, 25, 0, None)]
 
 DEC15_2 = K.DecimalType(15, 2)
 
@@ -45,7 +45,8 @@ def days(y, m, d):
 def _ltype_of(coldef):
     _, t, w, s, _ = coldef
     return {L.PG_T_INT32: K.IntegerType(), L.PG_T_INT64: K.BigintType(), L.PG_T_DATE32: K.DateType(),
-            L.PG_T_DECIMAL64: K.DecimalType(w, s), L.PG_T_CHAR1: K.VarcharType(), L.PG_T_DICT8: K.VarcharType()}[t]
+            L.PG_T_DECIMAL64: K.DecimalType(w, s), L.PG_T_CHAR1: K.VarcharType(), L.PG_T_DICT8: K.VarcharType(),
+            L.PG_T_VARCHAR: K.VarcharType()}[t]
 
 
 class Schema:
@@ -251,6 +252,47 @@ def semi_plan(anti=False, odate_lt=None, ship_gt=None, schema=FULL):
     aggs = [func("sum", K.DecimalType(38, 2), col(0, 1, DEC15_2)), func("count", K.HugeintType(), col(0, 0, K.IntegerType()))]
     outs = [col(0, 0, K.IntegerType()), col(1, 0, K.DecimalType(38, 2)), col(1, 1, K.HugeintType())]
     return PhysicalOperator(POT_Agg, Outputs=outs, Children=[j], Info=AggOpInfo(aggs, [col(0, 0, K.IntegerType())]))
+
+
+def q18_plan(qty_gt=314, limit=100, schema=FULL):
+    """TPC-H Q18 (cases/tpch/query/q18.sql) below its final Project:
+      Limit <- Order(o_totalprice desc, o_orderdate)
+        <- Agg(group by c_name, c_custkey, o_orderkey, o_orderdate, o_totalprice; sum(l_quantity))
+          <- SEMI Join(o_orderkey = l_orderkey)                 # `o_orderkey IN (subquery)`: builder_plan.go:234-262
+               <- { Join(l_orderkey = o_orderkey) <- { Scan(lineitem), Join(o_custkey = c_custkey) <- { Scan(orders), Scan(customer) } },
+                    Agg(group by l_orderkey; HAVING sum(l_quantity) > k) <- Scan(lineitem) }
+    The inner-join order follows Q3's (probe = larger relation, optimizer_joinorder.go:1028-1030)."""
+    S = schema
+    B = K.LType(K.LTID_BOOLEAN)
+    I, BI, D, H, V = K.IntegerType(), K.BigintType(), K.DateType(), K.HugeintType(), K.VarcharType()
+    OI, LI, CI = S.idx["orders"], S.idx["lineitem"], S.idx["customer"]
+    cust = PhysicalOperator(POT_Scan, Info=ScanOpInfo("customer"))
+    orders = PhysicalOperator(POT_Scan, Info=ScanOpInfo("orders"))
+    line = PhysicalOperator(POT_Scan, Info=ScanOpInfo("lineitem"))
+    j1 = PhysicalOperator(          # orders x customer -> o_orderkey, o_orderdate, o_totalprice, c_name, c_custkey
+        POT_Join, Children=[orders, cust],
+        Outputs=[col(0, OI["o_orderkey"], BI), col(0, OI["o_orderdate"], D), col(0, OI["o_totalprice"], DEC15_2),
+                 col(1, CI["c_name"], V), col(1, CI["c_custkey"], I)],
+        Info=JoinOpInfo(JOIN_INNER, [func("=", B, S.col("orders", "o_custkey", 0), S.col("customer", "c_custkey", 1))]))
+    j2 = PhysicalOperator(          # lineitem x j1 -> l_quantity, then j1's five columns
+        POT_Join, Children=[line, j1],
+        Outputs=[col(0, LI["l_quantity"], I), col(1, 0, BI), col(1, 1, D), col(1, 2, DEC15_2), col(1, 3, V), col(1, 4, I)],
+        Info=JoinOpInfo(JOIN_INNER, [func("=", B, S.col("lineitem", "l_orderkey", 0), col(1, 0, BI))]))
+    sub_scan = PhysicalOperator(POT_Scan, Info=ScanOpInfo("lineitem"))
+    sub = PhysicalOperator(         # select l_orderkey from lineitem group by l_orderkey having sum(l_quantity) > k
+        POT_Agg, Outputs=[col(0, 0, BI)], Children=[sub_scan],
+        Filters=[func(">", B, col(1, 0, H), cast(const(qty_gt, I), H))],
+        Info=AggOpInfo([func("sum", H, S.col("lineitem", "l_quantity"))], [S.col("lineitem", "l_orderkey")]))
+    semi = PhysicalOperator(
+        POT_Join, Children=[j2, sub], Outputs=[col(0, i, t) for i, t in enumerate([I, BI, D, DEC15_2, V, I])],
+        Info=JoinOpInfo(JOIN_SEMI, [func("=", B, col(0, 1, BI), col(1, 0, BI))]))
+    groups = [col(0, 4, V), col(0, 5, I), col(0, 1, BI), col(0, 2, D), col(0, 3, DEC15_2)]
+    outs = [col(0, 0, V), col(0, 1, I), col(0, 2, BI), col(0, 3, D), col(0, 4, DEC15_2), col(1, 0, H)]
+    agg = PhysicalOperator(POT_Agg, Outputs=outs, Children=[semi], Info=AggOpInfo([func("sum", H, col(0, 0, I))], groups))
+    if limit is None:
+        return agg
+    order = PhysicalOperator(POT_Order, Outputs=outs, Children=[agg], Info=OrderOpInfo([(col(0, 4, DEC15_2), True), (col(0, 3, D), False)]))
+    return PhysicalOperator(POT_Limit, Outputs=outs, Children=[order], Info=LimitOpInfo(limit))
 
 
 def q3_topk_plan(limit=10, **kw):

@@ -144,6 +144,8 @@ def test_reference_golden_files_sf1_on_gpu(pg):
         assert X.rows_text(X.order_limit(chunks, [(1, True), (2, False)], 10), 4) == open(os.path.join(GOLDEN, "ref_sf1_q3.txt")).read()
         chunks, _, _ = _run(T.q3_topk_plan(10), t)      # ORDER BY + LIMIT fused into the GPU pipeline
         assert X.rows_text(X.order_limit(chunks, []), 4) == open(os.path.join(GOLDEN, "ref_sf1_q3.txt")).read()
+        chunks, _, _ = _run(T.q18_plan(), t)            # cases/tpch/1g/plan/q18.txt
+        assert X.rows_text(X.order_limit(chunks, []), 6) == open(os.path.join(GOLDEN, "ref_sf1_q18.txt")).read()
     finally:
         for x in t.values():
             x.free()
@@ -393,3 +395,30 @@ def test_full_size_sf100_matches_the_oracle_fixtures(pg):
     finally:
         for x in t.values():
             x.free()
+
+
+def _q18_rows(chunks):
+    rows = []
+    for c in chunks:
+        name, ck, ok, od, tp, sq = (v.Data for v in c.Data)
+        for r in range(c.Card()):
+            rows.append({"c_name": name[r].decode(), "c_custkey": int(ck[r]), "o_orderkey": int(ok[r]), "o_orderdate": int(od[r]),
+                         "o_totalprice": int(tp[r]), "sum_qty": (int(sq[r]["upper"]) << 64) + int(sq[r]["lower"])})
+    return rows
+
+
+@pytest.mark.parametrize("qty_gt,limit", [(250, 100), (200, 100), (300, 5), (100, None), (10 ** 6, 100)])
+def test_q18_sf01(pg, oracle, uploaded, sf01_host, qty_gt, limit):
+    """TPC-H Q18's shape: SEMI join against a HAVING-filtered sub-aggregate pushed down to the orders scan,
+    INNER joins on unique keys, five group keys functionally dependent on the order row (one of them a
+    VARCHAR), ORDER BY a DECIMAL key DESC + date, LIMIT -- against the oracle at several thresholds."""
+    from plan_b200 import tpch as T
+    chunks, stats, explain = _run(T.q18_plan(qty_gt=qty_gt, limit=limit), uploaded)
+    assert "aggregate over lineitem" in explain and "dependent keys" in explain
+    want = oracle.q18(sf01_host["customer"], sf01_host["orders"], sf01_host["lineitem"], qty_gt=qty_gt, limit=limit)
+    got = _q18_rows(chunks)
+    if limit is None:       # unordered plan root: compare as sets
+        key = lambda r: r["o_orderkey"]   # noqa: E731
+        assert sorted(got, key=key) == sorted(want, key=key)
+    else:
+        assert got == want
