@@ -169,7 +169,9 @@ def test_device_generator_matches_cpu_generator(pg, oracle, sf01_host):
     try:
         for name in ("lineitem", "orders", "customer"):
             assert t[name].rows() == len(next(iter(sf01_host[name].values())))
-            for cname, *_ in t[name].columns:
+            for cname, ptype, *_ in t[name].columns:
+                if ptype == 10:      # PG_T_VARCHAR lives on the host (c_name: checked through the Q18 golden test)
+                    continue
                 assert np.array_equal(t[name].read_column(cname), sf01_host[name][cname]), (name, cname)
         check_q6(oracle, t, sf01_host["lineitem"])
         check_q1(oracle, t, sf01_host["lineitem"])

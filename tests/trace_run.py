@@ -23,7 +23,7 @@ def main():
     lo, hi = D.shard_range(n, rank, world)
     tables = T.generate_device_tables(sf, lo, hi)
     tables["customer"].set_replicated()
-    plans = {"q6": T.q6_plan, "q1": T.q1_plan, "q3": T.q3_plan, "q3k": lambda: T.q3_topk_plan(10),
+    plans = {"q6": T.q6_plan, "q1": T.q1_plan, "q3": T.q3_plan, "q3k": lambda: T.q3_topk_plan(10), "q18": T.q18_plan,
              "gok": lambda: T.groupby_plan(key="l_orderkey", value="l_quantity", having_gt=314, topk=100),
              "gpk": lambda: T.groupby_plan(key="l_partkey", value="l_quantity", topk=100),
              "gsk": lambda: T.groupby_plan(key="l_suppkey", value="l_extendedprice", topk=100)}
