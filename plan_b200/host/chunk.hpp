@@ -100,6 +100,7 @@ struct Vector {
     int NativeType = 0;                 // pg_type of Data
     std::vector<uint8_t> Data;          // native encoding
     std::vector<std::string> Dict;      // PG_T_DICT8
+    std::vector<std::string> Strings;   // PG_T_VARCHAR (copied out of the result: pg_string rows die with it)
 
     std::string ValueString(int64_t i) const   // GetValue(i).String()
     {
@@ -114,6 +115,7 @@ struct Vector {
         }
         case PG_T_CHAR1: return std::string(1, (char)p[i]);
         case PG_T_DICT8: return p[i] < Dict.size() ? Dict[p[i]] : std::string("?");
+        case PG_T_VARCHAR: return Strings[(size_t)i];
         case PG_T_FLOAT64: return go_float_string(((const double *)p)[i]);
         case PG_T_HUGEINT: {
             const pg_hugeint &h = ((const pg_hugeint *)p)[i];

@@ -211,8 +211,12 @@ public:
             Vector v;
             v.NativeType = t;
             v.Typ = (size_t)i < agg->Outputs.size() ? agg->Outputs[(size_t)i].DataTyp : LType();
-            size_t esz = t == PG_T_HUGEINT || t == PG_T_DECIMAL128 ? 16 : (t == PG_T_INT32 || t == PG_T_DATE32) ? 4 : (t == PG_T_CHAR1 || t == PG_T_DICT8) ? 1 : 8;
+            size_t esz = t == PG_T_HUGEINT || t == PG_T_DECIMAL128 || t == PG_T_VARCHAR ? 16 : (t == PG_T_INT32 || t == PG_T_DATE32) ? 4 : (t == PG_T_CHAR1 || t == PG_T_DICT8) ? 1 : 8;
             v.Data.assign((const uint8_t *)cols[(size_t)i], (const uint8_t *)cols[(size_t)i] + esz * (size_t)n);
+            if (t == PG_T_VARCHAR) {
+                const pg_string *sv = (const pg_string *)cols[(size_t)i];
+                for (int64_t r = 0; r < n; r++) v.Strings.emplace_back(sv[r].data, (size_t)sv[r].len);
+            }
             output->Data.push_back(std::move(v));
         }
         return haveMoreOutput;

@@ -123,4 +123,50 @@ inline Op q3_plan(int64_t limit = 10)   // Limit <- Order(revenue desc, o_orderd
     return lim;
 }
 
+// Limit <- Order(o_totalprice desc, o_orderdate) <- Agg(5 keys; sum(l_quantity))
+//   <- SEMI Join(o_orderkey = l_orderkey) <- { Join(lineitem, Join(orders, customer)), Agg(lineitem by l_orderkey having sum > k) }
+inline Op q18_plan(int64_t qty_gt = 314, int64_t limit = 100)
+{
+    LType B = LType::Boolean(), I = LType::Integer(), BI = LType::Bigint(), D = LType::Date(), H = LType::Hugeint(), V = LType::Varchar(),
+          P = LType::Decimal(15, 2);
+    Op cust = make(POT_Scan), ord = make(POT_Scan), line = make(POT_Scan), sub_scan = make(POT_Scan);
+    cust->Table = "customer";
+    ord->Table = "orders";
+    line->Table = "lineitem";
+    sub_scan->Table = "lineitem";
+    Op j1 = make(POT_Join);
+    j1->Children = {ord, cust};
+    j1->OnConds = {func("=", B, {col(0, PG_O_CUSTKEY, I), col(1, PG_C_CUSTKEY, I)})};
+    j1->Outputs = {col(0, PG_O_ORDERKEY, BI), col(0, PG_O_ORDERDATE, D), col(0, PG_O_TOTALPRICE, P), col(1, PG_C_NAME, V), col(1, PG_C_CUSTKEY, I)};
+    Op j2 = make(POT_Join);
+    j2->Children = {line, j1};
+    j2->OnConds = {func("=", B, {lcol(PG_L_ORDERKEY), col(1, 0, BI)})};
+    j2->Outputs = {lcol(PG_L_QUANTITY), col(1, 0, BI), col(1, 1, D), col(1, 2, P), col(1, 3, V), col(1, 4, I)};
+    Op sub = make(POT_Agg);
+    sub->GroupBys = {lcol(PG_L_ORDERKEY)};
+    sub->Aggs = {func("sum", H, {lcol(PG_L_QUANTITY)})};
+    sub->Filters = {func(">", B, {col(1, 0, H), cast(constI(qty_gt, I), H)})};
+    sub->Outputs = {col(0, 0, BI)};
+    sub->Children = {sub_scan};
+    Op semi = make(POT_Join);
+    semi->JoinTyp = PG_JOIN_SEMI;
+    semi->Children = {j2, sub};
+    semi->OnConds = {func("=", B, {col(0, 1, BI), col(1, 0, BI)})};
+    semi->Outputs = {col(0, 0, I), col(0, 1, BI), col(0, 2, D), col(0, 3, P), col(0, 4, V), col(0, 5, I)};
+    Op agg = make(POT_Agg);
+    agg->GroupBys = {col(0, 4, V), col(0, 5, I), col(0, 1, BI), col(0, 2, D), col(0, 3, P)};
+    agg->Aggs = {func("sum", H, {col(0, 0, I)})};
+    agg->Outputs = {col(0, 0, V), col(0, 1, I), col(0, 2, BI), col(0, 3, D), col(0, 4, P), col(1, 0, H)};
+    agg->Children = {semi};
+    Op order = make(POT_Order);
+    order->OrderBys = {{col(0, 4, P), true}, {col(0, 3, D), false}};
+    order->Outputs = agg->Outputs;
+    order->Children = {agg};
+    Op lim = make(POT_Limit);
+    lim->Limit = limit;
+    lim->Outputs = agg->Outputs;
+    lim->Children = {order};
+    return lim;
+}
+
 }  // namespace planhost

@@ -151,7 +151,7 @@ def test_reference_golden_files_sf1_on_gpu(pg):
             x.free()
 
 
-@pytest.mark.parametrize("query,golden", [(6, "ref_sf1_q6.txt"), (1, "ref_sf1_q1.txt"), (3, "ref_sf1_q3.txt")])
+@pytest.mark.parametrize("query,golden", [(6, "ref_sf1_q6.txt"), (1, "ref_sf1_q1.txt"), (3, "ref_sf1_q3.txt"), (18, "ref_sf1_q18.txt")])
 def test_cpp_host_shim_reproduces_golden_files(query, golden):
     """The C++ host shim (plan_b200/host: OperatorExec / PhysicalOperator / Chunk mirrors above the C
     ABI, standing in for the Go side) run like `tester tpch1g --query_id N`: its stdout is the
