@@ -74,6 +74,14 @@ inline int type_size(int t)
 
 inline i64 round_up(i64 x, i64 m) { return (x + m - 1) / m * m; }
 
+// Device memory comes from a size-keyed cache of cudaMalloc blocks (table.cu): column buffers and
+// pipeline scratch of a re-ingested table / re-prepared plan are the same sizes as before, and a
+// multi-GB cudaMalloc + cudaFree pair costs tens of milliseconds.  Blocks are rounded up to 2 MiB;
+// when an allocation fails the cache is emptied and the request retried.
+cudaError_t dev_alloc(void **p, size_t bytes);
+void dev_free(void *p);
+void dev_trim();          // give every cached block back to the driver
+
 struct Column {
     std::string name;
     int type = 0, width = 0, scale = 0;

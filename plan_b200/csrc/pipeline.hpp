@@ -47,12 +47,12 @@ struct DevBuf {
     {
         release();
         if (n == 0) n = 16;
-        cudaError_t e = cudaMalloc(&p, n);
+        cudaError_t e = dev_alloc(&p, n);
         if (e != cudaSuccess) { p = nullptr; set_error("cudaMalloc(%zu) failed: %s", n, cudaGetErrorString(e)); return PG_ENOMEM; }
         bytes = n;
         return PG_OK;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    void release() { if (p) dev_free(p); p = nullptr; bytes = 0; }
     ~DevBuf() { release(); }
     template <typename T> T *as() const { return (T *)p; }
 };

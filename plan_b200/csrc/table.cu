@@ -11,9 +11,79 @@
 
 #include <algorithm>
 
+#include <map>
+#include <mutex>
+#include <unordered_map>
+
 #include "common.cuh"
 
 namespace pg {
+
+// ---------------------------------------------------------------- device memory cache --
+namespace {
+struct DevCache {
+    std::mutex mu;
+    std::multimap<size_t, void *> free_blocks;          // size -> block
+    std::unordered_map<void *, size_t> size_of;         // every block handed out or cached
+    size_t cached_bytes = 0;
+};
+DevCache &dev_cache() { static DevCache c; return c; }
+constexpr size_t DEV_GRAIN = (size_t)2 << 20;
+constexpr size_t DEV_CACHE_LIMIT = (size_t)96 << 30;    // keep at most this much parked (B200: 180 GB)
+}  // namespace
+
+cudaError_t dev_alloc(void **p, size_t bytes)
+{
+    DevCache &c = dev_cache();
+    const size_t n = (std::max<size_t>(bytes, 1) + DEV_GRAIN - 1) / DEV_GRAIN * DEV_GRAIN;
+    {
+        std::lock_guard<std::mutex> g(c.mu);
+        auto it = c.free_blocks.find(n);
+        if (it != c.free_blocks.end()) {
+            *p = it->second;
+            c.free_blocks.erase(it);
+            c.cached_bytes -= n;
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = cudaMalloc(p, n);
+    if (e != cudaSuccess) {          // out of memory with blocks parked in the cache: release them and retry
+        cudaGetLastError();
+        dev_trim();
+        e = cudaMalloc(p, n);
+    }
+    if (e == cudaSuccess) {
+        std::lock_guard<std::mutex> g(c.mu);
+        c.size_of[*p] = n;
+    }
+    return e;
+}
+
+void dev_free(void *p)
+{
+    if (!p) return;
+    DevCache &c = dev_cache();
+    std::lock_guard<std::mutex> g(c.mu);
+    auto it = c.size_of.find(p);
+    if (it == c.size_of.end()) { cudaFree(p); return; }
+    if (c.cached_bytes + it->second > DEV_CACHE_LIMIT) {
+        c.size_of.erase(it);
+        cudaFree(p);
+        return;
+    }
+    c.free_blocks.emplace(it->second, p);
+    c.cached_bytes += it->second;
+}
+
+void dev_trim()
+{
+    DevCache &c = dev_cache();
+    std::lock_guard<std::mutex> g(c.mu);
+    for (auto &kv : c.free_blocks) { c.size_of.erase(kv.second); cudaFree(kv.second); }
+    c.free_blocks.clear();
+    c.cached_bytes = 0;
+}
+
 
 static thread_local char g_err[1024] = "";
 
@@ -169,20 +239,20 @@ static int grow(pg_table *t, i64 need_rows)
         if (col.type == PG_T_VARCHAR) continue;      // host-resident
         size_t esz = (size_t)type_size(col.type);
         void *nd = nullptr;
-        PG_CUDA(cudaMalloc(&nd, esz * (size_t)cap));
+        PG_CUDA(dev_alloc(&nd, esz * (size_t)cap));
         PG_CUDA(cudaMemsetAsync(nd, 0, esz * (size_t)cap, c.stream));
         if (col.d_data && t->nrows > 0)
             PG_CUDA(cudaMemcpyAsync(nd, col.d_data, esz * (size_t)t->nrows, cudaMemcpyDeviceToDevice, c.stream));
         PG_CUDA(cudaStreamSynchronize(c.stream));
-        if (col.d_data) cudaFree(col.d_data);
+        if (col.d_data) dev_free(col.d_data);
         col.d_data = nd;
         if (col.d_valid) {
             uint8_t *nv = nullptr;
-            PG_CUDA(cudaMalloc(&nv, (size_t)cap / 8));
+            PG_CUDA(dev_alloc((void **)&nv, (size_t)cap / 8));
             PG_CUDA(cudaMemsetAsync(nv, 0xff, (size_t)cap / 8, c.stream));
             PG_CUDA(cudaMemcpyAsync(nv, col.d_valid, (size_t)(t->capacity / 8), cudaMemcpyDeviceToDevice, c.stream));
             PG_CUDA(cudaStreamSynchronize(c.stream));
-            cudaFree(col.d_valid);
+            dev_free(col.d_valid);
             col.d_valid = nv;
         }
     }
@@ -367,7 +437,7 @@ int pg_table_append(pg_table *t, int64_t nrows, const void *const *cols, const u
         PG_TRY(h2d((char *)col.d_data + esz * (size_t)t->nrows, cols[i], esz * (size_t)nrows));
         if (valid && valid[i]) {
             if (!col.d_valid) {
-                PG_CUDA(cudaMalloc(&col.d_valid, (size_t)t->capacity / 8));
+                PG_CUDA(dev_alloc((void **)&col.d_valid, (size_t)t->capacity / 8));
                 PG_CUDA(cudaMemsetAsync(col.d_valid, 0xff, (size_t)t->capacity / 8, c.stream));
             }
             size_t vb = (size_t)(nrows + 7) / 8;
@@ -443,8 +513,8 @@ void pg_table_free(pg_table *t)
     if (!t) return;
     if (ctx().ready) cudaSetDevice(ctx().device);
     for (Column &col : t->cols) {
-        if (col.d_data) cudaFree(col.d_data);
-        if (col.d_valid) cudaFree(col.d_valid);
+        if (col.d_data) dev_free(col.d_data);
+        if (col.d_valid) dev_free(col.d_valid);
     }
     delete t;
 }

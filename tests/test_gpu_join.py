@@ -392,6 +392,17 @@ def test_full_size_sf100_matches_the_oracle_fixtures(pg):
         assert X.rows_text(X.order_limit(chunks, [(0, False), (1, False)]), 10) == open(os.path.join(GOLDEN, "oracle_sf100_q1.txt")).read()
         chunks, _, _ = _run(T.q3_topk_plan(10), t)
         assert X.rows_text(X.order_limit(chunks, []), 4) == open(os.path.join(GOLDEN, "oracle_sf100_q3.txt")).read()
+        chunks, _, _ = _run(T.q18_plan(), t)           # tests/golden/make_sf100_q18_fixture.py
+        assert X.rows_text(X.order_limit(chunks, []), 6) == open(os.path.join(GOLDEN, "oracle_sf100_q18.txt")).read()
+        # size-independent property at full size: the sorted-run group-by and the table-based one agree
+        gb = T.groupby_plan(key="l_orderkey", value="l_quantity", having_gt=300)
+        a, _, _ = _run(gb, t)
+        os.environ["PG_NO_SORTED_RUNS"] = "1"
+        try:
+            b, _, _ = _run(gb, t)
+        finally:
+            del os.environ["PG_NO_SORTED_RUNS"]
+        assert _groupby_result(a) == _groupby_result(b) and len(_groupby_result(a)) > 1000
     finally:
         for x in t.values():
             x.free()
