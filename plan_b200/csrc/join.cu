@@ -106,8 +106,6 @@ struct JoinAggPipeline : Pipeline {
     bool fd_mode = false;
     struct FdOut { int kind, slot, col, via_key_col, via_stage; };
     std::vector<FdOut> fd;
-    DevBuf d_fd;
-    PinBuf h_fd;
     DevBuf d_edges;
     std::vector<std::pair<int, int>> outs;
     std::vector<int> group_out_type;             // pg_type of each group key
@@ -796,7 +794,7 @@ struct JoinAggPipeline : Pipeline {
         if (max_out > out_cap) {
             PG_TRY(d_out_klo.alloc((size_t)max_out * 8));
             PG_TRY(d_out_khi.alloc((size_t)max_out * 8));
-            PG_TRY(d_out_acc.alloc((size_t)max_out * 8 * (size_t)(gs.nacc + 1)));
+            PG_TRY(d_out_acc.alloc((size_t)max_out * 8 * (size_t)(gs.nacc + 1 + (int)fd.size())));    // dependent key columns ride as extra planes
             out_cap = max_out;
         }
         PG_CUDA(cudaMemsetAsync(d_counters.p, 0, 32, st));
@@ -815,39 +813,32 @@ struct JoinAggPipeline : Pipeline {
         if (device_only) { dev_ngroups = ngroups; return PG_OK; }
         // (FD mode: the ORDER BY keys are fetched below, the host orders the groups)
         if (has_topk && !fd_mode) { PG_TRY(topk_preselect(&ngroups, res)); tr.mark("top-k preselect"); }
-        const i64 *h_fd_cols = nullptr;
-        if (fd_mode) {
-            const size_t nf = fd.size();
-            const size_t need = (size_t)std::max<i64>(ngroups, 1) * 8 * nf;
-            if (d_fd.bytes < need) PG_TRY(d_fd.alloc(need));
-            if (h_fd.bytes < need) PG_TRY(h_fd.alloc(need));
-            if (ngroups > 0) {
-                const int grid = (int)std::max<i64>(std::min<i64>((ngroups + 255) / 256, (i64)c.prop.multiProcessorCount * 8), 1);
-                const pg_table *bt = tab(stages.back()->src_slot);
-                for (size_t f = 0; f < nf; f++) {
-                    const FdOut &o = fd[f];
-                    const pg_table *ct = tab(o.slot);
-                    const bool host_col = ct->cols[(size_t)o.col].type == PG_T_VARCHAR;
-                    TypedCol none{nullptr, 8, nullptr};
-                    TypedCol colref = host_col ? none : typed(ct, o.col);
-                    if (o.kind == 0) {
-                        fd_gather_kernel<<<grid, 256, 0, st>>>(d_out_klo.as<i64>(), ngroups, colref, 0, none, JoinTable{}, none, host_col ? 1 : 0,
-                                                               d_fd.as<i64>() + f * (size_t)ngroups);
-                    } else {
-                        const Stage &d = *stages[(size_t)o.via_stage];
-                        if (!d.rank_index) PG_FAIL(PG_EUNSUPPORTED, "functionally dependent group key: the deeper build side has no unique-key index");
-                        fd_gather_kernel<<<grid, 256, 0, st>>>(d_out_klo.as<i64>(), ngroups, none, 1, typed(bt, o.via_key_col), d.jt, colref,
-                                                               host_col ? 1 : 0, d_fd.as<i64>() + f * (size_t)ngroups);
-                    }
-                    PG_CUDA(cudaGetLastError());
-                    res->stats.kernel_launches += 1;
+        if (fd_mode && ngroups > 0) {
+            // dependent key columns are written behind the accumulator planes of the group list, so every
+            // read-back / cross-rank gather path below carries them like one more aggregate
+            const int grid = (int)std::max<i64>(std::min<i64>((ngroups + 255) / 256, (i64)c.prop.multiProcessorCount * 8), 1);
+            const pg_table *bt = tab(stages.back()->src_slot);
+            for (size_t f = 0; f < fd.size(); f++) {
+                const FdOut &o = fd[f];
+                const pg_table *ct = tab(o.slot);
+                const bool host_col = ct->cols[(size_t)o.col].type == PG_T_VARCHAR;
+                TypedCol none{nullptr, 8, nullptr};
+                TypedCol colref = host_col ? none : typed(ct, o.col);
+                i64 *dst = d_out_acc.as<i64>() + (size_t)(gs.nacc + 1 + (int)f) * (size_t)out_cap;
+                if (o.kind == 0) {
+                    fd_gather_kernel<<<grid, 256, 0, st>>>(d_out_klo.as<i64>(), ngroups, colref, 0, none, JoinTable{}, none, host_col ? 1 : 0, dst);
+                } else {
+                    const Stage &d = *stages[(size_t)o.via_stage];
+                    if (!d.rank_index) PG_FAIL(PG_EUNSUPPORTED, "functionally dependent group key: the deeper build side has no unique-key index");
+                    fd_gather_kernel<<<grid, 256, 0, st>>>(d_out_klo.as<i64>(), ngroups, none, 1, typed(bt, o.via_key_col), d.jt, colref,
+                                                           host_col ? 1 : 0, dst);
                 }
-                PG_CUDA(cudaMemcpyAsync(h_fd.p, d_fd.p, (size_t)ngroups * 8 * nf, cudaMemcpyDeviceToHost, st));
+                PG_CUDA(cudaGetLastError());
+                res->stats.kernel_launches += 1;
             }
-            h_fd_cols = h_fd.as<i64>();
             tr.mark("dependent key gather");
         }
-        const int planes = gs.nacc + 1;
+        const int planes = gs.nacc + 1 + (int)fd.size();
         i64 *h_klo = nullptr, *h_khi = nullptr, *h_acc = nullptr;
         auto host_arrays = [&](i64 n) -> int {
             size_t need = (size_t)std::max<i64>(n, 1) * 8 * (size_t)(2 + planes);
@@ -980,7 +971,7 @@ struct JoinAggPipeline : Pipeline {
             if (o.first == 0 && fd_mode) {
                 const FdOut &fo = fd[(size_t)o.second];
                 const Column &cc = tab(fo.slot)->cols[(size_t)fo.col];
-                const i64 *src = h_fd_cols + (size_t)o.second * (size_t)ngroups;
+                const i64 *src = h_acc + (size_t)(gs.nacc + 1 + o.second) * (size_t)ngroups;
                 col.type = cc.type;
                 col.width = cc.width;
                 col.scale = cc.scale;
@@ -1161,6 +1152,8 @@ static int add_build_stage(JoinAggPipeline *p, const Node &n0, int key_idx, int 
         s->src_slot = src->slot;
         PG_TRY(build_join_agg(p->plan, *n, s->sub_scan, &s->sub, true));
         static_cast<JoinAggPipeline *>(s->sub.get())->device_only = true;
+        if (ctx().world > 1 && static_cast<JoinAggPipeline *>(s->sub.get())->shuffle)
+            PG_FAIL(PG_EUNSUPPORTED, "build-side aggregate whose groups span ranks (needs the shuffled key set on every rank)");
         s->existence_only = true;
     } else {
         PG_FAIL(PG_EUNSUPPORTED, "unsupported build side (op %d)", n->op);
@@ -1312,7 +1305,6 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &top, std::unique
             }
         }
         if (ok && anchor && need) {
-            if (ctx().world > 1) PG_FAIL(PG_EUNSUPPORTED, "functionally dependent group keys are single-GPU for now");
             p->fd_mode = true;
             p->fd = fd;
             for (auto &f : fd) if (f.kind == 1) p->stages[(size_t)f.via_stage]->payload_needed = true;
@@ -1566,6 +1558,16 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &top, std::unique
             if (force && atoi(force)) disjoint = false;
             p->gather_ranks = true;
             p->shuffle = !(ok && disjoint);
+            if (p->fd_mode) {
+                // groups stand for rows of the top build table: rank-local (and disjoint) when that table is sharded
+                // with the probe side (co-partitioning was proved above); host-resident key columns must come from
+                // replicated tables, whose row ids mean the same on every rank
+                if (bt->dist == PG_DIST_REPLICATED) PG_FAIL(PG_EUNSUPPORTED, "dependent group keys over a replicated build table and a sharded probe");
+                for (auto &f : p->fd)
+                    if (p->tab(f.slot)->cols[(size_t)f.col].type == PG_T_VARCHAR && p->tab(f.slot)->dist != PG_DIST_REPLICATED)
+                        PG_FAIL(PG_EUNSUPPORTED, "VARCHAR group key from a sharded table");
+                p->shuffle = false;
+            }
         }
     }
     if (plan->topk && !plan->topk->order.empty() && !nested && !p->fd_mode) {

@@ -54,6 +54,12 @@ def main():
     # SEMI / ANTI join of co-partitioned shards; its groups (o_custkey) collide across ranks -> shuffle
     J.check_semi(O, tables, host, anti=False)
     J.check_semi(O, tables, host, anti=True)
+    # TPC-H Q18's shape on shards: local sub-aggregate -> local existence bitmap, orders/lineitem co-partitioned,
+    # customer replicated (its VARCHAR names are fetched by row id on every rank), per-rank group lists gathered
+    for qty_gt, limit in ((250, 100), (200, 7)):
+        chunks, _, explain = J._run(T.q18_plan(qty_gt=qty_gt, limit=limit), tables)
+        assert "dependent keys" in explain
+        assert J._q18_rows(chunks) == O.q18(host["customer"], orders, line, qty_gt=qty_gt, limit=limit)
     os.environ["PG_FORCE_SHUFFLE"] = "1"          # the general path must also be right when it is not needed
     J.check_groupby(O, tables, line, key="l_orderkey", value="l_quantity", having_gt=200)
     J.check_q3(O, tables, host, check_counts=False)
