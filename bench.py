@@ -38,6 +38,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the Q18 / group-by timings reported beside the metric")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-sf", type=float, default=1.0, help="CPU baseline sample: this SF worth of rows")
     return ap.parse_args()
@@ -317,6 +318,28 @@ def main():
         pass
     launches = sum(a["launches"] for a in acc.values())
 
+    # ---- beside the metric (NOT part of `value`): the next queries SURVEY.md 8(d) names -----------
+    also = {}
+    if "q3" in queries and not args.no_extra:
+        extra_plans = {"q18": T.q18_plan,
+                       "groupby_l_orderkey_having": lambda: T.groupby_plan(key="l_orderkey", value="l_quantity", having_gt=314, topk=100)}
+        for name, mk in extra_plans.items():
+            try:
+                ex = X.gpuPipelineExec(mk(), tables)
+                ex.Init()
+                for _ in range(2):
+                    ex.Reset(); X.drain(ex)
+                tot = 0.0
+                for _ in range(5):
+                    barrier()
+                    ex.Reset(); X.drain(ex)
+                    tot += ex.stats.exec_ms
+                also[name] = {"exec_ms": max_over_ranks(tot / 5), "rows_scanned_per_gpu": int(ex.stats.rows_scanned),
+                              "pipeline": ex.Explain()[:160]}
+                ex.Close()
+            except Exception as e:      # reported, never fatal for the metric line
+                also[name] = {"error": str(e)[:200]}
+
     # ---- e2e: host buffers through the C ABI (H2D inside the timed region) -------------------
     e2e = None
     if not args.no_e2e:
@@ -401,7 +424,7 @@ def main():
                        "l2": "inputs larger than L2 (%.1f GB of columns per GPU vs 126 MB)" % (
                            per_query[dom]["main_kernel_bytes"] / 1e9),
                        "parallelism": "row-range shard x%d, NCCL all-gather merge of partial aggregates" % world},
-            "queries": per_query, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+            "queries": per_query, "also_measured": also, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "clocks": clocks, "datagen_s": gen_s,
         }
         print(json.dumps(out))
