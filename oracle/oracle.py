@@ -182,6 +182,44 @@ def gen_customer(sf, c_lo=0, c_hi=None):
     return out
 
 
+def gen_part(sf, like_word=None):
+    """dbgen-equivalent part: p_partkey, p_name (numpy object array of bytes) and, for `p_name like '%word%'`
+    (wildcardMatch, function_operator_boolean.go:336-377: a substring test for this pattern), the match flag."""
+    L = lib()
+    n = L.tg_num_parts_pub(C.c_double(sf))
+    keys = np.empty(n, np.int32)
+    buf = C.create_string_buffer(56 * n)
+    off = np.empty(n + 1, np.int64)
+    has = np.zeros(n, np.uint8)
+    L.tg_gen_part(C.c_double(sf), C.c_int64(0), C.c_int64(n), _p(keys), buf, _p(off),
+                  like_word.encode() if like_word else None, _p(has))
+    raw = buf.raw
+    names = np.array([raw[off[i]:off[i + 1]] for i in range(n)], dtype=object)
+    return {"p_partkey": keys, "p_name": names, "p_name_like": has.astype(bool)}
+
+
+def gen_supplier(sf):
+    L = lib()
+    n = L.tg_num_supp_pub(C.c_double(sf))
+    out = {"s_suppkey": np.empty(n, np.int32), "s_nationkey": np.empty(n, np.int32)}
+    L.tg_gen_supplier(C.c_double(sf), C.c_int64(0), C.c_int64(n), _p(out["s_suppkey"]), _p(out["s_nationkey"]))
+    return out
+
+
+def gen_partsupp(sf):
+    L = lib()
+    n = L.tg_num_parts_pub(C.c_double(sf))
+    out = {"ps_partkey": np.empty(4 * n, np.int32), "ps_suppkey": np.empty(4 * n, np.int32), "ps_supplycost": np.empty(4 * n, np.int64)}
+    L.tg_gen_partsupp(C.c_double(sf), C.c_int64(0), C.c_int64(n), _p(out["ps_partkey"]), _p(out["ps_suppkey"]), _p(out["ps_supplycost"]))
+    return out
+
+
+def nation_names():
+    L = lib()
+    L.tg_nation_name.restype = C.c_char_p
+    return [L.tg_nation_name(i).decode() for i in range(25)]
+
+
 # --------------------------------------------------------------- queries --
 
 def _i128(lo, hi):
@@ -421,6 +459,53 @@ def q18_text(rows):
         tp = r["o_totalprice"]
         lines.append("\t".join([r["c_name"], str(r["c_custkey"]), str(r["o_orderkey"]), fmt_date(r["o_orderdate"]),
                                 fmt_decimal((abs(tp), 2, tp < 0), 2), str(r["sum_qty"])]))
+    return "\n".join(lines) + "\n"
+
+
+def q9(part, supplier, partsupp, orders, line, like_word="pink"):
+    """TPC-H Q9 (cases/tpch/query/q9.sql): six-way INNER join, `p_name like '%pink%'`, group by
+    (n_name, extract(year from o_orderdate)), sum(l_extendedprice*(1-l_discount) - ps_supplycost*l_quantity).
+    Typing per the reference binder: the first product is DECIMAL scale 4; l_quantity is cast
+    INTEGER -> DECIMAL (value scale 0) so the second product has value scale 2; Sub -> scale 4
+    (govalues: max of the scales); sum(DECIMAL) -> DECIMAL(38,4) by sequential Add, exact here (totals
+    need 12 digits).  NULL-free inputs; every join is on keys that exist.  Returns [(nation, year, sum at scale 4)]
+    ordered by nation, year DESC."""
+    like = part["p_name_like"] if like_word == "pink" and "p_name_like" in part else np.array([like_word.encode() in n for n in part["p_name"]])
+    part_ok = np.zeros(int(part["p_partkey"].max()) + 1, dtype=bool)
+    part_ok[part["p_partkey"][like]] = True
+    m = part_ok[line["l_partkey"]]
+    lp, ls = line["l_partkey"][m].astype(np.int64), line["l_suppkey"][m].astype(np.int64)
+    ext, disc, qty, lok = line["l_extendedprice"][m], line["l_discount"][m], line["l_quantity"][m].astype(np.int64), line["l_orderkey"][m]
+    # partsupp lookup on (partkey, suppkey)
+    nsupp = int(supplier["s_suppkey"].max()) + 1
+    pskey = partsupp["ps_partkey"].astype(np.int64) * nsupp + partsupp["ps_suppkey"].astype(np.int64)
+    order_ps = np.argsort(pskey, kind="stable")
+    pos = np.searchsorted(pskey[order_ps], lp * nsupp + ls)
+    found = (pos < len(pskey)) & (pskey[order_ps][np.minimum(pos, len(pskey) - 1)] == lp * nsupp + ls)
+    cost = partsupp["ps_supplycost"][order_ps][np.minimum(pos, len(pskey) - 1)]
+    # supplier -> nation, orders -> year
+    nat_of = np.full(nsupp, -1, dtype=np.int64)
+    nat_of[supplier["s_suppkey"]] = supplier["s_nationkey"]
+    nat = nat_of[ls]
+    opos = np.searchsorted(orders["o_orderkey"], lok)
+    ofound = (opos < len(orders["o_orderkey"])) & (orders["o_orderkey"][np.minimum(opos, len(orders["o_orderkey"]) - 1)] == lok)
+    odate = orders["o_orderdate"][np.minimum(opos, len(orders["o_orderkey"]) - 1)]
+    year = (np.datetime64("1970-01-01") + odate.astype("timedelta64[D]")).astype("datetime64[Y]").astype(np.int64) + 1970
+    keep = found & ofound & (nat >= 0)
+    amount = ext * (100 - disc) - cost * qty * 100          # scale 4, exact int64
+    out = {}
+    for n_, y_, a_ in zip(nat[keep], year[keep], amount[keep]):
+        out[(int(n_), int(y_))] = out.get((int(n_), int(y_)), 0) + int(a_)
+    names = nation_names()
+    rows = [(names[n_], y_, v) for (n_, y_), v in out.items()]
+    rows.sort(key=lambda r: (r[0], -r[1]))
+    return rows
+
+
+def q9_text(rows):
+    lines = ["#" + "\t" * 2]
+    for nation, year, v in rows:
+        lines.append("\t".join([nation, str(year), fmt_decimal((abs(v), 4, v < 0), 4)]))
     return "\n".join(lines) + "\n"
 
 

@@ -176,3 +176,93 @@ void tg_gen_customer(double sf, int64_t c_lo, int64_t c_hi,
         if (c_nationkey) c_nationkey[i - c_lo] = (int32_t)nat;
     }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * part / supplier / partsupp / nation -- the columns TPC-H Q9 touches (cases/tpch/query/q9.sql).
+ * dbgen: P_NAME = 5 words of the 92-word "colors" distribution: the identity permutation of the 92
+ * indices is shuffled with 92 draws of stream P_NAME_SD (for i in 0..91: swap a[i], a[UnifInt(i, 91)])
+ * and the first five members are joined with blanks; PS_SUPPLYCOST = UnifInt(100, 100000) cents from
+ * PS_SCST_SD, 4 partsupp rows per part with the same supplier bridge as l_suppkey; S_NATIONKEY =
+ * UnifInt(0, 24) from S_NTRG_SD; the 25 nations are fixed.
+ */
+enum { SD_P_NAME = 709314158, SD_PS_SCST = 1051288424, SD_S_NTRG = 110356601 };
+
+static const char *TG_COLORS[92] = {
+    "almond", "antique", "aquamarine", "azure", "beige", "bisque", "black", "blanched", "blue", "blush", "brown", "burlywood",
+    "burnished", "chartreuse", "chiffon", "chocolate", "coral", "cornflower", "cornsilk", "cream", "cyan", "dark", "deep", "dim",
+    "dodger", "drab", "firebrick", "floral", "forest", "frosted", "gainsboro", "ghost", "goldenrod", "green", "grey", "honeydew",
+    "hot", "indian", "ivory", "khaki", "lace", "lavender", "lawn", "lemon", "light", "lime", "linen", "magenta", "maroon", "medium",
+    "metallic", "midnight", "mint", "misty", "moccasin", "navajo", "navy", "olive", "orange", "orchid", "pale", "papaya", "peach",
+    "peru", "pink", "plum", "powder", "puff", "purple", "red", "rose", "rosy", "royal", "saddle", "salmon", "sandy", "seashell",
+    "sienna", "sky", "slate", "smoke", "snow", "spring", "steel", "tan", "thistle", "tomato", "turquoise", "violet", "wheat", "white",
+    "yellow"};
+
+static const char *TG_NATIONS[25] = {
+    "ALGERIA", "ARGENTINA", "BRAZIL", "CANADA", "EGYPT", "ETHIOPIA", "FRANCE", "GERMANY", "INDIA", "INDONESIA", "IRAN", "IRAQ", "JAPAN",
+    "JORDAN", "KENYA", "MOROCCO", "MOZAMBIQUE", "PERU", "CHINA", "ROMANIA", "SAUDI ARABIA", "VIETNAM", "RUSSIA", "UNITED KINGDOM",
+    "UNITED STATES"};
+
+const char *tg_nation_name(int key) { return (key >= 0 && key < 25) ? TG_NATIONS[key] : ""; }
+int64_t tg_num_parts_pub(double sf) { return tg_num_parts(sf); }
+int64_t tg_num_supp_pub(double sf) { return tg_num_supp(sf); }
+
+/* parts [p_lo, p_hi) (0-based).  name_buf receives the names back to back, name_off[i]..name_off[i+1];
+ * name_off must hold (p_hi - p_lo + 1) entries, name_buf 56 bytes per part.  contains_word (optional):
+ * 1 when the name contains `word` as a substring (the `p_name like '%word%'` predicate). */
+void tg_gen_part(double sf, int64_t p_lo, int64_t p_hi, int32_t *p_partkey, char *name_buf, int64_t *name_off,
+                 const char *word, uint8_t *contains_word)
+{
+    (void)sf;
+    int64_t s = tg_jump(SD_P_NAME, 92 * p_lo), at = 0;
+    for (int64_t i = p_lo; i < p_hi; i++) {
+        int perm[92];
+        for (int k = 0; k < 92; k++) perm[k] = k;
+        for (int k = 0; k < 92; k++) {
+            int64_t src = tg_draw(&s, k, 91);
+            int t = perm[src]; perm[src] = perm[k]; perm[k] = t;
+        }
+        char nm[64];
+        size_t n = 0;
+        for (int w = 0; w < 5; w++) {
+            const char *c = TG_COLORS[perm[w]];
+            size_t l = strlen(c);
+            memcpy(nm + n, c, l);
+            n += l;
+            if (w < 4) nm[n++] = ' ';
+        }
+        nm[n] = 0;
+        if (p_partkey) p_partkey[i - p_lo] = (int32_t)(i + 1);
+        if (name_off) name_off[i - p_lo] = at;
+        if (name_buf) memcpy(name_buf + at, nm, n);
+        if (contains_word) contains_word[i - p_lo] = (word && strstr(nm, word)) ? 1 : 0;
+        at += (int64_t)n;
+    }
+    if (name_off) name_off[p_hi - p_lo] = at;
+}
+
+void tg_gen_supplier(double sf, int64_t s_lo, int64_t s_hi, int32_t *s_suppkey, int32_t *s_nationkey)
+{
+    (void)sf;
+    int64_t s = tg_jump(SD_S_NTRG, s_lo);
+    for (int64_t i = s_lo; i < s_hi; i++) {
+        int64_t nat = tg_draw(&s, 0, 24);
+        if (s_suppkey) s_suppkey[i - s_lo] = (int32_t)(i + 1);
+        if (s_nationkey) s_nationkey[i - s_lo] = (int32_t)nat;
+    }
+}
+
+/* the 4 partsupp rows of every part in [p_lo, p_hi): output arrays hold 4*(p_hi-p_lo) rows */
+void tg_gen_partsupp(double sf, int64_t p_lo, int64_t p_hi, int32_t *ps_partkey, int32_t *ps_suppkey, int64_t *ps_supplycost)
+{
+    const int64_t nsupp = tg_num_supp(sf);
+    int64_t s = tg_jump(SD_PS_SCST, 4 * p_lo), row = 0;
+    for (int64_t i = p_lo; i < p_hi; i++) {
+        const int64_t pk = i + 1;
+        for (int64_t j = 0; j < 4; j++, row++) {
+            int64_t cost = tg_draw(&s, 100, 100000);
+            if (ps_partkey) ps_partkey[row] = (int32_t)pk;
+            if (ps_suppkey) ps_suppkey[row] = (int32_t)((pk + j * (nsupp / 4 + (pk - 1) / nsupp)) % nsupp + 1);
+            if (ps_supplycost) ps_supplycost[row] = cost;
+        }
+    }
+}

@@ -79,6 +79,26 @@ def test_q18_reproduces_reference_golden(oracle, sf1):
     assert oracle.q18_text(rows) == open(os.path.join(GOLDEN, "ref_sf1_q18.txt")).read()
 
 
+def test_part_supplier_partsupp_first_rows_match_official_dbgen(oracle):
+    """First rows of the official SF1 part.tbl / supplier.tbl / partsupp.tbl."""
+    part = oracle.gen_part(0.01)
+    assert [n.decode() for n in part["p_name"][:5]] == [
+        "goldenrod lavender spring chocolate lace", "blush thistle blue yellow saddle", "spring green yellow purple cornsilk",
+        "cornflower chocolate smoke green pink", "forest brown coral puff cream"]
+    sup = oracle.gen_supplier(1.0)
+    assert list(sup["s_nationkey"][:5]) == [17, 5, 1, 15, 11] and len(sup["s_suppkey"]) == 10000
+    ps = oracle.gen_partsupp(1.0)
+    assert list(ps["ps_suppkey"][:5]) == [2, 2502, 5002, 7502, 3]
+    assert list(ps["ps_supplycost"][:5]) == [77164, 99349, 33709, 35784, 37849] and len(ps["ps_partkey"]) == 800000
+
+
+def test_q9_reproduces_reference_golden(oracle, sf1):
+    """cases/tpch/1g/plan/q9.txt: 175 (nation, year) groups of a six-way join with LIKE and EXTRACT(year)."""
+    line = sf1["lineitem"]
+    rows = oracle.q9(oracle.gen_part(1.0, "pink"), oracle.gen_supplier(1.0), oracle.gen_partsupp(1.0), sf1["orders"], line)
+    assert oracle.q9_text(rows) == open(os.path.join(GOLDEN, "ref_sf1_q9.txt")).read()
+
+
 def test_q3_reproduces_reference_golden(oracle, sf1):
     res = oracle.q3(sf1["customer"], sf1["orders"], sf1["lineitem"])
     assert oracle.q3_text(res) == open(os.path.join(GOLDEN, "ref_sf1_q3.txt")).read()
