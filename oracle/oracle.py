@@ -420,6 +420,55 @@ def q3_topk(res, limit=10):
     return sorted(res["groups"], key=key)[:limit]
 
 
+def wildcard_match(pattern, target):
+    """wildcardMatch (function_operator_boolean.go:336-377) restated: bytes; % any run, _ any byte."""
+    p = t = 0
+    star_p = star_t = -1
+    plen, tlen = len(pattern), len(target)
+    while t < tlen:
+        if p < plen and pattern[p] == 0x25:
+            p += 1
+            star_p = p
+            if p >= plen:
+                return True
+            star_t = t
+        elif p < plen and (pattern[p] == 0x5F or pattern[p] == target[t]):
+            p += 1
+            t += 1
+        else:
+            if star_p == -1 or star_t == -1:
+                return False
+            p = star_p
+            star_t += 1
+            t = star_t
+    while p < plen and pattern[p] == 0x25:
+        p += 1
+    return p >= plen
+
+
+def customer_filter(cust, filters, segments):
+    """select count(*), sum(c_nationkey), sum(c_custkey) from customer where <string predicates>
+    (likeOp / notLikeOp / equalStrOp, function_operator_boolean.go:99-104,336-392).  Returns None for an empty
+    selection (the aggregate emits no row), else (count, sum, sum)."""
+    n = len(cust["c_custkey"])
+    keep = np.ones(n, dtype=bool)
+    for cname, op, lit in filters:
+        lit = lit.encode()
+        if cname == "c_mktsegment":
+            vals = [segments[c].encode() for c in cust[cname]]
+        else:
+            vals = list(cust[cname])
+        if op in ("like", "not like"):
+            m = np.array([wildcard_match(lit, v) for v in vals], dtype=bool)
+            keep &= m if op == "like" else ~m
+        else:
+            m = np.array([v == lit for v in vals], dtype=bool)
+            keep &= m if op == "=" else ~m
+    if not keep.any():
+        return None
+    return (int(keep.sum()), int(cust["c_nationkey"][keep].astype(np.int64).sum()), int(cust["c_custkey"][keep].astype(np.int64).sum()))
+
+
 def customer_name(custkey):
     """dbgen C_NAME: the tag "Customer" + '#' + the key zero-padded to 9 digits (TPC-H spec 4.2.3)."""
     return "Customer#%09d" % int(custkey)

@@ -34,6 +34,7 @@ ET_Column, ET_Func, ET_Const = 0, 5, 7
 JOIN_INNER, JOIN_SEMI, JOIN_ANTI, JOIN_MARK, JOIN_LEFT = 1, 2, 3, 4, 5
 
 FUNC_IDS = {"+": 1, "-": 2, "*": 3, "/": 4, "=": 10, "<>": 11, "<": 12, "<=": 13, ">": 14, ">=": 15, "in": 16,
+            "like": 17, "not like": 18,      # FuncLike / FuncNotLike (function.go:89-128)
             "and": 20, "or": 21, "not": 22, "cast": 30}
 AGG_IDS = {"sum": 1, "avg": 2, "count": 3, "min": 4, "max": 5}
 

@@ -98,6 +98,9 @@ struct Column {
     // PG_T_VARCHAR: host-resident payload, row r = h_bytes[h_off[r] .. h_off[r+1]) (h_off holds nrows+1 entries)
     std::vector<int64_t> h_off;
     std::string h_bytes;
+    // ... and a device copy (uploaded at seal) for predicates evaluated on the GPU (LIKE, =, <>)
+    char *d_bytes = nullptr;
+    int64_t *d_off = nullptr;
 };
 
 }  // namespace pg

@@ -224,7 +224,7 @@ struct JoinAggPipeline : Pipeline {
         if (rs.size() > PIPE_MAXPRED) PG_FAIL(PG_EUNSUPPORTED, "more than %d predicate columns on one scan", PIPE_MAXPRED);
         pp.npred = (int)rs.size();
         for (size_t i = 0; i < rs.size(); i++) {
-            if (rs[i].is_set) PG_FAIL(PG_EUNSUPPORTED, "code-set predicates (IN, <>, OR) are not supported in join pipelines yet");
+            if (rs[i].is_set || rs[i].like) PG_FAIL(PG_EUNSUPPORTED, "code-set and string predicates (IN, <>, OR, LIKE) are not supported in join pipelines yet");
             pp.pred[i].col = typed(tab(slot), rs[i].col);
             pp.pred[i].lo = rs[i].lo;
             pp.pred[i].hi = rs[i].hi;

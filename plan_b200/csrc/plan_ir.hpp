@@ -197,7 +197,36 @@ struct Range {
     // byte-coded columns (VARCHAR(1) / dictionary): `<>`, IN lists and ORs of equalities are code SETS
     bool is_set = false;
     uint32_t set[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // PG_T_VARCHAR columns: 1 LIKE, 2 NOT LIKE (pattern with % and _), 3 =, 4 <> (byte equality) against `pat`
+    int like = 0;
+    std::string pat;
 };
+
+// The reference's LIKE matcher restated (wildcardMatch, function_operator_boolean.go:336-377): byte-wise,
+// '%' matches any run (greedy with backtracking to the last '%'), '_' any single byte.
+inline bool wildcard_match(const char *pat, size_t plen, const char *tgt, size_t tlen)
+{
+    size_t p = 0, t = 0;
+    long star_p = -1, star_t = -1;
+    while (t < tlen) {
+        if (p < plen && pat[p] == '%') {
+            p++;
+            star_p = (long)p;
+            if (p >= plen) return true;
+            star_t = (long)t;
+        } else if (p < plen && (pat[p] == '_' || pat[p] == tgt[t])) {
+            p++;
+            t++;
+        } else {
+            if (star_p == -1 || star_t == -1) return false;
+            p = (size_t)star_p;
+            star_t++;
+            t = (size_t)star_t;
+        }
+    }
+    while (p < plen && pat[p] == '%') p++;
+    return p >= plen;
+}
 
 struct Factor {
     int col = -1;      // -1: pure constant
@@ -360,6 +389,33 @@ inline bool lower_compare(LowerCtx &cx, const Expr &e, std::vector<Range> &range
         return true;
     }
     if (e.fn == PG_FN_OR || e.fn == PG_FN_IN) return lower_byte_set(cx, e, ranges);
+    if ((e.fn == PG_FN_LIKE || e.fn == PG_FN_NOT_LIKE) && e.args.size() == 2) {
+        const Expr *c = strip_value_preserving_casts(&e.args[0]), *k = strip_value_preserving_casts(&e.args[1]);
+        if (c->kind != PG_TK_COL || c->idx < 0 || c->idx >= (int)cx.table->cols.size() || k->kind != PG_TK_STR)
+            return fail(cx, "LIKE needs a column and a string literal");
+        const Column &col = cx.table->cols[(size_t)c->idx];
+        if (col.has_nulls) { if (!cx.allow_nulls) return fail(cx, "nullable column in predicate"); cx.saw_nulls = true; }
+        Range rg;
+        rg.col = c->idx;
+        if (is_byte_family(col.type)) {          // dictionary / char column: match every code's string once, on the host
+            rg.is_set = true;
+            for (int code = 0; code < 256; code++) {
+                std::string sv;
+                if (col.type == PG_T_CHAR1) sv = std::string(1, (char)code);
+                else if (code < (int)col.dict.size()) sv = col.dict[(size_t)code];
+                else continue;
+                bool m = wildcard_match(k->str.data(), k->str.size(), sv.data(), sv.size());
+                if (m == (e.fn == PG_FN_LIKE)) rg.set[code >> 5] |= 1u << (code & 31);
+            }
+        } else if (col.type == PG_T_VARCHAR) {
+            rg.like = e.fn == PG_FN_LIKE ? 1 : 2;
+            rg.pat = k->str;
+        } else {
+            return fail(cx, "LIKE on a non-string column");
+        }
+        ranges.push_back(rg);
+        return true;
+    }
     if (!is_cmp(e.fn) || e.args.size() != 2) return fail(cx, "filter is not a comparison/AND");
     const Expr *l = &e.args[0], *r = &e.args[1];
     int op = e.fn;
@@ -415,6 +471,14 @@ inline bool lower_compare(LowerCtx &cx, const Expr &e, std::vector<Range> &range
         ranges.push_back(rg);
         return true;
     }
+    if (col.type == PG_T_VARCHAR) {                  // equalStrOp / its negation: byte equality (function_operator_boolean.go:99-104)
+        if (k->kind != PG_TK_STR) return fail(cx, "VARCHAR column compared with non-string");
+        if (op != PG_FN_EQ && op != PG_FN_NE) return fail(cx, "only =, <>, LIKE and NOT LIKE are supported on VARCHAR columns");
+        rg.like = op == PG_FN_EQ ? 3 : 4;
+        rg.pat = k->str;
+        ranges.push_back(rg);
+        return true;
+    }
     if (!is_int_family(col.type)) return fail(cx, "unsupported column type in predicate");
     if (k->kind != PG_TK_CONST) return fail(cx, "integer column compared with non-numeric constant");
     i64 kv = k->v0;
@@ -445,7 +509,7 @@ inline bool lower_filters(LowerCtx &cx, const std::vector<Expr> &filters, std::v
     for (auto &f : filters) if (!lower_compare(cx, f, raw)) return false;
     for (auto &r : raw) {
         bool merged = false;
-        for (auto &o : out) if (o.col == r.col) {
+        for (auto &o : out) if (o.col == r.col && !o.like && !r.like) {
             if (o.is_set || r.is_set) {          // intersect as code sets
                 Range rr = r;
                 range_to_set(o);

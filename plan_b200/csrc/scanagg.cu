@@ -752,7 +752,7 @@ struct GenericPipeline : Pipeline {
     std::vector<int> plane_kind;         // GEN_* per plane
     std::vector<bool> agg_is_int;
     std::vector<std::pair<int, int>> outs;
-    i64 bytes_per_row = 0;
+    i64 bytes_per_row = 0, extra_bytes = 0;      // extra: string payload + offsets of LIKE'd VARCHAR columns
     DevBuf d_part, d_final, d_luts, d_gather, d_kinds;
     PinBuf h_final;
     EventPair ev_all, ev_main;
@@ -810,7 +810,7 @@ struct GenericPipeline : Pipeline {
         res->stats.kernel_ms = ev_all.ms();
         res->stats.main_kernel_ms = ev_main.ms();
         res->stats.rows_scanned = table->nrows;
-        res->stats.algorithmic_bytes = table->nrows * bytes_per_row;
+        res->stats.algorithmic_bytes = table->nrows * bytes_per_row + extra_bytes;
         res->stats.main_kernel_bytes = res->stats.algorithmic_bytes;
         res->stats.kernel_launches = 2;
         std::vector<int> order;
@@ -925,8 +925,28 @@ static int try_generic(pg_plan *plan, const Node &aggn, const Node &scan, const 
     GenParams &q = p->prm;
     q.nrows = t->nrows;
     q.row_base = t->global_offset;
-    q.npred = (int)ranges.size();
-    for (size_t i = 0; i < ranges.size(); i++) {
+    // string predicates first out of the range list
+    std::vector<Range> likes, plain;
+    for (auto &r : ranges) (r.like ? likes : plain).push_back(r);
+    if (likes.size() > GEN_MAXLIKE) { *why = "more than 2 string predicates"; return PG_EUNSUPPORTED; }
+    q.nlike = (int)likes.size();
+    for (size_t i = 0; i < likes.size(); i++) {
+        const Column &col = t->cols[(size_t)likes[i].col];
+        if (likes[i].pat.size() > GEN_PATMAX) { *why = "string pattern longer than 48 bytes"; return PG_EUNSUPPORTED; }
+        if (!col.d_off) { *why = "VARCHAR column has no device copy"; return PG_EUNSUPPORTED; }
+        q.like[i].bytes = col.d_bytes;
+        q.like[i].off = (const i64 *)col.d_off;
+        q.like[i].kind = likes[i].like;
+        q.like[i].plen = (int)likes[i].pat.size();
+        memcpy(q.like[i].pat, likes[i].pat.data(), likes[i].pat.size());
+        p->extra_bytes += (i64)col.h_bytes.size() + 8 * t->nrows;
+    }
+    const std::vector<Range> &ranges_ = plain;
+    q.npred = (int)ranges_.size();
+    for (size_t i = 0; i < ranges_.size(); i++) {
+        const Range *rp = &ranges_[i];
+        const std::vector<Range> &ranges = ranges_;
+        (void)rp;
         const Column &col = t->cols[(size_t)ranges[i].col];
         q.pcol[i].p = col.d_data;
         q.pcol[i].width = type_size(col.type);
@@ -1075,7 +1095,7 @@ int build_scan_agg(pg_plan *plan, const Node &aggn, const Node &scan, std::uniqu
     const char *force = getenv("PG_FORCE_GENERIC");      // testing: exercise the shape-agnostic kernel on every plan
     int s = PG_EUNSUPPORTED;
     bool any_set = false;
-    for (auto &r : ranges) any_set = any_set || r.is_set;
+    for (auto &r : ranges) any_set = any_set || r.is_set || r.like;
     if (!(force && atoi(force)) && !cx.saw_nulls && !any_set) {
         s = try_sumprod(plan, aggn, scan, ranges, args, out, &why1);
         if (s != PG_EUNSUPPORTED) return s;

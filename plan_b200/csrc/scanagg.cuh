@@ -414,8 +414,55 @@ struct GenAcc {
     int s[GEN_MAXFAC];
 };
 
+// string predicate on a VARCHAR column (device copy: bytes + offsets): kind 1 LIKE, 2 NOT LIKE, 3 =, 4 <>
+constexpr int GEN_MAXLIKE = 2, GEN_PATMAX = 48;
+struct GenLike {
+    const char *bytes;
+    const i64 *off;
+    int kind, plen;
+    char pat[GEN_PATMAX];
+};
+// wildcardMatch of the reference (function_operator_boolean.go:336-377), byte for byte
+__device__ __forceinline__ bool gen_wildcard_match(const char *pat, int plen, const char *tgt, i64 tlen)
+{
+    i64 p = 0, t = 0, star_p = -1, star_t = -1;
+    while (t < tlen) {
+        if (p < plen && pat[p] == '%') {
+            p++;
+            star_p = p;
+            if (p >= plen) return true;
+            star_t = t;
+        } else if (p < plen && (pat[p] == '_' || pat[p] == tgt[t])) {
+            p++;
+            t++;
+        } else {
+            if (star_p == -1 || star_t == -1) return false;
+            p = star_p;
+            star_t++;
+            t = star_t;
+        }
+    }
+    while (p < plen && pat[p] == '%') p++;
+    return p >= plen;
+}
+__device__ __forceinline__ bool gen_like_pass(const GenLike &l, i64 row)
+{
+    const i64 b = __ldg(l.off + row), e = __ldg(l.off + row + 1);
+    const char *tgt = l.bytes + b;
+    bool m;
+    if (l.kind <= 2) {
+        m = gen_wildcard_match(l.pat, l.plen, tgt, e - b);
+    } else {
+        m = (e - b) == l.plen;
+        for (int i = 0; m && i < l.plen; i++) m = tgt[i] == l.pat[i];
+    }
+    return m == (l.kind == 1 || l.kind == 3);
+}
+
 struct GenParams {
     i64 nrows, row_base;
+    int nlike;
+    GenLike like[GEN_MAXLIKE];
     int npred;
     GenCol pcol[GEN_MAXPRED];
     i64 plo[GEN_MAXPRED], phi[GEN_MAXPRED];
@@ -464,6 +511,7 @@ generic_scanagg_kernel(const GenParams p, i64 *__restrict__ partials /* [grid][G
             i64 v = gen_load(p.pcol[k], row);
             ok = p.pset[k] ? ((p.pmask[k][(v >> 5) & 7] >> (v & 31)) & 1u) != 0 : (v >= p.plo[k] && v <= p.phi[k]);
         }
+        for (int k = 0; k < p.nlike && ok; k++) ok = gen_like_pass(p.like[k], row);
         if (!ok) continue;
         int g = 0;
         if (p.nkeys > 0) g = s_lut[0][__ldg(p.key0 + row)];

@@ -488,6 +488,16 @@ int pg_table_seal(pg_table *t, int64_t global_row_offset)
             PG_FAIL(PG_ESTATE, "pg_table_seal: VARCHAR column %s holds %zu strings for %lld rows", col.name.c_str(), col.h_off.size() - 1, (long long)t->nrows);
     }
     PG_TRY(compute_stats(t));
+    for (Column &col : t->cols) {        // device copy of string columns for GPU-side predicates (LIKE, =, <>)
+        if (col.type != PG_T_VARCHAR) continue;
+        if (col.d_off) { dev_free(col.d_off); col.d_off = nullptr; }
+        if (col.d_bytes) { dev_free(col.d_bytes); col.d_bytes = nullptr; }
+        PG_CUDA(dev_alloc((void **)&col.d_off, col.h_off.size() * 8));
+        PG_CUDA(dev_alloc((void **)&col.d_bytes, col.h_bytes.size() + 64));
+        PG_CUDA(cudaMemcpyAsync(col.d_off, col.h_off.data(), col.h_off.size() * 8, cudaMemcpyHostToDevice, ctx().stream));
+        PG_CUDA(cudaMemcpyAsync(col.d_bytes, col.h_bytes.data(), col.h_bytes.size(), cudaMemcpyHostToDevice, ctx().stream));
+        PG_CUDA(cudaStreamSynchronize(ctx().stream));
+    }
     t->sealed = true;
     t->version++;
     return PG_OK;
@@ -515,6 +525,8 @@ void pg_table_free(pg_table *t)
     for (Column &col : t->cols) {
         if (col.d_data) dev_free(col.d_data);
         if (col.d_valid) dev_free(col.d_valid);
+        if (col.d_off) dev_free(col.d_off);
+        if (col.d_bytes) dev_free(col.d_bytes);
     }
     delete t;
 }

@@ -295,6 +295,21 @@ def q18_plan(qty_gt=314, limit=100, schema=FULL):
     return PhysicalOperator(POT_Limit, Outputs=outs, Children=[order], Info=LimitOpInfo(limit))
 
 
+def customer_filter_plan(filters, schema=FULL):
+    """select count(*), sum(c_nationkey), sum(c_custkey) from customer where <filters>:
+    a scan-aggregate over customer used to exercise string predicates (LIKE / NOT LIKE / = / <> on the
+    VARCHAR c_name, LIKE on the dictionary column c_mktsegment).  filters: list of (column, op, literal)."""
+    S = schema
+    B = K.LType(K.LTID_BOOLEAN)
+    fl = [func(op, B, S.col("customer", cname), const(lit, K.VarcharType())) for cname, op, lit in filters]
+    scan = PhysicalOperator(POT_Scan, Filters=fl, Info=ScanOpInfo("customer"))
+    H = K.HugeintType()
+    ck = S.col("customer", "c_custkey")
+    aggs = [func("count", H, ck), func("sum", H, S.col("customer", "c_nationkey")), func("sum", H, ck)]
+    outs = [col(1, i, a.DataTyp) for i, a in enumerate(aggs)]
+    return PhysicalOperator(POT_Agg, Outputs=outs, Children=[scan], Info=AggOpInfo(aggs, []))
+
+
 def q3_topk_plan(limit=10, **kw):
     """Limit <- Order(revenue desc, o_orderdate) <- Agg(...) : the whole Q3 tail below the final
     Project, fused into the GPU pipeline (device top-k)."""

@@ -370,3 +370,37 @@ def test_code_set_predicates(pg, oracle, uploaded, sf01_host, kw, okw):
     assert set(got) == set(want)
     for k in want:
         assert got[k][0] == want[k][0] and _same_decimal(got[k][1], want[k][1])
+
+
+@pytest.mark.parametrize("filters", [
+    [("c_name", "like", "%00001%")],                       # contains
+    [("c_name", "like", "Customer#00000_2%")],             # prefix, single-byte wildcard, trailing run
+    [("c_name", "not like", "%7")],                        # suffix, negated
+    [("c_name", "like", "%0%1%2%")],                       # several runs (backtracking)
+    [("c_name", "=", "Customer#000001234")],
+    [("c_name", "<>", "Customer#000001234"), ("c_name", "like", "%1234")],
+    [("c_name", "like", "nothing%")],                      # selects nothing: the aggregate emits no row
+    [("c_mktsegment", "like", "%U%"), ("c_name", "like", "%99%")],   # dictionary column: matched per code on the host
+    [("c_mktsegment", "not like", "_U%")],
+    [("c_name", "like", "%")], [("c_name", "like", "")], [("c_name", "like", "__________________")],
+])
+def test_string_predicates(pg, oracle, sf01_host, filters):
+    """LIKE / NOT LIKE / = / <> on a VARCHAR column evaluated on the GPU with the reference's wildcardMatch
+    (function_operator_boolean.go:336-377), LIKE on a dictionary column folded into a code set."""
+    from plan_b200 import tpch as T, compute as X
+    t = T.upload_tables({"customer": sf01_host["customer"]})
+    try:
+        ex = X.gpuPipelineExec(T.customer_filter_plan(filters), t)
+        ex.Init()
+        chunks = X.drain(ex)
+        ex.Close()
+        want = oracle.customer_filter(sf01_host["customer"], filters, T.SEGMENTS)
+        if want is None:
+            assert chunks == []
+        else:
+            c = chunks[0]
+            h = lambda v: (int(v["upper"]) << 64) + int(v["lower"])   # noqa: E731
+            got = (h(c.Data[0].Data[0]), h(c.Data[1].Data[0]), h(c.Data[2].Data[0]))
+            assert got == want
+    finally:
+        t["customer"].free()

@@ -137,3 +137,14 @@ def test_decimal_contract(oracle):
     lo, hi = f(0.03) - f(0.01), f(0.03) + f(0.01)
     passing = [c for c in range(0, 11) if lo <= f(L.orc_dec_float64(c, 2, 0)) <= hi]
     assert passing == [2, 3, 4]
+
+
+def test_wildcard_match_restatement(oracle):
+    """Truth table of the reference's LIKE matcher (wildcardMatch, function_operator_boolean.go:336-377)."""
+    cases = [("%pink%", "cornflower chocolate smoke green pink", True), ("%pink%", "forest brown coral puff cream", False),
+             ("", "", True), ("", "a", False), ("%", "", True), ("%", "abc", True), ("_", "", False), ("_", "a", True), ("_", "ab", False),
+             ("a%b", "ab", True), ("a%b", "axxb", True), ("a%b", "axxbc", False), ("a%b%", "axxbc", True), ("%a%a%", "banana", True),
+             ("%a_a%", "banana", True), ("%ab", "aab", True), ("%ab", "aba", False), ("a_c", "abc", True), ("a_c", "ac", False),
+             ("%%", "x", True), ("%_", "", False), ("abc", "abc", True), ("abc", "abd", False), ("abc%", "ab", False)]
+    for pat, tgt, want in cases:
+        assert oracle.wildcard_match(pat.encode(), tgt.encode()) is want, (pat, tgt)
