@@ -83,6 +83,7 @@
 #define PG_FN_IN 16 /* in(arg, const...) (function_operator_boolean.go:393-504: INT32, VARCHAR) */
 #define PG_FN_LIKE 17     /* like(arg, pattern): wildcardMatch, % = any run, _ = any byte (function_operator_boolean.go:336-381) */
 #define PG_FN_NOT_LIKE 18
+#define PG_FN_EXTRACT 19  /* extract('year', date) -> INTEGER (binStringInt32ExtractOp, function_operator_binary.go:259-265) */
 #define PG_FN_AND 20
 #define PG_FN_OR 21
 #define PG_FN_NOT 22

@@ -24,6 +24,11 @@ enum { PG_O_ORDERKEY = 0, PG_O_CUSTKEY, PG_O_ORDERDATE, PG_O_SHIPPRIORITY, PG_O_
        PG_O_NCOLS };
 enum { PG_C_CUSTKEY = 0, PG_C_MKTSEGMENT, PG_C_NATIONKEY, PG_C_NAME, PG_C_NCOLS };
 
+enum { PG_P_PARTKEY = 0, PG_P_NAME, PG_P_NCOLS };
+enum { PG_S_SUPPKEY = 0, PG_S_NATIONKEY, PG_S_NCOLS };
+enum { PG_PS_PARTKEY = 0, PG_PS_SUPPKEY, PG_PS_SUPPLYCOST, PG_PS_NCOLS };
+enum { PG_N_NATIONKEY = 0, PG_N_NAME, PG_N_NCOLS };
+
 int64_t pg_tpch_num_orders(double sf);
 int64_t pg_tpch_num_customers(double sf);
 
@@ -33,6 +38,14 @@ int64_t pg_tpch_num_customers(double sf);
  * (lineitem generation still needs the line counts). */
 int pg_tpch_orders_lineitem(double sf, int64_t order_lo, int64_t order_hi, pg_table **orders, pg_table **lineitem);
 int pg_tpch_customer(double sf, int64_t cust_lo, int64_t cust_hi, pg_table **customer);
+
+/* the dimension tables TPC-H Q9 joins (whole tables, SEALED): part(p_partkey, p_name VARCHAR),
+ * supplier(s_suppkey, s_nationkey), partsupp(ps_partkey, ps_suppkey, ps_supplycost DECIMAL(15,2)),
+ * nation(n_nationkey, n_name as a 25-entry dictionary column) */
+int pg_tpch_part(double sf, pg_table **part);
+int pg_tpch_supplier(double sf, pg_table **supplier);
+int pg_tpch_partsupp(double sf, pg_table **partsupp);
+int pg_tpch_nation(pg_table **nation);
 
 /* copy `nrows` rows of column `col` starting at `row` to a host buffer (tests, e2e bench) */
 int pg_table_read_column(pg_table *t, int col, int64_t row, int64_t nrows, void *host_out);

@@ -195,7 +195,7 @@ def gen_part(sf, like_word=None):
                   like_word.encode() if like_word else None, _p(has))
     raw = buf.raw
     names = np.array([raw[off[i]:off[i + 1]] for i in range(n)], dtype=object)
-    return {"p_partkey": keys, "p_name": names, "p_name_like": has.astype(bool)}
+    return {"p_partkey": keys, "p_name": names, "p_name_like": has.astype(bool), "like_word": like_word}
 
 
 def gen_supplier(sf):
@@ -519,7 +519,7 @@ def q9(part, supplier, partsupp, orders, line, like_word="pink"):
     (govalues: max of the scales); sum(DECIMAL) -> DECIMAL(38,4) by sequential Add, exact here (totals
     need 12 digits).  NULL-free inputs; every join is on keys that exist.  Returns [(nation, year, sum at scale 4)]
     ordered by nation, year DESC."""
-    like = part["p_name_like"] if like_word == "pink" and "p_name_like" in part else np.array([like_word.encode() in n for n in part["p_name"]])
+    like = part["p_name_like"] if part.get("like_word") == like_word else np.array([like_word.encode() in n for n in part["p_name"]], dtype=bool)
     part_ok = np.zeros(int(part["p_partkey"].max()) + 1, dtype=bool)
     part_ok[part["p_partkey"][like]] = True
     m = part_ok[line["l_partkey"]]

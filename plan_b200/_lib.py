@@ -83,6 +83,10 @@ SIGNATURES = [
     ("pg_tpch_num_customers", C.c_int64, [C.c_double]),
     ("pg_tpch_orders_lineitem", C.c_int, [C.c_double, C.c_int64, C.c_int64, C.POINTER(_P), C.POINTER(_P)]),
     ("pg_tpch_customer", C.c_int, [C.c_double, C.c_int64, C.c_int64, C.POINTER(_P)]),
+    ("pg_tpch_part", C.c_int, [C.c_double, C.POINTER(_P)]),
+    ("pg_tpch_supplier", C.c_int, [C.c_double, C.POINTER(_P)]),
+    ("pg_tpch_partsupp", C.c_int, [C.c_double, C.POINTER(_P)]),
+    ("pg_tpch_nation", C.c_int, [C.POINTER(_P)]),
     ("pg_table_read_column", C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, _P]),
 ]
 

@@ -35,6 +35,7 @@ JOIN_INNER, JOIN_SEMI, JOIN_ANTI, JOIN_MARK, JOIN_LEFT = 1, 2, 3, 4, 5
 
 FUNC_IDS = {"+": 1, "-": 2, "*": 3, "/": 4, "=": 10, "<>": 11, "<": 12, "<=": 13, ">": 14, ">=": 15, "in": 16,
             "like": 17, "not like": 18,      # FuncLike / FuncNotLike (function.go:89-128)
+            "extract": 19,                   # extract('year', date) (binStringInt32ExtractOp, function_operator_binary.go:259-265)
             "and": 20, "or": 21, "not": 22, "cast": 30}
 AGG_IDS = {"sum": 1, "avg": 2, "count": 3, "min": 4, "max": 5}
 
@@ -380,16 +381,22 @@ class gpuPipelineExec(OperatorExec):
         return op
 
     def _dict_for_output(self, i):
-        # a DICT8 group key comes straight from a scan column: find its dictionary
+        # a DICT8 group key is a scan column reached through joins: follow the output references down to its dictionary
         agg = self._agg_op()
         o = agg.Outputs[i]
-        if agg.Typ == POT_Agg and o.ColRef[0] == 0:
-            g = agg.Info.GroupBys[o.ColRef[1]]
-            node = agg.Children[0]
-            while node.Typ not in (POT_Scan,):
-                node = node.Children[g.ColRef[0]] if node.Typ == POT_Join else node.Children[0]
-            return self.tables[node.Info.Table].columns[g.ColRef[1]][4]
-        return None
+        if agg.Typ != POT_Agg or o.ColRef[0] != 0:
+            return None
+        g = agg.Info.GroupBys[o.ColRef[1]]
+        if g.Typ != ET_Column:
+            return None
+        node, idx = agg.Children[0], g.ColRef[1]
+        while node.Typ != POT_Scan:
+            if node.Typ == POT_Join:
+                ref = node.Outputs[idx].ColRef
+                node, idx = node.Children[ref[0]], ref[1]
+            else:
+                node = node.Children[0]
+        return self.tables[node.Info.Table].columns[idx][4]
 
     def Close(self):
         lib = L.lib()

@@ -47,6 +47,7 @@ struct Stage {
     // group keys are computed on the device by a nested pipeline and become an existence bitmap
     std::unique_ptr<Pipeline> sub;
     Node sub_scan;
+    int ins_key_col2 = -1;           // two-column build key (k << 32 | k2): hash table, no bitmap
     i64 capacity_rows = 0;
     i64 built_rows = 0;
     bool payload_needed = false;     // some column of this build side is read above the join
@@ -106,6 +107,22 @@ struct JoinAggPipeline : Pipeline {
     bool fd_mode = false;
     struct FdOut { int kind, slot, col, via_key_col, via_stage; };
     std::vector<FdOut> fd;
+    // Star joins (see hits_star_kernel): `main_stage` is the existence join the filter pass tests, `lookups`
+    // are all INNER joins of the fact-table spine bottom-up; origin 0 = the fact table, j = lookup j-1's table
+    bool star = false;
+    int main_stage = -1;
+    struct HRef { int origin = 0, col = -1; };
+    struct HLookup { int nkey = 1; HRef key[2]; int stage = -1; };
+    struct HPart { HRef v; int fn = 0; i64 lo = 0; int n = 1; int type = 0; };
+    struct HTerm { int nfac = 0; HRef fac[3]; i64 fc[3] = {0, 0, 0}; int fs[3] = {1, 1, 1}; i64 mul = 1; };
+    std::vector<HLookup> lookups;
+    std::vector<int> origin_slot;
+    std::vector<HPart> sparts;
+    std::vector<HTerm> sterms;
+    int star_ngroups = 0, star_scale = 0;
+    DevBuf d_star, d_star_all;
+    PinBuf h_star;
+    Stage &top_stage_ref() { return *stages[(size_t)(main_stage >= 0 ? main_stage : (int)stages.size() - 1)]; }
     DevBuf d_edges;
     std::vector<std::pair<int, int>> outs;
     std::vector<int> group_out_type;             // pg_type of each group key
@@ -219,12 +236,26 @@ struct JoinAggPipeline : Pipeline {
 
     const pg_table *tab(int slot) const { return plan->slots[(size_t)slot]; }
 
-    int fill_preds(PipeParams &pp, const std::vector<Range> &rs, int slot)
+    int fill_preds(PipeParams &pp, const std::vector<Range> &all, int slot)
     {
+        std::vector<Range> rs;
+        pp.nlike = 0;
+        for (auto &r : all) {
+            if (!r.like) { rs.push_back(r); continue; }
+            // string predicate on a VARCHAR column: evaluated by pipeline_kernel (the two-phase filter does not take them)
+            const Column &col = tab(slot)->cols[(size_t)r.col];
+            if (pp.nlike >= GEN_MAXLIKE || r.pat.size() > GEN_PATMAX || !col.d_off) PG_FAIL(PG_EUNSUPPORTED, "string predicate not off-loadable in a join pipeline");
+            GenLike &l = pp.like[pp.nlike++];
+            l.bytes = col.d_bytes;
+            l.off = (const i64 *)col.d_off;
+            l.kind = r.like;
+            l.plen = (int)r.pat.size();
+            memcpy(l.pat, r.pat.data(), r.pat.size());
+        }
         if (rs.size() > PIPE_MAXPRED) PG_FAIL(PG_EUNSUPPORTED, "more than %d predicate columns on one scan", PIPE_MAXPRED);
         pp.npred = (int)rs.size();
         for (size_t i = 0; i < rs.size(); i++) {
-            if (rs[i].is_set || rs[i].like) PG_FAIL(PG_EUNSUPPORTED, "code-set and string predicates (IN, <>, OR, LIKE) are not supported in join pipelines yet");
+            if (rs[i].is_set) PG_FAIL(PG_EUNSUPPORTED, "code-set predicates (IN, <>, OR) are not supported in join pipelines yet");
             pp.pred[i].col = typed(tab(slot), rs[i].col);
             pp.pred[i].lo = rs[i].lo;
             pp.pred[i].hi = rs[i].hi;
@@ -275,7 +306,7 @@ struct JoinAggPipeline : Pipeline {
         for (int k = 0; k < pp.npred; k++) any_valid = any_valid || pp.pred[k].col.valid != nullptr;
         // (a build stage without a probe of its own also qualifies: the filter pass then lists every row that
         //  passes the predicate -- pp.probe_key must name the key column so the vector loads have a source)
-        return (pp.has_probe ? pp.probe.bitmap != nullptr : ins_sink) && pp.npred <= 1 && (pp.npred == 0 || pp.pred[0].col.width == 4) &&
+        return (pp.has_probe ? pp.probe.bitmap != nullptr : ins_sink) && pp.nlike == 0 && pp.npred <= 1 && (pp.npred == 0 || pp.pred[0].col.width == 4) &&
                (pp.probe_key.width == 4 || pp.probe_key.width == 8) && !any_valid && t->nrows < ((i64)1 << 32) &&
                !getenv("PG_JOIN_GENERIC");
     }
@@ -342,6 +373,7 @@ struct JoinAggPipeline : Pipeline {
             while (((u64)1 << lg) < nb) lg++;
             bool asc = keycol.stats_ok && keycol.adjacent_descents * 100 <= std::max<i64>(nbuild, 1) && dom > 0 && dom <= ((i128)1 << 34) && lg <= 29;
             if (getenv("PG_JOIN_ORDER_PRESERVING")) asc = asc && atoi(getenv("PG_JOIN_ORDER_PRESERVING")) != 0;
+            if (s.ins_key_col2 >= 0) asc = false;            // composite keys: hashed buckets
             s.jt.order_preserving = asc ? 1 : 0;
             s.jt.log2buckets = lg;
             s.jt.domain = dom > 0 ? (u64)dom : 1;
@@ -354,7 +386,7 @@ struct JoinAggPipeline : Pipeline {
         s.jt.bm_min = keycol.vmin;
         s.jt.bm_max = keycol.vmax;
         i128 domain = (i128)keycol.vmax - (i128)keycol.vmin + 1;
-        if (keycol.stats_ok && domain > 0 && domain <= ((i128)1 << 32)) {
+        if (keycol.stats_ok && domain > 0 && domain <= ((i128)1 << 32) && s.ins_key_col2 < 0) {
             size_t words = ((size_t)((domain + 31) / 32) + 7) / 8 * 8;      // whole 256-bit blocks (rank index)
             if (s.d_bitmap.bytes < words * 4) PG_TRY(s.d_bitmap.alloc(words * 4));
             PG_CUDA(cudaMemsetAsync(s.d_bitmap.p, 0, words * 4, st));
@@ -377,6 +409,7 @@ struct JoinAggPipeline : Pipeline {
         const int grid = ctx().prop.multiProcessorCount * 8;
         if (s.d_keys_tmp.bytes < (size_t)std::max<i64>(nh, 1) * 8) PG_TRY(s.d_keys_tmp.alloc((size_t)std::max<i64>(nh, 1) * 8));
         pp.ins_key = typed(t, s.ins_key_col);
+        if (s.ins_key_col2 >= 0) pp.ins_key2 = typed(t, s.ins_key_col2);
         s.jt.dups = d_counters.as<unsigned long long>() + 2;
         pp.ins = s.jt;
         PG_CUDA(cudaMemsetAsync(d_counters.p, 0, 32, st));
@@ -438,7 +471,7 @@ struct JoinAggPipeline : Pipeline {
             s.no_table = true;
             s.dup_keys = 0;
             s.built_rows = nk;
-            if (idx < 4) { res->stats.aux[2 + 2 * idx] = sp->tab(sp->src_slot)->nrows; res->stats.aux[3 + 2 * idx] = nk; }
+            if (idx < 2) { res->stats.aux[2 + 2 * idx] = sp->tab(sp->src_slot)->nrows; res->stats.aux[3 + 2 * idx] = nk; }
             return PG_OK;
         }
         PipeParams pp{};
@@ -462,13 +495,14 @@ struct JoinAggPipeline : Pipeline {
             PG_TRY(prepare_table(s, 0, t->cols[(size_t)s.ins_key_col]));
             if (s.jt.bitmap) {
                 pp.ins_key = typed(t, s.ins_key_col);
+        if (s.ins_key_col2 >= 0) pp.ins_key2 = typed(t, s.ins_key_col2);
                 pp.ins = s.jt;
                 PG_CUDA(cudaMemsetAsync(d_counters.p, 0, 32, st));
                 PG_TRY(launch_pipe<SINK_BITMAP>(pp, t));
                 s.no_table = true;
                 s.dup_keys = 0;
                 res->stats.kernel_launches += 1;
-                if (idx < 4) {       // counters are read lazily with the next stage's; keep the API cheap
+                if (idx < 2) {       // counters are read lazily with the next stage's; keep the API cheap
                     unsigned long long c0[4];
                     PG_TRY(read_counters(c0));
                     s.built_rows = (i64)c0[1];
@@ -493,12 +527,13 @@ struct JoinAggPipeline : Pipeline {
                 PG_TRY(build_rank_index(s, pp, t, (i64)nh, res, &done));
                 if (done) {
                     res->stats.kernel_launches += 1;
-                    if (idx < 4) { res->stats.aux[2 + 2 * idx] = (i64)cnt[0]; res->stats.aux[3 + 2 * idx] = s.built_rows; }
+                    if (idx < 2) { res->stats.aux[2 + 2 * idx] = (i64)cnt[0]; res->stats.aux[3 + 2 * idx] = s.built_rows; }
                     return PG_OK;
                 }
             }
             PG_TRY(prepare_table(s, s.built_rows, t->cols[(size_t)s.ins_key_col]));
             pp.ins_key = typed(t, s.ins_key_col);
+        if (s.ins_key_col2 >= 0) pp.ins_key2 = typed(t, s.ins_key_col2);
             s.jt.dups = d_counters.as<unsigned long long>() + 2;
             pp.ins = s.jt;
             PG_CUDA(cudaMemsetAsync(d_counters.p, 0, 32, st));
@@ -510,7 +545,7 @@ struct JoinAggPipeline : Pipeline {
                 s.dup_keys = (i64)c2[2];
             }
             res->stats.kernel_launches += exact ? 2 : 3;
-            if (idx < 4) { res->stats.aux[2 + 2 * idx] = (i64)cnt[0]; res->stats.aux[3 + 2 * idx] = s.built_rows; }
+            if (idx < 2) { res->stats.aux[2 + 2 * idx] = (i64)cnt[0]; res->stats.aux[3 + 2 * idx] = s.built_rows; }
             return PG_OK;
         }
         // sizing pass: how many rows reach the sink
@@ -521,6 +556,7 @@ struct JoinAggPipeline : Pipeline {
         s.built_rows = (i64)cnt[1];
         PG_TRY(prepare_table(s, s.built_rows, t->cols[(size_t)s.ins_key_col]));
         pp.ins_key = typed(t, s.ins_key_col);
+        if (s.ins_key_col2 >= 0) pp.ins_key2 = typed(t, s.ins_key_col2);
         s.jt.dups = d_counters.as<unsigned long long>() + 2;
         pp.ins = s.jt;
         PG_CUDA(cudaMemsetAsync(d_counters.p, 0, 32, st));
@@ -532,7 +568,7 @@ struct JoinAggPipeline : Pipeline {
             s.dup_keys = (i64)c2[2];
         }
         res->stats.kernel_launches += 2;
-        if (idx < 4) { res->stats.aux[2 + 2 * idx] = (i64)cnt[0]; res->stats.aux[3 + 2 * idx] = (i64)cnt[1]; }
+        if (idx < 2) { res->stats.aux[2 + 2 * idx] = (i64)cnt[0]; res->stats.aux[3 + 2 * idx] = (i64)cnt[1]; }
         return PG_OK;
     }
 
@@ -617,6 +653,142 @@ struct JoinAggPipeline : Pipeline {
         return PG_OK;
     }
 
+    // fact-table pipeline of a star join: existence filter pass, then hits_star_kernel (lookups + dense group sums)
+    int run_star(pg_result *res, Trace &tr)
+    {
+        Context &c = ctx();
+        cudaStream_t st = c.stream;
+        const pg_table *t = tab(src_slot);
+        PipeParams pp{};
+        pp.nrows = t->nrows;
+        PG_TRY(fill_preds(pp, ranges, src_slot));
+        Stage &M = top_stage_ref();
+        pp.has_probe = 1;
+        pp.probe_key = typed(t, probe_key_col);
+        pp.probe = M.jt;
+        pp.probe_bitmap_only = 1;
+        pp.probe_mode = 0;
+        pp.counters = d_counters.as<unsigned long long>();
+        if (!two_phase_ok(pp, t, false) || t->nrows > HIT_CHUNK) PG_FAIL(PG_EUNSUPPORTED, "star join: the fact-table scan does not fit the filter pass (one 32-bit range predicate, bitmap-able main join)");
+        PG_CUDA(cudaMemsetAsync(d_counters.p, 0, 32, st));
+        PG_CUDA(cudaEventRecord(ev_main.a, st));
+        PG_TRY(launch_filter(pp, 0, t->nrows));
+        tr.mark("star filter");
+        StarParams sp{};
+        sp.hits = d_hits.as<unsigned>();
+        sp.hit_count = d_hit_count.as<unsigned long long>();
+        auto href = [&](const HRef &h) { ValRef v; v.col = typed(tab(origin_slot[(size_t)h.origin]), h.col); v.from_build = h.origin; return v; };
+        sp.nlookup = (int)lookups.size();
+        for (size_t l = 0; l < lookups.size(); l++) {
+            const Stage &b = *stages[(size_t)lookups[l].stage];
+            sp.lk[l].nkey = lookups[l].nkey;
+            for (int k = 0; k < lookups[l].nkey; k++) sp.lk[l].key[k] = href(lookups[l].key[k]);
+            sp.lk[l].jt = b.jt;
+            sp.lk[l].existence = b.bitmap_only() ? 1 : 0;
+            if (!sp.lk[l].existence && b.no_table) PG_FAIL(PG_ECUDA, "internal: star lookup needs a payload but its build side kept none");
+        }
+        sp.nparts = (int)sparts.size();
+        sp.ngroups = star_ngroups;
+        for (size_t k = 0; k < sparts.size(); k++) { sp.part[k].v = href(sparts[k].v); sp.part[k].fn = sparts[k].fn; sp.part[k].lo = sparts[k].lo; sp.part[k].n = sparts[k].n; }
+        sp.nterm = (int)sterms.size();
+        for (size_t i = 0; i < sterms.size(); i++) {
+            sp.term[i].nfac = sterms[i].nfac;
+            sp.term[i].mul = sterms[i].mul;
+            for (int f = 0; f < sterms[i].nfac; f++) { sp.term[i].fac[f] = href(sterms[i].fac[f]); sp.term[i].fc[f] = sterms[i].fc[f]; sp.term[i].fs[f] = sterms[i].fs[f]; }
+        }
+        const size_t gbytes = (size_t)star_ngroups * 24;      // sum low word, sum high word, row count
+        const int W = (t->dist != PG_DIST_REPLICATED && c.world > 1) ? c.world : 1;
+        if (!d_star.p) { PG_TRY(d_star.alloc(gbytes)); PG_TRY(d_star_all.alloc(gbytes * (size_t)c.world)); PG_TRY(h_star.alloc(gbytes * (size_t)c.world)); }
+        PG_CUDA(cudaMemsetAsync(d_star.p, 0, gbytes, st));
+        sp.gsum = d_star.as<unsigned long long>();
+        sp.gsum_hi = sp.gsum + star_ngroups;
+        sp.gcnt = sp.gsum + 2 * star_ngroups;
+        sp.counters = d_counters.as<unsigned long long>();
+        hits_star_kernel<<<c.prop.multiProcessorCount * 8, 256, (size_t)star_ngroups * 16, st>>>(sp);
+        PG_CUDA(cudaGetLastError());
+        PG_CUDA(cudaEventRecord(ev_main.b, st));
+        res->stats.kernel_launches += 2;
+        if (W > 1) {
+            PG_TRY(comm_allgather(d_star.p, d_star_all.p, gbytes, st));
+            PG_CUDA(cudaMemcpyAsync(h_star.p, d_star_all.p, gbytes * (size_t)W, cudaMemcpyDeviceToHost, st));
+        } else {
+            PG_CUDA(cudaMemcpyAsync(h_star.p, d_star.p, gbytes, cudaMemcpyDeviceToHost, st));
+        }
+        unsigned long long cnt[4];
+        PG_CUDA(cudaEventRecord(ev_all.b, st));
+        PG_TRY(read_counters(cnt));
+        tr.mark("star sink + d2h");
+        if (cnt[2] != 0) PG_FAIL(PG_EUNSUPPORTED, "star join: a lookup matched more than one build row (duplicate build keys)");
+        res->stats.kernel_ms = ev_all.ms();
+        res->stats.main_kernel_ms = ev_main.ms();
+        res->stats.rows_scanned = t->nrows;
+        res->stats.algorithmic_bytes = algorithmic_bytes;
+        res->stats.main_kernel_bytes = main_bytes;
+        res->stats.aux[0] = (i64)cnt[0];
+        res->stats.aux[1] = (i64)cnt[1];
+        // merge ranks (exact: 128-bit), emit the groups that received rows
+        std::vector<i128> sums((size_t)star_ngroups, 0);
+        std::vector<i64> cnts((size_t)star_ngroups, 0);
+        const i64 *hs = h_star.as<i64>();
+        for (int r = 0; r < W; r++)
+            for (int g = 0; g < star_ngroups; g++) {
+                const i64 *rec = hs + (size_t)r * 3 * (size_t)star_ngroups;
+                sums[(size_t)g] += (i128)(((u128)(u64)rec[star_ngroups + g] << 64) | (u128)(u64)rec[g]);
+                cnts[(size_t)g] += rec[2 * star_ngroups + g];
+            }
+        std::vector<int> live;
+        for (int g = 0; g < star_ngroups; g++) if (cnts[(size_t)g] > 0) live.push_back(g);
+        res->nrows = (i64)live.size();
+        res->stats.aux[6] = res->nrows;
+        for (auto &o : outs) {
+            ResCol col;
+            if (o.first == 0) {
+                const HPart &hp = sparts[(size_t)o.second];
+                i64 stride = 1;
+                for (size_t k = (size_t)o.second + 1; k < sparts.size(); k++) stride *= sparts[k].n;
+                col.type = hp.type;
+                const int w = type_size(col.type);
+                col.data.resize(live.size() * (size_t)w);
+                if (hp.type == PG_T_DICT8) col.dict = tab(origin_slot[(size_t)hp.v.origin])->cols[(size_t)hp.v.col].dict;
+                for (size_t i = 0; i < live.size(); i++) {
+                    const i64 v = ((i64)live[i] / stride) % hp.n + hp.lo;
+                    if (w == 8) ((i64 *)col.data.data())[i] = v;
+                    else if (w == 4) ((int32_t *)col.data.data())[i] = (int32_t)v;
+                    else col.data[i] = (uint8_t)v;
+                }
+            } else {
+                const AggExpr &a = aggs[(size_t)o.second];
+                col.width = a.width;
+                col.scale = a.scale;
+                if (a.fn == PG_AGG_COUNT || a.ltype == PG_LT_HUGEINT) {
+                    col.type = PG_T_HUGEINT;
+                    col.data.resize(live.size() * sizeof(pg_hugeint));
+                    pg_hugeint *d = (pg_hugeint *)col.data.data();
+                    for (size_t i = 0; i < live.size(); i++) {
+                        const i128 v = a.fn == PG_AGG_COUNT ? (i128)cnts[(size_t)live[i]] : sums[(size_t)live[i]];
+                        d[i].lower = (u64)v;
+                        d[i].upper = (i64)(v >> 64);
+                    }
+                } else {
+                    col.type = PG_T_DECIMAL128;
+                    col.data.resize(live.size() * sizeof(pg_decimal));
+                    pg_decimal *d = (pg_decimal *)col.data.data();
+                    for (size_t i = 0; i < live.size(); i++) {
+                        const i128 v = sums[(size_t)live[i]];
+                        const u128 m = v < 0 ? (u128)(-v) : (u128)v;
+                        if (m >= (u128)10000000000000000000ULL) PG_FAIL(PG_EOVERFLOW, "star join: a group sum needs more than 19 digits");
+                        d[i].neg = v < 0;
+                        d[i].coef = (u64)m;
+                        d[i].scale = star_scale;
+                    }
+                }
+            }
+            res->cols.push_back(std::move(col));
+        }
+        tr.mark("result columns");
+        return PG_OK;
+    }
+
     int run(pg_result *res) override
     {
         Context &c = ctx();
@@ -627,6 +799,7 @@ struct JoinAggPipeline : Pipeline {
         PG_CUDA(cudaEventRecord(ev_all.a, st));
         res->stats.kernel_launches = 0;
         for (size_t i = 0; i < stages.size(); i++) { PG_TRY(run_build_stage(*stages[i], res, (int)i)); tr.mark("build stage"); }
+        if (star) return run_star(res, tr);
 
         const pg_table *t = tab(src_slot);
         PipeParams pp{};
@@ -634,7 +807,7 @@ struct JoinAggPipeline : Pipeline {
         PG_TRY(fill_preds(pp, ranges, src_slot));
         pp.has_probe = no_join ? 0 : 1;
         if (!no_join) {
-            Stage &last = *stages.back();
+            Stage &last = top_stage_ref();
             pp.probe_key = typed(t, probe_key_col);
             pp.probe = last.jt;
             pp.probe_bitmap_only = last.bitmap_only() ? 1 : 0;
@@ -1169,6 +1342,298 @@ static int add_build_stage(JoinAggPipeline *p, const Node &n0, int key_idx, int 
     return PG_OK;
 }
 
+static i64 host_year_of_days(i64 z)
+{
+    z += 719468;
+    const i64 era = (z >= 0 ? z : z - 146096) / 146097;
+    const i64 doe = z - era * 146097;
+    const i64 yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+    const i64 y = yoe + era * 400;
+    const i64 doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
+    const i64 mp = (5 * doy + 2) / 153;
+    return y + (mp >= 10 ? 1 : 0);
+}
+
+// Star join: the aggregate's input is a LEFT-DEEP stack of INNER joins whose leftmost leaf is the fact
+// table scan and whose build sides are (filtered) scans -- the shape of TPC-H Q9.  Group keys must map
+// to a small dense domain (dictionary / narrow integer columns, EXTRACT(year) of a date) and the single
+// SUM argument to a signed sum of products of (constant +/- column) factors over the joined rows.
+static int build_star(pg_plan *plan, const Node &aggn, const Node &top, std::unique_ptr<JoinAggPipeline> p, std::unique_ptr<Pipeline> *out)
+{
+    typedef JoinAggPipeline::HRef HRef;
+    p->star = true;
+    std::vector<const Node *> spine;
+    const Node *x = &top;
+    while (x->op == PG_OP_JOIN) {
+        if (x->jointype != PG_JOIN_INNER) PG_FAIL(PG_EUNSUPPORTED, "star join: only INNER joins on the fact-table spine");
+        spine.push_back(x);
+        x = &x->children[0];
+    }
+    std::vector<Expr> pf;
+    while (x->op == PG_OP_FILTER) { for (auto &f : x->filters) pf.push_back(f); x = &x->children[0]; }
+    if (x->op != PG_OP_SCAN) PG_FAIL(PG_EUNSUPPORTED, "star join: the leftmost leaf must be a scan");
+    if (spine.size() > STAR_MAXLOOKUP) PG_FAIL(PG_EUNSUPPORTED, "star join: more than %d joins", STAR_MAXLOOKUP);
+    p->src_slot = x->slot;
+    const pg_table *st = p->tab(x->slot);
+    {
+        LowerCtx cx;
+        cx.table = st;
+        std::vector<Expr> fl = x->filters;
+        for (auto &f : pf) fl.push_back(f);
+        if (!lower_filters(cx, fl, p->ranges)) PG_FAIL(PG_EUNSUPPORTED, "fact-table filter not off-loadable: %s", cx.why.c_str());
+    }
+    p->origin_slot.push_back(p->src_slot);
+    // base column -> (origin, column): the fact table or the table of an earlier lookup
+    auto locate = [&](const Node &scope, int idx, HRef *h) -> bool {
+        BaseCol bc;
+        if (!resolve(scope, idx, &bc)) return false;
+        for (size_t o = 0; o < p->origin_slot.size(); o++)
+            if (p->origin_slot[o] == bc.slot) { h->origin = (int)o; h->col = bc.col; return true; }
+        return false;
+    };
+    auto int_nonnull = [&](const HRef &h) {
+        const Column &cc = p->tab(p->origin_slot[(size_t)h.origin])->cols[(size_t)h.col];
+        return is_int_family(cc.type) && !cc.has_nulls;
+    };
+    for (size_t i = spine.size(); i-- > 0;) {          // bottom-up
+        const Node &J = *spine[i];
+        if (J.conds.empty() || J.conds.size() > 2) PG_FAIL(PG_EUNSUPPORTED, "star join: join keys of 1 or 2 columns only");
+        JoinAggPipeline::HLookup lk;
+        lk.nkey = (int)J.conds.size();
+        const Expr *be0 = strip_value_preserving_casts(&J.conds[0].second);
+        if (be0->kind != PG_TK_COL) PG_FAIL(PG_EUNSUPPORTED, "join condition is not column = column");
+        PG_TRY(add_build_stage(p.get(), J.children[1], be0->idx, &lk.stage));
+        Stage &S = *p->stages[(size_t)lk.stage];
+        if (S.has_probe || S.sub) PG_FAIL(PG_EUNSUPPORTED, "star join: build sides must be (filtered) scans");
+        for (int k = 0; k < lk.nkey; k++) {
+            const Expr *pe = strip_value_preserving_casts(&J.conds[(size_t)k].first);
+            if (pe->kind != PG_TK_COL || !locate(J.children[0], pe->idx, &lk.key[k]) || !int_nonnull(lk.key[k]))
+                PG_FAIL(PG_EUNSUPPORTED, "star join: probe key %d is not a reachable non-null integer column", k);
+        }
+        if (lk.nkey == 2) {
+            const Expr *be1 = strip_value_preserving_casts(&J.conds[1].second);
+            BaseCol b2;
+            if (be1->kind != PG_TK_COL || !resolve(J.children[1], be1->idx, &b2) || b2.slot != S.src_slot) PG_FAIL(PG_EUNSUPPORTED, "second build key is not a column of the build scan");
+            const pg_table *bt = p->tab(S.src_slot);
+            const Column &k1 = bt->cols[(size_t)S.ins_key_col], &k2 = bt->cols[(size_t)b2.col];
+            auto fits32 = [](const Column &c) { return is_int_family(c.type) && !c.has_nulls && c.vmin >= INT32_MIN && c.vmax <= INT32_MAX; };
+            if (!fits32(k1) || !fits32(k2)) PG_FAIL(PG_EUNSUPPORTED, "two-column join keys must both fit 32 bits");
+            S.ins_key_col2 = b2.col;
+            S.unique_key = false;
+        }
+        p->lookups.push_back(lk);
+        p->origin_slot.push_back(S.src_slot);
+    }
+    // the filter pass: a one-column join on a FACT column, preferably one whose build side is filtered
+    int main = -1;
+    for (int pass = 0; pass < 2 && main < 0; pass++)
+        for (size_t l = 0; l < p->lookups.size(); l++) {
+            const auto &lk = p->lookups[l];
+            const Stage &S = *p->stages[(size_t)lk.stage];
+            const Column &bk = p->tab(S.src_slot)->cols[(size_t)S.ins_key_col];
+            const bool bitmapable = bk.stats_ok && (i128)bk.vmax - (i128)bk.vmin + 1 <= ((i128)1 << 32);
+            if (lk.nkey == 1 && lk.key[0].origin == 0 && bitmapable && (pass == 1 || !S.ranges.empty())) { main = (int)l; break; }
+        }
+    if (main < 0) PG_FAIL(PG_EUNSUPPORTED, "star join: no single-column join on a fact-table column to filter with");
+    p->main_stage = p->lookups[(size_t)main].stage;
+    p->probe_key_col = p->lookups[(size_t)main].key[0].col;
+    if (p->ranges.size() > 1) PG_FAIL(PG_EUNSUPPORTED, "star join: at most one range predicate on the fact table");
+
+    std::vector<bool> used(p->origin_slot.size(), false);
+    auto mark = [&](const HRef &h) { used[(size_t)h.origin] = true; };
+    for (auto &lk : p->lookups) for (int k = 0; k < lk.nkey; k++) mark(lk.key[k]);
+
+    // group keys -> dense index parts
+    if (aggn.groups.empty() || aggn.groups.size() > STAR_MAXPART) PG_FAIL(PG_EUNSUPPORTED, "star join: 1..%d group keys", STAR_MAXPART);
+    i64 ng = 1;
+    for (auto &g0 : aggn.groups) {
+        const Expr *ge = strip_value_preserving_casts(&g0);
+        JoinAggPipeline::HPart hp;
+        if (ge->kind == PG_TK_FUNC && ge->fn == PG_FN_EXTRACT && ge->args.size() == 2) {
+            const Expr *what = strip_value_preserving_casts(&ge->args[0]), *arg = strip_value_preserving_casts(&ge->args[1]);
+            if (what->kind != PG_TK_STR || what->str != "year") PG_FAIL(PG_EUNSUPPORTED, "only EXTRACT(year ...) is off-loaded");
+            ge = arg;
+            hp.fn = 1;
+        }
+        if (ge->kind != PG_TK_COL || !locate(top, ge->idx, &hp.v)) PG_FAIL(PG_EUNSUPPORTED, "star join: group key is not a reachable column");
+        const Column &cc = p->tab(p->origin_slot[(size_t)hp.v.origin])->cols[(size_t)hp.v.col];
+        if (cc.has_nulls) PG_FAIL(PG_EUNSUPPORTED, "star join: nullable group key");
+        if (hp.fn == 1) {
+            if (cc.type != PG_T_DATE32) PG_FAIL(PG_EUNSUPPORTED, "EXTRACT(year) of a non-date column");
+            hp.lo = host_year_of_days(cc.vmin);
+            hp.n = (int)(host_year_of_days(cc.vmax) - hp.lo + 1);
+            hp.type = PG_T_INT32;
+        } else if (cc.type == PG_T_DICT8 || cc.type == PG_T_CHAR1) {
+            hp.lo = 0;
+            hp.n = cc.type == PG_T_DICT8 ? std::max<int>((int)cc.dict.size(), 1) : 256;
+            hp.type = cc.type;
+        } else if (is_int_family(cc.type) && cc.stats_ok && (i128)cc.vmax - (i128)cc.vmin + 1 <= STAR_MAXGROUPS) {
+            hp.lo = cc.vmin;
+            hp.n = (int)(cc.vmax - cc.vmin + 1);
+            hp.type = cc.type;
+        } else {
+            PG_FAIL(PG_EUNSUPPORTED, "star join: group key domain is not small and dense");
+        }
+        ng *= hp.n;
+        if (ng > STAR_MAXGROUPS) PG_FAIL(PG_EUNSUPPORTED, "star join: more than %d dense groups", STAR_MAXGROUPS);
+        mark(hp.v);
+        p->sparts.push_back(hp);
+    }
+    p->star_ngroups = (int)ng;
+
+    // aggregates: one SUM (signed sum of products) and/or COUNT
+    p->aggs = aggn.aggs;
+    int nsum = 0;
+    const AggExpr *sum = nullptr;
+    for (auto &ae : aggn.aggs) {
+        if (ae.fn == PG_AGG_COUNT) continue;
+        if (ae.fn != PG_AGG_SUM || (ae.ltype != PG_LT_DECIMAL && ae.ltype != PG_LT_HUGEINT)) PG_FAIL(PG_EUNSUPPORTED, "star join: sum and count only");
+        nsum++;
+        sum = &ae;
+    }
+    if (nsum > 1) PG_FAIL(PG_EUNSUPPORTED, "star join: a single sum");
+    if (sum) {
+        struct Raw { std::vector<const Expr *> leaves; int sign; };
+        std::vector<Raw> raw;
+        std::vector<std::pair<const Expr *, int>> todo{{&sum->arg, 1}};
+        while (!todo.empty()) {
+            auto [e0, sg] = todo.back();
+            todo.pop_back();
+            const Expr *e = strip_value_preserving_casts(e0);
+            if (e->kind == PG_TK_FUNC && (e->fn == PG_FN_SUB || e->fn == PG_FN_ADD) && e->args.size() == 2) {
+                const Expr *l = strip_value_preserving_casts(&e->args[0]), *r = strip_value_preserving_casts(&e->args[1]);
+                const bool affine = (l->kind == PG_TK_CONST && r->kind == PG_TK_COL) || (l->kind == PG_TK_COL && r->kind == PG_TK_CONST);
+                if (!affine) { todo.push_back({&e->args[1], e->fn == PG_FN_SUB ? -sg : sg}); todo.push_back({&e->args[0], sg}); continue; }
+            }
+            Raw rw;
+            rw.sign = sg;
+            std::vector<const Expr *> prod{e};
+            while (!prod.empty()) {
+                const Expr *m = strip_value_preserving_casts(prod.back());
+                prod.pop_back();
+                if (m->kind == PG_TK_FUNC && m->fn == PG_FN_MUL && m->args.size() == 2) { prod.push_back(&m->args[1]); prod.push_back(&m->args[0]); }
+                else rw.leaves.push_back(m);
+            }
+            raw.push_back(rw);
+        }
+        if (raw.empty() || raw.size() > STAR_MAXTERM) PG_FAIL(PG_EUNSUPPORTED, "star join: the sum has %zu terms (max %d)", raw.size(), STAR_MAXTERM);
+        std::vector<int> tscale;
+        i128 worst = 0;
+        for (auto &rw : raw) {
+            if (rw.leaves.empty() || rw.leaves.size() > 3) PG_FAIL(PG_EUNSUPPORTED, "star join: a product of %zu factors", rw.leaves.size());
+            JoinAggPipeline::HTerm ht;
+            ht.nfac = (int)rw.leaves.size();
+            int scale = 0;
+            i128 bound = 1;
+            for (size_t f = 0; f < rw.leaves.size(); f++) {
+                const Expr *e = rw.leaves[f], *ce = nullptr, *ke = nullptr;
+                int sgn = 1;
+                bool negk = false;
+                if (e->kind == PG_TK_COL) ce = e;
+                else if (e->kind == PG_TK_FUNC && (e->fn == PG_FN_ADD || e->fn == PG_FN_SUB) && e->args.size() == 2) {
+                    const Expr *l = strip_value_preserving_casts(&e->args[0]), *r = strip_value_preserving_casts(&e->args[1]);
+                    if (l->kind == PG_TK_CONST && r->kind == PG_TK_COL) { ke = l; ce = r; sgn = e->fn == PG_FN_ADD ? 1 : -1; }
+                    else if (l->kind == PG_TK_COL && r->kind == PG_TK_CONST) { ce = l; ke = r; negk = e->fn == PG_FN_SUB; }
+                } else if (e->kind == PG_TK_FUNC && e->fn == PG_FN_CAST && e->args.size() == 1) {
+                    // INTEGER -> DECIMAL cast of a column keeps the integer value at value scale 0 (tryCastInt32ToDecimal, function_cast.go:337-347)
+                    const Expr *a = strip_value_preserving_casts(&e->args[0]);
+                    if (a->kind == PG_TK_COL && e->ltype == PG_LT_DECIMAL && (a->ltype == PG_LT_INTEGER || a->ltype == PG_LT_BIGINT)) ce = a;
+                }
+                if (!ce || !locate(top, ce->idx, &ht.fac[f])) PG_FAIL(PG_EUNSUPPORTED, "star join: factor is not (constant +/- reachable column)");
+                const Column &cc = p->tab(p->origin_slot[(size_t)ht.fac[f].origin])->cols[(size_t)ht.fac[f].col];
+                if (!is_int_family(cc.type) || cc.type == PG_T_DATE32 || cc.has_nulls) PG_FAIL(PG_EUNSUPPORTED, "star join: factor column type");
+                const int cs = cc.type == PG_T_DECIMAL64 ? cc.scale : 0;
+                i64 k = 0;
+                if (ke && !const_at_scale(ke, cs, &k)) PG_FAIL(PG_EUNSUPPORTED, "constant does not fit the column scale");
+                ht.fc[f] = negk ? -k : k;
+                ht.fs[f] = sgn;
+                scale += cs;
+                i128 lo = (i128)ht.fc[f] + (i128)sgn * cc.vmin, hi = (i128)ht.fc[f] + (i128)sgn * cc.vmax;
+                i128 m = std::max(lo < 0 ? -lo : lo, hi < 0 ? -hi : hi);
+                bound *= m > 1 ? m : 1;
+                mark(ht.fac[f]);
+            }
+            ht.mul = rw.sign;
+            tscale.push_back(scale);
+            p->sterms.push_back(ht);
+            worst += bound;
+        }
+        // Sub/Add of decimals: the result scale is the larger one (govalues Add/Sub); align the coarser terms
+        int maxs = 0;
+        for (int s : tscale) maxs = std::max(maxs, s);
+        i128 scaled_worst = 0;
+        for (size_t i = 0; i < p->sterms.size(); i++) {
+            i128 m = 1;
+            for (int s = tscale[i]; s < maxs; s++) m *= 10;
+            p->sterms[i].mul *= (i64)m;
+            scaled_worst = std::max(scaled_worst, worst * m);
+        }
+        if (sum->ltype == PG_LT_HUGEINT && maxs != 0) PG_FAIL(PG_EUNSUPPORTED, "integer sum over a scaled value");
+        p->star_scale = maxs;
+        // a block's shared-memory partial is int64: it receives at most its share of the fact rows (grid-stride over the hits)
+        const i64 threads = (i64)ctx().prop.multiProcessorCount * 8 * 256;
+        const i64 per_block = ((std::max<i64>(st->nrows, 1) + threads - 1) / threads) * 256;
+        if (scaled_worst * (i128)per_block >= ((i128)1 << 63)) PG_FAIL(PG_EUNSUPPORTED, "a block's partial group sum could exceed int64");
+    }
+    for (size_t o = 1; o < used.size(); o++) p->stages[(size_t)p->lookups[o - 1].stage]->payload_needed = used[o];
+    for (auto &o : aggn.outs) {
+        if (o.first == 0 && (o.second < 0 || o.second >= (int)p->sparts.size())) PG_FAIL(PG_EUNSUPPORTED, "bad group output index");
+        if (o.first == 1 && (o.second < 0 || o.second >= (int)aggn.aggs.size())) PG_FAIL(PG_EUNSUPPORTED, "bad aggregate output index");
+        if (o.first != 0 && o.first != 1) PG_FAIL(PG_EUNSUPPORTED, "bad output kind");
+    }
+    p->outs = aggn.outs;
+    if (aggn.having.size()) PG_FAIL(PG_EUNSUPPORTED, "star join: HAVING");
+    // bytes: the filter pass streams the fact key (+ predicate) column; everything else is gathered per hit
+    p->main_bytes = st->nrows * type_size(st->cols[(size_t)p->probe_key_col].type);
+    for (auto &r : p->ranges) p->main_bytes += st->nrows * type_size(st->cols[(size_t)r.col].type);
+    p->algorithmic_bytes = p->main_bytes;
+    for (auto &sp : p->stages) {
+        const pg_table *bt = p->tab(sp->src_slot);
+        p->algorithmic_bytes += bt->nrows * type_size(bt->cols[(size_t)sp->ins_key_col].type);
+    }
+    if (ctx().world > 1 && st->dist != PG_DIST_REPLICATED) {
+        // sharded fact table: every build side must be whole on every rank, or sharded on the same key ranges
+        for (auto &lk : p->lookups) {
+            const Stage &S = *p->stages[(size_t)lk.stage];
+            const pg_table *bt = p->tab(S.src_slot);
+            if (bt->dist == PG_DIST_REPLICATED) continue;
+            if (lk.nkey != 1 || lk.key[0].origin != 0) PG_FAIL(PG_EUNSUPPORTED, "star join: a sharded build side must be keyed by a fact-table column");
+            const int W = ctx().world;
+            const Column &pc = st->cols[(size_t)lk.key[0].col], &bc = bt->cols[(size_t)S.ins_key_col];
+            i64 mine[6] = {pc.vmin, pc.vmax, st->nrows, bc.vmin, bc.vmax, bt->nrows};
+            DevBuf ds, dr;
+            PG_TRY(ds.alloc(sizeof mine));
+            PG_TRY(dr.alloc(sizeof mine * (size_t)W));
+            PG_CUDA(cudaMemcpyAsync(ds.p, mine, sizeof mine, cudaMemcpyHostToDevice, ctx().stream));
+            PG_TRY(comm_allgather(ds.p, dr.p, sizeof mine, ctx().stream));
+            std::vector<i64> all(6 * (size_t)W);
+            PG_CUDA(cudaMemcpyAsync(all.data(), dr.p, sizeof mine * (size_t)W, cudaMemcpyDeviceToHost, ctx().stream));
+            PG_CUDA(cudaStreamSynchronize(ctx().stream));
+            for (int r = 0; r < W; r++)
+                for (int q = 0; q < W; q++) {
+                    if (r == q || all[(size_t)r * 6 + 2] == 0 || all[(size_t)q * 6 + 5] == 0) continue;
+                    if (all[(size_t)r * 6] <= all[(size_t)q * 6 + 4] && all[(size_t)q * 6 + 3] <= all[(size_t)r * 6 + 1])
+                        PG_FAIL(PG_EUNSUPPORTED, "sharded join sides are not co-partitioned on the key (needs the all-to-all shuffle path)");
+                }
+        }
+    }
+    PG_TRY(p->d_counters.alloc(64));
+    PG_TRY(p->d_overflow.alloc(4));
+    std::string ex = "StarJoin[existence filter -> per-hit lookups -> dense shared-memory groups] kernel=filter_hits_kernel+hits_star_kernel fact=" + st->name + " joins:";
+    for (size_t l = 0; l < p->lookups.size(); l++) {
+        const Stage &S = *p->stages[(size_t)p->lookups[l].stage];
+        char b[200];
+        snprintf(b, sizeof b, " %s(%d-col key%s%s)", p->tab(S.src_slot)->name.c_str(), p->lookups[l].nkey, (int)l == main ? ", filter pass" : "",
+                 S.payload_needed ? ", payload" : ", existence");
+        ex += b;
+    }
+    char b[96];
+    snprintf(b, sizeof b, " groups=%d (dense) terms=%zu", p->star_ngroups, p->sterms.size());
+    p->explain = ex + b;
+    *out = std::move(p);
+    return PG_OK;
+}
+
 // `join` is the aggregate's input: an INNER join tree, or (high-cardinality group-by straight over a
 // table) a SCAN whose filters the caller already merged.
 int build_join_agg(pg_plan *plan, const Node &aggn, const Node &top, std::unique_ptr<Pipeline> *out, bool nested)
@@ -1203,6 +1668,11 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &top, std::unique
         jn = &jn->children[0];
     }
     const Node &join = *jn;
+    if (join.op == PG_OP_JOIN && pending.empty() && !nested) {
+        const Node *ps = &join.children[0];
+        while (ps->op == PG_OP_FILTER) ps = &ps->children[0];
+        if (ps->op == PG_OP_JOIN) return build_star(plan, aggn, top, std::move(p), out);      // several joins on the fact-table side
+    }
     p->no_join = join.op == PG_OP_SCAN;
     if (!p->no_join) {
         if (join.jointype != PG_JOIN_INNER && join.jointype != PG_JOIN_SEMI && join.jointype != PG_JOIN_ANTI)

@@ -243,7 +243,11 @@ struct PipeParams {
     JoinTable probe;
     // SINK_INSERT
     TypedCol ins_key;
+    TypedCol ins_key2;       // p != null: two-column key, (k << 32) | (k2 & 0xffffffff)
     JoinTable ins;
+    // string predicates on VARCHAR columns of the source (build side `p_name like '%pink%'`)
+    int nlike;
+    GenLike like[GEN_MAXLIKE];
     // SINK_GROUP
     GroupTable gt;
     GroupSpec gs;
@@ -339,6 +343,7 @@ pipeline_kernel(const PipeParams p)
             i64 v = load_typed(p.pred[k].col, row);
             ok = typed_valid(p.pred[k].col, row) && v >= p.pred[k].lo && v <= p.pred[k].hi;   // NULL is never selected
         }
+        for (int k = 0; k < p.nlike && ok; k++) ok = gen_like_pass(p.like[k], row);
         if (!ok) continue;
         n_pass++;
         if (p.nextra && !extras_pass(p, row)) continue;
@@ -346,7 +351,9 @@ pipeline_kernel(const PipeParams p)
             if ((SINK == SINK_INSERT || SINK == SINK_BITMAP) && !typed_valid(p.ins_key, row)) return;   // NULL keys are not built (join_table.go:152-195)
             n_join++;
             if (SINK == SINK_INSERT) {
-                jt_insert(p.ins, load_typed(p.ins_key, row), (u64)row);
+                i64 key = load_typed(p.ins_key, row);
+                if (p.ins_key2.p) key = (key << 32) | (load_typed(p.ins_key2, row) & 0xffffffffLL);
+                jt_insert(p.ins, key, (u64)row);
             } else if (SINK == SINK_BITMAP) {
                 u64 off = (u64)(load_typed(p.ins_key, row) - p.ins.bm_min);
                 atomicOr(p.ins.bitmap + (off >> 5), 1u << (off & 31));
@@ -844,7 +851,9 @@ hits_sink_kernel(const PipeParams p)
         auto sink = [&](u64 build_row) {
             n_join++;
             if (SINK == SINK_INSERT) {
-                jt_insert(p.ins, load_typed(p.ins_key, row), (u64)row);
+                i64 key = load_typed(p.ins_key, row);
+                if (p.ins_key2.p) key = (key << 32) | (load_typed(p.ins_key2, row) & 0xffffffffLL);
+                jt_insert(p.ins, key, (u64)row);
             } else if (SINK == SINK_BITMAP) {
                 u64 off = (u64)(load_typed(p.ins_key, row) - p.ins.bm_min);
                 atomicOr(p.ins.bitmap + (off >> 5), 1u << (off & 31));
@@ -868,6 +877,129 @@ hits_sink_kernel(const PipeParams p)
     }
     n_join = (unsigned long long)warp_sum((i64)n_join);
     if ((threadIdx.x & 31) == 0 && n_join) atomicAdd(&p.counters[1], n_join);
+}
+
+// ---------------------------------------------------------------- star joins --
+// A fact-table pipeline with SEVERAL INNER joins on the way to a low-cardinality group-by (TPC-H Q9:
+// lineitem x part x supplier x partsupp x orders x nation, 175 groups).  The most selective existence
+// join is the filter pass (filter_hits_kernel); this sink then resolves the other joins for each hit --
+// key from the fact row or from an earlier lookup's build row, one or two key columns, rank index or
+// hash table -- evaluates sum-of-products terms over the joined rows and adds them to a block-private
+// shared-memory table indexed by the dense group id; blocks flush to the global table at the end.
+constexpr int STAR_MAXLOOKUP = 5, STAR_MAXTERM = 2, STAR_MAXPART = 2, STAR_MAXGROUPS = 4096;
+struct StarLookup {
+    int nkey;                 // 1, or 2: key = (k0 << 32) | (k1 & 0xffffffff)
+    ValRef key[2];            // from_build: 0 = fact row, j > 0 = build row of lookup j-1
+    JoinTable jt;
+    int existence;            // payload-free: the exact bitmap answers
+};
+struct StarPart {             // dense group index part: f(value) - lo in [0, n)
+    ValRef v;
+    int fn;                   // 0: the value itself, 1: calendar year of a DATE (days since 1970-01-01)
+    i64 lo;
+    int n;
+};
+struct StarTerm {             // mul * prod(fc + fs * value)
+    int nfac;
+    ValRef fac[3];
+    i64 fc[3];
+    int fs[3];
+    i64 mul;
+};
+struct StarParams {
+    const unsigned *hits;
+    const unsigned long long *hit_count;
+    int nlookup;
+    StarLookup lk[STAR_MAXLOOKUP];
+    int nparts, ngroups;
+    StarPart part[STAR_MAXPART];
+    int nterm;
+    StarTerm term[STAR_MAXTERM];
+    unsigned long long *gsum, *gsum_hi, *gcnt;   // [ngroups] global accumulators: 128-bit sums (two words) and row counts
+    unsigned long long *counters;             // [1] joined rows, [2] hits with more than one match in some lookup
+};
+
+// civil year of days-since-epoch (proleptic Gregorian; the reference extracts it through time.Time, common/date.go)
+__device__ __forceinline__ i64 year_of_days(i64 z)
+{
+    z += 719468;
+    const i64 era = (z >= 0 ? z : z - 146096) / 146097;
+    const i64 doe = z - era * 146097;
+    const i64 yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+    const i64 y = yoe + era * 400;
+    const i64 doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
+    const i64 mp = (5 * doy + 2) / 153;
+    return y + (mp >= 10 ? 1 : 0);
+}
+
+static __global__ void __launch_bounds__(256)
+hits_star_kernel(const StarParams sp)
+{
+    extern __shared__ unsigned long long s_star[];      // [ngroups] sums, [ngroups] counts
+    unsigned long long *s_sum = s_star, *s_cnt = s_star + sp.ngroups;
+    for (int i = threadIdx.x; i < 2 * sp.ngroups; i += blockDim.x) s_star[i] = 0;
+    __syncthreads();
+    const unsigned long long n = *sp.hit_count;
+    unsigned long long n_join = 0, n_multi = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        i64 rows[STAR_MAXLOOKUP + 1];
+        rows[0] = (i64)sp.hits[i];
+        auto val = [&](const ValRef &r) { return load_typed(r.col, rows[r.from_build]); };
+        bool ok = true;
+#pragma unroll
+        for (int l = 0; l < STAR_MAXLOOKUP; l++) {
+            if (l >= sp.nlookup || !ok) continue;
+            const StarLookup &L = sp.lk[l];
+            i64 key = val(L.key[0]);
+            if (L.nkey == 2) key = (key << 32) | (val(L.key[1]) & 0xffffffffLL);
+            rows[l + 1] = -1;
+            if (L.existence) {
+                ok = bitmap_test(L.jt, key);
+            } else {
+                int matches = 0;
+                jt_probe(L.jt, key, [&](u64 r) { rows[l + 1] = (i64)r; matches++; });
+                ok = matches > 0;
+                n_multi += matches > 1 ? 1 : 0;
+            }
+        }
+        if (!ok) continue;
+        n_join++;
+        int g = 0;
+#pragma unroll
+        for (int k = 0; k < STAR_MAXPART; k++) {
+            if (k >= sp.nparts) continue;
+            i64 v = val(sp.part[k].v);
+            if (sp.part[k].fn == 1) v = year_of_days(v);
+            g = g * sp.part[k].n + (int)(v - sp.part[k].lo);
+        }
+        i64 amount = 0;
+#pragma unroll
+        for (int t = 0; t < STAR_MAXTERM; t++) {
+            if (t >= sp.nterm) continue;
+            i64 x = sp.term[t].mul;
+            for (int f = 0; f < sp.term[t].nfac; f++) x *= sp.term[t].fc[f] + sp.term[t].fs[f] * val(sp.term[t].fac[f]);
+            amount += x;
+        }
+        atomicAdd(&s_sum[g], (unsigned long long)amount);
+        atomicAdd(&s_cnt[g], 1ULL);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < sp.ngroups; i += blockDim.x) {
+        if (s_cnt[i]) {
+            // the block's exact int64 partial (the host proved it cannot overflow) goes into a 128-bit total
+            const unsigned long long x = s_sum[i];
+            const unsigned long long old = atomicAdd(&sp.gsum[i], x);
+            const long long hi = (long long)(old + x < old ? 1 : 0) - ((long long)x < 0 ? 1 : 0);
+            if (hi) atomicAdd(&sp.gsum_hi[i], (unsigned long long)hi);
+            atomicAdd(&sp.gcnt[i], s_cnt[i]);
+        }
+    }
+    n_join = (unsigned long long)warp_sum((i64)n_join);
+    n_multi = (unsigned long long)warp_sum((i64)n_multi);
+    if ((threadIdx.x & 31) == 0) {
+        if (n_join) atomicAdd(&sp.counters[1], n_join);
+        if (n_multi) atomicAdd(&sp.counters[2], n_multi);
+    }
 }
 
 // ---------------------------------------------------------------- rank index build --

@@ -18,6 +18,7 @@ struct ResCol {
     std::vector<uint8_t> data;
     std::vector<uint8_t> valid;     // one byte per row (1 = not NULL); empty = no NULLs in this column
     std::vector<char> heap;         // PG_T_VARCHAR: the bytes the pg_string rows point into (sized once, never regrown)
+    std::vector<std::string> dict;  // PG_T_DICT8 results that may be ORDER BY keys: code -> string (ordering is by the string)
     void push_null(size_t rows_before, size_t elem)
     {
         if (valid.empty()) valid.assign(rows_before, 1);

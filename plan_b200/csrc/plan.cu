@@ -69,6 +69,11 @@ static int sort_result(pg_result *r, const std::vector<std::pair<int, int>> &ord
                 if (x != y) return o.second ? x > y : x < y;
                 continue;
             }
+            if (c.type == PG_T_DICT8 && !c.dict.empty()) {       // VARCHAR key: byte order of the strings, not of the codes
+                const std::string &x = c.dict[c.data[(size_t)a]], &y = c.dict[c.data[(size_t)b]];
+                if (x != y) return o.second ? x > y : x < y;
+                continue;
+            }
             i128 x = order_key(c, a), y = order_key(c, b);
             if (x != y) return o.second ? x > y : x < y;
         }

@@ -121,6 +121,63 @@ static i64 num_customers(double sf) { return (i64)(150000.0 * sf + 0.5); }
 static i64 num_parts(double sf) { return (i64)(200000.0 * sf + 0.5); }
 static i64 num_supp(double sf) { i64 n = (i64)(10000.0 * sf + 0.5); return n < 4 ? 4 : n; }
 
+// ---- part / supplier / partsupp (TPC-H Q9's dimension tables) --------------------------------
+constexpr i64 SD_P_NAME = 709314158, SD_PS_SCST = 1051288424, SD_S_NTRG = 110356601;
+constexpr int TG_NAME_SLOT = 56;
+__device__ const char tg_colors[92][12] = {
+    "almond", "antique", "aquamarine", "azure", "beige", "bisque", "black", "blanched", "blue", "blush", "brown", "burlywood",
+    "burnished", "chartreuse", "chiffon", "chocolate", "coral", "cornflower", "cornsilk", "cream", "cyan", "dark", "deep", "dim",
+    "dodger", "drab", "firebrick", "floral", "forest", "frosted", "gainsboro", "ghost", "goldenrod", "green", "grey", "honeydew",
+    "hot", "indian", "ivory", "khaki", "lace", "lavender", "lawn", "lemon", "light", "lime", "linen", "magenta", "maroon", "medium",
+    "metallic", "midnight", "mint", "misty", "moccasin", "navajo", "navy", "olive", "orange", "orchid", "pale", "papaya", "peach",
+    "peru", "pink", "plum", "powder", "puff", "purple", "red", "rose", "rosy", "royal", "saddle", "salmon", "sandy", "seashell",
+    "sienna", "sky", "slate", "smoke", "snow", "spring", "steel", "tan", "thistle", "tomato", "turquoise", "violet", "wheat", "white",
+    "yellow"};
+
+// P_NAME: the identity permutation of the 92 colours shuffled with 92 draws of the part's own slice of
+// stream P_NAME_SD (swap a[k], a[UnifInt(k, 91)]), first five joined with blanks
+__global__ void tg_part_kernel(i64 n, int *__restrict__ p_partkey, char *__restrict__ names, uint8_t *__restrict__ name_len)
+{
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    i64 s = tg_mulmod(SD_P_NAME, tg_pow(16807, 92 * i));
+    uint8_t perm[92];
+    for (int k = 0; k < 92; k++) perm[k] = (uint8_t)k;
+    for (int k = 0; k < 92; k++) {
+        int src = (int)tg_draw(s, k, 91);
+        uint8_t t = perm[src]; perm[src] = perm[k]; perm[k] = t;
+    }
+    char *out = names + i * TG_NAME_SLOT;
+    int at = 0;
+    for (int w = 0; w < 5; w++) {
+        const char *c = tg_colors[perm[w]];
+        for (int j = 0; c[j]; j++) out[at++] = c[j];
+        if (w < 4) out[at++] = ' ';
+    }
+    name_len[i] = (uint8_t)at;
+    p_partkey[i] = (int)(i + 1);
+}
+
+__global__ void tg_supplier_kernel(i64 n, int *__restrict__ s_suppkey, int *__restrict__ s_nationkey)
+{
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    i64 s = tg_mulmod(SD_S_NTRG, tg_pow(16807, i));
+    s_suppkey[i] = (int)(i + 1);
+    s_nationkey[i] = (int)tg_draw(s, 0, 24);
+}
+
+__global__ void tg_partsupp_kernel(i64 nrows, i64 nsupp, int *__restrict__ ps_partkey, int *__restrict__ ps_suppkey, i64 *__restrict__ ps_supplycost)
+{
+    i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrows) return;
+    const i64 pk = r / 4 + 1, j = r % 4;
+    i64 s = tg_mulmod(SD_PS_SCST, tg_pow(16807, r));
+    ps_partkey[r] = (int)pk;
+    ps_suppkey[r] = (int)((pk + j * (nsupp / 4 + (pk - 1) / nsupp)) % nsupp + 1);
+    ps_supplycost[r] = tg_draw(s, 100, 100000);
+}
+
 }  // namespace pg
 
 using namespace pg;
@@ -268,6 +325,103 @@ int pg_tpch_customer(double sf, int64_t cust_lo, int64_t cust_hi, pg_table **cus
     }
     PG_TRY(pg_table_seal(t, cust_lo));
     *customer = t;
+    return PG_OK;
+}
+
+int pg_tpch_part(double sf, pg_table **part)
+{
+    Context &c = ctx();
+    if (!c.ready) PG_FAIL(PG_ESTATE, "pg_tpch_part: call pg_init first");
+    if (!part) PG_FAIL(PG_EINVAL, "pg_tpch_part: bad arguments");
+    PG_CUDA(cudaSetDevice(c.device));
+    pg_coldesc cd[PG_P_NCOLS] = {{"p_partkey", PG_T_INT32, 0, 0, 0, nullptr}, {"p_name", PG_T_VARCHAR, 55, 0, 0, nullptr}};
+    pg_table *t = nullptr;
+    PG_TRY(pg_table_create("part", PG_P_NCOLS, cd, &t));
+    const i64 n = num_parts(sf);
+    PG_TRY(pg_table_reserve(t, n));
+    DevBuf d_names, d_len;
+    PG_TRY(d_names.alloc((size_t)n * TG_NAME_SLOT));
+    PG_TRY(d_len.alloc((size_t)n));
+    tg_part_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c.stream>>>(n, (int *)t->cols[PG_P_PARTKEY].d_data, d_names.as<char>(), d_len.as<uint8_t>());
+    PG_CUDA(cudaGetLastError());
+    std::vector<char> h_names((size_t)n * TG_NAME_SLOT);
+    std::vector<uint8_t> h_len((size_t)n);
+    PG_CUDA(cudaMemcpyAsync(h_names.data(), d_names.p, h_names.size(), cudaMemcpyDeviceToHost, c.stream));
+    PG_CUDA(cudaMemcpyAsync(h_len.data(), d_len.p, h_len.size(), cudaMemcpyDeviceToHost, c.stream));
+    PG_CUDA(cudaStreamSynchronize(c.stream));
+    PG_TRY(pg_table_set_rows(t, n));
+    Column &nm = t->cols[PG_P_NAME];          // VARCHAR columns live on the host (plus a device copy made at seal)
+    nm.h_off.resize((size_t)n + 1);
+    size_t total = 0;
+    for (i64 i = 0; i < n; i++) { nm.h_off[(size_t)i] = (int64_t)total; total += h_len[(size_t)i]; }
+    nm.h_off[(size_t)n] = (int64_t)total;
+    nm.h_bytes.resize(total);
+    for (i64 i = 0; i < n; i++) memcpy(&nm.h_bytes[(size_t)nm.h_off[(size_t)i]], h_names.data() + (size_t)i * TG_NAME_SLOT, h_len[(size_t)i]);
+    PG_TRY(pg_table_seal(t, 0));
+    *part = t;
+    return PG_OK;
+}
+
+int pg_tpch_supplier(double sf, pg_table **supplier)
+{
+    Context &c = ctx();
+    if (!c.ready) PG_FAIL(PG_ESTATE, "pg_tpch_supplier: call pg_init first");
+    if (!supplier) PG_FAIL(PG_EINVAL, "pg_tpch_supplier: bad arguments");
+    PG_CUDA(cudaSetDevice(c.device));
+    pg_coldesc cd[PG_S_NCOLS] = {{"s_suppkey", PG_T_INT32, 0, 0, 0, nullptr}, {"s_nationkey", PG_T_INT32, 0, 0, 0, nullptr}};
+    pg_table *t = nullptr;
+    PG_TRY(pg_table_create("supplier", PG_S_NCOLS, cd, &t));
+    const i64 n = num_supp(sf);
+    PG_TRY(pg_table_reserve(t, n));
+    tg_supplier_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(n, (int *)t->cols[PG_S_SUPPKEY].d_data, (int *)t->cols[PG_S_NATIONKEY].d_data);
+    PG_CUDA(cudaGetLastError());
+    PG_CUDA(cudaStreamSynchronize(c.stream));
+    PG_TRY(pg_table_set_rows(t, n));
+    PG_TRY(pg_table_seal(t, 0));
+    *supplier = t;
+    return PG_OK;
+}
+
+int pg_tpch_partsupp(double sf, pg_table **partsupp)
+{
+    Context &c = ctx();
+    if (!c.ready) PG_FAIL(PG_ESTATE, "pg_tpch_partsupp: call pg_init first");
+    if (!partsupp) PG_FAIL(PG_EINVAL, "pg_tpch_partsupp: bad arguments");
+    PG_CUDA(cudaSetDevice(c.device));
+    pg_coldesc cd[PG_PS_NCOLS] = {{"ps_partkey", PG_T_INT32, 0, 0, 0, nullptr}, {"ps_suppkey", PG_T_INT32, 0, 0, 0, nullptr},
+                                  {"ps_supplycost", PG_T_DECIMAL64, 15, 2, 0, nullptr}};
+    pg_table *t = nullptr;
+    PG_TRY(pg_table_create("partsupp", PG_PS_NCOLS, cd, &t));
+    const i64 np = num_parts(sf), n = 4 * np;
+    PG_TRY(pg_table_reserve(t, n));
+    tg_partsupp_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(n, num_supp(sf), (int *)t->cols[PG_PS_PARTKEY].d_data,
+                                                                        (int *)t->cols[PG_PS_SUPPKEY].d_data, (i64 *)t->cols[PG_PS_SUPPLYCOST].d_data);
+    PG_CUDA(cudaGetLastError());
+    PG_CUDA(cudaStreamSynchronize(c.stream));
+    PG_TRY(pg_table_set_rows(t, n));
+    PG_TRY(pg_table_seal(t, 0));
+    *partsupp = t;
+    return PG_OK;
+}
+
+int pg_tpch_nation(pg_table **nation)
+{
+    Context &c = ctx();
+    if (!c.ready) PG_FAIL(PG_ESTATE, "pg_tpch_nation: call pg_init first");
+    if (!nation) PG_FAIL(PG_EINVAL, "pg_tpch_nation: bad arguments");
+    static const char *names[25] = {"ALGERIA", "ARGENTINA", "BRAZIL", "CANADA", "EGYPT", "ETHIOPIA", "FRANCE", "GERMANY", "INDIA", "INDONESIA",
+                                    "IRAN", "IRAQ", "JAPAN", "JORDAN", "KENYA", "MOROCCO", "MOZAMBIQUE", "PERU", "CHINA", "ROMANIA",
+                                    "SAUDI ARABIA", "VIETNAM", "RUSSIA", "UNITED KINGDOM", "UNITED STATES"};
+    pg_coldesc cd[PG_N_NCOLS] = {{"n_nationkey", PG_T_INT32, 0, 0, 0, nullptr}, {"n_name", PG_T_DICT8, 0, 0, 25, names}};
+    pg_table *t = nullptr;
+    PG_TRY(pg_table_create("nation", PG_N_NCOLS, cd, &t));
+    int32_t keys[25];
+    uint8_t codes[25];
+    for (int i = 0; i < 25; i++) { keys[i] = i; codes[i] = (uint8_t)i; }
+    const void *cols[2] = {keys, codes};
+    PG_TRY(pg_table_append(t, 25, cols, nullptr));
+    PG_TRY(pg_table_seal(t, 0));
+    *nation = t;
     return PG_OK;
 }
 

@@ -35,6 +35,15 @@ ORDERS = [("o_orderkey", L.PG_T_INT64, 0, 0, None), ("o_custkey", L.PG_T_INT32, 
 CUSTOMER = [("c_custkey", L.PG_T_INT32, 0, 0, None), ("c_mktsegment", L.PG_T_DICT8, 0, 0, SEGMENTS),
             ("c_nationkey", L.PG_T_INT32, 0, 0, None), ("c_name", L.PG_T_VARCHAR, 25, 0, None)]
 
+NATIONS = ["ALGERIA", "ARGENTINA", "BRAZIL", "CANADA", "EGYPT", "ETHIOPIA", "FRANCE", "GERMANY", "INDIA", "INDONESIA", "IRAN", "IRAQ",
+           "JAPAN", "JORDAN", "KENYA", "MOROCCO", "MOZAMBIQUE", "PERU", "CHINA", "ROMANIA", "SAUDI ARABIA", "VIETNAM", "RUSSIA",
+           "UNITED KINGDOM", "UNITED STATES"]          # n_nationkey order (dbgen nations distribution)
+PART = [("p_partkey", L.PG_T_INT32, 0, 0, None), ("p_name", L.PG_T_VARCHAR, 55, 0, None)]
+SUPPLIER = [("s_suppkey", L.PG_T_INT32, 0, 0, None), ("s_nationkey", L.PG_T_INT32, 0, 0, None)]
+PARTSUPP = [("ps_partkey", L.PG_T_INT32, 0, 0, None), ("ps_suppkey", L.PG_T_INT32, 0, 0, None),
+            ("ps_supplycost", L.PG_T_DECIMAL64, 15, 2, None)]
+NATION = [("n_nationkey", L.PG_T_INT32, 0, 0, None), ("n_name", L.PG_T_DICT8, 0, 0, NATIONS)]
+
 DEC15_2 = K.DecimalType(15, 2)
 
 
@@ -54,8 +63,9 @@ class Schema:
     the full generated tables; a caller that uploads only the referenced columns passes the
     pruned layout so column references index the right positions."""
 
-    def __init__(self, lineitem=None, orders=None, customer=None):
-        self.tables = {"lineitem": lineitem or LINEITEM, "orders": orders or ORDERS, "customer": customer or CUSTOMER}
+    def __init__(self, lineitem=None, orders=None, customer=None, part=None, supplier=None, partsupp=None, nation=None):
+        self.tables = {"lineitem": lineitem or LINEITEM, "orders": orders or ORDERS, "customer": customer or CUSTOMER,
+                       "part": part or PART, "supplier": supplier or SUPPLIER, "partsupp": partsupp or PARTSUPP, "nation": nation or NATION}
         self.idx = {t: {c[0]: i for i, c in enumerate(cols)} for t, cols in self.tables.items()}
 
     def col(self, table, name, side=0):
@@ -295,6 +305,61 @@ def q18_plan(qty_gt=314, limit=100, schema=FULL):
     return PhysicalOperator(POT_Limit, Outputs=outs, Children=[order], Info=LimitOpInfo(limit))
 
 
+def q9_plan(word="pink", schema=FULL):
+    """TPC-H Q9 (cases/tpch/query/q9.sql) below its final Project, the subquery's expressions inlined in the aggregate:
+      Order(nation, o_year desc)
+        <- Agg(group by n_name, extract(year from o_orderdate); sum(l_extendedprice*(1-l_discount) - ps_supplycost*l_quantity))
+          <- Join(s_nationkey = n_nationkey) <- { Join(l_orderkey = o_orderkey) <- { Join(l_suppkey = ps_suppkey and l_partkey = ps_partkey)
+               <- { Join(l_suppkey = s_suppkey) <- { Join(l_partkey = p_partkey) <- { Scan(lineitem), Scan(part; p_name like '%word%') },
+                    Scan(supplier) }, Scan(partsupp) }, Scan(orders) }, Scan(nation) }
+    A left-deep stack with the fact table as the leftmost leaf (probe = larger side, optimizer_joinorder.go:1028-1030)."""
+    S = schema
+    B = K.LType(K.LTID_BOOLEAN)
+    I, BI, D, V = K.IntegerType(), K.BigintType(), K.DateType(), K.VarcharType()
+    LI = S.idx["lineitem"]
+    scan = lambda name, fl=None: PhysicalOperator(POT_Scan, Filters=fl or [], Info=ScanOpInfo(name))   # noqa: E731
+    line, supp, ps, orders, nation = scan("lineitem"), scan("supplier"), scan("partsupp"), scan("orders"), scan("nation")
+    part = scan("part", [func("like", B, S.col("part", "p_name"), const("%" + word + "%", V))])
+    base = [col(0, LI["l_orderkey"], BI), col(0, LI["l_partkey"], I), col(0, LI["l_suppkey"], I), col(0, LI["l_quantity"], I),
+            col(0, LI["l_extendedprice"], DEC15_2), col(0, LI["l_discount"], DEC15_2)]
+    types = [BI, I, I, I, DEC15_2, DEC15_2]
+    eq = lambda a, b: func("=", B, a, b)   # noqa: E731
+    j1 = PhysicalOperator(POT_Join, Children=[line, part], Outputs=list(base),
+                          Info=JoinOpInfo(JOIN_INNER, [eq(S.col("lineitem", "l_partkey", 0), S.col("part", "p_partkey", 1))]))
+    up = lambda ts: [col(0, i, t) for i, t in enumerate(ts)]   # noqa: E731
+    j2 = PhysicalOperator(POT_Join, Children=[j1, supp], Outputs=up(types) + [S.col("supplier", "s_nationkey", 1)],
+                          Info=JoinOpInfo(JOIN_INNER, [eq(col(0, 2, I), S.col("supplier", "s_suppkey", 1))]))
+    types = types + [I]
+    j3 = PhysicalOperator(POT_Join, Children=[j2, ps], Outputs=up(types) + [S.col("partsupp", "ps_supplycost", 1)],
+                          Info=JoinOpInfo(JOIN_INNER, [eq(col(0, 2, I), S.col("partsupp", "ps_suppkey", 1)),
+                                                       eq(col(0, 1, I), S.col("partsupp", "ps_partkey", 1))]))
+    types = types + [DEC15_2]
+    j4 = PhysicalOperator(POT_Join, Children=[j3, orders], Outputs=up(types) + [S.col("orders", "o_orderdate", 1)],
+                          Info=JoinOpInfo(JOIN_INNER, [eq(col(0, 0, BI), S.col("orders", "o_orderkey", 1))]))
+    types = types + [D]
+    j5 = PhysicalOperator(POT_Join, Children=[j4, nation], Outputs=up(types) + [S.col("nation", "n_name", 1)],
+                          Info=JoinOpInfo(JOIN_INNER, [eq(col(0, 6, I), S.col("nation", "n_nationkey", 1))]))
+    # amount: DECIMAL(18,4) product minus DECIMAL x cast(INTEGER) product (value scale 2), Sub -> scale 4
+    amount = func("-", K.DecimalType(18, 4), _disc_price(col(0, 4, DEC15_2), col(0, 5, DEC15_2)),
+                  func("*", K.DecimalType(18, 4), col(0, 7, DEC15_2), cast(col(0, 3, I), DEC15_2)))
+    sum_t = K.DecimalType(38, 4)
+    groups = [col(0, 9, V), func("extract", I, const("year", V), col(0, 8, D))]
+    outs = [col(0, 0, V), col(0, 1, I), col(1, 0, sum_t)]
+    agg = PhysicalOperator(POT_Agg, Outputs=outs, Children=[j5], Info=AggOpInfo([func("sum", sum_t, amount)], groups))
+    return PhysicalOperator(POT_Order, Outputs=outs, Children=[agg], Info=OrderOpInfo([(col(0, 0, V), False), (col(0, 1, I), True)]))
+
+
+def part_like_plan(pattern, schema=FULL):
+    """select count(p_partkey), sum(p_partkey) from part where p_name like <pattern>"""
+    S = schema
+    H = K.HugeintType()
+    scan = PhysicalOperator(POT_Scan, Info=ScanOpInfo("part"),
+                            Filters=[func("like", K.LType(K.LTID_BOOLEAN), S.col("part", "p_name"), const(pattern, K.VarcharType()))])
+    pk = S.col("part", "p_partkey")
+    aggs = [func("count", H, pk), func("sum", H, pk)]
+    return PhysicalOperator(POT_Agg, Outputs=[col(1, 0, H), col(1, 1, H)], Children=[scan], Info=AggOpInfo(aggs, []))
+
+
 def customer_filter_plan(filters, schema=FULL):
     """select count(*), sum(c_nationkey), sum(c_custkey) from customer where <filters>:
     a scan-aggregate over customer used to exercise string predicates (LIKE / NOT LIKE / = / <> on the
@@ -340,7 +405,20 @@ def generate_device_tables(sf, order_lo=0, order_hi=None, want=("lineitem", "ord
         hc = C.c_void_p()
         L.check(lib.pg_tpch_customer(sf, 0, lib.pg_tpch_num_customers(sf), C.byref(hc)))
         out["customer"] = DeviceTable("customer", hc, CUSTOMER)
+    for name, fn, schema in (("part", lib.pg_tpch_part, PART), ("supplier", lib.pg_tpch_supplier, SUPPLIER),
+                             ("partsupp", lib.pg_tpch_partsupp, PARTSUPP)):
+        if name in want:
+            h = C.c_void_p()
+            L.check(fn(sf, C.byref(h)))
+            out[name] = DeviceTable(name, h, schema)
+    if "nation" in want:
+        h = C.c_void_p()
+        L.check(lib.pg_tpch_nation(C.byref(h)))
+        out["nation"] = DeviceTable("nation", h, NATION)
     return out
+
+
+ALL_TABLES = ("lineitem", "orders", "customer", "part", "supplier", "partsupp", "nation")
 
 
 def upload_tables(host, global_offsets=None, schema=FULL):

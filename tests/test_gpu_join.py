@@ -433,3 +433,57 @@ def test_q18_sf01(pg, oracle, uploaded, sf01_host, qty_gt, limit):
         assert sorted(got, key=key) == sorted(want, key=key)
     else:
         assert got == want
+
+
+def _q9_rows(chunks):
+    rows = []
+    for c in chunks:
+        for r in range(c.Card()):
+            nat, yr, sm = c.Data[0], c.Data[1], c.Data[2].Data[r]
+            rows.append((nat.Dict[int(nat.Data[r])], int(yr.Data[r]), (-1 if sm["neg"] else 1) * int(sm["coef"])))
+    return rows
+
+
+def test_device_generator_q9_tables(pg, oracle):
+    """part / supplier / partsupp / nation generated in HBM == the dbgen-exact CPU generator; p_name is checked
+    through GPU LIKE counts (VARCHAR columns are not readable as flat arrays)."""
+    from plan_b200 import tpch as T
+    sf = 0.05
+    t = T.generate_device_tables(sf, want=("part", "supplier", "partsupp", "nation"))
+    try:
+        sup, ps = oracle.gen_supplier(sf), oracle.gen_partsupp(sf)
+        for k, v in sup.items():
+            assert np.array_equal(t["supplier"].read_column(k), v), k
+        for k, v in ps.items():
+            assert np.array_equal(t["partsupp"].read_column(k), v), k
+        assert list(t["nation"].read_column("n_nationkey")) == list(range(25))
+        for word in ("pink", "green", "almond", "yellow", "zzz"):
+            part = oracle.gen_part(sf, word)
+            chunks, _, _ = _run(T.part_like_plan("%" + word + "%"), t)
+            want = part["p_partkey"][part["p_name_like"]]
+            if len(want) == 0:
+                assert chunks == []
+            else:
+                h = lambda v: (int(v["upper"]) << 64) + int(v["lower"])   # noqa: E731
+                assert (h(chunks[0].Data[0].Data[0]), h(chunks[0].Data[1].Data[0])) == (len(want), int(want.astype(np.int64).sum()))
+    finally:
+        for x in t.values():
+            x.free()
+
+
+@pytest.mark.parametrize("word", ["pink", "green", "lace", "nosuchcolour"])
+def test_q9_sf005(pg, oracle, word):
+    """TPC-H Q9's shape (star join: five INNER joins on the lineitem spine, a two-column key, LIKE on the build
+    side, EXTRACT(year) group key, difference of products) against the oracle."""
+    from plan_b200 import tpch as T
+    sf = 0.05
+    t = T.generate_device_tables(sf, want=T.ALL_TABLES)
+    try:
+        chunks, stats, explain = _run(T.q9_plan(word), t)
+        assert "StarJoin" in explain
+        orders, line = oracle.gen_orders_lineitem(sf)
+        want = oracle.q9(oracle.gen_part(sf, word), oracle.gen_supplier(sf), oracle.gen_partsupp(sf), orders, line, like_word=word)
+        assert _q9_rows(chunks) == want
+    finally:
+        for x in t.values():
+            x.free()
