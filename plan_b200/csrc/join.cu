@@ -1438,6 +1438,23 @@ static int build_star(pg_plan *plan, const Node &aggn, const Node &top, std::uni
     p->main_stage = p->lookups[(size_t)main].stage;
     p->probe_key_col = p->lookups[(size_t)main].key[0].col;
     if (p->ranges.size() > 1) PG_FAIL(PG_EUNSUPPORTED, "star join: at most one range predicate on the fact table");
+    // Key equivalence: another join keyed (partly) by the SAME fact column as the filter join can only ever be
+    // probed with keys the filter join accepts, so its build side is reduced up front by an existence probe of the
+    // filter join's bitmap (Q9: partsupp rows whose ps_partkey is not a '%pink%' part are never inserted).
+    for (size_t l = 0; l < p->lookups.size(); l++) {
+        if ((int)l == main) continue;
+        const auto &lk = p->lookups[l];
+        Stage &S = *p->stages[(size_t)lk.stage];
+        if (S.has_probe || lk.stage < p->main_stage || p->stages[(size_t)p->main_stage]->ranges.empty()) continue;
+        for (int k = 0; k < lk.nkey; k++) {
+            if (lk.key[k].origin != 0 || lk.key[k].col != p->probe_key_col) continue;
+            S.has_probe = true;
+            S.probe_mode = 1;                                   // SEMI: existence only
+            S.probe_stage = p->main_stage;
+            S.probe_key_col = k == 0 ? S.ins_key_col : S.ins_key_col2;
+            break;
+        }
+    }
 
     std::vector<bool> used(p->origin_slot.size(), false);
     auto mark = [&](const HRef &h) { used[(size_t)h.origin] = true; };

@@ -129,11 +129,11 @@ def test_join_duplicate_build_keys_emit_every_pair(pg, oracle, sf01_host):
 
 
 def test_reference_golden_files_sf1_on_gpu(pg):
-    """Known-answer test: dbgen-equivalent SF1 data generated in HBM, Q1 / Q6 / Q3 through the
+    """Known-answer test: dbgen-equivalent SF1 data generated in HBM, Q1 / Q6 / Q3 / Q18 / Q9 through the
     C ABI, rendered with the reference's formatting rules == the reference's own result files
-    (/root/reference/cases/tpch/1g/plan/q{1,6,3}.txt, committed under tests/golden/)."""
+    (/root/reference/cases/tpch/1g/plan/q{1,6,3,18,9}.txt, committed under tests/golden/)."""
     from plan_b200 import compute as X, tpch as T
-    t = T.generate_device_tables(1.0)
+    t = T.generate_device_tables(1.0, want=T.ALL_TABLES)
     try:
         assert t["lineitem"].rows() == 6001215
         chunks, _, _ = _run(T.q6_plan(), t)
@@ -146,6 +146,8 @@ def test_reference_golden_files_sf1_on_gpu(pg):
         assert X.rows_text(X.order_limit(chunks, []), 4) == open(os.path.join(GOLDEN, "ref_sf1_q3.txt")).read()
         chunks, _, _ = _run(T.q18_plan(), t)            # cases/tpch/1g/plan/q18.txt
         assert X.rows_text(X.order_limit(chunks, []), 6) == open(os.path.join(GOLDEN, "ref_sf1_q18.txt")).read()
+        chunks, _, _ = _run(T.q9_plan(), t)             # cases/tpch/1g/plan/q9.txt (175 groups)
+        assert X.rows_text(X.order_limit(chunks, []), 3) == open(os.path.join(GOLDEN, "ref_sf1_q9.txt")).read()
     finally:
         for x in t.values():
             x.free()

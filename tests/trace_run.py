@@ -21,9 +21,11 @@ def main():
         D.init_comm(lib, L.check)
     n = lib.pg_tpch_num_orders(sf)
     lo, hi = D.shard_range(n, rank, world)
-    tables = T.generate_device_tables(sf, lo, hi)
-    tables["customer"].set_replicated()
-    plans = {"q6": T.q6_plan, "q1": T.q1_plan, "q3": T.q3_plan, "q3k": lambda: T.q3_topk_plan(10), "q18": T.q18_plan,
+    tables = T.generate_device_tables(sf, lo, hi, want=T.ALL_TABLES if "q9" in queries else ("lineitem", "orders", "customer"))
+    for name in ("customer", "part", "supplier", "partsupp", "nation"):
+        if name in tables:
+            tables[name].set_replicated()
+    plans = {"q6": T.q6_plan, "q1": T.q1_plan, "q3": T.q3_plan, "q3k": lambda: T.q3_topk_plan(10), "q18": T.q18_plan, "q9": T.q9_plan,
              "gok": lambda: T.groupby_plan(key="l_orderkey", value="l_quantity", having_gt=314, topk=100),
              "gpk": lambda: T.groupby_plan(key="l_partkey", value="l_quantity", topk=100),
              "gsk": lambda: T.groupby_plan(key="l_suppkey", value="l_extendedprice", topk=100)}
