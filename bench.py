@@ -321,11 +321,18 @@ def main():
     # ---- beside the metric (NOT part of `value`): the next queries SURVEY.md 8(d) names -----------
     also = {}
     if "q3" in queries and not args.no_extra:
-        extra_plans = {"q18": T.q18_plan,
+        extra_tables = dict(tables)
+        try:
+            extra_tables.update(T.generate_device_tables(args.sf, want=("part", "supplier", "partsupp", "nation")))
+            for name in ("part", "supplier", "partsupp", "nation"):
+                extra_tables[name].set_replicated()
+        except Exception as e:
+            also["q9_tables"] = {"error": str(e)[:200]}
+        extra_plans = {"q9": T.q9_plan, "q18": T.q18_plan,
                        "groupby_l_orderkey_having": lambda: T.groupby_plan(key="l_orderkey", value="l_quantity", having_gt=314, topk=100)}
         for name, mk in extra_plans.items():
             try:
-                ex = X.gpuPipelineExec(mk(), tables)
+                ex = X.gpuPipelineExec(mk(), extra_tables)
                 ex.Init()
                 for _ in range(2):
                     ex.Reset(); X.drain(ex)

@@ -27,8 +27,9 @@ def main():
     sf = 0.05
     n_orders = lib.pg_tpch_num_orders(sf)
     lo, hi = D.shard_range(n_orders, rank, world)
-    tables = T.generate_device_tables(sf, lo, hi)
-    tables["customer"].set_replicated()
+    tables = T.generate_device_tables(sf, lo, hi, want=T.ALL_TABLES)
+    for name in ("customer", "part", "supplier", "partsupp", "nation"):
+        tables[name].set_replicated()
     orders, line = O.gen_orders_lineitem(sf)
     host = {"orders": orders, "lineitem": line, "customer": O.gen_customer(sf)}
     total = torch.tensor([tables["lineitem"].rows()], device="cuda")
@@ -60,6 +61,12 @@ def main():
         chunks, _, explain = J._run(T.q18_plan(qty_gt=qty_gt, limit=limit), tables)
         assert "dependent keys" in explain
         assert J._q18_rows(chunks) == O.q18(host["customer"], orders, line, qty_gt=qty_gt, limit=limit)
+    # TPC-H Q9's shape on shards: lineitem/orders sharded (orders lookups are shard-local, proved from the key
+    # ranges), the other four build sides replicated; the 175 dense group sums are all-gathered and added in 128 bits
+    for word in ("pink", "lace"):
+        chunks, _, explain = J._run(T.q9_plan(word), tables)
+        assert "StarJoin" in explain
+        assert J._q9_rows(chunks) == O.q9(O.gen_part(sf, word), O.gen_supplier(sf), O.gen_partsupp(sf), orders, line, like_word=word)
     os.environ["PG_FORCE_SHUFFLE"] = "1"          # the general path must also be right when it is not needed
     J.check_groupby(O, tables, line, key="l_orderkey", value="l_quantity", having_gt=200)
     J.check_q3(O, tables, host, check_counts=False)
