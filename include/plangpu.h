@@ -183,6 +183,10 @@ int pg_result_rows(const pg_result *r, int64_t *nrows);
  * *nrows == 0 means Done (executor_operator.go:11-18).                            */
 int pg_result_next(pg_result *r, int64_t max_rows, int64_t *nrows, const void **cols, const uint8_t **valid);
 int pg_result_rewind(pg_result *r);
+/* PG_T_DICT8 result columns: the dictionary the codes index (code i -> entries[i], NUL-terminated, owned by
+ * the result).  *nentries == 0 for other columns.  The Go shim builds the VARCHAR vector from it
+ * (chunk/vector.go:208-217), so a result needs no side channel to the table it came from. */
+int pg_result_column_dict(const pg_result *r, int col, int32_t *nentries, const char *const **entries);
 
 typedef struct {
     double exec_ms;            /* wall time of pg_plan_execute                    */

@@ -77,6 +77,7 @@ SIGNATURES = [
     ("pg_result_rows", C.c_int, [_P, C.POINTER(C.c_int64)]),
     ("pg_result_next", C.c_int, [_P, C.c_int64, C.POINTER(C.c_int64), C.POINTER(_P), C.POINTER(_P)]),
     ("pg_result_rewind", C.c_int, [_P]),
+    ("pg_result_column_dict", C.c_int, [_P, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.POINTER(C.c_char_p))]),
     ("pg_result_stats", C.c_int, [_P, C.POINTER(Stats)]),
     ("pg_result_free", None, [_P]),
     ("pg_tpch_num_orders", C.c_int64, [C.c_double]),

@@ -365,7 +365,9 @@ class gpuPipelineExec(OperatorExec):
             typ = agg.Outputs[i].DataTyp if i < len(agg.Outputs) else K.LType(0)
             d = None
             if t == L.PG_T_DICT8:
-                d = self._dict_for_output(i)
+                nd, ents = C.c_int32(), C.POINTER(C.c_char_p)()
+                L.check(lib.pg_result_column_dict(self.result, i, C.byref(nd), C.byref(ents)))
+                d = [ents[k].decode() for k in range(nd.value)] if nd.value else self._dict_for_output(i)
             mask = None
             if valids[i]:       # packed validity bits, 1 = valid (pkg/util/bitmap.go)
                 nb = (n.value + 7) // 8

@@ -121,6 +121,7 @@ int comm_alltoallv(const void *d_send, const i64 *send_cnt, const i64 *send_off,
 struct pg_result {
     std::vector<pg::ResCol> cols;
     std::vector<std::vector<uint8_t>> valid_scratch;   // packed validity bitmaps handed out by pg_result_next
+    std::vector<std::vector<const char *>> dict_ptrs;  // pointer tables handed out by pg_result_column_dict
     pg::i64 nrows = 0, cursor = 0;
     pg_stats stats{};
 };

@@ -247,6 +247,19 @@ int pg_result_column_type(const pg_result *r, int col, int32_t *type, int32_t *w
     return PG_OK;
 }
 
+int pg_result_column_dict(const pg_result *r, int col, int32_t *nentries, const char *const **entries)
+{
+    if (!r || col < 0 || col >= (int)r->cols.size() || !nentries || !entries) PG_FAIL(PG_EINVAL, "pg_result_column_dict: bad arguments");
+    pg_result *w = const_cast<pg_result *>(r);
+    if ((size_t)col >= w->dict_ptrs.size()) w->dict_ptrs.resize(r->cols.size());
+    std::vector<const char *> &ptrs = w->dict_ptrs[(size_t)col];
+    ptrs.clear();
+    for (auto &e : r->cols[(size_t)col].dict) ptrs.push_back(e.c_str());
+    *nentries = (int32_t)ptrs.size();
+    *entries = ptrs.empty() ? nullptr : ptrs.data();
+    return PG_OK;
+}
+
 int pg_result_rows(const pg_result *r, int64_t *nrows)
 {
     if (!r || !nrows) PG_FAIL(PG_EINVAL, "pg_result_rows: bad arguments");

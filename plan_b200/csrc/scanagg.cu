@@ -500,6 +500,7 @@ struct LowcardPipeline : Pipeline {
             if (o.first == 0) {
                 const Column &kc = table->cols[(size_t)key_col[o.second]];
                 col.type = kc.type;
+                if (kc.type == PG_T_DICT8) col.dict = kc.dict;      // results are self-describing (pg_result_column_dict)
                 for (int g : order) {
                     int id = (nkeys == 2) ? (o.second == 0 ? g / prm.n1 : g % prm.n1) : g;
                     col.push<uint8_t>(vals[o.second][(size_t)id]);
@@ -825,6 +826,7 @@ struct GenericPipeline : Pipeline {
             if (o.first == 0) {
                 const Column &kc = table->cols[(size_t)key_col[o.second]];
                 col.type = kc.type;
+                if (kc.type == PG_T_DICT8) col.dict = kc.dict;      // results are self-describing (pg_result_column_dict)
                 for (int g : order) {
                     int id = (nkeys == 2) ? (o.second == 0 ? g / prm.n1 : g % prm.n1) : g;
                     col.push<uint8_t>(vals[o.second][(size_t)id]);

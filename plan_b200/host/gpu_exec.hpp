@@ -66,6 +66,7 @@ public:
     {
         static const std::map<std::string, int> m = {{"+", PG_FN_ADD}, {"-", PG_FN_SUB}, {"*", PG_FN_MUL}, {"/", PG_FN_DIV},
             {"=", PG_FN_EQ}, {"<>", PG_FN_NE}, {"<", PG_FN_LT}, {"<=", PG_FN_LE}, {">", PG_FN_GT}, {">=", PG_FN_GE}, {"in", PG_FN_IN},
+            {"like", PG_FN_LIKE}, {"not like", PG_FN_NOT_LIKE}, {"extract", PG_FN_EXTRACT},
             {"and", PG_FN_AND}, {"or", PG_FN_OR}, {"not", PG_FN_NOT}, {"cast", PG_FN_CAST}};
         auto it = m.find(n);
         if (it == m.end()) throw PlanError(PG_EUNSUPPORTED, "function " + n + " cannot be off-loaded");
@@ -213,6 +214,12 @@ public:
             v.Typ = (size_t)i < agg->Outputs.size() ? agg->Outputs[(size_t)i].DataTyp : LType();
             size_t esz = t == PG_T_HUGEINT || t == PG_T_DECIMAL128 || t == PG_T_VARCHAR ? 16 : (t == PG_T_INT32 || t == PG_T_DATE32) ? 4 : (t == PG_T_CHAR1 || t == PG_T_DICT8) ? 1 : 8;
             v.Data.assign((const uint8_t *)cols[(size_t)i], (const uint8_t *)cols[(size_t)i] + esz * (size_t)n);
+            if (t == PG_T_DICT8) {
+                int32_t nd = 0;
+                const char *const *ents = nullptr;
+                check(pg_result_column_dict(result_, i, &nd, &ents));
+                for (int32_t k = 0; k < nd; k++) v.Dict.emplace_back(ents[k]);
+            }
             if (t == PG_T_VARCHAR) {
                 const pg_string *sv = (const pg_string *)cols[(size_t)i];
                 for (int64_t r = 0; r < n; r++) v.Strings.emplace_back(sv[r].data, (size_t)sv[r].len);

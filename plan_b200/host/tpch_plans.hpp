@@ -169,4 +169,55 @@ inline Op q18_plan(int64_t qty_gt = 314, int64_t limit = 100)
     return lim;
 }
 
+// Order(nation, o_year desc) <- Agg(n_name, extract(year from o_orderdate); sum(ext*(1-disc) - ps_supplycost*l_quantity))
+//   <- five INNER joins stacked on the lineitem scan: part (p_name like '%pink%'), supplier, partsupp (2-column key), orders, nation
+inline Op q9_plan(const std::string &word = "pink")
+{
+    LType B = LType::Boolean(), I = LType::Integer(), BI = LType::Bigint(), D = LType::Date(), V = LType::Varchar(), P = LType::Decimal(15, 2);
+    auto scan = [](const char *name) { Op s = make(POT_Scan); s->Table = name; return s; };
+    Op line = scan("lineitem"), part = scan("part"), supp = scan("supplier"), ps = scan("partsupp"), ord = scan("orders"), nat = scan("nation");
+    part->Filters = {func("like", B, {col(0, PG_P_NAME, V), constS("%" + word + "%")})};
+    std::vector<LType> types = {BI, I, I, I, P, P};
+    auto up = [&]() { std::vector<Expr> o; for (size_t i = 0; i < types.size(); i++) o.push_back(col(0, (int)i, types[i])); return o; };
+    Op j1 = make(POT_Join);
+    j1->Children = {line, part};
+    j1->OnConds = {func("=", B, {lcol(PG_L_PARTKEY), col(1, PG_P_PARTKEY, I)})};
+    j1->Outputs = {lcol(PG_L_ORDERKEY), lcol(PG_L_PARTKEY), lcol(PG_L_SUPPKEY), lcol(PG_L_QUANTITY), lcol(PG_L_EXTENDEDPRICE), lcol(PG_L_DISCOUNT)};
+    Op j2 = make(POT_Join);
+    j2->Children = {j1, supp};
+    j2->OnConds = {func("=", B, {col(0, 2, I), col(1, PG_S_SUPPKEY, I)})};
+    j2->Outputs = up();
+    j2->Outputs.push_back(col(1, PG_S_NATIONKEY, I));
+    types.push_back(I);
+    Op j3 = make(POT_Join);
+    j3->Children = {j2, ps};
+    j3->OnConds = {func("=", B, {col(0, 2, I), col(1, PG_PS_SUPPKEY, I)}), func("=", B, {col(0, 1, I), col(1, PG_PS_PARTKEY, I)})};
+    j3->Outputs = up();
+    j3->Outputs.push_back(col(1, PG_PS_SUPPLYCOST, P));
+    types.push_back(P);
+    Op j4 = make(POT_Join);
+    j4->Children = {j3, ord};
+    j4->OnConds = {func("=", B, {col(0, 0, BI), col(1, PG_O_ORDERKEY, BI)})};
+    j4->Outputs = up();
+    j4->Outputs.push_back(col(1, PG_O_ORDERDATE, D));
+    types.push_back(D);
+    Op j5 = make(POT_Join);
+    j5->Children = {j4, nat};
+    j5->OnConds = {func("=", B, {col(0, 6, I), col(1, PG_N_NATIONKEY, I)})};
+    j5->Outputs = up();
+    j5->Outputs.push_back(col(1, PG_N_NAME, V));
+    Expr amount = func("-", LType::Decimal(18, 4), {disc_price(col(0, 4, P), col(0, 5, P)),
+                                                    func("*", LType::Decimal(18, 4), {col(0, 7, P), cast(col(0, 3, I), P)})});
+    Op agg = make(POT_Agg);
+    agg->GroupBys = {col(0, 9, V), func("extract", I, {constS("year"), col(0, 8, D)})};
+    agg->Aggs = {func("sum", LType::Decimal(38, 4), {amount})};
+    agg->Outputs = {col(0, 0, V), col(0, 1, I), col(1, 0, LType::Decimal(38, 4))};
+    agg->Children = {j5};
+    Op order = make(POT_Order);
+    order->OrderBys = {{col(0, 0, V), false}, {col(0, 1, I), true}};
+    order->Outputs = agg->Outputs;
+    order->Children = {agg};
+    return order;
+}
+
 }  // namespace planhost

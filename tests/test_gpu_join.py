@@ -153,7 +153,8 @@ def test_reference_golden_files_sf1_on_gpu(pg):
             x.free()
 
 
-@pytest.mark.parametrize("query,golden", [(6, "ref_sf1_q6.txt"), (1, "ref_sf1_q1.txt"), (3, "ref_sf1_q3.txt"), (18, "ref_sf1_q18.txt")])
+@pytest.mark.parametrize("query,golden", [(6, "ref_sf1_q6.txt"), (1, "ref_sf1_q1.txt"), (3, "ref_sf1_q3.txt"), (18, "ref_sf1_q18.txt"),
+                                          (9, "ref_sf1_q9.txt")])
 def test_cpp_host_shim_reproduces_golden_files(query, golden):
     """The C++ host shim (plan_b200/host: OperatorExec / PhysicalOperator / Chunk mirrors above the C
     ABI, standing in for the Go side) run like `tester tpch1g --query_id N`: its stdout is the
@@ -383,8 +384,8 @@ def test_full_size_sf100_matches_the_oracle_fixtures(pg):
     from plan_b200 import compute as X, tpch as T
     import torch
     if torch.cuda.mem_get_info(0)[0] < 60 * 2 ** 30:
-        pytest.skip("needs ~45 GB of free HBM")
-    t = T.generate_device_tables(100.0)
+        pytest.skip("needs ~60 GB of free HBM")
+    t = T.generate_device_tables(100.0, want=T.ALL_TABLES)
     try:
         assert t["lineitem"].rows() == 600037902
         chunks, _, _ = _run(T.q6_plan(), t)
@@ -396,6 +397,8 @@ def test_full_size_sf100_matches_the_oracle_fixtures(pg):
         assert X.rows_text(X.order_limit(chunks, []), 4) == open(os.path.join(GOLDEN, "oracle_sf100_q3.txt")).read()
         chunks, _, _ = _run(T.q18_plan(), t)           # tests/golden/make_sf100_q18_fixture.py
         assert X.rows_text(X.order_limit(chunks, []), 6) == open(os.path.join(GOLDEN, "oracle_sf100_q18.txt")).read()
+        chunks, _, _ = _run(T.q9_plan(), t)            # tests/golden/make_sf100_q9_fixture.py
+        assert X.rows_text(X.order_limit(chunks, []), 3) == open(os.path.join(GOLDEN, "oracle_sf100_q9.txt")).read()
         # size-independent property at full size: the sorted-run group-by and the table-based one agree
         gb = T.groupby_plan(key="l_orderkey", value="l_quantity", having_gt=300)
         a, _, _ = _run(gb, t)
