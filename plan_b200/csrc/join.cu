@@ -380,6 +380,7 @@ struct JoinAggPipeline : Pipeline {
         }
         s.jt.rank_prefix = nullptr;
         s.jt.rank_payload = nullptr;
+        s.jt.rank_identity = 0;
         s.rank_index = false;
         // exact key-domain bitmap when the build column's value range is small enough
         s.jt.bitmap = nullptr;
@@ -509,6 +510,36 @@ struct JoinAggPipeline : Pipeline {
                     res->stats.aux[2 + 2 * idx] = (i64)c0[0];
                     res->stats.aux[3 + 2 * idx] = (i64)c0[1];
                 }
+                return PG_OK;
+            }
+        }
+        if (!s.has_probe && s.unique_key && s.payload_needed && pp.npred == 0 && pp.nlike == 0 && pp.nextra == 0 && s.ins_key_col2 < 0 &&
+            !getenv("PG_JOIN_NO_RANK_INDEX")) {
+            // Every row of a strictly ascending key column is built: the rank of a key IS its row id, so the index is the
+            // bitmap plus its block prefix -- no hit list, no payload array (Q9: the 150 M unfiltered orders).
+            PG_TRY(prepare_table(s, 0, t->cols[(size_t)s.ins_key_col]));
+            if (s.jt.bitmap) {
+                pp.ins_key = typed(t, s.ins_key_col);
+                pp.ins = s.jt;
+                PG_CUDA(cudaMemsetAsync(d_counters.p, 0, 32, st));
+                PG_TRY(launch_pipe<SINK_BITMAP>(pp, t));
+                const u64 nblocks = (s.jt.domain + 255) / 256;
+                if (s.d_rank_prefix.bytes < nblocks * 4) PG_TRY(s.d_rank_prefix.alloc(nblocks * 4));
+                unsigned *prefix = s.d_rank_prefix.as<unsigned>();
+                const int grid = ctx().prop.multiProcessorCount * 8;
+                rank_count_kernel<<<(int)std::min<u64>((nblocks + 255) / 256, (u64)grid), 256, 0, st>>>(s.jt.bitmap, nblocks, prefix);
+                PG_CUDA(cudaGetLastError());
+                size_t tmp_bytes = 0;
+                PG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, prefix, prefix, (int)nblocks, st));
+                if (s.d_scan_tmp.bytes < tmp_bytes) PG_TRY(s.d_scan_tmp.alloc(tmp_bytes));
+                PG_CUDA(cub::DeviceScan::ExclusiveSum(s.d_scan_tmp.p, tmp_bytes, prefix, prefix, (int)nblocks, st));
+                s.jt.rank_prefix = prefix;
+                s.jt.rank_identity = 1;
+                s.rank_index = true;
+                s.dup_keys = 0;
+                s.built_rows = t->nrows;
+                res->stats.kernel_launches += 3;
+                if (idx < 2) { res->stats.aux[2 + 2 * idx] = t->nrows; res->stats.aux[3 + 2 * idx] = t->nrows; }
                 return PG_OK;
             }
         }

@@ -51,6 +51,7 @@ struct JoinTable {
     // 32-byte sector, so a lookup is branch-free: bitmap sector + prefix word -> payload word.
     const unsigned *rank_prefix;
     const unsigned *rank_payload;
+    int rank_identity;          // every row of a strictly ascending key column was inserted: rank == build row id, no payload array
 };
 
 // rank of key offset `off` (its bit must be set): number of set bits before it
@@ -116,7 +117,7 @@ __device__ __forceinline__ void jt_probe(const JoinTable &t, i64 key, F f)
         if (off >= t.domain) return;
         bool set;
         const unsigned r = jt_rank(t, off, &set);
-        if (set) f((u64)__ldg(t.rank_payload + r));
+        if (set) f(t.rank_identity ? (u64)r : (u64)__ldg(t.rank_payload + r));
         return;
     }
     u64 b = jt_home(t, key);
