@@ -467,9 +467,9 @@ void orc_q3(int64_t n_cust, const int32_t *c_custkey, const uint8_t *c_segment, 
                 if (ho.keys[p] != key) continue;
                 res->n_line_joined++;
                 /* aggregate argument */
-                dec_t ext = dec_from_i64(l_extprice[r], 2), disc = dec_from_i64(l_discount[r], 2), t, rev;
+                dec_t ext = dec_from_i64(l_extprice[r], 2), disc = dec_from_i64(l_discount[r], 2), t = one, rev = one;
                 if (dec_sub(one, disc, &t)) res->error = 1;
-                if (dec_mul(ext, t, &rev)) res->error = 1;
+                else if (dec_mul(ext, t, &rev)) res->error = 1;
                 /* FindOrCreateGroups on the 3-column key; resize at load 1/1.5 (aggregate.go:63) */
                 if ((ng + 1) * 3 > gcap * 2) {
                     int64_t ncap = gcap * 2;
