@@ -251,6 +251,12 @@ struct JoinAggPipeline : Pipeline {
             l.kind = r.like;
             l.plen = (int)r.pat.size();
             memcpy(l.pat, r.pat.data(), r.pat.size());
+            std::string lit;
+            if (r.like <= 2 && like_is_contains(r.pat, &lit)) {      // '%lit%': word-at-a-time search
+                l.kind = r.like == 1 ? 5 : 6;
+                l.plen = (int)lit.size();
+                memcpy(l.pat, lit.data(), lit.size());
+            }
         }
         if (rs.size() > PIPE_MAXPRED) PG_FAIL(PG_EUNSUPPORTED, "more than %d predicate columns on one scan", PIPE_MAXPRED);
         pp.npred = (int)rs.size();

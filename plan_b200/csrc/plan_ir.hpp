@@ -202,6 +202,16 @@ struct Range {
     std::string pat;
 };
 
+// `%lit%` with 1..8 wildcard-free bytes: the device takes a word-at-a-time substring search for these
+inline bool like_is_contains(const std::string &pat, std::string *lit)
+{
+    if (pat.size() < 3 || pat.size() > 10 || pat.front() != '%' || pat.back() != '%') return false;
+    const std::string mid = pat.substr(1, pat.size() - 2);
+    if (mid.find('%') != std::string::npos || mid.find('_') != std::string::npos) return false;
+    *lit = mid;
+    return true;
+}
+
 // The reference's LIKE matcher restated (wildcardMatch, function_operator_boolean.go:336-377): byte-wise,
 // '%' matches any run (greedy with backtracking to the last '%'), '_' any single byte.
 inline bool wildcard_match(const char *pat, size_t plen, const char *tgt, size_t tlen)

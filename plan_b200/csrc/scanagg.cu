@@ -941,6 +941,12 @@ static int try_generic(pg_plan *plan, const Node &aggn, const Node &scan, const 
         q.like[i].kind = likes[i].like;
         q.like[i].plen = (int)likes[i].pat.size();
         memcpy(q.like[i].pat, likes[i].pat.data(), likes[i].pat.size());
+        std::string lit;
+        if (likes[i].like <= 2 && like_is_contains(likes[i].pat, &lit)) {      // '%lit%': word-at-a-time search
+            q.like[i].kind = likes[i].like == 1 ? 5 : 6;
+            q.like[i].plen = (int)lit.size();
+            memcpy(q.like[i].pat, lit.data(), lit.size());
+        }
         p->extra_bytes += (i64)col.h_bytes.size() + 8 * t->nrows;
     }
     const std::vector<Range> &ranges_ = plain;

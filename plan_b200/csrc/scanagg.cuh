@@ -445,9 +445,44 @@ __device__ __forceinline__ bool gen_wildcard_match(const char *pat, int plen, co
     while (p < plen && pat[p] == '%') p++;
     return p >= plen;
 }
+// `%lit%` with a wildcard-free literal of 1..8 bytes (the shape of `p_name like '%pink%'`): word-at-a-time
+// search -- candidate positions of the literal's first byte come from the zero-byte trick on aligned 8-byte
+// words, only those are verified against the (masked) literal.  The byte buffer is 8-byte aligned and padded.
+__device__ __forceinline__ bool gen_contains(const char *bytes, i64 b, i64 e, u64 lit, int L)
+{
+    if (e - b < L) return false;
+    const u64 ONES = 0x0101010101010101ULL, HIGH = 0x8080808080808080ULL;
+    const u64 mask = L >= 8 ? ~0ULL : ((1ULL << (8 * L)) - 1);
+    const u64 first = ONES * (lit & 0xff);
+    const u64 *base = (const u64 *)bytes;
+    const i64 wb = b >> 3, we = (e - 1) >> 3;
+    u64 cur = __ldg(base + wb);
+    for (i64 w = wb; w <= we; w++) {
+        const u64 nxt = __ldg(base + w + 1);
+        const u64 x = cur ^ first;
+        u64 t = (x - ONES) & ~x & HIGH;          // bytes equal to the first literal byte (plus rare false positives, verified below)
+        while (t) {
+            const int j = (__ffsll((long long)t) - 1) >> 3;
+            t &= t - 1;
+            const i64 p = (w << 3) + j;
+            if (p < b || p + L > e) continue;
+            const int sh = j * 8;
+            const u64 win = sh == 0 ? cur : (cur >> sh) | (nxt << (64 - sh));
+            if ((win & mask) == lit) return true;
+        }
+        cur = nxt;
+    }
+    return false;
+}
+
 __device__ __forceinline__ bool gen_like_pass(const GenLike &l, i64 row)
 {
     const i64 b = __ldg(l.off + row), e = __ldg(l.off + row + 1);
+    if (l.kind >= 5) {                    // 5: contains, 6: does not contain (fast path of LIKE / NOT LIKE '%lit%')
+        u64 lit = 0;
+        for (int i = 0; i < l.plen; i++) lit |= (u64)(unsigned char)l.pat[i] << (8 * i);
+        return gen_contains(l.bytes, b, e, lit, l.plen) == (l.kind == 5);
+    }
     const char *tgt = l.bytes + b;
     bool m;
     if (l.kind <= 2) {

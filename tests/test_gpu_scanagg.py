@@ -383,6 +383,11 @@ def test_code_set_predicates(pg, oracle, uploaded, sf01_host, kw, okw):
     [("c_mktsegment", "like", "%U%"), ("c_name", "like", "%99%")],   # dictionary column: matched per code on the host
     [("c_mktsegment", "not like", "_U%")],
     [("c_name", "like", "%")], [("c_name", "like", "")], [("c_name", "like", "__________________")],
+    # '%lit%' with 1..8 literal bytes takes the word-at-a-time search: first / last bytes of the string, 8-byte literal,
+    # a literal longer than some... and NOT LIKE
+    [("c_name", "like", "%C%")], [("c_name", "like", "%4%")], [("c_name", "like", "%Customer%")], [("c_name", "like", "%mer#0000%")],
+    [("c_name", "like", "%014999%")], [("c_name", "not like", "%12%")], [("c_name", "like", "%#00001499%")],
+    [("c_name", "like", "%r#000014%"), ("c_name", "not like", "%9%")],
 ])
 def test_string_predicates(pg, oracle, sf01_host, filters):
     """LIKE / NOT LIKE / = / <> on a VARCHAR column evaluated on the GPU with the reference's wildcardMatch
