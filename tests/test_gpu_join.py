@@ -492,3 +492,68 @@ def test_q9_sf005(pg, oracle, word):
     finally:
         for x in t.values():
             x.free()
+
+
+def _q9_host(oracle, sf, word="pink"):
+    orders, line = oracle.gen_orders_lineitem(sf)
+    part = oracle.gen_part(sf, word)
+    host = {"lineitem": line, "orders": orders, "part": {"p_partkey": part["p_partkey"], "p_name": part["p_name"]},
+            "supplier": oracle.gen_supplier(sf), "partsupp": oracle.gen_partsupp(sf),
+            "nation": {"n_nationkey": np.arange(25, dtype=np.int32), "n_name": np.arange(25, dtype=np.uint8)}}
+    return host, part
+
+
+@pytest.mark.parametrize("empty", ["lineitem", "part", "partsupp", "orders", "nation"])
+def test_q9_with_an_empty_table(pg, oracle, empty):
+    """A star join with an empty fact table or an empty build side yields no group (INNER joins), not an error."""
+    from plan_b200 import tpch as T
+    host, _ = _q9_host(oracle, 0.01)
+    host[empty] = {k: v[:0] for k, v in host[empty].items()}
+    t = T.upload_tables(host)
+    try:
+        chunks, _, explain = _run(T.q9_plan(), t)
+        assert "StarJoin" in explain and chunks == []
+    finally:
+        for x in t.values():
+            x.free()
+
+
+def test_q9_uploaded_tables_and_duplicate_build_keys(pg, oracle):
+    """Host-uploaded (not device-generated) tables give the oracle's result; a build side with duplicate keys would need
+    row multiplication in the star sink and is refused at execution time with PG_EUNSUPPORTED -- never answered wrongly."""
+    from plan_b200 import _lib as L, compute as X, tpch as T
+    sf = 0.01
+    host, part = _q9_host(oracle, sf)
+    t = T.upload_tables(host)
+    try:
+        chunks, _, _ = _run(T.q9_plan(), t)
+        assert _q9_rows(chunks) == oracle.q9(part, host["supplier"], host["partsupp"], host["orders"], host["lineitem"])
+    finally:
+        for x in t.values():
+            x.free()
+    host["supplier"] = {k: np.concatenate([v, v[:10]]) for k, v in host["supplier"].items()}     # ten supplier keys twice
+    t = T.upload_tables(host)
+    try:
+        ex = X.gpuPipelineExec(T.q9_plan(), t)
+        ex.Init()
+        with pytest.raises(L.PlanGpuError) as ei:
+            X.drain(ex)
+        assert ei.value.status == L.PG_EUNSUPPORTED and "more than one build row" in str(ei.value)
+        ex.Close()
+    finally:
+        for x in t.values():
+            x.free()
+
+
+def test_q18_with_empty_tables_and_no_qualifying_order(pg, oracle, sf01_host):
+    from plan_b200 import tpch as T
+    for empty in ("customer", "orders", "lineitem"):
+        host = {k: dict(v) for k, v in sf01_host.items()}
+        host[empty] = {k: v[:0] for k, v in host[empty].items()}
+        t = T.upload_tables(host)
+        try:
+            chunks, _, _ = _run(T.q18_plan(qty_gt=200), t)
+            assert chunks == []
+        finally:
+            for x in t.values():
+                x.free()
