@@ -51,6 +51,7 @@
 #define PG_JOIN_ANTI 3
 #define PG_JOIN_MARK 4
 #define PG_JOIN_LEFT 5
+#define PG_JOIN_ANTI_MARK 6 /* NOT EXISTS: the same mark column as MARK, filtered with mark = false (builder_plan.go:421-429) */
 
 /* tokens */
 #define PG_TK_COL 1

@@ -31,7 +31,7 @@ POT_Scan, POT_Filter, POT_Join, POT_Agg, POT_Project, POT_Order, POT_Limit = 1, 
 ET_Column, ET_Func, ET_Const = 0, 5, 7
 
 # join types
-JOIN_INNER, JOIN_SEMI, JOIN_ANTI, JOIN_MARK, JOIN_LEFT = 1, 2, 3, 4, 5
+JOIN_INNER, JOIN_SEMI, JOIN_ANTI, JOIN_MARK, JOIN_LEFT, JOIN_ANTI_MARK = 1, 2, 3, 4, 5, 6
 
 FUNC_IDS = {"+": 1, "-": 2, "*": 3, "/": 4, "=": 10, "<>": 11, "<": 12, "<=": 13, ">": 14, ">=": 15, "in": 16,
             "like": 17, "not like": 18,      # FuncLike / FuncNotLike (function.go:89-128)

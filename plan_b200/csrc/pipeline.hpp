@@ -130,6 +130,7 @@ struct pg_plan {
     pg::Node root;
     const pg::Node *topk = nullptr;     // root when it is a PG_OP_TOPK, else null
     pg::Node scan_copy;                 // scan with merged filters (high-cardinality Agg <- Scan)
+    pg::Node mark_copy;                 // Filter(mark = b) <- MARK join rewritten as a SEMI / ANTI join
     const pg::Node &agg_root() const { return topk ? root.children[0] : root; }
     std::vector<pg_table *> slots;
     std::vector<uint64_t> bound_versions;

@@ -119,6 +119,36 @@ static int build_pipeline(pg_plan *plan)
         }
         return build_scan_agg(plan, root, scan, &plan->pipe);
     }
+    if (child->op == PG_OP_JOIN && (child->jointype == PG_JOIN_MARK || child->jointype == PG_JOIN_ANTI_MARK)) {
+        // EXISTS / NOT EXISTS: the reference plans a MARK join -- every probe row plus a boolean "found a match"
+        // column, NULL for a NULL key (constructMarkJoinResult, join_scan.go:132-165) -- under Filter(mark = true | false)
+        // (makeMarkCondFunc, builder_plan.go:380-400).  When the mark column is only filtered this is a SEMI join
+        // (mark = true) or an ANTI join (mark = false; the probe key must be NULL-free, a NULL mark selects nothing).
+        if (extra.size() != 1 || child->outs.empty() || child->outs.back().first != 2)
+            PG_FAIL(PG_EUNSUPPORTED, "MARK join: expected exactly Filter(mark = constant) above it and the mark column last");
+        for (size_t i = 0; i + 1 < child->outs.size(); i++)
+            if (child->outs[i].first == 2) PG_FAIL(PG_EUNSUPPORTED, "MARK join: the mark column is projected more than once");
+        const Expr &f = extra[0];
+        if (f.kind != PG_TK_FUNC || (f.fn != PG_FN_EQ && f.fn != PG_FN_NE) || f.args.size() != 2) PG_FAIL(PG_EUNSUPPORTED, "MARK join: filter is not mark = constant");
+        const Expr *c = strip_value_preserving_casts(&f.args[0]), *k = strip_value_preserving_casts(&f.args[1]);
+        if (c->kind != PG_TK_COL) std::swap(c, k);
+        if (c->kind != PG_TK_COL || c->idx != (int)child->outs.size() - 1 || k->kind != PG_TK_CONST || k->ltype != PG_LT_BOOLEAN)
+            PG_FAIL(PG_EUNSUPPORTED, "MARK join: filter is not mark = constant");
+        const bool want_match = (k->v0 != 0) == (f.fn == PG_FN_EQ);
+        plan->mark_copy = *child;
+        plan->mark_copy.jointype = want_match ? PG_JOIN_SEMI : PG_JOIN_ANTI;
+        plan->mark_copy.outs.pop_back();
+        if (!want_match) {
+            // ANTI keeps probe rows with a NULL key, `mark = false` does not: only equivalent without NULL keys
+            const Node *src = &plan->mark_copy.children[0];
+            while (src->op == PG_OP_FILTER) src = &src->children[0];
+            const Expr *pe = plan->mark_copy.conds.size() == 1 ? strip_value_preserving_casts(&plan->mark_copy.conds[0].first) : nullptr;
+            if (!pe || pe->kind != PG_TK_COL || src->op != PG_OP_SCAN || pe->idx < 0 || pe->idx >= (int)plan->slots[(size_t)src->slot]->cols.size() ||
+                plan->slots[(size_t)src->slot]->cols[(size_t)pe->idx].has_nulls)
+                PG_FAIL(PG_EUNSUPPORTED, "MARK join filtered with mark = false over a nullable (or non-scan) probe key");
+        }
+        return build_join_agg(plan, root, plan->mark_copy, &plan->pipe);
+    }
     if (child->op == PG_OP_JOIN) {
         if (!extra.empty()) PG_FAIL(PG_EUNSUPPORTED, "filter between aggregate and join is not supported");
         return build_join_agg(plan, root, *child, &plan->pipe);

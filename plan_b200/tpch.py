@@ -17,7 +17,7 @@ import numpy as np
 
 from . import _lib as L
 from . import chunk as K
-from .compute import (JOIN_ANTI, JOIN_SEMI, JOIN_INNER, POT_Agg, POT_Join, POT_Limit, POT_Order, POT_Scan, AggOpInfo, DeviceTable, JoinOpInfo,
+from .compute import (JOIN_ANTI, JOIN_ANTI_MARK, JOIN_MARK, JOIN_SEMI, JOIN_INNER, POT_Filter, POT_Agg, POT_Join, POT_Limit, POT_Order, POT_Scan, AggOpInfo, DeviceTable, JoinOpInfo,
                       LimitOpInfo, OrderOpInfo, PhysicalOperator, ScanOpInfo, cast, col, const, func)
 
 SEGMENTS = ["AUTOMOBILE", "BUILDING", "FURNITURE", "HOUSEHOLD", "MACHINERY"]
@@ -373,6 +373,33 @@ def customer_filter_plan(filters, schema=FULL):
     aggs = [func("count", H, ck), func("sum", H, S.col("customer", "c_nationkey")), func("sum", H, ck)]
     outs = [col(1, i, a.DataTyp) for i, a in enumerate(aggs)]
     return PhysicalOperator(POT_Agg, Outputs=outs, Children=[scan], Info=AggOpInfo(aggs, []))
+
+
+def exists_plan(negated=False, odate_lt=None, ship_gt=None, schema=FULL):
+    """EXISTS / NOT EXISTS as the reference plans it (builder_plan.go:380-429): a MARK / AntiMARK join whose extra
+    boolean output is filtered with `mark = true` / `mark = false` (the shape of TPC-H Q4, Q21, Q22):
+        select o_custkey, sum(o_totalprice), count(*) from orders
+        where o_orderdate < d and [not] exists (select * from lineitem where l_orderkey = o_orderkey and l_shipdate > s)
+        group by o_custkey
+    The same rows as semi_plan(anti=negated)."""
+    S = schema
+    odate_lt = days(1995, 3, 29) if odate_lt is None else odate_lt
+    ship_gt = days(1995, 3, 29) if ship_gt is None else ship_gt
+    B = K.LType(K.LTID_BOOLEAN)
+    orders = PhysicalOperator(POT_Scan, Info=ScanOpInfo("orders"),
+                              Filters=[func("<", B, S.col("orders", "o_orderdate"), const(odate_lt, K.DateType()))])
+    line = PhysicalOperator(POT_Scan, Info=ScanOpInfo("lineitem"),
+                            Filters=[func(">", B, S.col("lineitem", "l_shipdate"), const(ship_gt, K.DateType()))])
+    OI = S.idx["orders"]
+    j = PhysicalOperator(
+        POT_Join, Children=[orders, line],
+        Outputs=[col(0, OI["o_custkey"], K.IntegerType()), col(0, OI["o_totalprice"], DEC15_2), col(2, 0, B)],   # side 2: the mark column
+        Info=JoinOpInfo(JOIN_ANTI_MARK if negated else JOIN_MARK,
+                        [func("=", B, S.col("orders", "o_orderkey", 0), S.col("lineitem", "l_orderkey", 1))]))
+    flt = PhysicalOperator(POT_Filter, Outputs=j.Outputs, Children=[j], Filters=[func("=", B, col(0, 2, B), const(0 if negated else 1, B))])
+    aggs = [func("sum", K.DecimalType(38, 2), col(0, 1, DEC15_2)), func("count", K.HugeintType(), col(0, 0, K.IntegerType()))]
+    outs = [col(0, 0, K.IntegerType()), col(1, 0, K.DecimalType(38, 2)), col(1, 1, K.HugeintType())]
+    return PhysicalOperator(POT_Agg, Outputs=outs, Children=[flt], Info=AggOpInfo(aggs, [col(0, 0, K.IntegerType())]))
 
 
 def q3_topk_plan(limit=10, **kw):

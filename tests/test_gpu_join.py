@@ -557,3 +557,26 @@ def test_q18_with_empty_tables_and_no_qualifying_order(pg, oracle, sf01_host):
         finally:
             for x in t.values():
                 x.free()
+
+
+@pytest.mark.parametrize("negated", [False, True])
+@pytest.mark.parametrize("kw", [dict(), dict(odate_lt=8035 + 3000, ship_gt=8035 + 2400)])
+def test_exists_as_mark_join(pg, oracle, uploaded, sf01_host, negated, kw):
+    """EXISTS / NOT EXISTS: Filter(mark = true|false) <- MARK / AntiMARK join (builder_plan.go:380-429,
+    join_scan.go:124-165) gives the rows of the SEMI / ANTI join."""
+    from plan_b200 import tpch as T
+    chunks, _, _ = _run(T.exists_plan(negated=negated, **kw), uploaded)
+    want = oracle.semi_groupby(sf01_host["orders"], sf01_host["lineitem"], anti=negated, **kw)
+    got = _groupby_result(chunks)
+    assert len(got) == len(want) and got == want
+
+
+def test_mark_join_without_its_filter_is_refused(pg, uploaded):
+    from plan_b200 import _lib as L, compute as X, tpch as T
+    plan = T.exists_plan()
+    plan.Children[0] = plan.Children[0].Children[0]          # drop Filter(mark = true): the mark column would have to be produced
+    ex = X.gpuPipelineExec(plan, uploaded)
+    with pytest.raises(L.PlanGpuError) as ei:
+        ex.Init()
+    assert ei.value.status == L.PG_EUNSUPPORTED
+    ex.Close()

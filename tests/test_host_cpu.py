@@ -59,7 +59,7 @@ def test_calls_without_init_fail_loudly(lib):
 def test_descriptor_roundtrip_and_validation(lib):
     from plan_b200 import _lib as L, compute as X, tpch as T
     for plan, nslots in ((T.q6_plan(), 1), (T.q1_plan(), 1), (T.q3_plan(), 3), (T.q3_topk_plan(10), 3), (T.q18_plan(), 3), (T.q9_plan(), 6),
-                         (T.groupby_plan(having_gt=314, topk=100), 1), (T.semi_plan(anti=True), 2),
+                         (T.groupby_plan(having_gt=314, topk=100), 1), (T.semi_plan(anti=True), 2), (T.exists_plan(negated=True), 2),
                          (T.customer_filter_plan([("c_name", "like", "%00001%"), ("c_mktsegment", "not like", "_U%")]), 1)):
         d, slots = X.serialize_plan(plan)
         assert d[0] == 0x31504750 and d[1] == 1 and len(slots) == nslots
