@@ -1235,7 +1235,28 @@ struct JoinAggPipeline : Pipeline {
                 col.width = a.width;
                 col.scale = a.scale;
                 const i64 *src = h_acc + (size_t)agg_plane[(size_t)o.second] * (size_t)ngroups;
-                if (a.ltype == PG_LT_HUGEINT) {          // sum(INT) / count -> 128-bit integer
+                const i64 *rows_of = h_acc + (size_t)gs.nacc * (size_t)ngroups;      // the row-count plane
+                if (a.fn == PG_AGG_AVG && a.ltype == PG_LT_DOUBLE) {       // avg(INT): float64 sum / float64 count
+                    col.type = PG_T_FLOAT64;
+                    col.data.resize((size_t)ngroups * 8);
+                    double *d = (double *)col.data.data();
+                    for (i64 i = 0; i < ngroups; i++) {
+                        if (src[i] >= ((i64)1 << 53) || src[i] <= -((i64)1 << 53)) PG_FAIL(PG_EOVERFLOW, "avg(INT): sum not exact in float64");
+                        d[i] = (double)src[i] / (double)rows_of[i];
+                    }
+                } else if (a.fn == PG_AGG_AVG) {                           // avg(DECIMAL) = sum.Quo(count)
+                    col.type = PG_T_DECIMAL128;
+                    col.data.resize((size_t)ngroups * sizeof(pg_decimal));
+                    pg_decimal *d = (pg_decimal *)col.data.data();
+                    for (i64 i = 0; i < ngroups; i++) {
+                        HDec sd, nd, qd;
+                        if (!hd_from_i128((i128)src[i], agg_scale[(size_t)o.second], &sd) || !hd_from_i128((i128)rows_of[i], 0, &nd) || !hd_quo(sd, nd, &qd))
+                            PG_FAIL(PG_EOVERFLOW, "avg: decimal division failed");
+                        d[i].coef = qd.coef;
+                        d[i].scale = qd.scale;
+                        d[i].neg = qd.neg ? 1u : 0u;
+                    }
+                } else if (a.ltype == PG_LT_HUGEINT) {          // sum(INT) / count -> 128-bit integer
                     col.type = PG_T_HUGEINT;
                     col.data.resize((size_t)ngroups * sizeof(pg_hugeint));
                     pg_hugeint *d = (pg_hugeint *)col.data.data();
@@ -1890,7 +1911,11 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &top, std::unique
         }
         const size_t a = (size_t)next_plane;
         p->agg_plane[ai] = next_plane++;
-        if (ae.fn != PG_AGG_SUM || (ae.ltype != PG_LT_DECIMAL && ae.ltype != PG_LT_HUGEINT)) PG_FAIL(PG_EUNSUPPORTED, "high-cardinality aggregate supports sum and count only");
+        // sum -> DECIMAL / HUGEINT; avg = the same sum divided by the group's row count at result time
+        // (avg(DECIMAL) = sum.Quo(count), avg(INT) -> DOUBLE: function_aggr.go:63-86,881-895)
+        const bool is_sum = ae.fn == PG_AGG_SUM && (ae.ltype == PG_LT_DECIMAL || ae.ltype == PG_LT_HUGEINT);
+        const bool is_avg = ae.fn == PG_AGG_AVG && (ae.ltype == PG_LT_DECIMAL || ae.ltype == PG_LT_DOUBLE);
+        if (!is_sum && !is_avg) PG_FAIL(PG_EUNSUPPORTED, "high-cardinality aggregate supports sum, avg and count only");
         // lower against a virtual table made of the join's outputs: reuse lower_affprod on the
         // probe table for factors, resolving columns by hand
         struct Tmp { std::vector<Factor> f; } tmp;
@@ -1931,7 +1956,7 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &top, std::unique
             i128 m = std::max(lo < 0 ? -lo : lo, hi < 0 ? -hi : hi);
             bound *= m > 1 ? m : 1;
         }
-        if (ae.ltype == PG_LT_HUGEINT && scale != 0) PG_FAIL(PG_EUNSUPPORTED, "integer sum over a scaled value");
+        if ((ae.ltype == PG_LT_HUGEINT || ae.ltype == PG_LT_DOUBLE) && scale != 0) PG_FAIL(PG_EUNSUPPORTED, "integer sum over a scaled value");
         p->agg_scale[ai] = scale;
         worst = std::max(worst, bound);
     }
@@ -1946,6 +1971,7 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &top, std::unique
             PG_FAIL(PG_EUNSUPPORTED, "HAVING must compare an aggregate with a constant");
         i64 k;
         if (!const_at_scale(r, p->agg_scale[(size_t)l->idx], &k)) PG_FAIL(PG_EUNSUPPORTED, "HAVING constant does not fit the aggregate scale");
+        if (aggn.aggs[(size_t)l->idx].fn == PG_AGG_AVG) PG_FAIL(PG_EUNSUPPORTED, "HAVING on an average");
         p->hav_plane = p->agg_plane[(size_t)l->idx];
         switch (op) {
         case PG_FN_EQ: p->hav_lo = p->hav_hi = k; break;
@@ -2103,6 +2129,7 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &top, std::unique
         if (o.first == 0) {
             tk.src = o.second;            // 0: klo, 1: khi high, 2: khi low
         } else {
+            if (aggn.aggs[(size_t)o.second].fn == PG_AGG_AVG) goto no_device_topk;       // ordering by sum/count: left to the host sort
             tk.src = 3;
             tk.plane = p->agg_plane[(size_t)o.second];
             int sc = p->agg_scale[(size_t)o.second];
@@ -2112,6 +2139,7 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &top, std::unique
         p->topk_key = tk;
         p->topk_limit = plan->topk->limit;
     }
+no_device_topk:
     PG_TRY(p->d_counters.alloc(64));
     PG_TRY(p->d_overflow.alloc(4));
     std::string ex = "JoinAgg[inner hash join chain -> global group table] stages:";

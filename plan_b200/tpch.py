@@ -211,6 +211,20 @@ def stats_plan(d0, d1, d2, d3, q0, q1, disc_gt_cents, schema=FULL, linestatus_ne
     return PhysicalOperator(POT_Agg, Outputs=outs, Children=[scan], Info=AggOpInfo(aggs, [lc("l_returnflag")]))
 
 
+def groupby_avg_plan(key="l_suppkey", value="l_extendedprice", schema=FULL):
+    """select <key>, avg(<value>), count(*) from lineitem group by <key>  (high-cardinality aggregate with an average:
+    avg(DECIMAL) = sum.Quo(count) -> DECIMAL(38,s), avg(INTEGER) -> DOUBLE; function_aggr.go:63-86,881-895)"""
+    S = schema
+    lc = lambda n: S.col("lineitem", n)   # noqa: E731
+    vt = _ltype_of(S.tables["lineitem"][S.idx["lineitem"][value]])
+    avg_t = K.DoubleType() if vt.Id in (K.LTID_INTEGER, K.LTID_BIGINT) else K.DecimalType(38, vt.Scale)
+    kt = _ltype_of(S.tables["lineitem"][S.idx["lineitem"][key]])
+    aggs = [func("avg", avg_t, lc(value)), func("count", K.HugeintType(), col(0, 0, _ltype_of(S.tables["lineitem"][0])))]
+    outs = [col(0, 0, kt), col(1, 0, avg_t), col(1, 1, K.HugeintType())]
+    scan = PhysicalOperator(POT_Scan, Info=ScanOpInfo("lineitem"))
+    return PhysicalOperator(POT_Agg, Outputs=outs, Children=[scan], Info=AggOpInfo(aggs, [lc(key)]))
+
+
 def groupby_plan(key="l_orderkey", value="l_quantity", having_gt=None, ship_le=None, topk=None, schema=FULL):
     """High-cardinality group-by straight over lineitem (the inner aggregate of TPC-H Q18 when
     key = l_orderkey, having_gt = 314):

@@ -580,3 +580,28 @@ def test_mark_join_without_its_filter_is_refused(pg, uploaded):
         ex.Init()
     assert ei.value.status == L.PG_EUNSUPPORTED
     ex.Close()
+
+
+@pytest.mark.parametrize("key,value", [("l_suppkey", "l_extendedprice"), ("l_partkey", "l_quantity"), ("l_orderkey", "l_discount")])
+def test_high_cardinality_avg(pg, oracle, uploaded, sf01_host, key, value):
+    """avg in the global-table aggregate: avg(DECIMAL) = sum.Quo(count) bit for bit (govalues Quo restated in
+    hostdec.hpp vs the oracle's decimal.h), avg(INTEGER) = float64(sum) / float64(count) exactly."""
+    from plan_b200 import tpch as T
+    import ctypes as C
+    chunks, _, _ = _run(T.groupby_avg_plan(key=key, value=value), uploaded)
+    want = oracle.groupby_sum(sf01_host["lineitem"], key=key, value=value)
+    L = oracle.lib()
+    n = 0
+    for c in chunks:
+        k, a, cnt = (v.Data for v in c.Data)
+        for r in range(c.Card()):
+            s_, c_ = want[int(k[r])]
+            assert int(cnt[r]["lower"]) == c_
+            if value == "l_quantity":
+                assert float(a[r]) == float(s_) / float(c_)
+            else:
+                oc, os_, on = C.c_uint64(), C.c_int(), C.c_int()
+                assert L.orc_dec_quo(C.c_uint64(abs(s_)), 2, int(s_ < 0), C.c_uint64(c_), 0, 0, C.byref(oc), C.byref(os_), C.byref(on)) == 0
+                assert (int(a[r]["coef"]), int(a[r]["scale"]), int(a[r]["neg"])) == (oc.value, os_.value, on.value)
+            n += 1
+    assert n == len(want)
