@@ -261,10 +261,11 @@ struct JoinAggPipeline : Pipeline {
         if (rs.size() > PIPE_MAXPRED) PG_FAIL(PG_EUNSUPPORTED, "more than %d predicate columns on one scan", PIPE_MAXPRED);
         pp.npred = (int)rs.size();
         for (size_t i = 0; i < rs.size(); i++) {
-            if (rs[i].is_set) PG_FAIL(PG_EUNSUPPORTED, "code-set predicates (IN, <>, OR) are not supported in join pipelines yet");
             pp.pred[i].col = typed(tab(slot), rs[i].col);
             pp.pred[i].lo = rs[i].lo;
             pp.pred[i].hi = rs[i].hi;
+            pp.pred[i].is_set = rs[i].is_set ? 1 : 0;          // code sets live on 1-byte columns: never taken by the 32-bit filter pass
+            memcpy(pp.pred[i].mask, rs[i].set, sizeof pp.pred[i].mask);
         }
         return PG_OK;
     }
@@ -312,7 +313,7 @@ struct JoinAggPipeline : Pipeline {
         for (int k = 0; k < pp.npred; k++) any_valid = any_valid || pp.pred[k].col.valid != nullptr;
         // (a build stage without a probe of its own also qualifies: the filter pass then lists every row that
         //  passes the predicate -- pp.probe_key must name the key column so the vector loads have a source)
-        return (pp.has_probe ? pp.probe.bitmap != nullptr : ins_sink) && pp.nlike == 0 && pp.npred <= 1 && (pp.npred == 0 || pp.pred[0].col.width == 4) &&
+        return (pp.has_probe ? pp.probe.bitmap != nullptr : ins_sink) && pp.nlike == 0 && pp.npred <= 1 && (pp.npred == 0 || (pp.pred[0].col.width == 4 && !pp.pred[0].is_set)) &&
                (pp.probe_key.width == 4 || pp.probe_key.width == 8) && !any_valid && t->nrows < ((i64)1 << 32) &&
                !getenv("PG_JOIN_GENERIC");
     }
@@ -881,7 +882,7 @@ struct JoinAggPipeline : Pipeline {
             bool pred_valid = false;
             for (int k = 0; k < pp.npred; k++) pred_valid = pred_valid || pp.pred[k].col.valid != nullptr;
             one_shape = !pred_valid && gs.nparts == 1 && gs.nacc == 1 && gs.nfac[0] == 1 && pp.npred <= 1 &&
-                        (pp.npred == 0 || pp.pred[0].col.width == 4) && gs.part[0].col.width >= 4 &&
+                        (pp.npred == 0 || (pp.pred[0].col.width == 4 && !pp.pred[0].is_set)) && gs.part[0].col.width >= 4 &&
                         gs.fac[0][0].col.width >= 4 && !getenv("PG_GROUP_GENERIC");
         }
         const bool sorted_runs = one_shape && key_sorted && t->nrows > 0 && !(shuffle && c.world > 1) && !getenv("PG_NO_SORTED_RUNS");

@@ -152,10 +152,18 @@ __device__ __forceinline__ i64 load_typed(const TypedCol &c, i64 row)
     }
 }
 
-struct SrcPred {          // inclusive range on a source column
+struct SrcPred {          // inclusive range on a source column, or (byte-coded columns) a set of codes: IN, <>, OR of =
     TypedCol col;
     i64 lo, hi;
+    int is_set;
+    unsigned mask[8];
 };
+__device__ __forceinline__ bool pred_pass(const SrcPred &q, i64 row)
+{
+    if (!typed_valid(q.col, row)) return false;                 // NULL is never selected
+    const i64 v = load_typed(q.col, row);
+    return q.is_set ? ((q.mask[(v >> 5) & 7] >> (v & 31)) & 1u) != 0 : (v >= q.lo && v <= q.hi);
+}
 
 constexpr int PIPE_MAXPRED = 3;
 
@@ -341,8 +349,7 @@ pipeline_kernel(const PipeParams p)
     for (i64 row = (i64)blockIdx.x * blockDim.x + threadIdx.x; row < p.nrows; row += (i64)gridDim.x * blockDim.x) {
         bool ok = true;
         for (int k = 0; k < p.npred && ok; k++) {
-            i64 v = load_typed(p.pred[k].col, row);
-            ok = typed_valid(p.pred[k].col, row) && v >= p.pred[k].lo && v <= p.pred[k].hi;   // NULL is never selected
+            ok = pred_pass(p.pred[k], row);
         }
         for (int k = 0; k < p.nlike && ok; k++) ok = gen_like_pass(p.like[k], row);
         if (!ok) continue;
@@ -414,8 +421,7 @@ static scan_group_kernel(const PipeParams p)
         i64 row = it * stride + (i64)blockIdx.x * blockDim.x + threadIdx.x;
         bool ok = row < p.nrows;
         for (int k = 0; k < p.npred && ok; k++) {
-            i64 v = load_typed(p.pred[k].col, row);
-            ok = typed_valid(p.pred[k].col, row) && v >= p.pred[k].lo && v <= p.pred[k].hi;
+            ok = pred_pass(p.pred[k], row);
         }
         i64 klo = 0, khi = 0, vals[GT_MAXACC];
         if (ok) {

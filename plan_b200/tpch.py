@@ -141,7 +141,7 @@ def q1_plan(ship_le=None, schema=FULL):
     return PhysicalOperator(POT_Agg, Outputs=outs, Children=[scan], Info=AggOpInfo(aggs, groups))
 
 
-def q3_plan(segment="HOUSEHOLD", odate_lt=None, ship_gt=None, schema=FULL):
+def q3_plan(segment="HOUSEHOLD", odate_lt=None, ship_gt=None, schema=FULL, segment_in=None, segment_ne=None):
     """Agg(group by l_orderkey,o_orderdate,o_shippriority; sum(ext*(1-disc)))
          <- Join(l_orderkey = o_orderkey) <- { Scan(lineitem; l_shipdate > d),
               Join(o_custkey = c_custkey) <- { Scan(orders; o_orderdate < d),
@@ -151,8 +151,14 @@ def q3_plan(segment="HOUSEHOLD", odate_lt=None, ship_gt=None, schema=FULL):
     odate_lt = days(1995, 3, 29) if odate_lt is None else odate_lt
     ship_gt = days(1995, 3, 29) if ship_gt is None else ship_gt
     B = K.LType(K.LTID_BOOLEAN)
-    cust = PhysicalOperator(POT_Scan, Info=ScanOpInfo("customer"),
-                            Filters=[func("=", B, S.col("customer", "c_mktsegment"), const(segment, K.VarcharType()))])
+    seg_col = S.col("customer", "c_mktsegment")
+    if segment_in is not None:            # c_mktsegment in (...): a code set on the build-side scan
+        seg_filter = func("in", B, seg_col, *[const(x, K.VarcharType()) for x in segment_in])
+    elif segment_ne is not None:
+        seg_filter = func("<>", B, seg_col, const(segment_ne, K.VarcharType()))
+    else:
+        seg_filter = func("=", B, seg_col, const(segment, K.VarcharType()))
+    cust = PhysicalOperator(POT_Scan, Info=ScanOpInfo("customer"), Filters=[seg_filter])
     orders = PhysicalOperator(POT_Scan, Info=ScanOpInfo("orders"),
                               Filters=[func("<", B, S.col("orders", "o_orderdate"), const(odate_lt, K.DateType()))])
     line = PhysicalOperator(POT_Scan, Info=ScanOpInfo("lineitem"),

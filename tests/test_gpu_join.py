@@ -605,3 +605,23 @@ def test_high_cardinality_avg(pg, oracle, uploaded, sf01_host, key, value):
                 assert (int(a[r]["coef"]), int(a[r]["scale"]), int(a[r]["neg"])) == (oc.value, os_.value, on.value)
             n += 1
     assert n == len(want)
+
+
+@pytest.mark.parametrize("kw", [dict(segment_in=["BUILDING", "MACHINERY"]), dict(segment_ne="HOUSEHOLD"), dict(segment_in=["NOPE"])])
+def test_q3_with_code_set_filter_on_the_build_side(pg, oracle, uploaded, sf01_host, kw):
+    """IN / <> on a dictionary column of a join's build-side scan (a code set evaluated by pipeline_kernel).
+    The oracle's Q3 filters on ONE segment code, so the expected result is Q3 over a customer table whose
+    segment codes are rewritten to 0 = selected / 1 = not selected."""
+    from plan_b200 import tpch as T
+    chunks, _, _ = _run(T.q3_plan(**kw), uploaded)
+    seg = sf01_host["customer"]["c_mktsegment"]
+    if "segment_in" in kw:
+        sel = np.isin(seg, [T.SEGMENTS.index(s) for s in kw["segment_in"] if s in T.SEGMENTS])
+    else:
+        sel = seg != T.SEGMENTS.index(kw["segment_ne"])
+    cust = dict(sf01_host["customer"])
+    cust["c_mktsegment"] = np.where(sel, 0, 1).astype(np.uint8)
+    ref = oracle.q3(cust, sf01_host["orders"], sf01_host["lineitem"], segment=0)
+    got = _q3_groups(chunks)
+    want = {(g["l_orderkey"], g["o_orderdate"], g["o_shippriority"]): g["x_revenue"] for g in ref["groups"]}
+    assert got == want and len(got) == ref["stats"]["ngroups"]
