@@ -105,6 +105,9 @@ typedef struct pg_result pg_result;
 
 /* ---- library / device ------------------------------------------------------ */
 int pg_abi_version(void);
+/* Device memory freed by pg_table_free / pg_plan_free is parked in a size-keyed cache for the next ingest or
+ * plan (multi-GB cudaMalloc/cudaFree pairs cost tens of milliseconds); pg_trim gives all of it back to the driver. */
+int pg_trim(void);
 /* Bind the calling process to one GPU (one process per GPU). */
 int pg_init(int device);
 int pg_shutdown(void);

@@ -50,6 +50,7 @@ class PgHugeint(C.Structure):
 _P = C.c_void_p
 SIGNATURES = [
     ("pg_abi_version", C.c_int, []),
+    ("pg_trim", C.c_int, []),
     ("pg_init", C.c_int, [C.c_int]),
     ("pg_shutdown", C.c_int, []),
     ("pg_last_error", C.c_char_p, []),

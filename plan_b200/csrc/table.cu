@@ -307,6 +307,13 @@ extern "C" {
 
 int pg_abi_version(void) { return PG_ABI_VERSION; }
 
+int pg_trim(void)
+{
+    if (ctx().ready) cudaSetDevice(ctx().device);
+    dev_trim();
+    return PG_OK;
+}
+
 const char *pg_last_error(void) { return get_error(); }
 
 int pg_init(int device)
