@@ -625,3 +625,21 @@ def test_q3_with_code_set_filter_on_the_build_side(pg, oracle, uploaded, sf01_ho
     got = _q3_groups(chunks)
     want = {(g["l_orderkey"], g["o_orderdate"], g["o_shippriority"]): g["x_revenue"] for g in ref["groups"]}
     assert got == want and len(got) == ref["stats"]["ngroups"]
+
+
+def test_baseline_sf10_configs_match_the_oracle_fixtures(pg):
+    """BASELINE.json configs[1] and configs[2]: Q6 and Q3 (top 10) at SF10 (59,986,052 lineitem rows) on one B200,
+    plus Q1, against the CPU oracle's SF10 results (tests/golden/oracle_sf10_*.txt, `make_sf100_fixtures.py 10`)."""
+    from plan_b200 import compute as X, tpch as T
+    t = T.generate_device_tables(10.0)
+    try:
+        assert t["lineitem"].rows() == 59986052
+        chunks, _, _ = _run(T.q6_plan(), t)
+        assert X.rows_text(X.order_limit(chunks, []), 1) == open(os.path.join(GOLDEN, "oracle_sf10_q6.txt")).read()
+        chunks, _, _ = _run(T.q3_topk_plan(10), t)
+        assert X.rows_text(X.order_limit(chunks, []), 4) == open(os.path.join(GOLDEN, "oracle_sf10_q3.txt")).read()
+        chunks, _, _ = _run(T.q1_plan(), t)
+        assert X.rows_text(X.order_limit(chunks, [(0, False), (1, False)]), 10) == open(os.path.join(GOLDEN, "oracle_sf10_q1.txt")).read()
+    finally:
+        for x in t.values():
+            x.free()
