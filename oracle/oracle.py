@@ -511,7 +511,7 @@ def q18_text(rows):
     return "\n".join(lines) + "\n"
 
 
-def q9(part, supplier, partsupp, orders, line, like_word="pink"):
+def q9(part, supplier, partsupp, orders, line, like_word="pink", with_counts=False):
     """TPC-H Q9 (cases/tpch/query/q9.sql): six-way INNER join, `p_name like '%pink%'`, group by
     (n_name, extract(year from o_orderdate)), sum(l_extendedprice*(1-l_discount) - ps_supplycost*l_quantity).
     Typing per the reference binder: the first product is DECIMAL scale 4; l_quantity is cast
@@ -542,11 +542,13 @@ def q9(part, supplier, partsupp, orders, line, like_word="pink"):
     year = (np.datetime64("1970-01-01") + odate.astype("timedelta64[D]")).astype("datetime64[Y]").astype(np.int64) + 1970
     keep = found & ofound & (nat >= 0)
     amount = ext * (100 - disc) - cost * qty * 100          # scale 4, exact int64
-    out = {}
+    out, cnt = {}, {}
     for n_, y_, a_ in zip(nat[keep], year[keep], amount[keep]):
-        out[(int(n_), int(y_))] = out.get((int(n_), int(y_)), 0) + int(a_)
+        k_ = (int(n_), int(y_))
+        out[k_] = out.get(k_, 0) + int(a_)
+        cnt[k_] = cnt.get(k_, 0) + 1
     names = nation_names()
-    rows = [(names[n_], y_, v) for (n_, y_), v in out.items()]
+    rows = [(names[n_], y_, v) + ((cnt[(n_, y_)],) if with_counts else ()) for (n_, y_), v in out.items()]
     rows.sort(key=lambda r: (r[0], -r[1]))
     return rows
 

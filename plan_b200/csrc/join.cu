@@ -798,7 +798,28 @@ struct JoinAggPipeline : Pipeline {
                 const AggExpr &a = aggs[(size_t)o.second];
                 col.width = a.width;
                 col.scale = a.scale;
-                if (a.fn == PG_AGG_COUNT || a.ltype == PG_LT_HUGEINT) {
+                if (a.fn == PG_AGG_AVG && a.ltype == PG_LT_DOUBLE) {             // avg(INT): float64 sum / float64 count
+                    col.type = PG_T_FLOAT64;
+                    col.data.resize(live.size() * 8);
+                    double *d = (double *)col.data.data();
+                    for (size_t i = 0; i < live.size(); i++) {
+                        const i128 v = sums[(size_t)live[i]];
+                        if (v >= ((i128)1 << 53) || v <= -((i128)1 << 53)) PG_FAIL(PG_EOVERFLOW, "avg(INT): sum not exact in float64");
+                        d[i] = (double)(i64)v / (double)cnts[(size_t)live[i]];
+                    }
+                } else if (a.fn == PG_AGG_AVG) {                                 // avg(DECIMAL) = sum.Quo(count)
+                    col.type = PG_T_DECIMAL128;
+                    col.data.resize(live.size() * sizeof(pg_decimal));
+                    pg_decimal *d = (pg_decimal *)col.data.data();
+                    for (size_t i = 0; i < live.size(); i++) {
+                        HDec sd, nd, qd;
+                        if (!hd_from_i128(sums[(size_t)live[i]], star_scale, &sd) || !hd_from_i128((i128)cnts[(size_t)live[i]], 0, &nd) || !hd_quo(sd, nd, &qd))
+                            PG_FAIL(PG_EOVERFLOW, "avg: decimal division failed");
+                        d[i].coef = qd.coef;
+                        d[i].scale = qd.scale;
+                        d[i].neg = qd.neg ? 1u : 0u;
+                    }
+                } else if (a.fn == PG_AGG_COUNT || a.ltype == PG_LT_HUGEINT) {
                     col.type = PG_T_HUGEINT;
                     col.data.resize(live.size() * sizeof(pg_hugeint));
                     pg_hugeint *d = (pg_hugeint *)col.data.data();
@@ -1563,7 +1584,9 @@ static int build_star(pg_plan *plan, const Node &aggn, const Node &top, std::uni
     const AggExpr *sum = nullptr;
     for (auto &ae : aggn.aggs) {
         if (ae.fn == PG_AGG_COUNT) continue;
-        if (ae.fn != PG_AGG_SUM || (ae.ltype != PG_LT_DECIMAL && ae.ltype != PG_LT_HUGEINT)) PG_FAIL(PG_EUNSUPPORTED, "star join: sum and count only");
+        const bool is_sum = ae.fn == PG_AGG_SUM && (ae.ltype == PG_LT_DECIMAL || ae.ltype == PG_LT_HUGEINT);
+        const bool is_avg = ae.fn == PG_AGG_AVG && (ae.ltype == PG_LT_DECIMAL || ae.ltype == PG_LT_DOUBLE);     // sum / row count at result time
+        if (!is_sum && !is_avg) PG_FAIL(PG_EUNSUPPORTED, "star join: sum, avg and count only");
         nsum++;
         sum = &ae;
     }
@@ -1644,7 +1667,7 @@ static int build_star(pg_plan *plan, const Node &aggn, const Node &top, std::uni
             p->sterms[i].mul *= (i64)m;
             scaled_worst = std::max(scaled_worst, worst * m);
         }
-        if (sum->ltype == PG_LT_HUGEINT && maxs != 0) PG_FAIL(PG_EUNSUPPORTED, "integer sum over a scaled value");
+        if ((sum->ltype == PG_LT_HUGEINT || sum->ltype == PG_LT_DOUBLE) && maxs != 0) PG_FAIL(PG_EUNSUPPORTED, "integer sum over a scaled value");
         p->star_scale = maxs;
         // a block's shared-memory partial is int64: it receives at most its share of the fact rows (grid-stride over the hits)
         const i64 threads = (i64)ctx().prop.multiProcessorCount * 8 * 256;

@@ -325,7 +325,7 @@ def q18_plan(qty_gt=314, limit=100, schema=FULL):
     return PhysicalOperator(POT_Limit, Outputs=outs, Children=[order], Info=LimitOpInfo(limit))
 
 
-def q9_plan(word="pink", schema=FULL):
+def q9_plan(word="pink", schema=FULL, agg="sum"):
     """TPC-H Q9 (cases/tpch/query/q9.sql) below its final Project, the subquery's expressions inlined in the aggregate:
       Order(nation, o_year desc)
         <- Agg(group by n_name, extract(year from o_orderdate); sum(l_extendedprice*(1-l_discount) - ps_supplycost*l_quantity))
@@ -365,8 +365,12 @@ def q9_plan(word="pink", schema=FULL):
     sum_t = K.DecimalType(38, 4)
     groups = [col(0, 9, V), func("extract", I, const("year", V), col(0, 8, D))]
     outs = [col(0, 0, V), col(0, 1, I), col(1, 0, sum_t)]
-    agg = PhysicalOperator(POT_Agg, Outputs=outs, Children=[j5], Info=AggOpInfo([func("sum", sum_t, amount)], groups))
-    return PhysicalOperator(POT_Order, Outputs=outs, Children=[agg], Info=OrderOpInfo([(col(0, 0, V), False), (col(0, 1, I), True)]))
+    aggs = [func(agg, sum_t, amount)]            # agg="avg": avg(DECIMAL) = sum.Quo(count) -> DECIMAL(38,4)
+    if agg == "avg":
+        aggs.append(func("count", K.HugeintType(), col(0, 0, BI)))
+        outs.append(col(1, 1, K.HugeintType()))
+    node = PhysicalOperator(POT_Agg, Outputs=outs, Children=[j5], Info=AggOpInfo(aggs, groups))
+    return PhysicalOperator(POT_Order, Outputs=outs, Children=[node], Info=OrderOpInfo([(col(0, 0, V), False), (col(0, 1, I), True)]))
 
 
 def part_like_plan(pattern, schema=FULL):

@@ -643,3 +643,31 @@ def test_baseline_sf10_configs_match_the_oracle_fixtures(pg):
     finally:
         for x in t.values():
             x.free()
+
+
+def test_q9_with_an_average(pg, oracle):
+    """avg(DECIMAL) in the star sink = sum.Quo(count), bit for bit against the oracle's decimal restatement."""
+    from plan_b200 import tpch as T
+    import ctypes as C
+    sf = 0.05
+    t = T.generate_device_tables(sf, want=T.ALL_TABLES)
+    try:
+        chunks, _, _ = _run(T.q9_plan(agg="avg"), t)
+        orders, line = oracle.gen_orders_lineitem(sf)
+        want = oracle.q9(oracle.gen_part(sf, "pink"), oracle.gen_supplier(sf), oracle.gen_partsupp(sf), orders, line, with_counts=True)
+        got = []
+        for c in chunks:
+            for r in range(c.Card()):
+                a = c.Data[2].Data[r]
+                got.append((c.Data[0].Dict[int(c.Data[0].Data[r])], int(c.Data[1].Data[r]), (int(a["coef"]), int(a["scale"]), int(a["neg"])),
+                            int(c.Data[3].Data[r]["lower"])))
+        L = oracle.lib()
+        exp = []
+        for nation, year, s_, n_ in want:
+            oc, os_, on = C.c_uint64(), C.c_int(), C.c_int()
+            assert L.orc_dec_quo(C.c_uint64(abs(s_)), 4, int(s_ < 0), C.c_uint64(n_), 0, 0, C.byref(oc), C.byref(os_), C.byref(on)) == 0
+            exp.append((nation, year, (oc.value, os_.value, on.value), n_))
+        assert got == exp
+    finally:
+        for x in t.values():
+            x.free()
