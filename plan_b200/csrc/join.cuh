@@ -738,7 +738,8 @@ filter_hits_kernel(const PipeParams p)
     const unsigned *__restrict__ bm = p.probe.bitmap;
     const u64 bmin = (u64)p.probe.bm_min, dom = p.probe.domain;
     const i64 G = gridDim.x;
-    constexpr int WBUF = 1024;                       // >= 32 * 4 * NT hits of one step
+    constexpr int WBUF = 512;                        // >= 32 * 4 * NT hits of one step.  (1024 entries = 33 KB per CTA took L1 away from
+                                                     //  the bitmap lookups: Q9's filter pass 2.84 ms against 2.33 ms with 512, 2.29 with 256)
     __shared__ unsigned s_buf[SA_THREADS / 32][WBUF];
     int nbuf = 0;                                    // warp-uniform fill level
     unsigned n_pass = 0, n_hits = 0;
