@@ -121,3 +121,51 @@ def test_oracle_is_not_reachable_from_the_product():
                 src = open(os.path.join(root, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
                 assert not [ln for ln in src.splitlines() if ln.lstrip().startswith("#include") and "oracle" in ln], f
+
+
+def test_product_host_arithmetic_agrees_with_the_oracle(tmp_path):
+    """The product finalises averages with its own govalues restatement (plan_b200/csrc/hostdec.hpp) and matches LIKE
+    patterns with its own wildcardMatch restatement (plan_ir.hpp).  Both are written independently of the oracle's
+    (oracle/decimal.h, oracle.wildcard_match): a host-only harness over the product headers must agree with the oracle
+    on random cases -- on the CPU, no GPU involved."""
+    import random
+    import subprocess
+    from oracle import oracle as O
+    exe = str(tmp_path / "hostlogic_check")
+    src = os.path.join(ROOT, "tests", "hostlogic", "hostlogic_check.cu")
+    subprocess.run(["/usr/local/cuda/bin/nvcc", "-std=c++17", "-O1", "-Wno-deprecated-gpu-targets", "-o", exe, src], check=True, capture_output=True)
+    rng = random.Random(7)
+    L = O.lib()
+    cases, lines = [], []
+    for _ in range(3000):
+        ca = rng.choice([rng.randrange(10 ** rng.randrange(1, 20)), 10 ** 19 - 1, 0, 1])
+        sa, na = rng.randrange(0, 9), rng.randrange(2)
+        if rng.random() < 0.7:
+            cb, sb = rng.randrange(1, 10 ** rng.randrange(1, 10)), 0          # avg: divide by a row count
+        else:
+            cb, sb = rng.randrange(1, 10 ** rng.randrange(1, 19)), rng.randrange(0, 5)
+        nb = rng.randrange(2) if rng.random() < 0.1 else 0
+        cases.append(("Q", ca, sa, na, cb, sb, nb))
+        lines.append("Q %d %d %d %d %d %d" % (ca, sa, na, cb, sb, nb))
+    for _ in range(4000):
+        p = "".join(rng.choice("ab%_") for _ in range(rng.randrange(0, 7)))
+        t = "".join(rng.choice("ab") for _ in range(rng.randrange(0, 9)))
+        cases.append(("W", p, t))
+        lines.append("W %s %s" % (p or "~", t or "~"))
+    out = subprocess.run([exe], input="\n".join(lines) + "\n", capture_output=True, text=True, check=True).stdout.split("\n")
+    for case, got in zip(cases, out):
+        if case[0] == "Q":
+            _, ca, sa, na, cb, sb, nb = case
+            oc, os_, on = C.c_uint64(), C.c_int(), C.c_int()
+            rc = L.orc_dec_quo(C.c_uint64(ca), sa, na, C.c_uint64(cb), sb, nb, C.byref(oc), C.byref(os_), C.byref(on))
+            want = "fail" if rc != 0 else "ok %d %d %d" % (oc.value, os_.value, on.value if oc.value else on.value)
+            if rc == 0 and oc.value == 0:
+                assert got.split()[:3] == ["ok", "0", str(os_.value)], (case, got, want)      # sign of zero is not significant
+            else:
+                assert got == want, (case, got, want)
+        else:
+            _, p, t = case
+            m, fast = got.split()
+            assert (m == "1") == O.wildcard_match(p.encode(), t.encode()), (case, got)
+            if fast == "1":
+                assert p[0] == "%" and p[-1] == "%" and (m == "1") == (p[1:-1] in t), (case, got)
