@@ -3,6 +3,7 @@
 //   Q <coef_a> <scale_a> <neg_a> <coef_b> <scale_b> <neg_b>   ->  "ok <coef> <scale> <neg>" | "fail"       (hd_quo)
 //   N <neg> <hi> <lo> <scale>                                  ->  "ok <coef> <scale> <neg>" | "fail"       (hd_normalise of a u128)
 //   W <pattern> <target>   ('~' stands for the empty string)   ->  "<match> <is_contains_fast_path>"        (wildcard_match)
+//   F <op> <float literal bits as u32> <scale> <vmin> <vmax>    ->  "<lo> <hi>"   (float_cmp_to_range: cast(DECIMAL AS FLOAT) <op> literal)
 #include <stdio.h>
 #include <string.h>
 
@@ -34,6 +35,16 @@ int main()
             HDec d;
             if (hd_normalise(neg != 0, ((u128)hi << 64) | (u128)lo, scale, &d)) printf("ok %llu %d %d\n", (unsigned long long)d.coef, d.scale, d.neg ? 1 : 0);
             else printf("fail\n");
+        } else if (kind == "F") {
+            int op, scale;
+            unsigned bits;
+            long long vmin, vmax;
+            std::cin >> op >> bits >> scale >> vmin >> vmax;
+            float k;
+            memcpy(&k, &bits, 4);
+            i64 lo, hi;
+            float_cmp_to_range(op, k, scale, vmin, vmax, &lo, &hi);
+            printf("%lld %lld\n", (long long)lo, (long long)hi);
         } else if (kind == "W") {
             std::string p, t, lit;
             std::cin >> p >> t;

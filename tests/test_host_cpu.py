@@ -152,9 +152,26 @@ def test_product_host_arithmetic_agrees_with_the_oracle(tmp_path):
         t = "".join(rng.choice("ab") for _ in range(rng.randrange(0, 9)))
         cases.append(("W", p, t))
         lines.append("W %s %s" % (p or "~", t or "~"))
+    # DECIMAL-vs-FLOAT-literal comparisons run in float32 in the reference (function_cast.go:349-354: Float64() then
+    # float32()); the product lowers them to integer ranges -- brute-force every column value in float32 here
+    ops = {12: np.less, 13: np.less_equal, 14: np.greater, 15: np.greater_equal, 10: np.equal}
+    for _ in range(300):
+        scale = rng.choice([0, 1, 2, 2, 2, 4])
+        vmin, vmax = sorted((rng.randrange(-500, 3000), rng.randrange(-500, 3000)))
+        lit = np.float32(rng.choice([rng.randrange(-500, 3000) / 10 ** scale, rng.uniform(-1, 30),
+                                     float(np.float32(0.03) - np.float32(0.01)), float(np.float32(0.03) + np.float32(0.01))]))
+        op = rng.choice(list(ops))
+        cases.append(("F", op, lit, scale, vmin, vmax))
+        lines.append("F %d %d %d %d %d" % (op, int(np.frombuffer(lit.tobytes(), np.uint32)[0]), scale, vmin, vmax))
     out = subprocess.run([exe], input="\n".join(lines) + "\n", capture_output=True, text=True, check=True).stdout.split("\n")
     for case, got in zip(cases, out):
-        if case[0] == "Q":
+        if case[0] == "F":
+            _, op, lit, scale, vmin, vmax = case
+            v = np.arange(vmin, vmax + 1, dtype=np.int64)
+            sel = v[ops[op]((v.astype(np.float64) / float(10 ** scale)).astype(np.float32), lit)]
+            lo, hi = (int(x) for x in got.split())
+            assert sorted(sel.tolist()) == list(range(max(lo, vmin), min(hi, vmax) + 1)), (case, got)
+        elif case[0] == "Q":
             _, ca, sa, na, cb, sb, nb = case
             oc, os_, on = C.c_uint64(), C.c_int(), C.c_int()
             rc = L.orc_dec_quo(C.c_uint64(ca), sa, na, C.c_uint64(cb), sb, nb, C.byref(oc), C.byref(os_), C.byref(on))
