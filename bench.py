@@ -103,6 +103,34 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------
+# parity: every bench run re-checks its own results (untimed) against the committed fixtures
+# ----------------------------------------------------------------------------------------
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+# query -> (ORDER BY applied by the host parents that stay in Go, number of columns)
+PARITY_RENDER = {"q6": ([], 1), "q1": ([(0, False), (1, False)], 10), "q3": ([], 4), "q9": ([], 3), "q18": ([], 6)}
+
+
+def parity_fixture(q, sf):
+    """Path of the committed oracle result for query q at this scale factor, or None.  The fixtures were
+    produced once on the CPU by tests/golden/make_sf100*_fixture*.py (the oracle over the same dbgen-equivalent
+    data); bench.py only reads the text files, it never runs the oracle in this arm."""
+    if sf != int(sf):
+        return None
+    p = os.path.join(GOLDEN, "oracle_sf%d_%s.txt" % (int(sf), q))
+    return p if os.path.exists(p) else None
+
+
+def parity_check(X, q, chunks, sf):
+    """True / False (byte-for-byte equality of the rendered rows with the fixture) or None (no fixture)."""
+    fx = parity_fixture(q, sf)
+    if fx is None or q not in PARITY_RENDER:
+        return None
+    order, ncols = PARITY_RENDER[q]
+    return X.rows_text(X.order_limit(chunks, order), ncols) == open(fx).read()
+
+
+# ----------------------------------------------------------------------------------------
 # reference arm: the reference's own CPU implementation of the path = the oracle port
 # ----------------------------------------------------------------------------------------
 
@@ -215,6 +243,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def min_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return float(t.item())
+
     def sum_over_ranks(x):
         if world == 1:
             return x
@@ -287,6 +322,18 @@ def main():
     ms_per_step = dt / args.steps * 1e3
     value = total_rows * len(queries) * args.steps / dt
 
+    # ---- parity (untimed): the results of THIS run, on every rank, against the committed fixtures --------
+    def all_ranks_agree(flag):
+        """None stays None; otherwise True only if every rank's rendered result equals the fixture."""
+        if flag is None:
+            return None
+        return bool(min_over_ranks(1.0 if flag else 0.0) > 0.5)
+
+    parity = {}
+    for q in queries:
+        chunks, _ = run_query(q)
+        parity[q] = all_ranks_agree(parity_check(X, q, chunks, args.sf))
+
     # ---- roofline of the dominant kernel (largest share of device time) ---------------------
     peak, peak_src = measured_peak_gbs()
     per_query = {}
@@ -335,7 +382,9 @@ def main():
                 ex = X.gpuPipelineExec(mk(), extra_tables)
                 ex.Init()
                 for _ in range(2):
-                    ex.Reset(); X.drain(ex)
+                    ex.Reset(); chunks = X.drain(ex)
+                if name in PARITY_RENDER:
+                    parity[name] = all_ranks_agree(parity_check(X, name, chunks, args.sf))
                 tot = 0.0
                 for _ in range(5):
                     barrier()
@@ -431,6 +480,8 @@ def main():
                        "l2": "inputs larger than L2 (%.1f GB of columns per GPU vs 126 MB)" % (
                            per_query[dom]["main_kernel_bytes"] / 1e9),
                        "parallelism": "row-range shard x%d, NCCL all-gather merge of partial aggregates" % world},
+            "parity": parity, "parity_source": "rendered rows == tests/golden/oracle_sf%g_<query>.txt byte for byte, checked on every "
+                                               "rank after the timed loop (null: no fixture at this SF)" % args.sf,
             "queries": per_query, "also_measured": also, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "clocks": clocks, "datagen_s": gen_s,
         }
@@ -442,6 +493,10 @@ def main():
     if world > 1:
         lib.pg_comm_destroy()
         dist.destroy_process_group()
+    bad = sorted(q for q, ok in parity.items() if ok is False)
+    if bad:
+        sys.stderr.write("bench.py: PARITY MISMATCH against tests/golden fixtures for %s\n" % ", ".join(bad))
+        sys.exit(3)
 
 
 if __name__ == "__main__":
