@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define PG_ABI_VERSION 1
+#define PG_ABI_VERSION 2
 
 typedef enum {
     PG_OK = 0,
@@ -141,6 +141,21 @@ int pg_table_reserve(pg_table *t, int64_t nrows);
  * valid[i] may be NULL (all valid) or a packed bitmap, bit=1 valid, LSB first
  * (pkg/util/bitmap.go).  `valid` itself may be NULL.  Copies synchronously.     */
 int pg_table_append(pg_table *t, int64_t nrows, const void *const *cols, const uint8_t *const *valid);
+/* The same with NARROW host buffers: the shim knows each chunk's value range (it walks the vector anyway to
+ * flatten govalues Decimals / Dates, chunk/vector_format.go:64-97) and may hand a column over at 1, 2 or 4 bytes
+ * per value with a frame of reference:  value = base + data[i], data[i] read as uint8 / uint16 / int32 / int64
+ * for width 1 / 2 / 4 / 8.  Only the narrow bytes cross PCIe; the device widens them.  width 0 = the column's
+ * native width (base must be 0).  Narrow buffers are accepted for INT32 / INT64 / DATE32 / DECIMAL64 columns.
+ * Appends of at most 65536 rows (the reference's 2048-row chunks) are gathered in pinned host staging and
+ * copied asynchronously per 262144 rows: no per-call synchronisation or device allocation.                  */
+typedef struct {
+    const void *data;
+    int32_t width;
+    int32_t reserved;
+    int64_t base;
+    const uint8_t *valid;      /* packed validity for this column or NULL */
+} pg_colbuf;
+int pg_table_append_cols(pg_table *t, int64_t nrows, const pg_colbuf *cols);
 /* Device pointer of column `col` (capacity = reserved rows) for producers that
  * already hold the data in HBM (the in-box generator); follow with set_rows.    */
 int pg_table_device_column(pg_table *t, int col, void **dev_ptr);
@@ -158,6 +173,12 @@ int pg_table_seal(pg_table *t, int64_t global_row_offset);
 #define PG_DIST_REPLICATED 1
 int pg_table_set_distribution(pg_table *t, int dist);
 int pg_table_rows(const pg_table *t, int64_t *nrows);
+/* Physical encoding pg_table_seal chose for a column from its min/max statistics (frame of reference:
+ * value = base + stored): stored bytes per value (1, 2, 4 or 8; 0 for host-resident VARCHAR) and the base. */
+int pg_table_column_encoding(const pg_table *t, int col, int32_t *stored_width, int64_t *base);
+/* Bulk export: `nrows` rows of column `col` starting at `row`, in the column's NATIVE encoding, into a host
+ * buffer (the inverse of pg_table_append; the device decodes packed columns first).  Not for VARCHAR.      */
+int pg_table_read_column(pg_table *t, int col, int64_t row, int64_t nrows, void *host_out);
 void pg_table_free(pg_table *t);
 
 /* ---- plans ------------------------------------------------------------------

@@ -47,9 +47,6 @@ int pg_tpch_supplier(double sf, pg_table **supplier);
 int pg_tpch_partsupp(double sf, pg_table **partsupp);
 int pg_tpch_nation(pg_table **nation);
 
-/* copy `nrows` rows of column `col` starting at `row` to a host buffer (tests, e2e bench) */
-int pg_table_read_column(pg_table *t, int col, int64_t row, int64_t nrows, void *host_out);
-
 #ifdef __cplusplus
 }
 #endif

@@ -1,9 +1,11 @@
-"""ctypes bindings of include/plangpu.h and include/plangpu_tpch.h."""
+"""ctypes bindings of include/plangpu.h (libplangpu.so: the drop-in library) and include/plangpu_tpch.h
+(libplangpu_tpch.so: the in-box TPC-H generator used by tests and benchmarks only)."""
 import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libplangpu.so")
+TPCH_LIB_PATH = os.path.join(HERE, "libplangpu_tpch.so")
 
 PG_OK, PG_EINVAL, PG_ENOMEM, PG_ECUDA, PG_ENCCL, PG_EOVERFLOW, PG_EUNSUPPORTED, PG_ESTATE = range(8)
 STATUS_NAMES = ["PG_OK", "PG_EINVAL", "PG_ENOMEM", "PG_ECUDA", "PG_ENCCL", "PG_EOVERFLOW", "PG_EUNSUPPORTED",
@@ -38,6 +40,11 @@ class Stats(C.Structure):
                 ("aux", C.c_int64 * 8)]
 
 
+class ColBuf(C.Structure):
+    """pg_colbuf: a host column buffer at 1/2/4/8 bytes per value with a frame of reference."""
+    _fields_ = [("data", C.c_void_p), ("width", C.c_int32), ("reserved", C.c_int32), ("base", C.c_int64), ("valid", C.c_void_p)]
+
+
 class PgDecimal(C.Structure):
     _fields_ = [("coef", C.c_uint64), ("scale", C.c_int32), ("neg", C.c_uint32)]
 
@@ -61,6 +68,9 @@ SIGNATURES = [
     ("pg_table_create", C.c_int, [C.c_char_p, C.c_int, C.POINTER(ColDesc), C.POINTER(_P)]),
     ("pg_table_reserve", C.c_int, [_P, C.c_int64]),
     ("pg_table_append", C.c_int, [_P, C.c_int64, C.POINTER(_P), C.POINTER(_P)]),
+    ("pg_table_append_cols", C.c_int, [_P, C.c_int64, C.POINTER(ColBuf)]),
+    ("pg_table_column_encoding", C.c_int, [_P, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
+    ("pg_table_read_column", C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, _P]),
     ("pg_table_device_column", C.c_int, [_P, C.c_int, C.POINTER(_P)]),
     ("pg_table_set_rows", C.c_int, [_P, C.c_int64]),
     ("pg_table_seal", C.c_int, [_P, C.c_int64]),
@@ -81,6 +91,9 @@ SIGNATURES = [
     ("pg_result_column_dict", C.c_int, [_P, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.POINTER(C.c_char_p))]),
     ("pg_result_stats", C.c_int, [_P, C.POINTER(Stats)]),
     ("pg_result_free", None, [_P]),
+]
+# include/plangpu_tpch.h (libplangpu_tpch.so)
+TPCH_SIGNATURES = [
     ("pg_tpch_num_orders", C.c_int64, [C.c_double]),
     ("pg_tpch_num_customers", C.c_int64, [C.c_double]),
     ("pg_tpch_orders_lineitem", C.c_int, [C.c_double, C.c_int64, C.c_int64, C.POINTER(_P), C.POINTER(_P)]),
@@ -89,25 +102,42 @@ SIGNATURES = [
     ("pg_tpch_supplier", C.c_int, [C.c_double, C.POINTER(_P)]),
     ("pg_tpch_partsupp", C.c_int, [C.c_double, C.POINTER(_P)]),
     ("pg_tpch_nation", C.c_int, [C.POINTER(_P)]),
-    ("pg_table_read_column", C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, _P]),
 ]
 
 _LIB = None
 
 
+class _Libs:
+    """Attribute access over both libraries: the operator ABI first, then the generator."""
+
+    def __init__(self, core, tpch):
+        self.core, self.tpch = core, tpch
+
+    def __getattr__(self, name):
+        try:
+            return getattr(self.core, name)
+        except AttributeError:
+            return getattr(self.tpch, name)
+
+
+def _load(path, signatures):
+    if not os.path.exists(path):
+        raise ImportError("%s is missing: build it with `python -m plan_b200.build` or __graft_entry__.build(); "
+                          "the GPU path has no CPU fallback" % path)
+    L = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    for name, res, args in signatures:
+        f = getattr(L, name)
+        f.restype = res
+        f.argtypes = args
+    return L
+
+
 def lib():
-    """Load libplangpu.so.  Raises if it was not built -- there is no CPU fallback."""
+    """Load libplangpu.so (+ the generator library).  Raises if they were not built -- there is no CPU fallback."""
     global _LIB
     if _LIB is None:
-        if not os.path.exists(LIB_PATH):
-            raise ImportError("libplangpu.so is missing (%s): build it with `python -m plan_b200.build` "
-                              "or __graft_entry__.build(); the GPU path has no CPU fallback" % LIB_PATH)
-        L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
-        for name, res, args in SIGNATURES:
-            f = getattr(L, name)
-            f.restype = res
-            f.argtypes = args
-        _LIB = L
+        core = _load(LIB_PATH, SIGNATURES)
+        _LIB = _Libs(core, _load(TPCH_LIB_PATH, TPCH_SIGNATURES))
     return _LIB
 
 

@@ -68,7 +68,8 @@ static TypedCol typed(const pg_table *t, int col)
 {
     TypedCol c;
     c.p = t->cols[(size_t)col].d_data;
-    c.width = type_size(t->cols[(size_t)col].type);
+    c.width = t->cols[(size_t)col].phys_width();
+    c.base = t->cols[(size_t)col].base;
     c.valid = t->cols[(size_t)col].has_nulls ? t->cols[(size_t)col].d_valid : nullptr;
     return c;
 }
@@ -313,8 +314,7 @@ struct JoinAggPipeline : Pipeline {
         for (int k = 0; k < pp.npred; k++) any_valid = any_valid || pp.pred[k].col.valid != nullptr;
         // (a build stage without a probe of its own also qualifies: the filter pass then lists every row that
         //  passes the predicate -- pp.probe_key must name the key column so the vector loads have a source)
-        return (pp.has_probe ? pp.probe.bitmap != nullptr : ins_sink) && pp.nlike == 0 && pp.npred <= 1 && (pp.npred == 0 || (pp.pred[0].col.width == 4 && !pp.pred[0].is_set)) &&
-               (pp.probe_key.width == 4 || pp.probe_key.width == 8) && !any_valid && t->nrows < ((i64)1 << 32) &&
+        return (pp.has_probe ? pp.probe.bitmap != nullptr : ins_sink) && pp.nlike == 0 && pp.npred <= 1 && (pp.npred == 0 || !pp.pred[0].is_set) && !any_valid && t->nrows < ((i64)1 << 32) &&
                !getenv("PG_JOIN_GENERIC");
     }
 
@@ -332,13 +332,9 @@ struct JoinAggPipeline : Pipeline {
         pp.hit_count = d_hit_count.as<unsigned long long>();
         i64 ntiles = (hi - lo + SA_TILE - 1) / SA_TILE;
         int grid = (int)std::max<i64>(std::min<i64>(ntiles, (i64)ctx().prop.multiProcessorCount * 8), 1);
-        const bool k8 = pp.probe_key.width == 8, hp = pp.npred == 1;
-        // (two tiles per step were measured slower for both key widths: 90 registers cost more occupancy
-        //  than the extra loads in flight bring)
-#define PG_FH(K, P) filter_hits_kernel<K, P, 1><<<grid, SA_THREADS, 0, st>>>(pp)
-        if (k8) { if (hp) PG_FH(8, true); else PG_FH(8, false); }
-        else { if (hp) PG_FH(4, true); else PG_FH(4, false); }
-#undef PG_FH
+        // (two tiles per step were measured slower: 90 registers cost more occupancy than the extra loads in flight bring)
+        if (pp.npred == 1) filter_hits_kernel<true, 1><<<grid, SA_THREADS, 0, st>>>(pp);
+        else filter_hits_kernel<false, 1><<<grid, SA_THREADS, 0, st>>>(pp);
         PG_CUDA(cudaGetLastError());
         return PG_OK;
     }
@@ -742,6 +738,8 @@ struct JoinAggPipeline : Pipeline {
         sp.gsum_hi = sp.gsum + star_ngroups;
         sp.gcnt = sp.gsum + 2 * star_ngroups;
         sp.counters = d_counters.as<unsigned long long>();
+        if ((size_t)star_ngroups * 16 > 48 * 1024)      // above the default dynamic shared memory limit (up to 64 KB at STAR_MAXGROUPS)
+            PG_CUDA(cudaFuncSetAttribute(hits_star_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, star_ngroups * 16));
         hits_star_kernel<<<c.prop.multiProcessorCount * 8, 256, (size_t)star_ngroups * 16, st>>>(sp);
         PG_CUDA(cudaGetLastError());
         PG_CUDA(cudaEventRecord(ev_main.b, st));
@@ -903,8 +901,7 @@ struct JoinAggPipeline : Pipeline {
             bool pred_valid = false;
             for (int k = 0; k < pp.npred; k++) pred_valid = pred_valid || pp.pred[k].col.valid != nullptr;
             one_shape = !pred_valid && gs.nparts == 1 && gs.nacc == 1 && gs.nfac[0] == 1 && pp.npred <= 1 &&
-                        (pp.npred == 0 || (pp.pred[0].col.width == 4 && !pp.pred[0].is_set)) && gs.part[0].col.width >= 4 &&
-                        gs.fac[0][0].col.width >= 4 && !getenv("PG_GROUP_GENERIC");
+                        (pp.npred == 0 || !pp.pred[0].is_set) && !getenv("PG_GROUP_GENERIC");
         }
         const bool sorted_runs = one_shape && key_sorted && t->nrows > 0 && !(shuffle && c.world > 1) && !getenv("PG_NO_SORTED_RUNS");
         i64 ngroups = 0;
@@ -933,13 +930,8 @@ struct JoinAggPipeline : Pipeline {
                 RunOut ro{d_out_klo.as<i64>(), d_out_khi.as<i64>(), d_out_acc.as<i64>(), out_cap, d_counters.as<unsigned long long>() + 2,
                           hav_plane, hav_lo, hav_hi};
                 PG_CUDA(cudaEventRecord(ev_main.a, st));
-                const bool k8 = gs.part[0].col.width == 8, v8 = gs.fac[0][0].col.width == 8, hp = pp.npred == 1;
-#define PG_RG(K, V, P) run_group_kernel<K, V, P><<<(int)grid, SA_THREADS, 0, st>>>(pp, ro, first, last, chunk_tiles)
-                if (k8 && v8) { if (hp) PG_RG(8, 8, true); else PG_RG(8, 8, false); }
-                else if (k8) { if (hp) PG_RG(8, 4, true); else PG_RG(8, 4, false); }
-                else if (v8) { if (hp) PG_RG(4, 8, true); else PG_RG(4, 8, false); }
-                else { if (hp) PG_RG(4, 4, true); else PG_RG(4, 4, false); }
-#undef PG_RG
+                if (pp.npred == 1) run_group_kernel<true><<<(int)grid, SA_THREADS, 0, st>>>(pp, ro, first, last, chunk_tiles);
+                else run_group_kernel<false><<<(int)grid, SA_THREADS, 0, st>>>(pp, ro, first, last, chunk_tiles);
                 PG_CUDA(cudaGetLastError());
                 run_fixup_kernel<<<(int)((nchunks + 255) / 256), 256, 0, st>>>(first, last, (int)nchunks, ro);
                 PG_CUDA(cudaGetLastError());
@@ -993,13 +985,8 @@ struct JoinAggPipeline : Pipeline {
                 if (one_shape) {
                     i64 ntiles = (t->nrows + SA_TILE - 1) / SA_TILE;
                     int grid = (int)std::max<i64>(std::min<i64>(ntiles, (i64)c.prop.multiProcessorCount * 8), 1);
-                    const bool k8 = gs.part[0].col.width == 8, v8 = gs.fac[0][0].col.width == 8, hp = pp.npred == 1;
-#define PG_G1(K, V, P) group1_kernel<K, V, P><<<grid, SA_THREADS, 0, st>>>(pp)
-                    if (k8 && v8) { if (hp) PG_G1(8, 8, true); else PG_G1(8, 8, false); }
-                    else if (k8) { if (hp) PG_G1(8, 4, true); else PG_G1(8, 4, false); }
-                    else if (v8) { if (hp) PG_G1(4, 8, true); else PG_G1(4, 8, false); }
-                    else { if (hp) PG_G1(4, 4, true); else PG_G1(4, 4, false); }
-#undef PG_G1
+                    if (pp.npred == 1) group1_kernel<true><<<grid, SA_THREADS, 0, st>>>(pp);
+                    else group1_kernel<false><<<grid, SA_THREADS, 0, st>>>(pp);
                 } else {
                     scan_group_kernel<<<grid_rows(t->nrows), 256, 0, st>>>(pp);
                 }
@@ -1054,7 +1041,7 @@ struct JoinAggPipeline : Pipeline {
                 const FdOut &o = fd[f];
                 const pg_table *ct = tab(o.slot);
                 const bool host_col = ct->cols[(size_t)o.col].type == PG_T_VARCHAR;
-                TypedCol none{nullptr, 8, nullptr};
+                TypedCol none{nullptr, 8, 0, nullptr};
                 TypedCol colref = host_col ? none : typed(ct, o.col);
                 i64 *dst = d_out_acc.as<i64>() + (size_t)(gs.nacc + 1 + (int)f) * (size_t)out_cap;
                 if (o.kind == 0) {
@@ -1473,7 +1460,7 @@ static int build_star(pg_plan *plan, const Node &aggn, const Node &top, std::uni
     };
     auto int_nonnull = [&](const HRef &h) {
         const Column &cc = p->tab(p->origin_slot[(size_t)h.origin])->cols[(size_t)h.col];
-        return is_int_family(cc.type) && !cc.has_nulls;
+        return is_int_family(cc.type) && !cc.any_nulls();
     };
     for (size_t i = spine.size(); i-- > 0;) {          // bottom-up
         const Node &J = *spine[i];
@@ -1496,7 +1483,7 @@ static int build_star(pg_plan *plan, const Node &aggn, const Node &top, std::uni
             if (be1->kind != PG_TK_COL || !resolve(J.children[1], be1->idx, &b2) || b2.slot != S.src_slot) PG_FAIL(PG_EUNSUPPORTED, "second build key is not a column of the build scan");
             const pg_table *bt = p->tab(S.src_slot);
             const Column &k1 = bt->cols[(size_t)S.ins_key_col], &k2 = bt->cols[(size_t)b2.col];
-            auto fits32 = [](const Column &c) { return is_int_family(c.type) && !c.has_nulls && c.vmin >= INT32_MIN && c.vmax <= INT32_MAX; };
+            auto fits32 = [](const Column &c) { return is_int_family(c.type) && !c.any_nulls() && c.vmin >= INT32_MIN && c.vmax <= INT32_MAX; };
             if (!fits32(k1) || !fits32(k2)) PG_FAIL(PG_EUNSUPPORTED, "two-column join keys must both fit 32 bits");
             S.ins_key_col2 = b2.col;
             S.unique_key = false;
@@ -1554,19 +1541,19 @@ static int build_star(pg_plan *plan, const Node &aggn, const Node &top, std::uni
         }
         if (ge->kind != PG_TK_COL || !locate(top, ge->idx, &hp.v)) PG_FAIL(PG_EUNSUPPORTED, "star join: group key is not a reachable column");
         const Column &cc = p->tab(p->origin_slot[(size_t)hp.v.origin])->cols[(size_t)hp.v.col];
-        if (cc.has_nulls) PG_FAIL(PG_EUNSUPPORTED, "star join: nullable group key");
+        if (cc.any_nulls()) PG_FAIL(PG_EUNSUPPORTED, "star join: nullable group key");
         if (hp.fn == 1) {
             if (cc.type != PG_T_DATE32) PG_FAIL(PG_EUNSUPPORTED, "EXTRACT(year) of a non-date column");
-            hp.lo = host_year_of_days(cc.vmin);
-            hp.n = (int)(host_year_of_days(cc.vmax) - hp.lo + 1);
+            hp.lo = host_year_of_days(cc.gmin());
+            hp.n = (int)(host_year_of_days(cc.gmax()) - hp.lo + 1);
             hp.type = PG_T_INT32;
         } else if (cc.type == PG_T_DICT8 || cc.type == PG_T_CHAR1) {
             hp.lo = 0;
             hp.n = cc.type == PG_T_DICT8 ? std::max<int>((int)cc.dict.size(), 1) : 256;
             hp.type = cc.type;
-        } else if (is_int_family(cc.type) && cc.stats_ok && (i128)cc.vmax - (i128)cc.vmin + 1 <= STAR_MAXGROUPS) {
-            hp.lo = cc.vmin;
-            hp.n = (int)(cc.vmax - cc.vmin + 1);
+        } else if (is_int_family(cc.type) && cc.stats_ok && (i128)cc.gmax() - (i128)cc.gmin() + 1 <= STAR_MAXGROUPS) {
+            hp.lo = cc.gmin();
+            hp.n = (int)(cc.gmax() - cc.gmin() + 1);
             hp.type = cc.type;
         } else {
             PG_FAIL(PG_EUNSUPPORTED, "star join: group key domain is not small and dense");
@@ -1640,14 +1627,14 @@ static int build_star(pg_plan *plan, const Node &aggn, const Node &top, std::uni
                 }
                 if (!ce || !locate(top, ce->idx, &ht.fac[f])) PG_FAIL(PG_EUNSUPPORTED, "star join: factor is not (constant +/- reachable column)");
                 const Column &cc = p->tab(p->origin_slot[(size_t)ht.fac[f].origin])->cols[(size_t)ht.fac[f].col];
-                if (!is_int_family(cc.type) || cc.type == PG_T_DATE32 || cc.has_nulls) PG_FAIL(PG_EUNSUPPORTED, "star join: factor column type");
+                if (!is_int_family(cc.type) || cc.type == PG_T_DATE32 || cc.any_nulls()) PG_FAIL(PG_EUNSUPPORTED, "star join: factor column type");
                 const int cs = cc.type == PG_T_DECIMAL64 ? cc.scale : 0;
                 i64 k = 0;
                 if (ke && !const_at_scale(ke, cs, &k)) PG_FAIL(PG_EUNSUPPORTED, "constant does not fit the column scale");
                 ht.fc[f] = negk ? -k : k;
                 ht.fs[f] = sgn;
                 scale += cs;
-                i128 lo = (i128)ht.fc[f] + (i128)sgn * cc.vmin, hi = (i128)ht.fc[f] + (i128)sgn * cc.vmax;
+                i128 lo = (i128)ht.fc[f] + (i128)sgn * cc.gmin(), hi = (i128)ht.fc[f] + (i128)sgn * cc.gmax();
                 i128 m = std::max(lo < 0 ? -lo : lo, hi < 0 ? -hi : hi);
                 bound *= m > 1 ? m : 1;
                 mark(ht.fac[f]);
@@ -1683,12 +1670,12 @@ static int build_star(pg_plan *plan, const Node &aggn, const Node &top, std::uni
     p->outs = aggn.outs;
     if (aggn.having.size()) PG_FAIL(PG_EUNSUPPORTED, "star join: HAVING");
     // bytes: the filter pass streams the fact key (+ predicate) column; everything else is gathered per hit
-    p->main_bytes = st->nrows * type_size(st->cols[(size_t)p->probe_key_col].type);
-    for (auto &r : p->ranges) p->main_bytes += st->nrows * type_size(st->cols[(size_t)r.col].type);
+    p->main_bytes = st->nrows * st->cols[(size_t)p->probe_key_col].phys_width();
+    for (auto &r : p->ranges) p->main_bytes += st->nrows * st->cols[(size_t)r.col].phys_width();
     p->algorithmic_bytes = p->main_bytes;
     for (auto &sp : p->stages) {
         const pg_table *bt = p->tab(sp->src_slot);
-        p->algorithmic_bytes += bt->nrows * type_size(bt->cols[(size_t)sp->ins_key_col].type);
+        p->algorithmic_bytes += bt->nrows * bt->cols[(size_t)sp->ins_key_col].phys_width();
     }
     if (ctx().world > 1 && st->dist != PG_DIST_REPLICATED) {
         // sharded fact table: every build side must be whole on every rank, or sharded on the same key ranges
@@ -1854,7 +1841,7 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &top, std::unique
             BaseCol bc;
             if (ge->kind != PG_TK_COL || !resolve(top, ge->idx, &bc)) { ok = false; break; }
             const Column &cc = p->tab(bc.slot)->cols[(size_t)bc.col];
-            if (cc.has_nulls) { ok = false; break; }
+            if (cc.any_nulls()) { ok = false; break; }
             if (cc.type == PG_T_VARCHAR) need = true;
             if (bc.slot == build_slot) {
                 if (bc.col == T.ins_key_col) anchor = true;
@@ -1890,14 +1877,14 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &top, std::unique
         else return false;
         vr->col = typed(t, bc.col);
         *colp = &t->cols[(size_t)bc.col];
-        return !(*colp)->has_nulls;
+        return !(*colp)->any_nulls();
     };
 
     // group keys: up to 3 parts packed into two 64-bit words
     if (p->fd_mode) {
         p->nparts = 1;
         p->gs.nparts = 1;
-        p->gs.part[0].col = TypedCol{nullptr, 8, nullptr};
+        p->gs.part[0].col = TypedCol{nullptr, 8, 0, nullptr};
         p->gs.part[0].from_build = 2;                  // the build row id is the group key
         p->group_out_type.push_back(PG_T_INT64);
     } else if (aggn.groups.empty() || aggn.groups.size() > GT_MAXKEYPARTS) {
@@ -2065,15 +2052,15 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &top, std::unique
         }
         for (auto &u : used) {
             const pg_table *t = p->tab(u.first);
-            i64 b = t->nrows * type_size(t->cols[(size_t)u.second].type);
+            i64 b = t->nrows * t->cols[(size_t)u.second].phys_width();
             p->algorithmic_bytes += b;      // every referenced column read once
         }
         // the probe kernel itself STREAMS only the predicate and key columns; the other probe-side
         // columns are gathered for matching rows (added per run: 32-byte sector per value)
-        for (auto &r : p->ranges) p->main_bytes += st->nrows * type_size(st->cols[(size_t)r.col].type);
+        for (auto &r : p->ranges) p->main_bytes += st->nrows * st->cols[(size_t)r.col].phys_width();
         bool key_is_pred = p->no_join;
         for (auto &r : p->ranges) key_is_pred = key_is_pred || r.col == p->probe_key_col;
-        if (!key_is_pred) p->main_bytes += st->nrows * type_size(st->cols[(size_t)p->probe_key_col].type);
+        if (!key_is_pred) p->main_bytes += st->nrows * st->cols[(size_t)p->probe_key_col].phys_width();
         if (p->no_join) p->main_bytes = p->algorithmic_bytes;
     }
     // multi-GPU: which joins are shard-local?  A REPLICATED build side is complete everywhere.  Two

@@ -133,23 +133,45 @@ __device__ __forceinline__ void jt_probe(const JoinTable &t, i64 key, F f)
     }
 }
 
-// a column of a base table read by row id with its native width
+// a column of a base table in its physical encoding (NCol: logical = base + stored), plus validity
 struct TypedCol {
     const void *p;
-    int width;             // 1, 4 or 8 bytes
+    int width;             // stored bytes per value: 1, 2, 4 or 8
+    i64 base;
     const uint8_t *valid;  // packed validity (1 = not NULL) or null when the column holds no NULLs
 };
 __device__ __forceinline__ bool typed_valid(const TypedCol &c, i64 row)
 {
     return c.valid == nullptr || ((__ldg(c.valid + (row >> 3)) >> (row & 7)) & 1);
 }
+// LOGICAL value of one row (gathers by row id)
 __device__ __forceinline__ i64 load_typed(const TypedCol &c, i64 row)
 {
     switch (c.width) {
     case 8: return __ldg((const i64 *)c.p + row);
-    case 4: return (i64)__ldg((const int *)c.p + row);
-    default: return (i64)__ldg((const uint8_t *)c.p + row);
+    case 4: return (i64)__ldg((const int *)c.p + row) + c.base;
+    case 2: return (i64)__ldg((const unsigned short *)c.p + row) + c.base;
+    default: return (i64)__ldg((const uint8_t *)c.p + row) + c.base;
     }
+}
+// streaming access to 4 consecutive rows (row a multiple of 4): raw vector load now, LOGICAL values on unpack
+__device__ __forceinline__ NCol typed_ncol(const TypedCol &c)
+{
+    NCol n;
+    n.p = c.p; n.pw = c.width; n.pad_ = 0; n.base = c.base;
+    return n;
+}
+__device__ __forceinline__ void ld_typed4(const TypedCol &c, i64 row, Raw4<true> &r) { ld_raw4(typed_ncol(c), row, r); }
+__device__ __forceinline__ void unpack_typed4(const TypedCol &c, const Raw4<true> &r, i64 (&v)[4])
+{
+    unpack4(typed_ncol(c), r, v);
+    if (c.width != 8) { v[0] += c.base; v[1] += c.base; v[2] += c.base; v[3] += c.base; }
+}
+__device__ __forceinline__ void load_typed4(const TypedCol &c, i64 row, i64 (&v)[4])
+{
+    Raw4<true> r;
+    ld_typed4(c, row, r);
+    unpack_typed4(c, r, v);
 }
 
 struct SrcPred {          // inclusive range on a source column, or (byte-coded columns) a set of codes: IN, <>, OR of =
@@ -450,45 +472,33 @@ static scan_group_kernel(const PipeParams p)
 // `group by l_orderkey having sum(l_quantity) > 314`.  16-byte streaming loads (4 rows per thread),
 // runs of equal keys are first combined inside the thread's 4 rows, then one compact table update
 // per run.  Everything is compile-time except pointers and constants.
-template <int KEYW, int VALW, bool HAS_PRED>
+template <bool HAS_PRED>
 __global__ void __launch_bounds__(SA_THREADS)
 group1_kernel(const PipeParams p)
 {
     unsigned long long n_pass = 0;
     const i64 ntiles = (p.nrows + SA_TILE - 1) / SA_TILE;
-    const int plo = (int)(p.pred[0].lo < INT32_MIN ? INT32_MIN : p.pred[0].lo);
-    const int phi = (int)(p.pred[0].hi > INT32_MAX ? INT32_MAX : p.pred[0].hi);
-    const bool pempty = p.pred[0].lo > p.pred[0].hi;
-    const void *kp = p.gs.part[0].col.p, *vp = p.gs.fac[0][0].col.p;
+    const i64 plo = p.pred[0].lo, phi = p.pred[0].hi;
+    const TypedCol kc = p.gs.part[0].col, vc = p.gs.fac[0][0].col;
     const i64 fc = p.gs.fc[0][0];
     const int fs = p.gs.fs[0][0];
     for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         i64 row = tile * SA_TILE + threadIdx.x * SA_VEC;
         i64 rem = p.nrows - row;
-        int4 d = make_int4(0, 0, 0, 0);
-        if (HAS_PRED) d = ld_stream16((const int *)p.pred[0].col.p + row);
-        i64 k[4], v[4];
-        if (KEYW == 8) {
-            longlong2 a = ld_stream16_ll((const i64 *)kp + row), b = ld_stream16_ll((const i64 *)kp + row + 2);
-            k[0] = a.x; k[1] = a.y; k[2] = b.x; k[3] = b.y;
-        } else {
-            int4 a = ld_stream16((const int *)kp + row);
-            k[0] = a.x; k[1] = a.y; k[2] = a.z; k[3] = a.w;
-        }
-        if (VALW == 8) {
-            longlong2 a = ld_stream16_ll((const i64 *)vp + row), b = ld_stream16_ll((const i64 *)vp + row + 2);
-            v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
-        } else {
-            int4 a = ld_stream16((const int *)vp + row);
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-        }
-        int dv[4] = {d.x, d.y, d.z, d.w};
+        i64 dv[4] = {0, 0, 0, 0}, k[4], v[4];
+        Raw4<true> rd, rk, rv;
+        if (HAS_PRED) ld_typed4(p.pred[0].col, row, rd);
+        ld_typed4(kc, row, rk);
+        ld_typed4(vc, row, rv);
+        if (HAS_PRED) unpack_typed4(p.pred[0].col, rd, dv);
+        unpack_typed4(kc, rk, k);
+        unpack_typed4(vc, rv, v);
         // fold the 4 rows into runs of equal keys
         i64 run_key = 0, run_sum = 0, run_cnt = 0;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             bool ok = j < rem;
-            if (HAS_PRED) ok = ok && !pempty && dv[j] >= plo && dv[j] <= phi;
+            if (HAS_PRED) ok = ok && dv[j] >= plo && dv[j] <= phi;
             if (!ok) continue;
             n_pass++;
             i64 x = fc + fs * v[j];
@@ -537,7 +547,7 @@ constexpr int RUN_WTILE = 32 * SA_VEC;                 // rows per warp tile
 // (register double-buffering and prefetch.global.L2 of later tiles were both measured: no gain, the kernel
 //  is issue-bound at ~75 % issue utilisation, not latency-bound)
 
-template <int KEYW, int VALW, bool HAS_PRED>
+template <bool HAS_PRED>
 __global__ void __launch_bounds__(SA_THREADS, 4)
 run_group_kernel(const PipeParams p, const RunOut out, RunEdge *__restrict__ first, RunEdge *__restrict__ last, i64 chunk_tiles)
 {
@@ -550,13 +560,11 @@ run_group_kernel(const PipeParams p, const RunOut out, RunEdge *__restrict__ fir
     if (lane == 0) { first[gw].valid = 0; last[gw].valid = 0; }
     __syncwarp();
     if (tile_begin >= tile_end) return;
-    const int plo = (int)(p.pred[0].lo < INT32_MIN ? INT32_MIN : p.pred[0].lo);
-    const int phi = (int)(p.pred[0].hi > INT32_MAX ? INT32_MAX : p.pred[0].hi);
-    const bool pempty = p.pred[0].lo > p.pred[0].hi;
-    const void *kp = p.gs.part[0].col.p, *vp = p.gs.fac[0][0].col.p;
+    const i64 plo = p.pred[0].lo, phi = p.pred[0].hi;
+    const TypedCol kc = p.gs.part[0].col, vc = p.gs.fac[0][0].col;
     const i64 fc = p.gs.fc[0][0], fs = p.gs.fs[0][0];
     const bool plain = fc == 0 && fs == 1;             // sum(column): no multiply
-    const i64 tail_key = KEYW == 8 ? __ldg((const i64 *)kp + (p.nrows - 1)) : (i64)__ldg((const int *)kp + (p.nrows - 1));
+    const i64 tail_key = load_typed(kc, p.nrows - 1);
     // the warp's open run, carried across tiles (warp-uniform); cf == 0: none yet
     int cf = 0;
     i64 ck = 0, cs = 0, cc = 0;
@@ -565,31 +573,23 @@ run_group_kernel(const PipeParams p, const RunOut out, RunEdge *__restrict__ fir
     for (i64 tile = tile_begin; tile < tile_end; tile++) {
         const i64 row = tile * RUN_WTILE + lane * SA_VEC;
         const i64 rem = p.nrows - row;
-        int4 d = make_int4(0, 0, 0, 0);
-        i64 k[4], v[4];
-        if (HAS_PRED) d = ld_stream16((const int *)p.pred[0].col.p + row);
-        if (KEYW == 8) {
-            longlong2 a = ld_stream16_ll((const i64 *)kp + row), b = ld_stream16_ll((const i64 *)kp + row + 2);
-            k[0] = a.x; k[1] = a.y; k[2] = b.x; k[3] = b.y;
-        } else {
-            int4 a = ld_stream16((const int *)kp + row);
-            k[0] = a.x; k[1] = a.y; k[2] = a.z; k[3] = a.w;
+        i64 dv[4] = {0, 0, 0, 0}, k[4], v[4];
+        {
+            Raw4<true> rd, rk, rv;
+            if (HAS_PRED) ld_typed4(p.pred[0].col, row, rd);
+            ld_typed4(kc, row, rk);
+            ld_typed4(vc, row, rv);
+            if (HAS_PRED) unpack_typed4(p.pred[0].col, rd, dv);
+            unpack_typed4(kc, rk, k);
+            unpack_typed4(vc, rv, v);
         }
-        if (VALW == 8) {
-            longlong2 a = ld_stream16_ll((const i64 *)vp + row), b = ld_stream16_ll((const i64 *)vp + row + 2);
-            v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
-        } else {
-            int4 a = ld_stream16((const int *)vp + row);
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-        }
-        const int dv[4] = {d.x, d.y, d.z, d.w};
         i64 x[4];
         int c[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             bool ok = j < rem;
             if (!ok) k[j] = tail_key;                  // pad rows join the table's last run and add nothing
-            if (HAS_PRED) ok = ok && !pempty && dv[j] >= plo && dv[j] <= phi;
+            if (HAS_PRED) ok = ok && dv[j] >= plo && dv[j] <= phi;
             x[j] = ok ? (plain ? v[j] : fc + fs * v[j]) : 0;
             c[j] = ok ? 1 : 0;
             n_pass += ok ? 1u : 0u;
@@ -724,15 +724,13 @@ run_fixup_kernel(const RunEdge *__restrict__ first, const RunEdge *__restrict__ 
 // Phase 2 (latency-bound, massively parallel): one thread per hit does the hash-table probe / insert /
 // group update.  Splitting the two lets each kernel have the occupancy it needs: measured at SF100, the
 // fused warp-queue kernel streamed lineitem at 3.1 TB/s; see profiles/ for the split numbers.
-template <int KEYW, bool HAS_PRED, int NT>
+template <bool HAS_PRED, int NT>
 __global__ void __launch_bounds__(SA_THREADS)
 filter_hits_kernel(const PipeParams p)
 {
     const i64 nloc = p.row_end - p.row_begin;
     const i64 ntiles = (nloc + SA_TILE - 1) / SA_TILE;
-    const int plo = (int)(p.pred[0].lo < INT32_MIN ? INT32_MIN : p.pred[0].lo);
-    const int phi = (int)(p.pred[0].hi > INT32_MAX ? INT32_MAX : p.pred[0].hi);
-    const bool pempty = p.pred[0].lo > p.pred[0].hi;
+    const i64 plo = p.pred[0].lo, phi = p.pred[0].hi;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool anti = p.probe_mode == 2;
     const unsigned *__restrict__ bm = p.probe.bitmap;
@@ -755,23 +753,17 @@ filter_hits_kernel(const PipeParams p)
     };
     // one step = NT tiles (tile0 + u * G); the column buffers carry ROW_PAD rows of slack, so a
     // whole-vector load of a partial tile is in bounds
-    auto load = [&](i64 tile0, int4 (&d)[NT], i64 (&k)[NT][4]) {
+    auto load = [&](i64 tile0, Raw4<true> (&d)[NT], Raw4<true> (&k)[NT]) {
 #pragma unroll
         for (int u = 0; u < NT; u++) {
             const i64 tile = tile0 + u * G;
             if (tile >= ntiles) continue;
             const i64 row = p.row_begin + tile * SA_TILE + threadIdx.x * SA_VEC;
-            if (HAS_PRED) d[u] = ld_stream16((const int *)p.pred[0].col.p + row);
-            if (KEYW == 8) {
-                longlong2 a = ld_stream16_ll((const i64 *)p.probe_key.p + row), b = ld_stream16_ll((const i64 *)p.probe_key.p + row + 2);
-                k[u][0] = a.x; k[u][1] = a.y; k[u][2] = b.x; k[u][3] = b.y;
-            } else {
-                int4 a = ld_stream16((const int *)p.probe_key.p + row);
-                k[u][0] = a.x; k[u][1] = a.y; k[u][2] = a.z; k[u][3] = a.w;
-            }
+            if (HAS_PRED) ld_typed4(p.pred[0].col, row, d[u]);
+            ld_typed4(p.probe_key, row, k[u]);
         }
     };
-    auto process = [&](i64 tile0, const int4 (&d)[NT], const i64 (&k)[NT][4]) {
+    auto process = [&](i64 tile0, const Raw4<true> (&d)[NT], const Raw4<true> (&kr)[NT]) {
         bool ok[NT][4];
         unsigned w[NT][4];
         u64 off[NT][4];
@@ -781,12 +773,14 @@ filter_hits_kernel(const PipeParams p)
             const i64 tile = tile0 + u * G;
             const i64 row = p.row_begin + tile * SA_TILE + threadIdx.x * SA_VEC;
             const i64 rem = tile < ntiles ? p.row_end - row : 0;
-            const int dv[4] = {d[u].x, d[u].y, d[u].z, d[u].w};
+            i64 dv[4] = {0, 0, 0, 0}, k4[4];
+            if (HAS_PRED) unpack_typed4(p.pred[0].col, d[u], dv);
+            unpack_typed4(p.probe_key, kr[u], k4);
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 ok[u][j] = j < rem;
-                if (HAS_PRED) ok[u][j] = ok[u][j] && !pempty && dv[j] >= plo && dv[j] <= phi;
-                off[u][j] = (u64)k[u][j] - bmin;            // one unsigned compare covers both ends of the domain
+                if (HAS_PRED) ok[u][j] = ok[u][j] && dv[j] >= plo && dv[j] <= phi;
+                off[u][j] = (u64)k4[j] - bmin;            // one unsigned compare covers both ends of the domain
                 const bool in = ok[u][j] && bm != nullptr && off[u][j] < dom;
                 w[u][j] = in ? __ldg(bm + (unsigned)(off[u][j] >> 5)) : 0u;
             }
@@ -825,10 +819,12 @@ filter_hits_kernel(const PipeParams p)
         __syncwarp();
     };
     // software pipeline: the next step's vectors are in flight while the current step is screened
-    int4 dA[NT], dB[NT];
-    i64 kA[NT][4], kB[NT][4];
+    Raw4<true> dA[NT], dB[NT], kA[NT], kB[NT];
 #pragma unroll
-    for (int u = 0; u < NT; u++) dA[u] = dB[u] = make_int4(0, 0, 0, 0);
+    for (int u = 0; u < NT; u++) {
+        dA[u].a = dA[u].b = dB[u].a = dB[u].b = make_int4(0, 0, 0, 0);
+        kA[u].a = kA[u].b = kB[u].a = kB[u].b = make_int4(0, 0, 0, 0);
+    }
     i64 tile = blockIdx.x;
     const i64 step = G * NT;
     if (tile < ntiles) load(tile, dA, kA);

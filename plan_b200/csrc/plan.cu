@@ -96,6 +96,69 @@ static int sort_result(pg_result *r, const std::vector<std::pair<int, int>> &ord
     return PG_OK;
 }
 
+// Statistics of a SHARDED table over all ranks' shards (Column::g_*): one all-gather of 64 bytes per column when a
+// plan over the table is prepared.  Every choice that shapes a collective reads the agreed values, so all ranks
+// build the same pipeline with the same buffer sizes (a rank whose shard happens to hold NULLs, wider values or
+// other years than its peers no longer diverges).  Collective: every rank prepares its plans in the same order.
+int agree_table_stats(pg_table *t)
+{
+    Context &c = ctx();
+    const bool shared = c.world > 1 && t->dist == PG_DIST_SHARDED;
+    if (t->g_version == t->version && t->g_world == c.world) return PG_OK;
+    if (!shared) {
+        for (Column &col : t->cols) col.g_ok = false;
+        t->g_max_rows = t->g_total_rows = t->nrows;
+        t->g_version = t->version;
+        t->g_world = c.world;
+        return PG_OK;
+    }
+    struct Rec { i64 vmin, vmax; uint32_t present[8]; i64 has_nulls, nrows; };
+    static_assert(sizeof(Rec) == 64, "statistics record is exchanged as 64 bytes");
+    const size_t ncol = t->cols.size();
+    std::vector<Rec> mine(ncol), all(ncol * (size_t)c.world);
+    for (size_t i = 0; i < ncol; i++) {
+        const Column &col = t->cols[i];
+        mine[i].vmin = col.vmin;
+        mine[i].vmax = col.vmax;
+        memcpy(mine[i].present, col.present, 32);
+        mine[i].has_nulls = col.has_nulls ? 1 : 0;
+        mine[i].nrows = t->nrows;
+    }
+    DevBuf ds, dr;
+    PG_TRY(ds.alloc(ncol * 64));
+    PG_TRY(dr.alloc(ncol * 64 * (size_t)c.world));
+    PG_CUDA(cudaMemcpyAsync(ds.p, mine.data(), ncol * 64, cudaMemcpyHostToDevice, c.stream));
+    PG_TRY(comm_allgather(ds.p, dr.p, ncol * 64, c.stream));
+    PG_CUDA(cudaMemcpyAsync(all.data(), dr.p, ncol * 64 * (size_t)c.world, cudaMemcpyDeviceToHost, c.stream));
+    PG_CUDA(cudaStreamSynchronize(c.stream));
+    t->g_max_rows = t->g_total_rows = 0;
+    for (int r = 0; r < c.world; r++) {
+        const i64 n = all[(size_t)r * ncol].nrows;
+        t->g_max_rows = std::max(t->g_max_rows, n);
+        t->g_total_rows += n;
+    }
+    for (size_t i = 0; i < ncol; i++) {
+        Column &col = t->cols[i];
+        bool any = false;
+        col.g_has_nulls = false;
+        memset(col.g_present, 0, 32);
+        col.g_vmin = col.g_vmax = 0;
+        for (int r = 0; r < c.world; r++) {
+            const Rec &x = all[(size_t)r * ncol + i];
+            if (x.nrows == 0) continue;                  // an empty shard has no statistics
+            col.g_vmin = any ? std::min(col.g_vmin, x.vmin) : x.vmin;
+            col.g_vmax = any ? std::max(col.g_vmax, x.vmax) : x.vmax;
+            any = true;
+            col.g_has_nulls = col.g_has_nulls || x.has_nulls != 0;
+            for (int w = 0; w < 8; w++) col.g_present[w] |= x.present[w];
+        }
+        col.g_ok = true;
+    }
+    t->g_version = t->version;
+    t->g_world = c.world;
+    return PG_OK;
+}
+
 static int build_pipeline(pg_plan *plan)
 {
     const Node &root = plan->agg_root();
@@ -144,7 +207,7 @@ static int build_pipeline(pg_plan *plan)
             while (src->op == PG_OP_FILTER) src = &src->children[0];
             const Expr *pe = plan->mark_copy.conds.size() == 1 ? strip_value_preserving_casts(&plan->mark_copy.conds[0].first) : nullptr;
             if (!pe || pe->kind != PG_TK_COL || src->op != PG_OP_SCAN || pe->idx < 0 || pe->idx >= (int)plan->slots[(size_t)src->slot]->cols.size() ||
-                plan->slots[(size_t)src->slot]->cols[(size_t)pe->idx].has_nulls)
+                plan->slots[(size_t)src->slot]->cols[(size_t)pe->idx].any_nulls())
                 PG_FAIL(PG_EUNSUPPORTED, "MARK join filtered with mark = false over a nullable (or non-scan) probe key");
         }
         return build_join_agg(plan, root, plan->mark_copy, &plan->pipe);
@@ -217,6 +280,7 @@ static int ensure_pipeline(pg_plan *p)
     if (!stale) return PG_OK;
     p->pipe.reset();
     PG_CUDA(cudaSetDevice(ctx().device));
+    for (size_t i = 0; i < p->slots.size(); i++) PG_TRY(agree_table_stats(p->slots[i]));
     PG_TRY(build_pipeline(p));
     p->bound_versions.resize(p->slots.size());
     for (size_t i = 0; i < p->slots.size(); i++) p->bound_versions[i] = p->slots[i]->version;

@@ -288,7 +288,7 @@ inline float dec_to_f32_exact(i64 c, int scale)
 {
     static const double P10[20] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12,
                                    1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19};   // all exact in binary64
-    double d = (double)c / P10[scale];
+    double d = (double)c / P10[scale < 0 ? 0 : scale > 19 ? 19 : scale];   // pg_table_create admits 0..19 only
     return (float)d;
 }
 
@@ -364,7 +364,7 @@ inline bool lower_byte_set(LowerCtx &cx, const Expr &e, std::vector<Range> &rang
             if (c->kind != PG_TK_COL || c->idx < 0 || c->idx >= (int)cx.table->cols.size()) return fail(cx, "IN over a non-column");
             const Column &col = cx.table->cols[(size_t)c->idx];
             if (!is_byte_family(col.type)) return fail(cx, "IN is supported on dictionary/char columns only");
-            if (col.has_nulls) { if (!cx.allow_nulls) return fail(cx, "nullable column in predicate"); cx.saw_nulls = true; }
+            if (col.any_nulls()) { if (!cx.allow_nulls) return fail(cx, "nullable column in predicate"); cx.saw_nulls = true; }
             Range r;
             r.col = c->idx;
             r.is_set = true;
@@ -404,7 +404,7 @@ inline bool lower_compare(LowerCtx &cx, const Expr &e, std::vector<Range> &range
         if (c->kind != PG_TK_COL || c->idx < 0 || c->idx >= (int)cx.table->cols.size() || k->kind != PG_TK_STR)
             return fail(cx, "LIKE needs a column and a string literal");
         const Column &col = cx.table->cols[(size_t)c->idx];
-        if (col.has_nulls) { if (!cx.allow_nulls) return fail(cx, "nullable column in predicate"); cx.saw_nulls = true; }
+        if (col.any_nulls()) { if (!cx.allow_nulls) return fail(cx, "nullable column in predicate"); cx.saw_nulls = true; }
         Range rg;
         rg.col = c->idx;
         if (is_byte_family(col.type)) {          // dictionary / char column: match every code's string once, on the host
@@ -449,7 +449,7 @@ inline bool lower_compare(LowerCtx &cx, const Expr &e, std::vector<Range> &range
     if (c->kind != PG_TK_COL) return fail(cx, "comparison left side is not a column");
     if (c->idx < 0 || c->idx >= (int)cx.table->cols.size()) return fail(cx, "column index out of range");
     const Column &col = cx.table->cols[(size_t)c->idx];
-    if (col.has_nulls) {
+    if (col.any_nulls()) {
         if (!cx.allow_nulls) return fail(cx, "nullable column in predicate");
         cx.saw_nulls = true;
     }
@@ -460,11 +460,11 @@ inline bool lower_compare(LowerCtx &cx, const Expr &e, std::vector<Range> &range
         if (col.type != PG_T_DECIMAL64 || k->kind != PG_TK_CONST || k->ltype != PG_LT_FLOAT)
             return fail(cx, "float cast comparison of unsupported types");
         if (op == PG_FN_NE) return fail(cx, "<> on float cast");
-        if (col.vmax >= ((i64)1 << 53) || col.vmin <= -((i64)1 << 53)) return fail(cx, "decimal too wide for exact float cast");
+        if (col.gmax() >= ((i64)1 << 53) || col.gmin() <= -((i64)1 << 53)) return fail(cx, "decimal too wide for exact float cast");
         double kd;
         memcpy(&kd, &k->v0, 8);
         float kf = (float)kd;   // constants are stored as float32(val.F64) (chunk/vector.go:205-207)
-        float_cmp_to_range(op, kf, col.scale, col.vmin, col.vmax, &rg.lo, &rg.hi);
+        float_cmp_to_range(op, kf, col.scale, col.gmin(), col.gmax(), &rg.lo, &rg.hi);
         ranges.push_back(rg);
         return true;
     }
@@ -559,7 +559,7 @@ inline bool lower_affprod(LowerCtx &cx, const Expr &e0, AffProd &out)
         if (c->idx < 0 || c->idx >= (int)cx.table->cols.size()) return false;
         const Column &col = cx.table->cols[(size_t)c->idx];
         if (!is_int_family(col.type) || col.type == PG_T_DATE32) return false;
-        if (col.has_nulls) {
+        if (col.any_nulls()) {
             if (!cx.allow_nulls) return false;
             cx.saw_nulls = true;
         }

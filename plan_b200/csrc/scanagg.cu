@@ -18,14 +18,6 @@ static i128 maxabs(i64 lo, i64 hi)
     return a > b ? a : b;
 }
 
-static void clamp_to_stats(Range &r, const Column &c)
-{
-    if (c.stats_ok) {
-        if (r.lo < c.vmin) r.lo = c.vmin;
-        if (r.hi > c.vmax) r.hi = c.vmax;
-    }
-}
-
 static Range find_range(const std::vector<Range> &rs, int col)
 {
     for (auto &r : rs) if (r.col == col) return r;
@@ -34,12 +26,38 @@ static Range find_range(const std::vector<Range> &rs, int col)
     return r;
 }
 
-static int grid_for(const void *kernel, int threads, size_t smem, i64 ntiles)
+// A logical inclusive range on column c -> bounds on the STORED values (logical = base + stored), clamped to
+// what the stored type can hold; an empty range becomes [1, 0].
+static void stored_range(const Column &c, i64 lo, i64 hi, i64 *slo, i64 *shi)
+{
+    const int pw = c.phys_width();
+    const i128 tmin = pw == 8 ? (i128)INT64_MIN : pw == 4 ? (i128)INT32_MIN : 0;
+    const i128 tmax = pw == 8 ? (i128)INT64_MAX : pw == 4 ? (i128)INT32_MAX : pw == 2 ? 0xffff : 0xff;
+    i128 a = (i128)lo - c.base, b = (i128)hi - c.base;
+    if (a < tmin) a = tmin;
+    if (b > tmax) b = tmax;
+    if (lo > hi || a > b) { *slo = 1; *shi = 0; return; }
+    *slo = (i64)a;
+    *shi = (i64)b;
+}
+
+static bool fits_i32(i128 v) { return v >= (i128)INT32_MIN && v <= (i128)INT32_MAX; }
+// can the column's LOGICAL values be handled as 32-bit ints by a narrow kernel?
+static bool col_is_narrow(const Column &c)
+{
+    return c.phys_width() <= 4 && fits_i32(c.vmin) && fits_i32(c.vmax) && fits_i32(c.base);
+}
+
+static int sms_times(const void *kernel, int threads, size_t smem)
 {
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
     if (per_sm < 1) per_sm = 1;
-    i64 g = (i64)ctx().prop.multiProcessorCount * per_sm;
+    return ctx().prop.multiProcessorCount * per_sm;
+}
+static int grid_for(const void *kernel, int threads, size_t smem, i64 ntiles)
+{
+    i64 g = sms_times(kernel, threads, smem);
     if (g > ntiles) g = ntiles;
     if (g < 1) g = 1;
     return (int)g;
@@ -56,12 +74,27 @@ static pg_decimal to_pg_decimal(const HDec &d)
 
 static i128 make_i128(u64 lo, u64 hi) { return (i128)(((u128)hi << 64) | (u128)lo); }
 
+static int env_int(const char *name, int dflt)
+{
+    const char *e = getenv(name);
+    return e && *e ? atoi(e) : dflt;
+}
+
 // ------------------------------------------------------------------- sumprod --
+
+typedef void (*SumProdKernel)(const SumProdParams, i64 *);
+static SumProdKernel sumprod_variant(bool wide, bool has_a, bool has_b)
+{
+#define PG_SP(W, U) (has_a && has_b ? sumprod_kernel<W, true, true, U> : has_a ? sumprod_kernel<W, true, false, U> \
+                     : has_b ? sumprod_kernel<W, false, true, U> : sumprod_kernel<W, false, false, U>)
+    return wide ? PG_SP(true, 2) : PG_SP(false, 4);      // 32-byte raw vectors: two tiles in flight keep the wide kernel under 128 registers
+#undef PG_SP
+}
 
 struct SumProdPipeline : Pipeline {
     const pg_table *table = nullptr;
     SumProdParams prm{};
-    bool has_a = false, has_b = false;
+    bool has_a = false, has_b = false, wide = false;
     int grid = 1, vscale = 0;
     AggExpr agg;
     std::vector<std::pair<int, int>> outs;
@@ -69,19 +102,6 @@ struct SumProdPipeline : Pipeline {
     DevBuf d_part, d_final, d_gather;
     PinBuf h_final;
     EventPair ev_all, ev_main;
-
-    int launch()
-    {
-        cudaStream_t st = ctx().stream;
-#define PG_SP(A, B) sumprod_kernel<A, B, 4><<<grid, SA_THREADS, 0, st>>>(prm, d_part.as<i64>())
-        if (has_a && has_b) PG_SP(true, true);
-        else if (has_a) PG_SP(true, false);
-        else if (has_b) PG_SP(false, true);
-        else PG_SP(false, false);
-#undef PG_SP
-        PG_CUDA(cudaGetLastError());
-        return PG_OK;
-    }
 
     int run(pg_result *res) override
     {
@@ -91,7 +111,8 @@ struct SumProdPipeline : Pipeline {
         PG_TRY(ev_main.init());
         PG_CUDA(cudaEventRecord(ev_all.a, st));
         PG_CUDA(cudaEventRecord(ev_main.a, st));
-        PG_TRY(launch());
+        sumprod_variant(wide, has_a, has_b)<<<grid, SA_THREADS, 0, st>>>(prm, d_part.as<i64>());
+        PG_CUDA(cudaGetLastError());
         PG_CUDA(cudaEventRecord(ev_main.b, st));
         finalize128_kernel<<<1, 32, 0, st>>>(d_part.as<i64>(), grid, 2, d_final.as<u64>());
         PG_CUDA(cudaGetLastError());
@@ -128,8 +149,8 @@ struct SumProdPipeline : Pipeline {
             col.scale = agg.scale;
             if (cnt > 0) {
                 HDec d;
-                // TODO(rounding regime): a total beyond 19 digits needs the sequential
-                // half-even emulation; until then refuse instead of rounding differently.
+                // an ungrouped total beyond 19 digits would need the sequential half-even emulation of the
+                // low-cardinality pipeline; refuse instead of rounding differently
                 if (!hd_from_i128(sum, vscale, &d) || hd_digits((u128)(sum < 0 ? -sum : sum)) > HD_MAXPREC)
                     PG_FAIL(PG_EOVERFLOW, "sum exceeds 19 significant digits (order-dependent rounding regime)");
                 col.push(to_pg_decimal(d));
@@ -149,7 +170,6 @@ static int try_sumprod(pg_plan *plan, const Node &aggn, const Node &scan, const 
     const AffProd &ap = args[0];
     if (ap.f.size() != 2 || ap.f[0].c != 0 || ap.f[0].s != 1 || ap.f[1].c != 0 || ap.f[1].s != 1) { *why = "argument is not column*column"; return PG_EUNSUPPORTED; }
     const Column &ca = t->cols[(size_t)ap.f[0].col], &cb = t->cols[(size_t)ap.f[1].col];
-    if (type_size(ca.type) != 8 || type_size(cb.type) != 8) { *why = "factor columns are not 64-bit"; return PG_EUNSUPPORTED; }
     std::unique_ptr<SumProdPipeline> p(new SumProdPipeline());
     p->table = t;
     p->agg = aggn.aggs[0];
@@ -158,37 +178,40 @@ static int try_sumprod(pg_plan *plan, const Node &aggn, const Node &scan, const 
     p->vscale = ap.vscale();
     SumProdParams &q = p->prm;
     q.nrows = t->nrows;
-    q.fa = (const i64 *)ca.d_data;
-    q.fb = (const i64 *)cb.d_data;
+    q.fa = ca.ncol();
+    q.fb = cb.ncol();
     Range ra = find_range(ranges, ap.f[0].col), rb = find_range(ranges, ap.f[1].col);
-    clamp_to_stats(ra, ca);
-    clamp_to_stats(rb, cb);
-    q.fa_lo = ra.lo; q.fa_hi = ra.hi; q.fb_lo = rb.lo; q.fb_hi = rb.hi;
-    q.pa = q.pb = nullptr;
-    q.a_lo = q.b_lo = INT32_MIN;
-    q.a_hi = q.b_hi = INT32_MAX;
-    int n32 = 0;
+    stored_range(ca, ra.lo, ra.hi, &q.fa_lo, &q.fa_hi);
+    stored_range(cb, rb.lo, rb.hi, &q.fb_lo, &q.fb_hi);
+    q.pa = q.pb = q.fa;
+    q.a_lo = q.b_lo = 0;
+    q.a_hi = q.b_hi = -1;
+    bool narrow = col_is_narrow(ca) && col_is_narrow(cb);
+    p->bytes_per_row = ca.phys_width() + cb.phys_width();
+    int npred = 0;
     for (auto &r : ranges) {
         if (r.col == ap.f[0].col || r.col == ap.f[1].col) continue;
         const Column &col = t->cols[(size_t)r.col];
-        if (type_size(col.type) != 4) { *why = "predicate on a column that is neither a factor nor 32-bit"; return PG_EUNSUPPORTED; }
-        if (n32 == 2) { *why = "more than two 32-bit predicate columns"; return PG_EUNSUPPORTED; }
-        int lo = (int)std::max<i64>(r.lo, INT32_MIN), hi = (int)std::min<i64>(r.hi, INT32_MAX);
-        if (r.lo > r.hi) { lo = 1; hi = 0; }
-        if (n32 == 0) { q.pa = (const int *)col.d_data; q.a_lo = lo; q.a_hi = hi; p->has_a = true; }
-        else { q.pb = (const int *)col.d_data; q.b_lo = lo; q.b_hi = hi; p->has_b = true; }
-        n32++;
+        if (!is_int_family(col.type)) { *why = "predicate on a column that is neither a factor nor an integer-family column"; return PG_EUNSUPPORTED; }
+        if (npred == 2) { *why = "more than two predicate-only columns"; return PG_EUNSUPPORTED; }
+        if (col.phys_width() > 4) narrow = false;
+        if (npred == 0) { q.pa = col.ncol(); stored_range(col, r.lo, r.hi, &q.a_lo, &q.a_hi); p->has_a = true; }
+        else { q.pb = col.ncol(); stored_range(col, r.lo, r.hi, &q.b_lo, &q.b_hi); p->has_b = true; }
+        p->bytes_per_row += col.phys_width();
+        npred++;
     }
-    p->bytes_per_row = 16 + 4 * n32;
-    i64 ntiles = (t->nrows + SA_TILE - 1) / SA_TILE;
-    const void *kern = p->has_a && p->has_b ? (const void *)sumprod_kernel<true, true, 4>
-                       : p->has_a           ? (const void *)sumprod_kernel<true, false, 4>
-                       : p->has_b           ? (const void *)sumprod_kernel<false, true, 4>
-                                            : (const void *)sumprod_kernel<false, false, 4>;
-    p->grid = grid_for(kern, SA_THREADS, 0, ntiles);
-    // per-CTA int64 partials must be exact: bound them with the column statistics
-    i128 per_row = maxabs(ra.lo, ra.hi) * maxabs(rb.lo, rb.hi);
-    i128 rows_per_cta = (i128)((ntiles + p->grid - 1) / p->grid) * SA_TILE;
+    if (env_int("PG_FORCE_WIDE", 0)) narrow = false;
+    p->wide = !narrow;
+    const i64 ntiles = (t->nrows + SA_TILE - 1) / SA_TILE;
+    const void *kern = (const void *)sumprod_variant(p->wide, p->has_a, p->has_b);
+    const int full = sms_times(kern, SA_THREADS, 0);
+    p->grid = (int)std::max<i64>(1, std::min<i64>(full, ntiles));
+    // per-CTA int64 partials must be exact: bound them with the statistics of the whole table (every rank takes
+    // the same decision) and the largest shard
+    i128 per_row = maxabs(std::max(ra.lo, ca.gmin()), std::min(ra.hi, ca.gmax())) * maxabs(std::max(rb.lo, cb.gmin()), std::min(rb.hi, cb.gmax()));
+    const i64 max_tiles = (t->max_rows() + SA_TILE - 1) / SA_TILE;
+    const i64 gmin_grid = std::max<i64>(1, std::min<i64>(full, max_tiles));
+    i128 rows_per_cta = (i128)((max_tiles + gmin_grid - 1) / gmin_grid) * SA_TILE;       // a CTA takes ceil(ntiles / grid) tiles
     if (ra.lo <= ra.hi && rb.lo <= rb.hi && per_row * rows_per_cta >= ((i128)1 << 62)) {
         *why = "per-CTA partial sum could exceed int64";
         return PG_EUNSUPPORTED;
@@ -199,11 +222,11 @@ static int try_sumprod(pg_plan *plan, const Node &aggn, const Node &scan, const 
     PG_TRY(p->h_final.alloc(32 * (size_t)ctx().world));
     char buf[512];
     snprintf(buf, sizeof buf,
-             "ScanAgg[sumprod] table=%s rows=%lld kernel=sumprod_kernel<%d,%d,4> grid=%d block=%d "
-             "bytes/row=%d ranges: a=[%d,%d] b=[%d,%d] fa=[%lld,%lld] fb=[%lld,%lld] value_scale=%d",
-             t->name.c_str(), (long long)t->nrows, (int)p->has_a, (int)p->has_b, p->grid, SA_THREADS,
-             p->bytes_per_row, q.a_lo, q.a_hi, q.b_lo, q.b_hi, (long long)q.fa_lo, (long long)q.fa_hi,
-             (long long)q.fb_lo, (long long)q.fb_hi, p->vscale);
+             "ScanAgg[sumprod] table=%s rows=%lld kernel=sumprod_kernel<%s,%d,%d> grid=%d block=%d "
+             "stored bytes/row=%d (widths: fa=%d fb=%d) stored ranges: a=[%lld,%lld] b=[%lld,%lld] fa=[%lld,%lld] fb=[%lld,%lld] value_scale=%d",
+             t->name.c_str(), (long long)t->nrows, p->wide ? "wide" : "narrow", (int)p->has_a, (int)p->has_b, p->grid, SA_THREADS,
+             p->bytes_per_row, ca.phys_width(), cb.phys_width(), (long long)q.a_lo, (long long)q.a_hi, (long long)q.b_lo, (long long)q.b_hi,
+             (long long)q.fa_lo, (long long)q.fa_hi, (long long)q.fb_lo, (long long)q.fb_hi, p->vscale);
     p->explain = buf;
     *out = std::move(p);
     return PG_OK;
@@ -211,10 +234,21 @@ static int try_sumprod(pg_plan *plan, const Node &aggn, const Node &scan, const 
 
 // ------------------------------------------------------------- lowcard chain --
 
+typedef void (*LowcardKernel)(const LowcardParams, i64 *, i64 *);
+static LowcardKernel lowcard_variant(bool wide, bool acc32, bool key1, int unroll)
+{
+#define PG_LC(U) (wide ? (key1 ? lowcard_chain_kernel<true, false, true, U> : lowcard_chain_kernel<true, false, false, U>) \
+                  : acc32 ? (key1 ? lowcard_chain_kernel<false, true, true, U> : lowcard_chain_kernel<false, true, false, U>) \
+                          : (key1 ? lowcard_chain_kernel<false, false, true, U> : lowcard_chain_kernel<false, false, false, U>))
+    return unroll >= 4 ? PG_LC(4) : PG_LC(2);
+#undef PG_LC
+}
+
 struct LowcardPipeline : Pipeline {
     const pg_table *table = nullptr;
     LowcardParams prm{};
-    bool has_key1 = false;
+    bool has_key1 = false, wide = false, acc32 = false;
+    int unroll = 2;
     int grid = 1, G = 1;
     size_t smem = 0;
     int nkeys = 0;
@@ -229,206 +263,22 @@ struct LowcardPipeline : Pipeline {
     DevBuf d_part, d_final, d_first, d_luts, d_gather;
     PinBuf h_final;
     EventPair ev_all, ev_main;
-    bool nonneg[LC_K] = {true, true, true, true, true, true};   // slot values proven >= 0 from statistics
-    int emulations = 0;                                         // (group, slot) sums that took the ordered path
+    // the ordered-rounding stage (scanagg.cuh: ord_plan / ord_jobs / ord_fold), appended when the statistics allow
+    // a DECIMAL total of 20 digits; identical launches and collectives on every rank
+    bool ord_stage = false;
+    unsigned emu_mask = 0;               // slots whose sum is a DECIMAL result with non-negative addends and scale >= 1
+    i64 ord_stride = 0;                  // summaries reserved per job
+    DevBuf d_jobs, d_ord, d_contrib;     // OrdJob[ORD_MAXJOBS] + njobs | summaries | OrdContrib[ORD_MAXJOBS] + gathered copies
+    int emulations = 0;                  // (group, slot) sums that took the ordered path in the last run
 
     // ranks whose partials are merged: a replicated table is complete on every rank
     int nranks() const { return table->dist == PG_DIST_REPLICATED ? 1 : ctx().world; }
     int myrank() const { return table->dist == PG_DIST_REPLICATED ? 0 : ctx().rank; }
 
     size_t rank_bytes() const { return (size_t)G * LC_K * 16 + (size_t)LC_MAXG * 8; }
-
-    static constexpr int ORD_CHUNK = 16;   // tiles composed per summary on the device (tail pass)
-    bool part_on_host = false;             // run() already copied the per-CTA partials to h_part
-    // scratch of the ordered-rounding path, allocated once (no cudaMalloc while executing)
-    DevBuf d_ord, d_contrib;
-    PinBuf h_ord, h_part, h_tile, h_contrib;
-
-    int ensure_ord_buffers()
-    {
-        if (d_ord.p) return PG_OK;
-        const i64 ntiles = (prm.nrows + LC_TILE - 1) / LC_TILE;
-        PG_TRY(d_ord.alloc(sizeof(OrdSummary) * (size_t)std::max<i64>(ntiles, 1)));
-        PG_TRY(h_ord.alloc(sizeof(OrdSummary) * (size_t)std::max<i64>(ntiles, 1)));
-        PG_TRY(h_part.alloc(sizeof(i64) * (size_t)grid * (size_t)G * LC_K));
-        PG_TRY(h_tile.alloc((size_t)LC_TILE * 32 + 512));
-        PG_TRY(d_contrib.alloc(64 * (size_t)(ctx().world + 1)));
-        PG_TRY(h_contrib.alloc(64 * (size_t)(ctx().world + 1)));
-        return PG_OK;
-    }
-
-    // summaries of tiles [tb, te) for (group, slot), `chunk` consecutive tiles composed per summary
-    // (chunk = 1 where the crossing tile is searched) -> h_ord (pinned)
-    int ord_summaries(int g, int s, i64 tb, i64 te, int chunk, const OrdSummary **out, i64 *n, i64 at = 0, bool sync = true)
-    {
-        *n = te > tb ? (te - tb + chunk - 1) / chunk : 0;
-        *out = h_ord.as<OrdSummary>() + at;
-        if (te <= tb) return PG_OK;
-        cudaStream_t st = ctx().stream;
-        OrdParams op;
-        op.base = prm;
-        op.group = g;
-        op.slot = s;
-        op.tile_begin = tb;
-        op.tile_end = te;
-        op.chunk = chunk;
-        int gr = (int)std::min<i64>(*n, (i64)ctx().prop.multiProcessorCount * 8);
-        if (has_key1) ord_tile_kernel<true><<<gr, LC_THREADS, 0, st>>>(op, d_ord.as<OrdSummary>() + at);
-        else ord_tile_kernel<false><<<gr, LC_THREADS, 0, st>>>(op, d_ord.as<OrdSummary>() + at);
-        PG_CUDA(cudaGetLastError());
-        PG_CUDA(cudaMemcpyAsync(h_ord.as<OrdSummary>() + at, d_ord.as<OrdSummary>() + at, sizeof(OrdSummary) * (size_t)*n, cudaMemcpyDeviceToHost, st));
-        if (sync) PG_CUDA(cudaStreamSynchronize(st));
-        return PG_OK;
-    }
-
-    // The value the reference's sequential Decimal.Add fold holds for (group g, slot s) when the
-    // exact total needs 20 digits (see the comment above ord_tile_kernel).  Collective: every
-    // rank calls it with the same arguments.  rank_tot[r] = exact total of rank r.
-    int emulate_rounded_sum(int g, int s, const std::vector<i128> &rank_tot, int vscale, HDec *out)
-    {
-        Context &c = ctx();
-        cudaStream_t st = c.stream;
-        const i128 THR = (i128)10000000000000000000ULL;    // 10^19
-        i128 total = 0;
-        for (auto v : rank_tot) total += v;
-        if (!nonneg[s]) PG_FAIL(PG_EOVERFLOW, "sum needs 20 digits and its addends may be negative: rounding order emulation not available");
-        if (total >= THR * 10) PG_FAIL(PG_EOVERFLOW, "sum needs more than 20 digits");
-        if (!prm.contig) PG_FAIL(PG_EOVERFLOW, "internal: ordered partials were not produced");
-        if (vscale < 1) PG_FAIL(PG_EOVERFLOW, "decimal overflow: integer part exceeds 19 digits");
-        int rstar = 0;
-        i128 P0 = 0;
-        while (P0 + rank_tot[(size_t)rstar] < THR) { P0 += rank_tot[(size_t)rstar]; rstar++; }
-        const i64 ntiles = (prm.nrows + LC_TILE - 1) / LC_TILE;
-        PG_TRY(ensure_ord_buffers());
-        const OrdSummary *sums = nullptr;
-        i64 nsums = 0;
-        // per-rank contribution: absolute state (rank == rstar) or a transducer summary (rank > rstar)
-        struct Contrib { u64 kind, s_lo, s_hi, q_lo, q_hi; u64 c0, c1, p0p1; } mine{};
-        if (myrank() == rstar) {
-            // a. which CTA range crosses
-            const i64 *part = h_part.as<i64>();
-            if (!part_on_host) {
-                PG_CUDA(cudaMemcpyAsync(h_part.p, d_part.p, sizeof(i64) * (size_t)grid * (size_t)G * LC_K, cudaMemcpyDeviceToHost, st));
-                PG_CUDA(cudaStreamSynchronize(st));
-            }
-            i64 per = (ntiles + grid - 1) / grid;
-            i128 P = P0;
-            int cstar = 0;
-            for (; cstar < grid; cstar++) {
-                i128 v = part[(size_t)cstar * (size_t)G * LC_K + (size_t)g * LC_K + (size_t)s];
-                if (P + v >= THR) break;
-                P += v;
-            }
-            if (cstar == grid) PG_FAIL(PG_ECUDA, "internal: crossing CTA not found");
-            // b. per-tile summaries of the crossing CTA's tiles and, in the same round trip, chunk summaries
-            //    of every tile after that CTA's range
-            i64 tb = (i64)cstar * per, te = std::min<i64>(ntiles, tb + per);
-            const OrdSummary *tail = nullptr;
-            i64 ntail = 0;
-            PG_TRY(ord_summaries(g, s, tb, te, 1, &sums, &nsums, 0, false));
-            PG_TRY(ord_summaries(g, s, te, ntiles, ORD_CHUNK, &tail, &ntail, te - tb, true));
-            i64 tstar = tb;
-            for (; tstar < te; tstar++) {
-                i128 v = sums[tstar - tb].sum_x;
-                if (P + v >= THR) break;
-                P += v;
-            }
-            if (tstar == te) PG_FAIL(PG_ECUDA, "internal: crossing tile not found");
-            // c. that tile row by row, exactly as the reference would add them
-            i64 row0 = tstar * LC_TILE;
-            int n = (int)std::min<i64>(LC_TILE, prm.nrows - row0);
-            // pinned staging: [A | B | C] int64, [pred] int32, [key0 | key1] bytes, [luts]
-            i64 *h_a = h_tile.as<i64>(), *h_b = h_a + LC_TILE, *h_c = h_b + LC_TILE;
-            int *h_pred = (int *)(h_c + LC_TILE);
-            uint8_t *h_k0 = (uint8_t *)(h_pred + LC_TILE), *h_k1 = h_k0 + LC_TILE, *h_lut = h_k1 + LC_TILE;
-            PG_CUDA(cudaMemcpyAsync(h_pred, prm.pred + row0, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
-            PG_CUDA(cudaMemcpyAsync(h_k0, prm.key0 + row0, (size_t)n, cudaMemcpyDeviceToHost, st));
-            if (has_key1) PG_CUDA(cudaMemcpyAsync(h_k1, prm.key1 + row0, (size_t)n, cudaMemcpyDeviceToHost, st));
-            PG_CUDA(cudaMemcpyAsync(h_a, prm.A + row0, sizeof(i64) * (size_t)n, cudaMemcpyDeviceToHost, st));
-            PG_CUDA(cudaMemcpyAsync(h_b, prm.B + row0, sizeof(i64) * (size_t)n, cudaMemcpyDeviceToHost, st));
-            PG_CUDA(cudaMemcpyAsync(h_c, prm.C + row0, sizeof(i64) * (size_t)n, cudaMemcpyDeviceToHost, st));
-            PG_CUDA(cudaMemcpyAsync(h_lut, prm.luts, 512, cudaMemcpyDeviceToHost, st));
-            PG_CUDA(cudaStreamSynchronize(st));
-            bool rounded = false;
-            u128 S = 0;
-            for (int i = 0; i < n; i++) {
-                if (h_pred[(size_t)i] < prm.lo || h_pred[(size_t)i] > prm.hi) continue;
-                int gg = h_lut[h_k0[(size_t)i]];
-                if (has_key1) gg = gg * prm.n1 + h_lut[256 + h_k1[(size_t)i]];
-                if (gg != g) continue;
-                i64 a = h_a[(size_t)i], b = h_b[(size_t)i], cc = h_c[(size_t)i];
-                i64 t2 = a * (prm.c1 + prm.s1 * b);
-                i64 x = s == 2 ? a : s == 3 ? t2 : s == 4 ? t2 * (prm.c2 + prm.s2 * cc) : b;
-                if (!rounded) {
-                    P += x;
-                    if (P >= THR) { S = hd_shift_right_even((u128)P, 1); rounded = true; }
-                } else {
-                    u128 q = (u128)(x / 10), t = S + q;
-                    int d = (int)(x % 10);
-                    S = t + ((d > 5 || (d == 5 && (t & 1))) ? 1 : 0);
-                }
-            }
-            if (!rounded) PG_FAIL(PG_ECUDA, "internal: crossing row not found");
-            // d. the rest of the crossing CTA's tiles (per-tile summaries), then the chunk summaries after it
-            for (i64 t = tstar + 1; t < te; t++) S += (u128)sums[t - tb].sum_q + ((S & 1) ? sums[t - tb].c1 : sums[t - tb].c0);
-            for (i64 i = 0; i < ntail; i++) S += (u128)tail[i].sum_q + ((S & 1) ? tail[i].c1 : tail[i].c0);
-            mine.kind = 1;
-            mine.s_lo = (u64)S;
-            mine.s_hi = (u64)(S >> 64);
-        } else if (myrank() > rstar) {
-            PG_TRY(ord_summaries(g, s, 0, ntiles, ORD_CHUNK, &sums, &nsums));
-            i128 q = 0;
-            u64 cc[2] = {0, 0}, pp[2] = {0, 1};
-            for (i64 i = 0; i < nsums; i++) {
-                const OrdSummary &o = sums[i];
-                q += o.sum_q;
-                for (int k = 0; k < 2; k++) {
-                    cc[k] += pp[k] ? o.c1 : o.c0;
-                    pp[k] = pp[k] ? o.p1 : o.p0;
-                }
-            }
-            mine.kind = 2;
-            mine.q_lo = (u64)q;
-            mine.q_hi = (u64)((u128)q >> 64);
-            mine.c0 = cc[0];
-            mine.c1 = cc[1];
-            mine.p0p1 = pp[0] | (pp[1] << 1);
-        }
-        static_assert(sizeof(Contrib) == 64, "Contrib is exchanged as 64 bytes");
-        Contrib *all = h_contrib.as<Contrib>() + 1;
-        if (nranks() > 1) {
-            h_contrib.as<Contrib>()[0] = mine;
-            PG_CUDA(cudaMemcpyAsync(d_contrib.p, h_contrib.p, 64, cudaMemcpyHostToDevice, st));
-            PG_TRY(comm_allgather(d_contrib.p, (char *)d_contrib.p + 64, 64, st));
-            PG_CUDA(cudaMemcpyAsync(all, (char *)d_contrib.p + 64, 64 * (size_t)nranks(), cudaMemcpyDeviceToHost, st));
-            PG_CUDA(cudaStreamSynchronize(st));
-        } else {
-            all[0] = mine;
-        }
-        if (all[(size_t)rstar].kind != 1) PG_FAIL(PG_ECUDA, "internal: crossing rank did not report a state");
-        u128 S = ((u128)all[(size_t)rstar].s_hi << 64) | all[(size_t)rstar].s_lo;
-        for (int r = rstar + 1; r < nranks(); r++) {
-            const Contrib &k = all[(size_t)r];
-            u128 q = ((u128)k.q_hi << 64) | k.q_lo;
-            S += q + ((S & 1) ? k.c1 : k.c0);
-        }
-        if (S > (u128)HD_MAXCOEF) PG_FAIL(PG_EOVERFLOW, "sum needs more than 19 digits after rounding");
-        out->coef = (u64)S;
-        out->scale = vscale - 1;
-        out->neg = false;
-        emulations++;
-        return PG_OK;
-    }
-
-    // exact total -> the Decimal the reference would hold (rank_tot = per-rank exact totals)
-    int decimal_sum(int g, int s, const std::vector<i128> &rank_tot, HDec *out)
-    {
-        i128 v = 0;
-        for (auto x : rank_tot) v += x;
-        if (hd_digits((u128)(v < 0 ? -v : v)) > HD_MAXPREC) return emulate_rounded_sum(g, s, rank_tot, slot_scale[(size_t)s], out);
-        if (!hd_from_i128(v, slot_scale[(size_t)s], out)) PG_FAIL(PG_EOVERFLOW, "decimal overflow");
-        return PG_OK;
-    }
+    size_t contrib_bytes() const { return sizeof(OrdContrib) * ORD_MAXJOBS; }
+    // pinned result block: [nranks x rank_bytes] totals, then [nranks x contrib_bytes] contributions
+    size_t host_bytes() const { return (rank_bytes() + contrib_bytes()) * (size_t)nranks(); }
 
     int run(pg_result *res) override
     {
@@ -442,41 +292,51 @@ struct LowcardPipeline : Pipeline {
         PG_CUDA(cudaEventRecord(ev_all.a, st));
         PG_CUDA(cudaMemsetAsync(d_firstrow, 0x7f, LC_MAXG * 8, st));   // 0x7f7f.. = "unset"
         PG_CUDA(cudaEventRecord(ev_main.a, st));
-        if (has_key1) lowcard_chain_kernel<true, 2><<<grid, LC_THREADS, smem, st>>>(prm, d_part.as<i64>(), d_firstrow);
-        else lowcard_chain_kernel<false, 2><<<grid, LC_THREADS, smem, st>>>(prm, d_part.as<i64>(), d_firstrow);
+        lowcard_variant(wide, acc32, has_key1, unroll)<<<grid, LC_THREADS, smem, st>>>(prm, d_part.as<i64>(), d_firstrow);
         PG_CUDA(cudaGetLastError());
         PG_CUDA(cudaEventRecord(ev_main.b, st));
         finalize128_kernel<<<1, 64, 0, st>>>(d_part.as<i64>(), grid, G * LC_K, d_final.as<u64>());
         PG_CUDA(cudaGetLastError());
-        const void *src = d_final.p;
-        if (nranks() > 1) {
-            PG_TRY(comm_allgather(d_final.p, d_gather.p, rank_bytes(), st));
-            src = d_gather.p;
+        // every rank's totals on every rank (world 1: a device copy)
+        if (nranks() > 1) PG_TRY(comm_allgather(d_final.p, d_gather.p, rank_bytes(), st));
+        else PG_CUDA(cudaMemcpyAsync(d_gather.p, d_final.p, rank_bytes(), cudaMemcpyDeviceToDevice, st));
+        int launches = 2;
+        char *h_tot = (char *)h_final.p, *h_con = h_tot + rank_bytes() * (size_t)nranks();
+        if (ord_stage) {
+            const i64 ntiles = (prm.nrows + LC_TILE - 1) / LC_TILE;
+            const i64 per = (ntiles + grid - 1) / grid;
+            OrdJob *jobs = d_jobs.as<OrdJob>();
+            int *njobs = (int *)(jobs + ORD_MAXJOBS);
+            OrdContrib *mine = d_contrib.as<OrdContrib>(), *all = mine + ORD_MAXJOBS;
+            ord_plan_kernel<<<1, 32, 0, st>>>(d_gather.as<u64>(), (i64)(rank_bytes() / 8), nranks(), myrank(), G, emu_mask, d_part.as<i64>(), grid,
+                                              per, ntiles, jobs, njobs);
+            const int og = ctx().prop.multiProcessorCount * 4;
+            if (has_key1) {
+                ord_jobs_kernel<true><<<og, LC_THREADS, 0, st>>>(prm, jobs, njobs, d_ord.as<OrdSummary>(), ord_stride, ntiles);
+                ord_fold_kernel<true><<<ORD_MAXJOBS, LC_THREADS, 0, st>>>(prm, jobs, njobs, d_ord.as<OrdSummary>(), ord_stride, ntiles, mine);
+            } else {
+                ord_jobs_kernel<false><<<og, LC_THREADS, 0, st>>>(prm, jobs, njobs, d_ord.as<OrdSummary>(), ord_stride, ntiles);
+                ord_fold_kernel<false><<<ORD_MAXJOBS, LC_THREADS, 0, st>>>(prm, jobs, njobs, d_ord.as<OrdSummary>(), ord_stride, ntiles, mine);
+            }
+            PG_CUDA(cudaGetLastError());
+            if (nranks() > 1) PG_TRY(comm_allgather(mine, all, contrib_bytes(), st));
+            else PG_CUDA(cudaMemcpyAsync(all, mine, contrib_bytes(), cudaMemcpyDeviceToDevice, st));
+            PG_CUDA(cudaMemcpyAsync(h_con, all, contrib_bytes() * (size_t)nranks(), cudaMemcpyDeviceToHost, st));
+            launches += 3;
         }
-        PG_CUDA(cudaMemcpyAsync(h_final.p, src, rank_bytes() * (size_t)nranks(), cudaMemcpyDeviceToHost, st));
-        part_on_host = false;
-        if (prm.contig) {      // the ordered partials ride along: the rounding path then needs no extra round trip
-            PG_TRY(ensure_ord_buffers());
-            PG_CUDA(cudaMemcpyAsync(h_part.p, d_part.p, sizeof(i64) * (size_t)grid * (size_t)G * LC_K, cudaMemcpyDeviceToHost, st));
-            part_on_host = true;
-        }
+        PG_CUDA(cudaMemcpyAsync(h_tot, d_gather.p, rank_bytes() * (size_t)nranks(), cudaMemcpyDeviceToHost, st));
         PG_CUDA(cudaEventRecord(ev_all.b, st));
         PG_CUDA(cudaStreamSynchronize(st));
         tr.mark("kernels+gather+d2h");
 
         // merge ranks in order; 128-bit exact
         std::vector<i128> tot((size_t)G * LC_K, 0);
-        std::vector<std::vector<i128>> rtot((size_t)G * LC_K, std::vector<i128>((size_t)nranks(), 0));
         std::vector<i64> first((size_t)G, INT64_MAX);
-        emulations = 0;
         for (int r = 0; r < nranks(); r++) {
-            const char *base = (const char *)h_final.p + rank_bytes() * (size_t)r;
+            const char *base = h_tot + rank_bytes() * (size_t)r;
             const u64 *h = (const u64 *)base;
             const i64 *f = (const i64 *)(base + (size_t)G * LC_K * 16);
-            for (int v = 0; v < G * LC_K; v++) {
-                rtot[(size_t)v][(size_t)r] = make_i128(h[2 * v], h[2 * v + 1]);
-                tot[(size_t)v] += rtot[(size_t)v][(size_t)r];
-            }
+            for (int v = 0; v < G * LC_K; v++) tot[(size_t)v] += make_i128(h[2 * v], h[2 * v + 1]);
             for (int g = 0; g < G; g++) if (f[g] != 0x7f7f7f7f7f7f7f7fLL && f[g] < first[(size_t)g]) first[(size_t)g] = f[g];
         }
         res->stats.kernel_ms = ev_all.ms();
@@ -484,7 +344,63 @@ struct LowcardPipeline : Pipeline {
         res->stats.rows_scanned = table->nrows;
         res->stats.algorithmic_bytes = table->nrows * bytes_per_row;
         res->stats.main_kernel_bytes = res->stats.algorithmic_bytes;
-        res->stats.kernel_launches = 2;
+        res->stats.kernel_launches = launches;
+
+        // The value the reference's sequential Decimal.Add fold holds for every (group, slot) whose exact total
+        // needs 20 digits: the crossing rank's state, then the later ranks' transducers applied in rank order.
+        // The job list is enumerated exactly as ord_plan_kernel does (group-major, slots 2..5).
+        const i128 THR = (i128)10000000000000000000ULL;
+        std::vector<HDec> rounded((size_t)G * LC_K);
+        std::vector<char> has_rounded((size_t)G * LC_K, 0);
+        emulations = 0;
+        {
+            int job = 0;
+            for (int g = 0; g < G; g++)
+                for (int s = 2; s < LC_K; s++) {
+                    if (!((emu_mask >> s) & 1u) || !ord_stage) continue;
+                    const i128 total = tot[(size_t)g * LC_K + (size_t)s];
+                    if (total < THR) continue;
+                    if (total >= THR * 9) PG_FAIL(PG_EOVERFLOW, "sum needs more than 20 digits");
+                    if (job >= ORD_MAXJOBS) PG_FAIL(PG_EOVERFLOW, "more than %d sums need the ordered rounding emulation", ORD_MAXJOBS);
+                    bool have = false;
+                    u128 S = 0;
+                    for (int r = 0; r < nranks(); r++) {
+                        const OrdContrib &k = ((const OrdContrib *)(h_con + contrib_bytes() * (size_t)r))[job];
+                        if (k.kind == 9) PG_FAIL(PG_ECUDA, "internal: ordered rounding could not locate the crossing row");
+                        if (k.kind == 1) {
+                            if (have) PG_FAIL(PG_ECUDA, "internal: two ranks reported a crossing state");
+                            S = ((u128)k.s_hi << 64) | k.s_lo;
+                            have = true;
+                        } else if (k.kind == 2) {
+                            if (!have) PG_FAIL(PG_ECUDA, "internal: a transducer precedes the crossing rank");
+                            const u128 q = ((u128)k.q_hi << 64) | k.q_lo;
+                            S += q + ((S & 1) ? k.c1 : k.c0);
+                        }
+                    }
+                    if (!have) PG_FAIL(PG_ECUDA, "internal: crossing rank did not report a state");
+                    if (S > (u128)HD_MAXCOEF) PG_FAIL(PG_EOVERFLOW, "sum needs more than 19 digits after rounding");
+                    HDec d;
+                    d.coef = (u64)S;
+                    d.scale = slot_scale[(size_t)s] - 1;
+                    d.neg = false;
+                    rounded[(size_t)g * LC_K + (size_t)s] = d;
+                    has_rounded[(size_t)g * LC_K + (size_t)s] = 1;
+                    job++;
+                }
+        }
+        // exact total -> the Decimal the reference would hold
+        auto decimal_sum = [&](int g, int s, HDec *out) -> int {
+            const i128 v = tot[(size_t)g * LC_K + (size_t)s];
+            if (hd_digits((u128)(v < 0 ? -v : v)) > HD_MAXPREC) {
+                if (!has_rounded[(size_t)g * LC_K + (size_t)s])
+                    PG_FAIL(PG_EOVERFLOW, "sum needs 20 digits and the ordered rounding emulation does not apply (negative addends, scale 0, or not planned)");
+                *out = rounded[(size_t)g * LC_K + (size_t)s];
+                emulations++;
+                return PG_OK;
+            }
+            if (!hd_from_i128(v, slot_scale[(size_t)s], out)) PG_FAIL(PG_EOVERFLOW, "decimal overflow");
+            return PG_OK;
+        };
 
         // groups in first-insertion order (aggregate_hash.go:424-438)
         std::vector<int> order;
@@ -495,6 +411,7 @@ struct LowcardPipeline : Pipeline {
         res->stats.aux[0] = selected;
         res->nrows = (i64)order.size();
 
+        std::vector<char> counted((size_t)G * LC_K, 0);
         for (auto &o : outs) {
             ResCol col;
             if (o.first == 0) {
@@ -524,7 +441,7 @@ struct LowcardPipeline : Pipeline {
                         col.push(h);
                     } else if (a.fn == PG_AGG_SUM) {
                         HDec d;
-                        PG_TRY(decimal_sum(g, s, rtot[(size_t)g * LC_K + (size_t)s], &d));
+                        PG_TRY(decimal_sum(g, s, &d));
                         col.push(to_pg_decimal(d));
                     } else if (is_int) {   // avg(INT32): float64 sum / float64 count
                         i128 mag = v < 0 ? -v : v;
@@ -533,7 +450,7 @@ struct LowcardPipeline : Pipeline {
                         col.push(x);
                     } else {               // avg(DECIMAL) = sum.Quo(count)
                         HDec sd, nd, qd;
-                        PG_TRY(decimal_sum(g, s, rtot[(size_t)g * LC_K + (size_t)s], &sd));
+                        PG_TRY(decimal_sum(g, s, &sd));
                         hd_from_i128(n, 0, &nd);
                         if (!hd_quo(sd, nd, &qd)) PG_FAIL(PG_EOVERFLOW, "avg: decimal division failed");
                         col.push(to_pg_decimal(qd));
@@ -542,8 +459,14 @@ struct LowcardPipeline : Pipeline {
             }
             res->cols.push_back(col);
         }
+        // distinct (group, slot) sums that took the ordered path
+        {
+            int n = 0;
+            for (size_t i = 0; i < has_rounded.size(); i++) n += has_rounded[i] ? 1 : 0;
+            emulations = n;
+        }
         res->stats.aux[1] = emulations;
-        tr.mark("finalise(+rounding emulation)");
+        tr.mark("finalise");
         return PG_OK;
     }
 };
@@ -553,6 +476,18 @@ static bool prefix_match(const AffProd &a, const AffProd &chain, size_t n)
     if (a.f.size() != n || chain.f.size() < n) return false;
     for (size_t i = 0; i < n; i++) if (!(a.f[i] == chain.f[i])) return false;
     return true;
+}
+
+// dense ids over the byte codes that occur anywhere in the (sharded) table
+static void dense_codes(const Column &col, std::vector<uint8_t> *vals, uint8_t *lut /* [256] */)
+{
+    const uint32_t *present = col.gpresent();
+    for (int code = 0; code < 256; code++)
+        if (present[code >> 5] & (1u << (code & 31))) {
+            lut[code] = (uint8_t)vals->size();
+            vals->push_back((uint8_t)code);
+        }
+    if (vals->empty()) vals->push_back(0);   // empty table
 }
 
 static int try_lowcard(pg_plan *plan, const Node &aggn, const Node &scan, const std::vector<Range> &ranges,
@@ -570,28 +505,9 @@ static int try_lowcard(pg_plan *plan, const Node &aggn, const Node &scan, const 
         const Expr &ge = aggn.groups[(size_t)k];
         if (ge.kind != PG_TK_COL) { *why = "group key is not a column"; return PG_EUNSUPPORTED; }
         const Column &col = t->cols[(size_t)ge.idx];
-        if (!is_byte_family(col.type) || col.has_nulls) { *why = "group key is not a non-null byte-coded column"; return PG_EUNSUPPORTED; }
+        if (!is_byte_family(col.type) || col.any_nulls()) { *why = "group key is not a non-null byte-coded column"; return PG_EUNSUPPORTED; }
         p->key_col[k] = ge.idx;
-        // dense ids over the codes that occur anywhere (union over ranks so every rank agrees)
-        uint32_t present[8];
-        memcpy(present, col.present, sizeof present);
-        if (ctx().world > 1 && t->dist != PG_DIST_REPLICATED) {
-            DevBuf ds, dr;
-            PG_TRY(ds.alloc(32));
-            PG_TRY(dr.alloc(32 * (size_t)ctx().world));
-            PG_CUDA(cudaMemcpyAsync(ds.p, present, 32, cudaMemcpyHostToDevice, ctx().stream));
-            PG_TRY(comm_allgather(ds.p, dr.p, 32, ctx().stream));
-            std::vector<uint32_t> all(8 * (size_t)ctx().world);
-            PG_CUDA(cudaMemcpyAsync(all.data(), dr.p, 32 * (size_t)ctx().world, cudaMemcpyDeviceToHost, ctx().stream));
-            PG_CUDA(cudaStreamSynchronize(ctx().stream));
-            for (int r = 0; r < ctx().world; r++) for (int w = 0; w < 8; w++) present[w] |= all[(size_t)r * 8 + (size_t)w];
-        }
-        for (int code = 0; code < 256; code++)
-            if (present[code >> 5] & (1u << (code & 31))) {
-                luts[(size_t)k * 256 + (size_t)code] = (uint8_t)p->vals[k].size();
-                p->vals[k].push_back((uint8_t)code);
-            }
-        if (p->vals[k].empty()) p->vals[k].push_back(0);   // empty table
+        dense_codes(col, &p->vals[k], &luts[(size_t)k * 256]);
         dims[k] = (int)p->vals[k].size();
     }
     p->G = dims[0] * dims[1];
@@ -612,6 +528,7 @@ static int try_lowcard(pg_plan *plan, const Node &aggn, const Node &scan, const 
     p->aggs = aggn.aggs;
     p->outs = aggn.outs;
     p->slot_scale.assign(LC_K, 0);
+    std::vector<char> slot_is_decimal(LC_K, 0);
     for (size_t i = 0; i < aggn.aggs.size(); i++) {
         const AggExpr &a = aggn.aggs[i];
         const AffProd &ap = args[i];
@@ -619,7 +536,7 @@ static int try_lowcard(pg_plan *plan, const Node &aggn, const Node &scan, const 
         bool is_int = false;
         if (a.fn == PG_AGG_COUNT) { s = 0; is_int = true; }
         else if (a.fn != PG_AGG_SUM && a.fn != PG_AGG_AVG) { *why = "aggregate other than sum/avg/count"; return PG_EUNSUPPORTED; }
-        else if (ap.f.size() == 1 && ap.f[0].c == 0 && ap.f[0].s == 1 && type_size(t->cols[(size_t)ap.f[0].col].type) == 4) {
+        else if (ap.f.size() == 1 && ap.f[0].c == 0 && ap.f[0].s == 1 && t->cols[(size_t)ap.f[0].col].type == PG_T_INT32) {
             if (colQ >= 0 && colQ != ap.f[0].col) { *why = "two different 32-bit aggregate columns"; return PG_EUNSUPPORTED; }
             colQ = ap.f[0].col;
             s = 1;
@@ -636,6 +553,7 @@ static int try_lowcard(pg_plan *plan, const Node &aggn, const Node &scan, const 
             p->slot_scale[(size_t)s] = sc;
             is_int = a.ltype == PG_LT_HUGEINT || a.ltype == PG_LT_DOUBLE;
             if (is_int && sc != 0) { *why = "integer aggregate over a scaled value"; return PG_EUNSUPPORTED; }
+            if (!is_int) slot_is_decimal[(size_t)s] = 1;
         }
         if (a.fn == PG_AGG_SUM && !is_int && a.ltype != PG_LT_DECIMAL) { *why = "sum result type mismatch"; return PG_EUNSUPPORTED; }
         p->slot.push_back(s);
@@ -646,92 +564,136 @@ static int try_lowcard(pg_plan *plan, const Node &aggn, const Node &scan, const 
         if (o.first == 1 && (o.second < 0 || o.second >= (int)aggn.aggs.size())) { *why = "bad aggregate output index"; return PG_EUNSUPPORTED; }
         if (o.first != 0 && o.first != 1) { *why = "bad output kind"; return PG_EUNSUPPORTED; }
     }
-    // predicate: at most one range, on a 32-bit column
+    // predicate: at most one range, on an integer-family column
     if (ranges.size() > 1) { *why = "more than one predicate column"; return PG_EUNSUPPORTED; }
     int colP = -1;
-    int lo = INT32_MIN, hi = INT32_MAX;
     if (ranges.size() == 1) {
         colP = ranges[0].col;
-        if (type_size(t->cols[(size_t)colP].type) != 4) { *why = "predicate column is not 32-bit"; return PG_EUNSUPPORTED; }
-        lo = (int)std::max<i64>(ranges[0].lo, INT32_MIN);
-        hi = (int)std::min<i64>(ranges[0].hi, INT32_MAX);
-        if (ranges[0].lo > ranges[0].hi) { lo = 1; hi = 0; }
+        if (!is_int_family(t->cols[(size_t)colP].type)) { *why = "predicate column is not an integer-family column"; return PG_EUNSUPPORTED; }
     }
+    if (colA < 0) { *why = "no chain column"; return PG_EUNSUPPORTED; }
+    for (int cidx : {colA, colB, colC}) if (cidx >= 0 && !is_int_family(t->cols[(size_t)cidx].type)) { *why = "chain column is not an integer-family column"; return PG_EUNSUPPORTED; }
     // every kernel input must exist: alias the missing ones to a column that is read anyway
-    if (colA < 0) { *why = "no 64-bit aggregate column"; return PG_EUNSUPPORTED; }
-    for (int cidx : {colA, colB, colC}) if (cidx >= 0 && type_size(t->cols[(size_t)cidx].type) != 8) { *why = "chain column is not 64-bit"; return PG_EUNSUPPORTED; }
     LowcardParams &q = p->prm;
     q.nrows = t->nrows;
     q.row_base = t->global_offset;
-    q.A = (const i64 *)t->cols[(size_t)colA].d_data;
+    const Column &cA = t->cols[(size_t)colA];
+    q.A = cA.ncol();
     q.c1 = 1; q.s1 = 0; q.c2 = 1; q.s2 = 0;
     q.B = q.A; q.C = q.A;
-    int ncol8 = 1;
-    if (colB >= 0) { q.B = (const i64 *)t->cols[(size_t)colB].d_data; q.c1 = chain.f[1].c; q.s1 = chain.f[1].s; ncol8++; }
-    if (colC >= 0) { q.C = (const i64 *)t->cols[(size_t)colC].d_data; q.c2 = chain.f[2].c; q.s2 = chain.f[2].s; ncol8++; }
-    int ncol4 = 0;
-    if (colQ >= 0) { q.q = (const int *)t->cols[(size_t)colQ].d_data; ncol4++; }
-    if (colP >= 0) { q.pred = (const int *)t->cols[(size_t)colP].d_data; if (colP != colQ) ncol4++; }
-    if (colQ < 0 && colP < 0) { *why = "no 32-bit column at all"; return PG_EUNSUPPORTED; }
-    if (colQ < 0) q.q = q.pred;
-    if (colP < 0) q.pred = q.q;
-    q.lo = lo; q.hi = hi;
-    q.key0 = (const uint8_t *)t->cols[(size_t)p->key_col[0]].d_data;
-    q.key1 = p->has_key1 ? (const uint8_t *)t->cols[(size_t)p->key_col[1]].d_data : nullptr;
+    p->bytes_per_row = cA.phys_width() + p->nkeys;
+    bool narrow = col_is_narrow(cA);
+    if (colB >= 0) { const Column &cB = t->cols[(size_t)colB]; q.B = cB.ncol(); q.c1 = chain.f[1].c; q.s1 = chain.f[1].s; p->bytes_per_row += cB.phys_width(); narrow = narrow && col_is_narrow(cB); }
+    if (colC >= 0) { const Column &cC = t->cols[(size_t)colC]; q.C = cC.ncol(); q.c2 = chain.f[2].c; q.s2 = chain.f[2].s; p->bytes_per_row += cC.phys_width(); narrow = narrow && col_is_narrow(cC); }
+    if (colQ >= 0) { q.q = t->cols[(size_t)colQ].ncol(); p->bytes_per_row += q.q.pw; narrow = narrow && col_is_narrow(t->cols[(size_t)colQ]); }
+    else q.q = q.A;
+    i64 slo = 1, shi = 0;
+    if (colP >= 0) {
+        const Column &cP = t->cols[(size_t)colP];
+        q.pred = cP.ncol();
+        stored_range(cP, ranges[0].lo, ranges[0].hi, &slo, &shi);
+        if (colP != colQ && colP != colA && colP != colB && colP != colC) p->bytes_per_row += cP.phys_width();
+        narrow = narrow && cP.phys_width() <= 4;
+    } else {                       // no predicate: the chain column with its whole stored domain
+        q.pred = q.A;
+        stored_range(cA, INT64_MIN, INT64_MAX, &slo, &shi);
+    }
+    q.lo = slo; q.hi = shi;
+    q.key0 = t->cols[(size_t)p->key_col[0]].ncol();
+    if (p->has_key1) q.key1 = t->cols[(size_t)p->key_col[1]].ncol();
+    else { q.key1 = q.key0; q.key1.p = nullptr; }
     q.n1 = dims[1];
     q.ngroups = p->G;
-    p->bytes_per_row = 8 * ncol8 + 4 * ncol4 + p->nkeys;
-    p->smem = (size_t)p->G * LC_K * LC_THREADS * sizeof(i64);
-    const void *kern = p->has_key1 ? (const void *)lowcard_chain_kernel<true, 2> : (const void *)lowcard_chain_kernel<false, 2>;
-    PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
-    i64 ntiles = (t->nrows + LC_TILE - 1) / LC_TILE;
-    p->grid = grid_for(kern, LC_THREADS, p->smem, ntiles);
-    // exactness proof from column statistics
+    // the factors as 32-bit values in the narrow kernel
+    auto fac_fits = [&](i64 c, i64 s, const Column &col) {
+        return fits_i32(c) && fits_i32(s) && fits_i32((i128)c + (i128)s * col.vmin) && fits_i32((i128)c + (i128)s * col.vmax) && fits_i32((i128)c + (i128)s * col.base);
+    };
+    if (colB >= 0) narrow = narrow && fac_fits(q.c1, q.s1, t->cols[(size_t)colB]);
+    if (colC >= 0) narrow = narrow && fac_fits(q.c2, q.s2, t->cols[(size_t)colC]);
+    if (env_int("PG_FORCE_WIDE", 0)) narrow = false;
+    p->wide = !narrow;
+    p->unroll = env_int("PG_LC_UNROLL", 2) >= 4 ? 4 : 2;
+    const i64 ntiles = (t->nrows + LC_TILE - 1) / LC_TILE;
+
+    // exactness proof from the statistics of the WHOLE table (every rank decides alike) and the largest shard
+    const i64 max_tiles = (t->max_rows() + LC_TILE - 1) / LC_TILE;
+    i128 bound = maxabs(cA.gmin(), cA.gmax());
+    if (colB >= 0) {
+        const Column &cB = t->cols[(size_t)colB];
+        i128 f = std::max(maxabs(q.c1 + q.s1 * cB.gmin(), q.c1 + q.s1 * cB.gmax()), maxabs(cB.gmin(), cB.gmax()));
+        bound *= f > 1 ? f : 1;
+    }
+    if (colC >= 0) {
+        const Column &cC = t->cols[(size_t)colC];
+        i128 f = maxabs(q.c2 + q.s2 * cC.gmin(), q.c2 + q.s2 * cC.gmax());
+        bound *= f > 1 ? f : 1;
+    }
+    if (colQ >= 0) bound = std::max(bound, maxabs(t->cols[(size_t)colQ].gmin(), t->cols[(size_t)colQ].gmax()));
+    // can any DECIMAL total need 20 digits?  Then the CTAs take contiguous tile runs so that their partials are
+    // ordered, and the ordered-rounding stage is appended (on every rank: the bound is global)
+    i128 table_bound = bound * (i128)std::max<i64>(t->total_rows(), 1);
+    q.contig = table_bound >= (i128)1000000000000000000LL ? 1 : 0;   // 10^18: generous margin
+    if (getenv("PG_LOWCARD_CONTIG")) q.contig = env_int("PG_LOWCARD_CONTIG", 0) ? 1 : 0;
     {
-        const Column &cA = t->cols[(size_t)colA];
-        i128 bound = maxabs(cA.vmin, cA.vmax);
-        if (colB >= 0) {
-            const Column &cB = t->cols[(size_t)colB];
-            i128 f = std::max(maxabs(q.c1 + q.s1 * cB.vmin, q.c1 + q.s1 * cB.vmax), maxabs(cB.vmin, cB.vmax));
-            bound *= f > 1 ? f : 1;
-        }
-        if (colC >= 0) {
-            const Column &cC = t->cols[(size_t)colC];
-            i128 f = maxabs(q.c2 + q.s2 * cC.vmin, q.c2 + q.s2 * cC.vmax);
-            bound *= f > 1 ? f : 1;
-        }
-        i128 rows_per_cta = (i128)((ntiles + p->grid - 1) / p->grid) * LC_TILE;
+        const bool a_pos = cA.gmin() >= 0;
+        const bool f1_pos = colB < 0 || (q.c1 + q.s1 * t->cols[(size_t)colB].gmin() >= 0 && q.c1 + q.s1 * t->cols[(size_t)colB].gmax() >= 0);
+        const bool f2_pos = colC < 0 || (q.c2 + q.s2 * t->cols[(size_t)colC].gmin() >= 0 && q.c2 + q.s2 * t->cols[(size_t)colC].gmax() >= 0);
+        const bool nonneg[LC_K] = {true, true, a_pos, a_pos && f1_pos, a_pos && f1_pos && f2_pos, colB < 0 || t->cols[(size_t)colB].gmin() >= 0};
+        for (int s = 2; s < LC_K; s++)
+            if (slot_is_decimal[(size_t)s] && nonneg[s] && p->slot_scale[(size_t)s] >= 1) p->emu_mask |= 1u << s;
+    }
+    p->ord_stage = q.contig && p->emu_mask != 0;
+
+    // kernel variant, shared memory and grid.  ACC32: the three small accumulators as 32-bit table slots when a
+    // thread's total over its stored values provably fits (rows per thread from the occupancy of the 64-bit variant,
+    // which is never larger than the 32-bit variant's).
+    auto prep = [&](LowcardKernel k, bool a32) -> int {      // opt in to the shared memory the variant needs; full-GPU grid
+        const size_t sm = (size_t)lc_smem_per_thread(p->G, a32) * LC_THREADS;
+        cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        return sms_times((const void *)k, LC_THREADS, sm);
+    };
+    p->acc32 = false;
+    if (narrow && !env_int("PG_LC_NO_ACC32", 0)) {
+        const int g64 = (int)std::max<i64>(1, std::min<i64>(prep(lowcard_variant(false, false, p->has_key1, p->unroll), false), ntiles));
+        const i128 rows_thr = (i128)((ntiles + g64 - 1) / g64 + p->unroll) * SA_VEC;
+        const Column &cq = t->cols[(size_t)(colQ >= 0 ? colQ : colA)], &cb = t->cols[(size_t)(colB >= 0 ? colB : colA)];
+        const i128 m = std::max<i128>(1, std::max((i128)cq.vmax - cq.base, (i128)cb.vmax - cb.base));
+        const bool nonneg_stored = (i128)cq.vmin - cq.base >= 0 && (i128)cb.vmin - cb.base >= 0;
+        p->acc32 = nonneg_stored && rows_thr * m < ((i128)1 << 32);
+    }
+    p->smem = (size_t)lc_smem_per_thread(p->G, p->acc32) * LC_THREADS;
+    const int full = prep(lowcard_variant(p->wide, p->acc32, p->has_key1, p->unroll), p->acc32);
+    PG_CUDA(cudaGetLastError());
+    p->grid = (int)std::max<i64>(1, std::min<i64>(full, ntiles));
+    {
+        const int full64 = prep(lowcard_variant(true, false, p->has_key1, 2), false);
+        const i64 gmin_grid = std::max<i64>(1, std::min<i64>(full64, max_tiles));     // the smallest grid any rank could run
+        i128 rows_per_cta = (i128)((max_tiles + gmin_grid - 1) / gmin_grid) * LC_TILE;
         if (bound * rows_per_cta >= ((i128)1 << 62)) { *why = "per-CTA partial sum could exceed int64"; return PG_EUNSUPPORTED; }
-        // can any DECIMAL total need 20 digits?  Then the CTAs take contiguous tile runs so that
-        // their partials are ordered (sequential-rounding emulation); the bound uses the largest
-        // table any rank could hold relative to this one (shards are balanced to within 2x).
-        i128 table_bound = bound * (i128)std::max<i64>(t->nrows, 1) * (i128)ctx().world * 2;
-        q.contig = table_bound >= (i128)1000000000000000000LL ? 1 : 0;   // 10^18: generous margin
-        const char *force = getenv("PG_LOWCARD_CONTIG");
-        if (force) q.contig = atoi(force) ? 1 : 0;
-        bool a_pos = cA.vmin >= 0;
-        bool f1_pos = colB < 0 || (q.c1 + q.s1 * t->cols[(size_t)colB].vmin >= 0 && q.c1 + q.s1 * t->cols[(size_t)colB].vmax >= 0);
-        bool f2_pos = colC < 0 || (q.c2 + q.s2 * t->cols[(size_t)colC].vmin >= 0 && q.c2 + q.s2 * t->cols[(size_t)colC].vmax >= 0);
-        p->nonneg[2] = a_pos;
-        p->nonneg[3] = a_pos && f1_pos;
-        p->nonneg[4] = a_pos && f1_pos && f2_pos;
-        p->nonneg[5] = colB < 0 || t->cols[(size_t)colB].vmin >= 0;
     }
     PG_TRY(p->d_part.alloc(sizeof(i64) * (size_t)p->grid * (size_t)p->G * LC_K));
     PG_TRY(p->d_final.alloc(p->rank_bytes()));
     PG_TRY(p->d_gather.alloc(p->rank_bytes() * (size_t)p->nranks()));
-    PG_TRY(p->h_final.alloc(p->rank_bytes() * (size_t)p->nranks()));
+    PG_TRY(p->h_final.alloc(p->host_bytes()));
     PG_TRY(p->d_luts.alloc(512));
+    if (p->ord_stage) {
+        const i64 per = (ntiles + p->grid - 1) / p->grid;
+        p->ord_stride = per + ntiles / ORD_CHUNK + 4;
+        PG_TRY(p->d_jobs.alloc(sizeof(OrdJob) * ORD_MAXJOBS + 64));
+        PG_TRY(p->d_ord.alloc(sizeof(OrdSummary) * (size_t)p->ord_stride * ORD_MAXJOBS));
+        PG_TRY(p->d_contrib.alloc(p->contrib_bytes() * (size_t)(p->nranks() + 1)));
+    }
     PG_CUDA(cudaMemcpyAsync(p->d_luts.p, luts.data(), 512, cudaMemcpyHostToDevice, ctx().stream));
     PG_CUDA(cudaStreamSynchronize(ctx().stream));
     q.luts = p->d_luts.as<uint8_t>();
-    char buf[512];
+    char buf[640];
     snprintf(buf, sizeof buf,
-             "ScanAgg[lowcard-chain] table=%s rows=%lld kernel=lowcard_chain_kernel<%d,2> grid=%d block=%d smem=%zu "
-             "groups=%dx%d bytes/row=%d pred=[%d,%d] chain: A*(%lld%+lld*B)*(%lld%+lld*C) tiles=%s",
-             t->name.c_str(), (long long)t->nrows, (int)p->has_key1, p->grid, LC_THREADS, p->smem, dims[0], dims[1],
-             p->bytes_per_row, lo, hi, (long long)q.c1, (long long)q.s1, (long long)q.c2, (long long)q.s2,
-             q.contig ? "contiguous-per-CTA(ordered partials)" : "interleaved");
+             "ScanAgg[lowcard-chain] table=%s rows=%lld kernel=lowcard_chain_kernel<%s,%s,%d,%d> grid=%d block=%d smem=%zu "
+             "groups=%dx%d stored bytes/row=%d (widths: pred=%d q=%d A=%d B=%d C=%d) stored pred=[%lld,%lld] chain: A*(%lld%+lld*B)*(%lld%+lld*C) tiles=%s%s",
+             t->name.c_str(), (long long)t->nrows, p->wide ? "wide" : "narrow", p->acc32 ? "acc32" : "acc64", (int)p->has_key1, p->unroll, p->grid,
+             LC_THREADS, p->smem, dims[0], dims[1], p->bytes_per_row, q.pred.pw, q.q.pw, q.A.pw, q.B.pw, q.C.pw, (long long)slo, (long long)shi,
+             (long long)q.c1, (long long)q.s1, (long long)q.c2, (long long)q.s2,
+             q.contig ? "contiguous-per-CTA(ordered partials)" : "interleaved", p->ord_stage ? " +ordered-rounding stage (device)" : "");
     p->explain = buf;
     *out = std::move(p);
     return PG_OK;
@@ -893,33 +855,15 @@ static int try_generic(pg_plan *plan, const Node &aggn, const Node &scan, const 
     std::vector<uint8_t> luts(512, 0);
     int dims[2] = {1, 1};
     std::vector<std::pair<int, int>> used;   // (column, width) for the byte accounting
-    auto use = [&](int col) { for (auto &u : used) if (u.first == col) return; used.push_back({col, type_size(t->cols[(size_t)col].type)}); };
+    auto use = [&](int col) { for (auto &u : used) if (u.first == col) return; used.push_back({col, t->cols[(size_t)col].phys_width()}); };
     for (int k = 0; k < p->nkeys; k++) {
         const Expr &ge = aggn.groups[(size_t)k];
         if (ge.kind != PG_TK_COL) { *why = "group key is not a column"; return PG_EUNSUPPORTED; }
         const Column &col = t->cols[(size_t)ge.idx];
-        if (!is_byte_family(col.type) || col.has_nulls) { *why = "group key is not a non-null byte-coded column"; return PG_EUNSUPPORTED; }
+        if (!is_byte_family(col.type) || col.any_nulls()) { *why = "group key is not a non-null byte-coded column"; return PG_EUNSUPPORTED; }
         p->key_col[k] = ge.idx;
         use(ge.idx);
-        uint32_t present[8];
-        memcpy(present, col.present, sizeof present);
-        if (ctx().world > 1 && t->dist != PG_DIST_REPLICATED) {
-            DevBuf ds, dr;
-            PG_TRY(ds.alloc(32));
-            PG_TRY(dr.alloc(32 * (size_t)ctx().world));
-            PG_CUDA(cudaMemcpyAsync(ds.p, present, 32, cudaMemcpyHostToDevice, ctx().stream));
-            PG_TRY(comm_allgather(ds.p, dr.p, 32, ctx().stream));
-            std::vector<uint32_t> all(8 * (size_t)ctx().world);
-            PG_CUDA(cudaMemcpyAsync(all.data(), dr.p, 32 * (size_t)ctx().world, cudaMemcpyDeviceToHost, ctx().stream));
-            PG_CUDA(cudaStreamSynchronize(ctx().stream));
-            for (int r = 0; r < ctx().world; r++) for (int w = 0; w < 8; w++) present[w] |= all[(size_t)r * 8 + (size_t)w];
-        }
-        for (int code = 0; code < 256; code++)
-            if (present[code >> 5] & (1u << (code & 31))) {
-                luts[(size_t)k * 256 + (size_t)code] = (uint8_t)p->vals[k].size();
-                p->vals[k].push_back((uint8_t)code);
-            }
-        if (p->vals[k].empty()) p->vals[k].push_back(0);
+        dense_codes(col, &p->vals[k], &luts[(size_t)k * 256]);     // over the codes of the whole (sharded) table
         dims[k] = (int)p->vals[k].size();
     }
     p->G = dims[0] * dims[1];
@@ -956,12 +900,10 @@ static int try_generic(pg_plan *plan, const Node &aggn, const Node &scan, const 
         const std::vector<Range> &ranges = ranges_;
         (void)rp;
         const Column &col = t->cols[(size_t)ranges[i].col];
-        q.pcol[i].p = col.d_data;
-        q.pcol[i].width = type_size(col.type);
+        q.pcol[i].c = col.ncol();
         q.pcol[i].valid = col.has_nulls ? col.d_valid : nullptr;
-        if (col.has_nulls) p->nulls = true;
-        q.plo[i] = ranges[i].lo;
-        q.phi[i] = ranges[i].hi;
+        if (col.any_nulls()) p->nulls = true;           // agreed across ranks: the plane count shapes the merge
+        stored_range(col, ranges[i].lo, ranges[i].hi, &q.plo[i], &q.phi[i]);
         q.pset[i] = ranges[i].is_set ? 1 : 0;
         memcpy(q.pmask[i], ranges[i].set, sizeof q.pmask[i]);
         use(ranges[i].col);
@@ -994,14 +936,13 @@ static int try_generic(pg_plan *plan, const Node &aggn, const Node &scan, const 
             i128 bound = 1;
             for (size_t f = 0; f < ap.f.size(); f++) {
                 const Column &col = t->cols[(size_t)ap.f[f].col];
-                A.fac[f].p = col.d_data;
-                A.fac[f].width = type_size(col.type);
+                A.fac[f].c = col.ncol();
                 A.fac[f].valid = col.has_nulls ? col.d_valid : nullptr;
-                if (col.has_nulls) p->nulls = true;
-                A.c[f] = ap.f[f].c;
+                if (col.any_nulls()) p->nulls = true;
+                A.c[f] = ap.f[f].c + ap.f[f].s * col.base;      // the kernel multiplies STORED values
                 A.s[f] = ap.f[f].s;
                 use(ap.f[f].col);
-                i128 m = std::max(maxabs(ap.f[f].c + ap.f[f].s * col.vmin, ap.f[f].c + ap.f[f].s * col.vmax), (i128)1);
+                i128 m = std::max(maxabs(ap.f[f].c + ap.f[f].s * col.gmin(), ap.f[f].c + ap.f[f].s * col.gmax()), (i128)1);
                 bound *= m;
             }
             if (kind == GEN_SUM) worst = std::max(worst, bound);
@@ -1037,12 +978,11 @@ static int try_generic(pg_plan *plan, const Node &aggn, const Node &scan, const 
     const void *kern = p->nulls ? (p->NT == 256 ? (const void *)generic_scanagg_kernel<256, true> : p->NT == 128 ? (const void *)generic_scanagg_kernel<128, true> : (const void *)generic_scanagg_kernel<64, true>)
                                 : (p->NT == 256 ? (const void *)generic_scanagg_kernel<256, false> : p->NT == 128 ? (const void *)generic_scanagg_kernel<128, false> : (const void *)generic_scanagg_kernel<64, false>);
     PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
-    int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, p->NT, p->smem);
-    i64 g = (i64)ctx().prop.multiProcessorCount * std::max(per_sm, 1);
-    i64 maxg = (t->nrows + p->NT - 1) / p->NT;
-    p->grid = (int)std::max<i64>(std::min(g, maxg), 1);
-    i128 rows_per_cta = (i128)((t->nrows + p->grid - 1) / p->grid) + p->NT;
+    const i64 g = sms_times(kern, p->NT, p->smem);
+    const i64 tile = (i64)p->NT * SA_VEC;
+    p->grid = (int)std::max<i64>(std::min(g, (t->nrows + tile - 1) / tile), 1);
+    const i64 max_tiles = (t->max_rows() + tile - 1) / tile, gmin_grid = std::max<i64>(1, std::min<i64>(g, max_tiles));
+    i128 rows_per_cta = (i128)((max_tiles + gmin_grid - 1) / gmin_grid) * tile;                 // largest shard, full grid
     if (worst * rows_per_cta >= ((i128)1 << 62)) { *why = "per-CTA partial sum could exceed int64"; return PG_EUNSUPPORTED; }
     PG_TRY(p->d_part.alloc(sizeof(i64) * (size_t)p->grid * (size_t)p->G * (size_t)p->P));
     PG_TRY(p->d_final.alloc(p->rank_bytes()));
@@ -1059,7 +999,7 @@ static int try_generic(pg_plan *plan, const Node &aggn, const Node &scan, const 
     char buf[384];
     snprintf(buf, sizeof buf,
              "ScanAgg[generic] table=%s rows=%lld kernel=generic_scanagg_kernel<%d> grid=%d smem=%zu groups=%dx%d "
-             "predicates=%d accumulators=%d bytes/row=%lld%s",
+             "predicates=%d accumulators=%d stored bytes/row=%lld%s",
              t->name.c_str(), (long long)t->nrows, p->NT, p->grid, p->smem, dims[0], dims[1], q.npred, q.nacc, (long long)p->bytes_per_row,
              p->nulls ? " nulls=validity-bitmaps" : "");
     p->explain = buf;
@@ -1087,7 +1027,7 @@ int build_scan_agg(pg_plan *plan, const Node &aggn, const Node &scan, std::uniqu
                 const Expr *e = strip_value_preserving_casts(&a.arg);
                 if (e->kind != PG_TK_COL || e->idx < 0 || e->idx >= (int)t->cols.size())
                     PG_FAIL(PG_EUNSUPPORTED, "count() over a computed argument");
-                if (t->cols[(size_t)e->idx].has_nulls) {      // count(col) = rows where col is not NULL
+                if (t->cols[(size_t)e->idx].any_nulls()) {      // count(col) = rows where col is not NULL
                     Factor f;
                     f.col = e->idx;
                     args[i].f.push_back(f);

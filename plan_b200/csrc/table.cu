@@ -7,11 +7,13 @@
 // 16-byte vector loads.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
 
 #include <map>
+#include <memory>
 #include <mutex>
 #include <unordered_map>
 
@@ -168,19 +170,28 @@ __global__ void stats_nulls_kernel(const uint8_t *__restrict__ bits, i64 n, int 
     }
 }
 
+// scratch that is released on every exit path
+struct ScratchBuf {
+    void *p = nullptr;
+    ~ScratchBuf() { if (p) dev_free(p); }
+    cudaError_t alloc(size_t n) { return dev_alloc(&p, n ? n : 16); }
+    template <typename T> T *as() const { return (T *)p; }
+};
+
 static int compute_stats(pg_table *t)
 {
     Context &c = ctx();
-    i64 *d_mm = nullptr;
-    uint32_t *d_present = nullptr;
-    int *d_flag = nullptr;
-    unsigned long long *d_adj = nullptr;
     size_t ncol = t->cols.size();
-    PG_CUDA(cudaMalloc(&d_adj, sizeof(unsigned long long) * 2 * ncol));
+    ScratchBuf b_adj, b_mm, b_present, b_flag;
+    PG_CUDA(b_adj.alloc(sizeof(unsigned long long) * 2 * ncol));
+    PG_CUDA(b_mm.alloc(sizeof(i64) * 2 * ncol));
+    PG_CUDA(b_present.alloc(sizeof(uint32_t) * 8 * ncol));
+    PG_CUDA(b_flag.alloc(sizeof(int) * ncol));
+    unsigned long long *d_adj = b_adj.as<unsigned long long>();
+    i64 *d_mm = b_mm.as<i64>();
+    uint32_t *d_present = b_present.as<uint32_t>();
+    int *d_flag = b_flag.as<int>();
     PG_CUDA(cudaMemsetAsync(d_adj, 0, sizeof(unsigned long long) * 2 * ncol, c.stream));
-    PG_CUDA(cudaMalloc(&d_mm, sizeof(i64) * 2 * ncol));
-    PG_CUDA(cudaMalloc(&d_present, sizeof(uint32_t) * 8 * ncol));
-    PG_CUDA(cudaMalloc(&d_flag, sizeof(int) * ncol));
     std::vector<i64> h_mm(2 * ncol);
     for (size_t i = 0; i < ncol; i++) { h_mm[2 * i] = INT64_MAX; h_mm[2 * i + 1] = INT64_MIN; }
     PG_CUDA(cudaMemcpyAsync(d_mm, h_mm.data(), sizeof(i64) * 2 * ncol, cudaMemcpyHostToDevice, c.stream));
@@ -222,10 +233,85 @@ static int compute_stats(pg_table *t)
         col.adjacent_descents = (i64)h_adj[2 * i + 1];
         col.stats_ok = true;
     }
-    cudaFree(d_adj);
-    cudaFree(d_mm);
-    cudaFree(d_present);
-    cudaFree(d_flag);
+    return PG_OK;
+}
+
+// ---------------------------------------------------------------- physical encoding --
+// Frame-of-reference narrowing at seal: an integer-family column whose value span fits 1, 2 or 4 bytes
+// is re-encoded at that width (NCol: logical = base + stored).  TPC-H at SF100: l_quantity, l_discount,
+// l_tax -> 1 byte, dates -> 2, l_extendedprice, keys -> 4; Q1 reads 11 bytes per row instead of 34, Q6 8
+// instead of 24.  The scan kernels sit at the HBM roofline, so fewer stored bytes is the only speed left.
+template <typename S, typename D>
+__global__ void pack_kernel(const S *__restrict__ src, D *__restrict__ dst, i64 n, i64 base)
+{
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) dst[i] = (D)((i64)src[i] - base);
+}
+// value = base + stored, written at the column's NATIVE width (append of narrow host buffers, column export)
+template <typename S, typename D>
+__global__ void widen_kernel(const S *__restrict__ src, D *__restrict__ dst, i64 n, i64 base)
+{
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) dst[i] = (D)((i64)src[i] + base);
+}
+
+template <typename S>
+static void launch_pack(const S *src, void *dst, int pw, i64 n, i64 base, cudaStream_t st)
+{
+    const int grid = ctx().prop.multiProcessorCount * 8;
+    if (pw == 1) pack_kernel<S, uint8_t><<<grid, 256, 0, st>>>(src, (uint8_t *)dst, n, base);
+    else if (pw == 2) pack_kernel<S, uint16_t><<<grid, 256, 0, st>>>(src, (uint16_t *)dst, n, base);
+    else pack_kernel<S, int32_t><<<grid, 256, 0, st>>>(src, (int32_t *)dst, n, base);
+}
+template <typename D>
+static void launch_widen(const void *src, int pw, D *dst, i64 n, i64 base, cudaStream_t st)
+{
+    const int grid = ctx().prop.multiProcessorCount * 8;
+    if (pw == 1) widen_kernel<uint8_t, D><<<grid, 256, 0, st>>>((const uint8_t *)src, dst, n, base);
+    else if (pw == 2) widen_kernel<uint16_t, D><<<grid, 256, 0, st>>>((const uint16_t *)src, dst, n, base);
+    else if (pw == 4) widen_kernel<int32_t, D><<<grid, 256, 0, st>>>((const int32_t *)src, dst, n, base);
+    else widen_kernel<i64, D><<<grid, 256, 0, st>>>((const i64 *)src, dst, n, base);
+}
+
+// narrowest width for [vmin, vmax]; base 0 whenever the values themselves fit the stored type
+static void choose_encoding(i64 vmin, i64 vmax, int native, int *pw, i64 *base)
+{
+    const u64 span = (u64)vmax - (u64)vmin;
+    *pw = native;
+    *base = 0;
+    if (span <= 0xffu) { *pw = 1; *base = (vmin >= 0 && vmax <= 0xff) ? 0 : vmin; }
+    else if (span <= 0xffffu) { *pw = 2; *base = (vmin >= 0 && vmax <= 0xffff) ? 0 : vmin; }
+    else if (span <= 0xffffffffu && native == 8) {
+        *pw = 4;
+        if (vmin >= INT32_MIN && vmax <= INT32_MAX) *base = 0;
+        else *base = span <= (u64)INT32_MAX ? vmin : vmin + ((i64)1 << 31);      // stored stays a signed int32
+    }
+    if (*pw >= native) { *pw = native; *base = 0; }
+}
+
+static int pack_columns(pg_table *t)
+{
+    Context &c = ctx();
+    const char *off = getenv("PG_NO_PACK");
+    if (off && atoi(off)) return PG_OK;
+    if (t->nrows == 0) return PG_OK;
+    for (Column &col : t->cols) {
+        if (!is_packable(col.type) || col.pw != 0) continue;
+        const int native = type_size(col.type);
+        int pw;
+        i64 base;
+        choose_encoding(col.vmin, col.vmax, native, &pw, &base);
+        if (pw == native) continue;
+        void *nd = nullptr;
+        PG_CUDA(dev_alloc(&nd, (size_t)pw * (size_t)t->capacity));
+        PG_CUDA(cudaMemsetAsync(nd, 0, (size_t)pw * (size_t)t->capacity, c.stream));
+        if (native == 8) launch_pack<i64>((const i64 *)col.d_data, nd, pw, t->nrows, base, c.stream);
+        else launch_pack<int32_t>((const int32_t *)col.d_data, nd, pw, t->nrows, base, c.stream);
+        PG_CUDA(cudaGetLastError());
+        PG_CUDA(cudaStreamSynchronize(c.stream));
+        dev_free(col.d_data);
+        col.d_data = nd;
+        col.pw = pw;
+        col.base = base;
+    }
     return PG_OK;
 }
 
@@ -241,8 +327,8 @@ static int grow(pg_table *t, i64 need_rows)
         void *nd = nullptr;
         PG_CUDA(dev_alloc(&nd, esz * (size_t)cap));
         PG_CUDA(cudaMemsetAsync(nd, 0, esz * (size_t)cap, c.stream));
-        if (col.d_data && t->nrows > 0)
-            PG_CUDA(cudaMemcpyAsync(nd, col.d_data, esz * (size_t)t->nrows, cudaMemcpyDeviceToDevice, c.stream));
+        if (col.d_data && t->dev_rows > 0)
+            PG_CUDA(cudaMemcpyAsync(nd, col.d_data, esz * (size_t)t->dev_rows, cudaMemcpyDeviceToDevice, c.stream));
         PG_CUDA(cudaStreamSynchronize(c.stream));
         if (col.d_data) dev_free(col.d_data);
         col.d_data = nd;
@@ -261,8 +347,9 @@ static int grow(pg_table *t, i64 need_rows)
 }
 
 // Host -> device copy of one column slice.  Pinned (or registered) sources are DMAed
-// directly; pageable ones are pipelined through two pinned staging buffers.
-static int h2d(void *dst, const void *src, size_t bytes)
+// directly (*direct = true: the caller's buffer is still being read when this returns);
+// pageable ones are pipelined through two pinned staging buffers and are consumed on return.
+static int h2d(void *dst, const void *src, size_t bytes, bool *direct)
 {
     Context &c = ctx();
     if (bytes == 0) return PG_OK;
@@ -271,6 +358,7 @@ static int h2d(void *dst, const void *src, size_t bytes)
     cudaGetLastError();
     if (pinned) {
         PG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c.stream));
+        *direct = true;
         return PG_OK;
     }
     size_t off = 0;
@@ -297,6 +385,169 @@ __global__ void valid_scatter_kernel(uint8_t *dst, i64 at, const uint8_t *src, i
             atomicAnd((unsigned int *)(dst + ((j >> 3) & ~(i64)3)), ~(1u << (((j >> 3) & 3) * 8 + (j & 7))));
         }
     }
+}
+
+static int ensure_valid_bitmap(pg_table *t, Column &col)
+{
+    if (col.d_valid) return PG_OK;
+    PG_CUDA(dev_alloc((void **)&col.d_valid, (size_t)t->capacity / 8));
+    PG_CUDA(cudaMemsetAsync(col.d_valid, 0xff, (size_t)t->capacity / 8, ctx().stream));
+    return PG_OK;
+}
+
+// ---------------------------------------------------------------- small-append staging --
+// The Go shim appends what scanExecutor hands it: 2048-row chunks from pageable Go heap
+// (executor_scan.go:158-223), ~293 k calls for SF100 lineitem.  Such calls are copied into pinned,
+// column-wise host staging (the caller's buffers are consumed when the call returns -- the cgo rule)
+// and reach the device as one asynchronous copy per column per STAGE_ROWS rows: no per-call
+// synchronisation, no per-call device allocation.  Two staging sets alternate so the host keeps
+// filling one while the other is in flight.
+constexpr i64 STAGE_ROWS = (i64)1 << 18;          // rows per staging set
+constexpr i64 STAGE_SMALL = (i64)1 << 16;         // appends of at most this many rows are staged
+
+struct AppendStage {
+    struct Set {
+        std::vector<void *> col;                  // pinned, STAGE_ROWS x native width (null for VARCHAR)
+        std::vector<uint8_t *> valid;             // pinned packed validity, allocated on first use
+        std::vector<char> any_valid;
+        i64 rows = 0;
+        cudaEvent_t ev = nullptr;
+    } set[2];
+    int cur = 0;
+    std::vector<uint8_t *> d_valid_tmp;           // device scratch for the validity scatter, per column
+    ~AppendStage()
+    {
+        for (Set &s : set) {
+            for (void *p : s.col) if (p) cudaFreeHost(p);
+            for (uint8_t *p : s.valid) if (p) cudaFreeHost(p);
+            if (s.ev) cudaEventDestroy(s.ev);
+        }
+        for (uint8_t *p : d_valid_tmp) if (p) dev_free(p);
+    }
+};
+
+static int stage_create(pg_table *t)
+{
+    if (t->stage) return PG_OK;
+    std::unique_ptr<AppendStage> st(new AppendStage());
+    const size_t ncol = t->cols.size();
+    st->d_valid_tmp.assign(ncol, nullptr);
+    for (AppendStage::Set &s : st->set) {
+        s.col.assign(ncol, nullptr);
+        s.valid.assign(ncol, nullptr);
+        s.any_valid.assign(ncol, 0);
+        PG_CUDA(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
+        for (size_t i = 0; i < ncol; i++) {
+            if (t->cols[i].type == PG_T_VARCHAR) continue;
+            PG_CUDA(cudaMallocHost(&s.col[i], (size_t)STAGE_ROWS * (size_t)type_size(t->cols[i].type)));
+        }
+    }
+    t->stage = st.release();
+    return PG_OK;
+}
+
+// copy the current staging set to the device (asynchronously) and switch to the other one
+static int stage_flush(pg_table *t)
+{
+    Context &c = ctx();
+    AppendStage *st = t->stage;
+    if (!st) return PG_OK;
+    AppendStage::Set &s = st->set[st->cur];
+    if (s.rows == 0) return PG_OK;
+    PG_TRY(grow(t, t->dev_rows + s.rows));
+    for (size_t i = 0; i < t->cols.size(); i++) {
+        Column &col = t->cols[i];
+        if (col.type == PG_T_VARCHAR) continue;
+        const size_t esz = (size_t)type_size(col.type);
+        PG_CUDA(cudaMemcpyAsync((char *)col.d_data + esz * (size_t)t->dev_rows, s.col[i], esz * (size_t)s.rows, cudaMemcpyHostToDevice, c.stream));
+        if (s.any_valid[i]) {
+            PG_TRY(ensure_valid_bitmap(t, col));
+            if (!st->d_valid_tmp[i]) PG_CUDA(dev_alloc((void **)&st->d_valid_tmp[i], (size_t)STAGE_ROWS / 8));
+            PG_CUDA(cudaMemcpyAsync(st->d_valid_tmp[i], s.valid[i], (size_t)(s.rows + 7) / 8, cudaMemcpyHostToDevice, c.stream));
+            valid_scatter_kernel<<<64, 256, 0, c.stream>>>(col.d_valid, t->dev_rows, st->d_valid_tmp[i], s.rows);
+            PG_CUDA(cudaGetLastError());
+        }
+    }
+    PG_CUDA(cudaEventRecord(s.ev, c.stream));
+    t->dev_rows += s.rows;
+    st->cur ^= 1;
+    AppendStage::Set &n = st->set[st->cur];
+    PG_CUDA(cudaEventSynchronize(n.ev));          // the set we are about to refill has left the host
+    n.rows = 0;
+    std::fill(n.any_valid.begin(), n.any_valid.end(), 0);
+    return PG_OK;
+}
+
+// host-side widening of a narrow source into the native staging array
+template <typename D>
+static void widen_host(const pg_colbuf &b, int w, D *dst, i64 n)
+{
+    const i64 base = b.base;
+    switch (w) {
+    case 1: { const uint8_t *s = (const uint8_t *)b.data; for (i64 i = 0; i < n; i++) dst[i] = (D)(base + s[i]); break; }
+    case 2: { const uint16_t *s = (const uint16_t *)b.data; for (i64 i = 0; i < n; i++) dst[i] = (D)(base + s[i]); break; }
+    case 4: { const int32_t *s = (const int32_t *)b.data; for (i64 i = 0; i < n; i++) dst[i] = (D)(base + s[i]); break; }
+    default: { const i64 *s = (const i64 *)b.data; for (i64 i = 0; i < n; i++) dst[i] = (D)(base + s[i]); break; }
+    }
+}
+
+static void copy_bits(uint8_t *dst, i64 at, const uint8_t *src, i64 n)
+{
+    if ((at & 7) == 0) {
+        memcpy(dst + (at >> 3), src, (size_t)(n + 7) / 8);
+        if (n & 7) dst[(at + n) >> 3] |= (uint8_t)(0xffu << (n & 7));     // slots past the end stay "valid" until they are written
+        return;
+    }
+    for (i64 k = 0; k < n; k++) {
+        const i64 j = at + k;
+        if ((src[k >> 3] >> (k & 7)) & 1) dst[j >> 3] |= (uint8_t)(1u << (j & 7));
+        else dst[j >> 3] &= (uint8_t)~(1u << (j & 7));
+    }
+}
+
+static int stage_append(pg_table *t, i64 nrows, const pg_colbuf *cols)
+{
+    PG_TRY(stage_create(t));
+    AppendStage *st = t->stage;
+    i64 done = 0;
+    while (done < nrows) {
+        AppendStage::Set &s = st->set[st->cur];
+        const i64 n = std::min(nrows - done, STAGE_ROWS - s.rows);
+        for (size_t i = 0; i < t->cols.size(); i++) {
+            const Column &col = t->cols[i];
+            if (col.type == PG_T_VARCHAR) continue;
+            const int esz = type_size(col.type);
+            const int w = cols[i].width ? cols[i].width : esz;
+            char *dst = (char *)s.col[i] + (size_t)esz * (size_t)s.rows;
+            if (w == esz && cols[i].base == 0) {
+                memcpy(dst, (const char *)cols[i].data + (size_t)w * (size_t)done, (size_t)esz * (size_t)n);
+            } else {
+                pg_colbuf b = cols[i];
+                b.data = (const char *)cols[i].data + (size_t)w * (size_t)done;
+                if (esz == 8) widen_host<i64>(b, w, (i64 *)dst, n);
+                else if (esz == 4) widen_host<int32_t>(b, w, (int32_t *)dst, n);
+                else widen_host<uint8_t>(b, w, (uint8_t *)dst, n);
+            }
+            if (cols[i].valid) {
+                if (!s.valid[i]) {
+                    PG_CUDA(cudaMallocHost((void **)&s.valid[i], (size_t)STAGE_ROWS / 8));
+                }
+                if (!s.any_valid[i]) { memset(s.valid[i], 0xff, (size_t)STAGE_ROWS / 8); s.any_valid[i] = 1; }
+                if ((done & 7) == 0) copy_bits(s.valid[i], s.rows, cols[i].valid + (done >> 3), n);
+                else {
+                    for (i64 k = 0; k < n; k++) {
+                        const i64 j = s.rows + k, q = done + k;
+                        if ((cols[i].valid[q >> 3] >> (q & 7)) & 1) s.valid[i][j >> 3] |= (uint8_t)(1u << (j & 7));
+                        else s.valid[i][j >> 3] &= (uint8_t)~(1u << (j & 7));
+                    }
+                }
+            }
+        }
+        s.rows += n;
+        done += n;
+        if (s.rows == STAGE_ROWS) PG_TRY(stage_flush(t));
+    }
+    return PG_OK;
 }
 
 }  // namespace pg
@@ -386,7 +637,7 @@ int pg_table_create(const char *name, int ncol, const pg_coldesc *cols, pg_table
     if (!c.ready) PG_FAIL(PG_ESTATE, "pg_table_create: call pg_init first");
     if (!out || !cols || ncol <= 0 || ncol > 256) PG_FAIL(PG_EINVAL, "pg_table_create: bad arguments");
     PG_CUDA(cudaSetDevice(c.device));
-    pg_table *t = new pg_table();
+    std::unique_ptr<pg_table> t(new pg_table());
     t->name = name ? name : "";
     for (int i = 0; i < ncol; i++) {
         Column col;
@@ -394,80 +645,140 @@ int pg_table_create(const char *name, int ncol, const pg_coldesc *cols, pg_table
         col.type = cols[i].type;
         col.width = cols[i].width;
         col.scale = cols[i].scale;
-        if (type_size(col.type) == 0 || col.type == PG_T_HUGEINT || col.type == PG_T_DECIMAL128) {
-            delete t;
+        if (type_size(col.type) == 0 || col.type == PG_T_HUGEINT || col.type == PG_T_DECIMAL128)
             PG_FAIL(PG_EINVAL, "pg_table_create: column %d (%s) has unsupported input type %d", i, col.name.c_str(), col.type);
-        }
+        // a DECIMAL64 column is an unscaled int64: the coefficient has at most 19 digits (govalues), the scale 0..19
+        if (col.type == PG_T_DECIMAL64 && (col.scale < 0 || col.scale > 19 || col.width < 0 || col.width > 19 || (col.width > 0 && col.scale > col.width)))
+            PG_FAIL(PG_EINVAL, "pg_table_create: column %d (%s) DECIMAL(%d,%d) is outside DECIMAL64 (width <= 19, 0 <= scale <= width)", i,
+                    col.name.c_str(), col.width, col.scale);
         if (col.type == PG_T_DICT8) {
-            if (cols[i].dict_len < 0 || cols[i].dict_len > 256 || (cols[i].dict_len > 0 && !cols[i].dict)) {
-                delete t;
+            if (cols[i].dict_len < 0 || cols[i].dict_len > 256 || (cols[i].dict_len > 0 && !cols[i].dict))
                 PG_FAIL(PG_EINVAL, "pg_table_create: column %d (%s) bad dictionary", i, col.name.c_str());
-            }
             for (int k = 0; k < cols[i].dict_len; k++) col.dict.push_back(cols[i].dict[k] ? cols[i].dict[k] : "");
         }
         t->cols.push_back(col);
     }
-    *out = t;
+    *out = t.release();
     return PG_OK;
 }
 
 int pg_table_reserve(pg_table *t, int64_t nrows)
 {
     if (!t || nrows < 0) PG_FAIL(PG_EINVAL, "pg_table_reserve: bad arguments");
+    if (t->sealed) PG_FAIL(PG_ESTATE, "pg_table_reserve: table %s is sealed", t->name.c_str());
     PG_CUDA(cudaSetDevice(ctx().device));
     return grow(t, std::max<i64>(nrows, 1));
 }
 
-int pg_table_append(pg_table *t, int64_t nrows, const void *const *cols, const uint8_t *const *valid)
+int pg_table_append_cols(pg_table *t, int64_t nrows, const pg_colbuf *cols)
 {
     Context &c = ctx();
-    if (!t || nrows < 0 || (nrows > 0 && !cols)) PG_FAIL(PG_EINVAL, "pg_table_append: bad arguments");
-    if (t->sealed) PG_FAIL(PG_ESTATE, "pg_table_append: table %s is sealed", t->name.c_str());
+    if (!t || nrows < 0 || (nrows > 0 && !cols)) PG_FAIL(PG_EINVAL, "pg_table_append_cols: bad arguments");
+    if (t->sealed) PG_FAIL(PG_ESTATE, "pg_table_append_cols: table %s is sealed", t->name.c_str());
     if (nrows == 0) return PG_OK;
     PG_CUDA(cudaSetDevice(c.device));
-    PG_TRY(grow(t, t->nrows + nrows));
     for (size_t i = 0; i < t->cols.size(); i++) {
-        Column &col = t->cols[i];
-        if (!cols[i]) PG_FAIL(PG_EINVAL, "pg_table_append: column %zu (%s) is NULL", i, col.name.c_str());
+        const Column &col = t->cols[i];
+        if (!cols[i].data) PG_FAIL(PG_EINVAL, "pg_table_append_cols: column %zu (%s) is NULL", i, col.name.c_str());
+        const int esz = type_size(col.type), w = cols[i].width ? cols[i].width : esz;
+        if (w != 1 && w != 2 && w != 4 && w != 8 && w != 16) PG_FAIL(PG_EINVAL, "pg_table_append_cols: column %s: width %d", col.name.c_str(), w);
+        if ((w != esz || cols[i].base != 0) && (!is_packable(col.type) || w > esz))
+            PG_FAIL(PG_EINVAL, "pg_table_append_cols: column %s: a narrow / based buffer needs an integer-family column at least as wide", col.name.c_str());
         if (col.type == PG_T_VARCHAR) {
-            if (valid && valid[i]) PG_FAIL(PG_EUNSUPPORTED, "pg_table_append: NULLs in VARCHAR column %s", col.name.c_str());
-            const pg_string *sv = (const pg_string *)cols[i];
-            if (col.h_off.empty()) col.h_off.push_back(0);
-            for (int64_t r = 0; r < nrows; r++) {
-                if (sv[r].len < 0 || (sv[r].len > 0 && !sv[r].data)) PG_FAIL(PG_EINVAL, "pg_table_append: bad string in column %s", col.name.c_str());
-                col.h_bytes.append(sv[r].data ? sv[r].data : "", (size_t)sv[r].len);
-                col.h_off.push_back((int64_t)col.h_bytes.size());
-            }
-            continue;
-        }
-        size_t esz = (size_t)type_size(col.type);
-        PG_TRY(h2d((char *)col.d_data + esz * (size_t)t->nrows, cols[i], esz * (size_t)nrows));
-        if (valid && valid[i]) {
-            if (!col.d_valid) {
-                PG_CUDA(dev_alloc((void **)&col.d_valid, (size_t)t->capacity / 8));
-                PG_CUDA(cudaMemsetAsync(col.d_valid, 0xff, (size_t)t->capacity / 8, c.stream));
-            }
-            size_t vb = (size_t)(nrows + 7) / 8;
-            uint8_t *d_tmp = nullptr;
-            PG_CUDA(cudaMalloc(&d_tmp, vb));
-            PG_TRY(h2d(d_tmp, valid[i], vb));
-            valid_scatter_kernel<<<256, 256, 0, c.stream>>>(col.d_valid, t->nrows, d_tmp, nrows);
-            PG_CUDA(cudaGetLastError());
-            PG_CUDA(cudaStreamSynchronize(c.stream));
-            cudaFree(d_tmp);
+            if (cols[i].valid) PG_FAIL(PG_EUNSUPPORTED, "pg_table_append_cols: NULLs in VARCHAR column %s", col.name.c_str());
+            const pg_string *sv = (const pg_string *)cols[i].data;
+            for (int64_t r = 0; r < nrows; r++)
+                if (sv[r].len < 0 || (sv[r].len > 0 && !sv[r].data)) PG_FAIL(PG_EINVAL, "pg_table_append_cols: bad string in column %s", col.name.c_str());
         }
     }
-    // the host buffers may be reused by the caller as soon as we return (cgo rule)
-    PG_CUDA(cudaStreamSynchronize(c.stream));
+    // host-resident VARCHAR payloads (validated above, so a failure below cannot leave them half appended)
+    for (size_t i = 0; i < t->cols.size(); i++) {
+        Column &col = t->cols[i];
+        if (col.type != PG_T_VARCHAR) continue;
+        const pg_string *sv = (const pg_string *)cols[i].data;
+        if (col.h_off.empty()) col.h_off.push_back(0);
+        for (int64_t r = 0; r < nrows; r++) {
+            col.h_bytes.append(sv[r].data ? sv[r].data : "", (size_t)sv[r].len);
+            col.h_off.push_back((int64_t)col.h_bytes.size());
+        }
+    }
+    auto rollback_strings = [&]() {
+        for (Column &col : t->cols) {
+            if (col.type != PG_T_VARCHAR) continue;
+            col.h_off.resize((size_t)t->nrows + 1);
+            col.h_bytes.resize((size_t)col.h_off.back());
+        }
+    };
+    int rc = PG_OK;
+    if (nrows <= STAGE_SMALL) {
+        rc = stage_append(t, nrows, cols);
+    } else {
+        bool direct = false;
+        rc = stage_flush(t);
+        if (rc == PG_OK) rc = grow(t, t->dev_rows + nrows);
+        std::vector<std::unique_ptr<ScratchBuf>> scratch;
+        for (size_t i = 0; i < t->cols.size() && rc == PG_OK; i++) {
+            Column &col = t->cols[i];
+            if (col.type == PG_T_VARCHAR) continue;
+            const size_t esz = (size_t)type_size(col.type);
+            const int w = cols[i].width ? cols[i].width : (int)esz;
+            char *dst = (char *)col.d_data + esz * (size_t)t->dev_rows;
+            if ((size_t)w == esz && cols[i].base == 0) {
+                rc = h2d(dst, cols[i].data, esz * (size_t)nrows, &direct);
+            } else {
+                // narrow host buffer: the narrow bytes cross PCIe, the device widens them into the native array
+                scratch.emplace_back(new ScratchBuf());
+                if (scratch.back()->alloc((size_t)w * (size_t)nrows) != cudaSuccess) { cudaGetLastError(); set_error("out of device memory for the append scratch"); rc = PG_ENOMEM; break; }
+                rc = h2d(scratch.back()->p, cols[i].data, (size_t)w * (size_t)nrows, &direct);
+                if (rc != PG_OK) break;
+                if (esz == 8) launch_widen<i64>(scratch.back()->p, w, (i64 *)dst, nrows, cols[i].base, c.stream);
+                else launch_widen<int32_t>(scratch.back()->p, w, (int32_t *)dst, nrows, cols[i].base, c.stream);
+                if (cudaGetLastError() != cudaSuccess) { set_error("widen kernel launch failed"); rc = PG_ECUDA; }
+            }
+            if (rc == PG_OK && cols[i].valid) {
+                rc = ensure_valid_bitmap(t, col);
+                if (rc != PG_OK) break;
+                const size_t vb = (size_t)(nrows + 7) / 8;
+                scratch.emplace_back(new ScratchBuf());
+                if (scratch.back()->alloc(vb) != cudaSuccess) { cudaGetLastError(); set_error("out of device memory for the validity scratch"); rc = PG_ENOMEM; break; }
+                rc = h2d(scratch.back()->p, cols[i].valid, vb, &direct);
+                if (rc != PG_OK) break;
+                valid_scatter_kernel<<<256, 256, 0, c.stream>>>(col.d_valid, t->dev_rows, scratch.back()->as<uint8_t>(), nrows);
+                if (cudaGetLastError() != cudaSuccess) { set_error("validity scatter launch failed"); rc = PG_ECUDA; }
+            }
+        }
+        // pinned caller buffers are read by the DMA engine until the stream drains (cgo rule: C must not keep
+        // using Go memory after the call); the scratch blocks go back to the cache only once their kernels ran
+        if (direct || !scratch.empty()) {
+            if (cudaStreamSynchronize(c.stream) != cudaSuccess && rc == PG_OK) { set_error("append: stream synchronisation failed"); rc = PG_ECUDA; }
+        }
+        if (rc == PG_OK) t->dev_rows += nrows;
+    }
+    if (rc != PG_OK) { rollback_strings(); return rc; }
     t->nrows += nrows;
     t->version++;
     return PG_OK;
+}
+
+int pg_table_append(pg_table *t, int64_t nrows, const void *const *cols, const uint8_t *const *valid)
+{
+    if (!t || nrows < 0 || (nrows > 0 && !cols)) PG_FAIL(PG_EINVAL, "pg_table_append: bad arguments");
+    std::vector<pg_colbuf> b(t->cols.size());
+    for (size_t i = 0; i < b.size(); i++) {
+        b[i].data = nrows > 0 ? cols[i] : nullptr;
+        b[i].width = 0;
+        b[i].reserved = 0;
+        b[i].base = 0;
+        b[i].valid = valid ? valid[i] : nullptr;
+    }
+    return pg_table_append_cols(t, nrows, b.data());
 }
 
 int pg_table_device_column(pg_table *t, int col, void **dev_ptr)
 {
     if (!t || !dev_ptr || col < 0 || col >= (int)t->cols.size()) PG_FAIL(PG_EINVAL, "pg_table_device_column: bad arguments");
     if (t->capacity == 0) PG_FAIL(PG_ESTATE, "pg_table_device_column: reserve rows first");
+    if (t->sealed) PG_FAIL(PG_ESTATE, "pg_table_device_column: table is sealed (columns are stored in their packed encoding)");
     if (t->cols[col].type == PG_T_VARCHAR) PG_FAIL(PG_EUNSUPPORTED, "pg_table_device_column: VARCHAR columns are host-resident");
     *dev_ptr = t->cols[col].d_data;
     return PG_OK;
@@ -477,7 +788,9 @@ int pg_table_set_rows(pg_table *t, int64_t nrows)
 {
     if (!t || nrows < 0 || nrows > t->capacity) PG_FAIL(PG_EINVAL, "pg_table_set_rows: %lld rows exceed capacity", (long long)nrows);
     if (t->sealed) PG_FAIL(PG_ESTATE, "pg_table_set_rows: table is sealed");
+    if (t->stage && t->stage->set[t->stage->cur].rows) PG_FAIL(PG_ESTATE, "pg_table_set_rows: appended rows are still staged");
     t->nrows = nrows;
+    t->dev_rows = nrows;
     t->version++;
     return PG_OK;
 }
@@ -485,7 +798,14 @@ int pg_table_set_rows(pg_table *t, int64_t nrows)
 int pg_table_seal(pg_table *t, int64_t global_row_offset)
 {
     if (!t) PG_FAIL(PG_EINVAL, "pg_table_seal: null table");
+    if (t->sealed) PG_FAIL(PG_ESTATE, "pg_table_seal: table %s is already sealed", t->name.c_str());
     PG_CUDA(cudaSetDevice(ctx().device));
+    PG_TRY(stage_flush(t));
+    if (t->stage) {                       // staging is only needed while the table grows
+        PG_CUDA(cudaStreamSynchronize(ctx().stream));
+        delete t->stage;
+        t->stage = nullptr;
+    }
     if (t->capacity == 0) PG_TRY(grow(t, 1));
     t->global_offset = global_row_offset;
     for (Column &col : t->cols) {
@@ -495,6 +815,7 @@ int pg_table_seal(pg_table *t, int64_t global_row_offset)
             PG_FAIL(PG_ESTATE, "pg_table_seal: VARCHAR column %s holds %zu strings for %lld rows", col.name.c_str(), col.h_off.size() - 1, (long long)t->nrows);
     }
     PG_TRY(compute_stats(t));
+    PG_TRY(pack_columns(t));
     for (Column &col : t->cols) {        // device copy of string columns for GPU-side predicates (LIKE, =, <>)
         if (col.type != PG_T_VARCHAR) continue;
         if (col.d_off) { dev_free(col.d_off); col.d_off = nullptr; }
@@ -525,10 +846,51 @@ int pg_table_rows(const pg_table *t, int64_t *nrows)
     return PG_OK;
 }
 
+int pg_table_column_encoding(const pg_table *t, int col, int32_t *stored_width, int64_t *base)
+{
+    if (!t || col < 0 || col >= (int)t->cols.size()) PG_FAIL(PG_EINVAL, "pg_table_column_encoding: bad arguments");
+    if (stored_width) *stored_width = t->cols[(size_t)col].type == PG_T_VARCHAR ? 0 : t->cols[(size_t)col].phys_width();
+    if (base) *base = t->cols[(size_t)col].base;
+    return PG_OK;
+}
+
+// Bulk export of a column range in the NATIVE encoding (decodes packed columns on the device first).
+int pg_table_read_column(pg_table *t, int col, int64_t row, int64_t nrows, void *host_out)
+{
+    if (!t || !host_out || col < 0 || col >= (int)t->cols.size() || row < 0 || nrows < 0 || row + nrows > t->nrows)
+        PG_FAIL(PG_EINVAL, "pg_table_read_column: bad arguments");
+    Context &c = ctx();
+    PG_CUDA(cudaSetDevice(c.device));
+    Column &cl = t->cols[(size_t)col];
+    if (cl.type == PG_T_VARCHAR) PG_FAIL(PG_EUNSUPPORTED, "pg_table_read_column: VARCHAR columns are host-resident");
+    if (nrows == 0) return PG_OK;
+    PG_TRY(stage_flush(t));
+    const size_t esz = (size_t)type_size(cl.type);
+    const int pw = cl.phys_width();
+    if ((size_t)pw == esz && cl.base == 0) {
+        PG_CUDA(cudaMemcpyAsync(host_out, (const char *)cl.d_data + esz * (size_t)row, esz * (size_t)nrows, cudaMemcpyDeviceToHost, c.stream));
+        PG_CUDA(cudaStreamSynchronize(c.stream));
+        return PG_OK;
+    }
+    ScratchBuf tmp;
+    PG_CUDA(tmp.alloc(esz * (size_t)nrows));
+    const void *src = (const char *)cl.d_data + (size_t)pw * (size_t)row;
+    if (esz == 8) launch_widen<i64>(src, pw, tmp.as<i64>(), nrows, cl.base, c.stream);
+    else launch_widen<int32_t>(src, pw, tmp.as<int32_t>(), nrows, cl.base, c.stream);
+    PG_CUDA(cudaGetLastError());
+    PG_CUDA(cudaMemcpyAsync(host_out, tmp.p, esz * (size_t)nrows, cudaMemcpyDeviceToHost, c.stream));
+    PG_CUDA(cudaStreamSynchronize(c.stream));
+    return PG_OK;
+}
+
 void pg_table_free(pg_table *t)
 {
     if (!t) return;
-    if (ctx().ready) cudaSetDevice(ctx().device);
+    if (ctx().ready) {
+        cudaSetDevice(ctx().device);
+        if (t->stage) cudaStreamSynchronize(ctx().stream);
+    }
+    delete t->stage;
     for (Column &col : t->cols) {
         if (col.d_data) dev_free(col.d_data);
         if (col.d_valid) dev_free(col.d_valid);

@@ -425,17 +425,4 @@ int pg_tpch_nation(pg_table **nation)
     return PG_OK;
 }
 
-int pg_table_read_column(pg_table *t, int col, int64_t row, int64_t nrows, void *host_out)
-{
-    if (!t || !host_out || col < 0 || col >= (int)t->cols.size() || row < 0 || nrows < 0 || row + nrows > t->nrows)
-        PG_FAIL(PG_EINVAL, "pg_table_read_column: bad arguments");
-    PG_CUDA(cudaSetDevice(ctx().device));
-    if (t->cols[(size_t)col].type == PG_T_VARCHAR) PG_FAIL(PG_EUNSUPPORTED, "pg_table_read_column: VARCHAR columns are host-resident");
-    size_t esz = (size_t)type_size(t->cols[(size_t)col].type);
-    PG_CUDA(cudaMemcpyAsync(host_out, (const char *)t->cols[(size_t)col].d_data + esz * (size_t)row, esz * (size_t)nrows,
-                            cudaMemcpyDeviceToHost, ctx().stream));
-    PG_CUDA(cudaStreamSynchronize(ctx().stream));
-    return PG_OK;
-}
-
 }  // extern "C"

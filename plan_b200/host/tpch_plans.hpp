@@ -28,7 +28,16 @@ inline LType lineitem_type(int c)
     default: return LType::Integer();
     }
 }
-inline Expr lcol(int c, int side = 0) { return col(side, c, lineitem_type(c)); }
+// Column positions in the BOUND tables.  By default the full generated schemas (PG_L_* / PG_O_* / PG_C_*); a host that
+// uploads only the referenced columns (ScanOpInfo.Columns in the reference) installs the pruned layout here.
+struct ColumnLayout {
+    std::vector<int> line, orders, customer;      // full index -> bound index (-1: column not uploaded); empty = identity
+    int at(const std::vector<int> &m, int c) const { return m.empty() ? c : m[(size_t)c]; }
+};
+inline ColumnLayout &layout() { static ColumnLayout l; return l; }
+inline Expr lcol(int c, int side = 0) { return col(side, layout().at(layout().line, c), lineitem_type(c)); }
+inline int ocol(int c) { return layout().at(layout().orders, c); }
+inline int ccol(int c) { return layout().at(layout().customer, c); }
 
 inline Op make(POT t) { auto p = std::make_shared<PhysicalOperator>(); p->Typ = t; return p; }
 
@@ -92,17 +101,17 @@ inline Op q3_plan(int64_t limit = 10)   // Limit <- Order(revenue desc, o_orderd
     int32_t d = days_from_civil(1995, 3, 29);
     Op cust = make(POT_Scan);
     cust->Table = "customer";
-    cust->Filters = {func("=", B, {col(0, PG_C_MKTSEGMENT, LType::Varchar()), constS("HOUSEHOLD")})};
+    cust->Filters = {func("=", B, {col(0, ccol(PG_C_MKTSEGMENT), LType::Varchar()), constS("HOUSEHOLD")})};
     Op ord = make(POT_Scan);
     ord->Table = "orders";
-    ord->Filters = {func("<", B, {col(0, PG_O_ORDERDATE, LType::Date()), constI(d, LType::Date())})};
+    ord->Filters = {func("<", B, {col(0, ocol(PG_O_ORDERDATE), LType::Date()), constI(d, LType::Date())})};
     Op line = make(POT_Scan);
     line->Table = "lineitem";
     line->Filters = {func(">", B, {lcol(PG_L_SHIPDATE), constI(d, LType::Date())})};
     Op j1 = make(POT_Join);
     j1->Children = {ord, cust};
-    j1->OnConds = {func("=", B, {col(0, PG_O_CUSTKEY, LType::Integer()), col(1, PG_C_CUSTKEY, LType::Integer())})};
-    j1->Outputs = {col(0, PG_O_ORDERKEY, LType::Bigint()), col(0, PG_O_ORDERDATE, LType::Date()), col(0, PG_O_SHIPPRIORITY, LType::Integer())};
+    j1->OnConds = {func("=", B, {col(0, ocol(PG_O_CUSTKEY), LType::Integer()), col(1, ccol(PG_C_CUSTKEY), LType::Integer())})};
+    j1->Outputs = {col(0, ocol(PG_O_ORDERKEY), LType::Bigint()), col(0, ocol(PG_O_ORDERDATE), LType::Date()), col(0, ocol(PG_O_SHIPPRIORITY), LType::Integer())};
     Op j2 = make(POT_Join);
     j2->Children = {line, j1};
     j2->OnConds = {func("=", B, {lcol(PG_L_ORDERKEY), col(1, 0, LType::Bigint())})};

@@ -19,23 +19,26 @@ def lib():
     return L.lib()
 
 
-def _declared_symbols():
-    names = set()
-    for h in ("plangpu.h", "plangpu_tpch.h"):
-        src = open(os.path.join(ROOT, "include", h)).read()
-        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-        names |= set(re.findall(r"\b(pg_[a-z0-9_]+)\s*\(", src))
-    return names
+def _declared_symbols(header):
+    src = open(os.path.join(ROOT, "include", header)).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return set(re.findall(r"\b(pg_[a-z0-9_]+)\s*\(", src))
 
 
 def test_library_exports_every_declared_symbol(lib):
+    """libplangpu.so (the drop-in) exports exactly include/plangpu.h; the in-box TPC-H generator lives in its own
+    library (libplangpu_tpch.so, include/plangpu_tpch.h) and is not part of the operator ABI."""
     from plan_b200 import _lib as L
-    declared = _declared_symbols()
-    assert len(declared) >= 30
-    for name in declared:
-        assert hasattr(lib, name), "libplangpu.so does not export %s" % name
-    assert declared == {s[0] for s in L.SIGNATURES}, "ctypes bindings and headers disagree"
-    assert lib.pg_abi_version() == 1
+    core, tpch = _declared_symbols("plangpu.h"), _declared_symbols("plangpu_tpch.h")
+    assert len(core) >= 30 and len(tpch) >= 8
+    for name in core:
+        assert hasattr(lib.core, name), "libplangpu.so does not export %s" % name
+    for name in tpch:
+        assert hasattr(lib.tpch, name), "libplangpu_tpch.so does not export %s" % name
+        assert not hasattr(lib.core, name), "the generator leaked into the drop-in library: %s" % name
+    assert core == {s[0] for s in L.SIGNATURES}, "ctypes bindings and plangpu.h disagree"
+    assert tpch == {s[0] for s in L.TPCH_SIGNATURES}, "ctypes bindings and plangpu_tpch.h disagree"
+    assert lib.pg_abi_version() == 2
 
 
 def test_sass_is_sm100_only():
