@@ -1,0 +1,288 @@
+// scan_staged.cuh -- the scan-aggregate kernels over NARROW physical columns (every referenced column stored in
+// <= 4 bytes), fed by the bulk-copy tile ring of stage.cuh.
+//
+// Reference path replaced (as scanagg.cuh): scan filter ExprExec.executeSelect pkg/compute/expr_exec.go:342-530,
+// projection executeExprs :85-340, decimal ops function_operator_binary.go:134-191, group lookup
+// FindOrCreateGroups aggregate_hash.go:201-391, state update function_aggr.go:770-1161 -- one pass, every column
+// byte read once.
+//
+// Why a second family next to scanagg.cuh's register-staged kernels: at 8-11 stored bytes per row the HBM
+// roofline allows ~2 rows / clk / SM, i.e. a budget of ~60 issued instructions per row over the whole SM.  The
+// register-staged kernels spend that on address arithmetic and sub-word loads (ncu, r2: 52 instructions / row for
+// Q6, issue-bound at 0.49 of the roofline; Q1 0.25).  Here the producer lane issues one bulk copy per column per
+// 2048-row tile and the consumers' inner loops hold nothing but the predicate and the arithmetic.
+#pragma once
+#include "stage.cuh"
+
+namespace pg {
+
+// ------------------------------------------------------------------------------
+// sumprod: ungrouped sum(fa * fb) under inclusive range predicates (TPC-H Q6).
+// Stage columns: 0 = fa, 1 = fb, 2 = pa, 3 = pb (absent: pw 0).  A range is  (v - lo) <=u span  on the STORED value.
+// ------------------------------------------------------------------------------
+struct SumProdSParams {
+    StageDesc st;                     // the distinct physical columns
+    int roff[4], rpw[4];              // role -> stage offset / width: 0 = fa, 1 = fb, 2 = pa, 3 = pb (pw 0: absent)
+    unsigned a_lo, a_span, b_lo, b_span, x_lo, x_span, y_lo, y_span;
+    int xbase, ybase;                 // logical = stored + base
+    i64 nrows;
+};
+
+template <bool HAS_A, bool HAS_B, bool XR, bool YR, int QPT>
+__global__ void __launch_bounds__(ST_THREADS)
+sumprod_staged_kernel(const SumProdSParams p, i64 *__restrict__ partials /* [grid][2] = {sum, count} */)
+{
+    extern __shared__ __align__(128) unsigned char st_smem[];
+    const StageDesc &d = p.st;
+    const StageRing ring = stage_ring_init(st_smem, d);
+    const i64 ntiles = (p.nrows + d.tile_rows - 1) / d.tile_rows;
+    const TileSeq seq = tile_seq(ntiles, 0);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __shared__ i64 s_sum[ST_CONS_WARPS], s_cnt[ST_CONS_WARPS];
+    if (warp == ST_CONS_WARPS) {
+        stage_produce(ring, d, seq);
+    } else {
+        i64 sum = 0, cnt64 = 0;
+        StageCursor cur = {0, 0};
+        for (i64 k = 0; k < seq.count; k++) {
+            const i64 tile = seq.first + k * seq.step;
+            const char *stg = stage_acquire(ring, d, cur);
+            unsigned x[QPT][4], y[QPT][4], a[QPT][4], b[QPT][4];
+#pragma unroll
+            for (int q = 0; q < QPT; q++) {
+                const int qrow = (warp * QPT + q) * 128 + lane * 4;
+                quad_load(stg, p.roff[0], p.rpw[0], qrow, x[q]);
+                quad_load(stg, p.roff[1], p.rpw[1], qrow, y[q]);
+                if (HAS_A) quad_load(stg, p.roff[2], p.rpw[2], qrow, a[q]);
+                if (HAS_B) quad_load(stg, p.roff[3], p.rpw[3], qrow, b[q]);
+            }
+            stage_release(ring, d, cur);
+            const i64 row0 = tile * d.tile_rows;
+            const bool whole = row0 + d.tile_rows <= p.nrows;     // only the last tile can hold pad rows
+            unsigned cnt = 0;
+#pragma unroll
+            for (int q = 0; q < QPT; q++) {
+                const i64 rem = p.nrows - (row0 + (warp * QPT + q) * 128 + lane * 4);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    bool ok = whole || j < rem;
+                    if (HAS_A) ok = ok && (a[q][j] - p.a_lo) <= p.a_span;
+                    if (HAS_B) ok = ok && (b[q][j] - p.b_lo) <= p.b_span;
+                    if (XR) ok = ok && (x[q][j] - p.x_lo) <= p.x_span;
+                    if (YR) ok = ok && (y[q][j] - p.y_lo) <= p.y_span;
+                    const int xl = (int)x[q][j] + p.xbase;
+                    const int ym = ok ? (int)y[q][j] + p.ybase : 0;
+                    sum += (i64)xl * (i64)ym;                      // one IMAD.WIDE
+                    cnt += ok ? 1u : 0u;
+                }
+            }
+            cnt64 += cnt;
+        }
+        sum = warp_sum(sum);
+        cnt64 = warp_sum(cnt64);
+        if (lane == 0) { s_sum[warp] = sum; s_cnt[warp] = cnt64; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        i64 s = 0, c = 0;
+#pragma unroll
+        for (int w = 0; w < ST_CONS_WARPS; w++) { s += s_sum[w]; c += s_cnt[w]; }
+        partials[2 * blockIdx.x] = s;
+        partials[2 * blockIdx.x + 1] = c;
+    }
+}
+
+// ------------------------------------------------------------------------------
+// lowcard chain (TPC-H Q1): GROUP BY <= 2 byte-coded keys (<= 8 dense groups), accumulators
+//   [0] count(*)  [1] sum(q)  [2] sum(A)  [3] sum(A*(c1+s1*B))  [4] sum(A*(c1+s1*B)*(c2+s2*C))  [5] sum(B)
+// over rows passing one inclusive range.  Output format identical to lowcard_chain_kernel (scanagg.cuh).
+//
+// Group state: every consumer thread owns a private table in shared memory, updated for EVERY row with plain
+// LDS / STS (no atomics, no data-dependent branch: the cost does not depend on how the groups are clustered).
+// What bounds the kernel is shared-memory bandwidth, so an entry is packed into THREE 64-bit words, each
+// holding a wide sum in its low bits and a small one in its high (>= 32) bits:
+//     w0 = sum t3 | count << sh0      w1 = sum t2 | sum q << sh1      w2 = sum A | sum B << sh2
+// (all over non-negative values; the host proves from the statistics and the rows a thread can see that no
+// field overflows into its neighbour).  24 bytes read + 24 written per row instead of 2 x 48.
+// The table slot of a row is a multiplicative hash of its two key bytes, chosen by the host to be injective
+// on the key combinations that can occur:  slot = ((k0 | k1 << 8) * 0x10001 * M) >> 29.
+// Stage columns: 0 pred, 1 key0, 2 key1, 3 q, 4 A, 5 B, 6 C   (pw 0: absent, reads as 0).
+// ------------------------------------------------------------------------------
+struct LowcardSParams {
+    StageDesc st;                     // the distinct physical columns
+    int roff[7], rpw[7];              // role -> stage offset / width (pw 0: absent, reads as 0)
+    unsigned p_lo, p_span;
+    int abase;                        // logical A = stored + abase
+    int f1c, f1s, f2c, f2s;           // factors on the STORED values of B and C
+    unsigned hashM;
+    unsigned mul0, mul1, mul2;        // 1 << (sh - 32): what one unit of the small field adds to the high word
+    int sh0, sh1, sh2;
+    unsigned char slot_group[8];      // table slot -> dense group id, 0xff: unused
+    int ngroups;
+    int contig;
+    i64 qbase, Abase, Bbase;          // stored -> logical for the sums of q, A, B
+    i64 nrows;
+};
+
+__host__ __device__ inline unsigned lc_slot_of(unsigned k0, unsigned k1, bool has_key1, unsigned M)
+{
+    const unsigned kk = has_key1 ? (k0 | (k1 << 8)) * 0x00010001u : k0 * 0x01010101u;
+    return (kk * M) >> 29;
+}
+
+constexpr int LCS_TBL_BYTES = 8 * 3 * 8 * ST_CONS_THREADS;       // 8 slots x 3 words per consumer thread
+
+template <bool HAS_KEY1, int QPT>
+__global__ void __launch_bounds__(ST_THREADS, 2)
+lowcard_staged_kernel(const LowcardSParams p, i64 *__restrict__ partials /* [grid][G*6] */)
+{
+    extern __shared__ __align__(128) unsigned char st_smem[];
+    const StageDesc &d = p.st;
+    const StageRing ring = stage_ring_init(st_smem, d);
+    // tables behind the stage ring: [slot][thread] pairs {w0, w1} (16 B), then [slot][thread] w2 (8 B)
+    ulonglong2 *t01 = (ulonglong2 *)(st_smem + ST_HDR + (size_t)d.nstage * d.stage_bytes);
+    u64 *t2p = (u64 *)(t01 + 8 * ST_CONS_THREADS);
+    for (int i = threadIdx.x; i < 8 * ST_CONS_THREADS; i += ST_THREADS) { t01[i] = make_ulonglong2(0, 0); t2p[i] = 0; }
+    __shared__ i64 s_tot[8 * 6];
+    if (threadIdx.x < 48) s_tot[threadIdx.x] = 0;
+    __syncthreads();
+    const i64 ntiles = (p.nrows + d.tile_rows - 1) / d.tile_rows;
+    const TileSeq seq = tile_seq(ntiles, p.contig);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == ST_CONS_WARPS) {
+        stage_produce(ring, d, seq);
+    } else {
+        ulonglong2 *my01 = t01 + threadIdx.x;
+        u64 *my2 = t2p + threadIdx.x;
+        StageCursor cur = {0, 0};
+        for (i64 k = 0; k < seq.count; k++) {
+            const i64 tile = seq.first + k * seq.step;
+            const char *stg = stage_acquire(ring, d, cur);
+            unsigned dv[QPT][4], qv[QPT][4], av[QPT][4], bv[QPT][4], cv[QPT][4], k0[QPT], k1[QPT];
+#pragma unroll
+            for (int q = 0; q < QPT; q++) {
+                const int qrow = (warp * QPT + q) * 128 + lane * 4;
+                quad_load(stg, p.roff[0], p.rpw[0], qrow, dv[q]);
+                k0[q] = quad_load_bytes(stg, p.roff[1], qrow);
+                k1[q] = HAS_KEY1 ? quad_load_bytes(stg, p.roff[2], qrow) : 0u;
+                quad_load(stg, p.roff[3], p.rpw[3], qrow, qv[q]);
+                quad_load(stg, p.roff[4], p.rpw[4], qrow, av[q]);
+                quad_load(stg, p.roff[5], p.rpw[5], qrow, bv[q]);
+                quad_load(stg, p.roff[6], p.rpw[6], qrow, cv[q]);
+            }
+            stage_release(ring, d, cur);
+            const i64 row0 = tile * d.tile_rows;
+            const bool whole = row0 + d.tile_rows <= p.nrows;
+#pragma unroll
+            for (int q = 0; q < QPT; q++) {
+                const i64 rem = p.nrows - (row0 + (warp * QPT + q) * 128 + lane * 4);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const bool ok = (whole || j < rem) && (dv[q][j] - p.p_lo) <= p.p_span;
+                    if (ok) {
+                        // both key bytes twice (k0 k1 k0 k1) = kk * 0x10001: the hash needs no masking
+                        const unsigned kk = HAS_KEY1 ? __byte_perm(k0[q], k1[q], (unsigned)(j | ((4 + j) << 4) | (j << 8) | ((4 + j) << 12)))
+                                                     : __byte_perm(k0[q], 0u, (unsigned)(j * 0x1111));
+                        const unsigned slot = (kk * p.hashM) >> 29;
+                        ulonglong2 *e01 = my01 + slot * ST_CONS_THREADS;
+                        u64 *e2 = my2 + slot * ST_CONS_THREADS;
+                        ulonglong2 w01 = *e01;
+                        u64 w2 = *e2;
+                        const unsigned al = av[q][j] + (unsigned)p.abase;
+                        const unsigned t2 = al * (unsigned)(p.f1c + p.f1s * (int)bv[q][j]);      // proven < 2^32
+                        const unsigned f2 = (unsigned)(p.f2c + p.f2s * (int)cv[q][j]);
+                        w01.x += (u64)t2 * f2 + ((u64)p.mul0 << 32);
+                        w01.y += (u64)t2 + ((u64)(qv[q][j] * p.mul1) << 32);
+                        w2 += (u64)av[q][j] + ((u64)(bv[q][j] * p.mul2) << 32);
+                        *e01 = w01;
+                        *e2 = w2;
+                    }
+                }
+            }
+        }
+        // this thread's fields -> block totals (shared-memory atomics: once per thread, not per row)
+        for (int s = 0; s < 8; s++) {
+            const int g = p.slot_group[s];
+            if (g == 0xff) continue;                               // warp-uniform
+            const ulonglong2 w01 = my01[s * ST_CONS_THREADS];
+            const u64 w2 = my2[s * ST_CONS_THREADS];
+            i64 f[6];
+            f[0] = (i64)(w01.x >> p.sh0);                          // count
+            f[1] = (i64)(w01.y >> p.sh1);                          // sum q (stored)
+            f[2] = (i64)(w2 & (((u64)1 << p.sh2) - 1));            // sum A (stored)
+            f[3] = (i64)(w01.y & (((u64)1 << p.sh1) - 1));         // sum t2
+            f[4] = (i64)(w01.x & (((u64)1 << p.sh0) - 1));         // sum t3
+            f[5] = (i64)(w2 >> p.sh2);                             // sum B (stored)
+#pragma unroll
+            for (int kx = 0; kx < 6; kx++) {
+                const i64 v = warp_sum(f[kx]);
+                if (lane == 0) atomicAdd((unsigned long long *)&s_tot[g * 6 + kx], (unsigned long long)v);
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < p.ngroups * 6) {
+        const int g = threadIdx.x / 6, kx = threadIdx.x % 6;
+        i64 s = s_tot[threadIdx.x];
+        const i64 n = s_tot[g * 6];
+        if (kx == 1) s += n * p.qbase;                              // stored -> logical sums
+        else if (kx == 2) s += n * p.Abase;
+        else if (kx == 5) s += n * p.Bbase;
+        partials[(i64)blockIdx.x * (p.ngroups * 6) + threadIdx.x] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------
+// First occurrence of every group among the rows that pass the predicate (the reference emits groups in
+// first-insertion order, aggregate_hash.go:424-438).  Kept out of the scan's inner loop: CTAs walk 1024-row
+// chunks from the start of the table and stop as soon as every group the totals say is present has been seen
+// before their next chunk -- normally after one wave.
+// ------------------------------------------------------------------------------
+__device__ __forceinline__ i64 ncol_stored(const NCol &c, i64 row)
+{
+    switch (c.pw) {
+    case 8: return __ldg((const i64 *)c.p + row);
+    case 4: return (i64)__ldg((const int *)c.p + row);
+    case 2: return (i64)__ldg((const unsigned short *)c.p + row);
+    default: return (i64)__ldg((const uint8_t *)c.p + row);
+    }
+}
+
+template <bool HAS_KEY1>
+__global__ void __launch_bounds__(256)
+first_rows_kernel(const LowcardParams p, const u64 *__restrict__ totals /* [G*6][2], this rank */, i64 *__restrict__ first_row /* [G], preset huge */)
+{
+    __shared__ i64 s_first[LC_MAXG];
+    __shared__ int s_go;
+    const int G = p.ngroups;
+    const i64 nchunks = (p.nrows + 1023) / 1024;
+    for (i64 c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        if (threadIdx.x == 0) {
+            int go = 0;
+            for (int g = 0; g < G; g++) {
+                const bool present = (totals[(size_t)(g * LC_K) * 2] | totals[(size_t)(g * LC_K) * 2 + 1]) != 0;
+                if (present && *(volatile i64 *)&first_row[g] >= p.row_base + c * 1024) go = 1;
+            }
+            s_go = go;
+        }
+        if (threadIdx.x < LC_MAXG) s_first[threadIdx.x] = INT64_MAX;
+        __syncthreads();
+        if (!s_go) break;
+        const i64 row = c * 1024 + threadIdx.x * 4;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const i64 r = row + j;
+            if (r >= p.nrows) break;
+            const i64 dv = ncol_stored(p.pred, r);
+            if (dv < p.lo || dv > p.hi) continue;
+            int g = __ldg(p.luts + __ldg((const uint8_t *)p.key0.p + r));
+            if (HAS_KEY1) g = g * p.n1 + __ldg(p.luts + 256 + __ldg((const uint8_t *)p.key1.p + r));
+            if (p.row_base + r < s_first[g]) atomicMin((long long *)&s_first[g], (long long)(p.row_base + r));
+        }
+        __syncthreads();
+        if (threadIdx.x < G && s_first[threadIdx.x] != INT64_MAX) atomicMin((long long *)&first_row[threadIdx.x], (long long)s_first[threadIdx.x]);
+        __syncthreads();
+    }
+}
+
+}  // namespace pg

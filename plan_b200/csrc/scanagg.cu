@@ -91,9 +91,47 @@ static SumProdKernel sumprod_variant(bool wide, bool has_a, bool has_b)
 #undef PG_SP
 }
 
+// staged (bulk-copy fed) variants over narrow columns, scan_staged.cuh
+typedef void (*SumProdSKernel)(const SumProdSParams, i64 *);
+static SumProdSKernel sumprod_staged_variant(bool has_a, bool has_b, bool xr, bool yr, int qpt)
+{
+#define PG_SPS4(A, B, X, Y) (qpt >= 4 ? sumprod_staged_kernel<A, B, X, Y, 4> : qpt >= 2 ? sumprod_staged_kernel<A, B, X, Y, 2> : sumprod_staged_kernel<A, B, X, Y, 1>)
+#define PG_SPS2(A, B) (xr ? (yr ? PG_SPS4(A, B, true, true) : PG_SPS4(A, B, true, false)) : (yr ? PG_SPS4(A, B, false, true) : PG_SPS4(A, B, false, false)))
+    return has_a ? (has_b ? PG_SPS2(true, true) : PG_SPS2(true, false)) : (has_b ? PG_SPS2(false, true) : PG_SPS2(false, false));
+#undef PG_SPS2
+#undef PG_SPS4
+}
+
+// (v - lo) <=u span on a STORED value; false when the range is empty
+static bool unsigned_range(i64 slo, i64 shi, unsigned *lo, unsigned *span)
+{
+    if (slo > shi) return false;
+    *lo = (unsigned)(int32_t)slo;
+    *span = (unsigned)(u64)(shi - slo);
+    return true;
+}
+// does [slo, shi] leave out any stored value the column holds?
+static bool range_restricts(const Column &c, i64 slo, i64 shi)
+{
+    return slo > (i64)((i128)c.vmin - c.base) || shi < (i64)((i128)c.vmax - c.base);
+}
+// add a physical column to a stage description once; returns its index
+static int stage_add(StageDesc *d, const Column &c)
+{
+    for (int i = 0; i < d->ncol; i++) if (d->src[i] == (const char *)c.d_data) return i;
+    if (d->ncol >= ST_MAXCOL) return -1;
+    d->src[d->ncol] = (const char *)c.d_data;
+    d->pw[d->ncol] = c.phys_width();
+    return d->ncol++;
+}
+
 struct SumProdPipeline : Pipeline {
     const pg_table *table = nullptr;
     SumProdParams prm{};
+    SumProdSParams sprm{};
+    bool staged = false, xr = false, yr = false;
+    int qpt = 2;
+    size_t smem = 0;
     bool has_a = false, has_b = false, wide = false;
     int grid = 1, vscale = 0;
     AggExpr agg;
@@ -111,7 +149,8 @@ struct SumProdPipeline : Pipeline {
         PG_TRY(ev_main.init());
         PG_CUDA(cudaEventRecord(ev_all.a, st));
         PG_CUDA(cudaEventRecord(ev_main.a, st));
-        sumprod_variant(wide, has_a, has_b)<<<grid, SA_THREADS, 0, st>>>(prm, d_part.as<i64>());
+        if (staged) sumprod_staged_variant(has_a, has_b, xr, yr, qpt)<<<grid, ST_THREADS, smem, st>>>(sprm, d_part.as<i64>());
+        else sumprod_variant(wide, has_a, has_b)<<<grid, SA_THREADS, 0, st>>>(prm, d_part.as<i64>());
         PG_CUDA(cudaGetLastError());
         PG_CUDA(cudaEventRecord(ev_main.b, st));
         finalize128_kernel<<<1, 32, 0, st>>>(d_part.as<i64>(), grid, 2, d_final.as<u64>());
@@ -202,16 +241,58 @@ static int try_sumprod(pg_plan *plan, const Node &aggn, const Node &scan, const 
     }
     if (env_int("PG_FORCE_WIDE", 0)) narrow = false;
     p->wide = !narrow;
-    const i64 ntiles = (t->nrows + SA_TILE - 1) / SA_TILE;
+    i64 ntiles = (t->nrows + SA_TILE - 1) / SA_TILE;
     const void *kern = (const void *)sumprod_variant(p->wide, p->has_a, p->has_b);
-    const int full = sms_times(kern, SA_THREADS, 0);
+    int full = sms_times(kern, SA_THREADS, 0);
+    i64 tile_rows = SA_TILE;
+    // narrow columns: the bulk-copy staged kernel (scan_staged.cuh)
+    if (narrow && !env_int("PG_NO_STAGED", 0) && t->nrows > 0) {
+        SumProdSParams &sp = p->sprm;
+        sp = SumProdSParams{};
+        sp.nrows = t->nrows;
+        sp.xbase = (int)ca.base;
+        sp.ybase = (int)cb.base;
+        bool ok = unsigned_range(q.fa_lo, q.fa_hi, &sp.x_lo, &sp.x_span) && unsigned_range(q.fb_lo, q.fb_hi, &sp.y_lo, &sp.y_span);
+        if (p->has_a) ok = ok && unsigned_range(q.a_lo, q.a_hi, &sp.a_lo, &sp.a_span);
+        if (p->has_b) ok = ok && unsigned_range(q.b_lo, q.b_hi, &sp.b_lo, &sp.b_span);
+        const Column *rc[4] = {&ca, &cb, nullptr, nullptr};
+        {
+            int np = 0;
+            for (auto &r : ranges) {
+                if (r.col == ap.f[0].col || r.col == ap.f[1].col) continue;
+                rc[2 + np++] = &t->cols[(size_t)r.col];
+            }
+        }
+        for (int r = 0; r < 4 && ok; r++) {
+            if (!rc[r]) { sp.rpw[r] = 0; sp.roff[r] = 0; continue; }
+            const int ci = stage_add(&sp.st, *rc[r]);
+            if (ci < 0) { ok = false; break; }
+            sp.rpw[r] = -1 - ci;            // resolved to offsets after the layout below
+        }
+        if (ok) {
+            p->qpt = std::max(1, std::min(4, env_int("PG_QPT", 2)));
+            if (p->qpt == 3) p->qpt = 2;
+            tile_rows = (i64)ST_CONS_WARPS * 128 * p->qpt;
+            stage_layout(&sp.st, (int)tile_rows);
+            for (int r = 0; r < 4; r++) if (sp.rpw[r] < 0) { const int ci = -1 - sp.rpw[r]; sp.rpw[r] = sp.st.pw[ci]; sp.roff[r] = sp.st.off[ci]; }
+            sp.st.nstage = std::max(2, std::min(ST_MAXSTAGE, env_int("PG_NSTAGE", 4)));
+            p->xr = range_restricts(ca, q.fa_lo, q.fa_hi);
+            p->yr = range_restricts(cb, q.fb_lo, q.fb_hi);
+            p->smem = (size_t)ST_HDR + (size_t)sp.st.nstage * sp.st.stage_bytes;
+            kern = (const void *)sumprod_staged_variant(p->has_a, p->has_b, p->xr, p->yr, p->qpt);
+            PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+            full = sms_times(kern, ST_THREADS, p->smem);
+            ntiles = (t->nrows + tile_rows - 1) / tile_rows;
+            p->staged = true;
+        }
+    }
     p->grid = (int)std::max<i64>(1, std::min<i64>(full, ntiles));
     // per-CTA int64 partials must be exact: bound them with the statistics of the whole table (every rank takes
     // the same decision) and the largest shard
     i128 per_row = maxabs(std::max(ra.lo, ca.gmin()), std::min(ra.hi, ca.gmax())) * maxabs(std::max(rb.lo, cb.gmin()), std::min(rb.hi, cb.gmax()));
-    const i64 max_tiles = (t->max_rows() + SA_TILE - 1) / SA_TILE;
+    const i64 max_tiles = (t->max_rows() + tile_rows - 1) / tile_rows;
     const i64 gmin_grid = std::max<i64>(1, std::min<i64>(full, max_tiles));
-    i128 rows_per_cta = (i128)((max_tiles + gmin_grid - 1) / gmin_grid) * SA_TILE;       // a CTA takes ceil(ntiles / grid) tiles
+    i128 rows_per_cta = (i128)((max_tiles + gmin_grid - 1) / gmin_grid) * tile_rows;       // a CTA takes ceil(ntiles / grid) tiles
     if (ra.lo <= ra.hi && rb.lo <= rb.hi && per_row * rows_per_cta >= ((i128)1 << 62)) {
         *why = "per-CTA partial sum could exceed int64";
         return PG_EUNSUPPORTED;
@@ -222,9 +303,10 @@ static int try_sumprod(pg_plan *plan, const Node &aggn, const Node &scan, const 
     PG_TRY(p->h_final.alloc(32 * (size_t)ctx().world));
     char buf[512];
     snprintf(buf, sizeof buf,
-             "ScanAgg[sumprod] table=%s rows=%lld kernel=sumprod_kernel<%s,%d,%d> grid=%d block=%d "
+             "ScanAgg[sumprod] table=%s rows=%lld kernel=%s<%s,%d,%d> grid=%d block=%d "
              "stored bytes/row=%d (widths: fa=%d fb=%d) stored ranges: a=[%lld,%lld] b=[%lld,%lld] fa=[%lld,%lld] fb=[%lld,%lld] value_scale=%d",
-             t->name.c_str(), (long long)t->nrows, p->wide ? "wide" : "narrow", (int)p->has_a, (int)p->has_b, p->grid, SA_THREADS,
+             t->name.c_str(), (long long)t->nrows, p->staged ? "sumprod_staged_kernel" : "sumprod_kernel", p->staged ? "bulk-copy ring" : p->wide ? "wide" : "narrow",
+             (int)p->has_a, (int)p->has_b, p->grid, p->staged ? ST_THREADS : SA_THREADS,
              p->bytes_per_row, ca.phys_width(), cb.phys_width(), (long long)q.a_lo, (long long)q.a_hi, (long long)q.b_lo, (long long)q.b_hi,
              (long long)q.fa_lo, (long long)q.fa_hi, (long long)q.fb_lo, (long long)q.fb_hi, p->vscale);
     p->explain = buf;
@@ -235,6 +317,13 @@ static int try_sumprod(pg_plan *plan, const Node &aggn, const Node &scan, const 
 // ------------------------------------------------------------- lowcard chain --
 
 typedef void (*LowcardKernel)(const LowcardParams, i64 *, i64 *);
+typedef void (*LowcardSKernel)(const LowcardSParams, i64 *);
+static LowcardSKernel lowcard_staged_variant(bool key1, int qpt)
+{
+    if (qpt >= 2) return key1 ? lowcard_staged_kernel<true, 2> : lowcard_staged_kernel<false, 2>;
+    return key1 ? lowcard_staged_kernel<true, 1> : lowcard_staged_kernel<false, 1>;
+}
+static int bit_length(i128 v) { int n = 0; while (v > 0) { n++; v >>= 1; } return n; }
 static LowcardKernel lowcard_variant(bool wide, bool acc32, bool key1, int unroll)
 {
 #define PG_LC(U) (wide ? (key1 ? lowcard_chain_kernel<true, false, true, U> : lowcard_chain_kernel<true, false, false, U>) \
@@ -251,6 +340,10 @@ struct LowcardPipeline : Pipeline {
     int unroll = 2;
     int grid = 1, G = 1;
     size_t smem = 0;
+    bool staged = false;                 // lowcard_staged_kernel (scan_staged.cuh) + first_rows_kernel
+    LowcardSParams sprm{};
+    int qpt = 2;
+    i64 lc_per = 0;                      // LC_TILE-sized tiles per CTA (contiguous mode), whichever kernel runs
     int nkeys = 0;
     int key_col[2] = {-1, -1};
     std::vector<uint8_t> vals[2];        // dense id -> byte code, per key
@@ -292,19 +385,25 @@ struct LowcardPipeline : Pipeline {
         PG_CUDA(cudaEventRecord(ev_all.a, st));
         PG_CUDA(cudaMemsetAsync(d_firstrow, 0x7f, LC_MAXG * 8, st));   // 0x7f7f.. = "unset"
         PG_CUDA(cudaEventRecord(ev_main.a, st));
-        lowcard_variant(wide, acc32, has_key1, unroll)<<<grid, LC_THREADS, smem, st>>>(prm, d_part.as<i64>(), d_firstrow);
+        if (staged) lowcard_staged_variant(has_key1, qpt)<<<grid, ST_THREADS, smem, st>>>(sprm, d_part.as<i64>());
+        else lowcard_variant(wide, acc32, has_key1, unroll)<<<grid, LC_THREADS, smem, st>>>(prm, d_part.as<i64>(), d_firstrow);
         PG_CUDA(cudaGetLastError());
         PG_CUDA(cudaEventRecord(ev_main.b, st));
         finalize128_kernel<<<1, 64, 0, st>>>(d_part.as<i64>(), grid, G * LC_K, d_final.as<u64>());
         PG_CUDA(cudaGetLastError());
+        if (staged) {       // group order: first passing row of every group, found outside the scan's inner loop
+            if (has_key1) first_rows_kernel<true><<<64, 256, 0, st>>>(prm, d_final.as<u64>(), d_firstrow);
+            else first_rows_kernel<false><<<64, 256, 0, st>>>(prm, d_final.as<u64>(), d_firstrow);
+            PG_CUDA(cudaGetLastError());
+        }
         // every rank's totals on every rank (world 1: a device copy)
         if (nranks() > 1) PG_TRY(comm_allgather(d_final.p, d_gather.p, rank_bytes(), st));
         else PG_CUDA(cudaMemcpyAsync(d_gather.p, d_final.p, rank_bytes(), cudaMemcpyDeviceToDevice, st));
-        int launches = 2;
+        int launches = staged ? 3 : 2;
         char *h_tot = (char *)h_final.p, *h_con = h_tot + rank_bytes() * (size_t)nranks();
         if (ord_stage) {
             const i64 ntiles = (prm.nrows + LC_TILE - 1) / LC_TILE;
-            const i64 per = (ntiles + grid - 1) / grid;
+            const i64 per = lc_per;
             OrdJob *jobs = d_jobs.as<OrdJob>();
             int *njobs = (int *)(jobs + ORD_MAXJOBS);
             OrdContrib *mine = d_contrib.as<OrdContrib>(), *all = mine + ORD_MAXJOBS;
@@ -644,6 +743,110 @@ static int try_lowcard(pg_plan *plan, const Node &aggn, const Node &scan, const 
     }
     p->ord_stage = q.contig && p->emu_mask != 0;
 
+    // Narrow columns over non-negative values: the bulk-copy staged kernel with packed three-word table entries
+    // (scan_staged.cuh) whenever the statistics prove that no packed field can overflow.
+    if (narrow && !env_int("PG_NO_STAGED", 0) && t->nrows > 0) {
+        LowcardSParams &sp = p->sprm;
+        sp = LowcardSParams{};
+        std::string no;
+        const Column *cP = colP >= 0 ? &t->cols[(size_t)colP] : nullptr;
+        const Column *cQ = colQ >= 0 ? &t->cols[(size_t)colQ] : nullptr;
+        const Column *cB = colB >= 0 ? &t->cols[(size_t)colB] : nullptr;
+        const Column *cC = colC >= 0 ? &t->cols[(size_t)colC] : nullptr;
+        auto st_min = [](const Column *c) { return c ? (i128)c->vmin - c->base : (i128)0; };
+        auto st_max = [](const Column *c) { return c ? (i128)c->vmax - c->base : (i128)0; };
+        const i128 f1lo = cB ? std::min((i128)q.c1 + (i128)q.s1 * cB->vmin, (i128)q.c1 + (i128)q.s1 * cB->vmax) : 1;
+        const i128 f1hi = cB ? std::max((i128)q.c1 + (i128)q.s1 * cB->vmin, (i128)q.c1 + (i128)q.s1 * cB->vmax) : 1;
+        const i128 f2lo = cC ? std::min((i128)q.c2 + (i128)q.s2 * cC->vmin, (i128)q.c2 + (i128)q.s2 * cC->vmax) : 1;
+        const i128 f2hi = cC ? std::max((i128)q.c2 + (i128)q.s2 * cC->vmin, (i128)q.c2 + (i128)q.s2 * cC->vmax) : 1;
+        if (st_min(cQ) < 0 || st_min(&cA) < 0 || st_min(cB) < 0 || st_min(cC) < 0 || cA.vmin < 0 || f1lo < 0 || f2lo < 0) no = "negative values";
+        const i128 t2max = (i128)std::max<i64>(cA.vmax, 0) * f1hi;
+        if (no.empty() && (t2max >= ((i128)1 << 32) || f2hi >= ((i128)1 << 31))) no = "A*(c1+s1*B) does not fit 32 bits";
+        unsigned plo = 0, pspan = 0xffffffffu;
+        if (no.empty() && cP && !unsigned_range(q.lo, q.hi, &plo, &pspan)) no = "empty predicate range";
+        // the slot hash: injective on every key combination that can occur
+        unsigned M = 0;
+        if (no.empty()) {
+            u64 x = 0x9e3779b97f4a7c15ULL;
+            bool found = false;
+            for (int tries = 0; tries < 200000 && !found; tries++) {
+                x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+                const unsigned cand = (unsigned)(x >> 16) | 1u;
+                unsigned used = 0;
+                bool inj = true;
+                for (size_t i0 = 0; i0 < p->vals[0].size() && inj; i0++)
+                    for (size_t i1 = 0; i1 < (p->has_key1 ? p->vals[1].size() : (size_t)1) && inj; i1++) {
+                        const unsigned sl = lc_slot_of(p->vals[0][i0], p->has_key1 ? p->vals[1][i1] : 0, p->has_key1, cand);
+                        if (used & (1u << sl)) inj = false;
+                        used |= 1u << sl;
+                    }
+                if (inj) { M = cand; found = true; }
+            }
+            if (!found) no = "no injective slot hash";
+        }
+        if (no.empty()) {
+            for (int r = 0; r < 7; r++) { sp.rpw[r] = 0; sp.roff[r] = 0; }
+            const Column *roles[7] = {cP, &t->cols[(size_t)p->key_col[0]], p->has_key1 ? &t->cols[(size_t)p->key_col[1]] : nullptr, cQ, &cA, cB, cC};
+            for (int r = 0; r < 7; r++) {
+                if (!roles[r]) continue;
+                const int ci = stage_add(&sp.st, *roles[r]);
+                if (ci < 0) { no = "too many columns"; break; }
+                sp.rpw[r] = -1 - ci;
+            }
+        }
+        if (no.empty()) {
+            p->qpt = env_int("PG_QPT", 2) >= 2 ? 2 : 1;
+            const i64 tile_rows = (i64)ST_CONS_WARPS * 128 * p->qpt;
+            stage_layout(&sp.st, (int)tile_rows);
+            for (int r = 0; r < 7; r++) if (sp.rpw[r] < 0) { const int ci = -1 - sp.rpw[r]; sp.rpw[r] = sp.st.pw[ci]; sp.roff[r] = sp.st.off[ci]; }
+            // as many stages as let two CTAs share an SM
+            const size_t budget = (size_t)(ctx().prop.sharedMemPerMultiprocessor / 2) - 1024 - 1024;
+            int ns = env_int("PG_NSTAGE", 0);
+            if (ns <= 0) ns = (int)std::min<size_t>(ST_MAXSTAGE, (budget - ST_HDR - LCS_TBL_BYTES) / (size_t)sp.st.stage_bytes);
+            if (ns < 2) ns = 2;
+            sp.st.nstage = ns;
+            const size_t smem = (size_t)ST_HDR + (size_t)ns * sp.st.stage_bytes + LCS_TBL_BYTES;
+            const void *kern = (const void *)lowcard_staged_variant(p->has_key1, p->qpt);
+            if (smem > (size_t)ctx().prop.sharedMemPerBlockOptin) no = "stages do not fit in shared memory";
+            else {
+                PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                const i64 ntiles_s = (t->nrows + tile_rows - 1) / tile_rows;
+                const int full = sms_times(kern, ST_THREADS, smem);
+                const int grid = (int)std::max<i64>(1, std::min<i64>(full, ntiles_s));
+                const i64 per_s = (ntiles_s + grid - 1) / grid;
+                // a consumer thread sees per_s tiles x qpt quads x 4 rows: field widths of the packed entry
+                const i128 rows_thr = (i128)per_s * p->qpt * 4;
+                const int b_n = bit_length(rows_thr), b_q = bit_length(rows_thr * st_max(cQ)), b_B = bit_length(rows_thr * st_max(cB));
+                const int b_A = bit_length(rows_thr * st_max(&cA)), b_t2 = bit_length(rows_thr * t2max), b_t3 = bit_length(rows_thr * t2max * f2hi);
+                const int sh0 = std::max(32, b_t3), sh1 = std::max(32, b_t2), sh2 = std::max(32, b_A);
+                if (b_n > 64 - sh0 || b_q > 64 - sh1 || b_B > 64 - sh2) no = "packed table fields could overflow";
+                else if ((i128)bound * per_s * tile_rows >= ((i128)1 << 62)) no = "per-CTA partial sum could exceed int64";
+                else {
+                    sp.p_lo = plo; sp.p_span = pspan;
+                    sp.abase = (int)cA.base;
+                    sp.f1c = cB ? (int)(q.c1 + q.s1 * cB->base) : 1; sp.f1s = cB ? (int)q.s1 : 0;
+                    sp.f2c = cC ? (int)(q.c2 + q.s2 * cC->base) : 1; sp.f2s = cC ? (int)q.s2 : 0;
+                    sp.hashM = M;
+                    sp.sh0 = sh0; sp.sh1 = sh1; sp.sh2 = sh2;
+                    sp.mul0 = 1u << (sh0 - 32); sp.mul1 = 1u << (sh1 - 32); sp.mul2 = 1u << (sh2 - 32);
+                    memset(sp.slot_group, 0xff, 8);
+                    for (size_t i0 = 0; i0 < p->vals[0].size(); i0++)
+                        for (size_t i1 = 0; i1 < (p->has_key1 ? p->vals[1].size() : (size_t)1); i1++)
+                            sp.slot_group[lc_slot_of(p->vals[0][i0], p->has_key1 ? p->vals[1][i1] : 0, p->has_key1, M)] = (unsigned char)(i0 * (size_t)dims[1] + i1);
+                    sp.ngroups = p->G;
+                    sp.contig = q.contig;
+                    sp.qbase = cQ ? cQ->base : 0; sp.Abase = cA.base; sp.Bbase = cB ? cB->base : 0;
+                    sp.nrows = t->nrows;
+                    p->staged = true;
+                    p->smem = smem;
+                    p->grid = grid;
+                    p->lc_per = per_s * (tile_rows / LC_TILE);
+                }
+            }
+        }
+        if (!p->staged && getenv("PG_TRACE")) fprintf(stderr, "[pg] lowcard: staged kernel not used: %s\n", no.c_str());
+    }
+    if (!p->staged) {
     // kernel variant, shared memory and grid.  ACC32: the three small accumulators as 32-bit table slots when a
     // thread's total over its stored values provably fits (rows per thread from the occupancy of the 64-bit variant,
     // which is never larger than the 32-bit variant's).
@@ -671,13 +874,15 @@ static int try_lowcard(pg_plan *plan, const Node &aggn, const Node &scan, const 
         i128 rows_per_cta = (i128)((max_tiles + gmin_grid - 1) / gmin_grid) * LC_TILE;
         if (bound * rows_per_cta >= ((i128)1 << 62)) { *why = "per-CTA partial sum could exceed int64"; return PG_EUNSUPPORTED; }
     }
+    p->lc_per = (ntiles + p->grid - 1) / p->grid;
+    }
     PG_TRY(p->d_part.alloc(sizeof(i64) * (size_t)p->grid * (size_t)p->G * LC_K));
     PG_TRY(p->d_final.alloc(p->rank_bytes()));
     PG_TRY(p->d_gather.alloc(p->rank_bytes() * (size_t)p->nranks()));
     PG_TRY(p->h_final.alloc(p->host_bytes()));
     PG_TRY(p->d_luts.alloc(512));
     if (p->ord_stage) {
-        const i64 per = (ntiles + p->grid - 1) / p->grid;
+        const i64 per = p->lc_per;
         p->ord_stride = per + ntiles / ORD_CHUNK + 4;
         PG_TRY(p->d_jobs.alloc(sizeof(OrdJob) * ORD_MAXJOBS + 64));
         PG_TRY(p->d_ord.alloc(sizeof(OrdSummary) * (size_t)p->ord_stride * ORD_MAXJOBS));
@@ -688,10 +893,11 @@ static int try_lowcard(pg_plan *plan, const Node &aggn, const Node &scan, const 
     q.luts = p->d_luts.as<uint8_t>();
     char buf[640];
     snprintf(buf, sizeof buf,
-             "ScanAgg[lowcard-chain] table=%s rows=%lld kernel=lowcard_chain_kernel<%s,%s,%d,%d> grid=%d block=%d smem=%zu "
+             "ScanAgg[lowcard-chain] table=%s rows=%lld kernel=%s<%s,%s,%d,%d> grid=%d block=%d smem=%zu "
              "groups=%dx%d stored bytes/row=%d (widths: pred=%d q=%d A=%d B=%d C=%d) stored pred=[%lld,%lld] chain: A*(%lld%+lld*B)*(%lld%+lld*C) tiles=%s%s",
-             t->name.c_str(), (long long)t->nrows, p->wide ? "wide" : "narrow", p->acc32 ? "acc32" : "acc64", (int)p->has_key1, p->unroll, p->grid,
-             LC_THREADS, p->smem, dims[0], dims[1], p->bytes_per_row, q.pred.pw, q.q.pw, q.A.pw, q.B.pw, q.C.pw, (long long)slo, (long long)shi,
+             t->name.c_str(), (long long)t->nrows, p->staged ? "lowcard_staged_kernel" : "lowcard_chain_kernel", p->staged ? "bulk-copy ring" : p->wide ? "wide" : "narrow",
+             p->staged ? "packed3" : p->acc32 ? "acc32" : "acc64", (int)p->has_key1, p->staged ? p->qpt : p->unroll, p->grid,
+             p->staged ? ST_THREADS : LC_THREADS, p->smem, dims[0], dims[1], p->bytes_per_row, q.pred.pw, q.q.pw, q.A.pw, q.B.pw, q.C.pw, (long long)slo, (long long)shi,
              (long long)q.c1, (long long)q.s1, (long long)q.c2, (long long)q.s2,
              q.contig ? "contiguous-per-CTA(ordered partials)" : "interleaved", p->ord_stage ? " +ordered-rounding stage (device)" : "");
     p->explain = buf;

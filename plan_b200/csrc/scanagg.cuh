@@ -1127,3 +1127,5 @@ static __global__ void finalize128_kernel(const i64 *__restrict__ partials, int 
 }
 
 }  // namespace pg
+
+#include "scan_staged.cuh"
