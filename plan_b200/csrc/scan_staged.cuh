@@ -16,66 +16,91 @@
 
 namespace pg {
 
+template <int J> struct IC { static constexpr int v = J; };
+#define PG_FOR4(f) do { f(IC<0>()); f(IC<1>()); f(IC<2>()); f(IC<3>()); } while (0)
+
+// does this CTA's LAST tile hold pad rows?  (only the table's last tile can)
+__device__ __forceinline__ bool last_tile_is_partial(const TileSeq &seq, i64 ntiles, i64 nrows, int tile_rows)
+{
+    return seq.count > 0 && seq.first + (seq.count - 1) * seq.step == ntiles - 1 && nrows % tile_rows != 0;
+}
+
 // ------------------------------------------------------------------------------
 // sumprod: ungrouped sum(fa * fb) under inclusive range predicates (TPC-H Q6).
-// Stage columns: 0 = fa, 1 = fb, 2 = pa, 3 = pb (absent: pw 0).  A range is  (v - lo) <=u span  on the STORED value.
+// Roles: 0 = fa, 1 = fb, 2 = pa, 3 = pb (width 0: absent).  A range is  (v - lo) <=u span  on the STORED value.
 // ------------------------------------------------------------------------------
 struct SumProdSParams {
     StageDesc st;                     // the distinct physical columns
-    int roff[4], rpw[4];              // role -> stage offset / width: 0 = fa, 1 = fb, 2 = pa, 3 = pb (pw 0: absent)
+    int roff[4], rpw[4];              // role -> stage offset / width
     unsigned a_lo, a_span, b_lo, b_span, x_lo, x_span, y_lo, y_span;
     int xbase, ybase;                 // logical = stored + base
     i64 nrows;
 };
 
-template <bool HAS_A, bool HAS_B, bool XR, bool YR, int QPT>
+template <int WFA, int WFB, int WPA, int WPB, bool XR, bool YR, int QPT, bool MASK>
+__device__ __forceinline__ void sumprod_tile(const SumProdSParams &p, const StageRing &ring, StageCursor &cur, int warp, int lane,
+                                             int rows_in_tile, i64 &sum, unsigned &cnt)
+{
+    const char *stg = stage_acquire(ring, p.st, cur);
+    Quad<WFA> x[QPT];
+    Quad<WFB> y[QPT];
+    Quad<WPA> a[QPT];
+    Quad<WPB> b[QPT];
+#pragma unroll
+    for (int q = 0; q < QPT; q++) {
+        const int qrow = (warp * QPT + q) * 128 + lane * 4;
+        x[q].load(stg + p.roff[0], qrow, p.rpw[0]);
+        y[q].load(stg + p.roff[1], qrow, p.rpw[1]);
+        a[q].load(stg + p.roff[2], qrow, p.rpw[2]);
+        b[q].load(stg + p.roff[3], qrow, p.rpw[3]);
+    }
+    stage_release(ring, p.st, cur);
+#pragma unroll
+    for (int q = 0; q < QPT; q++) {
+        const int rem = rows_in_tile - ((warp * QPT + q) * 128 + lane * 4);
+        auto row = [&](auto jc) {
+            constexpr int J = decltype(jc)::v;
+            bool ok = !MASK || J < rem;
+            if (WPA != 0) ok = ok && (a[q].template get<J>() - p.a_lo) <= p.a_span;
+            if (WPB != 0) ok = ok && (b[q].template get<J>() - p.b_lo) <= p.b_span;
+            const unsigned xs = x[q].template get<J>(), ys = y[q].template get<J>();
+            if (XR) ok = ok && (xs - p.x_lo) <= p.x_span;
+            if (YR) ok = ok && (ys - p.y_lo) <= p.y_span;
+            const unsigned xl = xs + (unsigned)p.xbase;     // logical values are non-negative (host-checked)
+            const unsigned ym = ok ? ys + (unsigned)p.ybase : 0u;
+            sum += (i64)((u64)xl * (u64)ym);               // one IMAD.WIDE.U32
+            cnt += ok ? 1u : 0u;
+        };
+        PG_FOR4(row);
+    }
+}
+
+template <int WFA, int WFB, int WPA, int WPB, bool XR, bool YR, int QPT>
 __global__ void __launch_bounds__(ST_THREADS)
 sumprod_staged_kernel(const SumProdSParams p, i64 *__restrict__ partials /* [grid][2] = {sum, count} */)
 {
     extern __shared__ __align__(128) unsigned char st_smem[];
+    __shared__ i64 s_sum[ST_CONS_WARPS], s_cnt[ST_CONS_WARPS];
     const StageDesc &d = p.st;
     const StageRing ring = stage_ring_init(st_smem, d);
     const i64 ntiles = (p.nrows + d.tile_rows - 1) / d.tile_rows;
     const TileSeq seq = tile_seq(ntiles, 0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    __shared__ i64 s_sum[ST_CONS_WARPS], s_cnt[ST_CONS_WARPS];
     if (warp == ST_CONS_WARPS) {
         stage_produce(ring, d, seq);
     } else {
         i64 sum = 0, cnt64 = 0;
         StageCursor cur = {0, 0};
-        for (i64 k = 0; k < seq.count; k++) {
-            const i64 tile = seq.first + k * seq.step;
-            const char *stg = stage_acquire(ring, d, cur);
-            unsigned x[QPT][4], y[QPT][4], a[QPT][4], b[QPT][4];
-#pragma unroll
-            for (int q = 0; q < QPT; q++) {
-                const int qrow = (warp * QPT + q) * 128 + lane * 4;
-                quad_load(stg, p.roff[0], p.rpw[0], qrow, x[q]);
-                quad_load(stg, p.roff[1], p.rpw[1], qrow, y[q]);
-                if (HAS_A) quad_load(stg, p.roff[2], p.rpw[2], qrow, a[q]);
-                if (HAS_B) quad_load(stg, p.roff[3], p.rpw[3], qrow, b[q]);
-            }
-            stage_release(ring, d, cur);
-            const i64 row0 = tile * d.tile_rows;
-            const bool whole = row0 + d.tile_rows <= p.nrows;     // only the last tile can hold pad rows
+        const bool partial = last_tile_is_partial(seq, ntiles, p.nrows, d.tile_rows);
+        const int nwhole = (int)seq.count - (partial ? 1 : 0);
+        for (int k = 0; k < nwhole; k++) {
             unsigned cnt = 0;
-#pragma unroll
-            for (int q = 0; q < QPT; q++) {
-                const i64 rem = p.nrows - (row0 + (warp * QPT + q) * 128 + lane * 4);
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    bool ok = whole || j < rem;
-                    if (HAS_A) ok = ok && (a[q][j] - p.a_lo) <= p.a_span;
-                    if (HAS_B) ok = ok && (b[q][j] - p.b_lo) <= p.b_span;
-                    if (XR) ok = ok && (x[q][j] - p.x_lo) <= p.x_span;
-                    if (YR) ok = ok && (y[q][j] - p.y_lo) <= p.y_span;
-                    const int xl = (int)x[q][j] + p.xbase;
-                    const int ym = ok ? (int)y[q][j] + p.ybase : 0;
-                    sum += (i64)xl * (i64)ym;                      // one IMAD.WIDE
-                    cnt += ok ? 1u : 0u;
-                }
-            }
+            sumprod_tile<WFA, WFB, WPA, WPB, XR, YR, QPT, false>(p, ring, cur, warp, lane, 0, sum, cnt);
+            cnt64 += cnt;
+        }
+        if (partial) {
+            unsigned cnt = 0;
+            sumprod_tile<WFA, WFB, WPA, WPB, XR, YR, QPT, true>(p, ring, cur, warp, lane, (int)(p.nrows - (ntiles - 1) * d.tile_rows), sum, cnt);
             cnt64 += cnt;
         }
         sum = warp_sum(sum);
@@ -106,11 +131,11 @@ sumprod_staged_kernel(const SumProdSParams p, i64 *__restrict__ partials /* [gri
 // field overflows into its neighbour).  24 bytes read + 24 written per row instead of 2 x 48.
 // The table slot of a row is a multiplicative hash of its two key bytes, chosen by the host to be injective
 // on the key combinations that can occur:  slot = ((k0 | k1 << 8) * 0x10001 * M) >> 29.
-// Stage columns: 0 pred, 1 key0, 2 key1, 3 q, 4 A, 5 B, 6 C   (pw 0: absent, reads as 0).
+// Roles: 0 pred, 1 key0, 2 key1, 3 q, 4 A, 5 B, 6 C   (width 0: absent, reads as 0).
 // ------------------------------------------------------------------------------
 struct LowcardSParams {
     StageDesc st;                     // the distinct physical columns
-    int roff[7], rpw[7];              // role -> stage offset / width (pw 0: absent, reads as 0)
+    int roff[7], rpw[7];              // role -> stage offset / width
     unsigned p_lo, p_span;
     int abase;                        // logical A = stored + abase
     int f1c, f1s, f2c, f2s;           // factors on the STORED values of B and C
@@ -132,18 +157,70 @@ __host__ __device__ inline unsigned lc_slot_of(unsigned k0, unsigned k1, bool ha
 
 constexpr int LCS_TBL_BYTES = 8 * 3 * 8 * ST_CONS_THREADS;       // 8 slots x 3 words per consumer thread
 
-template <bool HAS_KEY1, int QPT>
+template <int WP, int WQ, int WA, int WB, int WC, bool HAS_KEY1, int QPT, bool MASK>
+__device__ __forceinline__ void lowcard_tile(const LowcardSParams &p, const StageRing &ring, StageCursor &cur, int warp, int lane,
+                                             int rows_in_tile, char *my01, char *my2)
+{
+    const char *stg = stage_acquire(ring, p.st, cur);
+    Quad<WP> dv[QPT];
+    Quad<WQ> qv[QPT];
+    Quad<WA> av[QPT];
+    Quad<WB> bv[QPT];
+    Quad<WC> cv[QPT];
+    unsigned k0[QPT], k1[QPT];
+#pragma unroll
+    for (int q = 0; q < QPT; q++) {
+        const int qrow = (warp * QPT + q) * 128 + lane * 4;
+        dv[q].load(stg + p.roff[0], qrow, p.rpw[0]);
+        k0[q] = *(const unsigned *)(stg + p.roff[1] + qrow);
+        k1[q] = HAS_KEY1 ? *(const unsigned *)(stg + p.roff[2] + qrow) : 0u;
+        qv[q].load(stg + p.roff[3], qrow, p.rpw[3]);
+        av[q].load(stg + p.roff[4], qrow, p.rpw[4]);
+        bv[q].load(stg + p.roff[5], qrow, p.rpw[5]);
+        cv[q].load(stg + p.roff[6], qrow, p.rpw[6]);
+    }
+    stage_release(ring, p.st, cur);
+#pragma unroll
+    for (int q = 0; q < QPT; q++) {
+        const int rem = rows_in_tile - ((warp * QPT + q) * 128 + lane * 4);
+        auto row = [&](auto jc) {
+            constexpr int J = decltype(jc)::v;
+            const bool ok = (!MASK || J < rem) && (dv[q].template get<J>() - p.p_lo) <= p.p_span;
+            if (ok) {
+                // both key bytes twice (k0 k1 k0 k1) = (k0 | k1 << 8) * 0x10001: the hash needs no masking
+                const unsigned kk = HAS_KEY1 ? __byte_perm(k0[q], k1[q], (unsigned)(J | ((4 + J) << 4) | (J << 8) | ((4 + J) << 12)))
+                                             : __byte_perm(k0[q], 0u, (unsigned)(J * 0x1111));
+                const unsigned slot = (kk * p.hashM) >> 29;
+                ulonglong2 *e01 = (ulonglong2 *)(my01 + slot * (16 * ST_CONS_THREADS));
+                u64 *e2 = (u64 *)(my2 + slot * (8 * ST_CONS_THREADS));
+                ulonglong2 w01 = *e01;
+                u64 w2 = *e2;
+                const unsigned as = av[q].template get<J>(), bs = bv[q].template get<J>();
+                const unsigned t2 = (as + (unsigned)p.abase) * (unsigned)(p.f1c + p.f1s * (int)bs);      // proven < 2^32
+                const unsigned f2 = (unsigned)(p.f2c + p.f2s * (int)cv[q].template get<J>());
+                w01.x += (u64)t2 * f2 + ((u64)p.mul0 << 32);
+                w01.y += (u64)t2 + ((u64)(qv[q].template get<J>() * p.mul1) << 32);
+                w2 += (u64)as + ((u64)(bs * p.mul2) << 32);
+                *e01 = w01;
+                *e2 = w2;
+            }
+        };
+        PG_FOR4(row);
+    }
+}
+
+template <int WP, int WQ, int WA, int WB, int WC, bool HAS_KEY1, int QPT>
 __global__ void __launch_bounds__(ST_THREADS, 2)
 lowcard_staged_kernel(const LowcardSParams p, i64 *__restrict__ partials /* [grid][G*6] */)
 {
     extern __shared__ __align__(128) unsigned char st_smem[];
+    __shared__ i64 s_tot[8 * 6];
     const StageDesc &d = p.st;
     const StageRing ring = stage_ring_init(st_smem, d);
     // tables behind the stage ring: [slot][thread] pairs {w0, w1} (16 B), then [slot][thread] w2 (8 B)
     ulonglong2 *t01 = (ulonglong2 *)(st_smem + ST_HDR + (size_t)d.nstage * d.stage_bytes);
     u64 *t2p = (u64 *)(t01 + 8 * ST_CONS_THREADS);
     for (int i = threadIdx.x; i < 8 * ST_CONS_THREADS; i += ST_THREADS) { t01[i] = make_ulonglong2(0, 0); t2p[i] = 0; }
-    __shared__ i64 s_tot[8 * 6];
     if (threadIdx.x < 48) s_tot[threadIdx.x] = 0;
     __syncthreads();
     const i64 ntiles = (p.nrows + d.tile_rows - 1) / d.tile_rows;
@@ -155,51 +232,12 @@ lowcard_staged_kernel(const LowcardSParams p, i64 *__restrict__ partials /* [gri
         ulonglong2 *my01 = t01 + threadIdx.x;
         u64 *my2 = t2p + threadIdx.x;
         StageCursor cur = {0, 0};
-        for (i64 k = 0; k < seq.count; k++) {
-            const i64 tile = seq.first + k * seq.step;
-            const char *stg = stage_acquire(ring, d, cur);
-            unsigned dv[QPT][4], qv[QPT][4], av[QPT][4], bv[QPT][4], cv[QPT][4], k0[QPT], k1[QPT];
-#pragma unroll
-            for (int q = 0; q < QPT; q++) {
-                const int qrow = (warp * QPT + q) * 128 + lane * 4;
-                quad_load(stg, p.roff[0], p.rpw[0], qrow, dv[q]);
-                k0[q] = quad_load_bytes(stg, p.roff[1], qrow);
-                k1[q] = HAS_KEY1 ? quad_load_bytes(stg, p.roff[2], qrow) : 0u;
-                quad_load(stg, p.roff[3], p.rpw[3], qrow, qv[q]);
-                quad_load(stg, p.roff[4], p.rpw[4], qrow, av[q]);
-                quad_load(stg, p.roff[5], p.rpw[5], qrow, bv[q]);
-                quad_load(stg, p.roff[6], p.rpw[6], qrow, cv[q]);
-            }
-            stage_release(ring, d, cur);
-            const i64 row0 = tile * d.tile_rows;
-            const bool whole = row0 + d.tile_rows <= p.nrows;
-#pragma unroll
-            for (int q = 0; q < QPT; q++) {
-                const i64 rem = p.nrows - (row0 + (warp * QPT + q) * 128 + lane * 4);
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const bool ok = (whole || j < rem) && (dv[q][j] - p.p_lo) <= p.p_span;
-                    if (ok) {
-                        // both key bytes twice (k0 k1 k0 k1) = kk * 0x10001: the hash needs no masking
-                        const unsigned kk = HAS_KEY1 ? __byte_perm(k0[q], k1[q], (unsigned)(j | ((4 + j) << 4) | (j << 8) | ((4 + j) << 12)))
-                                                     : __byte_perm(k0[q], 0u, (unsigned)(j * 0x1111));
-                        const unsigned slot = (kk * p.hashM) >> 29;
-                        ulonglong2 *e01 = my01 + slot * ST_CONS_THREADS;
-                        u64 *e2 = my2 + slot * ST_CONS_THREADS;
-                        ulonglong2 w01 = *e01;
-                        u64 w2 = *e2;
-                        const unsigned al = av[q][j] + (unsigned)p.abase;
-                        const unsigned t2 = al * (unsigned)(p.f1c + p.f1s * (int)bv[q][j]);      // proven < 2^32
-                        const unsigned f2 = (unsigned)(p.f2c + p.f2s * (int)cv[q][j]);
-                        w01.x += (u64)t2 * f2 + ((u64)p.mul0 << 32);
-                        w01.y += (u64)t2 + ((u64)(qv[q][j] * p.mul1) << 32);
-                        w2 += (u64)av[q][j] + ((u64)(bv[q][j] * p.mul2) << 32);
-                        *e01 = w01;
-                        *e2 = w2;
-                    }
-                }
-            }
-        }
+        const bool partial = last_tile_is_partial(seq, ntiles, p.nrows, d.tile_rows);
+        const int nwhole = (int)seq.count - (partial ? 1 : 0);
+        for (int k = 0; k < nwhole; k++)
+            lowcard_tile<WP, WQ, WA, WB, WC, HAS_KEY1, QPT, false>(p, ring, cur, warp, lane, 0, (char *)my01, (char *)my2);
+        if (partial)
+            lowcard_tile<WP, WQ, WA, WB, WC, HAS_KEY1, QPT, true>(p, ring, cur, warp, lane, (int)(p.nrows - (ntiles - 1) * d.tile_rows), (char *)my01, (char *)my2);
         // this thread's fields -> block totals (shared-memory atomics: once per thread, not per row)
         for (int s = 0; s < 8; s++) {
             const int g = p.slot_group[s];

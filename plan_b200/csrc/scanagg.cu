@@ -93,13 +93,19 @@ static SumProdKernel sumprod_variant(bool wide, bool has_a, bool has_b)
 
 // staged (bulk-copy fed) variants over narrow columns, scan_staged.cuh
 typedef void (*SumProdSKernel)(const SumProdSParams, i64 *);
-static SumProdSKernel sumprod_staged_variant(bool has_a, bool has_b, bool xr, bool yr, int qpt)
+// Width signatures with their own instantiation (everything else runs the run-time-width variant, W = -1):
+// {fa, fb, pa, pb} = {4, 1, 2, 1}: DECIMAL price x byte-wide factor under a 16-bit date and a byte predicate (TPC-H Q6 at any SF)
+static SumProdSKernel sumprod_staged_variant(const int *w /* [4] role widths */, bool xr, bool yr, int qpt, bool *specialised)
 {
-#define PG_SPS4(A, B, X, Y) (qpt >= 4 ? sumprod_staged_kernel<A, B, X, Y, 4> : qpt >= 2 ? sumprod_staged_kernel<A, B, X, Y, 2> : sumprod_staged_kernel<A, B, X, Y, 1>)
-#define PG_SPS2(A, B) (xr ? (yr ? PG_SPS4(A, B, true, true) : PG_SPS4(A, B, true, false)) : (yr ? PG_SPS4(A, B, false, true) : PG_SPS4(A, B, false, false)))
-    return has_a ? (has_b ? PG_SPS2(true, true) : PG_SPS2(true, false)) : (has_b ? PG_SPS2(false, true) : PG_SPS2(false, false));
-#undef PG_SPS2
-#undef PG_SPS4
+    const bool has_a = w[2] != 0, has_b = w[3] != 0;
+#define PG_SPSQ(FA, FB, PA, PB, X, Y) (qpt >= 4 ? sumprod_staged_kernel<FA, FB, PA, PB, X, Y, 4> : qpt >= 2 ? sumprod_staged_kernel<FA, FB, PA, PB, X, Y, 2> : sumprod_staged_kernel<FA, FB, PA, PB, X, Y, 1>)
+#define PG_SPSR(FA, FB, PA, PB) (xr ? (yr ? PG_SPSQ(FA, FB, PA, PB, true, true) : PG_SPSQ(FA, FB, PA, PB, true, false)) : (yr ? PG_SPSQ(FA, FB, PA, PB, false, true) : PG_SPSQ(FA, FB, PA, PB, false, false)))
+    *specialised = true;
+    if (w[0] == 4 && w[1] == 1 && w[2] == 2 && w[3] == 1) return PG_SPSR(4, 1, 2, 1);
+    *specialised = false;
+    return has_a ? (has_b ? PG_SPSR(-1, -1, -1, -1) : PG_SPSR(-1, -1, -1, 0)) : (has_b ? PG_SPSR(-1, -1, 0, -1) : PG_SPSR(-1, -1, 0, 0));
+#undef PG_SPSR
+#undef PG_SPSQ
 }
 
 // (v - lo) <=u span on a STORED value; false when the range is empty
@@ -129,7 +135,8 @@ struct SumProdPipeline : Pipeline {
     const pg_table *table = nullptr;
     SumProdParams prm{};
     SumProdSParams sprm{};
-    bool staged = false, xr = false, yr = false;
+    bool staged = false, xr = false, yr = false, specialised = false;
+    SumProdSKernel skern = nullptr;
     int qpt = 2;
     size_t smem = 0;
     bool has_a = false, has_b = false, wide = false;
@@ -149,7 +156,7 @@ struct SumProdPipeline : Pipeline {
         PG_TRY(ev_main.init());
         PG_CUDA(cudaEventRecord(ev_all.a, st));
         PG_CUDA(cudaEventRecord(ev_main.a, st));
-        if (staged) sumprod_staged_variant(has_a, has_b, xr, yr, qpt)<<<grid, ST_THREADS, smem, st>>>(sprm, d_part.as<i64>());
+        if (staged) skern<<<grid, ST_THREADS, smem, st>>>(sprm, d_part.as<i64>());
         else sumprod_variant(wide, has_a, has_b)<<<grid, SA_THREADS, 0, st>>>(prm, d_part.as<i64>());
         PG_CUDA(cudaGetLastError());
         PG_CUDA(cudaEventRecord(ev_main.b, st));
@@ -246,7 +253,7 @@ static int try_sumprod(pg_plan *plan, const Node &aggn, const Node &scan, const 
     int full = sms_times(kern, SA_THREADS, 0);
     i64 tile_rows = SA_TILE;
     // narrow columns: the bulk-copy staged kernel (scan_staged.cuh)
-    if (narrow && !env_int("PG_NO_STAGED", 0) && t->nrows > 0) {
+    if (narrow && !env_int("PG_NO_STAGED", 0) && t->nrows > 0 && ca.vmin >= 0 && cb.vmin >= 0) {
         SumProdSParams &sp = p->sprm;
         sp = SumProdSParams{};
         sp.nrows = t->nrows;
@@ -279,7 +286,14 @@ static int try_sumprod(pg_plan *plan, const Node &aggn, const Node &scan, const 
             p->xr = range_restricts(ca, q.fa_lo, q.fa_hi);
             p->yr = range_restricts(cb, q.fb_lo, q.fb_hi);
             p->smem = (size_t)ST_HDR + (size_t)sp.st.nstage * sp.st.stage_bytes;
-            kern = (const void *)sumprod_staged_variant(p->has_a, p->has_b, p->xr, p->yr, p->qpt);
+            if (!p->has_a && p->has_b) {            // a single predicate column is role 2
+                std::swap(sp.rpw[2], sp.rpw[3]); std::swap(sp.roff[2], sp.roff[3]);
+                std::swap(sp.a_lo, sp.b_lo); std::swap(sp.a_span, sp.b_span);
+            }
+            int wsig[4] = {sp.rpw[0], sp.rpw[1], sp.rpw[2], sp.rpw[3]};
+            if (env_int("PG_NO_SPECIALISED", 0)) wsig[0] = 8;
+            p->skern = sumprod_staged_variant(wsig, p->xr, p->yr, p->qpt, &p->specialised);
+            kern = (const void *)p->skern;
             PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
             full = sms_times(kern, ST_THREADS, p->smem);
             ntiles = (t->nrows + tile_rows - 1) / tile_rows;
@@ -305,7 +319,7 @@ static int try_sumprod(pg_plan *plan, const Node &aggn, const Node &scan, const 
     snprintf(buf, sizeof buf,
              "ScanAgg[sumprod] table=%s rows=%lld kernel=%s<%s,%d,%d> grid=%d block=%d "
              "stored bytes/row=%d (widths: fa=%d fb=%d) stored ranges: a=[%lld,%lld] b=[%lld,%lld] fa=[%lld,%lld] fb=[%lld,%lld] value_scale=%d",
-             t->name.c_str(), (long long)t->nrows, p->staged ? "sumprod_staged_kernel" : "sumprod_kernel", p->staged ? "bulk-copy ring" : p->wide ? "wide" : "narrow",
+             t->name.c_str(), (long long)t->nrows, p->staged ? "sumprod_staged_kernel" : "sumprod_kernel", p->staged ? (p->specialised ? "bulk-copy ring, widths compiled in" : "bulk-copy ring, run-time widths") : p->wide ? "wide" : "narrow",
              (int)p->has_a, (int)p->has_b, p->grid, p->staged ? ST_THREADS : SA_THREADS,
              p->bytes_per_row, ca.phys_width(), cb.phys_width(), (long long)q.a_lo, (long long)q.a_hi, (long long)q.b_lo, (long long)q.b_hi,
              (long long)q.fa_lo, (long long)q.fa_hi, (long long)q.fb_lo, (long long)q.fb_hi, p->vscale);
@@ -318,10 +332,16 @@ static int try_sumprod(pg_plan *plan, const Node &aggn, const Node &scan, const 
 
 typedef void (*LowcardKernel)(const LowcardParams, i64 *, i64 *);
 typedef void (*LowcardSKernel)(const LowcardSParams, i64 *);
-static LowcardSKernel lowcard_staged_variant(bool key1, int qpt)
+// {pred, q, A, B, C} = {2, 1, 4, 1, 1} has its own instantiation (TPC-H Q1 at any SF); everything else: run-time widths
+static LowcardSKernel lowcard_staged_variant(const int *w /* [7] role widths */, bool key1, int qpt, bool *specialised)
 {
-    if (qpt >= 2) return key1 ? lowcard_staged_kernel<true, 2> : lowcard_staged_kernel<false, 2>;
-    return key1 ? lowcard_staged_kernel<true, 1> : lowcard_staged_kernel<false, 1>;
+#define PG_LCS(P, Q, A, B, C) (qpt >= 2 ? (key1 ? lowcard_staged_kernel<P, Q, A, B, C, true, 2> : lowcard_staged_kernel<P, Q, A, B, C, false, 2>) \
+                                        : (key1 ? lowcard_staged_kernel<P, Q, A, B, C, true, 1> : lowcard_staged_kernel<P, Q, A, B, C, false, 1>))
+    *specialised = true;
+    if (w[0] == 2 && w[3] == 1 && w[4] == 4 && w[5] == 1 && w[6] == 1) return PG_LCS(2, 1, 4, 1, 1);
+    *specialised = false;
+    return PG_LCS(-1, -1, -1, -1, -1);
+#undef PG_LCS
 }
 static int bit_length(i128 v) { int n = 0; while (v > 0) { n++; v >>= 1; } return n; }
 static LowcardKernel lowcard_variant(bool wide, bool acc32, bool key1, int unroll)
@@ -340,7 +360,8 @@ struct LowcardPipeline : Pipeline {
     int unroll = 2;
     int grid = 1, G = 1;
     size_t smem = 0;
-    bool staged = false;                 // lowcard_staged_kernel (scan_staged.cuh) + first_rows_kernel
+    bool staged = false, specialised = false;   // lowcard_staged_kernel (scan_staged.cuh) + first_rows_kernel
+    LowcardSKernel skern = nullptr;
     LowcardSParams sprm{};
     int qpt = 2;
     i64 lc_per = 0;                      // LC_TILE-sized tiles per CTA (contiguous mode), whichever kernel runs
@@ -385,7 +406,7 @@ struct LowcardPipeline : Pipeline {
         PG_CUDA(cudaEventRecord(ev_all.a, st));
         PG_CUDA(cudaMemsetAsync(d_firstrow, 0x7f, LC_MAXG * 8, st));   // 0x7f7f.. = "unset"
         PG_CUDA(cudaEventRecord(ev_main.a, st));
-        if (staged) lowcard_staged_variant(has_key1, qpt)<<<grid, ST_THREADS, smem, st>>>(sprm, d_part.as<i64>());
+        if (staged) skern<<<grid, ST_THREADS, smem, st>>>(sprm, d_part.as<i64>());
         else lowcard_variant(wide, acc32, has_key1, unroll)<<<grid, LC_THREADS, smem, st>>>(prm, d_part.as<i64>(), d_firstrow);
         PG_CUDA(cudaGetLastError());
         PG_CUDA(cudaEventRecord(ev_main.b, st));
@@ -806,7 +827,11 @@ static int try_lowcard(pg_plan *plan, const Node &aggn, const Node &scan, const 
             if (ns < 2) ns = 2;
             sp.st.nstage = ns;
             const size_t smem = (size_t)ST_HDR + (size_t)ns * sp.st.stage_bytes + LCS_TBL_BYTES;
-            const void *kern = (const void *)lowcard_staged_variant(p->has_key1, p->qpt);
+            int wsig[7];
+            for (int r = 0; r < 7; r++) wsig[r] = sp.rpw[r];
+            if (env_int("PG_NO_SPECIALISED", 0)) wsig[0] = 8;
+            p->skern = lowcard_staged_variant(wsig, p->has_key1, p->qpt, &p->specialised);
+            const void *kern = (const void *)p->skern;
             if (smem > (size_t)ctx().prop.sharedMemPerBlockOptin) no = "stages do not fit in shared memory";
             else {
                 PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -895,7 +920,7 @@ static int try_lowcard(pg_plan *plan, const Node &aggn, const Node &scan, const 
     snprintf(buf, sizeof buf,
              "ScanAgg[lowcard-chain] table=%s rows=%lld kernel=%s<%s,%s,%d,%d> grid=%d block=%d smem=%zu "
              "groups=%dx%d stored bytes/row=%d (widths: pred=%d q=%d A=%d B=%d C=%d) stored pred=[%lld,%lld] chain: A*(%lld%+lld*B)*(%lld%+lld*C) tiles=%s%s",
-             t->name.c_str(), (long long)t->nrows, p->staged ? "lowcard_staged_kernel" : "lowcard_chain_kernel", p->staged ? "bulk-copy ring" : p->wide ? "wide" : "narrow",
+             t->name.c_str(), (long long)t->nrows, p->staged ? "lowcard_staged_kernel" : "lowcard_chain_kernel", p->staged ? (p->specialised ? "bulk-copy ring, widths compiled in" : "bulk-copy ring, run-time widths") : p->wide ? "wide" : "narrow",
              p->staged ? "packed3" : p->acc32 ? "acc32" : "acc64", (int)p->has_key1, p->staged ? p->qpt : p->unroll, p->grid,
              p->staged ? ST_THREADS : LC_THREADS, p->smem, dims[0], dims[1], p->bytes_per_row, q.pred.pw, q.q.pw, q.A.pw, q.B.pw, q.C.pw, (long long)slo, (long long)shi,
              (long long)q.c1, (long long)q.s1, (long long)q.c2, (long long)q.s2,

@@ -165,29 +165,53 @@ __device__ __forceinline__ void stage_release(const StageRing &r, const StageDes
     if (++c.s == d.nstage) { c.s = 0; c.ph ^= 1u; }
 }
 
-// One quad (4 consecutive rows) of a staged column -> 4 STORED values as 32-bit words.
-// pw is warp-uniform; pw == 0 stands for "column absent": zeros.  qrow = row index of the quad inside the tile.
-__device__ __forceinline__ void quad_load(const char *stage, int off, int pw, int qrow, unsigned (&v)[4])
-{
-    const char *p = stage + off + qrow * pw;
-    if (pw == 1) {
-        const unsigned x = *(const unsigned *)p;
-        v[0] = x & 255u; v[1] = (x >> 8) & 255u; v[2] = (x >> 16) & 255u; v[3] = x >> 24;
-    } else if (pw == 2) {
-        const uint2 x = *(const uint2 *)p;
-        v[0] = x.x & 0xffffu; v[1] = x.x >> 16; v[2] = x.y & 0xffffu; v[3] = x.y >> 16;
-    } else if (pw == 4) {
-        const uint4 x = *(const uint4 *)p;
-        v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
-    } else {
-        v[0] = v[1] = v[2] = v[3] = 0;
+// One quad (4 consecutive rows) of a staged column, held raw in registers; get<j>() yields the STORED value of
+// row j as a 32-bit word.  The width is a template parameter: 1 / 2 / 4 bytes, 0 = column absent (reads as 0),
+// -1 = decided at run time (warp-uniform switch; the fallback for width combinations that are not instantiated).
+template <int PW> struct Quad;
+template <> struct Quad<0> {
+    __device__ __forceinline__ void load(const char *, int, int) {}
+    template <int J> __device__ __forceinline__ unsigned get() const { return 0u; }
+};
+template <> struct Quad<1> {
+    unsigned r;
+    __device__ __forceinline__ void load(const char *col, int qrow, int) { r = *(const unsigned *)(col + qrow); }
+    template <int J> __device__ __forceinline__ unsigned get() const { return __byte_perm(r, 0u, 0x4440u + J); }
+};
+template <> struct Quad<2> {
+    uint2 r;
+    __device__ __forceinline__ void load(const char *col, int qrow, int) { r = *(const uint2 *)(col + 2 * qrow); }
+    template <int J> __device__ __forceinline__ unsigned get() const
+    {
+        const unsigned w = J < 2 ? r.x : r.y;
+        return (J & 1) ? w >> 16 : w & 0xffffu;
     }
-}
-// raw 32-bit word of a byte column's quad (4 codes)
-__device__ __forceinline__ unsigned quad_load_bytes(const char *stage, int off, int qrow)
-{
-    return *(const unsigned *)(stage + off + qrow);
-}
+};
+template <> struct Quad<4> {
+    uint4 r;
+    __device__ __forceinline__ void load(const char *col, int qrow, int) { r = *(const uint4 *)(col + 4 * qrow); }
+    template <int J> __device__ __forceinline__ unsigned get() const { return J == 0 ? r.x : J == 1 ? r.y : J == 2 ? r.z : r.w; }
+};
+template <> struct Quad<-1> {
+    unsigned v[4];
+    __device__ __forceinline__ void load(const char *col, int qrow, int pw)
+    {
+        const char *p = col + qrow * pw;
+        if (pw == 1) {
+            const unsigned x = *(const unsigned *)p;
+            v[0] = __byte_perm(x, 0u, 0x4440u); v[1] = __byte_perm(x, 0u, 0x4441u); v[2] = __byte_perm(x, 0u, 0x4442u); v[3] = x >> 24;
+        } else if (pw == 2) {
+            const uint2 x = *(const uint2 *)p;
+            v[0] = x.x & 0xffffu; v[1] = x.x >> 16; v[2] = x.y & 0xffffu; v[3] = x.y >> 16;
+        } else if (pw == 4) {
+            const uint4 x = *(const uint4 *)p;
+            v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+        } else {
+            v[0] = v[1] = v[2] = v[3] = 0;
+        }
+    }
+    template <int J> __device__ __forceinline__ unsigned get() const { return v[J]; }
+};
 #endif
 
 }  // namespace pg
