@@ -330,12 +330,103 @@ struct JoinAggPipeline : Pipeline {
         pp.row_end = hi;
         pp.hits = d_hits.as<unsigned>();
         pp.hit_count = d_hit_count.as<unsigned long long>();
+        if (try_staged_filter(pp, lo, hi) == PG_OK) return PG_OK;
         i64 ntiles = (hi - lo + SA_TILE - 1) / SA_TILE;
         int grid = (int)std::max<i64>(std::min<i64>(ntiles, (i64)ctx().prop.multiProcessorCount * 8), 1);
         // (two tiles per step were measured slower: 90 registers cost more occupancy than the extra loads in flight bring)
         if (pp.npred == 1) filter_hits_kernel<true, 1><<<grid, SA_THREADS, 0, st>>>(pp);
         else filter_hits_kernel<false, 1><<<grid, SA_THREADS, 0, st>>>(pp);
         PG_CUDA(cudaGetLastError());
+        return PG_OK;
+    }
+
+    // The bulk-copy staged filter (join.cuh) when predicate and key are stored in <= 4 bytes and the 32-bit
+    // domain test is provably exact.  Returns PG_OK when it was launched, PG_EUNSUPPORTED to use the kernel above.
+    bool staged_filter_used = false;
+    int try_staged_filter(const PipeParams &pp, i64 lo, i64 hi)
+    {
+        if (getenv("PG_NO_STAGED") && atoi(getenv("PG_NO_STAGED"))) return PG_EUNSUPPORTED;
+        if (hi <= lo || (lo & 15) != 0 || pp.npred > 1) return PG_EUNSUPPORTED;
+        const TypedCol &kc = pp.probe_key;
+        if (!kc.p || kc.width > 4 || kc.valid) return PG_EUNSUPPORTED;
+        FilterSParams fp{};
+        fp.bitmap = pp.has_probe ? pp.probe.bitmap : nullptr;
+        if (pp.has_probe && !fp.bitmap) return PG_EUNSUPPORTED;
+        fp.anti = pp.probe_mode == 2 ? 1 : 0;
+        auto stored_span = [](const TypedCol &c, i64 *tmin, i64 *tmax) {
+            if (c.width == 4) { *tmin = INT32_MIN; *tmax = INT32_MAX; }
+            else { *tmin = 0; *tmax = c.width == 2 ? 0xffff : 0xff; }
+        };
+        if (fp.bitmap) {
+            // off = logical - bm_min = stored + (base - bm_min); every stored value the type can hold must land, mod 2^32,
+            // outside [0, dom) unless its true offset is inside
+            if (pp.probe.domain > 0xffffffffULL) return PG_EUNSUPPORTED;
+            i64 tmin, tmax;
+            stored_span(kc, &tmin, &tmax);
+            const i128 delta = (i128)kc.base - (i128)pp.probe.bm_min;
+            const i128 omin = (i128)tmin + delta, omax = (i128)tmax + delta;
+            if (omax >= ((i128)1 << 32) || omin <= (i128)pp.probe.domain - ((i128)1 << 32)) return PG_EUNSUPPORTED;
+            fp.kdelta = (unsigned)(u64)(i64)delta;
+            fp.dom = (unsigned)pp.probe.domain;
+        }
+        fp.p_lo = 0; fp.p_span = 0xffffffffu;
+        fp.st.ncol = 0;
+        fp.rpw[0] = 0; fp.roff[0] = 0;
+        int pi = -1;
+        if (pp.npred == 1) {
+            const TypedCol &pc = pp.pred[0].col;
+            if (pp.pred[0].is_set || pc.width > 4 || pc.valid) return PG_EUNSUPPORTED;
+            i64 tmin, tmax;
+            stored_span(pc, &tmin, &tmax);
+            i128 a = (i128)pp.pred[0].lo - pc.base, b = (i128)pp.pred[0].hi - pc.base;
+            if (a < tmin) a = tmin;
+            if (b > tmax) b = tmax;
+            if (pp.pred[0].lo > pp.pred[0].hi || a > b) return PG_EUNSUPPORTED;      // empty range: the plain kernel
+            fp.p_lo = (unsigned)(int32_t)(i64)a;
+            fp.p_span = (unsigned)(u64)(i64)(b - a);
+            pi = fp.st.ncol;
+            fp.st.src[pi] = (const char *)pc.p + lo * pc.width;
+            fp.st.pw[pi] = pc.width;
+            fp.st.ncol++;
+        }
+        int ki = -1;
+        if (pi >= 0 && fp.st.src[pi] == (const char *)kc.p + lo * kc.width) ki = pi;
+        else {
+            ki = fp.st.ncol;
+            fp.st.src[ki] = (const char *)kc.p + lo * kc.width;
+            fp.st.pw[ki] = kc.width;
+            fp.st.ncol++;
+        }
+        const int qpt = 2;
+        const int tile_rows = ST_CONS_WARPS * 128 * qpt;
+        stage_layout(&fp.st, tile_rows);
+        if (pi >= 0) { fp.rpw[0] = fp.st.pw[pi]; fp.roff[0] = fp.st.off[pi]; }
+        fp.rpw[1] = fp.st.pw[ki]; fp.roff[1] = fp.st.off[ki];
+        fp.st.nstage = getenv("PG_NSTAGE") ? atoi(getenv("PG_NSTAGE")) : 4;
+        fp.row_begin = lo;
+        fp.nloc = hi - lo;
+        fp.hits = pp.hits;
+        fp.hit_count = pp.hit_count;
+        fp.counters = pp.counters;
+        typedef void (*FK)(const FilterSParams);
+        FK k;
+        if (const char *m = getenv("PG_STAGED_FILTER_MASK")) {     // diagnosis: which width classes may use the staged filter
+            const int cls = (fp.rpw[0] == 2 && fp.rpw[1] == 4) ? 1 : (fp.rpw[0] == 0 && fp.rpw[1] == 4) ? 2 : fp.rpw[0] == 0 ? 4 : 8;
+            if (!(atoi(m) & cls)) return PG_EUNSUPPORTED;
+        }
+        if (fp.rpw[0] == 2 && fp.rpw[1] == 4) k = filter_hits_staged_kernel<2, 4, 2>;
+        else if (fp.rpw[0] == 0 && fp.rpw[1] == 4) k = filter_hits_staged_kernel<0, 4, 2>;
+        else if (fp.rpw[0] == 0) k = filter_hits_staged_kernel<0, -1, 2>;
+        else k = filter_hits_staged_kernel<-1, -1, 2>;
+        const size_t smem = (size_t)ST_HDR + (size_t)fp.st.nstage * fp.st.stage_bytes;
+        PG_CUDA(cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)k, ST_THREADS, smem);
+        const i64 ntiles = (fp.nloc + tile_rows - 1) / tile_rows;
+        const int grid = (int)std::max<i64>(1, std::min<i64>(ntiles, (i64)ctx().prop.multiProcessorCount * std::max(per_sm, 1)));
+        k<<<grid, ST_THREADS, smem, ctx().stream>>>(fp);
+        PG_CUDA(cudaGetLastError());
+        staged_filter_used = true;
         return PG_OK;
     }
 

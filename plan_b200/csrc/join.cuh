@@ -843,6 +843,131 @@ filter_hits_kernel(const PipeParams p)
     if (lane == 0 && nh) atomicAdd(&p.counters[3], nh);
 }
 
+// Phase 1 over NARROW stored columns (predicate and key in <= 4 bytes, no NULLs): the same screen, fed by the
+// bulk-copy tile ring of stage.cuh instead of per-thread vector loads -- at 6 stored bytes per lineitem row the
+// register-staged kernel above is issue-bound (r2: 2.0 TB/s).  Predicate and key-domain tests run on the STORED
+// 32-bit values:  (v - p_lo) <=u p_span,  off = stored key + kdelta (mod 2^32) < dom  (the host proves the wrap
+// cannot alias a key outside the bitmap's domain into it).
+struct FilterSParams {
+    StageDesc st;
+    int roff[2], rpw[2];          // role 0 = predicate column (width 0: none), 1 = probe key
+    unsigned p_lo, p_span;
+    unsigned kdelta, dom;
+    const unsigned *bitmap;       // null: no probe, every row passing the predicate is a hit
+    int anti;
+    i64 row_begin, nloc;
+    unsigned *hits;
+    unsigned long long *hit_count;
+    unsigned long long *counters;
+};
+
+template <int WP, int WK, int QPT, bool MASK>
+__device__ __forceinline__ void filter_tile(const FilterSParams &p, const StageRing &ring, StageCursor &cur, int warp, int lane, i64 tile,
+                                            unsigned (*s_buf)[512], int &nbuf, unsigned &n_pass, unsigned &n_hits)
+{
+    constexpr int WBUF = 512;
+    const char *stg = stage_acquire(ring, p.st, cur);
+    Quad<WP> dv[QPT];
+    Quad<WK> kv[QPT];
+#pragma unroll
+    for (int q = 0; q < QPT; q++) {
+        const int qrow = (warp * QPT + q) * 128 + lane * 4;
+        dv[q].load(stg + p.roff[0], qrow, p.rpw[0]);
+        kv[q].load(stg + p.roff[1], qrow, p.rpw[1]);
+    }
+    stage_release(ring, p.st, cur);
+    const unsigned *__restrict__ bm = p.bitmap;
+    const bool anti = p.anti != 0;
+    const i64 row0 = tile * p.st.tile_rows;
+    const int rows_in_tile = MASK ? (int)(p.nloc - row0) : 0;
+    bool ok[QPT][4];
+    unsigned w[QPT][4], off[QPT][4];
+#pragma unroll
+    for (int q = 0; q < QPT; q++) {
+        const int rem = rows_in_tile - ((warp * QPT + q) * 128 + lane * 4);
+        auto row = [&](auto jc) {
+            constexpr int J = decltype(jc)::v;
+            ok[q][J] = (!MASK || J < rem) && (WP == 0 || (dv[q].template get<J>() - p.p_lo) <= p.p_span);
+            off[q][J] = kv[q].template get<J>() + p.kdelta;
+            const bool in = ok[q][J] && bm != nullptr && off[q][J] < p.dom;
+            w[q][J] = in ? __ldg(bm + (off[q][J] >> 5)) : 0u;      // predicated loads issued back to back
+        };
+        PG_FOR4(row);
+    }
+    unsigned hitmask = 0;
+#pragma unroll
+    for (int q = 0; q < QPT; q++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            n_pass += ok[q][j] ? 1u : 0u;
+            const bool set = bm == nullptr || ((w[q][j] >> (off[q][j] & 31u)) & 1u);
+            if (ok[q][j] && set != anti) hitmask |= 1u << (4 * q + j);
+        }
+    const int c = __popc(hitmask);
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return;
+    if (nbuf + total > WBUF) {          // flush: ONE cursor bump for the whole buffer
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(p.hit_count, (unsigned long long)nbuf);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int i = lane; i < nbuf; i += 32) p.hits[base + i] = s_buf[warp][i];
+        __syncwarp();
+        n_hits += lane == 0 ? (unsigned)nbuf : 0u;
+        nbuf = 0;
+    }
+    int pos = nbuf + incl - c;
+#pragma unroll
+    for (int q = 0; q < QPT; q++) {
+        const unsigned rowid = (unsigned)(p.row_begin + row0) + (unsigned)((warp * QPT + q) * 128 + lane * 4);
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (hitmask & (1u << (4 * q + j))) s_buf[warp][pos++] = rowid + j;
+    }
+    nbuf += total;
+    __syncwarp();
+}
+
+template <int WP, int WK, int QPT>
+__global__ void __launch_bounds__(ST_THREADS)
+filter_hits_staged_kernel(const FilterSParams p)
+{
+    extern __shared__ __align__(128) unsigned char st_smem[];
+    __shared__ unsigned s_buf[ST_CONS_WARPS][512];
+    const StageDesc &d = p.st;
+    const StageRing ring = stage_ring_init(st_smem, d);
+    const i64 ntiles = (p.nloc + d.tile_rows - 1) / d.tile_rows;
+    const TileSeq seq = tile_seq(ntiles, 0);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == ST_CONS_WARPS) {
+        stage_produce(ring, d, seq);
+        return;
+    }
+    StageCursor cur = {0, 0};
+    int nbuf = 0;
+    unsigned n_pass = 0, n_hits = 0;
+    const bool partial = last_tile_is_partial(seq, ntiles, p.nloc, d.tile_rows);
+    const int nwhole = (int)seq.count - (partial ? 1 : 0);
+    for (int k = 0; k < nwhole; k++)
+        filter_tile<WP, WK, QPT, false>(p, ring, cur, warp, lane, seq.first + (i64)k * seq.step, s_buf, nbuf, n_pass, n_hits);
+    if (partial) filter_tile<WP, WK, QPT, true>(p, ring, cur, warp, lane, ntiles - 1, s_buf, nbuf, n_pass, n_hits);
+    if (nbuf) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(p.hit_count, (unsigned long long)nbuf);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int i = lane; i < nbuf; i += 32) p.hits[base + i] = s_buf[warp][i];
+        n_hits += lane == 0 ? (unsigned)nbuf : 0u;
+    }
+    unsigned long long np = (unsigned long long)warp_sum((i64)n_pass), nh = (unsigned long long)warp_sum((i64)n_hits);
+    if (lane == 0 && np) atomicAdd(&p.counters[0], np);
+    if (lane == 0 && nh) atomicAdd(&p.counters[3], nh);
+}
+
 template <int SINK>
 __global__ void __launch_bounds__(256)
 hits_sink_kernel(const PipeParams p)

@@ -160,7 +160,7 @@ struct SumProdPipeline : Pipeline {
         else sumprod_variant(wide, has_a, has_b)<<<grid, SA_THREADS, 0, st>>>(prm, d_part.as<i64>());
         PG_CUDA(cudaGetLastError());
         PG_CUDA(cudaEventRecord(ev_main.b, st));
-        finalize128_kernel<<<1, 32, 0, st>>>(d_part.as<i64>(), grid, 2, d_final.as<u64>());
+        finalize128_kernel<<<2, 32, 0, st>>>(d_part.as<i64>(), grid, 2, d_final.as<u64>());
         PG_CUDA(cudaGetLastError());
         const void *src = d_final.p;
         const int nmerge = table->dist == PG_DIST_REPLICATED ? 1 : c.world;   // a replicated table is complete on every rank
@@ -410,7 +410,7 @@ struct LowcardPipeline : Pipeline {
         else lowcard_variant(wide, acc32, has_key1, unroll)<<<grid, LC_THREADS, smem, st>>>(prm, d_part.as<i64>(), d_firstrow);
         PG_CUDA(cudaGetLastError());
         PG_CUDA(cudaEventRecord(ev_main.b, st));
-        finalize128_kernel<<<1, 64, 0, st>>>(d_part.as<i64>(), grid, G * LC_K, d_final.as<u64>());
+        finalize128_kernel<<<G * LC_K, 32, 0, st>>>(d_part.as<i64>(), grid, G * LC_K, d_final.as<u64>());
         PG_CUDA(cudaGetLastError());
         if (staged) {       // group order: first passing row of every group, found outside the scan's inner loop
             if (has_key1) first_rows_kernel<true><<<64, 256, 0, st>>>(prm, d_final.as<u64>(), d_firstrow);
@@ -428,16 +428,16 @@ struct LowcardPipeline : Pipeline {
             OrdJob *jobs = d_jobs.as<OrdJob>();
             int *njobs = (int *)(jobs + ORD_MAXJOBS);
             OrdContrib *mine = d_contrib.as<OrdContrib>(), *all = mine + ORD_MAXJOBS;
-            ord_plan_kernel<<<1, 32, 0, st>>>(d_gather.as<u64>(), (i64)(rank_bytes() / 8), nranks(), myrank(), G, emu_mask, d_part.as<i64>(), grid,
+            ord_plan_kernel<<<1, ORD_PLAN_THREADS, 0, st>>>(d_gather.as<u64>(), (i64)(rank_bytes() / 8), nranks(), myrank(), G, emu_mask, d_part.as<i64>(), grid,
                                               per, ntiles, jobs, njobs);
             const int og = ctx().prop.multiProcessorCount * 4;
-            if (has_key1) {
-                ord_jobs_kernel<true><<<og, LC_THREADS, 0, st>>>(prm, jobs, njobs, d_ord.as<OrdSummary>(), ord_stride, ntiles);
-                ord_fold_kernel<true><<<ORD_MAXJOBS, LC_THREADS, 0, st>>>(prm, jobs, njobs, d_ord.as<OrdSummary>(), ord_stride, ntiles, mine);
-            } else {
-                ord_jobs_kernel<false><<<og, LC_THREADS, 0, st>>>(prm, jobs, njobs, d_ord.as<OrdSummary>(), ord_stride, ntiles);
-                ord_fold_kernel<false><<<ORD_MAXJOBS, LC_THREADS, 0, st>>>(prm, jobs, njobs, d_ord.as<OrdSummary>(), ord_stride, ntiles, mine);
-            }
+            const bool ow = prm.pred.pw > 4 || prm.A.pw > 4 || prm.B.pw > 4 || prm.C.pw > 4;       // 8-byte columns: 32-byte raw vectors
+#define PG_ORDJ(K, W) ord_jobs_kernel<K, W><<<og, LC_THREADS, 0, st>>>(prm, jobs, njobs, d_ord.as<OrdSummary>(), ord_stride, ntiles)
+            if (has_key1) { if (ow) PG_ORDJ(true, true); else PG_ORDJ(true, false); }
+            else { if (ow) PG_ORDJ(false, true); else PG_ORDJ(false, false); }
+#undef PG_ORDJ
+            if (has_key1) ord_fold_kernel<true><<<ORD_MAXJOBS, LC_THREADS, 0, st>>>(prm, jobs, njobs, d_ord.as<OrdSummary>(), ord_stride, ntiles, mine);
+            else ord_fold_kernel<false><<<ORD_MAXJOBS, LC_THREADS, 0, st>>>(prm, jobs, njobs, d_ord.as<OrdSummary>(), ord_stride, ntiles, mine);
             PG_CUDA(cudaGetLastError());
             if (nranks() > 1) PG_TRY(comm_allgather(mine, all, contrib_bytes(), st));
             else PG_CUDA(cudaMemcpyAsync(all, mine, contrib_bytes(), cudaMemcpyDeviceToDevice, st));

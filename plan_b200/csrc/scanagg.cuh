@@ -495,34 +495,61 @@ __device__ __forceinline__ OrdState ord_shfl_down(const OrdState &st, int o)
     return r;
 }
 
-// the 4 rows of one thread of one tile -> their ordered composite for (group, slot)
-template <bool HAS_KEY1>
-__device__ __forceinline__ OrdState ord_thread_rows(const OrdParams &op, const uint8_t (*s_lut)[256], i64 tile)
+// 4 consecutive rows starting at `row` -> their ordered composite for (group, slot).  WIDE = false: every column is
+// stored in <= 4 bytes (raw vectors of 16 bytes, 32-bit unpacking).
+template <bool HAS_KEY1, bool WIDE = true>
+__device__ __forceinline__ OrdState ord_quad_rows(const OrdParams &op, const uint8_t (*s_lut)[256], i64 row)
 {
+    typedef typename std::conditional<WIDE, i64, int>::type V;
     const LowcardParams &p = op.base;
-    const i64 row = tile * LC_TILE + threadIdx.x * SA_VEC;
     const i64 rem = p.nrows - row;
-    Raw4<true> d, a, b, c;
+    Raw4<WIDE> d, a, b, c;
     ld_raw4(p.pred, row, d);
     const unsigned k0 = ld_stream4((const uint8_t *)p.key0.p + row), k1 = HAS_KEY1 ? ld_stream4((const uint8_t *)p.key1.p + row) : 0;
     ld_raw4(p.A, row, a);
     ld_raw4(p.B, row, b);
     ld_raw4(p.C, row, c);
-    i64 dv[4], av[4], bv[4], cv[4];
+    V dv[4], av[4], bv[4], cv[4];
     unpack4(p.pred, d, dv);
     unpack4(p.A, a, av);
     unpack4(p.B, b, bv);
     unpack4(p.C, c, cv);
+    // Both entry parities are simulated directly (no per-row transducer objects): a row with digit d != 5 carries
+    // [d > 5] whatever the state and flips both parities alike; a row with d == 5 carries parity(S + q) and leaves the
+    // sum EVEN in both cases (half-to-even), after which the two simulations coincide.
     OrdState st = {0, 0, 0, 0, 0, 1};   // identity: parity preserved, no carries
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         const bool ok = j < rem && dv[j] >= p.lo && dv[j] <= p.hi;
         int g = s_lut[0][(k0 >> (8 * j)) & 255];
         if (HAS_KEY1) g = g * p.n1 + s_lut[1][(k1 >> (8 * j)) & 255];
-        if (ok && g == op.group)
-            st = ord_compose(st, ord_of(ord_value(p, op.slot, av[j] + p.A.base, bv[j] + p.B.base, cv[j] + p.C.base)));
+        if (ok && g == op.group) {
+            const u64 x = (u64)ord_value(p, op.slot, av[j] + p.A.base, bv[j] + p.B.base, cv[j] + p.C.base);
+            const u64 q = x / 10;
+            const unsigned d = (unsigned)(x - q * 10), t = (unsigned)q & 1u;
+            st.sq += (i64)q;
+            st.sx += (i64)x;
+            if (d == 5u) {
+                st.c0 += st.p0 ^ t;
+                st.c1 += st.p1 ^ t;
+                st.p0 = 0;
+                st.p1 = 0;
+            } else {
+                const unsigned c = d > 5u ? 1u : 0u;
+                st.c0 += c;
+                st.c1 += c;
+                st.p0 ^= t ^ c;
+                st.p1 ^= t ^ c;
+            }
+        }
     }
     return st;
+}
+// the 4 rows of one thread of one tile
+template <bool HAS_KEY1>
+__device__ __forceinline__ OrdState ord_thread_rows(const OrdParams &op, const uint8_t (*s_lut)[256], i64 tile)
+{
+    return ord_quad_rows<HAS_KEY1>(op, s_lut, tile * LC_TILE + threadIdx.x * SA_VEC);
 }
 
 template <bool HAS_KEY1>
@@ -572,7 +599,7 @@ ord_tile_kernel(const OrdParams op, OrdSummary *__restrict__ out /* [ceil((tile_
 //                     summaries into one transducer.  One 64-byte contribution per (job, rank).
 // The contributions are all-gathered and applied in rank order on the host (a few dozen integer ops).
 constexpr int ORD_MAXJOBS = 4;
-constexpr int ORD_CHUNK = 16;           // tiles composed per summary after the crossing CTA's range
+constexpr int ORD_CHUNK = 4;            // tiles composed per summary after the crossing CTA's range
 struct OrdJob {
     int g, s;
     int role;            // 0: this rank lies before the crossing, 1: the crossing rank, 2: a later rank
@@ -585,46 +612,82 @@ static_assert(sizeof(OrdContrib) == 64, "OrdContrib is exchanged as 64 bytes");
 
 __device__ __forceinline__ u128 ord_thr() { return (u128)10000000000000000000ULL; }
 
-static __global__ void ord_plan_kernel(const u64 *__restrict__ gathered, i64 rank_words, int nranks, int myrank, int G, unsigned emu_mask,
-                                       const i64 *__restrict__ part, int grid, i64 per, i64 ntiles, OrdJob *__restrict__ jobs, int *__restrict__ njobs)
+// launched as <<<1, ORD_PLAN_THREADS>>>: the block stages the gathered totals and, for a crossing job, the CTAs' partials
+// in shared memory (coalesced, all loads in flight at once); thread 0 then walks them -- the walks used to be chains of
+// dependent global loads (135 us at SF100 for 296 CTAs).
+constexpr int ORD_PLAN_THREADS = 256;
+constexpr int ORD_PLAN_MAXG = 1024, ORD_PLAN_MAXCTA = 2048;
+static __global__ void __launch_bounds__(ORD_PLAN_THREADS)
+ord_plan_kernel(const u64 *__restrict__ gathered, i64 rank_words, int nranks, int myrank, int G, unsigned emu_mask,
+                const i64 *__restrict__ part, int grid, i64 per, i64 ntiles, OrdJob *__restrict__ jobs, int *__restrict__ njobs)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    __shared__ u64 s_g[ORD_PLAN_MAXG];
+    __shared__ i64 s_x[ORD_PLAN_MAXCTA];
+    __shared__ OrdJob s_jobs[ORD_MAXJOBS];
+    __shared__ int s_n;
     const u128 THR = ord_thr();
-    int n = 0;
-    for (int g = 0; g < G; g++)
-        for (int s = 2; s < LC_K; s++) {
-            if (!((emu_mask >> s) & 1u)) continue;
-            const int v = g * LC_K + s;
-            u128 tot = 0;
-            for (int r = 0; r < nranks; r++) tot += ((u128)gathered[r * rank_words + 2 * v + 1] << 64) | gathered[r * rank_words + 2 * v];
-            if (tot < THR) continue;
-            if (n >= ORD_MAXJOBS) { n++; continue; }
-            OrdJob j;
-            j.g = g; j.s = s; j.tb = 0; j.te = 0; j.P = 0;
-            u128 P = 0;
-            int r = 0;
-            for (; r < nranks; r++) {
-                const u128 t = ((u128)gathered[r * rank_words + 2 * v + 1] << 64) | gathered[r * rank_words + 2 * v];
-                if (P + t >= THR) break;
-                P += t;
-            }
-            j.rstar = r;
-            j.role = myrank == r ? 1 : myrank > r ? 2 : 0;
-            if (j.role == 1) {
-                int c = 0;
-                for (; c < grid; c++) {
-                    const u128 x = (u128)(u64)part[(i64)c * (G * LC_K) + v];
-                    if (P + x >= THR) break;
-                    P += x;
+    const int GK = G * LC_K;
+    const bool g_in_smem = (i64)nranks * 2 * GK <= ORD_PLAN_MAXG;
+    if (g_in_smem)
+        for (int i = threadIdx.x; i < nranks * 2 * GK; i += ORD_PLAN_THREADS) s_g[i] = gathered[(i64)(i / (2 * GK)) * rank_words + i % (2 * GK)];
+    __syncthreads();
+    auto total_of = [&](int r, int v) -> u128 {
+        if (g_in_smem) return ((u128)s_g[r * 2 * GK + 2 * v + 1] << 64) | s_g[r * 2 * GK + 2 * v];
+        return ((u128)gathered[r * rank_words + 2 * v + 1] << 64) | gathered[r * rank_words + 2 * v];
+    };
+    if (threadIdx.x == 0) {
+        int n = 0;
+        for (int g = 0; g < G; g++)
+            for (int s = 2; s < LC_K; s++) {
+                if (!((emu_mask >> s) & 1u)) continue;
+                const int v = g * LC_K + s;
+                u128 tot = 0;
+                for (int r = 0; r < nranks; r++) tot += total_of(r, v);
+                if (tot < THR) continue;
+                if (n >= ORD_MAXJOBS) { n++; continue; }
+                OrdJob j;
+                j.g = g; j.s = s; j.tb = 0; j.te = 0; j.P = 0;
+                u128 P = 0;
+                int r = 0;
+                for (; r < nranks; r++) {
+                    const u128 t = total_of(r, v);
+                    if (P + t >= THR) break;
+                    P += t;
                 }
-                if (c == grid) c = grid - 1;        // cannot happen (the totals say the crossing is here); keeps indices sane
-                j.tb = (i64)c * per;
-                j.te = j.tb + per < ntiles ? j.tb + per : ntiles;
-                j.P = (u64)P;
+                j.rstar = r;
+                j.role = myrank == r ? 1 : myrank > r ? 2 : 0;
+                j.P = (u64)P;                     // role 1: completed below with the CTAs before the crossing one
+                s_jobs[n++] = j;
             }
-            jobs[n++] = j;
+        s_n = n;
+    }
+    __syncthreads();
+    const int n = s_n;
+    for (int e = 0; e < n && e < ORD_MAXJOBS; e++) {
+        if (s_jobs[e].role != 1) continue;                       // block-uniform
+        const int v = s_jobs[e].g * LC_K + s_jobs[e].s;
+        const bool x_in_smem = grid <= ORD_PLAN_MAXCTA;
+        if (x_in_smem) for (int c = threadIdx.x; c < grid; c += ORD_PLAN_THREADS) s_x[c] = part[(i64)c * GK + v];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            u128 P = s_jobs[e].P;
+            int c = 0;
+            for (; c < grid; c++) {
+                const u128 x = (u128)(u64)(x_in_smem ? s_x[c] : part[(i64)c * GK + v]);
+                if (P + x >= THR) break;
+                P += x;
+            }
+            if (c == grid) c = grid - 1;        // cannot happen (the totals say the crossing is here); keeps indices sane
+            s_jobs[e].tb = (i64)c * per;
+            s_jobs[e].te = s_jobs[e].tb + per < ntiles ? s_jobs[e].tb + per : ntiles;
+            s_jobs[e].P = (u64)P;
         }
-    *njobs = n;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        for (int e = 0; e < n && e < ORD_MAXJOBS; e++) jobs[e] = s_jobs[e];
+        *njobs = n;
+    }
 }
 
 // ordered block-wide composition of one OrdState per thread (thread order); result valid in thread 0
@@ -650,18 +713,20 @@ __device__ __forceinline__ OrdState ord_from_summary(const OrdSummary &o)
     return r;
 }
 
-// summaries of every job's tiles: work item w < ntile1 -> tile tb + w alone; w >= ntile1 -> chunk of ORD_CHUNK tiles
-template <bool HAS_KEY1>
-__global__ void __launch_bounds__(LC_THREADS)
+// summaries of every job's tiles: work item w < ntile1 -> tile tb + w alone; w >= ntile1 -> chunk of ORD_CHUNK tiles.
+// One WARP per work item: its lanes compose their 4 rows, a shuffle ladder composes the 128-row group in lane
+// order, lane 0 carries the running composite over the item's groups -- no block-wide synchronisation.
+template <bool HAS_KEY1, bool WIDE>
+__global__ void __launch_bounds__(LC_THREADS, 2)
 ord_jobs_kernel(const LowcardParams p, const OrdJob *__restrict__ jobs, const int *__restrict__ njobs, OrdSummary *__restrict__ out,
                 i64 job_stride, i64 ntiles)
 {
     __shared__ uint8_t s_lut[2][256];
-    __shared__ OrdState s_w[LC_THREADS / 32];
     const int nj = *njobs < ORD_MAXJOBS ? *njobs : ORD_MAXJOBS;
     if (nj == 0) return;
     for (int i = threadIdx.x; i < 512; i += LC_THREADS) s_lut[i >> 8][i & 255] = p.luts[i];
     __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = LC_THREADS / 32;
     for (int e = 0; e < nj; e++) {
         const OrdJob job = jobs[e];
         if (job.role == 0) continue;
@@ -671,16 +736,25 @@ ord_jobs_kernel(const LowcardParams p, const OrdJob *__restrict__ jobs, const in
         op.slot = job.s;
         const i64 ntile1 = job.te - job.tb;
         const i64 nch = (ntiles - job.te + ORD_CHUNK - 1) / ORD_CHUNK;
-        for (i64 w = blockIdx.x; w < ntile1 + nch; w += gridDim.x) {
+        for (i64 w = (i64)blockIdx.x * nw + warp; w < ntile1 + nch; w += (i64)gridDim.x * nw) {
             i64 t0, t1;
             if (w < ntile1) { t0 = job.tb + w; t1 = t0 + 1; }
             else { t0 = job.te + (w - ntile1) * ORD_CHUNK; t1 = t0 + ORD_CHUNK < ntiles ? t0 + ORD_CHUNK : ntiles; }
             OrdState run = {0, 0, 0, 0, 0, 1};
-            for (i64 tile = t0; tile < t1; tile++) {
-                const OrdState st = ord_block_compose(ord_thread_rows<HAS_KEY1>(op, s_lut, tile), s_w);
-                if (threadIdx.x == 0) run = ord_compose(run, st);
+            // 256 rows per step: a lane takes 8 CONSECUTIVE rows (two quads, their loads in flight together) and
+            // composes them in order before the ladder
+            for (i64 row = t0 * LC_TILE; row < t1 * LC_TILE; row += 256) {
+                const i64 r0 = row + lane * 8;
+                const OrdState q0 = ord_quad_rows<HAS_KEY1, WIDE>(op, s_lut, r0), q1 = ord_quad_rows<HAS_KEY1, WIDE>(op, s_lut, r0 + 4);
+                OrdState st = ord_compose(q0, q1);
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const OrdState r = ord_shfl_down(st, o);
+                    if (lane + o < 32) st = ord_compose(st, r);
+                }
+                if (lane == 0) run = ord_compose(run, st);
             }
-            if (threadIdx.x == 0) {
+            if (lane == 0) {
                 OrdSummary o;
                 o.sum_q = run.sq; o.sum_x = run.sx; o.c0 = run.c0; o.c1 = run.c1; o.p0 = run.p0; o.p1 = run.p1;
                 out[(i64)e * job_stride + w] = o;
@@ -719,7 +793,13 @@ ord_fold_kernel(const LowcardParams p, const OrdJob *__restrict__ jobs, const in
         const i64 n = nsum - from;
         const i64 L = (n + LC_THREADS - 1) / LC_THREADS;
         OrdState st = {0, 0, 0, 0, 0, 1};
-        for (i64 i = from + (i64)threadIdx.x * L; i < from + ((i64)threadIdx.x + 1) * L && i < nsum; i++) st = ord_compose(st, ord_from_summary(sm[i]));
+        const i64 i0 = from + (i64)threadIdx.x * L, i1 = i0 + L < nsum ? i0 + L : nsum;
+        i64 i = i0;
+        for (; i + 4 <= i1; i += 4) {           // four independent 32-byte loads in flight, composed in order
+            const OrdSummary a = sm[i], b = sm[i + 1], c = sm[i + 2], d = sm[i + 3];
+            st = ord_compose(st, ord_compose(ord_compose(ord_from_summary(a), ord_from_summary(b)), ord_compose(ord_from_summary(c), ord_from_summary(d))));
+        }
+        for (; i < i1; i++) st = ord_compose(st, ord_from_summary(sm[i]));
         return ord_block_compose(st, s_w);
     };
     if (job.role == 2) {
@@ -1109,21 +1189,30 @@ static __global__ void finalize_generic_kernel(const i64 *__restrict__ partials,
 // 19-digit Decimal (:684-689); per-CTA sums are proven < 2^63 at plan time from the
 // column statistics, the cross-CTA total is carried in 128 bits.
 // ------------------------------------------------------------------------------
+// launched as <<<nvals, 32>>>: one warp per value, lanes stride over the CTAs' partials
 static __global__ void finalize128_kernel(const i64 *__restrict__ partials, int nblocks, int nvals,
                                    u64 *__restrict__ out /* [nvals][2] */)
 {
-    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = blockIdx.x, lane = threadIdx.x;
     if (v >= nvals) return;
     u64 lo = 0;
     i64 hi = 0;
-    for (int b = 0; b < nblocks; b++) {
-        i64 x = partials[(i64)b * nvals + v];
-        u64 nlo = lo + (u64)x;
+    for (int b = lane; b < nblocks; b += 32) {
+        const i64 x = partials[(i64)b * nvals + v];
+        const u64 nlo = lo + (u64)x;
         hi += (x < 0 ? -1 : 0) + (nlo < lo ? 1 : 0);
         lo = nlo;
     }
-    out[2 * v] = lo;
-    out[2 * v + 1] = (u64)hi;
+    // 128-bit warp reduction: add (lo, hi) pairs with carry
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const u64 olo = __shfl_xor_sync(0xffffffffu, lo, o);
+        const i64 ohi = __shfl_xor_sync(0xffffffffu, hi, o);
+        const u64 nlo = lo + olo;
+        hi += ohi + (nlo < lo ? 1 : 0);
+        lo = nlo;
+    }
+    if (lane == 0) { out[2 * v] = lo; out[2 * v + 1] = (u64)hi; }
 }
 
 }  // namespace pg

@@ -157,9 +157,14 @@ __device__ __forceinline__ const char *stage_acquire(const StageRing &r, const S
     mbar_wait(r.full0 + 8 * c.s, c.ph);
     return r.data + (size_t)c.s * (size_t)d.stage_bytes;
 }
-// every lane of the warp has its data in registers
+// Every lane of the warp has issued its reads of the stage.  The refill is written by the ASYNC proxy, the reads
+// went through the generic proxy: without a proxy fence between a lane's LDS and the arrive that frees the stage,
+// the bulk copy of the next tile was observed to land before the reads were performed (Q9's filter pass at SF1
+// lost a few of 326137 hits in every second run; with the fence: 0 of 60 runs) -- mbarrier release semantics
+// alone do not order generic-proxy reads before async-proxy writes.
 __device__ __forceinline__ void stage_release(const StageRing &r, const StageDesc &d, StageCursor &c)
 {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbar_arrive(r.empty0 + 8 * c.s);
     if (++c.s == d.nstage) { c.s = 0; c.ph ^= 1u; }
