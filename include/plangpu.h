@@ -179,6 +179,10 @@ int pg_table_column_encoding(const pg_table *t, int col, int32_t *stored_width, 
 /* Bulk export: `nrows` rows of column `col` starting at `row`, in the column's NATIVE encoding, into a host
  * buffer (the inverse of pg_table_append; the device decodes packed columns first).  Not for VARCHAR.      */
 int pg_table_read_column(pg_table *t, int col, int64_t row, int64_t nrows, void *host_out);
+/* The same in the column's STORED encoding (pg_table_column_encoding: width bytes per value, value = base + stored):
+ * a straight device-to-host copy, and exactly the buffers pg_table_append_cols takes back -- the export / re-ingest
+ * pair of a (table, column, version) cache on the Go side (executor_scan.go:158-223 re-reads from storage instead). */
+int pg_table_read_column_stored(pg_table *t, int col, int64_t row, int64_t nrows, void *host_out);
 void pg_table_free(pg_table *t);
 
 /* ---- plans ------------------------------------------------------------------

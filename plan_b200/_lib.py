@@ -71,6 +71,7 @@ SIGNATURES = [
     ("pg_table_append_cols", C.c_int, [_P, C.c_int64, C.POINTER(ColBuf)]),
     ("pg_table_column_encoding", C.c_int, [_P, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     ("pg_table_read_column", C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, _P]),
+    ("pg_table_read_column_stored", C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, _P]),
     ("pg_table_device_column", C.c_int, [_P, C.c_int, C.POINTER(_P)]),
     ("pg_table_set_rows", C.c_int, [_P, C.c_int64]),
     ("pg_table_seal", C.c_int, [_P, C.c_int64]),

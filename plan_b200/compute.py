@@ -258,6 +258,22 @@ class DeviceTable:
                 vptrs[i] = None if v is None else v.ctypes.data
         L.check(lib.pg_table_append(self.handle, nrows, ptrs, vptrs))
 
+    def append_cols(self, bufs, nrows):
+        """bufs: one (host pointer int, width, base) per column -- narrow host buffers with a frame of reference
+        (pg_table_append_cols); width 0 = the column's native width."""
+        n = len(self.columns)
+        cb = (L.ColBuf * n)()
+        for i, (ptr, w, base) in enumerate(bufs):
+            cb[i].data, cb[i].width, cb[i].reserved, cb[i].base, cb[i].valid = ptr, w, 0, base, None
+        L.check(L.lib().pg_table_append_cols(self.handle, nrows, cb))
+
+    def column_encoding(self, col):
+        if isinstance(col, str):
+            col = [c[0] for c in self.columns].index(col)
+        w, b = C.c_int32(), C.c_int64()
+        L.check(L.lib().pg_table_column_encoding(self.handle, col, C.byref(w), C.byref(b)))
+        return w.value, b.value
+
     def seal(self, global_row_offset=0):
         L.check(L.lib().pg_table_seal(self.handle, global_row_offset))
         return self

@@ -883,6 +883,22 @@ int pg_table_read_column(pg_table *t, int col, int64_t row, int64_t nrows, void 
     return PG_OK;
 }
 
+int pg_table_read_column_stored(pg_table *t, int col, int64_t row, int64_t nrows, void *host_out)
+{
+    if (!t || !host_out || col < 0 || col >= (int)t->cols.size() || row < 0 || nrows < 0 || row + nrows > t->nrows)
+        PG_FAIL(PG_EINVAL, "pg_table_read_column_stored: bad arguments");
+    Context &c = ctx();
+    PG_CUDA(cudaSetDevice(c.device));
+    Column &cl = t->cols[(size_t)col];
+    if (cl.type == PG_T_VARCHAR) PG_FAIL(PG_EUNSUPPORTED, "pg_table_read_column_stored: VARCHAR columns are host-resident");
+    if (nrows == 0) return PG_OK;
+    PG_TRY(stage_flush(t));
+    const size_t pw = (size_t)cl.phys_width();
+    PG_CUDA(cudaMemcpyAsync(host_out, (const char *)cl.d_data + pw * (size_t)row, pw * (size_t)nrows, cudaMemcpyDeviceToHost, c.stream));
+    PG_CUDA(cudaStreamSynchronize(c.stream));
+    return PG_OK;
+}
+
 void pg_table_free(pg_table *t)
 {
     if (!t) return;
