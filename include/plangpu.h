@@ -72,9 +72,9 @@ typedef enum {
                             with PG_EUNSUPPORTED.                                            */
 } pg_type;
 
-typedef struct {
-    const char *data;          /* not NUL-terminated                                */
+typedef struct {               /* field order of common.String {Len int; Data unsafe.Pointer} (string.go:10-13, amd64) */
     int64_t len;
+    const char *data;          /* not NUL-terminated                                */
 } pg_string;
 
 /* A DECIMAL result value with govalues' own fields (value = (-1)^neg*coef*10^-scale),

@@ -191,8 +191,8 @@ def go_float_string(x):
     return r
 
 
-# pg_string {const char *data; int64_t len} (include/plangpu.h; the layout of common.String)
-PG_STRING = np.dtype([("data", np.uint64), ("len", np.int64)])
+# pg_string {int64_t len; const char *data} (include/plangpu.h; the layout of common.String, string.go:10-13)
+PG_STRING = np.dtype([("len", np.int64), ("data", np.uint64)])
 
 
 def native_dtype(pg_type):
