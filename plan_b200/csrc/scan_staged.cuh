@@ -271,6 +271,196 @@ lowcard_staged_kernel(const LowcardSParams p, i64 *__restrict__ partials /* [gri
 }
 
 // ------------------------------------------------------------------------------
+// Ordered-rounding summaries (scanagg.cuh, "sequential-rounding emulation") over narrow columns, fed by the tile ring.
+// One CTA per work item (a 1024-row tile, or ORD_CHUNK of them); tile = 8 warps x 128 rows, a lane simulates its 4
+// consecutive rows for both entering parities, a warp composes its 128-row slice with ballots (see ord_jobs_fast_kernel),
+// slices are composed in row order by one thread per item.  Digits and parities without 64-bit division:
+// x = 10 q + d, d from residues, parity(q) = parity((x - d) / 2), sum q = (sum x - sum d) / 10.
+// Roles: 0 pred, 1 key0, 2 key1, 3 A, 4 B, 5 C.
+// ------------------------------------------------------------------------------
+struct OrdStagedParams {
+    StageDesc st;
+    int roff[6], rpw[6];
+    unsigned p_lo, p_span;
+    int abase, bbase, f1c, f1s, f2c, f2s;
+    int has_key1, n1;
+    unsigned char code0[LC_MAXG], code1[LC_MAXG];
+    i64 nrows;
+};
+
+template <int WP, int WA, int WB, int WC>
+__global__ void __launch_bounds__(ST_THREADS)
+ord_jobs_staged_kernel(const OrdStagedParams p, const OrdJob *__restrict__ jobs, const int *__restrict__ njobs, OrdSummary *__restrict__ out,
+                       i64 job_stride, i64 ntiles)
+{
+    extern __shared__ __align__(128) unsigned char st_smem[];
+    __shared__ int4 s_slice[2][ORD_CHUNK][ST_CONS_WARPS];          // per (item parity, tile, warp): {D0, D1, G0, G1}
+    __shared__ unsigned long long s_acc[2][3];                      // per item parity: sum x, sum digits, base carries
+    const int nj = *njobs < ORD_MAXJOBS ? *njobs : ORD_MAXJOBS;
+    if (nj == 0) return;
+    const StageDesc &d = p.st;
+    const StageRing ring = stage_ring_init(st_smem, d);
+    if (threadIdx.x < 6) s_acc[threadIdx.x / 3][threadIdx.x % 3] = 0;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == ST_CONS_WARPS) {                 // producer: the tiles of this CTA's items, in the consumers' order
+        if (lane != 0) return;
+        int s = 0;
+        unsigned ph = 0, tx = 0;
+        for (int c = 0; c < d.ncol; c++) tx += (unsigned)(d.tile_rows * d.pw[c]);
+        for (int e = 0; e < nj; e++) {
+            const OrdJob job = jobs[e];
+            if (job.role == 0) continue;
+            const i64 ntile1 = job.te - job.tb, nch = (ntiles - job.te + ORD_CHUNK - 1) / ORD_CHUNK;
+            for (i64 w = blockIdx.x; w < ntile1 + nch; w += gridDim.x) {
+                i64 t0, t1;
+                if (w < ntile1) { t0 = job.tb + w; t1 = t0 + 1; }
+                else { t0 = job.te + (w - ntile1) * ORD_CHUNK; t1 = t0 + ORD_CHUNK < ntiles ? t0 + ORD_CHUNK : ntiles; }
+                for (i64 tile = t0; tile < t1; tile++) {
+                    mbar_wait(ring.empty0 + 8 * s, ph ^ 1u);
+                    const unsigned bar = ring.full0 + 8 * s;
+                    mbar_expect_tx(bar, tx);
+                    const unsigned dst = ring.data0 + (unsigned)s * (unsigned)d.stage_bytes;
+                    for (int c = 0; c < d.ncol; c++) {
+                        const unsigned bytes = (unsigned)(d.tile_rows * d.pw[c]);
+                        bulk_g2s(dst + (unsigned)d.off[c], d.src[c] + tile * (i64)bytes, bytes, bar);
+                    }
+                    if (++s == d.nstage) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+        return;
+    }
+    StageCursor cur = {0, 0};
+    const unsigned lt = (1u << lane) - 1u;
+    int par = 0;                                  // item parity: which half of the shared scratch this item uses
+    for (int e = 0; e < nj; e++) {
+        const OrdJob job = jobs[e];
+        if (job.role == 0) continue;
+        const int slot = job.s;
+        const int i0 = p.has_key1 ? job.g / p.n1 : job.g, i1 = p.has_key1 ? job.g % p.n1 : 0;
+        const unsigned target = (unsigned)p.code0[i0] | (p.has_key1 ? (unsigned)p.code1[i1] << 8 : 0u);
+        const i64 ntile1 = job.te - job.tb, nch = (ntiles - job.te + ORD_CHUNK - 1) / ORD_CHUNK;
+        for (i64 w = blockIdx.x; w < ntile1 + nch; w += gridDim.x) {
+            i64 t0, t1;
+            if (w < ntile1) { t0 = job.tb + w; t1 = t0 + 1; }
+            else { t0 = job.te + (w - ntile1) * ORD_CHUNK; t1 = t0 + ORD_CHUNK < ntiles ? t0 + ORD_CHUNK : ntiles; }
+            u64 sx = 0;
+            unsigned sd = 0, cbase = 0;
+            for (i64 tile = t0; tile < t1; tile++) {
+                const char *stg = stage_acquire(ring, d, cur);
+                Quad<WP> dv;
+                Quad<WA> av;
+                Quad<WB> bv;
+                Quad<WC> cv;
+                const int qrow = warp * 128 + lane * 4;
+                dv.load(stg + p.roff[0], qrow, p.rpw[0]);
+                const unsigned k0 = *(const unsigned *)(stg + p.roff[1] + qrow);
+                const unsigned k1 = p.has_key1 ? *(const unsigned *)(stg + p.roff[2] + qrow) : 0u;
+                av.load(stg + p.roff[3], qrow, p.rpw[3]);
+                bv.load(stg + p.roff[4], qrow, p.rpw[4]);
+                cv.load(stg + p.roff[5], qrow, p.rpw[5]);
+                stage_release(ring, d, cur);
+                const i64 rem = p.nrows - (tile * 1024 + qrow);
+                unsigned c0 = 0, c1 = 0, q0 = 0, q1 = 1;
+                auto row = [&](auto jc) {
+                    constexpr int J = decltype(jc)::v;
+                    const unsigned kk = __byte_perm(k0, k1, (unsigned)(J | ((4 + J) << 4) | 0x4400)) & 0xffffu;
+                    const bool ok = J < rem && (dv.template get<J>() - p.p_lo) <= p.p_span && kk == target;
+                    if (ok) {
+                        const unsigned bs = bv.template get<J>();
+                        const unsigned al = av.template get<J>() + (unsigned)p.abase;
+                        const unsigned t2 = al * (unsigned)(p.f1c + p.f1s * (int)bs);
+                        unsigned xlo, dg;
+                        if (slot == 4) {
+                            const unsigned f2 = (unsigned)(p.f2c + p.f2s * (int)cv.template get<J>());
+                            sx += (u64)t2 * f2;
+                            xlo = t2 * f2;
+                            dg = ((t2 % 10u) * (f2 % 10u)) % 10u;
+                        } else {
+                            xlo = slot == 3 ? t2 : slot == 2 ? al : bs + (unsigned)p.bbase;
+                            sx += xlo;
+                            dg = xlo % 10u;
+                        }
+                        const unsigned t = ((xlo - dg) >> 1) & 1u;
+                        sd += dg;
+                        if (dg == 5u) {
+                            c0 += q0 ^ t;
+                            c1 += q1 ^ t;
+                            q0 = 0;
+                            q1 = 0;
+                        } else {
+                            const unsigned cy = dg > 5u ? 1u : 0u;
+                            c0 += cy;
+                            c1 += cy;
+                            q0 ^= t ^ cy;
+                            q1 ^= t ^ cy;
+                        }
+                    }
+                };
+                PG_FOR4(row);
+                // this warp's 128-row slice: parity entering each lane for the slice entered even (E0) / odd (E1)
+                const bool reset = q0 == q1;
+                const unsigned R = __ballot_sync(0xffffffffu, reset), F = __ballot_sync(0xffffffffu, q0 != 0u);
+                unsigned E0, E1;
+                const unsigned belowR = R & lt;
+                if (belowR) {
+                    const int m = 31 - __clz(belowR);
+                    E0 = E1 = ((F >> m) & 1u) ^ (__popc(F & ~R & lt & ~((2u << m) - 1u)) & 1u);
+                } else {
+                    E0 = __popc(F & lt) & 1u;
+                    E1 = E0 ^ 1u;
+                }
+                // carries = c0 (order independent, kept per lane) + the part that depends on the entering parity
+                cbase += c0;
+                const bool up = c1 > c0, dn = c1 < c0;                 // |c1 - c0| <= 1
+                const int D0 = __popc(__ballot_sync(0xffffffffu, E0 && up)) - __popc(__ballot_sync(0xffffffffu, E0 && dn));
+                const int D1 = __popc(__ballot_sync(0xffffffffu, E1 && up)) - __popc(__ballot_sync(0xffffffffu, E1 && dn));
+                unsigned G0, G1;
+                if (R) {
+                    const int m = 31 - __clz(R);
+                    G0 = G1 = ((F >> m) & 1u) ^ (__popc(F & ~R & ~((2u << m) - 1u)) & 1u);
+                } else {
+                    G0 = __popc(F) & 1u;
+                    G1 = G0 ^ 1u;
+                }
+                if (lane == 0) s_slice[par][tile - t0][warp] = make_int4(D0, D1, (int)G0, (int)G1);
+            }
+            const i64 tx = warp_sum((i64)sx), td = warp_sum((i64)sd), tc = warp_sum((i64)cbase);
+            if (lane == 0) {
+                atomicAdd(&s_acc[par][0], (unsigned long long)tx);
+                atomicAdd(&s_acc[par][1], (unsigned long long)td);
+                atomicAdd(&s_acc[par][2], (unsigned long long)tc);
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(ST_CONS_THREADS) : "memory");     // the consumer warps only
+            if (threadIdx.x == 0) {
+                i64 C0 = 0, C1 = 0;
+                unsigned P0 = 0, P1 = 1;
+                for (int t = 0; t < (int)(t1 - t0); t++)
+                    for (int wq = 0; wq < ST_CONS_WARPS; wq++) {
+                        const int4 sl = s_slice[par][t][wq];
+                        C0 += P0 ? sl.y : sl.x;
+                        C1 += P1 ? sl.y : sl.x;
+                        P0 = P0 ? (unsigned)sl.w : (unsigned)sl.z;
+                        P1 = P1 ? (unsigned)sl.w : (unsigned)sl.z;
+                    }
+                OrdSummary o;
+                const i64 ax = (i64)s_acc[par][0], ad = (i64)s_acc[par][1], ac = (i64)s_acc[par][2];
+                o.sum_q = (ax - ad) / 10;
+                o.sum_x = ax;
+                o.c0 = (unsigned)(ac + C0);
+                o.c1 = (unsigned)(ac + C1);
+                o.p0 = P0;
+                o.p1 = P1;
+                out[(i64)e * job_stride + w] = o;
+                s_acc[par][0] = s_acc[par][1] = s_acc[par][2] = 0;      // this half is next used two items later: a barrier lies between
+            }
+            par ^= 1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------
 // First occurrence of every group among the rows that pass the predicate (the reference emits groups in
 // first-insertion order, aggregate_hash.go:424-438).  Kept out of the scan's inner loop: CTAs walk 1024-row
 // chunks from the start of the table and stop as soon as every group the totals say is present has been seen

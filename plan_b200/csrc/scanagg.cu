@@ -432,10 +432,43 @@ struct LowcardPipeline : Pipeline {
                                               per, ntiles, jobs, njobs);
             const int og = ctx().prop.multiProcessorCount * 4;
             const bool ow = prm.pred.pw > 4 || prm.A.pw > 4 || prm.B.pw > 4 || prm.C.pw > 4;       // 8-byte columns: 32-byte raw vectors
+            if (staged && !env_int("PG_NO_ORD_FAST", 0)) {          // the staged kernel's preconditions are the staged summaries' too
+                OrdStagedParams fp{};
+                const NCol *rc[6] = {&prm.pred, &prm.key0, has_key1 ? &prm.key1 : nullptr, &prm.A, &prm.B, &prm.C};
+                for (int r = 0; r < 6; r++) {
+                    fp.rpw[r] = 0; fp.roff[r] = 0;
+                    if (!rc[r] || !rc[r]->p) continue;
+                    int ci = -1;
+                    for (int i = 0; i < fp.st.ncol; i++) if (fp.st.src[i] == (const char *)rc[r]->p) ci = i;
+                    if (ci < 0) { ci = fp.st.ncol++; fp.st.src[ci] = (const char *)rc[r]->p; fp.st.pw[ci] = rc[r]->pw; }
+                    fp.rpw[r] = -1 - ci;
+                }
+                stage_layout(&fp.st, LC_TILE);
+                for (int r = 0; r < 6; r++) if (fp.rpw[r] < 0) { const int ci = -1 - fp.rpw[r]; fp.rpw[r] = fp.st.pw[ci]; fp.roff[r] = fp.st.off[ci]; }
+                // roles the chain does not use were aliased to A by the planner: they must read as zero here
+                if (sprm.rpw[0] == 0) fp.rpw[0] = 0;
+                if (sprm.rpw[5] == 0) fp.rpw[4] = 0;
+                if (sprm.rpw[6] == 0) fp.rpw[5] = 0;
+                fp.st.nstage = 6;
+                fp.p_lo = sprm.p_lo; fp.p_span = sprm.p_span;
+                fp.abase = sprm.abase; fp.bbase = (int)prm.B.base;
+                fp.f1c = sprm.f1c; fp.f1s = sprm.f1s; fp.f2c = sprm.f2c; fp.f2s = sprm.f2s;
+                fp.has_key1 = has_key1 ? 1 : 0;
+                fp.n1 = prm.n1;
+                for (size_t i = 0; i < vals[0].size() && i < (size_t)LC_MAXG; i++) fp.code0[i] = vals[0][i];
+                for (size_t i = 0; i < vals[1].size() && i < (size_t)LC_MAXG; i++) fp.code1[i] = vals[1][i];
+                fp.nrows = prm.nrows;
+                typedef void (*OK)(const OrdStagedParams, const OrdJob *, const int *, OrdSummary *, i64, i64);
+                OK k = (fp.rpw[0] == 2 && fp.rpw[3] == 4 && fp.rpw[4] == 1 && fp.rpw[5] == 1) ? ord_jobs_staged_kernel<2, 4, 1, 1> : ord_jobs_staged_kernel<-1, -1, -1, -1>;
+                const size_t osm = (size_t)ST_HDR + (size_t)fp.st.nstage * fp.st.stage_bytes;
+                PG_CUDA(cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)osm));
+                k<<<sms_times((const void *)k, ST_THREADS, osm), ST_THREADS, osm, st>>>(fp, jobs, njobs, d_ord.as<OrdSummary>(), ord_stride, ntiles);
+            } else {
 #define PG_ORDJ(K, W) ord_jobs_kernel<K, W><<<og, LC_THREADS, 0, st>>>(prm, jobs, njobs, d_ord.as<OrdSummary>(), ord_stride, ntiles)
             if (has_key1) { if (ow) PG_ORDJ(true, true); else PG_ORDJ(true, false); }
             else { if (ow) PG_ORDJ(false, true); else PG_ORDJ(false, false); }
 #undef PG_ORDJ
+            }
             if (has_key1) ord_fold_kernel<true><<<ORD_MAXJOBS, LC_THREADS, 0, st>>>(prm, jobs, njobs, d_ord.as<OrdSummary>(), ord_stride, ntiles, mine);
             else ord_fold_kernel<false><<<ORD_MAXJOBS, LC_THREADS, 0, st>>>(prm, jobs, njobs, d_ord.as<OrdSummary>(), ord_stride, ntiles, mine);
             PG_CUDA(cudaGetLastError());

@@ -763,6 +763,151 @@ ord_jobs_kernel(const LowcardParams p, const OrdJob *__restrict__ jobs, const in
     }
 }
 
+// The same summaries for the common narrow case (every column stored in <= 4 bytes, non-negative values,
+// A*(c1+s1*B) < 2^32 -- what the staged scan kernel requires too): 32-bit arithmetic up to the 64-bit addend, and NO
+// shuffle ladder.  A lane simulates its 8 consecutive rows for both entering parities; the 32 lane results are
+// composed in lane order with two ballots and bit arithmetic: a lane that saw a digit-5 row ends EVEN-or-odd
+// whatever it entered with (a "reset"), any other lane just flips or keeps the parity, so the parity entering
+// lane l is the exit parity of the last reset lane below l XOR the flips in between.  The order-independent parts
+// (sum of floor(x/10), of x, of the carries) stay in lane-local accumulators until the work item ends.
+struct OrdFastParams {
+    NCol pred, key0, key1, A, B, C;
+    unsigned p_lo, p_span;
+    int abase, bbase, f1c, f1s, f2c, f2s;      // f1 = f1c + f1s * stored B, f2 = f2c + f2s * stored C
+    int has_key1, n1;
+    unsigned char code0[LC_MAXG], code1[LC_MAXG];   // dense id -> byte code, per key
+    i64 nrows;
+};
+
+struct OrdFastRaw { Raw4<false> d, a, b, c; unsigned k0, k1; };
+__device__ __forceinline__ void ord_fast_load(const OrdFastParams &p, i64 row, OrdFastRaw &r)
+{
+    ld_raw4(p.pred, row, r.d);
+    r.k0 = ld_stream4((const uint8_t *)p.key0.p + row);
+    r.k1 = p.has_key1 ? ld_stream4((const uint8_t *)p.key1.p + row) : 0u;
+    ld_raw4(p.A, row, r.a);
+    ld_raw4(p.B, row, r.b);
+    ld_raw4(p.C, row, r.c);
+}
+__device__ __forceinline__ void ord_fast_quad(const OrdFastParams &p, int slot, unsigned target, i64 row, const OrdFastRaw &r, u64 &sq, u64 &sx,
+                                              unsigned &c0, unsigned &c1, unsigned &p0, unsigned &p1)
+{
+    const i64 rem = p.nrows - row;
+    int dv[4], av[4], bv[4], cv[4];
+    unpack4(p.pred, r.d, dv);
+    unpack4(p.A, r.a, av);
+    unpack4(p.B, r.b, bv);
+    unpack4(p.C, r.c, cv);
+    const unsigned k0 = r.k0, k1 = r.k1;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const unsigned kk = ((k0 >> (8 * j)) & 255u) | (((k1 >> (8 * j)) & 255u) << 8);
+        const bool ok = j < rem && ((unsigned)dv[j] - p.p_lo) <= p.p_span && kk == target;
+        if (ok) {
+            const unsigned al = (unsigned)(av[j] + p.abase);
+            const unsigned t2 = al * (unsigned)(p.f1c + p.f1s * bv[j]);
+            // x = 10 q + dg.  No 64-bit division: the digit comes from residues (x = t2 * f2: dg = (t2 mod 10)(f2 mod 10) mod 10),
+            // the parity of q from the low word ((x - dg) / 2 = 5 q has q's parity), and sum(q) = (sum(x) - sum(dg)) / 10 once per item.
+            u64 x;
+            unsigned xlo, dg;
+            if (slot == 4) {
+                const unsigned f2 = (unsigned)(p.f2c + p.f2s * cv[j]);
+                x = (u64)t2 * f2;
+                xlo = t2 * f2;
+                dg = ((t2 % 10u) * (f2 % 10u)) % 10u;
+            } else {
+                xlo = slot == 3 ? t2 : slot == 2 ? al : (unsigned)(bv[j] + p.bbase);
+                x = xlo;
+                dg = xlo % 10u;
+            }
+            const unsigned t = ((xlo - dg) >> 1) & 1u;
+            sq += dg;                 // the caller turns (sum x, sum digits) into sum q
+            sx += x;
+            if (dg == 5u) {
+                c0 += p0 ^ t;
+                c1 += p1 ^ t;
+                p0 = 0;
+                p1 = 0;
+            } else {
+                const unsigned cy = dg > 5u ? 1u : 0u;
+                c0 += cy;
+                c1 += cy;
+                p0 ^= t ^ cy;
+                p1 ^= t ^ cy;
+            }
+        }
+    }
+}
+
+static __global__ void __launch_bounds__(LC_THREADS, 3)
+ord_jobs_fast_kernel(const OrdFastParams p, const OrdJob *__restrict__ jobs, const int *__restrict__ njobs, OrdSummary *__restrict__ out,
+                     i64 job_stride, i64 ntiles)
+{
+    const int nj = *njobs < ORD_MAXJOBS ? *njobs : ORD_MAXJOBS;
+    if (nj == 0) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = LC_THREADS / 32;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int e = 0; e < nj; e++) {
+        const OrdJob job = jobs[e];
+        if (job.role == 0) continue;
+        const int i0 = p.has_key1 ? job.g / p.n1 : job.g, i1 = p.has_key1 ? job.g % p.n1 : 0;
+        const unsigned target = (unsigned)p.code0[i0] | (p.has_key1 ? (unsigned)p.code1[i1] << 8 : 0u);
+        const i64 ntile1 = job.te - job.tb;
+        const i64 nch = (ntiles - job.te + ORD_CHUNK - 1) / ORD_CHUNK;
+        for (i64 w = (i64)blockIdx.x * nw + warp; w < ntile1 + nch; w += (i64)gridDim.x * nw) {
+            i64 t0, t1;
+            if (w < ntile1) { t0 = job.tb + w; t1 = t0 + 1; }
+            else { t0 = job.te + (w - ntile1) * ORD_CHUNK; t1 = t0 + ORD_CHUNK < ntiles ? t0 + ORD_CHUNK : ntiles; }
+            u64 sq = 0, sx = 0;
+            unsigned lc0 = 0, lc1 = 0;          // this lane's carries given the ITEM was entered even / odd
+            unsigned P0 = 0, P1 = 1;            // running exit parity of the item for both entries (warp-uniform)
+            for (i64 row = t0 * LC_TILE; row < t1 * LC_TILE; row += 256) {
+                unsigned c0 = 0, c1 = 0, q0 = 0, q1 = 1;
+                const i64 r0 = row + lane * 8;
+                OrdFastRaw ra, rb;
+                ord_fast_load(p, r0, ra);
+                ord_fast_load(p, r0 + 4, rb);
+                ord_fast_quad(p, job.s, target, r0, ra, sq, sx, c0, c1, q0, q1);
+                ord_fast_quad(p, job.s, target, r0 + 4, rb, sq, sx, c0, c1, q0, q1);
+                const bool reset = q0 == q1;
+                const unsigned R = __ballot_sync(0xffffffffu, reset), F = __ballot_sync(0xffffffffu, q0 != 0u);
+                // parity entering this lane, for the step entered even (E0) / odd (E1)
+                unsigned E0, E1;
+                const unsigned belowR = R & lt;
+                if (belowR) {
+                    const int m = 31 - __clz(belowR);
+                    const unsigned between = F & ~R & lt & ~((2u << m) - 1u);
+                    E0 = E1 = ((F >> m) & 1u) ^ (__popc(between) & 1u);
+                } else {
+                    E0 = __popc(F & lt) & 1u;
+                    E1 = E0 ^ 1u;
+                }
+                const unsigned cE0 = E0 ? c1 : c0, cE1 = E1 ? c1 : c0;
+                lc0 += P0 ? cE1 : cE0;
+                lc1 += P1 ? cE1 : cE0;
+                // exit parity of the step
+                unsigned G0, G1;
+                if (R) {
+                    const int m = 31 - __clz(R);
+                    G0 = G1 = ((F >> m) & 1u) ^ (__popc(F & ~R & ~((2u << m) - 1u)) & 1u);
+                } else {
+                    G0 = __popc(F) & 1u;
+                    G1 = G0 ^ 1u;
+                }
+                P0 = P0 ? G1 : G0;
+                P1 = P1 ? G1 : G0;
+            }
+            const i64 td = warp_sum((i64)sq), tx = warp_sum((i64)sx);
+            const i64 tc0 = warp_sum((i64)lc0), tc1 = warp_sum((i64)lc1);
+            if (lane == 0) {
+                OrdSummary o;
+                o.sum_q = (tx - td) / 10; o.sum_x = tx; o.c0 = (unsigned)tc0; o.c1 = (unsigned)tc1; o.p0 = P0; o.p1 = P1;
+                out[(i64)e * job_stride + w] = o;
+            }
+        }
+    }
+}
+
 // one CTA per job: this rank's 64-byte contribution
 template <bool HAS_KEY1>
 __global__ void __launch_bounds__(LC_THREADS)
