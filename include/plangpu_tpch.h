@@ -45,6 +45,11 @@ int pg_tpch_customer(double sf, int64_t cust_lo, int64_t cust_hi, pg_table **cus
 int pg_tpch_part(double sf, pg_table **part);
 int pg_tpch_supplier(double sf, pg_table **supplier);
 int pg_tpch_partsupp(double sf, pg_table **partsupp);
+/* rows [row_lo, row_hi) of partsupp (4 rows per part, in ps_partkey order; row_hi < 0 = to the end): a row-range
+ * shard of the build side of Q9's lineitem x partsupp join, which is then keyed differently from the fact table's
+ * shards -- the case the all-to-all row exchange exists for (BASELINE config 5) */
+int pg_tpch_partsupp_range(double sf, int64_t row_lo, int64_t row_hi, pg_table **partsupp);
+int64_t pg_tpch_num_parts(double sf);
 int pg_tpch_nation(pg_table **nation);
 
 #ifdef __cplusplus

@@ -102,6 +102,8 @@ TPCH_SIGNATURES = [
     ("pg_tpch_part", C.c_int, [C.c_double, C.POINTER(_P)]),
     ("pg_tpch_supplier", C.c_int, [C.c_double, C.POINTER(_P)]),
     ("pg_tpch_partsupp", C.c_int, [C.c_double, C.POINTER(_P)]),
+    ("pg_tpch_partsupp_range", C.c_int, [C.c_double, C.c_int64, C.c_int64, C.POINTER(_P)]),
+    ("pg_tpch_num_parts", C.c_int64, [C.c_double]),
     ("pg_tpch_nation", C.c_int, [C.POINTER(_P)]),
 ]
 

@@ -17,6 +17,7 @@
 
 #include "hostdec.hpp"
 #include "join.cuh"
+#include "exchange.cuh"
 #include "pipeline.hpp"
 
 namespace pg {
@@ -121,6 +122,17 @@ struct JoinAggPipeline : Pipeline {
     std::vector<HPart> sparts;
     std::vector<HTerm> sterms;
     int star_ngroups = 0, star_scale = 0;
+    i128 star_worst = 0;                         // largest |value| one joined row can add to a group sum
+    // Exchange lookup (exchange.cuh): the ONE join of the star whose build side is sharded on another key than the
+    // fact table.  Both sides are hash-partitioned by the join key and shipped to the owner rank, which joins and sums.
+    int xl = -1;                                 // index into `lookups`, -1: every join is local
+    std::vector<int> xcols;                      // build-table columns carried to the owner (read by deferred factors)
+    int x_term_mask[STAR_MAXTERM] = {0, 0};      // bit f: factor f of the term reads the exchanged build side
+    int x_fac_col[STAR_MAXTERM][3] = {{0, 0, 0}, {0, 0, 0}};   // ... and which carried column it reads
+    DevBuf d_xb_rec, d_xb_dest, d_xb_send, d_xb_recv, d_xp_rec, d_xp_dest, d_xp_send, d_xp_recv;
+    i64 xb_recv_rows = 0;
+    EventPair ev_xb, ev_xp;
+    i64 x_sent_rows = 0, x_sent_bytes = 0;
     DevBuf d_star, d_star_all;
     PinBuf h_star;
     Stage &top_stage_ref() { return *stages[(size_t)(main_stage >= 0 ? main_stage : (int)stages.size() - 1)]; }
@@ -778,6 +790,185 @@ struct JoinAggPipeline : Pipeline {
         return PG_OK;
     }
 
+    // ---- all-to-all hash-partitioned exchange of JOIN ROWS (exchange.cuh; SURVEY.md 8e, BASELINE config 5) ----
+    // `d_rec` holds *d_n records of RW words with a destination byte each (X_DROP = not sent) and d_sx_cnt their
+    // per-destination counts, all made by one kernel.  Counts travel with an all-gather, records are moved into
+    // destination order and exchanged with grouped ncclSend/ncclRecv over NVLink.  Collective: every rank calls it.
+    int x_counts_reset()
+    {
+        const int W = ctx().world;
+        if (W > X_MAXWORLD) PG_FAIL(PG_EUNSUPPORTED, "row exchange: more than %d ranks", X_MAXWORLD);
+        if (!d_sx_cnt.p) {
+            PG_TRY(d_sx_cnt.alloc(8 * (size_t)W));
+            PG_TRY(d_sx_cursor.alloc(8 * (size_t)W));
+            PG_TRY(d_sx_allcnt.alloc(8 * (size_t)W * (size_t)W));
+        }
+        PG_CUDA(cudaMemsetAsync(d_sx_cnt.p, 0, 8 * (size_t)W, ctx().stream));
+        return PG_OK;
+    }
+    int exchange_rows(const i64 *d_rec, const unsigned char *d_dest, const unsigned long long *d_n, i64 n_host, int RW, DevBuf &send, DevBuf &recv,
+                      EventPair &ev, i64 *recv_rows)
+    {
+        Context &c = ctx();
+        cudaStream_t st = c.stream;
+        const int W = c.world;
+        PG_TRY(comm_allgather(d_sx_cnt.p, d_sx_allcnt.p, 8 * (size_t)W, st));
+        std::vector<i64> all((size_t)W * (size_t)W);
+        PG_CUDA(cudaMemcpyAsync(all.data(), d_sx_allcnt.p, 8 * (size_t)W * (size_t)W, cudaMemcpyDeviceToHost, st));
+        PG_CUDA(cudaStreamSynchronize(st));
+        std::vector<i64> send_cnt((size_t)W), send_off((size_t)W), recv_cnt((size_t)W), recv_off((size_t)W);
+        i64 so = 0, ro = 0;
+        for (int r = 0; r < W; r++) {
+            send_cnt[(size_t)r] = all[(size_t)c.rank * W + r]; send_off[(size_t)r] = so; so += send_cnt[(size_t)r];
+            recv_cnt[(size_t)r] = all[(size_t)r * W + c.rank]; recv_off[(size_t)r] = ro; ro += recv_cnt[(size_t)r];
+        }
+        if (send.bytes < (size_t)std::max<i64>(so, 1) * RW * 8) PG_TRY(send.alloc((size_t)std::max<i64>(so, 1) * RW * 8));
+        if (recv.bytes < (size_t)std::max<i64>(ro, 1) * RW * 8) PG_TRY(recv.alloc((size_t)std::max<i64>(ro, 1) * RW * 8));
+        PG_CUDA(cudaMemcpyAsync(d_sx_cursor.p, send_off.data(), 8 * (size_t)W, cudaMemcpyHostToDevice, st));
+        if (n_host > 0) {
+            x_scatter_kernel<<<grid_rows(n_host), 256, 0, st>>>(d_rec, d_dest, d_n, RW, d_sx_cursor.as<unsigned long long>(), send.as<i64>());
+            PG_CUDA(cudaGetLastError());
+        }
+        PG_TRY(ev.init());
+        PG_CUDA(cudaEventRecord(ev.a, st));
+        PG_TRY(comm_alltoallv(send.p, send_cnt.data(), send_off.data(), recv.p, recv_cnt.data(), recv_off.data(), (size_t)RW * 8, st));
+        PG_CUDA(cudaEventRecord(ev.b, st));
+        x_sent_rows += so - send_cnt[(size_t)c.rank];
+        x_sent_bytes += (so - send_cnt[(size_t)c.rank]) * RW * 8;
+        *recv_rows = ro;
+        return PG_OK;
+    }
+
+    // Build side of the exchange lookup: the local shard's rows that pass its filters travel to the owners of their
+    // keys; what arrives is inserted into a bucketized table whose payload indexes the receive buffer.
+    int run_exchange_build(Stage &s, pg_result *res)
+    {
+        cudaStream_t st = ctx().stream;
+        const pg_table *t = tab(s.src_slot);
+        PipeParams pp{};
+        pp.nrows = t->nrows;
+        PG_TRY(fill_preds(pp, s.ranges, s.src_slot));
+        pp.has_probe = s.has_probe ? 1 : 0;
+        if (s.has_probe) {
+            pp.probe_key = typed(t, s.probe_key_col);
+            pp.probe = stages[(size_t)s.probe_stage]->jt;
+            pp.probe_bitmap_only = 1;
+            pp.probe_mode = s.probe_mode;
+        } else {
+            pp.probe_key = typed(t, s.ins_key_col);
+        }
+        pp.ins_key = typed(t, s.ins_key_col);
+        pp.counters = d_counters.as<unsigned long long>();
+        if (!two_phase_ok(pp, t, true)) PG_FAIL(PG_EUNSUPPORTED, "row exchange: the build-side scan does not fit the filter pass");
+        PG_CUDA(cudaMemsetAsync(d_counters.p, 0, 32, st));
+        PG_TRY(launch_filter(pp, 0, t->nrows));
+        unsigned long long nh = 0;
+        PG_CUDA(cudaMemcpyAsync(&nh, d_hit_count.p, 8, cudaMemcpyDeviceToHost, st));
+        PG_CUDA(cudaStreamSynchronize(st));
+        const int RW = 1 + (int)xcols.size();
+        if (d_xb_rec.bytes < (size_t)std::max<u64>(nh, 1) * RW * 8) PG_TRY(d_xb_rec.alloc((size_t)std::max<u64>(nh, 1) * RW * 8));
+        if (d_xb_dest.bytes < (size_t)std::max<u64>(nh, 1)) PG_TRY(d_xb_dest.alloc((size_t)std::max<u64>(nh, 1)));
+        PG_TRY(x_counts_reset());
+        XBuildParams bp{};
+        bp.hits = d_hits.as<unsigned>();
+        bp.hit_count = d_hit_count.as<unsigned long long>();
+        bp.nkey = s.ins_key_col2 >= 0 ? 2 : 1;
+        bp.key[0] = typed(t, s.ins_key_col);
+        if (s.ins_key_col2 >= 0) bp.key[1] = typed(t, s.ins_key_col2);
+        bp.nx = (int)xcols.size();
+        for (size_t i = 0; i < xcols.size(); i++) bp.x[i] = typed(t, xcols[i]);
+        bp.world = ctx().world;
+        bp.rec = d_xb_rec.as<i64>();
+        bp.dest = d_xb_dest.as<unsigned char>();
+        bp.cnt = d_sx_cnt.as<unsigned long long>();
+        if (nh > 0) {
+            x_build_rows_kernel<<<grid_rows((i64)nh), 256, 0, st>>>(bp);
+            PG_CUDA(cudaGetLastError());
+        }
+        PG_TRY(exchange_rows(d_xb_rec.as<i64>(), d_xb_dest.as<unsigned char>(), d_hit_count.as<unsigned long long>(), (i64)nh, RW, d_xb_send, d_xb_recv,
+                             ev_xb, &xb_recv_rows));
+        // owner side: hashed buckets, no bitmap (the key domain is the whole table's, not this shard's)
+        u64 nb = next_pow2((u64)std::max<i64>((xb_recv_rows * 2 + HT_BUCKET - 1) / HT_BUCKET, 16));
+        if (s.d_slots.bytes < nb * HT_BUCKET * sizeof(longlong2)) PG_TRY(s.d_slots.alloc(nb * HT_BUCKET * sizeof(longlong2)));
+        PG_CUDA(cudaMemsetAsync(s.d_slots.p, 0x80, nb * HT_BUCKET * sizeof(longlong2), st));
+        s.jt = JoinTable{};
+        s.jt.slots = s.d_slots.as<longlong2>();
+        s.jt.bucket_mask = nb - 1;
+        s.jt.domain = 1;
+        if (xb_recv_rows > 0) {
+            x_insert_kernel<<<grid_rows(xb_recv_rows), 256, 0, st>>>(s.jt, d_xb_recv.as<i64>(), xb_recv_rows, RW);
+            PG_CUDA(cudaGetLastError());
+        }
+        s.built_rows = xb_recv_rows;
+        s.dup_keys = 1;
+        s.no_table = false;
+        res->stats.kernel_launches += 4;
+        return PG_OK;
+    }
+
+    // Probe side: every other join of the star, the group id and the local factors are evaluated where the fact row
+    // lives (star_pre_kernel); the records travel to the key's owner, which finishes the join (star_post_kernel).
+    int run_star_exchange(const StarParams &sp, pg_result *res, Trace &tr)
+    {
+        Context &c = ctx();
+        cudaStream_t st = c.stream;
+        unsigned long long nh = 0;
+        PG_CUDA(cudaMemcpyAsync(&nh, d_hit_count.p, 8, cudaMemcpyDeviceToHost, st));
+        PG_CUDA(cudaStreamSynchronize(st));
+        const int RW = 2 + sp.nterm;
+        if (d_xp_rec.bytes < (size_t)std::max<u64>(nh, 1) * RW * 8) PG_TRY(d_xp_rec.alloc((size_t)std::max<u64>(nh, 1) * RW * 8));
+        if (d_xp_dest.bytes < (size_t)std::max<u64>(nh, 1)) PG_TRY(d_xp_dest.alloc((size_t)std::max<u64>(nh, 1)));
+        PG_TRY(x_counts_reset());
+        XPreParams xp{};
+        xp.xl = xl;
+        xp.world = c.world;
+        for (int t = 0; t < STAR_MAXTERM; t++) xp.term_x[t] = x_term_mask[t];
+        xp.rec = d_xp_rec.as<i64>();
+        xp.dest = d_xp_dest.as<unsigned char>();
+        xp.cnt = d_sx_cnt.as<unsigned long long>();
+        if (nh > 0) {
+            star_pre_kernel<<<c.prop.multiProcessorCount * 8, 256, 0, st>>>(sp, xp);
+            PG_CUDA(cudaGetLastError());
+        }
+        tr.mark("star pre-join (local lookups)");
+        i64 np = 0;
+        PG_TRY(exchange_rows(d_xp_rec.as<i64>(), d_xp_dest.as<unsigned char>(), d_hit_count.as<unsigned long long>(), (i64)nh, RW, d_xp_send, d_xp_recv,
+                             ev_xp, &np));
+        tr.mark("star row exchange");
+        const Stage &X = *stages[(size_t)lookups[(size_t)xl].stage];
+        XPostParams pp{};
+        pp.prow = d_xp_recv.as<i64>();
+        pp.np = np;
+        pp.brow = d_xb_recv.as<i64>();
+        pp.nx = (int)xcols.size();
+        pp.jt = X.jt;
+        pp.nterm = sp.nterm;
+        for (int t = 0; t < sp.nterm; t++) {
+            int k = 0;
+            for (int f = 0; f < sp.term[t].nfac; f++) {
+                if (!((x_term_mask[t] >> f) & 1)) continue;
+                pp.xcol[t][k] = x_fac_col[t][f];
+                pp.xfc[t][k] = sp.term[t].fc[f];
+                pp.xfs[t][k] = sp.term[t].fs[f];
+                k++;
+            }
+            pp.nxf[t] = k;
+        }
+        pp.ngroups = sp.ngroups;
+        pp.gsum = sp.gsum;
+        pp.gsum_hi = sp.gsum_hi;
+        pp.gcnt = sp.gcnt;
+        pp.counters = sp.counters;
+        if ((size_t)star_ngroups * 16 > 48 * 1024)
+            PG_CUDA(cudaFuncSetAttribute(star_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, star_ngroups * 16));
+        if (np > 0) {
+            star_post_kernel<<<c.prop.multiProcessorCount * 8, 256, (size_t)star_ngroups * 16, st>>>(pp);
+            PG_CUDA(cudaGetLastError());
+        }
+        res->stats.kernel_launches += 3;
+        return PG_OK;
+    }
+
     // fact-table pipeline of a star join: existence filter pass, then hits_star_kernel (lookups + dense group sums)
     int run_star(pg_result *res, Trace &tr)
     {
@@ -831,8 +1022,12 @@ struct JoinAggPipeline : Pipeline {
         sp.counters = d_counters.as<unsigned long long>();
         if ((size_t)star_ngroups * 16 > 48 * 1024)      // above the default dynamic shared memory limit (up to 64 KB at STAR_MAXGROUPS)
             PG_CUDA(cudaFuncSetAttribute(hits_star_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, star_ngroups * 16));
-        hits_star_kernel<<<c.prop.multiProcessorCount * 8, 256, (size_t)star_ngroups * 16, st>>>(sp);
-        PG_CUDA(cudaGetLastError());
+        if (xl >= 0) {
+            PG_TRY(run_star_exchange(sp, res, tr));
+        } else {
+            hits_star_kernel<<<c.prop.multiProcessorCount * 8, 256, (size_t)star_ngroups * 16, st>>>(sp);
+            PG_CUDA(cudaGetLastError());
+        }
         PG_CUDA(cudaEventRecord(ev_main.b, st));
         res->stats.kernel_launches += 2;
         if (W > 1) {
@@ -847,6 +1042,11 @@ struct JoinAggPipeline : Pipeline {
         tr.mark("star sink + d2h");
         if (cnt[2] != 0) PG_FAIL(PG_EUNSUPPORTED, "star join: a lookup matched more than one build row (duplicate build keys)");
         res->stats.kernel_ms = ev_all.ms();
+        if (xl >= 0) {
+            res->stats.comm_ms = (double)ev_xb.ms() + (double)ev_xp.ms();     // the two row exchanges (NVLink)
+            res->stats.aux[7] = x_sent_rows;                                  // rows / bytes this rank sent to OTHER ranks
+            res->stats.aux[5] = x_sent_bytes;
+        }
         res->stats.main_kernel_ms = ev_main.ms();
         res->stats.rows_scanned = t->nrows;
         res->stats.algorithmic_bytes = algorithmic_bytes;
@@ -946,7 +1146,12 @@ struct JoinAggPipeline : Pipeline {
         Trace tr("joinagg");
         PG_CUDA(cudaEventRecord(ev_all.a, st));
         res->stats.kernel_launches = 0;
-        for (size_t i = 0; i < stages.size(); i++) { PG_TRY(run_build_stage(*stages[i], res, (int)i)); tr.mark("build stage"); }
+        x_sent_rows = x_sent_bytes = 0;
+        for (size_t i = 0; i < stages.size(); i++) {
+            if (xl >= 0 && (int)i == lookups[(size_t)xl].stage) { PG_TRY(run_exchange_build(*stages[i], res)); tr.mark("build stage (row exchange)"); continue; }
+            PG_TRY(run_build_stage(*stages[i], res, (int)i));
+            tr.mark("build stage");
+        }
         if (star) return run_star(res, tr);
 
         const pg_table *t = tab(src_slot);
@@ -1747,6 +1952,7 @@ static int build_star(pg_plan *plan, const Node &aggn, const Node &top, std::uni
         }
         if ((sum->ltype == PG_LT_HUGEINT || sum->ltype == PG_LT_DOUBLE) && maxs != 0) PG_FAIL(PG_EUNSUPPORTED, "integer sum over a scaled value");
         p->star_scale = maxs;
+        p->star_worst = scaled_worst;
         // a block's shared-memory partial is int64: it receives at most its share of the fact rows (grid-stride over the hits)
         const i64 threads = (i64)ctx().prop.multiProcessorCount * 8 * 256;
         const i64 per_block = ((std::max<i64>(st->nrows, 1) + threads - 1) / threads) * 256;
@@ -1768,31 +1974,86 @@ static int build_star(pg_plan *plan, const Node &aggn, const Node &top, std::uni
         const pg_table *bt = p->tab(sp->src_slot);
         p->algorithmic_bytes += bt->nrows * bt->cols[(size_t)sp->ins_key_col].phys_width();
     }
+    // Which joins are local?  With a sharded fact table a build side must be whole on every rank or sharded on the same
+    // key ranges (proved from the exchanged ranges); ONE join may instead be keyed differently on its two sides: it
+    // becomes the exchange lookup -- both sides are hash-partitioned on the join key and shipped to the owner rank
+    // (exchange.cuh).  PG_FORCE_EXCHANGE=1 sends a join through the exchange even where it is not needed (also on one rank).
+    const bool force_x = getenv("PG_FORCE_EXCHANGE") && atoi(getenv("PG_FORCE_EXCHANGE")) != 0;
+    std::string x_why;
+    auto x_candidate = [&](size_t l) -> bool {
+        const auto &lk = p->lookups[l];
+        const Stage &S = *p->stages[(size_t)lk.stage];
+        if ((int)l == main) { x_why = "the filter-pass join cannot be exchanged"; return false; }
+        if (S.sub || (S.has_probe && S.probe_stage != p->main_stage)) { x_why = "exchanged build side must be a (filtered) scan"; return false; }
+        for (size_t l2 = 0; l2 < p->lookups.size(); l2++)
+            for (int k = 0; k < p->lookups[l2].nkey; k++)
+                if (p->lookups[l2].key[k].origin == (int)l + 1) { x_why = "another join is keyed by a column of the exchanged build side"; return false; }
+        for (auto &hp : p->sparts) if (hp.v.origin == (int)l + 1) { x_why = "a group key comes from the exchanged build side"; return false; }
+        std::vector<int> cols;
+        for (auto &ht : p->sterms)
+            for (int f = 0; f < ht.nfac; f++)
+                if (ht.fac[f].origin == (int)l + 1 && std::find(cols.begin(), cols.end(), ht.fac[f].col) == cols.end()) cols.push_back(ht.fac[f].col);
+        if (cols.size() > X_MAXCOL) { x_why = "more than 3 columns of the exchanged build side are read"; return false; }
+        return true;
+    };
+    std::vector<size_t> must_x, may_x;
     if (ctx().world > 1 && st->dist != PG_DIST_REPLICATED) {
-        // sharded fact table: every build side must be whole on every rank, or sharded on the same key ranges
-        for (auto &lk : p->lookups) {
+        for (size_t l = 0; l < p->lookups.size(); l++) {
+            const auto &lk = p->lookups[l];
             const Stage &S = *p->stages[(size_t)lk.stage];
             const pg_table *bt = p->tab(S.src_slot);
             if (bt->dist == PG_DIST_REPLICATED) continue;
-            if (lk.nkey != 1 || lk.key[0].origin != 0) PG_FAIL(PG_EUNSUPPORTED, "star join: a sharded build side must be keyed by a fact-table column");
-            const int W = ctx().world;
-            const Column &pc = st->cols[(size_t)lk.key[0].col], &bc = bt->cols[(size_t)S.ins_key_col];
-            i64 mine[6] = {pc.vmin, pc.vmax, st->nrows, bc.vmin, bc.vmax, bt->nrows};
-            DevBuf ds, dr;
-            PG_TRY(ds.alloc(sizeof mine));
-            PG_TRY(dr.alloc(sizeof mine * (size_t)W));
-            PG_CUDA(cudaMemcpyAsync(ds.p, mine, sizeof mine, cudaMemcpyHostToDevice, ctx().stream));
-            PG_TRY(comm_allgather(ds.p, dr.p, sizeof mine, ctx().stream));
-            std::vector<i64> all(6 * (size_t)W);
-            PG_CUDA(cudaMemcpyAsync(all.data(), dr.p, sizeof mine * (size_t)W, cudaMemcpyDeviceToHost, ctx().stream));
-            PG_CUDA(cudaStreamSynchronize(ctx().stream));
-            for (int r = 0; r < W; r++)
-                for (int q = 0; q < W; q++) {
-                    if (r == q || all[(size_t)r * 6 + 2] == 0 || all[(size_t)q * 6 + 5] == 0) continue;
-                    if (all[(size_t)r * 6] <= all[(size_t)q * 6 + 4] && all[(size_t)q * 6 + 3] <= all[(size_t)r * 6 + 1])
-                        PG_FAIL(PG_EUNSUPPORTED, "sharded join sides are not co-partitioned on the key (needs the all-to-all shuffle path)");
-                }
+            bool copart = lk.nkey == 1 && lk.key[0].origin == 0;
+            if (copart) {
+                const int W = ctx().world;
+                const Column &pc = st->cols[(size_t)lk.key[0].col], &bc = bt->cols[(size_t)S.ins_key_col];
+                i64 mine[6] = {pc.vmin, pc.vmax, st->nrows, bc.vmin, bc.vmax, bt->nrows};
+                DevBuf ds, dr;
+                PG_TRY(ds.alloc(sizeof mine));
+                PG_TRY(dr.alloc(sizeof mine * (size_t)W));
+                PG_CUDA(cudaMemcpyAsync(ds.p, mine, sizeof mine, cudaMemcpyHostToDevice, ctx().stream));
+                PG_TRY(comm_allgather(ds.p, dr.p, sizeof mine, ctx().stream));
+                std::vector<i64> all(6 * (size_t)W);
+                PG_CUDA(cudaMemcpyAsync(all.data(), dr.p, sizeof mine * (size_t)W, cudaMemcpyDeviceToHost, ctx().stream));
+                PG_CUDA(cudaStreamSynchronize(ctx().stream));
+                for (int r = 0; r < W; r++)
+                    for (int q = 0; q < W; q++) {
+                        if (r == q || all[(size_t)r * 6 + 2] == 0 || all[(size_t)q * 6 + 5] == 0) continue;
+                        if (all[(size_t)r * 6] <= all[(size_t)q * 6 + 4] && all[(size_t)q * 6 + 3] <= all[(size_t)r * 6 + 1]) copart = false;
+                    }
+            }
+            if (!copart) must_x.push_back(l);
+            else may_x.push_back(l);
         }
+    } else if (ctx().world == 1) {
+        for (size_t l = 0; l < p->lookups.size(); l++) may_x.push_back(l);
+    }
+    if (must_x.size() > 1) PG_FAIL(PG_EUNSUPPORTED, "star join: %zu joins have sides sharded on different keys (one row exchange per star)", must_x.size());
+    if (must_x.size() == 1) {
+        if (!x_candidate(must_x[0])) PG_FAIL(PG_EUNSUPPORTED, "sharded join sides are not co-partitioned on the key and the row exchange does not apply: %s", x_why.c_str());
+        p->xl = (int)must_x[0];
+    } else if (force_x) {
+        // prefer a join whose build columns the aggregate reads (there is something to carry)
+        for (int pass = 0; pass < 2 && p->xl < 0; pass++)
+            for (size_t l : may_x)
+                if (x_candidate(l) && (pass == 1 || p->stages[(size_t)p->lookups[l].stage]->payload_needed)) { p->xl = (int)l; break; }
+    }
+    if (p->xl >= 0) {
+        const Stage &S = *p->stages[(size_t)p->lookups[(size_t)p->xl].stage];
+        const Column &k1 = p->tab(S.src_slot)->cols[(size_t)S.ins_key_col];
+        if (p->lookups[(size_t)p->xl].nkey == 1 && k1.gmin() <= HT_EMPTY && k1.gmax() >= HT_EMPTY) PG_FAIL(PG_EUNSUPPORTED, "join key range contains the empty-slot sentinel");
+        for (size_t t = 0; t < p->sterms.size(); t++)
+            for (int f = 0; f < p->sterms[t].nfac; f++) {
+                if (p->sterms[t].fac[f].origin != p->xl + 1) continue;
+                auto it = std::find(p->xcols.begin(), p->xcols.end(), p->sterms[t].fac[f].col);
+                if (it == p->xcols.end()) { p->xcols.push_back(p->sterms[t].fac[f].col); it = p->xcols.end() - 1; }
+                p->x_term_mask[t] |= 1 << f;
+                p->x_fac_col[t][f] = (int)(it - p->xcols.begin());
+            }
+        // the owner's blocks sum rows of every rank's shard: redo the int64 proof with the whole table's row count
+        const i64 threads = (i64)ctx().prop.multiProcessorCount * 8 * 256;
+        const i64 per_block = ((std::max<i64>(st->total_rows(), 1) + threads - 1) / threads) * 256 * std::max(ctx().world, 1);
+        if (p->star_worst * (i128)per_block >= ((i128)1 << 63)) PG_FAIL(PG_EUNSUPPORTED, "a block's partial group sum could exceed int64");
     }
     PG_TRY(p->d_counters.alloc(64));
     PG_TRY(p->d_overflow.alloc(4));
@@ -1800,8 +2061,8 @@ static int build_star(pg_plan *plan, const Node &aggn, const Node &top, std::uni
     for (size_t l = 0; l < p->lookups.size(); l++) {
         const Stage &S = *p->stages[(size_t)p->lookups[l].stage];
         char b[200];
-        snprintf(b, sizeof b, " %s(%d-col key%s%s)", p->tab(S.src_slot)->name.c_str(), p->lookups[l].nkey, (int)l == main ? ", filter pass" : "",
-                 S.payload_needed ? ", payload" : ", existence");
+        snprintf(b, sizeof b, " %s(%d-col key%s%s%s)", p->tab(S.src_slot)->name.c_str(), p->lookups[l].nkey, (int)l == main ? ", filter pass" : "",
+                 S.payload_needed ? ", payload" : ", existence", (int)l == p->xl ? ", ROW EXCHANGE: both sides hash-partitioned on the key, all-to-all over NVLink, joined on the owner rank" : "");
         ex += b;
     }
     char b[96];

@@ -167,15 +167,16 @@ __global__ void tg_supplier_kernel(i64 n, int *__restrict__ s_suppkey, int *__re
     s_nationkey[i] = (int)tg_draw(s, 0, 24);
 }
 
-__global__ void tg_partsupp_kernel(i64 nrows, i64 nsupp, int *__restrict__ ps_partkey, int *__restrict__ ps_suppkey, i64 *__restrict__ ps_supplycost)
+__global__ void tg_partsupp_kernel(i64 row_lo, i64 nrows, i64 nsupp, int *__restrict__ ps_partkey, int *__restrict__ ps_suppkey, i64 *__restrict__ ps_supplycost)
 {
-    i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= nrows) return;
+    i64 o = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= nrows) return;
+    const i64 r = row_lo + o;                     // global row: any row range is generated independently
     const i64 pk = r / 4 + 1, j = r % 4;
     i64 s = tg_mulmod(SD_PS_SCST, tg_pow(16807, r));
-    ps_partkey[r] = (int)pk;
-    ps_suppkey[r] = (int)((pk + j * (nsupp / 4 + (pk - 1) / nsupp)) % nsupp + 1);
-    ps_supplycost[r] = tg_draw(s, 100, 100000);
+    ps_partkey[o] = (int)pk;
+    ps_suppkey[o] = (int)((pk + j * (nsupp / 4 + (pk - 1) / nsupp)) % nsupp + 1);
+    ps_supplycost[o] = tg_draw(s, 100, 100000);
 }
 
 }  // namespace pg
@@ -186,6 +187,7 @@ extern "C" {
 
 int64_t pg_tpch_num_orders(double sf) { return num_orders(sf); }
 int64_t pg_tpch_num_customers(double sf) { return num_customers(sf); }
+int64_t pg_tpch_num_parts(double sf) { return num_parts(sf); }
 
 int pg_tpch_orders_lineitem(double sf, int64_t order_lo, int64_t order_hi, pg_table **orders, pg_table **lineitem)
 {
@@ -382,27 +384,33 @@ int pg_tpch_supplier(double sf, pg_table **supplier)
     return PG_OK;
 }
 
-int pg_tpch_partsupp(double sf, pg_table **partsupp)
+int pg_tpch_partsupp_range(double sf, int64_t row_lo, int64_t row_hi, pg_table **partsupp)
 {
     Context &c = ctx();
     if (!c.ready) PG_FAIL(PG_ESTATE, "pg_tpch_partsupp: call pg_init first");
     if (!partsupp) PG_FAIL(PG_EINVAL, "pg_tpch_partsupp: bad arguments");
+    const i64 total = 4 * num_parts(sf);
+    if (row_hi < 0) row_hi = total;
+    if (row_lo < 0 || row_hi < row_lo || row_hi > total) PG_FAIL(PG_EINVAL, "pg_tpch_partsupp_range: bad row range");
     PG_CUDA(cudaSetDevice(c.device));
     pg_coldesc cd[PG_PS_NCOLS] = {{"ps_partkey", PG_T_INT32, 0, 0, 0, nullptr}, {"ps_suppkey", PG_T_INT32, 0, 0, 0, nullptr},
                                   {"ps_supplycost", PG_T_DECIMAL64, 15, 2, 0, nullptr}};
     pg_table *t = nullptr;
     PG_TRY(pg_table_create("partsupp", PG_PS_NCOLS, cd, &t));
-    const i64 np = num_parts(sf), n = 4 * np;
+    const i64 n = row_hi - row_lo;
     PG_TRY(pg_table_reserve(t, n));
-    tg_partsupp_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(n, num_supp(sf), (int *)t->cols[PG_PS_PARTKEY].d_data,
-                                                                        (int *)t->cols[PG_PS_SUPPKEY].d_data, (i64 *)t->cols[PG_PS_SUPPLYCOST].d_data);
+    if (n > 0)
+        tg_partsupp_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(row_lo, n, num_supp(sf), (int *)t->cols[PG_PS_PARTKEY].d_data,
+                                                                            (int *)t->cols[PG_PS_SUPPKEY].d_data, (i64 *)t->cols[PG_PS_SUPPLYCOST].d_data);
     PG_CUDA(cudaGetLastError());
     PG_CUDA(cudaStreamSynchronize(c.stream));
     PG_TRY(pg_table_set_rows(t, n));
-    PG_TRY(pg_table_seal(t, 0));
+    PG_TRY(pg_table_seal(t, row_lo));
     *partsupp = t;
     return PG_OK;
 }
+
+int pg_tpch_partsupp(double sf, pg_table **partsupp) { return pg_tpch_partsupp_range(sf, 0, -1, partsupp); }
 
 int pg_tpch_nation(pg_table **nation)
 {

@@ -437,8 +437,10 @@ def q3_topk_plan(limit=10, **kw):
 
 # ----------------------------------------------------------------- tables --
 
-def generate_device_tables(sf, order_lo=0, order_hi=None, want=("lineitem", "orders", "customer")):
-    """dbgen-equivalent tables generated directly in HBM (plangpu_tpch.h)."""
+def generate_device_tables(sf, order_lo=0, order_hi=None, want=("lineitem", "orders", "customer"), partsupp_shard=None):
+    """dbgen-equivalent tables generated directly in HBM (plangpu_tpch.h).  partsupp_shard=(rank, world): only
+    that rank's row range of partsupp is generated (a SHARDED build side keyed differently from the lineitem
+    shards -- Q9 then takes the all-to-all row exchange instead of a replicated partsupp)."""
     lib = L.lib()
     if order_hi is None:
         order_hi = lib.pg_tpch_num_orders(sf)
@@ -460,7 +462,12 @@ def generate_device_tables(sf, order_lo=0, order_hi=None, want=("lineitem", "ord
                              ("partsupp", lib.pg_tpch_partsupp, PARTSUPP)):
         if name in want:
             h = C.c_void_p()
-            L.check(fn(sf, C.byref(h)))
+            if name == "partsupp" and partsupp_shard is not None:
+                r, w = partsupp_shard
+                n = 4 * lib.pg_tpch_num_parts(sf)
+                L.check(lib.pg_tpch_partsupp_range(sf, n * r // w, n * (r + 1) // w, C.byref(h)))
+            else:
+                L.check(fn(sf, C.byref(h)))
             out[name] = DeviceTable(name, h, schema)
     if "nation" in want:
         h = C.c_void_p()

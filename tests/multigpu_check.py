@@ -67,6 +67,17 @@ def main():
         chunks, _, explain = J._run(T.q9_plan(word), tables)
         assert "StarJoin" in explain
         assert J._q9_rows(chunks) == O.q9(O.gen_part(sf, word), O.gen_supplier(sf), O.gen_partsupp(sf), orders, line, like_word=word)
+    # BASELINE config 5 as written: partsupp SHARDED by row range (keyed by partkey, not by order index), so the
+    # lineitem x partsupp join has its sides on different ranks -> all-to-all hash-partitioned ROW exchange
+    ps_shard = T.generate_device_tables(sf, lo, hi, want=("partsupp",), partsupp_shard=(rank, world))["partsupp"]
+    tx = dict(tables)
+    tx["partsupp"] = ps_shard
+    for word in ("pink", "lace"):
+        chunks, st, explain = J._run(T.q9_plan(word), tx)
+        assert "ROW EXCHANGE" in explain, explain
+        assert st.aux[7] > 0, "no row crossed NVLink"
+        assert J._q9_rows(chunks) == O.q9(O.gen_part(sf, word), O.gen_supplier(sf), O.gen_partsupp(sf), orders, line, like_word=word)
+    ps_shard.free()
     os.environ["PG_FORCE_SHUFFLE"] = "1"          # the general path must also be right when it is not needed
     J.check_groupby(O, tables, line, key="l_orderkey", value="l_quantity", having_gt=200)
     J.check_q3(O, tables, host, check_counts=False)

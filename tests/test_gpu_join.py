@@ -494,6 +494,63 @@ def test_q9_sf005(pg, oracle, word):
             x.free()
 
 
+@pytest.mark.parametrize("word", ["pink", "lace", "nosuchcolour"])
+def test_q9_through_the_row_exchange(pg, oracle, word, monkeypatch):
+    """PG_FORCE_EXCHANGE=1: the lineitem x partsupp join runs through the all-to-all row exchange (exchange.cuh: both
+    sides hash-partitioned on (partkey, suppkey), records packed, scattered into destination order, joined from the
+    receive buffers) even on one rank, where the exchange degenerates to a device copy.  Same answer as the local join."""
+    from plan_b200 import tpch as T
+    sf = 0.05
+    t = T.generate_device_tables(sf, want=T.ALL_TABLES)
+    try:
+        monkeypatch.setenv("PG_FORCE_EXCHANGE", "1")
+        chunks, stats, explain = _run(T.q9_plan(word), t)
+        assert "partsupp(2-col key, payload, ROW EXCHANGE" in explain
+        orders, line = oracle.gen_orders_lineitem(sf)
+        want = oracle.q9(oracle.gen_part(sf, word), oracle.gen_supplier(sf), oracle.gen_partsupp(sf), orders, line, like_word=word)
+        assert _q9_rows(chunks) == want
+        monkeypatch.setenv("PG_FORCE_EXCHANGE", "0")
+        chunks2, _, explain2 = _run(T.q9_plan(word), t)
+        assert "ROW EXCHANGE" not in explain2 and _q9_rows(chunks2) == want
+    finally:
+        for x in t.values():
+            x.free()
+
+
+def test_q9_row_exchange_reproduces_the_reference_golden_file(pg, monkeypatch):
+    """cases/tpch/1g/plan/q9.txt through the exchanged join (SF1, device-generated tables)."""
+    from plan_b200 import compute as X, tpch as T
+    t = T.generate_device_tables(1.0, want=T.ALL_TABLES)
+    try:
+        monkeypatch.setenv("PG_FORCE_EXCHANGE", "1")
+        chunks, _, explain = _run(T.q9_plan(), t)
+        assert "ROW EXCHANGE" in explain
+        assert X.rows_text(X.order_limit(chunks, []), 3) == open(os.path.join(GOLDEN, "ref_sf1_q9.txt")).read()
+    finally:
+        for x in t.values():
+            x.free()
+
+
+def test_row_exchange_refuses_duplicate_build_keys(pg, oracle, monkeypatch):
+    """A probe row that matches two received build rows needs row multiplication in the sink: refused, never wrong."""
+    from plan_b200 import _lib as L, compute as X, tpch as T
+    host, part = _q9_host(oracle, 0.01)
+    host["partsupp"] = {k: np.concatenate([v, v[:50]]) for k, v in host["partsupp"].items()}
+    t = T.upload_tables(host)
+    try:
+        monkeypatch.setenv("PG_FORCE_EXCHANGE", "1")
+        ex = X.gpuPipelineExec(T.q9_plan("e"), t)       # '%e%' keeps nearly every part: the doubled keys are probed
+        ex.Init()
+        assert "ROW EXCHANGE" in ex.Explain()
+        with pytest.raises(L.PlanGpuError) as ei:
+            X.drain(ex)
+        assert ei.value.status == L.PG_EUNSUPPORTED and "more than one build row" in str(ei.value)
+        ex.Close()
+    finally:
+        for x in t.values():
+            x.free()
+
+
 def _q9_host(oracle, sf, word="pink"):
     orders, line = oracle.gen_orders_lineitem(sf)
     part = oracle.gen_part(sf, word)
