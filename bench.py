@@ -397,6 +397,40 @@ def main():
             except Exception as e:      # reported, never fatal for the metric line
                 also[name] = {"error": str(e)[:200]}
 
+        # BASELINE config 5 as written: partsupp SHARDED by row range, so Q9's lineitem x partsupp join has its two sides
+        # on different ranks and runs through the all-to-all hash-partitioned ROW exchange (exchange.cuh).  On one rank
+        # the same path is forced (PG_FORCE_EXCHANGE) and the exchange degenerates to a device copy.
+        if "partsupp" in extra_tables:
+            try:
+                xt = dict(extra_tables)
+                if world > 1:
+                    xt["partsupp"] = T.generate_device_tables(args.sf, want=("partsupp",), partsupp_shard=(rank, world))["partsupp"]
+                os.environ["PG_FORCE_EXCHANGE"] = "1"
+                ex = X.gpuPipelineExec(T.q9_plan(), xt)
+                ex.Init()
+                os.environ.pop("PG_FORCE_EXCHANGE")
+                for _ in range(2):
+                    ex.Reset(); chunks = X.drain(ex)
+                parity["q9_row_exchange"] = all_ranks_agree(parity_check(X, "q9", chunks, args.sf))
+                tot = comm = 0.0
+                for _ in range(5):
+                    barrier()
+                    ex.Reset(); X.drain(ex)
+                    tot += ex.stats.exec_ms
+                    comm += ex.stats.comm_ms
+                sent_b, sent_r = float(ex.stats.aux[5]), float(ex.stats.aux[7])
+                comm_ms = max_over_ranks(comm / 5)
+                also["q9_row_exchange"] = {"exec_ms": max_over_ranks(tot / 5), "exchange_ms": comm_ms,
+                                           "rows_sent_to_other_ranks": int(sum_over_ranks(sent_r)), "bytes_sent_to_other_ranks": int(sum_over_ranks(sent_b)),
+                                           "nvlink_gbs_per_rank": (sum_over_ranks(sent_b) / world) / (comm_ms * 1e-3) / 1e9 if comm_ms > 0 and world > 1 else None,
+                                           "explain": "ROW EXCHANGE" in ex.Explain(), "partsupp": "row-range sharded" if world > 1 else "whole (exchange forced)"}
+                ex.Close()
+                if world > 1:
+                    xt["partsupp"].free()
+            except Exception as e:
+                os.environ.pop("PG_FORCE_EXCHANGE", None)
+                also["q9_row_exchange"] = {"error": str(e)[:300]}
+
     # ---- e2e: host buffers through the C ABI (H2D inside the timed region) -------------------
     e2e = None
     if not args.no_e2e:

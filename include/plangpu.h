@@ -64,12 +64,13 @@ typedef enum {
     PG_T_FLOAT64 = 7,    /* LTID_DOUBLE                        8 B                  */
     PG_T_HUGEINT = 8,    /* LTID_HUGEINT {uint64 lower; int64 upper}   16 B (results) */
     PG_T_DECIMAL128 = 9, /* result DECIMAL: pg_decimal, 16 B                        */
-    PG_T_VARCHAR = 10    /* LTID_VARCHAR of any cardinality: one pg_string per row (the layout of
+    PG_T_VARCHAR = 10,   /* LTID_VARCHAR of any cardinality: one pg_string per row (the layout of
                             common.String, pkg/common/string.go:10-13).  Kept in HOST memory by the
                             library: such a column can only be CARRIED to the result (a group key
                             that is functionally dependent on a unique join key, e.g. c_name in
                             TPC-H Q18); predicates, join keys and aggregates on it are refused
                             with PG_EUNSUPPORTED.                                            */
+    PG_T_BOOL = 11       /* LTID_BOOLEAN, 1 B (results of row-emitting pipelines: MARK columns, projected predicates) */
 } pg_type;
 
 typedef struct {               /* field order of common.String {Len int; Data unsafe.Pointer} (string.go:10-13, amd64) */

@@ -14,7 +14,8 @@
  *          | PG_OP_SCAN   slot nfilters expr*
  *          | PG_OP_FILTER nfilters expr* node
  *          | PG_OP_JOIN   jointype nconds (expr_probe expr_build)* nout (side idx)* node_probe node_build
- *          | PG_OP_AGG    ngroups expr* naggs (aggfn ltype width scale expr)* nhaving expr* nout (kind idx)* node
+ *          | PG_OP_PROJECT nexprs expr* node                 -- row-emitting pipelines only (root)
+          | PG_OP_AGG    ngroups expr* naggs (aggfn ltype width scale expr)* nhaving expr* nout (kind idx)* node
  *                         -- (ltype width scale) = the aggregate's RESULT type, e.g. sum(DECIMAL(w,s)) ->
  *                            DECIMAL(38,s) (function_aggr.go:48-55); COUNT(*) passes ntokens = 0
  *   expr  := ntokens token*                       -- postfix (children before function)
@@ -44,6 +45,8 @@
 #define PG_OP_JOIN 3
 #define PG_OP_AGG 4
 #define PG_OP_TOPK 5
+#define PG_OP_PROJECT 6 /* POT_Project (executor_project.go:24-82): nexprs expr* node -- one output column per expression over the child's
+                           outputs.  Root of a ROW-EMITTING pipeline: [PROJECT] <- [FILTER]* <- (SCAN | JOIN(scan, scan)) returns rows, not groups */
 
 /* join types (LOT_JoinType) */
 #define PG_JOIN_INNER 1
@@ -88,6 +91,8 @@
 #define PG_FN_AND 20
 #define PG_FN_OR 21
 #define PG_FN_NOT 22
+#define PG_FN_CASE 23 /* case: args = [ELSE, WHEN1, THEN1, WHEN2, THEN2 ...] exactly Expr.Children of the reference's CASE
+                         (executeCase, expr_exec.go:144-246); a missing ELSE is a PG_TK_CONST with ltype 0 (NULL) */
 #define PG_FN_CAST 30 /* cast(arg AS ltype width scale) (function_cast.go:474-512) */
 
 /* aggregate functions (function_aggr.go:26-165) */

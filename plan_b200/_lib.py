@@ -13,7 +13,7 @@ STATUS_NAMES = ["PG_OK", "PG_EINVAL", "PG_ENOMEM", "PG_ECUDA", "PG_ENCCL", "PG_E
 
 PG_DIST_SHARDED, PG_DIST_REPLICATED = 0, 1
 PG_T_INT32, PG_T_INT64, PG_T_DATE32, PG_T_DECIMAL64, PG_T_CHAR1, PG_T_DICT8, PG_T_FLOAT64, PG_T_HUGEINT, \
-    PG_T_DECIMAL128, PG_T_VARCHAR = range(1, 11)
+    PG_T_DECIMAL128, PG_T_VARCHAR, PG_T_BOOL = range(1, 12)
 
 
 class PlanGpuError(RuntimeError):

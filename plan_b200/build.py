@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["table.cu", "plan.cu", "scanagg.cu", "join.cu", "comm.cu"]      # libplangpu.so: the drop-in operator library
+SOURCES = ["table.cu", "plan.cu", "scanagg.cu", "join.cu", "rows.cu", "comm.cu"]      # libplangpu.so: the drop-in operator library
 TPCH_SOURCES = ["tpchgen.cu"]                                           # libplangpu_tpch.so: in-box data generator (tests / bench only)
 OUT = os.path.join(HERE, "libplangpu.so")
 TPCH_OUT = os.path.join(HERE, "libplangpu_tpch.so")

@@ -42,6 +42,7 @@ class LType:
         return (self.Id, self.Width, self.Scale) == (o.Id, o.Width, o.Scale)
 
 
+def BooleanType(): return LType(LTID_BOOLEAN)
 def IntegerType(): return LType(LTID_INTEGER)
 def BigintType(): return LType(LTID_BIGINT)
 def DateType(): return LType(LTID_DATE)
@@ -118,6 +119,8 @@ class Value:
         if self.IsNull:
             return "NULL"
         t = self.Typ.Id
+        if t == LTID_BOOLEAN:
+            return "true" if self.I64 else "false"      # Value.String of a bool (chunk/value.go)
         if t in (LTID_INTEGER, LTID_BIGINT):
             return "%d" % self.I64
         if t == LTID_VARCHAR:
@@ -198,4 +201,4 @@ PG_STRING = np.dtype([("len", np.int64), ("data", np.uint64)])
 def native_dtype(pg_type):
     return {L.PG_T_INT32: np.int32, L.PG_T_INT64: np.int64, L.PG_T_DATE32: np.int32, L.PG_T_DECIMAL64: np.int64,
             L.PG_T_CHAR1: np.uint8, L.PG_T_DICT8: np.uint8, L.PG_T_FLOAT64: np.float64, L.PG_T_HUGEINT: HUGEINT,
-            L.PG_T_DECIMAL128: DECIMAL128, L.PG_T_VARCHAR: PG_STRING}[pg_type]
+            L.PG_T_DECIMAL128: DECIMAL128, L.PG_T_VARCHAR: PG_STRING, L.PG_T_BOOL: np.uint8}[pg_type]

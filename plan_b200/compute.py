@@ -36,7 +36,8 @@ JOIN_INNER, JOIN_SEMI, JOIN_ANTI, JOIN_MARK, JOIN_LEFT, JOIN_ANTI_MARK = 1, 2, 3
 FUNC_IDS = {"+": 1, "-": 2, "*": 3, "/": 4, "=": 10, "<>": 11, "<": 12, "<=": 13, ">": 14, ">=": 15, "in": 16,
             "like": 17, "not like": 18,      # FuncLike / FuncNotLike (function.go:89-128)
             "extract": 19,                   # extract('year', date) (binStringInt32ExtractOp, function_operator_binary.go:259-265)
-            "and": 20, "or": 21, "not": 22, "cast": 30}
+            "and": 20, "or": 21, "not": 22, "case": 23,   # case: Children = [ELSE, WHEN1, THEN1, ...] (executeCase, expr_exec.go:144-246)
+            "cast": 30}
 AGG_IDS = {"sum": 1, "avg": 2, "count": 3, "min": 4, "max": 5}
 
 PG_TK_COL, PG_TK_CONST, PG_TK_STR, PG_TK_FUNC = 1, 2, 3, 4
@@ -110,7 +111,9 @@ def _expr_tokens(e, out):
         out.append([PG_TK_COL, e.ColRef[0], e.ColRef[1]] + _ltype_words(e.DataTyp))
     elif e.Typ == ET_Const:
         t = e.DataTyp
-        if t.Id == K.LTID_VARCHAR:
+        if e.ConstValue is None:            # NULL constant (a CASE without ELSE): ltype 0
+            out.append([PG_TK_CONST, 0, 0, 0, 0])
+        elif t.Id == K.LTID_VARCHAR:
             b = e.ConstValue.encode()
             words = [int.from_bytes(b[i:i + 8].ljust(8, b"\0"), "little", signed=True) for i in range(0, len(b), 8)]
             out.append([PG_TK_STR, len(b)] + words)
@@ -158,6 +161,12 @@ def _node_words(op, slots):
         for f in op.Filters:
             w += _expr_words(f)
         return w
+    if op.Typ == POT_Project:
+        # row-emitting pipelines: Project <- [Filter]* <- (Scan | Join); Outputs are the projection expressions
+        w = [6, len(op.Outputs)]
+        for e in op.Outputs:
+            w += _expr_words(e)
+        return w + _node_words(op.Children[0], slots)
     if op.Typ == POT_Filter:
         w = [2, len(op.Filters)]
         for f in op.Filters:
@@ -393,8 +402,10 @@ class gpuPipelineExec(OperatorExec):
         return haveMoreOutput, None
 
     def _agg_op(self):
+        """The operator whose Outputs type the result columns: the aggregate, or the root of a row-emitting pipeline
+        (a Filter's outputs are its child's)."""
         op = self.op
-        while op.Typ in (POT_Limit, POT_Order):
+        while op.Typ in (POT_Limit, POT_Order) or (op.Typ == POT_Filter and not op.Outputs):
             op = op.Children[0]
         return op
 

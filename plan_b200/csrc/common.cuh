@@ -66,7 +66,7 @@ inline int type_size(int t)
     switch (t) {
     case PG_T_INT32: case PG_T_DATE32: return 4;
     case PG_T_INT64: case PG_T_DECIMAL64: case PG_T_FLOAT64: return 8;
-    case PG_T_CHAR1: case PG_T_DICT8: return 1;
+    case PG_T_CHAR1: case PG_T_DICT8: case PG_T_BOOL: return 1;
     case PG_T_HUGEINT: case PG_T_DECIMAL128: case PG_T_VARCHAR: return 16;
     default: return 0;
     }

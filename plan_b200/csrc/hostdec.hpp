@@ -12,6 +12,12 @@
 
 #include "common.cuh"
 
+#ifdef __CUDACC__
+#define HD_FN __host__ __device__ inline
+#else
+#define HD_FN inline
+#endif
+
 namespace pg {
 
 struct HDec {
@@ -21,16 +27,16 @@ struct HDec {
 };
 
 constexpr int HD_MAXPREC = 19;
-constexpr u64 HD_MAXCOEF = 9999999999999999999ULL;
+#define HD_MAXCOEF 9999999999999999999ULL
 
-inline u128 hd_pow10(int n)
+HD_FN u128 hd_pow10(int n)
 {
     u128 r = 1;
     for (int i = 0; i < n; i++) r *= 10;
     return r;
 }
 
-inline int hd_digits(u128 x)
+HD_FN int hd_digits(u128 x)
 {
     int d = 0;
     while (x > 0) { x /= 10; d++; }
@@ -38,7 +44,7 @@ inline int hd_digits(u128 x)
 }
 
 // divide by 10^shift, round half to even
-inline u128 hd_shift_right_even(u128 x, int shift)
+HD_FN u128 hd_shift_right_even(u128 x, int shift)
 {
     if (shift <= 0) return x;
     if (shift > 38) return 0;
@@ -49,7 +55,7 @@ inline u128 hd_shift_right_even(u128 x, int shift)
 
 // Bring an arbitrary-precision coefficient into the 19-digit format.  false = the integer
 // part alone needs more than 19 digits (the reference panics with a decimal overflow).
-inline bool hd_normalise(bool neg, u128 coef, int scale, HDec *out)
+HD_FN bool hd_normalise(bool neg, u128 coef, int scale, HDec *out)
 {
     for (int guard = 0; guard < 4; guard++) {
         int prec = hd_digits(coef);
@@ -72,14 +78,14 @@ inline bool hd_normalise(bool neg, u128 coef, int scale, HDec *out)
     return false;
 }
 
-inline bool hd_from_i128(i128 v, int scale, HDec *out)
+HD_FN bool hd_from_i128(i128 v, int scale, HDec *out)
 {
     bool neg = v < 0;
     u128 mag = neg ? (u128)(-(v + 1)) + 1 : (u128)v;
     return hd_normalise(neg, mag, scale, out);
 }
 
-inline HDec hd_trim(HDec d, int min_scale)
+HD_FN HDec hd_trim(HDec d, int min_scale)
 {
     while (d.scale > min_scale && d.coef % 10 == 0) { d.coef /= 10; d.scale--; }
     return d;
@@ -88,7 +94,7 @@ inline HDec hd_trim(HDec d, int min_scale)
 // a / b with govalues' Quo contract: exact when the quotient terminates within 19 digits,
 // otherwise the 38-digit truncated quotient rounded half-even to 19 digits; trailing zeros
 // trimmed down to max(0, a.scale - b.scale).
-inline bool hd_quo(const HDec &a, const HDec &b, HDec *out)
+HD_FN bool hd_quo(const HDec &a, const HDec &b, HDec *out)
 {
     if (b.coef == 0) return false;
     bool neg = a.neg != b.neg;

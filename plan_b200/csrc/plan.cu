@@ -20,6 +20,7 @@ Pipeline::~Pipeline() {}
 
 int build_scan_agg(pg_plan *plan, const Node &agg, const Node &scan, std::unique_ptr<Pipeline> *out);
 int build_join_agg(pg_plan *plan, const Node &agg, const Node &join, std::unique_ptr<Pipeline> *out, bool nested = false);
+int build_rows(pg_plan *plan, std::unique_ptr<Pipeline> *out);      // rows.cu: row-emitting Scan / Filter / Project / Join
 
 static const Node *skip_filters(const Node *n, std::vector<Expr> *extra)
 {
@@ -162,7 +163,10 @@ int agree_table_stats(pg_table *t)
 static int build_pipeline(pg_plan *plan)
 {
     const Node &root = plan->agg_root();
-    if (root.op != PG_OP_AGG) PG_FAIL(PG_EUNSUPPORTED, "plan root must be an aggregate (got op %d)", root.op);
+    if (root.op != PG_OP_AGG) {
+        if (plan->topk) PG_FAIL(PG_EUNSUPPORTED, "ORDER BY / LIMIT is fused over aggregates only");
+        return build_rows(plan, &plan->pipe);       // a Project / Filter / Join / Scan that returns rows
+    }
     std::vector<Expr> extra;
     const Node *child = skip_filters(&root.children[0], &extra);
     if (child->op == PG_OP_SCAN) {
@@ -253,7 +257,11 @@ int pg_plan_compile(const int64_t *desc, size_t nwords, pg_plan **out)
         for (auto &o : p->root.order)
             if (o.first < 0 || o.first >= (int)p->root.children[0].outs.size()) PG_FAIL(PG_EINVAL, "pg_plan_compile: ORDER BY refers to output %d", o.first);
     }
-    if (p->agg_root().op != PG_OP_AGG) PG_FAIL(PG_EUNSUPPORTED, "pg_plan_compile: only aggregate-rooted pipelines are off-loaded");
+    {
+        const int op = p->agg_root().op;
+        if (op != PG_OP_AGG && (p->topk || (op != PG_OP_PROJECT && op != PG_OP_FILTER && op != PG_OP_JOIN && op != PG_OP_SCAN)))
+            PG_FAIL(PG_EUNSUPPORTED, "pg_plan_compile: the root must be an aggregate (optionally under ORDER BY / LIMIT) or a row-emitting Project / Filter / Join / Scan");
+    }
     *out = p.release();
     return PG_OK;
 }

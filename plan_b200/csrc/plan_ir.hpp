@@ -47,6 +47,7 @@ struct Node {
     int jointype = 0;                                // JOIN
     std::vector<std::pair<Expr, Expr>> conds;        // JOIN (probe expr, build expr)
     std::vector<std::pair<int, int>> outs;           // JOIN (side idx) / AGG (kind idx)
+    std::vector<Expr> exprs;                         // PROJECT
     std::vector<Expr> groups;                        // AGG
     std::vector<AggExpr> aggs;
     std::vector<Expr> having;
@@ -133,6 +134,15 @@ public:
             out->filters.resize((size_t)nf);
             for (auto &e : out->filters) if (!expr(&e)) return false;
             return ok_;
+        }
+        case PG_OP_PROJECT: {
+            if (depth != 0) return ok_ = false;
+            i64 ne = next();
+            if (!ok_ || ne < 1 || ne > 256) return ok_ = false;
+            out->exprs.resize((size_t)ne);
+            for (auto &e : out->exprs) if (!expr(&e)) return false;
+            out->children.resize(1);
+            return node(&out->children[0], depth + 1);
         }
         case PG_OP_FILTER: {
             i64 nf = next();

@@ -1,0 +1,729 @@
+// rows.cu -- ROW-EMITTING operators: Scan / Filter / Project / Join whose parent is not an aggregate.
+//
+// Reference operators replaced:
+//   filterExecutor   /root/reference/pkg/compute/executor_filter.go:12-118   rows for which every filter is TRUE
+//   projectExecutor  /root/reference/pkg/compute/executor_project.go:24-82   one output column per expression
+//   joinExecutor     /root/reference/pkg/compute/executor_join.go:62-123,209-235 with Scan.Next* of join_scan.go:
+//       INNER (:182-299)  every (probe row, matching build row) pair
+//       LEFT  (:67-88)    the INNER pairs plus every probe row without a match, build columns NULL
+//       SEMI / ANTI (:90-121)  probe rows with / without a match (a NULL key never matches: ANTI keeps the row)
+//       MARK  (:123-165)  every probe row plus a boolean "found a match", NULL for a NULL probe key
+//   CASE / arithmetic / comparisons in their expressions: rowvm.cuh
+// NULL join keys never match (join_table.go:152-195).
+//
+// Plan shape:  [Project] <- [Filter]* <- ( Scan | Join( [Filter]* Scan , [Filter]* Scan ) ), 1 or 2 integer key columns.
+// Execution: the build side's passing rows go into a bucketized hash table (join.cuh jt_insert); one pass over the
+// probe side COUNTS the output rows of every probe row (filters above the join are evaluated per candidate pair, so
+// they see exactly the joined rows the reference's Filter operator sees), an exclusive scan turns counts into
+// offsets, a second pass writes the (probe row, build row) pairs in probe-row order, and the projection kernel
+// evaluates the output expressions per pair into columnar buffers that go back to the host in one copy per column
+// (the shim re-emits them as <= 2048-row chunks through pg_result_next).
+#include <algorithm>
+#include <functional>
+
+#include <cub/device/device_scan.cuh>
+
+#include "pipeline.hpp"
+#include "rowvm.cuh"
+
+namespace pg {
+
+enum { RO_I32 = 1, RO_I64, RO_DEC, RO_BOOL, RO_U8, RO_ROW0, RO_ROW1 };
+
+struct RowsParams {
+    const RvCode *code;
+    int jointype;                 // 0: no join
+    i64 build_rows, probe_rows;
+    int bf0, bf1, pf0, pf1, jf0, jf1;     // filter programs: build scan, probe scan, above the join
+    int nkey, bkey[2], pkey[2];   // column slots of the key parts
+    JoinTable jt;
+    unsigned *cnt;                // [probe_rows + 1]
+    const i64 *off;               // [probe_rows + 1]
+    i64 *pair0, *pair1;
+    int *err;
+    int nout;
+    int o0[RV_MAXOUT], o1[RV_MAXOUT], okind[RV_MAXOUT];
+    void *odata[RV_MAXOUT];
+    uint8_t *ovalid[RV_MAXOUT];
+    i64 nout_rows;
+};
+
+__device__ __forceinline__ bool rows_key(const RowsParams &p, const int *slots, i64 row, i64 *key)
+{
+    const RvCol &c0 = p.code->cols[slots[0]];
+    if (!typed_valid(c0.col, row)) return false;
+    i64 k = load_typed(c0.col, row);
+    if (p.nkey == 2) {
+        const RvCol &c1 = p.code->cols[slots[1]];
+        if (!typed_valid(c1.col, row)) return false;
+        k = (k << 32) | (load_typed(c1.col, row) & 0xffffffffLL);
+    }
+    *key = k;
+    return true;
+}
+
+static __global__ void __launch_bounds__(256)
+rows_build_kernel(const RowsParams p)
+{
+    int err = 0;
+    for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < p.build_rows; r += (i64)gridDim.x * blockDim.x) {
+        if (!rv_true(*p.code, p.bf0, p.bf1, -1, r, &err)) continue;
+        i64 key;
+        if (!rows_key(p, p.bkey, r, &key)) continue;            // NULL keys are not inserted
+        jt_insert(p.jt, key, (u64)r);
+    }
+    if (err) *p.err = err;
+}
+
+template <bool EMIT>
+static __global__ void __launch_bounds__(256)
+rows_probe_kernel(const RowsParams p)
+{
+    int err = 0;
+    for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < p.probe_rows; r += (i64)gridDim.x * blockDim.x) {
+        unsigned n = 0;
+        const i64 base = EMIT ? p.off[r] : 0;
+        auto emit = [&](i64 b) {
+            if (!rv_true(*p.code, p.jf0, p.jf1, r, b, &err)) return;
+            if (EMIT) { p.pair0[base + n] = r; p.pair1[base + n] = b; }
+            n++;
+        };
+        if (rv_true(*p.code, p.pf0, p.pf1, r, -1, &err)) {
+            if (p.jointype == 0) {
+                emit(-1);
+            } else {
+                i64 key = 0;
+                const bool has_key = rows_key(p, p.pkey, r, &key);
+                if (p.jointype == PG_JOIN_INNER || p.jointype == PG_JOIN_LEFT) {
+                    bool matched = false;
+                    if (has_key) jt_probe(p.jt, key, [&](u64 b) { matched = true; emit((i64)b); });
+                    if (!matched && p.jointype == PG_JOIN_LEFT) emit(-1);
+                } else {
+                    i64 first = -1;
+                    if (has_key) jt_probe(p.jt, key, [&](u64 b) { if (first < 0) first = (i64)b; });
+                    if (p.jointype == PG_JOIN_SEMI) { if (first >= 0) emit(-1); }
+                    else if (p.jointype == PG_JOIN_ANTI) { if (first < 0) emit(-1); }
+                    else emit(!has_key ? -2 : first);          // MARK: one row per probe row, the mark rides in the build row id
+                }
+            }
+        }
+        if (!EMIT) p.cnt[r] = n;
+    }
+    if (err) *p.err = err;
+}
+
+static __global__ void __launch_bounds__(256)
+rows_project_kernel(const RowsParams p)
+{
+    int err = 0;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < p.nout_rows; i += (i64)gridDim.x * blockDim.x) {
+        const i64 r0 = p.pair0[i], r1 = p.pair1[i];
+        for (int j = 0; j < p.nout; j++) {
+            const int kind = p.okind[j];
+            if (kind == RO_ROW0 || kind == RO_ROW1) {
+                const i64 r = kind == RO_ROW0 ? r0 : r1;
+                ((i64 *)p.odata[j])[i] = r;
+                p.ovalid[j][i] = r >= 0;
+                continue;
+            }
+            const RvVal v = rv_eval(*p.code, p.o0[j], p.o1[j], r0, r1, &err);
+            p.ovalid[j][i] = v.null ? 0 : 1;
+            switch (kind) {
+            case RO_I32: ((int32_t *)p.odata[j])[i] = v.null ? 0 : (int32_t)(i64)v.v; break;
+            case RO_I64: ((i64 *)p.odata[j])[i] = v.null ? 0 : (i64)v.v; break;
+            case RO_BOOL: case RO_U8: ((uint8_t *)p.odata[j])[i] = v.null ? 0 : (uint8_t)(i64)v.v; break;
+            default: {
+                pg_decimal d;
+                d.neg = (!v.null && v.v < 0) ? 1u : 0u;
+                d.coef = v.null ? 0 : (u64)(v.v < 0 ? -v.v : v.v);
+                d.scale = v.null ? 0 : v.scale;
+                ((pg_decimal *)p.odata[j])[i] = d;
+                break;
+            }
+            }
+        }
+    }
+    if (err) *p.err = err;
+}
+
+namespace {
+
+struct Src { int side = 0, col = -1; bool mark = false; };
+typedef std::function<bool(int, Src *)> Resolver;
+
+struct RowsPipeline : Pipeline {
+    pg_plan *plan = nullptr;
+    RvCode code{};
+    int ncode = 0, ncols = 0, nmasks = 0;
+    int slot[2] = {-1, -1};              // table slots of side 0 (probe / scanned) and side 1 (build)
+    RowsParams prm{};
+    struct Out { int type = 0, width = 0, scale = 0, side = 0, col = -1; };
+    std::vector<Out> outs;
+    DevBuf d_code, d_slots, d_cnt, d_off, d_pairs, d_err, d_scan_tmp, d_out;
+    EventPair ev_all;
+    std::string why;
+
+    const pg_table *tab(int side) const { return plan->slots[(size_t)slot[side]]; }
+
+    bool fail(const std::string &s) { why = s; return false; }
+    bool emit(int op, int a = 0, int b = 0, i64 imm = 0)
+    {
+        if (ncode >= RV_MAXCODE) return fail("expression program too long");
+        code.ins[ncode++] = RvIns{op, a, b, 0, imm};
+        return true;
+    }
+    int col_slot(int side, int col)
+    {
+        const pg_table *t = tab(side);
+        const Column &c = t->cols[(size_t)col];
+        for (int i = 0; i < ncols; i++)
+            if (code.cols[i].side == side && code.cols[i].col.p == c.d_data) return i;
+        if (ncols >= RV_MAXCOL) return -1;
+        RvCol rc;
+        rc.col.p = c.d_data;
+        rc.col.width = c.phys_width();
+        rc.col.base = c.base;
+        rc.col.valid = c.has_nulls ? c.d_valid : nullptr;
+        rc.side = side;
+        rc.scale = c.type == PG_T_DECIMAL64 ? c.scale : 0;
+        code.cols[ncols] = rc;
+        return ncols++;
+    }
+    static int kind_of_column(const Column &c)
+    {
+        switch (c.type) {
+        case PG_T_INT32: case PG_T_INT64: case PG_T_DATE32: return RVK_INT;
+        case PG_T_DECIMAL64: return RVK_DEC;
+        case PG_T_CHAR1: case PG_T_DICT8: return RVK_CODE;
+        default: return 0;
+        }
+    }
+    // code-set of a string predicate on a byte-coded column: fn applied to every code's string, once, on the host
+    bool code_mask(const Column &c, int fn, const std::vector<std::string> &lits, int *mask_slot)
+    {
+        if (nmasks >= RV_MAXMASK) return fail("too many string predicates");
+        unsigned *m = code.masks[nmasks];
+        for (int i = 0; i < 8; i++) m[i] = 0;
+        const int ncodes = c.type == PG_T_CHAR1 ? 256 : (int)c.dict.size();
+        for (int k = 0; k < ncodes; k++) {
+            const std::string s = c.type == PG_T_CHAR1 ? std::string(1, (char)k) : c.dict[(size_t)k];
+            bool t = false;
+            switch (fn) {
+            case PG_FN_EQ: case PG_FN_IN: for (auto &l : lits) t = t || s == l; break;
+            case PG_FN_NE: t = s != lits[0]; break;
+            case PG_FN_LIKE: t = wildcard_match(lits[0].data(), lits[0].size(), s.data(), s.size()); break;
+            case PG_FN_NOT_LIKE: t = !wildcard_match(lits[0].data(), lits[0].size(), s.data(), s.size()); break;
+            default: return fail("string comparison other than =, <>, IN, LIKE");
+            }
+            if (t) m[k >> 5] |= 1u << (k & 31);
+        }
+        *mask_slot = nmasks++;
+        return true;
+    }
+    // unify two numeric kinds (the binder casts INTEGER operands of a DECIMAL operation; be lenient about it)
+    bool numeric_pair(int *ka, int *kb)
+    {
+        if (*ka == *kb) return true;
+        if (*ka == RVK_INT && *kb == RVK_DEC) { *ka = RVK_DEC; return true; }      // INT values are DEC at scale 0 as they stand
+        if (*ka == RVK_DEC && *kb == RVK_INT) { *kb = RVK_DEC; return true; }
+        return fail("operand types differ (missing cast)");
+    }
+
+    // emits code that pushes the value of `e`; *kind = its static kind, *base = the byte-coded column it is (for string predicates)
+    bool compile(const Expr &e, const Resolver &rs, int *kind, const Column **base = nullptr, int depth = 0)
+    {
+        if (base) *base = nullptr;
+        if (depth > 24) return fail("expression too deep");
+        switch (e.kind) {
+        case PG_TK_COL: {
+            Src s;
+            if (e.side != 0 || !rs(e.idx, &s)) return fail("column reference out of scope");
+            if (s.mark) { *kind = RVK_BOOL; return emit(RV_MARK); }
+            const Column &c = tab(s.side)->cols[(size_t)s.col];
+            *kind = kind_of_column(c);
+            if (!*kind) return fail("column " + c.name + ": VARCHAR columns can be carried to the output but not computed on");
+            const int cs = col_slot(s.side, s.col);
+            if (cs < 0) return fail("too many columns referenced");
+            if (base) *base = &c;
+            return emit(RV_COL, cs);
+        }
+        case PG_TK_CONST:
+            switch (e.ltype) {
+            case PG_LT_BOOLEAN: *kind = RVK_BOOL; return emit(RV_CONST, 0, 0, e.v0 != 0);
+            case PG_LT_INTEGER: case PG_LT_BIGINT: case PG_LT_DATE: *kind = RVK_INT; return emit(RV_CONST, 0, 0, e.v0);
+            case PG_LT_DECIMAL: *kind = RVK_DEC; return emit(RV_CONST, 0, e.scale, e.v0);
+            case PG_LT_FLOAT: case PG_LT_DOUBLE: {      // float constants are float32(val) (chunk/vector.go:205-207)
+                double d;
+                memcpy(&d, &e.v0, 8);
+                const float f = (float)d;
+                unsigned bits;
+                memcpy(&bits, &f, 4);
+                *kind = RVK_F32;
+                return emit(RV_CONST, 0, 0, (i64)bits);
+            }
+            default: return fail("constant type");
+            }
+        case PG_TK_FUNC: break;
+        default: return fail("string literal outside a comparison with a dictionary / char column");
+        }
+        const int fn = e.fn;
+        const size_t na = e.args.size();
+        if (fn == PG_FN_ADD || fn == PG_FN_SUB || fn == PG_FN_MUL || fn == PG_FN_DIV) {
+            if (na != 2) return fail("arithmetic arity");
+            int ka, kb;
+            if (!compile(e.args[0], rs, &ka, nullptr, depth + 1) || !compile(e.args[1], rs, &kb, nullptr, depth + 1)) return false;
+            if (!numeric_pair(&ka, &kb)) return false;
+            if (ka != RVK_INT && ka != RVK_DEC && ka != RVK_F32) return fail("arithmetic on a non-numeric value");
+            if (ka == RVK_INT && fn == PG_FN_DIV) return fail("integer division");
+            *kind = ka;
+            const int op = fn == PG_FN_ADD ? RV_ADD : fn == PG_FN_SUB ? RV_SUB : fn == PG_FN_MUL ? RV_MUL : RV_DIV;
+            return emit(op, ka, (ka == RVK_INT && e.ltype == PG_LT_INTEGER) ? 32 : 0);
+        }
+        if (is_cmp(fn) || fn == PG_FN_LIKE || fn == PG_FN_NOT_LIKE) {
+            if (na != 2) return fail("comparison arity");
+            *kind = RVK_BOOL;
+            const Expr *l = &e.args[0], *r = &e.args[1];
+            int f2 = fn;
+            if (l->kind == PG_TK_STR) { std::swap(l, r); f2 = flip_cmp(fn); }
+            if (r->kind == PG_TK_STR) {
+                int k;
+                const Column *c;
+                if (!compile(*strip_value_preserving_casts(l), rs, &k, &c, depth + 1)) return false;
+                if (k != RVK_CODE || !c) return fail("string comparison on a column that is not dictionary / char coded");
+                int ms;
+                if (!code_mask(*c, f2, {r->str}, &ms)) return false;
+                return emit(RV_INSET, ms);
+            }
+            if (!is_cmp(fn)) return fail("LIKE needs a string pattern");
+            int ka, kb;
+            if (!compile(*l, rs, &ka, nullptr, depth + 1) || !compile(*r, rs, &kb, nullptr, depth + 1)) return false;
+            if (!numeric_pair(&ka, &kb)) return false;
+            return emit(RV_CMP, f2, ka);
+        }
+        if (fn == PG_FN_IN) {
+            if (na < 2) return fail("IN arity");
+            *kind = RVK_BOOL;
+            if (e.args[1].kind == PG_TK_STR) {
+                std::vector<std::string> lits;
+                for (size_t i = 1; i < na; i++) { if (e.args[i].kind != PG_TK_STR) return fail("IN list mixes types"); lits.push_back(e.args[i].str); }
+                int k;
+                const Column *c;
+                if (!compile(*strip_value_preserving_casts(&e.args[0]), rs, &k, &c, depth + 1)) return false;
+                if (k != RVK_CODE || !c) return fail("string IN on a column that is not dictionary / char coded");
+                int ms;
+                if (!code_mask(*c, PG_FN_IN, lits, &ms)) return false;
+                return emit(RV_INSET, ms);
+            }
+            for (size_t i = 1; i < na; i++) {          // x = c1 OR x = c2 ... (inInt32Op, function_operator_boolean.go:393-504)
+                int ka, kb;
+                if (!compile(e.args[0], rs, &ka, nullptr, depth + 1) || !compile(e.args[i], rs, &kb, nullptr, depth + 1)) return false;
+                if (!numeric_pair(&ka, &kb) || !emit(RV_CMP, PG_FN_EQ, ka)) return false;
+                if (i > 1 && !emit(RV_OR)) return false;
+            }
+            return true;
+        }
+        if (fn == PG_FN_AND || fn == PG_FN_OR) {
+            if (na < 2) return fail("AND / OR arity");
+            *kind = RVK_BOOL;
+            for (size_t i = 0; i < na; i++) {
+                int k;
+                if (!compile(e.args[i], rs, &k, nullptr, depth + 1)) return false;
+                if (k != RVK_BOOL) return fail("AND / OR of a non-boolean");
+                if (i > 0 && !emit(fn == PG_FN_AND ? RV_AND : RV_OR)) return false;
+            }
+            return true;
+        }
+        if (fn == PG_FN_NOT) {
+            int k;
+            if (na != 1 || !compile(e.args[0], rs, &k, nullptr, depth + 1) || k != RVK_BOOL) return why.empty() ? fail("NOT of a non-boolean") : false;
+            *kind = RVK_BOOL;
+            return emit(RV_NOT);
+        }
+        if (fn == PG_FN_EXTRACT) {
+            if (na != 2 || e.args[0].kind != PG_TK_STR || e.args[0].str != "year") return fail("only EXTRACT(year ...) is off-loaded");
+            int k;
+            if (!compile(e.args[1], rs, &k, nullptr, depth + 1)) return false;
+            if (k != RVK_INT || e.args[1].ltype != PG_LT_DATE) return fail("EXTRACT(year) of a non-date");
+            *kind = RVK_INT;
+            return emit(RV_YEAR);
+        }
+        if (fn == PG_FN_CAST) {
+            if (na != 1) return fail("cast arity");
+            int k;
+            const Column *c;
+            if (!compile(e.args[0], rs, &k, &c, depth + 1)) return false;
+            if (base) *base = c;
+            switch (e.ltype) {
+            case PG_LT_DECIMAL:
+                if (k == RVK_DEC) {
+                    if (e.scale < e.args[0].scale) return fail("DECIMAL cast that drops fractional digits");
+                    *kind = RVK_DEC;
+                    return true;                 // value preserving (tryCastDecimalToDecimal, function_cast.go:380-404)
+                }
+                if (k == RVK_INT) { *kind = RVK_DEC; return emit(RV_TODEC); }      // tryCastInt32ToDecimal (:337-347)
+                return fail("cast to DECIMAL from this type");
+            case PG_LT_FLOAT: case PG_LT_DOUBLE:
+                if (k == RVK_F32) { *kind = RVK_F32; return true; }
+                if (k != RVK_DEC && k != RVK_INT) return fail("cast to FLOAT from this type");
+                *kind = RVK_F32;
+                return emit(RV_TOF32, k);
+            case PG_LT_BIGINT: case PG_LT_HUGEINT: case PG_LT_INTEGER:
+                if (k != RVK_INT || (e.ltype == PG_LT_INTEGER && e.args[0].ltype != PG_LT_INTEGER)) return fail("narrowing integer cast");
+                *kind = RVK_INT;
+                return true;
+            case PG_LT_DATE: case PG_LT_VARCHAR: case PG_LT_BOOLEAN:
+                if (e.ltype != e.args[0].ltype) return fail("cast between unrelated types");
+                *kind = k;
+                return true;
+            default: return fail("cast target type");
+            }
+        }
+        if (fn == PG_FN_CASE) {
+            // children: [ELSE, WHEN1, THEN1, WHEN2, THEN2 ...] (executeCase, expr_exec.go:144-246)
+            if (na < 3 || (na & 1) == 0) return fail("CASE arity");
+            std::vector<int> to_end;
+            int rk = 0;
+            auto branch = [&](const Expr &x) -> bool {
+                int k;
+                if (x.kind == PG_TK_CONST && x.ltype == 0) { k = rk; if (!emit(RV_NULL)) return false; }       // typeless NULL constant
+                else if (!compile(x, rs, &k, nullptr, depth + 1)) return false;
+                if (rk == 0) rk = k;
+                else if (k != rk) {
+                    if ((rk == RVK_DEC && k == RVK_INT) || (rk == RVK_INT && k == RVK_DEC)) rk = RVK_DEC;
+                    else return fail("CASE branches of different types");
+                }
+                return true;
+            };
+            for (size_t i = 1; i + 1 < na; i += 2) {
+                int k;
+                if (!compile(e.args[i], rs, &k, nullptr, depth + 1)) return false;
+                if (k != RVK_BOOL) return fail("CASE WHEN is not a boolean");
+                const int jz = ncode;
+                if (!emit(RV_JZ)) return false;
+                if (!branch(e.args[i + 1])) return false;
+                to_end.push_back(ncode);
+                if (!emit(RV_JMP)) return false;
+                code.ins[jz].imm = ncode;
+            }
+            if (!branch(e.args[0])) return false;
+            for (int j : to_end) code.ins[j].imm = ncode;
+            *kind = rk;
+            return true;
+        }
+        return fail("function " + std::to_string(fn) + " is not off-loaded in row expressions");
+    }
+
+    // conjunction of filters -> one program [*p0, *p1)
+    bool compile_filters(const std::vector<const Expr *> &fs, const Resolver &rs, int *p0, int *p1)
+    {
+        *p0 = ncode;
+        for (size_t i = 0; i < fs.size(); i++) {
+            int k;
+            if (!compile(*fs[i], rs, &k)) return false;
+            if (k != RVK_BOOL) return fail("filter is not a boolean expression");
+            if (i > 0 && !emit(RV_AND)) return false;
+        }
+        *p1 = ncode;
+        return true;
+    }
+
+    int run(pg_result *res) override
+    {
+        Context &c = ctx();
+        cudaStream_t st = c.stream;
+        PG_TRY(ev_all.init());
+        Trace tr("rows");
+        RowsParams p = prm;
+        p.code = d_code.as<RvCode>();
+        p.err = d_err.as<int>();
+        PG_CUDA(cudaEventRecord(ev_all.a, st));
+        PG_CUDA(cudaMemsetAsync(d_err.p, 0, 4, st));
+        const int grid_cap = c.prop.multiProcessorCount * 8;
+        auto grid_for = [&](i64 n) { return (int)std::max<i64>(std::min<i64>((n + 255) / 256, grid_cap), 1); };
+        int launches = 0;
+        if (p.jointype) {
+            u64 nb = 16;
+            while (nb * HT_BUCKET < (u64)std::max<i64>(p.build_rows, 1) * 2) nb <<= 1;
+            if (d_slots.bytes < nb * HT_BUCKET * sizeof(longlong2)) PG_TRY(d_slots.alloc(nb * HT_BUCKET * sizeof(longlong2)));
+            PG_CUDA(cudaMemsetAsync(d_slots.p, 0x80, nb * HT_BUCKET * sizeof(longlong2), st));
+            p.jt = JoinTable{};
+            p.jt.slots = d_slots.as<longlong2>();
+            p.jt.bucket_mask = nb - 1;
+            p.jt.domain = 1;
+            if (p.build_rows > 0) {
+                rows_build_kernel<<<grid_for(p.build_rows), 256, 0, st>>>(p);
+                PG_CUDA(cudaGetLastError());
+                launches++;
+            }
+            tr.mark("build");
+        }
+        const i64 n = p.probe_rows;
+        if (d_cnt.bytes < (size_t)(n + 1) * 4) PG_TRY(d_cnt.alloc((size_t)(n + 1) * 4));
+        if (d_off.bytes < (size_t)(n + 1) * 8) PG_TRY(d_off.alloc((size_t)(n + 1) * 8));
+        p.cnt = d_cnt.as<unsigned>();
+        p.off = d_off.as<i64>();
+        PG_CUDA(cudaMemsetAsync(p.cnt + n, 0, 4, st));
+        if (n > 0) {
+            rows_probe_kernel<false><<<grid_for(n), 256, 0, st>>>(p);
+            PG_CUDA(cudaGetLastError());
+        }
+        size_t tmp = 0;
+        PG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, p.cnt, d_off.as<i64>(), (int)(n + 1), st));
+        if (d_scan_tmp.bytes < tmp) PG_TRY(d_scan_tmp.alloc(tmp));
+        PG_CUDA(cub::DeviceScan::ExclusiveSum(d_scan_tmp.p, tmp, p.cnt, d_off.as<i64>(), (int)(n + 1), st));
+        i64 total = 0;
+        int err = 0;
+        PG_CUDA(cudaMemcpyAsync(&total, d_off.as<i64>() + n, 8, cudaMemcpyDeviceToHost, st));
+        PG_CUDA(cudaMemcpyAsync(&err, d_err.p, 4, cudaMemcpyDeviceToHost, st));
+        PG_CUDA(cudaStreamSynchronize(st));
+        launches += 2;
+        tr.mark("count + scan");
+        PG_TRY(check_err(err));
+        if (d_pairs.bytes < (size_t)std::max<i64>(total, 1) * 16) PG_TRY(d_pairs.alloc((size_t)std::max<i64>(total, 1) * 16));
+        p.pair0 = d_pairs.as<i64>();
+        p.pair1 = p.pair0 + std::max<i64>(total, 1);
+        // output buffers: per column data (8-byte aligned blocks) then validity bytes
+        std::vector<size_t> doff(outs.size()), voff(outs.size());
+        size_t at = 0;
+        for (size_t j = 0; j < outs.size(); j++) {
+            const int k = p.okind[j];
+            const size_t w = k == RO_I32 ? 4 : (k == RO_BOOL || k == RO_U8) ? 1 : k == RO_DEC ? 16 : 8;
+            doff[j] = at; at += ((size_t)total * w + 15) / 16 * 16;
+            voff[j] = at; at += ((size_t)total + 15) / 16 * 16;
+        }
+        if (d_out.bytes < std::max<size_t>(at, 16)) PG_TRY(d_out.alloc(std::max<size_t>(at, 16)));
+        for (size_t j = 0; j < outs.size(); j++) { p.odata[j] = (char *)d_out.p + doff[j]; p.ovalid[j] = (uint8_t *)d_out.p + voff[j]; }
+        p.nout_rows = total;
+        if (total > 0) {
+            rows_probe_kernel<true><<<grid_for(n), 256, 0, st>>>(p);
+            PG_CUDA(cudaGetLastError());
+            rows_project_kernel<<<grid_for(total), 256, 0, st>>>(p);
+            PG_CUDA(cudaGetLastError());
+            launches += 2;
+        }
+        PG_CUDA(cudaEventRecord(ev_all.b, st));
+        std::vector<std::vector<uint8_t>> hv(outs.size());
+        std::vector<std::vector<uint8_t>> hd(outs.size());
+        for (size_t j = 0; j < outs.size(); j++) {
+            const int k = p.okind[j];
+            const size_t w = k == RO_I32 ? 4 : (k == RO_BOOL || k == RO_U8) ? 1 : k == RO_DEC ? 16 : 8;
+            hd[j].resize((size_t)total * w);
+            hv[j].resize((size_t)total);
+            if (total > 0) {
+                PG_CUDA(cudaMemcpyAsync(hd[j].data(), p.odata[j], (size_t)total * w, cudaMemcpyDeviceToHost, st));
+                PG_CUDA(cudaMemcpyAsync(hv[j].data(), p.ovalid[j], (size_t)total, cudaMemcpyDeviceToHost, st));
+            }
+        }
+        PG_CUDA(cudaMemcpyAsync(&err, d_err.p, 4, cudaMemcpyDeviceToHost, st));
+        PG_CUDA(cudaStreamSynchronize(st));
+        tr.mark("emit + project + d2h");
+        PG_TRY(check_err(err));
+        res->nrows = total;
+        for (size_t j = 0; j < outs.size(); j++) {
+            ResCol col;
+            col.type = outs[j].type;
+            col.width = outs[j].width;
+            col.scale = outs[j].scale;
+            bool any_null = false;
+            for (uint8_t v : hv[j]) any_null = any_null || !v;
+            if (p.okind[j] == RO_ROW0 || p.okind[j] == RO_ROW1) {
+                // VARCHAR carried to the output: fetched by row id from the host-resident column
+                const Column &cc = tab(outs[j].side)->cols[(size_t)outs[j].col];
+                const i64 *rows = (const i64 *)hd[j].data();
+                size_t bytes = 0;
+                for (i64 i = 0; i < total; i++)
+                    if (rows[i] >= 0) {
+                        if (rows[i] + 1 >= (i64)cc.h_off.size()) PG_FAIL(PG_ECUDA, "internal: VARCHAR row %lld out of range", (long long)rows[i]);
+                        bytes += (size_t)(cc.h_off[(size_t)rows[i] + 1] - cc.h_off[(size_t)rows[i]]);
+                    }
+                col.heap.resize(bytes + 1);
+                col.data.resize((size_t)total * sizeof(pg_string));
+                pg_string *d = (pg_string *)col.data.data();
+                size_t pos = 0;
+                for (i64 i = 0; i < total; i++) {
+                    if (rows[i] < 0) { d[i].data = col.heap.data(); d[i].len = 0; continue; }
+                    const size_t b = (size_t)cc.h_off[(size_t)rows[i]], len = (size_t)cc.h_off[(size_t)rows[i] + 1] - b;
+                    memcpy(col.heap.data() + pos, cc.h_bytes.data() + b, len);
+                    d[i].data = col.heap.data() + pos;
+                    d[i].len = (int64_t)len;
+                    pos += len;
+                }
+            } else {
+                col.data = std::move(hd[j]);
+                if (col.type == PG_T_DICT8) col.dict = tab(outs[j].side)->cols[(size_t)outs[j].col].dict;
+            }
+            if (any_null) col.valid = std::move(hv[j]);
+            res->cols.push_back(std::move(col));
+        }
+        res->stats.kernel_ms = ev_all.ms();
+        res->stats.main_kernel_ms = res->stats.kernel_ms;
+        res->stats.rows_scanned = n;
+        res->stats.kernel_launches = launches;
+        res->stats.aux[0] = n;
+        res->stats.aux[1] = total;
+        res->stats.aux[6] = total;
+        return PG_OK;
+    }
+
+    static int check_err(int err)
+    {
+        // the reference panics on these and the query fails (executor_bench.go:184-189 recover)
+        if (err == RV_ERR_OVERFLOW) PG_FAIL(PG_EOVERFLOW, "row expression: decimal overflow (integer part needs more than 19 digits)");
+        if (err == RV_ERR_DIVZERO) PG_FAIL(PG_EOVERFLOW, "row expression: division by zero");
+        if (err == RV_ERR_FLOAT) PG_FAIL(PG_EUNSUPPORTED, "row expression: value outside the exactly reproducible float32 cast range");
+        return PG_OK;
+    }
+};
+
+}  // namespace
+
+int build_rows(pg_plan *plan, std::unique_ptr<Pipeline> *out)
+{
+    std::unique_ptr<RowsPipeline> p(new RowsPipeline());
+    p->plan = plan;
+    const Node *n = &plan->root;
+    const Node *project = nullptr;
+    if (n->op == PG_OP_PROJECT) { project = n; n = &n->children[0]; }
+    std::vector<const Expr *> above;                 // filters above the join (or above the scan)
+    while (n->op == PG_OP_FILTER) { for (auto &f : n->filters) above.push_back(&f); n = &n->children[0]; }
+    const Node *top = n;
+    auto leaf_scan = [&](const Node *x, std::vector<const Expr *> *fl) -> const Node * {
+        while (x->op == PG_OP_FILTER) { for (auto &f : x->filters) fl->push_back(&f); x = &x->children[0]; }
+        if (x->op != PG_OP_SCAN) return nullptr;
+        for (auto &f : x->filters) fl->push_back(&f);
+        return x;
+    };
+    std::vector<const Expr *> pf, bf;
+    const Node *pscan = nullptr, *bscan = nullptr;
+    if (top->op == PG_OP_JOIN) {
+        pscan = leaf_scan(&top->children[0], &pf);
+        bscan = leaf_scan(&top->children[1], &bf);
+        if (!pscan || !bscan) PG_FAIL(PG_EUNSUPPORTED, "row-emitting join: both inputs must be (filtered) scans");
+        if (top->jointype != PG_JOIN_INNER && top->jointype != PG_JOIN_LEFT && top->jointype != PG_JOIN_SEMI && top->jointype != PG_JOIN_ANTI &&
+            top->jointype != PG_JOIN_MARK)
+            PG_FAIL(PG_EUNSUPPORTED, "row-emitting join: join type %d", top->jointype);
+        p->slot[0] = pscan->slot;
+        p->slot[1] = bscan->slot;
+    } else if (top->op == PG_OP_SCAN) {
+        pscan = top;
+        for (auto &f : top->filters) pf.push_back(&f);
+        p->slot[0] = pscan->slot;
+    } else {
+        PG_FAIL(PG_EUNSUPPORTED, "row-emitting pipeline over operator %d", top->op);
+    }
+    const pg_table *pt = p->tab(0), *bt = bscan ? p->tab(1) : nullptr;
+    if (ctx().world > 1 && bt && bt->dist != PG_DIST_REPLICATED && pt->dist != PG_DIST_REPLICATED)
+        PG_FAIL(PG_EUNSUPPORTED, "row-emitting join of two sharded tables (replicate the build side)");
+    if (bt && bt->nrows >= ((i64)1 << 31)) PG_FAIL(PG_EUNSUPPORTED, "row-emitting join: build side of 2^31 rows or more");
+    if (pt->nrows >= ((i64)1 << 31) - 1) PG_FAIL(PG_EUNSUPPORTED, "row-emitting pipeline over 2^31 rows or more");
+    // scopes
+    Resolver probe_scope = [&](int idx, Src *s) { if (idx < 0 || idx >= (int)pt->cols.size()) return false; s->side = 0; s->col = idx; s->mark = false; return true; };
+    Resolver build_scope = [&](int idx, Src *s) { if (!bt || idx < 0 || idx >= (int)bt->cols.size()) return false; s->side = 1; s->col = idx; s->mark = false; return true; };
+    Resolver top_scope = probe_scope;
+    if (top->op == PG_OP_JOIN) {
+        top_scope = [&](int idx, Src *s) {
+            if (idx < 0 || idx >= (int)top->outs.size()) return false;
+            const auto &o = top->outs[(size_t)idx];
+            if (o.first == 2) { s->mark = true; return top->jointype == PG_JOIN_MARK; }
+            if (o.first == 1 && top->jointype != PG_JOIN_INNER && top->jointype != PG_JOIN_LEFT) return false;
+            return o.first == 0 ? probe_scope(o.second, s) : o.first == 1 ? build_scope(o.second, s) : false;
+        };
+    }
+    RowsParams &prm = p->prm;
+    prm.jointype = top->op == PG_OP_JOIN ? top->jointype : 0;
+    prm.probe_rows = pt->nrows;
+    prm.build_rows = bt ? bt->nrows : 0;
+#define PG_ROWS_TRY(x) do { if (!(x)) PG_FAIL(PG_EUNSUPPORTED, "row-emitting pipeline: %s", p->why.c_str()); } while (0)
+    PG_ROWS_TRY(p->compile_filters(pf, probe_scope, &prm.pf0, &prm.pf1));
+    // build-side filters run with the build row on side 1
+    PG_ROWS_TRY(p->compile_filters(bf, build_scope, &prm.bf0, &prm.bf1));
+    PG_ROWS_TRY(p->compile_filters(above, top_scope, &prm.jf0, &prm.jf1));
+    if (top->op == PG_OP_JOIN) {
+        if (top->conds.empty() || top->conds.size() > 2) PG_FAIL(PG_EUNSUPPORTED, "row-emitting join: 1 or 2 key columns");
+        prm.nkey = (int)top->conds.size();
+        for (int k = 0; k < prm.nkey; k++) {
+            const Expr *pe = strip_value_preserving_casts(&top->conds[(size_t)k].first), *be = strip_value_preserving_casts(&top->conds[(size_t)k].second);
+            Src ps, bs;
+            if (pe->kind != PG_TK_COL || be->kind != PG_TK_COL || !probe_scope(pe->idx, &ps) || !build_scope(be->idx, &bs))
+                PG_FAIL(PG_EUNSUPPORTED, "row-emitting join: condition is not column = column");
+            const Column &pc = pt->cols[(size_t)ps.col], &bc = bt->cols[(size_t)bs.col];
+            if (!is_int_family(pc.type) || !is_int_family(bc.type)) PG_FAIL(PG_EUNSUPPORTED, "row-emitting join: key columns must be integer / date / decimal");
+            if (pc.type == PG_T_DECIMAL64 || bc.type == PG_T_DECIMAL64) {
+                if (pc.type != bc.type || pc.scale != bc.scale) PG_FAIL(PG_EUNSUPPORTED, "row-emitting join: DECIMAL keys of different scales");
+            }
+            if (prm.nkey == 2) {
+                auto fits32 = [](const Column &c) { return c.stats_ok && c.gmin() >= INT32_MIN && c.gmax() <= INT32_MAX; };
+                if (!fits32(pc) || !fits32(bc)) PG_FAIL(PG_EUNSUPPORTED, "two-column join keys must both fit 32 bits");
+            } else if (bc.gmin() <= HT_EMPTY && bc.gmax() >= HT_EMPTY) {
+                PG_FAIL(PG_EUNSUPPORTED, "join key range contains the empty-slot sentinel");
+            }
+            prm.pkey[k] = p->col_slot(0, ps.col);
+            prm.bkey[k] = p->col_slot(1, bs.col);
+            if (prm.pkey[k] < 0 || prm.bkey[k] < 0) PG_FAIL(PG_EUNSUPPORTED, "row-emitting pipeline: too many columns referenced");
+        }
+    }
+    // outputs
+    std::vector<Expr> owned;
+    size_t nout = project ? project->exprs.size() : top->op == PG_OP_JOIN ? top->outs.size() : pt->cols.size();
+    if (nout == 0 || nout > RV_MAXOUT) PG_FAIL(PG_EUNSUPPORTED, "row-emitting pipeline: %zu output columns", nout);
+    owned.resize(nout);
+    prm.nout = (int)nout;
+    for (size_t j = 0; j < nout; j++) {
+        const Expr *e;
+        if (project) e = &project->exprs[j];
+        else { owned[j].kind = PG_TK_COL; owned[j].side = 0; owned[j].idx = (int)j; e = &owned[j]; }
+        RowsPipeline::Out o;
+        const Expr *bare = strip_value_preserving_casts(e);
+        Src s;
+        if (bare->kind == PG_TK_COL && bare->side == 0 && top_scope(bare->idx, &s) && !s.mark) {
+            // a column carried through: keeps its column type (and dictionary / host-resident strings)
+            const Column &c = p->tab(s.side)->cols[(size_t)s.col];
+            o.type = c.type; o.width = c.width; o.scale = c.scale; o.side = s.side; o.col = s.col;
+            if (c.type == PG_T_VARCHAR) {
+                prm.okind[j] = s.side ? RO_ROW1 : RO_ROW0;
+                prm.o0[j] = prm.o1[j] = 0;
+                p->outs.push_back(o);
+                continue;
+            }
+            int k;
+            prm.o0[j] = p->ncode;
+            PG_ROWS_TRY(p->compile(*bare, top_scope, &k));
+            prm.o1[j] = p->ncode;
+            prm.okind[j] = type_size(c.type) == 4 ? RO_I32 : type_size(c.type) == 1 ? RO_U8 : RO_I64;
+            p->outs.push_back(o);
+            continue;
+        }
+        int k;
+        prm.o0[j] = p->ncode;
+        PG_ROWS_TRY(p->compile(*e, top_scope, &k));
+        prm.o1[j] = p->ncode;
+        switch (k) {
+        case RVK_BOOL: o.type = PG_T_BOOL; prm.okind[j] = RO_BOOL; break;
+        case RVK_INT:
+            if (e->ltype == PG_LT_DATE) { o.type = PG_T_DATE32; prm.okind[j] = RO_I32; }
+            else if (e->ltype == PG_LT_INTEGER) { o.type = PG_T_INT32; prm.okind[j] = RO_I32; }
+            else { o.type = PG_T_INT64; prm.okind[j] = RO_I64; }
+            break;
+        case RVK_DEC: o.type = PG_T_DECIMAL128; o.width = e->width; o.scale = e->scale; prm.okind[j] = RO_DEC; break;
+        default: PG_FAIL(PG_EUNSUPPORTED, "row-emitting pipeline: output column %zu has a type that is not returned (FLOAT / computed string)", j);
+        }
+        p->outs.push_back(o);
+    }
+#undef PG_ROWS_TRY
+    PG_TRY(p->d_code.alloc(sizeof(RvCode)));
+    PG_TRY(p->d_err.alloc(4));
+    PG_CUDA(cudaMemcpyAsync(p->d_code.p, &p->code, sizeof(RvCode), cudaMemcpyHostToDevice, ctx().stream));
+    PG_CUDA(cudaStreamSynchronize(ctx().stream));
+    static const char *jn[] = {"", "INNER", "SEMI", "ANTI", "MARK", "LEFT", "ANTI-MARK"};
+    char b[320];
+    if (top->op == PG_OP_JOIN)
+        snprintf(b, sizeof b, "Rows[%s%s join %s x %s (%d key column%s, bucketized hash table) -> count / scan / emit pairs -> project %zu columns] instructions=%d",
+                 project ? "project <- " : "", jn[top->jointype], pt->name.c_str(), bt->name.c_str(), prm.nkey, prm.nkey > 1 ? "s" : "", nout, p->ncode);
+    else
+        snprintf(b, sizeof b, "Rows[%sfilter scan(%s) -> count / scan / emit -> project %zu columns] instructions=%d", project ? "project <- " : "", pt->name.c_str(), nout, p->ncode);
+    p->explain = b;
+    *out = std::move(p);
+    return PG_OK;
+}
+
+}  // namespace pg

@@ -189,3 +189,43 @@ def test_product_host_arithmetic_agrees_with_the_oracle(tmp_path):
             assert (m == "1") == O.wildcard_match(p.encode(), t.encode()), (case, got)
             if fast == "1":
                 assert p[0] == "%" and p[-1] == "%" and (m == "1") == (p[1:-1] in t), (case, got)
+
+
+def test_row_oracle_and_descriptor_of_a_row_emitting_plan():
+    """CPU: the tree-walking row oracle (oracle/rowexec.py) on hand-checked cases -- LEFT / MARK / ANTI join NULL
+    semantics (join_scan.go:67-165), CASE evaluating only the taken branch (expr_exec.go:144-246), govalues Quo
+    (function_operator_binary.go:195-210) -- and pg_plan_compile accepting the Project / CASE descriptor."""
+    import ctypes as C
+    from oracle import rowexec as R
+    from plan_b200 import _lib as L, chunk as K, compute as X
+    B, I, D = K.LType(K.LTID_BOOLEAN), K.IntegerType(), K.DecimalType(15, 2)
+    left = [[1, R.Dec(250, 2)], [2, R.Dec(0, 2)], [None, R.Dec(100, 2)], [7, R.Dec(999, 2)]]
+    right = [[1, 10], [1, 11], [2, 20], [None, 99]]
+    tables = {"l": left, "r": right}
+    lscan = X.PhysicalOperator(X.POT_Scan, Info=X.ScanOpInfo("l"))
+    rscan = X.PhysicalOperator(X.POT_Scan, Info=X.ScanOpInfo("r"))
+
+    def join(jt, outs):
+        return X.PhysicalOperator(X.POT_Join, Children=[lscan, rscan], Outputs=outs,
+                                  Info=X.JoinOpInfo(jt, [X.func("=", B, X.col(0, 0, I), X.col(1, 0, I))]))
+    both = [X.col(0, 0, I), X.col(1, 1, I)]
+    assert sorted(map(str, R.execute(join(X.JOIN_INNER, both), tables))) == ["[1, 10]", "[1, 11]", "[2, 20]"]
+    assert sorted(map(str, R.execute(join(X.JOIN_LEFT, both), tables))) == ["[1, 10]", "[1, 11]", "[2, 20]", "[7, None]", "[None, None]"]
+    assert R.execute(join(X.JOIN_ANTI, [X.col(0, 0, I)]), tables) == [[None], [7]]          # a NULL key never matches: ANTI keeps it
+    assert R.execute(join(X.JOIN_SEMI, [X.col(0, 0, I)]), tables) == [[1], [2]]
+    assert R.execute(join(X.JOIN_MARK, [X.col(0, 0, I), X.col(2, 0, B)]), tables) == [[1, True], [2, True], [None, None], [7, False]]
+    # CASE: the division sits in the branch taken only where the divisor is non-zero
+    ratio = X.func("case", K.DecimalType(38, 6), X.const(None, D), X.func(">", B, X.col(0, 1, D), X.const(0, D)),
+                   X.func("/", K.DecimalType(38, 6), X.cast(X.const(1, I), D), X.col(0, 1, D)))
+    proj = X.PhysicalOperator(X.POT_Project, Outputs=[ratio], Children=[lscan])
+    got = R.format_rows(R.execute(proj, tables), [K.DecimalType(38, 6)])
+    assert got == sorted(["0.4", "NULL", "1", "0.1001"])                                     # 1/9.99 = 0.1001001... -> 6 digits, zeros trimmed
+    q = R.dec_quo(R.Dec(1, 0), R.Dec(3, 0))
+    assert (q.coef, q.scale) == (3333333333333333333, 19)
+    q = R.dec_quo(R.Dec(2, 0), R.Dec(3, 0))
+    assert (q.coef, q.scale) == (6666666666666666667, 19)
+    # the descriptor of a row-emitting plan parses (no GPU needed to compile)
+    desc, slots = X.serialize_plan(proj)
+    plan = C.c_void_p()
+    L.check(L.lib().pg_plan_compile(desc.ctypes.data_as(C.POINTER(C.c_int64)), len(desc), C.byref(plan)))
+    L.lib().pg_plan_free(plan)
