@@ -350,8 +350,12 @@ func newGpuPipelineExec(op *PhysicalOperator, cfg *util.Config, txn *storage.Txn
 	switch op.Typ {
 	case POT_Agg, POT_Order, POT_Limit:
 		return &gpuPipelineExec{op: op, cfg: cfg, txn: txn}, nil
+	case POT_Project, POT_Filter, POT_Join, POT_Scan:
+		// row-emitting pipelines (rows.cu): the library returns the operator's output ROWS in <= 2048-row chunks.
+		// serializePlan / Prepare refuse what it does not take (deeper join trees, VARCHAR expressions ...).
+		return &gpuPipelineExec{op: op, cfg: cfg, txn: txn}, nil
 	}
-	return nil, errNotOffloadable{"subtree root is not an aggregate (optionally under Order / Limit)"}
+	return nil, errNotOffloadable{"subtree root is neither an aggregate (optionally under Order / Limit) nor a row-emitting Project / Filter / Join / Scan"}
 }
 
 // Init serialises the subtree, binds device tables and lets the library choose its kernels.  An error (including
@@ -462,6 +466,8 @@ func fillVector(vec *chunk.Vector, lt common.LType, typ, scale int32, data unsaf
 		case plangpu.TDate32:
 			d := time.Unix(int64(*(*int32)(unsafe.Add(data, 4*i)))*86400, 0).UTC()
 			val.I64, val.I64_1, val.I64_2 = int64(d.Year()), int64(d.Month()), int64(d.Day())
+		case plangpu.TBool:
+			val.Bool = *(*byte)(unsafe.Add(data, i)) != 0 // MARK columns, projected predicates (vector.go SetValue LTID_BOOLEAN)
 		case plangpu.TChar1:
 			val.Str = string([]byte{*(*byte)(unsafe.Add(data, i))})
 		case plangpu.TDict8:

@@ -21,7 +21,7 @@ const (
 	pgDescMagic   = 0x31504750
 	pgDescVersion = 1
 
-	pgOpScan, pgOpFilter, pgOpJoin, pgOpAgg, pgOpTopK = 1, 2, 3, 4, 5
+	pgOpScan, pgOpFilter, pgOpJoin, pgOpAgg, pgOpTopK, pgOpProject = 1, 2, 3, 4, 5, 6
 
 	pgTkCol, pgTkConst, pgTkStr, pgTkFunc = 1, 2, 3, 4
 
@@ -33,7 +33,9 @@ var pgFuncIDs = map[string]int64{
 	FuncAdd: 1, FuncSubtract: 2, FuncMultiply: 3, FuncDivide: 4,
 	FuncEqual: 10, FuncNotEqual: 11, FuncLess: 12, FuncLessEqual: 13, FuncGreater: 14, FuncGreaterEqual: 15,
 	FuncIn: 16, FuncLike: 17, FuncNotLike: 18, FuncExtract: 19,
-	FuncAnd: 20, FuncOr: 21, FuncNot: 22, FuncCast: 30,
+	FuncAnd: 20, FuncOr: 21, FuncNot: 22,
+	FuncCase: 23, // Children = [ELSE, WHEN1, THEN1, ...] as bindCaseExpr builds them (builder_expr.go:95-113)
+	FuncCast: 30,
 }
 
 var pgAggIDs = map[string]int64{"sum": 1, "avg": 2, "count": 3, "min": 4, "max": 5}
@@ -155,6 +157,16 @@ func (ps *planSerializer) exprTokens(e *Expr, agg *PhysicalOperator, ntok *int64
 			*out = append(*out, pgTkConst)
 			*out = append(*out, lt...)
 			*out = append(*out, u)
+		case ConstTypeBoolean:
+			v := int64(0)
+			if e.ConstValue.Boolean {
+				v = 1
+			}
+			*out = append(*out, pgTkConst)
+			*out = append(*out, lt...)
+			*out = append(*out, v)
+		case ConstTypeNull:
+			*out = append(*out, pgTkConst, 0, 0, 0, 0) // ltype 0 = NULL (a CASE without ELSE)
 		default:
 			return errNotOffloadable{fmt.Sprintf("constant type %v", e.ConstValue.Type)}
 		}
@@ -248,6 +260,16 @@ func (ps *planSerializer) node(op *PhysicalOperator, w *[]int64) error {
 			}
 		}
 		return nil
+	case POT_Project:
+		// root of a ROW-EMITTING pipeline (rows.cu): Project <- [Filter]* <- (Scan | Join(scan, scan)).  A Project right
+		// under an aggregate never gets here: POT_Agg inlines it below.
+		*w = append(*w, pgOpProject, int64(len(op.Projects)))
+		for _, e := range op.Projects {
+			if err := ps.exprWords(e, nil, w); err != nil {
+				return err
+			}
+		}
+		return ps.node(op.Children[0], w)
 	case POT_Filter:
 		*w = append(*w, pgOpFilter, int64(len(op.Filters)))
 		for _, f := range op.Filters {

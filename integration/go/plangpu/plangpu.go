@@ -55,6 +55,7 @@ const (
 	THugeint    = int32(C.PG_T_HUGEINT)
 	TDecimal128 = int32(C.PG_T_DECIMAL128)
 	TVarchar    = int32(C.PG_T_VARCHAR)
+	TBool       = int32(C.PG_T_BOOL)
 )
 
 // Error carries the pg_status and the library's message for the calling thread.

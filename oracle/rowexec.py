@@ -220,6 +220,56 @@ def execute(op, tables):
         return [r for r in execute(op.Children[0], tables) if _all_true(op.Filters, r)]
     if op.Typ == POT_Project:
         return [[eval_expr(e, r) for e in op.Outputs] for r in execute(op.Children[0], tables)]
+    if op.Typ == POT_Agg:
+        # aggExecutor over its child's rows (executor_aggr.go:106-262): groups in first-seen order; sum(DECIMAL) is a
+        # left fold of Decimal.Add in row order, sum(INTEGER) a HUGEINT, avg(DECIMAL) = sum.Quo(count), avg(INTEGER) =
+        # float64 sum / float64 count, NULL arguments are ignored, an aggregate without any input is NULL
+        # (function_aggr.go:620-1032)
+        groups = {}
+        for r in execute(op.Children[0], tables):
+            key = tuple(_gkey(eval_expr(g, r)) for g in op.Info.GroupBys)
+            st = groups.get(key)
+            if st is None:
+                st = groups[key] = {"key": [eval_expr(g, r) for g in op.Info.GroupBys], "acc": [None] * len(op.Info.Aggs), "n": [0] * len(op.Info.Aggs)}
+            for i, a in enumerate(op.Info.Aggs):
+                fn = a.FunImpl
+                if fn == "count" and not a.Children:
+                    st["n"][i] += 1
+                    continue
+                v = eval_expr(a.Children[0], r)
+                if v is None:
+                    continue
+                st["n"][i] += 1
+                if fn == "count":
+                    continue
+                cur = st["acc"][i]
+                if cur is None:
+                    st["acc"][i] = v
+                elif fn in ("sum", "avg"):
+                    st["acc"][i] = dec_add(cur, v) if isinstance(v, Dec) else cur + v
+                elif fn == "min":
+                    st["acc"][i] = v if _compare("<", v, cur) else cur
+                elif fn == "max":
+                    st["acc"][i] = v if _compare(">", v, cur) else cur
+        out = []
+        for st in groups.values():
+            vals = []
+            for i, a in enumerate(op.Info.Aggs):
+                fn, acc, n = a.FunImpl, st["acc"][i], st["n"][i]
+                if fn == "count":
+                    vals.append(n)
+                elif n == 0:
+                    vals.append(None)
+                elif fn == "avg":
+                    vals.append(dec_quo(acc, Dec.from_int(n)) if isinstance(acc, Dec) else float(acc) / float(n))
+                else:
+                    vals.append(acc)
+            if not all(eval_having(f, st["key"], vals) for f in op.Filters):
+                continue
+            out.append([st["key"][o.ColRef[1]] if o.ColRef[0] == 0 else vals[o.ColRef[1]] for o in op.Outputs])
+        if not op.Info.GroupBys and not out and not op.Filters:
+            pass        # an aggregate over no rows at all: the reference emits nothing for these plans (executor_aggr.go:222-262)
+        return out
     if op.Typ == POT_Join:
         left, right = execute(op.Children[0], tables), execute(op.Children[1], tables)
         lk = [c.Children[0] for c in op.Info.OnConds]
@@ -265,6 +315,14 @@ def execute(op, tables):
     raise ValueError("operator %r" % op.Typ)
 
 
+def _gkey(v):
+    return ("d", v.signed() * 10 ** (19 - v.scale)) if isinstance(v, Dec) else v
+
+
+def eval_having(f, key, vals):
+    raise NotImplementedError("HAVING in the row oracle")
+
+
 def _key(v):
     return v.signed() * 10 ** (19 - v.scale) if isinstance(v, Dec) else v
 
@@ -275,6 +333,8 @@ def format_value(v, typ):
         return "NULL"
     if isinstance(v, bool):
         return "true" if v else "false"
+    if isinstance(v, float) and not isinstance(v, np.float32):
+        return O.fmt_double(v)
     if isinstance(v, Dec):
         buf = C.create_string_buffer(96)
         O.lib().orc_format_decimal(v.coef, v.scale, int(v.neg), typ.Scale, buf, 96)

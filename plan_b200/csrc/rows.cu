@@ -24,7 +24,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include "pipeline.hpp"
-#include "rowvm.cuh"
+#include "rowvm_compile.hpp"
 
 namespace pg {
 
@@ -148,284 +148,17 @@ rows_project_kernel(const RowsParams p)
 
 namespace {
 
-struct Src { int side = 0, col = -1; bool mark = false; };
-typedef std::function<bool(int, Src *)> Resolver;
-
 struct RowsPipeline : Pipeline {
     pg_plan *plan = nullptr;
-    RvCode code{};
-    int ncode = 0, ncols = 0, nmasks = 0;
+    RvCompiler cc;
     int slot[2] = {-1, -1};              // table slots of side 0 (probe / scanned) and side 1 (build)
     RowsParams prm{};
     struct Out { int type = 0, width = 0, scale = 0, side = 0, col = -1; };
     std::vector<Out> outs;
     DevBuf d_code, d_slots, d_cnt, d_off, d_pairs, d_err, d_scan_tmp, d_out;
     EventPair ev_all;
-    std::string why;
 
     const pg_table *tab(int side) const { return plan->slots[(size_t)slot[side]]; }
-
-    bool fail(const std::string &s) { why = s; return false; }
-    bool emit(int op, int a = 0, int b = 0, i64 imm = 0)
-    {
-        if (ncode >= RV_MAXCODE) return fail("expression program too long");
-        code.ins[ncode++] = RvIns{op, a, b, 0, imm};
-        return true;
-    }
-    int col_slot(int side, int col)
-    {
-        const pg_table *t = tab(side);
-        const Column &c = t->cols[(size_t)col];
-        for (int i = 0; i < ncols; i++)
-            if (code.cols[i].side == side && code.cols[i].col.p == c.d_data) return i;
-        if (ncols >= RV_MAXCOL) return -1;
-        RvCol rc;
-        rc.col.p = c.d_data;
-        rc.col.width = c.phys_width();
-        rc.col.base = c.base;
-        rc.col.valid = c.has_nulls ? c.d_valid : nullptr;
-        rc.side = side;
-        rc.scale = c.type == PG_T_DECIMAL64 ? c.scale : 0;
-        code.cols[ncols] = rc;
-        return ncols++;
-    }
-    static int kind_of_column(const Column &c)
-    {
-        switch (c.type) {
-        case PG_T_INT32: case PG_T_INT64: case PG_T_DATE32: return RVK_INT;
-        case PG_T_DECIMAL64: return RVK_DEC;
-        case PG_T_CHAR1: case PG_T_DICT8: return RVK_CODE;
-        default: return 0;
-        }
-    }
-    // code-set of a string predicate on a byte-coded column: fn applied to every code's string, once, on the host
-    bool code_mask(const Column &c, int fn, const std::vector<std::string> &lits, int *mask_slot)
-    {
-        if (nmasks >= RV_MAXMASK) return fail("too many string predicates");
-        unsigned *m = code.masks[nmasks];
-        for (int i = 0; i < 8; i++) m[i] = 0;
-        const int ncodes = c.type == PG_T_CHAR1 ? 256 : (int)c.dict.size();
-        for (int k = 0; k < ncodes; k++) {
-            const std::string s = c.type == PG_T_CHAR1 ? std::string(1, (char)k) : c.dict[(size_t)k];
-            bool t = false;
-            switch (fn) {
-            case PG_FN_EQ: case PG_FN_IN: for (auto &l : lits) t = t || s == l; break;
-            case PG_FN_NE: t = s != lits[0]; break;
-            case PG_FN_LIKE: t = wildcard_match(lits[0].data(), lits[0].size(), s.data(), s.size()); break;
-            case PG_FN_NOT_LIKE: t = !wildcard_match(lits[0].data(), lits[0].size(), s.data(), s.size()); break;
-            default: return fail("string comparison other than =, <>, IN, LIKE");
-            }
-            if (t) m[k >> 5] |= 1u << (k & 31);
-        }
-        *mask_slot = nmasks++;
-        return true;
-    }
-    // unify two numeric kinds (the binder casts INTEGER operands of a DECIMAL operation; be lenient about it)
-    bool numeric_pair(int *ka, int *kb)
-    {
-        if (*ka == *kb) return true;
-        if (*ka == RVK_INT && *kb == RVK_DEC) { *ka = RVK_DEC; return true; }      // INT values are DEC at scale 0 as they stand
-        if (*ka == RVK_DEC && *kb == RVK_INT) { *kb = RVK_DEC; return true; }
-        return fail("operand types differ (missing cast)");
-    }
-
-    // emits code that pushes the value of `e`; *kind = its static kind, *base = the byte-coded column it is (for string predicates)
-    bool compile(const Expr &e, const Resolver &rs, int *kind, const Column **base = nullptr, int depth = 0)
-    {
-        if (base) *base = nullptr;
-        if (depth > 24) return fail("expression too deep");
-        switch (e.kind) {
-        case PG_TK_COL: {
-            Src s;
-            if (e.side != 0 || !rs(e.idx, &s)) return fail("column reference out of scope");
-            if (s.mark) { *kind = RVK_BOOL; return emit(RV_MARK); }
-            const Column &c = tab(s.side)->cols[(size_t)s.col];
-            *kind = kind_of_column(c);
-            if (!*kind) return fail("column " + c.name + ": VARCHAR columns can be carried to the output but not computed on");
-            const int cs = col_slot(s.side, s.col);
-            if (cs < 0) return fail("too many columns referenced");
-            if (base) *base = &c;
-            return emit(RV_COL, cs);
-        }
-        case PG_TK_CONST:
-            switch (e.ltype) {
-            case PG_LT_BOOLEAN: *kind = RVK_BOOL; return emit(RV_CONST, 0, 0, e.v0 != 0);
-            case PG_LT_INTEGER: case PG_LT_BIGINT: case PG_LT_DATE: *kind = RVK_INT; return emit(RV_CONST, 0, 0, e.v0);
-            case PG_LT_DECIMAL: *kind = RVK_DEC; return emit(RV_CONST, 0, e.scale, e.v0);
-            case PG_LT_FLOAT: case PG_LT_DOUBLE: {      // float constants are float32(val) (chunk/vector.go:205-207)
-                double d;
-                memcpy(&d, &e.v0, 8);
-                const float f = (float)d;
-                unsigned bits;
-                memcpy(&bits, &f, 4);
-                *kind = RVK_F32;
-                return emit(RV_CONST, 0, 0, (i64)bits);
-            }
-            default: return fail("constant type");
-            }
-        case PG_TK_FUNC: break;
-        default: return fail("string literal outside a comparison with a dictionary / char column");
-        }
-        const int fn = e.fn;
-        const size_t na = e.args.size();
-        if (fn == PG_FN_ADD || fn == PG_FN_SUB || fn == PG_FN_MUL || fn == PG_FN_DIV) {
-            if (na != 2) return fail("arithmetic arity");
-            int ka, kb;
-            if (!compile(e.args[0], rs, &ka, nullptr, depth + 1) || !compile(e.args[1], rs, &kb, nullptr, depth + 1)) return false;
-            if (!numeric_pair(&ka, &kb)) return false;
-            if (ka != RVK_INT && ka != RVK_DEC && ka != RVK_F32) return fail("arithmetic on a non-numeric value");
-            if (ka == RVK_INT && fn == PG_FN_DIV) return fail("integer division");
-            *kind = ka;
-            const int op = fn == PG_FN_ADD ? RV_ADD : fn == PG_FN_SUB ? RV_SUB : fn == PG_FN_MUL ? RV_MUL : RV_DIV;
-            return emit(op, ka, (ka == RVK_INT && e.ltype == PG_LT_INTEGER) ? 32 : 0);
-        }
-        if (is_cmp(fn) || fn == PG_FN_LIKE || fn == PG_FN_NOT_LIKE) {
-            if (na != 2) return fail("comparison arity");
-            *kind = RVK_BOOL;
-            const Expr *l = &e.args[0], *r = &e.args[1];
-            int f2 = fn;
-            if (l->kind == PG_TK_STR) { std::swap(l, r); f2 = flip_cmp(fn); }
-            if (r->kind == PG_TK_STR) {
-                int k;
-                const Column *c;
-                if (!compile(*strip_value_preserving_casts(l), rs, &k, &c, depth + 1)) return false;
-                if (k != RVK_CODE || !c) return fail("string comparison on a column that is not dictionary / char coded");
-                int ms;
-                if (!code_mask(*c, f2, {r->str}, &ms)) return false;
-                return emit(RV_INSET, ms);
-            }
-            if (!is_cmp(fn)) return fail("LIKE needs a string pattern");
-            int ka, kb;
-            if (!compile(*l, rs, &ka, nullptr, depth + 1) || !compile(*r, rs, &kb, nullptr, depth + 1)) return false;
-            if (!numeric_pair(&ka, &kb)) return false;
-            return emit(RV_CMP, f2, ka);
-        }
-        if (fn == PG_FN_IN) {
-            if (na < 2) return fail("IN arity");
-            *kind = RVK_BOOL;
-            if (e.args[1].kind == PG_TK_STR) {
-                std::vector<std::string> lits;
-                for (size_t i = 1; i < na; i++) { if (e.args[i].kind != PG_TK_STR) return fail("IN list mixes types"); lits.push_back(e.args[i].str); }
-                int k;
-                const Column *c;
-                if (!compile(*strip_value_preserving_casts(&e.args[0]), rs, &k, &c, depth + 1)) return false;
-                if (k != RVK_CODE || !c) return fail("string IN on a column that is not dictionary / char coded");
-                int ms;
-                if (!code_mask(*c, PG_FN_IN, lits, &ms)) return false;
-                return emit(RV_INSET, ms);
-            }
-            for (size_t i = 1; i < na; i++) {          // x = c1 OR x = c2 ... (inInt32Op, function_operator_boolean.go:393-504)
-                int ka, kb;
-                if (!compile(e.args[0], rs, &ka, nullptr, depth + 1) || !compile(e.args[i], rs, &kb, nullptr, depth + 1)) return false;
-                if (!numeric_pair(&ka, &kb) || !emit(RV_CMP, PG_FN_EQ, ka)) return false;
-                if (i > 1 && !emit(RV_OR)) return false;
-            }
-            return true;
-        }
-        if (fn == PG_FN_AND || fn == PG_FN_OR) {
-            if (na < 2) return fail("AND / OR arity");
-            *kind = RVK_BOOL;
-            for (size_t i = 0; i < na; i++) {
-                int k;
-                if (!compile(e.args[i], rs, &k, nullptr, depth + 1)) return false;
-                if (k != RVK_BOOL) return fail("AND / OR of a non-boolean");
-                if (i > 0 && !emit(fn == PG_FN_AND ? RV_AND : RV_OR)) return false;
-            }
-            return true;
-        }
-        if (fn == PG_FN_NOT) {
-            int k;
-            if (na != 1 || !compile(e.args[0], rs, &k, nullptr, depth + 1) || k != RVK_BOOL) return why.empty() ? fail("NOT of a non-boolean") : false;
-            *kind = RVK_BOOL;
-            return emit(RV_NOT);
-        }
-        if (fn == PG_FN_EXTRACT) {
-            if (na != 2 || e.args[0].kind != PG_TK_STR || e.args[0].str != "year") return fail("only EXTRACT(year ...) is off-loaded");
-            int k;
-            if (!compile(e.args[1], rs, &k, nullptr, depth + 1)) return false;
-            if (k != RVK_INT || e.args[1].ltype != PG_LT_DATE) return fail("EXTRACT(year) of a non-date");
-            *kind = RVK_INT;
-            return emit(RV_YEAR);
-        }
-        if (fn == PG_FN_CAST) {
-            if (na != 1) return fail("cast arity");
-            int k;
-            const Column *c;
-            if (!compile(e.args[0], rs, &k, &c, depth + 1)) return false;
-            if (base) *base = c;
-            switch (e.ltype) {
-            case PG_LT_DECIMAL:
-                if (k == RVK_DEC) {
-                    if (e.scale < e.args[0].scale) return fail("DECIMAL cast that drops fractional digits");
-                    *kind = RVK_DEC;
-                    return true;                 // value preserving (tryCastDecimalToDecimal, function_cast.go:380-404)
-                }
-                if (k == RVK_INT) { *kind = RVK_DEC; return emit(RV_TODEC); }      // tryCastInt32ToDecimal (:337-347)
-                return fail("cast to DECIMAL from this type");
-            case PG_LT_FLOAT: case PG_LT_DOUBLE:
-                if (k == RVK_F32) { *kind = RVK_F32; return true; }
-                if (k != RVK_DEC && k != RVK_INT) return fail("cast to FLOAT from this type");
-                *kind = RVK_F32;
-                return emit(RV_TOF32, k);
-            case PG_LT_BIGINT: case PG_LT_HUGEINT: case PG_LT_INTEGER:
-                if (k != RVK_INT || (e.ltype == PG_LT_INTEGER && e.args[0].ltype != PG_LT_INTEGER)) return fail("narrowing integer cast");
-                *kind = RVK_INT;
-                return true;
-            case PG_LT_DATE: case PG_LT_VARCHAR: case PG_LT_BOOLEAN:
-                if (e.ltype != e.args[0].ltype) return fail("cast between unrelated types");
-                *kind = k;
-                return true;
-            default: return fail("cast target type");
-            }
-        }
-        if (fn == PG_FN_CASE) {
-            // children: [ELSE, WHEN1, THEN1, WHEN2, THEN2 ...] (executeCase, expr_exec.go:144-246)
-            if (na < 3 || (na & 1) == 0) return fail("CASE arity");
-            std::vector<int> to_end;
-            int rk = 0;
-            auto branch = [&](const Expr &x) -> bool {
-                int k;
-                if (x.kind == PG_TK_CONST && x.ltype == 0) { k = rk; if (!emit(RV_NULL)) return false; }       // typeless NULL constant
-                else if (!compile(x, rs, &k, nullptr, depth + 1)) return false;
-                if (rk == 0) rk = k;
-                else if (k != rk) {
-                    if ((rk == RVK_DEC && k == RVK_INT) || (rk == RVK_INT && k == RVK_DEC)) rk = RVK_DEC;
-                    else return fail("CASE branches of different types");
-                }
-                return true;
-            };
-            for (size_t i = 1; i + 1 < na; i += 2) {
-                int k;
-                if (!compile(e.args[i], rs, &k, nullptr, depth + 1)) return false;
-                if (k != RVK_BOOL) return fail("CASE WHEN is not a boolean");
-                const int jz = ncode;
-                if (!emit(RV_JZ)) return false;
-                if (!branch(e.args[i + 1])) return false;
-                to_end.push_back(ncode);
-                if (!emit(RV_JMP)) return false;
-                code.ins[jz].imm = ncode;
-            }
-            if (!branch(e.args[0])) return false;
-            for (int j : to_end) code.ins[j].imm = ncode;
-            *kind = rk;
-            return true;
-        }
-        return fail("function " + std::to_string(fn) + " is not off-loaded in row expressions");
-    }
-
-    // conjunction of filters -> one program [*p0, *p1)
-    bool compile_filters(const std::vector<const Expr *> &fs, const Resolver &rs, int *p0, int *p1)
-    {
-        *p0 = ncode;
-        for (size_t i = 0; i < fs.size(); i++) {
-            int k;
-            if (!compile(*fs[i], rs, &k)) return false;
-            if (k != RVK_BOOL) return fail("filter is not a boolean expression");
-            if (i > 0 && !emit(RV_AND)) return false;
-        }
-        *p1 = ncode;
-        return true;
-    }
 
     int run(pg_result *res) override
     {
@@ -612,6 +345,8 @@ int build_rows(pg_plan *plan, std::unique_ptr<Pipeline> *out)
         PG_FAIL(PG_EUNSUPPORTED, "row-emitting pipeline over operator %d", top->op);
     }
     const pg_table *pt = p->tab(0), *bt = bscan ? p->tab(1) : nullptr;
+    p->cc.tables[0] = pt;
+    p->cc.tables[1] = bt;
     if (ctx().world > 1 && bt && bt->dist != PG_DIST_REPLICATED && pt->dist != PG_DIST_REPLICATED)
         PG_FAIL(PG_EUNSUPPORTED, "row-emitting join of two sharded tables (replicate the build side)");
     if (bt && bt->nrows >= ((i64)1 << 31)) PG_FAIL(PG_EUNSUPPORTED, "row-emitting join: build side of 2^31 rows or more");
@@ -633,11 +368,11 @@ int build_rows(pg_plan *plan, std::unique_ptr<Pipeline> *out)
     prm.jointype = top->op == PG_OP_JOIN ? top->jointype : 0;
     prm.probe_rows = pt->nrows;
     prm.build_rows = bt ? bt->nrows : 0;
-#define PG_ROWS_TRY(x) do { if (!(x)) PG_FAIL(PG_EUNSUPPORTED, "row-emitting pipeline: %s", p->why.c_str()); } while (0)
-    PG_ROWS_TRY(p->compile_filters(pf, probe_scope, &prm.pf0, &prm.pf1));
+#define PG_ROWS_TRY(x) do { if (!(x)) PG_FAIL(PG_EUNSUPPORTED, "row-emitting pipeline: %s", p->cc.why.c_str()); } while (0)
+    PG_ROWS_TRY(p->cc.compile_filters(pf, probe_scope, &prm.pf0, &prm.pf1));
     // build-side filters run with the build row on side 1
-    PG_ROWS_TRY(p->compile_filters(bf, build_scope, &prm.bf0, &prm.bf1));
-    PG_ROWS_TRY(p->compile_filters(above, top_scope, &prm.jf0, &prm.jf1));
+    PG_ROWS_TRY(p->cc.compile_filters(bf, build_scope, &prm.bf0, &prm.bf1));
+    PG_ROWS_TRY(p->cc.compile_filters(above, top_scope, &prm.jf0, &prm.jf1));
     if (top->op == PG_OP_JOIN) {
         if (top->conds.empty() || top->conds.size() > 2) PG_FAIL(PG_EUNSUPPORTED, "row-emitting join: 1 or 2 key columns");
         prm.nkey = (int)top->conds.size();
@@ -657,8 +392,8 @@ int build_rows(pg_plan *plan, std::unique_ptr<Pipeline> *out)
             } else if (bc.gmin() <= HT_EMPTY && bc.gmax() >= HT_EMPTY) {
                 PG_FAIL(PG_EUNSUPPORTED, "join key range contains the empty-slot sentinel");
             }
-            prm.pkey[k] = p->col_slot(0, ps.col);
-            prm.bkey[k] = p->col_slot(1, bs.col);
+            prm.pkey[k] = p->cc.col_slot(0, ps.col);
+            prm.bkey[k] = p->cc.col_slot(1, bs.col);
             if (prm.pkey[k] < 0 || prm.bkey[k] < 0) PG_FAIL(PG_EUNSUPPORTED, "row-emitting pipeline: too many columns referenced");
         }
     }
@@ -686,17 +421,17 @@ int build_rows(pg_plan *plan, std::unique_ptr<Pipeline> *out)
                 continue;
             }
             int k;
-            prm.o0[j] = p->ncode;
-            PG_ROWS_TRY(p->compile(*bare, top_scope, &k));
-            prm.o1[j] = p->ncode;
+            prm.o0[j] = p->cc.ncode;
+            PG_ROWS_TRY(p->cc.compile(*bare, top_scope, &k));
+            prm.o1[j] = p->cc.ncode;
             prm.okind[j] = type_size(c.type) == 4 ? RO_I32 : type_size(c.type) == 1 ? RO_U8 : RO_I64;
             p->outs.push_back(o);
             continue;
         }
         int k;
-        prm.o0[j] = p->ncode;
-        PG_ROWS_TRY(p->compile(*e, top_scope, &k));
-        prm.o1[j] = p->ncode;
+        prm.o0[j] = p->cc.ncode;
+        PG_ROWS_TRY(p->cc.compile(*e, top_scope, &k));
+        prm.o1[j] = p->cc.ncode;
         switch (k) {
         case RVK_BOOL: o.type = PG_T_BOOL; prm.okind[j] = RO_BOOL; break;
         case RVK_INT:
@@ -712,15 +447,15 @@ int build_rows(pg_plan *plan, std::unique_ptr<Pipeline> *out)
 #undef PG_ROWS_TRY
     PG_TRY(p->d_code.alloc(sizeof(RvCode)));
     PG_TRY(p->d_err.alloc(4));
-    PG_CUDA(cudaMemcpyAsync(p->d_code.p, &p->code, sizeof(RvCode), cudaMemcpyHostToDevice, ctx().stream));
+    PG_CUDA(cudaMemcpyAsync(p->d_code.p, &p->cc.code, sizeof(RvCode), cudaMemcpyHostToDevice, ctx().stream));
     PG_CUDA(cudaStreamSynchronize(ctx().stream));
     static const char *jn[] = {"", "INNER", "SEMI", "ANTI", "MARK", "LEFT", "ANTI-MARK"};
     char b[320];
     if (top->op == PG_OP_JOIN)
         snprintf(b, sizeof b, "Rows[%s%s join %s x %s (%d key column%s, bucketized hash table) -> count / scan / emit pairs -> project %zu columns] instructions=%d",
-                 project ? "project <- " : "", jn[top->jointype], pt->name.c_str(), bt->name.c_str(), prm.nkey, prm.nkey > 1 ? "s" : "", nout, p->ncode);
+                 project ? "project <- " : "", jn[top->jointype], pt->name.c_str(), bt->name.c_str(), prm.nkey, prm.nkey > 1 ? "s" : "", nout, p->cc.ncode);
     else
-        snprintf(b, sizeof b, "Rows[%sfilter scan(%s) -> count / scan / emit -> project %zu columns] instructions=%d", project ? "project <- " : "", pt->name.c_str(), nout, p->ncode);
+        snprintf(b, sizeof b, "Rows[%sfilter scan(%s) -> count / scan / emit -> project %zu columns] instructions=%d", project ? "project <- " : "", pt->name.c_str(), nout, p->cc.ncode);
     p->explain = b;
     *out = std::move(p);
     return PG_OK;

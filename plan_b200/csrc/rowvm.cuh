@@ -68,7 +68,7 @@ __device__ __forceinline__ bool rv_fit(i128 v, int scale, RvVal *out)
 }
 
 // evaluates program [pc0, pc1); row0 / row1 = row ids on side 0 / 1
-__device__ __noinline__ RvVal rv_eval(const RvCode &c, int pc0, int pc1, i64 row0, i64 row1, int *err)
+static __device__ __noinline__ RvVal rv_eval(const RvCode &c, int pc0, int pc1, i64 row0, i64 row1, int *err)
 {
     RvVal st[RV_MAXSTACK];
     int sp = 0;

@@ -9,6 +9,8 @@
 #include "hostdec.hpp"
 #include "pipeline.hpp"
 #include "scanagg.cuh"
+#include "rowvm_compile.hpp"
+#include "scanagg_vm.cuh"
 
 namespace pg {
 
@@ -983,6 +985,11 @@ struct GenericPipeline : Pipeline {
     DevBuf d_part, d_final, d_luts, d_gather, d_kinds;
     PinBuf h_final;
     EventPair ev_all, ev_main;
+    // expression-driven mode (scanagg_vm.cuh): predicate and aggregate arguments are row programs
+    bool vm = false;
+    RvCompiler cc;
+    VmAggParams vprm{};
+    DevBuf d_code, d_err;
 
     int nranks() const { return table->dist == PG_DIST_REPLICATED ? 1 : ctx().world; }
     size_t rank_bytes() const { return (size_t)G * P * 16 + 64 * 8; }
@@ -997,7 +1004,9 @@ struct GenericPipeline : Pipeline {
         PG_CUDA(cudaEventRecord(ev_all.a, st));
         PG_CUDA(cudaMemsetAsync(d_firstrow, 0x7f, 64 * 8, st));
         PG_CUDA(cudaEventRecord(ev_main.a, st));
-#define PG_GEN(N) do { if (nulls) generic_scanagg_kernel<N, true><<<grid, N, smem, st>>>(prm, d_part.as<i64>(), d_firstrow); \
+        if (vm) PG_CUDA(cudaMemsetAsync(d_err.p, 0, 4, st));
+#define PG_GEN(N) do { if (vm) vm_scanagg_kernel<N><<<grid, N, smem, st>>>(vprm, d_part.as<i64>(), d_firstrow); \
+                       else if (nulls) generic_scanagg_kernel<N, true><<<grid, N, smem, st>>>(prm, d_part.as<i64>(), d_firstrow); \
                        else generic_scanagg_kernel<N, false><<<grid, N, smem, st>>>(prm, d_part.as<i64>(), d_firstrow); } while (0)
         if (NT == 256) PG_GEN(256);
         else if (NT == 128) PG_GEN(128);
@@ -1013,8 +1022,14 @@ struct GenericPipeline : Pipeline {
             src = d_gather.p;
         }
         PG_CUDA(cudaMemcpyAsync(h_final.p, src, rank_bytes() * (size_t)nranks(), cudaMemcpyDeviceToHost, st));
+        int vm_err = 0;
+        if (vm) PG_CUDA(cudaMemcpyAsync(&vm_err, d_err.p, 4, cudaMemcpyDeviceToHost, st));
         PG_CUDA(cudaEventRecord(ev_all.b, st));
         PG_CUDA(cudaStreamSynchronize(st));
+        // (a rank that fails here leaves its peers' collectives matched: the all-gather above has already run)
+        if (vm_err == RV_ERR_DIVZERO) PG_FAIL(PG_EOVERFLOW, "aggregate expression: division by zero");
+        if (vm_err == RV_ERR_FLOAT) PG_FAIL(PG_EUNSUPPORTED, "aggregate expression: value outside the exactly reproducible float32 cast range");
+        if (vm_err) PG_FAIL(PG_EOVERFLOW, "aggregate expression: a value exceeds the exact accumulation range");
         std::vector<i128> tot((size_t)G * P);
         std::vector<i64> first((size_t)G, INT64_MAX);
         for (int v = 0; v < G * P; v++) {
@@ -1271,6 +1286,127 @@ static int try_generic(pg_plan *plan, const Node &aggn, const Node &scan, const 
     return PG_OK;
 }
 
+// Expression-driven scan aggregate (scanagg_vm.cuh): taken when the filters or an aggregate argument do not lower to
+// ranges / affine products.  Same group keys, planes and finalisation as the generic pipeline.
+static int try_vm(pg_plan *plan, const Node &aggn, const Node &scan, std::unique_ptr<Pipeline> *out, std::string *why)
+{
+    const pg_table *t = plan->slots[(size_t)scan.slot];
+    if (aggn.groups.size() > 2) { *why = "more than two group keys"; return PG_EUNSUPPORTED; }
+    if (!aggn.having.empty()) { *why = "HAVING"; return PG_EUNSUPPORTED; }
+    std::unique_ptr<GenericPipeline> p(new GenericPipeline());
+    p->table = t;
+    p->vm = true;
+    p->nulls = true;                    // valid-input counts are always kept: an expression can be NULL without a NULL column
+    p->nkeys = (int)aggn.groups.size();
+    p->cc.tables[0] = t;
+    std::vector<uint8_t> luts(512, 0);
+    int dims[2] = {1, 1};
+    for (int k = 0; k < p->nkeys; k++) {
+        const Expr &ge = aggn.groups[(size_t)k];
+        if (ge.kind != PG_TK_COL) { *why = "group key is not a column"; return PG_EUNSUPPORTED; }
+        const Column &col = t->cols[(size_t)ge.idx];
+        if (!is_byte_family(col.type) || col.any_nulls()) { *why = "group key is not a non-null byte-coded column"; return PG_EUNSUPPORTED; }
+        p->key_col[k] = ge.idx;
+        dense_codes(col, &p->vals[k], &luts[(size_t)k * 256]);
+        dims[k] = (int)p->vals[k].size();
+    }
+    p->G = dims[0] * dims[1];
+    if (p->G > 64) { *why = "more than 64 dense groups"; return PG_EUNSUPPORTED; }
+    Resolver scope = [&](int idx, Src *s) { if (idx < 0 || idx >= (int)t->cols.size()) return false; s->side = 0; s->col = idx; s->mark = false; return true; };
+    VmAggParams &q = p->vprm;
+    q.nrows = t->nrows;
+    q.row_base = t->global_offset;
+    std::vector<const Expr *> fl;
+    for (auto &f : scan.filters) fl.push_back(&f);
+    if (!p->cc.compile_filters(fl, scope, &q.pred0, &q.pred1)) { *why = "filter: " + p->cc.why; return PG_EUNSUPPORTED; }
+    q.nkeys = p->nkeys;
+    q.key0 = p->nkeys > 0 ? (const uint8_t *)t->cols[(size_t)p->key_col[0]].d_data : nullptr;
+    q.key1 = p->nkeys > 1 ? (const uint8_t *)t->cols[(size_t)p->key_col[1]].d_data : nullptr;
+    q.n1 = dims[1];
+    q.ngroups = p->G;
+    p->prm.n1 = dims[1];
+    p->plane_kind = {GEN_SUM};
+    p->plane_scale = {0};
+    p->aggs = aggn.aggs;
+    int nacc = 0;
+    for (size_t i = 0; i < aggn.aggs.size(); i++) {
+        const AggExpr &a = aggn.aggs[i];
+        if (a.fn == PG_AGG_COUNT && a.star) { p->plane.push_back(0); p->agg_is_int.push_back(true); continue; }
+        const int kind = a.fn == PG_AGG_COUNT ? GEN_COUNTV : a.fn == PG_AGG_MIN ? GEN_MIN : a.fn == PG_AGG_MAX ? GEN_MAX : GEN_SUM;
+        if (a.fn != PG_AGG_COUNT && a.fn != PG_AGG_MIN && a.fn != PG_AGG_MAX && a.fn != PG_AGG_SUM && a.fn != PG_AGG_AVG) { *why = "aggregate function"; return PG_EUNSUPPORTED; }
+        int k = 0;
+        if (nacc >= GEN_MAXACC) { *why = "more than 8 aggregate arguments"; return PG_EUNSUPPORTED; }
+        q.a0[nacc] = p->cc.ncode;
+        if (!p->cc.compile(a.arg, scope, &k)) { *why = "aggregate argument: " + p->cc.why; return PG_EUNSUPPORTED; }
+        q.a1[nacc] = p->cc.ncode;
+        const int sb = p->cc.scale_bound(a.arg, scope);
+        if (kind != GEN_COUNTV) {
+            if (k != RVK_INT && k != RVK_DEC) { *why = "aggregate over a non-numeric expression"; return PG_EUNSUPPORTED; }
+            if (sb < 0 || sb > 18) { *why = "aggregate over a quotient (no fixed scale to accumulate at)"; return PG_EUNSUPPORTED; }
+        }
+        q.kind[nacc] = kind;
+        q.ascale[nacc] = kind == GEN_COUNTV ? 0 : sb;
+        const bool is_int = a.ltype == PG_LT_HUGEINT || a.ltype == PG_LT_DOUBLE || a.ltype == PG_LT_INTEGER || a.ltype == PG_LT_BIGINT;
+        if (is_int && kind != GEN_COUNTV && (k != RVK_INT || sb != 0)) { *why = "integer aggregate over a scaled value"; return PG_EUNSUPPORTED; }
+        if (!is_int && a.ltype != PG_LT_DECIMAL) { *why = "aggregate result type"; return PG_EUNSUPPORTED; }
+        if ((kind == GEN_MIN || kind == GEN_MAX) && is_int) { *why = "min/max are DECIMAL only in the reference"; return PG_EUNSUPPORTED; }
+        p->plane.push_back(nacc + 1);
+        p->plane_kind.push_back(kind == GEN_COUNTV ? (int)GEN_SUM : kind);
+        p->plane_scale.push_back(q.ascale[nacc]);
+        p->agg_is_int.push_back(is_int);
+        nacc++;
+    }
+    q.nacc = nacc;
+    p->prm.nacc = nacc;
+    p->P = 1 + 2 * nacc;
+    for (int a = 0; a < nacc; a++) { p->plane_kind.push_back(GEN_SUM); p->plane_scale.push_back(0); }
+    for (auto &o : aggn.outs) {
+        if (o.first == 0 && (o.second < 0 || o.second >= p->nkeys)) { *why = "bad group output index"; return PG_EUNSUPPORTED; }
+        if (o.first == 1 && (o.second < 0 || o.second >= (int)aggn.aggs.size())) { *why = "bad aggregate output index"; return PG_EUNSUPPORTED; }
+        if (o.first != 0 && o.first != 1) { *why = "bad output kind"; return PG_EUNSUPPORTED; }
+    }
+    p->outs = aggn.outs;
+    for (int i = 0; i < p->cc.ncols; i++) p->bytes_per_row += p->cc.code.cols[i].col.width;
+    for (int k = 0; k < p->nkeys; k++) p->bytes_per_row += 1;
+    p->NT = 256;
+    while (p->NT >= 64 && (size_t)p->G * p->P * p->NT * 8 > (size_t)200 * 1024) p->NT /= 2;
+    if (p->NT < 64) { *why = "group tables do not fit in shared memory"; return PG_EUNSUPPORTED; }
+    p->smem = (size_t)p->G * p->P * p->NT * 8;
+    const void *kern = p->NT == 256 ? (const void *)vm_scanagg_kernel<256> : p->NT == 128 ? (const void *)vm_scanagg_kernel<128> : (const void *)vm_scanagg_kernel<64>;
+    PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+    const i64 g = sms_times(kern, p->NT, p->smem);
+    p->grid = (int)std::max<i64>(std::min(g, (t->nrows + p->NT - 1) / p->NT), 1);
+    // a CTA's int64 partial sums stay exact while |value| * rows per CTA < 2^62 (largest shard, smallest full grid)
+    const i64 gmin_grid = std::max<i64>(1, std::min<i64>(g, (t->max_rows() + p->NT - 1) / p->NT));
+    const i64 rows_per_cta = (t->max_rows() + gmin_grid - 1) / gmin_grid + p->NT;
+    q.absmax = (i64)(((i128)1 << 62) / (i128)std::max<i64>(rows_per_cta, 1));
+    PG_TRY(p->d_part.alloc(sizeof(i64) * (size_t)p->grid * (size_t)p->G * (size_t)p->P));
+    PG_TRY(p->d_final.alloc(p->rank_bytes()));
+    PG_TRY(p->d_gather.alloc(p->rank_bytes() * (size_t)p->nranks()));
+    PG_TRY(p->h_final.alloc(p->rank_bytes() * (size_t)p->nranks()));
+    PG_TRY(p->d_luts.alloc(512));
+    PG_TRY(p->d_kinds.alloc(sizeof(int) * (size_t)p->G * (size_t)p->P));
+    PG_TRY(p->d_code.alloc(sizeof(RvCode)));
+    PG_TRY(p->d_err.alloc(4));
+    std::vector<int> kinds((size_t)p->G * (size_t)p->P);
+    for (int v = 0; v < p->G * p->P; v++) kinds[(size_t)v] = p->plane_kind[(size_t)(v % p->P)];
+    PG_CUDA(cudaMemcpyAsync(p->d_luts.p, luts.data(), 512, cudaMemcpyHostToDevice, ctx().stream));
+    PG_CUDA(cudaMemcpyAsync(p->d_kinds.p, kinds.data(), sizeof(int) * kinds.size(), cudaMemcpyHostToDevice, ctx().stream));
+    PG_CUDA(cudaMemcpyAsync(p->d_code.p, &p->cc.code, sizeof(RvCode), cudaMemcpyHostToDevice, ctx().stream));
+    PG_CUDA(cudaStreamSynchronize(ctx().stream));
+    q.luts = p->d_luts.as<uint8_t>();
+    q.code = p->d_code.as<RvCode>();
+    q.err = p->d_err.as<int>();
+    char buf[384];
+    snprintf(buf, sizeof buf,
+             "ScanAgg[expression programs] table=%s rows=%lld kernel=vm_scanagg_kernel<%d> grid=%d smem=%zu groups=%dx%d "
+             "instructions=%d columns=%d accumulators=%d stored bytes/row=%lld",
+             t->name.c_str(), (long long)t->nrows, p->NT, p->grid, p->smem, dims[0], dims[1], p->cc.ncode, p->cc.ncols, nacc, (long long)p->bytes_per_row);
+    p->explain = buf;
+    *out = std::move(p);
+    return PG_OK;
+}
+
 // ---------------------------------------------------------------------- entry --
 
 int build_scan_agg(pg_plan *plan, const Node &aggn, const Node &scan, std::unique_ptr<Pipeline> *out)
@@ -1280,7 +1416,15 @@ int build_scan_agg(pg_plan *plan, const Node &aggn, const Node &scan, std::uniqu
     cx.table = t;
     cx.allow_nulls = true;     // columns that hold NULLs route the plan to the NULL-aware generic kernel
     std::vector<Range> ranges;
-    if (!lower_filters(cx, scan.filters, ranges)) PG_FAIL(PG_EUNSUPPORTED, "scan filter not off-loadable: %s", cx.why.c_str());
+    std::string why_vm;
+    auto vm_path = [&](const std::string &because) -> int {
+        // not a conjunction of ranges / not a product of affine factors: evaluate the expressions themselves per row
+        const int s = try_vm(plan, aggn, scan, out, &why_vm);
+        if (s != PG_EUNSUPPORTED) return s;
+        PG_FAIL(PG_EUNSUPPORTED, "%s; expression-driven kernel: %s", because.c_str(), why_vm.c_str());
+    };
+    if (getenv("PG_FORCE_VM") && atoi(getenv("PG_FORCE_VM"))) return vm_path("PG_FORCE_VM");
+    if (!lower_filters(cx, scan.filters, ranges)) return vm_path("scan filter not a conjunction of ranges (" + cx.why + ")");
     std::vector<AffProd> args(aggn.aggs.size());
     for (size_t i = 0; i < aggn.aggs.size(); i++) {
         const AggExpr &a = aggn.aggs[i];
@@ -1290,7 +1434,7 @@ int build_scan_agg(pg_plan *plan, const Node &aggn, const Node &scan, std::uniqu
             if (!a.star) {
                 const Expr *e = strip_value_preserving_casts(&a.arg);
                 if (e->kind != PG_TK_COL || e->idx < 0 || e->idx >= (int)t->cols.size())
-                    PG_FAIL(PG_EUNSUPPORTED, "count() over a computed argument");
+                    return vm_path("count() over a computed argument");
                 if (t->cols[(size_t)e->idx].any_nulls()) {      // count(col) = rows where col is not NULL
                     Factor f;
                     f.col = e->idx;
@@ -1301,7 +1445,7 @@ int build_scan_agg(pg_plan *plan, const Node &aggn, const Node &scan, std::uniqu
             continue;
         }
         if (a.star) PG_FAIL(PG_EINVAL, "aggregate %zu has no argument", i);
-        if (!lower_affprod(cx, a.arg, args[i])) PG_FAIL(PG_EUNSUPPORTED, "aggregate argument not off-loadable: %s", cx.why.c_str());
+        if (!lower_affprod(cx, a.arg, args[i])) return vm_path("aggregate argument not a product of affine factors (" + cx.why + ")");
     }
     std::string why1 = "NULLs or code-set predicates present", why2 = why1, why3;
     const char *force = getenv("PG_FORCE_GENERIC");      // testing: exercise the shape-agnostic kernel on every plan

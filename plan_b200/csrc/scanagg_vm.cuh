@@ -1,0 +1,88 @@
+// scanagg_vm.cuh -- expression-driven scan aggregate: the shapes whose filters or aggregate arguments do not lower to
+// ranges and affine products (general OR / NOT, IN and <> on integers, CASE WHEN inside sum / avg / min / max,
+// column-to-column comparisons).  The predicate and every aggregate argument are rowvm.cuh programs evaluated per row
+// with the reference's value semantics (ExprExec, expr_exec.go:85-530; executeCase :144-246); the group tables,
+// partials layout, NULL handling (an aggregate skips NULL arguments, function_aggr.go IgnoreNull) and the exact
+// 128-bit finalisation are the generic scan aggregate's (generic_scanagg_kernel, GenericPipeline).
+// An aggregate accumulates at ONE scale: every value is rescaled to the plane's scale (the static bound of the
+// expression's run-time scale), and a value too large for the int64 partial-sum proof raises the overflow status.
+#pragma once
+#include "rowvm.cuh"
+
+namespace pg {
+
+struct VmAggParams {
+    const RvCode *code;
+    int *err;
+    i64 nrows, row_base;
+    int pred0, pred1;
+    int nkeys;
+    const uint8_t *key0, *key1;
+    const uint8_t *luts;
+    int n1, ngroups;
+    int nacc;
+    int kind[GEN_MAXACC], a0[GEN_MAXACC], a1[GEN_MAXACC], ascale[GEN_MAXACC];
+    i64 absmax;                 // |value| bound under which a CTA's int64 partial sums are provably exact
+};
+
+template <int NT>
+__global__ void __launch_bounds__(NT)
+vm_scanagg_kernel(const VmAggParams p, i64 *__restrict__ partials /* [grid][G*P] */, i64 *__restrict__ first_row /* [G] preset to 0x7f.. */)
+{
+    extern __shared__ i64 s_acc[];                 // [G*P][NT]
+    __shared__ uint8_t s_lut[2][256];
+    __shared__ i64 s_first[64];
+    const int G = p.ngroups, P = 1 + 2 * p.nacc;
+    auto plane_kind = [&](int plane) { return (plane == 0 || plane > p.nacc || p.kind[plane - 1] == GEN_COUNTV) ? (int)GEN_SUM : p.kind[plane - 1]; };
+    for (int i = threadIdx.x; i < G * P * NT; i += NT) {
+        const int kind = plane_kind((i / NT) % P);
+        s_acc[i] = kind == GEN_MIN ? INT64_MAX : kind == GEN_MAX ? INT64_MIN : 0;
+    }
+    if (p.nkeys > 0) for (int i = threadIdx.x; i < 512; i += NT) s_lut[i >> 8][i & 255] = p.luts[i];
+    if (threadIdx.x < 64) s_first[threadIdx.x] = INT64_MAX;
+    __syncthreads();
+    i64 *my = s_acc + threadIdx.x;
+    int err = 0;
+    for (i64 row = (i64)blockIdx.x * NT + threadIdx.x; row < p.nrows; row += (i64)gridDim.x * NT) {
+        if (!rv_true(*p.code, p.pred0, p.pred1, row, -1, &err)) continue;
+        int g = 0;
+        if (p.nkeys > 0) g = s_lut[0][p.key0[row]];
+        if (p.nkeys > 1) g = g * p.n1 + s_lut[1][p.key1[row]];
+        i64 *t = my + (i64)g * P * NT;
+        if (t[0] == 0) atomicMin((long long *)&s_first[g], (long long)(p.row_base + row));
+        t[0] += 1;
+        for (int a = 0; a < p.nacc; a++) {
+            const RvVal v = rv_eval(*p.code, p.a0[a], p.a1[a], row, -1, &err);
+            if (v.null) continue;
+            i64 *slot = t + (i64)(a + 1) * NT;
+            t[(i64)(p.nacc + 1 + a) * NT] += 1;
+            if (p.kind[a] == GEN_COUNTV) { *slot += 1; continue; }
+            i128 x = v.v;
+            if (v.scale > p.ascale[a]) { err = RV_ERR_OVERFLOW; continue; }
+            x *= rv_pow10(p.ascale[a] - v.scale);
+            if (x > (i128)p.absmax || x < -(i128)p.absmax) { err = RV_ERR_OVERFLOW; continue; }
+            const i64 xv = (i64)x, cur = *slot;
+            *slot = p.kind[a] == GEN_SUM ? cur + xv : p.kind[a] == GEN_MIN ? (xv < cur ? xv : cur) : (xv > cur ? xv : cur);
+        }
+    }
+    if (err) *p.err = err;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int v = warp; v < G * P; v += NT / 32) {
+        const int kind = plane_kind(v % P);
+        i64 r = kind == GEN_SUM ? 0 : kind == GEN_MIN ? INT64_MAX : INT64_MIN;
+        for (int j = 0; j < NT / 32; j++) {
+            const i64 x = s_acc[v * NT + lane + 32 * j];
+            r = kind == GEN_SUM ? r + x : kind == GEN_MIN ? (x < r ? x : r) : (x > r ? x : r);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const i64 x = __shfl_xor_sync(0xffffffffu, r, o);
+            r = kind == GEN_SUM ? r + x : kind == GEN_MIN ? (x < r ? x : r) : (x > r ? x : r);
+        }
+        if (lane == 0) partials[(i64)blockIdx.x * (G * P) + v] = r;
+    }
+    if (threadIdx.x < G && s_first[threadIdx.x] != INT64_MAX)
+        atomicMin((long long *)&first_row[threadIdx.x], (long long)s_first[threadIdx.x]);
+}
+
+}  // namespace pg

@@ -239,3 +239,74 @@ def test_unsupported_row_shapes_are_refused(pg, data):
         ex.Init()
     assert ei.value.status == pg.PG_EUNSUPPORTED
     ex.Close()
+
+
+# ---- expression-driven scan aggregate (scanagg_vm.cuh): the same row programs under sum / avg / min / max / count ----
+
+def _agg_check(op, tables, rows, expect="expression programs"):
+    return _check(op, tables, rows, expect_explain=expect)
+
+
+def test_aggregates_over_case_and_general_predicates(pg, data):
+    """TPC-H Q12 / Q14 style: sum(CASE WHEN ... THEN x ELSE 0 END), avg / min / max of a CASE, count(expr) and count(*),
+    under a filter with OR, IN and <> on INTEGER and a column-to-column comparison -- none of which lowers to ranges or
+    affine products.  NULLs in l_quantity / l_discount: NULL arguments are ignored, NULL predicates are not TRUE."""
+    tables, rows, S = data
+    K, X, B = _ops()
+    lc = lambda n: S.col("lineitem", n)   # noqa: E731
+    I, D152, V, H = K.IntegerType(), K.DecimalType(15, 2), K.VarcharType(), K.HugeintType()
+    filt = [X.func("or", B, X.func("in", B, lc("l_quantity"), *[X.const(q, I) for q in (1, 2, 3, 5, 8, 13, 21, 34)]),
+                   X.func("and", B, X.func("<>", B, lc("l_linenumber"), X.const(2, I)), X.func("<", B, lc("l_commitdate"), lc("l_receiptdate")))),
+            X.func("<", B, lc("l_shipdate"), X.const(10400, K.DateType()))]
+    scan = X.PhysicalOperator(X.POT_Scan, Info=X.ScanOpInfo("lineitem"), Filters=filt)
+    one = X.cast(X.const(1, I), D152)
+    disc_price = X.func("*", K.DecimalType(18, 4), X.cast(lc("l_extendedprice"), K.DecimalType(16, 2)), X.func("-", K.DecimalType(16, 2), one, lc("l_discount")))
+    late = X.func("case", I, X.const(0, I), X.func("<", B, lc("l_commitdate"), lc("l_receiptdate")), X.const(1, I))
+    promo = X.func("case", K.DecimalType(18, 4), X.cast(X.const(0, I), K.DecimalType(18, 4)), X.func("=", B, lc("l_linestatus"), X.const("F", V)), disc_price)
+    some = X.func("case", D152, X.const(None, D152), X.func(">", B, lc("l_quantity"), X.const(25, I)), lc("l_extendedprice"))
+    aggs = [X.func("sum", H, late), X.func("sum", K.DecimalType(38, 4), promo), X.func("sum", K.DecimalType(38, 4), disc_price),
+            X.func("avg", K.DecimalType(38, 2), some), X.func("min", D152, some), X.func("max", D152, some),
+            X.func("count", H, some), X.func("count", H), X.func("avg", K.DoubleType(), lc("l_quantity"))]
+    outs = [X.col(0, 0, V)] + [X.col(1, i, a.DataTyp) for i, a in enumerate(aggs)]
+    op = X.PhysicalOperator(X.POT_Agg, Outputs=outs, Children=[scan], Info=X.AggOpInfo(aggs, [lc("l_returnflag")]))
+    got = _agg_check(op, tables, rows)
+    assert len(got) == 3
+    # ungrouped, and a predicate nothing passes
+    op = X.PhysicalOperator(X.POT_Agg, Outputs=outs[1:], Children=[scan], Info=X.AggOpInfo(aggs, []))
+    op.Outputs = [X.col(1, i, a.DataTyp) for i, a in enumerate(aggs)]
+    assert len(_agg_check(op, tables, rows)) == 1
+    none = X.PhysicalOperator(X.POT_Scan, Info=X.ScanOpInfo("lineitem"),
+                              Filters=[X.func("or", B, X.func("<", B, lc("l_quantity"), X.const(0, I)), X.func(">", B, lc("l_linenumber"), X.const(9, I)))])
+    op = X.PhysicalOperator(X.POT_Agg, Outputs=[X.col(0, 0, V), X.col(1, 0, H)], Children=[none], Info=X.AggOpInfo([X.func("count", H)], [lc("l_returnflag")]))
+    assert _agg_check(op, tables, rows) == []
+
+
+def test_q1_and_q6_through_the_expression_kernel(pg, monkeypatch):
+    """PG_FORCE_VM=1: TPC-H Q6 (float32 BETWEEN via cast(DECIMAL AS FLOAT)) and Q1 (8 aggregates, 3-factor products) run as
+    row programs and must give exactly what the specialised kernels and the C oracle give."""
+    import test_gpu_scanagg as SA
+    from oracle import oracle as O
+    from plan_b200 import tpch as T
+    sf = 0.02
+    t = T.generate_device_tables(sf, want=("lineitem",))
+    try:
+        _, line = O.gen_orders_lineitem(sf)
+        monkeypatch.setenv("PG_FORCE_VM", "1")
+        for kw in ({}, {"disc_lit": 0.05, "disc_eps": 0.02}, {"qty_lt": 1}):
+            chunks, stats, explain = SA._run(T.q6_plan(**kw), t)
+            assert "expression programs" in explain
+            ref = O.q6(line, **kw)
+            assert stats.aux[0] == ref["rows_selected"]
+            if ref["has_row"]:
+                got = SA._dec(chunks[0].Data[0], 0)
+                assert SA._dec_value(got)[0] * 10 ** (4 - got[1]) == ref["exact"]
+            else:
+                assert chunks == []
+        chunks, stats, explain = SA._run(T.q1_plan(), t)
+        assert "expression programs" in explain
+        ref = O.q1(line)
+        rows = sorted("\t".join(v.GetValue(r).String() for v in chunks[0].Data) for r in range(chunks[0].Card()))
+        assert rows == sorted(O.q1_text(ref).strip("\n").split("\n")[1:])
+    finally:
+        for x in t.values():
+            x.free()
