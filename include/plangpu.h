@@ -129,6 +129,16 @@ int pg_device_info(pg_devinfo *out);
  * Rank 0 creates the id, the host (Go: any side channel; Python: torch.distributed)
  * broadcasts the 128 bytes, every rank calls pg_comm_init.  Row-range sharded
  * tables then merge partial aggregates with an all-gather inside pg_plan_execute. */
+/* Single-process multi-device mode (the reference is ONE process: pkg/compute runs a query on one goroutine).
+ * pg_init_devices binds the library to `ndev` GPUs at once and sets up one NCCL communicator over them
+ * (ncclCommInitAll's job); device i is rank i.  Every other call works on the device the CALLING THREAD selected with
+ * pg_use_device(i) -- the Go shim runs one goroutine per device, locked to its OS thread (runtime.LockOSThread),
+ * which ingests that device's row-range shard and calls pg_plan_execute; the collectives inside a plan (partial
+ * aggregate merges, the all-to-all exchanges) match up across those threads exactly as across processes.  Use either
+ * pg_init (+ pg_comm_init, one process per GPU) or pg_init_devices, not both.  pg_shutdown ends either mode. */
+int pg_init_devices(int ndev, const int *devices);
+int pg_use_device(int index);
+int pg_num_devices(void);
 int pg_comm_unique_id(void *out128);
 int pg_comm_init(int world_size, int rank, const void *id128);
 int pg_comm_destroy(void);

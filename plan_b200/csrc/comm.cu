@@ -106,6 +106,29 @@ int comm_alltoallv(const void *d_send, const i64 *send_cnt, const i64 *send_off,
     return PG_OK;
 }
 
+// ncclCommInitAll's job for contexts this process owns: one rank per context, initialised inside one group from the
+// calling thread (the documented single-thread multi-device form); rank i = contexts[i].
+int comm_init_all(const std::vector<Context *> &ctxs)
+{
+    const int n = (int)ctxs.size();
+    PG_TRY(load_nccl());
+    ncclUniqueId id;
+    PG_NCCL(nccl().GetUniqueId(&id));
+    std::vector<ncclComm_t> comms((size_t)n, nullptr);
+    PG_NCCL(nccl().GroupStart());
+    for (int i = 0; i < n; i++) {
+        PG_CUDA(cudaSetDevice(ctxs[(size_t)i]->device));
+        PG_NCCL(nccl().CommInitRank(&comms[(size_t)i], n, id, i));
+    }
+    PG_NCCL(nccl().GroupEnd());
+    for (int i = 0; i < n; i++) {
+        ctxs[(size_t)i]->nccl_comm = comms[(size_t)i];
+        ctxs[(size_t)i]->world = n;
+        ctxs[(size_t)i]->rank = i;
+    }
+    return PG_OK;
+}
+
 }  // namespace pg
 
 using namespace pg;

@@ -60,6 +60,7 @@ struct Context {
     void *nccl_comm = nullptr;
 };
 Context &ctx();
+int comm_init_all(const std::vector<Context *> &ctxs);      // comm.cu: one NCCL communicator over the contexts of pg_init_devices
 
 inline int type_size(int t)
 {

@@ -29,7 +29,11 @@ struct DevCache {
     std::unordered_map<void *, size_t> size_of;         // every block handed out or cached
     size_t cached_bytes = 0;
 };
-DevCache &dev_cache() { static DevCache c; return c; }
+// one cache per CUDA device: a block is only ever handed back to the device it was allocated on
+// (single-process multi-device mode, pg_init_devices: one host thread per device)
+constexpr int DEV_MAXDEV = 64;
+DevCache &dev_cache_of(int device) { static DevCache c[DEV_MAXDEV]; return c[device >= 0 && device < DEV_MAXDEV ? device : 0]; }
+DevCache &dev_cache() { return dev_cache_of(ctx().device); }
 constexpr size_t DEV_GRAIN = (size_t)2 << 20;
 constexpr size_t DEV_CACHE_LIMIT = (size_t)96 << 30;    // keep at most this much parked (B200: 180 GB)
 }  // namespace
@@ -64,7 +68,18 @@ cudaError_t dev_alloc(void **p, size_t bytes)
 void dev_free(void *p)
 {
     if (!p) return;
-    DevCache &c = dev_cache();
+    DevCache *own = &dev_cache();
+    {   // freed from a thread bound to another device: the block goes back to the cache of the device that owns it
+        std::lock_guard<std::mutex> g(own->mu);
+        if (own->size_of.find(p) == own->size_of.end()) own = nullptr;
+    }
+    for (int d = 0; d < DEV_MAXDEV && !own; d++) {
+        DevCache &c = dev_cache_of(d);
+        std::lock_guard<std::mutex> g(c.mu);
+        if (c.size_of.find(p) != c.size_of.end()) own = &c;
+    }
+    if (!own) { cudaFree(p); return; }
+    DevCache &c = *own;
     std::lock_guard<std::mutex> g(c.mu);
     auto it = c.size_of.find(p);
     if (it == c.size_of.end()) { cudaFree(p); return; }
@@ -98,11 +113,13 @@ void set_error(const char *fmt, ...)
 }
 const char *get_error() { return g_err; }
 
-Context &ctx()
-{
-    static Context c;
-    return c;
-}
+// The context a call works on: the one this THREAD was bound to with pg_use_device (single-process multi-device
+// mode: pg_init_devices creates one context per GPU and the host drives each from its own thread, which is what the
+// NCCL collectives inside a plan need), else the process-wide context of pg_init (one process per GPU).
+static Context g_default_ctx;
+static std::vector<std::unique_ptr<Context>> g_dev_ctx;
+static thread_local Context *tl_ctx = nullptr;
+Context &ctx() { return tl_ctx ? *tl_ctx : g_default_ctx; }
 
 // ---------------------------------------------------------------- statistics --
 
@@ -567,6 +584,41 @@ int pg_trim(void)
 
 const char *pg_last_error(void) { return get_error(); }
 
+int pg_init_devices(int ndev, const int *devices)
+{
+    if (ndev < 1 || ndev > DEV_MAXDEV || !devices) PG_FAIL(PG_EINVAL, "pg_init_devices: bad arguments");
+    if (!g_dev_ctx.empty() || g_default_ctx.ready) PG_FAIL(PG_ESTATE, "pg_init_devices: the library is already initialised");
+    for (int i = 0; i < ndev; i++)
+        for (int j = 0; j < i; j++) if (devices[i] == devices[j]) PG_FAIL(PG_EINVAL, "pg_init_devices: device %d listed twice", devices[i]);
+    std::vector<std::unique_ptr<Context>> made;
+    for (int i = 0; i < ndev; i++) {
+        made.emplace_back(new Context());
+        tl_ctx = made.back().get();
+        const int s = pg_init(devices[i]);
+        if (s != PG_OK) { tl_ctx = nullptr; return s; }
+    }
+    g_dev_ctx = std::move(made);
+    tl_ctx = g_dev_ctx[0].get();
+    if (ndev > 1) {
+        std::vector<Context *> cs;
+        for (auto &c : g_dev_ctx) cs.push_back(c.get());
+        const int s = comm_init_all(cs);
+        if (s != PG_OK) return s;
+    }
+    PG_CUDA(cudaSetDevice(g_dev_ctx[0]->device));
+    return PG_OK;
+}
+
+int pg_use_device(int index)
+{
+    if (index < 0 || index >= (int)g_dev_ctx.size()) PG_FAIL(PG_EINVAL, "pg_use_device: index %d out of range (%zu devices initialised)", index, g_dev_ctx.size());
+    tl_ctx = g_dev_ctx[(size_t)index].get();
+    PG_CUDA(cudaSetDevice(tl_ctx->device));
+    return PG_OK;
+}
+
+int pg_num_devices(void) { return g_dev_ctx.empty() ? (g_default_ctx.ready ? 1 : 0) : (int)g_dev_ctx.size(); }
+
 int pg_init(int device)
 {
     Context &c = ctx();
@@ -594,9 +646,25 @@ int pg_init(int device)
     return PG_OK;
 }
 
+static int shutdown_context(Context &c);
+
 int pg_shutdown(void)
 {
-    Context &c = ctx();
+    if (!g_dev_ctx.empty()) {            // multi-device mode: every context, whichever thread calls
+        for (auto &c : g_dev_ctx) {
+            tl_ctx = c.get();
+            pg_comm_destroy();
+            shutdown_context(*c);
+        }
+        tl_ctx = nullptr;
+        g_dev_ctx.clear();
+        return PG_OK;
+    }
+    return shutdown_context(ctx());
+}
+
+static int shutdown_context(Context &c)
+{
     if (!c.ready) return PG_OK;
     cudaSetDevice(c.device);
     cudaDeviceSynchronize();

@@ -24,3 +24,14 @@ def test_sharded_queries_match_oracle(world):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("multi-GPU parity OK") == world
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_single_process_drives_all_devices(world):
+    """pg_init_devices / pg_use_device: one process, one host thread per GPU, NCCL between the threads
+    (tests/multidev_check.py).  world = 1 runs on any GPU box."""
+    if _ngpus() < world:
+        pytest.skip("needs %d GPUs" % world)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "multidev_check.py"), str(world)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "parity OK" in r.stdout
