@@ -3,7 +3,7 @@
 // Drop into pkg/compute of daviszhen/plan (package compute).  The one change to existing code is the arm at the
 // top of buildOperatorExec (executor.go:305-350), BEFORE the children are built:
 //
-//	if cfg.Gpu.Enable {
+//	if cfg.Gpu.Enable {        // len(cfg.Gpu.Devices) > 1: newMultiGpuPipelineExec (executor_gpu_multi.go) instead
 //		if ex, err := newGpuPipelineExec(op, cfg, txn); err == nil {
 //			if err = ex.Init(); err == nil {
 //				return ex, nil          // the whole subtree runs on the device
@@ -12,7 +12,7 @@
 //		}
 //	}
 //
-// (util.Config gains `Gpu struct{ Enable bool; Device int }`, pkg/util/config.go:56-59.)
+// (util.Config gains `Gpu struct{ Enable bool; Device int; Devices []int; ReplicateBelow int }`, pkg/util/config.go:56-59.)
 //
 // Interface implemented: OperatorExec{Init, Execute, Close} (executor_operator.go:52-56) with the results of
 // executor_operator.go:11-18.  Parents (Project / Order / Limit executors, Runner.Execute executor.go:242-296)
@@ -249,52 +249,9 @@ func flattenVector(vec *chunk.Vector, count int, d *plangpu.ColDesc, dict map[st
 // flattened chunks are kept until the scan is drained and appended then.
 func ingest(scanOp *PhysicalOperator, cfg *util.Config, txn *storage.Txn) (*deviceTable, error) {
 	si := scanOp.Info.(*ScanOpInfo)
-	plain := *scanOp
-	plain.Filters = nil
-	scan, err := newScanExecutor(&plain, cfg, txn, nil)
+	descs, stages, err := drainScan(scanOp, cfg, txn)
 	if err != nil {
 		return nil, err
-	}
-	if err = scan.Init(); err != nil {
-		return nil, err
-	}
-	defer scan.Close()
-	descs := make([]plangpu.ColDesc, len(scanOp.Outputs))
-	dicts := make([]map[string]uint8, len(descs))
-	dictLists := make([][]string, len(descs))
-	for i, out := range scanOp.Outputs {
-		if descs[i], err = columnEncoding(si.Columns[i], out.DataTyp); err != nil {
-			return nil, err
-		}
-		dicts[i] = map[string]uint8{}
-	}
-	var stages []chunkStage
-	for {
-		ch := &chunk.Chunk{}
-		res, err := scan.Execute(nil, ch)
-		if err != nil {
-			return nil, err
-		}
-		if res == Done {
-			break
-		}
-		n := ch.Card()
-		if n == 0 {
-			continue
-		}
-		st := chunkStage{n: n}
-		for i := range descs {
-			cb, owner, err := flattenVector(ch.Data[i], n, &descs[i], dicts[i], &dictLists[i])
-			if err != nil {
-				return nil, err
-			}
-			st.cols = append(st.cols, cb)
-			st.keep = append(st.keep, owner)
-		}
-		stages = append(stages, st)
-	}
-	for i := range descs {
-		descs[i].Dict = dictLists[i]
 	}
 	tab, err := plangpu.NewTable(si.Database+"."+si.Table, descs)
 	if err != nil {
@@ -311,6 +268,60 @@ func ingest(scanOp *PhysicalOperator, cfg *util.Config, txn *storage.Txn) (*devi
 		return nil, err
 	}
 	return &deviceTable{tab: tab, cols: descs}, nil
+}
+
+// drainScan runs the scan to completion and returns the column descriptors (dictionaries filled in) with every
+// 2048-row chunk flattened to narrow column buffers, in storage order.
+func drainScan(scanOp *PhysicalOperator, cfg *util.Config, txn *storage.Txn) ([]plangpu.ColDesc, []chunkStage, error) {
+	si := scanOp.Info.(*ScanOpInfo)
+	plain := *scanOp
+	plain.Filters = nil
+	scan, err := newScanExecutor(&plain, cfg, txn, nil)
+	if err != nil {
+		return nil, nil, err
+	}
+	if err = scan.Init(); err != nil {
+		return nil, nil, err
+	}
+	defer scan.Close()
+	descs := make([]plangpu.ColDesc, len(scanOp.Outputs))
+	dicts := make([]map[string]uint8, len(descs))
+	dictLists := make([][]string, len(descs))
+	for i, out := range scanOp.Outputs {
+		if descs[i], err = columnEncoding(si.Columns[i], out.DataTyp); err != nil {
+			return nil, nil, err
+		}
+		dicts[i] = map[string]uint8{}
+	}
+	var stages []chunkStage
+	for {
+		ch := &chunk.Chunk{}
+		res, err := scan.Execute(nil, ch)
+		if err != nil {
+			return nil, nil, err
+		}
+		if res == Done {
+			break
+		}
+		n := ch.Card()
+		if n == 0 {
+			continue
+		}
+		st := chunkStage{n: n}
+		for i := range descs {
+			cb, owner, err := flattenVector(ch.Data[i], n, &descs[i], dicts[i], &dictLists[i])
+			if err != nil {
+				return nil, nil, err
+			}
+			st.cols = append(st.cols, cb)
+			st.keep = append(st.keep, owner)
+		}
+		stages = append(stages, st)
+	}
+	for i := range descs {
+		descs[i].Dict = dictLists[i]
+	}
+	return descs, stages, nil
 }
 
 // deviceTableFor returns the cached device copy of the scan's table or ingests it.

@@ -90,6 +90,29 @@ func call(f func() C.int) error {
 // Init binds the process to one GPU (pg_init).
 func Init(device int) error { return call(func() C.int { return C.pg_init(C.int(device)) }) }
 
+// InitDevices binds this ONE process to several GPUs (pg_init_devices): one context per device and one NCCL
+// communicator over them, device i = rank i.  Every later call works on the device the calling OS THREAD selected
+// with UseDevice, so each device is driven by a goroutine locked to its thread (compute.deviceWorker).
+func InitDevices(devices []int) error {
+	n := len(devices)
+	if n == 0 {
+		return &Error{Code: -1, Msg: "InitDevices: no devices"}
+	}
+	cd := (*C.int)(C.malloc(C.size_t(n) * C.size_t(unsafe.Sizeof(C.int(0)))))
+	defer C.free(unsafe.Pointer(cd))
+	for i, d := range devices {
+		*(*C.int)(unsafe.Add(unsafe.Pointer(cd), uintptr(i)*unsafe.Sizeof(C.int(0)))) = C.int(d)
+	}
+	return call(func() C.int { return C.pg_init_devices(C.int(n), cd) })
+}
+
+// UseDevice selects the device for the calling OS thread (the caller must hold runtime.LockOSThread for as long as
+// it works on that device).  Not wrapped in call(): call's own Lock/Unlock pair nests inside the caller's lock.
+func UseDevice(index int) error { return check(C.pg_use_device(C.int(index))) }
+
+// NumDevices: devices bound by InitDevices (1 after Init).
+func NumDevices() int { return int(C.pg_num_devices()) }
+
 // Shutdown releases streams and pinned staging.
 func Shutdown() error { return call(func() C.int { return C.pg_shutdown() }) }
 
