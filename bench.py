@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--e2e-native", action="store_true", help="e2e leg with native-width host buffers (int64 DECIMALs) instead of narrow ones")
     ap.add_argument("--no-extra", action="store_true", help="skip the Q18 / group-by timings reported beside the metric")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-chunked-e2e", action="store_true", help="skip the 2048-row-chunk pageable-memory e2e leg (C++ host shim subprocess)")
     ap.add_argument("--cpu-sample-sf", type=float, default=1.0, help="CPU baseline sample: this SF worth of rows")
     return ap.parse_args()
 
@@ -506,6 +507,33 @@ def main():
                "host_buffers": "native widths (int64 DECIMAL, int32 DATE/INT)" if args.e2e_native else
                                "narrow frame-of-reference column buffers (pg_table_append_cols), pinned",
                "includes": "pg_table_create+append_cols(H2D from pinned host, device widening)+seal(stats, packing)+plan compile/execute+result fetch"}
+
+    # ---- the same e2e step the way the reference's executor would feed it (rank 0, N=1 only): 2048-row chunks from
+    # PAGEABLE host memory, one pg_table_append_cols call per chunk, through the C++ host shim (plan_b200/host/
+    # append_bench.cc); its Q6 / Q1 / Q3 results are checked against the same fixtures
+    if e2e is not None and rank == 0 and world == 1 and not args.no_chunked_e2e and queries == ["q6", "q1", "q3"]:
+        exe = os.path.join(ROOT, "plan_b200", "host", "planhost_append")
+        try:
+            r = subprocess.run([exe, "%g" % args.sf, "2048", "narrow", "1"], capture_output=True, text=True, timeout=600)
+            if r.returncode != 0:
+                raise RuntimeError(r.stderr[-300:])
+            ch = json.loads(r.stdout.strip().splitlines()[-1])
+            texts = {}
+            for part in r.stderr.split("== ")[1:]:
+                name, _, body = part.partition("\n")
+                texts[name.strip()] = body
+            ok = {}
+            for q in ("q6", "q1", "q3"):
+                fx = parity_fixture(q, args.sf)
+                ok[q] = None if fx is None else (texts.get(q) == open(fx).read())
+            parity["chunked_e2e"] = None if any(v is None for v in ok.values()) else all(ok.values())
+            e2e["chunked_pageable"] = {"value": total_rows * 3 / (ch["ms_per_step"] * 1e-3), "unit": "rows/s", "ms_per_step": ch["ms_per_step"],
+                                       "append_calls_per_step": ch["append_calls_per_step"], "chunk_rows": ch["chunk_rows"],
+                                       "h2d_bytes_per_step": ch["h2d_bytes_per_step"], "host_memory": ch["host_memory"],
+                                       "note": "what a per-chunk shim costs: one append call per 2048-row scan chunk from pageable memory, "
+                                               "gathered in pinned staging inside the library; `e2e.value` above is the bulk export path (f2)"}
+        except Exception as ex_:      # reported, never fatal for the metric line
+            e2e["chunked_pageable"] = {"error": str(ex_)[:300]}
 
     # ---- CPU baseline beside it (rank 0, N=1 only) -------------------------------------------
     cpu = None

@@ -37,7 +37,8 @@ struct Stage {
     int probe_stage = -1;            // which earlier stage built the probed table
     int ins_key_col = -1;            // SINK_INSERT: key column on the source table
     // device state of the table this stage builds
-    DevBuf d_slots, d_bitmap, d_rank_prefix, d_rank_payload, d_keys_tmp, d_scan_tmp;
+    DevBuf d_slots, d_bitmap, d_rank_prefix, d_rank_payload, d_keys_tmp, d_scan_tmp, d_bm_all;
+    size_t bitmap_words = 0;
     JoinTable jt{};
     bool rank_index = false;         // unique keys + bitmap: the table is bitmap + rank prefix + payload (join.cuh jt_rank)
     // further existence tests on this stage's source rows (pushed-down SEMI / ANTI joins, INNER joins
@@ -300,10 +301,21 @@ struct JoinAggPipeline : Pipeline {
         return PG_OK;
     }
 
+    // d_counters: words 0..3 are the running stage's counters; words 4..7 keep {rows passing, rows built} of the first two
+    // build stages whose own read-back was skipped -- they ride along with whichever read comes next
+    pg_result *cur_res = nullptr;
+    unsigned deferred_stats = 0;
     int read_counters(unsigned long long *out2)
     {
-        PG_CUDA(cudaMemcpyAsync(out2, d_counters.p, 32, cudaMemcpyDeviceToHost, ctx().stream));
+        unsigned long long h[8];
+        PG_CUDA(cudaMemcpyAsync(h, d_counters.p, 64, cudaMemcpyDeviceToHost, ctx().stream));
         PG_CUDA(cudaStreamSynchronize(ctx().stream));
+        memcpy(out2, h, 32);
+        for (int idx = 0; idx < 2; idx++)
+            if (((deferred_stats >> idx) & 1u) && cur_res) {
+                cur_res->stats.aux[2 + 2 * idx] = (i64)h[4 + 2 * idx];
+                cur_res->stats.aux[3 + 2 * idx] = (i64)h[5 + 2 * idx];
+            }
         return PG_OK;
     }
 
@@ -454,7 +466,7 @@ struct JoinAggPipeline : Pipeline {
     template <int SINK>
     int launch_pipe(const PipeParams &pp, const pg_table *t)
     {
-        pipeline_kernel<SINK><<<grid_rows(t->nrows), 256, 0, ctx().stream>>>(pp);
+        pipeline_kernel<SINK><<<grid_rows(pp.pipe_hi > 0 ? pp.pipe_hi - pp.pipe_lo : t->nrows), 256, 0, ctx().stream>>>(pp);
         PG_CUDA(cudaGetLastError());
         return PG_OK;
     }
@@ -495,9 +507,10 @@ struct JoinAggPipeline : Pipeline {
         i128 domain = (i128)keycol.vmax - (i128)keycol.vmin + 1;
         if (keycol.stats_ok && domain > 0 && domain <= ((i128)1 << 32) && s.ins_key_col2 < 0) {
             size_t words = ((size_t)((domain + 31) / 32) + 7) / 8 * 8;      // whole 256-bit blocks (rank index)
-            if (s.d_bitmap.bytes < words * 4) PG_TRY(s.d_bitmap.alloc(words * 4));
-            PG_CUDA(cudaMemsetAsync(s.d_bitmap.p, 0, words * 4, st));
+            if (s.d_bitmap.bytes < words * 4 + 32) PG_TRY(s.d_bitmap.alloc(words * 4 + 32));   // + a 32-byte tail: counters of a split build
+            PG_CUDA(cudaMemsetAsync(s.d_bitmap.p, 0, words * 4 + 32, st));
             s.jt.bitmap = s.d_bitmap.as<unsigned>();
+            s.bitmap_words = words;
         }
         return PG_OK;
     }
@@ -605,16 +618,53 @@ struct JoinAggPipeline : Pipeline {
         if (s.ins_key_col2 >= 0) pp.ins_key2 = typed(t, s.ins_key_col2);
                 pp.ins = s.jt;
                 PG_CUDA(cudaMemsetAsync(d_counters.p, 0, 32, st));
-                PG_TRY(launch_pipe<SINK_BITMAP>(pp, t));
+                // A REPLICATED build side is the same on every rank: instead of W identical scans, every rank marks the keys
+                // of its 1/W of the rows and the partial bitmaps are all-gathered and OR-ed (2 MB for SF100's customer).
+                const int W = ctx().world;
+                const bool split = W > 1 && t->dist == PG_DIST_REPLICATED && !s.has_probe && s.extras.empty() && t->nrows >= (i64)W * (getenv("PG_SPLIT_MIN_ROWS") ? atoll(getenv("PG_SPLIT_MIN_ROWS")) : 65536) &&
+                                   !getenv("PG_NO_SPLIT_BUILD");
+                if (split) {
+                    pp.pipe_lo = (t->nrows * ctx().rank / W) & ~(i64)3;
+                    pp.pipe_hi = ctx().rank + 1 == W ? t->nrows : ((t->nrows * (ctx().rank + 1) / W) & ~(i64)3);
+                    if (pp.pipe_hi <= 0) pp.pipe_hi = pp.pipe_lo = 0;       // (an empty slice: pipe_hi == 0 would mean "every row")
+                }
+                bool any_valid = pp.ins_key.valid != nullptr;
+                for (int k = 0; k < pp.npred; k++) any_valid = any_valid || pp.pred[k].col.valid != nullptr;
+                if (!s.has_probe && pp.nextra == 0 && pp.nlike == 0 && pp.npred <= 1 && !any_valid && s.ins_key_col2 < 0 && !getenv("PG_JOIN_GENERIC")) {
+                    const i64 lo = split ? pp.pipe_lo : 0, hi = split ? pp.pipe_hi : t->nrows;
+                    const int grid = (int)std::max<i64>(std::min<i64>((hi - lo + 1023) / 1024, (i64)ctx().prop.multiProcessorCount * 8), 1);
+                    if (hi > lo) {
+                        if (pp.npred == 1) bitmap_build_kernel<true><<<grid, 256, 0, st>>>(pp, lo, hi);
+                        else bitmap_build_kernel<false><<<grid, 256, 0, st>>>(pp, lo, hi);
+                        PG_CUDA(cudaGetLastError());
+                    }
+                } else if (!split || pp.pipe_hi > pp.pipe_lo) {
+                    PG_TRY(launch_pipe<SINK_BITMAP>(pp, t));
+                }
+                if (split) {
+                    const size_t part = s.bitmap_words * 4 + 32;
+                    if (s.d_bm_all.bytes < part * (size_t)W) PG_TRY(s.d_bm_all.alloc(part * (size_t)W));
+                    PG_CUDA(cudaMemcpyAsync((char *)s.d_bitmap.p + s.bitmap_words * 4, d_counters.p, 32, cudaMemcpyDeviceToDevice, st));
+                    PG_TRY(comm_allgather(s.d_bitmap.p, s.d_bm_all.p, part, st));
+                    bitmap_or_kernel<<<(int)std::min<u64>((s.bitmap_words + 255) / 256, (u64)ctx().prop.multiProcessorCount * 4), 256, 0, st>>>(
+                        s.d_bm_all.as<unsigned>(), W, (u64)s.bitmap_words, s.jt.bitmap, d_counters.as<unsigned long long>());
+                    PG_CUDA(cudaGetLastError());
+                    res->stats.kernel_launches += 1;
+                }
                 s.no_table = true;
                 s.dup_keys = 0;
                 res->stats.kernel_launches += 1;
-                if (idx < 2) {       // counters are read lazily with the next stage's; keep the API cheap
+                const bool need_rows = !star && &s == stages.back().get();      // sizes the group table of the final probe
+                if (need_rows) {
                     unsigned long long c0[4];
                     PG_TRY(read_counters(c0));
                     s.built_rows = (i64)c0[1];
-                    res->stats.aux[2 + 2 * idx] = (i64)c0[0];
-                    res->stats.aux[3 + 2 * idx] = (i64)c0[1];
+                    if (idx < 2) { res->stats.aux[2 + 2 * idx] = (i64)c0[0]; res->stats.aux[3 + 2 * idx] = (i64)c0[1]; }
+                } else if (idx < 2) {
+                    // no host round trip for a statistic: park the two counters, the next read-back carries them
+                    PG_CUDA(cudaMemcpyAsync(d_counters.as<unsigned long long>() + 4 + 2 * idx, d_counters.p, 16, cudaMemcpyDeviceToDevice, st));
+                    deferred_stats |= 1u << idx;
+                    s.built_rows = t->nrows;                                    // upper bound (only statistics read it)
                 }
                 return PG_OK;
             }
@@ -1146,6 +1196,9 @@ struct JoinAggPipeline : Pipeline {
         Trace tr("joinagg");
         PG_CUDA(cudaEventRecord(ev_all.a, st));
         res->stats.kernel_launches = 0;
+        cur_res = res;
+        deferred_stats = 0;
+        PG_CUDA(cudaMemsetAsync(d_counters.p, 0, 128, st));
         x_sent_rows = x_sent_bytes = 0;
         for (size_t i = 0; i < stages.size(); i++) {
             if (xl >= 0 && (int)i == lookups[(size_t)xl].stage) { PG_TRY(run_exchange_build(*stages[i], res)); tr.mark("build stage (row exchange)"); continue; }
@@ -2055,7 +2108,7 @@ static int build_star(pg_plan *plan, const Node &aggn, const Node &top, std::uni
         const i64 per_block = ((std::max<i64>(st->total_rows(), 1) + threads - 1) / threads) * 256 * std::max(ctx().world, 1);
         if (p->star_worst * (i128)per_block >= ((i128)1 << 63)) PG_FAIL(PG_EUNSUPPORTED, "a block's partial group sum could exceed int64");
     }
-    PG_TRY(p->d_counters.alloc(64));
+    PG_TRY(p->d_counters.alloc(128));
     PG_TRY(p->d_overflow.alloc(4));
     std::string ex = "StarJoin[existence filter -> per-hit lookups -> dense shared-memory groups] kernel=filter_hits_kernel+hits_star_kernel fact=" + st->name + " joins:";
     for (size_t l = 0; l < p->lookups.size(); l++) {
@@ -2503,7 +2556,7 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &top, std::unique
         p->topk_limit = plan->topk->limit;
     }
 no_device_topk:
-    PG_TRY(p->d_counters.alloc(64));
+    PG_TRY(p->d_counters.alloc(128));
     PG_TRY(p->d_overflow.alloc(4));
     std::string ex = "JoinAgg[inner hash join chain -> global group table] stages:";
     for (auto &sp : p->stages) {

@@ -26,7 +26,7 @@ struct VmAggParams {
 };
 
 template <int NT>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 512 / NT)       // <= 128 registers: two 256-thread CTAs per SM hide the interpreter's latencies
 vm_scanagg_kernel(const VmAggParams p, i64 *__restrict__ partials /* [grid][G*P] */, i64 *__restrict__ first_row /* [G] preset to 0x7f.. */)
 {
     extern __shared__ i64 s_acc[];                 // [G*P][NT]

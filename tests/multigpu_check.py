@@ -78,6 +78,16 @@ def main():
         assert st.aux[7] > 0, "no row crossed NVLink"
         assert J._q9_rows(chunks) == O.q9(O.gen_part(sf, word), O.gen_supplier(sf), O.gen_partsupp(sf), orders, line, like_word=word)
     ps_shard.free()
+    # replicated build sides scanned 1/W per rank, key bitmaps OR-merged over NCCL (small tables here: force it)
+    os.environ["PG_SPLIT_MIN_ROWS"] = "1"
+    _, ref3 = J.check_q3(O, tables, host, check_counts=False)
+    _, st3, _ = J._run(T.q3_plan(), tables)
+    assert st3.aux[3] == ref3["stats"]["n_cust_sel"], "split build: the ranks' built-row counters were not summed"
+    J.check_q3_topk(O, tables, host, 10)
+    for word in ("pink", "lace"):
+        chunks, _, explain = J._run(T.q9_plan(word), tables)
+        assert J._q9_rows(chunks) == O.q9(O.gen_part(sf, word), O.gen_supplier(sf), O.gen_partsupp(sf), orders, line, like_word=word)
+    os.environ.pop("PG_SPLIT_MIN_ROWS")
     os.environ["PG_FORCE_SHUFFLE"] = "1"          # the general path must also be right when it is not needed
     J.check_groupby(O, tables, line, key="l_orderkey", value="l_quantity", having_gt=200)
     J.check_q3(O, tables, host, check_counts=False)

@@ -198,18 +198,28 @@ def test_device_generator_order_ranges(pg, oracle):
             x.free()
 
 
-def test_unsupported_shape_is_refused_not_emulated(pg, uploaded):
-    """A shape without a fused kernel yields PG_EUNSUPPORTED (plan selection falls back to the
-    stock executors at plan-build time) -- never a silent CPU path."""
+def test_unsupported_shape_is_refused_not_emulated(pg, oracle, uploaded, sf01_host):
+    """A filter that is not a conjunction of ranges (an OR of comparisons) takes the expression-driven kernel and gives
+    the oracle's answer; a shape without ANY kernel (sum over a quotient: no fixed scale to accumulate at) yields
+    PG_EUNSUPPORTED -- plan selection falls back to the stock executors at plan-build time, never a silent CPU path."""
     from plan_b200 import _lib as L, chunk as K, compute as X, tpch as T
     plan = T.q6_plan()
     B = K.LType(K.LTID_BOOLEAN)
-    scan = plan.Children[0]                         # an OR of comparisons is not a conjunction of ranges
-    scan.Filters.append(X.func("or", B, scan.Filters[0], scan.Filters[1]))
+    scan = plan.Children[0]
+    scan.Filters.append(X.func("or", B, scan.Filters[0], scan.Filters[1]))      # true for every row: the result is Q6's
+    chunks, stats, explain = _run(plan, uploaded)
+    assert "expression programs" in explain
+    ref = oracle.q6(sf01_host["lineitem"])
+    got = _dec(chunks[0].Data[0], 0)
+    assert stats.aux[0] == ref["rows_selected"] and _dec_value(got)[0] * 10 ** (4 - got[1]) == ref["exact"]
+    plan = T.q6_plan()
+    S = T.FULL
+    agg = plan.Info.Aggs[0]
+    agg.Children[0] = X.func("/", K.DecimalType(38, 6), S.col("lineitem", "l_extendedprice"), S.col("lineitem", "l_discount"))
     ex = X.gpuPipelineExec(plan, uploaded)
     with pytest.raises(L.PlanGpuError) as ei:
         ex.Init()
-    assert ei.value.status == L.PG_EUNSUPPORTED
+    assert ei.value.status == L.PG_EUNSUPPORTED and "quotient" in str(ei.value)
     ex.Close()
 
 
