@@ -42,7 +42,8 @@ def parse_args():
     ap.add_argument("--no-extra", action="store_true", help="skip the Q18 / group-by timings reported beside the metric")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-chunked-e2e", action="store_true", help="skip the 2048-row-chunk pageable-memory e2e leg (C++ host shim subprocess)")
-    ap.add_argument("--cpu-sample-sf", type=float, default=1.0, help="CPU baseline sample: this SF worth of rows")
+    ap.add_argument("--cpu-sample-sf", type=float, default=None,
+                    help="CPU sample: this SF worth of rows (default: 4 for the cpu_baseline leg, 10 for --impl reference, shrunk to fit the time bound)")
     return ap.parse_args()
 
 
@@ -173,10 +174,11 @@ def run_reference_arm(args, queries):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_sf = min(args.cpu_sample_sf, args.sf)
-    steps, warmup = max(1, args.steps), max(0, min(args.warmup, 1))
-    # bound the whole run to a few minutes: ~6 s per SF1 step for q6+q1+q3 on one core
-    while steps * sample_sf * 7.0 > 240 and sample_sf > 0.05:
+    sample_sf = min(args.cpu_sample_sf if args.cpu_sample_sf else 10.0, args.sf)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)          # the same warm-up as our arm
+    # bound the whole run to a few minutes: ~3.2-4 s per SF1 step for q6+q1+q3 on one core (the reference executes on one
+    # goroutine), plus ~2.5 s per SF1 to generate the sample
+    while (steps + warmup) * sample_sf * 4.0 + sample_sf * 2.5 > 400 and sample_sf > 0.05:
         sample_sf /= 2
     r = cpu_reference_run(queries, sample_sf, steps, warmup)
     sample = "dbgen-equivalent SF%g sample (%d lineitem rows) of the SF%g workload, per step" % (
@@ -187,7 +189,9 @@ def run_reference_arm(args, queries):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int64/decimal(19)",
         "data": "synthetic (dbgen-equivalent generator, in-box)",
         "config": {"workload": "TPC-H " + "+".join(q.upper() for q in queries) + " at SF%g" % args.sf,
-                   "queries": queries, "sf": args.sf, "sample": sample},
+                   "queries": queries, "sf": args.sf, "sample": sample, "kind": "port",
+                   "implementation": "oracle/refexec.c: C restatement of the reference's Go executor for this path, 2048-row chunks, "
+                                     "govalues-equivalent decimals, 1 thread (the Go toolchain is absent on the box)"},
         "cpu_baseline": {"value": r["rows_per_s"], "unit": "rows/s", "cores": 1, "kind": "port", "sample": sample,
                          "note": "C restatement of the reference's single-goroutine executor (no Go toolchain on "
                                  "the box); per query: " + json.dumps(r["per_query_rows_per_s"])},
@@ -538,7 +542,7 @@ def main():
     # ---- CPU baseline beside it (rank 0, N=1 only) -------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sample_sf = min(args.cpu_sample_sf, args.sf)
+        sample_sf = min(args.cpu_sample_sf if args.cpu_sample_sf else 4.0, args.sf)
         r = cpu_reference_run(queries, sample_sf, 1, 0)
         cpu = {"value": r["rows_per_s"], "unit": "rows/s", "cores": 1, "kind": "port",
                "sample": "dbgen-equivalent SF%g sample (%d lineitem rows), one pass of %s" % (
