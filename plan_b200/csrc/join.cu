@@ -137,7 +137,8 @@ struct JoinAggPipeline : Pipeline {
     DevBuf d_star, d_star_all;
     PinBuf h_star;
     Stage &top_stage_ref() { return *stages[(size_t)(main_stage >= 0 ? main_stage : (int)stages.size() - 1)]; }
-    DevBuf d_edges;
+    DevBuf d_edges, d_dense;
+    int dense_passes = 0;
     std::vector<std::pair<int, int>> outs;
     std::vector<int> group_out_type;             // pg_type of each group key
     i64 algorithmic_bytes = 0, main_bytes = 0;
@@ -1294,7 +1295,50 @@ struct JoinAggPipeline : Pipeline {
             }
             tr.mark("sorted-run group-by");
         }
-        for (int attempt = 0; !sorted_runs; attempt++) {
+        // unsorted key with a modest dense domain: direct-addressed accumulators, one pass per L2-sized key slice
+        const bool dense_group = !sorted_runs && one_shape && !(shuffle && c.world > 1) && key_domain > 0 && key_domain <= ((u64)1 << 28) &&
+                                 t->nrows > 0 && t->nrows < ((i64)1 << 32) && gs.nacc == 1 && !getenv("PG_NO_DENSE_GROUP");
+        if (dense_group) {
+            const u64 D = key_domain;
+            if (d_dense.bytes < D * 12 + 64) PG_TRY(d_dense.alloc(D * 12 + 64));
+            unsigned long long *dsum = d_dense.as<unsigned long long>();
+            unsigned *dcnt = (unsigned *)(dsum + D);
+            PG_CUDA(cudaMemsetAsync(d_dense.p, 0, D * 12, st));
+            PG_CUDA(cudaMemsetAsync(d_counters.p, 0, 32, st));
+            const u64 slice_bytes = (u64)(getenv("PG_DENSE_SLICE_MB") ? atoll(getenv("PG_DENSE_SLICE_MB")) : 48) << 20;
+            const int npass = (int)std::max<u64>((D * 12 + slice_bytes - 1) / slice_bytes, 1);
+            const i64 ntiles = (t->nrows + SA_TILE - 1) / SA_TILE;
+            const int grid = (int)std::max<i64>(std::min<i64>(ntiles, (i64)c.prop.multiProcessorCount * 8), 1);
+            PG_CUDA(cudaEventRecord(ev_main.a, st));
+            for (int ps = 0; ps < npass; ps++) {
+                const i64 lo = key_min + (i64)(D * (u64)ps / (u64)npass), hi = key_min + (i64)(D * (u64)(ps + 1) / (u64)npass);
+                if (pp.npred == 1) group1_dense_kernel<true><<<grid, SA_THREADS, 0, st>>>(pp, dsum, dcnt, key_min, lo, hi, ps == 0);
+                else group1_dense_kernel<false><<<grid, SA_THREADS, 0, st>>>(pp, dsum, dcnt, key_min, lo, hi, ps == 0);
+                PG_CUDA(cudaGetLastError());
+            }
+            PG_CUDA(cudaEventRecord(ev_main.b, st));
+            res->stats.kernel_launches += npass;
+            PG_TRY(read_counters(cnt));
+            tr.mark("dense group-by passes");
+            const i64 want = (i64)std::min<u64>(D, (u64)std::max<i64>((i64)cnt[0], 1));
+            if (want > out_cap) {
+                PG_TRY(d_out_klo.alloc((size_t)want * 8));
+                PG_TRY(d_out_khi.alloc((size_t)want * 8));
+                PG_TRY(d_out_acc.alloc((size_t)want * 8 * (size_t)(gs.nacc + 1)));
+                out_cap = want;
+            }
+            PG_CUDA(cudaMemsetAsync(d_counters.p, 0, 32, st));
+            dense_compact_kernel<<<(int)std::min<u64>((D + 255) / 256, (u64)c.prop.multiProcessorCount * 8), 256, 0, st>>>(
+                dsum, dcnt, D, key_min, d_out_klo.as<i64>(), d_out_khi.as<i64>(), d_out_acc.as<i64>(), out_cap, d_counters.as<unsigned long long>(),
+                hav_plane, hav_lo, hav_hi);
+            PG_CUDA(cudaGetLastError());
+            res->stats.kernel_launches += 1;
+            unsigned long long ng2[4];
+            PG_TRY(read_counters(ng2));
+            ngroups = (i64)ng2[0];
+            dense_passes = npass;
+        }
+        for (int attempt = 0; !sorted_runs && !dense_group; attempt++) {
             PG_TRY(ensure_group_table(cap));
             cap = gt_cap;
             PG_CUDA(cudaMemsetAsync(d_gt.p, 0x80, cap * 8 * (size_t)gt_slot_words(gs.nacc), st));
@@ -1356,7 +1400,7 @@ struct JoinAggPipeline : Pipeline {
         }
         // compact
         const bool do_shuffle = shuffle && c.world > 1;
-        if (!sorted_runs) {
+        if (!sorted_runs && !dense_group) {
         i64 max_out = (i64)std::min<u64>(cap, (u64)cnt[1]);
         if (max_out < 1) max_out = 1;
         if (max_out > out_cap) {
@@ -2571,7 +2615,8 @@ no_device_topk:
     if (p->no_join)
         snprintf(b, sizeof b, "GroupBy[global open-addressing table] scan(%s) kernel=pipeline_kernel<SINK_GROUP> group_keys=%d sums=%d%s%s%s",
                  st->name.c_str(), p->nparts, p->gs.nacc, p->hav_plane >= 0 ? " having" : "",
-                 p->key_sorted ? " sorted-run reduce-by-key when the shape allows (run_group_kernel)" : "",
+                 p->key_sorted ? " sorted-run reduce-by-key when the shape allows (run_group_kernel)"
+                               : (p->key_domain > 0 && p->key_domain <= ((u64)1 << 28)) ? " dense direct-addressed accumulators in L2-sized key slices when the shape allows (group1_dense_kernel)" : "",
                  p->shuffle ? " exchange=all-to-all(hash-partitioned)" : "");
     else
         snprintf(b, sizeof b, " probe(%s key=%s) kernel=filter_hits_kernel+hits_sink_kernel<SINK_GROUP> group_keys=%d sums=%d%s", st->name.c_str(),
