@@ -139,6 +139,12 @@ int pg_device_info(pg_devinfo *out);
 int pg_init_devices(int ndev, const int *devices);
 int pg_use_device(int index);
 int pg_num_devices(void);
+/* The library's own cross-rank merge of partial aggregates, callable WITHOUT a GPU (host arithmetic only; the pipelines
+ * call the same function after their all-gather).  `gathered`: nranks records of `rank_bytes` bytes, each
+ * [nvals x {uint64 lo, uint64 hi}] two's-complement 128-bit totals followed by [ngroups] int64 first-row ids
+ * (0x7f7f7f7f7f7f7f7f = the group has no row on that rank).  Sums are exact in 128 bits, first rows take the minimum. */
+int pg_host_merge_partials(const void *gathered, int64_t rank_bytes, int nranks, int nvals, int ngroups,
+                           uint64_t *out_totals, int64_t *out_first);
 int pg_comm_unique_id(void *out128);
 int pg_comm_init(int world_size, int rank, const void *id128);
 int pg_comm_destroy(void);

@@ -92,6 +92,7 @@ SIGNATURES = [
     ("pg_result_column_dict", C.c_int, [_P, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.POINTER(C.c_char_p))]),
     ("pg_result_stats", C.c_int, [_P, C.POINTER(Stats)]),
     ("pg_result_free", None, [_P]),
+    ("pg_host_merge_partials", C.c_int, [_P, C.c_int64, C.c_int, C.c_int, C.c_int, _P, _P]),
     ("pg_init_devices", C.c_int, [C.c_int, C.POINTER(C.c_int)]),
     ("pg_use_device", C.c_int, [C.c_int]),
     ("pg_num_devices", C.c_int, []),

@@ -355,6 +355,22 @@ static LowcardKernel lowcard_variant(bool wide, bool acc32, bool key1, int unrol
 #undef PG_LC
 }
 
+// Rank-ordered exact merge of the ranks' partial aggregates as they come out of the all-gather: per rank
+// [nvals x {u64 lo, u64 hi}] 128-bit totals followed by [ngroups] first-row ids (0x7f7f.. = group absent on that rank).
+// Sums add in 128 bits (NCCL has no int128 sum), the first row of a group is the smallest over the ranks.
+static void merge_rank_partials(const char *gathered, size_t rank_bytes, int nranks, int nvals, int ngroups, i128 *tot, i64 *first)
+{
+    for (int v = 0; v < nvals; v++) tot[v] = 0;
+    for (int g = 0; g < ngroups; g++) first[g] = INT64_MAX;
+    for (int r = 0; r < nranks; r++) {
+        const char *base = gathered + rank_bytes * (size_t)r;
+        const u64 *h = (const u64 *)base;
+        const i64 *f = (const i64 *)(base + (size_t)nvals * 16);
+        for (int v = 0; v < nvals; v++) tot[v] += make_i128(h[2 * v], h[2 * v + 1]);
+        for (int g = 0; g < ngroups; g++) if (f[g] != 0x7f7f7f7f7f7f7f7fLL && f[g] < first[g]) first[g] = f[g];
+    }
+}
+
 struct LowcardPipeline : Pipeline {
     const pg_table *table = nullptr;
     LowcardParams prm{};
@@ -484,16 +500,10 @@ struct LowcardPipeline : Pipeline {
         PG_CUDA(cudaStreamSynchronize(st));
         tr.mark("kernels+gather+d2h");
 
-        // merge ranks in order; 128-bit exact
+        // merge ranks in order; 128-bit exact (merge_rank_partials: also exported host-only as pg_host_merge_partials)
         std::vector<i128> tot((size_t)G * LC_K, 0);
         std::vector<i64> first((size_t)G, INT64_MAX);
-        for (int r = 0; r < nranks(); r++) {
-            const char *base = h_tot + rank_bytes() * (size_t)r;
-            const u64 *h = (const u64 *)base;
-            const i64 *f = (const i64 *)(base + (size_t)G * LC_K * 16);
-            for (int v = 0; v < G * LC_K; v++) tot[(size_t)v] += make_i128(h[2 * v], h[2 * v + 1]);
-            for (int g = 0; g < G; g++) if (f[g] != 0x7f7f7f7f7f7f7f7fLL && f[g] < first[(size_t)g]) first[(size_t)g] = f[g];
-        }
+        merge_rank_partials(h_tot, rank_bytes(), nranks(), G * LC_K, G, tot.data(), first.data());
         res->stats.kernel_ms = ev_all.ms();
         res->stats.main_kernel_ms = ev_main.ms();
         res->stats.rows_scanned = table->nrows;
@@ -1465,3 +1475,20 @@ int build_scan_agg(pg_plan *plan, const Node &aggn, const Node &scan, std::uniqu
 }
 
 }  // namespace pg
+
+// Host-only entry point (no CUDA call): the product's own cross-rank merge, for tests that run without a GPU
+// (tests/test_dist_cpu.py feeds it per-rank partials exchanged over gloo).
+extern "C" int pg_host_merge_partials(const void *gathered, int64_t rank_bytes, int nranks, int nvals, int ngroups,
+                                      uint64_t *out_totals /* [nvals][2] */, int64_t *out_first /* [ngroups] */)
+{
+    using namespace pg;
+    if (!gathered || !out_totals || !out_first || nranks < 1 || nvals < 0 || ngroups < 0 || rank_bytes < (int64_t)nvals * 16 + (int64_t)ngroups * 8)
+        PG_FAIL(PG_EINVAL, "pg_host_merge_partials: bad arguments");
+    std::vector<i128> tot((size_t)nvals);
+    std::vector<i64> first((size_t)ngroups);
+    merge_rank_partials((const char *)gathered, (size_t)rank_bytes, nranks, nvals, ngroups, tot.data(), first.data());
+    for (int v = 0; v < nvals; v++) { out_totals[2 * v] = (u64)tot[(size_t)v]; out_totals[2 * v + 1] = (u64)(tot[(size_t)v] >> 64); }
+    for (int g = 0; g < ngroups; g++) out_first[g] = first[(size_t)g];
+    return PG_OK;
+}
+

@@ -37,6 +37,33 @@ def _worker(rank, world, port, q):
         merged = D.merge_lowcard_partials([g[0] for g in gathered])
         _, whole = O.gen_orders_lineitem(sf)
         ref = O.q1(whole)
+        # the same merge through the PRODUCT's own code (pg_host_merge_partials: the function the pipelines call after
+        # their all-gather; host arithmetic only, no GPU): per-rank records in the library's wire layout
+        import ctypes as C
+        from plan_b200 import _lib as L
+        keys = sorted({k for g in gathered for k in g[0]})
+        nvals, ng = len(keys) * 6, len(keys)
+        rank_bytes = nvals * 16 + ng * 8
+        blob = bytearray()
+        for part, _, _, _ in gathered:
+            tot, first = [], []
+            for k in keys:
+                p = part.get(k)
+                vals = [0] * 6 if p is None else [p["count"]] + list(p["sums"])
+                tot += vals
+                first.append(0x7f7f7f7f7f7f7f7f if p is None else p["first_row"])
+            for v in tot:
+                blob += int(v & ((1 << 128) - 1)).to_bytes(16, "little")
+            for f in first:
+                blob += int(f).to_bytes(8, "little", signed=True)
+        out_tot = (C.c_uint64 * (2 * nvals))()
+        out_first = (C.c_int64 * ng)()
+        buf = (C.c_char * len(blob)).from_buffer(blob)
+        L.check(L.lib().pg_host_merge_partials(C.addressof(buf), rank_bytes, world, nvals, ng, C.addressof(out_tot), C.addressof(out_first)))
+        for i, k in enumerate(keys):
+            got = [out_tot[2 * (6 * i + j)] | (out_tot[2 * (6 * i + j) + 1] << 64) for j in range(6)]
+            assert got == [merged[k]["count"]] + merged[k]["sums"], (k, got)
+            assert out_first[i] == merged[k]["first_row"]
         assert sum(g[3] for g in gathered) == len(whole["l_orderkey"])
         assert len(merged) == len(ref["groups"])
         for g in ref["groups"]:
