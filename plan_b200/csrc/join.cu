@@ -158,7 +158,7 @@ struct JoinAggPipeline : Pipeline {
     bool has_topk = false;
     TopkKey topk_key{};
     i64 topk_limit = -1;
-    DevBuf d_hist, d_cand_klo, d_cand_khi, d_cand_acc;
+    DevBuf d_hist, d_cand_klo, d_cand_khi, d_cand_acc, d_tstate;
     PinBuf h_hist;
     i64 cand_cap = 0;
 
@@ -1424,7 +1424,11 @@ struct JoinAggPipeline : Pipeline {
         tr.mark("compact");
         if (device_only) { dev_ngroups = ngroups; return PG_OK; }
         // (FD mode: the ORDER BY keys are fetched below, the host orders the groups)
-        if (has_topk && !fd_mode) { PG_TRY(topk_preselect(&ngroups, res)); tr.mark("top-k preselect"); }
+        // LIMIT k with a small k over many groups: the radix select runs with its state on the device and the candidates
+        // leave in one fixed-size message (below) -- no host round trip per pass
+        const bool topk_fast = has_topk && !fd_mode && topk_limit > 0 && topk_limit <= SG_CAP / 2 && ngroups > topk_limit &&
+                               !(getenv("PG_TOPK_HOST") && atoi(getenv("PG_TOPK_HOST")));
+        if (has_topk && !fd_mode && !topk_fast) { PG_TRY(topk_preselect(&ngroups, res)); tr.mark("top-k preselect"); }
         if (fd_mode && ngroups > 0) {
             // dependent key columns are written behind the accumulator planes of the group list, so every
             // read-back / cross-rank gather path below carries them like one more aggregate
@@ -1460,8 +1464,77 @@ struct JoinAggPipeline : Pipeline {
             h_acc = h_khi + n;
             return PG_OK;
         };
-        bool small_done = false;
-        if (gather_ranks && c.world > 1 && has_topk && topk_limit >= 0 && topk_limit <= SG_CAP / 2) {
+        bool small_done = false, skip_small = false;
+        if (topk_fast) {
+            const i64 n = ngroups, k = topk_limit;
+            constexpr int NB = 1 << TOPK_DIGIT_BITS;
+            constexpr i64 FAST_CAP = 4 * SG_CAP;
+            if (!d_hist.p) { PG_TRY(d_hist.alloc(NB * 4 + 16)); PG_TRY(h_hist.alloc(NB * 4 + 16)); }
+            if (!d_tstate.p) PG_TRY(d_tstate.alloc(sizeof(TopkState)));
+            if (cand_cap < FAST_CAP) {
+                PG_TRY(d_cand_klo.alloc((size_t)FAST_CAP * 8));
+                PG_TRY(d_cand_khi.alloc((size_t)FAST_CAP * 8));
+                PG_TRY(d_cand_acc.alloc((size_t)FAST_CAP * 8 * (size_t)planes));
+                cand_cap = FAST_CAP;
+            }
+            const int grid = (int)std::max<i64>(std::min<i64>((n + 255) / 256, (i64)c.prop.multiProcessorCount * 4), 1);
+            unsigned *hist = d_hist.as<unsigned>();
+            unsigned long long *minmax = (unsigned long long *)(hist + NB);
+            TopkState *ts = d_tstate.as<TopkState>();
+            const i64 stop_at = std::max<i64>(128 - k, 16);
+            topk_state_init_kernel<<<1, 256, 0, st>>>(ts, k, n, hist, minmax);
+            topk_hist_dev_kernel<true><<<grid, 256, 0, st>>>(topk_key, d_out_klo.as<i64>(), d_out_khi.as<i64>(), d_out_acc.as<i64>(), out_cap, n, ts, hist, minmax);
+            topk_select_kernel<<<1, 256, 0, st>>>(ts, hist, minmax, k, n, stop_at, 0);
+            for (int i = 0; i < TOPK_DEV_MORE; i++) {
+                topk_hist_dev_kernel<false><<<grid, 256, 0, st>>>(topk_key, d_out_klo.as<i64>(), d_out_khi.as<i64>(), d_out_acc.as<i64>(), out_cap, n, ts, hist, minmax);
+                topk_select_kernel<<<1, 256, 0, st>>>(ts, hist, minmax, k, n, stop_at, i == TOPK_DEV_MORE - 1);
+            }
+            PG_CUDA(cudaMemsetAsync(d_counters.p, 0, 32, st));
+            topk_collect_dev_kernel<<<grid, 256, 0, st>>>(topk_key, d_out_klo.as<i64>(), d_out_khi.as<i64>(), d_out_acc.as<i64>(), out_cap, n, planes, ts,
+                                                          d_cand_klo.as<i64>(), d_cand_khi.as<i64>(), d_cand_acc.as<i64>(), cand_cap,
+                                                          d_counters.as<unsigned long long>());
+            const size_t words = 1 + (size_t)SG_CAP * (size_t)(2 + planes);
+            const int W = (gather_ranks && c.world > 1) ? c.world : 1;
+            if (!d_sg.p) { PG_TRY(d_sg.alloc(words * 8 * (size_t)(c.world + 1))); PG_TRY(h_sg.alloc(words * 8 * (size_t)c.world)); }
+            i64 *send = d_sg.as<i64>();
+            topk_pack_kernel<<<4, 256, 0, st>>>(d_cand_klo.as<i64>(), d_cand_khi.as<i64>(), d_cand_acc.as<i64>(), cand_cap, d_counters.as<unsigned long long>(), planes,
+                                                SG_CAP, send);
+            PG_CUDA(cudaGetLastError());
+            res->stats.kernel_launches += 5 + 2 * TOPK_DEV_MORE;
+            if (W > 1) {
+                PG_TRY(comm_allgather(send, send + words, words * 8, st));
+                PG_CUDA(cudaMemcpyAsync(h_sg.p, send + words, words * 8 * (size_t)W, cudaMemcpyDeviceToHost, st));
+            } else {
+                PG_CUDA(cudaMemcpyAsync(h_sg.p, send, words * 8, cudaMemcpyDeviceToHost, st));
+            }
+            PG_CUDA(cudaStreamSynchronize(st));
+            tr.mark("top-k (device select) + gather");
+            const i64 *hs = h_sg.as<i64>();
+            i64 total = 0;
+            bool ok = true;
+            for (int r = 0; r < W; r++) { i64 x = hs[(size_t)r * words]; if (x < 0) ok = false; else total += x; }
+            if (ok) {
+                PG_TRY(host_arrays(total));
+                i64 off = 0;
+                for (int r = 0; r < W; r++) {
+                    const i64 *rec = hs + (size_t)r * words;
+                    i64 nr = rec[0];
+                    memcpy(h_klo + off, rec + 1, (size_t)nr * 8);
+                    memcpy(h_khi + off, rec + 1 + SG_CAP, (size_t)nr * 8);
+                    for (int a = 0; a < planes; a++) memcpy(h_acc + (size_t)a * (size_t)total + (size_t)off, rec + 1 + (size_t)SG_CAP * (size_t)(2 + a), (size_t)nr * 8);
+                    off += nr;
+                }
+                ngroups = total;
+                small_done = true;
+            } else {
+                // more candidates than the message holds on some rank (every rank sees every count, so every rank leaves
+                // the single-message path here): the host-driven select, then the general gather below
+                PG_TRY(topk_preselect(&ngroups, res));
+                skip_small = true;
+            }
+        }
+        if (small_done || skip_small) {
+        } else if (gather_ranks && c.world > 1 && has_topk && topk_limit >= 0 && topk_limit <= SG_CAP / 2) {
             // LIMIT k with small k: every rank has at most k (+ties) candidates -> ONE fixed-size all-gather
             // [count | klo[SG_CAP] | khi[SG_CAP] | planes x acc[SG_CAP]] and one read-back.  A rank with more
             // than SG_CAP candidates publishes count = -1 and everybody takes the general path below.

@@ -1450,6 +1450,126 @@ static __global__ void topk_collect_kernel(TopkKey key, const i64 *klo, const i6
     }
 }
 
+// ---- the same radix select with its state on the DEVICE: no host round trip between the passes ----
+// The host loop above reads every histogram back (3 synchronisations for Q3's revenue key, ~25 us each: more than the
+// passes themselves once the shards are small).  Here a one-block kernel takes the host's decision after every pass and
+// the next pass reads prefix / shift from device memory; the launch sequence is fixed (first pass, TOPK_DEV_MORE further
+// passes that return at once when the selection is finished), the threshold lands in the state for the collect kernel.
+constexpr int TOPK_DEV_MORE = 4;
+struct TopkState {
+    u64 prefix;          // digits chosen so far (high bits of the key)
+    u64 threshold;       // valid when done: keys <= threshold are the candidates
+    i64 remaining;       // we look for the remaining-th smallest key among those matching the prefix
+    i64 n_equal;         // keys matching the prefix
+    int pass;            // digits of TOPK_DIGIT_BITS consumed
+    int done;
+};
+static __global__ void topk_state_init_kernel(TopkState *st, i64 k, i64 n, unsigned *hist, unsigned long long *minmax)
+{
+    if (threadIdx.x == 0) { st->prefix = 0; st->threshold = ~0ULL; st->remaining = k; st->n_equal = n; st->pass = 0; st->done = 0; minmax[0] = ~0ULL; minmax[1] = 0; }
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+}
+template <bool MINMAX>
+static __global__ void topk_hist_dev_kernel(TopkKey key, const i64 *klo, const i64 *khi, const i64 *acc, i64 stride, i64 n,
+                                            const TopkState *st, unsigned *hist, unsigned long long *minmax)
+{
+    if (st->done) return;
+    const u64 prefix = st->prefix;
+    const int prefix_bits = st->pass * TOPK_DIGIT_BITS;
+    __shared__ unsigned s_h[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_h[i] = 0;
+    __syncthreads();
+    u64 lo = ~0ULL, hi = 0;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        u64 u = topk_u64(key, klo, khi, acc, stride, i);
+        if (MINMAX) { lo = u < lo ? u : lo; hi = u > hi ? u : hi; }
+        if (prefix_bits == 0 || (u >> (64 - prefix_bits)) == prefix) atomicAdd(&s_h[(u >> (56 - prefix_bits)) & 255], 1u);
+    }
+    if (MINMAX) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            u64 l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+            lo = l2 < lo ? l2 : lo;
+            hi = h2 > hi ? h2 : hi;
+        }
+        if ((threadIdx.x & 31) == 0) { atomicMin(&minmax[0], lo); atomicMax(&minmax[1], hi); }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        if (s_h[i]) atomicAdd(&hist[i], s_h[i]);
+}
+// one block: the host loop's step (choose the digit holding the k-th key, skip digits common to every key after the
+// first pass, stop when the bin is small or the digits are used up), then clears the histogram for the next pass
+static __global__ void topk_select_kernel(TopkState *st, unsigned *hist, const unsigned long long *minmax, i64 k, i64 n, i64 stop_at, int last)
+{
+    __shared__ unsigned s_h[256];
+    const int npass = 64 / TOPK_DIGIT_BITS;
+    if (st->done) return;
+    s_h[threadIdx.x] = hist[threadIdx.x];
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    i64 remaining = st->remaining;
+    int d = 0;
+    for (; d < 256; d++) {
+        if ((i64)s_h[d] >= remaining) break;
+        remaining -= (i64)s_h[d];
+    }
+    if (d == 256) d = 255;                       // cannot happen (the bins hold n_equal >= remaining keys)
+    u64 prefix = (st->prefix << TOPK_DIGIT_BITS) | (u64)d;
+    i64 n_equal = (i64)s_h[d];
+    int pass = st->pass + 1;
+    if (pass == 1) {
+        const u64 diff = minmax[0] ^ minmax[1];
+        int common = 64;
+        if (diff) { common = 0; while (!((diff << common) >> 63)) common++; }
+        int skip_to = common / TOPK_DIGIT_BITS;
+        if (skip_to > npass) skip_to = npass;
+        if (skip_to > pass) {
+            pass = skip_to;
+            prefix = pass == npass ? minmax[0] : minmax[0] >> (64 - pass * TOPK_DIGIT_BITS);
+            remaining = k;
+            n_equal = n;
+        }
+    }
+    st->prefix = prefix;
+    st->remaining = remaining;
+    st->n_equal = n_equal;
+    st->pass = pass;
+    if (!(pass < npass && n_equal > stop_at) || last) {
+        const int rest_bits = 64 - pass * TOPK_DIGIT_BITS;
+        st->threshold = rest_bits > 0 ? (prefix << rest_bits) | ((((u64)1) << rest_bits) - 1) : prefix;
+        st->done = 1;
+    }
+}
+static __global__ void topk_collect_dev_kernel(TopkKey key, const i64 *klo, const i64 *khi, const i64 *acc, i64 stride, i64 n, int planes,
+                                               const TopkState *st, i64 *out_klo, i64 *out_khi, i64 *out_acc, i64 out_cap,
+                                               unsigned long long *counter)
+{
+    const u64 threshold = st->threshold;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        if (topk_u64(key, klo, khi, acc, stride, i) > threshold) continue;
+        unsigned long long o = atomicAdd(counter, 1ULL);
+        if ((i64)o >= out_cap) continue;
+        out_klo[o] = klo[i];
+        out_khi[o] = khi[i];
+        for (int a = 0; a < planes; a++) out_acc[(i64)a * out_cap + (i64)o] = acc[(i64)a * stride + i];
+    }
+}
+// candidates -> ONE fixed-size message [count | klo[cap] | khi[cap] | planes x acc[cap]]; count = -1 when they do not fit
+static __global__ void topk_pack_kernel(const i64 *klo, const i64 *khi, const i64 *acc, i64 stride, const unsigned long long *counter, int planes,
+                                        int cap, i64 *msg)
+{
+    const i64 n = (i64)*counter;
+    if (blockIdx.x == 0 && threadIdx.x == 0) msg[0] = n <= cap ? n : -1;
+    if (n > cap) return;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        msg[1 + i] = klo[i];
+        msg[1 + cap + i] = khi[i];
+        for (int a = 0; a < planes; a++) msg[1 + (i64)cap * (2 + a) + i] = acc[(i64)a * stride + i];
+    }
+}
+
 // -------------------------------------------------------------- shuffle --
 __device__ __forceinline__ int shuffle_dest(i64 klo, i64 khi, int world)
 {
