@@ -300,15 +300,26 @@ struct RvCompiler {
         }
     }
 
-    // conjunction of filters -> one program [*p0, *p1)
+    // conjunction of filters -> one program [*p0, *p1).  A filter keeps a row only when EVERY conjunct is TRUE, so the
+    // program leaves at the first conjunct that is not (execSelectAnd narrows the selection the same way,
+    // expr_exec.go:444-480): most rows of a selective scan cost one comparison.
     bool compile_filters(const std::vector<const Expr *> &fs, const Resolver &rs, int *p0, int *p1)
     {
         *p0 = ncode;
+        std::vector<int> exits;
         for (size_t i = 0; i < fs.size(); i++) {
             int k;
             if (!compile(*fs[i], rs, &k)) return false;
             if (k != RVK_BOOL) return fail("filter is not a boolean expression");
-            if (i > 0 && !emit(RV_AND)) return false;
+            if (fs.size() > 1) { exits.push_back(ncode); if (!emit(RV_JZ)) return false; }
+        }
+        if (fs.size() > 1) {
+            if (!emit(RV_CONST, 0, 0, 1)) return false;              // every conjunct was TRUE
+            const int jmp = ncode;
+            if (!emit(RV_JMP)) return false;
+            for (int j : exits) code.ins[j].imm = ncode;
+            if (!emit(RV_CONST, 0, 0, 0)) return false;              // some conjunct was FALSE or NULL
+            code.ins[jmp].imm = ncode;
         }
         *p1 = ncode;
         return true;
