@@ -20,7 +20,7 @@ Pipeline::~Pipeline() {}
 
 int build_scan_agg(pg_plan *plan, const Node &agg, const Node &scan, std::unique_ptr<Pipeline> *out);
 int build_join_agg(pg_plan *plan, const Node &agg, const Node &join, std::unique_ptr<Pipeline> *out, bool nested = false);
-int build_rows(pg_plan *plan, std::unique_ptr<Pipeline> *out);      // rows.cu: row-emitting Scan / Filter / Project / Join
+int build_rows(pg_plan *plan, std::unique_ptr<Pipeline> *out, const Node *aggn = nullptr);      // rows.cu: row-emitting Scan / Filter / Project / Join; aggn: aggregate over the joined rows
 
 static const Node *skip_filters(const Node *n, std::vector<Expr> *extra)
 {
@@ -217,8 +217,19 @@ static int build_pipeline(pg_plan *plan)
         return build_join_agg(plan, root, plan->mark_copy, &plan->pipe);
     }
     if (child->op == PG_OP_JOIN) {
-        if (!extra.empty()) PG_FAIL(PG_EUNSUPPORTED, "filter between aggregate and join is not supported");
-        return build_join_agg(plan, root, *child, &plan->pipe);
+        int s = PG_EUNSUPPORTED;
+        std::string why = "filter between aggregate and join";
+        if (extra.empty()) {
+            s = build_join_agg(plan, root, *child, &plan->pipe);
+            if (s != PG_EUNSUPPORTED) return s;
+            why = get_error();
+        }
+        // not a shape of the affine-product join pipelines (CASE / OR / IN in the aggregates, a filter above the join,
+        // a LEFT join ...): one join of two scans can still run as row programs over the joined rows (rows.cu)
+        plan->pipe.reset();
+        s = build_rows(plan, &plan->pipe, &root);
+        if (s == PG_EUNSUPPORTED) PG_FAIL(PG_EUNSUPPORTED, "%s; expression-driven join aggregate: %s", why.c_str(), std::string(get_error()).c_str());
+        return s;
     }
     PG_FAIL(PG_EUNSUPPORTED, "unsupported aggregate input (op %d)", child->op);
 }

@@ -18,13 +18,22 @@
 // offsets, a second pass writes the (probe row, build row) pairs in probe-row order, and the projection kernel
 // evaluates the output expressions per pair into columnar buffers that go back to the host in one copy per column
 // (the shim re-emits them as <= 2048-row chunks through pg_result_next).
+//
+// AGGREGATE MODE (Agg <- [Filter]* <- Join(scan, scan) whose expressions do not lower to the affine-product kernels of
+// join.cu: CASE WHEN / OR / IN inside the aggregates, TPC-H Q12 / Q14 style): the same pair list feeds vm_scanagg_kernel
+// (scanagg_vm.cuh) instead of the projection -- <= 2 byte-coded group keys from either side, sum / avg / min / max /
+// count of row programs over the joined row, thread-private shared-memory planes, exact 128-bit totals, the ranks'
+// partials all-gathered and merged in rank order, finalisation as in the generic scan aggregate (aggExecutor,
+// executor_aggr.go:106-262; SumOp / AvgOp / CountOp / MinMaxOp, function_aggr.go:620-1032).
 #include <algorithm>
 #include <functional>
 
 #include <cub/device/device_scan.cuh>
 
+#include "hostdec.hpp"
 #include "pipeline.hpp"
 #include "rowvm_compile.hpp"
+#include "scanagg_vm.cuh"
 
 namespace pg {
 
@@ -157,6 +166,20 @@ struct RowsPipeline : Pipeline {
     std::vector<Out> outs;
     DevBuf d_code, d_slots, d_cnt, d_off, d_pairs, d_err, d_scan_tmp, d_out;
     EventPair ev_all;
+    // aggregate mode
+    bool agg_mode = false;
+    VmAggParams aprm{};
+    int G = 1, P = 1, NT = 256, agrid = 1, nkeys = 0, key_side[2] = {0, 0}, key_col[2] = {-1, -1};
+    size_t asmem = 0;
+    std::vector<uint8_t> vals[2];
+    std::vector<AggExpr> aggs;
+    std::vector<int> plane, plane_scale, plane_kind;
+    std::vector<bool> agg_is_int;
+    std::vector<std::pair<int, int>> agg_outs;
+    DevBuf d_part, d_final, d_gather, d_luts, d_kinds;
+    PinBuf h_final;
+    int nranks() const { return tab(0)->dist == PG_DIST_REPLICATED ? 1 : ctx().world; }
+    size_t rank_bytes() const { return (size_t)G * P * 16 + 64 * 8; }
 
     const pg_table *tab(int side) const { return plan->slots[(size_t)slot[side]]; }
 
@@ -215,6 +238,14 @@ struct RowsPipeline : Pipeline {
         if (d_pairs.bytes < (size_t)std::max<i64>(total, 1) * 16) PG_TRY(d_pairs.alloc((size_t)std::max<i64>(total, 1) * 16));
         p.pair0 = d_pairs.as<i64>();
         p.pair1 = p.pair0 + std::max<i64>(total, 1);
+        if (agg_mode) {
+            if (total > 0) {
+                rows_probe_kernel<true><<<grid_for(n), 256, 0, st>>>(p);
+                PG_CUDA(cudaGetLastError());
+                launches++;
+            }
+            return run_agg(res, p, total, launches, tr);
+        }
         // output buffers: per column data (8-byte aligned blocks) then validity bytes
         std::vector<size_t> doff(outs.size()), voff(outs.size());
         size_t at = 0;
@@ -298,6 +329,132 @@ struct RowsPipeline : Pipeline {
         return PG_OK;
     }
 
+    // the pair list -> group totals (collective when the probe table is sharded: every rank all-gathers its partials)
+    int run_agg(pg_result *res, const RowsParams &p, i64 total, int launches, Trace &tr)
+    {
+        cudaStream_t st = ctx().stream;
+        VmAggParams q = aprm;
+        q.code = d_code.as<RvCode>();
+        q.err = d_err.as<int>();
+        q.nrows = total;
+        q.pair0 = p.pair0;
+        q.pair1 = p.pair1;
+        q.luts = d_luts.as<uint8_t>();
+        i64 *d_firstrow = (i64 *)((char *)d_final.p + (size_t)G * P * 16);
+        PG_CUDA(cudaMemsetAsync(d_firstrow, 0x7f, 64 * 8, st));
+        const int grid = (int)std::max<i64>(std::min<i64>((total + NT - 1) / NT, agrid), 1);
+        // a CTA's int64 partial sums are exact while |value| x its pairs < 2^62
+        if ((i128)q.absmax * (i128)((total + grid - 1) / grid + NT) >= ((i128)1 << 62))
+            PG_FAIL(PG_EUNSUPPORTED, "aggregate over %lld joined rows: exactness of the per-CTA partial sums cannot be proven", (long long)total);
+        if (NT == 256) vm_scanagg_kernel<256><<<grid, 256, asmem, st>>>(q, d_part.as<i64>(), d_firstrow);
+        else if (NT == 128) vm_scanagg_kernel<128><<<grid, 128, asmem, st>>>(q, d_part.as<i64>(), d_firstrow);
+        else vm_scanagg_kernel<64><<<grid, 64, asmem, st>>>(q, d_part.as<i64>(), d_firstrow);
+        PG_CUDA(cudaGetLastError());
+        finalize_generic_kernel<<<(G * P + 63) / 64, 64, 0, st>>>(d_part.as<i64>(), grid, G * P, d_kinds.as<int>(), d_final.as<u64>());
+        PG_CUDA(cudaGetLastError());
+        const void *src = d_final.p;
+        const int R = nranks();
+        if (R > 1) {
+            PG_TRY(comm_allgather(d_final.p, d_gather.p, rank_bytes(), st));
+            src = d_gather.p;
+        }
+        PG_CUDA(cudaMemcpyAsync(h_final.p, src, rank_bytes() * (size_t)R, cudaMemcpyDeviceToHost, st));
+        int err = 0;
+        PG_CUDA(cudaMemcpyAsync(&err, d_err.p, 4, cudaMemcpyDeviceToHost, st));
+        PG_CUDA(cudaEventRecord(ev_all.b, st));
+        PG_CUDA(cudaStreamSynchronize(st));
+        tr.mark("aggregate over the pairs + gather");
+        PG_TRY(check_err(err));
+        std::vector<i128> tot((size_t)G * P);
+        std::vector<i64> first((size_t)G, INT64_MAX);
+        for (int v = 0; v < G * P; v++) {
+            const int kind = plane_kind[(size_t)(v % P)];
+            tot[(size_t)v] = kind == GEN_SUM ? 0 : kind == GEN_MIN ? (i128)INT64_MAX : (i128)INT64_MIN;
+        }
+        for (int r = 0; r < R; r++) {
+            const char *base = (const char *)h_final.p + rank_bytes() * (size_t)r;
+            const u64 *h = (const u64 *)base;
+            const i64 *f = (const i64 *)(base + (size_t)G * P * 16);
+            for (int v = 0; v < G * P; v++) {
+                const i128 x = (i128)(((u128)h[2 * v + 1] << 64) | (u128)h[2 * v]);
+                const int kind = plane_kind[(size_t)(v % P)];
+                if (kind == GEN_SUM) tot[(size_t)v] += x;
+                else if (kind == GEN_MIN) tot[(size_t)v] = std::min(tot[(size_t)v], x);
+                else tot[(size_t)v] = std::max(tot[(size_t)v], x);
+            }
+            // group order: first joined row, ranks in order (shards are contiguous row ranges)
+            for (int g = 0; g < G; g++) if (f[g] != 0x7f7f7f7f7f7f7f7fLL && first[(size_t)g] == INT64_MAX) first[(size_t)g] = ((i64)r << 48) + f[g];
+        }
+        const int nacc = aprm.nacc;
+        std::vector<int> order;
+        for (int g = 0; g < G; g++) if (tot[(size_t)g * P] > 0) order.push_back(g);
+        std::sort(order.begin(), order.end(), [&](int a, int b) { return first[(size_t)a] < first[(size_t)b]; });
+        res->nrows = (i64)order.size();
+        for (auto &o : agg_outs) {
+            ResCol col;
+            if (o.first == 0) {
+                const Column &kc = tab(key_side[o.second])->cols[(size_t)key_col[o.second]];
+                col.type = kc.type;
+                if (kc.type == PG_T_DICT8) col.dict = kc.dict;
+                for (int g : order) {
+                    const int id = (nkeys == 2) ? (o.second == 0 ? g / aprm.n1 : g % aprm.n1) : g;
+                    col.push<uint8_t>(vals[o.second][(size_t)id]);
+                }
+            } else {
+                const AggExpr &a = aggs[(size_t)o.second];
+                const int pl = plane[(size_t)o.second];
+                const bool is_int = agg_is_int[(size_t)o.second];
+                col.width = a.width;
+                col.scale = a.scale;
+                if (a.fn == PG_AGG_COUNT) col.type = PG_T_HUGEINT;
+                else if (a.fn == PG_AGG_AVG) col.type = is_int ? PG_T_FLOAT64 : PG_T_DECIMAL128;
+                else col.type = is_int ? PG_T_HUGEINT : PG_T_DECIMAL128;
+                size_t nrow = 0;
+                for (int g : order) {
+                    i128 v = tot[(size_t)g * P + (size_t)pl], cnt = tot[(size_t)g * P];
+                    if (pl > 0) {
+                        cnt = tot[(size_t)g * P + (size_t)(nacc + pl)];       // NULL arguments were skipped
+                        if (cnt == 0 && a.fn != PG_AGG_COUNT) { col.push_null(nrow++, (size_t)type_size(col.type)); continue; }
+                    }
+                    col.mark_valid();
+                    nrow++;
+                    if (a.fn == PG_AGG_COUNT || (a.fn != PG_AGG_AVG && is_int)) {
+                        pg_hugeint h;
+                        h.lower = (u64)v;
+                        h.upper = (i64)(v >> 64);
+                        col.push(h);
+                    } else if (a.fn == PG_AGG_AVG && is_int) {
+                        const i128 mag = v < 0 ? -v : v;
+                        if (mag >= ((i128)1 << 53)) PG_FAIL(PG_EOVERFLOW, "avg(INT): sum not exact in float64");
+                        col.push((double)(i64)v / (double)(i64)cnt);
+                    } else {
+                        HDec d;
+                        if (hd_digits((u128)(v < 0 ? -v : v)) > HD_MAXPREC || !hd_from_i128(v, plane_scale[(size_t)pl], &d))
+                            PG_FAIL(PG_EOVERFLOW, "decimal aggregate exceeds 19 significant digits (order-dependent rounding regime)");
+                        if (a.fn == PG_AGG_AVG) {
+                            HDec nd, qd;
+                            hd_from_i128(cnt, 0, &nd);
+                            if (!hd_quo(d, nd, &qd)) PG_FAIL(PG_EOVERFLOW, "avg: decimal division failed");
+                            d = qd;
+                        }
+                        pg_decimal pd;
+                        pd.coef = d.coef; pd.scale = d.scale; pd.neg = d.neg ? 1u : 0u;
+                        col.push(pd);
+                    }
+                }
+            }
+            res->cols.push_back(col);
+        }
+        res->stats.kernel_ms = ev_all.ms();
+        res->stats.main_kernel_ms = res->stats.kernel_ms;
+        res->stats.rows_scanned = p.probe_rows;
+        res->stats.kernel_launches = launches + 2;
+        res->stats.aux[0] = p.probe_rows;
+        res->stats.aux[1] = total;
+        res->stats.aux[6] = res->nrows;
+        return PG_OK;
+    }
+
     static int check_err(int err)
     {
         // the reference panics on these and the query fails (executor_bench.go:184-189 recover)
@@ -310,11 +467,11 @@ struct RowsPipeline : Pipeline {
 
 }  // namespace
 
-int build_rows(pg_plan *plan, std::unique_ptr<Pipeline> *out)
+int build_rows(pg_plan *plan, std::unique_ptr<Pipeline> *out, const Node *aggn)
 {
     std::unique_ptr<RowsPipeline> p(new RowsPipeline());
     p->plan = plan;
-    const Node *n = &plan->root;
+    const Node *n = aggn ? &aggn->children[0] : &plan->root;
     const Node *project = nullptr;
     if (n->op == PG_OP_PROJECT) { project = n; n = &n->children[0]; }
     std::vector<const Expr *> above;                 // filters above the join (or above the scan)
@@ -397,10 +554,107 @@ int build_rows(pg_plan *plan, std::unique_ptr<Pipeline> *out)
             if (prm.pkey[k] < 0 || prm.bkey[k] < 0) PG_FAIL(PG_EUNSUPPORTED, "row-emitting pipeline: too many columns referenced");
         }
     }
+    if (aggn) {
+        // ---- aggregate mode: group keys and aggregate arguments over the joined row ----
+        if (top->op != PG_OP_JOIN) PG_FAIL(PG_EUNSUPPORTED, "aggregate over rows: expected a join below the aggregate");
+        if (aggn->groups.size() > 2) PG_FAIL(PG_EUNSUPPORTED, "aggregate over a join with expression arguments: more than two group keys");
+        if (!aggn->having.empty()) PG_FAIL(PG_EUNSUPPORTED, "aggregate over a join with expression arguments: HAVING");
+        p->agg_mode = true;
+        p->nkeys = (int)aggn->groups.size();
+        std::vector<uint8_t> luts(512, 0);
+        int dims[2] = {1, 1};
+        VmAggParams &q = p->aprm;
+        for (int k = 0; k < p->nkeys; k++) {
+            const Expr *ge = strip_value_preserving_casts(&aggn->groups[(size_t)k]);
+            Src s;
+            if (ge->kind != PG_TK_COL || ge->side != 0 || !top_scope(ge->idx, &s) || s.mark) PG_FAIL(PG_EUNSUPPORTED, "aggregate over a join: group key %d is not a column", k);
+            const Column &col = p->tab(s.side)->cols[(size_t)s.col];
+            if (!is_byte_family(col.type) || col.any_nulls()) PG_FAIL(PG_EUNSUPPORTED, "aggregate over a join with expression arguments: group key %s is not a non-null dictionary / char column", col.name.c_str());
+            if (s.side == 1 && top->jointype != PG_JOIN_INNER) PG_FAIL(PG_EUNSUPPORTED, "aggregate over a join: a build-side group key needs an INNER join");
+            p->key_side[k] = s.side;
+            p->key_col[k] = s.col;
+            const uint32_t *present = col.gpresent();
+            for (int code = 0; code < 256; code++)
+                if (present[code >> 5] & (1u << (code & 31))) { luts[(size_t)k * 256 + (size_t)code] = (uint8_t)p->vals[k].size(); p->vals[k].push_back((uint8_t)code); }
+            if (p->vals[k].empty()) p->vals[k].push_back(0);
+            dims[k] = (int)p->vals[k].size();
+            (k == 0 ? q.key0 : q.key1) = (const uint8_t *)col.d_data;
+            q.key_side[k] = s.side;
+        }
+        p->G = dims[0] * dims[1];
+        if (p->G > 64) PG_FAIL(PG_EUNSUPPORTED, "aggregate over a join with expression arguments: more than 64 dense groups");
+        q.nkeys = p->nkeys;
+        q.n1 = dims[1];
+        q.ngroups = p->G;
+        q.pred0 = q.pred1 = 0;                        // the filters were applied while the pairs were made
+        q.row_base = 0;
+        p->plane_kind = {GEN_SUM};
+        p->plane_scale = {0};
+        p->aggs = aggn->aggs;
+        int nacc = 0;
+        for (size_t i = 0; i < aggn->aggs.size(); i++) {
+            const AggExpr &a = aggn->aggs[i];
+            if (a.fn == PG_AGG_COUNT && a.star) { p->plane.push_back(0); p->agg_is_int.push_back(true); continue; }
+            const int kind = a.fn == PG_AGG_COUNT ? GEN_COUNTV : a.fn == PG_AGG_MIN ? GEN_MIN : a.fn == PG_AGG_MAX ? GEN_MAX : GEN_SUM;
+            if (a.fn != PG_AGG_COUNT && a.fn != PG_AGG_MIN && a.fn != PG_AGG_MAX && a.fn != PG_AGG_SUM && a.fn != PG_AGG_AVG) PG_FAIL(PG_EUNSUPPORTED, "aggregate function %d", a.fn);
+            if (nacc >= GEN_MAXACC) PG_FAIL(PG_EUNSUPPORTED, "more than 8 aggregate arguments");
+            int k = 0;
+            q.a0[nacc] = p->cc.ncode;
+            PG_ROWS_TRY(p->cc.compile(a.arg, top_scope, &k));
+            q.a1[nacc] = p->cc.ncode;
+            const int sb = p->cc.scale_bound(a.arg, top_scope);
+            if (kind != GEN_COUNTV) {
+                if (k != RVK_INT && k != RVK_DEC) PG_FAIL(PG_EUNSUPPORTED, "aggregate over a non-numeric expression");
+                if (sb < 0 || sb > 18) PG_FAIL(PG_EUNSUPPORTED, "aggregate over a quotient (no fixed scale to accumulate at)");
+            }
+            q.kind[nacc] = kind;
+            q.ascale[nacc] = kind == GEN_COUNTV ? 0 : sb;
+            const bool is_int = a.ltype == PG_LT_HUGEINT || a.ltype == PG_LT_DOUBLE || a.ltype == PG_LT_INTEGER || a.ltype == PG_LT_BIGINT;
+            if (is_int && kind != GEN_COUNTV && (k != RVK_INT || sb != 0)) PG_FAIL(PG_EUNSUPPORTED, "integer aggregate over a scaled value");
+            if (!is_int && a.ltype != PG_LT_DECIMAL) PG_FAIL(PG_EUNSUPPORTED, "aggregate result type");
+            if ((kind == GEN_MIN || kind == GEN_MAX) && is_int) PG_FAIL(PG_EUNSUPPORTED, "min/max are DECIMAL only in the reference");
+            p->plane.push_back(nacc + 1);
+            p->plane_kind.push_back(kind == GEN_COUNTV ? (int)GEN_SUM : kind);
+            p->plane_scale.push_back(q.ascale[nacc]);
+            p->agg_is_int.push_back(is_int);
+            nacc++;
+        }
+        q.nacc = nacc;
+        p->P = 1 + 2 * nacc;
+        for (int a = 0; a < nacc; a++) { p->plane_kind.push_back(GEN_SUM); p->plane_scale.push_back(0); }
+        for (auto &o : aggn->outs) {
+            if ((o.first == 0 && (o.second < 0 || o.second >= p->nkeys)) || (o.first == 1 && (o.second < 0 || o.second >= (int)aggn->aggs.size())) || (o.first != 0 && o.first != 1))
+                PG_FAIL(PG_EUNSUPPORTED, "bad aggregate output reference");
+        }
+        p->agg_outs = aggn->outs;
+        p->NT = 256;
+        while (p->NT >= 64 && (size_t)p->G * p->P * p->NT * 8 > (size_t)200 * 1024) p->NT /= 2;
+        if (p->NT < 64) PG_FAIL(PG_EUNSUPPORTED, "group tables do not fit in shared memory");
+        p->asmem = (size_t)p->G * p->P * p->NT * 8;
+        const void *kern = p->NT == 256 ? (const void *)vm_scanagg_kernel<256> : p->NT == 128 ? (const void *)vm_scanagg_kernel<128> : (const void *)vm_scanagg_kernel<64>;
+        PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->asmem));
+        int per_sm = 1;
+        PG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, p->NT, p->asmem));
+        p->agrid = std::max(per_sm, 1) * ctx().prop.multiProcessorCount;
+        // int64 partial sums of a CTA stay exact while |value| x pairs per CTA < 2^62; the pair count is not known at
+        // plan time, so bound it by what the emit pass can address (2^31 probe rows x matches is checked at run time:
+        // the count pass refuses more than 2^40 pairs below) -- values above 2^22 per pair slot are refused instead
+        q.absmax = (i64)1 << 40;
+        PG_TRY(p->d_part.alloc(sizeof(i64) * (size_t)p->agrid * (size_t)p->G * (size_t)p->P));
+        PG_TRY(p->d_final.alloc(p->rank_bytes()));
+        PG_TRY(p->d_gather.alloc(p->rank_bytes() * (size_t)std::max(ctx().world, 1)));
+        PG_TRY(p->h_final.alloc(p->rank_bytes() * (size_t)std::max(ctx().world, 1)));
+        PG_TRY(p->d_luts.alloc(512));
+        PG_TRY(p->d_kinds.alloc(sizeof(int) * (size_t)p->G * (size_t)p->P));
+        std::vector<int> kinds((size_t)p->G * (size_t)p->P);
+        for (int v = 0; v < p->G * p->P; v++) kinds[(size_t)v] = p->plane_kind[(size_t)(v % p->P)];
+        PG_CUDA(cudaMemcpyAsync(p->d_luts.p, luts.data(), 512, cudaMemcpyHostToDevice, ctx().stream));
+        PG_CUDA(cudaMemcpyAsync(p->d_kinds.p, kinds.data(), sizeof(int) * kinds.size(), cudaMemcpyHostToDevice, ctx().stream));
+    }
     // outputs
     std::vector<Expr> owned;
-    size_t nout = project ? project->exprs.size() : top->op == PG_OP_JOIN ? top->outs.size() : pt->cols.size();
-    if (nout == 0 || nout > RV_MAXOUT) PG_FAIL(PG_EUNSUPPORTED, "row-emitting pipeline: %zu output columns", nout);
+    size_t nout = aggn ? 0 : project ? project->exprs.size() : top->op == PG_OP_JOIN ? top->outs.size() : pt->cols.size();
+    if ((nout == 0 && !aggn) || nout > RV_MAXOUT) PG_FAIL(PG_EUNSUPPORTED, "row-emitting pipeline: %zu output columns", nout);
     owned.resize(nout);
     prm.nout = (int)nout;
     for (size_t j = 0; j < nout; j++) {
@@ -451,7 +705,10 @@ int build_rows(pg_plan *plan, std::unique_ptr<Pipeline> *out)
     PG_CUDA(cudaStreamSynchronize(ctx().stream));
     static const char *jn[] = {"", "INNER", "SEMI", "ANTI", "MARK", "LEFT", "ANTI-MARK"};
     char b[320];
-    if (top->op == PG_OP_JOIN)
+    if (aggn)
+        snprintf(b, sizeof b, "JoinAgg[expression programs] %s join %s x %s (%d key column%s, bucketized hash table) -> count / scan / emit pairs -> vm_scanagg_kernel over the pairs, groups=%d accumulators=%d instructions=%d",
+                 jn[top->jointype], pt->name.c_str(), bt->name.c_str(), prm.nkey, prm.nkey > 1 ? "s" : "", p->G, p->aprm.nacc, p->cc.ncode);
+    else if (top->op == PG_OP_JOIN)
         snprintf(b, sizeof b, "Rows[%s%s join %s x %s (%d key column%s, bucketized hash table) -> count / scan / emit pairs -> project %zu columns] instructions=%d",
                  project ? "project <- " : "", jn[top->jointype], pt->name.c_str(), bt->name.c_str(), prm.nkey, prm.nkey > 1 ? "s" : "", nout, p->cc.ncode);
     else

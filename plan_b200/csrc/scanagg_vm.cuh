@@ -16,6 +16,10 @@ struct VmAggParams {
     int *err;
     i64 nrows, row_base;
     int pred0, pred1;
+    // rows.cu (aggregate over a join): iterate the (probe row, build row) pairs instead of the table's rows; the filters
+    // were applied while the pairs were made
+    const i64 *pair0, *pair1;
+    int key_side[2];            // which row id indexes key0 / key1 (0: probe / scanned row, 1: build row)
     int nkeys;
     const uint8_t *key0, *key1;
     const uint8_t *luts;
@@ -43,16 +47,17 @@ vm_scanagg_kernel(const VmAggParams p, i64 *__restrict__ partials /* [grid][G*P]
     __syncthreads();
     i64 *my = s_acc + threadIdx.x;
     int err = 0;
-    for (i64 row = (i64)blockIdx.x * NT + threadIdx.x; row < p.nrows; row += (i64)gridDim.x * NT) {
-        if (!rv_true(*p.code, p.pred0, p.pred1, row, -1, &err)) continue;
+    for (i64 it = (i64)blockIdx.x * NT + threadIdx.x; it < p.nrows; it += (i64)gridDim.x * NT) {
+        const i64 row = p.pair0 ? p.pair0[it] : it, row1 = p.pair0 ? p.pair1[it] : -1;
+        if (!rv_true(*p.code, p.pred0, p.pred1, row, row1, &err)) continue;
         int g = 0;
-        if (p.nkeys > 0) g = s_lut[0][p.key0[row]];
-        if (p.nkeys > 1) g = g * p.n1 + s_lut[1][p.key1[row]];
+        if (p.nkeys > 0) g = s_lut[0][p.key0[p.key_side[0] ? row1 : row]];
+        if (p.nkeys > 1) g = g * p.n1 + s_lut[1][p.key1[p.key_side[1] ? row1 : row]];
         i64 *t = my + (i64)g * P * NT;
-        if (t[0] == 0) atomicMin((long long *)&s_first[g], (long long)(p.row_base + row));
+        if (t[0] == 0) atomicMin((long long *)&s_first[g], (long long)(p.row_base + it));
         t[0] += 1;
         for (int a = 0; a < p.nacc; a++) {
-            const RvVal v = rv_eval(*p.code, p.a0[a], p.a1[a], row, -1, &err);
+            const RvVal v = rv_eval(*p.code, p.a0[a], p.a1[a], row, row1, &err);
             if (v.null) continue;
             i64 *slot = t + (i64)(a + 1) * NT;
             t[(i64)(p.nacc + 1 + a) * NT] += 1;

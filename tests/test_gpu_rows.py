@@ -310,3 +310,35 @@ def test_q1_and_q6_through_the_expression_kernel(pg, monkeypatch):
     finally:
         for x in t.values():
             x.free()
+
+
+def test_aggregates_with_case_over_a_join(pg, data):
+    """TPC-H Q12 / Q14 shapes: Agg <- [Filter] <- Join(lineitem, orders) with CASE / IN inside the aggregates, grouped by a
+    char column of the probe side (Q12: l_shipmode; here l_returnflag) or ungrouped (Q14), INNER and LEFT.  build_join_agg
+    refuses these (not affine products); the pairs of the row pipeline feed vm_scanagg_kernel instead."""
+    tables, rows, S = data
+    K, X, B = _ops()
+    OI, LI = S.idx["orders"], S.idx["lineitem"]
+    I, D152, V, H = K.IntegerType(), K.DecimalType(15, 2), K.VarcharType(), K.HugeintType()
+    jouts = [X.col(0, LI["l_returnflag"], V), X.col(0, LI["l_extendedprice"], D152), X.col(0, LI["l_discount"], D152),
+             X.col(1, OI["o_orderstatus"], V), X.col(1, OI["o_totalprice"], D152), X.col(0, LI["l_quantity"], I), X.col(0, LI["l_shipdate"], K.DateType()),
+             X.col(1, OI["o_orderdate"], K.DateType())]
+    for jt in (X.JOIN_INNER, X.JOIN_LEFT):
+        j = _join(X, K, B, S, jt, jouts, probe="lineitem", build="orders", pk="l_orderkey", bk="o_orderkey",
+                  pfilters=[X.func("<", B, S.col("lineitem", "l_linenumber"), X.const(6, I))],
+                  bfilters=[X.func(">", B, S.col("orders", "o_totalprice"), X.const(2000000, D152))])
+        one = X.cast(X.const(1, I), D152)
+        rev = X.func("*", K.DecimalType(18, 4), X.cast(X.col(0, 1, D152), K.DecimalType(16, 2)), X.func("-", K.DecimalType(16, 2), one, X.col(0, 2, D152)))
+        high = X.func("case", I, X.const(0, I), X.func("in", B, X.col(0, 3, V), X.const("F", V), X.const("P", V)), X.const(1, I))
+        promo = X.func("case", K.DecimalType(18, 4), X.cast(X.const(0, I), K.DecimalType(18, 4)), X.func(">", B, X.col(0, 6, K.DateType()), X.col(0, 7, K.DateType())), rev)
+        aggs = [X.func("sum", H, high), X.func("sum", K.DecimalType(38, 4), promo), X.func("sum", K.DecimalType(38, 4), rev),
+                X.func("avg", K.DecimalType(38, 2), X.col(0, 4, D152)), X.func("count", H), X.func("max", D152, X.col(0, 4, D152)),
+                X.func("avg", K.DoubleType(), X.col(0, 5, I))]
+        outs = [X.col(0, 0, V)] + [X.col(1, i, a.DataTyp) for i, a in enumerate(aggs)]
+        op = X.PhysicalOperator(X.POT_Agg, Outputs=outs, Children=[j], Info=X.AggOpInfo(aggs, [X.col(0, 0, V)]))
+        got = _check(op, tables, rows, expect_explain="JoinAgg[expression programs]")
+        assert len(got) == 3
+        # ungrouped, with a filter between the aggregate and the join (it sees the joined, NULL-padded rows)
+        flt = X.PhysicalOperator(X.POT_Filter, Children=[j], Filters=[X.func("or", B, X.func("<", B, X.col(0, 5, I), X.const(10, I)), X.func(">", B, X.col(0, 4, D152), X.const(20000000, D152)))])
+        op = X.PhysicalOperator(X.POT_Agg, Outputs=[X.col(1, i, a.DataTyp) for i, a in enumerate(aggs)], Children=[flt], Info=X.AggOpInfo(aggs, []))
+        assert len(_check(op, tables, rows, expect_explain="JoinAgg[expression programs]")) == 1
