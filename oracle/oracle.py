@@ -214,6 +214,74 @@ def gen_partsupp(sf):
     return out
 
 
+# dbgen distributions (dists.dss) the draws of tg_gen_q12_q14_draws index; member order pinned by the reference's
+# golden cases/tpch/1g/plan/q12.txt (FOB / TRUCK counts) and q14.txt (PROMO share)
+SHIPMODES = ["REG AIR", "AIR", "RAIL", "TRUCK", "MAIL", "FOB", "SHIP"]
+PRIORITIES = ["1-URGENT", "2-HIGH", "3-MEDIUM", "4-NOT SPECIFIED", "5-LOW"]
+PTYPES = ["%s %s %s" % (a, b, c) for a in ("STANDARD", "SMALL", "MEDIUM", "LARGE", "ECONOMY", "PROMO")
+          for b in ("ANODIZED", "BURNISHED", "PLATED", "POLISHED", "BRUSHED") for c in ("TIN", "NICKEL", "BRASS", "STEEL", "COPPER")]
+
+
+def gen_q12_q14_columns(sf):
+    """dictionary codes of l_shipmode (per lineitem row), o_orderpriority (per order) and p_type (per part)"""
+    L = lib()
+    L.tg_gen_q12_q14_draws.restype = None
+    L.tg_gen_q12_q14_draws.argtypes = [C.c_double, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
+    no = L.tg_num_orders(sf)
+    nl = L.tg_count_lineitems(sf, 0, no)
+    npart = L.tg_num_parts_pub(C.c_double(sf))
+    out = {"o_orderpriority": np.empty(no, np.uint8), "l_shipmode": np.empty(nl, np.uint8), "p_type": np.empty(npart, np.uint8)}
+    L.tg_gen_q12_q14_draws(sf, 0, no, _p(out["o_orderpriority"]), _p(out["l_shipmode"]), 0, npart, _p(out["p_type"]))
+    return out
+
+
+def q12(orders, line, extra, modes=("FOB", "TRUCK"), year=1996):
+    """cases/tpch/query/q12.sql restated with exact integer arithmetic: rows (l_shipmode, high_line_count, low_line_count)
+    in l_shipmode order; sum(INTEGER) is a HUGEINT (function_aggr.go:620-650)."""
+    sm, pr = extra["l_shipmode"], extra["o_orderpriority"]
+    m = ((line["l_commitdate"] < line["l_receiptdate"]) & (line["l_shipdate"] < line["l_commitdate"]) &
+         (line["l_receiptdate"] >= days(year, 1, 1)) & (line["l_receiptdate"] < days(year + 1, 1, 1)) &
+         np.isin(sm, [SHIPMODES.index(x) for x in modes]))
+    oidx = np.searchsorted(orders["o_orderkey"], line["l_orderkey"][m])
+    ok = (oidx < len(orders["o_orderkey"])) & (orders["o_orderkey"][np.minimum(oidx, len(orders["o_orderkey"]) - 1)] == line["l_orderkey"][m])
+    lp, lm = pr[oidx[ok]], sm[m][ok]
+    rows = []
+    for name in sorted(modes):
+        sel = lm == SHIPMODES.index(name)
+        if not sel.any():
+            continue
+        high = int(((lp[sel] == 0) | (lp[sel] == 1)).sum())
+        rows.append((name, high, int(sel.sum()) - high))
+    return rows
+
+
+def q12_text(rows):
+    return "#\t\t\n" + "".join("%s\t%d\t%d\n" % r for r in rows)
+
+
+def q14(line, extra, date_lo=None, date_hi=None, like_prefix="PROMO"):
+    """cases/tpch/query/q14.sql: the two DECIMAL sums exactly (scale 4), and promo_revenue the way the reference computes it
+    above the aggregate: the literal 100.00 is FLOAT, so both sums are cast to FLOAT and the arithmetic is float32
+    (builder_binder.go:264-273; binFloat32MultiOp / binFloat32DivOp)."""
+    date_lo = days(1996, 4, 1) if date_lo is None else date_lo
+    date_hi = days(1996, 5, 1) if date_hi is None else date_hi
+    m = (line["l_shipdate"] >= date_lo) & (line["l_shipdate"] < date_hi)
+    rev = line["l_extendedprice"][m].astype(object) * (100 - line["l_discount"][m].astype(object))
+    ptype = extra["p_type"][line["l_partkey"][m] - 1]
+    promo_codes = [i for i, t in enumerate(PTYPES) if t.startswith(like_prefix)]
+    promo = int(rev[np.isin(ptype, promo_codes)].sum()) if m.any() else 0
+    total = int(rev.sum()) if m.any() else 0
+    return {"promo": promo, "total": total, "rows": int(m.sum())}
+
+
+def q14_promo_revenue(promo, total):
+    """100.00 * promo / total in float32, printed like a Go float64 holding that float32 (Value.String of a FLOAT)"""
+    with np.errstate(all="ignore"):
+        f = np.float32(100.0) * np.float32(float(C.c_double(lib().orc_dec_float64(abs(promo), 4, int(promo < 0))).value)) / \
+            np.float32(float(C.c_double(lib().orc_dec_float64(abs(total), 4, int(total < 0))).value))
+    return fmt_double(float(f))
+
+
 def nation_names():
     L = lib()
     L.tg_nation_name.restype = C.c_char_p

@@ -15,6 +15,12 @@ It evaluates the same PhysicalOperator / Expr trees the GPU path is given (plan_
   INTEGER + -                  int32 wrap-around (binInt32Int32AddOp, :143-146)
   cast(DECIMAL AS FLOAT)       float32(Float64(d)) (function_cast.go:349-354); FLOAT comparisons in float32
 
+Pinning: the reference holds no golden vector for these operators in isolation (its Go tests assert no numeric results), so
+this module is pinned indirectly -- its decimal arithmetic is oracle/decimal.h (checked against the reference's golden Q1 / Q6
+files), CASE / OR / IN / LIKE inside aggregates over a join are pinned by the reference's golden q12.txt / q14.txt through
+oracle.q12 / oracle.q14 and the GPU test that reproduces both files; row-level DECIMAL division and LEFT / MARK join outputs
+are PARITY UNPINNED against the reference.
+
 Values: None (NULL) | bool | int | Dec(coef, scale, neg) | np.float32 | str.
 """
 import ctypes as C

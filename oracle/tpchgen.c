@@ -266,3 +266,37 @@ void tg_gen_partsupp(double sf, int64_t p_lo, int64_t p_hi, int32_t *ps_partkey,
         }
     }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Columns of TPC-H Q12 / Q14 beyond the ones above (cases/tpch/query/q12.sql, q14.sql): the raw draws of
+ *   l_shipmode      pick_str(smode,  L_SMODE_SD): UnifInt(1, 7)   per line, 7 draws per order like every lineitem stream
+ *   o_orderpriority pick_str(o_oprio, O_PRIO_SD): UnifInt(1, 5)   per order
+ *   p_type          pick_str(p_types, P_TYPE_SD): UnifInt(1, 150) per part
+ * as 0-based indices into dbgen's distributions (dists.dss); the callers hold the member lists.  Pinned by the
+ * reference's golden cases/tpch/1g/plan/q12.txt and q14.txt (tests/test_oracle_golden.py).
+ */
+enum { SD_L_SMODE = 675466456, SD_O_PRIO = 591449447, SD_P_TYPE = 1841581359 };
+
+void tg_gen_q12_q14_draws(double sf, int64_t o_lo, int64_t o_hi, uint8_t *o_prio /* [orders] */, uint8_t *l_smode /* [lines] */,
+                          int64_t p_lo, int64_t p_hi, uint8_t *p_type /* [parts] */)
+{
+    (void)sf;
+    if (o_prio || l_smode) {
+        int64_t s_lcnt = tg_jump(SD_O_LCNT, o_lo), s_prio = tg_jump(SD_O_PRIO, o_lo);
+        int64_t row = 0;
+        for (int64_t i = o_lo; i < o_hi; i++) {
+            const int64_t lines = tg_draw(&s_lcnt, 1, 7);
+            const int64_t pr = tg_draw(&s_prio, 1, 5);
+            if (o_prio) o_prio[i - o_lo] = (uint8_t)(pr - 1);
+            int64_t s_sm = tg_jump(SD_L_SMODE, 7 * i);
+            for (int64_t j = 0; j < lines; j++, row++) {
+                const int64_t m = tg_draw(&s_sm, 1, 7);
+                if (l_smode) l_smode[row] = (uint8_t)(m - 1);
+            }
+        }
+    }
+    if (p_type) {
+        int64_t s = tg_jump(SD_P_TYPE, p_lo);
+        for (int64_t i = p_lo; i < p_hi; i++) p_type[i - p_lo] = (uint8_t)(tg_draw(&s, 1, 150) - 1);
+    }
+}

@@ -489,3 +489,66 @@ def upload_tables(host, global_offsets=None, schema=FULL):
         t.seal((global_offsets or {}).get(name, 0))
         out[name] = t
     return out
+
+
+# ---- TPC-H Q12 / Q14: CASE inside aggregates over a join (row programs over the joined rows, rows.cu aggregate mode) ----
+
+SHIPMODES = ["REG AIR", "AIR", "RAIL", "TRUCK", "MAIL", "FOB", "SHIP"]           # dbgen smode / o_oprio / p_types member order
+PRIORITIES = ["1-URGENT", "2-HIGH", "3-MEDIUM", "4-NOT SPECIFIED", "5-LOW"]
+PTYPES = ["%s %s %s" % (a, b, c) for a in ("STANDARD", "SMALL", "MEDIUM", "LARGE", "ECONOMY", "PROMO")
+          for b in ("ANODIZED", "BURNISHED", "PLATED", "POLISHED", "BRUSHED") for c in ("TIN", "NICKEL", "BRASS", "STEEL", "COPPER")]
+Q12_LINEITEM = [("l_orderkey", L.PG_T_INT64, 0, 0, None), ("l_shipmode", L.PG_T_DICT8, 0, 0, SHIPMODES), ("l_shipdate", L.PG_T_DATE32, 0, 0, None),
+                ("l_commitdate", L.PG_T_DATE32, 0, 0, None), ("l_receiptdate", L.PG_T_DATE32, 0, 0, None)]
+Q12_ORDERS = [("o_orderkey", L.PG_T_INT64, 0, 0, None), ("o_orderpriority", L.PG_T_DICT8, 0, 0, PRIORITIES)]
+Q14_LINEITEM = [("l_partkey", L.PG_T_INT32, 0, 0, None), ("l_extendedprice", L.PG_T_DECIMAL64, 15, 2, None),
+                ("l_discount", L.PG_T_DECIMAL64, 15, 2, None), ("l_shipdate", L.PG_T_DATE32, 0, 0, None)]
+Q14_PART = [("p_partkey", L.PG_T_INT32, 0, 0, None), ("p_type", L.PG_T_DICT8, 0, 0, PTYPES)]
+
+
+def q12_plan(modes=("FOB", "TRUCK"), year=1996):
+    """cases/tpch/query/q12.sql:  Agg(group by l_shipmode; sum(case when o_orderpriority = '1-URGENT' or o_orderpriority =
+    '2-HIGH' then 1 else 0 end), sum(case when o_orderpriority <> '1-URGENT' and o_orderpriority <> '2-HIGH' then 1 else 0 end))
+      <- Join(l_orderkey = o_orderkey) <- { Scan(lineitem; l_shipmode in (..), l_commitdate < l_receiptdate,
+                                                 l_shipdate < l_commitdate, l_receiptdate in [year, year+1)), Scan(orders) }
+    The ORDER BY l_shipmode stays with the host parents."""
+    S = Schema(lineitem=Q12_LINEITEM, orders=Q12_ORDERS)
+    B, V, I, H, D = K.LType(K.LTID_BOOLEAN), K.VarcharType(), K.IntegerType(), K.HugeintType(), K.DateType()
+    lc = lambda n: S.col("lineitem", n)   # noqa: E731
+    line = PhysicalOperator(POT_Scan, Info=ScanOpInfo("lineitem"), Filters=[
+        func("in", B, lc("l_shipmode"), *[const(m, V) for m in modes]),
+        func("<", B, lc("l_commitdate"), lc("l_receiptdate")),
+        func("<", B, lc("l_shipdate"), lc("l_commitdate")),
+        func(">=", B, lc("l_receiptdate"), const(days(year, 1, 1), D)),
+        func("<", B, lc("l_receiptdate"), const(days(year + 1, 1, 1), D))])
+    orders = PhysicalOperator(POT_Scan, Info=ScanOpInfo("orders"))
+    LI, OI = S.idx["lineitem"], S.idx["orders"]
+    j = PhysicalOperator(POT_Join, Children=[line, orders], Outputs=[col(0, LI["l_shipmode"], V), col(1, OI["o_orderpriority"], V)],
+                         Info=JoinOpInfo(JOIN_INNER, [func("=", B, S.col("lineitem", "l_orderkey", 0), S.col("orders", "o_orderkey", 1))]))
+    prio = col(0, 1, V)
+    high = func("case", I, const(0, I), func("or", B, func("=", B, prio, const("1-URGENT", V)), func("=", B, prio, const("2-HIGH", V))), const(1, I))
+    low = func("case", I, const(0, I), func("and", B, func("<>", B, prio, const("1-URGENT", V)), func("<>", B, prio, const("2-HIGH", V))), const(1, I))
+    aggs = [func("sum", H, high), func("sum", H, low)]
+    outs = [col(0, 0, V), col(1, 0, H), col(1, 1, H)]
+    return PhysicalOperator(POT_Agg, Outputs=outs, Children=[j], Info=AggOpInfo(aggs, [col(0, 0, V)]))
+
+
+def q14_plan(date_lo=None, date_hi=None, pattern="PROMO%"):
+    """cases/tpch/query/q14.sql below its final projection:  Agg(sum(case when p_type like 'PROMO%' then l_extendedprice * (1 -
+    l_discount) else 0 end), sum(l_extendedprice * (1 - l_discount))) <- Join(l_partkey = p_partkey) <- { Scan(lineitem; l_shipdate
+    in [d, d + 1 month)), Scan(part) }.  `100.00 * a / b` is a FLOAT projection above the aggregate and stays with the host."""
+    S = Schema(lineitem=Q14_LINEITEM, part=Q14_PART)
+    B, V, I, D = K.LType(K.LTID_BOOLEAN), K.VarcharType(), K.IntegerType(), K.DateType()
+    date_lo = days(1996, 4, 1) if date_lo is None else date_lo
+    date_hi = days(1996, 5, 1) if date_hi is None else date_hi
+    lc = lambda n: S.col("lineitem", n)   # noqa: E731
+    line = PhysicalOperator(POT_Scan, Info=ScanOpInfo("lineitem"), Filters=[func(">=", B, lc("l_shipdate"), const(date_lo, D)),
+                                                                           func("<", B, lc("l_shipdate"), const(date_hi, D))])
+    part = PhysicalOperator(POT_Scan, Info=ScanOpInfo("part"))
+    LI, PI = S.idx["lineitem"], S.idx["part"]
+    j = PhysicalOperator(POT_Join, Children=[line, part],
+                         Outputs=[col(0, LI["l_extendedprice"], DEC15_2), col(0, LI["l_discount"], DEC15_2), col(1, PI["p_type"], V)],
+                         Info=JoinOpInfo(JOIN_INNER, [func("=", B, S.col("lineitem", "l_partkey", 0), S.col("part", "p_partkey", 1))]))
+    rev = _disc_price(col(0, 0, DEC15_2), col(0, 1, DEC15_2))
+    promo = func("case", K.DecimalType(18, 4), cast(const(0, I), K.DecimalType(18, 4)), func("like", B, col(0, 2, V), const(pattern, V)), rev)
+    aggs = [func("sum", K.DecimalType(38, 4), promo), func("sum", K.DecimalType(38, 4), rev)]
+    return PhysicalOperator(POT_Agg, Outputs=[col(1, 0, K.DecimalType(38, 4)), col(1, 1, K.DecimalType(38, 4))], Children=[j], Info=AggOpInfo(aggs, []))

@@ -342,3 +342,46 @@ def test_aggregates_with_case_over_a_join(pg, data):
         flt = X.PhysicalOperator(X.POT_Filter, Children=[j], Filters=[X.func("or", B, X.func("<", B, X.col(0, 5, I), X.const(10, I)), X.func(">", B, X.col(0, 4, D152), X.const(20000000, D152)))])
         op = X.PhysicalOperator(X.POT_Agg, Outputs=[X.col(1, i, a.DataTyp) for i, a in enumerate(aggs)], Children=[flt], Info=X.AggOpInfo(aggs, []))
         assert len(_check(op, tables, rows, expect_explain="JoinAgg[expression programs]")) == 1
+
+
+def test_q12_and_q14_reproduce_the_reference_golden_files(pg):
+    """cases/tpch/1g/plan/q12.txt and q14.txt, byte for byte, from dbgen-exact SF1 columns uploaded through the C ABI:
+    the reference's OWN known answers for CASE / OR / IN / LIKE inside aggregates over a join (the expression-driven join
+    aggregate of rows.cu), Q14's final FLOAT projection `100.00 * a / b` done by the host parent in float32 as the reference does."""
+    import os
+    from oracle import oracle as O
+    from plan_b200 import compute as X, tpch as T
+    golden = os.path.join(os.path.dirname(__file__), "golden")
+    sf = 1.0
+    orders, line = O.gen_orders_lineitem(sf)
+    extra = O.gen_q12_q14_columns(sf)
+    npart = len(extra["p_type"])
+    host = {"q12": {"lineitem": (T.Q12_LINEITEM, dict(line, l_shipmode=extra["l_shipmode"])),
+                    "orders": (T.Q12_ORDERS, dict(orders, o_orderpriority=extra["o_orderpriority"]))},
+            "q14": {"lineitem": (T.Q14_LINEITEM, line),
+                    "part": (T.Q14_PART, {"p_partkey": np.arange(1, npart + 1, dtype=np.int32), "p_type": extra["p_type"]})}}
+    for q, plan in (("q12", T.q12_plan()), ("q14", T.q14_plan())):
+        tables = {}
+        for name, (sch, cols) in host[q].items():
+            t = X.DeviceTable.create(name, sch)
+            t.append([cols[c[0]] for c in sch])
+            t.seal(0)
+            tables[name] = t
+        try:
+            ex = X.gpuPipelineExec(plan, tables)
+            ex.Init()
+            assert "JoinAgg[expression programs]" in ex.Explain(), ex.Explain()
+            chunks = X.drain(ex)
+            ex.Close()
+            if q == "q12":
+                rows = X.order_limit(chunks, [(0, False)])
+                assert X.rows_text(rows, 3) == open(os.path.join(golden, "ref_sf1_q12.txt")).read()
+            else:
+                a, b = chunks[0].Data[0].Data[0], chunks[0].Data[1].Data[0]
+                ref = O.q14(line, extra)
+                assert int(a["coef"]) * 10 ** (4 - int(a["scale"])) == ref["promo"] and int(b["coef"]) * 10 ** (4 - int(b["scale"])) == ref["total"]
+                got = O.q14_promo_revenue(int(a["coef"]) * 10 ** (4 - int(a["scale"])), int(b["coef"]) * 10 ** (4 - int(b["scale"])))
+                assert "#\n" + got + "\n" == open(os.path.join(golden, "ref_sf1_q14.txt")).read()
+        finally:
+            for t in tables.values():
+                t.free()
