@@ -255,6 +255,20 @@ def q12(orders, line, extra, modes=("FOB", "TRUCK"), year=1996):
     return rows
 
 
+def q4(orders, line, extra, date_lo=None, date_hi=None):
+    """cases/tpch/query/q4.sql: orders of the quarter with at least one late lineitem, counted per priority"""
+    date_lo = days(1997, 7, 1) if date_lo is None else date_lo
+    date_hi = days(1997, 10, 1) if date_hi is None else date_hi
+    late = np.unique(line["l_orderkey"][line["l_commitdate"] < line["l_receiptdate"]])
+    m = (orders["o_orderdate"] >= date_lo) & (orders["o_orderdate"] < date_hi) & np.isin(orders["o_orderkey"], late)
+    pr = extra["o_orderpriority"][m]
+    return [(PRIORITIES[p], int((pr == p).sum())) for p in range(5) if (pr == p).any()]
+
+
+def q4_text(rows):
+    return "#\t\n" + "".join("%s\t%d\n" % r for r in rows)
+
+
 def q12_text(rows):
     return "#\t\t\n" + "".join("%s\t%d\t%d\n" % r for r in rows)
 

@@ -214,7 +214,17 @@ static int build_pipeline(pg_plan *plan)
                 plan->slots[(size_t)src->slot]->cols[(size_t)pe->idx].any_nulls())
                 PG_FAIL(PG_EUNSUPPORTED, "MARK join filtered with mark = false over a nullable (or non-scan) probe key");
         }
-        return build_join_agg(plan, root, plan->mark_copy, &plan->pipe);
+        {
+            const int s = build_join_agg(plan, root, plan->mark_copy, &plan->pipe);
+            if (s != PG_EUNSUPPORTED || child->jointype != PG_JOIN_MARK) return s;
+            // e.g. a build side filtered by a column-to-column comparison (TPC-H Q4's `l_commitdate < l_receiptdate`): the
+            // MARK join as it stands, its mark filter and the aggregate run as row programs over the joined rows (rows.cu)
+            const std::string why = get_error();
+            plan->pipe.reset();
+            const int s2 = build_rows(plan, &plan->pipe, &root);
+            if (s2 == PG_EUNSUPPORTED) PG_FAIL(PG_EUNSUPPORTED, "%s; expression-driven join aggregate: %s", why.c_str(), std::string(get_error()).c_str());
+            return s2;
+        }
     }
     if (child->op == PG_OP_JOIN) {
         int s = PG_EUNSUPPORTED;

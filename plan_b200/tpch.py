@@ -552,3 +552,27 @@ def q14_plan(date_lo=None, date_hi=None, pattern="PROMO%"):
     promo = func("case", K.DecimalType(18, 4), cast(const(0, I), K.DecimalType(18, 4)), func("like", B, col(0, 2, V), const(pattern, V)), rev)
     aggs = [func("sum", K.DecimalType(38, 4), promo), func("sum", K.DecimalType(38, 4), rev)]
     return PhysicalOperator(POT_Agg, Outputs=[col(1, 0, K.DecimalType(38, 4)), col(1, 1, K.DecimalType(38, 4))], Children=[j], Info=AggOpInfo(aggs, []))
+
+
+Q4_ORDERS = [("o_orderkey", L.PG_T_INT64, 0, 0, None), ("o_orderdate", L.PG_T_DATE32, 0, 0, None), ("o_orderpriority", L.PG_T_DICT8, 0, 0, PRIORITIES)]
+Q4_LINEITEM = [("l_orderkey", L.PG_T_INT64, 0, 0, None), ("l_commitdate", L.PG_T_DATE32, 0, 0, None), ("l_receiptdate", L.PG_T_DATE32, 0, 0, None)]
+
+
+def q4_plan(date_lo=None, date_hi=None):
+    """cases/tpch/query/q4.sql as the reference plans it: the EXISTS becomes a MARK join under Filter(mark = true)
+    (builder_plan.go:380-429); the build side carries the column-to-column filter l_commitdate < l_receiptdate.
+      Agg(group by o_orderpriority; count(*)) <- Filter(mark = true) <- MarkJoin(o_orderkey = l_orderkey)
+          <- { Scan(orders; o_orderdate in [d, d + 3 months)), Scan(lineitem; l_commitdate < l_receiptdate) }"""
+    S = Schema(orders=Q4_ORDERS, lineitem=Q4_LINEITEM)
+    B, V, H, D = K.LType(K.LTID_BOOLEAN), K.VarcharType(), K.HugeintType(), K.DateType()
+    date_lo = days(1997, 7, 1) if date_lo is None else date_lo
+    date_hi = days(1997, 10, 1) if date_hi is None else date_hi
+    orders = PhysicalOperator(POT_Scan, Info=ScanOpInfo("orders"), Filters=[func(">=", B, S.col("orders", "o_orderdate"), const(date_lo, D)),
+                                                                           func("<", B, S.col("orders", "o_orderdate"), const(date_hi, D))])
+    line = PhysicalOperator(POT_Scan, Info=ScanOpInfo("lineitem"), Filters=[func("<", B, S.col("lineitem", "l_commitdate"), S.col("lineitem", "l_receiptdate"))])
+    OI = S.idx["orders"]
+    j = PhysicalOperator(POT_Join, Children=[orders, line], Outputs=[col(0, OI["o_orderpriority"], V), col(0, OI["o_orderkey"], K.BigintType()), col(2, 0, B)],
+                         Info=JoinOpInfo(JOIN_MARK, [func("=", B, S.col("orders", "o_orderkey", 0), S.col("lineitem", "l_orderkey", 1))]))
+    flt = PhysicalOperator(POT_Filter, Outputs=j.Outputs, Children=[j], Filters=[func("=", B, col(0, 2, B), const(1, B))])
+    aggs = [func("count", H, col(0, 1, K.BigintType()))]         # count(*) -> count(<first column>) (builder_binder.go:207-228)
+    return PhysicalOperator(POT_Agg, Outputs=[col(0, 0, V), col(1, 0, H)], Children=[flt], Info=AggOpInfo(aggs, [col(0, 0, V)]))
