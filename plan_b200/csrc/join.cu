@@ -622,7 +622,12 @@ struct JoinAggPipeline : Pipeline {
                 // A REPLICATED build side is the same on every rank: instead of W identical scans, every rank marks the keys
                 // of its 1/W of the rows and the partial bitmaps are all-gathered and OR-ed (2 MB for SF100's customer).
                 const int W = ctx().world;
-                const bool split = W > 1 && t->dist == PG_DIST_REPLICATED && !s.has_probe && s.extras.empty() && t->nrows >= (i64)W * (getenv("PG_SPLIT_MIN_ROWS") ? atoll(getenv("PG_SPLIT_MIN_ROWS")) : 65536) &&
+                // Worth it only when the scan is expensive: measured at 8 GPUs on SF100's 15 M customers, the vectorised
+                // bitmap_build_kernel scans the whole table in 0.075 ms per rank while 1/8 of it + a 2 MB all-gather + the
+                // OR-merge takes 0.119 ms -- so plain range / code-set builds split only from 64 M rows per rank up, builds
+                // with a string predicate evaluated per row (Q9's p_name LIKE: 0.65 ms for 20 M parts) from 64 K rows up.
+                const i64 split_min = getenv("PG_SPLIT_MIN_ROWS") ? atoll(getenv("PG_SPLIT_MIN_ROWS")) : (pp.nlike > 0 ? (i64)65536 : (i64)64 << 20);
+                const bool split = W > 1 && t->dist == PG_DIST_REPLICATED && !s.has_probe && s.extras.empty() && t->nrows >= (i64)W * split_min &&
                                    !getenv("PG_NO_SPLIT_BUILD");
                 if (split) {
                     pp.pipe_lo = (t->nrows * ctx().rank / W) & ~(i64)3;
