@@ -2520,8 +2520,10 @@ int build_join_agg(pg_plan *plan, const Node &aggn, const Node &top, std::unique
         default: PG_FAIL(PG_EUNSUPPORTED, "HAVING <> is not a range");
         }
     }
-    // 64-bit accumulators: a group can at most receive every probe row
-    if (worst * (i128)std::max<i64>(st->nrows, 1) >= ((i128)1 << 63)) PG_FAIL(PG_EUNSUPPORTED, "group sums could exceed int64");
+    // 64-bit accumulators: a group can at most receive every probe row of EVERY rank (the shuffle adds the ranks' partials
+    // into the same slots).  (A build side with duplicate keys multiplies the joined rows; that case is detected while
+    // the table is built -- dup_keys -- and is bounded by the same product only for unique keys: see DESIGN 9.)
+    if (worst * (i128)std::max<i64>(st->total_rows(), 1) >= ((i128)1 << 63)) PG_FAIL(PG_EUNSUPPORTED, "group sums could exceed int64");
     {   // does anything above the top join read a build-side column?
         bool need = false;
         for (int k = 0; k < p->nparts; k++) need = need || p->gs.part[k].from_build != 0;
