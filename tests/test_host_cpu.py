@@ -229,3 +229,23 @@ def test_row_oracle_and_descriptor_of_a_row_emitting_plan():
     plan = C.c_void_p()
     L.check(L.lib().pg_plan_compile(desc.ctypes.data_as(C.POINTER(C.c_int64)), len(desc), C.byref(plan)))
     L.lib().pg_plan_free(plan)
+
+
+def test_descriptors_of_the_reference_plans_compile_without_a_gpu():
+    """pg_plan_compile parses the descriptor of every plan builder (aggregate-rooted, TOPK-fused, MARK joins, the row programs
+    of Q4 / Q12 / Q14) -- structure only, kernels are chosen at bind / prepare time on the device."""
+    import ctypes as C
+    from plan_b200 import _lib as L, compute as X, tpch as T
+    plans = [T.q6_plan(), T.q1_plan(), T.q3_plan(), T.q3_topk_plan(10), T.q18_plan(), T.q9_plan(), T.exists_plan(), T.exists_plan(negated=True),
+             T.q4_plan(), T.q12_plan(), T.q14_plan(), T.groupby_plan(key="l_partkey", value="l_quantity", topk=100)]
+    for op in plans:
+        desc, slots = X.serialize_plan(op)
+        assert desc[0] == X.PG_DESC_MAGIC and len(slots) >= 1
+        plan = C.c_void_p()
+        L.check(L.lib().pg_plan_compile(desc.ctypes.data_as(C.POINTER(C.c_int64)), len(desc), C.byref(plan)))
+        L.lib().pg_plan_free(plan)
+    # a truncated descriptor is refused, not read past its end
+    desc, _ = X.serialize_plan(T.q12_plan())
+    plan = C.c_void_p()
+    rc = L.lib().pg_plan_compile(desc.ctypes.data_as(C.POINTER(C.c_int64)), len(desc) - 3, C.byref(plan))
+    assert rc == L.PG_EINVAL
