@@ -222,6 +222,41 @@ PTYPES = ["%s %s %s" % (a, b, c) for a in ("STANDARD", "SMALL", "MEDIUM", "LARGE
           for b in ("ANODIZED", "BURNISHED", "PLATED", "POLISHED", "BRUSHED") for c in ("TIN", "NICKEL", "BRASS", "STEEL", "COPPER")]
 
 
+BRANDS = ["Brand#%d%d" % (m, n) for m in range(1, 6) for n in range(1, 6)]
+CONTAINERS = ["%s %s" % (a, b) for a in ("SM", "LG", "MED", "JUMBO", "WRAP") for b in ("CASE", "BOX", "BAG", "JAR", "PKG", "PACK", "CAN", "DRUM")]
+SHIPINSTRUCT = ["DELIVER IN PERSON", "COLLECT COD", "NONE", "TAKE BACK RETURN"]     # only index 0 is pinned (by q19.txt)
+
+
+def gen_q19_columns(sf):
+    """dictionary codes of l_shipinstruct (per lineitem row), p_brand / p_container (per part) and p_size"""
+    L = lib()
+    L.tg_gen_q19_draws.restype = None
+    L.tg_gen_q19_draws.argtypes = [C.c_double, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    no = L.tg_num_orders(sf)
+    nl = L.tg_count_lineitems(sf, 0, no)
+    npart = L.tg_num_parts_pub(C.c_double(sf))
+    out = {"l_shipinstruct": np.empty(nl, np.uint8), "p_brand": np.empty(npart, np.uint8), "p_size": np.empty(npart, np.int32),
+           "p_container": np.empty(npart, np.uint8)}
+    L.tg_gen_q19_draws(sf, 0, no, _p(out["l_shipinstruct"]), 0, npart, _p(out["p_brand"]), _p(out["p_size"]), _p(out["p_container"]))
+    return out
+
+
+Q19_GROUPS = (("Brand#23", ("SM CASE", "SM BOX", "SM PACK", "SM PKG"), 5, 5), ("Brand#15", ("MED BAG", "MED BOX", "MED PKG", "MED PACK"), 14, 10),
+              ("Brand#44", ("LG CASE", "LG BOX", "LG PACK", "LG PKG"), 28, 15))
+
+
+def q19(line, extra12, extra19):
+    """cases/tpch/query/q19.sql: exact revenue (scale 4).  'AIR REG' is not a ship mode dbgen produces ('REG AIR' is): only AIR matches."""
+    pk = line["l_partkey"] - 1
+    base = (extra19["l_shipinstruct"] == SHIPINSTRUCT.index("DELIVER IN PERSON")) & np.isin(extra12["l_shipmode"], [SHIPMODES.index("AIR")])
+    m = np.zeros(len(pk), bool)
+    for brand, conts, q0, smax in Q19_GROUPS:
+        m |= (base & (extra19["p_brand"][pk] == BRANDS.index(brand)) & np.isin(extra19["p_container"][pk], [CONTAINERS.index(c) for c in conts]) &
+              (line["l_quantity"] >= q0) & (line["l_quantity"] <= q0 + 10) & (extra19["p_size"][pk] >= 1) & (extra19["p_size"][pk] <= smax))
+    rev = line["l_extendedprice"][m].astype(object) * (100 - line["l_discount"][m].astype(object))
+    return {"revenue": int(rev.sum()) if m.any() else 0, "rows": int(m.sum())}
+
+
 def gen_q12_q14_columns(sf):
     """dictionary codes of l_shipmode (per lineitem row), o_orderpriority (per order) and p_type (per part)"""
     L = lib()

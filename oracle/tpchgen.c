@@ -300,3 +300,37 @@ void tg_gen_q12_q14_draws(double sf, int64_t o_lo, int64_t o_hi, uint8_t *o_prio
         for (int64_t i = p_lo; i < p_hi; i++) p_type[i - p_lo] = (uint8_t)(tg_draw(&s, 1, 150) - 1);
     }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Columns of TPC-H Q19 (cases/tpch/query/q19.sql): raw draws as 0-based indices / values
+ *   p_brand      "Brand#MN": M = UnifInt(1,5) from P_MFG_SD, N = UnifInt(1,5) from P_BRND_SD  -> code (M-1)*5 + (N-1)
+ *   p_size       UnifInt(1,50) from P_SIZE_SD
+ *   p_container  pick_str(p_cntr, P_CNTR_SD): UnifInt(1,40) -> index into {SM,LG,MED,JUMBO,WRAP} x {CASE,BOX,BAG,JAR,PKG,PACK,CAN,DRUM}
+ *   l_shipinstruct pick_str(instruct, L_SHIP_SD): UnifInt(1,4) per line (7 draws per order); index 0 = DELIVER IN PERSON
+ * Seeds and member orders pinned by the reference's golden cases/tpch/1g/plan/q19.txt (tests/test_oracle_golden.py).
+ */
+enum { SD_P_MFG = 1, SD_P_BRND = 46831694, SD_P_SIZE = 1193163244, SD_P_CNTR = 727633698, SD_L_SHIP = 1371272478 };
+
+void tg_gen_q19_draws(double sf, int64_t o_lo, int64_t o_hi, uint8_t *l_shipinstruct /* [lines] */,
+                      int64_t p_lo, int64_t p_hi, uint8_t *p_brand, int32_t *p_size, uint8_t *p_container /* [parts] */)
+{
+    (void)sf;
+    if (l_shipinstruct) {
+        int64_t s_lcnt = tg_jump(SD_O_LCNT, o_lo);
+        int64_t row = 0;
+        for (int64_t i = o_lo; i < o_hi; i++) {
+            const int64_t lines = tg_draw(&s_lcnt, 1, 7);
+            int64_t s = tg_jump(SD_L_SHIP, 7 * i);
+            for (int64_t j = 0; j < lines; j++, row++) l_shipinstruct[row] = (uint8_t)(tg_draw(&s, 1, 4) - 1);
+        }
+    }
+    if (p_brand || p_size || p_container) {
+        int64_t s_m = tg_jump(SD_P_MFG, p_lo), s_b = tg_jump(SD_P_BRND, p_lo), s_s = tg_jump(SD_P_SIZE, p_lo), s_c = tg_jump(SD_P_CNTR, p_lo);
+        for (int64_t i = p_lo; i < p_hi; i++) {
+            const int64_t m = tg_draw(&s_m, 1, 5), b = tg_draw(&s_b, 1, 5), sz = tg_draw(&s_s, 1, 50), c = tg_draw(&s_c, 1, 40);
+            if (p_brand) p_brand[i - p_lo] = (uint8_t)((m - 1) * 5 + (b - 1));
+            if (p_size) p_size[i - p_lo] = (int32_t)sz;
+            if (p_container) p_container[i - p_lo] = (uint8_t)(c - 1);
+        }
+    }
+}

@@ -576,3 +576,40 @@ def q4_plan(date_lo=None, date_hi=None):
     flt = PhysicalOperator(POT_Filter, Outputs=j.Outputs, Children=[j], Filters=[func("=", B, col(0, 2, B), const(1, B))])
     aggs = [func("count", H, col(0, 1, K.BigintType()))]         # count(*) -> count(<first column>) (builder_binder.go:207-228)
     return PhysicalOperator(POT_Agg, Outputs=[col(0, 0, V), col(1, 0, H)], Children=[flt], Info=AggOpInfo(aggs, [col(0, 0, V)]))
+
+
+BRANDS = ["Brand#%d%d" % (m, n) for m in range(1, 6) for n in range(1, 6)]
+CONTAINERS = ["%s %s" % (a, b) for a in ("SM", "LG", "MED", "JUMBO", "WRAP") for b in ("CASE", "BOX", "BAG", "JAR", "PKG", "PACK", "CAN", "DRUM")]
+SHIPINSTRUCT = ["DELIVER IN PERSON", "COLLECT COD", "NONE", "TAKE BACK RETURN"]
+Q19_LINEITEM = [("l_partkey", L.PG_T_INT32, 0, 0, None), ("l_quantity", L.PG_T_INT32, 0, 0, None), ("l_extendedprice", L.PG_T_DECIMAL64, 15, 2, None),
+                ("l_discount", L.PG_T_DECIMAL64, 15, 2, None), ("l_shipmode", L.PG_T_DICT8, 0, 0, SHIPMODES), ("l_shipinstruct", L.PG_T_DICT8, 0, 0, SHIPINSTRUCT)]
+Q19_PART = [("p_partkey", L.PG_T_INT32, 0, 0, None), ("p_brand", L.PG_T_DICT8, 0, 0, BRANDS), ("p_size", L.PG_T_INT32, 0, 0, None),
+            ("p_container", L.PG_T_DICT8, 0, 0, CONTAINERS)]
+Q19_GROUPS = (("Brand#23", ("SM CASE", "SM BOX", "SM PACK", "SM PKG"), 5, 5), ("Brand#15", ("MED BAG", "MED BOX", "MED PKG", "MED PACK"), 14, 10),
+              ("Brand#44", ("LG CASE", "LG BOX", "LG PACK", "LG PKG"), 28, 15))
+
+
+def q19_plan():
+    """cases/tpch/query/q19.sql with the join condition common to the three OR branches taken out (what lets the reference plan
+    a hash join at all):  Agg(sum(l_extendedprice * (1 - l_discount))) <- Filter(g1 OR g2 OR g3) <- Join(l_partkey = p_partkey)
+    <- { Scan(lineitem), Scan(part) }; every g_i is an AND of string equalities / IN lists on dictionary columns of BOTH sides and
+    integer ranges -- a general OR above a join, evaluated per joined row."""
+    S = Schema(lineitem=Q19_LINEITEM, part=Q19_PART)
+    B, V, I = K.LType(K.LTID_BOOLEAN), K.VarcharType(), K.IntegerType()
+    LI, PI = S.idx["lineitem"], S.idx["part"]
+    line = PhysicalOperator(POT_Scan, Info=ScanOpInfo("lineitem"))
+    part = PhysicalOperator(POT_Scan, Info=ScanOpInfo("part"))
+    jouts = [col(0, LI["l_quantity"], I), col(0, LI["l_extendedprice"], DEC15_2), col(0, LI["l_discount"], DEC15_2), col(0, LI["l_shipmode"], V),
+             col(0, LI["l_shipinstruct"], V), col(1, PI["p_brand"], V), col(1, PI["p_size"], I), col(1, PI["p_container"], V)]
+    j = PhysicalOperator(POT_Join, Children=[line, part], Outputs=jouts,
+                         Info=JoinOpInfo(JOIN_INNER, [func("=", B, S.col("lineitem", "l_partkey", 0), S.col("part", "p_partkey", 1))]))
+    qty, mode, instr, brand, size, cont = col(0, 0, I), col(0, 3, V), col(0, 4, V), col(0, 5, V), col(0, 6, I), col(0, 7, V)
+    groups = []
+    for b, conts, q0, smax in Q19_GROUPS:
+        groups.append(func("and", B, func("=", B, brand, const(b, V)), func("in", B, cont, *[const(c, V) for c in conts]),
+                           func(">=", B, qty, const(q0, I)), func("<=", B, qty, const(q0 + 10, I)),
+                           func(">=", B, size, const(1, I)), func("<=", B, size, const(smax, I)),          # between 1 and smax
+                           func("in", B, mode, const("AIR", V), const("AIR REG", V)), func("=", B, instr, const("DELIVER IN PERSON", V))))
+    flt = PhysicalOperator(POT_Filter, Outputs=jouts, Children=[j], Filters=[func("or", B, *groups)])
+    agg = func("sum", K.DecimalType(38, 4), _disc_price(col(0, 1, DEC15_2), col(0, 2, DEC15_2)))
+    return PhysicalOperator(POT_Agg, Outputs=[col(1, 0, K.DecimalType(38, 4))], Children=[flt], Info=AggOpInfo([agg], []))

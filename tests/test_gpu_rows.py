@@ -344,8 +344,9 @@ def test_aggregates_with_case_over_a_join(pg, data):
         assert len(_check(op, tables, rows, expect_explain="JoinAgg[expression programs]")) == 1
 
 
-def test_q4_q12_and_q14_reproduce_the_reference_golden_files(pg):
-    """cases/tpch/1g/plan/q4.txt (EXISTS as a MARK join whose build side carries a column-to-column filter), q12.txt and q14.txt, byte for byte, from dbgen-exact SF1 columns uploaded through the C ABI:
+def test_q4_q12_q14_and_q19_reproduce_the_reference_golden_files(pg):
+    """cases/tpch/1g/plan/q4.txt (EXISTS as a MARK join whose build side carries a column-to-column filter), q12.txt, q14.txt and q19.txt
+    (an OR of three AND groups over columns of both join sides, evaluated per joined row), byte for byte, from dbgen-exact SF1 columns uploaded through the C ABI:
     the reference's OWN known answers for CASE / OR / IN / LIKE inside aggregates over a join (the expression-driven join
     aggregate of rows.cu), Q14's final FLOAT projection `100.00 * a / b` done by the host parent in float32 as the reference does."""
     import os
@@ -355,13 +356,17 @@ def test_q4_q12_and_q14_reproduce_the_reference_golden_files(pg):
     sf = 1.0
     orders, line = O.gen_orders_lineitem(sf)
     extra = O.gen_q12_q14_columns(sf)
+    x19 = O.gen_q19_columns(sf)
     npart = len(extra["p_type"])
     host = {"q12": {"lineitem": (T.Q12_LINEITEM, dict(line, l_shipmode=extra["l_shipmode"])),
                     "orders": (T.Q12_ORDERS, dict(orders, o_orderpriority=extra["o_orderpriority"]))},
             "q4": {"orders": (T.Q4_ORDERS, dict(orders, o_orderpriority=extra["o_orderpriority"])), "lineitem": (T.Q4_LINEITEM, line)},
+            "q19": {"lineitem": (T.Q19_LINEITEM, dict(line, l_shipmode=extra["l_shipmode"], l_shipinstruct=x19["l_shipinstruct"])),
+                    "part": (T.Q19_PART, {"p_partkey": np.arange(1, npart + 1, dtype=np.int32), "p_brand": x19["p_brand"], "p_size": x19["p_size"],
+                                          "p_container": x19["p_container"]})},
             "q14": {"lineitem": (T.Q14_LINEITEM, line),
                     "part": (T.Q14_PART, {"p_partkey": np.arange(1, npart + 1, dtype=np.int32), "p_type": extra["p_type"]})}}
-    for q, plan in (("q4", T.q4_plan()), ("q12", T.q12_plan()), ("q14", T.q14_plan())):
+    for q, plan in (("q4", T.q4_plan()), ("q12", T.q12_plan()), ("q14", T.q14_plan()), ("q19", T.q19_plan())):
         tables = {}
         for name, (sch, cols) in host[q].items():
             t = X.DeviceTable.create(name, sch)
@@ -377,6 +382,8 @@ def test_q4_q12_and_q14_reproduce_the_reference_golden_files(pg):
             if q in ("q4", "q12"):
                 rows = X.order_limit(chunks, [(0, False)])
                 assert X.rows_text(rows, 2 if q == "q4" else 3) == open(os.path.join(golden, "ref_sf1_%s.txt" % q)).read()
+            elif q == "q19":      # a general OR over both sides of the join, above the join
+                assert X.rows_text(X.order_limit(chunks, []), 1) == open(os.path.join(golden, "ref_sf1_q19.txt")).read()
             else:
                 a, b = chunks[0].Data[0].Data[0], chunks[0].Data[1].Data[0]
                 ref = O.q14(line, extra)

@@ -99,8 +99,8 @@ def test_q9_reproduces_reference_golden(oracle, sf1):
     assert oracle.q9_text(rows) == open(os.path.join(GOLDEN, "ref_sf1_q9.txt")).read()
 
 
-def test_q4_q12_q14_reproduce_reference_golden(oracle, sf1):
-    """cases/tpch/1g/plan/q4.txt, q12.txt and q14.txt: pin l_shipmode / o_orderpriority / p_type of the generator (dbgen streams
+def test_q4_q12_q14_q19_reproduce_reference_golden(oracle, sf1):
+    """cases/tpch/1g/plan/q4.txt, q12.txt, q14.txt and q19.txt: pin l_shipmode / o_orderpriority / p_type of the generator (dbgen streams
     L_SMODE_SD, O_PRIO_SD, P_TYPE_SD and the member order of the smode / o_oprio / p_types distributions) and, through
     Q14, the reference's float32 arithmetic above the aggregate -- the known answers the CASE / aggregate-over-join GPU
     path is checked against (tests/test_gpu_rows.py)."""
@@ -108,6 +108,8 @@ def test_q4_q12_q14_reproduce_reference_golden(oracle, sf1):
     extra = oracle.gen_q12_q14_columns(1.0)
     assert oracle.q12_text(oracle.q12(orders, line, extra)) == open(os.path.join(GOLDEN, "ref_sf1_q12.txt")).read()
     assert oracle.q4_text(oracle.q4(orders, line, extra)) == open(os.path.join(GOLDEN, "ref_sf1_q4.txt")).read()
+    r19 = oracle.q19(line, extra, oracle.gen_q19_columns(1.0))      # cases/tpch/1g/plan/q19.txt: pins p_brand / p_size / p_container / l_shipinstruct
+    assert "#\n" + oracle.fmt_decimal((r19["revenue"], 4, 0), 4) + "\n" == open(os.path.join(GOLDEN, "ref_sf1_q19.txt")).read()
     r = oracle.q14(line, extra)
     assert "#\n" + oracle.q14_promo_revenue(r["promo"], r["total"]) + "\n" == open(os.path.join(GOLDEN, "ref_sf1_q14.txt")).read()
 
