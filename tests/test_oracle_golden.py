@@ -61,6 +61,16 @@ def test_generator_ranges_are_independent(oracle, sf1):
         assert np.array_equal(v, sf1["orders"][k][700000:700100]), k
 
 
+def test_golden_copies_are_the_reference_files():
+    """the ref_sf1_* fixtures are verbatim copies of the reference's own result files (checked where the reference is present:
+    this container; the GPU box has no /root/reference)"""
+    ref = "/root/reference/cases/tpch/1g/plan"
+    if not os.path.isdir(ref):
+        pytest.skip("reference tree not present")
+    for q in (1, 3, 4, 6, 9, 12, 14, 18, 19):
+        assert open(os.path.join(GOLDEN, "ref_sf1_q%d.txt" % q), "rb").read() == open(os.path.join(ref, "q%d.txt" % q), "rb").read(), q
+
+
 def test_q6_reproduces_reference_golden(oracle, sf1):
     assert oracle.q6_text(oracle.q6(sf1["lineitem"])) == open(os.path.join(GOLDEN, "ref_sf1_q6.txt")).read()
 
