@@ -36,19 +36,23 @@ enum {
     RV_YEAR,       // DATE (days since 1970-01-01) -> calendar year
     RV_TOF32,      // a: kind of the operand (RVK_DEC / RVK_INT)
     RV_TODEC,      // INT -> DEC at scale 0
+    RV_PRE,        // a, b: range of RvCode::pre -- only as the FIRST instruction of a filter program (rv_true): conjuncts of the
+                   // form `column <cmp> constant` / `coded column in {codes}` are tested inline before the interpreter runs
 };
 enum { RV_ERR_OVERFLOW = 1, RV_ERR_DIVZERO = 2, RV_ERR_FLOAT = 3 };
 
-constexpr int RV_MAXSTACK = 8, RV_MAXCODE = 384, RV_MAXCOL = 32, RV_MAXMASK = 16, RV_MAXOUT = 32;
+constexpr int RV_MAXSTACK = 8, RV_MAXCODE = 384, RV_MAXCOL = 32, RV_MAXMASK = 16, RV_MAXOUT = 32, RV_MAXPRE = 24;
 
 struct RvIns { int op, a, b, pad; i64 imm; };
 struct RvCol { TypedCol col; int side; int scale; };     // side 0: the probe / scanned row, 1: the build row
 struct RvVal { i128 v; int scale; int null; };
 
+struct RvPre { int col, mask; i64 lo, hi; };             // mask >= 0: code-set test on a byte-coded column; else lo <= value <= hi
 struct RvCode {
     RvIns ins[RV_MAXCODE];
     RvCol cols[RV_MAXCOL];
     unsigned masks[RV_MAXMASK][8];
+    RvPre pre[RV_MAXPRE];
 };
 
 __device__ __forceinline__ float rv_as_f32(const RvVal &x) { return __int_as_float((int)(i64)x.v); }
@@ -200,6 +204,21 @@ static __device__ __noinline__ RvVal rv_eval(const RvCode &c, int pc0, int pc1, 
 __device__ __forceinline__ bool rv_true(const RvCode &c, int pc0, int pc1, i64 row0, i64 row1, int *err)
 {
     if (pc1 <= pc0) return true;
+    if (c.ins[pc0].op == RV_PRE) {
+        // the cheap conjuncts first: most rows of a selective filter never reach the interpreter.  A NULL operand (or the
+        // NULL padding of a LEFT / MARK join, row < 0) makes the conjunct NULL, which is not TRUE.
+        const int p1 = c.ins[pc0].b;
+        for (int i = c.ins[pc0].a; i < p1; i++) {
+            const RvPre q = c.pre[i];
+            const RvCol &rc = c.cols[q.col];
+            const i64 row = rc.side ? row1 : row0;
+            if (row < 0 || !typed_valid(rc.col, row)) return false;
+            const i64 v = load_typed(rc.col, row);
+            if (q.mask >= 0) { if (!((c.masks[q.mask][(v >> 5) & 7] >> (v & 31)) & 1u)) return false; }
+            else if (v < q.lo || v > q.hi) return false;
+        }
+        if (++pc0 >= pc1) return true;
+    }
     const RvVal v = rv_eval(c, pc0, pc1, row0, row1, err);
     return !v.null && v.v != 0;
 }

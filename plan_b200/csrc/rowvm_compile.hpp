@@ -300,20 +300,93 @@ struct RvCompiler {
         }
     }
 
+    // `column <cmp> constant` on an integer / date / decimal column, or a string predicate on a dictionary / char column:
+    // lowered to an inline test (RvPre) instead of interpreter instructions.  false = not of that form (no error).
+    int npre = 0;
+    bool lower_pre(const Expr &f, const Resolver &rs, RvPre *out)
+    {
+        if (f.kind != PG_TK_FUNC) return false;
+        auto column_of = [&](const Expr &x, Src *src) -> const Column * {
+            const Expr *e = strip_value_preserving_casts(&x);
+            if (e->kind != PG_TK_COL || e->side != 0 || !rs(e->idx, src) || src->mark) return nullptr;
+            return &tab(src->side)->cols[(size_t)src->col];
+        };
+        const int fn = f.fn;
+        if ((is_cmp(fn) || fn == PG_FN_LIKE || fn == PG_FN_NOT_LIKE || fn == PG_FN_IN) && f.args.size() >= 2) {
+            // string predicates on byte-coded columns -> a code set
+            bool all_str = true;
+            for (size_t i = 1; i < f.args.size(); i++) all_str = all_str && f.args[i].kind == PG_TK_STR;
+            if (all_str && (fn == PG_FN_IN || f.args.size() == 2) && (fn == PG_FN_EQ || fn == PG_FN_NE || fn == PG_FN_LIKE || fn == PG_FN_NOT_LIKE || fn == PG_FN_IN)) {
+                Src src;
+                const Column *c = column_of(f.args[0], &src);
+                if (!c || !is_byte_family(c->type)) return false;
+                std::vector<std::string> lits;
+                for (size_t i = 1; i < f.args.size(); i++) lits.push_back(f.args[i].str);
+                int ms;
+                const int cs = col_slot(src.side, src.col);
+                if (cs < 0 || !code_mask(*c, fn, lits, &ms)) { why.clear(); return false; }
+                *out = RvPre{cs, ms, 0, 0};
+                return true;
+            }
+        }
+        if (!is_cmp(fn) || fn == PG_FN_NE || f.args.size() != 2) return false;
+        const Expr *l = &f.args[0], *r = &f.args[1];
+        int op = fn;
+        Src src;
+        const Column *c = column_of(*l, &src);
+        if (!c) { c = column_of(*r, &src); std::swap(l, r); op = flip_cmp(fn); }
+        if (!c || !is_int_family(c->type)) return false;
+        const Expr *k = strip_value_preserving_casts(r);
+        if (k->kind != PG_TK_CONST) return false;
+        i128 v = k->v0;
+        if (c->type == PG_T_DECIMAL64) {
+            int ks;
+            if (k->ltype == PG_LT_DECIMAL) ks = k->scale;
+            else if (k->ltype == PG_LT_INTEGER || k->ltype == PG_LT_BIGINT) ks = 0;
+            else return false;
+            for (; ks < c->scale; ks++) v *= 10;
+            for (; ks > c->scale; ks--) { if (v % 10 != 0) return false; v /= 10; }       // finer than the column: leave it to the interpreter
+        } else if (!(k->ltype == PG_LT_INTEGER || k->ltype == PG_LT_BIGINT || k->ltype == PG_LT_DATE)) {
+            return false;
+        }
+        if (v > (i128)INT64_MAX - 1 || v < (i128)INT64_MIN + 1) return false;
+        const int cs = col_slot(src.side, src.col);
+        if (cs < 0) return false;
+        RvPre q{cs, -1, INT64_MIN, INT64_MAX};
+        switch (op) {
+        case PG_FN_EQ: q.lo = q.hi = (i64)v; break;
+        case PG_FN_LT: q.hi = (i64)v - 1; break;
+        case PG_FN_LE: q.hi = (i64)v; break;
+        case PG_FN_GT: q.lo = (i64)v + 1; break;
+        default: q.lo = (i64)v; break;      // GE
+        }
+        *out = q;
+        return true;
+    }
+
     // conjunction of filters -> one program [*p0, *p1).  A filter keeps a row only when EVERY conjunct is TRUE, so the
-    // program leaves at the first conjunct that is not (execSelectAnd narrows the selection the same way,
-    // expr_exec.go:444-480): most rows of a selective scan cost one comparison.
+    // cheap conjuncts become inline tests (RV_PRE, lower_pre) and the interpreted rest leaves at the first conjunct
+    // that is not TRUE (execSelectAnd narrows the selection the same way, expr_exec.go:444-480).
     bool compile_filters(const std::vector<const Expr *> &fs, const Resolver &rs, int *p0, int *p1)
     {
         *p0 = ncode;
-        std::vector<int> exits;
-        for (size_t i = 0; i < fs.size(); i++) {
-            int k;
-            if (!compile(*fs[i], rs, &k)) return false;
-            if (k != RVK_BOOL) return fail("filter is not a boolean expression");
-            if (fs.size() > 1) { exits.push_back(ncode); if (!emit(RV_JZ)) return false; }
+        std::vector<const Expr *> rest;
+        const int pre0 = npre;
+        const bool no_pre = getenv("PG_VM_NO_PRE") && atoi(getenv("PG_VM_NO_PRE"));
+        for (const Expr *f : fs) {
+            RvPre q;
+            if (!no_pre && npre < RV_MAXPRE && lower_pre(*f, rs, &q)) code.pre[npre++] = q;
+            else rest.push_back(f);
         }
-        if (fs.size() > 1) {
+        if (npre > pre0 && !emit(RV_PRE, pre0, npre)) return false;
+        std::vector<int> exits;
+        for (size_t i = 0; i < rest.size(); i++) {
+            int k;
+            if (!compile(*rest[i], rs, &k)) return false;
+            if (k != RVK_BOOL) return fail("filter is not a boolean expression");
+            if (rest.size() > 1) { exits.push_back(ncode); if (!emit(RV_JZ)) return false; }
+        }
+        if (rest.size() > 1) {
             if (!emit(RV_CONST, 0, 0, 1)) return false;              // every conjunct was TRUE
             const int jmp = ncode;
             if (!emit(RV_JMP)) return false;
