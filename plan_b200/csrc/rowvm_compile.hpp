@@ -23,9 +23,19 @@ struct RvCompiler {
     const pg_table *tab(int side) const { return tables[side]; }
 
     bool fail(const std::string &s) { why = s; return false; }
+    // depth of the evaluation stack where the next instruction runs: the interpreter's stack is RV_MAXSTACK values in
+    // local memory and is never bounds-checked on the device, so a program that needs more is refused here
+    int cur_sp = 0;
     bool emit(int op, int a = 0, int b = 0, i64 imm = 0)
     {
         if (ncode >= RV_MAXCODE) return fail("expression program too long");
+        switch (op) {
+        case RV_COL: case RV_CONST: case RV_NULL: case RV_MARK: cur_sp += 1; break;
+        case RV_ADD: case RV_SUB: case RV_MUL: case RV_DIV: case RV_CMP: case RV_AND: case RV_OR: case RV_JZ: cur_sp -= 1; break;
+        default: break;      // NOT, INSET, YEAR, TOF32, TODEC, JMP, PRE keep the depth
+        }
+        if (cur_sp > RV_MAXSTACK) return fail("expression needs a deeper evaluation stack than the interpreter has");
+        if (cur_sp < 0) return fail("internal: evaluation stack underflow while compiling");
         code.ins[ncode++] = RvIns{op, a, b, 0, imm};
         return true;
     }
@@ -90,6 +100,7 @@ struct RvCompiler {
     bool compile(const Expr &e, const Resolver &rs, int *kind, const Column **base = nullptr, int depth = 0)
     {
         if (base) *base = nullptr;
+        if (depth == 0) cur_sp = 0;                  // a program starts on an empty stack
         if (depth > 24) return fail("expression too deep");
         switch (e.kind) {
         case PG_TK_COL: {
@@ -240,6 +251,7 @@ struct RvCompiler {
             if (na < 3 || (na & 1) == 0) return fail("CASE arity");
             std::vector<int> to_end;
             int rk = 0;
+            const int sp0 = cur_sp;                   // every path through the CASE leaves exactly one value above this depth
             auto branch = [&](const Expr &x) -> bool {
                 int k;
                 if (x.kind == PG_TK_CONST && x.ltype == 0) { k = rk; if (!emit(RV_NULL)) return false; }       // typeless NULL constant
@@ -261,6 +273,7 @@ struct RvCompiler {
                 to_end.push_back(ncode);
                 if (!emit(RV_JMP)) return false;
                 code.ins[jz].imm = ncode;
+                cur_sp = sp0;                         // the next WHEN starts where this one did (its THEN value is on another path)
             }
             if (!branch(e.args[0])) return false;
             for (int j : to_end) code.ins[j].imm = ncode;
@@ -391,10 +404,12 @@ struct RvCompiler {
             const int jmp = ncode;
             if (!emit(RV_JMP)) return false;
             for (int j : exits) code.ins[j].imm = ncode;
+            cur_sp -= 1;                                             // (the FALSE path does not carry the TRUE path's value)
             if (!emit(RV_CONST, 0, 0, 0)) return false;              // some conjunct was FALSE or NULL
             code.ins[jmp].imm = ncode;
         }
         *p1 = ncode;
+        cur_sp = 0;                                                  // a filter program leaves its one value to rv_true
         return true;
     }
 };

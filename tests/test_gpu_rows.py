@@ -232,6 +232,23 @@ def test_unsupported_row_shapes_are_refused(pg, data):
         ex.Init()
     assert ei.value.status == pg.PG_EUNSUPPORTED
     ex.Close()
+    # an expression that needs a deeper evaluation stack than the interpreter has (right-nested: every operand is pushed first)
+    I = K.IntegerType()
+    e = S.col("orders", "o_shippriority")
+    for _ in range(10):
+        e = X.func("+", I, S.col("orders", "o_custkey"), e)
+    deep = X.PhysicalOperator(X.POT_Project, Outputs=[e], Children=[X.PhysicalOperator(X.POT_Scan, Info=X.ScanOpInfo("orders"))])
+    ex = X.gpuPipelineExec(deep, tables)
+    with pytest.raises(pg.PlanGpuError) as ei:
+        ex.Init()
+    assert ei.value.status == pg.PG_EUNSUPPORTED and "evaluation stack" in str(ei.value)
+    ex.Close()
+    # ... while the same sum written left-nested (what the parser produces for a + b + c ...) needs two slots and runs
+    e = S.col("orders", "o_shippriority")
+    for _ in range(10):
+        e = X.func("+", I, e, S.col("orders", "o_custkey"))
+    flat = X.PhysicalOperator(X.POT_Project, Outputs=[e], Children=[X.PhysicalOperator(X.POT_Scan, Info=X.ScanOpInfo("orders"))])
+    assert len(_check(flat, tables, rows)) == len(rows["orders"])
     # build columns above a SEMI join
     j = _join(X, K, B, S, X.JOIN_SEMI, [X.col(0, OI["o_orderkey"], K.BigintType()), X.col(1, CI["c_nationkey"], K.IntegerType())])
     ex = X.gpuPipelineExec(j, tables)
