@@ -201,26 +201,51 @@ static __device__ __noinline__ RvVal rv_eval(const RvCode &c, int pc0, int pc1, 
     return st[sp - 1];
 }
 
-__device__ __forceinline__ bool rv_true(const RvCode &c, int pc0, int pc1, i64 row0, i64 row1, int *err)
+// The inline pre-tests of a filter program (RV_PRE: conjuncts of the form `column <cmp> constant` / `coded column in {codes}`):
+// most rows of a selective filter never reach the interpreter.  A NULL operand (or the NULL padding of a LEFT / MARK join,
+// row < 0) makes the conjunct NULL, which is not TRUE.  true when the program has no pre-tests.
+__device__ __forceinline__ bool rv_has_pre(const RvCode &c, int pc0, int pc1) { return pc1 > pc0 && c.ins[pc0].op == RV_PRE; }
+__device__ __forceinline__ bool rv_pre(const RvCode &c, int pc0, int pc1, i64 row0, i64 row1)
 {
-    if (pc1 <= pc0) return true;
-    if (c.ins[pc0].op == RV_PRE) {
-        // the cheap conjuncts first: most rows of a selective filter never reach the interpreter.  A NULL operand (or the
-        // NULL padding of a LEFT / MARK join, row < 0) makes the conjunct NULL, which is not TRUE.
-        const int p1 = c.ins[pc0].b;
-        for (int i = c.ins[pc0].a; i < p1; i++) {
-            const RvPre q = c.pre[i];
-            const RvCol &rc = c.cols[q.col];
-            const i64 row = rc.side ? row1 : row0;
-            if (row < 0 || !typed_valid(rc.col, row)) return false;
-            const i64 v = load_typed(rc.col, row);
-            if (q.mask >= 0) { if (!((c.masks[q.mask][(v >> 5) & 7] >> (v & 31)) & 1u)) return false; }
-            else if (v < q.lo || v > q.hi) return false;
-        }
-        if (++pc0 >= pc1) return true;
+    if (!rv_has_pre(c, pc0, pc1)) return true;
+    const int p1 = c.ins[pc0].b;
+    for (int i = c.ins[pc0].a; i < p1; i++) {
+        const RvPre q = c.pre[i];
+        const RvCol &rc = c.cols[q.col];
+        const i64 row = rc.side ? row1 : row0;
+        if (row < 0 || !typed_valid(rc.col, row)) return false;
+        const i64 v = load_typed(rc.col, row);
+        if (q.mask >= 0) { if (!((c.masks[q.mask][(v >> 5) & 7] >> (v & 31)) & 1u)) return false; }
+        else if (v < q.lo || v > q.hi) return false;
     }
+    return true;
+}
+// the same over descriptors a block copied into shared memory (pre-tests [i0, i1), column table, masks): one dependent
+// global load per test -- the data -- instead of three
+__device__ __forceinline__ bool rv_pre_smem(const RvPre *pre, int i0, int i1, const RvCol *cols, const unsigned (*masks)[8], i64 row0, i64 row1)
+{
+    for (int i = i0; i < i1; i++) {
+        const RvPre &q = pre[i];
+        const RvCol &rc = cols[q.col];
+        const i64 row = rc.side ? row1 : row0;
+        if (row < 0 || !typed_valid(rc.col, row)) return false;
+        const i64 v = load_typed(rc.col, row);
+        if (q.mask >= 0) { if (!((masks[q.mask][(v >> 5) & 7] >> (v & 31)) & 1u)) return false; }
+        else if (v < q.lo || v > q.hi) return false;
+    }
+    return true;
+}
+// the interpreted rest of a filter program (everything after its RV_PRE instruction)
+__device__ __forceinline__ bool rv_post(const RvCode &c, int pc0, int pc1, i64 row0, i64 row1, int *err)
+{
+    if (rv_has_pre(c, pc0, pc1)) pc0++;
+    if (pc1 <= pc0) return true;
     const RvVal v = rv_eval(c, pc0, pc1, row0, row1, err);
     return !v.null && v.v != 0;
+}
+__device__ __forceinline__ bool rv_true(const RvCode &c, int pc0, int pc1, i64 row0, i64 row1, int *err)
+{
+    return rv_pre(c, pc0, pc1, row0, row1) && rv_post(c, pc0, pc1, row0, row1, err);
 }
 
 }  // namespace pg

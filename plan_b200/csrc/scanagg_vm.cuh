@@ -47,9 +47,8 @@ vm_scanagg_kernel(const VmAggParams p, i64 *__restrict__ partials /* [grid][G*P]
     __syncthreads();
     i64 *my = s_acc + threadIdx.x;
     int err = 0;
-    for (i64 it = (i64)blockIdx.x * NT + threadIdx.x; it < p.nrows; it += (i64)gridDim.x * NT) {
-        const i64 row = p.pair0 ? p.pair0[it] : it, row1 = p.pair0 ? p.pair1[it] : -1;
-        if (!rv_true(*p.code, p.pred0, p.pred1, row, row1, &err)) continue;
+    // one selected row -> its group's planes (`it`: position used for the first-row order of the groups)
+    auto accumulate = [&](i64 it, i64 row, i64 row1) {
         int g = 0;
         if (p.nkeys > 0) g = s_lut[0][p.key0[p.key_side[0] ? row1 : row]];
         if (p.nkeys > 1) g = g * p.n1 + s_lut[1][p.key1[p.key_side[1] ? row1 : row]];
@@ -68,6 +67,71 @@ vm_scanagg_kernel(const VmAggParams p, i64 *__restrict__ partials /* [grid][G*P]
             if (x > (i128)p.absmax || x < -(i128)p.absmax) { err = RV_ERR_OVERFLOW; continue; }
             const i64 xv = (i64)x, cur = *slot;
             *slot = p.kind[a] == GEN_SUM ? cur + xv : p.kind[a] == GEN_MIN ? (xv < cur ? xv : cur) : (xv > cur ? xv : cur);
+        }
+    };
+    if (!p.pair0 && rv_has_pre(*p.code, p.pred0, p.pred1)) {
+        // Scan with inline pre-tests: a warp would run the interpreter while ANY of its 32 rows survives them, so the
+        // survivors of a block are first compacted into a shared-memory queue and interpreted NT at a time, densely.
+        // VM_R rows per thread and step: the pre-tests of the VM_R rows are independent (their loads overlap) and the
+        // barriers of the append are paid once per VM_R * NT rows.
+        constexpr int VM_R = 4;
+        __shared__ i64 s_q[(VM_R + 1) * NT];
+        __shared__ int s_woff[VM_R][NT / 32];
+        __shared__ int s_cnt;
+        __shared__ RvPre s_pre[RV_MAXPRE];
+        __shared__ RvCol s_cols[RV_MAXCOL];
+        __shared__ unsigned s_masks[RV_MAXMASK][8];
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int pre0 = p.code->ins[p.pred0].a, pre1 = p.code->ins[p.pred0].b;
+        if (threadIdx.x == 0) s_cnt = 0;
+        if (threadIdx.x < RV_MAXPRE) s_pre[threadIdx.x] = p.code->pre[threadIdx.x];
+        if (threadIdx.x < RV_MAXCOL) s_cols[threadIdx.x] = p.code->cols[threadIdx.x];
+        for (int i = threadIdx.x; i < RV_MAXMASK * 8; i += NT) s_masks[i / 8][i % 8] = p.code->masks[i / 8][i % 8];
+        __syncthreads();
+        for (i64 base = (i64)blockIdx.x * NT * VM_R; base < p.nrows; base += (i64)gridDim.x * NT * VM_R) {      // block-uniform trip count
+            bool pass[VM_R];
+            unsigned m[VM_R];
+#pragma unroll
+            for (int k = 0; k < VM_R; k++) {
+                const i64 row = base + (i64)k * NT + threadIdx.x;
+                pass[k] = row < p.nrows && rv_pre_smem(s_pre, pre0, pre1, s_cols, s_masks, row, -1);
+            }
+#pragma unroll
+            for (int k = 0; k < VM_R; k++) {
+                m[k] = __ballot_sync(0xffffffffu, pass[k]);
+                if (lane == 0) s_woff[k][warp] = __popc(m[k]);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int acc = s_cnt;
+                for (int k = 0; k < VM_R; k++)
+                    for (int w = 0; w < NT / 32; w++) { const int c = s_woff[k][w]; s_woff[k][w] = acc; acc += c; }
+                s_cnt = acc;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < VM_R; k++)
+                if (pass[k]) s_q[s_woff[k][warp] + __popc(m[k] & ((1u << lane) - 1u))] = base + (i64)k * NT + threadIdx.x;
+            __syncthreads();
+            int n = s_cnt;
+            while (n >= NT) {                       // block-uniform
+                const i64 r = s_q[n - NT + threadIdx.x];
+                if (rv_post(*p.code, p.pred0, p.pred1, r, -1, &err)) accumulate(r, r, -1);
+                n -= NT;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) s_cnt = n;
+            __syncthreads();
+        }
+        if ((int)threadIdx.x < s_cnt) {
+            const i64 r = s_q[threadIdx.x];
+            if (rv_post(*p.code, p.pred0, p.pred1, r, -1, &err)) accumulate(r, r, -1);
+        }
+    } else {
+        for (i64 it = (i64)blockIdx.x * NT + threadIdx.x; it < p.nrows; it += (i64)gridDim.x * NT) {
+            const i64 row = p.pair0 ? p.pair0[it] : it, row1 = p.pair0 ? p.pair1[it] : -1;
+            if (!rv_true(*p.code, p.pred0, p.pred1, row, row1, &err)) continue;
+            accumulate(it, row, row1);
         }
     }
     if (err) *p.err = err;
