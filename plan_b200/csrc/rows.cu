@@ -234,7 +234,9 @@ struct RowsPipeline : Pipeline {
         PG_CUDA(cudaStreamSynchronize(st));
         launches += 2;
         tr.mark("count + scan");
-        PG_TRY(check_err(err));
+        // (aggregate mode: a fault of ONE rank's rows must not keep that rank out of the all-gather its peers are about to
+        //  enter -- d_err is sticky, the check follows the collective in run_agg)
+        if (!agg_mode) PG_TRY(check_err(err));
         if (d_pairs.bytes < (size_t)std::max<i64>(total, 1) * 16) PG_TRY(d_pairs.alloc((size_t)std::max<i64>(total, 1) * 16));
         p.pair0 = d_pairs.as<i64>();
         p.pair1 = p.pair0 + std::max<i64>(total, 1);
@@ -343,9 +345,8 @@ struct RowsPipeline : Pipeline {
         i64 *d_firstrow = (i64 *)((char *)d_final.p + (size_t)G * P * 16);
         PG_CUDA(cudaMemsetAsync(d_firstrow, 0x7f, 64 * 8, st));
         const int grid = (int)std::max<i64>(std::min<i64>((total + NT - 1) / NT, agrid), 1);
-        // a CTA's int64 partial sums are exact while |value| x its pairs < 2^62
-        if ((i128)q.absmax * (i128)((total + grid - 1) / grid + NT) >= ((i128)1 << 62))
-            PG_FAIL(PG_EUNSUPPORTED, "aggregate over %lld joined rows: exactness of the per-CTA partial sums cannot be proven", (long long)total);
+        // a CTA's int64 partial sums are exact while |value| x its pairs < 2^62 (rank-local fact: reported after the collective)
+        const bool inexact = (i128)q.absmax * (i128)((total + grid - 1) / grid + NT) >= ((i128)1 << 62);
         if (NT == 256) vm_scanagg_kernel<256><<<grid, 256, asmem, st>>>(q, d_part.as<i64>(), d_firstrow);
         else if (NT == 128) vm_scanagg_kernel<128><<<grid, 128, asmem, st>>>(q, d_part.as<i64>(), d_firstrow);
         else vm_scanagg_kernel<64><<<grid, 64, asmem, st>>>(q, d_part.as<i64>(), d_firstrow);
@@ -365,6 +366,7 @@ struct RowsPipeline : Pipeline {
         PG_CUDA(cudaStreamSynchronize(st));
         tr.mark("aggregate over the pairs + gather");
         PG_TRY(check_err(err));
+        if (inexact) PG_FAIL(PG_EUNSUPPORTED, "aggregate over %lld joined rows: exactness of the per-CTA partial sums cannot be proven", (long long)total);
         std::vector<i128> tot((size_t)G * P);
         std::vector<i64> first((size_t)G, INT64_MAX);
         for (int v = 0; v < G * P; v++) {
