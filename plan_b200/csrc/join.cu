@@ -2160,6 +2160,16 @@ static int build_star(pg_plan *plan, const Node &aggn, const Node &top, std::uni
         const Stage &S = *p->stages[(size_t)lk.stage];
         if ((int)l == main) { x_why = "the filter-pass join cannot be exchanged"; return false; }
         if (S.sub || (S.has_probe && S.probe_stage != p->main_stage)) { x_why = "exchanged build side must be a (filtered) scan"; return false; }
+        {   // the exchange's filter pass takes NULL-free key / predicate columns; decided on the statistics agreed across ranks,
+            // so that every rank enters (or refuses) the collectives together
+            const pg_table *bt = p->tab(S.src_slot);
+            bool nulls = bt->cols[(size_t)S.ins_key_col].any_nulls() || (S.ins_key_col2 >= 0 && bt->cols[(size_t)S.ins_key_col2].any_nulls());
+            for (auto &r : S.ranges) nulls = nulls || bt->cols[(size_t)r.col].any_nulls();
+            if (nulls) { x_why = "exchanged build side has NULLs in its key or predicate columns"; return false; }
+            if (S.ranges.size() > 1) { x_why = "exchanged build side has more than one range predicate"; return false; }
+            for (auto &r : S.ranges) if (r.like || r.is_set) { x_why = "exchanged build side has a string / code-set predicate"; return false; }
+            if (bt->total_rows() >= ((i64)1 << 32)) { x_why = "exchanged build side has 2^32 rows or more"; return false; }
+        }
         for (size_t l2 = 0; l2 < p->lookups.size(); l2++)
             for (int k = 0; k < p->lookups[l2].nkey; k++)
                 if (p->lookups[l2].key[k].origin == (int)l + 1) { x_why = "another join is keyed by a column of the exchanged build side"; return false; }
@@ -2169,6 +2179,7 @@ static int build_star(pg_plan *plan, const Node &aggn, const Node &top, std::uni
             for (int f = 0; f < ht.nfac; f++)
                 if (ht.fac[f].origin == (int)l + 1 && std::find(cols.begin(), cols.end(), ht.fac[f].col) == cols.end()) cols.push_back(ht.fac[f].col);
         if (cols.size() > X_MAXCOL) { x_why = "more than 3 columns of the exchanged build side are read"; return false; }
+        for (int cidx : cols) if (p->tab(S.src_slot)->cols[(size_t)cidx].any_nulls()) { x_why = "a carried build column holds NULLs"; return false; }
         return true;
     };
     std::vector<size_t> must_x, may_x;
