@@ -506,8 +506,10 @@ int build_rows(pg_plan *plan, std::unique_ptr<Pipeline> *out, const Node *aggn)
     const pg_table *pt = p->tab(0), *bt = bscan ? p->tab(1) : nullptr;
     p->cc.tables[0] = pt;
     p->cc.tables[1] = bt;
-    if (ctx().world > 1 && bt && bt->dist != PG_DIST_REPLICATED && pt->dist != PG_DIST_REPLICATED)
-        PG_FAIL(PG_EUNSUPPORTED, "row-emitting join of two sharded tables (replicate the build side)");
+    // several ranks: every rank joins ITS probe rows (its shard, or the whole replicated table) against the WHOLE build side --
+    // a sharded build side would make "no match on this rank" (LEFT / ANTI / MARK, and SEMI duplicates) wrong
+    if (ctx().world > 1 && bt && bt->dist != PG_DIST_REPLICATED)
+        PG_FAIL(PG_EUNSUPPORTED, "row-emitting join against a sharded build side (replicate it)");
     if (bt && bt->nrows >= ((i64)1 << 31)) PG_FAIL(PG_EUNSUPPORTED, "row-emitting join: build side of 2^31 rows or more");
     if (pt->nrows >= ((i64)1 << 31) - 1) PG_FAIL(PG_EUNSUPPORTED, "row-emitting pipeline over 2^31 rows or more");
     // scopes
