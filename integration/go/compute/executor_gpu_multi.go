@@ -181,7 +181,8 @@ type multiGpuPipelineExec struct {
 	plans []*plangpu.Plan
 	res   []*plangpu.Result
 	cur   int  // device whose result is being emitted
-	rows  bool // row-emitting root: every device returns ITS rows (concatenated); aggregates: merged result on every device, device 0 is emitted
+	rows  bool // row-emitting root over a SHARDED probe table: every device returns the rows of its shard (concatenated);
+	// aggregates (merged result on every device) and row pipelines over a replicated probe table: device 0 is emitted
 }
 
 func newMultiGpuPipelineExec(op *PhysicalOperator, cfg *util.Config, txn *storage.Txn) (*multiGpuPipelineExec, error) {
@@ -206,6 +207,11 @@ func (e *multiGpuPipelineExec) Init() error {
 		if tabs[slot], err = shardedTableFor(e.ws, scanOp, e.cfg, e.txn); err != nil {
 			return err
 		}
+	}
+	// slot 0 is the leftmost (probe / scanned) table: serializePlan visits Children[0] first.  When it is replicated every
+	// device computes the same rows, so only one copy is emitted.
+	if e.rows && len(tabs) > 0 && tabs[0].replicated {
+		e.rows = false
 	}
 	e.plans = make([]*plangpu.Plan, len(e.ws))
 	// compile + bind + prepare on every device at once: Prepare agrees the statistics of sharded tables with one
