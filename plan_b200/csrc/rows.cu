@@ -89,7 +89,9 @@ static __global__ void __launch_bounds__(256)
 rows_probe_kernel(const RowsParams p)
 {
     int err = 0;
-    for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < p.probe_rows; r += (i64)gridDim.x * blockDim.x) {
+    // one probe row that passed the inline pre-tests of its scan filter: the interpreted rest of the filter, the join, the
+    // filters above the join per candidate pair; COUNT mode writes how many rows it yields, EMIT mode the pairs
+    auto process = [&](i64 r, bool pre_done) {
         unsigned n = 0;
         const i64 base = EMIT ? p.off[r] : 0;
         auto emit = [&](i64 b) {
@@ -97,7 +99,7 @@ rows_probe_kernel(const RowsParams p)
             if (EMIT) { p.pair0[base + n] = r; p.pair1[base + n] = b; }
             n++;
         };
-        if (rv_true(*p.code, p.pf0, p.pf1, r, -1, &err)) {
+        if (pre_done ? rv_post(*p.code, p.pf0, p.pf1, r, -1, &err) : rv_true(*p.code, p.pf0, p.pf1, r, -1, &err)) {
             if (p.jointype == 0) {
                 emit(-1);
             } else {
@@ -117,6 +119,57 @@ rows_probe_kernel(const RowsParams p)
             }
         }
         if (!EMIT) p.cnt[r] = n;
+    };
+    if (rv_has_pre(*p.code, p.pf0, p.pf1)) {
+        // A selective scan filter: a warp would run the interpreter and the probe while ANY of its 32 rows survives the
+        // pre-tests, so the survivors of a block are compacted into a shared-memory queue and processed 256 at a time
+        // (the same scheme as vm_scanagg_kernel).  Counts and offsets are indexed by row, so the output order is unchanged.
+        constexpr int NT = 256, R = 4;
+        __shared__ i64 s_q[(R + 1) * NT];
+        __shared__ int s_woff[R][NT / 32];
+        __shared__ int s_cnt;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        for (i64 base = (i64)blockIdx.x * NT * R; base < p.probe_rows; base += (i64)gridDim.x * NT * R) {      // block-uniform trip count
+            bool pass[R];
+            unsigned m[R];
+#pragma unroll
+            for (int k = 0; k < R; k++) {
+                const i64 row = base + (i64)k * NT + threadIdx.x;
+                const bool in = row < p.probe_rows;
+                pass[k] = in && rv_pre(*p.code, p.pf0, p.pf1, row, -1);
+                if (!EMIT && in && !pass[k]) p.cnt[row] = 0;
+            }
+#pragma unroll
+            for (int k = 0; k < R; k++) {
+                m[k] = __ballot_sync(0xffffffffu, pass[k]);
+                if (lane == 0) s_woff[k][warp] = __popc(m[k]);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int acc = s_cnt;
+                for (int k = 0; k < R; k++)
+                    for (int w = 0; w < NT / 32; w++) { const int c = s_woff[k][w]; s_woff[k][w] = acc; acc += c; }
+                s_cnt = acc;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < R; k++)
+                if (pass[k]) s_q[s_woff[k][warp] + __popc(m[k] & ((1u << lane) - 1u))] = base + (i64)k * NT + threadIdx.x;
+            __syncthreads();
+            int n = s_cnt;
+            while (n >= NT) {                       // block-uniform
+                process(s_q[n - NT + threadIdx.x], true);
+                n -= NT;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) s_cnt = n;
+            __syncthreads();
+        }
+        if ((int)threadIdx.x < s_cnt) process(s_q[threadIdx.x], true);
+    } else {
+        for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < p.probe_rows; r += (i64)gridDim.x * blockDim.x) process(r, false);
     }
     if (err) *p.err = err;
 }
