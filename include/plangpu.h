@@ -237,13 +237,17 @@ typedef struct {
     double exec_ms;            /* wall time of pg_plan_execute                    */
     double kernel_ms;          /* CUDA-event time of all kernels of the pipeline  */
     double main_kernel_ms;     /* CUDA-event time of the dominant (scan) kernel   */
-    double comm_ms;            /* NCCL merge / shuffle                            */
+    double comm_ms;            /* CUDA-event time of the all-to-all ROW exchanges of a join (build + probe side;
+                                  exchange.cuh); 0 for pipelines without one                            */
     int64_t rows_scanned;      /* rows read from the probe/fact table             */
     int64_t algorithmic_bytes; /* bytes of referenced columns, each read once     */
     int64_t main_kernel_bytes; /* algorithmic bytes of the dominant kernel        */
     int32_t kernel_launches;
     int32_t reserved;
-    int64_t aux[8];            /* pipeline specific counters (join sizes ...)     */
+    int64_t aux[8];            /* pipeline specific counters: [0] rows passing the scan / probe filters, [1] joined rows
+                                  (row pipelines: output rows), [2..5] rows passing / rows built of the first two build
+                                  stages, [6] result groups (rows) before any LIMIT, [7] rows sent to OTHER ranks by a
+                                  shuffle / row exchange ([5] = bytes sent, for a star join with a row exchange)        */
 } pg_stats;
 int pg_result_stats(const pg_result *r, pg_stats *out);
 void pg_result_free(pg_result *r);
