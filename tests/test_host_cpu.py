@@ -249,3 +249,133 @@ def test_descriptors_of_the_reference_plans_compile_without_a_gpu():
     plan = C.c_void_p()
     rc = L.lib().pg_plan_compile(desc.ctypes.data_as(C.POINTER(C.c_int64)), len(desc) - 3, C.byref(plan))
     assert rc == L.PG_EINVAL
+
+
+def _rowvm_listing(tmp_path, schema, mode, op):
+    """compile the harness once per test dir, feed it a schema + descriptor, parse the listing"""
+    import subprocess
+    from plan_b200 import compute as X
+    exe = str(tmp_path / "rowvm_check")
+    if not os.path.exists(exe):
+        src = os.path.join(ROOT, "tests", "hostlogic", "rowvm_check.cu")
+        subprocess.run(["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O1", "--expt-relaxed-constexpr",
+                        "-w", "-o", exe, src], check=True, capture_output=True)
+    desc, _ = X.serialize_plan(op)
+    cols = []
+    for _, t, _w, s, d in schema:
+        cols.append("%d %d %d %s" % (t, s, len(d or []), " ".join(x.replace(" ", "_") for x in (d or []))))
+    text = "%d %s\n%s %s\n" % (len(schema), " ".join(cols), mode, " ".join(str(int(w)) for w in desc))
+    out = subprocess.run([exe], input=text, capture_output=True, text=True, check=True).stdout.strip().split("\n")
+    if out[0] != "ok":
+        return {"fail": out[0]}
+    pre = [tuple(int(x) for x in ln.split()[1:]) for ln in out if ln.startswith("pre ")]
+    ins = [tuple(int(x) for x in ln.split()[1:]) for ln in out if ln.startswith("ins ")]
+    progs = [ln.split()[1:] for ln in out if ln.startswith("prog ")]
+    return {"pre": pre, "ins": ins, "progs": progs}
+
+
+# rowvm.cuh opcodes (restated: the test reads listings, it does not include the header)
+RV = dict(COL=1, CONST=2, NULL=3, MARK=4, ADD=5, SUB=6, MUL=7, DIV=8, CMP=9, AND=10, OR=11, NOT=12, INSET=13, JZ=14, JMP=15, YEAR=16,
+          TOF32=17, TODEC=18, PRE=19)
+
+
+def _max_depth(ins, p0, p1):
+    """evaluation-stack depth over every path of program [p0, p1): (max depth, depth at the end)"""
+    effect = {RV["COL"]: 1, RV["CONST"]: 1, RV["NULL"]: 1, RV["MARK"]: 1, RV["ADD"]: -1, RV["SUB"]: -1, RV["MUL"]: -1, RV["DIV"]: -1,
+              RV["CMP"]: -1, RV["AND"]: -1, RV["OR"]: -1, RV["JZ"]: -1}
+    best, ends = 0, set()
+    todo, seen = [(p0, 0)], set()
+    while todo:
+        pc, d = todo.pop()
+        while True:
+            if pc >= p1:
+                ends.add(d)
+                break
+            if (pc, d) in seen:
+                break
+            seen.add((pc, d))
+            _, op, a, b, imm = ins[pc]
+            d += effect.get(op, 0)
+            assert d >= 0
+            best = max(best, d)
+            if op == RV["JZ"]:
+                assert p0 <= imm <= p1
+                todo.append((imm, d))
+            if op == RV["JMP"]:
+                assert p0 <= imm <= p1
+                pc = imm
+            else:
+                pc += 1
+    return best, ends
+
+
+def test_row_program_compiler_on_the_cpu(tmp_path):
+    """The product's row-program compiler (rowvm_compile.hpp) run on the host by tests/hostlogic/rowvm_check.cu -- no GPU: which
+    conjuncts of a filter become inline pre-tests, jump targets and evaluation-stack depth on every path of CASE / filter
+    programs, the static scale bound an aggregate accumulates at, and the refusal of programs deeper than the interpreter's stack."""
+    from plan_b200 import _lib as L, chunk as K, compute as X, tpch as T
+    B, V, I, D = K.LType(K.LTID_BOOLEAN), K.VarcharType(), K.IntegerType(), K.DateType()
+    # Q12's lineitem scan filter: IN on a dictionary column and two date ranges are pre-tests, the column-to-column comparisons are interpreted
+    plan = T.q12_plan()
+    scan = plan.Children[0].Children[0]
+    r = _rowvm_listing(tmp_path, T.Q12_LINEITEM, "filters", scan)
+    assert "fail" not in r, r
+    smode, rdate = 1, 4
+    assert len(r["pre"]) == 3
+    mask = sum(1 << T.SHIPMODES.index(m) for m in ("FOB", "TRUCK"))
+    assert (smode, 0, 0, 0, mask) in r["pre"]
+    assert (rdate, -1, T.days(1996, 1, 1), (1 << 63) - 1, 0) in r["pre"] and (rdate, -1, -(1 << 63), T.days(1997, 1, 1) - 1, 0) in r["pre"]
+    p0, p1 = int(r["progs"][0][0]), int(r["progs"][0][1])
+    assert r["ins"][p0][1] == RV["PRE"] and (r["ins"][p0][2], r["ins"][p0][3]) == (0, 3)
+    assert sum(1 for x in r["ins"][p0:p1] if x[1] == RV["CMP"]) == 2 and sum(1 for x in r["ins"][p0:p1] if x[1] == RV["JZ"]) == 2
+    depth, ends = _max_depth(r["ins"], p0 + 1, p1)
+    assert depth <= 2 and ends == {1}
+    # PG_VM_NO_PRE-free check of the other extreme: a filter made only of range conjuncts is ONE instruction
+    only = X.PhysicalOperator(X.POT_Scan, Info=X.ScanOpInfo("lineitem"), Filters=scan.Filters[3:])
+    r = _rowvm_listing(tmp_path, T.Q12_LINEITEM, "filters", only)
+    assert len(r["ins"]) == 1 and r["ins"][0][1] == RV["PRE"] and len(r["pre"]) == 2
+    # projections: CASE with and without ELSE, decimal arithmetic, scale bounds, jump structure
+    S = T.Schema(lineitem=T.Q19_LINEITEM)
+    lc = lambda n: S.col("lineitem", n)   # noqa: E731
+    D152 = K.DecimalType(15, 2)
+    one = X.cast(X.const(1, I), D152)
+    rev = X.func("*", K.DecimalType(18, 4), X.cast(lc("l_extendedprice"), K.DecimalType(16, 2)), X.func("-", K.DecimalType(16, 2), one, lc("l_discount")))
+    case3 = X.func("case", K.DecimalType(18, 4), X.cast(X.const(0, I), K.DecimalType(18, 4)),
+                   X.func("=", B, lc("l_shipmode"), X.const("AIR", V)), rev,
+                   X.func("<", B, lc("l_quantity"), X.const(10, I)), lc("l_extendedprice"))
+    noelse = X.func("case", I, X.const(None, I), X.func(">", B, lc("l_quantity"), X.const(25, I)), lc("l_quantity"))
+    quo = X.func("/", K.DecimalType(38, 6), lc("l_extendedprice"), lc("l_discount"))
+    proj = X.PhysicalOperator(X.POT_Project, Outputs=[rev, case3, noelse, quo], Children=[X.PhysicalOperator(X.POT_Scan, Info=X.ScanOpInfo("lineitem"))])
+    r = _rowvm_listing(tmp_path, T.Q19_LINEITEM, "exprs", proj)
+    assert "fail" not in r, r
+    kinds = [int(p[2]) for p in r["progs"]]
+    bounds = [int(p[4]) for p in r["progs"]]
+    assert kinds == [3, 3, 2, 3]                     # DEC, DEC, INT, DEC
+    assert bounds == [4, 4, 0, -1]                   # a quotient has no fixed scale: aggregates over it are refused
+    for p in r["progs"]:
+        depth, ends = _max_depth(r["ins"], int(p[0]), int(p[1]))
+        assert depth <= 8 and ends == {1}, (p, depth, ends)
+    assert sum(1 for x in r["ins"] if x[1] == RV["JZ"]) == 3 and sum(1 for x in r["ins"] if x[1] == RV["NULL"]) == 1
+    # a right-nested sum needs one stack slot per operand: refused at 10 operands, accepted left-nested
+    e = lc("l_quantity")
+    for _ in range(10):
+        e = X.func("+", I, lc("l_partkey"), e)
+    r = _rowvm_listing(tmp_path, T.Q19_LINEITEM, "exprs", X.PhysicalOperator(X.POT_Project, Outputs=[e], Children=[proj.Children[0]]))
+    assert "evaluation stack" in r.get("fail", "")
+    e = lc("l_quantity")
+    for _ in range(10):
+        e = X.func("+", I, e, lc("l_partkey"))
+    r = _rowvm_listing(tmp_path, T.Q19_LINEITEM, "exprs", X.PhysicalOperator(X.POT_Project, Outputs=[e], Children=[proj.Children[0]]))
+    assert "fail" not in r and _max_depth(r["ins"], 0, len(r["ins"]))[0] == 2
+    # Q19's three-branch OR above the join compiles within the interpreter's limits (program length, masks, stack)
+    flt = T.q19_plan().Children[0]
+    joined = [("l_quantity", L.PG_T_INT32, 0, 0, None), ("l_extendedprice", L.PG_T_DECIMAL64, 15, 2, None), ("l_discount", L.PG_T_DECIMAL64, 15, 2, None),
+              ("l_shipmode", L.PG_T_DICT8, 0, 0, T.SHIPMODES), ("l_shipinstruct", L.PG_T_DICT8, 0, 0, T.SHIPINSTRUCT), ("p_brand", L.PG_T_DICT8, 0, 0, T.BRANDS),
+              ("p_size", L.PG_T_INT32, 0, 0, None), ("p_container", L.PG_T_DICT8, 0, 0, T.CONTAINERS)]
+    as_scan = X.PhysicalOperator(X.POT_Scan, Info=X.ScanOpInfo("joined"), Filters=flt.Filters)
+    r = _rowvm_listing(tmp_path, joined, "filters", as_scan)
+    assert "fail" not in r, r
+    p0, p1 = int(r["progs"][0][0]), int(r["progs"][0][1])
+    depth, ends = _max_depth(r["ins"], p0, p1)
+    assert r["pre"] == [] and depth <= 4 and ends == {1} and p1 - p0 < 384
+    assert sum(1 for x in r["ins"] if x[1] == RV["INSET"]) == 12 and sum(1 for x in r["ins"] if x[1] == RV["OR"]) == 2
