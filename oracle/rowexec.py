@@ -325,8 +325,25 @@ def _gkey(v):
     return ("d", v.signed() * 10 ** (19 - v.scale)) if isinstance(v, Dec) else v
 
 
+class _HavingRow:
+    """HAVING references group keys as (0, i) and aggregates as (1, i) (expr_exec.go:248-265)"""
+
+    def __init__(self, key, vals):
+        self.key, self.vals = key, vals
+
+
 def eval_having(f, key, vals):
-    raise NotImplementedError("HAVING in the row oracle")
+    def sub(e):
+        if e.Typ == ET_Column:
+            side, idx = e.ColRef
+            return (key if side == 0 else vals)[idx]
+        if e.Typ == ET_Const:
+            return eval_expr(e, [])
+        # rebuild the node over already evaluated children: reuse eval_expr through a positional row
+        row = [sub(c) for c in e.Children]
+        shadow = type(e)(e.Typ, e.DataTyp, Children=[type(e)(ET_Column, c.DataTyp, ColRef=(0, i)) for i, c in enumerate(e.Children)], FunImpl=e.FunImpl)
+        return eval_expr(shadow, row)
+    return sub(f) is True
 
 
 def _key(v):

@@ -220,6 +220,16 @@ def test_row_oracle_and_descriptor_of_a_row_emitting_plan():
     proj = X.PhysicalOperator(X.POT_Project, Outputs=[ratio], Children=[lscan])
     got = R.format_rows(R.execute(proj, tables), [K.DecimalType(38, 6)])
     assert got == sorted(["0.4", "NULL", "1", "0.1001"])                                     # 1/9.99 = 0.1001001... -> 6 digits, zeros trimmed
+    # aggregates: NULL arguments ignored, a group without any valid input sums to NULL, HAVING on an aggregate
+    H = K.HugeintType()
+    t2 = {"t": [[1, 5], [1, 7], [2, 1], [3, None]]}
+    scan2 = X.PhysicalOperator(X.POT_Scan, Info=X.ScanOpInfo("t"))
+    aggs = [X.func("sum", H, X.col(0, 1, I)), X.func("count", H), X.func("count", H, X.col(0, 1, I))]
+    outs = [X.col(0, 0, I)] + [X.col(1, i, H) for i in range(3)]
+    agg = X.PhysicalOperator(X.POT_Agg, Outputs=outs, Children=[scan2], Info=X.AggOpInfo(aggs, [X.col(0, 0, I)]))
+    assert R.execute(agg, t2) == [[1, 12, 2, 2], [2, 1, 1, 1], [3, None, 1, 0]]
+    agg.Filters = [X.func(">", B, X.col(1, 0, H), X.const(3, H))]
+    assert R.execute(agg, t2) == [[1, 12, 2, 2]]
     q = R.dec_quo(R.Dec(1, 0), R.Dec(3, 0))
     assert (q.coef, q.scale) == (3333333333333333333, 19)
     q = R.dec_quo(R.Dec(2, 0), R.Dec(3, 0))
