@@ -3,6 +3,9 @@
 //   line 1: ncols, then per column "<pg_type> <scale> <ndict> <dict entries...>" (entries without blanks; '_' stands for a blank)
 //   line 2: mode ("filters" | "exprs"), then the int64 words of a descriptor whose root is PG_OP_SCAN (mode filters: its filter
 //           list is compiled as ONE conjunction) or PG_OP_PROJECT over a scan (mode exprs: every projection is one program)
+//   mode "lower": the root is PG_OP_AGG over a scan; prints what the LOWERED kernels are given (plan_ir.hpp): "range <col> <lo> <hi>
+//           <is_set> <like>" per filter column (lower_filters) and "agg <i> vscale <s> factors <col> <c> <s> <scale> ..." per aggregate
+//           argument (lower_affprod), or "fail <reason>" when the shape does not lower (the expression kernels take it then)
 // stdout: "ok" + the listing ("pre <col> <mask> <lo> <hi>" lines, "ins <pc> <op> <a> <b> <imm>" lines, "prog <p0> <p1> <kind>")
 //         or "fail <reason>".  tests/test_host_cpu.py checks structure: which conjuncts became inline pre-tests, jump targets,
 //         evaluation-stack depth on every path, refusals.
@@ -47,6 +50,27 @@ int main()
     DescReader rd(words.data() + 2, words.size() - 2);
     Node root;
     if (!rd.node(&root) || !rd.ok()) { printf("fail malformed descriptor\n"); return 0; }
+    if (mode == "lower") {
+        if (root.op != PG_OP_AGG) { printf("fail root is not an aggregate\n"); return 0; }
+        const Node *scan = &root.children[0];
+        while (scan->op != PG_OP_SCAN && !scan->children.empty()) scan = &scan->children[0];
+        LowerCtx cx;
+        cx.table = &t;
+        cx.allow_nulls = true;
+        std::vector<Range> ranges;
+        if (!lower_filters(cx, scan->filters, ranges)) { printf("fail filters: %s\n", cx.why.c_str()); return 0; }
+        std::vector<AffProd> args(root.aggs.size());
+        for (size_t i = 0; i < root.aggs.size(); i++)
+            if (!root.aggs[i].star && root.aggs[i].fn != PG_AGG_COUNT && !lower_affprod(cx, root.aggs[i].arg, args[i])) { printf("fail aggregate %zu: %s\n", i, cx.why.c_str()); return 0; }
+        printf("ok\n");
+        for (auto &r : ranges) printf("range %d %lld %lld %d %d\n", r.col, (long long)r.lo, (long long)r.hi, r.is_set ? 1 : 0, r.like);
+        for (size_t i = 0; i < args.size(); i++) {
+            printf("agg %zu vscale %d factors", i, args[i].vscale());
+            for (auto &f : args[i].f) printf(" %d %lld %d %d", f.col, (long long)f.c, f.s, f.scale);
+            printf("\n");
+        }
+        return 0;
+    }
     RvCompiler cc;
     cc.tables[0] = &t;
     Resolver scope = [&](int idx, Src *s) { if (idx < 0 || idx >= (int)t.cols.size()) return false; s->side = 0; s->col = idx; s->mark = false; return true; };

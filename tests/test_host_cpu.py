@@ -389,3 +389,36 @@ def test_row_program_compiler_on_the_cpu(tmp_path):
     depth, ends = _max_depth(r["ins"], p0, p1)
     assert r["pre"] == [] and depth <= 4 and ends == {1} and p1 - p0 < 384
     assert sum(1 for x in r["ins"] if x[1] == RV["INSET"]) == 12 and sum(1 for x in r["ins"] if x[1] == RV["OR"]) == 2
+
+
+def test_lowering_of_q6_and_q1_on_the_cpu(tmp_path):
+    """What the specialised scan kernels are given, computed by the product's plan-time lowering (plan_ir.hpp) on the host: Q6's
+    float32 BETWEEN on a DECIMAL(15,2) column becomes the integer range [2, 4] (cents), its date / quantity comparisons inclusive
+    ranges, its aggregate a product of two plain columns at value scale 4; Q1's sum_charge a product of three affine factors
+    l_extendedprice * (100 - l_discount) * (100 + l_tax) at value scale 6 (SURVEY 8c typing trace)."""
+    import subprocess
+    from plan_b200 import compute as X, tpch as T
+    _rowvm_listing(tmp_path, T.LINEITEM, "filters", X.PhysicalOperator(X.POT_Scan, Info=X.ScanOpInfo("lineitem")))       # builds the harness
+    exe = str(tmp_path / "rowvm_check")
+
+    def lower(op):
+        desc, _ = X.serialize_plan(op)
+        cols = " ".join("%d %d 0" % (t, s) for _, t, _w, s, d in T.LINEITEM)
+        text = "%d %s\nlower %s\n" % (len(T.LINEITEM), cols, " ".join(str(int(w)) for w in desc))
+        out = subprocess.run([exe], input=text, capture_output=True, text=True, check=True).stdout.strip().split("\n")
+        assert out[0] == "ok", out
+        ranges = {int(ln.split()[1]): tuple(int(x) for x in ln.split()[2:]) for ln in out if ln.startswith("range ")}
+        aggs = [ln.split() for ln in out if ln.startswith("agg ")]
+        return ranges, aggs
+    LI = T.FULL.idx["lineitem"]
+    ranges, aggs = lower(T.q6_plan())
+    assert ranges[LI["l_shipdate"]][:2] == (T.days(1994, 1, 1), T.days(1995, 1, 1) - 1)
+    assert ranges[LI["l_discount"]][:2] == (2, 4)                       # float32(0.03) -+ float32(0.01) selects exactly 0.02 .. 0.04
+    assert ranges[LI["l_quantity"]][1] == 23
+    assert aggs[0][3] == "4" and [int(x) for x in aggs[0][5:]] == [LI["l_extendedprice"], 0, 1, 2, LI["l_discount"], 0, 1, 2]
+    ranges, aggs = lower(T.q1_plan())
+    assert ranges[LI["l_shipdate"]][1] == T.days(1998, 8, 11)
+    charge = [int(x) for x in aggs[3][5:]]
+    assert aggs[3][3] == "6" and charge == [LI["l_extendedprice"], 0, 1, 2, LI["l_discount"], 100, -1, 2, LI["l_tax"], 100, 1, 2]
+    disc_price = [int(x) for x in aggs[2][5:]]
+    assert aggs[2][3] == "4" and disc_price == charge[:8]
