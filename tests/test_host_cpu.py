@@ -422,3 +422,36 @@ def test_lowering_of_q6_and_q1_on_the_cpu(tmp_path):
     assert aggs[3][3] == "6" and charge == [LI["l_extendedprice"], 0, 1, 2, LI["l_discount"], 100, -1, 2, LI["l_tax"], 100, 1, 2]
     disc_price = [int(x) for x in aggs[2][5:]]
     assert aggs[2][3] == "4" and disc_price == charge[:8]
+
+
+def test_descriptor_parser_survives_mutated_input():
+    """The descriptor is the one structure that crosses the boundary as raw words: truncations and random word mutations of valid
+    descriptors must come back as a status (OK / PG_EINVAL / PG_EUNSUPPORTED), never crash or read past the buffer."""
+    import ctypes as C
+    import random
+    from plan_b200 import _lib as L, compute as X, tpch as T
+    lib = L.lib()
+    rng = random.Random(3)
+    seeds = [X.serialize_plan(p)[0] for p in (T.q6_plan(), T.q1_plan(), T.q3_topk_plan(10), T.q9_plan(), T.q12_plan(), T.q19_plan(), T.q4_plan())]
+    tried = 0
+    for base in seeds:
+        for _ in range(300):
+            d = base.copy()
+            kind = rng.randrange(3)
+            if kind == 0:
+                d = d[:rng.randrange(0, len(d))]
+            elif kind == 1:
+                for _ in range(rng.randrange(1, 4)):
+                    d[rng.randrange(2, len(d))] = rng.choice([0, 1, -1, 2, 7, 255, 4096, 1 << 40, -(1 << 62), rng.randrange(-50, 50)])
+            else:
+                i = rng.randrange(2, len(d))
+                d = np.concatenate([d[:i], np.array([rng.randrange(-5, 300) for _ in range(rng.randrange(1, 6))], dtype=np.int64), d[i:]])
+            d = np.ascontiguousarray(d, dtype=np.int64)
+            plan = C.c_void_p()
+            ptr = d.ctypes.data_as(C.POINTER(C.c_int64)) if len(d) else None
+            rc = lib.pg_plan_compile(ptr, len(d), C.byref(plan))
+            assert rc in (L.PG_OK, L.PG_EINVAL, L.PG_EUNSUPPORTED), rc
+            if rc == L.PG_OK:
+                lib.pg_plan_free(plan)
+            tried += 1
+    assert tried == 2100
