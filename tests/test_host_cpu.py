@@ -167,6 +167,13 @@ def test_product_host_arithmetic_agrees_with_the_oracle(tmp_path):
         cases.append(("F", op, lit, scale, vmin, vmax))
         lines.append("F %d %d %d %d %d" % (op, int(np.frombuffer(lit.tobytes(), np.uint32)[0]), scale, vmin, vmax))
     out = subprocess.run([exe], input="\n".join(lines) + "\n", capture_output=True, text=True, check=True).stdout.split("\n")
+    # the same harness as plain C++ under AddressSanitizer / UBSan: no out-of-bounds, no signed overflow, same answers
+    san = str(tmp_path / "hostlogic_asan")
+    subprocess.run(["g++", "-x", "c++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all",
+                    "-I/usr/local/cuda/include", "-o", san, src], check=True, capture_output=True)
+    res = subprocess.run([san], input="\n".join(lines) + "\n", capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert res.stdout.split("\n") == out
     for case, got in zip(cases, out):
         if case[0] == "F":
             _, op, lit, scale, vmin, vmax = case
@@ -261,15 +268,20 @@ def test_descriptors_of_the_reference_plans_compile_without_a_gpu():
     assert rc == L.PG_EINVAL
 
 
+_RV_EXE = {}
+
+
 def _rowvm_listing(tmp_path, schema, mode, op):
     """compile the harness once per test dir, feed it a schema + descriptor, parse the listing"""
     import subprocess
     from plan_b200 import compute as X
-    exe = str(tmp_path / "rowvm_check")
+    exe = _RV_EXE.get("exe") or str(tmp_path / "rowvm_check")
     if not os.path.exists(exe):
+        _RV_EXE["exe"] = exe                                                 # built once per session, shared by the tests below
         src = os.path.join(ROOT, "tests", "hostlogic", "rowvm_check.cu")
         subprocess.run(["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O1", "--expt-relaxed-constexpr",
-                        "-w", "-o", exe, src], check=True, capture_output=True)
+                        "-w", "-g", "-Xcompiler", "-fsanitize=address", "-Xcompiler", "-fsanitize=undefined", "-Xcompiler", "-fno-sanitize-recover=all",
+                        "-o", exe, src], check=True, capture_output=True)        # host code under ASan / UBSan: the fixed RvCode arrays
     desc, _ = X.serialize_plan(op)
     cols = []
     for _, t, _w, s, d in schema:
@@ -391,6 +403,50 @@ def test_row_program_compiler_on_the_cpu(tmp_path):
     assert sum(1 for x in r["ins"] if x[1] == RV["INSET"]) == 12 and sum(1 for x in r["ins"] if x[1] == RV["OR"]) == 2
 
 
+def test_row_program_capacity_limits_are_refusals(tmp_path):
+    """RvCode is a fixed-size structure (rowvm.cuh: 384 instructions, 32 column slots, 16 dictionary masks, 24 pre-tests, 24 levels
+    of nesting).  The harness is built with AddressSanitizer / UBSan: a plan that exceeds any of them must come back as a refusal
+    with a message -- never a write past a table -- and a plan at the limit must still compile."""
+    from plan_b200 import _lib as L, chunk as K, compute as X, tpch as T
+    B, V, I = K.LType(K.LTID_BOOLEAN), K.VarcharType(), K.IntegerType()
+    S = T.Schema(lineitem=T.Q19_LINEITEM)
+    lc = lambda n: S.col("lineitem", n)   # noqa: E731
+    scan0 = X.PhysicalOperator(X.POT_Scan, Info=X.ScanOpInfo("lineitem"))
+    wide = [("c%d" % i, L.PG_T_INT32, 0, 0, None) for i in range(40)]
+    SW = T.Schema(lineitem=wide)
+
+    def filters(f, schema=T.Q19_LINEITEM):
+        return _rowvm_listing(tmp_path, schema, "filters", X.PhysicalOperator(X.POT_Scan, Info=X.ScanOpInfo("lineitem"), Filters=f))
+
+    def exprs(outs, schema=T.Q19_LINEITEM):
+        return _rowvm_listing(tmp_path, schema, "exprs", X.PhysicalOperator(X.POT_Project, Outputs=outs, Children=[scan0]))
+    # more range conjuncts than pre-test slots: the first 24 are inline pre-tests, the rest are interpreted
+    r = filters([X.func(">", B, lc("l_quantity"), X.const(i, I)) for i in range(40)])
+    assert "fail" not in r and len(r["pre"]) == 24 and sum(1 for x in r["ins"] if x[1] == RV["CMP"]) == 16
+    # dictionary masks: 30 IN-lists as pre-tests, 40 inside ORs
+    inset = lambda c, names: X.func("in", B, lc(c), *[X.const(n, V) for n in names])   # noqa: E731
+    assert "too many string predicates" in filters([inset("l_shipmode", ("AIR", "MAIL")) for _ in range(30)]).get("fail", "")
+    ors = [X.func("or", B, inset("l_shipmode", ("AIR", T.SHIPMODES[i % 7])), inset("l_shipinstruct", (T.SHIPINSTRUCT[i % 4], T.SHIPINSTRUCT[0])))
+           for i in range(20)]
+    assert "too many string predicates" in filters(ors).get("fail", "")
+    assert "fail" not in filters(ors[:8])                                     # 16 masks: exactly full
+    # program length
+    assert "too long" in exprs([X.func("+", I, lc("l_quantity"), lc("l_partkey")) for _ in range(200)]).get("fail", "")
+    # column slots
+    outs = [X.func("+", I, SW.col("lineitem", "c%d" % i), SW.col("lineitem", "c%d" % ((i + 1) % 40))) for i in range(40)]
+    assert "too many columns" in exprs(outs, wide).get("fail", "")
+    assert "fail" not in exprs(outs[:31], wide)                               # 32 distinct columns: exactly full
+    # nesting
+    def nest(n):
+        e = lc("l_extendedprice")
+        for i in range(n):
+            e = X.func("case", K.DecimalType(15, 2), lc("l_discount"), X.func("<", B, lc("l_quantity"), X.const(i, I)), e)
+        return e
+    assert "too deep" in exprs([nest(60)]).get("fail", "")
+    r = exprs([nest(12)])
+    assert "fail" not in r and _max_depth(r["ins"], 0, len(r["ins"]))[1] == {1}
+
+
 def test_lowering_of_q6_and_q1_on_the_cpu(tmp_path):
     """What the specialised scan kernels are given, computed by the product's plan-time lowering (plan_ir.hpp) on the host: Q6's
     float32 BETWEEN on a DECIMAL(15,2) column becomes the integer range [2, 4] (cents), its date / quantity comparisons inclusive
@@ -399,7 +455,7 @@ def test_lowering_of_q6_and_q1_on_the_cpu(tmp_path):
     import subprocess
     from plan_b200 import compute as X, tpch as T
     _rowvm_listing(tmp_path, T.LINEITEM, "filters", X.PhysicalOperator(X.POT_Scan, Info=X.ScanOpInfo("lineitem")))       # builds the harness
-    exe = str(tmp_path / "rowvm_check")
+    exe = _RV_EXE["exe"]
 
     def lower(op):
         desc, _ = X.serialize_plan(op)
