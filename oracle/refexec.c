@@ -593,7 +593,7 @@ void orc_stats(int64_t n, const int32_t *shipdate, const int32_t *commitdate, co
         }
         int c2 = 0;
         for (int i = 0; i < c; i++) {      /* greatDecimalOp: left.Sub(right).IsPos() */
-            dec_t d;
+            dec_t d = {0, 0, 0};
             if (dec_sub(dec_from_i64(discount[off + sb[i]], 2), kdisc, &d)) res->error = 1;
             if (d.coef != 0 && !d.neg) sa[c2++] = sb[i];
         }
@@ -601,7 +601,7 @@ void orc_stats(int64_t n, const int32_t *shipdate, const int32_t *commitdate, co
             int64_t r = off + sa[i];
             int gi = -1;
             for (int k = 0; k < res->ngroups; k++) if (res->g[k].rf == returnflag[r]) gi = k;
-            dec_t ext = dec_from_i64(extprice[r], 2), disc = dec_from_i64(discount[r], 2), tx = dec_from_i64(tax[r], 2), f, taxed;
+            dec_t ext = dec_from_i64(extprice[r], 2), disc = dec_from_i64(discount[r], 2), tx = dec_from_i64(tax[r], 2), f = {0, 0, 0}, taxed = {0, 0, 0};
             if (dec_add(one, tx, &f)) res->error = 1;
             if (dec_mul(ext, f, &taxed)) res->error = 1;
             int ext_ok = !v_ext || v_ext[r], tax_ok = !v_tax || v_tax[r];

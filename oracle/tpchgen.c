@@ -334,3 +334,26 @@ void tg_gen_q19_draws(double sf, int64_t o_lo, int64_t o_hi, uint8_t *l_shipinst
         }
     }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Columns of TPC-H Q11 / Q22 (cases/tpch/query/q11.sql, q22.sql):
+ *   c_acctbal    UnifInt(-99999, 999999) cents from C_ABAL_SD, one draw per customer
+ *   ps_availqty  UnifInt(1, 9999) from PS_QTY_SD, one draw per partsupp row (4 per part)
+ * (substring(c_phone, 1, 2) needs no stream: dbgen's phone number starts with the two digits of 10 + c_nationkey.)
+ * Pinned by the reference's golden cases/tpch/1g/plan/q11.txt and q22.txt (tests/test_oracle_golden.py).
+ */
+enum { SD_C_ABAL = 298370230, SD_PS_QTY = 1671059989 };
+
+void tg_gen_q11_q22_draws(double sf, int64_t c_lo, int64_t c_hi, int64_t *c_acctbal /* [customers] */,
+                          int64_t p_lo, int64_t p_hi, int32_t *ps_availqty /* [4 * parts] */)
+{
+    (void)sf;
+    if (c_acctbal) {
+        int64_t s = tg_jump(SD_C_ABAL, c_lo);
+        for (int64_t i = c_lo; i < c_hi; i++) c_acctbal[i - c_lo] = tg_draw(&s, -99999, 999999);
+    }
+    if (ps_availqty) {
+        int64_t s = tg_jump(SD_PS_QTY, 4 * p_lo);
+        for (int64_t r = 0; r < 4 * (p_hi - p_lo); r++) ps_availqty[r] = (int32_t)tg_draw(&s, 1, 9999);
+    }
+}

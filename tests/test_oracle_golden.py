@@ -67,7 +67,7 @@ def test_golden_copies_are_the_reference_files():
     ref = "/root/reference/cases/tpch/1g/plan"
     if not os.path.isdir(ref):
         pytest.skip("reference tree not present")
-    for q in (1, 3, 4, 6, 9, 12, 14, 18, 19):
+    for q in (1, 3, 4, 5, 6, 7, 8, 9, 11, 12, 14, 17, 18, 19, 21, 22):
         assert open(os.path.join(GOLDEN, "ref_sf1_q%d.txt" % q), "rb").read() == open(os.path.join(ref, "q%d.txt" % q), "rb").read(), q
 
 
@@ -122,6 +122,29 @@ def test_q4_q12_q14_q19_reproduce_reference_golden(oracle, sf1):
     assert "#\n" + oracle.fmt_decimal((r19["revenue"], 4, 0), 4) + "\n" == open(os.path.join(GOLDEN, "ref_sf1_q19.txt")).read()
     r = oracle.q14(line, extra)
     assert "#\n" + oracle.q14_promo_revenue(r["promo"], r["total"]) + "\n" == open(os.path.join(GOLDEN, "ref_sf1_q14.txt")).read()
+
+
+def test_q5_q7_q8_q11_q17_q21_q22_reproduce_reference_golden(oracle, sf1):
+    """Seven more of the reference's SF1 result files (cases/tpch/1g/plan/q{5,7,8,11,17,21,22}.txt), byte for byte.  They pin what
+    the earlier files do not reach: the c_nationkey stream (Q5 / Q7 / Q8 / Q22), l_suppkey joined to s_nationkey on the lineitem
+    side (Q5 / Q7 / Q21), c_acctbal and ps_availqty (Q22, Q11), o_orderstatus and the commit / receipt dates per order (Q21),
+    a DECIMAL quotient printed at scale 4 (Q8) and a DECIMAL sum divided by a FLOAT literal in float32 (Q17)."""
+    orders, line, cust = sf1["orders"], sf1["lineitem"], sf1["customer"]
+    supp, ps = oracle.gen_supplier(1.0), oracle.gen_partsupp(1.0)
+    e12, e19, e22 = oracle.gen_q12_q14_columns(1.0), oracle.gen_q19_columns(1.0), oracle.gen_q11_q22_columns(1.0)
+    # first rows of the official customer.tbl / partsupp.tbl
+    assert e22["c_acctbal"][:5].tolist() == [71156, 12165, 749812, 286683, 79447]
+    assert e22["ps_availqty"][:4].tolist() == [3325, 8076, 3956, 4069]
+    gold = lambda q: open(os.path.join(GOLDEN, "ref_sf1_q%d.txt" % q)).read()   # noqa: E731
+    dec = lambda v, s: oracle.fmt_decimal((v, s, 0), s)                          # noqa: E731
+    assert oracle.rows_text(1, [(n, dec(v, 4)) for n, v in oracle.q5(cust, supp, orders, line)]) == gold(5)
+    assert oracle.rows_text(3, [(a, b, y, dec(v, 4)) for a, b, y, v in oracle.q7(cust, supp, orders, line)]) == gold(7)
+    assert oracle.rows_text(1, [(y, oracle.fmt_decimal(q, 4)) for y, q in oracle.q8(cust, supp, orders, line, e12)]) == gold(8)
+    assert oracle.rows_text(1, [(k, dec(v, 2)) for k, v in oracle.q11(supp, ps, e22)]) == gold(11)
+    r17 = oracle.q17(line, e19)
+    assert r17["rows"] == 558 and oracle.rows_text(0, [(r17["avg_yearly"],)]) == gold(17)
+    assert oracle.rows_text(1, oracle.q21(supp, orders, line)) == gold(21)
+    assert oracle.rows_text(2, [(c, n, dec(v, 2)) for c, n, v in oracle.q22(cust, orders, e22)]) == gold(22)
 
 
 def test_q3_reproduces_reference_golden(oracle, sf1):
