@@ -387,7 +387,7 @@ def q7(cust, supp, orders, line, a="FRANCE", b="ARGENTINA"):
 
 
 def q8(cust, supp, orders, line, extra12, nation="ARGENTINA", region="AMERICA", ptype="ECONOMY BURNISHED TIN"):
-    """cases/tpch/query/q8.sql: (o_year, mkt_share); the share is a DECIMAL quotient of the two exact sums (govalues Quo), printed at
+    """cases/tpch/query/q8.sql: (o_year, mkt_share, the two exact sums at scale 4); the share is a DECIMAL quotient of the two exact sums (govalues Quo), printed at
     the type's scale 4"""
     names, nreg = nation_names(), np.array(NATION_REGION)
     oidx, cn, sn = _line_dims(cust, supp, orders, line)
@@ -400,7 +400,7 @@ def q8(cust, supp, orders, line, extra12, nation="ARGENTINA", region="AMERICA", 
         part, tot = int(rev[(yr == y) & mine].sum()) if ((yr == y) & mine).any() else 0, int(rev[yr == y].sum())
         oc, os_, on = C.c_uint64(), C.c_int(), C.c_int()
         assert lib().orc_dec_quo(C.c_uint64(part), 4, 0, C.c_uint64(tot), 4, 0, C.byref(oc), C.byref(os_), C.byref(on)) == 0
-        rows.append((int(y), (oc.value, os_.value, on.value)))
+        rows.append((int(y), (oc.value, os_.value, on.value), part, tot))
     return rows
 
 

@@ -613,3 +613,126 @@ def q19_plan():
     flt = PhysicalOperator(POT_Filter, Outputs=jouts, Children=[j], Filters=[func("or", B, *groups)])
     agg = func("sum", K.DecimalType(38, 4), _disc_price(col(0, 1, DEC15_2), col(0, 2, DEC15_2)))
     return PhysicalOperator(POT_Agg, Outputs=[col(1, 0, K.DecimalType(38, 4))], Children=[flt], Info=AggOpInfo([agg], []))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Q5 / Q7 / Q8: multi-way joins through customer / supplier to nation (and region).  Plan trees only: they are executed by the
+# tree-walking oracle on the CPU (tests/test_oracle_golden.py) and their descriptors compile on the CPU; they were written after
+# the round's GPU budget was spent and have NOT been run through the GPU path.
+REGIONS = ["AFRICA", "AMERICA", "ASIA", "EUROPE", "MIDDLE EAST"]
+NATION_REGION = [0, 1, 1, 1, 4, 0, 3, 3, 2, 2, 4, 4, 2, 4, 0, 0, 0, 1, 2, 3, 4, 2, 3, 3, 1]          # n_regionkey by n_nationkey (dbgen)
+NATION_R = NATION + [("n_regionkey", L.PG_T_INT32, 0, 0, None)]
+REGION = [("r_regionkey", L.PG_T_INT32, 0, 0, None), ("r_name", L.PG_T_DICT8, 0, 0, REGIONS)]
+Q8_PART = [("p_partkey", L.PG_T_INT32, 0, 0, None), ("p_type", L.PG_T_DICT8, 0, 0, PTYPES)]
+
+
+class _Stack:
+    """a left-deep join stack that keeps track of the running output layout by column NAME"""
+
+    def __init__(self, table, cols, names, filters=None):
+        self.cols = cols                                      # {table: schema}
+        idx = {c[0]: i for i, c in enumerate(cols[table])}
+        self.node = PhysicalOperator(POT_Scan, Info=ScanOpInfo(table), Filters=filters or [])
+        self.layout = None                                    # None: the node is the bare scan, columns by table position
+        self.table, self.idx0 = table, idx
+        self.keep = list(names)
+
+    def ref(self, name):
+        if self.layout is None:
+            i = self.idx0[name]
+            return col(0, i, _ltype_of(self.cols[self.table][i]))
+        i, t = self.layout[name]
+        return col(0, i, t)
+
+    def join(self, table, on, take, filters=None, alias=None, jt=JOIN_INNER):
+        """on: [(left name, right column)], take: right columns appended to the layout (as alias + name when aliased)"""
+        B = K.LType(K.LTID_BOOLEAN)
+        sch = self.cols[table]
+        ridx = {c[0]: i for i, c in enumerate(sch)}
+        right = PhysicalOperator(POT_Scan, Info=ScanOpInfo(table), Filters=filters or [])
+        rref = lambda n: col(1, ridx[n], _ltype_of(sch[ridx[n]]))   # noqa: E731
+        conds = [func("=", B, self.ref(l), rref(r)) for l, r in on]
+        names = self.keep if self.layout is None else list(self.layout)
+        outs, layout = [], {}
+        for n in names:
+            e = self.ref(n)
+            layout[n] = (len(outs), e.DataTyp)
+            outs.append(e)
+        for n in take:
+            e = rref(n)
+            layout[(alias or "") + n] = (len(outs), e.DataTyp)
+            outs.append(e)
+        self.node = PhysicalOperator(POT_Join, Children=[self.node, right], Outputs=outs, Info=JoinOpInfo(jt, conds))
+        self.layout = layout
+        return self
+
+
+def q5_plan(region="AMERICA", year=1994):
+    """cases/tpch/query/q5.sql:  Agg(group by n_name; sum(l_extendedprice * (1 - l_discount)))
+      <- lineitem x orders[o_orderdate in year] x customer x supplier (l_suppkey = s_suppkey AND c_nationkey = s_nationkey)
+         x nation x region[r_name = region], left-deep with the fact table leftmost.  ORDER BY revenue desc stays with the host."""
+    B, V, D = K.LType(K.LTID_BOOLEAN), K.VarcharType(), K.DateType()
+    cols = {"lineitem": LINEITEM, "orders": ORDERS, "customer": CUSTOMER, "supplier": SUPPLIER, "nation": NATION_R, "region": REGION}
+    oi = {c[0]: i for i, c in enumerate(ORDERS)}
+    od = col(0, oi["o_orderdate"], D)
+    st = _Stack("lineitem", cols, ["l_orderkey", "l_suppkey", "l_extendedprice", "l_discount"])
+    st.join("orders", [("l_orderkey", "o_orderkey")], ["o_custkey"],
+            filters=[func(">=", B, od, const(days(year, 1, 1), D)), func("<", B, od, const(days(year + 1, 1, 1), D))])
+    st.join("customer", [("o_custkey", "c_custkey")], ["c_nationkey"])
+    st.join("supplier", [("l_suppkey", "s_suppkey"), ("c_nationkey", "s_nationkey")], ["s_nationkey"])
+    st.join("nation", [("s_nationkey", "n_nationkey")], ["n_name", "n_regionkey"])
+    st.join("region", [("n_regionkey", "r_regionkey")], [], filters=[func("=", B, col(0, 1, V), const(region, V))])
+    sum_t = K.DecimalType(38, 4)
+    agg = func("sum", sum_t, _disc_price(st.ref("l_extendedprice"), st.ref("l_discount")))
+    return PhysicalOperator(POT_Agg, Outputs=[col(0, 0, V), col(1, 0, sum_t)], Children=[st.node], Info=AggOpInfo([agg], [st.ref("n_name")]))
+
+
+def q7_plan(a="FRANCE", b="ARGENTINA"):
+    """cases/tpch/query/q7.sql:  Agg(group by supp_nation, cust_nation, extract(year from l_shipdate); sum(volume))
+      <- Filter((n1.n_name = a AND n2.n_name = b) OR (n1.n_name = b AND n2.n_name = a))
+      <- lineitem[l_shipdate between 1995-01-01 and 1996-12-31] x supplier x orders x customer x nation n1 x nation n2."""
+    B, V, I, D = K.LType(K.LTID_BOOLEAN), K.VarcharType(), K.IntegerType(), K.DateType()
+    cols = {"lineitem": LINEITEM, "orders": ORDERS, "customer": CUSTOMER, "supplier": SUPPLIER, "nation": NATION}
+    li = {c[0]: i for i, c in enumerate(LINEITEM)}
+    sd = col(0, li["l_shipdate"], D)
+    st = _Stack("lineitem", cols, ["l_orderkey", "l_suppkey", "l_extendedprice", "l_discount", "l_shipdate"],
+                filters=[func(">=", B, sd, const(days(1995, 1, 1), D)), func("<=", B, sd, const(days(1996, 12, 31), D))])
+    st.join("supplier", [("l_suppkey", "s_suppkey")], ["s_nationkey"])
+    st.join("orders", [("l_orderkey", "o_orderkey")], ["o_custkey"])
+    st.join("customer", [("o_custkey", "c_custkey")], ["c_nationkey"])
+    st.join("nation", [("s_nationkey", "n_nationkey")], ["n_name"], alias="n1.")
+    st.join("nation", [("c_nationkey", "n_nationkey")], ["n_name"], alias="n2.")
+    n1, n2 = st.ref("n1.n_name"), st.ref("n2.n_name")
+    pair = lambda x, y: func("and", B, func("=", B, n1, const(x, V)), func("=", B, n2, const(y, V)))   # noqa: E731
+    flt = PhysicalOperator(POT_Filter, Outputs=list(st.node.Outputs), Children=[st.node], Filters=[func("or", B, pair(a, b), pair(b, a))])
+    sum_t = K.DecimalType(38, 4)
+    groups = [n1, n2, func("extract", I, const("year", V), st.ref("l_shipdate"))]
+    agg = func("sum", sum_t, _disc_price(st.ref("l_extendedprice"), st.ref("l_discount")))
+    outs = [col(0, 0, V), col(0, 1, V), col(0, 2, I), col(1, 0, sum_t)]
+    return PhysicalOperator(POT_Agg, Outputs=outs, Children=[flt], Info=AggOpInfo([agg], groups))
+
+
+def q8_plan(nation="ARGENTINA", region="AMERICA", ptype="ECONOMY BURNISHED TIN"):
+    """cases/tpch/query/q8.sql below its final division:  Agg(group by extract(year from o_orderdate); sum(case when nation = X
+    then volume else 0 end), sum(volume)) <- lineitem x part[p_type = ..] x supplier x orders[o_orderdate between 1995-01-01 and
+    1996-12-31] x customer x nation n1 x region[r_name = ..] x nation n2.  mkt_share = a / b is a DECIMAL quotient above the
+    aggregate (host side)."""
+    B, V, I, D = K.LType(K.LTID_BOOLEAN), K.VarcharType(), K.IntegerType(), K.DateType()
+    cols = {"lineitem": LINEITEM, "orders": ORDERS, "customer": CUSTOMER, "supplier": SUPPLIER, "nation": NATION_R, "region": REGION, "part": Q8_PART}
+    oi = {c[0]: i for i, c in enumerate(ORDERS)}
+    od = col(0, oi["o_orderdate"], D)
+    st = _Stack("lineitem", cols, ["l_orderkey", "l_partkey", "l_suppkey", "l_extendedprice", "l_discount"])
+    st.join("part", [("l_partkey", "p_partkey")], [], filters=[func("=", B, col(0, 1, V), const(ptype, V))])
+    st.join("supplier", [("l_suppkey", "s_suppkey")], ["s_nationkey"])
+    st.join("orders", [("l_orderkey", "o_orderkey")], ["o_custkey", "o_orderdate"],
+            filters=[func(">=", B, od, const(days(1995, 1, 1), D)), func("<=", B, od, const(days(1996, 12, 31), D))])
+    st.join("customer", [("o_custkey", "c_custkey")], ["c_nationkey"])
+    st.join("nation", [("c_nationkey", "n_nationkey")], ["n_regionkey"], alias="n1.")
+    st.join("region", [("n1.n_regionkey", "r_regionkey")], [], filters=[func("=", B, col(0, 1, V), const(region, V))])
+    st.join("nation", [("s_nationkey", "n_nationkey")], ["n_name"], alias="n2.")
+    sum_t, v_t = K.DecimalType(38, 4), K.DecimalType(18, 4)
+    vol = _disc_price(st.ref("l_extendedprice"), st.ref("l_discount"))
+    mine = func("case", v_t, cast(const(0, I), v_t), func("=", B, st.ref("n2.n_name"), const(nation, V)), vol)
+    groups = [func("extract", I, const("year", V), st.ref("o_orderdate"))]
+    outs = [col(0, 0, I), col(1, 0, sum_t), col(1, 1, sum_t)]
+    return PhysicalOperator(POT_Agg, Outputs=outs, Children=[st.node], Info=AggOpInfo([func("sum", sum_t, mine), func("sum", sum_t, vol)], groups))

@@ -139,7 +139,7 @@ def test_q5_q7_q8_q11_q17_q21_q22_reproduce_reference_golden(oracle, sf1):
     dec = lambda v, s: oracle.fmt_decimal((v, s, 0), s)                          # noqa: E731
     assert oracle.rows_text(1, [(n, dec(v, 4)) for n, v in oracle.q5(cust, supp, orders, line)]) == gold(5)
     assert oracle.rows_text(3, [(a, b, y, dec(v, 4)) for a, b, y, v in oracle.q7(cust, supp, orders, line)]) == gold(7)
-    assert oracle.rows_text(1, [(y, oracle.fmt_decimal(q, 4)) for y, q in oracle.q8(cust, supp, orders, line, e12)]) == gold(8)
+    assert oracle.rows_text(1, [(y, oracle.fmt_decimal(q, 4)) for y, q, _a, _b in oracle.q8(cust, supp, orders, line, e12)]) == gold(8)
     assert oracle.rows_text(1, [(k, dec(v, 2)) for k, v in oracle.q11(supp, ps, e22)]) == gold(11)
     r17 = oracle.q17(line, e19)
     assert r17["rows"] == 558 and oracle.rows_text(0, [(r17["avg_yearly"],)]) == gold(17)
@@ -236,3 +236,33 @@ def test_row_oracle_agrees_with_the_golden_pinned_restatements(oracle):
         assert got == [] or got[0][0] is None
     else:
         assert got[0][0].signed() * 10 ** (4 - got[0][0].scale) == ref["revenue"]
+
+
+def test_row_oracle_runs_the_q5_q7_q8_plans(oracle):
+    """Six- to eight-table left-deep join stacks (a two-key join, the same dimension joined twice under two aliases, an OR of
+    two-sided string equalities above the joins, CASE inside a sum, extract(year)) as PhysicalOperator trees through the tree-walking
+    oracle: it must give what the numpy restatements give, which reproduce the reference's q5.txt / q7.txt / q8.txt at SF1."""
+    import numpy as np
+    from oracle import rowexec as R
+    from plan_b200 import tpch as T
+    sf = 0.02
+    orders, line = oracle.gen_orders_lineitem(sf)
+    cust, supp, x12 = oracle.gen_customer(sf), oracle.gen_supplier(sf), oracle.gen_q12_q14_columns(sf)
+    assert T.NATION_REGION == oracle.NATION_REGION and T.REGIONS == oracle.REGIONS
+    nation = {"n_nationkey": np.arange(25, dtype=np.int32), "n_name": np.arange(25, dtype=np.uint8), "n_regionkey": np.array(T.NATION_REGION, np.int32)}
+    region = {"r_regionkey": np.arange(5, dtype=np.int32), "r_name": np.arange(5, dtype=np.uint8)}
+    part = {"p_partkey": np.arange(1, len(x12["p_type"]) + 1, dtype=np.int32), "p_type": x12["p_type"]}
+    rows = R.table_rows
+    tabs = {"lineitem": rows(line, T.LINEITEM), "orders": rows(orders, T.ORDERS), "customer": rows(cust, T.CUSTOMER), "supplier": rows(supp, T.SUPPLIER),
+            "nation": rows(nation, T.NATION_R), "region": rows(region, T.REGION), "part": rows(part, T.Q8_PART)}
+    s4 = lambda v: v.signed() * 10 ** (4 - v.scale)   # noqa: E731
+    want = oracle.q5(cust, supp, orders, line)
+    assert len(want) == 5 and sorted((r[0], s4(r[1])) for r in R.execute(T.q5_plan(), tabs)) == sorted(want)
+    want = oracle.q7(cust, supp, orders, line)
+    assert len(want) == 4 and sorted((r[0], r[1], r[2], s4(r[3])) for r in R.execute(T.q7_plan(), tabs)) == want
+    want = oracle.q8(cust, supp, orders, line, x12)
+    got = sorted((r[0], s4(r[1]), s4(r[2])) for r in R.execute(T.q8_plan(), tabs))
+    assert len(want) == 2 and got == [(y, a, b) for y, _q, a, b in want]
+    for y, q, a, b in want:                                     # the host-side division above the aggregate: govalues Quo
+        d = R.dec_quo(R.Dec(a, 4), R.Dec(b, 4))
+        assert (d.coef, d.scale) == (q[0], q[1]) or (a == 0 and d.coef == 0)
