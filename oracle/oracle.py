@@ -467,6 +467,61 @@ def q22(cust, orders, extra22, codes=(10, 11, 26, 22, 19, 20, 27)):
     return [(int(c), int((m & (code == c)).sum()), int(ab[m & (code == c)].sum())) for c in sorted(set(code[m].tolist()))]
 
 
+def gen_supplier_text(sf):
+    """s_address (list of str), s_phone (list of str) and the `s_comment like '%Customer%Complaints%'` flag per supplier"""
+    L = lib()
+    n = L.tg_num_supp_pub(C.c_double(sf))
+    buf, ph, cp = C.create_string_buffer(41 * n), np.empty(3 * n, np.int32), np.empty(n, np.uint8)
+    L.tg_gen_supplier_text.restype = None
+    L.tg_gen_supplier_text.argtypes = [C.c_double, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.tg_gen_supplier_text(sf, 0, n, buf, _p(ph), _p(cp))
+    raw = buf.raw
+    nat = gen_supplier(sf)["s_nationkey"]
+    return {"s_address": [raw[41 * i:41 * i + 41].split(b"\0")[0].decode() for i in range(n)],
+            "s_phone": ["%d-%d-%d-%d" % (nat[i] + 10, ph[3 * i], ph[3 * i + 1], ph[3 * i + 2]) for i in range(n)],
+            "complaint": cp.astype(bool)}
+
+
+def q15(line, stext, date_lo=None, date_hi=None):
+    """cases/tpch/query/q15.sql: the supplier(s) with the largest revenue (scale 4) of the quarter;
+    (s_suppkey, s_name, s_address, s_phone, total_revenue)"""
+    date_lo = days(1995, 12, 1) if date_lo is None else date_lo
+    date_hi = days(1996, 3, 1) if date_hi is None else date_hi
+    m = (line["l_shipdate"] >= date_lo) & (line["l_shipdate"] < date_hi)
+    rev = np.zeros(len(stext["s_address"]) + 1, np.int64)          # < 2^63: a supplier holds ~600 lines of < 1e11 each
+    np.add.at(rev, line["l_suppkey"][m], line["l_extendedprice"][m] * (100 - line["l_discount"][m]))
+    best = int(rev.max())
+    return [(int(k), "Supplier#%09d" % k, stext["s_address"][k - 1], stext["s_phone"][k - 1], best) for k in np.nonzero(rev == best)[0]]
+
+
+def q16(partsupp, extra12, extra19, stext, brand="Brand#35", type_prefix="ECONOMY BURNISHED", sizes=(14, 7, 21, 24, 35, 33, 2, 20)):
+    """cases/tpch/query/q16.sql: count(distinct ps_suppkey) per (p_brand, p_type, p_size) without the complaint suppliers;
+    supplier_cnt desc, then the keys"""
+    pk = partsupp["ps_partkey"] - 1
+    b, t, z = extra19["p_brand"][pk], extra12["p_type"][pk], extra19["p_size"][pk]
+    m = ((b != BRANDS.index(brand)) & ~np.isin(t, [i for i, n in enumerate(PTYPES) if n.startswith(type_prefix)]) & np.isin(z, list(sizes)) &
+         ~stext["complaint"][partsupp["ps_suppkey"] - 1])
+    key = (b[m].astype(np.int64) * 150 + t[m]) * 64 + z[m]
+    g, cnt = np.unique(np.unique(key * (1 << 32) + partsupp["ps_suppkey"][m]) >> 32, return_counts=True)
+    rows = sorted((-int(c), BRANDS[int(k) // 64 // 150], PTYPES[int(k) // 64 % 150], int(k) % 64) for k, c in zip(g, cnt))
+    return [(bn, tn, sz, -c) for c, bn, tn, sz in rows]
+
+
+def q20(part, supp, partsupp, line, extra11, stext, prefix=b"lime", nation="VIETNAM", year=1993):
+    """cases/tpch/query/q20.sql: suppliers of the nation holding more than 0.5 * (the year's shipped quantity) of a part named
+    prefix%; (s_name, s_address) by s_name.  0.5 is a FLOAT literal: the comparison is float32, exact here (0.5 and sums < 2^24)."""
+    lime = np.array([nm.startswith(prefix) for nm in part["p_name"]])
+    m = (line["l_shipdate"] >= days(year, 1, 1)) & (line["l_shipdate"] < days(year + 1, 1, 1)) & lime[line["l_partkey"] - 1]
+    u, inv = np.unique(line["l_partkey"][m].astype(np.int64) * (1 << 32) + line["l_suppkey"][m], return_inverse=True)
+    sq = np.zeros(len(u), np.int64)
+    np.add.at(sq, inv, line["l_quantity"][m])
+    pkey = partsupp["ps_partkey"].astype(np.int64) * (1 << 32) + partsupp["ps_suppkey"]
+    pos = np.minimum(np.searchsorted(u, pkey), max(len(u) - 1, 0))
+    sel = (u[pos] == pkey) & (extra11["ps_availqty"].astype(np.float32) > np.float32(0.5) * sq[pos].astype(np.float32))   # no lines: NULL, not true
+    nk = nation_names().index(nation)
+    return [("Supplier#%09d" % k, stext["s_address"][k - 1]) for k in np.unique(partsupp["ps_suppkey"][sel]).tolist() if supp["s_nationkey"][k - 1] == nk]
+
+
 def rows_text(header_tabs, rows):
     """the reference's result file: '#' + one tab per column after the first, then tab-separated rows"""
     return "#" + "\t" * header_tabs + "\n" + "".join("\t".join(str(x) for x in r) + "\n" for r in rows)

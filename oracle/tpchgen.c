@@ -357,3 +357,47 @@ void tg_gen_q11_q22_draws(double sf, int64_t c_lo, int64_t c_hi, int64_t *c_acct
         for (int64_t r = 0; r < 4 * (p_hi - p_lo); r++) ps_availqty[r] = (int32_t)tg_draw(&s, 1, 9999);
     }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Supplier text columns of TPC-H Q15 / Q16 / Q20 (cases/tpch/query/q15.sql, q16.sql, q20.sql):
+ *   s_address  dbgen a_rnd(10, 40, S_ADDR_SD): a length draw, then one UnifInt(0, MAX_LONG) draw per 5 characters, 6 bits per character
+ *              indexing the 64-character alphabet below (the draw is NEGATIVE: dbgen's int32 range wraps; `& 077` and `>>= 6`
+ *              then act on the two's complement, which the golden addresses confirm); the stream advances 9 draws per supplier
+ *   s_phone    "CC-LLL-LLL-LLLL": CC = 10 + s_nationkey, then UnifInt(100,999), UnifInt(100,999), UnifInt(1000,9999) from S_PHNE_SD
+ *              (3 draws per supplier)
+ *   complaint  dbgen plants "Customer ... Complaints" into s_comment when UnifInt(1,10000, BBB_CMNT_SD) <= 10 and
+ *              UnifInt(0,100, BBB_TYPE_SD) < 50 (else "Customer ... Recommends"); the grammar-generated comment text itself never
+ *              holds the word "Customer", so the flag IS `s_comment like '%Customer%Complaints%'`
+ * Pinned by the reference's golden cases/tpch/1g/plan/q15.txt (one address + phone), q20.txt (177 addresses) and q16.txt (whose counts
+ * imply exactly the complaint suppliers 358, 2820, 3804, 9504 at SF1: the two BBB seeds below are the ones that select them).
+ */
+enum { SD_S_ADDR = 706178559, SD_S_PHNE = 884434366, SD_BBB_CMNT = 202794285, SD_BBB_TYPE = 753643799 };
+static const char TG_ALNUM[65] = "0123456789abcdefghijklmnopqrstuvwxyz ABCDEFGHIJKLMNOPQRSTUVWXYZ,";
+
+/* addr_buf: 41 bytes per supplier (NUL-terminated); phone: 3 ints per supplier; complaint: 1 byte per supplier */
+void tg_gen_supplier_text(double sf, int64_t s_lo, int64_t s_hi, char *addr_buf, int32_t *phone, uint8_t *complaint)
+{
+    (void)sf;
+    int64_t s_ph = tg_jump(SD_S_PHNE, 3 * s_lo), s_bc = tg_jump(SD_BBB_CMNT, s_lo), s_bt = tg_jump(SD_BBB_TYPE, s_lo);
+    for (int64_t i = s_lo; i < s_hi; i++) {
+        if (addr_buf) {
+            int64_t s = tg_jump(SD_S_ADDR, 9 * i);
+            char *dst = addr_buf + 41 * (i - s_lo);
+            const int64_t len = tg_draw(&s, 10, 40);
+            int64_t bits = 0;
+            for (int64_t k = 0; k < len; k++) {
+                if (k % 5 == 0) {       /* UnifInt(0, MAX_LONG): dbgen computes the range in int32, 2^31-1 - 0 + 1 wraps to -2^31 */
+                    s = (s * TG_A) % TG_M;
+                    bits = (int64_t)(((double)s / 2147483647.0) * -2147483648.0);
+                }
+                dst[k] = TG_ALNUM[bits & 63];
+                bits >>= 6;
+            }
+            dst[len] = 0;
+        }
+        const int64_t p1 = tg_draw(&s_ph, 100, 999), p2 = tg_draw(&s_ph, 100, 999), p3 = tg_draw(&s_ph, 1000, 9999);
+        if (phone) { phone[3 * (i - s_lo)] = (int32_t)p1; phone[3 * (i - s_lo) + 1] = (int32_t)p2; phone[3 * (i - s_lo) + 2] = (int32_t)p3; }
+        const int64_t bad = tg_draw(&s_bc, 1, 10000), type = tg_draw(&s_bt, 0, 100);
+        if (complaint) complaint[i - s_lo] = (uint8_t)(bad <= 10 && type < 50);
+    }
+}

@@ -67,8 +67,10 @@ def test_golden_copies_are_the_reference_files():
     ref = "/root/reference/cases/tpch/1g/plan"
     if not os.path.isdir(ref):
         pytest.skip("reference tree not present")
-    for q in (1, 3, 4, 5, 6, 7, 8, 9, 11, 12, 14, 17, 18, 19, 21, 22):
+    for q in (1, 3, 4, 5, 6, 7, 8, 9, 11, 12, 14, 15, 17, 18, 19, 20, 21, 22):
         assert open(os.path.join(GOLDEN, "ref_sf1_q%d.txt" % q), "rb").read() == open(os.path.join(ref, "q%d.txt" % q), "rb").read(), q
+    import gzip
+    assert gzip.open(os.path.join(GOLDEN, "ref_sf1_q16.txt.gz"), "rb").read() == open(os.path.join(ref, "q16.txt"), "rb").read()
 
 
 def test_q6_reproduces_reference_golden(oracle, sf1):
@@ -145,6 +147,24 @@ def test_q5_q7_q8_q11_q17_q21_q22_reproduce_reference_golden(oracle, sf1):
     assert r17["rows"] == 558 and oracle.rows_text(0, [(r17["avg_yearly"],)]) == gold(17)
     assert oracle.rows_text(1, oracle.q21(supp, orders, line)) == gold(21)
     assert oracle.rows_text(2, [(c, n, dec(v, 2)) for c, n, v in oracle.q22(cust, orders, e22)]) == gold(22)
+
+
+def test_q15_q16_q20_reproduce_reference_golden(oracle, sf1):
+    """cases/tpch/1g/plan/q15.txt, q16.txt (18341 rows, kept gzipped) and q20.txt (177 rows), byte for byte: they pin dbgen's
+    generated supplier TEXT -- s_address (a_rnd over the 64-character alphabet, with dbgen's wrapped int32 range), s_phone, and the
+    suppliers whose comment holds "Customer ... Complaints" (BBB streams) -- plus p_name prefixes and ps_availqty against the
+    per-(part, supplier) shipped quantity."""
+    import gzip
+    line = sf1["lineitem"]
+    supp, ps, part = oracle.gen_supplier(1.0), oracle.gen_partsupp(1.0), oracle.gen_part(1.0)
+    e12, e19, e22, st = oracle.gen_q12_q14_columns(1.0), oracle.gen_q19_columns(1.0), oracle.gen_q11_q22_columns(1.0), oracle.gen_supplier_text(1.0)
+    assert st["s_address"][0] == " N kD4on9OM Ipw3,gf0JBoQDd7tgrzrddZ" and st["s_phone"][0] == "27-918-335-1736"      # official supplier.tbl row 1
+    assert (np.nonzero(st["complaint"])[0] + 1).tolist() == [358, 2820, 3804, 9504]
+    gold = lambda q: open(os.path.join(GOLDEN, "ref_sf1_q%d.txt" % q)).read()   # noqa: E731
+    rows = [(k, n, a, p, oracle.fmt_decimal((v, 4, 0), 4)) for k, n, a, p, v in oracle.q15(line, st)]
+    assert oracle.rows_text(4, rows) == gold(15)
+    assert oracle.rows_text(3, oracle.q16(ps, e12, e19, st)) == gzip.open(os.path.join(GOLDEN, "ref_sf1_q16.txt.gz"), "rt").read()
+    assert oracle.rows_text(1, oracle.q20(part, supp, ps, line, e22, st)) == gold(20)
 
 
 def test_q3_reproduces_reference_golden(oracle, sf1):
