@@ -467,19 +467,35 @@ def q22(cust, orders, extra22, codes=(10, 11, 26, 22, 19, 20, 27)):
     return [(int(c), int((m & (code == c)).sum()), int(ab[m & (code == c)].sum())) for c in sorted(set(code[m].tolist()))]
 
 
+def _addresses(buf, n):
+    raw = buf.raw
+    return [raw[41 * i:41 * i + 41].split(b"\0")[0].decode() for i in range(n)]
+
+
+def _phones(nat, ph):
+    return ["%d-%d-%d-%d" % (nat[i] + 10, ph[3 * i], ph[3 * i + 1], ph[3 * i + 2]) for i in range(len(nat))]
+
+
 def gen_supplier_text(sf):
-    """s_address (list of str), s_phone (list of str) and the `s_comment like '%Customer%Complaints%'` flag per supplier"""
+    """s_address / s_phone (lists of str), s_acctbal (cents) and the `s_comment like '%Customer%Complaints%'` flag per supplier"""
     L = lib()
     n = L.tg_num_supp_pub(C.c_double(sf))
-    buf, ph, cp = C.create_string_buffer(41 * n), np.empty(3 * n, np.int32), np.empty(n, np.uint8)
+    buf, ph, cp, ab = C.create_string_buffer(41 * n), np.empty(3 * n, np.int32), np.empty(n, np.uint8), np.empty(n, np.int64)
     L.tg_gen_supplier_text.restype = None
-    L.tg_gen_supplier_text.argtypes = [C.c_double, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
-    L.tg_gen_supplier_text(sf, 0, n, buf, _p(ph), _p(cp))
-    raw = buf.raw
-    nat = gen_supplier(sf)["s_nationkey"]
-    return {"s_address": [raw[41 * i:41 * i + 41].split(b"\0")[0].decode() for i in range(n)],
-            "s_phone": ["%d-%d-%d-%d" % (nat[i] + 10, ph[3 * i], ph[3 * i + 1], ph[3 * i + 2]) for i in range(n)],
-            "complaint": cp.astype(bool)}
+    L.tg_gen_supplier_text.argtypes = [C.c_double, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.tg_gen_supplier_text(sf, 0, n, buf, _p(ph), _p(cp), _p(ab))
+    return {"s_address": _addresses(buf, n), "s_phone": _phones(gen_supplier(sf)["s_nationkey"], ph), "complaint": cp.astype(bool), "s_acctbal": ab}
+
+
+def gen_customer_text(sf, cust):
+    """c_address / c_phone (lists of str) per customer"""
+    L = lib()
+    n = len(cust["c_custkey"])
+    buf, ph = C.create_string_buffer(41 * n), np.empty(3 * n, np.int32)
+    L.tg_gen_customer_text.restype = None
+    L.tg_gen_customer_text.argtypes = [C.c_double, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
+    L.tg_gen_customer_text(sf, 0, n, buf, _p(ph))
+    return {"c_address": _addresses(buf, n), "c_phone": _phones(cust["c_nationkey"], ph)}
 
 
 def q15(line, stext, date_lo=None, date_hi=None):
@@ -520,6 +536,39 @@ def q20(part, supp, partsupp, line, extra11, stext, prefix=b"lime", nation="VIET
     sel = (u[pos] == pkey) & (extra11["ps_availqty"].astype(np.float32) > np.float32(0.5) * sq[pos].astype(np.float32))   # no lines: NULL, not true
     nk = nation_names().index(nation)
     return [("Supplier#%09d" % k, stext["s_address"][k - 1]) for k in np.unique(partsupp["ps_suppkey"][sel]).tolist() if supp["s_nationkey"][k - 1] == nk]
+
+
+def q10(cust, orders, line, extra22, ctext, date_lo=None, date_hi=None, limit=20):
+    """cases/tpch/query/q10.sql WITHOUT its last column (c_comment is grammar-generated text the generator does not restate):
+    (c_custkey, c_name, revenue scale 4, c_acctbal scale 2 signed, n_name, c_address, c_phone), revenue desc, limit 20"""
+    date_lo = days(1993, 3, 1) if date_lo is None else date_lo
+    date_hi = days(1993, 6, 1) if date_hi is None else date_hi
+    oidx = np.searchsorted(orders["o_orderkey"], line["l_orderkey"])
+    od = orders["o_orderdate"][oidx]
+    m = (od >= date_lo) & (od < date_hi) & (line["l_returnflag"] == ord("R"))
+    rev = np.zeros(len(cust["c_custkey"]) + 1, np.int64)
+    np.add.at(rev, orders["o_custkey"][oidx][m], line["l_extendedprice"][m] * (100 - line["l_discount"][m]))
+    names = nation_names()
+    top = sorted((-int(rev[k]), int(k)) for k in np.nonzero(rev)[0])[:limit]
+    return [(k, "Customer#%09d" % k, -r, int(extra22["c_acctbal"][k - 1]), names[cust["c_nationkey"][k - 1]], ctext["c_address"][k - 1],
+             ctext["c_phone"][k - 1]) for r, k in top]
+
+
+def q2(supp, partsupp, extra12, extra19, stext, size=48, type_suffix="TIN", region="MIDDLE EAST", limit=100):
+    """cases/tpch/query/q2.sql WITHOUT its last column (s_comment): (s_acctbal scale 2 signed, s_name, n_name, p_partkey, p_mfgr,
+    s_address, s_phone) of the region's cheapest supplier(s) of every matching part; s_acctbal desc, n_name, s_name, p_partkey"""
+    names, nreg = nation_names(), np.array(NATION_REGION)
+    in_reg = nreg[supp["s_nationkey"][partsupp["ps_suppkey"] - 1]] == REGIONS.index(region)
+    mincost = np.full(len(extra19["p_size"]) + 1, 1 << 62, np.int64)
+    np.minimum.at(mincost, partsupp["ps_partkey"][in_reg], partsupp["ps_supplycost"][in_reg])
+    pk = partsupp["ps_partkey"] - 1
+    suffix = np.array([t.endswith(type_suffix) for t in PTYPES])
+    m = in_reg & (extra19["p_size"][pk] == size) & suffix[extra12["p_type"][pk]] & (partsupp["ps_supplycost"] == mincost[partsupp["ps_partkey"]])
+    rows = []
+    for p, k in zip(partsupp["ps_partkey"][m].tolist(), partsupp["ps_suppkey"][m].tolist()):
+        rows.append((-int(stext["s_acctbal"][k - 1]), names[supp["s_nationkey"][k - 1]], "Supplier#%09d" % k, p,
+                     "Manufacturer#%d" % (extra19["p_brand"][p - 1] // 5 + 1), stext["s_address"][k - 1], stext["s_phone"][k - 1]))
+    return [(-b, sn, nn, p, mf, a, ph) for b, nn, sn, p, mf, a, ph in sorted(rows)[:limit]]
 
 
 def rows_text(header_tabs, rows):

@@ -374,30 +374,49 @@ void tg_gen_q11_q22_draws(double sf, int64_t c_lo, int64_t c_hi, int64_t *c_acct
 enum { SD_S_ADDR = 706178559, SD_S_PHNE = 884434366, SD_BBB_CMNT = 202794285, SD_BBB_TYPE = 753643799 };
 static const char TG_ALNUM[65] = "0123456789abcdefghijklmnopqrstuvwxyz ABCDEFGHIJKLMNOPQRSTUVWXYZ,";
 
-/* addr_buf: 41 bytes per supplier (NUL-terminated); phone: 3 ints per supplier; complaint: 1 byte per supplier */
-void tg_gen_supplier_text(double sf, int64_t s_lo, int64_t s_hi, char *addr_buf, int32_t *phone, uint8_t *complaint)
+/* dbgen a_rnd(10, 40, stream) for row i of a 9-draws-per-row stream; dst holds 41 bytes */
+static void tg_address(int64_t seed0, int64_t i, char *dst)
+{
+    int64_t s = tg_jump(seed0, 9 * i);
+    const int64_t len = tg_draw(&s, 10, 40);
+    int64_t bits = 0;
+    for (int64_t k = 0; k < len; k++) {
+        if (k % 5 == 0) {       /* UnifInt(0, MAX_LONG): dbgen computes the range in int32, 2^31-1 - 0 + 1 wraps to -2^31 */
+            s = (s * TG_A) % TG_M;
+            bits = (int64_t)(((double)s / 2147483647.0) * -2147483648.0);
+        }
+        dst[k] = TG_ALNUM[bits & 63];
+        bits >>= 6;
+    }
+    dst[len] = 0;
+}
+
+/* addr_buf: 41 bytes per supplier (NUL-terminated); phone: 3 ints per supplier; complaint: 1 byte per supplier;
+ * acctbal: UnifInt(-99999, 999999) cents from S_ABAL_SD */
+enum { SD_S_ABAL = 962338209, SD_C_ADDR = 881155353, SD_C_PHNE = 1521138112 };
+
+void tg_gen_supplier_text(double sf, int64_t s_lo, int64_t s_hi, char *addr_buf, int32_t *phone, uint8_t *complaint, int64_t *acctbal)
 {
     (void)sf;
-    int64_t s_ph = tg_jump(SD_S_PHNE, 3 * s_lo), s_bc = tg_jump(SD_BBB_CMNT, s_lo), s_bt = tg_jump(SD_BBB_TYPE, s_lo);
+    int64_t s_ph = tg_jump(SD_S_PHNE, 3 * s_lo), s_bc = tg_jump(SD_BBB_CMNT, s_lo), s_bt = tg_jump(SD_BBB_TYPE, s_lo), s_ab = tg_jump(SD_S_ABAL, s_lo);
     for (int64_t i = s_lo; i < s_hi; i++) {
-        if (addr_buf) {
-            int64_t s = tg_jump(SD_S_ADDR, 9 * i);
-            char *dst = addr_buf + 41 * (i - s_lo);
-            const int64_t len = tg_draw(&s, 10, 40);
-            int64_t bits = 0;
-            for (int64_t k = 0; k < len; k++) {
-                if (k % 5 == 0) {       /* UnifInt(0, MAX_LONG): dbgen computes the range in int32, 2^31-1 - 0 + 1 wraps to -2^31 */
-                    s = (s * TG_A) % TG_M;
-                    bits = (int64_t)(((double)s / 2147483647.0) * -2147483648.0);
-                }
-                dst[k] = TG_ALNUM[bits & 63];
-                bits >>= 6;
-            }
-            dst[len] = 0;
-        }
+        if (addr_buf) tg_address(SD_S_ADDR, i, addr_buf + 41 * (i - s_lo));
         const int64_t p1 = tg_draw(&s_ph, 100, 999), p2 = tg_draw(&s_ph, 100, 999), p3 = tg_draw(&s_ph, 1000, 9999);
         if (phone) { phone[3 * (i - s_lo)] = (int32_t)p1; phone[3 * (i - s_lo) + 1] = (int32_t)p2; phone[3 * (i - s_lo) + 2] = (int32_t)p3; }
-        const int64_t bad = tg_draw(&s_bc, 1, 10000), type = tg_draw(&s_bt, 0, 100);
+        const int64_t bad = tg_draw(&s_bc, 1, 10000), type = tg_draw(&s_bt, 0, 100), bal = tg_draw(&s_ab, -99999, 999999);
         if (complaint) complaint[i - s_lo] = (uint8_t)(bad <= 10 && type < 50);
+        if (acctbal) acctbal[i - s_lo] = bal;
+    }
+}
+
+/* c_address / c_phone of customers [c_lo, c_hi) (Q10), same construction from C_ADDR_SD / C_PHNE_SD */
+void tg_gen_customer_text(double sf, int64_t c_lo, int64_t c_hi, char *addr_buf, int32_t *phone)
+{
+    (void)sf;
+    int64_t s_ph = tg_jump(SD_C_PHNE, 3 * c_lo);
+    for (int64_t i = c_lo; i < c_hi; i++) {
+        if (addr_buf) tg_address(SD_C_ADDR, i, addr_buf + 41 * (i - c_lo));
+        const int64_t p1 = tg_draw(&s_ph, 100, 999), p2 = tg_draw(&s_ph, 100, 999), p3 = tg_draw(&s_ph, 1000, 9999);
+        if (phone) { phone[3 * (i - c_lo)] = (int32_t)p1; phone[3 * (i - c_lo) + 1] = (int32_t)p2; phone[3 * (i - c_lo) + 2] = (int32_t)p3; }
     }
 }
