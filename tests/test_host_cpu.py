@@ -448,6 +448,52 @@ def test_row_program_capacity_limits_are_refusals(tmp_path):
     assert "fail" not in r and _max_depth(r["ins"], 0, len(r["ins"]))[1] == {1}
 
 
+def test_row_program_compiler_survives_mutated_descriptors(tmp_path):
+    """Word-level mutations of valid descriptors that still PARSE reach the stages behind the parser -- plan-time lowering
+    (lower_filters / lower_affprod) and the row-program compiler -- with out-of-range columns, wrong types, unknown functions and
+    absurd constants.  Under ASan / UBSan every one must end in a listing or a refusal message (16000 such cases were run once
+    while writing this test; 750 are kept here)."""
+    import random
+    import subprocess
+    from plan_b200 import _lib as L, chunk as K, compute as X, tpch as T
+    B, V, I = K.LType(K.LTID_BOOLEAN), K.VarcharType(), K.IntegerType()
+    S = T.Schema(lineitem=T.Q19_LINEITEM)
+    lc = lambda n: S.col("lineitem", n)   # noqa: E731
+    one = X.cast(X.const(1, I), K.DecimalType(15, 2))
+    rev = X.func("*", K.DecimalType(18, 4), X.cast(lc("l_extendedprice"), K.DecimalType(16, 2)), X.func("-", K.DecimalType(16, 2), one, lc("l_discount")))
+    case3 = X.func("case", K.DecimalType(18, 4), X.cast(X.const(0, I), K.DecimalType(18, 4)), X.func("=", B, lc("l_shipmode"), X.const("AIR", V)), rev,
+                   X.func("<", B, lc("l_quantity"), X.const(10, I)), lc("l_extendedprice"))
+    quo = X.func("/", K.DecimalType(38, 6), lc("l_extendedprice"), lc("l_discount"))
+    scan0 = X.PhysicalOperator(X.POT_Scan, Info=X.ScanOpInfo("lineitem"))
+    proj = X.PhysicalOperator(X.POT_Project, Outputs=[rev, case3, quo], Children=[scan0])
+    joined = [("l_quantity", L.PG_T_INT32, 0, 0, None), ("l_extendedprice", L.PG_T_DECIMAL64, 15, 2, None), ("l_discount", L.PG_T_DECIMAL64, 15, 2, None),
+              ("l_shipmode", L.PG_T_DICT8, 0, 0, T.SHIPMODES), ("l_shipinstruct", L.PG_T_DICT8, 0, 0, T.SHIPINSTRUCT), ("p_brand", L.PG_T_DICT8, 0, 0, T.BRANDS),
+              ("p_size", L.PG_T_INT32, 0, 0, None), ("p_container", L.PG_T_DICT8, 0, 0, T.CONTAINERS)]
+    flt19 = X.PhysicalOperator(X.POT_Scan, Info=X.ScanOpInfo("joined"), Filters=T.q19_plan().Children[0].Filters)
+    cases = [("filters", T.Q12_LINEITEM, T.q12_plan().Children[0].Children[0]), ("exprs", T.Q19_LINEITEM, proj), ("filters", joined, flt19),
+             ("lower", T.LINEITEM, T.q6_plan()), ("lower", T.LINEITEM, T.q1_plan())]
+    _rowvm_listing(tmp_path, T.Q19_LINEITEM, "exprs", proj)                       # builds the harness
+    exe = _RV_EXE["exe"]
+    rng = random.Random(11)
+    outcomes = set()
+    for mode, schema, op in cases:
+        base = [int(w) for w in X.serialize_plan(op)[0]]
+        head = "%d %s\n" % (len(schema), " ".join("%d %d %d %s" % (t, sc, len(d or []), " ".join(x.replace(" ", "_") for x in (d or [])))
+                                                    for _, t, _w, sc, d in schema))
+        for _ in range(150):
+            d = list(base)
+            for _ in range(rng.randrange(1, 4)):
+                i = rng.randrange(2, len(d))
+                d[i] = rng.choice([0, 1, -1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 19, 20, 23, 24, 38, 39, 40, 63, 64, 255, 1 << 31, 1 << 40, -(1 << 62),
+                                   d[i] + 1, d[i] - 1])
+            r = subprocess.run([exe], input=head + mode + " " + " ".join(map(str, d)) + "\n", capture_output=True, text=True)
+            assert r.returncode == 0, (mode, [(i, a, b) for i, (a, b) in enumerate(zip(base, d)) if a != b], r.stderr[-1500:])
+            first = r.stdout.split("\n")[0]
+            assert first == "ok" or first.startswith("fail "), first
+            outcomes.add(first[:24])
+    assert "ok" in outcomes and len(outcomes) > 8                                 # the mutations did reach the later stages
+
+
 def test_lowering_of_q6_and_q1_on_the_cpu(tmp_path):
     """What the specialised scan kernels are given, computed by the product's plan-time lowering (plan_ir.hpp) on the host: Q6's
     float32 BETWEEN on a DECIMAL(15,2) column becomes the integer range [2, 4] (cents), its date / quantity comparisons inclusive
