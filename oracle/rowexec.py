@@ -18,8 +18,9 @@ It evaluates the same PhysicalOperator / Expr trees the GPU path is given (plan_
 Pinning: the reference holds no golden vector for these operators in isolation (its Go tests assert no numeric results), so
 this module is pinned indirectly -- its decimal arithmetic is oracle/decimal.h (checked against the reference's golden Q1 / Q6
 files), CASE / OR / IN / LIKE inside aggregates over a join are pinned by the reference's golden q12.txt / q14.txt through
-oracle.q12 / oracle.q14 and the GPU test that reproduces both files; row-level DECIMAL division and LEFT / MARK join outputs
-are PARITY UNPINNED against the reference.
+oracle.q12 / oracle.q14 and the GPU test that reproduces both files; MARK joins by q4.txt, multi-way join stacks by q5.txt / q7.txt /
+q8.txt (tests/test_oracle_golden.py runs those plans through this module); a DECIMAL quotient by q8.txt.  LEFT join outputs and
+DECIMAL division evaluated per row are PARITY UNPINNED against the reference.
 
 Values: None (NULL) | bool | int | Dec(coef, scale, neg) | np.float32 | str.
 """
