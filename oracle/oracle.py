@@ -538,9 +538,46 @@ def q20(part, supp, partsupp, line, extra11, stext, prefix=b"lime", nation="VIET
     return [("Supplier#%09d" % k, stext["s_address"][k - 1]) for k in np.unique(partsupp["ps_suppkey"][sel]).tolist() if supp["s_nationkey"][k - 1] == nk]
 
 
+COMMENT_STREAMS = {"c_comment": (1335826707, 73), "s_comment": (1341315363, 63), "o_comment": (276090261, 49)}   # (stream seed, average length)
+
+
+def comments(column, rows):
+    """the generated text of `column` for the given 0-based rows (dbgen cuts every comment out of one 300 MiB text pool;
+    oracle/tpchgen.c restates the pool).  The ~10 in 10000 suppliers whose comment dbgen overwrites with "Customer ... Complaints /
+    Recommends" (gen_supplier_text's flag covers the Complaints half) come back with their un-overwritten text."""
+    L = lib()
+    L.tg_text_pool.restype = C.c_void_p
+    L.tg_comment_spans.restype = None
+    L.tg_comment_spans.argtypes = [C.c_int64, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
+    base = L.tg_text_pool()
+    assert base, "text pool allocation failed"
+    seed, avg = COMMENT_STREAMS[column]
+    out = []
+    off, ln = np.empty(1, np.int64), np.empty(1, np.int32)
+    for r in rows:
+        L.tg_comment_spans(seed, avg, int(r), int(r) + 1, _p(off), _p(ln))
+        out.append(C.string_at(base + int(off[0]), int(ln[0])).decode())
+    return out
+
+
+def q13(orders, ncust, w1=b"pending", w2=b"accounts"):
+    """cases/tpch/query/q13.sql: customers LEFT JOIN orders (o_comment not like '%pending%accounts%'), count(o_orderkey) per
+    customer, then customers per count; custdist desc, c_count desc.  A customer without a surviving order has c_count NULL in the
+    reference (count over no non-NULL input, function_aggr.go), printed "NULL"."""
+    L = lib()
+    L.tg_comments_like2.argtypes = [C.c_int64, C.c_int, C.c_int64, C.c_int64, C.c_char_p, C.c_char_p, C.c_void_p]
+    flags = np.empty(len(orders["o_custkey"]), np.uint8)
+    seed, avg = COMMENT_STREAMS["o_comment"]
+    assert L.tg_comments_like2(seed, avg, 0, len(flags), w1, w2, _p(flags)) == 0
+    cnt = np.bincount(orders["o_custkey"][flags == 0], minlength=ncust + 1)[1:]
+    dist = np.bincount(cnt)
+    rows = sorted((-int(n), -int(c)) for c, n in enumerate(dist) if n)
+    return [(None if c == 0 else -c, -n) for n, c in rows]
+
+
 def q10(cust, orders, line, extra22, ctext, date_lo=None, date_hi=None, limit=20):
-    """cases/tpch/query/q10.sql WITHOUT its last column (c_comment is grammar-generated text the generator does not restate):
-    (c_custkey, c_name, revenue scale 4, c_acctbal scale 2 signed, n_name, c_address, c_phone), revenue desc, limit 20"""
+    """cases/tpch/query/q10.sql: (c_custkey, c_name, revenue scale 4, c_acctbal scale 2 signed, n_name, c_address, c_phone, c_comment),
+    revenue desc, limit 20"""
     date_lo = days(1993, 3, 1) if date_lo is None else date_lo
     date_hi = days(1993, 6, 1) if date_hi is None else date_hi
     oidx = np.searchsorted(orders["o_orderkey"], line["l_orderkey"])
@@ -550,13 +587,14 @@ def q10(cust, orders, line, extra22, ctext, date_lo=None, date_hi=None, limit=20
     np.add.at(rev, orders["o_custkey"][oidx][m], line["l_extendedprice"][m] * (100 - line["l_discount"][m]))
     names = nation_names()
     top = sorted((-int(rev[k]), int(k)) for k in np.nonzero(rev)[0])[:limit]
+    cm = comments("c_comment", [k - 1 for _, k in top])
     return [(k, "Customer#%09d" % k, -r, int(extra22["c_acctbal"][k - 1]), names[cust["c_nationkey"][k - 1]], ctext["c_address"][k - 1],
-             ctext["c_phone"][k - 1]) for r, k in top]
+             ctext["c_phone"][k - 1], cm[i]) for i, (r, k) in enumerate(top)]
 
 
 def q2(supp, partsupp, extra12, extra19, stext, size=48, type_suffix="TIN", region="MIDDLE EAST", limit=100):
-    """cases/tpch/query/q2.sql WITHOUT its last column (s_comment): (s_acctbal scale 2 signed, s_name, n_name, p_partkey, p_mfgr,
-    s_address, s_phone) of the region's cheapest supplier(s) of every matching part; s_acctbal desc, n_name, s_name, p_partkey"""
+    """cases/tpch/query/q2.sql: (s_acctbal scale 2 signed, s_name, n_name, p_partkey, p_mfgr, s_address, s_phone, s_comment) of the
+    region's cheapest supplier(s) of every matching part; s_acctbal desc, n_name, s_name, p_partkey"""
     names, nreg = nation_names(), np.array(NATION_REGION)
     in_reg = nreg[supp["s_nationkey"][partsupp["ps_suppkey"] - 1]] == REGIONS.index(region)
     mincost = np.full(len(extra19["p_size"]) + 1, 1 << 62, np.int64)
@@ -567,8 +605,10 @@ def q2(supp, partsupp, extra12, extra19, stext, size=48, type_suffix="TIN", regi
     rows = []
     for p, k in zip(partsupp["ps_partkey"][m].tolist(), partsupp["ps_suppkey"][m].tolist()):
         rows.append((-int(stext["s_acctbal"][k - 1]), names[supp["s_nationkey"][k - 1]], "Supplier#%09d" % k, p,
-                     "Manufacturer#%d" % (extra19["p_brand"][p - 1] // 5 + 1), stext["s_address"][k - 1], stext["s_phone"][k - 1]))
-    return [(-b, sn, nn, p, mf, a, ph) for b, nn, sn, p, mf, a, ph in sorted(rows)[:limit]]
+                     "Manufacturer#%d" % (extra19["p_brand"][p - 1] // 5 + 1), stext["s_address"][k - 1], stext["s_phone"][k - 1], k))
+    rows = sorted(rows)[:limit]
+    cm = comments("s_comment", [r[7] - 1 for r in rows])
+    return [(-b, sn, nn, p, mf, a, ph, cm[i]) for i, (b, nn, sn, p, mf, a, ph, _k) in enumerate(rows)]
 
 
 def rows_text(header_tabs, rows):

@@ -420,3 +420,166 @@ void tg_gen_customer_text(double sf, int64_t c_lo, int64_t c_hi, char *addr_buf,
         if (phone) { phone[3 * (i - c_lo)] = (int32_t)p1; phone[3 * (i - c_lo) + 1] = (int32_t)p2; phone[3 * (i - c_lo) + 2] = (int32_t)p3; }
     }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * dbgen's comment text (every *_comment column; TPC-H Q2 / Q10 print one, Q13 filters on o_comment).
+ * dbgen pre-generates ONE 300 MiB pool of pseudo-English from stream 5 and cuts every comment out of it:
+ *   pool      sentences appended with one blank between them until 300 * 2^20 bytes are filled (the last one truncated).
+ *             sentence = a form of `grammar` (N V T | N V P T | N V N T | N P V N T | N P V P T): N = noun phrase (a form of
+ *             `np`: N | J N | J, J N | D J N), V = verb phrase (a form of `vp`: V | X V | V D | X V D), P = preposition + " the "
+ *             + noun phrase, T = terminator glued to the previous word.  Every choice is pick_str: UnifInt(1, total weight)
+ *             against the cumulative weights of dists.dss, one draw each, all from the same stream.
+ *   comment   offset = UnifInt(0, pool size - max), length = UnifInt(min, max) from the column's own stream (2 draws per row),
+ *             min / max = int(0.4 * avg) / int(1.6 * avg); avg = 73 (c_comment), 63 (s_comment), 49 (o_comment).
+ * Word lists and weights are dists.dss's.  Pinned by the reference's golden q2.txt (100 s_comment values) and q10.txt (20
+ * c_comment values): all 120 are reproduced byte for byte, at offsets spread over the whole pool, which fixes every list member's
+ * LENGTH and weight; the spelling of one weight-1 preposition ("whithout", dists.dss's own typo) shows in none of the 120 and is
+ * fixed by its length only.  Q13's `o_comment not like '%pending%accounts%'` is pinned by q13.txt.
+ * Not restated: dbgen overwrites part of s_comment with "Customer ... Complaints / Recommends" for the ~10 in 10000 suppliers
+ * tg_gen_supplier_text flags (none of q2.txt's rows); tg_gen_supplier_text's flag is what Q16 needs.
+ */
+typedef struct { const char *text; int w; } tg_ent;
+typedef struct { const tg_ent *e; int n; int cum[48]; } tg_dist;
+static const tg_ent TGE_GRAMMAR[] = {{"N V T",3},{"N V P T",3},{"N V N T",3},{"N P V N T",1},{"N P V P T",1}};
+static const tg_ent TGE_NP[] = {{"N",10},{"J N",20},{"J, J N",10},{"D J N",50}};
+static const tg_ent TGE_VP[] = {{"V",30},{"X V",1},{"V D",40},{"X V D",1}};
+static const tg_ent TGE_NOUNS[] = {{"packages",40},{"requests",40},{"accounts",40},{"deposits",40},{"foxes",20},{"ideas",20},{"theodolites",20},
+    {"pinto beans",20},{"instructions",20},{"dependencies",10},{"excuses",10},{"platelets",10},{"asymptotes",10},{"courts",5},{"dolphins",5},
+    {"multipliers",1},{"sauternes",1},{"warthogs",1},{"frets",1},{"dinos",1},{"attainments",1},{"somas",1},{"Tiresias",1},{"patterns",1},{"forges",1},
+    {"braids",1},{"frays",1},{"warhorses",1},{"dugouts",1},{"notornis",1},{"epitaphs",1},{"pearls",1},{"tithes",1},{"waters",1},{"orbits",1},{"gifts",1},
+    {"sheaves",1},{"depths",1},{"sentiments",1},{"decoys",1},{"realms",1},{"pains",1},{"grouches",1},{"escapades",1},{"hockey players",1}};
+static const tg_ent TGE_VERBS[] = {{"sleep",20},{"wake",20},{"are",20},{"cajole",20},{"haggle",20},{"nag",10},{"use",10},{"boost",10},{"affix",5},
+    {"detect",5},{"integrate",5},{"maintain",1},{"nod",1},{"was",1},{"lose",1},{"sublate",1},{"solve",1},{"thrash",1},{"promise",1},{"engage",1},
+    {"hinder",1},{"print",1},{"x-ray",1},{"breach",1},{"eat",1},{"grow",1},{"impress",1},{"mold",1},{"poach",1},{"serve",1},{"run",1},{"dazzle",1},
+    {"snooze",1},{"doze",1},{"unwind",1},{"kindle",1},{"play",1},{"hang",1},{"believe",1},{"doubt",1}};
+static const tg_ent TGE_ADJ[] = {{"special",20},{"pending",20},{"unusual",20},{"express",20},{"furious",1},{"sly",1},{"careful",1},{"blithe",1},
+    {"quick",1},{"fluffy",1},{"slow",1},{"quiet",1},{"ruthless",1},{"thin",1},{"close",1},{"dogged",1},{"daring",1},{"brave",1},{"stealthy",1},
+    {"permanent",1},{"enticing",1},{"idle",1},{"busy",1},{"regular",50},{"final",40},{"ironic",40},{"even",30},{"bold",20},{"silent",10}};
+static const tg_ent TGE_ADV[] = {{"sometimes",1},{"always",1},{"never",1},{"furiously",50},{"slyly",50},{"carefully",50},{"blithely",40},
+    {"quickly",30},{"fluffily",20},{"slowly",1},{"quietly",1},{"ruthlessly",1},{"thinly",1},{"closely",1},{"doggedly",1},{"daringly",1},{"bravely",1},
+    {"stealthily",1},{"permanently",1},{"enticingly",1},{"idly",1},{"busily",1},{"regularly",1},{"finally",1},{"ironically",1},{"evenly",1},
+    {"boldly",1},{"silently",1}};
+static const tg_ent TGE_PREP[] = {{"about",50},{"above",50},{"according to",50},{"across",50},{"after",50},{"against",40},{"along",40},
+    {"alongside of",30},{"among",30},{"around",20},{"at",10},{"atop",1},{"before",1},{"behind",1},{"beneath",1},{"beside",1},{"besides",1},
+    {"between",1},{"beyond",1},{"by",1},{"despite",1},{"during",1},{"except",1},{"for",1},{"from",1},{"in place of",1},{"inside",1},{"instead of",1},
+    {"into",1},{"near",1},{"of",1},{"on",1},{"outside",1},{"over",1},{"past",1},{"since",1},{"through",1},{"throughout",1},{"to",1},{"toward",1},
+    {"under",1},{"until",1},{"up",1},{"upon",1},{"whithout",1},{"with",1},{"within",1}};
+static const tg_ent TGE_AUX[] = {{"do",1},{"may",1},{"might",1},{"shall",1},{"will",1},{"would",1},{"can",1},{"could",1},{"should",1},{"ought to",1},
+    {"must",1},{"will have to",1},{"shall have to",1},{"could have to",1},{"should have to",1},{"must have to",1},{"need to",1},{"try to",1}};
+static const tg_ent TGE_TERM[] = {{".",50},{";",1},{":",1},{"?",1},{"!",1},{"--",1}};
+#define TG_DIST(name, arr) static tg_dist name = { arr, (int)(sizeof(arr) / sizeof(arr[0])), {0} }
+TG_DIST(TGD_GRAMMAR, TGE_GRAMMAR); TG_DIST(TGD_NP, TGE_NP); TG_DIST(TGD_VP, TGE_VP); TG_DIST(TGD_NOUNS, TGE_NOUNS); TG_DIST(TGD_VERBS, TGE_VERBS);
+TG_DIST(TGD_ADJ, TGE_ADJ); TG_DIST(TGD_ADV, TGE_ADV); TG_DIST(TGD_PREP, TGE_PREP); TG_DIST(TGD_AUX, TGE_AUX); TG_DIST(TGD_TERM, TGE_TERM);
+
+enum { SD_TEXT_POOL = 933588178, SD_C_CMNT = 1335826707, SD_S_CMNT = 1341315363, SD_O_CMNT = 276090261 };
+#define TG_POOL_SIZE (300LL * 1024 * 1024)
+static char *tg_pool;
+static int64_t tg_pool_seed;
+
+static int tg_pick(tg_dist *d, char *target)
+{
+    const int64_t j = tg_draw(&tg_pool_seed, 1, d->cum[d->n - 1]);
+    int i = 0;
+    while (d->cum[i] < j) i++;
+    strcpy(target, d->e[i].text);
+    return i;
+}
+
+/* a noun or verb phrase: every word followed by the punctuation glued to its form letter (the comma of "J,") and one blank */
+static int tg_phrase(char *dest, tg_dist *forms)
+{
+    char syntax[16];
+    int res = 0;
+    tg_pick(forms, syntax);
+    for (const char *c = syntax; *c; ) {
+        while (*c == ' ') c++;
+        if (!*c) break;
+        tg_dist *src = *c == 'D' ? &TGD_ADV : *c == 'V' ? &TGD_VERBS : *c == 'X' ? &TGD_AUX : *c == 'J' ? &TGD_ADJ : &TGD_NOUNS;
+        const int len = (int)strlen(src->e[tg_pick(src, dest)].text);
+        dest += len; res += len;
+        c++;
+        if (*c && *c != ' ') { *dest++ = *c++; res++; }
+        *dest++ = ' '; res++;
+    }
+    return res;
+}
+
+static int tg_sentence(char *dest)
+{
+    char syntax[16];
+    int res = 0;
+    tg_pick(&TGD_GRAMMAR, syntax);
+    for (const char *c = syntax; *c; c++) {
+        if (*c == ' ') continue;
+        int len = 0;
+        if (*c == 'V') len = tg_phrase(dest, &TGD_VP);
+        else if (*c == 'N') len = tg_phrase(dest, &TGD_NP);
+        else if (*c == 'P') {
+            len = (int)strlen(TGD_PREP.e[tg_pick(&TGD_PREP, dest)].text);
+            memcpy(dest + len, " the ", 5);
+            len += 5;
+            len += tg_phrase(dest + len, &TGD_NP);
+        } else {                                        /* 'T': the terminator replaces the blank after the last word */
+            dest--;
+            len = (int)strlen(TGD_TERM.e[tg_pick(&TGD_TERM, dest)].text);
+            res--;
+        }
+        dest += len; res += len;
+    }
+    *dest = 0;
+    return res;
+}
+
+/* the 300 MiB pool (built once, about 3 s); NULL when the allocation fails */
+const char *tg_text_pool(void)
+{
+    if (tg_pool) return tg_pool;
+    tg_dist *all[] = {&TGD_GRAMMAR, &TGD_NP, &TGD_VP, &TGD_NOUNS, &TGD_VERBS, &TGD_ADJ, &TGD_ADV, &TGD_PREP, &TGD_AUX, &TGD_TERM};
+    for (int k = 0; k < 10; k++) { int c = 0; for (int i = 0; i < all[k]->n; i++) { c += all[k]->e[i].w; all[k]->cum[i] = c; } }
+    char *pool = (char *)malloc((size_t)TG_POOL_SIZE + 1), *cp = pool, sentence[512];
+    if (!pool) return NULL;
+    tg_pool_seed = SD_TEXT_POOL;
+    int64_t filled = 0;
+    while (filled < TG_POOL_SIZE) {
+        const int len = tg_sentence(sentence);
+        const int64_t room = TG_POOL_SIZE - filled;
+        if (room >= len + 1) { memcpy(cp, sentence, (size_t)len); cp += len; *cp++ = ' '; filled += len + 1; }
+        else { memcpy(cp, sentence, (size_t)room); cp += room; filled += room; }
+    }
+    *cp = 0;
+    tg_pool = pool;
+    return tg_pool;
+}
+
+/* comment spans of rows [lo, hi) of the column whose stream starts at `seed` (2 draws per row) and whose average length is avg */
+void tg_comment_spans(int64_t seed, int avg, int64_t lo, int64_t hi, int64_t *off, int32_t *len)
+{
+    const int mn = (int)(avg * 0.4), mx = (int)(avg * 1.6);
+    int64_t s = tg_jump(seed, 2 * lo);
+    for (int64_t i = lo; i < hi; i++) {
+        off[i - lo] = tg_draw(&s, 0, TG_POOL_SIZE - mx);
+        len[i - lo] = (int32_t)tg_draw(&s, mn, mx);
+    }
+}
+
+/* flags[i] = comment i matches '%w1%w2%' (w2 after the end of the first w1; wildcardMatch's greedy-with-backtracking result for
+ * two literal words is the same as: some occurrence of w1 is followed by an occurrence of w2, i.e. the FIRST w1 is) */
+int tg_comments_like2(int64_t seed, int avg, int64_t lo, int64_t hi, const char *w1, const char *w2, uint8_t *flags)
+{
+    const char *pool = tg_text_pool();
+    if (!pool) return -1;
+    const int mn = (int)(avg * 0.4), mx = (int)(avg * 1.6);
+    const size_t n1 = strlen(w1), n2 = strlen(w2);
+    int64_t s = tg_jump(seed, 2 * lo);
+    char buf[256];
+    for (int64_t i = lo; i < hi; i++) {
+        const int64_t off = tg_draw(&s, 0, TG_POOL_SIZE - mx);
+        const int len = (int)tg_draw(&s, mn, mx);
+        memcpy(buf, pool + off, (size_t)len);
+        buf[len] = 0;
+        const char *p = strstr(buf, w1);
+        flags[i - lo] = (uint8_t)(p != NULL && strstr(p + n1, w2) != NULL);
+        (void)n2;
+    }
+    return 0;
+}
