@@ -1,10 +1,10 @@
 /*
  * oracle/tpchgen.c -- TEST INFRASTRUCTURE (CPU). Not part of the product path.
  *
- * dbgen-equivalent TPC-H generator for the columns the hot path touches
- * (lineitem, orders, customer).  The reference loads official dbgen SF1 data
+ * dbgen-equivalent TPC-H generator for the columns the reference's TPC-H cases
+ * read.  The reference loads official dbgen SF1 data
  * (/root/reference/Makefile:47,57-67) and its golden results
- * (cases/tpch/1g/plan/q{1,3,6}.txt) are computed on it, so this generator
+ * (cases/tpch/1g/plan/q*.txt) are computed on it, so this generator
  * restates dbgen's published algorithm bit for bit for those columns:
  *   - Park-Miller LCG  seed' = seed*16807 mod (2^31-1), one stream per column,
  *     UnifInt = lo + (int64)((double)seed/2147483647.0 * (hi-lo+1));
@@ -15,9 +15,13 @@
  *   - sparse order keys (8 of every 32), customer mortality (custkey%3 != 0),
  *     retail price from partkey, R/A return flag drawn only when
  *     receiptdate <= 1995-06-17.
- * Pinned by tests/test_tpchgen.py against the first rows of the official SF1
- * lineitem/orders/customer tables and, end to end, by the reference's golden
- * Q1/Q6/Q3 results.
+ * Pinned by tests/test_oracle_golden.py against the first rows of the official SF1
+ * tables and, end to end, by ALL 22 of the reference's golden result files
+ * (cases/tpch/1g/plan/q1.txt ... q22.txt): the sections further down add, query by
+ * query, the other columns those files read -- part / supplier / partsupp / nation,
+ * ship modes, priorities, part types / brands / containers, balances, generated
+ * addresses and phone numbers, the Customer-Complaints suppliers and dbgen's 300 MiB
+ * comment text pool.
  */
 #include <stdint.h>
 #include <stdlib.h>
