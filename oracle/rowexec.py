@@ -19,8 +19,8 @@ Pinning: the reference holds no golden vector for these operators in isolation (
 this module is pinned indirectly -- its decimal arithmetic is oracle/decimal.h (checked against the reference's golden Q1 / Q6
 files), CASE / OR / IN / LIKE inside aggregates over a join are pinned by the reference's golden q12.txt / q14.txt through
 oracle.q12 / oracle.q14 and the GPU test that reproduces both files; MARK joins by q4.txt, multi-way join stacks by q5.txt / q7.txt /
-q8.txt (tests/test_oracle_golden.py runs those plans through this module); a DECIMAL quotient by q8.txt.  LEFT join outputs and
-DECIMAL division evaluated per row are PARITY UNPINNED against the reference.
+q8.txt, the LEFT join (NULL padding, count(x) = NULL over it) by q13.txt (tests/test_oracle_golden.py runs those plans through this
+module); a DECIMAL quotient by q8.txt.  DECIMAL division evaluated per row is PARITY UNPINNED against the reference.
 
 Values: None (NULL) | bool | int | Dec(coef, scale, neg) | np.float32 | str.
 """
@@ -263,7 +263,11 @@ def execute(op, tables):
             vals = []
             for i, a in enumerate(op.Info.Aggs):
                 fn, acc, n = a.FunImpl, st["acc"][i], st["n"][i]
-                if fn == "count":
+                if fn == "count" and not a.Children:
+                    vals.append(n)                      # count(*): a group exists only through a row
+                elif n == 0:                            # no non-NULL input: NULL, count(x) included (CountOp.Finalize, function_aggr.go:949-960)
+                    vals.append(None)
+                elif fn == "count":
                     vals.append(n)
                 elif n == 0:
                     vals.append(None)

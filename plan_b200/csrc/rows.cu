@@ -468,8 +468,10 @@ struct RowsPipeline : Pipeline {
                 for (int g : order) {
                     i128 v = tot[(size_t)g * P + (size_t)pl], cnt = tot[(size_t)g * P];
                     if (pl > 0) {
-                        cnt = tot[(size_t)g * P + (size_t)(nacc + pl)];       // NULL arguments were skipped
-                        if (cnt == 0 && a.fn != PG_AGG_COUNT) { col.push_null(nrow++, (size_t)type_size(col.type)); continue; }
+                        // NULL arguments were skipped; no valid input at all => NULL, count(x) included (CountOp.Finalize,
+                        // function_aggr.go:949-960 -- the reference's q13.txt prints NULL for customers without orders)
+                        cnt = tot[(size_t)g * P + (size_t)(nacc + pl)];
+                        if (cnt == 0) { col.push_null(nrow++, (size_t)type_size(col.type)); continue; }
                     }
                     col.mark_valid();
                     nrow++;

@@ -308,3 +308,25 @@ def test_row_oracle_runs_the_q5_q7_q8_plans(oracle):
     for y, q, a, b in want:                                     # the host-side division above the aggregate: govalues Quo
         d = R.dec_quo(R.Dec(a, 4), R.Dec(b, 4))
         assert (d.coef, d.scale) == (q[0], q[1]) or (a == 0 and d.coef == 0)
+
+
+def test_row_oracle_runs_the_q13_plan(oracle):
+    """Q13 as the reference plans it -- Agg over Agg over a LEFT join whose build side carries `o_comment not like '%pending%accounts%'`
+    -- through the tree-walking oracle: NULL padding of customers without a surviving order, count(o_orderkey) = NULL over them
+    (CountOp.Finalize), NULL as a group key of the outer aggregate.  It must give what oracle.q13 gives, which reproduces q13.txt at SF1:
+    this is what pins the row oracle's LEFT join."""
+    import numpy as np
+    from oracle import rowexec as R
+    from plan_b200 import tpch as T
+    sf = 0.02
+    orders, _ = oracle.gen_orders_lineitem(sf, lineitem_cols=[])
+    cust = oracle.gen_customer(sf)
+    text = oracle.comments("o_comment", range(len(orders["o_orderkey"])))
+    assert text[0] == "nstructions sleep furiously among " and text[1] == " foxes. pending accounts at the pending, silent asymptot"   # official orders.tbl rows 1-2
+    oc = dict(orders, o_comment=np.array([c.encode() for c in text], dtype=object))
+    tabs = {"customer": R.table_rows(cust, T.Q13_CUSTOMER), "orders": R.table_rows(oc, T.Q13_ORDERS)}
+    want = oracle.q13(orders, len(cust["c_custkey"]))
+    assert want[0] == (None, 1000) and sum(1 for t in text if oracle.wildcard_match(b"%pending%accounts%", t.encode())) > 100
+    got = R.execute(T.q13_plan(), tabs)
+    key = lambda r: (-r[1], -(r[0] or 0))   # noqa: E731
+    assert sorted(((r[0], r[1]) for r in got), key=key) == want
