@@ -754,3 +754,32 @@ def q13_plan(pattern="%pending%accounts%"):
                          Info=JoinOpInfo(JOIN_LEFT, [func("=", B, col(0, 0, I), col(1, 1, I))]))
     per_cust = PhysicalOperator(POT_Agg, Outputs=[col(0, 0, I), col(1, 0, H)], Children=[j], Info=AggOpInfo([func("count", H, col(0, 1, BI))], [col(0, 0, I)]))
     return PhysicalOperator(POT_Agg, Outputs=[col(0, 0, H), col(1, 0, H)], Children=[per_cust], Info=AggOpInfo([func("count", H)], [col(0, 1, H)]))
+
+
+Q10_CUSTOMER = [("c_custkey", L.PG_T_INT32, 0, 0, None), ("c_name", L.PG_T_VARCHAR, 25, 0, None), ("c_acctbal", L.PG_T_DECIMAL64, 15, 2, None),
+                ("c_nationkey", L.PG_T_INT32, 0, 0, None), ("c_address", L.PG_T_VARCHAR, 40, 0, None), ("c_phone", L.PG_T_VARCHAR, 15, 0, None),
+                ("c_comment", L.PG_T_VARCHAR, 117, 0, None)]
+
+
+def q10_plan(date_lo=None, date_hi=None, limit=20):
+    """cases/tpch/query/q10.sql:  Limit(20) <- Order(revenue desc) <- Agg(group by c_custkey, c_name, c_acctbal, c_phone, n_name,
+    c_address, c_comment; sum(l_extendedprice * (1 - l_discount))) <- lineitem[l_returnflag = 'R'] x orders[o_orderdate in the
+    quarter] x customer x nation.  Seven group keys, four of them strings, one a signed DECIMAL.  Plan tree only (see Q5 / Q7 / Q8)."""
+    B, V, D = K.LType(K.LTID_BOOLEAN), K.VarcharType(), K.DateType()
+    date_lo = days(1993, 3, 1) if date_lo is None else date_lo
+    date_hi = days(1993, 6, 1) if date_hi is None else date_hi
+    cols = {"lineitem": LINEITEM, "orders": ORDERS, "customer": Q10_CUSTOMER, "nation": NATION}
+    li, oi = {c[0]: i for i, c in enumerate(LINEITEM)}, {c[0]: i for i, c in enumerate(ORDERS)}
+    od = col(0, oi["o_orderdate"], D)
+    st = _Stack("lineitem", cols, ["l_orderkey", "l_extendedprice", "l_discount"], filters=[func("=", B, col(0, li["l_returnflag"], V), const("R", V))])
+    st.join("orders", [("l_orderkey", "o_orderkey")], ["o_custkey"], filters=[func(">=", B, od, const(date_lo, D)), func("<", B, od, const(date_hi, D))])
+    st.join("customer", [("o_custkey", "c_custkey")], ["c_custkey", "c_name", "c_acctbal", "c_nationkey", "c_address", "c_phone", "c_comment"])
+    st.join("nation", [("c_nationkey", "n_nationkey")], ["n_name"])
+    keys = [st.ref(n) for n in ("c_custkey", "c_name", "c_acctbal", "c_phone", "n_name", "c_address", "c_comment")]
+    sum_t = K.DecimalType(38, 4)
+    agg = func("sum", sum_t, _disc_price(st.ref("l_extendedprice"), st.ref("l_discount")))
+    # select list order: c_custkey, c_name, revenue, c_acctbal, n_name, c_address, c_phone, c_comment
+    outs = [col(0, 0, keys[0].DataTyp), col(0, 1, V), col(1, 0, sum_t), col(0, 2, keys[2].DataTyp), col(0, 4, V), col(0, 5, V), col(0, 3, V), col(0, 6, V)]
+    node = PhysicalOperator(POT_Agg, Outputs=outs, Children=[st.node], Info=AggOpInfo([agg], keys))
+    order = PhysicalOperator(POT_Order, Outputs=outs, Children=[node], Info=OrderOpInfo([(col(0, 2, sum_t), True)]))
+    return PhysicalOperator(POT_Limit, Outputs=outs, Children=[order], Info=LimitOpInfo(limit))

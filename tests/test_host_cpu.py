@@ -256,7 +256,7 @@ def test_descriptors_of_the_reference_plans_compile_without_a_gpu():
     import ctypes as C
     from plan_b200 import _lib as L, compute as X, tpch as T
     plans = [T.q6_plan(), T.q1_plan(), T.q3_plan(), T.q3_topk_plan(10), T.q18_plan(), T.q9_plan(), T.exists_plan(), T.exists_plan(negated=True),
-             T.q4_plan(), T.q12_plan(), T.q14_plan(), T.q19_plan(), T.q5_plan(), T.q7_plan(), T.q8_plan(), T.q13_plan(),
+             T.q4_plan(), T.q12_plan(), T.q14_plan(), T.q19_plan(), T.q5_plan(), T.q7_plan(), T.q8_plan(), T.q13_plan(), T.q10_plan(),
              T.groupby_plan(key="l_partkey", value="l_quantity", topk=100)]
     for op in plans:
         desc, slots = X.serialize_plan(op)

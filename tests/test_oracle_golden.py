@@ -330,3 +330,27 @@ def test_row_oracle_runs_the_q13_plan(oracle):
     got = R.execute(T.q13_plan(), tabs)
     key = lambda r: (-r[1], -(r[0] or 0))   # noqa: E731
     assert sorted(((r[0], r[1]) for r in got), key=key) == want
+
+
+def test_row_oracle_runs_the_q10_plan(oracle):
+    """Q10's aggregate (seven group keys: INTEGER, four VARCHARs, a signed DECIMAL, a dictionary name) over a four-table join through
+    the tree-walking oracle; ordered by revenue and cut to 20 rows it must equal oracle.q10, which reproduces q10.txt at SF1."""
+    import numpy as np
+    from oracle import rowexec as R
+    from plan_b200 import tpch as T
+    sf = 0.02
+    orders, line = oracle.gen_orders_lineitem(sf)
+    cust = oracle.gen_customer(sf)
+    ct, x22 = oracle.gen_customer_text(sf, cust), oracle.gen_q11_q22_columns(sf)
+    obj = lambda xs: np.array([x.encode() for x in xs], dtype=object)   # noqa: E731
+    cx = {"c_custkey": cust["c_custkey"], "c_name": cust["c_name"], "c_acctbal": x22["c_acctbal"], "c_nationkey": cust["c_nationkey"],
+          "c_address": obj(ct["c_address"]), "c_phone": obj(ct["c_phone"]), "c_comment": obj(oracle.comments("c_comment", range(len(cust["c_custkey"]))))}
+    nation = {"n_nationkey": np.arange(25, dtype=np.int32), "n_name": np.arange(25, dtype=np.uint8)}
+    tabs = {"lineitem": R.table_rows(line, T.LINEITEM), "orders": R.table_rows(orders, T.ORDERS), "customer": R.table_rows(cx, T.Q10_CUSTOMER),
+            "nation": R.table_rows(nation, T.NATION)}
+    plan = T.q10_plan()
+    got = R.execute(plan.Children[0].Children[0], tabs)                 # the aggregate below Limit <- Order (host parents)
+    s4 = lambda v: v.signed() * 10 ** (4 - v.scale)   # noqa: E731
+    top = sorted((-s4(r[2]), r[0]) + tuple(r) for r in got)[:20]
+    mine = [(r[2], r[3], s4(r[4]), r[5].signed() * 10 ** (2 - r[5].scale), r[6], r[7], r[8], r[9]) for r in top]
+    assert len(got) > 500 and mine == oracle.q10(cust, orders, line, x22, ct)
