@@ -184,7 +184,7 @@ def _compare(fn, a, b):
         a, b = np.float32(a), np.float32(b)
         if np.isnan(a) or np.isnan(b):
             return fn == "<>"
-        c = (a > b) - (a < b)
+        c = int(a > b) - int(a < b)
     else:
         c = (a > b) - (a < b)
     return {"=": c == 0, "<>": c != 0, "<": c < 0, "<=": c <= 0, ">": c > 0, ">=": c >= 0}[fn]

@@ -354,3 +354,49 @@ def test_row_oracle_runs_the_q10_plan(oracle):
     top = sorted((-s4(r[2]), r[0]) + tuple(r) for r in got)[:20]
     mine = [(r[2], r[3], s4(r[4]), r[5].signed() * 10 ** (2 - r[5].scale), r[6], r[7], r[8], r[9]) for r in top]
     assert len(got) > 500 and mine == oracle.q10(cust, orders, line, x22, ct)
+
+
+def test_row_oracle_agrees_with_the_c_oracle_on_the_headline_plans(oracle):
+    """The two oracles are independent restatements: oracle/refexec.c + numpy (pinned by q1 / q3 / q6 / q9 / q18.txt at SF1) and the
+    tree-walking oracle/rowexec.py that executes PhysicalOperator trees.  Running the five headline PLANS (tpch.q6_plan ... q18_plan,
+    the trees the GPU path is given) through rowexec must give the C oracle's answers exactly: Q6's float32 BETWEEN on a DECIMAL
+    column, Q1's eight aggregates incl. avg(DECIMAL) as a 19-digit quotient and avg(INTEGER) as a double, Q3's three-table join, Q9's
+    six-table star with LIKE and extract(year), Q18's join against a HAVING sub-aggregate."""
+    import numpy as np
+    from oracle import rowexec as R
+    from plan_b200 import tpch as T
+    sf = 0.01
+    orders, line = oracle.gen_orders_lineitem(sf)
+    cust, supp, ps, part = oracle.gen_customer(sf), oracle.gen_supplier(sf), oracle.gen_partsupp(sf), oracle.gen_part(sf, like_word="pink")
+    nation = {"n_nationkey": np.arange(25, dtype=np.int32), "n_name": np.arange(25, dtype=np.uint8)}
+    rows = R.table_rows
+    tabs = {"lineitem": rows(line, T.LINEITEM), "orders": rows(orders, T.ORDERS), "customer": rows(cust, T.CUSTOMER),
+            "part": rows({"p_partkey": part["p_partkey"], "p_name": part["p_name"]}, T.PART), "supplier": rows(supp, T.SUPPLIER),
+            "partsupp": rows(ps, T.PARTSUPP), "nation": rows(nation, T.NATION)}
+    s4 = lambda v: v.signed() * 10 ** (4 - v.scale)   # noqa: E731
+    dec = lambda v: (v.coef, v.scale, int(v.neg))     # noqa: E731
+    # Q6
+    got = R.execute(T.q6_plan(), tabs)
+    want = oracle.q6(line)
+    assert want["rows_selected"] > 500 and len(got) == 1 and s4(got[0][0]) == want["exact"]
+    # Q1
+    got, want = R.execute(T.q1_plan(), tabs), oracle.q1(line)
+    assert len(got) == len(want["groups"]) == 4
+    for g in want["groups"]:
+        r = [x for x in got if (x[0], x[1]) == (g["l_returnflag"], g["l_linestatus"])][0]
+        assert (r[2], dec(r[3]), dec(r[4]), dec(r[5]), r[6], dec(r[7]), dec(r[8]), r[9]) == (
+            g["sum_qty"], g["sum_base_price"], g["sum_disc_price"], g["sum_charge"], g["avg_qty"], g["avg_price"], g["avg_disc"], g["count_order"])
+    # Q3 (every group, not only the top 10)
+    want = sorted((g["l_orderkey"], g["x_revenue"], g["o_orderdate"], g["o_shippriority"]) for g in oracle.q3(cust, orders, line)["groups"])
+    assert len(want) > 50 and sorted((r[0], s4(r[1]), r[2], r[3]) for r in R.execute(T.q3_plan(), tabs)) == want
+    # Q9 (below its Order)
+    want = sorted(oracle.q9(part, supp, ps, orders, line))
+    assert len(want) > 100 and sorted((r[0], r[1], s4(r[2])) for r in R.execute(T.q9_plan().Children[0], tabs)) == want
+    # Q18 (the aggregate below Limit <- Order; threshold lowered so the small sample has groups)
+    node = T.q18_plan(qty_gt=150)
+    while node.Typ != R.POT_Agg:
+        node = node.Children[0]
+    got = sorted((-r[4].signed(), r[3], r[0], r[1], r[2], r[5]) for r in R.execute(node, tabs))[:100]
+    want = oracle.q18(cust, orders, line, qty_gt=150, limit=100)
+    assert len(want) == 100 and [(a[2], a[3], a[4], a[1], -a[0], a[5]) for a in got] == [
+        (g["c_name"], g["c_custkey"], g["o_orderkey"], g["o_orderdate"], g["o_totalprice"], g["sum_qty"]) for g in want]
