@@ -34,7 +34,7 @@ from . import oracle as O
 # numbering shared with plan_b200.compute / plangpu_desc.h (restated here: the oracle does not import the product)
 POT_Scan, POT_Filter, POT_Join, POT_Agg, POT_Project = 1, 2, 3, 4, 5
 ET_Column, ET_Func, ET_Const = 0, 5, 7
-JOIN_INNER, JOIN_SEMI, JOIN_ANTI, JOIN_MARK, JOIN_LEFT = 1, 2, 3, 4, 5
+JOIN_INNER, JOIN_SEMI, JOIN_ANTI, JOIN_MARK, JOIN_LEFT, JOIN_ANTI_MARK = 1, 2, 3, 4, 5, 6
 LT_BOOLEAN, LT_INTEGER, LT_BIGINT, LT_DATE, LT_DECIMAL, LT_FLOAT, LT_DOUBLE, LT_VARCHAR, LT_HUGEINT = range(1, 10)
 T_INT32, T_INT64, T_DATE32, T_DECIMAL64, T_CHAR1, T_DICT8, T_FLOAT64, T_HUGEINT, T_DECIMAL128, T_VARCHAR = range(1, 11)
 
@@ -318,7 +318,7 @@ def execute(op, tables):
             elif jt == JOIN_ANTI:
                 if not matches:
                     emit(l, None)
-            elif jt == JOIN_MARK:
+            elif jt in (JOIN_MARK, JOIN_ANTI_MARK):        # NOT EXISTS is planned as AntiMARK + `mark = false`; same scan (join_scan.go:54)
                 emit(l, None, None if null_key else bool(matches))
             else:
                 raise ValueError("join type %r" % jt)

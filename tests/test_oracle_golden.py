@@ -400,3 +400,50 @@ def test_row_oracle_agrees_with_the_c_oracle_on_the_headline_plans(oracle):
     want = oracle.q18(cust, orders, line, qty_gt=150, limit=100)
     assert len(want) == 100 and [(a[2], a[3], a[4], a[1], -a[0], a[5]) for a in got] == [
         (g["c_name"], g["c_custkey"], g["o_orderkey"], g["o_orderdate"], g["o_totalprice"], g["sum_qty"]) for g in want]
+
+
+def test_row_oracle_agrees_with_the_restatements_on_the_other_plan_builders(oracle):
+    """The remaining plan builders the GPU tests use -- high-cardinality group-bys with HAVING, SEMI / ANTI joins, EXISTS / NOT EXISTS as
+    MARK / AntiMARK joins under `mark = true / false`, string predicates, the wide min / max / sum / avg shape with NULLs -- through the
+    tree-walking oracle against their numpy / C restatements: two independent statements of each."""
+    import numpy as np
+    from oracle import rowexec as R
+    from plan_b200 import tpch as T
+    sf = 0.01
+    orders, line = oracle.gen_orders_lineitem(sf)
+    cust = oracle.gen_customer(sf)
+    tabs = {"lineitem": R.table_rows(line, T.LINEITEM), "orders": R.table_rows(orders, T.ORDERS), "customer": R.table_rows(cust, T.CUSTOMER)}
+
+    def agg_node(p):
+        while p.Typ != R.POT_Agg:
+            p = p.Children[0]
+        return p
+    num = lambda v: v.signed() if isinstance(v, R.Dec) else v   # noqa: E731
+    plain = lambda want: {int(k): (int(v[0]), int(v[1])) for k, v in want.items()}   # noqa: E731
+    for kw in (dict(key="l_orderkey", value="l_quantity", having_gt=200), dict(key="l_partkey", value="l_quantity"),
+               dict(key="l_suppkey", value="l_extendedprice", ship_le=9500)):
+        got = {r[0]: (num(r[1]), r[2]) for r in R.execute(agg_node(T.groupby_plan(**kw)), tabs)}
+        assert len(got) >= 100 and got == plain(oracle.groupby_sum(line, **kw)), kw
+    for anti in (False, True):
+        want = plain(oracle.semi_groupby(orders, line, anti=anti))
+        assert len(want) > 400
+        assert {r[0]: (num(r[1]), r[2]) for r in R.execute(agg_node(T.semi_plan(anti=anti)), tabs)} == want
+        assert {r[0]: (num(r[1]), r[2]) for r in R.execute(agg_node(T.exists_plan(negated=anti)), tabs)} == want
+    for fl in ([("c_name", "like", "%00001%")], [("c_mktsegment", "not like", "_U%"), ("c_name", "like", "Customer#0000005__")],
+               [("c_mktsegment", "=", "BUILDING")], [("c_name", "like", "nothing%")]):
+        got, want = R.execute(T.customer_filter_plan(fl), tabs), oracle.customer_filter(cust, fl, oracle.SEGMENTS)
+        assert (got == [] and want is None) or tuple(got[0]) == want, fl
+    # the wide shape, with NULLs in three columns: aggregates over no valid input are NULL
+    rng = np.random.default_rng(5)
+    n = len(line["l_orderkey"])
+    valid = {"l_quantity": rng.random(n) >= 0.1, "l_extendedprice": rng.random(n) >= 0.3, "l_tax": rng.random(n) >= 0.2}
+    valid["l_tax"][line["l_returnflag"] == ord("A")] = False                     # one group without any valid l_tax
+    args = (T.days(1993, 1, 1), T.days(1997, 6, 30), T.days(1997, 9, 1), T.days(1993, 2, 1), 5, 45, 3)
+    want = oracle.stats(line, *args, valid=valid)
+    got = R.execute(T.stats_plan(*args), {"lineitem": R.table_rows(line, T.LINEITEM, valid=valid)})
+    tup = lambda v: None if v is None else (v.coef, v.scale, int(v.neg))         # noqa: E731
+    assert len(got) == len(want["groups"]) == 3
+    for g in want["groups"]:
+        r = [x for x in got if x[0] == g["l_returnflag"]][0]
+        assert [tup(v) for v in r[1:7]] == [g["min_ext"], g["max_ext"], g["max_disc"], g["sum_tax"], g["avg_tax"], g["sum_taxed"]] and r[7] == g["count"]
+    assert [g["sum_tax"] for g in want["groups"] if g["l_returnflag"] == "A"] == [None]
