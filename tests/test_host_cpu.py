@@ -103,6 +103,27 @@ def test_value_formatting_follows_the_reference():
     assert K.decimal_int64(125, 3, False, 2) == (0, 12) and K.decimal_int64(135, 3, False, 2) == (0, 14)
 
 
+def test_value_formatting_agrees_with_the_oracle_on_random_values():
+    """Value.String of the host mirror (plan_b200/chunk.py) and the oracle's C restatement (orc_format_decimal, fmt_double) are written
+    independently; the oracle's is pinned by all 22 golden files.  5000 random decimals (any scale, sign, printed at any type scale) and
+    a set of floats that exercise Go's 'g' formatting thresholds must print identically."""
+    import random
+    from oracle import oracle as O
+    from plan_b200 import chunk as K
+    rng = random.Random(3)
+    for _ in range(5000):
+        scale = rng.randrange(0, 20)
+        coef = rng.choice([0, 1, 5, 15, 25, 125, 135, 10 ** 19 - 1, rng.randrange(10 ** rng.randrange(1, 20))])
+        neg = rng.randrange(2)
+        ts = rng.choice([0, 2, 2, 4, 6, 8, scale])
+        dec = np.zeros(1, dtype=K.DECIMAL128)
+        dec[0] = (coef, scale, neg)
+        assert K.Vector(K.DecimalType(38, ts), dec).GetValue(0).String() == O.fmt_decimal((coef, scale, neg), ts), (coef, scale, neg, ts)
+    for x in (1e21, 1e20, 1e-5, 1e-4, 100.0, 0.1, 343478.59375, float(np.float32(16.38077)), 123456789012345680000.0, 5e-324, 25.522005853257337,
+              float(np.float32(0.0351)), 1.7976931348623157e308):
+        assert K.go_float_string(x) == O.fmt_double(x), x
+
+
 def test_order_limit_standins():
     from plan_b200 import chunk as K, compute as X
     dec = np.zeros(4, dtype=K.DECIMAL128)
