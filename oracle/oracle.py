@@ -779,19 +779,36 @@ def fmt_date(d):
 
 
 def fmt_double(x):
-    """Go fmt %v for float64: shortest round-trip, 'e' form for exp < -4 || exp >= 21."""
-    r = repr(float(x))
-    if "e" in r or "inf" in r or "nan" in r:
-        m, _, e = r.partition("e")
-        if e:
-            e = int(e)
-            return "%se%s%02d" % (m, "+" if e >= 0 else "-", abs(e))
-        return {"inf": "+Inf", "-inf": "-Inf", "nan": "NaN"}[r]
-    if r.endswith(".0"):
-        r = r[:-2]
-        if len(r.lstrip("-")) > 21:
-            return "%e" % x
-    return r
+    """Go fmt.Sprintf("%v", float64) (chunk/value.go:55-58) = strconv.FormatFloat(x, 'g', -1, 64): the shortest digits that
+    round-trip, in %e form when the decimal exponent is < -4 or >= 6 -- strconv's formatDigits takes eprec = 6 when the precision is
+    "shortest" (float64(time.Second) prints 1e+09, 123456789.0 prints 1.23456789e+08; the 1e21 cut-off is encoding/json's and
+    JavaScript's, not fmt's).  %e: d.ddde+XX with at least two exponent digits; %f: plain digits without a trailing ".0".
+    No golden file of the reference holds a DOUBLE of 1e6 or more: the upper cut-off is restated from the Go library, not pinned."""
+    import math
+    x = float(x)
+    if math.isnan(x):
+        return "NaN"
+    if math.isinf(x):
+        return "+Inf" if x > 0 else "-Inf"
+    sign = "-" if math.copysign(1.0, x) < 0 else ""
+    if x == 0:
+        return sign + "0"
+    m, _, e = ("%r" % abs(x)).partition("e")            # Python's repr is the shortest round-trip digit string too
+    ip, _, fp = m.partition(".")
+    e10 = int(e) if e else 0
+    if ip.strip("0"):
+        dp = len(ip) + e10                              # value = 0.DIGITS * 10^dp
+    else:
+        dp = e10 - (len(fp) - len(fp.lstrip("0")))
+    digits = (ip + fp).strip("0") or "0"
+    exp = dp - 1
+    if exp < -4 or exp >= 6:
+        return "%s%s%se%s%02d" % (sign, digits[0], "." + digits[1:] if len(digits) > 1 else "", "+" if exp >= 0 else "-", abs(exp))
+    if dp <= 0:
+        return sign + "0." + "0" * (-dp) + digits
+    if len(digits) <= dp:
+        return sign + digits + "0" * (dp - len(digits))
+    return sign + digits[:dp] + "." + digits[dp:]
 
 
 def q1_text(res):

@@ -178,20 +178,32 @@ def decimal_string(coef, scale, neg):
 
 
 def go_float_string(x):
-    """fmt %v of a float64: shortest repr, exponent form when exp < -4 or >= 21."""
-    r = repr(float(x))
-    if r in ("inf", "-inf", "nan"):
-        return {"inf": "+Inf", "-inf": "-Inf", "nan": "NaN"}[r]
-    if "e" in r:
-        m, e = r.split("e")
-        return "%se%s%02d" % (m, "-" if int(e) < 0 else "+", abs(int(e)))
-    if r.endswith(".0"):
-        r = r[:-2]
-    digits = r.lstrip("-").split(".")[0]
-    if len(digits) > 21:
-        m = "%.16e" % x
-        return go_float_string(float(m))
-    return r
+    """fmt.Sprintf("%v", float64) (chunk/value.go:55-58): strconv's shortest 'g' -- the shortest digits that round-trip, %e form
+    (d.ddde+XX, two exponent digits at least) when the decimal exponent is < -4 or >= 6, plain digits otherwise."""
+    import decimal
+    import math
+    x = float(x)
+    if math.isnan(x):
+        return "NaN"
+    if math.isinf(x):
+        return "+Inf" if x > 0 else "-Inf"
+    if x == 0:
+        return "-0" if math.copysign(1.0, x) < 0 else "0"
+    sign, digs, e10 = decimal.Decimal(repr(x)).as_tuple()        # repr: the shortest round-trip digits
+    digs = list(digs)
+    while len(digs) > 1 and digs[-1] == 0:
+        digs.pop()
+        e10 += 1
+    text = "".join(map(str, digs))
+    exp = len(text) + e10 - 1                                      # value = d.ddd * 10^exp
+    neg = "-" if sign else ""
+    if exp < -4 or exp >= 6:
+        return "%s%s%se%s%02d" % (neg, text[0], "." + text[1:] if len(text) > 1 else "", "-" if exp < 0 else "+", abs(exp))
+    if exp < 0:
+        return neg + "0." + "0" * (-exp - 1) + text
+    if e10 >= 0:
+        return neg + text + "0" * e10
+    return neg + text[:exp + 1] + "." + text[exp + 1:]
 
 
 # pg_string {int64_t len; const char *data} (include/plangpu.h; the layout of common.String, string.go:10-13)

@@ -66,20 +66,20 @@ inline std::string decimal_value_string(uint64_t coef, int scale, bool neg, int 
     return decimal_string(whole * pow10_128(s) + frac, s, neg);
 }
 
-inline std::string go_float_string(double x)   // fmt %v: shortest round-trip, exponent form beyond 1e21 / below 1e-4
+inline std::string go_float_string(double x)   // fmt %v = strconv 'g', shortest: %e form when the decimal exponent is < -4 or >= 6
 {
+    if (x != x) return "NaN";
+    if (x == __builtin_inf()) return "+Inf";
+    if (x == -__builtin_inf()) return "-Inf";
+    if (x == 0) return __builtin_signbit(x) ? "-0" : "0";
     char buf[64];
-    auto r = std::to_chars(buf, buf + sizeof buf, x);
+    auto r = std::to_chars(buf, buf + sizeof buf, x, std::chars_format::scientific);     // shortest round-trip digits, d.ddde[+-]XX
     std::string s(buf, r.ptr);
-    size_t e = s.find('e');
-    if (e != std::string::npos) {   // Go pads the exponent to two digits: 1e+21, 1e-05
-        std::string m = s.substr(0, e), ex = s.substr(e + 1);
-        char sign = '+';
-        if (!ex.empty() && (ex[0] == '+' || ex[0] == '-')) { sign = ex[0]; ex = ex.substr(1); }
-        if (ex.size() < 2) ex = "0" + ex;
-        return m + "e" + sign + ex;
-    }
-    return s;
+    const size_t e = s.find('e');
+    const int exp = std::stoi(s.substr(e + 1));
+    if (exp < -4 || exp >= 6) return s;                 // to_chars already pads the exponent to two digits like Go
+    r = std::to_chars(buf, buf + sizeof buf, x, std::chars_format::fixed);               // shortest digits, no exponent
+    return std::string(buf, r.ptr);
 }
 
 inline std::string date_string(int32_t days)

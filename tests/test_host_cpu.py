@@ -99,7 +99,9 @@ def test_value_formatting_follows_the_reference():
     assert K.Vector(K.HugeintType(), h).GetValue(0).String() == "37734107"
     assert K.Vector(K.DateType(), np.array([9217], np.int32)).GetValue(0).String() == "1995-03-28"
     assert K.Vector(K.DoubleType(), np.array([25.522005853257337])).GetValue(0).String() == "25.522005853257337"
-    assert K.go_float_string(1e21) == "1e+21" and K.go_float_string(0.00001) == "1e-05"
+    assert K.go_float_string(1e21) == "1e+21" and K.go_float_string(0.00001) == "1e-05" and K.go_float_string(0.0001) == "0.0001"
+    # strconv's shortest %g switches to %e at exponent 6, not 21 (float64(time.Second) prints 1e+09 in Go)
+    assert K.go_float_string(999999.5) == "999999.5" and K.go_float_string(1e6) == "1e+06" and K.go_float_string(123456789.0) == "1.23456789e+08"
     assert K.decimal_int64(125, 3, False, 2) == (0, 12) and K.decimal_int64(135, 3, False, 2) == (0, 14)
 
 
@@ -120,8 +122,43 @@ def test_value_formatting_agrees_with_the_oracle_on_random_values():
         dec[0] = (coef, scale, neg)
         assert K.Vector(K.DecimalType(38, ts), dec).GetValue(0).String() == O.fmt_decimal((coef, scale, neg), ts), (coef, scale, neg, ts)
     for x in (1e21, 1e20, 1e-5, 1e-4, 100.0, 0.1, 343478.59375, float(np.float32(16.38077)), 123456789012345680000.0, 5e-324, 25.522005853257337,
-              float(np.float32(0.0351)), 1.7976931348623157e308):
+              float(np.float32(0.0351)), 1.7976931348623157e308, 1e6, 999999.9, 1234567.0, 16777216.0, -0.0, 0.0, -2.5e-7, 120000.0):
         assert K.go_float_string(x) == O.fmt_double(x), x
+    for _ in range(5000):
+        x = rng.choice([rng.uniform(-1e8, 1e8), rng.uniform(-1, 1) * 10 ** rng.randrange(-30, 30), float(rng.randrange(10 ** rng.randrange(1, 18)))])
+        assert K.go_float_string(x) == O.fmt_double(x) and float(K.go_float_string(x)) == x, x
+
+
+def test_cpp_shim_value_formatting_agrees_with_the_oracle(tmp_path):
+    """The third implementation of Value.String -- the C++ host shim's (plan_b200/host/chunk.hpp), built into a stdin harness
+    (tests/hostlogic/shimfmt_check.cc) -- against the oracle's on random decimals, floats and dates."""
+    import random
+    import struct
+    import subprocess
+    from oracle import oracle as O
+    exe = str(tmp_path / "shimfmt")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), "-I/usr/local/cuda/include", "-o", exe,
+                    os.path.join(ROOT, "tests", "hostlogic", "shimfmt_check.cc")], check=True, capture_output=True)
+    rng = random.Random(4)
+    lines, want = [], []
+    for _ in range(3000):
+        scale = rng.randrange(0, 20)
+        coef = rng.choice([0, 1, 5, 15, 25, 125, 135, 10 ** 19 - 1, rng.randrange(10 ** rng.randrange(1, 20))])
+        neg, ts = rng.randrange(2), rng.choice([0, 2, 2, 4, 6, 8, scale])
+        lines.append("D %d %d %d %d" % (coef, scale, neg, ts))
+        want.append(O.fmt_decimal((coef, scale, neg), ts))
+    floats = [1e21, 1e20, 1e-5, 1e-4, 100.0, 0.1, 343478.59375, 5e-324, 25.522005853257337, 1.7976931348623157e308, 1e6, 999999.9, 1234567.0,
+              16777216.0, -0.0, 0.0, -2.5e-7, 120000.0]
+    floats += [rng.choice([rng.uniform(-1e8, 1e8), rng.uniform(-1, 1) * 10 ** rng.randrange(-30, 30), float(rng.randrange(10 ** rng.randrange(1, 18)))])
+               for _ in range(3000)]
+    for x in floats:
+        lines.append("F %d" % struct.unpack("<Q", struct.pack("<d", x))[0])
+        want.append(O.fmt_double(x))
+    for d in (0, 9217, -1, 10957, 11016, -25567, 2932896):
+        lines.append("T %d" % d)
+        want.append(O.fmt_date(d))
+    out = subprocess.run([exe], input="\n".join(lines) + "\n", capture_output=True, text=True, check=True).stdout.split("\n")
+    assert [(l, g, w) for l, g, w in zip(lines, out, want) if g != w] == []
 
 
 def test_order_limit_standins():

@@ -222,6 +222,7 @@ def test_decimal_contract(oracle):
     assert oracle.fmt_decimal((125, 3, 0), 2) == "0.12" and oracle.fmt_decimal((135, 3, 0), 2) == "0.14"
     assert oracle.fmt_double(25.522005853257337) == "25.522005853257337"
     assert oracle.fmt_double(1e21) == "1e+21" and oracle.fmt_double(100.0) == "100"
+    assert oracle.fmt_double(1e9) == "1e+09" and oracle.fmt_double(16777216.0) == "1.6777216e+07" and oracle.fmt_double(343478.59375) == "343478.59375"
     # the float32 cast the reference applies to DECIMAL columns in range predicates
     f = np.float32
     lo, hi = f(0.03) - f(0.01), f(0.03) + f(0.01)
