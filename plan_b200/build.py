@@ -23,8 +23,21 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def host_stale():
+    """the host shim binaries are older than their own sources (plan_b200/host/*.cc, *.hpp) or than the library they link"""
+    outs = [os.path.join(HERE, "host", "planhost_run"), os.path.join(HERE, "host", "planhost_append")]
+    if not all(os.path.exists(o) for o in outs):
+        return True
+    t = min(os.path.getmtime(o) for o in outs)
+    hdir = os.path.join(HERE, "host")
+    deps = [os.path.join(hdir, f) for f in os.listdir(hdir) if f.endswith((".cc", ".hpp"))] + [OUT, TPCH_OUT]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
 def build(force=False, verbose=False):
     if not force and not needs_build():
+        if host_stale():
+            build_host()
         return OUT
     objs = []
     procs = []
