@@ -161,6 +161,28 @@ def test_cpp_shim_value_formatting_agrees_with_the_oracle(tmp_path):
     assert [(l, g, w) for l, g, w in zip(lines, out, want) if g != w] == []
 
 
+def test_cpp_shim_and_python_mirror_serialise_the_same_descriptors(tmp_path):
+    """Two host sides exist above the C ABI -- the Python mirror (plan_b200/compute.py + tpch.py) and the C++ shim (plan_b200/host/
+    gpu_exec.hpp + tpch_plans.hpp).  They build the five headline plans independently; the descriptor words they hand to
+    pg_plan_compile, and the table -> slot assignment, must be identical."""
+    import subprocess
+    from plan_b200 import chunk as K, compute as X, tpch as T
+    exe = str(tmp_path / "shimplan")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), "-I/usr/local/cuda/include", "-o", exe,
+                    os.path.join(ROOT, "tests", "hostlogic", "shimplan_check.cc")], check=True, capture_output=True)
+    cpp = {}
+    for ln in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.strip().split("\n"):
+        p = ln.split(" ")
+        cpp[p[0]] = (p[1].split(","), [int(w) for w in p[2:]])
+    V = K.VarcharType()
+    q1 = T.q1_plan()                                          # the shim keeps Q1's ORDER BY l_returnflag, l_linestatus in the fused plan
+    q1 = X.PhysicalOperator(X.POT_Order, Outputs=q1.Outputs, Children=[q1], Info=X.OrderOpInfo([(X.col(0, 0, V), False), (X.col(0, 1, V), False)]))
+    for name, op in (("q6", T.q6_plan()), ("q1", q1), ("q3", T.q3_topk_plan(10)), ("q18", T.q18_plan()), ("q9", T.q9_plan())):
+        d, slots = X.serialize_plan(op)
+        assert [n for n, _ in sorted(slots.items(), key=lambda kv: kv[1])] == cpp[name][0], name
+        assert [int(w) for w in d] == cpp[name][1], name
+
+
 def test_order_limit_standins():
     from plan_b200 import chunk as K, compute as X
     dec = np.zeros(4, dtype=K.DECIMAL128)
