@@ -230,6 +230,23 @@ def test_product_host_arithmetic_agrees_with_the_oracle(tmp_path):
         nb = rng.randrange(2) if rng.random() < 0.1 else 0
         cases.append(("Q", ca, sa, na, cb, sb, nb))
         lines.append("Q %d %d %d %d %d %d" % (ca, sa, na, cb, sb, nb))
+    # govalues Add / Mul as the row programs compute them (rowvm.cuh: the exact 128-bit sum / product, then rv_fit -> hd_normalise when
+    # it has more than 19 digits or a scale above 19) against the oracle's orc_dec_add / orc_dec_mul, overflow verdicts included
+    maxc = 10 ** 19 - 1
+    for _ in range(4000):
+        ca, cb = (rng.choice([rng.randrange(10 ** rng.randrange(1, 20)), maxc, 0, 1, 5 * 10 ** rng.randrange(0, 19), rng.randrange(10 ** 18, 10 ** 19)])
+                  for _ in range(2))
+        sa, sb, na, nb = rng.randrange(0, 20), rng.randrange(0, 20), rng.randrange(2), rng.randrange(2)
+        if rng.random() < 0.5:
+            kind, mag, scale, neg = "mul", ca * cb, sa + sb, na ^ nb
+        else:
+            sc = max(sa, sb)
+            v = (-1) ** na * ca * 10 ** (sc - sa) + (-1) ** nb * cb * 10 ** (sc - sb)
+            kind, mag, scale, neg = "add", abs(v), sc, int(v < 0)
+        if mag >= 1 << 127:
+            continue
+        cases.append(("N", kind, ca, sa, na, cb, sb, nb, mag, scale, neg))
+        lines.append("N %d %d %d %d" % (neg, mag >> 64, mag & ((1 << 64) - 1), scale))
     for _ in range(4000):
         p = "".join(rng.choice("ab%_") for _ in range(rng.randrange(0, 7)))
         t = "".join(rng.choice("ab") for _ in range(rng.randrange(0, 9)))
@@ -261,6 +278,16 @@ def test_product_host_arithmetic_agrees_with_the_oracle(tmp_path):
             sel = v[ops[op]((v.astype(np.float64) / float(10 ** scale)).astype(np.float32), lit)]
             lo, hi = (int(x) for x in got.split())
             assert sorted(sel.tolist()) == list(range(max(lo, vmin), min(hi, vmax) + 1)), (case, got)
+        elif case[0] == "N":
+            _, kind, ca, sa, na, cb, sb, nb, mag, scale, neg = case
+            oc, os_, on = C.c_uint64(), C.c_int(), C.c_int()
+            rc = getattr(L, "orc_dec_" + kind)(C.c_uint64(ca), sa, na, C.c_uint64(cb), sb, nb, C.byref(oc), C.byref(os_), C.byref(on))
+            mine = ("ok %d %d %d" % (mag, scale, neg)) if mag <= maxc and scale <= 19 else got      # rv_fit keeps what already fits
+            if rc != 0:
+                assert mine == "fail", (case, mine)
+            else:
+                m = mine.split()
+                assert m[:3] == ["ok", str(oc.value), str(os_.value)] and (oc.value == 0 or m[3] == str(on.value)), (case, mine, oc.value, os_.value, on.value)
         elif case[0] == "Q":
             _, ca, sa, na, cb, sb, nb = case
             oc, os_, on = C.c_uint64(), C.c_int(), C.c_int()
