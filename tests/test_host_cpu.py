@@ -183,6 +183,57 @@ def test_cpp_shim_and_python_mirror_serialise_the_same_descriptors(tmp_path):
         assert [int(w) for w in d] == cpp[name][1], name
 
 
+def test_descriptor_constants_agree_across_header_python_go_and_the_row_oracle():
+    """include/plangpu_desc.h is the one definition of the descriptor vocabulary; the Python mirror (compute.py, chunk.py), the Go
+    serializer that cannot be compiled here (integration/go/compute/gpu_serialize.go) and the row oracle restate the numbers.  A drift
+    in any of them would mis-encode plans silently: compare them all with the header."""
+    from oracle import rowexec as R
+    from plan_b200 import _lib as L, chunk as K, compute as X
+    hdr = open(os.path.join(ROOT, "include", "plangpu_desc.h")).read()
+    H = {m.group(1): int(m.group(2), 0) for m in re.finditer(r"#define\s+(PG_[A-Z0-9_]+)\s+(0x[0-9a-fA-F]+|\d+)", hdr)}
+    fn_names = {"+": "ADD", "-": "SUB", "*": "MUL", "/": "DIV", "=": "EQ", "<>": "NE", "<": "LT", "<=": "LE", ">": "GT", ">=": "GE", "in": "IN",
+                "like": "LIKE", "not like": "NOT_LIKE", "extract": "EXTRACT", "and": "AND", "or": "OR", "not": "NOT", "case": "CASE", "cast": "CAST"}
+    assert set(X.FUNC_IDS) == set(fn_names)
+    for name, cid in fn_names.items():
+        assert X.FUNC_IDS[name] == H["PG_FN_" + cid], name
+    assert X.AGG_IDS == {k.lower(): H["PG_AGG_" + k] for k in ("SUM", "AVG", "COUNT", "MIN", "MAX")}
+    assert (X.PG_TK_COL, X.PG_TK_CONST, X.PG_TK_STR, X.PG_TK_FUNC) == tuple(H["PG_TK_" + k] for k in ("COL", "CONST", "STR", "FUNC"))
+    assert (X.PG_DESC_MAGIC, X.PG_DESC_VERSION) == (H["PG_DESC_MAGIC"], H["PG_DESC_VERSION"])
+    joins = ("INNER", "SEMI", "ANTI", "MARK", "LEFT", "ANTI_MARK")
+    assert tuple(getattr(X, "JOIN_" + k) for k in joins) == tuple(H["PG_JOIN_" + k] for k in joins) == tuple(getattr(R, "JOIN_" + k) for k in joins)
+    lts = ("BOOLEAN", "INTEGER", "BIGINT", "DATE", "DECIMAL", "FLOAT", "DOUBLE", "VARCHAR", "HUGEINT")
+    assert tuple(getattr(K, "LTID_" + k) for k in lts) == tuple(H["PG_LT_" + k] for k in lts) == tuple(getattr(R, "LT_" + k) for k in lts)
+    # the row oracle's pg_type numbering against include/plangpu.h (through the ctypes mirror)
+    for k in ("INT32", "INT64", "DATE32", "DECIMAL64", "CHAR1", "DICT8", "FLOAT64", "HUGEINT", "DECIMAL128", "VARCHAR"):
+        assert getattr(R, "T_" + k) == getattr(L, "PG_T_" + k), k
+    # the Go serializer
+    go = open(os.path.join(ROOT, "integration", "go", "compute", "gpu_serialize.go")).read()
+
+    def go_tuple(lhs):
+        m = re.search(re.escape(lhs) + r"\s*=\s*([0-9, ]+)", go)
+        assert m, lhs
+        return tuple(int(x) for x in m.group(1).replace(" ", "").split(",") if x)
+    assert go_tuple("pgOpScan, pgOpFilter, pgOpJoin, pgOpAgg, pgOpTopK, pgOpProject") == tuple(
+        H["PG_OP_" + k] for k in ("SCAN", "FILTER", "JOIN", "AGG", "TOPK", "PROJECT"))
+    assert go_tuple("pgTkCol, pgTkConst, pgTkStr, pgTkFunc") == tuple(H["PG_TK_" + k] for k in ("COL", "CONST", "STR", "FUNC"))
+    assert go_tuple("pgLtBoolean, pgLtInteger, pgLtBigint, pgLtDate, pgLtDecimal") + go_tuple("pgLtFloat, pgLtDouble, pgLtVarchar, pgLtHugeint") == tuple(
+        H["PG_LT_" + k] for k in lts)
+    assert re.search(r"pgDescMagic\s*=\s*0x31504750", go) and re.search(r"pgDescVersion\s*=\s*1\b", go)
+    go_fn = {"FuncAdd": "ADD", "FuncSubtract": "SUB", "FuncMultiply": "MUL", "FuncDivide": "DIV", "FuncEqual": "EQ", "FuncNotEqual": "NE", "FuncLess": "LT",
+             "FuncLessEqual": "LE", "FuncGreater": "GT", "FuncGreaterEqual": "GE", "FuncIn": "IN", "FuncLike": "LIKE", "FuncNotLike": "NOT_LIKE",
+             "FuncExtract": "EXTRACT", "FuncAnd": "AND", "FuncOr": "OR", "FuncNot": "NOT", "FuncCase": "CASE", "FuncCast": "CAST"}
+    body = go[go.index("var pgFuncIDs"):go.index("var pgAggIDs")]
+    got = {m.group(1): int(m.group(2)) for m in re.finditer(r"(Func[A-Za-z]+):\s*(\d+)", body)}
+    assert got == {k: H["PG_FN_" + v] for k, v in go_fn.items()}
+    body = go[go.index("var pgAggIDs"):go.index("var pgJoinTypes")]
+    assert {m.group(1): int(m.group(2)) for m in re.finditer(r'"([a-z]+)":\s*(\d+)', body)} == X.AGG_IDS
+    body = go[go.index("var pgJoinTypes"):go.index("// errNotOffloadable")]
+    got = {m.group(1): int(m.group(2)) for m in re.finditer(r"LOT_JoinType([A-Za-z]+):\s*(\d+)", body)}
+    assert got == {"Inner": 1, "SEMI": 2, "ANTI": 3, "MARK": 4, "Left": 5, "AntiMARK": 6} == {
+        "Inner": H["PG_JOIN_INNER"], "SEMI": H["PG_JOIN_SEMI"], "ANTI": H["PG_JOIN_ANTI"], "MARK": H["PG_JOIN_MARK"], "Left": H["PG_JOIN_LEFT"],
+        "AntiMARK": H["PG_JOIN_ANTI_MARK"]}
+
+
 def test_order_limit_standins():
     from plan_b200 import chunk as K, compute as X
     dec = np.zeros(4, dtype=K.DECIMAL128)
