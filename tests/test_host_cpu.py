@@ -234,6 +234,40 @@ def test_descriptor_constants_agree_across_header_python_go_and_the_row_oracle()
         "AntiMARK": H["PG_JOIN_ANTI_MARK"]}
 
 
+def test_go_bindings_call_only_declared_functions_with_the_declared_arity():
+    """The cgo bindings (integration/go) cannot be compiled in this image; at least every C.pg_* call they make must name a function
+    include/plangpu.h declares, with the number of arguments it declares."""
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "plangpu.h")).read(), flags=re.S)
+    decl = {}
+    for m in re.finditer(r"\b(pg_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S):
+        args = m.group(2).strip()
+        decl[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    go = ""
+    for d, _, fs in os.walk(os.path.join(ROOT, "integration", "go")):
+        for f in fs:
+            if f.endswith(".go"):
+                go += open(os.path.join(d, f)).read()
+    calls = {}
+    for m in re.finditer(r"C\.(pg_[a-z0-9_]+)\(", go):
+        i, depth, commas, seen = m.end(), 1, 0, False
+        while depth:
+            c = go[i]
+            if c == "(":
+                depth += 1
+            elif c == ")":
+                depth -= 1
+            elif c == "," and depth == 1:
+                commas += 1
+            elif not c.isspace():
+                seen = True
+            i += 1
+        calls.setdefault(m.group(1), set()).add(commas + 1 if seen else 0)
+    assert len(calls) >= 25
+    for name, arities in calls.items():
+        assert name in decl, "Go calls undeclared %s" % name
+        assert arities == {decl[name]}, (name, arities, decl[name])
+
+
 def test_order_limit_standins():
     from plan_b200 import chunk as K, compute as X
     dec = np.zeros(4, dtype=K.DECIMAL128)
