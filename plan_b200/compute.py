@@ -453,6 +453,20 @@ def drain(exec_):
     return chunks
 
 
+class _Descending:
+    """sort key wrapper that inverts the order of values without a unary minus (VARCHAR keys of ORDER BY ... DESC)"""
+    __slots__ = ("v",)
+
+    def __init__(self, v):
+        self.v = v
+
+    def __lt__(self, other):
+        return other.v < self.v
+
+    def __eq__(self, other):
+        return self.v == other.v
+
+
 def order_limit(chunks, order_by, limit=None):
     """Host stand-in for the parents that stay in Go: Order (normalized keys,
     /root/reference/pkg/compute/sort_encoder.go:65-81: a DECIMAL key is Int64(2), i.e. rounded
@@ -480,7 +494,7 @@ def order_limit(chunks, order_by, limit=None):
             else:
                 part = (v.I64,)
             if desc:
-                part = tuple(-x for x in part)
+                part = tuple(_Descending(x) if isinstance(x, str) else -x for x in part)
             k.append(part)
         return k
     rows.sort(key=key)

@@ -279,6 +279,11 @@ def test_order_limit_standins():
     ch.Count = 4
     rows = X.order_limit([ch], [(1, True), (2, False)], 3)
     assert [r[0].I64 for r in rows] == [2, 4, 1]              # 10.01 first; tie on 10.00 broken by date
+    ch2 = K.Chunk()
+    ch2.Data = [K.Vector(K.VarcharType(), np.array([b"PERU", b"BRAZIL", b"CANADA", b"PERU"], dtype=object)), K.Vector(K.IntegerType(), np.array([1, 2, 3, 4], np.int32))]
+    ch2.Count = 4
+    rows = X.order_limit([ch2], [(0, True), (1, True)])        # ORDER BY name DESC, n DESC
+    assert [r[1].I64 for r in rows] == [4, 1, 3, 2]
 
 
 def test_oracle_is_not_reachable_from_the_product():
